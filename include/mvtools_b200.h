@@ -1,0 +1,298 @@
+/*
+ * mvtools_b200.h -- C ABI of the B200 (sm_100a) engine behind the mv.* hot path.
+ *
+ * One shared library, libmvtools_b200.so, exports exactly the functions declared
+ * here: plain C, POD structs, raw pointers and sizes -- no C++ and no torch types
+ * cross this boundary.  Each entry point names the reference interface it
+ * replaces (file:line under dubhater/vapoursynth-mvtools @ e516e90).
+ *
+ *   reference (CPU)                                   this ABI (GPU)
+ *   ------------------------------------------------  -----------------------------
+ *   mvsuperCreate      MVSuper.c:140-275              mvb200_super_init
+ *   mvsuperGetFrame    MVSuper.c:43-126               mvb200_super_frame / _batch
+ *   mvanalyseCreate    MVAnalyse.c:267-635            mvb200_analyse_init
+ *   mvanalyseGetFrame  MVAnalyse.c:76-254             mvb200_analyse_frame / _batch
+ *     gopSearchMVs     GroupOfPlanes.c:69-125           (inside the search kernel)
+ *     doPobSearchMVs   PlaneOfBlocks.cpp:971-1131       (inside the search kernel)
+ *   mvdegrainCreate<r> MVDegrains.cpp:512-809         mvb200_degrain_init
+ *   mvdegrainGetFrame  MVDegrains.cpp:85-330          mvb200_degrain_frame / _batch
+ *   mvcompensateCreate/GetFrame MVCompensate.c:73-575 mvb200_compensate_init / _frame
+ *   mvrecalculateCreate/GetFrame MVRecalculate.c:68-553 mvb200_recalculate_init / _frame
+ *
+ * The VapourSynth plugin (vapoursynth-mvtools_b200/plugin, exporting
+ * VapourSynthPluginInit2 like EntryPoint.c:28-50) is a thin host-side glue over
+ * these functions; INTEGRATION.md shows the binding a maintainer of the
+ * reference would add to call them from the existing filters.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     retrievable with mvb200_last_error() (thread-local) and, for the *_init
+ *     functions, is byte-identical to the reference's mapSetError text;
+ *   - "host" pointers are ordinary CPU memory (pinned or not); "dev" pointers are
+ *     CUDA device memory on the context's device;
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry
+ *     point fails loudly.
+ */
+#ifndef MVTOOLS_B200_H
+#define MVTOOLS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define MVB200_API __attribute__((visibility("default")))
+#else
+#define MVB200_API
+#endif
+
+/* "argument not given" marker for every optional filter argument below */
+#define MVB200_UNSET INT32_MIN
+#define MVB200_UNSET64 INT64_MIN
+
+#define MVB200_MAX_LEVELS 32
+#define MVB200_MAX_RADIUS 6
+
+/* MVPlaneSet, MVFrame.h:23-28 */
+enum { MVB200_YPLANE = 1, MVB200_UPLANE = 2, MVB200_VPLANE = 4, MVB200_YUVPLANES = 7 };
+
+/* VECTOR, MVAnalysisData.h:40-44 -- 16 bytes, the unit of the MVTools_vectors blob */
+typedef struct mvb200_vector {
+    int32_t x;
+    int32_t y;
+    int64_t sad;
+} mvb200_vector;
+
+/* MVAnalysisData, MVAnalysisData.h:83-134 -- the 84-byte MVTools_MVAnalysisData prop */
+typedef struct mvb200_analysis_data {
+    int32_t nMagicKey, nVersion;
+    int32_t nBlkSizeX, nBlkSizeY, nPel, nLvCount, nDeltaFrame, isBackward, nCPUFlags, nMotionFlags;
+    int32_t nWidth, nHeight, nOverlapX, nOverlapY, nBlkX, nBlkY, bitsPerSample, yRatioUV, xRatioUV;
+    int32_t nHPadding, nVPadding;
+} mvb200_analysis_data;
+
+/* ------------------------------------------------------------------ Super */
+
+/* Arguments of mv.Super (MVSuper.c:279-291) + the input clip's format.
+ * Set the "in" fields (MVB200_UNSET for "argument not given"), call mvb200_super_init. */
+typedef struct mvb200_super_params {
+    /* in: clip format */
+    int32_t width, height, bits;  /* bits 8..16 */
+    int32_t ssw, ssh;             /* log2 chroma subsampling (0 or 1) */
+    int32_t gray;                 /* 1 = single plane */
+    /* in: filter arguments, MVB200_UNSET = default (MVSuper.c:149-177) */
+    int32_t hpad, vpad, pel, levels, chroma, sharp, rfilter;
+    /* out (derived): */
+    int32_t nplanes;              /* 1 or 3 */
+    int32_t xRatioUV, yRatioUV;
+    int32_t modeyuv;              /* Super_modeyuv */
+    int32_t super_width, super_height; /* luma size of the super frame (MVSuper.c:254-262) */
+} mvb200_super_params;
+
+/* Geometry of one (plane, level) inside a super frame.  All rows of a plane share
+ * one pitch; `row0` is the first row of the level's sub-plane 0 inside the plane
+ * (PlaneSuperOffset, MVFrame.cpp:1229-1247, divided by the pitch). */
+typedef struct mvb200_level_geom {
+    int32_t width, height;        /* interior */
+    int32_t hpad, vpad;
+    int32_t padded_w, padded_h;
+    int32_t pel;                  /* pel of this level (level>0: 1) */
+    int32_t row0;
+} mvb200_level_geom;
+
+typedef struct mvb200_super_geom {
+    int32_t nplanes, levels;
+    int32_t plane_w[3], plane_h[3];            /* super-frame plane sizes in samples/rows */
+    mvb200_level_geom lv[3][MVB200_MAX_LEVELS];
+} mvb200_super_geom;
+
+/* ---------------------------------------------------------------- Analyse */
+
+/* Arguments of mv.Analyse (MVAnalyse.c:639-671).  MVB200_UNSET = not given. */
+typedef struct mvb200_analyse_args {
+    int32_t blksize, blksizev, levels, search, searchparam, pelsearch, isb, lambda, chroma, delta,
+        truemotion, lsad, plevel, global, pnew, pzero, pglobal, overlap, overlapv, divide, badsad,
+        badrange, opt, meander, trymany, fields, tff, search_coarse, dct;
+} mvb200_analyse_args;
+
+/* Fully resolved search parameters (what MVAnalyseData holds after mvanalyseCreate). */
+typedef struct mvb200_analyse_params {
+    mvb200_analysis_data ad;      /* the prop written on every vector frame */
+    int32_t divide;               /* divideExtra */
+    mvb200_analysis_data ad_divided;
+    int32_t search, search_coarse, nSearchParam, nPelSearch;
+    int32_t nLambda, lsad, pnew, plevel, global, pglobal, pzero;
+    int64_t badSAD;
+    int32_t badrange, meander, tryMany, dctmode, chroma;
+    int32_t fields, tff, tff_exists;
+    /* super-clip facts (Super_* props) */
+    int32_t super_hpad, super_vpad, super_pel, super_modeyuv, super_levels;
+    int32_t ssw, ssh, gray;
+    int32_t num_frames;
+    /* level geometry of the search (gopInit, GroupOfPlanes.c:25-56) */
+    int32_t nBlkX[MVB200_MAX_LEVELS], nBlkY[MVB200_MAX_LEVELS];
+    int32_t vectors_size;         /* gopGetArraySize: bytes of the MVTools_vectors blob */
+} mvb200_analyse_params;
+
+/* ---------------------------------------------------------------- Degrain */
+
+typedef struct mvb200_degrain_args {
+    int32_t radius;               /* 1..6 (Degrain1..Degrain6) */
+    int64_t thsad, thsadc;        /* MVB200_UNSET64 = default */
+    int32_t plane;                /* MVB200_UNSET = default (4) */
+    int32_t limit, limitc;        /* MVB200_UNSET = default */
+    int64_t thscd1;               /* MVB200_UNSET64 = default */
+    int32_t thscd2;               /* MVB200_UNSET = default */
+} mvb200_degrain_args;
+
+typedef struct mvb200_degrain_params {
+    int32_t radius;
+    mvb200_analysis_data vd[2 * MVB200_MAX_RADIUS]; /* per vector clip, order mvbw,mvfw,mvbw2,... */
+    int64_t thSAD[3];
+    int32_t nLimit[3];
+    int64_t nSCD1;
+    int32_t nSCD2;
+    int32_t process[3];
+    int32_t YUVplanes;
+    int32_t bits, ssw, ssh, gray, nplanes;
+    int32_t super_hpad, super_vpad, super_pel, super_modeyuv, super_levels;
+    int32_t nWidth[3], nHeight[3], nOverlapX[3], nOverlapY[3], nBlkSizeX[3], nBlkSizeY[3], nWidth_B[3], nHeight_B[3];
+} mvb200_degrain_params;
+
+/* ------------------------------------------------------- Compensate / Recalculate */
+
+typedef struct mvb200_compensate_args {
+    int32_t scbehavior;           /* MVB200_UNSET = default (1) */
+    int64_t thsad;                /* MVB200_UNSET64 = default (10000) */
+    int32_t fields;               /* MVB200_UNSET = default (0) */
+    double time;                  /* NaN = default (100.0) */
+    int64_t thscd1;               /* MVB200_UNSET64 = default */
+    int32_t thscd2;
+    int32_t tff;                  /* MVB200_UNSET = not given */
+} mvb200_compensate_args;
+
+typedef struct mvb200_compensate_params {
+    mvb200_analysis_data vd;
+    int32_t scBehavior, fields, tff, tff_exists, time256;
+    int64_t thSAD;
+    int64_t nSCD1;
+    int32_t nSCD2;
+    int32_t bits, ssw, ssh, gray, nplanes;
+    int32_t super_hpad, super_vpad, super_pel, super_modeyuv, super_levels;
+    int32_t nWidth[3], nHeight[3], nOverlapX[3], nOverlapY[3], nBlkSizeX[3], nBlkSizeY[3], nWidth_B[3], nHeight_B[3];
+    int32_t num_frames;
+} mvb200_compensate_params;
+
+typedef struct mvb200_recalculate_args {
+    int64_t thsad;                /* MVB200_UNSET64 = default (200) */
+    int32_t smooth, blksize, blksizev, search, searchparam, lambda, chroma, truemotion, pnew, overlap,
+        overlapv, divide, opt, meander, fields, tff, dct;
+} mvb200_recalculate_args;
+
+typedef struct mvb200_recalculate_params {
+    mvb200_analysis_data ad;      /* new analysis data (written as the prop) */
+    mvb200_analysis_data ad_divided;
+    mvb200_analysis_data old;     /* analysis data of the input vector clip */
+    int32_t divide, search, nSearchParam, nLambda, pnew, smooth, meander, dctmode, chroma;
+    int64_t thSAD;
+    int32_t fields, tff, tff_exists;
+    int32_t super_hpad, super_vpad, super_pel, super_modeyuv, super_levels;
+    int32_t ssw, ssh, gray;
+    int32_t num_frames;
+    int32_t vectors_size;
+} mvb200_recalculate_params;
+
+/* ------------------------------------------------------------- host logic */
+/* (pure host code: usable without a GPU; restates the reference's *Create) */
+
+MVB200_API const char *mvb200_last_error(void);
+MVB200_API const char *mvb200_version(void);
+
+/* MVSuper.c:140-264.  Returns non-zero and sets the reference's message on bad input. */
+MVB200_API int mvb200_super_init(mvb200_super_params *p);
+MVB200_API void mvb200_super_geometry(const mvb200_super_params *p, mvb200_super_geom *g);
+
+/* MVAnalyse.c:267-624.  `sp` describes the super clip (the Super_* props), num_frames its length. */
+MVB200_API int mvb200_analyse_init(const mvb200_analyse_args *a, const mvb200_super_params *sp, int num_frames, mvb200_analyse_params *out);
+
+/* MVDegrains.cpp:512-782.  vd[2*radius]: MVAnalysisData of mvbw,mvfw,mvbw2,...;
+ * (clip_w, clip_h) the source clip size. */
+MVB200_API int mvb200_degrain_init(const mvb200_degrain_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd, int clip_w, int clip_h, mvb200_degrain_params *out);
+
+/* MVCompensate.c:419-575 */
+MVB200_API int mvb200_compensate_init(const mvb200_compensate_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd, int clip_w, int clip_h, int num_frames, mvb200_compensate_params *out);
+
+/* MVRecalculate.c:263-553 */
+MVB200_API int mvb200_recalculate_init(const mvb200_recalculate_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *old, int num_frames, mvb200_recalculate_params *out);
+
+/* ---------------------------------------------------------------- context */
+
+typedef struct mvb200_ctx mvb200_ctx;
+
+/* Binds a context to CUDA device `device` (own stream, scratch pools).  Fails if
+ * the device is missing or is not compute capability 10.x. */
+MVB200_API int mvb200_ctx_create(int device, mvb200_ctx **out);
+MVB200_API void mvb200_ctx_destroy(mvb200_ctx *ctx);
+MVB200_API int mvb200_ctx_synchronize(mvb200_ctx *ctx);
+/* the cudaStream_t the context launches on (for CUDA-event timing by the caller) */
+MVB200_API void *mvb200_ctx_stream(mvb200_ctx *ctx);
+/* number of kernels this context has launched so far */
+MVB200_API int64_t mvb200_ctx_launch_count(mvb200_ctx *ctx);
+
+/* Device frame layout used by the *_batch functions: planes are stored one after
+ * another, each with its own pitch (bytes), frames one after another.
+ * pitch[p] = round_up(plane_w[p]*bytes, 256); offsets are from the frame start. */
+typedef struct mvb200_frame_layout {
+    int32_t nplanes, bytes_per_sample;
+    int32_t plane_w[3], plane_h[3];
+    int64_t pitch[3], offset[3];
+    int64_t frame_bytes;
+} mvb200_frame_layout;
+
+MVB200_API void mvb200_clip_layout(const mvb200_super_params *p, mvb200_frame_layout *l);  /* source / output frames */
+MVB200_API void mvb200_super_layout(const mvb200_super_params *p, mvb200_frame_layout *l); /* super frames */
+
+/* ------------------------------------------- device-resident batch entry points */
+/* n frames, contiguous in device memory in the layouts above. */
+
+/* mvsuperGetFrame (MVSuper.c:43-126) for frames [0,n). */
+MVB200_API int mvb200_super_batch(mvb200_ctx *ctx, const mvb200_super_params *p, const void *dev_src, void *dev_super, int n);
+
+/* mvanalyseGetFrame (MVAnalyse.c:76-254) for frames [first, first+n) of a clip whose
+ * super frames [0,num_frames) are resident at dev_super.  dev_vectors receives n
+ * blobs of ap->vectors_size bytes each (stride vectors_stride bytes, >= size). */
+MVB200_API int mvb200_analyse_batch(mvb200_ctx *ctx, const mvb200_analyse_params *ap, const mvb200_super_params *sp, const void *dev_super, int first, int n, void *dev_vectors, int64_t vectors_stride);
+
+/* Several mv.Analyse instances over the same super clip in ONE launch (the
+ * 2*radius vector clips a DegrainN consumes): nap parameter sets, dev_vectors[i]
+ * receives the n blobs of instance i. */
+MVB200_API int mvb200_analyse_multi_batch(mvb200_ctx *ctx, const mvb200_analyse_params *const *ap, int nap, const mvb200_super_params *sp, const void *dev_super, int first, int n, void *const *dev_vectors, int64_t vectors_stride);
+
+/* mvdegrainGetFrame<radius> (MVDegrains.cpp:85-330) for frames [first, first+n).
+ * dev_vectors[r] = blobs of vector clip r for frames [first, first+n) (same stride). */
+MVB200_API int mvb200_degrain_batch(mvb200_ctx *ctx, const mvb200_degrain_params *dp, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int num_frames, int first, int n, const void *const *dev_vectors, int64_t vectors_stride, void *dev_dst);
+
+/* --------------------------------------------- host-buffer per-frame entry points */
+/* (what the VapourSynth plugin calls from GetFrame; H2D/D2H copies inside) */
+
+MVB200_API int mvb200_super_frame(mvb200_ctx *ctx, const mvb200_super_params *p, const uint8_t *const src[3], const ptrdiff_t src_stride[3], uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
+
+/* src_super/ref_super: host super frames (ref may be NULL when nref is out of range:
+ * the default blob of gopWriteDefaultToArray, GroupOfPlanes.c:150-164, is written). */
+MVB200_API int mvb200_analyse_frame(mvb200_ctx *ctx, const mvb200_analyse_params *ap, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], int field_shift, uint8_t *vectors_out);
+
+/* refs[r] may be NULL (frame out of range); vectors[r] are host blobs. */
+MVB200_API int mvb200_degrain_frame(mvb200_ctx *ctx, const mvb200_degrain_params *dp, const mvb200_super_params *sp, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const *const ref_super /* [2r][3] flattened */, const ptrdiff_t *ref_stride /* [2r][3] */, const uint8_t *const *vectors /* [2r] */, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
+
+MVB200_API int mvb200_compensate_frame(mvb200_ctx *ctx, const mvb200_compensate_params *cp, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *vectors, int field_shift, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
+
+MVB200_API int mvb200_recalculate_frame(mvb200_ctx *ctx, const mvb200_recalculate_params *rp, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *old_vectors, int field_shift, uint8_t *vectors_out);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* MVTOOLS_B200_H */

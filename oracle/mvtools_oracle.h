@@ -1,0 +1,36 @@
+/* TEST INFRASTRUCTURE -- CPU oracle for the mv.* hot path.  See mvtools_oracle.c.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load
+ * this; the product (libmvtools_b200.so, the plugin) never does. */
+#ifndef MVTOOLS_ORACLE_H
+#define MVTOOLS_ORACLE_H
+
+#include "../include/mvtools_b200.h" /* POD parameter structs only */
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVO_API __attribute__((visibility("default")))
+
+MVO_API const char *mvo_last_error(void);
+
+/* mvsuperGetFrame, MVSuper.c:43-126 */
+MVO_API int mvo_super_frame(const mvb200_super_params *p, const uint8_t *const src[3], const ptrdiff_t src_stride[3], uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
+
+/* mvanalyseGetFrame, MVAnalyse.c:76-254 (ref_super == NULL -> default blob) */
+MVO_API int mvo_analyse_frame(const mvb200_analyse_params *ap, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], int field_shift, uint8_t *vectors_out);
+
+/* mvdegrainGetFrame<radius>, MVDegrains.cpp:85-330 */
+MVO_API int mvo_degrain_frame(const mvb200_degrain_params *dp, const mvb200_super_params *sp, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const *ref_super, const ptrdiff_t *ref_stride, const uint8_t *const *vectors, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
+
+/* overInit, Overlap.cpp:40-125: 9 windows of nx*ny int16 */
+MVO_API void mvo_overlap_windows(int nx, int ny, int ox, int oy, int16_t *out9);
+
+/* kernels exposed for unit parity tests */
+MVO_API unsigned mvo_sad(const uint8_t *a, ptrdiff_t apitch, const uint8_t *b, ptrdiff_t bpitch, int w, int h, int bytes);
+MVO_API unsigned mvo_satd(const uint8_t *a, ptrdiff_t apitch, const uint8_t *b, ptrdiff_t bpitch, int w, int h, int bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

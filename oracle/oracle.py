@@ -1,0 +1,86 @@
+"""TEST INFRASTRUCTURE: ctypes binding of the CPU oracle (oracle/_ref/liboracle.so).
+Takes the same POD parameter structs as the C ABI (vapoursynth-mvtools_b200/mvtools_b200.py)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(_HERE, "..", "vapoursynth-mvtools_b200"))
+import mvtools_b200 as mb  # noqa: E402  (struct definitions only)
+
+_LIB = None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(os.path.join(_HERE, "_ref", "liboracle.so"))
+        L.mvo_last_error.restype = C.c_char_p
+        vp, PP = C.c_void_p, C.POINTER
+        L.mvo_super_frame.argtypes = [PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
+        L.mvo_analyse_frame.argtypes = [PP(mb.AnalyseParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp),
+                                        PP(C.c_ssize_t), C.c_int, vp]
+        L.mvo_degrain_frame.argtypes = [PP(mb.DegrainParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp),
+                                        PP(C.c_ssize_t), PP(vp), PP(vp), PP(C.c_ssize_t)]
+        L.mvo_overlap_windows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        L.mvo_overlap_windows.restype = None
+        for n in ("mvo_sad", "mvo_satd"):
+            f = getattr(L, n)
+            f.restype = C.c_uint
+            f.argtypes = [vp, C.c_ssize_t, vp, C.c_ssize_t, C.c_int, C.c_int, C.c_int]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc:
+        raise RuntimeError(lib().mvo_last_error().decode())
+
+
+def super_frame(sp, src_planes):
+    g = mb.SuperGeom()
+    # geometry comes with the params; plane sizes follow MVSuper.c:254-262
+    pw = [sp.super_width] + [sp.super_width >> sp.ssw] * 2
+    ph = [sp.super_height] + [sp.super_height >> sp.ssh] * 2
+    dst = mb.alloc_planes(pw[: sp.nplanes], ph[: sp.nplanes], sp.bits, fill=0xA5)
+    s, ss = mb.plane_ptrs(src_planes)
+    d, ds = mb.plane_ptrs(dst)
+    _check(lib().mvo_super_frame(C.byref(sp), s, ss, d, ds))
+    return dst
+
+
+def analyse_frame(ap, sp, src_super, ref_super, field_shift=0):
+    out = np.zeros(ap.vectors_size, dtype=np.uint8)
+    s, ss = mb.plane_ptrs(src_super)
+    if ref_super is None:
+        r, rs = None, None
+    else:
+        r, rs = mb.plane_ptrs(ref_super)
+    _check(lib().mvo_analyse_frame(C.byref(ap), C.byref(sp), s, ss, r, rs, field_shift, out.ctypes.data))
+    return out
+
+
+def degrain_frame(dp, sp, src_planes, ref_supers, vectors):
+    n = 2 * dp.radius
+    refs = (C.c_void_p * (3 * n))()
+    rstr = (C.c_ssize_t * (3 * n))()
+    for r in range(n):
+        if ref_supers[r] is None:
+            continue
+        for p, a in enumerate(ref_supers[r]):
+            refs[r * 3 + p] = a.ctypes.data
+            rstr[r * 3 + p] = a.strides[0]
+    vecs = (C.c_void_p * n)(*[v.ctypes.data for v in vectors])
+    dst = mb.alloc_planes([a.shape[1] for a in src_planes], [a.shape[0] for a in src_planes], dp.bits, fill=0xA5)
+    s, ss = mb.plane_ptrs(src_planes)
+    d, ds = mb.plane_ptrs(dst)
+    _check(lib().mvo_degrain_frame(C.byref(dp), C.byref(sp), s, ss, refs, rstr, vecs, d, ds))
+    return dst
+
+
+def overlap_windows(nx, ny, ox, oy):
+    out = np.zeros((9, ny, nx), dtype=np.int16)
+    lib().mvo_overlap_windows(nx, ny, ox, oy, out.ctypes.data)
+    return out

@@ -1,0 +1,293 @@
+"""ctypes binding of include/mvtools_b200.h (libmvtools_b200.so).
+
+This is the thin Python face of the C ABI: the structs below mirror the header field
+for field, and `lib()` loads the in-tree shared library.  There is no Python or CPU
+implementation behind it -- if the CUDA library cannot be loaded, importing works but
+every call raises, loudly (`lib()` raises RuntimeError)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmvtools_b200.so")
+PLUGIN_PATH = os.path.join(_HERE, "libmvtools.so")
+
+UNSET = -(2 ** 31)
+UNSET64 = -(2 ** 63)
+MAX_LEVELS = 32
+MAX_RADIUS = 6
+
+i32, i64 = C.c_int32, C.c_int64
+
+
+class Vector(C.Structure):
+    _fields_ = [("x", i32), ("y", i32), ("sad", i64)]
+
+
+class AnalysisData(C.Structure):
+    _fields_ = [(n, i32) for n in (
+        "nMagicKey", "nVersion", "nBlkSizeX", "nBlkSizeY", "nPel", "nLvCount", "nDeltaFrame", "isBackward",
+        "nCPUFlags", "nMotionFlags", "nWidth", "nHeight", "nOverlapX", "nOverlapY", "nBlkX", "nBlkY",
+        "bitsPerSample", "yRatioUV", "xRatioUV", "nHPadding", "nVPadding")]
+
+
+class SuperParams(C.Structure):
+    _fields_ = [(n, i32) for n in (
+        "width", "height", "bits", "ssw", "ssh", "gray",
+        "hpad", "vpad", "pel", "levels", "chroma", "sharp", "rfilter",
+        "nplanes", "xRatioUV", "yRatioUV", "modeyuv", "super_width", "super_height")]
+
+
+class LevelGeom(C.Structure):
+    _fields_ = [(n, i32) for n in ("width", "height", "hpad", "vpad", "padded_w", "padded_h", "pel", "row0")]
+
+
+class SuperGeom(C.Structure):
+    _fields_ = [("nplanes", i32), ("levels", i32), ("plane_w", i32 * 3), ("plane_h", i32 * 3),
+                ("lv", (LevelGeom * MAX_LEVELS) * 3)]
+
+
+ANALYSE_ARGS = ("blksize", "blksizev", "levels", "search", "searchparam", "pelsearch", "isb", "lambda", "chroma",
+                "delta", "truemotion", "lsad", "plevel", "global", "pnew", "pzero", "pglobal", "overlap", "overlapv",
+                "divide", "badsad", "badrange", "opt", "meander", "trymany", "fields", "tff", "search_coarse", "dct")
+
+
+class AnalyseArgs(C.Structure):
+    _fields_ = [(n, i32) for n in ANALYSE_ARGS]
+
+
+class AnalyseParams(C.Structure):
+    _fields_ = [("ad", AnalysisData), ("divide", i32), ("ad_divided", AnalysisData)] + \
+        [(n, i32) for n in ("search", "search_coarse", "nSearchParam", "nPelSearch", "nLambda", "lsad", "pnew",
+                            "plevel", "global_", "pglobal", "pzero")] + \
+        [("badSAD", i64)] + \
+        [(n, i32) for n in ("badrange", "meander", "tryMany", "dctmode", "chroma", "fields", "tff", "tff_exists",
+                            "super_hpad", "super_vpad", "super_pel", "super_modeyuv", "super_levels",
+                            "ssw", "ssh", "gray", "num_frames")] + \
+        [("nBlkX", i32 * MAX_LEVELS), ("nBlkY", i32 * MAX_LEVELS), ("vectors_size", i32)]
+
+
+class DegrainArgs(C.Structure):
+    _fields_ = [("radius", i32), ("thsad", i64), ("thsadc", i64), ("plane", i32), ("limit", i32), ("limitc", i32),
+                ("thscd1", i64), ("thscd2", i32)]
+
+
+class DegrainParams(C.Structure):
+    _fields_ = [("radius", i32), ("vd", AnalysisData * (2 * MAX_RADIUS)), ("thSAD", i64 * 3), ("nLimit", i32 * 3),
+                ("nSCD1", i64), ("nSCD2", i32), ("process", i32 * 3), ("YUVplanes", i32)] + \
+        [(n, i32) for n in ("bits", "ssw", "ssh", "gray", "nplanes", "super_hpad", "super_vpad", "super_pel",
+                            "super_modeyuv", "super_levels")] + \
+        [(n, i32 * 3) for n in ("nWidth", "nHeight", "nOverlapX", "nOverlapY", "nBlkSizeX", "nBlkSizeY",
+                                "nWidth_B", "nHeight_B")]
+
+
+class FrameLayout(C.Structure):
+    _fields_ = [("nplanes", i32), ("bytes_per_sample", i32), ("plane_w", i32 * 3), ("plane_h", i32 * 3),
+                ("pitch", i64 * 3), ("offset", i64 * 3), ("frame_bytes", i64)]
+
+
+class Error(RuntimeError):
+    pass
+
+
+_LIB = None
+
+
+def lib():
+    """Loads libmvtools_b200.so (built in-tree by __graft_entry__.build()).  Raises if absent."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libmvtools_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        vp = C.c_void_p
+        PP = C.POINTER
+        L.mvb200_last_error.restype = C.c_char_p
+        L.mvb200_version.restype = C.c_char_p
+        L.mvb200_super_init.argtypes = [PP(SuperParams)]
+        L.mvb200_super_geometry.argtypes = [PP(SuperParams), PP(SuperGeom)]
+        L.mvb200_super_geometry.restype = None
+        L.mvb200_analyse_init.argtypes = [PP(AnalyseArgs), PP(SuperParams), i32, PP(AnalyseParams)]
+        L.mvb200_degrain_init.argtypes = [PP(DegrainArgs), PP(SuperParams), PP(AnalysisData), i32, i32, PP(DegrainParams)]
+        L.mvb200_clip_layout.argtypes = [PP(SuperParams), PP(FrameLayout)]
+        L.mvb200_clip_layout.restype = None
+        L.mvb200_super_layout.argtypes = [PP(SuperParams), PP(FrameLayout)]
+        L.mvb200_super_layout.restype = None
+        L.mvb200_ctx_create.argtypes = [i32, PP(vp)]
+        L.mvb200_ctx_destroy.argtypes = [vp]
+        L.mvb200_ctx_destroy.restype = None
+        L.mvb200_ctx_synchronize.argtypes = [vp]
+        L.mvb200_ctx_stream.argtypes = [vp]
+        L.mvb200_ctx_stream.restype = vp
+        L.mvb200_ctx_launch_count.argtypes = [vp]
+        L.mvb200_ctx_launch_count.restype = i64
+        L.mvb200_super_batch.argtypes = [vp, PP(SuperParams), vp, vp, i32]
+        L.mvb200_analyse_batch.argtypes = [vp, PP(AnalyseParams), PP(SuperParams), vp, i32, i32, vp, i64]
+        L.mvb200_analyse_multi_batch.argtypes = [vp, PP(PP(AnalyseParams)), i32, PP(SuperParams), vp, i32, i32, PP(vp), i64]
+        L.mvb200_degrain_batch.argtypes = [vp, PP(DegrainParams), PP(SuperParams), vp, vp, i32, i32, i32, PP(vp), i64, vp]
+        L.mvb200_super_frame.argtypes = [vp, PP(SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
+        L.mvb200_analyse_frame.argtypes = [vp, PP(AnalyseParams), PP(SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp),
+                                           PP(C.c_ssize_t), i32, vp]
+        L.mvb200_degrain_frame.argtypes = [vp, PP(DegrainParams), PP(SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp),
+                                           PP(C.c_ssize_t), PP(vp), PP(vp), PP(C.c_ssize_t)]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc:
+        raise Error(lib().mvb200_last_error().decode())
+
+
+# ----------------------------------------------------------------- host logic
+
+def super_params(width, height, bits=8, ssw=1, ssh=1, gray=False, **kw):
+    p = SuperParams()
+    p.width, p.height, p.bits, p.ssw, p.ssh, p.gray = width, height, bits, ssw, ssh, int(gray)
+    for n in ("hpad", "vpad", "pel", "levels", "chroma", "sharp", "rfilter"):
+        setattr(p, n, int(kw.pop(n)) if n in kw and kw[n] is not None else UNSET)
+    if kw:
+        raise TypeError("Super: unknown argument(s) %s" % sorted(kw))
+    _check(lib().mvb200_super_init(C.byref(p)))
+    return p
+
+
+def super_geometry(sp):
+    g = SuperGeom()
+    lib().mvb200_super_geometry(C.byref(sp), C.byref(g))
+    return g
+
+
+def analyse_params(sp, num_frames, **kw):
+    a = AnalyseArgs()
+    for n in ANALYSE_ARGS:
+        v = kw.pop(n, None)
+        setattr(a, n, UNSET if v is None else int(v))
+    if kw:
+        raise TypeError("Analyse: unknown argument(s) %s" % sorted(kw))
+    out = AnalyseParams()
+    _check(lib().mvb200_analyse_init(C.byref(a), C.byref(sp), num_frames, C.byref(out)))
+    return out
+
+
+def degrain_params(sp, vds, clip_w, clip_h, radius, **kw):
+    a = DegrainArgs()
+    a.radius = radius
+    for n, unset in (("thsad", UNSET64), ("thsadc", UNSET64), ("plane", UNSET), ("limit", UNSET), ("limitc", UNSET),
+                     ("thscd1", UNSET64), ("thscd2", UNSET)):
+        v = kw.pop(n, None)
+        setattr(a, n, unset if v is None else int(v))
+    if kw:
+        raise TypeError("Degrain: unknown argument(s) %s" % sorted(kw))
+    arr = (AnalysisData * len(vds))(*vds)
+    out = DegrainParams()
+    _check(lib().mvb200_degrain_init(C.byref(a), C.byref(sp), arr, clip_w, clip_h, C.byref(out)))
+    return out
+
+
+def clip_layout(sp):
+    l = FrameLayout()
+    lib().mvb200_clip_layout(C.byref(sp), C.byref(l))
+    return l
+
+
+def super_layout(sp):
+    l = FrameLayout()
+    lib().mvb200_super_layout(C.byref(sp), C.byref(l))
+    return l
+
+
+# ------------------------------------------------------ plane <-> pointer glue
+
+def plane_ptrs(planes):
+    """[np.ndarray]*n -> (void*[3], ssize_t[3]); arrays must be C-contiguous rows."""
+    ptrs = (C.c_void_p * 3)()
+    strides = (C.c_ssize_t * 3)()
+    for i, a in enumerate(planes):
+        if a is None:
+            continue
+        assert a.strides[-1] == a.itemsize
+        ptrs[i] = a.ctypes.data
+        strides[i] = a.strides[0]
+    return ptrs, strides
+
+
+def alloc_planes(widths, heights, bits, fill=None):
+    dt = np.uint8 if bits <= 8 else np.uint16
+    out = []
+    for w, h in zip(widths, heights):
+        a = np.empty((h, w), dtype=dt)
+        if fill is not None:
+            a[...] = fill
+        out.append(a)
+    return out
+
+
+class Context:
+    """One CUDA device context (stream + scratch) of the engine."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        _check(lib().mvb200_ctx_create(device, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().mvb200_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def synchronize(self):
+        _check(lib().mvb200_ctx_synchronize(self._h))
+
+    def stream(self):
+        return lib().mvb200_ctx_stream(self._h)
+
+    def launch_count(self):
+        return lib().mvb200_ctx_launch_count(self._h)
+
+    # ---- host-buffer per-frame calls (what the VapourSynth plugin makes)
+    def super_frame(self, sp, src_planes):
+        g = super_geometry(sp)
+        dst = alloc_planes(list(g.plane_w)[: sp.nplanes], list(g.plane_h)[: sp.nplanes], sp.bits, fill=0xA5)
+        s, ss = plane_ptrs(src_planes)
+        d, ds = plane_ptrs(dst)
+        _check(lib().mvb200_super_frame(self._h, C.byref(sp), s, ss, d, ds))
+        return dst
+
+    def analyse_frame(self, ap, sp, src_super, ref_super, field_shift=0):
+        out = np.empty(ap.vectors_size, dtype=np.uint8)
+        s, ss = plane_ptrs(src_super)
+        if ref_super is None:
+            r, rs = None, None
+        else:
+            r, rs = plane_ptrs(ref_super)
+        _check(lib().mvb200_analyse_frame(self._h, C.byref(ap), C.byref(sp), s, ss, r, rs, field_shift, out.ctypes.data))
+        return out
+
+    def degrain_frame(self, dp, sp, src_planes, ref_supers, vectors):
+        n = 2 * dp.radius
+        refs = (C.c_void_p * (3 * n))()
+        rstr = (C.c_ssize_t * (3 * n))()
+        for r in range(n):
+            if ref_supers[r] is None:
+                continue
+            for p, a in enumerate(ref_supers[r]):
+                refs[r * 3 + p] = a.ctypes.data
+                rstr[r * 3 + p] = a.strides[0]
+        vecs = (C.c_void_p * n)(*[v.ctypes.data for v in vectors])
+        dst = alloc_planes([a.shape[1] for a in src_planes], [a.shape[0] for a in src_planes], dp.bits, fill=0xA5)
+        s, ss = plane_ptrs(src_planes)
+        d, ds = plane_ptrs(dst)
+        _check(lib().mvb200_degrain_frame(self._h, C.byref(dp), C.byref(sp), s, ss, refs, rstr, vecs, d, ds))
+        return dst
