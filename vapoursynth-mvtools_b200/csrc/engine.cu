@@ -1,0 +1,475 @@
+// libmvtools_b200.so: context, device layouts and the C-ABI entry points declared in
+// include/mvtools_b200.h (the compute half; the parameter derivation half is
+// host_logic.cpp).  There is no CPU path in this library: every compute entry point
+// needs a CUDA device of compute capability 10.x and fails loudly otherwise.
+#include "engine.h"
+
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+namespace mvb200 {
+
+static long long round_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+void make_clip_desc(const mvb200_super_params *sp, ClipDesc *d) {
+    memset(d, 0, sizeof(*d));
+    d->nplanes = sp->nplanes;
+    d->bits = sp->bits;
+    d->bps = (sp->bits + 7) / 8;
+    long long off = 0;
+    for (int p = 0; p < sp->nplanes; p++) {
+        d->w[p] = p ? sp->width >> sp->ssw : sp->width;
+        d->h[p] = p ? sp->height >> sp->ssh : sp->height;
+        d->pitch[p] = round_up((long long)d->w[p] * d->bps, 256);
+        d->offset[p] = off;
+        off += d->pitch[p] * d->h[p];
+    }
+    d->frame_bytes = round_up(off, 256);
+}
+
+void make_super_desc(const mvb200_super_params *sp, SuperDesc *d) {
+    memset(d, 0, sizeof(*d));
+    mvb200_super_geom g;
+    mvb200_super_geometry(sp, &g);
+    d->nplanes = sp->nplanes;
+    d->levels = sp->levels;
+    d->bits = sp->bits;
+    d->bps = (sp->bits + 7) / 8;
+    d->xRatioUV = sp->xRatioUV;
+    d->yRatioUV = sp->yRatioUV;
+    d->logxR = sp->ssw;
+    d->logyR = sp->ssh;
+    long long off = 0;
+    for (int p = 0; p < sp->nplanes; p++) {
+        // + 4 bytes of slack so the unaligned-word loads of the search may touch the word
+        // after the last sample of a row; pitch multiple of 256
+        d->pitch[p] = round_up((long long)g.plane_w[p] * d->bps + 4, 256);
+        d->offset[p] = off;
+        off += d->pitch[p] * g.plane_h[p];
+        for (int l = 0; l < sp->levels && l < kDevMaxLevels; l++)
+            d->lv[p][l] = g.lv[p][l];
+    }
+    d->frame_bytes = round_up(off, 256);
+}
+
+void *Ctx::get_scratch(int slot, size_t bytes) {
+    if (bytes <= scratch_bytes[slot])
+        return scratch[slot];
+    // device memory may still be in use by queued kernels: drain first
+    cudaStreamSynchronize(stream);
+    if (scratch[slot])
+        cudaFree(scratch[slot]);
+    scratch[slot] = nullptr;
+    scratch_bytes[slot] = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    void *p = nullptr;
+    if (cudaMalloc(&p, want) != cudaSuccess) {
+        set_error("mvtools_b200: out of device memory (%zu bytes of scratch)", want);
+        return nullptr;
+    }
+    if (cudaMemsetAsync(p, 0, want, stream) != cudaSuccess) {
+        cudaFree(p);
+        set_error("mvtools_b200: cudaMemset failed");
+        return nullptr;
+    }
+    scratch[slot] = p;
+    scratch_bytes[slot] = want;
+    return p;
+}
+
+void *Ctx::get_pinned(size_t bytes) {
+    if (bytes <= pinned_bytes)
+        return pinned;
+    cudaStreamSynchronize(stream);
+    if (pinned)
+        cudaFreeHost(pinned);
+    pinned = nullptr;
+    pinned_bytes = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    if (cudaMallocHost(&pinned, want) != cudaSuccess) {
+        pinned = nullptr;
+        set_error("mvtools_b200: cannot allocate %zu bytes of pinned host memory", want);
+        return nullptr;
+    }
+    pinned_bytes = want;
+    return pinned;
+}
+
+static int check_levels(const mvb200_super_params *sp) {
+    if (sp->levels > kDevMaxLevels)
+        return set_error("mvtools_b200: more than %d pyramid levels are not supported on the device", kDevMaxLevels);
+    return 0;
+}
+
+static void make_search_params(const mvb200_analyse_params *ap, SearchParams *P) {
+    memset(P, 0, sizeof(*P));
+    const mvb200_analysis_data &ad = ap->ad;
+    P->blkW = ad.nBlkSizeX;
+    P->blkH = ad.nBlkSizeY;
+    P->ovX = ad.nOverlapX;
+    P->ovY = ad.nOverlapY;
+    P->pel = ad.nPel;
+    P->logPel = ad.nPel == 4 ? 2 : (ad.nPel == 2 ? 1 : 0);
+    P->levels = ad.nLvCount;
+    P->chroma = ap->chroma;
+    P->bits = ad.bitsPerSample;
+    P->bps = (ad.bitsPerSample + 7) / 8;
+    P->search = ap->search;
+    P->search_coarse = ap->search_coarse;
+    P->nSearchParam = ap->nSearchParam;
+    P->nPelSearch = ap->nPelSearch;
+    P->nLambda = ap->nLambda;
+    P->lsad = ap->lsad;
+    P->pnew = ap->pnew;
+    P->plevel = ap->plevel;
+    P->global = ap->global;
+    P->pglobal = ap->pglobal;
+    P->pzero = ap->pzero;
+    P->badSAD = ap->badSAD;
+    P->badrange = ap->badrange;
+    P->meander = ap->meander;
+    P->tryMany = ap->tryMany;
+    P->dctmode = ap->dctmode;
+    P->divide = ap->divide;
+    P->vectors_size = ap->vectors_size;
+    P->verybigSAD = (long long)ad.nBlkSizeX * ad.nBlkSizeY * (1LL << ad.bitsPerSample);
+    int off = 8;
+    for (int l = ad.nLvCount - 1; l >= 0; l--) { // coarsest first (GroupOfPlanes.c:76-85)
+        P->nBlkX[l] = ap->nBlkX[l];
+        P->nBlkY[l] = ap->nBlkY[l];
+        P->level_off[l] = off;
+        off += 4 + ap->nBlkX[l] * ap->nBlkY[l] * 16;
+    }
+}
+
+static int check_analyse(const mvb200_analyse_params *ap, const mvb200_super_params *sp) {
+    if (ap->dctmode >= 1 && ap->dctmode <= 4)
+        return set_error("Analyse: dct=%d (FFTW DCT modes 1..4) is not implemented by the B200 engine; use dct=0 or the SATD modes 5..10", ap->dctmode);
+    if (ap->ad.nLvCount > kDevMaxLevels)
+        return set_error("Analyse: more than %d levels are not supported on the device", kDevMaxLevels);
+    if (ap->super_pel != sp->pel || ap->super_hpad != sp->hpad || ap->super_vpad != sp->vpad || ap->ad.bitsPerSample != sp->bits)
+        return set_error("Analyse: parameters were initialised for a different super clip");
+    return check_levels(sp);
+}
+
+// mvanalyseGetFrame's choice of the reference frame (MVAnalyse.c:84-109,127-133)
+static int ref_frame_of(const mvb200_analyse_params *ap, int n) {
+    int nref;
+    if (ap->ad.nDeltaFrame > 0)
+        nref = n + (ap->ad.isBackward ? ap->ad.nDeltaFrame : -ap->ad.nDeltaFrame);
+    else
+        nref = -ap->ad.nDeltaFrame;
+    return (nref >= 0 && nref < ap->num_frames) ? nref : -1;
+}
+
+// field shift with an explicit tff (MVAnalyse.c:146-179); frame props are the plugin's business
+static int field_shift_of(const mvb200_analyse_params *ap, int n, int nref) {
+    if (!(ap->fields && ap->ad.nPel > 1 && (ap->ad.nDeltaFrame % 2)) || !ap->tff_exists)
+        return 0;
+    int src_top = ap->tff ^ (n % 2), ref_top = ap->tff ^ (nref % 2);
+    return (src_top && !ref_top) ? ap->ad.nPel / 2 : ((ref_top && !src_top) ? -(ap->ad.nPel / 2) : 0);
+}
+
+} // namespace mvb200
+
+using namespace mvb200;
+
+struct mvb200_ctx {
+    Ctx c;
+};
+
+extern "C" {
+
+int mvb200_ctx_create(int device, mvb200_ctx **out) {
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return set_error("mvtools_b200: no CUDA device available (%s); this engine has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count)
+        return set_error("mvtools_b200: CUDA device %d does not exist (%d visible)", device, count);
+    cudaDeviceProp prop;
+    MVB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return set_error("mvtools_b200: device %d (%s, sm_%d%d) is not a Blackwell sm_100 part; kernels are built for sm_100a only", device, prop.name, prop.major, prop.minor);
+    MVB_CUDA_CHECK(cudaSetDevice(device));
+    mvb200_ctx *ctx = new mvb200_ctx;
+    ctx->c.device = device;
+    ctx->c.sm_count = prop.multiProcessorCount;
+    cudaError_t se = cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking);
+    if (se != cudaSuccess) {
+        delete ctx;
+        return set_error("mvtools_b200: cudaStreamCreate failed: %s", cudaGetErrorString(se));
+    }
+    *out = ctx;
+    return 0;
+}
+
+void mvb200_ctx_destroy(mvb200_ctx *ctx) {
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->c.device);
+    cudaStreamSynchronize(ctx->c.stream);
+    for (auto &p : ctx->c.scratch)
+        if (p)
+            cudaFree(p);
+    if (ctx->c.pinned)
+        cudaFreeHost(ctx->c.pinned);
+    cudaStreamDestroy(ctx->c.stream);
+    delete ctx;
+}
+
+int mvb200_ctx_synchronize(mvb200_ctx *ctx) {
+    MVB_CUDA_CHECK(cudaSetDevice(ctx->c.device));
+    MVB_CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    return 0;
+}
+
+void *mvb200_ctx_stream(mvb200_ctx *ctx) { return (void *)ctx->c.stream; }
+
+int64_t mvb200_ctx_launch_count(mvb200_ctx *ctx) { return ctx->c.launches; }
+
+void mvb200_clip_layout(const mvb200_super_params *p, mvb200_frame_layout *l) {
+    ClipDesc d;
+    make_clip_desc(p, &d);
+    memset(l, 0, sizeof(*l));
+    l->nplanes = d.nplanes;
+    l->bytes_per_sample = d.bps;
+    for (int i = 0; i < d.nplanes; i++) {
+        l->plane_w[i] = d.w[i];
+        l->plane_h[i] = d.h[i];
+        l->pitch[i] = d.pitch[i];
+        l->offset[i] = d.offset[i];
+    }
+    l->frame_bytes = d.frame_bytes;
+}
+
+void mvb200_super_layout(const mvb200_super_params *p, mvb200_frame_layout *l) {
+    SuperDesc d;
+    make_super_desc(p, &d);
+    mvb200_super_geom g;
+    mvb200_super_geometry(p, &g);
+    memset(l, 0, sizeof(*l));
+    l->nplanes = d.nplanes;
+    l->bytes_per_sample = d.bps;
+    for (int i = 0; i < d.nplanes; i++) {
+        l->plane_w[i] = g.plane_w[i];
+        l->plane_h[i] = g.plane_h[i];
+        l->pitch[i] = d.pitch[i];
+        l->offset[i] = d.offset[i];
+    }
+    l->frame_bytes = d.frame_bytes;
+}
+
+// ------------------------------------------------------------- batch path
+
+int mvb200_super_batch(mvb200_ctx *ctx, const mvb200_super_params *p, const void *dev_src, void *dev_super, int n) {
+    if (check_levels(p))
+        return 1;
+    MVB_CUDA_CHECK(cudaSetDevice(ctx->c.device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(p, &sd);
+    make_clip_desc(p, &cd);
+    return launch_super(&ctx->c, p, sd, cd, (const uint8_t *)dev_src, (uint8_t *)dev_super, n);
+}
+
+int mvb200_analyse_multi_batch(mvb200_ctx *ctx, const mvb200_analyse_params *const *ap, int nap, const mvb200_super_params *sp, const void *dev_super, int first, int n, void *const *dev_vectors, int64_t vectors_stride) {
+    MVB_CUDA_CHECK(cudaSetDevice(ctx->c.device));
+    SuperDesc sd;
+    make_super_desc(sp, &sd);
+    std::vector<SearchParams> params((size_t)nap);
+    std::vector<SearchJob> jobs;
+    jobs.reserve((size_t)nap * n);
+    for (int i = 0; i < nap; i++) {
+        if (check_analyse(ap[i], sp))
+            return 1;
+        if (vectors_stride < ap[i]->vectors_size)
+            return set_error("Analyse: vectors_stride (%lld) is smaller than the blob (%d bytes)", (long long)vectors_stride, ap[i]->vectors_size);
+        make_search_params(ap[i], &params[i]);
+    }
+    // frame-major order so that chains touching the same super frames are scheduled together
+    for (int f = 0; f < n; f++)
+        for (int i = 0; i < nap; i++) {
+            int fn = first + f;
+            int nref = ref_frame_of(ap[i], fn);
+            SearchJob j;
+            j.src = (const uint8_t *)dev_super + (long long)fn * sd.frame_bytes;
+            j.ref = nref >= 0 ? (const uint8_t *)dev_super + (long long)nref * sd.frame_bytes : nullptr;
+            j.out = (uint8_t *)dev_vectors[i] + (long long)f * vectors_stride;
+            j.param = i;
+            j.field_shift = nref >= 0 ? field_shift_of(ap[i], fn, nref) : 0;
+            jobs.push_back(j);
+        }
+    return launch_search(&ctx->c, sd, params.data(), nap, jobs.data(), (int)jobs.size());
+}
+
+int mvb200_analyse_batch(mvb200_ctx *ctx, const mvb200_analyse_params *ap, const mvb200_super_params *sp, const void *dev_super, int first, int n, void *dev_vectors, int64_t vectors_stride) {
+    const mvb200_analyse_params *aps[1] = {ap};
+    void *outs[1] = {dev_vectors};
+    return mvb200_analyse_multi_batch(ctx, aps, 1, sp, dev_super, first, n, outs, vectors_stride);
+}
+
+int mvb200_degrain_batch(mvb200_ctx *ctx, const mvb200_degrain_params *dp, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int num_frames, int first, int n, const void *const *dev_vectors, int64_t vectors_stride, void *dev_dst) {
+    if (check_levels(sp))
+        return 1;
+    MVB_CUDA_CHECK(cudaSetDevice(ctx->c.device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(sp, &sd);
+    make_clip_desc(sp, &cd);
+    return launch_degrain(&ctx->c, dp, sd, cd, (const uint8_t *)dev_src, (const uint8_t *)dev_super, num_frames, first, n, (const uint8_t *const *)dev_vectors, vectors_stride, (uint8_t *)dev_dst);
+}
+
+// ------------------------------------------------------- host-buffer path
+
+static int upload_planes(Ctx *c, uint8_t *dev_frame, const long long *pitch, const long long *offset, const int *w, const int *h, int bps, int nplanes, const uint8_t *const src[3], const ptrdiff_t stride[3]) {
+    for (int p = 0; p < nplanes; p++) {
+        if (!src[p])
+            continue;
+        MVB_CUDA_CHECK(cudaMemcpy2DAsync(dev_frame + offset[p], (size_t)pitch[p], src[p], (size_t)stride[p], (size_t)w[p] * bps, (size_t)h[p], cudaMemcpyHostToDevice, c->stream));
+    }
+    return 0;
+}
+
+static int download_planes(Ctx *c, const uint8_t *dev_frame, const long long *pitch, const long long *offset, const int *w, const int *h, int bps, int nplanes, uint8_t *const dst[3], const ptrdiff_t stride[3]) {
+    for (int p = 0; p < nplanes; p++)
+        MVB_CUDA_CHECK(cudaMemcpy2DAsync(dst[p], (size_t)stride[p], dev_frame + offset[p], (size_t)pitch[p], (size_t)w[p] * bps, (size_t)h[p], cudaMemcpyDeviceToHost, c->stream));
+    return 0;
+}
+
+static void super_plane_dims(const mvb200_super_params *sp, int w[3], int h[3]) {
+    for (int p = 0; p < 3; p++) {
+        w[p] = p ? sp->super_width >> sp->ssw : sp->super_width;
+        h[p] = p ? sp->super_height >> sp->ssh : sp->super_height;
+    }
+}
+
+int mvb200_super_frame(mvb200_ctx *ctx, const mvb200_super_params *p, const uint8_t *const src[3], const ptrdiff_t src_stride[3], uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
+    if (check_levels(p))
+        return 1;
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(p, &sd);
+    make_clip_desc(p, &cd);
+    uint8_t *buf = (uint8_t *)c->get_scratch(5, (size_t)(cd.frame_bytes + sd.frame_bytes));
+    if (!buf)
+        return 1;
+    uint8_t *dsrc = buf, *dsup = buf + cd.frame_bytes;
+    if (upload_planes(c, dsrc, cd.pitch, cd.offset, cd.w, cd.h, cd.bps, cd.nplanes, src, src_stride))
+        return 1;
+    if (launch_super(c, p, sd, cd, dsrc, dsup, 1))
+        return 1;
+    int w[3], h[3];
+    super_plane_dims(p, w, h);
+    if (download_planes(c, dsup, sd.pitch, sd.offset, w, h, sd.bps, sd.nplanes, dst, dst_stride))
+        return 1;
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mvb200_analyse_frame(mvb200_ctx *ctx, const mvb200_analyse_params *ap, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], int field_shift, uint8_t *vectors_out) {
+    if (check_analyse(ap, sp))
+        return 1;
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    make_super_desc(sp, &sd);
+    size_t blob = ((size_t)ap->vectors_size + 255) & ~(size_t)255;
+    uint8_t *buf = (uint8_t *)c->get_scratch(5, (size_t)sd.frame_bytes * 2 + blob);
+    if (!buf)
+        return 1;
+    int w[3], h[3];
+    super_plane_dims(sp, w, h);
+    int nplanes_used = ap->chroma ? sd.nplanes : 1;
+    if (upload_planes(c, buf, sd.pitch, sd.offset, w, h, sd.bps, nplanes_used, src_super, src_stride))
+        return 1;
+    if (ref_super && upload_planes(c, buf + sd.frame_bytes, sd.pitch, sd.offset, w, h, sd.bps, nplanes_used, ref_super, ref_stride))
+        return 1;
+    SearchParams P;
+    make_search_params(ap, &P);
+    SearchJob j;
+    j.src = buf;
+    j.ref = ref_super ? buf + sd.frame_bytes : nullptr;
+    j.out = buf + sd.frame_bytes * 2;
+    j.param = 0;
+    j.field_shift = field_shift;
+    if (launch_search(c, sd, &P, 1, &j, 1))
+        return 1;
+    MVB_CUDA_CHECK(cudaMemcpyAsync(vectors_out, j.out, (size_t)ap->vectors_size, cudaMemcpyDeviceToHost, c->stream));
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mvb200_degrain_frame(mvb200_ctx *ctx, const mvb200_degrain_params *dp, const mvb200_super_params *sp, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const *const ref_super, const ptrdiff_t *ref_stride, const uint8_t *const *vectors, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
+    if (check_levels(sp))
+        return 1;
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(sp, &sd);
+    make_clip_desc(sp, &cd);
+    const int R2 = dp->radius * 2;
+    int maxdelta = 0;
+    for (int r = 0; r < R2; r++)
+        maxdelta = dp->vd[r].nDeltaFrame > maxdelta ? dp->vd[r].nDeltaFrame : maxdelta;
+    // a virtual clip of 2*maxdelta+1 super frames with the current frame in the middle, so the
+    // batch kernel's "frame n +- delta" addressing finds each reference where it expects it
+    const int vframes = 2 * maxdelta + 1;
+    // blob size: walk the level headers of the first blob (sizes are stored in the blob itself)
+    size_t blob_bytes = (size_t)(*(const int32_t *)vectors[0]);
+    size_t blob_stride = (blob_bytes + 255) & ~(size_t)255;
+    size_t need = (size_t)sd.frame_bytes * vframes + (size_t)cd.frame_bytes * 2 + blob_stride * R2;
+    uint8_t *buf = (uint8_t *)c->get_scratch(5, need);
+    if (!buf)
+        return 1;
+    uint8_t *dsup = buf, *dsrc = buf + (size_t)sd.frame_bytes * vframes, *ddst = dsrc + cd.frame_bytes, *dvec = ddst + cd.frame_bytes;
+    int w[3], h[3];
+    super_plane_dims(sp, w, h);
+    if (upload_planes(c, dsrc, cd.pitch, cd.offset, cd.w, cd.h, cd.bps, cd.nplanes, src, src_stride))
+        return 1;
+    const void *dv[2 * MVB200_MAX_RADIUS];
+    for (int r = 0; r < R2; r++) {
+        if ((size_t)(*(const int32_t *)vectors[r]) != blob_bytes)
+            return set_error("Degrain: vector blobs of different sizes");
+        MVB_CUDA_CHECK(cudaMemcpyAsync(dvec + blob_stride * r, vectors[r], blob_bytes, cudaMemcpyHostToDevice, c->stream));
+        dv[r] = dvec + blob_stride * r;
+        const uint8_t *const *rp = ref_super + r * 3;
+        if (rp[0]) {
+            int idx = maxdelta + (dp->vd[r].isBackward ? dp->vd[r].nDeltaFrame : -dp->vd[r].nDeltaFrame);
+            if (upload_planes(c, dsup + (size_t)sd.frame_bytes * idx, sd.pitch, sd.offset, w, h, sd.bps, sd.nplanes, rp, ref_stride + r * 3))
+                return 1;
+        }
+    }
+    // `first` = maxdelta in the virtual clip; the source frame pointer is biased accordingly
+    if (launch_degrain(c, dp, sd, cd, dsrc - (long long)maxdelta * cd.frame_bytes, dsup, vframes, maxdelta, 1, (const uint8_t *const *)dv, (long long)blob_stride, ddst))
+        return 1;
+    if (download_planes(c, ddst, cd.pitch, cd.offset, cd.w, cd.h, cd.bps, cd.nplanes, dst, dst_stride))
+        return 1;
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// ---- not implemented yet in this round: fail loudly ------------------------
+
+int mvb200_compensate_init(const mvb200_compensate_args *, const mvb200_super_params *, const mvb200_analysis_data *, int, int, int, mvb200_compensate_params *) {
+    return set_error("Compensate: not implemented by the B200 engine yet");
+}
+
+int mvb200_recalculate_init(const mvb200_recalculate_args *, const mvb200_super_params *, const mvb200_analysis_data *, int, mvb200_recalculate_params *) {
+    return set_error("Recalculate: not implemented by the B200 engine yet");
+}
+
+int mvb200_compensate_frame(mvb200_ctx *, const mvb200_compensate_params *, const mvb200_super_params *, const uint8_t *const[3], const ptrdiff_t[3], const uint8_t *const[3], const ptrdiff_t[3], const uint8_t *, int, uint8_t *const[3], const ptrdiff_t[3]) {
+    return set_error("Compensate: not implemented by the B200 engine yet");
+}
+
+int mvb200_recalculate_frame(mvb200_ctx *, const mvb200_recalculate_params *, const mvb200_super_params *, const uint8_t *const[3], const ptrdiff_t[3], const uint8_t *const[3], const ptrdiff_t[3], const uint8_t *, int, uint8_t *) {
+    return set_error("Recalculate: not implemented by the B200 engine yet");
+}
+
+} // extern "C"

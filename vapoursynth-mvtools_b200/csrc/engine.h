@@ -4,11 +4,98 @@
 
 #include "../../include/mvtools_b200.h"
 
+#include <cstddef>
+#include <cstdint>
+
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#endif
+
 namespace mvb200 {
 
 // sets the thread-local message returned by mvb200_last_error(); returns 1
 int set_error(const char *fmt, ...) __attribute__((format(printf, 1, 2)));
 
 int plane_dim_luma(int src, int level, int ratio, int pad);
+
+constexpr int kDevMaxLevels = 16;
+
+// Device-side description of where every (plane, level) of a super frame lives.
+// Frames are `frame_bytes` apart; plane p starts `offset[p]` bytes into a frame and
+// has row pitch `pitch[p]` bytes (mvb200_super_layout).
+struct SuperDesc {
+    int nplanes, levels, bps, bits;
+    int xRatioUV, yRatioUV, logxR, logyR;
+    long long pitch[3], offset[3], frame_bytes;
+    mvb200_level_geom lv[3][kDevMaxLevels];
+};
+
+// Source / output clip layout on the device (mvb200_clip_layout).
+struct ClipDesc {
+    int nplanes, bps, bits;
+    int w[3], h[3];
+    long long pitch[3], offset[3], frame_bytes;
+};
+
+void make_super_desc(const mvb200_super_params *sp, SuperDesc *d);
+void make_clip_desc(const mvb200_super_params *sp, ClipDesc *d);
+
+#ifdef __CUDACC__
+
+// Parameters of one mv.Analyse instance as the search kernel consumes them.
+struct SearchParams {
+    int blkW, blkH, ovX, ovY, pel, logPel, levels; // levels = nLvCount
+    int chroma, bps, bits;
+    int search, search_coarse, nSearchParam, nPelSearch;
+    int nLambda, lsad, pnew, plevel, global, pglobal, pzero;
+    long long badSAD;
+    int badrange, meander, tryMany, dctmode, divide;
+    int nBlkX[kDevMaxLevels], nBlkY[kDevMaxLevels];
+    int level_off[kDevMaxLevels]; // byte offset of level l's size header inside the blob
+    int vectors_size;
+    long long verybigSAD;
+};
+
+// One search chain = one (analyse instance, frame): walked by one warp.
+struct SearchJob {
+    const uint8_t *src; // super frame n (device)
+    const uint8_t *ref; // super frame nref, or nullptr (-> default vectors, validity 0)
+    uint8_t *out;       // blob
+    int param;          // index into the SearchParams array
+    int field_shift;
+};
+
+struct Ctx;
+
+// kernels' host launchers (each returns 0 or sets the error)
+int launch_super(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, uint8_t *dev_super, int n);
+int launch_search(Ctx *ctx, const SuperDesc &sd, const SearchParams *host_params, int nparams, const SearchJob *host_jobs, int njobs);
+int launch_degrain(Ctx *ctx, const mvb200_degrain_params *dp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, const uint8_t *dev_super, int num_frames, int first, int n, const uint8_t *const *dev_vectors, long long vectors_stride, uint8_t *dev_dst);
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    long long launches = 0;
+    // growable device scratch buffers
+    void *scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // pinned host staging
+    void *pinned = nullptr;
+    size_t pinned_bytes = 0;
+    int sm_count = 0;
+
+    void *get_scratch(int slot, size_t bytes); // nullptr + error on failure
+    void *get_pinned(size_t bytes);
+};
+
+#define MVB_CUDA_CHECK(call)                                                                          \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return ::mvb200::set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorName(e_), __FILE__, \
+                                       __LINE__, cudaGetErrorString(e_));                             \
+    } while (0)
+
+#endif // __CUDACC__
 
 } // namespace mvb200

@@ -1,0 +1,995 @@
+// mv.Analyse on the GPU: the hierarchical predictor-driven block-matching search
+// (gopSearchMVs GroupOfPlanes.c:69-125, doPobSearchMVs PlaneOfBlocks.cpp:971-1131,
+// pobPseudoEPZSearch :819-968 and everything below it).
+//
+// Execution model.  One search (analyse instance x frame) is a strict serial chain:
+// block k's predictors are the results of block k-1 (meander scan) and of the row
+// above, `badcount` is a running counter and every accept is a strict '<' against
+// the running minimum.  Bit-exactness forbids reordering, so
+//   * ONE WARP walks one chain from the coarsest level to the finest, keeping the
+//     chain state (best vector, running minimum cost, lambda, badcount, global MV)
+//     in per-lane registers -- every lane computes the same scalars, so there is
+//     no cross-lane protocol for control flow;
+//   * the 32 lanes split the PIXELS of each candidate block: unaligned 32-bit
+//     loads of source and reference words, VABSDIFF4.U8.ACC (`__vsadu4`) /
+//     2x16-bit absolute differences, one REDUX.SUM per plane class;
+//   * between levels the lanes split the BLOCKS: global-MV histogram
+//     (pobEstimateGlobalMVDoubled :1559-1636) and the 2x vector-field upsampling
+//     (pobInterpolatePrediction :1447-1514) are block-parallel;
+//   * throughput comes from running thousands of chains at once: a batch of F
+//     frames x 2*radius vector clips gives F*2*radius independent warps.
+// The MVTools_vectors blob itself is the working memory: before a level is
+// searched its VECTOR array holds the interpolated predictors, and each block's
+// result overwrites its slot (exactly the role of pob->vectors in the reference).
+//
+// Host-identical scalar arithmetic: the few FP64 operations (lambda scaling
+// :461-462, overlap-aware interpolation :1457,1500-1502) use IEEE double mul/div
+// with round-to-nearest and C truncation; the file is compiled with -fmad=false.
+#include "engine.h"
+
+namespace mvb200 {
+
+namespace {
+
+struct VEC {
+    int x, y;
+    long long sad;
+};
+
+struct PlaneView {
+    const uint8_t *base; // sub-plane 0, padded origin
+    long long pitch;     // bytes
+    long long sub;       // bytes between pel sub-planes = pitch * padded_h
+    int hpad, vpad, pw, ph;
+};
+
+struct State {
+    // per level
+    int nBlkX, nBlkY, blkW, blkH, ovX, ovY, logPel, logScale, logxR, logyR, bps, chroma, smallest;
+    int cw, ch;
+    PlaneView src[3], ref[3];
+    VEC *vectors;
+    int searchType, searchParam;
+    int penaltyZero, pglobal, penaltyNew, badrange, tryMany, dctmode, dctweight16;
+    long long badSAD, LSAD, verybigSAD;
+    VEC globalMV, zeroMVfs;
+    // per block
+    int x[3], y[3], blkx, blky, blkIdx, scanDir;
+    int dxMin, dxMax, dyMin, dyMax;
+    long long nLambda, nMinCost;
+    VEC bestMV, predictor, predictors[4];
+    const uint8_t *pSrc[3];
+    int srcLuma, badcount;
+    int lane;
+};
+
+// ------------------------------------------------------------------ pixels
+
+__device__ __forceinline__ unsigned ldu32(const uint8_t *p) {
+    unsigned long long a = (unsigned long long)p;
+    const unsigned *q = (const unsigned *)(a & ~3ull);
+    unsigned sh = ((unsigned)a & 3u) * 8u;
+    unsigned lo = __ldg(q);
+    if (sh == 0)
+        return lo;
+    unsigned hi = __ldg(q + 1);
+    return __funnelshift_r(lo, hi, sh);
+}
+
+__device__ __forceinline__ unsigned absdiff_word(unsigned a, unsigned b, int bps) {
+    return bps == 1 ? __vsadu4(a, b) : __vsadu2(a, b);
+}
+
+// per-lane partial SAD over a (rowbytes x h) block; caller reduces.   sad_c, SADFunctions.cpp:354-367
+__device__ __forceinline__ unsigned lane_sad(const uint8_t *a, long long ap, const uint8_t *b, long long bp, int rowbytes, int h, int bps, int lane) {
+    int wpr = rowbytes >> 2;
+    int lw = 31 - __clz(wpr);
+    int total = wpr * h;
+    unsigned acc = 0;
+    for (int i = lane; i < total; i += 32) {
+        int row = i >> lw, col = (i & (wpr - 1)) << 2;
+        acc += absdiff_word(ldu32(a + row * ap + col), ldu32(b + row * bp + col), bps);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ unsigned lane_luma(const uint8_t *a, long long ap, int rowbytes, int h, int bps, int lane) {
+    int wpr = rowbytes >> 2;
+    int lw = 31 - __clz(wpr);
+    int total = wpr * h;
+    unsigned acc = 0;
+    for (int i = lane; i < total; i += 32) {
+        int row = i >> lw, col = (i & (wpr - 1)) << 2;
+        unsigned v = ldu32(a + row * ap + col);
+        acc += bps == 1 ? __dp4a(v, 0x01010101u, 0u) : ((v & 0xffffu) + (v >> 16));
+    }
+    return acc;
+}
+
+__device__ __forceinline__ void hadamard4(int &d0, int &d1, int &d2, int &d3, int s0, int s1, int s2, int s3) {
+    int t0 = s0 + s1, t1 = s0 - s1, t2 = s2 + s3, t3 = s2 - s3;
+    d0 = t0 + t2;
+    d2 = t0 - t2;
+    d1 = t1 + t3;
+    d3 = t1 - t3;
+}
+
+// per-lane partial SATD: one lane per 4x4 tile.  Satd_C, SADFunctions.cpp:605-710: every
+// 8x4 (or lone 4x4) tile is halved; each 4x4 half is even, so halving per 4x4 is identical.
+__device__ unsigned lane_satd(const uint8_t *a, long long ap, const uint8_t *b, long long bp, int w, int h, int bps, int lane) {
+    int tx = w >> 2, tiles = tx * (h >> 2);
+    unsigned acc = 0;
+    for (int t = lane; t < tiles; t += 32) {
+        int ox = (t % tx) * 4, oy = (t / tx) * 4;
+        int m[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint8_t *pa = a + (oy + r) * ap + ox * bps, *pb = b + (oy + r) * bp + ox * bps;
+            int d0, d1, d2, d3;
+            if (bps == 1) {
+                unsigned va = ldu32(pa), vb = ldu32(pb);
+                d0 = (int)(va & 255) - (int)(vb & 255);
+                d1 = (int)((va >> 8) & 255) - (int)((vb >> 8) & 255);
+                d2 = (int)((va >> 16) & 255) - (int)((vb >> 16) & 255);
+                d3 = (int)(va >> 24) - (int)(vb >> 24);
+            } else {
+                unsigned va = ldu32(pa), vb = ldu32(pb), va2 = ldu32(pa + 4), vb2 = ldu32(pb + 4);
+                d0 = (int)(va & 0xffff) - (int)(vb & 0xffff);
+                d1 = (int)(va >> 16) - (int)(vb >> 16);
+                d2 = (int)(va2 & 0xffff) - (int)(vb2 & 0xffff);
+                d3 = (int)(va2 >> 16) - (int)(vb2 >> 16);
+            }
+            hadamard4(m[r][0], m[r][1], m[r][2], m[r][3], d0, d1, d2, d3);
+        }
+        unsigned s = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            int a0, a1, a2, a3;
+            hadamard4(a0, a1, a2, a3, m[0][c], m[1][c], m[2][c], m[3][c]);
+            s += (unsigned)(abs(a0) + abs(a1) + abs(a2) + abs(a3));
+        }
+        acc += s >> 1;
+    }
+    return acc;
+}
+
+__device__ __forceinline__ unsigned wsum(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
+
+// mvpGetAbsolutePointerPel1/2/4, MVFrame.cpp:1706-1730
+__device__ __forceinline__ const uint8_t *pel_ptr(const PlaneView &v, int bps, int logpel, int x, int y) {
+    int m = (1 << logpel) - 1;
+    int idx = (x & m) | ((y & m) << logpel);
+    return v.base + idx * v.sub + (long long)(y >> logpel) * v.pitch + (long long)(x >> logpel) * bps;
+}
+
+__device__ __forceinline__ const uint8_t *ref_luma(const State &S, int vx, int vy) { // pobGetRefBlock :35-53
+    return pel_ptr(S.ref[0], S.bps, S.logPel, (S.x[0] << S.logPel) + vx, (S.y[0] << S.logPel) + vy);
+}
+
+__device__ __forceinline__ const uint8_t *ref_chroma(const State &S, int p, int vx, int vy) { // pobGetRefBlockU/V :56-101
+    int xbias = (vx < 0) * ((1 << S.logxR) - 1);
+    int ybias = (vy < 0) * ((1 << S.logyR) - 1);
+    return pel_ptr(S.ref[p], S.bps, S.logPel, (S.x[p] << S.logPel) + ((vx + xbias) >> S.logxR), (S.y[p] << S.logPel) + ((vy + ybias) >> S.logyR));
+}
+
+// pobLumaSAD<dctmode>, PlaneOfBlocks.cpp:117-203 (dct 0 and the SATD modes 5..10)
+__device__ long long luma_sad(State &S, const uint8_t *pRef) {
+    long long sp = S.src[0].pitch, rp = S.ref[0].pitch;
+    int d = S.dctmode;
+    if (d == 5)
+        return wsum(lane_satd(S.pSrc[0], sp, pRef, rp, S.blkW, S.blkH, S.bps, S.lane));
+    long long sad = wsum(lane_sad(S.pSrc[0], sp, pRef, rp, S.blkW * S.bps, S.blkH, S.bps, S.lane));
+    if (d == 0)
+        return sad;
+    if (d == 6) {
+        if (S.dctweight16 > 0) {
+            long long dctsad = wsum(lane_satd(S.pSrc[0], sp, pRef, rp, S.blkW, S.blkH, S.bps, S.lane));
+            sad = (sad * (16 - S.dctweight16) + dctsad * S.dctweight16) / 16;
+        }
+        return sad;
+    }
+    if (d == 9) {
+        if (S.dctweight16 > 1) {
+            int half = S.dctweight16 / 2;
+            long long dctsad = wsum(lane_satd(S.pSrc[0], sp, pRef, rp, S.blkW, S.blkH, S.bps, S.lane));
+            sad = (sad * (16 - half) + dctsad * half) / 16;
+        }
+        return sad;
+    }
+    int refLuma = (int)wsum(lane_luma(pRef, rp, S.blkW * S.bps, S.blkH, S.bps, S.lane));
+    int shift = d == 10 ? 4 : 5;
+    if (abs(S.srcLuma - refLuma) > ((S.srcLuma + refLuma) >> shift)) {
+        long long dctsad = wsum(lane_satd(S.pSrc[0], sp, pRef, rp, S.blkW, S.blkH, S.bps, S.lane));
+        if (d == 7)
+            sad = sad / 2 + dctsad / 2;
+        else if (d == 8)
+            sad = sad / 4 + dctsad / 2 + dctsad / 4;
+        else
+            sad = sad / 2 + dctsad / 4 + sad / 4;
+    }
+    return sad;
+}
+
+__device__ __forceinline__ long long chroma_sad(const State &S, int vx, int vy) {
+    unsigned acc = lane_sad(S.pSrc[1], S.src[1].pitch, ref_chroma(S, 1, vx, vy), S.ref[1].pitch, S.cw * S.bps, S.ch, S.bps, S.lane);
+    acc += lane_sad(S.pSrc[2], S.src[2].pitch, ref_chroma(S, 2, vx, vy), S.ref[2].pitch, S.cw * S.bps, S.ch, S.bps, S.lane);
+    return wsum(acc);
+}
+
+// ------------------------------------------------------------------ search
+
+#define F_PENALTYNEW 2
+#define F_UPDATEDIR 4
+#define F_UPDATEBEST 8
+
+// pobCheckMV_Template, PlaneOfBlocks.cpp:219-261 (early outs kept: they are warp-uniform)
+__device__ __noinline__ void check_mv(State &S, int vx, int vy, int flags, int *dir, int val) {
+    if (!(vx >= S.dxMin && vy >= S.dyMin && vx < S.dxMax && vy < S.dyMax))
+        return;
+    int ddx = S.predictor.x - vx, ddy = S.predictor.y - vy;
+    int dist = (int)((unsigned)(ddx * ddx) + (unsigned)(ddy * ddy));
+    long long cost = (int)((S.nLambda * dist) >> 8); // pobMotionDistorsion :111-114
+    if (cost >= S.nMinCost)
+        return;
+    long long sad = luma_sad(S, ref_luma(S, vx, vy));
+    cost += sad + ((flags & F_PENALTYNEW) ? ((S.penaltyNew * sad) >> 8) : 0);
+    if (cost >= S.nMinCost)
+        return;
+    long long saduv = 0;
+    if (S.chroma) {
+        saduv = chroma_sad(S, vx, vy);
+        cost += saduv + ((flags & F_PENALTYNEW) ? ((S.penaltyNew * saduv) >> 8) : 0);
+        if (cost >= S.nMinCost)
+            return;
+    }
+    if (flags & F_UPDATEBEST) {
+        S.bestMV.x = vx;
+        S.bestMV.y = vy;
+    }
+    S.nMinCost = cost;
+    S.bestMV.sad = sad + saduv;
+    if (flags & F_UPDATEDIR)
+        *dir = val;
+}
+
+__device__ __forceinline__ void CheckMV0(State &S, int vx, int vy) { check_mv(S, vx, vy, F_UPDATEBEST, nullptr, 0); }
+__device__ __forceinline__ void CheckMV(State &S, int vx, int vy) { check_mv(S, vx, vy, F_PENALTYNEW | F_UPDATEBEST, nullptr, 0); }
+__device__ __forceinline__ void CheckMV2(State &S, int vx, int vy, int *dir, int val) { check_mv(S, vx, vy, F_PENALTYNEW | F_UPDATEDIR | F_UPDATEBEST, dir, val); }
+__device__ __forceinline__ void CheckMVdir(State &S, int vx, int vy, int *dir, int val) { check_mv(S, vx, vy, F_PENALTYNEW | F_UPDATEDIR, dir, val); }
+
+__device__ __forceinline__ int clipx(const State &S, int v) { return min(max(v, S.dxMin), S.dxMax - 1); }
+__device__ __forceinline__ int clipy(const State &S, int v) { return min(max(v, S.dyMin), S.dyMax - 1); }
+__device__ __forceinline__ VEC clipmv(const State &S, VEC v) { // pobClipMV :293-311
+    VEC r;
+    r.x = clipx(S, v.x);
+    r.y = clipy(S, v.y);
+    r.sad = v.sad;
+    return r;
+}
+__device__ __forceinline__ int median3(int a, int b, int c) { return max(min(a, b), min(max(a, b), c)); }
+__device__ __forceinline__ bool vec_ok(const State &S, int vx, int vy) { return vx >= S.dxMin && vy >= S.dyMin && vx < S.dxMax && vy < S.dyMax; }
+
+__device__ __forceinline__ VEC ldvec(const VEC *p) {
+    // vectors are written by this warp earlier in the chain: L2-coherent (.cg) loads.  The VECTOR
+    // arrays of the blob are only 4-byte aligned (8-byte blob header + 4-byte level headers).
+    const int *q = (const int *)p;
+    int4 v;
+    v.x = __ldcg(q);
+    v.y = __ldcg(q + 1);
+    v.z = __ldcg(q + 2);
+    v.w = __ldcg(q + 3);
+    VEC r;
+    r.x = v.x;
+    r.y = v.y;
+    r.sad = (long long)(((unsigned long long)(unsigned)v.w << 32) | (unsigned)v.z);
+    return r;
+}
+
+// pobFetchPredictors, PlaneOfBlocks.cpp:419-463
+__device__ void fetch_predictors(State &S) {
+    bool hasNext = (S.scanDir == 1 && S.blkx < S.nBlkX - 1) || (S.scanDir == -1 && S.blkx > 0);
+    if ((S.scanDir == 1 && S.blkx > 0) || (S.scanDir == -1 && S.blkx < S.nBlkX - 1))
+        S.predictors[1] = clipmv(S, ldvec(&S.vectors[S.blkIdx - S.scanDir]));
+    else
+        S.predictors[1] = clipmv(S, S.zeroMVfs);
+    if (S.blky > 0)
+        S.predictors[2] = clipmv(S, ldvec(&S.vectors[S.blkIdx - S.nBlkX]));
+    else
+        S.predictors[2] = clipmv(S, S.zeroMVfs);
+    if (S.blky < S.nBlkY - 1 && hasNext)
+        S.predictors[3] = clipmv(S, ldvec(&S.vectors[S.blkIdx + S.nBlkX + S.scanDir]));
+    else if (S.blky > 0 && hasNext)
+        S.predictors[3] = clipmv(S, ldvec(&S.vectors[S.blkIdx - S.nBlkX + S.scanDir]));
+    else
+        S.predictors[3] = clipmv(S, S.zeroMVfs);
+    if (S.blky > 0) {
+        S.predictors[0].x = median3(S.predictors[1].x, S.predictors[2].x, S.predictors[3].x);
+        S.predictors[0].y = median3(S.predictors[1].y, S.predictors[2].y, S.predictors[3].y);
+        S.predictors[0].sad = max(S.predictors[1].sad, max(S.predictors[2].sad, S.predictors[3].sad));
+    } else {
+        S.predictors[0] = S.predictors[1];
+    }
+    if (S.smallest)
+        S.predictor = S.predictors[0];
+    double scale = __ddiv_rn((double)S.LSAD, (double)(S.LSAD + (S.predictor.sad >> 1)));
+    S.nLambda = __double2ll_rz(__dmul_rn(__dmul_rn((double)S.nLambda, scale), scale));
+}
+
+__device__ void nstep_search(State &S, int stp) { // :466-485
+    for (int length = stp; length > 0; length--) {
+        int dx = S.bestMV.x, dy = S.bestMV.y;
+        CheckMV(S, dx + length, dy + length);
+        CheckMV(S, dx + length, dy);
+        CheckMV(S, dx + length, dy - length);
+        CheckMV(S, dx, dy - length);
+        CheckMV(S, dx, dy + length);
+        CheckMV(S, dx - length, dy + length);
+        CheckMV(S, dx - length, dy);
+        CheckMV(S, dx - length, dy - length);
+    }
+}
+
+__device__ void onetime_search(State &S, int length) { // :488-527
+    int direction = 0;
+    int dx = S.bestMV.x, dy = S.bestMV.y;
+    CheckMV2(S, dx - length, dy, &direction, 2);
+    CheckMV2(S, dx + length, dy, &direction, 1);
+    if (direction == 1) {
+        while (direction) {
+            direction = 0;
+            dx += length;
+            CheckMV2(S, dx + length, dy, &direction, 1);
+        }
+    } else if (direction == 2) {
+        while (direction) {
+            direction = 0;
+            dx -= length;
+            CheckMV2(S, dx - length, dy, &direction, 1);
+        }
+    }
+    CheckMV2(S, dx, dy - length, &direction, 2);
+    CheckMV2(S, dx, dy + length, &direction, 1);
+    if (direction == 1) {
+        while (direction) {
+            direction = 0;
+            dy += length;
+            CheckMV2(S, dx, dy + length, &direction, 1);
+        }
+    } else if (direction == 2) {
+        while (direction) {
+            direction = 0;
+            dy -= length;
+            CheckMV2(S, dx, dy - length, &direction, 1);
+        }
+    }
+}
+
+__device__ void diamond_search(State &S, int length) { // :530-632
+    enum { R = 1, L = 2, D = 4, U = 8 };
+    int direction = 15, last;
+    while (direction > 0) {
+        int dx = S.bestMV.x, dy = S.bestMV.y;
+        last = direction;
+        direction = 0;
+        if (last & R) CheckMV2(S, dx + length, dy, &direction, R);
+        if (last & L) CheckMV2(S, dx - length, dy, &direction, L);
+        if (last & D) CheckMV2(S, dx, dy + length, &direction, D);
+        if (last & U) CheckMV2(S, dx, dy - length, &direction, U);
+        if (direction) {
+            last = direction;
+            dx = S.bestMV.x;
+            dy = S.bestMV.y;
+            if (last & (R + L)) {
+                CheckMV2(S, dx, dy + length, &direction, D);
+                CheckMV2(S, dx, dy - length, &direction, U);
+            } else {
+                CheckMV2(S, dx + length, dy, &direction, R);
+                CheckMV2(S, dx - length, dy, &direction, L);
+            }
+        } else {
+            // the diagonal probes of every case, as (sx, sy, value) triples in the reference's order
+            int sx[4], sy[4], vv[4], cnt = 0;
+#define DG(a, b, c) (sx[cnt] = (a), sy[cnt] = (b), vv[cnt] = (c), cnt++)
+            switch (last) {
+            case R: DG(1, 1, R + D); DG(1, -1, R + U); break;
+            case L: DG(-1, 1, L + D); DG(-1, -1, L + U); break;
+            case D: DG(1, 1, R + D); DG(-1, 1, L + D); break;
+            case U: DG(1, -1, R + U); DG(-1, -1, L + U); break;
+            case R + D: DG(1, 1, R + D); DG(-1, 1, L + D); DG(1, -1, R + U); break;
+            case L + D: DG(1, 1, R + D); DG(-1, 1, L + D); DG(-1, -1, L + U); break;
+            case R + U: DG(1, 1, R + D); DG(-1, -1, L + U); DG(1, -1, R + U); break;
+            case L + U: DG(-1, -1, L + U); DG(-1, 1, L + D); DG(1, -1, R + U); break;
+            default: DG(1, 1, R + D); DG(-1, 1, L + D); DG(1, -1, R + U); DG(-1, -1, L + U); break;
+            }
+#undef DG
+            for (int k = 0; k < cnt; k++)
+                CheckMV2(S, dx + sx[k] * length, dy + sy[k] * length, &direction, vv[k]);
+        }
+    }
+}
+
+__device__ void expanding_search(State &S, int r, int s, int mvx, int mvy) { // :635-658
+    for (int i = -r + s; i < r; i += s) {
+        CheckMV(S, mvx + i, mvy - r);
+        CheckMV(S, mvx + i, mvy + r);
+    }
+    for (int j = -r + s; j < r; j += s) {
+        CheckMV(S, mvx - r, mvy + j);
+        CheckMV(S, mvx + r, mvy + j);
+    }
+    CheckMV(S, mvx - r, mvy - r);
+    CheckMV(S, mvx - r, mvy + r);
+    CheckMV(S, mvx + r, mvy - r);
+    CheckMV(S, mvx + r, mvy + r);
+}
+
+__constant__ int c_mod6m1[8] = {5, 0, 1, 2, 3, 4, 5, 0};
+__constant__ int c_hex2[8][2] = {{-1, -2}, {-2, 0}, {-1, 2}, {1, 2}, {2, 0}, {1, -2}, {-1, -2}, {-2, 0}};
+__constant__ int c_hex4[16][2] = {{-4, 2}, {-4, 1}, {-4, 0}, {-4, -1}, {-4, -2}, {4, -2}, {4, -1}, {4, 0},
+                                  {4, 1},  {4, 2},  {2, 3},  {0, 4},   {-2, 3},  {-2, -3}, {0, -4}, {2, -3}};
+
+__device__ void hex2_search(State &S, int range) { // :661-724
+    int dir = -2;
+    int bmx = S.bestMV.x, bmy = S.bestMV.y;
+    if (range > 1) {
+        CheckMVdir(S, bmx - 2, bmy, &dir, 0);
+        CheckMVdir(S, bmx - 1, bmy + 2, &dir, 1);
+        CheckMVdir(S, bmx + 1, bmy + 2, &dir, 2);
+        CheckMVdir(S, bmx + 2, bmy, &dir, 3);
+        CheckMVdir(S, bmx + 1, bmy - 2, &dir, 4);
+        CheckMVdir(S, bmx - 1, bmy - 2, &dir, 5);
+        if (dir != -2) {
+            bmx += c_hex2[dir + 1][0];
+            bmy += c_hex2[dir + 1][1];
+            for (int i = 1; i < range / 2 && vec_ok(S, bmx, bmy); i++) {
+                const int odir = c_mod6m1[dir + 1];
+                dir = -2;
+                CheckMVdir(S, bmx + c_hex2[odir + 0][0], bmy + c_hex2[odir + 0][1], &dir, odir - 1);
+                CheckMVdir(S, bmx + c_hex2[odir + 1][0], bmy + c_hex2[odir + 1][1], &dir, odir);
+                CheckMVdir(S, bmx + c_hex2[odir + 2][0], bmy + c_hex2[odir + 2][1], &dir, odir + 1);
+                if (dir == -2)
+                    break;
+                bmx += c_hex2[dir + 1][0];
+                bmy += c_hex2[dir + 1][1];
+            }
+        }
+        S.bestMV.x = bmx;
+        S.bestMV.y = bmy;
+    }
+    expanding_search(S, 1, 1, bmx, bmy);
+}
+
+__device__ void umh_search(State &S, int range, int omx, int omy) { // :727-769
+    for (int i = 1; i < range; i += 2) {
+        CheckMV(S, omx - i, omy);
+        CheckMV(S, omx + i, omy);
+    }
+    for (int j = 1; j < range; j += 2) {
+        CheckMV(S, omx, omy - j);
+        CheckMV(S, omx, omy + j);
+    }
+    int i = 1;
+    do {
+        for (int j = 0; j < 16; j++)
+            CheckMV(S, omx + c_hex4[j][0] * i, omy + c_hex4[j][1] * i);
+    } while (++i <= range / 4);
+    hex2_search(S, range);
+}
+
+__device__ void refine(State &S) { // pobRefine :772-816
+    switch (S.searchType) {
+    case 0:
+        for (int i = S.searchParam; i > 0; i /= 2)
+            onetime_search(S, i);
+        break;
+    case 1:
+        nstep_search(S, S.searchParam);
+        break;
+    case 2:
+        for (int i = S.searchParam; i > 0; i /= 2)
+            diamond_search(S, i);
+        break;
+    case 3: {
+        int mvx = S.bestMV.x, mvy = S.bestMV.y;
+        for (int i = 1; i <= S.searchParam; i++)
+            expanding_search(S, i, 1, mvx, mvy);
+        break;
+    }
+    case 4:
+        hex2_search(S, S.searchParam);
+        break;
+    case 5:
+        umh_search(S, S.searchParam, S.bestMV.x, S.bestMV.y);
+        break;
+    case 6: {
+        int mvx = S.bestMV.x, mvy = S.bestMV.y;
+        for (int i = 1; i <= S.searchParam; i++) {
+            CheckMV(S, mvx - i, mvy);
+            CheckMV(S, mvx + i, mvy);
+        }
+        break;
+    }
+    case 7: {
+        int mvx = S.bestMV.x, mvy = S.bestMV.y;
+        for (int i = 1; i <= S.searchParam; i++) {
+            CheckMV(S, mvx, mvy - i);
+            CheckMV(S, mvx, mvy + i);
+        }
+        break;
+    }
+    }
+}
+
+__device__ long long full_sad_at(State &S, int lx, int ly, int cx, int cy) {
+    long long sad = luma_sad(S, ref_luma(S, lx, ly));
+    if (S.chroma)
+        sad += chroma_sad(S, cx, cy);
+    return sad;
+}
+
+// pobPseudoEPZSearch, PlaneOfBlocks.cpp:819-968
+__device__ void epz_search(State &S) {
+    fetch_predictors(S);
+    if (S.dctmode >= 3)
+        S.srcLuma = (int)wsum(lane_luma(S.pSrc[0], S.src[0].pitch, S.blkW * S.bps, S.blkH, S.bps, S.lane));
+
+    S.bestMV.x = S.zeroMVfs.x;
+    S.bestMV.y = S.zeroMVfs.y;
+    long long sad = full_sad_at(S, 0, S.zeroMVfs.y, 0, 0);
+    S.bestMV.sad = sad;
+    S.nMinCost = sad + ((S.penaltyZero * sad) >> 8);
+
+    VEC bestMany[7];
+    long long costMany[7];
+    if (S.tryMany) {
+        for (int i = 0; i < 7; i++)
+            costMany[i] = 0;
+        refine(S);
+        bestMany[0] = S.bestMV;
+        costMany[0] = S.nMinCost;
+    }
+
+    S.globalMV = clipmv(S, S.globalMV);
+    sad = full_sad_at(S, S.globalMV.x, S.globalMV.y, S.globalMV.x, S.globalMV.y);
+    long long cost = sad + ((S.pglobal * sad) >> 8);
+    if (cost < S.nMinCost || S.tryMany) {
+        S.bestMV.x = S.globalMV.x;
+        S.bestMV.y = S.globalMV.y;
+        S.bestMV.sad = sad;
+        S.nMinCost = cost;
+    }
+    if (S.tryMany) {
+        refine(S);
+        bestMany[1] = S.bestMV;
+        costMany[1] = S.nMinCost;
+    }
+
+    sad = full_sad_at(S, S.predictor.x, S.predictor.y, S.predictor.x, S.predictor.y);
+    cost = sad;
+    if (cost < S.nMinCost || S.tryMany) {
+        S.bestMV.x = S.predictor.x;
+        S.bestMV.y = S.predictor.y;
+        S.bestMV.sad = sad;
+        S.nMinCost = cost;
+    }
+    if (S.tryMany) {
+        refine(S);
+        bestMany[2] = S.bestMV;
+        costMany[2] = S.nMinCost;
+    }
+
+    for (int i = 0; i < 4; i++) {
+        if (S.tryMany)
+            S.nMinCost = S.verybigSAD + 1;
+        CheckMV0(S, S.predictors[i].x, S.predictors[i].y);
+        if (S.tryMany) {
+            refine(S);
+            bestMany[i + 3] = S.bestMV;
+            costMany[i + 3] = S.nMinCost;
+        }
+    }
+
+    if (S.tryMany) {
+        S.nMinCost = S.verybigSAD + 1;
+        for (int i = 0; i < 7; i++)
+            if (costMany[i] < S.nMinCost) {
+                S.bestMV = bestMany[i];
+                S.nMinCost = costMany[i];
+            }
+    } else {
+        refine(S);
+    }
+
+    long long foundSAD = S.bestMV.sad;
+    if (S.blkIdx > 1 && foundSAD > (S.badSAD + S.badSAD * S.badcount / 16)) {
+        S.badcount++;
+        if (S.badrange > 0) {
+            umh_search(S, S.badrange * (1 << S.logPel), 0, 0);
+        } else if (S.badrange < 0) {
+            for (int i = 1; i < -S.badrange * (1 << S.logPel); i += (1 << S.logPel)) {
+                expanding_search(S, i, 1 << S.logPel, 0, 0);
+                if (S.bestMV.sad < foundSAD / 4)
+                    break;
+            }
+        }
+        int mvx = S.bestMV.x, mvy = S.bestMV.y;
+        for (int i = 1; i < (1 << S.logPel); i++)
+            expanding_search(S, i, 1, mvx, mvy);
+    }
+}
+
+__device__ __forceinline__ void stvec(VEC *p, const VEC &v) {
+    int *q = (int *)p;
+    __stcg(q, v.x);
+    __stcg(q + 1, v.y);
+    __stcg(q + 2, (int)(unsigned)(unsigned long long)v.sad);
+    __stcg(q + 3, (int)(unsigned)((unsigned long long)v.sad >> 32));
+}
+
+__device__ void bind_planes(PlaneView v[3], const uint8_t *frame, const SuperDesc &sd, int level, int nplanes_used) {
+    for (int p = 0; p < 3; p++) {
+        v[p].base = nullptr;
+        if (p < nplanes_used) {
+            const mvb200_level_geom &g = sd.lv[p][level];
+            v[p].pitch = sd.pitch[p];
+            v[p].base = frame + sd.offset[p] + (long long)g.row0 * sd.pitch[p];
+            v[p].sub = sd.pitch[p] * g.padded_h;
+            v[p].hpad = g.hpad;
+            v[p].vpad = g.vpad;
+            v[p].pw = g.padded_w;
+            v[p].ph = g.padded_h;
+        }
+    }
+}
+
+// pobEstimateGlobalMVDoubled, PlaneOfBlocks.cpp:1559-1636, lanes split the blocks.
+// hist: this chain's zero-initialised scratch of `freqSize` ints; left zeroed again.
+__device__ void estimate_global_mv(const VEC *v, int n, int freqSize, int *hist, VEC &g, int lane) {
+    int med[2];
+    for (int c = 0; c < 2; c++) {
+        int indmin = freqSize - 1, indmax = 0;
+        for (int i = lane; i < n; i += 32) {
+            VEC t = ldvec(&v[i]);
+            int ind = (freqSize >> 1) + (c ? t.y : t.x);
+            if (ind >= 0 && ind < freqSize) {
+                atomicAdd(&hist[ind], 1);
+                indmax = max(indmax, ind);
+                indmin = min(indmin, ind);
+            }
+        }
+        indmin = __reduce_min_sync(0xffffffffu, indmin);
+        indmax = __reduce_max_sync(0xffffffffu, indmax);
+        __syncwarp();
+        // first maximum in [indmin, indmax]: highest count, ties to the lowest index
+        int bestc = -1, besti = 0x7fffffff;
+        for (int i = indmin + lane; i <= indmax; i += 32) {
+            int cnt = *(volatile int *)&hist[i];
+            if (cnt > bestc) {
+                bestc = cnt;
+                besti = i;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            int oc = __shfl_xor_sync(0xffffffffu, bestc, o), oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (oc > bestc || (oc == bestc && oi < besti)) {
+                bestc = oc;
+                besti = oi;
+            }
+        }
+        if (indmin > indmax) // no vector fell into the histogram (cannot happen for n >= 1 with sane vectors)
+            besti = indmin;
+        med[c] = besti - (freqSize >> 1);
+        __syncwarp();
+        for (int i = indmin + lane; i <= indmax; i += 32)
+            hist[i] = 0;
+        __syncwarp();
+    }
+    int meanvx = 0, meanvy = 0, num = 0;
+    for (int i = lane; i < n; i += 32) {
+        VEC t = ldvec(&v[i]);
+        if (abs(t.x - med[0]) < 6 && abs(t.y - med[1]) < 6) {
+            meanvx += t.x;
+            meanvy += t.y;
+            num++;
+        }
+    }
+    meanvx = __reduce_add_sync(0xffffffffu, meanvx);
+    meanvy = __reduce_add_sync(0xffffffffu, meanvy);
+    num = __reduce_add_sync(0xffffffffu, num);
+    if (num > 0) {
+        g.x = 2 * meanvx / num;
+        g.y = 2 * meanvy / num;
+    } else {
+        g.x = 2 * med[0];
+        g.y = 2 * med[1];
+    }
+}
+
+// pobInterpolatePrediction, PlaneOfBlocks.cpp:1447-1514, lanes split the blocks
+__device__ void interpolate_prediction(VEC *dst, int nBlkX, int nBlkY, int logPel, const VEC *v2, int nBlkX2, int nBlkY2, int blkW, int blkH, int ovX, int ovY, int lane) {
+    int normFactor = 3 - logPel; // logPel of the coarser level is always 0
+    int mulFactor = normFactor < 0 ? -normFactor : 0;
+    normFactor = normFactor < 0 ? 0 : normFactor;
+    int normov = (blkW - ovX) * (blkH - ovY);
+    int aoddx = blkW * 3 - ovX * 2, aevenx = blkW * 3 - ovX * 4;
+    int aoddy = blkH * 3 - ovY * 2, aeveny = blkH * 3 - ovY * 4;
+    double scaleov = __ddiv_rn(1.0, (double)normov);
+    int total = nBlkX * nBlkY;
+    for (int index = lane; index < total; index += 32) {
+        int l = index / nBlkX, k = index - l * nBlkX;
+        int i = k, j = l;
+        if (i >= 2 * nBlkX2) i = 2 * nBlkX2 - 1;
+        if (j >= 2 * nBlkY2) j = 2 * nBlkY2 - 1;
+        int offy = -1 + 2 * (j % 2), offx = -1 + 2 * (i % 2);
+        bool edgex = (i == 0) || (i >= 2 * nBlkX2 - 1), edgey = (j == 0) || (j >= 2 * nBlkY2 - 1);
+        VEC v1, w2, v3, v4;
+        v1 = ldvec(&v2[i / 2 + (j / 2) * nBlkX2]);
+        if (edgex) {
+            w2 = v1;
+            if (edgey) {
+                v3 = v4 = v1;
+            } else {
+                v3 = v4 = ldvec(&v2[i / 2 + (j / 2 + offy) * nBlkX2]);
+            }
+        } else if (edgey) {
+            w2 = v1;
+            v3 = v4 = ldvec(&v2[i / 2 + offx + (j / 2) * nBlkX2]);
+        } else {
+            w2 = ldvec(&v2[i / 2 + offx + (j / 2) * nBlkX2]);
+            v3 = ldvec(&v2[i / 2 + (j / 2 + offy) * nBlkX2]);
+            v4 = ldvec(&v2[i / 2 + offx + (j / 2 + offy) * nBlkX2]);
+        }
+        long long temp_sad;
+        int vx, vy;
+        if (ovX == 0 && ovY == 0) {
+            vx = 9 * v1.x + 3 * w2.x + 3 * v3.x + v4.x;
+            vy = 9 * v1.y + 3 * w2.y + 3 * v3.y + v4.y;
+            temp_sad = 9 * v1.sad + 3 * w2.sad + 3 * v3.sad + v4.sad + 8;
+        } else {
+            int ax1 = offx > 0 ? aoddx : aevenx;
+            int ax2 = (blkW - ovX) * 4 - ax1;
+            int ay1 = offy > 0 ? aoddy : aeveny;
+            int ay2 = (blkH - ovY) * 4 - ay1;
+            long long a11 = ax1 * ay1, a12 = ax1 * ay2, a21 = ax2 * ay1, a22 = ax2 * ay2;
+            vx = __double2int_rz(__dmul_rn((double)(a11 * v1.x + a21 * w2.x + a12 * v3.x + a22 * v4.x), scaleov));
+            vy = __double2int_rz(__dmul_rn((double)(a11 * v1.y + a21 * w2.y + a12 * v3.y + a22 * v4.y), scaleov));
+            temp_sad = __double2ll_rz(__dmul_rn((double)(a11 * v1.sad + a21 * w2.sad + a12 * v3.sad + a22 * v4.sad), scaleov));
+        }
+        VEC o;
+        o.x = (vx >> normFactor) * (1 << mulFactor);
+        o.y = (vy >> normFactor) * (1 << mulFactor);
+        o.sad = temp_sad >> 4;
+        stvec(&dst[index], o);
+    }
+}
+
+// GetMedian, GroupOfPlanes.c:179-203
+__device__ __forceinline__ int med3(int a, int b, int c) {
+    if (((b <= a) && (a <= c)) || ((c <= a) && (a <= b))) return a;
+    if (((a <= b) && (b <= c)) || ((c <= b) && (b <= a))) return b;
+    return c;
+}
+__device__ __forceinline__ void get_median(int &vx, int &vy, int x1, int y1, int x2, int y2, int x3, int y3) {
+    vx = med3(x1, x2, x3);
+    vy = med3(y1, y2, y3);
+    if ((vx == x1 && vy == y1) || (vx == x2 && vy == y2) || (vx == x3 && vy == y3))
+        return;
+    vx = x1;
+    vy = y1;
+}
+
+// doPobSearchMVs, PlaneOfBlocks.cpp:971-1131
+__device__ void search_level(State &S, const SearchParams &P, int st, int stp, const VEC &globalMVec, int fieldShift, int *pmeanLumaChange, int pglobal, int tryMany) {
+    S.dctweight16 = min(16, abs(*pmeanLumaChange) / (S.blkW * S.blkH));
+    S.badSAD = P.badSAD;
+    S.badrange = P.badrange;
+    S.zeroMVfs.x = 0;
+    S.zeroMVfs.y = fieldShift;
+    S.zeroMVfs.sad = 0;
+    S.globalMV.x = (1 << S.logPel) * globalMVec.x;
+    S.globalMV.y = (1 << S.logPel) * globalMVec.y + fieldShift;
+    S.globalMV.sad = globalMVec.sad;
+    S.searchType = st;
+    S.searchParam = stp;
+    int nScale = 1 << S.logScale;
+    int nLambdaLevel = P.nLambda / ((1 << S.logPel) * (1 << S.logPel));
+    if (P.plevel == 1)
+        nLambdaLevel = nLambdaLevel * nScale;
+    else if (P.plevel == 2)
+        nLambdaLevel = nLambdaLevel * nScale * nScale;
+    S.penaltyZero = P.pzero;
+    S.pglobal = pglobal;
+    S.badcount = 0;
+    S.tryMany = tryMany;
+    S.penaltyNew = P.pnew;
+    S.LSAD = P.lsad;
+    int sumLumaChange = 0;
+    const int stepX = S.blkW - S.ovX, stepY = S.blkH - S.ovY;
+    const PlaneView &g0 = S.src[0];
+    const int hps = g0.hpad >> S.logScale, vps = g0.vpad >> S.logScale;
+    for (int p = 0; p < 3; p++)
+        S.y[p] = S.src[p].base ? S.src[p].vpad : 0;
+    for (S.blky = 0; S.blky < S.nBlkY; S.blky++) {
+        S.scanDir = (S.blky % 2 == 0 || P.meander == 0) ? 1 : -1;
+        int blkxStart = (S.scanDir == 1) ? 0 : S.nBlkX - 1;
+        for (int iblkx = 0; iblkx < S.nBlkX; iblkx++) {
+            S.blkx = blkxStart + iblkx * S.scanDir;
+            S.blkIdx = S.blky * S.nBlkX + S.blkx;
+            S.x[0] = g0.hpad + stepX * S.blkx;
+            if (S.chroma) {
+                S.x[1] = S.src[1].hpad + (stepX >> S.logxR) * S.blkx;
+                S.x[2] = S.src[2].hpad + (stepX >> S.logxR) * S.blkx;
+            }
+            for (int p = 0; p < (S.chroma ? 3 : 1); p++)
+                S.pSrc[p] = S.src[p].base + (long long)S.y[p] * S.src[p].pitch + (long long)S.x[p] * S.bps;
+            S.nLambda = S.blky == 0 ? 0 : nLambdaLevel;
+            S.dxMax = (g0.pw - S.x[0] - S.blkW - g0.hpad + hps) << S.logPel;
+            S.dyMax = (g0.ph - S.y[0] - S.blkH - g0.vpad + vps) << S.logPel;
+            S.dxMin = -((S.x[0] - g0.hpad + hps) << S.logPel);
+            S.dyMin = -((S.y[0] - g0.vpad + vps) << S.logPel);
+            S.predictor = clipmv(S, ldvec(&S.vectors[S.blkIdx]));
+            epz_search(S);
+            __syncwarp();
+            if (S.lane == 0)
+                stvec(&S.vectors[S.blkIdx], S.bestMV);
+            __syncwarp();
+            if (S.smallest)
+                sumLumaChange += (int)wsum(lane_luma(ref_luma(S, 0, 0), S.ref[0].pitch, S.blkW * S.bps, S.blkH, S.bps, S.lane)) -
+                                 (int)wsum(lane_luma(S.pSrc[0], S.src[0].pitch, S.blkW * S.bps, S.blkH, S.bps, S.lane));
+        }
+        S.y[0] += stepY;
+        if (S.src[1].base) S.y[1] += stepY >> S.logyR;
+        if (S.src[2].base) S.y[2] += stepY >> S.logyR;
+    }
+    if (S.smallest)
+        *pmeanLumaChange = sumLumaChange / (S.nBlkX * S.nBlkY);
+}
+
+__global__ void __launch_bounds__(32) k_search(const SuperDesc *__restrict__ sdp, const SearchParams *__restrict__ params, const SearchJob *__restrict__ jobs, int njobs, int *__restrict__ hist_all, int hist_ints) {
+    int chain = blockIdx.x;
+    if (chain >= njobs)
+        return;
+    const int lane = threadIdx.x;
+    const SearchJob job = jobs[chain];
+    const SearchParams &P = params[job.param];
+    const SuperDesc &sd = *sdp;
+    const int L = P.levels;
+    int *hdr = (int *)job.out;
+    if (lane == 0) {
+        hdr[0] = P.vectors_size;
+        hdr[1] = job.ref ? 1 : 0;
+    }
+    // level headers (pobWriteHeaderToArray :413-416) and, without a reference frame, the
+    // default vectors of gopWriteDefaultToArray (GroupOfPlanes.c:150-164)
+    for (int l = 0; l < L; l++) {
+        int n = P.nBlkX[l] * P.nBlkY[l];
+        uint8_t *o = job.out + P.level_off[l];
+        if (lane == 0)
+            *(int *)o = 4 + n * 16;
+        VEC *v = (VEC *)(o + 4);
+        VEC init;
+        init.x = 0;
+        init.y = 0;
+        init.sad = job.ref ? 0 : P.verybigSAD; // pobInit zeroes vectors[] (:354-355)
+        for (int i = lane; i < n; i += 32)
+            stvec(&v[i], init);
+        if (l == 0 && P.divide) {
+            uint8_t *o2 = o + 4 + n * 16;
+            if (lane == 0)
+                *(int *)o2 = 4 + n * 16 * 4;
+            if (!job.ref) {
+                VEC *v2 = (VEC *)(o2 + 4);
+                for (int i = lane; i < n * 4; i += 32)
+                    stvec(&v2[i], init);
+            }
+        }
+    }
+    __syncwarp();
+    if (!job.ref)
+        return;
+
+    int *hist = hist_all + (long long)chain * hist_ints;
+    const int nplanes_used = P.chroma ? 3 : 1;
+    VEC globalMV;
+    globalMV.x = 0;
+    globalMV.y = 0;
+    globalMV.sad = -1;
+    const int pglobal = P.global ? P.pglobal : P.pzero;
+    int meanLumaChange = 0;
+
+    State S;
+    S.lane = lane;
+    S.blkW = P.blkW;
+    S.blkH = P.blkH;
+    S.ovX = P.ovX;
+    S.ovY = P.ovY;
+    S.logxR = sd.logxR;
+    S.logyR = sd.logyR;
+    S.bps = P.bps;
+    S.chroma = P.chroma;
+    S.cw = P.blkW >> sd.logxR;
+    S.ch = P.blkH >> sd.logyR;
+    S.dctmode = P.dctmode;
+    S.verybigSAD = P.verybigSAD;
+    S.srcLuma = 0;
+
+    for (int l = L - 1; l >= 0; l--) {
+        S.nBlkX = P.nBlkX[l];
+        S.nBlkY = P.nBlkY[l];
+        S.logPel = l == 0 ? P.logPel : 0;
+        S.logScale = l;
+        S.smallest = (l == L - 1);
+        S.vectors = (VEC *)(job.out + P.level_off[l] + 4);
+        bind_planes(S.src, job.src, sd, l, nplanes_used);
+        bind_planes(S.ref, job.ref, sd, l, nplanes_used);
+        int st, stp, fs, tm;
+        if (l == L - 1) {
+            st = (L == 1 || P.search == 6 || P.search == 7) ? P.search : P.search_coarse;
+            stp = (L == 1) ? P.nPelSearch : P.nSearchParam;
+            fs = (L - 1 == 0) ? job.field_shift : 0;
+            tm = P.tryMany && L > 1;
+        } else {
+            st = (l == 0 || P.search == 6 || P.search == 7) ? P.search : P.search_coarse;
+            stp = (l == 0) ? P.nPelSearch : P.nSearchParam;
+            const VEC *coarse = (const VEC *)(job.out + P.level_off[l + 1] + 4);
+            if (P.global)
+                estimate_global_mv(coarse, P.nBlkX[l + 1] * P.nBlkY[l + 1], 8192 * 1 * 2, hist, globalMV, lane);
+            interpolate_prediction(S.vectors, S.nBlkX, S.nBlkY, S.logPel, coarse, P.nBlkX[l + 1], P.nBlkY[l + 1], S.blkW, S.blkH, S.ovX, S.ovY, lane);
+            __syncwarp();
+            fs = (l == 0) ? job.field_shift : 0;
+            tm = P.tryMany && l > 0;
+        }
+        search_level(S, P, st, stp, globalMV, fs, &meanLumaChange, pglobal, tm);
+        __syncwarp();
+    }
+    if (P.divide) { // gopExtraDivide, GroupOfPlanes.c:206-302, lanes split the blocks
+        const int nBlkX = P.nBlkX[0], nBlkY = P.nBlkY[0], n = nBlkX * nBlkY;
+        const VEC *in = (const VEC *)(job.out + P.level_off[0] + 4);
+        VEC *out = (VEC *)(job.out + P.level_off[0] + 4 + n * 16 + 4);
+        for (int i = lane; i < n; i += 32) {
+            int by = i / nBlkX, bx = i - by * nBlkX;
+            VEC b = ldvec(&in[i]);
+            b.sad >>= 2;
+            VEC o[4] = {b, b, b, b};
+            if (P.divide > 1 && by >= 1 && by < nBlkY - 1 && bx >= 1 && bx < nBlkX - 1) {
+                VEC c = ldvec(&in[i]), lf = ldvec(&in[i - 1]), rt = ldvec(&in[i + 1]), up = ldvec(&in[i - nBlkX]), dn = ldvec(&in[i + nBlkX]);
+                get_median(o[0].x, o[0].y, c.x, c.y, lf.x, lf.y, up.x, up.y);
+                get_median(o[1].x, o[1].y, c.x, c.y, rt.x, rt.y, up.x, up.y);
+                get_median(o[2].x, o[2].y, c.x, c.y, lf.x, lf.y, dn.x, dn.y);
+                get_median(o[3].x, o[3].y, c.x, c.y, rt.x, rt.y, dn.x, dn.y);
+            }
+            VEC *q = out + (by * 2) * (nBlkX * 2) + bx * 2;
+            stvec(&q[0], o[0]);
+            stvec(&q[1], o[1]);
+            stvec(&q[nBlkX * 2], o[2]);
+            stvec(&q[nBlkX * 2 + 1], o[3]);
+        }
+    }
+}
+
+} // namespace
+
+int launch_search(Ctx *ctx, const SuperDesc &sd, const SearchParams *host_params, int nparams, const SearchJob *host_jobs, int njobs) {
+    if (njobs <= 0)
+        return 0;
+    const int hist_ints = 8192 * 2;
+    size_t bytes_sd = sizeof(SuperDesc), bytes_p = sizeof(SearchParams) * (size_t)nparams, bytes_j = sizeof(SearchJob) * (size_t)njobs;
+    size_t off_p = (bytes_sd + 255) & ~(size_t)255, off_j = (off_p + bytes_p + 255) & ~(size_t)255, total = off_j + bytes_j;
+    uint8_t *host = (uint8_t *)ctx->get_pinned(total);
+    uint8_t *dev = (uint8_t *)ctx->get_scratch(0, total);
+    int *hist = (int *)ctx->get_scratch(1, sizeof(int) * (size_t)hist_ints * (size_t)njobs);
+    if (!host || !dev || !hist)
+        return 1;
+    // the pinned staging buffer is reused by the next call: wait for earlier uploads to be consumed
+    MVB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    memcpy(host, &sd, bytes_sd);
+    memcpy(host + off_p, host_params, bytes_p);
+    memcpy(host + off_j, host_jobs, bytes_j);
+    MVB_CUDA_CHECK(cudaMemcpyAsync(dev, host, total, cudaMemcpyHostToDevice, ctx->stream));
+    k_search<<<njobs, 32, 0, ctx->stream>>>((const SuperDesc *)dev, (const SearchParams *)(dev + off_p), (const SearchJob *)(dev + off_j), njobs, hist, hist_ints);
+    ctx->launches++;
+    MVB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+} // namespace mvb200

@@ -1,0 +1,296 @@
+// mv.Super on the GPU: builds the padded, multi-level, sub-pel "super" frames of a
+// whole batch of source frames, in the reference's exact memory layout
+// (MVFrame.cpp:1229-1247 / MVSuper.c:78-103), so any stage's bytes can be handed
+// back to VapourSynth or diffed against the oracle without repacking.
+//
+// All kernels here are streaming integer stencils: one thread per output sample,
+// consecutive threads on consecutive samples of a row (coalesced), grid.z = frame.
+// They are HBM-bound; the pyramid levels and the three refine passes are separate
+// launches in the reference's order because each consumes the previous one's padded
+// output (reduce l -> pad l+1 -> reduce l+1 ...; pad 0 -> refine).
+//
+//   k_fill     <- mvfFillPlane            MVFrame.cpp:1367-1371
+//   k_reduce   <- RB2F_C / RB2Filtered / RB2BilinearFiltered / RB2Quadratic / RB2Cubic
+//                                         MVFrame.cpp:576-1014 (vertical pass at double
+//                                         width + in-place horizontal pass, fused; the
+//                                         stale right half of the intermediate is
+//                                         reproduced because it is part of the frame)
+//   k_pad      <- PadReferenceFrame       MVFrame.cpp:1264-1318
+//   k_refine_* <- Horizontal/Vertical/DiagonalBilinear :508-572, *Bicubic :1115-1176,
+//                 *Wiener :1019-1111, Average2 :1180-1197, driver mvpRefine :1386-1527
+#include "engine.h"
+
+namespace mvb200 {
+
+namespace {
+
+template <typename T>
+__device__ __forceinline__ int ld(const T *p, long long i) {
+    return (int)p[i];
+}
+
+// ---- fill ---------------------------------------------------------------
+template <typename T>
+__global__ void k_fill(const uint8_t *__restrict__ src, long long src_pitch, long long src_frame, uint8_t *__restrict__ dst,
+                       long long dst_pitch, long long dst_frame, int w, int h) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h)
+        return;
+    const T *s = (const T *)(src + (long long)blockIdx.z * src_frame + (long long)y * src_pitch);
+    T *d = (T *)(dst + (long long)blockIdx.z * dst_frame + (long long)y * dst_pitch);
+    d[x] = s[x];
+}
+
+// ---- reduce -------------------------------------------------------------
+// vertical tap of the separable reduce filters at intermediate column x, output row y
+template <typename T>
+__device__ __forceinline__ int reduce_v(const T *s, long long sp, int x, int y, int h, int rfilter) {
+    const T *r = s + (long long)(2 * y) * sp + x;
+    bool edge = (rfilter == 1) ? (y == 0) : (y == 0 || y >= max(h - 1, 1));
+    if (edge)
+        return (ld(r, 0) + ld(r, sp) + 1) / 2;
+    if (rfilter == 1)
+        return (ld(r, -sp) + ld(r, 0) * 2 + ld(r, sp) + 2) / 4;
+    if (rfilter == 2)
+        return (ld(r, -sp) + (ld(r, 0) + ld(r, sp)) * 3 + ld(r, sp * 2) + 4) / 8;
+    int m0 = ld(r, -sp * 2), m1 = ld(r, -sp), m2 = ld(r, 0), m3 = ld(r, sp), m4 = ld(r, sp * 2), m5 = ld(r, sp * 3);
+    if (rfilter == 3) {
+        m2 = (m2 + m3) * 22;
+        m1 = (m1 + m4) * 9;
+        m0 += m5 + m2 + m1 + 32;
+        return m0 >> 6;
+    }
+    m2 = (m2 + m3) * 10;
+    m1 = (m1 + m4) * 5;
+    m0 += m5 + m2 + m1 + 16;
+    return m0 >> 5;
+}
+
+template <typename T>
+__global__ void k_reduce(const uint8_t *__restrict__ src_base, uint8_t *__restrict__ dst_base, long long pitch_bytes,
+                         long long frame_bytes, int w, int h, int rfilter) {
+    // src_base / dst_base: interior origin of level l / l+1 in frame 0.  pitch in bytes.
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    int wide = rfilter == 0 ? w : 2 * w;
+    if (x >= wide || y >= h)
+        return;
+    long long sp = pitch_bytes / (long long)sizeof(T);
+    const T *s = (const T *)(src_base + (long long)blockIdx.z * frame_bytes);
+    T *d = (T *)(dst_base + (long long)blockIdx.z * frame_bytes) + (long long)y * sp;
+    int v;
+    if (rfilter == 0) {
+        const T *r = s + (long long)(2 * y) * sp + 2 * x;
+        v = (ld(r, 0) + ld(r, 1) + ld(r, sp + 1) + ld(r, sp) + 2) / 4;
+    } else if (x >= w) {
+        v = reduce_v(s, sp, x, y, h, rfilter); // stale intermediate the in-place pass leaves behind
+    } else if (x == 0) {
+        v = (reduce_v(s, sp, 0, y, h, rfilter) + reduce_v(s, sp, 1, y, h, rfilter) + 1) / 2;
+    } else if (rfilter == 1) {
+        v = (reduce_v(s, sp, 2 * x - 1, y, h, rfilter) + reduce_v(s, sp, 2 * x, y, h, rfilter) * 2 + reduce_v(s, sp, 2 * x + 1, y, h, rfilter) + 2) / 4;
+    } else if (x >= max(w - 1, 1)) {
+        v = (reduce_v(s, sp, 2 * x, y, h, rfilter) + reduce_v(s, sp, 2 * x + 1, y, h, rfilter) + 1) / 2;
+    } else if (rfilter == 2) {
+        v = (reduce_v(s, sp, 2 * x - 1, y, h, rfilter) + (reduce_v(s, sp, 2 * x, y, h, rfilter) + reduce_v(s, sp, 2 * x + 1, y, h, rfilter)) * 3 +
+             reduce_v(s, sp, 2 * x + 2, y, h, rfilter) + 4) / 8;
+    } else {
+        int m0 = reduce_v(s, sp, 2 * x - 2, y, h, rfilter), m1 = reduce_v(s, sp, 2 * x - 1, y, h, rfilter);
+        int m2 = reduce_v(s, sp, 2 * x, y, h, rfilter), m3 = reduce_v(s, sp, 2 * x + 1, y, h, rfilter);
+        int m4 = reduce_v(s, sp, 2 * x + 2, y, h, rfilter), m5 = reduce_v(s, sp, 2 * x + 3, y, h, rfilter);
+        if (rfilter == 3) {
+            m2 = (m2 + m3) * 22;
+            m1 = (m1 + m4) * 9;
+            m0 += m5 + m2 + m1 + 32;
+            v = m0 >> 6;
+        } else {
+            m2 = (m2 + m3) * 10;
+            m1 = (m1 + m4) * 5;
+            m0 += m5 + m2 + m1 + 16;
+            v = m0 >> 5;
+        }
+    }
+    d[x] = (T)v;
+}
+
+// ---- pad ----------------------------------------------------------------
+template <typename T>
+__global__ void k_pad(uint8_t *__restrict__ base, long long pitch_bytes, long long frame_bytes, int hpad, int vpad, int w, int h) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w + 2 * hpad || y >= h + 2 * vpad)
+        return;
+    bool interior = (x >= hpad && x < hpad + w && y >= vpad && y < vpad + h);
+    if (interior)
+        return;
+    long long sp = pitch_bytes / (long long)sizeof(T);
+    T *p = (T *)(base + (long long)blockIdx.z * frame_bytes);
+    int sx = min(max(x - hpad, 0), w - 1) + hpad;
+    int sy = min(max(y - vpad, 0), h - 1) + vpad;
+    p[(long long)y * sp + x] = p[(long long)sy * sp + sx];
+}
+
+// ---- refine -------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ int wiener6(int m0, int m1, int m2, int m3, int m4, int m5, int pixelMax) {
+    m2 = (m2 + m3) * 4;
+    m2 -= m1 + m4;
+    m2 *= 5;
+    m0 += m5 + m2 + 16;
+    m0 >>= 5;
+    return max(0, min(m0, pixelMax));
+}
+
+// dir: 0 = horizontal (step 1), 1 = vertical (step pitch)
+template <typename T>
+__global__ void k_refine_hv(uint8_t *__restrict__ dst_base, const uint8_t *__restrict__ src_base, long long pitch_bytes,
+                            long long frame_bytes, int w, int h, int bits, int sharp, int dir) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h)
+        return;
+    long long sp = pitch_bytes / (long long)sizeof(T);
+    const T *s = (const T *)(src_base + (long long)blockIdx.z * frame_bytes) + (long long)y * sp + x;
+    T *d = (T *)(dst_base + (long long)blockIdx.z * frame_bytes) + (long long)y * sp + x;
+    long long st = dir ? sp : 1;
+    int i = dir ? y : x, n = dir ? h : w;
+    int pixelMax = (1 << bits) - 1;
+    int mode; // 0 copy, 1 average, 2 filter
+    if (i == n - 1)
+        mode = 0;
+    else if (sharp == 0)
+        mode = 1;
+    else if (sharp == 1)
+        mode = (i >= 1 && i < n - 3) ? 2 : 1;
+    else
+        mode = (i >= 2 && i < n - 4) ? 2 : 1;
+    int v;
+    if (mode == 0)
+        v = ld(s, 0);
+    else if (mode == 1)
+        v = (ld(s, 0) + ld(s, st) + 1) >> 1;
+    else if (sharp == 1)
+        v = min(pixelMax, max(0, (-ld(s, -st) - ld(s, st * 2) + (ld(s, 0) + ld(s, st)) * 9 + 8) >> 4));
+    else
+        v = wiener6<T>(ld(s, -st * 2), ld(s, -st), ld(s, 0), ld(s, st), ld(s, st * 2), ld(s, st * 3), pixelMax);
+    *d = (T)v;
+}
+
+template <typename T>
+__global__ void k_refine_diag(uint8_t *__restrict__ dst_base, const uint8_t *__restrict__ src_base, long long pitch_bytes,
+                              long long frame_bytes, int w, int h) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h)
+        return;
+    long long sp = pitch_bytes / (long long)sizeof(T);
+    const T *s = (const T *)(src_base + (long long)blockIdx.z * frame_bytes) + (long long)y * sp + x;
+    T *d = (T *)(dst_base + (long long)blockIdx.z * frame_bytes) + (long long)y * sp + x;
+    int v;
+    if (y < h - 1) {
+        if (x < w - 1)
+            v = (ld(s, 0) + ld(s, 1) + ld(s, sp) + ld(s, sp + 1) + 2) >> 2;
+        else
+            v = (ld(s, 0) + ld(s, sp) + 1) >> 1;
+    } else {
+        if (x < w - 1)
+            v = (ld(s, 0) + ld(s, 1) + 1) >> 1;
+        else
+            v = ld(s, 0);
+    }
+    *d = (T)v;
+}
+
+template <typename T>
+__global__ void k_avg2(uint8_t *__restrict__ dst_base, const uint8_t *__restrict__ a_base, const uint8_t *__restrict__ b_base,
+                       long long pitch_bytes, long long frame_bytes, int w, int h) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h)
+        return;
+    long long sp = pitch_bytes / (long long)sizeof(T);
+    long long o = (long long)y * sp + x;
+    const T *a = (const T *)(a_base + (long long)blockIdx.z * frame_bytes);
+    const T *b = (const T *)(b_base + (long long)blockIdx.z * frame_bytes);
+    T *d = (T *)(dst_base + (long long)blockIdx.z * frame_bytes);
+    d[o] = (T)((ld(a, o) + ld(b, o) + 1) >> 1);
+}
+
+inline dim3 grid2d(int w, int h, int n, dim3 blk) { return dim3((w + blk.x - 1) / blk.x, (h + blk.y - 1) / blk.y, n); }
+
+template <typename T>
+int super_typed(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, uint8_t *dev_super, int n) {
+    cudaStream_t st = ctx->stream;
+    const dim3 blk(64, 4);
+    const int bps = sd.bps;
+    // MVSuper.c:75 -- the whole super frame starts zeroed (the gaps between levels stay zero)
+    MVB_CUDA_CHECK(cudaMemsetAsync(dev_super, 0, (size_t)sd.frame_bytes * n, st));
+    ctx->launches++;
+    for (int plane = 0; plane < sd.nplanes; plane++) {
+        if (!(p->modeyuv & (1 << plane)))
+            continue;
+        const long long pitch = sd.pitch[plane];
+        uint8_t *pl = dev_super + sd.offset[plane];
+        auto level_base = [&](int l) { return pl + (long long)sd.lv[plane][l].row0 * pitch; };
+        auto interior = [&](int l) { return level_base(l) + (long long)sd.lv[plane][l].vpad * pitch + (long long)sd.lv[plane][l].hpad * bps; };
+        const mvb200_level_geom &g0 = sd.lv[plane][0];
+        k_fill<T><<<grid2d(g0.width, g0.height, n, blk), blk, 0, st>>>(dev_src + cd.offset[plane], cd.pitch[plane], cd.frame_bytes, interior(0), pitch,
+                                                                      sd.frame_bytes, g0.width, g0.height);
+        ctx->launches++;
+        for (int l = 0; l < sd.levels - 1; l++) {
+            const mvb200_level_geom &g1 = sd.lv[plane][l + 1];
+            int wide = p->rfilter == 0 ? g1.width : 2 * g1.width;
+            k_reduce<T><<<grid2d(wide, g1.height, n, blk), blk, 0, st>>>(interior(l), interior(l + 1), pitch, sd.frame_bytes, g1.width, g1.height, p->rfilter);
+            k_pad<T><<<grid2d(g1.padded_w, g1.padded_h, n, blk), blk, 0, st>>>(level_base(l + 1), pitch, sd.frame_bytes, g1.hpad, g1.vpad, g1.width, g1.height);
+            ctx->launches += 2;
+        }
+        k_pad<T><<<grid2d(g0.padded_w, g0.padded_h, n, blk), blk, 0, st>>>(level_base(0), pitch, sd.frame_bytes, g0.hpad, g0.vpad, g0.width, g0.height);
+        ctx->launches++;
+        if (p->pel > 1) { // mvpRefine, MVFrame.cpp:1386-1527
+            const long long sub = pitch * g0.padded_h;
+            auto P = [&](int i) { return level_base(0) + sub * i; };
+            const int w = g0.padded_w, h = g0.padded_h;
+            const int iH = p->pel == 2 ? 1 : 2, iV = p->pel == 2 ? 2 : 8, iD = p->pel == 2 ? 3 : 10;
+            dim3 g = grid2d(w, h, n, blk);
+            k_refine_hv<T><<<g, blk, 0, st>>>(P(iH), P(0), pitch, sd.frame_bytes, w, h, sd.bits, p->sharp, 0);
+            k_refine_hv<T><<<g, blk, 0, st>>>(P(iV), P(0), pitch, sd.frame_bytes, w, h, sd.bits, p->sharp, 1);
+            if (p->sharp == 0)
+                k_refine_diag<T><<<g, blk, 0, st>>>(P(iD), P(0), pitch, sd.frame_bytes, w, h);
+            else
+                k_refine_hv<T><<<g, blk, 0, st>>>(P(iD), P(iV), pitch, sd.frame_bytes, w, h, sd.bits, p->sharp, 0);
+            ctx->launches += 3;
+            if (p->pel == 4) {
+                auto avg = [&](int d, const uint8_t *a, const uint8_t *b, int ww, int hh) {
+                    k_avg2<T><<<grid2d(ww, hh, n, blk), blk, 0, st>>>(P(d), a, b, pitch, sd.frame_bytes, ww, hh);
+                    ctx->launches++;
+                };
+                avg(1, P(0), P(2), w, h);
+                avg(9, P(8), P(10), w, h);
+                avg(4, P(0), P(8), w, h);
+                avg(6, P(2), P(10), w, h);
+                avg(5, P(4), P(6), w, h);
+                avg(3, P(0) + bps, P(2), w - 1, h);
+                avg(11, P(8) + bps, P(10), w - 1, h);
+                avg(12, P(0) + pitch, P(8), w, h - 1);
+                avg(14, P(2) + pitch, P(10), w, h - 1);
+                avg(13, P(12), P(14), w, h);
+                avg(7, P(4) + bps, P(6), w - 1, h);
+                avg(15, P(12) + bps, P(14), w - 1, h);
+            }
+        }
+    }
+    MVB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+} // namespace
+
+int launch_super(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, uint8_t *dev_super, int n) {
+    if (n <= 0)
+        return 0;
+    if (sd.bps == 1)
+        return super_typed<uint8_t>(ctx, p, sd, cd, dev_src, dev_super, n);
+    return super_typed<uint16_t>(ctx, p, sd, cd, dev_src, dev_super, n);
+}
+
+} // namespace mvb200
