@@ -1,0 +1,121 @@
+"""Shared test helpers: run Super -> Analyse x 2r -> DegrainN on a seeded clip through
+ (a) the CPU oracle, (b) the compiled reference via the mini host, (c) the CUDA C ABI,
+and hash every stage the same way so results can be compared or pinned as goldens."""
+import hashlib
+
+import numpy as np
+
+import clipgen
+import mvtools_b200 as mb
+
+# (name, clip kwargs, Super kwargs, Analyse kwargs, radius, Degrain kwargs)
+CASES = {
+    # BASELINE.json configs[0]: Super+Analyse blksize=8 pel=1 search=4, 640x360 P8
+    "c1_640x360_p8_blk8_pel1": (dict(width=640, height=360, nframes=6, bits=8), dict(pel=1), dict(blksize=8, search=4), 1, {}),
+    "blk8_ov4_pel2_p8": (dict(width=320, height=192, nframes=6, bits=8), dict(pel=2), dict(blksize=8, overlap=4), 1, {}),
+    "blk16_ov8_pel2_p16_r3": (dict(width=320, height=192, nframes=8, bits=16), dict(pel=2), dict(blksize=16, overlap=8), 3, {}),
+    "blk16_ov8_pel2_p8_r3": (dict(width=320, height=200, nframes=8, bits=8), dict(pel=2), dict(blksize=16, overlap=8), 3, {}),
+    "p10_444_blk8_pel4_bicubic": (dict(width=176, height=120, nframes=5, bits=10, ssw=0, ssh=0), dict(pel=4, sharp=1, rfilter=4), dict(blksize=8, overlap=2, search=5, searchparam=4), 1, dict(limit=40, thsad=600)),
+    "gray_blk4_pel1_rf0": (dict(width=128, height=96, nframes=5, bits=8, gray=True), dict(pel=1, rfilter=0), dict(blksize=4, search=2, searchparam=2, truemotion=0), 1, dict()),
+    "blk4_420_chroma2x2_pel2": (dict(width=80, height=64, nframes=4, bits=8), dict(pel=2, hpad=8, vpad=8), dict(blksize=4, overlap=2), 1, dict()),
+    "blk32_p16_umh": (dict(width=256, height=160, nframes=4, bits=16), dict(pel=1), dict(blksize=32, overlap=16, search=5, searchparam=8, search_coarse=4), 1, dict()),
+    "p8_422_blk8x4_sharp0_rf1": (dict(width=208, height=120, nframes=5, bits=8, ssw=1, ssh=0), dict(pel=2, sharp=0, rfilter=1, hpad=8, vpad=8), dict(blksize=8, blksizev=4, overlap=4, overlapv=2, search=3, searchparam=2, meander=0), 2, dict(plane=0)),
+    "satd_dct5_blk16": (dict(width=256, height=144, nframes=5, bits=8), dict(pel=2, rfilter=3), dict(blksize=16, dct=5, search=1, searchparam=2), 1, dict()),
+    "noise_badblocks_blk8": (dict(width=192, height=128, nframes=5, bits=8, pure_noise=True), dict(pel=2), dict(blksize=8, overlap=2, badsad=300, badrange=6), 1, dict(thscd1=16000, thscd2=255)),
+    "trymany_nochroma_dct7_p16": (dict(width=192, height=128, nframes=5, bits=16), dict(pel=2), dict(blksize=16, overlap=4, trymany=1, chroma=0, dct=7, search=0, searchparam=3, global_=0), 1, dict()),
+    "divide2_blk16_esa_neg_badrange": (dict(width=256, height=160, nframes=5, bits=8, pure_noise=True), dict(pel=2), dict(blksize=16, overlap=8, divide=2, badsad=500, badrange=-4, search=6, searchparam=3), 1, dict(thscd1=16000, thscd2=255)),
+}
+
+
+def _fix(kw):
+    kw = dict(kw)
+    if "global_" in kw:
+        kw["global"] = kw.pop("global_")
+    return kw
+
+
+def make_frames(ck):
+    ck = dict(ck)
+    return clipgen.make_clip(ck.pop("width"), ck.pop("height"), ck.pop("nframes"), **ck)
+
+
+def sha(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+def mask_blob(blob, ap):
+    """The reference leaves the 4-byte size header of the `divide` level uninitialised."""
+    b = np.array(blob, copy=True)
+    if ap.divide:
+        n0 = ap.nBlkX[0] * ap.nBlkY[0]
+        off = ap.vectors_size - (4 + n0 * 16 * 4)
+        b[off:off + 4] = 0
+    return b
+
+
+def params_for(case):
+    ck, skw, akw, radius, dkw = CASES[case]
+    W, H, N = ck["width"], ck["height"], ck["nframes"]
+    bits, ssw, ssh, gray = ck.get("bits", 8), ck.get("ssw", 1), ck.get("ssh", 1), ck.get("gray", False)
+    sp = mb.super_params(W, H, bits, ssw, ssh, gray, **skw)
+    aps = [mb.analyse_params(sp, N, isb=isb, delta=d, **_fix(akw)) for d in range(1, radius + 1) for isb in (1, 0)]
+    vds = [(ap.ad_divided if ap.divide else ap.ad) for ap in aps]
+    dp = mb.degrain_params(sp, vds, W, H, radius, **dkw)
+    return sp, aps, dp
+
+
+def nref_of(ap, n, N):
+    d = ap.ad.nDeltaFrame
+    r = n + d if ap.ad.isBackward else n - d
+    return r if 0 <= r < N else None
+
+
+def run_engine(case, super_fn, analyse_fn, degrain_fn):
+    """Runs the per-frame pipeline with the given stage functions; returns {stage: [hash per frame]}"""
+    frames = make_frames(CASES[case][0])
+    N = len(frames)
+    sp, aps, dp = params_for(case)
+    sups = [super_fn(sp, f) for f in frames]
+    out = {"super": [[sha(p) for p in s] for s in sups], "vectors": [], "degrain": []}
+    vecs = []
+    for n in range(N):
+        row = []
+        for ap in aps:
+            r = nref_of(ap, n, N)
+            row.append(analyse_fn(ap, sp, sups[n], sups[r] if r is not None else None))
+        vecs.append(row)
+        out["vectors"].append([sha(mask_blob(v, ap)) for v, ap in zip(row, aps)])
+    for n in range(N):
+        refs = [sups[nref_of(ap, n, N)] if nref_of(ap, n, N) is not None else None for ap in aps]
+        d = degrain_fn(dp, sp, frames[n], refs, vecs[n])
+        out["degrain"].append([sha(p) for p in d])
+    return out
+
+
+def run_reference(case):
+    """The same pipeline through the compiled reference plugin and the mini VapourSynth host."""
+    import minivs
+    ck, skw, akw, radius, dkw = CASES[case]
+    frames = make_frames(ck)
+    N = len(frames)
+    sp, aps, dp = params_for(case)
+    core = minivs.Core()
+    mv = core.load(minivs.REF_PLUGIN)
+    clip = core.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1))
+    sup = mv.Super(clip, **skw)
+    vn = [mv.Analyse(sup, isb=isb, delta=d, **_fix(akw)) for d in range(1, radius + 1) for isb in (1, 0)]
+    dn = mv.invoke("Degrain%d" % radius, clip, sup, *vn, **dkw)
+    out = {"super": [], "vectors": [], "degrain": [], "adata": []}
+    for n in range(N):
+        out["super"].append([sha(p) for p in sup.get_frame(n).planes()])
+        row = []
+        for v, ap in zip(vn, aps):
+            blob = np.frombuffer(v.get_frame(n).prop_data("MVTools_vectors"), dtype=np.uint8)
+            row.append(sha(mask_blob(blob, ap)))
+        out["vectors"].append(row)
+        out["degrain"].append([sha(p) for p in dn.get_frame(n).planes()])
+    for v in vn:
+        ad = np.frombuffer(v.get_frame(0).prop_data("MVTools_MVAnalysisData"), dtype=np.int32).copy()
+        ad[[0, 1, 8]] = 0  # nMagicKey / nVersion are never written, nCPUFlags is host specific
+        out["adata"].append(ad.tolist())
+    return out

@@ -1,0 +1,99 @@
+"""CPU tests of the host side of the C ABI: the library loads, exports every symbol the
+header declares, derives parameters like the reference's *Create functions and reports the
+reference's error messages."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import mvtools_b200 as mb
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    hdr = open(os.path.join(ROOT, "include", "mvtools_b200.h")).read()
+    names = re.findall(r"MVB200_API\s+[\w\s\*]+?\b(mvb200_\w+)\s*\(", hdr)
+    assert len(names) >= 20
+    L = C.CDLL(mb.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), "libmvtools_b200.so does not export %s" % n
+    assert b"mvtools_b200" in mb.lib().mvb200_version()
+
+
+def test_plugin_exports_entry_point(built):
+    L = C.CDLL(mb.PLUGIN_PATH)
+    assert hasattr(L, "VapourSynthPluginInit2")
+
+
+def test_super_geometry_matches_survey_table(built):
+    # super frame sizes for the BASELINE configs
+    for (w, h, pel, sw, sh, lv) in ((640, 360, 1, 672, 978, 8), (1920, 1080, 2, 1952, 5822, 10), (3840, 2160, 2, 3872, 11254, 11)):
+        sp = mb.super_params(w, h, 8, 1, 1, pel=pel)
+        assert (sp.super_width, sp.super_height, sp.levels) == (sw, sh, lv)
+
+
+def test_analyse_geometry_matches_survey_table(built):
+    sp = mb.super_params(1920, 1080, 8, 1, 1, pel=2)
+    ap = mb.analyse_params(sp, 10, blksize=8, overlap=4)
+    assert (ap.ad.nBlkX, ap.ad.nBlkY, ap.ad.nLvCount) == (479, 269, 8)
+    assert [ap.nBlkX[i] * ap.nBlkY[i] for i in range(8)] == [128851, 32026, 7854, 1888, 435, 98, 18, 2]
+    ap = mb.analyse_params(sp, 10, blksize=16, overlap=8)
+    assert (ap.ad.nBlkX, ap.ad.nBlkY, ap.ad.nLvCount) == (239, 134, 7)
+    # truemotion defaults, MVAnalyse.c:303-330,477-483
+    assert (ap.nLambda, ap.lsad, ap.pnew, ap.plevel, ap.global_, ap.badSAD) == (4000, 4800, 50, 1, 1, 40000)
+    sp16 = mb.super_params(1920, 1080, 16, 1, 1, pel=2)
+    ap = mb.analyse_params(sp16, 10, blksize=16, overlap=8)
+    assert (ap.nLambda, ap.lsad, ap.badSAD) == (1028000, 1233600, 10280000)
+
+
+@pytest.mark.parametrize("kw,msg", [
+    (dict(search=9), "Analyse: search must be between 0 and 7 (inclusive)."),
+    (dict(blksize=12), "Analyse: the block size must be 4x4, 8x4, 8x8, 16x2, 16x8, 16x16, 32x16, 32x32, 64x32, 64x64, 128x64, or 128x128."),
+    (dict(blksize=8, overlap=6), "Analyse: overlap must be at most half of blksize, overlapv must be at most half of blksizev, and they both need to be at least 0."),
+    (dict(blksize=8, overlap=3), "Analyse: The requested overlap is incompatible with the super clip's subsampling."),
+    (dict(dct=11), "Analyse: dct must be between 0 and 10 (inclusive)."),
+    (dict(pnew=300), "Analyse: pnew must be between 0 and 256 (inclusive)."),
+    (dict(levels=40), "Analyse: invalid number of levels."),
+    (dict(blksize=4, divide=1), "Analyse: blksize and blksizev must be at least 8 when divide=True."),
+])
+def test_analyse_errors_are_the_references(built, kw, msg):
+    sp = mb.super_params(640, 360, 8, 1, 1)
+    with pytest.raises(mb.Error) as e:
+        mb.analyse_params(sp, 10, **kw)
+    assert str(e.value) == msg
+
+
+def test_super_errors(built):
+    with pytest.raises(mb.Error) as e:
+        mb.super_params(640, 360, 8, 1, 1, pel=3)
+    assert str(e.value) == "Super: pel must be 1, 2, or 4."
+
+
+def test_degrain_errors_and_thresholds(built):
+    sp = mb.super_params(640, 360, 8, 1, 1)
+    bw = mb.analyse_params(sp, 10, isb=1, blksize=16, overlap=8)
+    fw = mb.analyse_params(sp, 10, isb=0, blksize=16, overlap=8)
+    dp = mb.degrain_params(sp, [bw.ad, fw.ad], 640, 360, 1)
+    # scaleThSCD (MVAnalysisData.c:7-31): 400*256/64 = 1600, +1600/4*2 = 2400; thsad 400 -> 2400
+    assert (dp.nSCD1, dp.nSCD2, dp.thSAD[0], dp.thSAD[1]) == (2400, 130 * bw.ad.nBlkX * bw.ad.nBlkY // 256, 2400, 2400)
+    with pytest.raises(mb.Error) as e:
+        mb.degrain_params(sp, [fw.ad, bw.ad], 640, 360, 1)
+    assert str(e.value) == "Degrain1: mvfw must be generated with isb=False."
+    with pytest.raises(mb.Error) as e:
+        mb.degrain_params(sp, [bw.ad, fw.ad], 640, 360, 1, thscd1=20000)
+    assert str(e.value) == "Degrain1: thscd1 can be at most 16320."
+    with pytest.raises(mb.Error) as e:
+        mb.degrain_params(sp, [bw.ad, fw.ad], 320, 360, 1)
+    assert str(e.value) == "Degrain1: wrong source or super clip frame size."
+
+
+def test_compute_fails_loudly_without_gpu(built):
+    """No CPU fallback: on a box without a CUDA device the context cannot be created."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(mb.Error) as e:
+        mb.Context(0)
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
