@@ -300,9 +300,13 @@ int mvb200_analyse_multi_batch(mvb200_ctx *ctx, const mvb200_analyse_params *con
             j.out = (uint8_t *)dev_vectors[i] + (long long)f * vectors_stride;
             j.param = i;
             j.field_shift = nref >= 0 ? field_shift_of(ap[i], fn, nref) : 0;
+            j.src_index = fn;
+            j.ref_index = nref >= 0 ? nref : 0;
             jobs.push_back(j);
         }
-    return launch_search(&ctx->c, sd, params.data(), nap, jobs.data(), (int)jobs.size());
+    mvb200_super_geom geom;
+    mvb200_super_geometry(sp, &geom);
+    return launch_search(&ctx->c, sd, geom, (const uint8_t *)dev_super, nap > 0 ? ap[0]->num_frames : 0, params.data(), nap, jobs.data(), (int)jobs.size());
 }
 
 int mvb200_analyse_batch(mvb200_ctx *ctx, const mvb200_analyse_params *ap, const mvb200_super_params *sp, const void *dev_super, int first, int n, void *dev_vectors, int64_t vectors_stride) {
@@ -397,7 +401,11 @@ int mvb200_analyse_frame(mvb200_ctx *ctx, const mvb200_analyse_params *ap, const
     j.out = buf + sd.frame_bytes * 2;
     j.param = 0;
     j.field_shift = field_shift;
-    if (launch_search(c, sd, &P, 1, &j, 1))
+    j.src_index = 0;
+    j.ref_index = 1;
+    mvb200_super_geom geom;
+    mvb200_super_geometry(sp, &geom);
+    if (launch_search(c, sd, geom, buf, 2, &P, 1, &j, 1))
         return 1;
     MVB_CUDA_CHECK(cudaMemcpyAsync(vectors_out, j.out, (size_t)ap->vectors_size, cudaMemcpyDeviceToHost, c->stream));
     MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));

@@ -63,13 +63,17 @@ struct SearchJob {
     uint8_t *out;       // blob
     int param;          // index into the SearchParams array
     int field_shift;
+    int src_index, ref_index; // frame indices relative to the super-clip base (TMA coordinates)
 };
 
 struct Ctx;
 
 // kernels' host launchers (each returns 0 or sets the error)
 int launch_super(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, uint8_t *dev_super, int n);
-int launch_search(Ctx *ctx, const SuperDesc &sd, const SearchParams *host_params, int nparams, const SearchJob *host_jobs, int njobs);
+// frames_base / nframes describe the resident super clip the jobs point into (needed for the TMA descriptors)
+int launch_search(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &geom, const uint8_t *frames_base, int nframes, const SearchParams *host_params, int nparams, const SearchJob *host_jobs, int njobs);
+int launch_search_tma(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &geom, const uint8_t *frames_base, int nframes, const SearchParams *host_params, int nparams,
+                      const SuperDesc *dev_sd, const SearchParams *dev_params, const SearchJob *dev_jobs, int njobs, int *hist, int hist_ints, bool *handled);
 int launch_search_fast(Ctx *ctx, const SuperDesc &sd, const SearchParams *host_params, int nparams, const SuperDesc *dev_sd, const SearchParams *dev_params,
                        const SearchJob *dev_jobs, int njobs, int *hist, int hist_ints, bool *handled);
 int launch_degrain(Ctx *ctx, const mvb200_degrain_params *dp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, const uint8_t *dev_super, int num_frames, int first, int n, const uint8_t *const *dev_vectors, long long vectors_stride, uint8_t *dev_dst);

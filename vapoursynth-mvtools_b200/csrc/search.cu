@@ -757,7 +757,7 @@ __global__ void __launch_bounds__(32) k_search(const SuperDesc *__restrict__ sdp
 
 } // namespace
 
-int launch_search(Ctx *ctx, const SuperDesc &sd, const SearchParams *host_params, int nparams, const SearchJob *host_jobs, int njobs) {
+int launch_search(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &geom, const uint8_t *frames_base, int nframes, const SearchParams *host_params, int nparams, const SearchJob *host_jobs, int njobs) {
     if (njobs <= 0)
         return 0;
     const int hist_ints = 8192 * 2;
@@ -778,6 +778,12 @@ int launch_search(Ctx *ctx, const SuperDesc &sd, const SearchParams *host_params
     // generic kernel otherwise, or when MVB200_FORCE_GENERIC=1 (used by the tests to cover both)
     bool handled = false;
     const char *force = getenv("MVB200_FORCE_GENERIC");
+    const char *notma = getenv("MVB200_NO_TMA");
+    if (!(force && force[0] == '1') && !(notma && notma[0] == '1'))
+        if (launch_search_tma(ctx, sd, geom, frames_base, nframes, host_params, nparams, (const SuperDesc *)dev, (const SearchParams *)(dev + off_p), (const SearchJob *)(dev + off_j), njobs, hist, hist_ints, &handled))
+            return 1;
+    if (handled)
+        return 0;
     if (!(force && force[0] == '1'))
         if (launch_search_fast(ctx, sd, host_params, nparams, (const SuperDesc *)dev, (const SearchParams *)(dev + off_p), (const SearchJob *)(dev + off_j), njobs, hist, hist_ints, &handled))
             return 1;

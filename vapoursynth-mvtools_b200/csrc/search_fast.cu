@@ -471,6 +471,7 @@ __global__ void __launch_bounds__(32) k_search_fast(const SuperDesc *__restrict_
         S.logScale = l;
         S.smallest = (l == L - 1);
         S.vectors = (VEC *)(job.out + P.level_off[l] + 4);
+#pragma unroll
         for (int p = 0; p < 3; p++) {
             const int q = (p < sd.nplanes) ? p : 0;
             const mvb200_level_geom &g = sd.lv[q][l];
@@ -508,9 +509,13 @@ __global__ void __launch_bounds__(32) k_search_fast(const SuperDesc *__restrict_
                 act = false;
             }
             int row = w / wpr, col = w - row * wpr;
-            int o = row * S.pl[p].pitch + col * 4;
-            S.sp[k] = S.pl[p].sbase + o;
-            S.rp[k] = S.pl[p].rbase + o;
+            // (no dynamic indexing of S.pl[]: that would force the whole state into local memory)
+            const int pitch_p = p == 0 ? S.pl[0].pitch : S.pl[1].pitch;
+            const uint8_t *sb = p == 0 ? S.pl[0].sbase : (p == 1 ? S.pl[1].sbase : S.pl[2].sbase);
+            const uint8_t *rb = p == 0 ? S.pl[0].rbase : (p == 1 ? S.pl[1].rbase : S.pl[2].rbase);
+            int o = row * pitch_p + col * 4;
+            S.sp[k] = sb + o;
+            S.rp[k] = rb + o;
             if (act)
                 S.actMask |= 1u << k;
             if (act && p == 0)
@@ -711,6 +716,9 @@ int launch_search_fast(Ctx *ctx, const SuperDesc &sd, const SearchParams *host_p
         k_search_fast<NW_, BPS_, PACK_><<<njobs, 32, 0, ctx->stream>>>(dev_sd, dev_params, dev_jobs, njobs, hist, hist_ints); \
         *handled = true;                                                                                                           \
     } while (0)
+#ifdef MVB_FAST_QUICK
+    if (bps == 1 && pack && nw == 3) LAUNCH(3, 1, true);
+#else
     if (bps == 1 && pack) {
         if (nw == 1) LAUNCH(1, 1, true);
         else if (nw == 2) LAUNCH(2, 1, true);
@@ -731,6 +739,7 @@ int launch_search_fast(Ctx *ctx, const SuperDesc &sd, const SearchParams *host_p
         else if (nw == 6) LAUNCH(6, 2, false);
         else if (nw == 8) LAUNCH(8, 2, false);
     }
+#endif
 #undef LAUNCH
     if (*handled) {
         ctx->launches++;
