@@ -66,11 +66,14 @@ __constant__ int t_hex4[16][2] = {{-4, 2}, {-4, 1}, {-4, 0}, {-4, -1}, {-4, -2},
 template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
 struct Cfg {
     static constexpr int CW = BW >> LXR, CH = BH >> LYR;
-    static constexpr int R = 4; // luma window radius in full pixels (left/top); right/bottom get the 16-byte round-up too
+    static constexpr int R = 4; // guaranteed luma window radius in full pixels
     static constexpr int RCX = R >> LXR, RCY = R >> LYR;
-    static constexpr int LWB = ((BW + 2 * R) * BPS + 15) / 16 * 16; // luma window row bytes
+    // window row bytes: block + 2R, plus up to 15 bytes because a TMA tile must START on a 16-byte
+    // boundary of the innermost dimension (measured: an unaligned start coordinate raises
+    // "illegal instruction" on sm_100), rounded up to the 16-byte box granularity
+    static constexpr int LWB = ((BW + 2 * R) * BPS + 15 + 15) / 16 * 16;
     static constexpr int LWH = BH + 2 * R;
-    static constexpr int CWB = ((CW + 2 * RCX) * BPS + 15) / 16 * 16;
+    static constexpr int CWB = ((CW + 2 * RCX) * BPS + 15 + 15) / 16 * 16;
     static constexpr int CWH = CH + 2 * RCY;
     static constexpr int LT = (LWB * LWH + 127) / 128 * 128; // tile bytes (TMA destinations are 128-byte aligned)
     static constexpr int CT = CHROMA ? (CWB * CWH + 127) / 128 * 128 : 0;
@@ -79,7 +82,7 @@ struct Cfg {
     static constexpr int LW = BW * BPS / 4, LN = LW * BH, NLI = (LN + 31) / 32;
     static constexpr int CWw = CW * BPS / 4, CN = CWw * CH, NCI = CHROMA ? (2 * CN + 31) / 32 : 0;
     static constexpr bool PACK = BPS == 1 && BW * BH <= 256 && 2 * CW * CH <= 256;
-    static constexpr int SMEM = 2 * BUF + 128;
+    static constexpr int SMEM = 2 * BUF + 256;
 };
 
 struct TmaMaps {
@@ -148,6 +151,9 @@ struct Chain {
         oy = (((y0_ << logPel) + cy) >> logPel) - C::R;
         oxc = (((xc_ << logPel) + cdiv(cx, LXR)) >> logPel) - C::RCX;
         oyc = (((yc_ << logPel) + cdiv(cy, LYR)) >> logPel) - C::RCY;
+        // 16-byte aligned start of the innermost (x) coordinate, rounding toward -infinity
+        ox = ((ox * BPS) & ~15) >> (BPS == 2 ? 1 : 0);
+        oxc = ((oxc * BPS) & ~15) >> (BPS == 2 ? 1 : 0);
     }
 
     // one lane issues the tile loads of a window into buffer `dst`
