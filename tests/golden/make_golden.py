@@ -16,6 +16,10 @@ out = {}
 for case in pipeline.CASES:
     out[case] = pipeline.run_reference(case)
     print(case, "ok", flush=True)
+import minivs  # noqa: E402
+reg = minivs.Core().load(minivs.REF_PLUGIN)
+with open(os.path.join(HERE, "registration.json"), "w") as f:
+    json.dump({"identifier": reg.identifier, "namespace": reg.namespace, "functions": reg.functions()}, f, indent=0, sort_keys=True)
 with open(os.path.join(HERE, "golden.json"), "w") as f:
     json.dump(out, f, indent=0, sort_keys=True)
 print("wrote golden.json")

@@ -92,15 +92,15 @@ def run_engine(case, super_fn, analyse_fn, degrain_fn):
     return out
 
 
-def run_reference(case):
-    """The same pipeline through the compiled reference plugin and the mini VapourSynth host."""
+def run_reference(case, plugin_path=None):
+    """The same pipeline through a VapourSynth plugin (default: the compiled reference) and the mini host."""
     import minivs
     ck, skw, akw, radius, dkw = CASES[case]
     frames = make_frames(ck)
     N = len(frames)
     sp, aps, dp = params_for(case)
     core = minivs.Core()
-    mv = core.load(minivs.REF_PLUGIN)
+    mv = core.load(plugin_path or minivs.REF_PLUGIN)
     clip = core.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1))
     sup = mv.Super(clip, **skw)
     vn = [mv.Analyse(sup, isb=isb, delta=d, **_fix(akw)) for d in range(1, radius + 1) for isb in (1, 0)]

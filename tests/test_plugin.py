@@ -1,0 +1,61 @@
+"""The drop-in boundary: this repo's VapourSynth plugin (libmvtools.so) against the reference plugin.
+
+CPU part: identity, namespace, function names and argument strings are byte-identical to what the
+reference registers (EntryPoint.c:28-50 and the *Register functions), create-time errors included.
+GPU part: the same "script" (Super -> Analyse x 2r -> DegrainN) driven through the plugin API by the
+test-only mini VapourSynth host gives the reference's bytes."""
+import json
+import os
+
+import pytest
+
+import mvtools_b200 as mb
+import pipeline
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REG = json.load(open(os.path.join(HERE, "golden", "registration.json")))
+GOLD = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+
+
+def test_registration_is_the_references(built):
+    import minivs
+    p = minivs.Core().load(mb.PLUGIN_PATH)
+    assert (p.identifier, p.namespace) == (REG["identifier"], REG["namespace"])
+    mine = p.functions()
+    for name, args in REG["functions"].items():
+        assert name in mine, "mv.%s is not registered" % name
+        assert mine[name] == args, "mv.%s: argument string differs from the reference" % name
+    assert set(mine) == set(REG["functions"])
+
+
+def test_registration_golden_is_current(have_ref):
+    if not have_ref:
+        pytest.skip("reference build not available")
+    import minivs
+    p = minivs.Core().load(minivs.REF_PLUGIN)
+    assert p.functions() == REG["functions"]
+
+
+def test_create_time_errors_through_the_plugin(built):
+    import clipgen
+    import minivs
+    core = minivs.Core()
+    mv = core.load(mb.PLUGIN_PATH)
+    clip = core.source(clipgen.make_clip(64, 48, 2))
+    with pytest.raises(minivs.Error) as e:
+        mv.Super(clip, pel=3)
+    assert str(e.value) == "Super: pel must be 1, 2, or 4."
+    with pytest.raises(minivs.Error) as e:
+        mv.Analyse(clip)  # not a super clip: no Super_* props
+    assert "required properties not found in first frame of super clip" in str(e.value)
+    with pytest.raises(minivs.Error) as e:
+        mv.Super(clip, bogus=1)
+    assert "does not take argument" in str(e.value)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["c1_640x360_p8_blk8_pel1", "blk16_ov8_pel2_p8_r3", "blk16_ov8_pel2_p16_r3", "divide2_blk16_esa_neg_badrange", "p8_422_blk8x4_sharp0_rf1"])
+def test_script_through_plugin_matches_reference(built, case):
+    got = pipeline.run_reference(case, plugin_path=mb.PLUGIN_PATH)
+    for stage in ("super", "vectors", "degrain", "adata"):
+        assert got[stage] == GOLD[case][stage], "%s: plugin %s differs from the reference plugin" % (case, stage)

@@ -49,11 +49,10 @@ struct VEC { // the blob's VECTOR arrays are only 4-byte aligned: 32-bit fields 
     __device__ __forceinline__ long long sad() const { return (long long)(((unsigned long long)(unsigned)sad_hi << 32) | (unsigned)sad_lo); }
 };
 
-__device__ __forceinline__ const VEC *blob_level0(const uint8_t *blob, int nLvCount) {
-    const uint8_t *p = blob + 8;
-    for (int i = nLvCount - 1; i >= 1; i--)
-        p += *(const int *)p;
-    return (const VEC *)(p + 4);
+// The finest level (the one Degrain reads: fgopGetBlock(fgop, 0, i), Fakery.c:110-133) is stored LAST in
+// the blob (coarsest first, GroupOfPlanes.c:76-85), also for `divide` clips: it is the final 16*nBlk bytes.
+__device__ __forceinline__ const VEC *blob_level0(const uint8_t *blob, int nBlk) {
+    return (const VEC *)(blob + __ldg((const int *)blob) - 16 * nBlk);
 }
 
 // one CTA per (r, frame)
@@ -61,7 +60,7 @@ __global__ void k_scd(DegrainDev D, int *__restrict__ usable) {
     int r = blockIdx.x, f = blockIdx.y;
     const uint8_t *blob = D.vectors[r] + (long long)f * D.vectors_stride;
     int valid = ((const int *)blob)[1] == 1;
-    const VEC *v = blob_level0(blob, D.nLvCount);
+    const VEC *v = blob_level0(blob, D.nBlkX * D.nBlkY);
     int n = D.nBlkX * D.nBlkY;
     int cnt = 0;
     for (int i = threadIdx.x; i < n; i += blockDim.x)
@@ -98,7 +97,7 @@ __global__ void k_weights(DegrainDev D, const int *__restrict__ usable, BlockW *
     long long sad[kMaxR2];
     for (int r = 0; r < D.R2; r++) {
         if (usable[f * D.R2 + r]) {
-            const VEC *v = blob_level0(D.vectors[r] + (long long)f * D.vectors_stride, D.nLvCount);
+            const VEC *v = blob_level0(D.vectors[r] + (long long)f * D.vectors_stride, n);
             sad[r] = v[i].sad();
         } else {
             sad[r] = -1;
@@ -150,7 +149,7 @@ __device__ __forceinline__ int blend_block(const DegrainDev &D, const BlendPlane
         int wr = w.w[B.cls][r];
         if (wr == 0)
             continue; // unusable reference or zero weight: contributes nothing
-        const VEC *v = blob_level0(D.vectors[r] + (long long)f * D.vectors_stride, D.nLvCount);
+        const VEC *v = blob_level0(D.vectors[r] + (long long)f * D.vectors_stride, D.nBlkX * D.nBlkY);
         int vx = v[bi].x, vy = v[bi].y;
         // useBlock, MVDegrains.h:192-206 + mvpGetPointer, MVFrame.cpp:1733-1755
         int blx = ((bx * B.stepX0) << D.logPel) + vx;
@@ -214,6 +213,144 @@ __global__ void k_blend(DegrainDev D, BlendPlane B, const uint8_t *__restrict__ 
     if (B.limit < pixelMax) // LimitChanges_C, MVDegrains.h:168-181
         out = min(max(out, srcv - B.limit), srcv + B.limit);
     drow[x] = (T)out;
+}
+
+
+// ---- four samples per thread ------------------------------------------------------------
+// When block size, step and overlap are multiples of 4 samples, the 4 samples x..x+3 (x % 4 == 0)
+// are covered by the same blocks, so the per-block work (weights, vectors, sub-plane addressing) is
+// done once per 4 outputs and the pixels move as 32/64-bit words.
+template <typename T>
+struct Quad {
+    int v[4];
+};
+
+template <typename T>
+__device__ __forceinline__ void load4(const uint8_t *p, int (&o)[4]) {
+    // p: address of 4 consecutive samples with sample alignment only
+    unsigned long long a = (unsigned long long)p;
+    if (sizeof(T) == 1) {
+        const unsigned *q = (const unsigned *)(a & ~3ull);
+        unsigned w = __funnelshift_r(__ldg(q), __ldg(q + 1), ((unsigned)a & 3u) * 8u);
+        o[0] = w & 255;
+        o[1] = (w >> 8) & 255;
+        o[2] = (w >> 16) & 255;
+        o[3] = w >> 24;
+    } else {
+        const unsigned *q = (const unsigned *)(a & ~3ull);
+        unsigned sh = ((unsigned)a & 2u) * 8u;
+        unsigned w0 = __ldg(q), w1 = __ldg(q + 1), w2 = sh ? __ldg(q + 2) : 0u;
+        unsigned lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        o[0] = lo & 0xffff;
+        o[1] = lo >> 16;
+        o[2] = hi & 0xffff;
+        o[3] = hi >> 16;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void blend_block4(const DegrainDev &D, const BlendPlane &B, const BlockW &w, const uint8_t *sup_frames, long long sup_frame_bytes, int f, int bx,
+                                             int by, int ix, int iy, const int (&srcv)[4], int (&out)[4]) {
+    int sum[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        sum[i] = 128 + srcv[i] * w.wsrc[B.cls];
+    const int bi = by * D.nBlkX + bx;
+    for (int r = 0; r < D.R2; r++) {
+        const int wr = w.w[B.cls][r];
+        if (wr == 0)
+            continue;
+        const VEC *v = blob_level0(D.vectors[r] + (long long)f * D.vectors_stride, D.nBlkX * D.nBlkY);
+        const int vx = v[bi].x, vy = v[bi].y;
+        const int blx = ((bx * B.stepX0) << D.logPel) + vx;
+        const int bly = ((by * B.stepY0) << D.logPel) + vy;
+        const int ax = (B.plane ? blx >> B.xSub : blx) + B.hpad_pel;
+        const int ay = (B.plane ? bly >> B.ySub : bly) + B.vpad_pel;
+        const int m = D.pel - 1;
+        const int idx = (ax & m) | ((ay & m) << D.logPel);
+        const int n_ref = D.first + f + (D.backward[r] ? D.delta[r] : -D.delta[r]);
+        const uint8_t *p = sup_frames + (long long)n_ref * sup_frame_bytes + B.sup_off + idx * B.sup_sub + (long long)((ay >> D.logPel) + iy) * B.sup_pitch +
+                           (long long)((ax >> D.logPel) + ix) * (int)sizeof(T);
+        int rv[4];
+        load4<T>(p, rv);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            sum[i] += rv[i] * wr;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        out[i] = (int)(T)(sum[i] >> 8);
+}
+
+template <typename T>
+__global__ void k_blend4(DegrainDev D, BlendPlane B, const uint8_t *__restrict__ src_frames, long long src_frame_bytes, const uint8_t *__restrict__ sup_frames,
+                         long long sup_frame_bytes, uint8_t *__restrict__ dst_frames, long long dst_frame_bytes, const BlockW *__restrict__ weights) {
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int f = blockIdx.z;
+    if (x >= B.W || y >= B.H)
+        return;
+    const uint8_t *srow = src_frames + (long long)(D.first + f) * src_frame_bytes + B.src_off + (long long)y * B.src_pitch;
+    uint8_t *drow = dst_frames + (long long)f * dst_frame_bytes + B.dst_off + (long long)y * B.dst_pitch;
+    int srcv[4], out[4];
+    load4<T>(srow + (long long)x * (int)sizeof(T), srcv);
+    const int pixelMax = (1 << D.bits) - 1;
+    const int nvalid = min(4, B.W - x);
+    // a quad never straddles the covered / uncovered boundary unless WB % 4 != 0: handle per sample below
+    const bool covered = B.process && x + 3 < B.WB && y < B.HB;
+    if (covered) {
+        const BlockW *wf = weights + (long long)f * D.nBlkX * D.nBlkY;
+        if (!B.win) {
+            const int bx = x / B.bw, by = y / B.bh;
+            blend_block4<T>(D, B, wf[by * D.nBlkX + bx], sup_frames, sup_frame_bytes, f, bx, by, x - bx * B.bw, y - by * B.bh, srcv, out);
+        } else {
+            const int sx = B.bw - B.ox, sy = B.bh - B.oy;
+            const int bx1 = min(x / sx, D.nBlkX - 1), by1 = min(y / sy, D.nBlkY - 1);
+            const int bx0 = (bx1 >= 1 && x - bx1 * sx < B.ox) ? bx1 - 1 : bx1;
+            const int by0 = (by1 >= 1 && y - by1 * sy < B.oy) ? by1 - 1 : by1;
+            unsigned acc[4] = {0, 0, 0, 0};
+            for (int by = by0; by <= by1; by++) {
+                const int wby = ((by + D.nBlkY - 3) / (D.nBlkY - 2)) * 3;
+                const int iy = y - by * sy;
+                for (int bx = bx0; bx <= bx1; bx++) {
+                    const int wbx = bx == D.nBlkX - 1 ? 2 : (bx == 0 ? 0 : 1);
+                    const int ix = x - bx * sx;
+                    int v[4];
+                    blend_block4<T>(D, B, wf[by * D.nBlkX + bx], sup_frames, sup_frame_bytes, f, bx, by, ix, iy, srcv, v);
+                    const short4 wv = *(const short4 *)(B.win + (wby + wbx) * B.bw * B.bh + iy * B.bw + ix);
+                    const int ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        acc[i] += (unsigned)((v[i] * ww[i]) >> 6);
+                        if (sizeof(T) == 1)
+                            acc[i] &= 0xffffu;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                out[i] = min(pixelMax, (int)((acc[i] + 16) >> 5));
+        }
+        if (B.limit < pixelMax) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                out[i] = min(max(out[i], srcv[i] - B.limit), srcv[i] + B.limit);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            out[i] = srcv[i];
+    }
+    T *d = (T *)drow + x;
+    if (nvalid == 4) {
+        if (sizeof(T) == 1)
+            *(unsigned *)d = (unsigned)out[0] | ((unsigned)out[1] << 8) | ((unsigned)out[2] << 16) | ((unsigned)out[3] << 24);
+        else
+            *(uint2 *)d = make_uint2((unsigned)out[0] | ((unsigned)out[1] << 16), (unsigned)out[2] | ((unsigned)out[3] << 16));
+    } else {
+        for (int i = 0; i < nvalid; i++)
+            d[i] = (T)out[i];
+    }
 }
 
 // overInit, Overlap.cpp:40-125 -- evaluated on the HOST with the same float/double
@@ -357,6 +494,18 @@ int launch_degrain(Ctx *ctx, const mvb200_degrain_params *dp, const SuperDesc &s
             B.WB = B.W;
         if (!(dp->nHeight_B[0] < dp->nHeight[0]))
             B.HB = B.H;
+        // 4 samples per thread when every block boundary is a multiple of 4 samples (and rows start 4-aligned)
+        const bool quad = B.process && (B.bw % 4 == 0) && (B.ox % 4 == 0) && (B.WB % 4 == 0) && (!overlap || ((B.bw - B.ox) % 4 == 0));
+        if (quad) {
+            dim3 blk4(32, 8);
+            dim3 grid4(((B.W + 3) / 4 + blk4.x - 1) / blk4.x, (B.H + blk4.y - 1) / blk4.y, n);
+            if (sd.bps == 1)
+                k_blend4<uint8_t><<<grid4, blk4, 0, st>>>(D, B, dev_src, cd.frame_bytes, dev_super, sd.frame_bytes, dev_dst, cd.frame_bytes, weights);
+            else
+                k_blend4<uint16_t><<<grid4, blk4, 0, st>>>(D, B, dev_src, cd.frame_bytes, dev_super, sd.frame_bytes, dev_dst, cd.frame_bytes, weights);
+            ctx->launches++;
+            continue;
+        }
         dim3 blk(32, 8);
         dim3 grid((B.W + blk.x - 1) / blk.x, (B.H + blk.y - 1) / blk.y, n);
         if (sd.bps == 1)

@@ -25,6 +25,10 @@
 
 #include <cuda.h>
 
+#ifndef MVB_TMA_MIN_BLOCKS
+#define MVB_TMA_MIN_BLOCKS 16 // caps registers at 128 so that 16 chains fit on an SM
+#endif
+
 namespace mvb200 {
 
 namespace {
@@ -119,7 +123,7 @@ struct Chain {
     long long nLambda, nMinCost;
     VEC best, predictor;
     int badcount, lane;
-    const uint8_t *sbuf; // the current window buffer (shared memory)
+    uint32_t sbuf; // shared-space address of the current window buffer
 
     __device__ __forceinline__ bool ok(int vx, int vy) const { return vx >= dxMin && vy >= dyMin && vx < dxMax && vy < dyMax; }
     __device__ __forceinline__ VEC clip(VEC v) const {
@@ -136,7 +140,16 @@ struct Chain {
     // chroma vector of a luma vector: division toward zero (pobGetRefBlockU/V, :56-101)
     __device__ __forceinline__ static int cdiv(int v, int lg) { return (v + ((v < 0) ? ((1 << lg) - 1) : 0)) >> lg; }
 
-    __device__ __forceinline__ static unsigned lds(const uint8_t *a) { return *(const unsigned *)a; }
+    // window reads use 32-bit shared-space addresses (no 64-bit generic pointer arithmetic per word).
+    // `volatile` keeps them after the mbarrier wait that publishes the TMA data.
+    __device__ __forceinline__ static unsigned lds(uint32_t a) {
+        unsigned v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+        return v;
+    }
+    __device__ __forceinline__ static void lds2(uint32_t a, unsigned &lo, unsigned &hi) {
+        asm volatile("ld.shared.u32 %0, [%2];\n\tld.shared.u32 %1, [%2+4];" : "=r"(lo), "=r"(hi) : "r"(a));
+    }
     __device__ __forceinline__ static unsigned ldg_un(const uint8_t *p) { // unaligned 32-bit global load
         unsigned long long a = (unsigned long long)p;
         const unsigned *q = (const unsigned *)(a & ~3ull);
@@ -199,6 +212,7 @@ struct Chain {
 
     // Evaluates the candidates held by lanes 0..7 (lane j: candidate j).  Returns, in every lane,
     // this lane's own candidate's (sadY, sadUV) -- lanes without a valid candidate get garbage.
+    template <int NS>
     __device__ __forceinline__ void eval_step(const Cand &c, unsigned &mySy, unsigned &mySuv) const {
         // my candidate's window addressing
         const int m = (1 << logPel) - 1;
@@ -213,43 +227,47 @@ struct Chain {
             inside = inside && fxc >= wxc0 && fxc + C::CW <= wxc0 + C::CWB / BPS && fyc >= wyc0 && fyc + C::CH <= wyc0 + C::CWH;
             cbc += ((Xc & m) | ((Yc & m) << logPel)) * C::CT + (fyc - wyc0) * C::CWB + (fxc - wxc0) * BPS;
         }
-        const bool mine = lane < 8 && c.valid;
+        const bool mine = lane < NS && c.valid;
         if (!mine) { // harmless in-window dummy
             cbl = 0;
             cbc = C::NSUB * C::LT;
         }
         const unsigned needMask = __ballot_sync(0xffffffffu, mine);
         const unsigned outside = __ballot_sync(0xffffffffu, mine && !inside);
-        unsigned res[8];
+        unsigned res[NS];
         if (outside == 0) {
-            unsigned aL[8], aC[8];
+            unsigned aL[NS], aC[NS];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < NS; j++) {
                 const int pl = __shfl_sync(0xffffffffu, cbl, j);
-                const uint8_t *al = sbuf + (pl & ~3);
+                const uint32_t al = sbuf + (pl & ~3);
                 const unsigned shl = (pl & 3) * 8;
                 aL[j] = 0;
                 aC[j] = 0;
 #pragma unroll
                 for (int k = 0; k < NLI; k++) {
-                    unsigned w = __funnelshift_r(lds(al + lo_l[k]), lds(al + lo_l[k] + 4), shl);
+                    unsigned w0, w1;
+                    lds2(al + lo_l[k], w0, w1);
+                    unsigned w = __funnelshift_r(w0, w1, shl);
                     unsigned d = absd(w, srcL[k]);
                     aL[j] += act_l[k] ? d : 0u;
                 }
                 if (CHROMA) {
                     const int pc = __shfl_sync(0xffffffffu, cbc, j);
-                    const uint8_t *ac = sbuf + (pc & ~3);
+                    const uint32_t ac = sbuf + (pc & ~3);
                     const unsigned shc = (pc & 3) * 8;
 #pragma unroll
                     for (int k = 0; k < NCI; k++) {
-                        unsigned w = __funnelshift_r(lds(ac + lo_c[k]), lds(ac + lo_c[k] + 4), shc);
+                        unsigned w0, w1;
+                        lds2(ac + lo_c[k], w0, w1);
+                        unsigned w = __funnelshift_r(w0, w1, shc);
                         unsigned d = absd(w, srcC[k]);
                         aC[j] += act_c[k] ? d : 0u;
                     }
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < NS; j++) {
                 if (C::PACK) {
                     res[j] = __reduce_add_sync(0xffffffffu, aL[j] + (aC[j] << 16));
                 } else {
@@ -260,14 +278,14 @@ struct Chain {
             if (C::PACK) {
                 unsigned r = res[0];
 #pragma unroll
-                for (int j = 1; j < 8; j++)
+                for (int j = 1; j < NS; j++)
                     r = lane == j ? res[j] : r;
                 mySy = r & 0xffffu;
                 mySuv = r >> 16;
             } else {
                 unsigned r = res[0], u = aC[0];
 #pragma unroll
-                for (int j = 1; j < 8; j++) {
+                for (int j = 1; j < NS; j++) {
                     r = lane == j ? res[j] : r;
                     u = lane == j ? aC[j] : u;
                 }
@@ -277,7 +295,7 @@ struct Chain {
         } else {
             // at least one candidate leaves the staged window: evaluate the step from global memory
             unsigned ry = 0, ruv = 0;
-            for (int j = 0; j < 8; j++) {
+            for (int j = 0; j < NS; j++) {
                 if (!(needMask & (1u << j)))
                     continue;
                 unsigned sy, suv;
@@ -388,7 +406,12 @@ struct Chain {
             if (__ballot_sync(0xffffffffu, lane < 8 && c.valid) == 0)
                 continue;
             unsigned sy, suv;
-            eval_step(c, sy, suv);
+            if (PAT == PAT_HEX6)
+                eval_step<6>(c, sy, suv);
+            else if (PAT == PAT_HEX3)
+                eval_step<3>(c, sy, suv);
+            else
+                eval_step<8>(c, sy, suv);
             int d2 = dir;
             if (resolve(c, cost_new(c.lvx, c.lvy, sy, suv), sy, suv, !dirMode, v, d2) && dirMode)
                 dir = d2;
@@ -475,7 +498,7 @@ struct Chain {
         }
         c.valid = j < 3 || (j < 7 && ok(px, py));
         unsigned sy, suv;
-        eval_step(c, sy, suv);
+        eval_step<7>(c, sy, suv);
         // per-candidate cost rules (:846, :870, :894, CheckMV0)
         const long long sad = (long long)sy + suv;
         long long cost;
@@ -512,7 +535,7 @@ struct Chain {
 };
 
 template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
-__global__ void __launch_bounds__(32) k_search_tma(const __grid_constant__ TmaMaps maps, const SuperDesc *__restrict__ sdp, const SearchParams *__restrict__ params,
+__global__ void __launch_bounds__(32, MVB_TMA_MIN_BLOCKS) k_search_tma(const __grid_constant__ TmaMaps maps, const SuperDesc *__restrict__ sdp, const SearchParams *__restrict__ params,
                                                    const SearchJob *__restrict__ jobs, int njobs, int *__restrict__ hist_all, int hist_ints) {
     using C = Cfg<BPS, BW, BH, LXR, LYR, CHROMA>;
     using CH = Chain<BPS, BW, BH, LXR, LYR, CHROMA>;
@@ -531,8 +554,7 @@ __global__ void __launch_bounds__(32) k_search_tma(const __grid_constant__ TmaMa
     int *hist = hist_all + (long long)chain * hist_ints;
 
     // shared memory: [buffer 0][buffer 1][2 mbarriers]
-    const uint8_t *smem_gen = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u); // 128-byte aligned
-    const uint32_t smem0 = smem_u32(smem_gen);
+    const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;
     const uint32_t bar0 = smem0 + 2 * C::BUF;
     if (lane == 0) {
         mbar_init(bar0, 1);
@@ -766,7 +788,7 @@ __global__ void __launch_bounds__(32) k_search_tma(const __grid_constant__ TmaMa
             // the window of this block was issued one block ago: wait for it
             mbar_wait(bar0 + 8 * cbuf, phase[cbuf]);
             phase[cbuf] ^= 1;
-            S.sbuf = smem_gen + cbuf * C::BUF;
+            S.sbuf = smem0 + cbuf * C::BUF;
             S.wx0 = wo[cbuf][0];
             S.wy0 = wo[cbuf][1];
             S.wxc0 = wo[cbuf][2];
