@@ -272,6 +272,15 @@ def run_gpu_arm(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (search_ms / 1e3) / 1e9
+    # DRAM traffic of the same kernel from the committed ncu --set full capture (per chain, scaled to this launch)
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_search_tma_saturated.json")))
+        rd = prof["dram__bytes_read.sum"]; wr = prof["dram__bytes_write.sum"]
+        tobytes = lambda m: m["value"] * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[m["unit"]]
+        traffic = (tobytes(rd) + tobytes(wr)) / prof["_chains"] * len(aps) * F
+    except (OSError, KeyError, ValueError):
+        pass
     line = {
         "metric": "frames/sec Analyse+Degrain3 1080p YUV420P8", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": region_ms / args.steps, "higher_is_better": True,
@@ -285,7 +294,8 @@ def run_gpu_arm(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"kernel": "k_search (6 analyse instances x F frames, one warp per search chain)", "bound": "hbm", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_source": "dram__bytes_read+write of profiles/r1_ncu_search_tma_saturated.json, per chain x chains of this launch" if traffic else None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "algorithmic_bytes_per_launch": alg_bytes,
                      "note": "the search is a serial dependency chain per (frame, direction, delta): latency/issue bound, far below the HBM roofline by construction"},
@@ -310,7 +320,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=256, help="frames per step per GPU")
+    ap.add_argument("--frames", type=int, default=690, help="frames per step per GPU (690 x 6 chains = 2 full waves of 14 warps x 148 SMs)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
