@@ -151,8 +151,13 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import sharding
     L = mb.lib()
-    F = args.frames
+    # weak scaling: a global clip of world x `frames` frames, split into contiguous ranges; a rank holds its
+    # range plus a radius*delta halo of source frames on each side (recomputed locally, no data-path collective)
+    plan = sharding.local_plan(world * args.frames, world, rank, reach=RADIUS * 1)
+    F_out = plan["count"]
+    F = plan["local_frames"]
     sp = mb.super_params(WIDTH, HEIGHT, BITS, 1, 1, pel=PEL)
     aps = [mb.analyse_params(sp, F, isb=isb, delta=d, blksize=BLK, overlap=OVERLAP) for d in range(1, RADIUS + 1) for isb in (1, 0)]
     dp = mb.degrain_params(sp, [a.ad for a in aps], WIDTH, HEIGHT, RADIUS)
@@ -160,8 +165,7 @@ def run_gpu_arm(args):
     ctx = mb.Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local))
 
-    # synthetic clip, each rank its own shard of F frames (weak scaling); rank r starts r*F frames into the cycle
-    frames = make_frames(F + rank)[rank:]
+    frames = make_frames(world * args.frames)[plan["lo"]:plan["hi"]]
     host = torch.zeros((F, cl.frame_bytes), dtype=torch.uint8).pin_memory()
     hv = host.numpy()
     for n, fr in enumerate(frames):
@@ -228,7 +232,7 @@ def run_gpu_arm(args):
     super_ms = sum(e[0].elapsed_time(e[1]) for e in stage_events) / args.steps
     degrain_ms = sum(e[2].elapsed_time(e[3]) for e in stage_events) / args.steps
     region_ms = max_over_ranks(region_ms)
-    value = world * F * args.steps / (region_ms / 1e3)
+    value = world * F_out * args.steps / (region_ms / 1e3)
 
     # ---- end-to-end timing: pinned host source -> H2D -> pipeline -> D2H denoised frames
     def e2e_step():
@@ -247,7 +251,7 @@ def run_gpu_arm(args):
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
-    e2e_value = world * F * args.steps / (e2e_ms / 1e3)
+    e2e_value = world * F_out * args.steps / (e2e_ms / 1e3)
     checksum = int(host_out.numpy()[:, ::4099].astype(np.uint64).sum())
     if world > 1:  # the only collective of the job: reassemble the sharded clip's output planes (here: a digest of them)
         t = torch.tensor([checksum % (1 << 53)], dtype=torch.float64, device="cuda")
@@ -285,7 +289,7 @@ def run_gpu_arm(args):
         "metric": "frames/sec Analyse+Degrain3 1080p YUV420P8", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": region_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F, "distinct_frames": DISTINCT,
+        "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F_out, "halo_frames_per_gpu": F - F_out, "distinct_frames": DISTINCT,
                    "search_chains_per_step_per_gpu": len(aps) * F,
                    "l2": "inputs larger than L2 (%d MB of super frames + vectors per step vs 126 MB L2), no flush" % int(F * (sl.frame_bytes + 6 * vs) / 1e6),
                    "stage_ms": {"super": super_ms, "analyse_x6": search_ms, "degrain3": degrain_ms}},
