@@ -1513,3 +1513,251 @@ int mvo_degrain_frame(const mvb200_degrain_params *dp, const mvb200_super_params
     }
     return 0;
 }
+
+/* ======================================================================== */
+/* Recalculate                                                               */
+
+/* doPobRecalculateMVs (PlaneOfBlocks.cpp:1158-1424) + gopRecalculateMVs (GroupOfPlanes.c:128-147) +
+ * mvrecalculateGetFrame (MVRecalculate.c:68-254).  ref_super == NULL or an invalid old blob -> defaults. */
+int mvo_recalculate_frame(const mvb200_recalculate_params *rp, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *old_vectors, int field_shift, uint8_t *vectors_out) {
+    const mvb200_analysis_data *ad = &rp->ad;
+    const mvb200_analysis_data *od = &rp->old;
+    int32_t *hdr = (int32_t *)vectors_out;
+    int bps = (ad->bitsPerSample + 7) / 8;
+    int n = ad->nBlkX * ad->nBlkY;
+    int64_t verybig = (int64_t)ad->nBlkSizeX * ad->nBlkSizeY * (1 << ad->bitsPerSample);
+    hdr[0] = rp->vectors_size;
+    uint8_t *out = vectors_out + 8;
+    *(int32_t *)out = 4 + n * 16;
+    VECTOR *res = (VECTOR *)(out + 4);
+    int old_valid;
+    const VECTOR *oldv = blob_level0(old_vectors, od, &old_valid);
+    if (!ref_super || !old_valid) { /* gopWriteDefaultToArray */
+        hdr[1] = 0;
+        for (int i = 0; i < n; i++) {
+            res[i].x = 0;
+            res[i].y = 0;
+            res[i].sad = verybig;
+        }
+        if (rp->divide) {
+            uint8_t *o = (uint8_t *)(res + n);
+            *(int32_t *)o = 4 + n * 16 * 4;
+            VECTOR *v = (VECTOR *)(o + 4);
+            for (int i = 0; i < n * 4; i++) {
+                v[i].x = 0;
+                v[i].y = 0;
+                v[i].sad = verybig;
+            }
+        }
+        return 0;
+    }
+    if (rp->dctmode >= 1 && rp->dctmode <= 4)
+        return fail("oracle: dct 1..4 (FFTW DCT) is not restated");
+    hdr[1] = 1;
+    Search S;
+    memset(&S, 0, sizeof(S));
+    S.nBlkX = ad->nBlkX;
+    S.nBlkY = ad->nBlkY;
+    S.blkW = ad->nBlkSizeX;
+    S.blkH = ad->nBlkSizeY;
+    S.ovX = ad->nOverlapX;
+    S.ovY = ad->nOverlapY;
+    S.logPel = ad->nPel == 4 ? 2 : ad->nPel == 2 ? 1 : 0;
+    S.xR = ad->xRatioUV;
+    S.yR = ad->yRatioUV;
+    S.logxR = S.xR == 2;
+    S.logyR = S.yR == 2;
+    S.bps = bps;
+    S.chroma = rp->chroma;
+    S.cw = S.blkW / S.xR;
+    S.ch = S.blkH / S.yR;
+    S.dctmode = rp->dctmode;
+    S.dctweight16 = 8; /* :1166 */
+    S.verybigSAD = verybig;
+    S.vectors = res;
+    S.searchType = rp->search;
+    S.searchParam = rp->nSearchParam;
+    S.penaltyNew = rp->pnew;
+    bind_planes(S.src, src_super, src_stride, sp, 0, rp->chroma ? 3 : 1);
+    bind_planes(S.ref, ref_super, ref_stride, sp, 0, rp->chroma ? 3 : 1);
+    int nLambdaLevel = rp->nLambda / ((1 << S.logPel) * (1 << S.logPel));
+    int nBlkXold = od->nBlkX, nBlkYold = od->nBlkY;
+    int nStepXold = od->nBlkSizeX - od->nOverlapX, nStepYold = od->nBlkSizeY - od->nOverlapY;
+    int nLogPelold = od->nPel == 4 ? 2 : od->nPel == 2 ? 1 : 0;
+    int stepX = S.blkW - S.ovX, stepY = S.blkH - S.ovY;
+    const Lv *g0 = &S.src[0].g;
+    (void)field_shift; /* only zeroMVfieldShifted / globalMVPredictor use it, neither is read by the refinement */
+    for (S.blky = 0; S.blky < S.nBlkY; S.blky++)
+        for (S.blkx = 0; S.blkx < S.nBlkX; S.blkx++) { /* blocks are independent: scan order does not matter */
+            S.blkIdx = S.blky * S.nBlkX + S.blkx;
+            S.x[0] = g0->hpad + stepX * S.blkx;
+            S.y[0] = g0->vpad + stepY * S.blky;
+            if (S.chroma) {
+                S.x[1] = S.x[2] = S.src[1].g.hpad + (stepX >> S.logxR) * S.blkx;
+                S.y[1] = S.y[2] = S.src[1].g.vpad + (stepY >> S.logyR) * S.blky;
+            }
+            for (int p = 0; p < (S.chroma ? 3 : 1); p++)
+                S.pSrc[p] = S.src[p].base + (ptrdiff_t)S.y[p] * S.src[p].pitch + (ptrdiff_t)S.x[p] * S.bps;
+            S.nLambda = S.blky == 0 ? 0 : nLambdaLevel;
+            /* :1274-1277 -- the whole padded plane */
+            S.dxMax = (g0->pw - S.x[0] - S.blkW) << S.logPel;
+            S.dyMax = (g0->ph - S.y[0] - S.blkH) << S.logPel;
+            S.dxMin = -(S.x[0] << S.logPel);
+            S.dyMin = -(S.y[0] << S.logPel);
+            /* :1279-1330 -- predictor from the old vector field */
+            int centerX = S.blkW / 2 + stepX * S.blkx;
+            int blkxold = (centerX - od->nBlkSizeX / 2) / nStepXold;
+            int centerY = S.blkH / 2 + stepY * S.blky;
+            int blkyold = (centerY - od->nBlkSizeY / 2) / nStepYold;
+            int deltaX = IMAX(0, centerX - (od->nBlkSizeX / 2 + nStepXold * blkxold));
+            int deltaY = IMAX(0, centerY - (od->nBlkSizeY / 2 + nStepYold * blkyold));
+            int bx1 = IMIN(nBlkXold - 1, IMAX(0, blkxold)), bx2 = IMIN(nBlkXold - 1, IMAX(0, blkxold + 1));
+            int by1 = IMIN(nBlkYold - 1, IMAX(0, blkyold)), by2 = IMIN(nBlkYold - 1, IMAX(0, blkyold + 1));
+            VECTOR vo;
+            if (rp->smooth == 1) {
+                VECTOR v1 = oldv[bx1 + by1 * nBlkXold], v2 = oldv[bx2 + by1 * nBlkXold], v3 = oldv[bx1 + by2 * nBlkXold], v4 = oldv[bx2 + by2 * nBlkXold];
+                int a_x = v1.x * nStepXold + deltaX * (v2.x - v1.x);
+                int a_y = v1.y * nStepXold + deltaX * (v2.y - v1.y);
+                int64_t a_s = v1.sad * nStepXold + deltaX * (v2.sad - v1.sad);
+                int b_x = v3.x * nStepXold + deltaX * (v4.x - v3.x);
+                int b_y = v3.y * nStepXold + deltaX * (v4.y - v3.y);
+                int64_t b_s = v3.sad * nStepXold + deltaX * (v4.sad - v3.sad);
+                vo.x = (a_x + deltaY * (b_x - a_x) / nStepYold) / nStepXold;
+                vo.y = (a_y + deltaY * (b_y - a_y) / nStepYold) / nStepXold;
+                vo.sad = (a_s + deltaY * (b_s - a_s) / nStepYold) / nStepXold;
+            } else {
+                int rx = deltaX * 2 >= nStepXold, ry = deltaY * 2 >= nStepYold;
+                vo = oldv[(rx ? bx2 : bx1) + (ry ? by2 : by1) * nBlkXold];
+            }
+            vo.x = (vo.x << S.logPel) >> nLogPelold;
+            vo.y = (vo.y << S.logPel) >> nLogPelold;
+            S.predictor = clipmv(&S, vo);
+            S.predictor.sad = vo.sad * (S.blkW * S.blkH) / (od->nBlkSizeX * od->nBlkSizeY);
+            S.bestMV = S.predictor;
+            if (S.dctmode >= 3)
+                S.srcLuma = (int)luma_sum(S.pSrc[0], S.src[0].pitch, S.blkW, S.blkH, S.bps);
+            int64_t sad = full_sad_at(&S, S.predictor.x, S.predictor.y, S.predictor.x, S.predictor.y);
+            S.bestMV.sad = sad;
+            S.nMinCost = sad;
+            if (S.bestMV.sad > rp->thSAD)
+                refine(&S);
+            res[S.blkIdx] = S.bestMV;
+        }
+    if (rp->divide) {
+        uint8_t *o = (uint8_t *)(res + n);
+        *(int32_t *)o = 4 + n * 16 * 4;
+        extra_divide(res, (VECTOR *)(o + 4), ad->nBlkX, ad->nBlkY, rp->divide);
+    }
+    return 0;
+}
+
+/* ======================================================================== */
+/* Compensate                                                                */
+
+/* mvcompensateGetFrame, MVCompensate.c:73-374.  src_super = super frame n, ref_super = super frame nref
+ * (NULL when out of range).  Only the planes of the super clip's modeyuv are written (the reference leaves
+ * the others uninitialised). */
+int mvo_compensate_frame(const mvb200_compensate_params *cp, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *vectors, int field_shift, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
+    const mvb200_analysis_data *vd = &cp->vd;
+    int bps = (cp->bits + 7) / 8;
+    int nBlkX = vd->nBlkX, nBlkY = vd->nBlkY;
+    int nPel = vd->nPel, nLogPel = nPel == 4 ? 2 : nPel == 2 ? 1 : 0;
+    int pixelMax = (1 << cp->bits) - 1;
+    int num_planes = (cp->super_modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) ? 3 : 1;
+    int valid;
+    const VECTOR *vec = blob_level0(vectors, vd, &valid);
+    int sum = 0;
+    for (int i = 0; i < nBlkX * nBlkY; i++)
+        sum += vec[i].sad > cp->nSCD1 ? 1 : 0;
+    int usable = valid && !(sum > cp->nSCD2);
+    if (usable && !ref_super)
+        return fail("oracle compensate: usable vectors but no reference super frame");
+    if (!usable) { /* :348-364 */
+        const uint8_t *const *s = (!cp->scBehavior && ref_super) ? ref_super : src_super;
+        const ptrdiff_t *ss = (!cp->scBehavior && ref_super) ? ref_stride : src_stride;
+        for (int plane = 0; plane < num_planes; plane++) {
+            Lv g;
+            level_geom(sp->width, sp->height, sp->xRatioUV, sp->yRatioUV, sp->hpad, sp->vpad, sp->pel, plane, 0, &g);
+            for (int y = 0; y < cp->nHeight[plane]; y++)
+                memcpy(dst[plane] + (ptrdiff_t)y * dst_stride[plane], s[plane] + (ptrdiff_t)(y + g.vpad) * ss[plane] + (ptrdiff_t)g.hpad * bps, (size_t)cp->nWidth[plane] * bps);
+        }
+        return 0;
+    }
+    int overlap = cp->nOverlapX[0] > 0 || cp->nOverlapY[0] > 0;
+    int stepX0 = cp->nBlkSizeX[0] - cp->nOverlapX[0], stepY0 = cp->nBlkSizeY[0] - cp->nOverlapY[0];
+    for (int plane = 0; plane < num_planes; plane++) {
+        int W = cp->nWidth[plane], H = cp->nHeight[plane], WB = cp->nWidth_B[plane], HB = cp->nHeight_B[plane];
+        int bw = cp->nBlkSizeX[plane], bh = cp->nBlkSizeY[plane], ox = cp->nOverlapX[plane], oy = cp->nOverlapY[plane];
+        int xSub = plane ? cp->ssw : 0, ySub = plane ? cp->ssh : 0;
+        PlaneView rv, sv;
+        level_geom(sp->width, sp->height, sp->xRatioUV, sp->yRatioUV, sp->hpad, sp->vpad, sp->pel, plane, 0, &rv.g);
+        sv.g = rv.g;
+        rv.pitch = ref_stride[plane];
+        rv.base = ref_super[plane];
+        sv.pitch = src_stride[plane];
+        sv.base = src_super[plane];
+        int16_t *win = NULL;
+        uint32_t *acc = NULL;
+        if (overlap) {
+            win = (int16_t *)malloc(sizeof(int16_t) * 9 * (size_t)bw * bh);
+            mvo_overlap_windows(bw, bh, ox, oy, win);
+            acc = (uint32_t *)calloc((size_t)W * H + 1, sizeof(uint32_t));
+        }
+        for (int by = 0; by < nBlkY; by++)
+            for (int bx = 0; bx < nBlkX; bx++) {
+                int i = by * nBlkX + bx;
+                int blx, bly;
+                const PlaneView *pv;
+                if (vec[i].sad < cp->thSAD) { /* :238-242 / :286-290 */
+                    blx = (bx * stepX0) * nPel + vec[i].x * cp->time256 / 256;
+                    bly = (by * stepY0) * nPel + vec[i].y * cp->time256 / 256 + field_shift;
+                    pv = &rv;
+                } else {
+                    blx = (bx * stepX0) * nPel;
+                    bly = (by * stepY0) * nPel + field_shift;
+                    pv = &sv;
+                }
+                int ax = (plane ? blx >> xSub : blx) + pv->g.hpad * nPel;
+                int ay = (plane ? bly >> ySub : bly) + pv->g.vpad * nPel;
+                const uint8_t *p = pel_ptr(pv, bps, nLogPel, ax, ay);
+                int px = overlap ? bx * (bw - ox) : bx * bw, py = overlap ? by * (bh - oy) : by * bh;
+                if (!overlap) {
+                    for (int y = 0; y < bh; y++)
+                        memcpy(dst[plane] + (ptrdiff_t)(py + y) * dst_stride[plane] + (ptrdiff_t)px * bps, p + (ptrdiff_t)y * pv->pitch, (size_t)bw * bps);
+                } else {
+                    int wby = ((by + nBlkY - 3) / (nBlkY - 2)) * 3;
+                    int wbx = bx == 0 ? 0 : (bx == nBlkX - 1 ? 2 : 1);
+                    if (nBlkX == 1) wbx = 2;
+                    const int16_t *w = win + (size_t)(wby + wbx) * bw * bh;
+                    for (int y = 0; y < bh; y++)
+                        for (int x = 0; x < bw; x++) {
+                            uint32_t add = (uint32_t)((LD(p + (ptrdiff_t)y * pv->pitch, bps, x) * w[y * bw + x]) >> 6);
+                            uint32_t *a = &acc[(size_t)(py + y) * W + px + x];
+                            if (bps == 1)
+                                *a = (uint16_t)(*a + add);
+                            else
+                                *a += add;
+                        }
+                }
+            }
+        if (overlap) {
+            for (int y = 0; y < HB; y++)
+                for (int x = 0; x < WB; x++) {
+                    int a = (int)((acc[(size_t)y * W + x] + 16) >> 5);
+                    ST(dst[plane] + (ptrdiff_t)y * dst_stride[plane], bps, x, IMIN(pixelMax, a));
+                }
+        }
+        /* uncovered strips from the source (scbehavior=1) or reference super frame's interior (:330-342) */
+        const uint8_t *sc = cp->scBehavior ? src_super[plane] : ref_super[plane];
+        ptrdiff_t scs = cp->scBehavior ? src_stride[plane] : ref_stride[plane];
+        if (cp->nWidth_B[0] < cp->nWidth[0])
+            for (int y = 0; y < HB; y++)
+                memcpy(dst[plane] + (ptrdiff_t)y * dst_stride[plane] + (ptrdiff_t)WB * bps, sc + (ptrdiff_t)(y + rv.g.vpad) * scs + (ptrdiff_t)(WB + rv.g.hpad) * bps, (size_t)(W - WB) * bps);
+        if (cp->nHeight_B[0] < cp->nHeight[0])
+            for (int y = HB; y < H; y++)
+                memcpy(dst[plane] + (ptrdiff_t)y * dst_stride[plane], sc + (ptrdiff_t)(y + rv.g.vpad) * scs + (ptrdiff_t)rv.g.hpad * bps, (size_t)W * bps);
+        free(win);
+        free(acc);
+    }
+    return 0;
+}

@@ -23,6 +23,12 @@ MVO_API int mvo_analyse_frame(const mvb200_analyse_params *ap, const mvb200_supe
 /* mvdegrainGetFrame<radius>, MVDegrains.cpp:85-330 */
 MVO_API int mvo_degrain_frame(const mvb200_degrain_params *dp, const mvb200_super_params *sp, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const *ref_super, const ptrdiff_t *ref_stride, const uint8_t *const *vectors, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
 
+/* mvrecalculateGetFrame, MVRecalculate.c:68-254 */
+MVO_API int mvo_recalculate_frame(const mvb200_recalculate_params *rp, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *old_vectors, int field_shift, uint8_t *vectors_out);
+
+/* mvcompensateGetFrame, MVCompensate.c:73-374 */
+MVO_API int mvo_compensate_frame(const mvb200_compensate_params *cp, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *vectors, int field_shift, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
+
 /* overInit, Overlap.cpp:40-125: 9 windows of nx*ny int16 */
 MVO_API void mvo_overlap_windows(int nx, int ny, int ox, int oy, int16_t *out9);
 

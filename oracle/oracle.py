@@ -24,6 +24,9 @@ def lib():
                                         PP(C.c_ssize_t), C.c_int, vp]
         L.mvo_degrain_frame.argtypes = [PP(mb.DegrainParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp),
                                         PP(C.c_ssize_t), PP(vp), PP(vp), PP(C.c_ssize_t)]
+        L.mvo_recalculate_frame.argtypes = [PP(mb.RecalculateParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, C.c_int, vp]
+        L.mvo_compensate_frame.argtypes = [PP(mb.CompensateParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, C.c_int,
+                                           PP(vp), PP(C.c_ssize_t)]
         L.mvo_overlap_windows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.mvo_overlap_windows.restype = None
         for n in ("mvo_sad", "mvo_satd"):
@@ -77,6 +80,23 @@ def degrain_frame(dp, sp, src_planes, ref_supers, vectors):
     s, ss = mb.plane_ptrs(src_planes)
     d, ds = mb.plane_ptrs(dst)
     _check(lib().mvo_degrain_frame(C.byref(dp), C.byref(sp), s, ss, refs, rstr, vecs, d, ds))
+    return dst
+
+
+def recalculate_frame(rp, sp, src_super, ref_super, old_vectors, field_shift=0):
+    out = np.zeros(rp.vectors_size, dtype=np.uint8)
+    s, ss = mb.plane_ptrs(src_super)
+    r, rs = (None, None) if ref_super is None else mb.plane_ptrs(ref_super)
+    _check(lib().mvo_recalculate_frame(C.byref(rp), C.byref(sp), s, ss, r, rs, old_vectors.ctypes.data, field_shift, out.ctypes.data))
+    return out
+
+
+def compensate_frame(cp, sp, src_super, ref_super, vectors, field_shift=0):
+    dst = mb.alloc_planes(list(cp.nWidth)[: cp.nplanes], list(cp.nHeight)[: cp.nplanes], cp.bits, fill=0xA5)
+    s, ss = mb.plane_ptrs(src_super)
+    r, rs = (None, None) if ref_super is None else mb.plane_ptrs(ref_super)
+    d, ds = mb.plane_ptrs(dst)
+    _check(lib().mvo_compensate_frame(C.byref(cp), C.byref(sp), s, ss, r, rs, vectors.ctypes.data, field_shift, d, ds))
     return dst
 
 

@@ -27,6 +27,19 @@ CASES = {
 }
 
 
+# optional extra stages on vector clip 0 (backward, delta 1): mv.Recalculate(sup, vec0, **recalc) and
+# mv.Compensate(clip, sup, vec0, **comp)
+EXTRA = {
+    "c1_640x360_p8_blk8_pel1": dict(recalc=dict(blksize=8, thsad=50, smooth=0), comp=dict(time=50.0)),
+    "blk16_ov8_pel2_p8_r3": dict(recalc=dict(blksize=8, overlap=4, thsad=100), comp=dict(thsad=20000)),
+    "blk16_ov8_pel2_p16_r3": dict(recalc=dict(blksize=16, overlap=8, thsad=150, search=3, searchparam=2, divide=1), comp=dict(scbehavior=0, thscd1=200, thscd2=60)),
+    "noise_badblocks_blk8": dict(recalc=dict(blksize=8, overlap=2, dct=5, thsad=10, search=5, searchparam=4), comp=dict(thsad=300, thscd1=16000, thscd2=255)),
+    "p8_422_blk8x4_sharp0_rf1": dict(recalc=dict(blksize=8, blksizev=4, overlap=4, overlapv=2, thsad=80, search=2, meander=0), comp=dict(time=75.0)),
+    "gray_blk4_pel1_rf0": dict(recalc=dict(blksize=8, thsad=20, search=0, searchparam=2, chroma=0), comp=dict()),
+    "divide2_blk16_esa_neg_badrange": dict(recalc=dict(blksize=8, overlap=4, thsad=100, divide=2, smooth=1), comp=dict(thscd1=16000, thscd2=255)),
+}
+
+
 def _fix(kw):
     kw = dict(kw)
     if "global_" in kw:
@@ -64,13 +77,33 @@ def params_for(case):
     return sp, aps, dp
 
 
+def extra_params_for(case):
+    ck = CASES[case][0]
+    W, H, N = ck["width"], ck["height"], ck["nframes"]
+    sp, aps, dp = params_for(case)
+    ex = EXTRA[case]
+    vd0 = aps[0].ad_divided if aps[0].divide else aps[0].ad
+    rp = mb.recalculate_params(sp, vd0, N, **ex["recalc"])
+    cp = mb.compensate_params(sp, vd0, W, H, N, **ex["comp"])
+    return rp, cp
+
+
+def mask_recalc_blob(blob, rp):
+    b = np.array(blob, copy=True)
+    if rp.divide:
+        n0 = rp.ad.nBlkX * rp.ad.nBlkY
+        off = rp.vectors_size - (4 + n0 * 16 * 4)
+        b[off:off + 4] = 0
+    return b
+
+
 def nref_of(ap, n, N):
     d = ap.ad.nDeltaFrame
     r = n + d if ap.ad.isBackward else n - d
     return r if 0 <= r < N else None
 
 
-def run_engine(case, super_fn, analyse_fn, degrain_fn):
+def run_engine(case, super_fn, analyse_fn, degrain_fn, recalculate_fn=None, compensate_fn=None):
     """Runs the per-frame pipeline with the given stage functions; returns {stage: [hash per frame]}"""
     frames = make_frames(CASES[case][0])
     N = len(frames)
@@ -89,6 +122,14 @@ def run_engine(case, super_fn, analyse_fn, degrain_fn):
         refs = [sups[nref_of(ap, n, N)] if nref_of(ap, n, N) is not None else None for ap in aps]
         d = degrain_fn(dp, sp, frames[n], refs, vecs[n])
         out["degrain"].append([sha(p) for p in d])
+    if recalculate_fn and case in EXTRA:
+        rp, cp = extra_params_for(case)
+        out["recalc"], out["compensate"] = [], []
+        for n in range(N):
+            r = nref_of(aps[0], n, N)
+            ref = sups[r] if r is not None else None
+            out["recalc"].append(sha(mask_recalc_blob(recalculate_fn(rp, sp, sups[n], ref, vecs[n][0]), rp)))
+            out["compensate"].append([sha(p) for p in compensate_fn(cp, sp, sups[n], ref, vecs[n][0])])
     return out
 
 
@@ -114,6 +155,20 @@ def run_reference(case, plugin_path=None):
             row.append(sha(mask_blob(blob, ap)))
         out["vectors"].append(row)
         out["degrain"].append([sha(p) for p in dn.get_frame(n).planes()])
+    if case in EXTRA:
+        ex = EXTRA[case]
+        rp, cp = extra_params_for(case)
+        rn = mv.Recalculate(sup, vn[0], **ex["recalc"])
+        cn = mv.Compensate(clip, sup, vn[0], **ex["comp"])
+        out["recalc"], out["compensate"] = [], []
+        nplanes = 1 if ck.get("gray") else 3
+        for n in range(N):
+            blob = np.frombuffer(rn.get_frame(n).prop_data("MVTools_vectors"), dtype=np.uint8)
+            out["recalc"].append(sha(mask_recalc_blob(blob, rp)))
+            out["compensate"].append([sha(p) for p in cn.get_frame(n).planes()[:nplanes]])
+        ad = np.frombuffer(rn.get_frame(0).prop_data("MVTools_MVAnalysisData"), dtype=np.int32).copy()
+        ad[[0, 1, 8]] = 0
+        out["recalc_adata"] = ad.tolist()
     for v in vn:
         ad = np.frombuffer(v.get_frame(0).prop_data("MVTools_MVAnalysisData"), dtype=np.int32).copy()
         ad[[0, 1, 8]] = 0  # nMagicKey / nVersion are never written, nCPUFlags is host specific

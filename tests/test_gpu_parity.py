@@ -20,9 +20,10 @@ GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.
 def test_cuda_matches_reference_goldens(gpu_ctx, case):
     """per-frame host-buffer entry points (what the VapourSynth plugin calls): bit-exact"""
     ctx = gpu_ctx
-    got = pipeline.run_engine(case, ctx.super_frame, ctx.analyse_frame, ctx.degrain_frame)
-    for stage in ("super", "vectors", "degrain"):
-        assert got[stage] == GOLD[case][stage], "%s: CUDA %s differs from the reference" % (case, stage)
+    got = pipeline.run_engine(case, ctx.super_frame, ctx.analyse_frame, ctx.degrain_frame, ctx.recalculate_frame, ctx.compensate_frame)
+    for stage in ("super", "vectors", "degrain", "recalc", "compensate"):
+        if stage in got:
+            assert got[stage] == GOLD[case][stage], "%s: CUDA %s differs from the reference" % (case, stage)
 
 
 @pytest.mark.parametrize("case", ["c1_640x360_p8_blk8_pel1", "blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "blk16_ov8_pel2_p8_r3",

@@ -19,14 +19,15 @@ GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden.
 
 def oracle_run(case):
     import oracle
-    return pipeline.run_engine(case, oracle.super_frame, oracle.analyse_frame, oracle.degrain_frame)
+    return pipeline.run_engine(case, oracle.super_frame, oracle.analyse_frame, oracle.degrain_frame, oracle.recalculate_frame, oracle.compensate_frame)
 
 
 @pytest.mark.parametrize("case", sorted(pipeline.CASES))
 def test_oracle_matches_golden(built, case):
     got = oracle_run(case)
-    for stage in ("super", "vectors", "degrain"):
-        assert got[stage] == GOLD[case][stage], "%s: oracle %s differs from the reference's golden hashes" % (case, stage)
+    for stage in ("super", "vectors", "degrain", "recalc", "compensate"):
+        if stage in got:
+            assert got[stage] == GOLD[case][stage], "%s: oracle %s differs from the reference's golden hashes" % (case, stage)
 
 
 @pytest.mark.parametrize("case", ["c1_640x360_p8_blk8_pel1", "blk16_ov8_pel2_p16_r3", "p10_444_blk8_pel4_bicubic", "divide2_blk16_esa_neg_badrange"])
@@ -49,6 +50,11 @@ def test_analysis_data_prop_matches_reference(built):
             ad = np.frombuffer(bytes(ap.ad_divided if ap.divide else ap.ad), dtype=np.int32).copy()
             ad[[0, 1, 8]] = 0
             assert ad.tolist() == ref, case
+        if case in pipeline.EXTRA:
+            rp, cp = pipeline.extra_params_for(case)
+            ad = np.frombuffer(bytes(rp.ad_divided if rp.divide else rp.ad), dtype=np.int32).copy()
+            ad[[0, 1, 8]] = 0
+            assert ad.tolist() == GOLD[case]["recalc_adata"], case
 
 
 def test_sad_satd_kernels(built):

@@ -399,6 +399,8 @@ void overlap_windows(int nx, int ny, int ox, int oy, std::vector<short> &out) {
 
 } // namespace
 
+void overlap_windows_host(int nx, int ny, int ox, int oy, std::vector<short> &out) { overlap_windows(nx, ny, ox, oy, out); }
+
 int launch_degrain(Ctx *ctx, const mvb200_degrain_params *dp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, const uint8_t *dev_super, int num_frames,
                    int first, int n, const uint8_t *const *dev_vectors, long long vectors_stride, uint8_t *dev_dst) {
     if (n <= 0)

@@ -462,22 +462,100 @@ int mvb200_degrain_frame(mvb200_ctx *ctx, const mvb200_degrain_params *dp, const
     return 0;
 }
 
-// ---- not implemented yet in this round: fail loudly ------------------------
-
-int mvb200_compensate_init(const mvb200_compensate_args *, const mvb200_super_params *, const mvb200_analysis_data *, int, int, int, mvb200_compensate_params *) {
-    return set_error("Compensate: not implemented by the B200 engine yet");
+int mvb200_compensate_frame(mvb200_ctx *ctx, const mvb200_compensate_params *cp, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *vectors, int field_shift, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
+    if (check_levels(sp))
+        return 1;
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(sp, &sd);
+    make_clip_desc(sp, &cd);
+    const size_t blob_bytes = (size_t)(*(const int32_t *)vectors), blob_stride = (blob_bytes + 255) & ~(size_t)255;
+    uint8_t *buf = (uint8_t *)c->get_scratch(5, (size_t)sd.frame_bytes * 2 + (size_t)cd.frame_bytes + blob_stride);
+    if (!buf)
+        return 1;
+    uint8_t *dsrc = buf, *dref = buf + sd.frame_bytes, *ddst = dref + sd.frame_bytes, *dvec = ddst + cd.frame_bytes;
+    int w[3], h[3];
+    super_plane_dims(sp, w, h);
+    const int num_planes = (cp->super_modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) ? sd.nplanes : 1;
+    if (upload_planes(c, dsrc, sd.pitch, sd.offset, w, h, sd.bps, num_planes, src_super, src_stride))
+        return 1;
+    if (ref_super && upload_planes(c, dref, sd.pitch, sd.offset, w, h, sd.bps, num_planes, ref_super, ref_stride))
+        return 1;
+    MVB_CUDA_CHECK(cudaMemcpyAsync(dvec, vectors, blob_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (launch_compensate(c, cp, sd, cd, dsrc, ref_super ? dref : nullptr, dvec, field_shift, ddst))
+        return 1;
+    // only the planes of the super clip's modeyuv are produced (the reference leaves the others untouched)
+    if (download_planes(c, ddst, cd.pitch, cd.offset, cd.w, cd.h, cd.bps, num_planes, dst, dst_stride))
+        return 1;
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
-int mvb200_recalculate_init(const mvb200_recalculate_args *, const mvb200_super_params *, const mvb200_analysis_data *, int, mvb200_recalculate_params *) {
-    return set_error("Recalculate: not implemented by the B200 engine yet");
-}
-
-int mvb200_compensate_frame(mvb200_ctx *, const mvb200_compensate_params *, const mvb200_super_params *, const uint8_t *const[3], const ptrdiff_t[3], const uint8_t *const[3], const ptrdiff_t[3], const uint8_t *, int, uint8_t *const[3], const ptrdiff_t[3]) {
-    return set_error("Compensate: not implemented by the B200 engine yet");
-}
-
-int mvb200_recalculate_frame(mvb200_ctx *, const mvb200_recalculate_params *, const mvb200_super_params *, const uint8_t *const[3], const ptrdiff_t[3], const uint8_t *const[3], const ptrdiff_t[3], const uint8_t *, int, uint8_t *) {
-    return set_error("Recalculate: not implemented by the B200 engine yet");
+int mvb200_recalculate_frame(mvb200_ctx *ctx, const mvb200_recalculate_params *rp, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *old_vectors, int field_shift, uint8_t *vectors_out) {
+    if (rp->dctmode >= 1 && rp->dctmode <= 4)
+        return set_error("Recalculate: dct=%d (FFTW DCT modes 1..4) is not implemented by the B200 engine; use dct=0 or the SATD modes 5..10", rp->dctmode);
+    if (check_levels(sp))
+        return 1;
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    make_super_desc(sp, &sd);
+    const size_t old_bytes = (size_t)(*(const int32_t *)old_vectors), old_stride = (old_bytes + 255) & ~(size_t)255;
+    const size_t new_stride = ((size_t)rp->vectors_size + 255) & ~(size_t)255;
+    uint8_t *buf = (uint8_t *)c->get_scratch(5, (size_t)sd.frame_bytes * 2 + old_stride + new_stride);
+    if (!buf)
+        return 1;
+    int w[3], h[3];
+    super_plane_dims(sp, w, h);
+    const int nplanes_used = rp->chroma ? sd.nplanes : 1;
+    if (upload_planes(c, buf, sd.pitch, sd.offset, w, h, sd.bps, nplanes_used, src_super, src_stride))
+        return 1;
+    if (ref_super && upload_planes(c, buf + sd.frame_bytes, sd.pitch, sd.offset, w, h, sd.bps, nplanes_used, ref_super, ref_stride))
+        return 1;
+    uint8_t *dold = buf + sd.frame_bytes * 2, *dnew = dold + old_stride;
+    MVB_CUDA_CHECK(cudaMemcpyAsync(dold, old_vectors, old_bytes, cudaMemcpyHostToDevice, c->stream));
+    RecalcParams P;
+    memset(&P, 0, sizeof(P));
+    const mvb200_analysis_data &ad = rp->ad, &od = rp->old;
+    P.blkW = ad.nBlkSizeX;
+    P.blkH = ad.nBlkSizeY;
+    P.ovX = ad.nOverlapX;
+    P.ovY = ad.nOverlapY;
+    P.logPel = ad.nPel == 4 ? 2 : (ad.nPel == 2 ? 1 : 0);
+    P.chroma = rp->chroma;
+    P.bps = (ad.bitsPerSample + 7) / 8;
+    P.search = rp->search;
+    P.nSearchParam = rp->nSearchParam;
+    P.nLambda = rp->nLambda;
+    P.pnew = rp->pnew;
+    P.smooth = rp->smooth;
+    P.dctmode = rp->dctmode;
+    P.divide = rp->divide;
+    P.thSAD = rp->thSAD;
+    P.verybigSAD = (long long)ad.nBlkSizeX * ad.nBlkSizeY * (1LL << ad.bitsPerSample);
+    P.nBlkX = ad.nBlkX;
+    P.nBlkY = ad.nBlkY;
+    P.vectors_size = rp->vectors_size;
+    P.oBlkX = od.nBlkX;
+    P.oBlkY = od.nBlkY;
+    P.oBlkW = od.nBlkSizeX;
+    P.oBlkH = od.nBlkSizeY;
+    P.oOvX = od.nOverlapX;
+    P.oOvY = od.nOverlapY;
+    P.oLogPel = od.nPel == 4 ? 2 : (od.nPel == 2 ? 1 : 0);
+    RecalcJob j;
+    j.src = buf;
+    j.ref = ref_super ? buf + sd.frame_bytes : nullptr;
+    j.old = dold;
+    j.out = dnew;
+    j.field_shift = field_shift;
+    if (launch_recalc(c, sd, P, &j, 1))
+        return 1;
+    MVB_CUDA_CHECK(cudaMemcpyAsync(vectors_out, dnew, (size_t)rp->vectors_size, cudaMemcpyDeviceToHost, c->stream));
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
 }
 
 } // extern "C"

@@ -66,6 +66,20 @@ struct SearchJob {
     int src_index, ref_index; // frame indices relative to the super-clip base (TMA coordinates)
 };
 
+// mv.Recalculate: parameters and one job per frame
+struct RecalcParams {
+    int blkW, blkH, ovX, ovY, logPel, chroma, bps, search, nSearchParam, nLambda, pnew, smooth, dctmode, divide;
+    long long thSAD, verybigSAD;
+    int nBlkX, nBlkY, vectors_size;
+    int oBlkX, oBlkY, oBlkW, oBlkH, oOvX, oOvY, oLogPel; // geometry of the OLD vector field (its finest level)
+};
+struct RecalcJob {
+    const uint8_t *src, *ref; // super frames (ref may be null)
+    const uint8_t *old;       // old blob
+    uint8_t *out;             // new blob
+    int field_shift;
+};
+
 struct Ctx;
 
 // kernels' host launchers (each returns 0 or sets the error)
@@ -76,6 +90,8 @@ int launch_search_tma(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &ge
                       const SuperDesc *dev_sd, const SearchParams *dev_params, const SearchJob *dev_jobs, int njobs, int *hist, int hist_ints, bool *handled);
 int launch_search_fast(Ctx *ctx, const SuperDesc &sd, const SearchParams *host_params, int nparams, const SuperDesc *dev_sd, const SearchParams *dev_params,
                        const SearchJob *dev_jobs, int njobs, int *hist, int hist_ints, bool *handled);
+int launch_recalc(Ctx *ctx, const SuperDesc &sd, const RecalcParams &P, const RecalcJob *host_jobs, int njobs);
+int launch_compensate(Ctx *ctx, const mvb200_compensate_params *cp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src_super, const uint8_t *dev_ref_super, const uint8_t *dev_vectors, int field_shift, uint8_t *dev_dst);
 int launch_degrain(Ctx *ctx, const mvb200_degrain_params *dp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, const uint8_t *dev_super, int num_frames, int first, int n, const uint8_t *const *dev_vectors, long long vectors_stride, uint8_t *dev_dst);
 
 struct Ctx {

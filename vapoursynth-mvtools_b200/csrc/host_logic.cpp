@@ -408,4 +408,156 @@ int mvb200_degrain_init(const mvb200_degrain_args *a, const mvb200_super_params 
     return 0;
 }
 
+// mvcompensateCreate, MVCompensate.c:419-575
+int mvb200_compensate_init(const mvb200_compensate_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd, int clip_w, int clip_h, int num_frames, mvb200_compensate_params *d) {
+    memset(d, 0, sizeof(*d));
+    d->scBehavior = GIVEN(a->scbehavior) ? !!a->scbehavior : 1;
+    d->thSAD = GIVEN64(a->thsad) ? a->thsad : 10000;
+    d->fields = GIVEN(a->fields) && a->fields != 0;
+    double time = (a->time == a->time) ? a->time : 100.0; // NaN = not given
+    d->nSCD1 = GIVEN64(a->thscd1) ? a->thscd1 : 400;
+    d->nSCD2 = GIVEN(a->thscd2) ? a->thscd2 : 130;
+    d->tff = GIVEN(a->tff) && a->tff != 0;
+    d->tff_exists = GIVEN(a->tff);
+    if (time < 0.0 || time > 100.0)
+        return set_error("Compensate: time must be between 0.0 and 100.0 (inclusive).");
+    d->vd = *vd;
+    int64_t nSCD1_old = d->nSCD1;
+    if (scale_thscd(&d->nSCD1, &d->nSCD2, &d->vd, "Compensate"))
+        return 1;
+    if (d->fields && vd->nPel < 2)
+        return set_error("Compensate: fields option requires pel > 1.");
+    d->thSAD = d->thSAD * d->nSCD1 / nSCD1_old;
+    if (vd->nHeight != sp->height || vd->nHeight != clip_h || vd->nWidth != sp->super_width - sp->hpad * 2 || vd->nWidth != clip_w || vd->nPel != sp->pel)
+        return set_error("Compensate: wrong source or super clip frame size.");
+    if (sp->bits > 16 || sp->ssw > 1 || sp->ssh > 1)
+        return set_error("Compensate: input clip must be GRAY, 420, 422, 440, or 444, up to 16 bits, with constant dimensions.");
+    d->time256 = (int)(time * 256 / 100);
+    d->bits = sp->bits;
+    d->ssw = sp->ssw;
+    d->ssh = sp->ssh;
+    d->gray = sp->gray;
+    d->nplanes = sp->nplanes;
+    d->super_hpad = sp->hpad;
+    d->super_vpad = sp->vpad;
+    d->super_pel = sp->pel;
+    d->super_modeyuv = sp->modeyuv;
+    d->super_levels = sp->levels;
+    d->num_frames = num_frames;
+    const int xs = vd->xRatioUV == 2 ? 1 : 0, ys = vd->yRatioUV == 2 ? 1 : 0;
+    for (int p = 0; p < 3; p++) {
+        int x = p ? xs : 0, y = p ? ys : 0;
+        d->nWidth[p] = vd->nWidth >> x;
+        d->nHeight[p] = vd->nHeight >> y;
+        d->nOverlapX[p] = vd->nOverlapX >> x;
+        d->nOverlapY[p] = vd->nOverlapY >> y;
+        d->nBlkSizeX[p] = vd->nBlkSizeX >> x;
+        d->nBlkSizeY[p] = vd->nBlkSizeY >> y;
+        d->nWidth_B[p] = (vd->nBlkX * (vd->nBlkSizeX - vd->nOverlapX) + vd->nOverlapX) >> x;
+        d->nHeight_B[p] = (vd->nBlkY * (vd->nBlkSizeY - vd->nOverlapY) + vd->nOverlapY) >> y;
+    }
+    return 0;
+}
+
+// mvrecalculateCreate, MVRecalculate.c:265-553
+int mvb200_recalculate_init(const mvb200_recalculate_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *old, int num_frames, mvb200_recalculate_params *d) {
+    memset(d, 0, sizeof(*d));
+    mvb200_analysis_data &ad = d->ad;
+    d->thSAD = GIVEN64(a->thsad) ? a->thsad : 200;
+    d->smooth = GIVEN(a->smooth) ? a->smooth : 1;
+    ad.nBlkSizeX = GIVEN(a->blksize) ? a->blksize : 8;
+    ad.nBlkSizeY = GIVEN(a->blksizev) ? a->blksizev : ad.nBlkSizeX;
+    d->search = GIVEN(a->search) ? a->search : 4;
+    int searchparam = GIVEN(a->searchparam) ? a->searchparam : 2;
+    d->chroma = GIVEN(a->chroma) ? !!a->chroma : 1;
+    int truemotion = GIVEN(a->truemotion) ? !!a->truemotion : 1;
+    d->nLambda = GIVEN(a->lambda) ? a->lambda : (truemotion ? (1000 * ad.nBlkSizeX * ad.nBlkSizeY / 64) : 0);
+    d->pnew = GIVEN(a->pnew) ? a->pnew : (truemotion ? 50 : 0);
+    ad.nOverlapX = GIVEN(a->overlap) ? a->overlap : 0;
+    ad.nOverlapY = GIVEN(a->overlapv) ? a->overlapv : ad.nOverlapX;
+    d->dctmode = GIVEN(a->dct) ? a->dct : 0;
+    d->divide = GIVEN(a->divide) ? a->divide : 0;
+    int opt = GIVEN(a->opt) ? !!a->opt : 1;
+    d->meander = GIVEN(a->meander) ? !!a->meander : 1;
+    d->fields = GIVEN(a->fields) && a->fields != 0;
+    d->tff = GIVEN(a->tff) && a->tff != 0;
+    d->tff_exists = GIVEN(a->tff);
+    if (d->search < 0 || d->search > 7) return set_error("Recalculate: search must be between 0 and 7 (inclusive).");
+    if (d->dctmode < 0 || d->dctmode > 10) return set_error("Recalculate: dct must be between 0 and 10 (inclusive).");
+    if (d->dctmode >= 5 && ad.nBlkSizeX == 16 && ad.nBlkSizeY == 2) return set_error("Recalculate: dct 5..10 cannot work with 16x2 blocks.");
+    if (d->divide < 0 || d->divide > 2) return set_error("Recalculate: divide must be between 0 and 2 (inclusive).");
+    {
+        static const int ok[12][2] = {{4, 4}, {8, 4}, {8, 8}, {16, 2}, {16, 8}, {16, 16}, {32, 16}, {32, 32}, {64, 32}, {64, 64}, {128, 64}, {128, 128}};
+        bool found = false;
+        for (auto &s : ok)
+            found |= (s[0] == ad.nBlkSizeX && s[1] == ad.nBlkSizeY);
+        if (!found)
+            return set_error("Recalculate: the block size must be 4x4, 8x4, 8x8, 16x2, 16x8, 16x16, 32x16, 32x32, 64x32, 64x64, 128x64, or 128x128.");
+    }
+    if (d->pnew < 0 || d->pnew > 256) return set_error("Recalculate: pnew must be between 0 and 256 (inclusive).");
+    if (ad.nOverlapX < 0 || ad.nOverlapX > ad.nBlkSizeX / 2 || ad.nOverlapY < 0 || ad.nOverlapY > ad.nBlkSizeY / 2)
+        return set_error("Recalculate: overlap must be at most half of blksize, overlapv must be at most half of blksizev, and they both need to be at least 0.");
+    if (d->divide && (ad.nBlkSizeX < 8 || ad.nBlkSizeY < 8))
+        return set_error("Recalculate: blksize and blksizev must be at least 8 when divide=True.");
+    if (d->search == 1)
+        d->nSearchParam = searchparam < 0 ? 0 : searchparam;
+    else
+        d->nSearchParam = searchparam < 1 ? 1 : searchparam;
+    if (ad.nOverlapX % (1 << sp->ssw) || ad.nOverlapY % (1 << sp->ssh))
+        return set_error("Recalculate: The requested overlap is incompatible with the super clip's subsampling.");
+    if (d->divide && (ad.nOverlapX % (2 << sp->ssw) || ad.nOverlapY % (2 << sp->ssh)))
+        return set_error("Recalculate: overlap and overlapv must be multiples of 2 or 4 when divide=True, depending on the super clip's subsampling.");
+    if (sp->gray)
+        d->chroma = 0;
+    int nModeYUV = d->chroma ? MVB200_YUVPLANES : MVB200_YPLANE;
+    if ((nModeYUV & sp->modeyuv) != nModeYUV)
+        return set_error("Recalculate: super clip does not contain needed colour data.");
+    d->old = *old;
+    ad.yRatioUV = old->yRatioUV;
+    ad.xRatioUV = old->xRatioUV;
+    ad.nWidth = old->nWidth;
+    ad.nHeight = old->nHeight;
+    ad.nDeltaFrame = old->nDeltaFrame;
+    ad.isBackward = old->isBackward;
+    ad.bitsPerSample = sp->bits;
+    int pixelMax = (1 << sp->bits) - 1;
+    d->thSAD = (int64_t)((double)d->thSAD * pixelMax / 255.0 + 0.5);
+    d->nLambda = (int)((double)d->nLambda * pixelMax / 255.0 + 0.5);
+    d->thSAD = d->thSAD * (ad.nBlkSizeX * ad.nBlkSizeY) / 64;
+    if (d->chroma)
+        d->thSAD += d->thSAD / (ad.xRatioUV * ad.yRatioUV) * 2;
+    ad.nMotionFlags = (opt ? 0x01 : 0) | (ad.isBackward ? 0x02 : 0) | (d->chroma ? 0x08 : 0);
+    ad.nCPUFlags = 0;
+    ad.nPel = sp->pel;
+    if (sp->height != ad.nHeight || sp->super_width - 2 * sp->hpad != ad.nWidth)
+        return set_error("Recalculate: wrong frame size.");
+    ad.nHPadding = sp->hpad;
+    ad.nVPadding = sp->vpad;
+    ad.nBlkX = (ad.nWidth - ad.nOverlapX) / (ad.nBlkSizeX - ad.nOverlapX);
+    ad.nBlkY = (ad.nHeight - ad.nOverlapY) / (ad.nBlkSizeY - ad.nOverlapY);
+    ad.nLvCount = 1;
+    if (d->divide) {
+        d->ad_divided = ad;
+        d->ad_divided.nBlkX = ad.nBlkX * 2;
+        d->ad_divided.nBlkY = ad.nBlkY * 2;
+        d->ad_divided.nBlkSizeX = ad.nBlkSizeX / 2;
+        d->ad_divided.nBlkSizeY = ad.nBlkSizeY / 2;
+        d->ad_divided.nOverlapX = ad.nOverlapX / 2;
+        d->ad_divided.nOverlapY = ad.nOverlapY / 2;
+        d->ad_divided.nLvCount = ad.nLvCount + 1;
+    }
+    d->super_hpad = sp->hpad;
+    d->super_vpad = sp->vpad;
+    d->super_pel = sp->pel;
+    d->super_modeyuv = sp->modeyuv;
+    d->super_levels = sp->levels;
+    d->ssw = sp->ssw;
+    d->ssh = sp->ssh;
+    d->gray = sp->gray;
+    d->num_frames = num_frames;
+    int n = ad.nBlkX * ad.nBlkY;
+    d->vectors_size = 8 + 4 + n * 16 + (d->divide ? 4 + n * 16 * 4 : 0);
+    return 0;
+}
+
 } // extern "C"

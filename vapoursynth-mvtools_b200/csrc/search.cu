@@ -755,6 +755,158 @@ __global__ void __launch_bounds__(32) k_search(const SuperDesc *__restrict__ sdp
     chain_divide(job, P, lane);
 }
 
+
+// ------------------------------------------------------------------ Recalculate
+// doPobRecalculateMVs, PlaneOfBlocks.cpp:1158-1424: the predictor of every block comes from the OLD
+// vector field, there is no neighbour predictor and no badcount, so blocks are independent: one warp per
+// block, grid = blocks x frames.  The refinement itself is the generic pattern code above.
+__global__ void __launch_bounds__(32) k_recalc(const SuperDesc *__restrict__ sdp, const RecalcParams *__restrict__ pp, const RecalcJob *__restrict__ jobs) {
+    const SuperDesc &sd = *sdp;
+    const RecalcParams &P = *pp;
+    const RecalcJob job = jobs[blockIdx.y];
+    const int lane = threadIdx.x;
+    const int blkIdx = blockIdx.x;
+    const int n = P.nBlkX * P.nBlkY;
+    int *hdr = (int *)job.out;
+    VEC *res = (VEC *)(job.out + 12);
+    const int old_valid = __ldg((const int *)job.old + 1) == 1;
+    const bool live = job.ref != nullptr && old_valid;
+    if (blkIdx == 0 && lane == 0) {
+        hdr[0] = P.vectors_size;
+        hdr[1] = live ? 1 : 0;
+        hdr[2] = 4 + n * 16;
+        if (P.divide)
+            *(int *)(job.out + 12 + n * 16) = 4 + n * 16 * 4;
+    }
+    if (!live) { // gopWriteDefaultToArray, GroupOfPlanes.c:150-164
+        VEC d;
+        d.x = 0;
+        d.y = 0;
+        d.sad = P.verybigSAD;
+        if (lane == 0)
+            stvec(&res[blkIdx], d);
+        if (P.divide && lane < 4) {
+            VEC *q = (VEC *)(job.out + 12 + n * 16 + 4);
+            const int by = blkIdx / P.nBlkX, bx = blkIdx - by * P.nBlkX;
+            stvec(&q[(by * 2 + (lane >> 1)) * (P.nBlkX * 2) + bx * 2 + (lane & 1)], d);
+        }
+        return;
+    }
+    State S;
+    S.lane = lane;
+    S.nBlkX = P.nBlkX;
+    S.nBlkY = P.nBlkY;
+    S.blkW = P.blkW;
+    S.blkH = P.blkH;
+    S.ovX = P.ovX;
+    S.ovY = P.ovY;
+    S.logPel = P.logPel;
+    S.logScale = 0;
+    S.logxR = sd.logxR;
+    S.logyR = sd.logyR;
+    S.bps = P.bps;
+    S.chroma = P.chroma;
+    S.smallest = 1;
+    S.cw = P.blkW >> sd.logxR;
+    S.ch = P.blkH >> sd.logyR;
+    S.dctmode = P.dctmode;
+    S.dctweight16 = 8; // :1166
+    S.verybigSAD = P.verybigSAD;
+    S.vectors = res;
+    S.searchType = P.search;
+    S.searchParam = P.nSearchParam;
+    S.penaltyNew = P.pnew;
+    S.srcLuma = 0;
+    bind_planes(S.src, job.src, sd, 0, P.chroma ? 3 : 1);
+    bind_planes(S.ref, job.ref, sd, 0, P.chroma ? 3 : 1);
+    S.blky = blkIdx / P.nBlkX;
+    S.blkx = blkIdx - S.blky * P.nBlkX;
+    S.blkIdx = blkIdx;
+    const int stepX = P.blkW - P.ovX, stepY = P.blkH - P.ovY;
+    S.x[0] = S.src[0].hpad + stepX * S.blkx;
+    S.y[0] = S.src[0].vpad + stepY * S.blky;
+    if (P.chroma) {
+        S.x[1] = S.x[2] = S.src[1].hpad + (stepX >> sd.logxR) * S.blkx;
+        S.y[1] = S.y[2] = S.src[1].vpad + (stepY >> sd.logyR) * S.blky;
+    }
+    for (int p = 0; p < (P.chroma ? 3 : 1); p++)
+        S.pSrc[p] = S.src[p].base + (long long)S.y[p] * S.src[p].pitch + (long long)S.x[p] * S.bps;
+    S.nLambda = S.blky == 0 ? 0 : P.nLambda / ((1 << P.logPel) * (1 << P.logPel));
+    S.dxMax = (S.src[0].pw - S.x[0] - P.blkW) << P.logPel; // :1274-1277, the whole padded plane
+    S.dyMax = (S.src[0].ph - S.y[0] - P.blkH) << P.logPel;
+    S.dxMin = -(S.x[0] << P.logPel);
+    S.dyMin = -(S.y[0] << P.logPel);
+    // predictor from the old field (:1279-1330)
+    const VEC *oldv = (const VEC *)(job.old + __ldg((const int *)job.old) - 16 * P.oBlkX * P.oBlkY);
+    const int nStepXold = P.oBlkW - P.oOvX, nStepYold = P.oBlkH - P.oOvY;
+    const int centerX = P.blkW / 2 + stepX * S.blkx;
+    const int blkxold = (centerX - P.oBlkW / 2) / nStepXold;
+    const int centerY = P.blkH / 2 + stepY * S.blky;
+    const int blkyold = (centerY - P.oBlkH / 2) / nStepYold;
+    const int deltaX = max(0, centerX - (P.oBlkW / 2 + nStepXold * blkxold));
+    const int deltaY = max(0, centerY - (P.oBlkH / 2 + nStepYold * blkyold));
+    const int bx1 = min(P.oBlkX - 1, max(0, blkxold)), bx2 = min(P.oBlkX - 1, max(0, blkxold + 1));
+    const int by1 = min(P.oBlkY - 1, max(0, blkyold)), by2 = min(P.oBlkY - 1, max(0, blkyold + 1));
+    VEC vo;
+    if (P.smooth == 1) {
+        const VEC v1 = ldvec(&oldv[bx1 + by1 * P.oBlkX]), v2 = ldvec(&oldv[bx2 + by1 * P.oBlkX]), v3 = ldvec(&oldv[bx1 + by2 * P.oBlkX]), v4 = ldvec(&oldv[bx2 + by2 * P.oBlkX]);
+        const int a_x = v1.x * nStepXold + deltaX * (v2.x - v1.x);
+        const int a_y = v1.y * nStepXold + deltaX * (v2.y - v1.y);
+        const long long a_s = v1.sad * nStepXold + deltaX * (v2.sad - v1.sad);
+        const int b_x = v3.x * nStepXold + deltaX * (v4.x - v3.x);
+        const int b_y = v3.y * nStepXold + deltaX * (v4.y - v3.y);
+        const long long b_s = v3.sad * nStepXold + deltaX * (v4.sad - v3.sad);
+        vo.x = (a_x + deltaY * (b_x - a_x) / nStepYold) / nStepXold;
+        vo.y = (a_y + deltaY * (b_y - a_y) / nStepYold) / nStepXold;
+        vo.sad = (a_s + deltaY * (b_s - a_s) / nStepYold) / nStepXold;
+    } else {
+        const bool rx = deltaX * 2 >= nStepXold, ry = deltaY * 2 >= nStepYold;
+        vo = ldvec(&oldv[(rx ? bx2 : bx1) + (ry ? by2 : by1) * P.oBlkX]);
+    }
+    vo.x = (vo.x << P.logPel) >> P.oLogPel;
+    vo.y = (vo.y << P.logPel) >> P.oLogPel;
+    S.predictor = clipmv(S, vo);
+    S.predictor.sad = vo.sad * (P.blkW * P.blkH) / (P.oBlkW * P.oBlkH);
+    S.bestMV = S.predictor;
+    if (S.dctmode >= 3)
+        S.srcLuma = (int)wsum(lane_luma(S.pSrc[0], S.src[0].pitch, S.blkW * S.bps, S.blkH, S.bps, S.lane));
+    const long long sad = full_sad_at(S, S.predictor.x, S.predictor.y, S.predictor.x, S.predictor.y);
+    S.bestMV.sad = sad;
+    S.nMinCost = sad;
+    if (S.bestMV.sad > P.thSAD)
+        refine(S);
+    if (lane == 0)
+        stvec(&res[blkIdx], S.bestMV);
+}
+
+// gopExtraDivide (GroupOfPlanes.c:206-302) for Recalculate: thread per block, after k_recalc
+__global__ void k_recalc_divide(const RecalcParams *__restrict__ pp, const RecalcJob *__restrict__ jobs) {
+    const RecalcParams &P = *pp;
+    const RecalcJob job = jobs[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nBlkX = P.nBlkX, nBlkY = P.nBlkY, n = nBlkX * nBlkY;
+    if (i >= n || ((const int *)job.out)[1] != 1)
+        return;
+    const VEC *in = (const VEC *)(job.out + 12);
+    VEC *out = (VEC *)(job.out + 12 + n * 16 + 4);
+    const int by = i / nBlkX, bx = i - by * nBlkX;
+    VEC b = ldvec(&in[i]);
+    b.sad >>= 2;
+    VEC o[4] = {b, b, b, b};
+    if (P.divide > 1 && by >= 1 && by < nBlkY - 1 && bx >= 1 && bx < nBlkX - 1) {
+        VEC c = ldvec(&in[i]), lf = ldvec(&in[i - 1]), rt = ldvec(&in[i + 1]), up = ldvec(&in[i - nBlkX]), dn = ldvec(&in[i + nBlkX]);
+        get_median(o[0].x, o[0].y, c.x, c.y, lf.x, lf.y, up.x, up.y);
+        get_median(o[1].x, o[1].y, c.x, c.y, rt.x, rt.y, up.x, up.y);
+        get_median(o[2].x, o[2].y, c.x, c.y, lf.x, lf.y, dn.x, dn.y);
+        get_median(o[3].x, o[3].y, c.x, c.y, rt.x, rt.y, dn.x, dn.y);
+    }
+    VEC *q = out + (by * 2) * (nBlkX * 2) + bx * 2;
+    stvec(&q[0], o[0]);
+    stvec(&q[1], o[1]);
+    stvec(&q[nBlkX * 2], o[2]);
+    stvec(&q[nBlkX * 2 + 1], o[3]);
+}
+
 } // namespace
 
 int launch_search(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &geom, const uint8_t *frames_base, int nframes, const SearchParams *host_params, int nparams, const SearchJob *host_jobs, int njobs) {
@@ -791,6 +943,31 @@ int launch_search(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &geom, 
         return 0;
     k_search<<<njobs, 32, 0, ctx->stream>>>((const SuperDesc *)dev, (const SearchParams *)(dev + off_p), (const SearchJob *)(dev + off_j), njobs, hist, hist_ints);
     ctx->launches++;
+    MVB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+int launch_recalc(Ctx *ctx, const SuperDesc &sd, const RecalcParams &P, const RecalcJob *host_jobs, int njobs) {
+    if (njobs <= 0)
+        return 0;
+    size_t bytes_sd = sizeof(SuperDesc), bytes_p = sizeof(RecalcParams), bytes_j = sizeof(RecalcJob) * (size_t)njobs;
+    size_t off_p = (bytes_sd + 255) & ~(size_t)255, off_j = (off_p + bytes_p + 255) & ~(size_t)255, total = off_j + bytes_j;
+    uint8_t *host = (uint8_t *)ctx->get_pinned(total);
+    uint8_t *dev = (uint8_t *)ctx->get_scratch(0, total);
+    if (!host || !dev)
+        return 1;
+    MVB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    memcpy(host, &sd, bytes_sd);
+    memcpy(host + off_p, &P, bytes_p);
+    memcpy(host + off_j, host_jobs, bytes_j);
+    MVB_CUDA_CHECK(cudaMemcpyAsync(dev, host, total, cudaMemcpyHostToDevice, ctx->stream));
+    const int n = P.nBlkX * P.nBlkY;
+    k_recalc<<<dim3(n, njobs), 32, 0, ctx->stream>>>((const SuperDesc *)dev, (const RecalcParams *)(dev + off_p), (const RecalcJob *)(dev + off_j));
+    ctx->launches++;
+    if (P.divide) {
+        k_recalc_divide<<<dim3((n + 127) / 128, njobs), 128, 0, ctx->stream>>>((const RecalcParams *)(dev + off_p), (const RecalcJob *)(dev + off_j));
+        ctx->launches++;
+    }
     MVB_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -82,6 +82,34 @@ class DegrainParams(C.Structure):
                                 "nWidth_B", "nHeight_B")]
 
 
+class CompensateArgs(C.Structure):
+    _fields_ = [("scbehavior", i32), ("thsad", i64), ("fields", i32), ("time", C.c_double), ("thscd1", i64), ("thscd2", i32), ("tff", i32)]
+
+
+class CompensateParams(C.Structure):
+    _fields_ = [("vd", AnalysisData)] + [(n, i32) for n in ("scBehavior", "fields", "tff", "tff_exists", "time256")] + \
+        [("thSAD", i64), ("nSCD1", i64), ("nSCD2", i32)] + \
+        [(n, i32) for n in ("bits", "ssw", "ssh", "gray", "nplanes", "super_hpad", "super_vpad", "super_pel", "super_modeyuv", "super_levels")] + \
+        [(n, i32 * 3) for n in ("nWidth", "nHeight", "nOverlapX", "nOverlapY", "nBlkSizeX", "nBlkSizeY", "nWidth_B", "nHeight_B")] + \
+        [("num_frames", i32)]
+
+
+RECALC_ARGS = ("smooth", "blksize", "blksizev", "search", "searchparam", "lambda", "chroma", "truemotion", "pnew", "overlap",
+               "overlapv", "divide", "opt", "meander", "fields", "tff", "dct")
+
+
+class RecalculateArgs(C.Structure):
+    _fields_ = [("thsad", i64)] + [(n, i32) for n in RECALC_ARGS]
+
+
+class RecalculateParams(C.Structure):
+    _fields_ = [("ad", AnalysisData), ("ad_divided", AnalysisData), ("old", AnalysisData)] + \
+        [(n, i32) for n in ("divide", "search", "nSearchParam", "nLambda", "pnew", "smooth", "meander", "dctmode", "chroma")] + \
+        [("thSAD", i64)] + \
+        [(n, i32) for n in ("fields", "tff", "tff_exists", "super_hpad", "super_vpad", "super_pel", "super_modeyuv", "super_levels",
+                            "ssw", "ssh", "gray", "num_frames", "vectors_size")]
+
+
 class FrameLayout(C.Structure):
     _fields_ = [("nplanes", i32), ("bytes_per_sample", i32), ("plane_w", i32 * 3), ("plane_h", i32 * 3),
                 ("pitch", i64 * 3), ("offset", i64 * 3), ("frame_bytes", i64)]
@@ -111,6 +139,12 @@ def lib():
         L.mvb200_super_geometry.restype = None
         L.mvb200_analyse_init.argtypes = [PP(AnalyseArgs), PP(SuperParams), i32, PP(AnalyseParams)]
         L.mvb200_degrain_init.argtypes = [PP(DegrainArgs), PP(SuperParams), PP(AnalysisData), i32, i32, PP(DegrainParams)]
+        L.mvb200_compensate_init.argtypes = [PP(CompensateArgs), PP(SuperParams), PP(AnalysisData), i32, i32, i32, PP(CompensateParams)]
+        L.mvb200_recalculate_init.argtypes = [PP(RecalculateArgs), PP(SuperParams), PP(AnalysisData), i32, PP(RecalculateParams)]
+        L.mvb200_compensate_frame.argtypes = [vp, PP(CompensateParams), PP(SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, i32,
+                                              PP(vp), PP(C.c_ssize_t)]
+        L.mvb200_recalculate_frame.argtypes = [vp, PP(RecalculateParams), PP(SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp,
+                                               i32, vp]
         L.mvb200_clip_layout.argtypes = [PP(SuperParams), PP(FrameLayout)]
         L.mvb200_clip_layout.restype = None
         L.mvb200_super_layout.argtypes = [PP(SuperParams), PP(FrameLayout)]
@@ -184,6 +218,43 @@ def degrain_params(sp, vds, clip_w, clip_h, radius, **kw):
     arr = (AnalysisData * len(vds))(*vds)
     out = DegrainParams()
     _check(lib().mvb200_degrain_init(C.byref(a), C.byref(sp), arr, clip_w, clip_h, C.byref(out)))
+    return out
+
+
+def compensate_params(sp, vd, clip_w, clip_h, num_frames, **kw):
+    a = CompensateArgs()
+    a.scbehavior = UNSET if kw.get("scbehavior") is None else int(kw.pop("scbehavior"))
+    kw.pop("scbehavior", None)
+    a.thsad = UNSET64 if kw.get("thsad") is None else int(kw.pop("thsad"))
+    kw.pop("thsad", None)
+    a.fields = UNSET if kw.get("fields") is None else int(kw.pop("fields"))
+    kw.pop("fields", None)
+    t = kw.pop("time", None)
+    a.time = float("nan") if t is None else float(t)
+    a.thscd1 = UNSET64 if kw.get("thscd1") is None else int(kw.pop("thscd1"))
+    kw.pop("thscd1", None)
+    a.thscd2 = UNSET if kw.get("thscd2") is None else int(kw.pop("thscd2"))
+    kw.pop("thscd2", None)
+    a.tff = UNSET if kw.get("tff") is None else int(kw.pop("tff"))
+    kw.pop("tff", None)
+    if kw:
+        raise TypeError("Compensate: unknown argument(s) %s" % sorted(kw))
+    out = CompensateParams()
+    _check(lib().mvb200_compensate_init(C.byref(a), C.byref(sp), C.byref(vd), clip_w, clip_h, num_frames, C.byref(out)))
+    return out
+
+
+def recalculate_params(sp, old_vd, num_frames, **kw):
+    a = RecalculateArgs()
+    v = kw.pop("thsad", None)
+    a.thsad = UNSET64 if v is None else int(v)
+    for n in RECALC_ARGS:
+        v = kw.pop(n, None)
+        setattr(a, n, UNSET if v is None else int(v))
+    if kw:
+        raise TypeError("Recalculate: unknown argument(s) %s" % sorted(kw))
+    out = RecalculateParams()
+    _check(lib().mvb200_recalculate_init(C.byref(a), C.byref(sp), C.byref(old_vd), num_frames, C.byref(out)))
     return out
 
 
@@ -274,6 +345,21 @@ class Context:
             r, rs = plane_ptrs(ref_super)
         _check(lib().mvb200_analyse_frame(self._h, C.byref(ap), C.byref(sp), s, ss, r, rs, field_shift, out.ctypes.data))
         return out
+
+    def recalculate_frame(self, rp, sp, src_super, ref_super, old_vectors, field_shift=0):
+        out = np.empty(rp.vectors_size, dtype=np.uint8)
+        s, ss = plane_ptrs(src_super)
+        r, rs = (None, None) if ref_super is None else plane_ptrs(ref_super)
+        _check(lib().mvb200_recalculate_frame(self._h, C.byref(rp), C.byref(sp), s, ss, r, rs, old_vectors.ctypes.data, field_shift, out.ctypes.data))
+        return out
+
+    def compensate_frame(self, cp, sp, src_super, ref_super, vectors, field_shift=0):
+        dst = alloc_planes(list(cp.nWidth)[: cp.nplanes], list(cp.nHeight)[: cp.nplanes], cp.bits, fill=0xA5)
+        s, ss = plane_ptrs(src_super)
+        r, rs = (None, None) if ref_super is None else plane_ptrs(ref_super)
+        d, ds = plane_ptrs(dst)
+        _check(lib().mvb200_compensate_frame(self._h, C.byref(cp), C.byref(sp), s, ss, r, rs, vectors.ctypes.data, field_shift, d, ds))
+        return dst
 
     def degrain_frame(self, dp, sp, src_planes, ref_supers, vectors):
         n = 2 * dp.radius

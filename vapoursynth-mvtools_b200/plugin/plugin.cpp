@@ -2,9 +2,8 @@
 //
 // Exports exactly what the reference's module exports (EntryPoint.c:28-50):
 // VapourSynthPluginInit2, which configures the plugin as "com.nodame.mvtools" / namespace
-// "mv" and registers Super, Analyse, Degrain1..6 (and Compensate / Recalculate, which report
-// "not implemented" until the engine grows them) with the reference's byte-identical argument
-// strings, so existing .vpy scripts load unchanged.  Every filter keeps the reference's
+// "mv" and registers Super, Analyse, Recalculate, Compensate and Degrain1..6 with the reference's
+// byte-identical argument strings, so existing .vpy scripts load unchanged.  Every filter keeps the reference's
 // create-time validation (messages included, they come from mvb200_*_init), frame
 // properties (Super_*, MVTools_MVAnalysisData, MVTools_vectors) and request pattern; the
 // pixel work is done by libmvtools_b200.so on the GPU through the C ABI in
@@ -496,9 +495,274 @@ void VS_CC degrainCreate(const VSMap *in, VSMap *out, void *userData, VSCore *co
     vsapi->createVideoFilter(out, filter.c_str(), data->vi, degrainGetFrame, degrainFree, fmParallel, deps, 2 + 2 * radius, data, core);
 }
 
-// ------------------------------------------- Compensate / Recalculate (not implemented yet)
-void VS_CC notImplemented(const VSMap *, VSMap *out, void *userData, VSCore *, const VSAPI *vsapi) {
-    vsapi->mapSetError(out, (std::string((const char *)userData) + ": not implemented by the B200 engine yet.").c_str());
+// adataFromVectorClip, MVAnalysisData.c:34-65
+bool adataFromClip(VSNode *clip, const VSAPI *vsapi, const std::string &filter, const char *name, mvb200_analysis_data *ad, std::string &err) {
+    char msg[1024];
+    const VSFrame *evil = vsapi->getFrame(0, clip, msg, sizeof(msg));
+    if (!evil) {
+        err = filter + ": Failed to retrieve first frame from " + name + ". Error message: " + msg;
+        return false;
+    }
+    int e = 0;
+    const VSMap *props = vsapi->getFramePropertiesRO(evil);
+    const char *data = vsapi->mapGetData(props, "MVTools_MVAnalysisData", 0, &e);
+    int size = e ? 0 : vsapi->mapGetDataSize(props, "MVTools_MVAnalysisData", 0, nullptr);
+    if (e)
+        err = filter + ": Property 'MVTools_MVAnalysisData' not found in first frame of " + name + ".";
+    else if (size != (int)sizeof(mvb200_analysis_data))
+        err = filter + ": Property 'MVTools_MVAnalysisData' in first frame of " + name + " has wrong size (" + std::to_string(size) + " instead of " +
+              std::to_string(sizeof(mvb200_analysis_data)) + ").";
+    else
+        memcpy(ad, data, sizeof(*ad));
+    vsapi->freeFrame(evil);
+    return err.empty();
+}
+
+// field shift from _Field props / tff (MVAnalyse.c:146-179, MVCompensate.c:191-229, MVRecalculate.c:112-166)
+bool fieldShiftOf(const VSAPI *vsapi, const VSFrame *src, const VSFrame *ref, int n, int nref, bool fields, bool tffExists, int tff, int nPel, bool oddDelta, int *shift) {
+    *shift = 0;
+    int err = 0;
+    int srcTop = !!vsapi->mapGetInt(vsapi->getFramePropertiesRO(src), "_Field", 0, &err);
+    bool missing = err && fields && !tffExists;
+    int refTop = 0;
+    if (ref) {
+        refTop = !!vsapi->mapGetInt(vsapi->getFramePropertiesRO(ref), "_Field", 0, &err);
+        missing = missing || (err && fields && !tffExists);
+    }
+    if (missing)
+        return false;
+    if (tffExists) {
+        srcTop = tff ^ (n % 2);
+        refTop = tff ^ (nref % 2);
+    }
+    if (ref && fields && nPel > 1 && oddDelta)
+        *shift = (srcTop && !refTop) ? nPel / 2 : ((refTop && !srcTop) ? -(nPel / 2) : 0);
+    return true;
+}
+
+// ------------------------------------------------------------ Recalculate
+struct RecalcData {
+    VSNode *node, *vectors;
+    const VSVideoInfo *vi;
+    mvb200_super_params sp;
+    mvb200_recalculate_params rp;
+};
+
+const VSFrame *VS_CC recalcGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    RecalcData *d = (RecalcData *)instanceData;
+    const int off = d->rp.ad.nDeltaFrame;
+    const int nref = off > 0 ? (d->rp.ad.isBackward ? n + off : n - off) : -off;
+    const bool refOk = nref >= 0 && nref < d->vi->numFrames;
+    if (activationReason == arInitial) { // MVRecalculate.c:73-94
+        vsapi->requestFrameFilter(n, d->vectors, frameCtx);
+        if (refOk) {
+            vsapi->requestFrameFilter(n < nref ? n : nref, d->node, frameCtx);
+            vsapi->requestFrameFilter(n < nref ? nref : n, d->node, frameCtx);
+        } else {
+            vsapi->requestFrameFilter(n, d->node, frameCtx);
+        }
+    } else if (activationReason == arAllFramesReady) {
+        const VSFrame *src = vsapi->getFrameFilter(n, d->node, frameCtx);
+        const VSFrame *ref = refOk ? vsapi->getFrameFilter(nref, d->node, frameCtx) : nullptr;
+        const VSFrame *mvn = vsapi->getFrameFilter(n, d->vectors, frameCtx);
+        int e = 0;
+        const uint8_t *old = (const uint8_t *)vsapi->mapGetData(vsapi->getFramePropertiesRO(mvn), "MVTools_vectors", 0, &e);
+        int fieldShift = 0;
+        std::string msg;
+        int rc = 1;
+        if (e) {
+            msg = "MVTools_vectors property missing";
+        } else if (!fieldShiftOf(vsapi, src, ref, n, nref, d->rp.fields, d->rp.tff_exists, d->rp.tff, d->rp.ad.nPel, d->rp.ad.nDeltaFrame % 2, &fieldShift)) {
+            msg = "_Field property not found in input frame. Therefore, you must pass tff argument.";
+        } else {
+            std::vector<uint8_t> vectors((size_t)d->rp.vectors_size);
+            const uint8_t *sp_[3], *rp_[3];
+            ptrdiff_t ss[3], rs[3];
+            planesRO(vsapi, src, d->vi->format.numPlanes, sp_, ss);
+            planesRO(vsapi, ref, d->vi->format.numPlanes, rp_, rs);
+            {
+                std::lock_guard<std::mutex> lock(g_engine_mutex);
+                mvb200_ctx *ctx = engine(msg);
+                rc = ctx ? mvb200_recalculate_frame(ctx, &d->rp, &d->sp, sp_, ss, ref ? rp_ : nullptr, ref ? rs : nullptr, old, fieldShift, vectors.data()) : 1;
+                if (ctx && rc)
+                    msg = mvb200_last_error();
+            }
+            if (!rc) {
+                VSFrame *dst = vsapi->copyFrame(src, core);
+                VSMap *props = vsapi->getFramePropertiesRW(dst);
+                const mvb200_analysis_data *ad = d->rp.divide ? &d->rp.ad_divided : &d->rp.ad;
+                vsapi->mapSetData(props, "MVTools_MVAnalysisData", (const char *)ad, sizeof(*ad), dtBinary, maReplace);
+                vsapi->mapSetData(props, "MVTools_vectors", (const char *)vectors.data(), (int)vectors.size(), dtBinary, maReplace);
+                vsapi->freeFrame(mvn);
+                vsapi->freeFrame(ref);
+                vsapi->freeFrame(src);
+                return dst;
+            }
+        }
+        vsapi->freeFrame(mvn);
+        vsapi->freeFrame(ref);
+        vsapi->freeFrame(src);
+        vsapi->setFilterError(("Recalculate: " + msg).c_str(), frameCtx);
+        return nullptr;
+    }
+    return nullptr;
+}
+
+void VS_CC recalcFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
+    RecalcData *d = (RecalcData *)instanceData;
+    vsapi->freeNode(d->node);
+    vsapi->freeNode(d->vectors);
+    delete d;
+}
+
+void VS_CC recalcCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const VSAPI *vsapi) {
+    mvb200_recalculate_args a;
+    a.thsad = argInt64(vsapi, in, "thsad");
+    static const char *names[] = {"smooth", "blksize", "blksizev", "search", "searchparam", "lambda", "chroma", "truemotion", "pnew", "overlap", "overlapv", "divide",
+                                  "opt", "meander", "fields", "tff", "dct"};
+    int32_t *fields = &a.smooth;
+    for (size_t i = 0; i < sizeof(names) / sizeof(names[0]); i++)
+        fields[i] = argInt(vsapi, in, names[i]);
+    RecalcData d;
+    memset(&d, 0, sizeof(d));
+    d.node = vsapi->mapGetNode(in, "super", 0, nullptr);
+    d.vectors = vsapi->mapGetNode(in, "vectors", 0, nullptr);
+    d.vi = vsapi->getVideoInfo(d.node);
+    std::string err;
+    mvb200_analysis_data old;
+    if (!superFromClip(d.node, vsapi, "Recalculate", &d.sp, err) || !adataFromClip(d.vectors, vsapi, "Recalculate", "vectors", &old, err) ||
+        mvb200_recalculate_init(&a, &d.sp, &old, d.vi->numFrames, &d.rp)) {
+        vsapi->mapSetError(out, err.empty() ? mvb200_last_error() : err.c_str());
+        vsapi->freeNode(d.node);
+        vsapi->freeNode(d.vectors);
+        return;
+    }
+    RecalcData *data = new RecalcData(d);
+    VSFilterDependency deps[2] = {{data->node, rpGeneral}, {data->vectors, rpStrictSpatial}};
+    vsapi->createVideoFilter(out, "Recalculate", data->vi, recalcGetFrame, recalcFree, fmParallel, deps, 2, data, core);
+}
+
+// ------------------------------------------------------------- Compensate
+struct CompData {
+    VSNode *node, *super, *vectors;
+    const VSVideoInfo *vi, *supervi;
+    mvb200_super_params sp;
+    mvb200_compensate_params cp;
+};
+
+const VSFrame *VS_CC compGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    CompData *d = (CompData *)instanceData;
+    const int delta = d->cp.vd.nDeltaFrame;
+    const int nref = delta > 0 ? n + (d->cp.vd.isBackward ? delta : -delta) : -delta;
+    if (activationReason == arInitial) { // MVCompensate.c:78-97
+        vsapi->requestFrameFilter(n, d->vectors, frameCtx);
+        if (nref < n && nref >= 0)
+            vsapi->requestFrameFilter(nref, d->super, frameCtx);
+        vsapi->requestFrameFilter(n, d->super, frameCtx);
+        if (nref >= n && nref < d->vi->numFrames)
+            vsapi->requestFrameFilter(nref, d->super, frameCtx);
+    } else if (activationReason == arAllFramesReady) {
+        const VSFrame *src = vsapi->getFrameFilter(n, d->super, frameCtx);
+        const VSFrame *ref = (nref >= 0 && nref < d->vi->numFrames) ? vsapi->getFrameFilter(nref, d->super, frameCtx) : nullptr;
+        const VSFrame *mvn = vsapi->getFrameFilter(n, d->vectors, frameCtx);
+        VSFrame *dst = vsapi->newVideoFrame(&d->vi->format, d->vi->width, d->vi->height, src, core);
+        int e = 0;
+        const uint8_t *vec = (const uint8_t *)vsapi->mapGetData(vsapi->getFramePropertiesRO(mvn), "MVTools_vectors", 0, &e);
+        int fieldShift = 0;
+        std::string msg;
+        int rc = 1;
+        if (e) {
+            msg = "MVTools_vectors property missing";
+        } else if (!fieldShiftOf(vsapi, src, ref, n, nref, d->cp.fields && d->cp.vd.nPel > 1 && (nref - n) % 2 != 0 && ref, d->cp.tff_exists, d->cp.tff, d->cp.vd.nPel, true, &fieldShift)) {
+            msg = "_Field property not found in input frame. Therefore, you must pass tff argument.";
+        } else {
+            const uint8_t *sp_[3], *rp_[3];
+            ptrdiff_t ss[3], rs[3];
+            uint8_t *dp_[3];
+            ptrdiff_t ds[3];
+            planesRO(vsapi, src, d->supervi->format.numPlanes, sp_, ss);
+            planesRO(vsapi, ref, d->supervi->format.numPlanes, rp_, rs);
+            planesRW(vsapi, dst, d->vi->format.numPlanes, dp_, ds);
+            std::lock_guard<std::mutex> lock(g_engine_mutex);
+            mvb200_ctx *ctx = engine(msg);
+            rc = ctx ? mvb200_compensate_frame(ctx, &d->cp, &d->sp, sp_, ss, ref ? rp_ : nullptr, ref ? rs : nullptr, vec, fieldShift, dp_, ds) : 1;
+            if (ctx && rc)
+                msg = mvb200_last_error();
+        }
+        vsapi->freeFrame(mvn);
+        vsapi->freeFrame(ref);
+        vsapi->freeFrame(src);
+        if (rc) {
+            vsapi->setFilterError(("Compensate: " + msg).c_str(), frameCtx);
+            vsapi->freeFrame(dst);
+            return nullptr;
+        }
+        return dst;
+    }
+    return nullptr;
+}
+
+void VS_CC compFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
+    CompData *d = (CompData *)instanceData;
+    vsapi->freeNode(d->node);
+    vsapi->freeNode(d->super);
+    vsapi->freeNode(d->vectors);
+    delete d;
+}
+
+void VS_CC compCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const VSAPI *vsapi) {
+    mvb200_compensate_args a;
+    a.scbehavior = argInt(vsapi, in, "scbehavior");
+    a.thsad = argInt64(vsapi, in, "thsad");
+    a.fields = argInt(vsapi, in, "fields");
+    int err = 0;
+    a.time = vsapi->mapGetFloat(in, "time", 0, &err);
+    if (err)
+        a.time = NAN;
+    a.thscd1 = argInt64(vsapi, in, "thscd1");
+    a.thscd2 = argInt(vsapi, in, "thscd2");
+    a.tff = argInt(vsapi, in, "tff");
+    if (a.time == a.time && (a.time < 0.0 || a.time > 100.0)) { // checked before any clip is touched (MVCompensate.c:457-460)
+        vsapi->mapSetError(out, "Compensate: time must be between 0.0 and 100.0 (inclusive).");
+        return;
+    }
+    CompData d;
+    memset(&d, 0, sizeof(d));
+    auto freeAll = [&]() {
+        vsapi->freeNode(d.node);
+        vsapi->freeNode(d.super);
+        vsapi->freeNode(d.vectors);
+    };
+    d.super = vsapi->mapGetNode(in, "super", 0, nullptr);
+    d.supervi = vsapi->getVideoInfo(d.super);
+    std::string msg;
+    mvb200_analysis_data vd;
+    if (!superFromClip(d.super, vsapi, "Compensate", &d.sp, msg)) {
+        vsapi->mapSetError(out, msg.c_str());
+        freeAll();
+        return;
+    }
+    d.vectors = vsapi->mapGetNode(in, "vectors", 0, nullptr);
+    if (!adataFromClip(d.vectors, vsapi, "Compensate", "vectors", &vd, msg)) {
+        vsapi->mapSetError(out, msg.c_str());
+        freeAll();
+        return;
+    }
+    d.node = vsapi->mapGetNode(in, "clip", 0, nullptr);
+    d.vi = vsapi->getVideoInfo(d.node);
+    if (mvb200_compensate_init(&a, &d.sp, &vd, d.vi->width, d.vi->height, d.vi->numFrames, &d.cp)) {
+        vsapi->mapSetError(out, mvb200_last_error());
+        freeAll();
+        return;
+    }
+    if (!formatOk(d.vi)) {
+        vsapi->mapSetError(out, "Compensate: input clip must be GRAY, 420, 422, 440, or 444, up to 16 bits, with constant dimensions.");
+        freeAll();
+        return;
+    }
+    CompData *data = new CompData(d);
+    VSFilterDependency deps[2] = {{data->super, rpGeneral}, {data->vectors, rpGeneral}};
+    vsapi->createVideoFilter(out, "Compensate", data->vi, compGetFrame, compFree, fmParallel, deps, 2, data, core);
 }
 
 } // namespace
@@ -529,10 +793,10 @@ VS_EXTERNAL_API(void) VapourSynthPluginInit2(VSPlugin *plugin, const VSPLUGINAPI
     vspapi->registerFunction("Compensate",
                              "clip:vnode;super:vnode;vectors:vnode;scbehavior:int:opt;thsad:int:opt;fields:int:opt;time:float:opt;thscd1:int:opt;thscd2:int:opt;opt:int:opt;"
                              "tff:int:opt;",
-                             "clip:vnode;", notImplemented, (void *)"Compensate", plugin);
+                             "clip:vnode;", compCreate, nullptr, plugin);
     vspapi->registerFunction("Recalculate",
                              "super:vnode;vectors:vnode;thsad:int:opt;smooth:int:opt;blksize:int:opt;blksizev:int:opt;search:int:opt;searchparam:int:opt;lambda:int:opt;"
                              "chroma:int:opt;truemotion:int:opt;pnew:int:opt;overlap:int:opt;overlapv:int:opt;divide:int:opt;opt:int:opt;meander:int:opt;fields:int:opt;"
                              "tff:int:opt;dct:int:opt;",
-                             "clip:vnode;", notImplemented, (void *)"Recalculate", plugin);
+                             "clip:vnode;", recalcCreate, nullptr, plugin);
 }
