@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=690, help="frames per step per GPU (690 x 6 chains = 2 full waves of 14 warps x 148 SMs)")
+    ap.add_argument("--frames", type=int, default=592, help="frames per step per GPU (592 x 6 chains = 2 full waves of 12 warps x 148 SMs)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
