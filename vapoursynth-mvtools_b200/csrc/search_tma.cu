@@ -66,6 +66,10 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm,
 }
 // shared-space loads/stores with 32-bit addresses.  `volatile` keeps the loads after the mbarrier
 // wait that publishes the TMA data.
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src) { // LDGSTS: global -> shared without a register
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void sts32(uint32_t a, unsigned v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 template <int OFF>
 __device__ __forceinline__ unsigned lds_o(uint32_t a) {
@@ -146,7 +150,10 @@ struct Cfg {
     static constexpr int SRCW = (LBYTES + 2 * CBYTES) / 4, NSI = (SRCW + 31) / 32; // source block words, per lane for the cooperative load
     static constexpr bool PACK = BPS == 1 && BW * BH <= 256 && 2 * CW * CH <= 256;
     static constexpr bool SRC_SMEM = BPS == 2 && BW * BH >= 256; // too many registers: read source rows from shared memory
-    static constexpr int SRCOFF = 2 * BUF, BAROFF = SRCOFF + r128(LBYTES + 2 * CBYTES);
+    static constexpr int SRCB = r128(LBYTES + 2 * CBYTES);                   // one source-block buffer
+    static constexpr int SRCOFF = 2 * BUF, RAWOFF = SRCOFF + 2 * SRCB;        // [src 0][src 1][raw lo/hi words of an unaligned block]
+    static constexpr int VECOFF = RAWOFF + r128(8 * SRCW);                    // hier[2], up, p3: 4 x 16 bytes
+    static constexpr int COLDOFF = VECOFF + 128, BAROFF = COLDOFF + 384;      // level constants, 2 mbarriers
     static constexpr int SMEM = BAROFF + 64 + 128;
     static_assert(BH % 4 == 0 && (BW * BPS) % 4 == 0, "block shape");
     static_assert(!CHROMA || (CH % 4 == 0 && (CW * BPS) % 4 == 0), "chroma block shape");
@@ -157,13 +164,24 @@ struct TmaMaps {
     CUtensorMap plane4[3]; // 4-D {x, row, sub-plane, frame} over level 0: pel 2
 };
 
-struct Pre {
-    VEC hier, up, p3;
-};
-
 struct Geom {
     int x0, y0, xc, yc, dxMin, dxMax, dyMin, dyMax;
 };
+
+// Level constants and other state that is touched once per block (or less): kept in this warp's
+// shared memory instead of registers -- the block loop needs its registers for the search itself.
+struct Cold {
+    const uint8_t *sbase[3], *rbase[3]; // level bases (padded origin, sub-plane 0) of the source / reference frame
+    VEC *vectors;
+    long long badSAD, LSAD;
+    int pitch0, pitch1, sub0, sub1;
+    int hp0, vp0, hpc, vpc, pw0, ph0, hps, vps, row0_0, row0_1;
+    int nBlkX, nBlkY, nBlk, stepX, stepY, meander, nLambdaLevel, fs, ref_frame, use4d, smallest, srcAligned;
+    int penaltyZero, pglobal, badrange, searchType, searchParam;
+    int gmx, gmy;  // globalMV (sticky clipping, :859)
+    int wo[2][4];  // window origins of the two window buffers
+};
+static_assert(sizeof(Cold) <= 384, "Cold");
 
 template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
 struct Chain {
@@ -173,20 +191,15 @@ struct Chain {
 
     // ---- source block rows of this lane (rows q, q+4, ...), unless C::SRC_SMEM
     unsigned srcL[C::SRC_SMEM ? 1 : C::LR][C::RW], srcC[2][C::SRC_SMEM ? 1 : C::CR][C::CRW];
-    uint32_t srcbuf; // shared-space address of the source block
-    // ---- level constants
-    const uint8_t *rbase[3]; // level bases (padded origin, sub-plane 0) of the reference frame
-    int pitch0, pitch1, sub0, sub1;
-    int logPel, searchType, searchParam;
-    int penaltyZero, pglobal, penaltyNew, badrange, fieldShift;
-    long long badSAD, LSAD;
-    VEC globalMV;
+    uint32_t srcbuf; // shared-space address of the current source block
+    Cold *K;
+    int logPel, penaltyNew;
     // ---- block state
     Geom g;
     int wx0, wy0, wxc0, wyc0; // window origins (full-pel, padded-plane coordinates) of the CURRENT buffer
     long long nLambda, nMinCost;
     VEC best, predictor;
-    int badcount, lane, j, q;
+    int badcount, j, q;
     uint32_t sbuf; // shared-space address of the current window buffer
 
     __device__ __forceinline__ bool ok(int vx, int vy) const { return vx >= g.dxMin && vy >= g.dyMin && vx < g.dxMax && vy < g.dyMax; }
@@ -288,7 +301,8 @@ struct Chain {
             }
         } else {
             // at least one candidate leaves the staged window: the whole step reads global memory
-            const uint8_t *pl = rbase[0] + (long long)subl * sub0 + (long long)(fy + q) * pitch0 + fx * BPS;
+            const int pitch0 = K->pitch0, pitch1 = K->pitch1;
+            const uint8_t *pl = K->rbase[0] + (long long)subl * K->sub0 + (long long)(fy + q) * pitch0 + fx * BPS;
 #pragma unroll
             for (int i = 0; i < C::LR; i++) {
                 unsigned sw[C::RW];
@@ -299,7 +313,7 @@ struct Chain {
                     aL += absd(ldg_un(pl + (long long)(4 * i) * pitch0 + 4 * w), C::SRC_SMEM ? sw[w] : srcL[i][w]);
             }
             if (CHROMA) {
-                const long long oc = (long long)subc * sub1 + (long long)(fyc + q) * pitch1 + fxc * BPS;
+                const long long oc = (long long)subc * K->sub1 + (long long)(fyc + q) * pitch1 + fxc * BPS;
 #pragma unroll
                 for (int p = 0; p < 2; p++) {
 #pragma unroll
@@ -309,7 +323,7 @@ struct Chain {
                             lds_vec(srcbuf + C::LBYTES + p * C::CBYTES + (q + 4 * i) * (C::CRW * 4), sw);
 #pragma unroll
                         for (int w = 0; w < C::CRW; w++)
-                            aC += absd(ldg_un(rbase[1 + p] + oc + (long long)(4 * i) * pitch1 + 4 * w), C::SRC_SMEM ? sw[w] : srcC[p][i][w]);
+                            aC += absd(ldg_un(K->rbase[1 + p] + oc + (long long)(4 * i) * pitch1 + 4 * w), C::SRC_SMEM ? sw[w] : srcC[p][i][w]);
                     }
                 }
             }
@@ -513,6 +527,7 @@ struct Chain {
     }
 
     __device__ __forceinline__ void refine() { // pobRefine :772-816, types 3/4/5
+        const int searchType = K->searchType, searchParam = K->searchParam;
         if (searchType == 3) {
             int mvx = best.x, mvy = best.y;
             for (int i = 1; i <= searchParam; i++)
@@ -525,29 +540,35 @@ struct Chain {
     }
 
     // pobPseudoEPZSearch, PlaneOfBlocks.cpp:819-968, given the fetched predictors
-    __device__ __forceinline__ void epz(const VEC (&pr)[4], int blkIdx) {
-        globalMV = clip(globalMV); // sticky (:859)
+    __device__ __forceinline__ void epz(const int (&prx)[4], const int (&pry)[4], int blkIdx) {
+        // globalMV is clipped to every block's bounds in turn and stays clipped (:859)
+        const int gmx = min(max(K->gmx, g.dxMin), g.dxMax - 1), gmy = min(max(K->gmy, g.dyMin), g.dyMax - 1);
+        __syncwarp();
+        if (j == 0 && q == 0) {
+            K->gmx = gmx;
+            K->gmy = gmy;
+        }
         // slot j owns start candidate j: 0 zero, 1 global, 2 hierarchical, 3..6 predictors[0..3]
         Cand c;
         int px = 0, py = 0;
-        px = j == 1 ? globalMV.x : px;
-        py = j == 1 ? globalMV.y : py;
+        px = j == 1 ? gmx : px;
+        py = j == 1 ? gmy : py;
         px = j == 2 ? predictor.x : px;
         py = j == 2 ? predictor.y : py;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            px = j == 3 + i ? pr[i].x : px;
-            py = j == 3 + i ? pr[i].y : py;
+            px = j == 3 + i ? prx[i] : px;
+            py = j == 3 + i ? pry[i] : py;
         }
         c.lvx = c.cvx = px;
         c.cvy = py;
-        c.lvy = j == 0 ? fieldShift : py; // zero: luma at (0, fieldShift), chroma at (0, 0)  (:836-839)
+        c.lvy = j == 0 ? K->fs : py; // zero: luma at (0, fieldShift), chroma at (0, 0)  (:836-839)
         c.valid = j < 3 || (j < 7 && ok(px, py));
         unsigned sy, suv;
         eval_step<7>(c, sy, suv);
         // per-candidate cost rules (:846, :870, :894, CheckMV0)
         const long long sad = (long long)sy + suv;
-        const int pen = j == 0 ? penaltyZero : (j == 1 ? pglobal : 0);
+        const int pen = j == 0 ? K->penaltyZero : (j == 1 ? K->pglobal : 0);
         const long long cost = sad + ((pen * sad) >> 8) + (j >= 3 ? mv_cost(px, py) : 0ll);
         nMinCost = INF; // zero is accepted unconditionally, then strict '<' in order == first minimum
         int dummy = 0;
@@ -555,8 +576,10 @@ struct Chain {
         refine();
         // bad-block wide search (:938-963)
         const long long foundSAD = best.sad;
+        const long long badSAD = K->badSAD;
         if (blkIdx > 1 && foundSAD > (badSAD + badSAD * badcount / 16)) {
             badcount++;
+            const int badrange = K->badrange;
             if (badrange > 0) {
                 umh(badrange * (1 << logPel), 0, 0);
             } else if (badrange < 0) {
@@ -592,9 +615,12 @@ __global__ void __launch_bounds__(32, MVB_TMA_MIN_BLOCKS) k_search_tma(const __g
         return;
     int *hist = hist_all + (long long)chain * hist_ints;
 
-    // shared memory: [window buffer 0][window buffer 1][source block][2 mbarriers]
+    // shared memory: [window 0][window 1][source 0][source 1][raw source words][vector slots][Cold][2 mbarriers]
     const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;
+    uint8_t *const smem_gen = smem_raw + (smem0 - smem_u32(smem_raw));
+    Cold &K = *(Cold *)(smem_gen + C::COLDOFF);
     const uint32_t bar0 = smem0 + C::BAROFF;
+    const uint32_t vslot = smem0 + C::VECOFF; // hier(even t), hier(odd t), up, p3
     if (lane == 0) {
         mbar_init(bar0, 1);
         mbar_init(bar0 + 8, 1);
@@ -609,19 +635,10 @@ __global__ void __launch_bounds__(32, MVB_TMA_MIN_BLOCKS) k_search_tma(const __g
     globalMVec.sad = -1;
 
     CH S;
-    S.lane = lane;
     S.j = lane >> 2;
     S.q = lane & 3;
-    S.srcbuf = smem0 + C::SRCOFF;
-    S.penaltyZero = P.pzero;
-    S.pglobal = P.global ? P.pglobal : P.pzero;
+    S.K = &K;
     S.penaltyNew = P.pnew;
-    S.badSAD = P.badSAD;
-    S.badrange = P.badrange;
-    S.LSAD = P.lsad;
-    const int ref_frame = job.ref_index;
-    const int stepX = BW - P.ovX, stepY = BH - P.ovY;
-    const int meander = P.meander;
 
     // cooperative source-block load: word w of the block (luma rows, then U rows, then V rows) -> lane w % 32
     int sw_plane[C::NSI], sw_row[C::NSI], sw_col[C::NSI];
@@ -644,130 +661,211 @@ __global__ void __launch_bounds__(32, MVB_TMA_MIN_BLOCKS) k_search_tma(const __g
     }
 
     for (int l = L - 1; l >= 0; l--) {
-        const int nBlkX = P.nBlkX[l], nBlkY = P.nBlkY[l];
         S.logPel = l == 0 ? P.logPel : 0;
-        const bool smallest = (l == L - 1);
-        VEC *const vectors = (VEC *)(job.out + P.level_off[l] + 4);
-        const uint8_t *sbase[3];
+        const int nBlkX = P.nBlkX[l], nBlkY = P.nBlkY[l];
+        int fs;
+        {
+            const mvb200_level_geom &g0 = sd.lv[0][l];
+            const mvb200_level_geom &g1 = sd.lv[CHROMA ? 1 : 0][l];
+            int st, stp;
+            if (l == L - 1) {
+                st = (L == 1) ? P.search : P.search_coarse;
+                stp = (L == 1) ? P.nPelSearch : P.nSearchParam;
+                fs = (L - 1 == 0) ? job.field_shift : 0;
+            } else {
+                st = (l == 0) ? P.search : P.search_coarse;
+                stp = (l == 0) ? P.nPelSearch : P.nSearchParam;
+                fs = (l == 0) ? job.field_shift : 0;
+            }
+            const int nScale = 1 << l;
+            int nLambdaLevel = P.nLambda / ((1 << S.logPel) * (1 << S.logPel));
+            if (P.plevel == 1)
+                nLambdaLevel = nLambdaLevel * nScale;
+            else if (P.plevel == 2)
+                nLambdaLevel = nLambdaLevel * nScale * nScale;
+            __syncwarp();
+            if (lane == 0) {
 #pragma unroll
-        for (int p = 0; p < 3; p++) {
-            const int qp = (CHROMA || p == 0) ? p : 0;
-            const mvb200_level_geom &gl = sd.lv[qp][l];
-            const long long off = sd.offset[qp] + (long long)gl.row0 * sd.pitch[qp];
-            sbase[p] = job.src + off;
-            S.rbase[p] = job.ref + off;
+                for (int p = 0; p < 3; p++) {
+                    const int qp = (CHROMA || p == 0) ? p : 0;
+                    const long long off = sd.offset[qp] + (long long)sd.lv[qp][l].row0 * sd.pitch[qp];
+                    K.sbase[p] = job.src + off;
+                    K.rbase[p] = job.ref + off;
+                }
+                K.vectors = (VEC *)(job.out + P.level_off[l] + 4);
+                K.badSAD = P.badSAD;
+                K.LSAD = P.lsad;
+                K.pitch0 = (int)sd.pitch[0];
+                K.pitch1 = (int)sd.pitch[CHROMA ? 1 : 0];
+                K.sub0 = K.pitch0 * g0.padded_h;
+                K.sub1 = K.pitch1 * g1.padded_h;
+                K.hp0 = g0.hpad;
+                K.vp0 = g0.vpad;
+                K.hpc = g1.hpad;
+                K.vpc = g1.vpad;
+                K.pw0 = g0.padded_w;
+                K.ph0 = g0.padded_h;
+                K.hps = g0.hpad >> l;
+                K.vps = g0.vpad >> l;
+                K.row0_0 = g0.row0;
+                K.row0_1 = g1.row0;
+                K.nBlkX = nBlkX;
+                K.nBlkY = nBlkY;
+                K.nBlk = nBlkX * nBlkY;
+                K.stepX = BW - P.ovX;
+                K.stepY = BH - P.ovY;
+                K.meander = P.meander;
+                K.nLambdaLevel = nLambdaLevel;
+                K.fs = fs;
+                K.ref_frame = job.ref_index;
+                K.use4d = S.logPel == 1; // level 0 of a pel-2 clip: the 4-D maps (their row origin is level 0's row0)
+                K.smallest = (l == L - 1);
+                K.srcAligned = (((g0.hpad * BPS) | ((BW - P.ovX) * BPS) | (g1.hpad * BPS) | (((BW - P.ovX) >> LXR) * BPS)) & 3) == 0;
+                K.penaltyZero = P.pzero;
+                K.pglobal = P.global ? P.pglobal : P.pzero;
+                K.badrange = P.badrange;
+                K.searchType = st;
+                K.searchParam = stp;
+            }
+            __syncwarp();
         }
-        const mvb200_level_geom &g0 = sd.lv[0][l];
-        const mvb200_level_geom &g1 = sd.lv[CHROMA ? 1 : 0][l];
-        S.pitch0 = (int)sd.pitch[0];
-        S.pitch1 = (int)sd.pitch[CHROMA ? 1 : 0];
-        S.sub0 = S.pitch0 * g0.padded_h;
-        S.sub1 = S.pitch1 * g1.padded_h;
-        const int hp0 = g0.hpad, vp0 = g0.vpad, hpc = g1.hpad, vpc = g1.vpad, pw0 = g0.padded_w, ph0 = g0.padded_h;
-        const int row0_0 = g0.row0, row0_1 = g1.row0;
-        const bool use4d = S.logPel == 1; // level 0 of a pel-2 clip: the 4-D maps (their row origin is level 0's row0 = 0)
-        int st, stp, fs;
-        if (l == L - 1) {
-            st = (L == 1) ? P.search : P.search_coarse;
-            stp = (L == 1) ? P.nPelSearch : P.nSearchParam;
-            fs = (L - 1 == 0) ? job.field_shift : 0;
-        } else {
-            st = (l == 0) ? P.search : P.search_coarse;
-            stp = (l == 0) ? P.nPelSearch : P.nSearchParam;
+        if (l != L - 1) {
             const VEC *coarse = (const VEC *)(job.out + P.level_off[l + 1] + 4);
             if (P.global)
                 estimate_global_mv(coarse, P.nBlkX[l + 1] * P.nBlkY[l + 1], 8192 * 1 * 2, hist, globalMVec, lane);
-            interpolate_prediction(vectors, nBlkX, nBlkY, S.logPel, coarse, P.nBlkX[l + 1], P.nBlkY[l + 1], BW, BH, P.ovX, P.ovY, lane);
+            interpolate_prediction(K.vectors, nBlkX, nBlkY, S.logPel, coarse, P.nBlkX[l + 1], P.nBlkY[l + 1], BW, BH, P.ovX, P.ovY, lane);
             __syncwarp();
-            fs = (l == 0) ? job.field_shift : 0;
         }
         // ---- doPobSearchMVs, PlaneOfBlocks.cpp:971-1131
-        S.searchType = st;
-        S.searchParam = stp;
-        S.fieldShift = fs;
-        S.globalMV.x = (1 << S.logPel) * globalMVec.x;
-        S.globalMV.y = (1 << S.logPel) * globalMVec.y + fs;
-        S.globalMV.sad = globalMVec.sad;
-        const int nScale = 1 << l;
-        int nLambdaLevel = P.nLambda / ((1 << S.logPel) * (1 << S.logPel));
-        if (P.plevel == 1)
-            nLambdaLevel = nLambdaLevel * nScale;
-        else if (P.plevel == 2)
-            nLambdaLevel = nLambdaLevel * nScale * nScale;
+        if (lane == 0) {
+            K.gmx = (1 << S.logPel) * globalMVec.x;
+            K.gmy = (1 << S.logPel) * globalMVec.y + fs;
+        }
+        __syncwarp();
         S.badcount = 0;
-        const int hps = hp0 >> l, vps = vp0 >> l;
         const int nBlk = nBlkX * nBlkY;
-        VEC zeroFs;
-        zeroFs.x = 0;
-        zeroFs.y = fs;
-        zeroFs.sad = 0;
+        const bool smallest = (l == L - 1);
 
         auto block_geom = [&](int bx, int by, Geom &gg) {
-            gg.x0 = hp0 + stepX * bx;
-            gg.y0 = vp0 + stepY * by;
-            gg.xc = hpc + (stepX >> LXR) * bx;
-            gg.yc = vpc + (stepY >> LYR) * by;
-            gg.dxMax = (pw0 - gg.x0 - BW - hp0 + hps) << S.logPel;
-            gg.dyMax = (ph0 - gg.y0 - BH - vp0 + vps) << S.logPel;
-            gg.dxMin = -((gg.x0 - hp0 + hps) << S.logPel);
-            gg.dyMin = -((gg.y0 - vp0 + vps) << S.logPel);
+            const int hp0 = K.hp0, vp0 = K.vp0;
+            gg.x0 = hp0 + K.stepX * bx;
+            gg.y0 = vp0 + K.stepY * by;
+            gg.xc = K.hpc + (K.stepX >> LXR) * bx;
+            gg.yc = K.vpc + (K.stepY >> LYR) * by;
+            gg.dxMax = (K.pw0 - gg.x0 - BW - hp0 + K.hps) << S.logPel;
+            gg.dyMax = (K.ph0 - gg.y0 - BH - vp0 + K.vps) << S.logPel;
+            gg.dxMin = -((gg.x0 - hp0 + K.hps) << S.logPel);
+            gg.dyMin = -((gg.y0 - vp0 + K.vps) << S.logPel);
         };
-        // raw (unshifted) words of the source block at gg; the funnel shift happens when they are consumed
-        auto load_src_raw = [&](const Geom &gg, unsigned (&lo)[C::NSI], unsigned (&hi)[C::NSI]) {
-#pragma unroll
-            for (int k = 0; k < C::NSI; k++) {
-                const int pl = sw_plane[k];
-                const uint8_t *p = (pl == 0 ? sbase[0] : (pl == 1 ? sbase[1] : sbase[2])) +
-                                   (long long)((pl == 0 ? gg.y0 : gg.yc) + sw_row[k]) * (pl == 0 ? S.pitch0 : S.pitch1) + (pl == 0 ? gg.x0 : gg.xc) * BPS + sw_col[k];
-                const unsigned *w = (const unsigned *)((unsigned long long)p & ~3ull);
-                lo[k] = __ldg(w);
-                hi[k] = __ldg(w + 1);
+        // meander scan order (:1037-1055): successor of (bx, by, dir)
+        auto succ = [&](int bx, int by, int dir, int &nbx, int &nby, int &ndir) {
+            nbx = bx + dir;
+            nby = by;
+            ndir = dir;
+            if (nbx < 0 || nbx >= nBlkX) {
+                nby = by + 1;
+                ndir = (K.meander == 0 || (nby & 1) == 0) ? 1 : -1;
+                nbx = ndir == 1 ? 0 : nBlkX - 1;
             }
         };
-        // shifts the raw words, publishes the block in shared memory and loads this lane's rows
-        auto commit_src = [&](const Geom &gg, const unsigned (&lo)[C::NSI], const unsigned (&hi)[C::NSI]) {
-            const unsigned shl = ((unsigned)(gg.x0 * BPS) & 3u) * 8u, shc = ((unsigned)(gg.xc * BPS) & 3u) * 8u;
-            __syncwarp(); // every lane is done reading the previous block from shared memory
+        // Asynchronous copy (LDGSTS) of the source block at (x0, y0)/(xc, yc) into source buffer `buf`:
+        // straight into place when every block of the level is 4-byte aligned, else as raw lo/hi words.
+        auto issue_src = [&](int x0, int y0, int xc, int yc, int buf) {
+            const bool aligned = K.srcAligned;
+            const int pitch0 = K.pitch0, pitch1 = K.pitch1;
 #pragma unroll
-            for (int k = 0; k < C::NSI; k++)
-                if (lane + 32 * k < C::SRCW)
-                    sts32(S.srcbuf + 4 * (lane + 32 * k), __funnelshift_r(lo[k], hi[k], sw_plane[k] == 0 ? shl : shc));
+            for (int k = 0; k < C::NSI; k++) {
+                if (lane + 32 * k < C::SRCW) {
+                    const int pl = sw_plane[k];
+                    const uint8_t *p = K.sbase[pl] + (long long)((pl == 0 ? y0 : yc) + sw_row[k]) * (pl == 0 ? pitch0 : pitch1) + (pl == 0 ? x0 : xc) * BPS + sw_col[k];
+                    if (aligned) {
+                        cp_async4(smem0 + C::SRCOFF + buf * C::SRCB + 4 * (lane + 32 * k), p);
+                    } else {
+                        const unsigned *w = (const unsigned *)((unsigned long long)p & ~3ull);
+                        cp_async4(smem0 + C::RAWOFF + 8 * (lane + 32 * k), w);
+                        cp_async4(smem0 + C::RAWOFF + 8 * (lane + 32 * k) + 4, w + 1);
+                    }
+                }
+            }
+        };
+        // completes the copy of the source block (x0, xc give the byte misalignment) and loads this lane's rows
+        auto commit_src = [&](int x0, int xc, int buf) {
+            cp_async_wait_all();
             __syncwarp();
+            const uint32_t dst = smem0 + C::SRCOFF + buf * C::SRCB;
+            if (!K.srcAligned) {
+                const unsigned shl = ((unsigned)(x0 * BPS) & 3u) * 8u, shc = ((unsigned)(xc * BPS) & 3u) * 8u;
+#pragma unroll
+                for (int k = 0; k < C::NSI; k++)
+                    if (lane + 32 * k < C::SRCW) {
+                        unsigned lh[2];
+                        lds_vec(smem0 + C::RAWOFF + 8 * (lane + 32 * k), lh);
+                        sts32(dst + 4 * (lane + 32 * k), __funnelshift_r(lh[0], lh[1], sw_plane[k] == 0 ? shl : shc));
+                    }
+                __syncwarp();
+            }
+            S.srcbuf = dst;
             if (!C::SRC_SMEM) {
 #pragma unroll
                 for (int i = 0; i < C::LR; i++)
-                    lds_vec(S.srcbuf + (S.q + 4 * i) * (C::RW * 4), S.srcL[i]);
+                    lds_vec(dst + (S.q + 4 * i) * (C::RW * 4), S.srcL[i]);
                 if (CHROMA) {
 #pragma unroll
                     for (int p = 0; p < 2; p++)
 #pragma unroll
                         for (int i = 0; i < C::CR; i++)
-                            lds_vec(S.srcbuf + C::LBYTES + p * C::CBYTES + (S.q + 4 * i) * (C::CRW * 4), S.srcC[p][i]);
+                            lds_vec(dst + C::LBYTES + p * C::CBYTES + (S.q + 4 * i) * (C::CRW * 4), S.srcC[p][i]);
                 }
             }
         };
-        auto prefetch = [&](int bx, int by, int dir, Pre &pre) {
-            const int idx = by * nBlkX + bx;
-            pre.hier = ldvec(&vectors[idx]);
-            const bool hasNext = (dir == 1 && bx < nBlkX - 1) || (dir == -1 && bx > 0);
-            pre.up = zeroFs;
-            if (by > 0)
-                pre.up = ldvec(&vectors[idx - nBlkX]);
-            pre.p3 = zeroFs;
-            if (by < nBlkY - 1 && hasNext)
-                pre.p3 = ldvec(&vectors[idx + nBlkX + dir]);
-            else if (by > 0 && hasNext)
-                pre.p3 = ldvec(&vectors[idx - nBlkX + dir]);
+        // The word this lane fetches for the vector slots: lanes 0-3 the hierarchical predictor of the block at
+        // (hx, hy) (if hv), lanes 4-7 / 8-11 the "up" and "down-right / up-right" neighbours of the block at
+        // (bx, by, dir) (if nv) -- pobFetchPredictors' reads (:419-463); zeroMVfieldShifted where there is none.
+        auto fetch_word = [&](bool hv, int hx, int hy, bool nv, int bx, int by, int dir) -> int {
+            const int grp = lane >> 2, wi = lane & 3;
+            const int *vw = (const int *)K.vectors;
+            const int zero = wi == 1 ? K.fs : 0;
+            int idx = -1;
+            if (grp == 0) {
+                idx = hv ? hy * nBlkX + hx : -1;
+            } else if (grp == 1) {
+                idx = (nv && by > 0) ? (by - 1) * nBlkX + bx : -1;
+            } else if (grp == 2 && nv) {
+                const bool hasNext = (dir == 1 && bx < nBlkX - 1) || (dir == -1 && bx > 0);
+                if (by < nBlkY - 1 && hasNext)
+                    idx = (by + 1) * nBlkX + bx + dir;
+                else if (by > 0 && hasNext)
+                    idx = (by - 1) * nBlkX + bx + dir;
+            }
+            return idx >= 0 ? __ldcg(vw + 4 * idx + wi) : zero; // written by this warp earlier in the chain: L2-coherent loads
         };
-        // stages the window of the block with geometry gg around its clipped hierarchical predictor
-        auto stage = [&](const Geom &gg, const VEC &hier, int buf, int (&wo)[4]) {
-            const int cx = min(max(hier.x, gg.dxMin), gg.dxMax - 1), cy = min(max(hier.y, gg.dyMin), gg.dyMax - 1);
+        auto slot_of_lane = [&](int hslot) -> uint32_t { // where fetch_word's result goes
+            const int grp = lane >> 2, wi = lane & 3;
+            return vslot + 16 * (grp == 0 ? hslot : grp + 1) + 4 * wi;
+        };
+        auto read_vec = [&](int slot) -> VEC {
+            unsigned v[4];
+            lds_vec(vslot + 16 * slot, v);
+            VEC r;
+            r.x = (int)v[0];
+            r.y = (int)v[1];
+            r.sad = (long long)(((unsigned long long)v[3] << 32) | v[2]);
+            return r;
+        };
+        // stages the window of the block with geometry gg around its clipped hierarchical predictor (hx, hy)
+        auto stage = [&](const Geom &gg, int hx, int hy, int buf) {
+            const int cx = min(max(hx, gg.dxMin), gg.dxMax - 1), cy = min(max(hy, gg.dyMin), gg.dyMax - 1);
+            int wo[4];
             S.window_origin(gg, cx, cy, wo[0], wo[1], wo[2], wo[3]);
             fence_proxy_async(); // earlier generic-proxy reads of this buffer are ordered before the async writes
             __syncwarp();
             if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    K.wo[buf][k] = wo[k];
                 const uint32_t dst = smem0 + buf * C::BUF, bar = bar0 + 8 * buf;
-                if (use4d) {
+                const int ref_frame = K.ref_frame;
+                if (K.use4d) {
                     mbar_expect_tx(bar, (uint32_t)(4 * (C::LT + 2 * C::CT)));
                     tma_load_4d(dst, &maps.plane4[0], wo[0], wo[1], 0, ref_frame, bar);
                     if (CHROMA) {
@@ -776,101 +874,126 @@ __global__ void __launch_bounds__(32, MVB_TMA_MIN_BLOCKS) k_search_tma(const __g
                     }
                 } else {
                     mbar_expect_tx(bar, (uint32_t)(C::LT + 2 * C::CT));
-                    tma_load_3d(dst, &maps.plane[0], wo[0], row0_0 + wo[1], ref_frame, bar);
+                    tma_load_3d(dst, &maps.plane[0], wo[0], K.row0_0 + wo[1], ref_frame, bar);
                     if (CHROMA) {
-                        tma_load_3d(dst + C::LREG, &maps.plane[1], wo[2], row0_1 + wo[3], ref_frame, bar);
-                        tma_load_3d(dst + C::LREG + C::CREG, &maps.plane[2], wo[2], row0_1 + wo[3], ref_frame, bar);
+                        tma_load_3d(dst + C::LREG, &maps.plane[1], wo[2], K.row0_1 + wo[3], ref_frame, bar);
+                        tma_load_3d(dst + C::LREG + C::CREG, &maps.plane[2], wo[2], K.row0_1 + wo[3], ref_frame, bar);
                     }
                 }
             }
+            __syncwarp();
         };
 
-        Pre cur, nxt;
-        Geom gn;
+        // ---- level prologue: vectors of block 0 (and the hierarchical predictor of block 1), source block 0, window 0
         int bx = 0, by = 0, dir = 1;
-        prefetch(bx, by, dir, cur);
-        block_geom(bx, by, S.g);
         {
-            unsigned lo[C::NSI], hi[C::NSI];
-            load_src_raw(S.g, lo, hi);
-            commit_src(S.g, lo, hi);
+            int n1x, n1y, n1d;
+            succ(bx, by, dir, n1x, n1y, n1d);
+            const int w0 = fetch_word(true, 0, 0, true, 0, 0, 1);
+            const int w1 = fetch_word(nBlk > 1, n1x, n1y, false, 0, 0, 1);
+            if (lane < 12)
+                sts32(slot_of_lane(0), (unsigned)w0);
+            if (lane < 4)
+                sts32(slot_of_lane(1), (unsigned)w1);
+            block_geom(0, 0, S.g);
+            issue_src(S.g.x0, S.g.y0, S.g.xc, S.g.yc, 0);
+            commit_src(S.g.x0, S.g.xc, 0); // (its __syncwarp also publishes the vector slots)
+            if (!smallest) {
+                const VEC h0 = read_vec(0);
+                stage(S.g, h0.x, h0.y, 0);
+            }
         }
-        int wcur[4], wnxt[4]; // window origins of the current / the other buffer
         int cbuf = 0;
-        if (!smallest)
-            stage(S.g, cur.hier, cbuf, wcur);
-        VEC prev = zeroFs;
         for (int t = 0; t < nBlk; t++) {
             const int blkIdx = by * nBlkX + bx;
-            // next scan position (meander order, :1037-1055)
-            int nbx = bx + dir, nby = by, ndir = dir;
-            if (nbx < 0 || nbx >= nBlkX) {
-                nby = by + 1;
-                ndir = (meander == 0 || (nby & 1) == 0) ? 1 : -1;
-                nbx = ndir == 1 ? 0 : nBlkX - 1;
-            }
             const bool hasMore = t + 1 < nBlk;
-            unsigned nlo[C::NSI], nhi[C::NSI];
-            if (hasMore) {
-                prefetch(nbx, nby, ndir, nxt);
-                block_geom(nbx, nby, gn);
-                load_src_raw(gn, nlo, nhi);
-            }
-            S.nLambda = by == 0 ? 0 : nLambdaLevel;
-            S.predictor = S.clip(cur.hier);
-            // pobFetchPredictors, PlaneOfBlocks.cpp:419-463
-            VEC pr[4];
-            const bool hasPrev = (dir == 1 && bx > 0) || (dir == -1 && bx < nBlkX - 1);
-            pr[1] = S.clip(hasPrev ? prev : zeroFs);
-            pr[2] = S.clip(cur.up);
-            pr[3] = S.clip(cur.p3);
-            if (by > 0) {
-                pr[0].x = max(min(pr[1].x, pr[2].x), min(max(pr[1].x, pr[2].x), pr[3].x));
-                pr[0].y = max(min(pr[1].y, pr[2].y), min(max(pr[1].y, pr[2].y), pr[3].y));
-                pr[0].sad = max(pr[1].sad, max(pr[2].sad, pr[3].sad));
-            } else {
-                pr[0] = pr[1];
-            }
-            if (smallest) {
-                S.predictor = pr[0];
-                // the window centre depends on the previous block here: stage now (few blocks on this level)
-                stage(S.g, S.predictor, cbuf, wcur);
-            }
+            int nbx, nby, ndir;
+            succ(bx, by, dir, nbx, nby, ndir);
+            // this block's vectors (fetched during the previous block)
+            const VEC hier = read_vec(t & 1), up = read_vec(2), p3 = read_vec(3);
+            __syncwarp(); // slots are rewritten at the end of this block
+            // fetch for later: hier(t+2), up/p3(t+1), source block t+1
+            int pv;
             {
-                double scale = __ddiv_rn((double)S.LSAD, (double)(S.LSAD + (S.predictor.sad >> 1)));
+                int n2x, n2y, n2d;
+                succ(nbx, nby, ndir, n2x, n2y, n2d);
+                pv = fetch_word(t + 2 < nBlk, n2x, n2y, hasMore, nbx, nby, ndir);
+            }
+            block_geom(bx, by, S.g);
+            S.nLambda = by == 0 ? 0 : K.nLambdaLevel;
+            S.predictor = S.clip(hier);
+            // pobFetchPredictors, PlaneOfBlocks.cpp:419-463
+            int prx[4], pry[4];
+            {
+                const int fs = K.fs;
+                const bool hasPrev = (dir == 1 && bx > 0) || (dir == -1 && bx < nBlkX - 1);
+                VEC p1; // predictors[1]: the previous block of the scan
+                p1.x = hasPrev ? S.best.x : 0;
+                p1.y = hasPrev ? S.best.y : fs;
+                p1.sad = hasPrev ? S.best.sad : 0;
+                p1 = S.clip(p1);
+                const VEC p2 = S.clip(up), p3c = S.clip(p3);
+                prx[1] = p1.x;
+                pry[1] = p1.y;
+                prx[2] = p2.x;
+                pry[2] = p2.y;
+                prx[3] = p3c.x;
+                pry[3] = p3c.y;
+                long long p0sad = p1.sad;
+                if (by > 0) {
+                    prx[0] = max(min(p1.x, p2.x), min(max(p1.x, p2.x), p3c.x));
+                    pry[0] = max(min(p1.y, p2.y), min(max(p1.y, p2.y), p3c.y));
+                    p0sad = max(p1.sad, max(p2.sad, p3c.sad));
+                } else {
+                    prx[0] = p1.x;
+                    pry[0] = p1.y;
+                }
+                if (smallest) {
+                    S.predictor.x = prx[0];
+                    S.predictor.y = pry[0];
+                    S.predictor.sad = p0sad;
+                    // the window centre depends on the previous block here: stage now (few blocks on this level)
+                    stage(S.g, S.predictor.x, S.predictor.y, cbuf);
+                }
+                const long long LSAD = K.LSAD;
+                double scale = __ddiv_rn((double)LSAD, (double)(LSAD + (S.predictor.sad >> 1)));
                 S.nLambda = __double2ll_rz(__dmul_rn(__dmul_rn((double)S.nLambda, scale), scale));
             }
             // the window of this block was issued one block ago: wait for it
             mbar_wait(bar0 + 8 * cbuf, (phasebits >> cbuf) & 1u);
             phasebits ^= 1u << cbuf;
             S.sbuf = smem0 + cbuf * C::BUF;
-            S.wx0 = wcur[0];
-            S.wy0 = wcur[1];
-            S.wxc0 = wcur[2];
-            S.wyc0 = wcur[3];
-            // ... and the next block's window goes into the other buffer while this block is searched
-            if (hasMore && !smallest)
-                stage(gn, nxt.hier, cbuf ^ 1, wnxt);
-            S.epz(pr, blkIdx);
-            if (lane == 0)
-                stvec(&vectors[blkIdx], S.best);
-            __syncwarp(); // orders the vector store before later loads by other lanes
-            prev = S.best;
+            S.wx0 = K.wo[cbuf][0];
+            S.wy0 = K.wo[cbuf][1];
+            S.wxc0 = K.wo[cbuf][2];
+            S.wyc0 = K.wo[cbuf][3];
+            // ... and the next block's window and source block are fetched while this block is searched
             if (hasMore) {
-                if (nby > 0 && (nby * nBlkX + nbx) - nBlkX == blkIdx)
-                    nxt.up = S.best; // meander turn: the next block's "up" neighbour is this block
-                cur = nxt;
-                commit_src(gn, nlo, nhi);
-                S.g = gn;
+                Geom gn;
+                block_geom(nbx, nby, gn);
+                issue_src(gn.x0, gn.y0, gn.xc, gn.yc, (t + 1) & 1);
+                if (!smallest) {
+                    const VEC hn = read_vec((t + 1) & 1);
+                    stage(gn, hn.x, hn.y, cbuf ^ 1);
+                }
+            }
+            S.epz(prx, pry, blkIdx);
+            if (lane == 0)
+                stvec(&K.vectors[blkIdx], S.best);
+            if (hasMore) {
+                // publish the fetched vector words; at a meander turn the next block's "up" neighbour is this block
+                if (nby > 0 && (nby * nBlkX + nbx) - nBlkX == blkIdx && (lane >> 2) == 1) {
+                    const int wi = lane & 3;
+                    pv = wi == 0 ? S.best.x : (wi == 1 ? S.best.y : (wi == 2 ? (int)(unsigned)(unsigned long long)S.best.sad : (int)(unsigned)((unsigned long long)S.best.sad >> 32)));
+                }
+                if (lane < 12)
+                    sts32(slot_of_lane(t & 1), (unsigned)pv);
+                commit_src(K.hp0 + K.stepX * nbx, K.hpc + (K.stepX >> LXR) * nbx, (t + 1) & 1); // (syncs: publishes the slots, orders the vector store)
                 bx = nbx;
                 by = nby;
                 dir = ndir;
-                if (!smallest) {
+                if (!smallest)
                     cbuf ^= 1;
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        wcur[k] = wnxt[k];
-                }
             }
         }
         __syncwarp();
