@@ -151,10 +151,11 @@ struct Cfg {
     static constexpr bool PACK = BPS == 1 && BW * BH <= 256 && 2 * CW * CH <= 256;
     static constexpr bool SRC_SMEM = BPS == 2 && BW * BH >= 256; // too many registers: read source rows from shared memory
     static constexpr int SRCB = r128(LBYTES + 2 * CBYTES);                   // one source-block buffer
-    static constexpr int SRCOFF = 2 * BUF, RAWOFF = SRCOFF + 2 * SRCB;        // [src 0][src 1][raw lo/hi words of an unaligned block]
-    static constexpr int VECOFF = RAWOFF + r128(8 * SRCW);                    // hier[2], up, p3: 4 x 16 bytes
-    static constexpr int COLDOFF = VECOFF + 128, BAROFF = COLDOFF + 384;      // level constants, 2 mbarriers
-    static constexpr int SMEM = BAROFF + 64 + 128;
+    static constexpr int SRCOFF = 2 * BUF;                                   // [src 0][src 1]
+    static constexpr int VECOFF = SRCOFF + 2 * SRCB;                          // hier[2], up, p3: 4 x 16 bytes
+    static constexpr int COLDOFF = VECOFF + 64, BAROFF = COLDOFF + 256;       // level constants, 2 mbarriers
+    static constexpr int RAWOFF = BAROFF + 64;                                // raw lo/hi words of an unaligned source block (optional)
+    static constexpr int SMEM = RAWOFF + 128, SMEM_RAW = SMEM + r128(8 * SRCW);
     static_assert(BH % 4 == 0 && (BW * BPS) % 4 == 0, "block shape");
     static_assert(!CHROMA || (CH % 4 == 0 && (CW * BPS) % 4 == 0), "chroma block shape");
 };
@@ -181,7 +182,7 @@ struct Cold {
     int gmx, gmy;  // globalMV (sticky clipping, :859)
     int wo[2][4];  // window origins of the two window buffers
 };
-static_assert(sizeof(Cold) <= 384, "Cold");
+static_assert(sizeof(Cold) <= 256, "Cold");
 
 template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
 struct Chain {
@@ -266,6 +267,7 @@ struct Chain {
         const unsigned outside = __ballot_sync(FULL, mine && !inside);
         unsigned aL = 0, aC = 0;
         if (outside == 0) {
+            unsigned accL[C::LR], accC[2][C::CR]; // one accumulator per row: independent VABSDIFF4 chains
             if (!mine) { // harmless in-window dummy
                 cbl = 0;
                 cbc = 0;
@@ -278,10 +280,14 @@ struct Chain {
                 lds_row(al + 4 * i * C::LWB, r);
                 if (C::SRC_SMEM)
                     lds_vec(srcbuf + (q + 4 * i) * (C::RW * 4), sw);
+                accL[i] = 0;
 #pragma unroll
                 for (int w = 0; w < C::RW; w++)
-                    aL += absd(__funnelshift_r(r[w], r[w + 1], shl), C::SRC_SMEM ? sw[w] : srcL[i][w]);
+                    accL[i] += absd(__funnelshift_r(r[w], r[w + 1], shl), C::SRC_SMEM ? sw[w] : srcL[i][w]);
             }
+#pragma unroll
+            for (int i = 0; i < C::LR; i++)
+                aL += accL[i];
             if (CHROMA) {
                 const uint32_t ac = sbuf + C::LREG + (cbc & ~3) + q * C::CWB;
                 const unsigned shc = (unsigned)cbc << 3;
@@ -293,11 +299,17 @@ struct Chain {
                         lds_row(ac + p * C::CREG + 4 * i * C::CWB, r);
                         if (C::SRC_SMEM)
                             lds_vec(srcbuf + C::LBYTES + p * C::CBYTES + (q + 4 * i) * (C::CRW * 4), sw);
+                        accC[p][i] = 0;
 #pragma unroll
                         for (int w = 0; w < C::CRW; w++)
-                            aC += absd(__funnelshift_r(r[w], r[w + 1], shc), C::SRC_SMEM ? sw[w] : srcC[p][i][w]);
+                            accC[p][i] += absd(__funnelshift_r(r[w], r[w + 1], shc), C::SRC_SMEM ? sw[w] : srcC[p][i][w]);
                     }
                 }
+#pragma unroll
+                for (int p = 0; p < 2; p++)
+#pragma unroll
+                    for (int i = 0; i < C::CR; i++)
+                        aC += accC[p][i];
             }
         } else {
             // at least one candidate leaves the staged window: the whole step reads global memory
@@ -1019,7 +1031,7 @@ EncodeTiledFn get_encode_fn() {
 
 template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
 int launch_cfg(Ctx *ctx, const SuperDesc &sd, const uint8_t *frames_base, int nframes, const SuperDesc *dev_sd, const SearchParams *dev_params, const SearchJob *dev_jobs,
-               int njobs, int *hist, int hist_ints, const mvb200_super_geom &geom, int pel) {
+               int njobs, int *hist, int hist_ints, const mvb200_super_geom &geom, int pel, bool need_raw) {
     using C = Cfg<BPS, BW, BH, LXR, LYR, CHROMA>;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc)
@@ -1054,11 +1066,11 @@ int launch_cfg(Ctx *ctx, const SuperDesc &sd, const uint8_t *frames_base, int nf
     auto kern = k_search_tma<BPS, BW, BH, LXR, LYR, CHROMA>;
     static bool configured = false;
     if (!configured) {
-        MVB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        MVB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_RAW));
         MVB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
-    kern<<<njobs, 32, C::SMEM, ctx->stream>>>(maps, dev_sd, dev_params, dev_jobs, njobs, hist, hist_ints);
+    kern<<<njobs, 32, need_raw ? C::SMEM_RAW : C::SMEM, ctx->stream>>>(maps, dev_sd, dev_params, dev_jobs, njobs, hist, hist_ints);
     ctx->launches++;
     MVB_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -1085,11 +1097,19 @@ int launch_search_tma(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &ge
     if ((sd.lv[0][0].padded_w << P0.logPel) >= 32768 || (sd.lv[0][0].padded_h << P0.logPel) >= 32768)
         return 0;
     const int bw = P0.blkW, bh = P0.blkH, bps = P0.bps, lx = sd.logxR, ly = sd.logyR;
+    // source blocks that are not 4-byte aligned in some level need the raw staging area (same test as K.srcAligned)
+    bool need_raw = false;
+    for (int i = 0; i < nparams; i++)
+        for (int l = 0; l < host_params[i].levels; l++) {
+            const int stepX = bw - host_params[i].ovX, c = P0.chroma ? 1 : 0;
+            if ((((sd.lv[0][l].hpad * bps) | (stepX * bps) | (sd.lv[c][l].hpad * bps) | ((stepX >> (c ? lx : 0)) * bps)) & 3) != 0)
+                need_raw = true;
+        }
     const bool chroma = P0.chroma;
 #define TRY(BPS_, BW_, BH_, LX_, LY_, CH_)                                                                                                                       \
     if (!*handled && bps == BPS_ && bw == BW_ && bh == BH_ && chroma == CH_ && (!CH_ || (lx == LX_ && ly == LY_))) {                                             \
         *handled = true;                                                                                                                                          \
-        return launch_cfg<BPS_, BW_, BH_, LX_, LY_, CH_>(ctx, sd, frames_base, nframes, dev_sd, dev_params, dev_jobs, njobs, hist, hist_ints, geom, P0.pel);     \
+        return launch_cfg<BPS_, BW_, BH_, LX_, LY_, CH_>(ctx, sd, frames_base, nframes, dev_sd, dev_params, dev_jobs, njobs, hist, hist_ints, geom, P0.pel, need_raw); \
     }
     TRY(1, 16, 16, 1, 1, true)
     TRY(2, 16, 16, 1, 1, true)
