@@ -353,6 +353,168 @@ __global__ void k_blend4(DegrainDev D, BlendPlane B, const uint8_t *__restrict__
     }
 }
 
+// ---- tiled variant of the quad kernel -----------------------------------------------------
+// A CTA owns a TW x TH tile of the plane.  Phase 1: the CTA's threads resolve, ONCE per (block, reference)
+// pair that can touch the tile, the weight and the address of the motion-compensated block (vector load,
+// sub-plane selection, padding) into shared memory.  Phase 2: every thread blends one quad, walking the
+// <= 4 covering blocks x 2r references with one LDS.128 + two loads + a funnel shift per reference; for
+// 8-bit clips two samples share a register (the weighted sum fits 16 bits, MVDegrains.h:31-53).
+constexpr int kTileW = 64, kTileH = 8, kTileMaxEntries = 1024, kTileMaxBlocks = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(kTileW / 4 * kTileH) k_blend_tile(DegrainDev D, BlendPlane B, const uint8_t *__restrict__ src_frames, long long src_frame_bytes,
+                                                                  const uint8_t *__restrict__ sup_frames, long long sup_frame_bytes, uint8_t *__restrict__ dst_frames,
+                                                                  long long dst_frame_bytes, const BlockW *__restrict__ weights) {
+    __shared__ int4 ent[kTileMaxEntries]; // {offset lo, offset hi, weight, -}
+    __shared__ int wsrc_s[kTileMaxBlocks];
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthreads = blockDim.x * blockDim.y;
+    const int tx0 = blockIdx.x * kTileW, ty0 = blockIdx.y * kTileH;
+    const int f = blockIdx.z;
+    const int sx = B.bw - B.ox, sy = B.bh - B.oy;
+    const int bxlo = max(0, tx0 / sx - 1), bxhi = min(D.nBlkX - 1, (tx0 + kTileW - 1) / sx);
+    const int bylo = max(0, ty0 / sy - 1), byhi = min(D.nBlkY - 1, (ty0 + kTileH - 1) / sy);
+    const int nbx = bxhi - bxlo + 1, nby = byhi - bylo + 1;
+    const int nblk = D.nBlkX * D.nBlkY;
+    if (B.process) {
+        const BlockW *wf = weights + (long long)f * nblk;
+        for (int e = tid; e < nbx * nby * D.R2; e += nthreads) {
+            const int b = e / D.R2, r = e - b * D.R2;
+            const int lby = b / nbx, lbx = b - lby * nbx;
+            const int bx = bxlo + lbx, by = bylo + lby, bi = by * D.nBlkX + bx;
+            const int wr = wf[bi].w[B.cls][r];
+            long long off = 0;
+            if (wr != 0) {
+                const VEC *v = blob_level0(D.vectors[r] + (long long)f * D.vectors_stride, nblk);
+                const int vx = v[bi].x, vy = v[bi].y;
+                // useBlock, MVDegrains.h:192-206 + mvpGetPointer, MVFrame.cpp:1733-1755
+                const int blx = ((bx * B.stepX0) << D.logPel) + vx;
+                const int bly = ((by * B.stepY0) << D.logPel) + vy;
+                const int ax = (B.plane ? blx >> B.xSub : blx) + B.hpad_pel;
+                const int ay = (B.plane ? bly >> B.ySub : bly) + B.vpad_pel;
+                const int m = D.pel - 1;
+                const int idx = (ax & m) | ((ay & m) << D.logPel);
+                const int n_ref = D.first + f + (D.backward[r] ? D.delta[r] : -D.delta[r]);
+                off = (long long)n_ref * sup_frame_bytes + B.sup_off + idx * B.sup_sub + (long long)(ay >> D.logPel) * B.sup_pitch + (long long)(ax >> D.logPel) * (int)sizeof(T);
+            }
+            ent[e] = make_int4((int)(unsigned)(unsigned long long)off, (int)(unsigned)((unsigned long long)off >> 32), wr, 0);
+            if (r == 0)
+                wsrc_s[b] = wf[bi].wsrc[B.cls];
+        }
+    }
+    __syncthreads();
+    const int x = tx0 + threadIdx.x * 4, y = ty0 + threadIdx.y;
+    if (x >= B.W || y >= B.H)
+        return;
+    const uint8_t *srow = src_frames + (long long)(D.first + f) * src_frame_bytes + B.src_off + (long long)y * B.src_pitch;
+    uint8_t *drow = dst_frames + (long long)f * dst_frame_bytes + B.dst_off + (long long)y * B.dst_pitch;
+    int srcv[4], out[4];
+    load4<T>(srow + (long long)x * (int)sizeof(T), srcv);
+    const int pixelMax = (1 << D.bits) - 1;
+    const int nvalid = min(4, B.W - x);
+    const bool covered = B.process && x + 3 < B.WB && y < B.HB;
+    if (covered) {
+        int bx0, bx1, by0, by1;
+        if (!B.win) {
+            bx0 = bx1 = x / B.bw;
+            by0 = by1 = y / B.bh;
+        } else {
+            bx1 = min(x / sx, D.nBlkX - 1);
+            by1 = min(y / sy, D.nBlkY - 1);
+            bx0 = (bx1 >= 1 && x - bx1 * sx < B.ox) ? bx1 - 1 : bx1;
+            by0 = (by1 >= 1 && y - by1 * sy < B.oy) ? by1 - 1 : by1;
+        }
+        unsigned acc[4] = {0, 0, 0, 0};
+        for (int by = by0; by <= by1; by++) {
+            const int iy = y - by * sy;
+            for (int bx = bx0; bx <= bx1; bx++) {
+                const int ix = x - bx * sx;
+                const int lb = (by - bylo) * nbx + (bx - bxlo);
+                const int ws = wsrc_s[lb];
+                const long long rowoff = (long long)iy * B.sup_pitch + ix * (int)sizeof(T);
+                int v[4];
+                if (sizeof(T) == 1) {
+                    // two samples per register: even samples in sumA, odd in sumB; each half stays below 2^16
+                    const unsigned sw = (unsigned)srcv[0] | ((unsigned)srcv[2] << 16), so = (unsigned)srcv[1] | ((unsigned)srcv[3] << 16);
+                    unsigned sumA = 0x00800080u + sw * (unsigned)ws, sumB = 0x00800080u + so * (unsigned)ws;
+                    for (int r = 0; r < D.R2; r++) {
+                        const int4 e = ent[lb * D.R2 + r];
+                        if (e.z == 0)
+                            continue; // unusable reference or zero weight: contributes nothing
+                        const uint8_t *p = sup_frames + (((long long)e.y << 32) | (unsigned)e.x) + rowoff;
+                        const unsigned long long a = (unsigned long long)p;
+                        const unsigned *q = (const unsigned *)(a & ~3ull);
+                        const unsigned w = __funnelshift_r(__ldg(q), __ldg(q + 1), ((unsigned)a & 3u) * 8u);
+                        sumA += (w & 0x00ff00ffu) * (unsigned)e.z;
+                        sumB += ((w >> 8) & 0x00ff00ffu) * (unsigned)e.z;
+                    }
+                    v[0] = (sumA >> 8) & 0xff;
+                    v[2] = sumA >> 24;
+                    v[1] = (sumB >> 8) & 0xff;
+                    v[3] = sumB >> 24;
+                } else {
+                    int sum[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        sum[i] = 128 + srcv[i] * ws;
+                    for (int r = 0; r < D.R2; r++) {
+                        const int4 e = ent[lb * D.R2 + r];
+                        if (e.z == 0)
+                            continue;
+                        int rv[4];
+                        load4<T>(sup_frames + (((long long)e.y << 32) | (unsigned)e.x) + rowoff, rv);
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            sum[i] += rv[i] * e.z;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        v[i] = (int)(T)(sum[i] >> 8);
+                }
+                if (!B.win) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        out[i] = v[i];
+                } else {
+                    const int wby = ((by + D.nBlkY - 3) / (D.nBlkY - 2)) * 3;       // MVDegrains.cpp:256
+                    const int wbx = bx == D.nBlkX - 1 ? 2 : (bx == 0 ? 0 : 1);       // :257-262
+                    const short4 wv = *(const short4 *)(B.win + (wby + wbx) * B.bw * B.bh + iy * B.bw + ix);
+                    const int ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        acc[i] += (unsigned)((v[i] * ww[i]) >> 6); // overlaps_c, Overlap.cpp:144-158
+                        if (sizeof(T) == 1)
+                            acc[i] &= 0xffffu; // the reference accumulates 8-bit video in uint16_t
+                    }
+                }
+            }
+        }
+        if (B.win) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                out[i] = min(pixelMax, (int)((acc[i] + 16) >> 5)); // ToPixels, Overlap.cpp:335-356
+        }
+        if (B.limit < pixelMax) { // LimitChanges_C, MVDegrains.h:168-181
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                out[i] = min(max(out[i], srcv[i] - B.limit), srcv[i] + B.limit);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            out[i] = srcv[i];
+    }
+    T *d = (T *)drow + x;
+    if (nvalid == 4) {
+        if (sizeof(T) == 1)
+            *(unsigned *)d = (unsigned)out[0] | ((unsigned)out[1] << 8) | ((unsigned)out[2] << 16) | ((unsigned)out[3] << 24);
+        else
+            *(uint2 *)d = make_uint2((unsigned)out[0] | ((unsigned)out[1] << 16), (unsigned)out[2] | ((unsigned)out[3] << 16));
+    } else {
+        for (int i = 0; i < nvalid; i++)
+            d[i] = (T)out[i];
+    }
+}
+
 // overInit, Overlap.cpp:40-125 -- evaluated on the HOST with the same float/double
 // expression (cosf of a double argument), never on the GPU.
 void overlap_windows(int nx, int ny, int ox, int oy, std::vector<short> &out) {
@@ -498,6 +660,18 @@ int launch_degrain(Ctx *ctx, const mvb200_degrain_params *dp, const SuperDesc &s
             B.HB = B.H;
         // 4 samples per thread when every block boundary is a multiple of 4 samples (and rows start 4-aligned)
         const bool quad = B.process && (B.bw % 4 == 0) && (B.ox % 4 == 0) && (B.WB % 4 == 0) && (!overlap || ((B.bw - B.ox) % 4 == 0));
+        const int tsx = B.bw - B.ox, tsy = B.bh - B.oy;
+        const int tile_blocks = (kTileW / tsx + 2) * (kTileH / tsy + 2);
+        if (quad && tile_blocks <= kTileMaxBlocks && tile_blocks * D.R2 <= kTileMaxEntries) {
+            dim3 blkt(kTileW / 4, kTileH);
+            dim3 gridt((B.W + kTileW - 1) / kTileW, (B.H + kTileH - 1) / kTileH, n);
+            if (sd.bps == 1)
+                k_blend_tile<uint8_t><<<gridt, blkt, 0, st>>>(D, B, dev_src, cd.frame_bytes, dev_super, sd.frame_bytes, dev_dst, cd.frame_bytes, weights);
+            else
+                k_blend_tile<uint16_t><<<gridt, blkt, 0, st>>>(D, B, dev_src, cd.frame_bytes, dev_super, sd.frame_bytes, dev_dst, cd.frame_bytes, weights);
+            ctx->launches++;
+            continue;
+        }
         if (quad) {
             dim3 blk4(32, 8);
             dim3 grid4(((B.W + 3) / 4 + blk4.x - 1) / blk4.x, (B.H + blk4.y - 1) / blk4.y, n);

@@ -42,6 +42,18 @@ __global__ void k_fill(const uint8_t *__restrict__ src, long long src_pitch, lon
     d[x] = s[x];
 }
 
+// one 32-bit word (4 / 2 samples) per thread; rows of both clips start 4-byte aligned
+__global__ void k_fill_w(const uint8_t *__restrict__ src, long long src_pitch, long long src_frame, uint8_t *__restrict__ dst, long long dst_pitch, long long dst_frame,
+                         int wwords, int h) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= wwords || y >= h)
+        return;
+    const unsigned *s = (const unsigned *)(src + (long long)blockIdx.z * src_frame + (long long)y * src_pitch);
+    unsigned *d = (unsigned *)(dst + (long long)blockIdx.z * dst_frame + (long long)y * dst_pitch);
+    d[x] = __ldg(s + x);
+}
+
 // ---- reduce -------------------------------------------------------------
 // vertical tap of the separable reduce filters at intermediate column x, output row y
 template <typename T>
@@ -130,6 +142,39 @@ __global__ void k_pad(uint8_t *__restrict__ base, long long pitch_bytes, long lo
     p[(long long)y * sp + x] = p[(long long)sy * sp + sx];
 }
 
+// Border-only, one 32-bit word per thread.  grid.y covers the 2*vpad full-width border rows first, then the
+// h interior rows whose 2*hpad side columns are written.  Requires hpad and w to be whole words.
+template <typename T>
+__global__ void k_pad_w(uint8_t *__restrict__ base, long long pitch_bytes, long long frame_bytes, int hpad, int vpad, int w, int h) {
+    constexpr int SPW = 4 / (int)sizeof(T);
+    const int pww = (w + 2 * hpad) / SPW, hpw = hpad / SPW;
+    int xw = blockIdx.x * blockDim.x + threadIdx.x;
+    int r = blockIdx.y * blockDim.y + threadIdx.y;
+    int y;
+    if (r < 2 * vpad) {
+        y = r < vpad ? r : h + r; // rows [0, vpad) and [vpad + h, 2 vpad + h)
+        if (xw >= pww)
+            return;
+    } else {
+        y = r - 2 * vpad + vpad;
+        if (y >= vpad + h || xw >= 2 * hpw)
+            return;
+        xw = xw < hpw ? xw : xw - hpw + (hpad + w) / SPW; // left words, then right words
+    }
+    uint8_t *fb = base + (long long)blockIdx.z * frame_bytes;
+    const int sy = min(max(y - vpad, 0), h - 1) + vpad;
+    const T *srow = (const T *)(fb + (long long)sy * pitch_bytes);
+    const int x = xw * SPW;
+    unsigned v;
+    if (x >= hpad && x + SPW <= hpad + w) {
+        v = *(const unsigned *)(srow + x);
+    } else { // all samples of the word replicate the nearest edge sample
+        const unsigned e = (unsigned)srow[x < hpad ? hpad : hpad + w - 1];
+        v = sizeof(T) == 1 ? e * 0x01010101u : e * 0x00010001u;
+    }
+    *(unsigned *)(fb + (long long)y * pitch_bytes + (long long)x * (int)sizeof(T)) = v;
+}
+
 // ---- refine -------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ int wiener6(int m0, int m1, int m2, int m3, int m4, int m5, int pixelMax) {
@@ -174,6 +219,77 @@ __global__ void k_refine_hv(uint8_t *__restrict__ dst_base, const uint8_t *__res
     else
         v = wiener6<T>(ld(s, -st * 2), ld(s, -st), ld(s, 0), ld(s, st), ld(s, st * 2), ld(s, st * 3), pixelMax);
     *d = (T)v;
+}
+
+// One 32-bit word of output (4 / 2 samples) per thread; same arithmetic as k_refine_hv.
+template <typename T>
+__global__ void k_refine_hv_w(uint8_t *__restrict__ dst_base, const uint8_t *__restrict__ src_base, long long pitch_bytes, long long frame_bytes, int w, int h, int bits,
+                              int sharp, int dir) {
+    constexpr int SPW = 4 / (int)sizeof(T), MASK = sizeof(T) == 1 ? 0xff : 0xffff, SH = 8 * (int)sizeof(T);
+    const int xw = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = xw * SPW;
+    if (x >= w || y >= h)
+        return;
+    const uint8_t *srow = src_base + (long long)blockIdx.z * frame_bytes + (long long)y * pitch_bytes;
+    unsigned *d = (unsigned *)(dst_base + (long long)blockIdx.z * frame_bytes + (long long)y * pitch_bytes) + xw;
+    const int pixelMax = (1 << bits) - 1;
+    int t[6][SPW]; // the six taps (positions -2..+3) of each output sample
+    if (dir == 0) {
+        // samples x-SPW*? .. : words xw-2/SPW.. ; gather samples x-2 .. x+SPW+2 from whole words
+        constexpr int NW = sizeof(T) == 1 ? 3 : 4; // words covering [x - 2 (rounded down to a word), x + SPW + 3)
+        const int w0 = sizeof(T) == 1 ? xw - 1 : xw - 1;
+        int smp[NW * SPW];
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            const int wi = w0 + k;
+            const bool inb = wi >= 0 && wi * SPW < w; // samples outside the row are never used by a filtered output
+            const unsigned v = inb ? __ldg((const unsigned *)srow + wi) : 0u;
+#pragma unroll
+            for (int b = 0; b < SPW; b++)
+                smp[k * SPW + b] = (int)((v >> (SH * b)) & MASK);
+        }
+#pragma unroll
+        for (int j = 0; j < SPW; j++)
+#pragma unroll
+            for (int k = 0; k < 6; k++)
+                t[k][j] = smp[SPW + j + k - 2];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int yy = y + k - 2;
+            const bool inb = yy >= 0 && yy < h;
+            const unsigned v = inb ? __ldg((const unsigned *)(srow + (long long)(k - 2) * pitch_bytes) + xw) : 0u;
+#pragma unroll
+            for (int b = 0; b < SPW; b++)
+                t[k][b] = (int)((v >> (SH * b)) & MASK);
+        }
+    }
+    unsigned out = 0;
+#pragma unroll
+    for (int j = 0; j < SPW; j++) {
+        const int i = dir ? y : x + j, n = dir ? h : w;
+        int mode; // 0 copy, 1 average, 2 filter
+        if (i >= n - 1)
+            mode = 0;
+        else if (sharp == 0)
+            mode = 1;
+        else if (sharp == 1)
+            mode = (i >= 1 && i < n - 3) ? 2 : 1;
+        else
+            mode = (i >= 2 && i < n - 4) ? 2 : 1;
+        int v;
+        if (mode == 0)
+            v = t[2][j];
+        else if (mode == 1)
+            v = (t[2][j] + t[3][j] + 1) >> 1;
+        else if (sharp == 1)
+            v = min(pixelMax, max(0, (-t[1][j] - t[4][j] + (t[2][j] + t[3][j]) * 9 + 8) >> 4));
+        else
+            v = wiener6<T>(t[0][j], t[1][j], t[2][j], t[3][j], t[4][j], t[5][j], pixelMax);
+        out |= (unsigned)v << (SH * j);
+    }
+    *d = out;
 }
 
 template <typename T>
@@ -234,8 +350,13 @@ int super_typed(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, con
         auto level_base = [&](int l) { return pl + (long long)sd.lv[plane][l].row0 * pitch; };
         auto interior = [&](int l) { return level_base(l) + (long long)sd.lv[plane][l].vpad * pitch + (long long)sd.lv[plane][l].hpad * bps; };
         const mvb200_level_geom &g0 = sd.lv[plane][0];
-        k_fill<T><<<grid2d(g0.width, g0.height, n, blk), blk, 0, st>>>(dev_src + cd.offset[plane], cd.pitch[plane], cd.frame_bytes, interior(0), pitch,
-                                                                      sd.frame_bytes, g0.width, g0.height);
+        const bool words0 = (g0.width * bps) % 4 == 0 && (g0.hpad * bps) % 4 == 0; // level 0: whole 32-bit words per row segment
+        if (words0)
+            k_fill_w<<<grid2d(g0.width * bps / 4, g0.height, n, blk), blk, 0, st>>>(dev_src + cd.offset[plane], cd.pitch[plane], cd.frame_bytes, interior(0), pitch, sd.frame_bytes,
+                                                                                  g0.width * bps / 4, g0.height);
+        else
+            k_fill<T><<<grid2d(g0.width, g0.height, n, blk), blk, 0, st>>>(dev_src + cd.offset[plane], cd.pitch[plane], cd.frame_bytes, interior(0), pitch,
+                                                                          sd.frame_bytes, g0.width, g0.height);
         ctx->launches++;
         for (int l = 0; l < sd.levels - 1; l++) {
             const mvb200_level_geom &g1 = sd.lv[plane][l + 1];
@@ -244,7 +365,10 @@ int super_typed(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, con
             k_pad<T><<<grid2d(g1.padded_w, g1.padded_h, n, blk), blk, 0, st>>>(level_base(l + 1), pitch, sd.frame_bytes, g1.hpad, g1.vpad, g1.width, g1.height);
             ctx->launches += 2;
         }
-        k_pad<T><<<grid2d(g0.padded_w, g0.padded_h, n, blk), blk, 0, st>>>(level_base(0), pitch, sd.frame_bytes, g0.hpad, g0.vpad, g0.width, g0.height);
+        if (words0)
+            k_pad_w<T><<<grid2d(g0.padded_w * bps / 4, 2 * g0.vpad + g0.height, n, blk), blk, 0, st>>>(level_base(0), pitch, sd.frame_bytes, g0.hpad, g0.vpad, g0.width, g0.height);
+        else
+            k_pad<T><<<grid2d(g0.padded_w, g0.padded_h, n, blk), blk, 0, st>>>(level_base(0), pitch, sd.frame_bytes, g0.hpad, g0.vpad, g0.width, g0.height);
         ctx->launches++;
         if (p->pel > 1) { // mvpRefine, MVFrame.cpp:1386-1527
             const long long sub = pitch * g0.padded_h;
@@ -252,12 +376,20 @@ int super_typed(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, con
             const int w = g0.padded_w, h = g0.padded_h;
             const int iH = p->pel == 2 ? 1 : 2, iV = p->pel == 2 ? 2 : 8, iD = p->pel == 2 ? 3 : 10;
             dim3 g = grid2d(w, h, n, blk);
-            k_refine_hv<T><<<g, blk, 0, st>>>(P(iH), P(0), pitch, sd.frame_bytes, w, h, sd.bits, p->sharp, 0);
-            k_refine_hv<T><<<g, blk, 0, st>>>(P(iV), P(0), pitch, sd.frame_bytes, w, h, sd.bits, p->sharp, 1);
+            const bool words = (w * bps) % 4 == 0;
+            dim3 gw = grid2d(w * bps / 4, h, n, blk);
+            auto refine_hv = [&](int di, int si, int dir) {
+                if (words)
+                    k_refine_hv_w<T><<<gw, blk, 0, st>>>(P(di), P(si), pitch, sd.frame_bytes, w, h, sd.bits, p->sharp, dir);
+                else
+                    k_refine_hv<T><<<g, blk, 0, st>>>(P(di), P(si), pitch, sd.frame_bytes, w, h, sd.bits, p->sharp, dir);
+            };
+            refine_hv(iH, 0, 0);
+            refine_hv(iV, 0, 1);
             if (p->sharp == 0)
                 k_refine_diag<T><<<g, blk, 0, st>>>(P(iD), P(0), pitch, sd.frame_bytes, w, h);
             else
-                k_refine_hv<T><<<g, blk, 0, st>>>(P(iD), P(iV), pitch, sd.frame_bytes, w, h, sd.bits, p->sharp, 0);
+                refine_hv(iD, iV, 0);
             ctx->launches += 3;
             if (p->pel == 4) {
                 auto avg = [&](int d, const uint8_t *a, const uint8_t *b, int ww, int hh) {
