@@ -174,8 +174,9 @@ def run_gpu_arm(args):
             rows[:, : a.shape[1] * a.itemsize] = a.view(np.uint8).reshape(a.shape[0], -1)
     host_out = torch.zeros((F, cl.frame_bytes), dtype=torch.uint8).pin_memory()
     vs = (aps[0].vectors_size + 255) // 256 * 256
+    dsrc = host.to("cuda")  # (torch's own stream: the pinned block must not be tied to the engine's stream, which dies with ctx)
+    torch.cuda.synchronize()
     with torch.cuda.stream(stream):
-        dsrc = host.to("cuda", non_blocking=True)
         dsup = torch.empty((F, sl.frame_bytes), dtype=torch.uint8, device="cuda")
         dvec = [torch.empty((F, vs), dtype=torch.uint8, device="cuda") for _ in aps]
         ddst = torch.empty((F, cl.frame_bytes), dtype=torch.uint8, device="cuda")
@@ -235,20 +236,31 @@ def run_gpu_arm(args):
     value = world * F_out * args.steps / (region_ms / 1e3)
 
     # ---- end-to-end timing: pinned host source -> H2D -> pipeline -> D2H denoised frames
-    def e2e_step():
-        with torch.cuda.stream(stream):
-            dsrc.copy_(host, non_blocking=True)
-            pipeline()
-            host_out.copy_(ddst, non_blocking=True)
+    # One C-ABI call per step with HOST buffers (mvb200_degrain_clip_host_async): H2D of the step's source
+    # frames, Super + 6x Analyse + Degrain3, D2H of the denoised frames.  The call is asynchronous and the
+    # engine double-buffers the clips, so the copies of neighbouring steps overlap the kernels; everything
+    # (all copies included) completes inside the timed region.
+    host_outs = [host_out, torch.zeros((F, cl.frame_bytes), dtype=torch.uint8).pin_memory()]
+    e2e_calls = [0]
 
-    e2e_step()
+    def e2e_step():
+        o = host_outs[e2e_calls[0] & 1]
+        e2e_calls[0] += 1
+        mb._check(L.mvb200_degrain_clip_host_async(ctx.handle, C.byref(sp), apa, len(aps), C.byref(dp), host.data_ptr(), o.data_ptr(), F))
+
+    for _ in range(max(2, args.warmup)):
+        e2e_step()
     barrier()
+    e2e_launches0 = ctx.launch_count()
+    t0 = time.perf_counter()
     e0, e1 = ev(), ev()
     e0.record(stream)
     for _ in range(args.steps):
         e2e_step()
+    ctx.synchronize()  # compute stream and both copy streams of the engine
     e1.record(stream)
     barrier()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * F_out * args.steps / (e2e_ms / 1e3)
@@ -314,9 +326,11 @@ def run_gpu_arm(args):
                                               "its own sources (x264 NASM kernels replaced by the reference's C fallbacks)" % sample}
         else:
             line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": cores, "kind": "reference", "sample": "unavailable: " + err}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    ctx.synchronize()
+    torch.cuda.synchronize()
 
 
 def main():

@@ -116,6 +116,33 @@ def test_batch_path_matches_goldens(gpu_ctx, case):
         assert [pipeline.sha(p) for p in _planes(dst[n], cl)] == GOLD[case]["degrain"][n]
 
 
+@pytest.mark.parametrize("case", ["blk16_ov8_pel2_p8_r3", "p8_422_blk8x4_sharp0_rf1"])
+def test_host_clip_pipeline_matches_goldens(gpu_ctx, case):
+    """mvb200_degrain_clip_host_async: host buffers in, host buffers out, three overlapping calls (both
+    device slots reused) -- every call's output equals the goldens"""
+    import torch
+    L = mb.lib()
+    frames = pipeline.make_frames(pipeline.CASES[case][0])
+    sp, aps, dp = pipeline.params_for(case)
+    N = len(frames)
+    cl = mb.clip_layout(sp)
+    host = torch.zeros((N, cl.frame_bytes), dtype=torch.uint8).pin_memory()
+    hv = host.numpy()
+    for n, fr in enumerate(frames):
+        for p, a in enumerate(fr):
+            rows = hv[n, cl.offset[p]: cl.offset[p] + cl.pitch[p] * cl.plane_h[p]].reshape(cl.plane_h[p], cl.pitch[p])
+            rows[:, : a.shape[1] * a.itemsize] = a.view(np.uint8).reshape(a.shape[0], -1)
+    outs = [torch.zeros((N, cl.frame_bytes), dtype=torch.uint8).pin_memory() for _ in range(3)]
+    apa = (C.POINTER(mb.AnalyseParams) * len(aps))(*[C.pointer(a) for a in aps])
+    for o in outs:
+        mb._check(L.mvb200_degrain_clip_host_async(gpu_ctx.handle, C.byref(sp), apa, len(aps), C.byref(dp), host.data_ptr(), o.data_ptr(), N))
+    gpu_ctx.synchronize()
+    for o in outs:
+        dst = o.numpy()
+        for n in range(N):
+            assert [pipeline.sha(p) for p in _planes(dst[n], cl)] == GOLD[case]["degrain"][n]
+
+
 def test_full_size_1080p_properties(gpu_ctx):
     """BASELINE.json configs[1]-sized run (1920x1080 P8, blk 8 ov 4 pel 2, Degrain1) checked by
     properties that do not need the slow CPU path at full size, plus one oracle frame."""

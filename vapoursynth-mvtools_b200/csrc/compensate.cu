@@ -157,7 +157,7 @@ int launch_compensate(Ctx *ctx, const mvb200_compensate_params *cp, const SuperD
             overlap_windows_host(cp->nBlkSizeX[1], cp->nBlkSizeY[1], cp->nOverlapX[1], cp->nOverlapY[1], wc);
         size_t bl = wl.size() * sizeof(short), bc = wc.size() * sizeof(short), offc = (bl + 255) & ~(size_t)255;
         uint8_t *host = (uint8_t *)ctx->get_pinned(offc + bc + 256);
-        uint8_t *dev = (uint8_t *)ctx->get_scratch(4, offc + bc + 256);
+        uint8_t *dev = (uint8_t *)ctx->get_scratch(6, offc + bc + 256);
         if (!host || !dev)
             return 1;
         MVB_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -605,23 +605,30 @@ int launch_degrain(Ctx *ctx, const mvb200_degrain_params *dp, const SuperDesc &s
     // overlap windows: luma and chroma tables, built on the host (libm cosf), uploaded once per call
     short *dev_win[2] = {nullptr, nullptr};
     if (overlap) {
-        std::vector<short> wl, wc;
-        overlap_windows(dp->nBlkSizeX[0], dp->nBlkSizeY[0], dp->nOverlapX[0], dp->nOverlapY[0], wl);
-        if (dp->nplanes > 1)
-            overlap_windows(dp->nBlkSizeX[1], dp->nBlkSizeY[1], dp->nOverlapX[1], dp->nOverlapY[1], wc);
-        size_t bl = wl.size() * sizeof(short), bc = wc.size() * sizeof(short);
-        size_t offc = (bl + 255) & ~(size_t)255;
-        uint8_t *host = (uint8_t *)ctx->get_pinned(offc + bc + 256);
-        uint8_t *dev = (uint8_t *)ctx->get_scratch(4, offc + bc + 256);
-        if (!host || !dev)
-            return 1;
-        MVB_CUDA_CHECK(cudaStreamSynchronize(st));
-        memcpy(host, wl.data(), bl);
-        if (bc)
-            memcpy(host + offc, wc.data(), bc);
-        MVB_CUDA_CHECK(cudaMemcpyAsync(dev, host, offc + bc, cudaMemcpyHostToDevice, st));
-        dev_win[0] = (short *)dev;
-        dev_win[1] = (short *)(dev + offc);
+        const int key[8] = {dp->nBlkSizeX[0], dp->nBlkSizeY[0], dp->nOverlapX[0], dp->nOverlapY[0], dp->nplanes > 1 ? dp->nBlkSizeX[1] : 0, dp->nplanes > 1 ? dp->nBlkSizeY[1] : 0,
+                            dp->nplanes > 1 ? dp->nOverlapX[1] : 0, dp->nplanes > 1 ? dp->nOverlapY[1] : 0};
+        if (!ctx->win_valid || memcmp(key, ctx->win_key, sizeof(key)) != 0) {
+            std::vector<short> wl, wc;
+            overlap_windows(dp->nBlkSizeX[0], dp->nBlkSizeY[0], dp->nOverlapX[0], dp->nOverlapY[0], wl);
+            if (dp->nplanes > 1)
+                overlap_windows(dp->nBlkSizeX[1], dp->nBlkSizeY[1], dp->nOverlapX[1], dp->nOverlapY[1], wc);
+            size_t bl = wl.size() * sizeof(short), bc = wc.size() * sizeof(short);
+            size_t offc = (bl + 255) & ~(size_t)255;
+            // first use of this configuration (or a change): drain, rebuild the tables, upload synchronously
+            MVB_CUDA_CHECK(cudaStreamSynchronize(st));
+            uint8_t *dev = (uint8_t *)ctx->get_scratch(4, offc + bc + 256);
+            if (!dev)
+                return 1;
+            MVB_CUDA_CHECK(cudaMemcpy(dev, wl.data(), bl, cudaMemcpyHostToDevice));
+            if (bc)
+                MVB_CUDA_CHECK(cudaMemcpy(dev + offc, wc.data(), bc, cudaMemcpyHostToDevice));
+            ctx->win_dev[0] = (short *)dev;
+            ctx->win_dev[1] = (short *)(dev + offc);
+            memcpy(ctx->win_key, key, sizeof(key));
+            ctx->win_valid = true;
+        }
+        dev_win[0] = ctx->win_dev[0];
+        dev_win[1] = ctx->win_dev[1];
     }
     for (int plane = 0; plane < dp->nplanes; plane++) {
         BlendPlane B;

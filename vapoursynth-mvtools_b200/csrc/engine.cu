@@ -4,6 +4,8 @@
 // needs a CUDA device of compute capability 10.x and fails loudly otherwise.
 #include "engine.h"
 
+#include <algorithm>
+
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -94,6 +96,19 @@ void *Ctx::get_pinned(size_t bytes) {
     }
     pinned_bytes = want;
     return pinned;
+}
+
+int Ctx::staging_wait() {
+    if (staging_ev)
+        MVB_CUDA_CHECK(cudaEventSynchronize(staging_ev));
+    return 0;
+}
+
+int Ctx::staging_posted() {
+    if (!staging_ev)
+        MVB_CUDA_CHECK(cudaEventCreateWithFlags(&staging_ev, cudaEventDisableTiming));
+    MVB_CUDA_CHECK(cudaEventRecord(staging_ev, stream));
+    return 0;
 }
 
 static int check_levels(const mvb200_super_params *sp) {
@@ -216,6 +231,24 @@ void mvb200_ctx_destroy(mvb200_ctx *ctx) {
             cudaFree(p);
     if (ctx->c.pinned)
         cudaFreeHost(ctx->c.pinned);
+    if (ctx->c.copy_in) {
+        cudaStreamSynchronize(ctx->c.copy_in);
+        cudaStreamDestroy(ctx->c.copy_in);
+    }
+    if (ctx->c.copy_out) {
+        cudaStreamSynchronize(ctx->c.copy_out);
+        cudaStreamDestroy(ctx->c.copy_out);
+    }
+    for (int i = 0; i < 2; i++) {
+        if (ctx->c.ev_h2d[i])
+            cudaEventDestroy(ctx->c.ev_h2d[i]);
+        if (ctx->c.ev_compute[i])
+            cudaEventDestroy(ctx->c.ev_compute[i]);
+        if (ctx->c.ev_d2h[i])
+            cudaEventDestroy(ctx->c.ev_d2h[i]);
+    }
+    if (ctx->c.staging_ev)
+        cudaEventDestroy(ctx->c.staging_ev);
     cudaStreamDestroy(ctx->c.stream);
     delete ctx;
 }
@@ -223,6 +256,10 @@ void mvb200_ctx_destroy(mvb200_ctx *ctx) {
 int mvb200_ctx_synchronize(mvb200_ctx *ctx) {
     MVB_CUDA_CHECK(cudaSetDevice(ctx->c.device));
     MVB_CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    if (ctx->c.copy_in)
+        MVB_CUDA_CHECK(cudaStreamSynchronize(ctx->c.copy_in));
+    if (ctx->c.copy_out)
+        MVB_CUDA_CHECK(cudaStreamSynchronize(ctx->c.copy_out));
     return 0;
 }
 
@@ -324,6 +361,77 @@ int mvb200_degrain_batch(mvb200_ctx *ctx, const mvb200_degrain_params *dp, const
     make_super_desc(sp, &sd);
     make_clip_desc(sp, &cd);
     return launch_degrain(&ctx->c, dp, sd, cd, (const uint8_t *)dev_src, (const uint8_t *)dev_super, num_frames, first, n, (const uint8_t *const *)dev_vectors, vectors_stride, (uint8_t *)dev_dst);
+}
+
+// ------------------------------------------------ host-buffer clip pipeline
+// Super + nap x Analyse + DegrainN over a whole segment of n frames in HOST memory (clip layout, frames
+// frame_bytes apart; pinned memory for truly asynchronous copies).  Asynchronous: the call returns when the
+// work is enqueued; host_dst is valid after mvb200_ctx_synchronize().  Consecutive calls overlap: the H2D copy
+// of segment k+1 and the D2H copy of segment k-1 run on their own streams beside the kernels of segment k
+// (source / output clips are double buffered on the device).
+int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const mvb200_degrain_params *dp,
+                                   const void *host_src, void *host_dst, int n) {
+    if (check_levels(sp))
+        return 1;
+    if (n <= 0)
+        return 0;
+    if (nap != dp->radius * 2)
+        return set_error("mvtools_b200: Degrain%d needs %d vector clips, %d given", dp->radius, dp->radius * 2, nap);
+    Ctx &c = ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c.device));
+    if (!c.copy_in) {
+        MVB_CUDA_CHECK(cudaStreamCreateWithFlags(&c.copy_in, cudaStreamNonBlocking));
+        MVB_CUDA_CHECK(cudaStreamCreateWithFlags(&c.copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            MVB_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_h2d[i], cudaEventDisableTiming));
+            MVB_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_compute[i], cudaEventDisableTiming));
+            MVB_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_d2h[i], cudaEventDisableTiming));
+        }
+    }
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(sp, &sd);
+    make_clip_desc(sp, &cd);
+    int64_t vstride = 0;
+    for (int i = 0; i < nap; i++)
+        vstride = std::max<int64_t>(vstride, ((int64_t)ap[i]->vectors_size + 255) / 256 * 256);
+    const int slot = (int)(c.clip_calls & 1);
+    const bool reuse = c.clip_calls >= 2; // this slot's buffers were used by the call before the previous one
+    c.clip_calls++;
+    const size_t clip_bytes = (size_t)cd.frame_bytes * n;
+    void *before[4] = {c.scratch[8 + slot], c.scratch[10 + slot], c.scratch[12], c.scratch[13]};
+    uint8_t *dsrc = (uint8_t *)c.get_scratch(8 + slot, clip_bytes);
+    uint8_t *ddst = (uint8_t *)c.get_scratch(10 + slot, clip_bytes);
+    uint8_t *dsup = (uint8_t *)c.get_scratch(12, (size_t)sd.frame_bytes * n);
+    uint8_t *dvec = (uint8_t *)c.get_scratch(13, (size_t)vstride * n * nap);
+    if (!dsrc || !ddst || !dsup || !dvec)
+        return 1;
+    if (before[0] != dsrc || before[1] != ddst || before[2] != dsup || before[3] != dvec)
+        MVB_CUDA_CHECK(cudaStreamSynchronize(c.stream)); // fresh buffers are cleared on the compute stream: finish that before the copy stream writes
+    // H2D: once the kernels that last read this slot's source clip are done
+    if (reuse)
+        MVB_CUDA_CHECK(cudaStreamWaitEvent(c.copy_in, c.ev_compute[slot], 0));
+    MVB_CUDA_CHECK(cudaMemcpyAsync(dsrc, host_src, clip_bytes, cudaMemcpyHostToDevice, c.copy_in));
+    MVB_CUDA_CHECK(cudaEventRecord(c.ev_h2d[slot], c.copy_in));
+    // compute: after this segment's H2D and after the D2H that last read this slot's output clip
+    MVB_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_h2d[slot], 0));
+    if (reuse)
+        MVB_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_d2h[slot], 0));
+    std::vector<void *> outs((size_t)nap);
+    for (int i = 0; i < nap; i++)
+        outs[i] = dvec + (size_t)vstride * n * i;
+    if (mvb200_super_batch(ctx, sp, dsrc, dsup, n))
+        return 1;
+    if (mvb200_analyse_multi_batch(ctx, ap, nap, sp, dsup, 0, n, outs.data(), vstride))
+        return 1;
+    if (mvb200_degrain_batch(ctx, dp, sp, dsrc, dsup, n, 0, n, (const void *const *)outs.data(), vstride, ddst))
+        return 1;
+    MVB_CUDA_CHECK(cudaEventRecord(c.ev_compute[slot], c.stream));
+    // D2H
+    MVB_CUDA_CHECK(cudaStreamWaitEvent(c.copy_out, c.ev_compute[slot], 0));
+    MVB_CUDA_CHECK(cudaMemcpyAsync(host_dst, ddst, clip_bytes, cudaMemcpyDeviceToHost, c.copy_out));
+    MVB_CUDA_CHECK(cudaEventRecord(c.ev_d2h[slot], c.copy_out));
+    return 0;
 }
 
 // ------------------------------------------------------- host-buffer path

@@ -99,15 +99,28 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     long long launches = 0;
     // growable device scratch buffers
-    void *scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    void *scratch[16] = {};
+    size_t scratch_bytes[16] = {};
     // pinned host staging
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
     int sm_count = 0;
+    // the pinned staging buffer is reused from call to call: an event marks the last upload out of it,
+    // so that the next writer waits for that copy only (not for the kernels queued behind it)
+    cudaEvent_t staging_ev = nullptr;
+    // overlap windows of the last Degrain configuration, resident on the device
+    int win_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    short *win_dev[2] = {nullptr, nullptr};
+    bool win_valid = false;
+    // host-buffer clip pipeline (mvb200_degrain_clip_host_async): copy streams + double-buffered clips
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    long long clip_calls = 0;
 
     void *get_scratch(int slot, size_t bytes); // nullptr + error on failure
     void *get_pinned(size_t bytes);
+    int staging_wait();   // before the host writes the pinned staging buffer
+    int staging_posted(); // after the upload out of it was enqueued on `stream`
 };
 
 #define MVB_CUDA_CHECK(call)                                                                          \

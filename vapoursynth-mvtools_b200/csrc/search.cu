@@ -920,12 +920,15 @@ int launch_search(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &geom, 
     int *hist = (int *)ctx->get_scratch(1, sizeof(int) * (size_t)hist_ints * (size_t)njobs);
     if (!host || !dev || !hist)
         return 1;
-    // the pinned staging buffer is reused by the next call: wait for earlier uploads to be consumed
-    MVB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    // the pinned staging buffer is reused from call to call: wait until the previous upload out of it is done
+    if (ctx->staging_wait())
+        return 1;
     memcpy(host, &sd, bytes_sd);
     memcpy(host + off_p, host_params, bytes_p);
     memcpy(host + off_j, host_jobs, bytes_j);
     MVB_CUDA_CHECK(cudaMemcpyAsync(dev, host, total, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->staging_posted())
+        return 1;
     // specialised kernel when every parameter set qualifies (all mv.Analyse defaults do); the
     // generic kernel otherwise, or when MVB200_FORCE_GENERIC=1 (used by the tests to cover both)
     bool handled = false;
@@ -956,11 +959,14 @@ int launch_recalc(Ctx *ctx, const SuperDesc &sd, const RecalcParams &P, const Re
     uint8_t *dev = (uint8_t *)ctx->get_scratch(0, total);
     if (!host || !dev)
         return 1;
-    MVB_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->staging_wait())
+        return 1;
     memcpy(host, &sd, bytes_sd);
     memcpy(host + off_p, &P, bytes_p);
     memcpy(host + off_j, host_jobs, bytes_j);
     MVB_CUDA_CHECK(cudaMemcpyAsync(dev, host, total, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->staging_posted())
+        return 1;
     const int n = P.nBlkX * P.nBlkY;
     k_recalc<<<dim3(n, njobs), 32, 0, ctx->stream>>>((const SuperDesc *)dev, (const RecalcParams *)(dev + off_p), (const RecalcJob *)(dev + off_j));
     ctx->launches++;
