@@ -39,6 +39,9 @@ WORKLOAD = ("mv.Super(pel=2) + 6x mv.Analyse(blksize=16, overlap=8, delta=1..3, 
             "1920x1080 YUV420P8 (metric's Analyse+Degrain3 1080p P8 with configs[2]'s block geometry)")
 
 
+NCU_PROFILE = "r1_ncu_search_v5_1776chains.json"  # ncu --set full capture of the search kernel the traffic / pipe numbers come from
+
+
 def make_frames(n):
     import clipgen
     base = clipgen.make_clip(WIDTH, HEIGHT, DISTINCT, bits=BITS, seed=0)
@@ -291,12 +294,16 @@ def run_gpu_arm(args):
     # DRAM traffic of the same kernel from the committed ncu --set full capture (per chain, scaled to this launch)
     traffic = None
     try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_search_tma_saturated.json")))
+        prof = json.load(open(os.path.join(ROOT, "profiles", NCU_PROFILE)))
         rd = prof["dram__bytes_read.sum"]; wr = prof["dram__bytes_write.sum"]
         tobytes = lambda m: m["value"] * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[m["unit"]]
         traffic = (tobytes(rd) + tobytes(wr)) / prof["_chains"] * len(aps) * F
+        # the bound that actually binds a latency-serial integer search: issue slots / the integer ALU pipe (same capture)
+        int_pipe = {"alu_pipe_active_pct_of_peak": prof["sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"]["value"],
+                    "issue_active_pct_of_peak": prof["smsp__issue_active.avg.pct_of_peak_sustained_active"]["value"],
+                    "warps_per_sm": prof["launch__occupancy_limit_registers"]["value"], "source": "profiles/" + NCU_PROFILE}
     except (OSError, KeyError, ValueError):
-        pass
+        int_pipe = None
     line = {
         "metric": "frames/sec Analyse+Degrain3 1080p YUV420P8", "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": region_ms / args.steps, "higher_is_better": True,
@@ -311,10 +318,11 @@ def run_gpu_arm(args):
         "clocks": clocks,
         "roofline": {"kernel": "k_search (6 analyse instances x F frames, one warp per search chain)", "bound": "hbm", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "traffic_source": "dram__bytes_read+write of profiles/r1_ncu_search_tma_saturated.json, per chain x chains of this launch" if traffic else None,
+                     "traffic_source": ("dram__bytes_read+write of profiles/%s, per chain x chains of this launch" % NCU_PROFILE) if traffic else None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                      "algorithmic_bytes_per_launch": alg_bytes,
-                     "note": "the search is a serial dependency chain per (frame, direction, delta): latency/issue bound, far below the HBM roofline by construction"},
+                     "int_pipe": int_pipe,
+                     "note": "the search is a serial dependency chain per (frame, direction, delta): issue/integer-pipe bound (see int_pipe), far below the HBM roofline by construction"},
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
