@@ -289,6 +289,12 @@ MVB200_API int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_supe
 /* (what the VapourSynth plugin calls from GetFrame; H2D/D2H copies inside) */
 
 MVB200_API int mvb200_super_frame(mvb200_ctx *ctx, const mvb200_super_params *p, const uint8_t *const src[3], const ptrdiff_t src_stride[3], uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
+/* mv.Super's `pelclip` (MVSuper.c:229-253 create-time checks; :91-104 + mvpRefineExt, MVFrame.cpp:1530-1631 per frame):
+ * the check takes the pel clip's dimensions (same_format: it has the input clip's format and constant dimensions) and
+ * says whether the clip is used (pel >= 2) and whether it already carries the padding; the frame call takes the pel
+ * clip's frame planes beside the source frame's. */
+MVB200_API int mvb200_super_pelclip_check(const mvb200_super_params *p, int same_format, int pel_width, int pel_height, int *use_pelclip, int *pel_padded);
+MVB200_API int mvb200_super_frame_pel(mvb200_ctx *ctx, const mvb200_super_params *p, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const pel[3], const ptrdiff_t pel_stride[3], int pel_padded, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
 
 /* src_super/ref_super: host super frames (ref may be NULL when nref is out of range:
  * the default blob of gopWriteDefaultToArray, GroupOfPlanes.c:150-164, is written). */

@@ -360,8 +360,45 @@ static void refine_plane(uint8_t *base, ptrdiff_t pitch, const Lv *g, int bps, i
     }
 }
 
+/* mvpRefineExtPel2 / mvpRefineExtPel4, MVFrame.cpp:1530-1614: sub-planes 1..pel^2-1 of level 0 are picked out of a
+ * pel-times upsized clip.  Literal restatement, including what the reference does for an already padded pel clip:
+ * it still copies only width x height samples, from the pel clip's origin to the planes' padded origin. */
+static void refine_ext_plane(uint8_t *level0, ptrdiff_t pitch, const Lv *g, int bps, int pel, const uint8_t *pel_plane, ptrdiff_t pel_stride, int is_padded) {
+    ptrdiff_t sub = pitch * g->ph; /* samples between sub-planes */
+    ptrdiff_t offset = is_padded ? 0 : (ptrdiff_t)g->vpad * pitch + g->hpad;
+    for (int i = 1; i < pel * pel; i++) {
+        int sx = i % pel, sy = i / pel;
+        for (int y = 0; y < g->h; y++) {
+            uint8_t *d = level0 + ((ptrdiff_t)i * sub + offset + (ptrdiff_t)y * pitch) * bps;
+            const uint8_t *s = pel_plane + (ptrdiff_t)(y * pel + sy) * pel_stride;
+            for (int x = 0; x < g->w; x++) {
+                if (bps == 1)
+                    d[x] = s[x * pel + sx];
+                else
+                    ((uint16_t *)d)[x] = ((const uint16_t *)s)[x * pel + sx];
+            }
+        }
+        if (!is_padded)
+            pad_plane(level0 + (ptrdiff_t)i * sub * bps, pitch, g->hpad, g->vpad, g->w, g->h, bps);
+    }
+}
+
+static int super_frame_impl(const mvb200_super_params *p, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const pel[3], const ptrdiff_t pel_stride[3],
+                            int pel_padded, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
+
 /* mvsuperGetFrame, MVSuper.c:43-126 */
 int mvo_super_frame(const mvb200_super_params *p, const uint8_t *const src[3], const ptrdiff_t src_stride[3], uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
+    return super_frame_impl(p, src, src_stride, NULL, NULL, 0, dst, dst_stride);
+}
+
+/* ... with a pelclip (MVSuper.c:91-104) */
+int mvo_super_frame_pel(const mvb200_super_params *p, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const pel[3], const ptrdiff_t pel_stride[3],
+                        int pel_padded, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
+    return super_frame_impl(p, src, src_stride, pel, pel_stride, pel_padded, dst, dst_stride);
+}
+
+static int super_frame_impl(const mvb200_super_params *p, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const pel[3], const ptrdiff_t pel_stride[3],
+                            int pel_padded, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
     int bps = (p->bits + 7) / 8;
     for (int plane = 0; plane < p->nplanes; plane++) {
         int ph = plane ? p->super_height >> p->ssh : p->super_height;
@@ -384,7 +421,10 @@ int mvo_super_frame(const mvb200_super_params *p, const uint8_t *const src[3], c
         }
         /* mvgofPad (level 0), MVSuper.c:89; mvgofRefine, MVSuper.c:103 */
         pad_plane(LEVEL_BASE(0), pitch, g[0].hpad, g[0].vpad, g[0].w, g[0].h, bps);
-        refine_plane(LEVEL_BASE(0), pitch, &g[0], bps, p->bits, p->sharp);
+        if (pel && p->pel >= 2)
+            refine_ext_plane(LEVEL_BASE(0), pitch, &g[0], bps, p->pel, pel[plane], pel_stride[plane], pel_padded);
+        else
+            refine_plane(LEVEL_BASE(0), pitch, &g[0], bps, p->bits, p->sharp);
 #undef LEVEL_BASE
 #undef INTERIOR
     }

@@ -17,6 +17,9 @@ MVO_API const char *mvo_last_error(void);
 /* mvsuperGetFrame, MVSuper.c:43-126 */
 MVO_API int mvo_super_frame(const mvb200_super_params *p, const uint8_t *const src[3], const ptrdiff_t src_stride[3], uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
 
+/* the same with a pelclip: mvpRefineExt, MVFrame.cpp:1530-1631 (pel planes of level 0 taken from an upsized clip) */
+MVO_API int mvo_super_frame_pel(const mvb200_super_params *p, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const pel[3], const ptrdiff_t pel_stride[3], int pel_padded, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
+
 /* mvanalyseGetFrame, MVAnalyse.c:76-254 (ref_super == NULL -> default blob) */
 MVO_API int mvo_analyse_frame(const mvb200_analyse_params *ap, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], int field_shift, uint8_t *vectors_out);
 

@@ -20,6 +20,7 @@ def lib():
         L.mvo_last_error.restype = C.c_char_p
         vp, PP = C.c_void_p, C.POINTER
         L.mvo_super_frame.argtypes = [PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
+        L.mvo_super_frame_pel.argtypes = [PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), C.c_int, PP(vp), PP(C.c_ssize_t)]
         L.mvo_analyse_frame.argtypes = [PP(mb.AnalyseParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp),
                                         PP(C.c_ssize_t), C.c_int, vp]
         L.mvo_degrain_frame.argtypes = [PP(mb.DegrainParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp),
@@ -42,7 +43,9 @@ def _check(rc):
         raise RuntimeError(lib().mvo_last_error().decode())
 
 
-def super_frame(sp, src_planes):
+def super_frame(sp, src_planes, pel_planes=None, pel_padded=False):
+    if pel_planes is not None:
+        return super_frame_pel(sp, src_planes, pel_planes, pel_padded)
     g = mb.SuperGeom()
     # geometry comes with the params; plane sizes follow MVSuper.c:254-262
     pw = [sp.super_width] + [sp.super_width >> sp.ssw] * 2
@@ -51,6 +54,17 @@ def super_frame(sp, src_planes):
     s, ss = mb.plane_ptrs(src_planes)
     d, ds = mb.plane_ptrs(dst)
     _check(lib().mvo_super_frame(C.byref(sp), s, ss, d, ds))
+    return dst
+
+
+def super_frame_pel(sp, src_planes, pel_planes, pel_padded):
+    pw = [sp.super_width] + [sp.super_width >> sp.ssw] * 2
+    ph = [sp.super_height] + [sp.super_height >> sp.ssh] * 2
+    dst = mb.alloc_planes(pw[: sp.nplanes], ph[: sp.nplanes], sp.bits, fill=0xA5)
+    s, ss = mb.plane_ptrs(src_planes)
+    q, qs = mb.plane_ptrs(pel_planes)
+    d, ds = mb.plane_ptrs(dst)
+    _check(lib().mvo_super_frame_pel(C.byref(sp), s, ss, q, qs, int(pel_padded), d, ds))
     return dst
 
 

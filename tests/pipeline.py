@@ -24,7 +24,13 @@ CASES = {
     "noise_badblocks_blk8": (dict(width=192, height=128, nframes=5, bits=8, pure_noise=True), dict(pel=2), dict(blksize=8, overlap=2, badsad=300, badrange=6), 1, dict(thscd1=16000, thscd2=255)),
     "trymany_nochroma_dct7_p16": (dict(width=192, height=128, nframes=5, bits=16), dict(pel=2), dict(blksize=16, overlap=4, trymany=1, chroma=0, dct=7, search=0, searchparam=3, global_=0), 1, dict()),
     "divide2_blk16_esa_neg_badrange": (dict(width=256, height=160, nframes=5, bits=8, pure_noise=True), dict(pel=2), dict(blksize=16, overlap=8, divide=2, badsad=500, badrange=-4, search=6, searchparam=3), 1, dict(thscd1=16000, thscd2=255)),
+    # mv.Super(pelclip=...): the pel planes come from an upsized clip (MVSuper.c:229-253, mvpRefineExt)
+    "pelclip2_p8": (dict(width=160, height=96, nframes=4, bits=8), dict(pel=2, hpad=8, vpad=8), dict(blksize=8, overlap=4), 1, {}),
+    "pelclip4_padded_p16": (dict(width=96, height=64, nframes=4, bits=16), dict(pel=4, hpad=8, vpad=8), dict(blksize=8), 1, {}),
 }
+
+# case -> is the pel clip already padded ((w + 2 hpad) * pel wide) or not (w * pel)
+PELCLIP = {"pelclip2_p8": False, "pelclip4_padded_p16": True}
 
 
 # optional extra stages on vector clip 0 (backward, delta 1): mv.Recalculate(sup, vec0, **recalc) and
@@ -50,6 +56,15 @@ def _fix(kw):
 def make_frames(ck):
     ck = dict(ck)
     return clipgen.make_clip(ck.pop("width"), ck.pop("height"), ck.pop("nframes"), **ck)
+
+
+def make_pel_frames(case):
+    """The pel-times upsized clip of a PELCLIP case (any deterministic content will do: another seed)."""
+    ck, skw = dict(CASES[case][0]), CASES[case][1]
+    pel, padded = skw["pel"], PELCLIP[case]
+    w = (ck.pop("width") + (2 * skw["hpad"] if padded else 0)) * pel
+    h = (ck.pop("height") + (2 * skw["vpad"] if padded else 0)) * pel
+    return clipgen.make_clip(w, h, ck.pop("nframes"), seed=77, **ck)
 
 
 def sha(a):
@@ -108,7 +123,11 @@ def run_engine(case, super_fn, analyse_fn, degrain_fn, recalculate_fn=None, comp
     frames = make_frames(CASES[case][0])
     N = len(frames)
     sp, aps, dp = params_for(case)
-    sups = [super_fn(sp, f) for f in frames]
+    if case in PELCLIP:  # super_fn is then called with the pel frame and the padded flag as well
+        pel_frames = make_pel_frames(case)
+        sups = [super_fn(sp, f, q, PELCLIP[case]) for f, q in zip(frames, pel_frames)]
+    else:
+        sups = [super_fn(sp, f) for f in frames]
     out = {"super": [[sha(p) for p in s] for s in sups], "vectors": [], "degrain": []}
     vecs = []
     for n in range(N):
@@ -143,7 +162,11 @@ def run_reference(case, plugin_path=None):
     core = minivs.Core()
     mv = core.load(plugin_path or minivs.REF_PLUGIN)
     clip = core.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1))
-    sup = mv.Super(clip, **skw)
+    if case in PELCLIP:
+        pelclip = core.source(make_pel_frames(case), bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1))
+        sup = mv.Super(clip, pelclip=pelclip, **skw)
+    else:
+        sup = mv.Super(clip, **skw)
     vn = [mv.Analyse(sup, isb=isb, delta=d, **_fix(akw)) for d in range(1, radius + 1) for isb in (1, 0)]
     dn = mv.invoke("Degrain%d" % radius, clip, sup, *vn, **dkw)
     out = {"super": [], "vectors": [], "degrain": [], "adata": []}

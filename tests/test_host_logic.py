@@ -71,6 +71,21 @@ def test_super_errors(built):
     assert str(e.value) == "Super: pel must be 1, 2, or 4."
 
 
+def test_super_pelclip_check(built):
+    """mvsuperCreate's pelclip rules (MVSuper.c:229-253)"""
+    sp = mb.super_params(160, 96, 8, 1, 1, pel=2, hpad=8, vpad=8)
+    assert mb.super_pelclip_check(sp, 320, 192) == (True, False)
+    assert mb.super_pelclip_check(sp, (160 + 16) * 2, (96 + 16) * 2) == (True, True)
+    with pytest.raises(mb.Error) as e:
+        mb.super_pelclip_check(sp, 321, 192)
+    assert str(e.value) == "Super: pelclip's dimensions must be multiples of the input clip's dimensions."
+    with pytest.raises(mb.Error) as e:
+        mb.super_pelclip_check(sp, 320, 192, same_format=False)
+    assert str(e.value) == "Super: pelclip must have the same format as the input clip, and it must have constant dimensions."
+    sp1 = mb.super_params(160, 96, 8, 1, 1, pel=1)
+    assert mb.super_pelclip_check(sp1, 123, 45) == (False, False)  # ignored for pel 1
+
+
 def test_degrain_errors_and_thresholds(built):
     sp = mb.super_params(640, 360, 8, 1, 1)
     bw = mb.analyse_params(sp, 10, isb=1, blksize=16, overlap=8)

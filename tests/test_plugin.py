@@ -49,12 +49,19 @@ def test_create_time_errors_through_the_plugin(built):
         mv.Analyse(clip)  # not a super clip: no Super_* props
     assert "required properties not found in first frame of super clip" in str(e.value)
     with pytest.raises(minivs.Error) as e:
+        mv.Super(clip, pelclip=core.source(clipgen.make_clip(130, 96, 2)))
+    assert str(e.value) == "Super: pelclip's dimensions must be multiples of the input clip's dimensions."
+    with pytest.raises(minivs.Error) as e:
+        mv.Super(clip, pelclip=core.source(clipgen.make_clip(128, 96, 2, bits=10), bits=10))
+    assert str(e.value) == "Super: pelclip must have the same format as the input clip, and it must have constant dimensions."
+    with pytest.raises(minivs.Error) as e:
         mv.Super(clip, bogus=1)
     assert "does not take argument" in str(e.value)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["c1_640x360_p8_blk8_pel1", "blk16_ov8_pel2_p8_r3", "blk16_ov8_pel2_p16_r3", "divide2_blk16_esa_neg_badrange", "p8_422_blk8x4_sharp0_rf1"])
+@pytest.mark.parametrize("case", ["c1_640x360_p8_blk8_pel1", "blk16_ov8_pel2_p8_r3", "blk16_ov8_pel2_p16_r3", "divide2_blk16_esa_neg_badrange", "p8_422_blk8x4_sharp0_rf1",
+                                  "pelclip2_p8", "pelclip4_padded_p16"])
 def test_script_through_plugin_matches_reference(built, case):
     got = pipeline.run_reference(case, plugin_path=mb.PLUGIN_PATH)
     for stage in ("super", "vectors", "degrain", "adata", "recalc", "compensate", "recalc_adata"):

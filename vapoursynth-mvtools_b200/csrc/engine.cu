@@ -483,6 +483,51 @@ int mvb200_super_frame(mvb200_ctx *ctx, const mvb200_super_params *p, const uint
     return 0;
 }
 
+// mvsuperGetFrame with a pelclip (MVSuper.c:91-104)
+int mvb200_super_frame_pel(mvb200_ctx *ctx, const mvb200_super_params *p, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const pel[3],
+                           const ptrdiff_t pel_stride[3], int pel_padded, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
+    if (check_levels(p))
+        return 1;
+    if (p->pel < 2) // MVSuper.c:240: the pelclip is ignored for pel 1
+        return mvb200_super_frame(ctx, p, src, src_stride, dst, dst_stride);
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(p, &sd);
+    make_clip_desc(p, &cd);
+    PelClip pc;
+    int pw[3], ph[3];
+    long long pel_bytes = 0;
+    for (int i = 0; i < 3; i++) {
+        const int lw = (pel_padded ? p->width + 2 * p->hpad : p->width) * p->pel, lh = (pel_padded ? p->height + 2 * p->vpad : p->height) * p->pel;
+        pw[i] = i ? lw >> p->ssw : lw; // the pel clip has the input clip's format (MVSuper.c:232)
+        ph[i] = i ? lh >> p->ssh : lh;
+        pc.pitch[i] = round_up((long long)pw[i] * cd.bps, 256);
+        pc.offset[i] = pel_bytes;
+        if (i < cd.nplanes)
+            pel_bytes += pc.pitch[i] * ph[i];
+    }
+    pc.padded = pel_padded;
+    uint8_t *buf = (uint8_t *)c->get_scratch(5, (size_t)(cd.frame_bytes + sd.frame_bytes + pel_bytes));
+    if (!buf)
+        return 1;
+    uint8_t *dsrc = buf, *dsup = buf + cd.frame_bytes, *dpel = dsup + sd.frame_bytes;
+    pc.dev = dpel;
+    if (upload_planes(c, dsrc, cd.pitch, cd.offset, cd.w, cd.h, cd.bps, cd.nplanes, src, src_stride))
+        return 1;
+    if (upload_planes(c, dpel, pc.pitch, pc.offset, pw, ph, cd.bps, cd.nplanes, pel, pel_stride))
+        return 1;
+    if (launch_super(c, p, sd, cd, dsrc, dsup, 1, &pc))
+        return 1;
+    int w[3], h[3];
+    super_plane_dims(p, w, h);
+    if (download_planes(c, dsup, sd.pitch, sd.offset, w, h, sd.bps, sd.nplanes, dst, dst_stride))
+        return 1;
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int mvb200_analyse_frame(mvb200_ctx *ctx, const mvb200_analyse_params *ap, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], int field_shift, uint8_t *vectors_out) {
     if (check_analyse(ap, sp))
         return 1;

@@ -83,7 +83,13 @@ struct RecalcJob {
 struct Ctx;
 
 // kernels' host launchers (each returns 0 or sets the error)
-int launch_super(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, uint8_t *dev_super, int n);
+// one frame of a pel-times upsized clip on the device (mv.Super's pelclip argument)
+struct PelClip {
+    const uint8_t *dev;
+    long long pitch[3], offset[3];
+    int padded; // the pel clip already carries the padding (MVSuper.c:246-248)
+};
+int launch_super(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, uint8_t *dev_super, int n, const PelClip *pelclip = nullptr);
 // frames_base / nframes describe the resident super clip the jobs point into (needed for the TMA descriptors)
 int launch_search(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &geom, const uint8_t *frames_base, int nframes, const SearchParams *host_params, int nparams, const SearchJob *host_jobs, int njobs);
 int launch_search_tma(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &geom, const uint8_t *frames_base, int nframes, const SearchParams *host_params, int nparams,

@@ -136,6 +136,25 @@ int mvb200_super_init(mvb200_super_params *p) {
     return 0;
 }
 
+// the pelclip part of mvsuperCreate, MVSuper.c:229-253
+int mvb200_super_pelclip_check(const mvb200_super_params *p, int same_format, int pel_width, int pel_height, int *use_pelclip, int *pel_padded) {
+    *use_pelclip = 0;
+    *pel_padded = 0;
+    if (!same_format)
+        return set_error("Super: pelclip must have the same format as the input clip, and it must have constant dimensions.");
+    if (p->pel >= 2) {
+        if (pel_width == p->width * p->pel && pel_height == p->height * p->pel) {
+            *use_pelclip = 1;
+        } else if (pel_width == (p->width + p->hpad * 2) * p->pel && pel_height == (p->height + p->vpad * 2) * p->pel) {
+            *use_pelclip = 1;
+            *pel_padded = 1;
+        } else {
+            return set_error("Super: pelclip's dimensions must be multiples of the input clip's dimensions.");
+        }
+    }
+    return 0;
+}
+
 void mvb200_super_geometry(const mvb200_super_params *p, mvb200_super_geom *g) {
     memset(g, 0, sizeof(*g));
     g->nplanes = p->nplanes;

@@ -332,10 +332,25 @@ __global__ void k_avg2(uint8_t *__restrict__ dst_base, const uint8_t *__restrict
     d[o] = (T)((ld(a, o) + ld(b, o) + 1) >> 1);
 }
 
+// mvpRefineExtPel2 / Pel4, MVFrame.cpp:1530-1614: sub-plane i = (sx, sy) of level 0 is the (sx, sy) phase of a
+// pel-times upsized clip; blockIdx.z = sub-plane index - 1 (the frame loop is on the host: per-frame entry point)
+template <typename T>
+__global__ void k_refine_ext(uint8_t *__restrict__ level0, long long pitch_bytes, long long sub_bytes, long long dst_off_bytes, const uint8_t *__restrict__ pel_plane,
+                             long long pel_pitch, int w, int h, int pel) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= w || y >= h)
+        return;
+    const int i = blockIdx.z + 1, sx = i % pel, sy = i / pel;
+    T *d = (T *)(level0 + (long long)i * sub_bytes + dst_off_bytes + (long long)y * pitch_bytes);
+    const T *s = (const T *)(pel_plane + (long long)(y * pel + sy) * pel_pitch);
+    d[x] = s[x * pel + sx];
+}
+
 inline dim3 grid2d(int w, int h, int n, dim3 blk) { return dim3((w + blk.x - 1) / blk.x, (h + blk.y - 1) / blk.y, n); }
 
 template <typename T>
-int super_typed(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, uint8_t *dev_super, int n) {
+int super_typed(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, uint8_t *dev_super, int n, const PelClip *pelclip) {
     cudaStream_t st = ctx->stream;
     const dim3 blk(64, 4);
     const int bps = sd.bps;
@@ -370,7 +385,18 @@ int super_typed(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, con
         else
             k_pad<T><<<grid2d(g0.padded_w, g0.padded_h, n, blk), blk, 0, st>>>(level_base(0), pitch, sd.frame_bytes, g0.hpad, g0.vpad, g0.width, g0.height);
         ctx->launches++;
-        if (p->pel > 1) { // mvpRefine, MVFrame.cpp:1386-1527
+        if (p->pel > 1 && pelclip) { // mvpRefineExt, MVFrame.cpp:1530-1631 (n == 1)
+            const long long sub = pitch * g0.padded_h;
+            const long long off = pelclip->padded ? 0 : (long long)g0.vpad * pitch + (long long)g0.hpad * bps;
+            dim3 g((g0.width + blk.x - 1) / blk.x, (g0.height + blk.y - 1) / blk.y, p->pel * p->pel - 1);
+            k_refine_ext<T><<<g, blk, 0, st>>>(level_base(0), pitch, sub, off, pelclip->dev + pelclip->offset[plane], pelclip->pitch[plane], g0.width, g0.height, p->pel);
+            ctx->launches++;
+            if (!pelclip->padded)
+                for (int i = 1; i < p->pel * p->pel; i++) {
+                    k_pad<T><<<grid2d(g0.padded_w, g0.padded_h, 1, blk), blk, 0, st>>>(level_base(0) + sub * i, pitch, sd.frame_bytes, g0.hpad, g0.vpad, g0.width, g0.height);
+                    ctx->launches++;
+                }
+        } else if (p->pel > 1) { // mvpRefine, MVFrame.cpp:1386-1527
             const long long sub = pitch * g0.padded_h;
             auto P = [&](int i) { return level_base(0) + sub * i; };
             const int w = g0.padded_w, h = g0.padded_h;
@@ -417,12 +443,14 @@ int super_typed(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, con
 
 } // namespace
 
-int launch_super(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, uint8_t *dev_super, int n) {
+int launch_super(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, uint8_t *dev_super, int n, const PelClip *pelclip) {
     if (n <= 0)
         return 0;
+    if (pelclip && n != 1)
+        return set_error("mvtools_b200: a pelclip is supported by the per-frame entry point only");
     if (sd.bps == 1)
-        return super_typed<uint8_t>(ctx, p, sd, cd, dev_src, dev_super, n);
-    return super_typed<uint16_t>(ctx, p, sd, cd, dev_src, dev_super, n);
+        return super_typed<uint8_t>(ctx, p, sd, cd, dev_src, dev_super, n, pelclip);
+    return super_typed<uint16_t>(ctx, p, sd, cd, dev_src, dev_super, n, pelclip);
 }
 
 } // namespace mvb200

@@ -163,12 +163,21 @@ def lib():
         L.mvb200_degrain_batch.argtypes = [vp, PP(DegrainParams), PP(SuperParams), vp, vp, i32, i32, i32, PP(vp), i64, vp]
         L.mvb200_degrain_clip_host_async.argtypes = [vp, PP(SuperParams), PP(PP(AnalyseParams)), i32, PP(DegrainParams), vp, vp, i32]
         L.mvb200_super_frame.argtypes = [vp, PP(SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
+        L.mvb200_super_frame_pel.argtypes = [vp, PP(SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), i32, PP(vp), PP(C.c_ssize_t)]
+        L.mvb200_super_pelclip_check.argtypes = [PP(SuperParams), i32, i32, i32, PP(i32), PP(i32)]
         L.mvb200_analyse_frame.argtypes = [vp, PP(AnalyseParams), PP(SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp),
                                            PP(C.c_ssize_t), i32, vp]
         L.mvb200_degrain_frame.argtypes = [vp, PP(DegrainParams), PP(SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp),
                                            PP(C.c_ssize_t), PP(vp), PP(vp), PP(C.c_ssize_t)]
         _LIB = L
     return _LIB
+
+
+def super_pelclip_check(sp, pel_width, pel_height, same_format=True):
+    """-> (use_pelclip, pel_padded); raises Error with the reference's message"""
+    use, padded = C.c_int32(0), C.c_int32(0)
+    _check(lib().mvb200_super_pelclip_check(C.byref(sp), int(same_format), pel_width, pel_height, C.byref(use), C.byref(padded)))
+    return bool(use.value), bool(padded.value)
 
 
 def _check(rc):
@@ -329,12 +338,23 @@ class Context:
         return lib().mvb200_ctx_launch_count(self._h)
 
     # ---- host-buffer per-frame calls (what the VapourSynth plugin makes)
-    def super_frame(self, sp, src_planes):
+    def super_frame(self, sp, src_planes, pel_planes=None, pel_padded=False):
+        if pel_planes is not None:
+            return self.super_frame_pel(sp, src_planes, pel_planes, pel_padded)
         g = super_geometry(sp)
         dst = alloc_planes(list(g.plane_w)[: sp.nplanes], list(g.plane_h)[: sp.nplanes], sp.bits, fill=0xA5)
         s, ss = plane_ptrs(src_planes)
         d, ds = plane_ptrs(dst)
         _check(lib().mvb200_super_frame(self._h, C.byref(sp), s, ss, d, ds))
+        return dst
+
+    def super_frame_pel(self, sp, src_planes, pel_planes, pel_padded):
+        g = super_geometry(sp)
+        dst = alloc_planes(list(g.plane_w)[: sp.nplanes], list(g.plane_h)[: sp.nplanes], sp.bits, fill=0xA5)
+        s, ss = plane_ptrs(src_planes)
+        q, qs = plane_ptrs(pel_planes)
+        d, ds = plane_ptrs(dst)
+        _check(lib().mvb200_super_frame_pel(self._h, C.byref(sp), s, ss, q, qs, int(pel_padded), d, ds))
         return dst
 
     def analyse_frame(self, ap, sp, src_super, ref_super, field_shift=0):

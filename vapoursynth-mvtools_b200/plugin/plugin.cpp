@@ -123,34 +123,45 @@ bool superFromClip(VSNode *super, const VSAPI *vsapi, const char *filter, mvb200
 
 // ------------------------------------------------------------------ Super
 struct SuperData {
-    VSNode *node;
+    VSNode *node, *pelclip;
     VSVideoInfo vi;
     mvb200_super_params sp;
+    int usePelClip, pelPadded;
 };
 
 const VSFrame *VS_CC superGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
     SuperData *d = (SuperData *)instanceData;
     if (activationReason == arInitial) {
         vsapi->requestFrameFilter(n, d->node, frameCtx);
+        if (d->usePelClip)
+            vsapi->requestFrameFilter(n, d->pelclip, frameCtx);
     } else if (activationReason == arAllFramesReady) {
         const VSFrame *src = vsapi->getFrameFilter(n, d->node, frameCtx);
+        const VSFrame *srcPel = d->usePelClip ? vsapi->getFrameFilter(n, d->pelclip, frameCtx) : nullptr;
         VSFrame *dst = vsapi->newVideoFrame(&d->vi.format, d->vi.width, d->vi.height, src, core);
-        const uint8_t *sp_[3];
-        ptrdiff_t ss[3];
+        const uint8_t *sp_[3], *pp_[3];
+        ptrdiff_t ss[3], ps[3];
         uint8_t *dp[3];
         ptrdiff_t ds[3];
         planesRO(vsapi, src, d->vi.format.numPlanes, sp_, ss);
+        planesRO(vsapi, srcPel, d->vi.format.numPlanes, pp_, ps);
         planesRW(vsapi, dst, d->vi.format.numPlanes, dp, ds);
         std::string err;
         int rc;
         {
             std::lock_guard<std::mutex> lock(g_engine_mutex);
             mvb200_ctx *ctx = engine(err);
-            rc = ctx ? mvb200_super_frame(ctx, &d->sp, sp_, ss, dp, ds) : 1;
+            if (!ctx)
+                rc = 1;
+            else if (srcPel)
+                rc = mvb200_super_frame_pel(ctx, &d->sp, sp_, ss, pp_, ps, d->pelPadded, dp, ds);
+            else
+                rc = mvb200_super_frame(ctx, &d->sp, sp_, ss, dp, ds);
             if (ctx && rc)
                 err = mvb200_last_error();
         }
         vsapi->freeFrame(src);
+        vsapi->freeFrame(srcPel);
         if (rc) {
             vsapi->setFilterError(("Super: " + err).c_str(), frameCtx);
             vsapi->freeFrame(dst);
@@ -173,19 +184,15 @@ const VSFrame *VS_CC superGetFrame(int n, int activationReason, void *instanceDa
 void VS_CC superFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
     SuperData *d = (SuperData *)instanceData;
     vsapi->freeNode(d->node);
+    vsapi->freeNode(d->pelclip);
     delete d;
 }
 
 void VS_CC superCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const VSAPI *vsapi) {
-    int err = 0;
-    VSNode *pelclip = vsapi->mapGetNode(in, "pelclip", 0, &err);
-    if (pelclip) {
-        vsapi->freeNode(pelclip);
-        vsapi->mapSetError(out, "Super: pelclip is not implemented by the B200 engine.");
-        return;
-    }
     SuperData d;
     memset(&d.sp, 0, sizeof(d.sp));
+    d.pelclip = nullptr;
+    d.usePelClip = d.pelPadded = 0;
     d.sp.hpad = argInt(vsapi, in, "hpad");
     d.sp.vpad = argInt(vsapi, in, "vpad");
     d.sp.pel = argInt(vsapi, in, "pel");
@@ -211,10 +218,24 @@ void VS_CC superCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const 
         vsapi->freeNode(d.node);
         return;
     }
+    int err = 0;
+    d.pelclip = vsapi->mapGetNode(in, "pelclip", 0, &err); // MVSuper.c:229-253
+    if (d.pelclip) {
+        const VSVideoInfo *pelvi = vsapi->getVideoInfo(d.pelclip);
+        const bool same = vsh::isConstantVideoFormat(pelvi) && pelvi->format.colorFamily == d.vi.format.colorFamily && pelvi->format.sampleType == d.vi.format.sampleType &&
+                          pelvi->format.bitsPerSample == d.vi.format.bitsPerSample && pelvi->format.subSamplingW == d.vi.format.subSamplingW &&
+                          pelvi->format.subSamplingH == d.vi.format.subSamplingH;
+        if (mvb200_super_pelclip_check(&d.sp, same, pelvi->width, pelvi->height, &d.usePelClip, &d.pelPadded)) {
+            vsapi->mapSetError(out, mvb200_last_error());
+            vsapi->freeNode(d.node);
+            vsapi->freeNode(d.pelclip);
+            return;
+        }
+    }
     d.vi.width = d.sp.super_width;
     d.vi.height = d.sp.super_height;
     SuperData *data = new SuperData(d);
-    VSFilterDependency deps[1] = {{data->node, rpStrictSpatial}};
+    VSFilterDependency deps[1] = {{data->node, rpStrictSpatial}}; // (the reference declares the source clip only, MVSuper.c:270-272)
     vsapi->createVideoFilter(out, "Super", &data->vi, superGetFrame, superFree, fmParallel, deps, 1, data, core);
 }
 
