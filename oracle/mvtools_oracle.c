@@ -526,7 +526,101 @@ static const uint8_t *pel_ptr(const PlaneView *v, int bps, int logpel, int x, in
     return v->base + (ptrdiff_t)idx * v->pitch * v->g.ph + (ptrdiff_t)y * v->pitch + (ptrdiff_t)x * bps;
 }
 
+/* ---- dct = 1..4: the FFTW DCT path (DCTFFTW.cpp).  The transform itself lives in FFTW3f, which the reference does not
+ * vendor or pin (meson.build:185-188): it is restated from FFTW's documented definition of REDFT10 -- unnormalised
+ * DCT-II, Y_k = 2 sum_j x_j cos(pi (j + 1/2) k / n), applied to rows then columns -- as plain float dot products in index
+ * order.  FFTW's codelets add in a different order, so against a build with the real FFTW this path agrees to float
+ * rounding only (PARITY UNPINNED for dct 1..4; the tests pin it against oracle/_ref, whose FFTW is the same definition,
+ * oracle/shim/fftw_shim.c).  Everything around the transform is the reference's integer code, restated exactly. */
+typedef struct Dct {
+    int sizex, sizey, bits, dctshift, dctshift0;
+    float *cx, *cy, *fsrc, *ftmp, *fdct; /* cx[k * sizex + j] = (float)(2 cos(pi (2j + 1) k / (2 sizex))) */
+    uint8_t *dctSrc, *dctRef;            /* blkW x blkH pixel-typed "DCT images", pitch = blkW * bps */
+} Dct;
+
+static float *dct_costab(int n) {
+    float *t = (float *)malloc(sizeof(float) * (size_t)n * (size_t)n);
+    for (int k = 0; k < n; k++)
+        for (int i = 0; i < n; i++)
+            t[k * n + i] = (float)(2.0 * cos(M_PI * (2.0 * i + 1.0) * k / (2.0 * n)));
+    return t;
+}
+
+/* dctInit, DCTFFTW.cpp:135-173 */
+static void dct_init(Dct *d, int sizex, int sizey, int bits) {
+    d->sizex = sizex;
+    d->sizey = sizey;
+    d->bits = bits;
+    int size2d = sizex * sizey, cur = 1;
+    d->dctshift = 0;
+    while (cur < size2d) {
+        d->dctshift++;
+        cur <<= 1;
+    }
+    d->dctshift0 = d->dctshift + 2;
+    d->cx = dct_costab(sizex);
+    d->cy = dct_costab(sizey);
+    d->fsrc = (float *)malloc(sizeof(float) * (size_t)size2d);
+    d->ftmp = (float *)malloc(sizeof(float) * (size_t)size2d);
+    d->fdct = (float *)malloc(sizeof(float) * (size_t)size2d);
+    int bps = (bits + 7) / 8;
+    d->dctSrc = (uint8_t *)malloc((size_t)size2d * bps);
+    d->dctRef = (uint8_t *)malloc((size_t)size2d * bps);
+}
+
+static void dct_free(Dct *d) {
+    free(d->cx);
+    free(d->cy);
+    free(d->fsrc);
+    free(d->ftmp);
+    free(d->fdct);
+    free(d->dctSrc);
+    free(d->dctRef);
+}
+
+/* dctBytes2D, DCTFFTW.cpp:200-208: Pixels2Float (:185-197), REDFT10 x REDFT10, Float2Pixels_C (:31-54) */
+static void dct_bytes2d(const Dct *d, const uint8_t *src, ptrdiff_t src_pitch, uint8_t *dst) {
+    const int nx = d->sizex, ny = d->sizey, bps = (d->bits + 7) / 8;
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++)
+            d->fsrc[j * nx + i] = (float)LD(src + (ptrdiff_t)j * src_pitch, bps, i);
+    for (int i = 0; i < ny; i++) /* rows */
+        for (int k = 0; k < nx; k++) {
+            float acc = 0.f;
+            for (int j = 0; j < nx; j++)
+                acc += d->fsrc[i * nx + j] * d->cx[k * nx + j];
+            d->ftmp[i * nx + k] = acc;
+        }
+    for (int k = 0; k < ny; k++) /* columns */
+        for (int j = 0; j < nx; j++) {
+            float acc = 0.f;
+            for (int i = 0; i < ny; i++)
+                acc += d->ftmp[i * nx + j] * d->cy[k * ny + i];
+            d->fdct[k * nx + j] = acc;
+        }
+    const int pixelMax = (1 << d->bits) - 1, pixelHalf = 1 << (d->bits - 1);
+    const float sqrt_2_div_2 = 0.70710678118654752440084436210485f;
+    for (int j = 0; j < ny; j++)
+        for (int i = 0; i < nx; i++) {
+            float f = d->fdct[j * nx + i] * sqrt_2_div_2;
+            int integ = (int)nearbyintf(f);
+            int v = IMIN(pixelMax, IMAX(0, (integ >> d->dctshift) + pixelHalf));
+            if (bps == 1)
+                dst[j * nx + i] = (uint8_t)v;
+            else
+                ((uint16_t *)dst)[j * nx + i] = (uint16_t)v;
+        }
+    float f = d->fdct[0] * 0.5f;
+    int integ = (int)nearbyintf(f);
+    int v = IMIN(pixelMax, IMAX(0, (integ >> d->dctshift0) + pixelHalf)); /* DC */
+    if (bps == 1)
+        dst[0] = (uint8_t)v;
+    else
+        ((uint16_t *)dst)[0] = (uint16_t)v;
+}
+
 typedef struct Search {
+    Dct *dct; /* dct 1..4 */
     /* constant per level */
     int nBlkX, nBlkY, blkW, blkH, ovX, ovY, logPel, logScale, xR, yR, logxR, logyR, bps, chroma, smallest;
     int cw, ch; /* chroma block size */
@@ -570,13 +664,37 @@ static const uint8_t *ref_chroma(const Search *S, int plane, int vx, int vy) { /
                    (S->y[plane] << S->logPel) + ((vy + ybias) >> S->logyR));
 }
 
-/* pobLumaSAD<dctmode>, PlaneOfBlocks.cpp:117-203 (dct 0 and 5..10) */
+/* pobLumaSAD<dctmode>, PlaneOfBlocks.cpp:117-203 (all dct modes) */
 static int64_t luma_sad(Search *S, const uint8_t *pRef) {
     ptrdiff_t sp = S->src[0].pitch, rp = S->ref[0].pitch;
     int64_t sad = mvo_sad(S->pSrc[0], sp, pRef, rp, S->blkW, S->blkH, S->bps);
     int d = S->dctmode;
     if (d == 0)
         return sad;
+    if (d >= 1 && d <= 4) { /* :123-163 */
+        const Dct *D = S->dct;
+        const ptrdiff_t dp = (ptrdiff_t)S->blkW * S->bps;
+        if (d == 1 || (d == 2 && S->dctweight16 > 0)) {
+            dct_bytes2d(D, pRef, rp, D->dctRef);
+            unsigned dcdiff = (unsigned)abs(LD(D->dctSrc, S->bps, 0) - LD(D->dctRef, S->bps, 0));
+            int64_t dctsad = (int64_t)(unsigned)(mvo_sad(D->dctSrc, dp, D->dctRef, dp, S->blkW, S->blkH, S->bps) + dcdiff * 3u) * (int64_t)S->blkW / 2;
+            if (d == 1)
+                return dctsad;
+            return (sad * (16 - S->dctweight16) + dctsad * S->dctweight16) / 16;
+        }
+        if (d == 2)
+            return sad;
+        int refLuma = (int)luma_sum(pRef, rp, S->blkW, S->blkH, S->bps);
+        if (abs(S->srcLuma - refLuma) > ((S->srcLuma + refLuma) >> 5)) {
+            dct_bytes2d(D, pRef, rp, D->dctRef);
+            int64_t dctsad = (int64_t)mvo_sad(D->dctSrc, dp, D->dctRef, dp, S->blkW, S->blkH, S->bps) * (int64_t)S->blkW / 2;
+            if (d == 3)
+                sad = sad / 2 + dctsad / 2;
+            else
+                sad = sad / 4 + dctsad / 2 + dctsad / 4;
+        }
+        return sad;
+    }
     if (d == 5)
         return mvo_satd(S->pSrc[0], sp, pRef, rp, S->blkW, S->blkH, S->bps);
     if (d == 6) {
@@ -935,6 +1053,8 @@ static int64_t full_sad_at(Search *S, int lx, int ly, int cx, int cy) {
 /* pobPseudoEPZSearch, PlaneOfBlocks.cpp:819-968 */
 static void epz_search(Search *S) {
     fetch_predictors(S);
+    if (S->dctmode >= 1 && S->dctmode <= 4) /* :824-828 */
+        dct_bytes2d(S->dct, S->pSrc[0], S->src[0].pitch, S->dct->dctSrc);
     if (S->dctmode >= 3)
         S->srcLuma = (int)luma_sum(S->pSrc[0], S->src[0].pitch, S->blkW, S->blkH, S->bps);
 
@@ -1270,8 +1390,10 @@ int mvo_analyse_frame(const mvb200_analyse_params *ap, const mvb200_super_params
         }
         return 0;
     }
-    if (ap->dctmode >= 1 && ap->dctmode <= 4)
-        return fail("oracle: dct 1..4 (FFTW DCT) is not restated");
+    Dct dctc;
+    const int use_dct = ap->dctmode >= 1 && ap->dctmode <= 4; /* MVAnalyse.c:196-201 */
+    if (use_dct)
+        dct_init(&dctc, ap->ad.nBlkSizeX, ap->ad.nBlkSizeY, sp->bits);
 
     hdr[1] = 1;
     VECTOR *lvVec[MVB200_MAX_LEVELS];
@@ -1312,6 +1434,7 @@ int mvo_analyse_frame(const mvb200_analyse_params *ap, const mvb200_super_params
         S.ch = S.blkH / S.yR;
         S.smallest = (l == L - 1);
         S.dctmode = ap->dctmode;
+        S.dct = use_dct ? &dctc : NULL;
         S.verybigSAD = verybig;
         S.vectors = lvVec[l];
         bind_planes(S.src, src_super, src_stride, sp, l, nplanes_used);
@@ -1343,6 +1466,8 @@ int mvo_analyse_frame(const mvb200_analyse_params *ap, const mvb200_super_params
     }
     for (int l = 0; l < L; l++)
         free(lvVec[l]);
+    if (use_dct)
+        dct_free(&dctc);
     return 0;
 }
 
@@ -1591,11 +1716,14 @@ int mvo_recalculate_frame(const mvb200_recalculate_params *rp, const mvb200_supe
         }
         return 0;
     }
-    if (rp->dctmode >= 1 && rp->dctmode <= 4)
-        return fail("oracle: dct 1..4 (FFTW DCT) is not restated");
+    Dct dctc;
+    const int use_dct = rp->dctmode >= 1 && rp->dctmode <= 4; /* MVRecalculate.c:193-198 */
+    if (use_dct)
+        dct_init(&dctc, rp->ad.nBlkSizeX, rp->ad.nBlkSizeY, sp->bits);
     hdr[1] = 1;
     Search S;
     memset(&S, 0, sizeof(S));
+    S.dct = use_dct ? &dctc : NULL;
     S.nBlkX = ad->nBlkX;
     S.nBlkY = ad->nBlkY;
     S.blkW = ad->nBlkSizeX;
@@ -1674,6 +1802,8 @@ int mvo_recalculate_frame(const mvb200_recalculate_params *rp, const mvb200_supe
             S.predictor = clipmv(&S, vo);
             S.predictor.sad = vo.sad * (S.blkW * S.blkH) / (od->nBlkSizeX * od->nBlkSizeY);
             S.bestMV = S.predictor;
+            if (use_dct) /* :1336-1338 */
+                dct_bytes2d(&dctc, S.pSrc[0], S.src[0].pitch, dctc.dctSrc);
             if (S.dctmode >= 3)
                 S.srcLuma = (int)luma_sum(S.pSrc[0], S.src[0].pitch, S.blkW, S.blkH, S.bps);
             int64_t sad = full_sad_at(&S, S.predictor.x, S.predictor.y, S.predictor.x, S.predictor.y);
@@ -1688,6 +1818,8 @@ int mvo_recalculate_frame(const mvb200_recalculate_params *rp, const mvb200_supe
         *(int32_t *)o = 4 + n * 16 * 4;
         extra_divide(res, (VECTOR *)(o + 4), ad->nBlkX, ad->nBlkY, rp->divide);
     }
+    if (use_dct)
+        dct_free(&dctc);
     return 0;
 }
 

@@ -24,6 +24,11 @@ CASES = {
     "noise_badblocks_blk8": (dict(width=192, height=128, nframes=5, bits=8, pure_noise=True), dict(pel=2), dict(blksize=8, overlap=2, badsad=300, badrange=6), 1, dict(thscd1=16000, thscd2=255)),
     "trymany_nochroma_dct7_p16": (dict(width=192, height=128, nframes=5, bits=16), dict(pel=2), dict(blksize=16, overlap=4, trymany=1, chroma=0, dct=7, search=0, searchparam=3, global_=0), 1, dict()),
     "divide2_blk16_esa_neg_badrange": (dict(width=256, height=160, nframes=5, bits=8, pure_noise=True), dict(pel=2), dict(blksize=16, overlap=8, divide=2, badsad=500, badrange=-4, search=6, searchparam=3), 1, dict(thscd1=16000, thscd2=255)),
+    # dct 1..4: the FFTW DCT path (DCTFFTW.cpp); pinned against oracle/_ref, whose FFTW is oracle/shim/fftw_shim.c
+    "dct1_blk8_p8": (dict(width=160, height=96, nframes=4, bits=8), dict(pel=2, hpad=8, vpad=8), dict(blksize=8, overlap=4, dct=1), 1, {}),
+    "dct2_blk16_p16": (dict(width=160, height=96, nframes=4, bits=16, scene_cut=True), dict(pel=1, hpad=8, vpad=8), dict(blksize=16, dct=2, search=3, searchparam=1), 1, {}),
+    "dct3_blk8x4_p8": (dict(width=128, height=80, nframes=4, bits=8, noise_sigma=12.0), dict(pel=2, hpad=8, vpad=8), dict(blksize=8, blksizev=4, dct=3), 1, {}),
+    "dct4_blk4_p10": (dict(width=96, height=64, nframes=4, bits=10, ssw=0, ssh=0), dict(pel=1, hpad=8, vpad=8), dict(blksize=4, dct=4, search=5, searchparam=2), 1, {}),
     # mv.Super(pelclip=...): the pel planes come from an upsized clip (MVSuper.c:229-253, mvpRefineExt)
     "pelclip2_p8": (dict(width=160, height=96, nframes=4, bits=8), dict(pel=2, hpad=8, vpad=8), dict(blksize=8, overlap=4), 1, {}),
     "pelclip4_padded_p16": (dict(width=96, height=64, nframes=4, bits=16), dict(pel=4, hpad=8, vpad=8), dict(blksize=8), 1, {}),
@@ -43,6 +48,7 @@ EXTRA = {
     "p8_422_blk8x4_sharp0_rf1": dict(recalc=dict(blksize=8, blksizev=4, overlap=4, overlapv=2, thsad=80, search=2, meander=0), comp=dict(time=75.0)),
     "gray_blk4_pel1_rf0": dict(recalc=dict(blksize=8, thsad=20, search=0, searchparam=2, chroma=0), comp=dict()),
     "divide2_blk16_esa_neg_badrange": dict(recalc=dict(blksize=8, overlap=4, thsad=100, divide=2, smooth=1), comp=dict(thscd1=16000, thscd2=255)),
+    "dct1_blk8_p8": dict(recalc=dict(blksize=8, overlap=2, dct=3, thsad=30), comp=dict()),
 }
 
 

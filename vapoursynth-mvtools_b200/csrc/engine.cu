@@ -159,8 +159,6 @@ static void make_search_params(const mvb200_analyse_params *ap, SearchParams *P)
 }
 
 static int check_analyse(const mvb200_analyse_params *ap, const mvb200_super_params *sp) {
-    if (ap->dctmode >= 1 && ap->dctmode <= 4)
-        return set_error("Analyse: dct=%d (FFTW DCT modes 1..4) is not implemented by the B200 engine; use dct=0 or the SATD modes 5..10", ap->dctmode);
     if (ap->ad.nLvCount > kDevMaxLevels)
         return set_error("Analyse: more than %d levels are not supported on the device", kDevMaxLevels);
     if (ap->super_pel != sp->pel || ap->super_hpad != sp->hpad || ap->super_vpad != sp->vpad || ap->ad.bitsPerSample != sp->bits)
@@ -647,8 +645,6 @@ int mvb200_compensate_frame(mvb200_ctx *ctx, const mvb200_compensate_params *cp,
 }
 
 int mvb200_recalculate_frame(mvb200_ctx *ctx, const mvb200_recalculate_params *rp, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *old_vectors, int field_shift, uint8_t *vectors_out) {
-    if (rp->dctmode >= 1 && rp->dctmode <= 4)
-        return set_error("Recalculate: dct=%d (FFTW DCT modes 1..4) is not implemented by the B200 engine; use dct=0 or the SATD modes 5..10", rp->dctmode);
     if (check_levels(sp))
         return 1;
     Ctx *c = &ctx->c;
@@ -685,6 +681,10 @@ int mvb200_recalculate_frame(mvb200_ctx *ctx, const mvb200_recalculate_params *r
     P.pnew = rp->pnew;
     P.smooth = rp->smooth;
     P.dctmode = rp->dctmode;
+    P.bits = sp->bits;
+    P.dct_cos = nullptr;
+    P.dct_scratch = nullptr;
+    P.dct_scratch_stride = 0;
     P.divide = rp->divide;
     P.thSAD = rp->thSAD;
     P.verybigSAD = (long long)ad.nBlkSizeX * ad.nBlkSizeY * (1LL << ad.bitsPerSample);

@@ -54,6 +54,11 @@ struct SearchParams {
     int level_off[kDevMaxLevels]; // byte offset of level l's size header inside the blob
     int vectors_size;
     long long verybigSAD;
+    // dct 1..4 (DCTFFTW.cpp): cosine tables (blkW^2 then blkH^2 floats) and the per-chain scratch
+    // (blkW*blkH floats of row-pass results + blkW*blkH ints holding the source block's DCT image)
+    const float *dct_cos;
+    uint8_t *dct_scratch;
+    long long dct_scratch_stride;
 };
 
 // One search chain = one (analyse instance, frame): walked by one warp.
@@ -72,6 +77,10 @@ struct RecalcParams {
     long long thSAD, verybigSAD;
     int nBlkX, nBlkY, vectors_size;
     int oBlkX, oBlkY, oBlkW, oBlkH, oOvX, oOvY, oLogPel; // geometry of the OLD vector field (its finest level)
+    int bits;
+    const float *dct_cos; // as in SearchParams; the scratch is per (block, frame) here
+    uint8_t *dct_scratch;
+    long long dct_scratch_stride;
 };
 struct RecalcJob {
     const uint8_t *src, *ref; // super frames (ref may be null)

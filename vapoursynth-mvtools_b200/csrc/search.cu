@@ -27,6 +27,9 @@
 // with round-to-nearest and C truncation; the file is compiled with -fmad=false.
 #include "search_common.cuh"
 
+#include <cmath>
+#include <vector>
+
 #include <cstdlib>
 
 namespace mvb200 {
@@ -58,6 +61,11 @@ struct State {
     const uint8_t *pSrc[3];
     int srcLuma, badcount;
     int lane;
+    // dct 1..4
+    const float *dcx, *dcy; // dcx[k * blkW + j] = (float)(2 cos(pi (2j + 1) k / (2 blkW)))
+    float *dtmp;            // blkW * blkH row-pass results
+    int *dsrc;              // the source block's DCT image
+    int dctshift, bits;
 };
 
 // ------------------------------------------------------------------ pixels
@@ -172,7 +180,54 @@ __device__ __forceinline__ const uint8_t *ref_chroma(const State &S, int p, int 
     return pel_ptr(S.ref[p], S.bps, S.logPel, (S.x[p] << S.logPel) + ((vx + xbias) >> S.logxR), (S.y[p] << S.logPel) + ((vy + ybias) >> S.logyR));
 }
 
-// pobLumaSAD<dctmode>, PlaneOfBlocks.cpp:117-203 (dct 0 and the SATD modes 5..10)
+// dctBytes2D, DCTFFTW.cpp:200-208, by one warp: Pixels2Float, FFTW's REDFT10 x REDFT10 evaluated from its definition
+// (unnormalised DCT-II, rows then columns, float dot products in index order, no FMA -- the same arithmetic as the
+// oracle and as the FFTW stand-in the reference is built with here; against the real FFTW: float rounding, "parity
+// unpinned"), Float2Pixels_C (:31-54).  is_src: the DCT image is stored (S.dsrc); otherwise it is compared
+// with the stored one on the fly: returns this lane's part of SAD(dctSrc, dctRef), and |DC difference| in dc (lane 0).
+__device__ unsigned dct_block(State &S, const uint8_t *p, long long pitch, bool is_src, unsigned &dc) {
+    const int nx = S.blkW, ny = S.blkH, n = nx * ny, lx = 31 - __clz(nx), ly = 31 - __clz(ny);
+    for (int idx = S.lane; idx < n; idx += 32) { // rows: tmp[i][k] = sum_j x[i][j] cx[k][j]
+        const int i = idx >> lx, k = idx & (nx - 1);
+        const uint8_t *row = p + i * pitch;
+        const float *c = S.dcx + k * nx;
+        float acc = 0.f;
+        for (int j = 0; j < nx; j++) {
+            const float x = (float)(S.bps == 1 ? (int)row[j] : (int)((const uint16_t *)row)[j]);
+            acc = __fadd_rn(acc, __fmul_rn(x, c[j]));
+        }
+        S.dtmp[idx] = acc;
+    }
+    __syncwarp();
+    const int pixelMax = (1 << S.bits) - 1, pixelHalf = 1 << (S.bits - 1);
+    unsigned sad = 0;
+    dc = 0;
+    for (int idx = S.lane; idx < n; idx += 32) { // columns: y[k][j] = sum_i tmp[i][j] cy[k][i]
+        const int k = idx >> lx, j = idx & (nx - 1);
+        const float *c = S.dcy + k * ny;
+        float acc = 0.f;
+        for (int i = 0; i < ny; i++)
+            acc = __fadd_rn(acc, __fmul_rn(S.dtmp[(i << lx) + j], c[i]));
+        int v;
+        if (idx == 0) // DC (:50-53)
+            v = min(pixelMax, max(0, (__float2int_rn(__fmul_rn(acc, 0.5f)) >> (S.dctshift + 2)) + pixelHalf));
+        else
+            v = min(pixelMax, max(0, (__float2int_rn(__fmul_rn(acc, 0.70710678118654752440084436210485f)) >> S.dctshift) + pixelHalf));
+        if (is_src) {
+            S.dsrc[idx] = v;
+        } else {
+            const unsigned d = (unsigned)abs(S.dsrc[idx] - v);
+            sad += d;
+            if (idx == 0)
+                dc = d;
+        }
+    }
+    (void)ly;
+    __syncwarp();
+    return sad;
+}
+
+// pobLumaSAD<dctmode>, PlaneOfBlocks.cpp:117-203
 __device__ long long luma_sad(State &S, const uint8_t *pRef) {
     long long sp = S.src[0].pitch, rp = S.ref[0].pitch;
     int d = S.dctmode;
@@ -181,6 +236,29 @@ __device__ long long luma_sad(State &S, const uint8_t *pRef) {
     long long sad = wsum(lane_sad(S.pSrc[0], sp, pRef, rp, S.blkW * S.bps, S.blkH, S.bps, S.lane));
     if (d == 0)
         return sad;
+    if (d <= 4) { // the FFTW DCT modes (:123-163)
+        if (d == 1 || (d == 2 && S.dctweight16 > 0)) {
+            unsigned dc;
+            unsigned part = dct_block(S, pRef, rp, false, dc);
+            const unsigned tot = wsum(part) + 3u * wsum(dc);
+            const long long dctsad = (long long)tot * (long long)S.blkW / 2;
+            if (d == 1)
+                return dctsad;
+            return (sad * (16 - S.dctweight16) + dctsad * S.dctweight16) / 16;
+        }
+        if (d == 2)
+            return sad;
+        int refLuma = (int)wsum(lane_luma(pRef, rp, S.blkW * S.bps, S.blkH, S.bps, S.lane));
+        if (abs(S.srcLuma - refLuma) > ((S.srcLuma + refLuma) >> 5)) {
+            unsigned dc;
+            const long long dctsad = (long long)wsum(dct_block(S, pRef, rp, false, dc)) * (long long)S.blkW / 2;
+            if (d == 3)
+                sad = sad / 2 + dctsad / 2;
+            else
+                sad = sad / 4 + dctsad / 2 + dctsad / 4;
+        }
+        return sad;
+    }
     if (d == 6) {
         if (S.dctweight16 > 0) {
             long long dctsad = wsum(lane_satd(S.pSrc[0], sp, pRef, rp, S.blkW, S.blkH, S.bps, S.lane));
@@ -514,6 +592,10 @@ __device__ long long full_sad_at(State &S, int lx, int ly, int cx, int cy) {
 // pobPseudoEPZSearch, PlaneOfBlocks.cpp:819-968
 __device__ void epz_search(State &S) {
     fetch_predictors(S);
+    if (S.dctmode >= 1 && S.dctmode <= 4) { // make dct of source block (:824-828 / :1336-1338)
+        unsigned dc;
+        dct_block(S, S.pSrc[0], S.src[0].pitch, true, dc);
+    }
     if (S.dctmode >= 3)
         S.srcLuma = (int)wsum(lane_luma(S.pSrc[0], S.src[0].pitch, S.blkW * S.bps, S.blkH, S.bps, S.lane));
 
@@ -722,6 +804,14 @@ __global__ void __launch_bounds__(32) k_search(const SuperDesc *__restrict__ sdp
     S.dctmode = P.dctmode;
     S.verybigSAD = P.verybigSAD;
     S.srcLuma = 0;
+    S.bits = P.bits;
+    S.dcx = P.dct_cos;
+    S.dcy = P.dct_cos ? P.dct_cos + P.blkW * P.blkW : nullptr;
+    S.dtmp = (float *)(P.dct_scratch + (long long)chain * P.dct_scratch_stride);
+    S.dsrc = (int *)(S.dtmp + P.blkW * P.blkH);
+    S.dctshift = 0;
+    while ((1 << S.dctshift) < P.blkW * P.blkH) // dctInit, DCTFFTW.cpp:142-149
+        S.dctshift++;
 
     for (int l = L - 1; l >= 0; l--) {
         S.nBlkX = P.nBlkX[l];
@@ -811,6 +901,14 @@ __global__ void __launch_bounds__(32) k_recalc(const SuperDesc *__restrict__ sdp
     S.ch = P.blkH >> sd.logyR;
     S.dctmode = P.dctmode;
     S.dctweight16 = 8; // :1166
+    S.bits = P.bits;
+    S.dcx = P.dct_cos;
+    S.dcy = P.dct_cos ? P.dct_cos + P.blkW * P.blkW : nullptr;
+    S.dtmp = (float *)(P.dct_scratch + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * P.dct_scratch_stride);
+    S.dsrc = (int *)(S.dtmp + P.blkW * P.blkH);
+    S.dctshift = 0;
+    while ((1 << S.dctshift) < P.blkW * P.blkH)
+        S.dctshift++;
     S.verybigSAD = P.verybigSAD;
     S.vectors = res;
     S.searchType = P.search;
@@ -868,6 +966,10 @@ __global__ void __launch_bounds__(32) k_recalc(const SuperDesc *__restrict__ sdp
     S.predictor = clipmv(S, vo);
     S.predictor.sad = vo.sad * (P.blkW * P.blkH) / (P.oBlkW * P.oBlkH);
     S.bestMV = S.predictor;
+    if (S.dctmode >= 1 && S.dctmode <= 4) { // make dct of source block (:824-828 / :1336-1338)
+        unsigned dc;
+        dct_block(S, S.pSrc[0], S.src[0].pitch, true, dc);
+    }
     if (S.dctmode >= 3)
         S.srcLuma = (int)wsum(lane_luma(S.pSrc[0], S.src[0].pitch, S.blkW * S.bps, S.blkH, S.bps, S.lane));
     const long long sad = full_sad_at(S, S.predictor.x, S.predictor.y, S.predictor.x, S.predictor.y);
@@ -909,23 +1011,63 @@ __global__ void k_recalc_divide(const RecalcParams *__restrict__ pp, const Recal
 
 } // namespace
 
-int launch_search(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &geom, const uint8_t *frames_base, int nframes, const SearchParams *host_params, int nparams, const SearchJob *host_jobs, int njobs) {
+// cosine tables of the DCT modes: cx (w*w) then cy (h*h), t[k * n + i] = (float)(2 cos(pi (2i + 1) k / (2n))) evaluated in
+// double on the host, exactly like the oracle and the FFTW stand-in (oracle/shim/fftw_shim.c)
+static void dct_tables(int w, int h, std::vector<float> &t) {
+    t.resize((size_t)w * w + (size_t)h * h);
+    for (int pass = 0; pass < 2; pass++) {
+        const int n = pass ? h : w;
+        float *o = t.data() + (pass ? (size_t)w * w : 0);
+        for (int k = 0; k < n; k++)
+            for (int i = 0; i < n; i++)
+                o[k * n + i] = (float)(2.0 * cos(M_PI * (2.0 * i + 1.0) * k / (2.0 * n)));
+    }
+}
+
+int launch_search(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &geom, const uint8_t *frames_base, int nframes, const SearchParams *host_params_in, int nparams, const SearchJob *host_jobs, int njobs) {
     if (njobs <= 0)
         return 0;
     const int hist_ints = 8192 * 2;
+    std::vector<SearchParams> params_copy(host_params_in, host_params_in + nparams);
+    SearchParams *host_params = params_copy.data();
+    bool any_dct = false;
+    for (int i = 0; i < nparams; i++)
+        any_dct = any_dct || (host_params[i].dctmode >= 1 && host_params[i].dctmode <= 4);
+    std::vector<float> cos_tab;
+    size_t bytes_cos = 0;
+    if (any_dct) { // all instances of a launch share the block size (checked by the callers' similarity rules; enforce)
+        for (int i = 1; i < nparams; i++)
+            if (host_params[i].blkW != host_params[0].blkW || host_params[i].blkH != host_params[0].blkH)
+                return set_error("mvtools_b200: dct 1..4 instances of one launch must share the block size");
+        dct_tables(host_params[0].blkW, host_params[0].blkH, cos_tab);
+        bytes_cos = cos_tab.size() * sizeof(float);
+    }
     size_t bytes_sd = sizeof(SuperDesc), bytes_p = sizeof(SearchParams) * (size_t)nparams, bytes_j = sizeof(SearchJob) * (size_t)njobs;
-    size_t off_p = (bytes_sd + 255) & ~(size_t)255, off_j = (off_p + bytes_p + 255) & ~(size_t)255, total = off_j + bytes_j;
+    size_t off_p = (bytes_sd + 255) & ~(size_t)255, off_j = (off_p + bytes_p + 255) & ~(size_t)255, off_c = (off_j + bytes_j + 255) & ~(size_t)255, total = off_c + bytes_cos;
     uint8_t *host = (uint8_t *)ctx->get_pinned(total);
     uint8_t *dev = (uint8_t *)ctx->get_scratch(0, total);
     int *hist = (int *)ctx->get_scratch(1, sizeof(int) * (size_t)hist_ints * (size_t)njobs);
     if (!host || !dev || !hist)
         return 1;
+    if (any_dct) {
+        const long long stride = (long long)host_params[0].blkW * host_params[0].blkH * 8;
+        uint8_t *scr = (uint8_t *)ctx->get_scratch(7, (size_t)stride * njobs);
+        if (!scr)
+            return 1;
+        for (int i = 0; i < nparams; i++) {
+            host_params[i].dct_cos = (const float *)(dev + off_c);
+            host_params[i].dct_scratch = scr;
+            host_params[i].dct_scratch_stride = stride;
+        }
+    }
     // the pinned staging buffer is reused from call to call: wait until the previous upload out of it is done
     if (ctx->staging_wait())
         return 1;
     memcpy(host, &sd, bytes_sd);
     memcpy(host + off_p, host_params, bytes_p);
     memcpy(host + off_j, host_jobs, bytes_j);
+    if (bytes_cos)
+        memcpy(host + off_c, cos_tab.data(), bytes_cos);
     MVB_CUDA_CHECK(cudaMemcpyAsync(dev, host, total, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->staging_posted())
         return 1;
@@ -950,20 +1092,37 @@ int launch_search(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &geom, 
     return 0;
 }
 
-int launch_recalc(Ctx *ctx, const SuperDesc &sd, const RecalcParams &P, const RecalcJob *host_jobs, int njobs) {
+int launch_recalc(Ctx *ctx, const SuperDesc &sd, const RecalcParams &P_in, const RecalcJob *host_jobs, int njobs) {
     if (njobs <= 0)
         return 0;
+    RecalcParams P = P_in;
+    const bool dct = P.dctmode >= 1 && P.dctmode <= 4;
+    std::vector<float> cos_tab;
+    if (dct)
+        dct_tables(P.blkW, P.blkH, cos_tab);
+    const size_t bytes_cos = cos_tab.size() * sizeof(float);
     size_t bytes_sd = sizeof(SuperDesc), bytes_p = sizeof(RecalcParams), bytes_j = sizeof(RecalcJob) * (size_t)njobs;
-    size_t off_p = (bytes_sd + 255) & ~(size_t)255, off_j = (off_p + bytes_p + 255) & ~(size_t)255, total = off_j + bytes_j;
+    size_t off_p = (bytes_sd + 255) & ~(size_t)255, off_j = (off_p + bytes_p + 255) & ~(size_t)255, off_c = (off_j + bytes_j + 255) & ~(size_t)255, total = off_c + bytes_cos;
     uint8_t *host = (uint8_t *)ctx->get_pinned(total);
     uint8_t *dev = (uint8_t *)ctx->get_scratch(0, total);
     if (!host || !dev)
         return 1;
+    if (dct) {
+        const long long stride = (long long)P.blkW * P.blkH * 8;
+        uint8_t *scr = (uint8_t *)ctx->get_scratch(7, (size_t)stride * P.nBlkX * P.nBlkY * njobs);
+        if (!scr)
+            return 1;
+        P.dct_cos = (const float *)(dev + off_c);
+        P.dct_scratch = scr;
+        P.dct_scratch_stride = stride;
+    }
     if (ctx->staging_wait())
         return 1;
     memcpy(host, &sd, bytes_sd);
     memcpy(host + off_p, &P, bytes_p);
     memcpy(host + off_j, host_jobs, bytes_j);
+    if (bytes_cos)
+        memcpy(host + off_c, cos_tab.data(), bytes_cos);
     MVB_CUDA_CHECK(cudaMemcpyAsync(dev, host, total, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->staging_posted())
         return 1;
