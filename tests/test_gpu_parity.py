@@ -192,6 +192,72 @@ def test_full_size_1080p_properties(gpu_ctx):
         assert np.array_equal(out[p], od[p])
 
 
+def test_full_size_4k_p16_degrain3_properties(gpu_ctx):
+    """BASELINE.json configs[4] geometry (3840x2160 P16, blk 16 ov 8, Degrain3) on a short clip: batch path,
+    properties, and one frame of every stage against the oracle at full size."""
+    import clipgen
+    import oracle
+    W, H, N = 3840, 2160, 7
+    base = clipgen.make_clip(W, H, 4, bits=16, scene_cut=False)
+    frames = [base[0], base[1], base[2], base[3], base[3], base[2], base[1]]  # frames 3, 4 identical
+    sp = mb.super_params(W, H, 16, 1, 1, pel=2)
+    aps = [mb.analyse_params(sp, N, isb=isb, delta=d, blksize=16, overlap=8) for d in (1, 2, 3) for isb in (1, 0)]
+    dp = mb.degrain_params(sp, [a.ad for a in aps], W, H, 3)
+    sup, vecs, dst, cl, sl = _run_batch(gpu_ctx, sp, aps, dp, frames)
+    ap = aps[0]
+    n0 = ap.nBlkX[0] * ap.nBlkY[0]
+    assert (ap.nBlkX[0], ap.nBlkY[0]) == (479, 269)  # SURVEY.md 8, C5
+    # static pair: frame 3 backward (-> 4) has all-zero vectors and SADs at the finest level
+    blob = vecs[0][3][: ap.vectors_size]
+    lvl0 = np.frombuffer(blob[ap.vectors_size - n0 * 16:].tobytes(), dtype=np.int32).reshape(n0, 4)
+    assert not lvl0.any()
+    # validity: delta-3 forward vectors of frames 0..2 have no reference
+    for n in range(N):
+        want = 1 if n >= 3 else 0
+        assert np.frombuffer(vecs[5][n][:8].tobytes(), dtype=np.int32).tolist() == [ap.vectors_size, want]
+    # one frame of each stage against the oracle (frame 3: all six references exist)
+    n = 3
+    osup = {k: oracle.super_frame(sp, frames[k]) for k in range(N)}
+    for p in range(3):
+        assert np.array_equal(_planes(sup[n], sl)[p], osup[n][p])
+    ov = []
+    for i, a in enumerate(aps):
+        r = pipeline.nref_of(a, n, N)
+        ov.append(oracle.analyse_frame(a, sp, osup[n], osup[r]))
+        assert np.array_equal(vecs[i][n][: a.vectors_size], ov[i]), "vectors of instance %d" % i
+    od = oracle.degrain_frame(dp, sp, frames[n], [osup[pipeline.nref_of(a, n, N)] for a in aps], ov)
+    out = _planes(dst[n], cl)
+    for p in range(3):
+        assert np.array_equal(out[p], od[p])
+
+
+def test_full_size_4k_satd_recalculate_compensate(gpu_ctx):
+    """BASELINE.json configs[3] (3840x2160 P8: Analyse with SATD -- dct=5 in the reference's numbering --, Recalculate,
+    Compensate) through the per-frame entry points, against the oracle at full size."""
+    import clipgen
+    import oracle
+    W, H, N = 3840, 2160, 2
+    frames = clipgen.make_clip(W, H, N, bits=8, scene_cut=False)
+    sp = mb.super_params(W, H, 8, 1, 1, pel=2)
+    ap = mb.analyse_params(sp, N, isb=1, delta=1, dct=5)
+    rp = mb.recalculate_params(sp, ap.ad, N, blksize=8, overlap=4, thsad=120, dct=5)
+    cp = mb.compensate_params(sp, rp.ad, W, H, N)
+    gs = [gpu_ctx.super_frame(sp, f) for f in frames]
+    os_ = [oracle.super_frame(sp, f) for f in frames]
+    for a, b in zip(gs[0], os_[0]):
+        assert np.array_equal(a, b)
+    gv = gpu_ctx.analyse_frame(ap, sp, gs[0], gs[1])
+    ov = oracle.analyse_frame(ap, sp, os_[0], os_[1])
+    assert np.array_equal(gv, ov)
+    gr = gpu_ctx.recalculate_frame(rp, sp, gs[0], gs[1], gv)
+    orr = oracle.recalculate_frame(rp, sp, os_[0], os_[1], ov)
+    assert np.array_equal(pipeline.mask_recalc_blob(gr, rp), pipeline.mask_recalc_blob(orr, rp))
+    gc = gpu_ctx.compensate_frame(cp, sp, gs[0], gs[1], gr)
+    oc = oracle.compensate_frame(cp, sp, os_[0], os_[1], orr)
+    for a, b in zip(gc, oc):
+        assert np.array_equal(a, b)
+
+
 def test_smoke_entry(built):
     import __graft_entry__
     __graft_entry__.smoke()
