@@ -161,6 +161,7 @@ def run_gpu_arm(args):
     plan = sharding.local_plan(world * args.frames, world, rank, reach=RADIUS * 1)
     F_out = plan["count"]
     F = plan["local_frames"]
+    OFF = plan["offset"]
     sp = mb.super_params(WIDTH, HEIGHT, BITS, 1, 1, pel=PEL)
     aps = [mb.analyse_params(sp, F, isb=isb, delta=d, blksize=BLK, overlap=OVERLAP) for d in range(1, RADIUS + 1) for isb in (1, 0)]
     dp = mb.degrain_params(sp, [a.ad for a in aps], WIDTH, HEIGHT, RADIUS)
@@ -195,10 +196,11 @@ def run_gpu_arm(args):
         mb._check(L.mvb200_super_batch(ctx.handle, C.byref(sp), dsrc.data_ptr(), dsup.data_ptr(), F))
         if timers is not None:
             timers[1].record(stream)
-        mb._check(L.mvb200_analyse_multi_batch(ctx.handle, apa, len(aps), C.byref(sp), dsup.data_ptr(), 0, F, outs, vs))
+        # vectors and output only for this rank's own frames; the halo frames are references (their super frames above)
+        mb._check(L.mvb200_analyse_multi_batch(ctx.handle, apa, len(aps), C.byref(sp), dsup.data_ptr(), OFF, F_out, outs, vs))
         if timers is not None:
             timers[2].record(stream)
-        mb._check(L.mvb200_degrain_batch(ctx.handle, C.byref(dp), C.byref(sp), dsrc.data_ptr(), dsup.data_ptr(), F, 0, F, outs, vs, ddst.data_ptr()))
+        mb._check(L.mvb200_degrain_batch(ctx.handle, C.byref(dp), C.byref(sp), dsrc.data_ptr(), dsup.data_ptr(), F, OFF, F_out, outs, vs, ddst.data_ptr()))
         if timers is not None:
             timers[3].record(stream)
 
@@ -249,7 +251,7 @@ def run_gpu_arm(args):
     def e2e_step():
         o = host_outs[e2e_calls[0] & 1]
         e2e_calls[0] += 1
-        mb._check(L.mvb200_degrain_clip_host_async(ctx.handle, C.byref(sp), apa, len(aps), C.byref(dp), host.data_ptr(), o.data_ptr(), F))
+        mb._check(L.mvb200_degrain_clip_host_async(ctx.handle, C.byref(sp), apa, len(aps), C.byref(dp), host.data_ptr(), o.data_ptr(), F, OFF, F_out))
 
     for _ in range(max(2, args.warmup)):
         e2e_step()
@@ -267,7 +269,7 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     e2e_value = world * F_out * args.steps / (e2e_ms / 1e3)
-    checksum = int(host_out.numpy()[:, ::4099].astype(np.uint64).sum())
+    checksum = int(host_out.numpy()[:F_out, ::4099].astype(np.uint64).sum())
     if world > 1:  # the only collective of the job: reassemble the sharded clip's output planes (here: a digest of them)
         t = torch.tensor([checksum % (1 << 53)], dtype=torch.float64, device="cuda")
         g = [torch.zeros_like(t) for _ in range(world)]
@@ -283,7 +285,7 @@ def run_gpu_arm(args):
     S = (PEL * PEL + 1.0 / 3.0) * A          # reference side: the whole super frame
     S1 = (1 + 1.0 / 3.0) * A                  # source side: plane 0 of every level
     V = aps[0].vectors_size
-    alg_bytes = len(aps) * F * (S1 + S + V)
+    alg_bytes = len(aps) * F_out * (S1 + S + V)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -297,7 +299,7 @@ def run_gpu_arm(args):
         prof = json.load(open(os.path.join(ROOT, "profiles", NCU_PROFILE)))
         rd = prof["dram__bytes_read.sum"]; wr = prof["dram__bytes_write.sum"]
         tobytes = lambda m: m["value"] * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[m["unit"]]
-        traffic = (tobytes(rd) + tobytes(wr)) / prof["_chains"] * len(aps) * F
+        traffic = (tobytes(rd) + tobytes(wr)) / prof["_chains"] * len(aps) * F_out
         # the bound that actually binds a latency-serial integer search: issue slots / the integer ALU pipe (same capture)
         int_pipe = {"alu_pipe_active_pct_of_peak": prof["sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"]["value"],
                     "issue_active_pct_of_peak": prof["smsp__issue_active.avg.pct_of_peak_sustained_active"]["value"],
@@ -309,10 +311,10 @@ def run_gpu_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": region_ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": F_out, "halo_frames_per_gpu": F - F_out, "distinct_frames": DISTINCT,
-                   "search_chains_per_step_per_gpu": len(aps) * F,
+                   "search_chains_per_step_per_gpu": len(aps) * F_out,
                    "l2": "inputs larger than L2 (%d MB of super frames + vectors per step vs 126 MB L2), no flush" % int(F * (sl.frame_bytes + 6 * vs) / 1e6),
                    "stage_ms": {"super": super_ms, "analyse_x6": search_ms, "degrain3": degrain_ms}},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(F * cl.frame_bytes), "d2h_bytes_per_step": int(F * cl.frame_bytes),
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(F * cl.frame_bytes), "d2h_bytes_per_step": int(F_out * cl.frame_bytes),
                 "output_digest": checksum},
         "gpu_launches": int(launches),
         "clocks": clocks,

@@ -277,13 +277,15 @@ MVB200_API int mvb200_degrain_batch(mvb200_ctx *ctx, const mvb200_degrain_params
 
 /* Host-buffer clip pipeline: mv.Super + nap x mv.Analyse + mv.DegrainN (nap == 2 * radius) over a whole
  * segment of n frames held in HOST memory in the clip layout (mvb200_clip_layout; frames frame_bytes
- * apart; use pinned memory for truly asynchronous copies).  Replaces, for a segment, the
+ * apart; use pinned memory for truly asynchronous copies); frames [first, first + count) are denoised into
+ * host_dst (count frames), the rest of the segment only serves as references (the halo of a sharded clip:
+ * vapoursynth-mvtools_b200/sharding.py).  Replaces, for a segment, the
  * mvsuperGetFrame / mvanalyseGetFrame / mvdegrainGetFrame calls a frame server would make per frame
  * (MVSuper.c:43-126, MVAnalyse.c:76-254, MVDegrains.cpp:85-330).  ASYNCHRONOUS: returns once the copies
  * and kernels are enqueued; host_dst is valid after mvb200_ctx_synchronize().  Consecutive calls
  * overlap (H2D of segment k+1 and D2H of segment k-1 beside the kernels of segment k). */
 MVB200_API int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap,
-                                              const mvb200_degrain_params *dp, const void *host_src, void *host_dst, int n);
+                                              const mvb200_degrain_params *dp, const void *host_src, void *host_dst, int n, int first, int count);
 
 /* --------------------------------------------- host-buffer per-frame entry points */
 /* (what the VapourSynth plugin calls from GetFrame; H2D/D2H copies inside) */

@@ -363,16 +363,19 @@ int mvb200_degrain_batch(mvb200_ctx *ctx, const mvb200_degrain_params *dp, const
 
 // ------------------------------------------------ host-buffer clip pipeline
 // Super + nap x Analyse + DegrainN over a whole segment of n frames in HOST memory (clip layout, frames
-// frame_bytes apart; pinned memory for truly asynchronous copies).  Asynchronous: the call returns when the
+// frame_bytes apart; pinned memory for truly asynchronous copies); frames [first, first + count) are denoised
+// into host_dst (count frames), the others only serve as references (the halo of a sharded clip).  Asynchronous: the call returns when the
 // work is enqueued; host_dst is valid after mvb200_ctx_synchronize().  Consecutive calls overlap: the H2D copy
 // of segment k+1 and the D2H copy of segment k-1 run on their own streams beside the kernels of segment k
 // (source / output clips are double buffered on the device).
 int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const mvb200_degrain_params *dp,
-                                   const void *host_src, void *host_dst, int n) {
+                                   const void *host_src, void *host_dst, int n, int first, int count) {
     if (check_levels(sp))
         return 1;
-    if (n <= 0)
+    if (n <= 0 || count <= 0)
         return 0;
+    if (first < 0 || first + count > n)
+        return set_error("mvtools_b200: output range [%d, %d) is outside the segment of %d frames", first, first + count, n);
     if (nap != dp->radius * 2)
         return set_error("mvtools_b200: Degrain%d needs %d vector clips, %d given", dp->radius, dp->radius * 2, nap);
     Ctx &c = ctx->c;
@@ -401,7 +404,7 @@ int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *s
     uint8_t *dsrc = (uint8_t *)c.get_scratch(8 + slot, clip_bytes);
     uint8_t *ddst = (uint8_t *)c.get_scratch(10 + slot, clip_bytes);
     uint8_t *dsup = (uint8_t *)c.get_scratch(12, (size_t)sd.frame_bytes * n);
-    uint8_t *dvec = (uint8_t *)c.get_scratch(13, (size_t)vstride * n * nap);
+    uint8_t *dvec = (uint8_t *)c.get_scratch(13, (size_t)vstride * count * nap);
     if (!dsrc || !ddst || !dsup || !dvec)
         return 1;
     if (before[0] != dsrc || before[1] != ddst || before[2] != dsup || before[3] != dvec)
@@ -417,17 +420,17 @@ int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *s
         MVB_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_d2h[slot], 0));
     std::vector<void *> outs((size_t)nap);
     for (int i = 0; i < nap; i++)
-        outs[i] = dvec + (size_t)vstride * n * i;
-    if (mvb200_super_batch(ctx, sp, dsrc, dsup, n))
+        outs[i] = dvec + (size_t)vstride * count * i;
+    if (mvb200_super_batch(ctx, sp, dsrc, dsup, n)) // every frame of the segment: the frames outside [first, first + count) are references
         return 1;
-    if (mvb200_analyse_multi_batch(ctx, ap, nap, sp, dsup, 0, n, outs.data(), vstride))
+    if (mvb200_analyse_multi_batch(ctx, ap, nap, sp, dsup, first, count, outs.data(), vstride))
         return 1;
-    if (mvb200_degrain_batch(ctx, dp, sp, dsrc, dsup, n, 0, n, (const void *const *)outs.data(), vstride, ddst))
+    if (mvb200_degrain_batch(ctx, dp, sp, dsrc, dsup, n, first, count, (const void *const *)outs.data(), vstride, ddst))
         return 1;
     MVB_CUDA_CHECK(cudaEventRecord(c.ev_compute[slot], c.stream));
     // D2H
     MVB_CUDA_CHECK(cudaStreamWaitEvent(c.copy_out, c.ev_compute[slot], 0));
-    MVB_CUDA_CHECK(cudaMemcpyAsync(host_dst, ddst, clip_bytes, cudaMemcpyDeviceToHost, c.copy_out));
+    MVB_CUDA_CHECK(cudaMemcpyAsync(host_dst, ddst, (size_t)cd.frame_bytes * count, cudaMemcpyDeviceToHost, c.copy_out));
     MVB_CUDA_CHECK(cudaEventRecord(c.ev_d2h[slot], c.copy_out));
     return 0;
 }
