@@ -69,6 +69,9 @@ def run(W, H, N, bits, radius, blk, ov, pel, check=True):
         print("  degrain match:", all(np.array_equal(a, b) for a, b in zip(gd, oo)))
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "prof":  # one 1080p P8 Degrain3 pass for ncu
+        run(1920, 1080, int(sys.argv[2]) if len(sys.argv) > 2 else 64, 8, 3, 16, 8, 2, check=False)
+        sys.exit(0)
     sys.path.insert(0, ROOT); import __graft_entry__ as g
     g.smoke()
     run(640, 360, 8, 8, 1, 8, 0, 1)

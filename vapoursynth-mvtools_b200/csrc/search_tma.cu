@@ -24,7 +24,13 @@
 #include <cuda.h>
 
 #ifndef MVB_TMA_MIN_BLOCKS
-#define MVB_TMA_MIN_BLOCKS 12 // caps registers at 168: the kernel needs ~170 to stay out of local memory (measured: 128 regs = spills in the block loop, 1.8x slower)
+#define MVB_TMA_MIN_BLOCKS 16 // chains (warps) per SM the compact configurations are built for: caps registers at 128
+#endif
+#ifndef MVB_TMA_MIN_BLOCKS_BIG
+#define MVB_TMA_MIN_BLOCKS_BIG 12 // 16-bit 16x16 blocks: shared memory allows 9 chains per SM anyway; 168 registers
+#endif
+#ifndef MVB_CLD
+#define MVB_CLD 1 // chroma windows of the 8-bit 16x16 configuration by LDGSTS into compact 16-byte rows (see Cfg::CLD)
 #endif
 
 namespace mvb200 {
@@ -136,8 +142,14 @@ struct Cfg {
     // "illegal instruction" on sm_100), rounded up to the 16-byte box granularity
     static constexpr int LWB = ((BW + 2 * R) * BPS + 15 + 15) / 16 * 16;
     static constexpr int LWH = BH + 2 * R;
-    static constexpr int CWB = ((CW + 2 * RCX) * BPS + 15 + 15) / 16 * 16;
+    // CLD: the chroma windows do not come by TMA but by 4-byte LDGSTS of all lanes, into rows that carry 3 bytes of
+    // alignment slack instead of 15.  For 8-bit 16x16 blocks that halves the chroma part of a window buffer and brings a
+    // chain's shared memory from 17.6 KB to 13.1 KB -- 16 chains per SM instead of 12 (228 KB, 1 KB reserved per CTA).
+    static constexpr bool CLD = MVB_CLD && CHROMA && BPS == 1 && BW == 16 && BH == 16;
+    static constexpr int CWB = CLD ? ((CW + 2 * RCX) * BPS + 3 + 3) / 4 * 4 : ((CW + 2 * RCX) * BPS + 15 + 15) / 16 * 16;
     static constexpr int CWH = CH + 2 * RCY;
+    static_assert(!CLD || (CWB == 16 && CWH == 12), "the LDGSTS lane mapping below is written for 16-byte x 12-row chroma windows");
+    static constexpr int MINB = (BPS == 2 && BW * BH >= 256) ? MVB_TMA_MIN_BLOCKS_BIG : MVB_TMA_MIN_BLOCKS;
     static constexpr int LT = LWB * LWH;               // bytes of one sub-plane's luma tile
     static constexpr int CT = CHROMA ? CWB * CWH : 0;  // ... chroma tile
     static constexpr int NSUB = 4;                     // pel <= 2
@@ -154,8 +166,8 @@ struct Cfg {
     static constexpr int SRCOFF = 2 * BUF;                                   // [src 0][src 1]
     static constexpr int VECOFF = SRCOFF + 2 * SRCB;                          // hier[2], up, p3: 4 x 16 bytes
     static constexpr int COLDOFF = VECOFF + 64, BAROFF = COLDOFF + 256;       // level constants, 2 mbarriers
-    static constexpr int RAWOFF = BAROFF + 64;                                // raw lo/hi words of an unaligned source block (optional)
-    static constexpr int SMEM = RAWOFF + 128, SMEM_RAW = SMEM + r128(8 * SRCW);
+    static constexpr int RAWOFF = BAROFF + 16;                                // raw lo/hi words of an unaligned source block (optional)
+    static constexpr int SMEM = r128(RAWOFF), SMEM_RAW = r128(RAWOFF + 8 * SRCW);
     static_assert(BH % 4 == 0 && (BW * BPS) % 4 == 0, "block shape");
     static_assert(!CHROMA || (CH % 4 == 0 && (CW * BPS) % 4 == 0), "chroma block shape");
 };
@@ -181,6 +193,7 @@ struct Cold {
     int penaltyZero, pglobal, badrange, searchType, searchParam;
     int gmx, gmy;  // globalMV (sticky clipping, :859)
     int wo[2][4];  // window origins of the two window buffers
+    int cxmax, cymin, cymax; // CLD: limits of a chroma window origin that keep every LDGSTS address inside the plane
 };
 static_assert(sizeof(Cold) <= 256, "Cold");
 
@@ -234,7 +247,15 @@ struct Chain {
         oyc = (((gg.yc << logPel) + cdiv(cy, LYR)) >> logPel) - C::RCY;
         // 16-byte aligned start of the innermost (x) coordinate, rounding toward -infinity
         ox = ((ox * BPS) & ~15) >> (BPS == 2 ? 1 : 0);
-        oxc = ((oxc * BPS) & ~15) >> (BPS == 2 ? 1 : 0);
+        if (C::CLD) {
+            // LDGSTS windows start on a 4-byte boundary and must lie inside the plane (TMA zero-fills what is outside,
+            // a plain load may not go there): a clamped window still serves every candidate it covers -- the rest
+            // takes the global-memory path like any other candidate outside its window
+            oxc = min(max(((oxc * BPS) & ~3) >> (BPS == 2 ? 1 : 0), 0), K->cxmax);
+            oyc = min(max(oyc, K->cymin), K->cymax);
+        } else {
+            oxc = ((oxc * BPS) & ~15) >> (BPS == 2 ? 1 : 0);
+        }
     }
 
     // Per-lane description of "my" candidate in a step
@@ -609,8 +630,8 @@ struct Chain {
 };
 
 template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
-__global__ void __launch_bounds__(32, MVB_TMA_MIN_BLOCKS) k_search_tma(const __grid_constant__ TmaMaps maps, const SuperDesc *__restrict__ sdp, const SearchParams *__restrict__ params,
-                                                   const SearchJob *__restrict__ jobs, int njobs, int *__restrict__ hist_all, int hist_ints) {
+__global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)) k_search_tma(const __grid_constant__ TmaMaps maps, const SuperDesc *__restrict__ sdp, const SearchParams *__restrict__ params,
+                                                   const SearchJob *__restrict__ jobs, int njobs, int *__restrict__ hist_all, int hist_ints, int chroma_rows) {
     using C = Cfg<BPS, BW, BH, LXR, LYR, CHROMA>;
     using CH = Chain<BPS, BW, BH, LXR, LYR, CHROMA>;
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -732,6 +753,12 @@ __global__ void __launch_bounds__(32, MVB_TMA_MIN_BLOCKS) k_search_tma(const __g
                 K.ref_frame = job.ref_index;
                 K.use4d = S.logPel == 1; // level 0 of a pel-2 clip: the 4-D maps (their row origin is level 0's row0)
                 K.smallest = (l == L - 1);
+                if (C::CLD) {
+                    const int nsub = S.logPel == 1 ? 4 : 1;
+                    K.cxmax = (int)sd.pitch[1] / BPS - C::CWB / BPS;
+                    K.cymin = -g1.row0;
+                    K.cymax = chroma_rows - g1.row0 - (nsub - 1) * g1.padded_h - C::CWH;
+                }
                 K.srcAligned = (((g0.hpad * BPS) | ((BW - P.ovX) * BPS) | (g1.hpad * BPS) | (((BW - P.ovX) >> LXR) * BPS)) & 3) == 0;
                 K.penaltyZero = P.pzero;
                 K.pglobal = P.global ? P.pglobal : P.pzero;
@@ -877,19 +904,47 @@ __global__ void __launch_bounds__(32, MVB_TMA_MIN_BLOCKS) k_search_tma(const __g
                     K.wo[buf][k] = wo[k];
                 const uint32_t dst = smem0 + buf * C::BUF, bar = bar0 + 8 * buf;
                 const int ref_frame = K.ref_frame;
+                constexpr int TMA_CT = (CHROMA && !C::CLD) ? 2 * C::CT : 0; // chroma bytes per sub-plane that arrive by TMA
                 if (K.use4d) {
-                    mbar_expect_tx(bar, (uint32_t)(4 * (C::LT + 2 * C::CT)));
+                    mbar_expect_tx(bar, (uint32_t)(4 * (C::LT + TMA_CT)));
                     tma_load_4d(dst, &maps.plane4[0], wo[0], wo[1], 0, ref_frame, bar);
-                    if (CHROMA) {
+                    if (CHROMA && !C::CLD) {
                         tma_load_4d(dst + C::LREG, &maps.plane4[1], wo[2], wo[3], 0, ref_frame, bar);
                         tma_load_4d(dst + C::LREG + C::CREG, &maps.plane4[2], wo[2], wo[3], 0, ref_frame, bar);
                     }
                 } else {
-                    mbar_expect_tx(bar, (uint32_t)(C::LT + 2 * C::CT));
+                    mbar_expect_tx(bar, (uint32_t)(C::LT + TMA_CT));
                     tma_load_3d(dst, &maps.plane[0], wo[0], K.row0_0 + wo[1], ref_frame, bar);
-                    if (CHROMA) {
+                    if (CHROMA && !C::CLD) {
                         tma_load_3d(dst + C::LREG, &maps.plane[1], wo[2], K.row0_1 + wo[3], ref_frame, bar);
                         tma_load_3d(dst + C::LREG + C::CREG, &maps.plane[2], wo[2], K.row0_1 + wo[3], ref_frame, bar);
+                    }
+                }
+            }
+            if (C::CLD) {
+                // chroma windows: 16-byte rows, 12 rows per sub-plane, word w of a plane's window (sub-plane, row, column
+                // in that order) travels in lane w % 32: lane = (row within a group of 8) * 4 + column word.  The data is
+                // complete at the next cp.async.wait_all -- commit_src() at the end of the block, or the callers' own.
+                const int a = lane >> 2;
+                const int pitch1 = K.pitch1, sub1 = K.sub1;
+                const bool all = K.use4d; // level 0 of a pel-2 clip: four sub-planes, else one
+                const int off0 = a * pitch1;                                           // words 0..31: sub-plane 0 (and 2), rows 0..7
+                const int off1 = a < 4 ? off0 + 8 * pitch1 : off0 - 4 * pitch1 + sub1; // words 32..63: rows 8..11, then rows 0..3 of the next sub-plane
+                const int off2 = off0 + 4 * pitch1 + sub1;                             // words 64..95: rows 4..11 of sub-plane 1 (and 3)
+                const long long org = (long long)wo[3] * pitch1 + wo[2] * BPS + (lane & 3) * 4;
+#pragma unroll
+                for (int p = 0; p < 2; p++) {
+                    const uint8_t *gp = K.rbase[1 + p] + org;
+                    const uint32_t d = smem0 + buf * C::BUF + C::LREG + p * C::CREG + 4 * lane;
+                    cp_async4(d, gp + off0);
+                    if (all || a < 4)
+                        cp_async4(d + 128, gp + off1);
+                    if (all) {
+                        cp_async4(d + 256, gp + off2);
+                        gp += 2 * (long long)sub1;
+                        cp_async4(d + 384, gp + off0);
+                        cp_async4(d + 512, gp + off1);
+                        cp_async4(d + 640, gp + off2);
                     }
                 }
             }
@@ -913,6 +968,10 @@ __global__ void __launch_bounds__(32, MVB_TMA_MIN_BLOCKS) k_search_tma(const __g
             if (!smallest) {
                 const VEC h0 = read_vec(0);
                 stage(S.g, h0.x, h0.y, 0);
+                if (C::CLD) {
+                    cp_async_wait_all();
+                    __syncwarp();
+                }
             }
         }
         int cbuf = 0;
@@ -966,6 +1025,10 @@ __global__ void __launch_bounds__(32, MVB_TMA_MIN_BLOCKS) k_search_tma(const __g
                     S.predictor.sad = p0sad;
                     // the window centre depends on the previous block here: stage now (few blocks on this level)
                     stage(S.g, S.predictor.x, S.predictor.y, cbuf);
+                    if (C::CLD) {
+                        cp_async_wait_all();
+                        __syncwarp();
+                    }
                 }
                 const long long LSAD = K.LSAD;
                 double scale = __ddiv_rn((double)LSAD, (double)(LSAD + (S.predictor.sad >> 1)));
@@ -1070,7 +1133,7 @@ int launch_cfg(Ctx *ctx, const SuperDesc &sd, const uint8_t *frames_base, int nf
         MVB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
-    kern<<<njobs, 32, need_raw ? C::SMEM_RAW : C::SMEM, ctx->stream>>>(maps, dev_sd, dev_params, dev_jobs, njobs, hist, hist_ints);
+    kern<<<njobs, 32, need_raw ? C::SMEM_RAW : C::SMEM, ctx->stream>>>(maps, dev_sd, dev_params, dev_jobs, njobs, hist, hist_ints, geom.plane_h[CHROMA ? 1 : 0]);
     ctx->launches++;
     MVB_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmvtools_b200.so")
+LIB_PATH = os.path.join(_HERE, os.environ.get("MVB200_LIB", "libmvtools_b200.so"))  # MVB200_LIB: an experiment build (Makefile, V=)
 PLUGIN_PATH = os.path.join(_HERE, "libmvtools.so")
 
 UNSET = -(2 ** 31)
