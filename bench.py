@@ -34,7 +34,7 @@ import numpy as np  # noqa: E402
 
 WIDTH, HEIGHT, BITS = 1920, 1080, 8
 RADIUS, BLK, OVERLAP, PEL = 3, 16, 8, 2
-DISTINCT = 16  # distinct synthetic frames; the clip cycles through them (neighbours always differ)
+DISTINCT = 64  # a 64-frame synthetic clip (pan + moving rectangle + noise, one scene cut at frame 32); longer batches cycle through it
 WORKLOAD = ("mv.Super(pel=2) + 6x mv.Analyse(blksize=16, overlap=8, delta=1..3, isb=0/1) + mv.Degrain3, "
             "1920x1080 YUV420P8 (metric's Analyse+Degrain3 1080p P8 with configs[2]'s block geometry)")
 
@@ -42,10 +42,15 @@ WORKLOAD = ("mv.Super(pel=2) + 6x mv.Analyse(blksize=16, overlap=8, delta=1..3, 
 NCU_PROFILE = "r1_ncu_search_v5_1776chains.json"  # ncu --set full capture of the search kernel the traffic / pipe numbers come from
 
 
+_BASE_CLIP = None
+
+
 def make_frames(n):
-    import clipgen
-    base = clipgen.make_clip(WIDTH, HEIGHT, DISTINCT, bits=BITS, seed=0)
-    return [base[i % DISTINCT] for i in range(n)]
+    global _BASE_CLIP
+    if _BASE_CLIP is None:
+        import clipgen
+        _BASE_CLIP = clipgen.make_clip(WIDTH, HEIGHT, DISTINCT, bits=BITS, seed=0)
+    return [_BASE_CLIP[i % DISTINCT] for i in range(n)]
 
 
 # ----------------------------------------------------------------- clocks
@@ -115,7 +120,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = max(16, min(2 * cores, 96))
+    sample = DISTINCT  # one whole cycle of the synthetic clip (both of its discontinuities: the scene cut and the wrap-around)
     times = []
     for _ in range(args.warmup):
         reference_fps(max(4, sample // 4), 0, cores)
@@ -328,7 +333,7 @@ def run_gpu_arm(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = max(8, min(cores, 48))
+        sample = DISTINCT  # one whole cycle of the synthetic clip, like the GPU arm's batch
         fps, err = reference_fps(sample, 4, cores)
         if fps is not None:
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "reference",
@@ -348,7 +353,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=592, help="frames per step per GPU (592 x 6 chains = 2 full waves of 12 warps x 148 SMs)")
+    ap.add_argument("--frames", type=int, default=1184, help="frames per step per GPU (1184 x 6 chains = 4 full rounds of 12 warps x 148 SMs)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -14,7 +14,7 @@ echo "== bench (b200 arm, default library)"
 timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 echo "bench exit $?"; cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
 for spec in "$@"; do   # name[:frames]
-    name=${spec%%:*}; frames=${spec#*:}; [ "$frames" = "$spec" ] && frames=592
+    name=${spec%%:*}; frames=${spec#*:}; [ "$frames" = "$spec" ] && frames=1184
     lib=libmvtools_b200_$name.so; [ "$name" = default ] && lib=libmvtools_b200.so
     MVB200_LIB=$lib timeout 300 python bench.py --no-cpu-baseline --frames $frames > gpurun_out/${TAG}_bench_${name}_$frames.json 2> gpurun_out/${TAG}_bench_${name}_$frames.err
     python - <<PY
@@ -26,13 +26,16 @@ except Exception as e:
     print("variant $name F=$frames FAILED", e); print(open("gpurun_out/${TAG}_bench_${name}_$frames.err").read()[-600:])
 PY
 done
+echo "== bench (reference arm)"
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
+cat gpurun_out/${TAG}_bench_ref.json
 echo "== ncu launch list of the bench command (not a bench value)"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 1 --warmup 1 --frames 296 --no-cpu-baseline > gpurun_out/${TAG}_launches_run.log 2>&1
 echo "launch list exit $?"
 echo "== ncu --set full: search kernel (one launch)"
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_search_tma -c 1 -f -o gpurun_out/${TAG}_prof_search \
-    python tools/gpu_prof.py ${PROF_FRAMES:-395} > gpurun_out/${TAG}_prof_search.log 2>&1
+    python tools/gpu_prof.py ${PROF_FRAMES:-296} > gpurun_out/${TAG}_prof_search.log 2>&1
 echo "search prof exit $?"
 find gpurun_out -size +40M -print -delete
 du -sh gpurun_out; ls -la gpurun_out | tail -25

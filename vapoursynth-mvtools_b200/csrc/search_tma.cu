@@ -24,13 +24,13 @@
 #include <cuda.h>
 
 #ifndef MVB_TMA_MIN_BLOCKS
-#define MVB_TMA_MIN_BLOCKS 16 // chains (warps) per SM the compact configurations are built for: caps registers at 128
+#define MVB_TMA_MIN_BLOCKS 12 // chains (warps) per SM: caps registers at 168 (16 chains at 128 registers measured slower: instruction-cache and LSU pressure)
 #endif
 #ifndef MVB_TMA_MIN_BLOCKS_BIG
 #define MVB_TMA_MIN_BLOCKS_BIG 12 // 16-bit 16x16 blocks: shared memory allows 9 chains per SM anyway; 168 registers
 #endif
 #ifndef MVB_CLD
-#define MVB_CLD 1 // chroma windows of the 8-bit 16x16 configuration by LDGSTS into compact 16-byte rows (see Cfg::CLD)
+#define MVB_CLD 0 // (experiment, measured slower) chroma windows of the 8-bit 16x16 configuration by LDGSTS into compact 16-byte rows (see Cfg::CLD)
 #endif
 
 namespace mvb200 {
@@ -161,7 +161,10 @@ struct Cfg {
     static constexpr int LBYTES = BW * BH * BPS, CBYTES = CHROMA ? CW * CH * BPS : 0;
     static constexpr int SRCW = (LBYTES + 2 * CBYTES) / 4, NSI = (SRCW + 31) / 32; // source block words, per lane for the cooperative load
     static constexpr bool PACK = BPS == 1 && BW * BH <= 256 && 2 * CW * CH <= 256;
-    static constexpr bool SRC_SMEM = BPS == 2 && BW * BH >= 256; // too many registers: read source rows from shared memory
+#ifndef MVB_SRC_SMEM
+#define MVB_SRC_SMEM 0
+#endif
+    static constexpr bool SRC_SMEM = MVB_SRC_SMEM || (BPS == 2 && BW * BH >= 256); // too many registers: read source rows from shared memory
     static constexpr int SRCB = r128(LBYTES + 2 * CBYTES);                   // one source-block buffer
     static constexpr int SRCOFF = 2 * BUF;                                   // [src 0][src 1]
     static constexpr int VECOFF = SRCOFF + 2 * SRCB;                          // hier[2], up, p3: 4 x 16 bytes
@@ -196,6 +199,17 @@ struct Cold {
     int cxmax, cymin, cymax; // CLD: limits of a chroma window origin that keep every LDGSTS address inside the plane
 };
 static_assert(sizeof(Cold) <= 256, "Cold");
+
+#ifndef MVB_FALLBACK_NOINLINE
+#define MVB_FALLBACK_NOINLINE 0
+#endif
+
+struct Cold;
+// The global-memory path of a step as a real function (MVB_FALLBACK_NOINLINE): it runs for a few percent of the
+// steps but, inlined, sits in the middle of every step's code.  Source rows come from the shared-memory copy of the
+// source block, so the call passes a handful of scalars.  Returns sadY | sadUV << 32 of this lane's rows.
+template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
+__device__ __noinline__ unsigned long long eval_global(const Cold *K, uint32_t srcbuf, int q, int subl, int fx, int fy, int subc, int fxc, int fyc);
 
 template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
 struct Chain {
@@ -333,33 +347,64 @@ struct Chain {
                         aC += accC[p][i];
             }
         } else {
-            // at least one candidate leaves the staged window: the whole step reads global memory
+#if MVB_FALLBACK_NOINLINE
+            const unsigned long long r2 = eval_global<BPS, BW, BH, LXR, LYR, CHROMA>(K, srcbuf, q, subl, fx, fy, subc, fxc, fyc);
+            aL = (unsigned)r2;
+            aC = (unsigned)(r2 >> 32);
+#else
+            // at least one candidate leaves the staged window: the whole step reads global memory.  Like the window
+            // path: RW + 1 aligned words per row (the row pitch carries 4 bytes of slack for the last one), funnel
+            // shifts for the byte misalignment, one accumulator per row.
             const int pitch0 = K->pitch0, pitch1 = K->pitch1;
-            const uint8_t *pl = K->rbase[0] + (long long)subl * K->sub0 + (long long)(fy + q) * pitch0 + fx * BPS;
+            const unsigned long long la = (unsigned long long)(K->rbase[0] + (long long)subl * K->sub0 + (long long)(fy + q) * pitch0 + fx * BPS);
+            const uint8_t *lw = (const uint8_t *)(la & ~3ull);
+            const unsigned shl = ((unsigned)la & 3u) * 8u;
+            unsigned accL[C::LR], accC[2][C::CR];
 #pragma unroll
             for (int i = 0; i < C::LR; i++) {
-                unsigned sw[C::RW];
+                const unsigned *rw = (const unsigned *)(lw + (long long)(4 * i) * pitch0);
+                unsigned r[C::RW + 1], sw[C::RW];
+#pragma unroll
+                for (int w = 0; w <= C::RW; w++)
+                    r[w] = __ldg(rw + w);
                 if (C::SRC_SMEM)
                     lds_vec(srcbuf + (q + 4 * i) * (C::RW * 4), sw);
+                accL[i] = 0;
 #pragma unroll
                 for (int w = 0; w < C::RW; w++)
-                    aL += absd(ldg_un(pl + (long long)(4 * i) * pitch0 + 4 * w), C::SRC_SMEM ? sw[w] : srcL[i][w]);
+                    accL[i] += absd(__funnelshift_r(r[w], r[w + 1], shl), C::SRC_SMEM ? sw[w] : srcL[i][w]);
             }
+#pragma unroll
+            for (int i = 0; i < C::LR; i++)
+                aL += accL[i];
             if (CHROMA) {
                 const long long oc = (long long)subc * K->sub1 + (long long)(fyc + q) * pitch1 + fxc * BPS;
+                const unsigned shc = ((unsigned)oc & 3u) * 8u; // the plane bases are 4-byte aligned
 #pragma unroll
                 for (int p = 0; p < 2; p++) {
+                    const uint8_t *cw = K->rbase[1 + p] + (oc & ~3ll);
 #pragma unroll
                     for (int i = 0; i < C::CR; i++) {
-                        unsigned sw[C::CRW];
+                        const unsigned *rw = (const unsigned *)(cw + (long long)(4 * i) * pitch1);
+                        unsigned r[C::CRW + 1], sw[C::CRW];
+#pragma unroll
+                        for (int w = 0; w <= C::CRW; w++)
+                            r[w] = __ldg(rw + w);
                         if (C::SRC_SMEM)
                             lds_vec(srcbuf + C::LBYTES + p * C::CBYTES + (q + 4 * i) * (C::CRW * 4), sw);
+                        accC[p][i] = 0;
 #pragma unroll
                         for (int w = 0; w < C::CRW; w++)
-                            aC += absd(ldg_un(K->rbase[1 + p] + oc + (long long)(4 * i) * pitch1 + 4 * w), C::SRC_SMEM ? sw[w] : srcC[p][i][w]);
+                            accC[p][i] += absd(__funnelshift_r(r[w], r[w + 1], shc), C::SRC_SMEM ? sw[w] : srcC[p][i][w]);
                     }
                 }
+#pragma unroll
+                for (int p = 0; p < 2; p++)
+#pragma unroll
+                    for (int i = 0; i < C::CR; i++)
+                        aC += accC[p][i];
             }
+#endif
         }
         if (C::PACK) {
             unsigned v = aL + (aC << 16);
@@ -628,6 +673,53 @@ struct Chain {
         }
     }
 };
+
+template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
+__device__ __noinline__ unsigned long long eval_global(const Cold *K, uint32_t srcbuf, int q, int subl, int fx, int fy, int subc, int fxc, int fyc) {
+    using C = Cfg<BPS, BW, BH, LXR, LYR, CHROMA>;
+    const int pitch0 = K->pitch0, pitch1 = K->pitch1;
+    const unsigned long long la = (unsigned long long)(K->rbase[0] + (long long)subl * K->sub0 + (long long)(fy + q) * pitch0 + fx * BPS);
+    const uint8_t *lw = (const uint8_t *)(la & ~3ull);
+    const unsigned shl = ((unsigned)la & 3u) * 8u;
+    unsigned aL = 0, aC = 0;
+#pragma unroll
+    for (int i = 0; i < C::LR; i++) {
+        const unsigned *rw = (const unsigned *)(lw + (long long)(4 * i) * pitch0);
+        unsigned r[C::RW + 1], sw[C::RW];
+#pragma unroll
+        for (int w = 0; w <= C::RW; w++)
+            r[w] = __ldg(rw + w);
+        lds_vec(srcbuf + (q + 4 * i) * (C::RW * 4), sw);
+        unsigned acc = 0;
+#pragma unroll
+        for (int w = 0; w < C::RW; w++)
+            acc += (BPS == 1 ? __vsadu4(__funnelshift_r(r[w], r[w + 1], shl), sw[w]) : __vsadu2(__funnelshift_r(r[w], r[w + 1], shl), sw[w]));
+        aL += acc;
+    }
+    if (CHROMA) {
+        const long long oc = (long long)subc * K->sub1 + (long long)(fyc + q) * pitch1 + fxc * BPS;
+        const unsigned shc = ((unsigned)oc & 3u) * 8u;
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            const uint8_t *cw = K->rbase[1 + p] + (oc & ~3ll);
+#pragma unroll
+            for (int i = 0; i < C::CR; i++) {
+                const unsigned *rw = (const unsigned *)(cw + (long long)(4 * i) * pitch1);
+                unsigned r[C::CRW + 1], sw[C::CRW];
+#pragma unroll
+                for (int w = 0; w <= C::CRW; w++)
+                    r[w] = __ldg(rw + w);
+                lds_vec(srcbuf + C::LBYTES + p * C::CBYTES + (q + 4 * i) * (C::CRW * 4), sw);
+                unsigned acc = 0;
+#pragma unroll
+                for (int w = 0; w < C::CRW; w++)
+                    acc += (BPS == 1 ? __vsadu4(__funnelshift_r(r[w], r[w + 1], shc), sw[w]) : __vsadu2(__funnelshift_r(r[w], r[w + 1], shc), sw[w]));
+                aC += acc;
+            }
+        }
+    }
+    return (unsigned long long)aL | ((unsigned long long)aC << 32);
+}
 
 template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
 __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)) k_search_tma(const __grid_constant__ TmaMaps maps, const SuperDesc *__restrict__ sdp, const SearchParams *__restrict__ params,
