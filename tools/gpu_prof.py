@@ -11,8 +11,9 @@ ov = int(sys.argv[4]) if len(sys.argv) > 4 else 8
 radius = int(sys.argv[5]) if len(sys.argv) > 5 else 3
 W, H = 1920, 1080
 L = mb.lib()
-base = clipgen.make_clip(W, H, 8, bits=bits)
-frames = [base[i % 8] for i in range(F)]
+DISTINCT = 64  # the bench's clip (bench.py): 64 frames, cycled
+base = clipgen.make_clip(W, H, DISTINCT, bits=bits, seed=0)
+frames = [base[i % DISTINCT] for i in range(F)]
 sp = mb.super_params(W, H, bits, 1, 1, pel=2)
 cl, sl = mb.clip_layout(sp), mb.super_layout(sp)
 ctx = mb.Context(0)

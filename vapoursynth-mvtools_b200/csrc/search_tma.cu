@@ -169,8 +169,16 @@ struct Cfg {
     static constexpr int SRCOFF = 2 * BUF;                                   // [src 0][src 1]
     static constexpr int VECOFF = SRCOFF + 2 * SRCB;                          // hier[2], up, p3: 4 x 16 bytes
     static constexpr int COLDOFF = VECOFF + 64, BAROFF = COLDOFF + 256;       // level constants, 2 mbarriers
-    static constexpr int RAWOFF = BAROFF + 16;                                // raw lo/hi words of an unaligned source block (optional)
-    static constexpr int SMEM = r128(RAWOFF), SMEM_RAW = r128(RAWOFF + 8 * SRCW);
+#ifndef MVB_ZB
+#define MVB_ZB 1
+#endif
+    // ZB: the reference block at the zero vector -- the one start candidate that is usually far from a window placed
+    // around the hierarchical predictor of fast motion -- is prefetched beside the source block (same position, same
+    // word layout, LDGSTS), so that it alone no longer sends the whole first step to global memory
+    static constexpr bool ZB = MVB_ZB != 0 && BPS == 1; // (16-bit 16x16 blocks would drop from 9 to 8 chains per SM for its 1.5 KB)
+    static constexpr int ZBOFF = BAROFF + 16;                                 // [zero block 0][zero block 1]
+    static constexpr int RAWOFF = ZBOFF + (ZB ? 2 * SRCB : 0);                // raw lo/hi words of an unaligned source block (optional)
+    static constexpr int SMEM = r128(RAWOFF + 16), SMEM_RAW = r128(RAWOFF + 8 * SRCW + 16); // (+16: a row read fetches one word past the last block row)
     static_assert(BH % 4 == 0 && (BW * BPS) % 4 == 0, "block shape");
     static_assert(!CHROMA || (CH % 4 == 0 && (CW * BPS) % 4 == 0), "chroma block shape");
 };
@@ -197,6 +205,7 @@ struct Cold {
     int gmx, gmy;  // globalMV (sticky clipping, :859)
     int wo[2][4];  // window origins of the two window buffers
     int cxmax, cymin, cymax; // CLD: limits of a chroma window origin that keep every LDGSTS address inside the plane
+    int zb;                  // this level prefetches the zero-vector reference block (aligned source blocks, no field shift)
 };
 static_assert(sizeof(Cold) <= 256, "Cold");
 
@@ -229,6 +238,7 @@ struct Chain {
     VEC best, predictor;
     int badcount, j, q;
     uint32_t sbuf; // shared-space address of the current window buffer
+    uint32_t zbuf; // shared-space address of the current block's zero-vector reference block, or 0
 
     __device__ __forceinline__ bool ok(int vx, int vy) const { return vx >= g.dxMin && vy >= g.dyMin && vx < g.dxMax && vy < g.dyMax; }
     __device__ __forceinline__ VEC clip(VEC v) const {
@@ -280,9 +290,11 @@ struct Chain {
 
     // Evaluates the candidates of a step: the four lanes 4j..4j+3 hold candidate j (identical Cand).
     // Returns, in every lane, its own candidate's (sadY, sadUV) -- lanes without a valid candidate get garbage.
-    template <int NS>
+    // ZSLOT: slot 0 is the zero-vector candidate (the first step of a block) and may be served by the prefetched block.
+    template <int NS, bool ZSLOT = false>
     __device__ __forceinline__ void eval_step(const Cand &c, unsigned &mySy, unsigned &mySuv) const {
         const bool mine = j < NS && c.valid;
+        const bool zlane = ZSLOT && C::ZB && j == 0 && zbuf != 0;
         const int lvx = mine ? c.lvx : 0, lvy = mine ? c.lvy : 0, cvx = mine ? c.cvx : 0, cvy = mine ? c.cvy : 0;
         const int m = (1 << logPel) - 1;
         const int X = (g.x0 << logPel) + lvx, Y = (g.y0 << logPel) + lvy;
@@ -299,7 +311,7 @@ struct Chain {
             inside = inside && fxc >= wxc0 && fxc + C::CW <= wxc0 + C::CWB / BPS && fyc >= wyc0 && fyc + C::CH <= wyc0 + C::CWH;
             cbc = subc * C::CT + (fyc - wyc0) * C::CWB + (fxc - wxc0) * BPS;
         }
-        const unsigned outside = __ballot_sync(FULL, mine && !inside);
+        const unsigned outside = __ballot_sync(FULL, mine && !inside && !zlane);
         unsigned aL = 0, aC = 0;
         if (outside == 0) {
             unsigned accL[C::LR], accC[2][C::CR]; // one accumulator per row: independent VABSDIFF4 chains
@@ -307,12 +319,21 @@ struct Chain {
                 cbl = 0;
                 cbc = 0;
             }
-            const uint32_t al = sbuf + (cbl & ~3) + q * C::LWB;
-            const unsigned shl = (unsigned)cbl << 3; // funnel shifts use the amount mod 32
+            uint32_t al = sbuf + (cbl & ~3) + q * C::LWB;
+            unsigned shl = (unsigned)cbl << 3; // funnel shifts use the amount mod 32
+            int lrow = 4 * C::LWB;             // bytes between two rows of this lane
+            if (zlane) {                       // the prefetched block: rows of BW samples, no misalignment
+                al = zbuf + q * (C::RW * 4);
+                shl = 0;
+                lrow = 4 * (C::RW * 4);
+            }
 #pragma unroll
             for (int i = 0; i < C::LR; i++) {
                 unsigned r[C::RW + 1], sw[C::RW];
-                lds_row(al + 4 * i * C::LWB, r);
+                if (ZSLOT && C::ZB)
+                    lds_row(al + i * lrow, r);
+                else
+                    lds_row(al + 4 * i * C::LWB, r);
                 if (C::SRC_SMEM)
                     lds_vec(srcbuf + (q + 4 * i) * (C::RW * 4), sw);
                 accL[i] = 0;
@@ -324,14 +345,24 @@ struct Chain {
             for (int i = 0; i < C::LR; i++)
                 aL += accL[i];
             if (CHROMA) {
-                const uint32_t ac = sbuf + C::LREG + (cbc & ~3) + q * C::CWB;
-                const unsigned shc = (unsigned)cbc << 3;
+                uint32_t ac = sbuf + C::LREG + (cbc & ~3) + q * C::CWB;
+                unsigned shc = (unsigned)cbc << 3;
+                int crow = 4 * C::CWB, cplane = C::CREG;
+                if (zlane) {
+                    ac = zbuf + C::LBYTES + q * (C::CRW * 4);
+                    shc = 0;
+                    crow = 4 * (C::CRW * 4);
+                    cplane = C::CBYTES;
+                }
 #pragma unroll
                 for (int p = 0; p < 2; p++) {
 #pragma unroll
                     for (int i = 0; i < C::CR; i++) {
                         unsigned r[C::CRW + 1], sw[C::CRW];
-                        lds_row(ac + p * C::CREG + 4 * i * C::CWB, r);
+                        if (ZSLOT && C::ZB)
+                            lds_row(ac + p * cplane + i * crow, r);
+                        else
+                            lds_row(ac + p * C::CREG + 4 * i * C::CWB, r);
                         if (C::SRC_SMEM)
                             lds_vec(srcbuf + C::LBYTES + p * C::CBYTES + (q + 4 * i) * (C::CRW * 4), sw);
                         accC[p][i] = 0;
@@ -643,7 +674,7 @@ struct Chain {
         c.lvy = j == 0 ? K->fs : py; // zero: luma at (0, fieldShift), chroma at (0, 0)  (:836-839)
         c.valid = j < 3 || (j < 7 && ok(px, py));
         unsigned sy, suv;
-        eval_step<7>(c, sy, suv);
+        eval_step<7, true>(c, sy, suv);
         // per-candidate cost rules (:846, :870, :894, CheckMV0)
         const long long sad = (long long)sy + suv;
         const int pen = j == 0 ? K->penaltyZero : (j == 1 ? K->pglobal : 0);
@@ -852,6 +883,7 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
                     K.cymax = chroma_rows - g1.row0 - (nsub - 1) * g1.padded_h - C::CWH;
                 }
                 K.srcAligned = (((g0.hpad * BPS) | ((BW - P.ovX) * BPS) | (g1.hpad * BPS) | (((BW - P.ovX) >> LXR) * BPS)) & 3) == 0;
+                K.zb = C::ZB && K.srcAligned && fs == 0;
                 K.penaltyZero = P.pzero;
                 K.pglobal = P.global ? P.pglobal : P.pzero;
                 K.badrange = P.badrange;
@@ -903,6 +935,7 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
         // straight into place when every block of the level is 4-byte aligned, else as raw lo/hi words.
         auto issue_src = [&](int x0, int y0, int xc, int yc, int buf) {
             const bool aligned = K.srcAligned;
+            const bool zb = K.zb != 0;
             const int pitch0 = K.pitch0, pitch1 = K.pitch1;
 #pragma unroll
             for (int k = 0; k < C::NSI; k++) {
@@ -911,6 +944,8 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
                     const uint8_t *p = K.sbase[pl] + (long long)((pl == 0 ? y0 : yc) + sw_row[k]) * (pl == 0 ? pitch0 : pitch1) + (pl == 0 ? x0 : xc) * BPS + sw_col[k];
                     if (aligned) {
                         cp_async4(smem0 + C::SRCOFF + buf * C::SRCB + 4 * (lane + 32 * k), p);
+                        if (C::ZB && zb) // same position in the reference frame: the block at the zero vector (sub-plane 0)
+                            cp_async4(smem0 + C::ZBOFF + buf * C::SRCB + 4 * (lane + 32 * k), K.rbase[pl] + (p - K.sbase[pl]));
                     } else {
                         const unsigned *w = (const unsigned *)((unsigned long long)p & ~3ull);
                         cp_async4(smem0 + C::RAWOFF + 8 * (lane + 32 * k), w);
@@ -1130,6 +1165,7 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
             mbar_wait(bar0 + 8 * cbuf, (phasebits >> cbuf) & 1u);
             phasebits ^= 1u << cbuf;
             S.sbuf = smem0 + cbuf * C::BUF;
+            S.zbuf = (C::ZB && K.zb) ? smem0 + C::ZBOFF + (t & 1) * C::SRCB : 0u;
             S.wx0 = K.wo[cbuf][0];
             S.wy0 = K.wo[cbuf][1];
             S.wxc0 = K.wo[cbuf][2];
