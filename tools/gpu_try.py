@@ -6,9 +6,9 @@ for p in ("vapoursynth-mvtools_b200", "oracle", "oracle/minivs"):
 import numpy as np, torch
 import clipgen, mvtools_b200 as mb
 
-def run(W, H, N, bits, radius, blk, ov, pel, check=True):
+def run(W, H, N, bits, radius, blk, ov, pel, check=True, distinct=8):
     L = mb.lib()
-    frames = clipgen.make_clip(W, H, min(N, 8), bits=bits)
+    frames = clipgen.make_clip(W, H, min(N, distinct), bits=bits)
     frames = [frames[i % len(frames)] for i in range(N)]
     sp = mb.super_params(W, H, bits, 1, 1, pel=pel)
     cl, sl = mb.clip_layout(sp), mb.super_layout(sp)
@@ -69,6 +69,11 @@ def run(W, H, N, bits, radius, blk, ov, pel, check=True):
         print("  degrain match:", all(np.array_equal(a, b) for a, b in zip(gd, oo)))
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "configs":  # resident-clip throughput of BASELINE.json's other configurations (not a bench line)
+        run(1920, 1080, 888, 8, 1, 8, 4, 2, check=False, distinct=64)      # configs[1]: Degrain1 blk 8 ov 4 pel 2, 1080p P8
+        run(1920, 1080, 222, 16, 3, 16, 8, 2, check=False, distinct=64)    # configs[2]: Degrain3 blk 16 ov 8 pel 2, 1080p P16
+        run(3840, 2160, 64, 16, 3, 16, 8, 2, check=False, distinct=16)     # configs[4]: one GPU's 64-frame shard of the 4K P16 batch
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "prof":  # one 1080p P8 Degrain3 pass for ncu
         run(1920, 1080, int(sys.argv[2]) if len(sys.argv) > 2 else 64, 8, 3, 16, 8, 2, check=False)
         sys.exit(0)
