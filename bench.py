@@ -39,7 +39,7 @@ WORKLOAD = ("mv.Super(pel=2) + 6x mv.Analyse(blksize=16, overlap=8, delta=1..3, 
             "1920x1080 YUV420P8 (metric's Analyse+Degrain3 1080p P8 with configs[2]'s block geometry)")
 
 
-NCU_PROFILE = "r1_ncu_search_v5_1776chains.json"  # ncu --set full capture of the search kernel the traffic / pipe numbers come from
+NCU_PROFILE = "r1_ncu_search_v7_1776chains.json"  # ncu --set full capture of the search kernel the traffic / pipe numbers come from
 
 
 _BASE_CLIP = None

@@ -70,7 +70,7 @@ def run(W, H, N, bits, radius, blk, ov, pel, check=True, distinct=8):
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "configs":  # resident-clip throughput of BASELINE.json's other configurations (not a bench line)
-        run(1920, 1080, 888, 8, 1, 8, 4, 2, check=False, distinct=64)      # configs[1]: Degrain1 blk 8 ov 4 pel 2, 1080p P8
+        run(1920, 1080, 3552, 8, 1, 8, 4, 2, check=False, distinct=64)     # configs[1]: Degrain1 blk 8 ov 4 pel 2, 1080p P8
         run(1920, 1080, 222, 16, 3, 16, 8, 2, check=False, distinct=64)    # configs[2]: Degrain3 blk 16 ov 8 pel 2, 1080p P16
         run(3840, 2160, 64, 16, 3, 16, 8, 2, check=False, distinct=16)     # configs[4]: one GPU's 64-frame shard of the 4K P16 batch
         sys.exit(0)
