@@ -144,6 +144,41 @@ def test_host_clip_pipeline_matches_goldens(gpu_ctx, case):
             assert [pipeline.sha(p) for p in _planes(dst[k], cl)] == GOLD[case]["degrain"][first + k]
 
 
+def test_host_clip_pipeline_pieces_match_batch_path(gpu_ctx):
+    """a segment long enough to move in pieces (kClipChunks x 8 frames or more: chunked H2D + Super, chunked
+    Degrain + D2H) gives the bytes of the device-resident batch path, for a full and for an inner output range"""
+    import torch
+    L = mb.lib()
+    case = "blk16_ov8_pel2_p8_r3"
+    ck = dict(pipeline.CASES[case][0], nframes=38)
+    frames = pipeline.make_frames(ck)
+    N = len(frames)
+    W, H = ck["width"], ck["height"]
+    _, skw, akw, radius, dkw = pipeline.CASES[case]
+    sp = mb.super_params(W, H, ck["bits"], 1, 1, False, **skw)
+    aps = [mb.analyse_params(sp, N, isb=isb, delta=d, **akw) for d in range(1, radius + 1) for isb in (1, 0)]
+    dp = mb.degrain_params(sp, [ap.ad for ap in aps], W, H, radius, **dkw)
+    _, _, want, cl, _ = _run_batch(gpu_ctx, sp, aps, dp, frames)
+    host = torch.zeros((N, cl.frame_bytes), dtype=torch.uint8).pin_memory()
+    hv = host.numpy()
+    for n, fr in enumerate(frames):
+        for p, a in enumerate(fr):
+            rows = hv[n, cl.offset[p]: cl.offset[p] + cl.pitch[p] * cl.plane_h[p]].reshape(cl.plane_h[p], cl.pitch[p])
+            rows[:, : a.shape[1] * a.itemsize] = a.view(np.uint8).reshape(a.shape[0], -1)
+    outs = [torch.zeros((N, cl.frame_bytes), dtype=torch.uint8).pin_memory() for _ in range(3)]
+    apa = (C.POINTER(mb.AnalyseParams) * len(aps))(*[C.pointer(a) for a in aps])
+    ranges = [(0, N), (3, N - 6), (0, N)]
+    for o, (first, count) in zip(outs, ranges):
+        mb._check(L.mvb200_degrain_clip_host_async(gpu_ctx.handle, C.byref(sp), apa, len(aps), C.byref(dp), host.data_ptr(), o.data_ptr(), N, first, count))
+    gpu_ctx.synchronize()
+    for o, (first, count) in zip(outs, ranges):
+        dst = o.numpy()
+        for k in range(count):
+            for a, b in zip(_planes(dst[k], cl), _planes(want[first + k], cl)):
+                assert np.array_equal(a, b), "frame %d of range (%d, %d)" % (first + k, first, count)
+
+
+
 def test_full_size_1080p_properties(gpu_ctx):
     """BASELINE.json configs[1]-sized run (1920x1080 P8, blk 8 ov 4 pel 2, Degrain1) checked by
     properties that do not need the slow CPU path at full size, plus one oracle frame."""

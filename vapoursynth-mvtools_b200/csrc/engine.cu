@@ -245,6 +245,12 @@ void mvb200_ctx_destroy(mvb200_ctx *ctx) {
         if (ctx->c.ev_d2h[i])
             cudaEventDestroy(ctx->c.ev_d2h[i]);
     }
+    for (int i = 0; i < kClipChunks; i++) {
+        if (ctx->c.ev_piece_in[i])
+            cudaEventDestroy(ctx->c.ev_piece_in[i]);
+        if (ctx->c.ev_piece_out[i])
+            cudaEventDestroy(ctx->c.ev_piece_out[i]);
+    }
     if (ctx->c.staging_ev)
         cudaEventDestroy(ctx->c.staging_ev);
     cudaStreamDestroy(ctx->c.stream);
@@ -383,6 +389,10 @@ int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *s
     if (!c.copy_in) {
         MVB_CUDA_CHECK(cudaStreamCreateWithFlags(&c.copy_in, cudaStreamNonBlocking));
         MVB_CUDA_CHECK(cudaStreamCreateWithFlags(&c.copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < kClipChunks; i++) {
+            MVB_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_piece_in[i], cudaEventDisableTiming));
+            MVB_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_piece_out[i], cudaEventDisableTiming));
+        }
         for (int i = 0; i < 2; i++) {
             MVB_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_h2d[i], cudaEventDisableTiming));
             MVB_CUDA_CHECK(cudaEventCreateWithFlags(&c.ev_compute[i], cudaEventDisableTiming));
@@ -409,28 +419,46 @@ int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *s
         return 1;
     if (before[0] != dsrc || before[1] != ddst || before[2] != dsup || before[3] != dvec)
         MVB_CUDA_CHECK(cudaStreamSynchronize(c.stream)); // fresh buffers are cleared on the compute stream: finish that before the copy stream writes
+    // The segment moves in up to kClipChunks pieces so that only a piece's copy -- not the whole segment's -- is exposed
+    // before the first kernel and after the last one: Super of piece i runs while piece i+1 is still arriving, and the
+    // denoised frames of piece i leave while piece i+1 is being blended.  (Between consecutive calls the copies already
+    // overlap the neighbouring segments' kernels.)
+    const int nin = n >= 8 * kClipChunks ? kClipChunks : 1, nout = count >= 8 * kClipChunks ? kClipChunks : 1;
     // H2D: once the kernels that last read this slot's source clip are done
     if (reuse)
         MVB_CUDA_CHECK(cudaStreamWaitEvent(c.copy_in, c.ev_compute[slot], 0));
-    MVB_CUDA_CHECK(cudaMemcpyAsync(dsrc, host_src, clip_bytes, cudaMemcpyHostToDevice, c.copy_in));
-    MVB_CUDA_CHECK(cudaEventRecord(c.ev_h2d[slot], c.copy_in));
-    // compute: after this segment's H2D and after the D2H that last read this slot's output clip
-    MVB_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_h2d[slot], 0));
+    // compute: after the D2H that last read this slot's output clip (and, piece by piece, after this segment's H2D)
     if (reuse)
         MVB_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_d2h[slot], 0));
+    for (int i = 0; i < nin; i++) {
+        const int f0 = (int)((long long)n * i / nin), f1 = (int)((long long)n * (i + 1) / nin);
+        MVB_CUDA_CHECK(cudaMemcpyAsync(dsrc + (size_t)cd.frame_bytes * f0, (const uint8_t *)host_src + (size_t)cd.frame_bytes * f0, (size_t)cd.frame_bytes * (f1 - f0),
+                                       cudaMemcpyHostToDevice, c.copy_in));
+        MVB_CUDA_CHECK(cudaEventRecord(c.ev_piece_in[i], c.copy_in));
+        MVB_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_piece_in[i], 0));
+        // every frame of the segment gets its super frame: the frames outside [first, first + count) are references
+        if (mvb200_super_batch(ctx, sp, dsrc + (size_t)cd.frame_bytes * f0, dsup + (size_t)sd.frame_bytes * f0, f1 - f0))
+            return 1;
+    }
+    MVB_CUDA_CHECK(cudaEventRecord(c.ev_h2d[slot], c.copy_in));
     std::vector<void *> outs((size_t)nap);
     for (int i = 0; i < nap; i++)
         outs[i] = dvec + (size_t)vstride * count * i;
-    if (mvb200_super_batch(ctx, sp, dsrc, dsup, n)) // every frame of the segment: the frames outside [first, first + count) are references
-        return 1;
     if (mvb200_analyse_multi_batch(ctx, ap, nap, sp, dsup, first, count, outs.data(), vstride))
         return 1;
-    if (mvb200_degrain_batch(ctx, dp, sp, dsrc, dsup, n, first, count, (const void *const *)outs.data(), vstride, ddst))
-        return 1;
-    MVB_CUDA_CHECK(cudaEventRecord(c.ev_compute[slot], c.stream));
-    // D2H
-    MVB_CUDA_CHECK(cudaStreamWaitEvent(c.copy_out, c.ev_compute[slot], 0));
-    MVB_CUDA_CHECK(cudaMemcpyAsync(host_dst, ddst, (size_t)cd.frame_bytes * count, cudaMemcpyDeviceToHost, c.copy_out));
+    std::vector<const void *> vin((size_t)nap);
+    for (int i = 0; i < nout; i++) {
+        const int o0 = (int)((long long)count * i / nout), o1 = (int)((long long)count * (i + 1) / nout);
+        for (int k = 0; k < nap; k++)
+            vin[k] = (const uint8_t *)outs[k] + (size_t)vstride * o0;
+        if (mvb200_degrain_batch(ctx, dp, sp, dsrc, dsup, n, first + o0, o1 - o0, vin.data(), vstride, ddst + (size_t)cd.frame_bytes * o0))
+            return 1;
+        MVB_CUDA_CHECK(cudaEventRecord(i == nout - 1 ? c.ev_compute[slot] : c.ev_piece_out[i], c.stream));
+        // D2H of the piece
+        MVB_CUDA_CHECK(cudaStreamWaitEvent(c.copy_out, i == nout - 1 ? c.ev_compute[slot] : c.ev_piece_out[i], 0));
+        MVB_CUDA_CHECK(cudaMemcpyAsync((uint8_t *)host_dst + (size_t)cd.frame_bytes * o0, ddst + (size_t)cd.frame_bytes * o0, (size_t)cd.frame_bytes * (o1 - o0),
+                                       cudaMemcpyDeviceToHost, c.copy_out));
+    }
     MVB_CUDA_CHECK(cudaEventRecord(c.ev_d2h[slot], c.copy_out));
     return 0;
 }

@@ -109,6 +109,8 @@ int launch_recalc(Ctx *ctx, const SuperDesc &sd, const RecalcParams &P, const Re
 int launch_compensate(Ctx *ctx, const mvb200_compensate_params *cp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src_super, const uint8_t *dev_ref_super, const uint8_t *dev_vectors, int field_shift, uint8_t *dev_dst);
 int launch_degrain(Ctx *ctx, const mvb200_degrain_params *dp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, const uint8_t *dev_super, int num_frames, int first, int n, const uint8_t *const *dev_vectors, long long vectors_stride, uint8_t *dev_dst);
 
+constexpr int kClipChunks = 4;
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -130,6 +132,7 @@ struct Ctx {
     // host-buffer clip pipeline (mvb200_degrain_clip_host_async): copy streams + double-buffered clips
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    cudaEvent_t ev_piece_in[4] = {}, ev_piece_out[4] = {}; // a segment's copies move in kClipChunks pieces
     long long clip_calls = 0;
 
     void *get_scratch(int slot, size_t bytes); // nullptr + error on failure
