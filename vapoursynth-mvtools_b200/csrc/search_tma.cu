@@ -167,10 +167,7 @@ struct Cfg {
     static constexpr int LBYTES = BW * BH * BPS, CBYTES = CHROMA ? CW * CH * BPS : 0;
     static constexpr int SRCW = (LBYTES + 2 * CBYTES) / 4, NSI = (SRCW + 31) / 32; // source block words, per lane for the cooperative load
     static constexpr bool PACK = BPS == 1 && BW * BH <= 256 && 2 * CW * CH <= 256;
-#ifndef MVB_SRC_SMEM
-#define MVB_SRC_SMEM 0
-#endif
-    static constexpr bool SRC_SMEM = MVB_SRC_SMEM || (BPS == 2 && BW * BH >= 256); // too many registers: read source rows from shared memory
+    static constexpr bool SRC_SMEM = BPS == 2 && BW * BH >= 256; // too many registers: read source rows from shared memory
     static constexpr int SRCB = r128(LBYTES + 2 * CBYTES);                   // one source-block buffer
     static constexpr int SRCOFF = 2 * BUF;                                   // [src 0][src 1]
     static constexpr int VECOFF = SRCOFF + 2 * SRCB;                          // hier[2], up, p3: 4 x 16 bytes
@@ -214,17 +211,6 @@ struct Cold {
     int zb;                  // this level prefetches the zero-vector reference block (aligned source blocks, no field shift)
 };
 static_assert(sizeof(Cold) <= 256, "Cold");
-
-#ifndef MVB_FALLBACK_NOINLINE
-#define MVB_FALLBACK_NOINLINE 0
-#endif
-
-struct Cold;
-// The global-memory path of a step as a real function (MVB_FALLBACK_NOINLINE): it runs for a few percent of the
-// steps but, inlined, sits in the middle of every step's code.  Source rows come from the shared-memory copy of the
-// source block, so the call passes a handful of scalars.  Returns sadY | sadUV << 32 of this lane's rows.
-template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
-__device__ __noinline__ unsigned long long eval_global(const Cold *K, uint32_t srcbuf, int q, int subl, int fx, int fy, int subc, int fxc, int fyc);
 
 template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
 struct Chain {
@@ -384,11 +370,6 @@ struct Chain {
                         aC += accC[p][i];
             }
         } else {
-#if MVB_FALLBACK_NOINLINE
-            const unsigned long long r2 = eval_global<BPS, BW, BH, LXR, LYR, CHROMA>(K, srcbuf, q, subl, fx, fy, subc, fxc, fyc);
-            aL = (unsigned)r2;
-            aC = (unsigned)(r2 >> 32);
-#else
             // at least one candidate leaves the staged window: the whole step reads global memory.  Like the window
             // path: RW + 1 aligned words per row (the row pitch carries 4 bytes of slack for the last one), funnel
             // shifts for the byte misalignment, one accumulator per row.
@@ -441,7 +422,6 @@ struct Chain {
                     for (int i = 0; i < C::CR; i++)
                         aC += accC[p][i];
             }
-#endif
         }
         if (C::PACK) {
             unsigned v = aL + (aC << 16);
@@ -710,53 +690,6 @@ struct Chain {
         }
     }
 };
-
-template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
-__device__ __noinline__ unsigned long long eval_global(const Cold *K, uint32_t srcbuf, int q, int subl, int fx, int fy, int subc, int fxc, int fyc) {
-    using C = Cfg<BPS, BW, BH, LXR, LYR, CHROMA>;
-    const int pitch0 = K->pitch0, pitch1 = K->pitch1;
-    const unsigned long long la = (unsigned long long)(K->rbase[0] + (long long)subl * K->sub0 + (long long)(fy + q) * pitch0 + fx * BPS);
-    const uint8_t *lw = (const uint8_t *)(la & ~3ull);
-    const unsigned shl = ((unsigned)la & 3u) * 8u;
-    unsigned aL = 0, aC = 0;
-#pragma unroll
-    for (int i = 0; i < C::LR; i++) {
-        const unsigned *rw = (const unsigned *)(lw + (long long)(4 * i) * pitch0);
-        unsigned r[C::RW + 1], sw[C::RW];
-#pragma unroll
-        for (int w = 0; w <= C::RW; w++)
-            r[w] = __ldg(rw + w);
-        lds_vec(srcbuf + (q + 4 * i) * (C::RW * 4), sw);
-        unsigned acc = 0;
-#pragma unroll
-        for (int w = 0; w < C::RW; w++)
-            acc += (BPS == 1 ? __vsadu4(__funnelshift_r(r[w], r[w + 1], shl), sw[w]) : __vsadu2(__funnelshift_r(r[w], r[w + 1], shl), sw[w]));
-        aL += acc;
-    }
-    if (CHROMA) {
-        const long long oc = (long long)subc * K->sub1 + (long long)(fyc + q) * pitch1 + fxc * BPS;
-        const unsigned shc = ((unsigned)oc & 3u) * 8u;
-#pragma unroll
-        for (int p = 0; p < 2; p++) {
-            const uint8_t *cw = K->rbase[1 + p] + (oc & ~3ll);
-#pragma unroll
-            for (int i = 0; i < C::CR; i++) {
-                const unsigned *rw = (const unsigned *)(cw + (long long)(4 * i) * pitch1);
-                unsigned r[C::CRW + 1], sw[C::CRW];
-#pragma unroll
-                for (int w = 0; w <= C::CRW; w++)
-                    r[w] = __ldg(rw + w);
-                lds_vec(srcbuf + C::LBYTES + p * C::CBYTES + (q + 4 * i) * (C::CRW * 4), sw);
-                unsigned acc = 0;
-#pragma unroll
-                for (int w = 0; w < C::CRW; w++)
-                    acc += (BPS == 1 ? __vsadu4(__funnelshift_r(r[w], r[w + 1], shc), sw[w]) : __vsadu2(__funnelshift_r(r[w], r[w + 1], shc), sw[w]));
-                aC += acc;
-            }
-        }
-    }
-    return (unsigned long long)aL | ((unsigned long long)aC << 32);
-}
 
 template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
 __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)) k_search_tma(const __grid_constant__ TmaMaps maps, const SuperDesc *__restrict__ sdp, const SearchParams *__restrict__ params,
