@@ -275,6 +275,14 @@ MVB200_API int mvb200_analyse_multi_batch(mvb200_ctx *ctx, const mvb200_analyse_
  * dev_vectors[r] = blobs of vector clip r for frames [first, first+n) (same stride). */
 MVB200_API int mvb200_degrain_batch(mvb200_ctx *ctx, const mvb200_degrain_params *dp, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int num_frames, int first, int n, const void *const *dev_vectors, int64_t vectors_stride, void *dev_dst);
 
+/* mv.Recalculate / mv.Compensate over frames [first, first + n) of a device-resident super clip (gopRecalculateMVs per
+ * frame, MVRecalculate.c:68-254; mvcompensateGetFrame, MVCompensate.c:73-374).  Old blobs are old_stride bytes apart, new
+ * ones vectors_stride (>= rp->vectors_size); compensated frames are written in the clip layout, frame_bytes apart.
+ * Reference frames follow the filters' own rule (n +/- delta, or the fixed frame -delta), an out-of-range or invalid
+ * one gives the default blob / the scene-change copy; field shifts need an explicit tff (frame props are the plugin's). */
+MVB200_API int mvb200_recalculate_batch(mvb200_ctx *ctx, const mvb200_recalculate_params *rp, const mvb200_super_params *sp, const void *dev_super, int first, int n, const void *dev_old_vectors, int64_t old_stride, void *dev_vectors, int64_t vectors_stride);
+MVB200_API int mvb200_compensate_batch(mvb200_ctx *ctx, const mvb200_compensate_params *cp, const mvb200_super_params *sp, const void *dev_super, int first, int n, const void *dev_vectors, int64_t vectors_stride, void *dev_dst);
+
 /* Host-buffer clip pipeline: mv.Super + nap x mv.Analyse + mv.DegrainN (nap == 2 * radius) over a whole
  * segment of n frames held in HOST memory in the clip layout (mvb200_clip_layout; frames frame_bytes
  * apart; use pinned memory for truly asynchronous copies); frames [first, first + count) are denoised into

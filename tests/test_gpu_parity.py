@@ -144,6 +144,46 @@ def test_host_clip_pipeline_matches_goldens(gpu_ctx, case):
             assert [pipeline.sha(p) for p in _planes(dst[k], cl)] == GOLD[case]["degrain"][first + k]
 
 
+@pytest.mark.parametrize("case", sorted(pipeline.EXTRA))
+def test_recalculate_compensate_batch_match_goldens(gpu_ctx, case):
+    """mvb200_recalculate_batch / mvb200_compensate_batch on a device-resident clip (vector clip 0 of the case, as in
+    the per-frame test) give the reference's bytes for every frame"""
+    import torch
+    L = mb.lib()
+    ctx = gpu_ctx
+    if case in pipeline.PELCLIP:
+        pytest.skip("pelclip cases go through the per-frame Super entry point")
+    frames = pipeline.make_frames(pipeline.CASES[case][0])
+    N = len(frames)
+    sp, aps, dp = pipeline.params_for(case)
+    rp, cp = pipeline.extra_params_for(case)
+    cl, sl = mb.clip_layout(sp), mb.super_layout(sp)
+    dsrc = _device_clip(frames, cl)
+    dsup = torch.empty((N, sl.frame_bytes), dtype=torch.uint8, device="cuda")
+    vs = (aps[0].vectors_size + 255) // 256 * 256
+    dvec = torch.zeros((N, vs), dtype=torch.uint8, device="cuda")
+    rs = (rp.vectors_size + 255) // 256 * 256
+    dnew = torch.zeros((N, rs), dtype=torch.uint8, device="cuda")
+    dcomp = torch.full((N, cl.frame_bytes), 0xA5, dtype=torch.uint8, device="cuda")
+    apa = (C.POINTER(mb.AnalyseParams) * 1)(C.pointer(aps[0]))
+    outs = (C.c_void_p * 1)(dvec.data_ptr())
+    mb._check(L.mvb200_super_batch(ctx.handle, C.byref(sp), dsrc.data_ptr(), dsup.data_ptr(), N))
+    mb._check(L.mvb200_analyse_multi_batch(ctx.handle, apa, 1, C.byref(sp), dsup.data_ptr(), 0, N, outs, vs))
+    mb._check(L.mvb200_recalculate_batch(ctx.handle, C.byref(rp), C.byref(sp), dsup.data_ptr(), 0, N, dvec.data_ptr(), vs, dnew.data_ptr(), rs))
+    mb._check(L.mvb200_compensate_batch(ctx.handle, C.byref(cp), C.byref(sp), dsup.data_ptr(), 0, N, dvec.data_ptr(), vs, dcomp.data_ptr()))
+    ctx.synchronize()
+    new, comp = dnew.cpu().numpy(), dcomp.cpu().numpy()
+    for n in range(N):
+        assert pipeline.sha(pipeline.mask_recalc_blob(new[n][: rp.vectors_size], rp)) == GOLD[case]["recalc"][n], "frame %d: Recalculate" % n
+        assert [pipeline.sha(p) for p in _planes(comp[n], cl)][: cp.nplanes] == GOLD[case]["compensate"][n], "frame %d: Compensate" % n
+    # an inner range addresses the same frames
+    dnew2 = torch.zeros((N, rs), dtype=torch.uint8, device="cuda")
+    mb._check(L.mvb200_recalculate_batch(ctx.handle, C.byref(rp), C.byref(sp), dsup.data_ptr(), 1, N - 2, dvec[1:].data_ptr(), vs, dnew2.data_ptr(), rs))
+    ctx.synchronize()
+    assert np.array_equal(dnew2.cpu().numpy()[: N - 2, : rp.vectors_size], new[1: N - 1, : rp.vectors_size])
+
+
+
 def test_host_clip_pipeline_pieces_match_batch_path(gpu_ctx):
     """a segment long enough to move in pieces (kClipChunks x 8 frames or more: chunked H2D + Super, chunked
     Degrain + D2H) gives the bytes of the device-resident batch path, for a full and for an inner output range"""

@@ -150,23 +150,30 @@ int launch_compensate(Ctx *ctx, const mvb200_compensate_params *cp, const SuperD
     const bool overlap = cp->nOverlapX[0] > 0 || cp->nOverlapY[0] > 0;
     const int num_planes = (cp->super_modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) ? 3 : 1;
     short *dev_win[2] = {nullptr, nullptr};
-    if (overlap) {
-        std::vector<short> wl, wc;
-        overlap_windows_host(cp->nBlkSizeX[0], cp->nBlkSizeY[0], cp->nOverlapX[0], cp->nOverlapY[0], wl);
-        if (num_planes > 1)
-            overlap_windows_host(cp->nBlkSizeX[1], cp->nBlkSizeY[1], cp->nOverlapX[1], cp->nOverlapY[1], wc);
-        size_t bl = wl.size() * sizeof(short), bc = wc.size() * sizeof(short), offc = (bl + 255) & ~(size_t)255;
-        uint8_t *host = (uint8_t *)ctx->get_pinned(offc + bc + 256);
-        uint8_t *dev = (uint8_t *)ctx->get_scratch(6, offc + bc + 256);
-        if (!host || !dev)
-            return 1;
-        MVB_CUDA_CHECK(cudaStreamSynchronize(st));
-        memcpy(host, wl.data(), bl);
-        if (bc)
-            memcpy(host + offc, wc.data(), bc);
-        MVB_CUDA_CHECK(cudaMemcpyAsync(dev, host, offc + bc, cudaMemcpyHostToDevice, st));
-        dev_win[0] = (short *)dev;
-        dev_win[1] = (short *)(dev + offc);
+    if (overlap) { // window tables (built on the host, libm cosf): resident on the device until the configuration changes
+        const int key[8] = {cp->nBlkSizeX[0], cp->nBlkSizeY[0], cp->nOverlapX[0], cp->nOverlapY[0], num_planes > 1 ? cp->nBlkSizeX[1] : 0, num_planes > 1 ? cp->nBlkSizeY[1] : 0,
+                            num_planes > 1 ? cp->nOverlapX[1] : 0, num_planes > 1 ? cp->nOverlapY[1] : 0};
+        if (!ctx->cwin_valid || memcmp(key, ctx->cwin_key, sizeof(key)) != 0) {
+            std::vector<short> wl, wc;
+            overlap_windows_host(cp->nBlkSizeX[0], cp->nBlkSizeY[0], cp->nOverlapX[0], cp->nOverlapY[0], wl);
+            if (num_planes > 1)
+                overlap_windows_host(cp->nBlkSizeX[1], cp->nBlkSizeY[1], cp->nOverlapX[1], cp->nOverlapY[1], wc);
+            size_t bl = wl.size() * sizeof(short), bc = wc.size() * sizeof(short), offc = (bl + 255) & ~(size_t)255;
+            // first use of this configuration (or a change): drain, rebuild the tables, upload synchronously
+            uint8_t *dev = (uint8_t *)ctx->get_scratch(6, offc + bc + 256);
+            if (!dev)
+                return 1;
+            MVB_CUDA_CHECK(cudaStreamSynchronize(st)); // (also past the clearing of a fresh scratch buffer)
+            MVB_CUDA_CHECK(cudaMemcpy(dev, wl.data(), bl, cudaMemcpyHostToDevice));
+            if (bc)
+                MVB_CUDA_CHECK(cudaMemcpy(dev + offc, wc.data(), bc, cudaMemcpyHostToDevice));
+            ctx->cwin_dev[0] = (short *)dev;
+            ctx->cwin_dev[1] = (short *)(dev + offc);
+            memcpy(ctx->cwin_key, key, sizeof(key));
+            ctx->cwin_valid = true;
+        }
+        dev_win[0] = ctx->cwin_dev[0];
+        dev_win[1] = ctx->cwin_dev[1];
     }
     for (int plane = 0; plane < num_planes; plane++) {
         CompPlane B;

@@ -615,10 +615,10 @@ int launch_degrain(Ctx *ctx, const mvb200_degrain_params *dp, const SuperDesc &s
             size_t bl = wl.size() * sizeof(short), bc = wc.size() * sizeof(short);
             size_t offc = (bl + 255) & ~(size_t)255;
             // first use of this configuration (or a change): drain, rebuild the tables, upload synchronously
-            MVB_CUDA_CHECK(cudaStreamSynchronize(st));
             uint8_t *dev = (uint8_t *)ctx->get_scratch(4, offc + bc + 256);
             if (!dev)
                 return 1;
+            MVB_CUDA_CHECK(cudaStreamSynchronize(st)); // (also past the clearing of a fresh scratch buffer)
             MVB_CUDA_CHECK(cudaMemcpy(dev, wl.data(), bl, cudaMemcpyHostToDevice));
             if (bc)
                 MVB_CUDA_CHECK(cudaMemcpy(dev + offc, wc.data(), bc, cudaMemcpyHostToDevice));

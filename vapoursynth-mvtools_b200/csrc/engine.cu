@@ -184,6 +184,56 @@ static int field_shift_of(const mvb200_analyse_params *ap, int n, int nref) {
     return (src_top && !ref_top) ? ap->ad.nPel / 2 : ((ref_top && !src_top) ? -(ap->ad.nPel / 2) : 0);
 }
 
+// the same two rules for the consumers of a vector clip (MVRecalculate.c:76-83,168-174; MVCompensate.c:80-87,188-223),
+// with an explicit tff; `odd` = the parity test each filter uses (nDeltaFrame % 2, or (nref - n) % 2 in Compensate)
+static int ref_frame_of_vd(const mvb200_analysis_data &vd, int num_frames, int n) {
+    const int nref = vd.nDeltaFrame > 0 ? n + (vd.isBackward ? vd.nDeltaFrame : -vd.nDeltaFrame) : -vd.nDeltaFrame;
+    return (nref >= 0 && nref < num_frames) ? nref : -1;
+}
+static int field_shift_tff(int fields, int tff_exists, int tff, int pel, bool odd, int n, int nref) {
+    if (!(fields && pel > 1 && odd) || !tff_exists)
+        return 0;
+    const int src_top = tff ^ (n % 2), ref_top = tff ^ (nref % 2);
+    return (src_top && !ref_top) ? pel / 2 : ((ref_top && !src_top) ? -(pel / 2) : 0);
+}
+
+// mvb200_recalculate_params -> the kernel's parameter block (dct tables are attached by launch_recalc)
+static void make_recalc_params(const mvb200_recalculate_params *rp, const mvb200_super_params *sp, RecalcParams *out) {
+    RecalcParams &P = *out;
+    memset(&P, 0, sizeof(P));
+    const mvb200_analysis_data &ad = rp->ad, &od = rp->old;
+    P.blkW = ad.nBlkSizeX;
+    P.blkH = ad.nBlkSizeY;
+    P.ovX = ad.nOverlapX;
+    P.ovY = ad.nOverlapY;
+    P.logPel = ad.nPel == 4 ? 2 : (ad.nPel == 2 ? 1 : 0);
+    P.chroma = rp->chroma;
+    P.bps = (ad.bitsPerSample + 7) / 8;
+    P.search = rp->search;
+    P.nSearchParam = rp->nSearchParam;
+    P.nLambda = rp->nLambda;
+    P.pnew = rp->pnew;
+    P.smooth = rp->smooth;
+    P.dctmode = rp->dctmode;
+    P.bits = sp->bits;
+    P.dct_cos = nullptr;
+    P.dct_scratch = nullptr;
+    P.dct_scratch_stride = 0;
+    P.divide = rp->divide;
+    P.thSAD = rp->thSAD;
+    P.verybigSAD = (long long)ad.nBlkSizeX * ad.nBlkSizeY * (1LL << ad.bitsPerSample);
+    P.nBlkX = ad.nBlkX;
+    P.nBlkY = ad.nBlkY;
+    P.vectors_size = rp->vectors_size;
+    P.oBlkX = od.nBlkX;
+    P.oBlkY = od.nBlkY;
+    P.oBlkW = od.nBlkSizeX;
+    P.oBlkH = od.nBlkSizeY;
+    P.oOvX = od.nOverlapX;
+    P.oOvY = od.nOverlapY;
+    P.oLogPel = od.nPel == 4 ? 2 : (od.nPel == 2 ? 1 : 0);
+}
+
 } // namespace mvb200
 
 using namespace mvb200;
@@ -365,6 +415,63 @@ int mvb200_degrain_batch(mvb200_ctx *ctx, const mvb200_degrain_params *dp, const
     make_super_desc(sp, &sd);
     make_clip_desc(sp, &cd);
     return launch_degrain(&ctx->c, dp, sd, cd, (const uint8_t *)dev_src, (const uint8_t *)dev_super, num_frames, first, n, (const uint8_t *const *)dev_vectors, vectors_stride, (uint8_t *)dev_dst);
+}
+
+// mv.Recalculate / mv.Compensate over frames [first, first + n) of a device-resident super clip (the counterparts of
+// mvb200_analyse_multi_batch / mvb200_degrain_batch): the old vector blobs are `old_stride` apart, the new ones
+// `vectors_stride`; reference frames and field shifts follow the filters' own rules with an explicit tff.
+int mvb200_recalculate_batch(mvb200_ctx *ctx, const mvb200_recalculate_params *rp, const mvb200_super_params *sp, const void *dev_super, int first, int n,
+                             const void *dev_old_vectors, int64_t old_stride, void *dev_vectors, int64_t vectors_stride) {
+    if (check_levels(sp))
+        return 1;
+    if (n <= 0)
+        return 0;
+    if (first < 0 || first + n > rp->num_frames)
+        return set_error("Recalculate: frames [%d, %d) are outside the clip of %d frames", first, first + n, rp->num_frames);
+    if (vectors_stride < rp->vectors_size)
+        return set_error("Recalculate: vectors_stride (%lld) is smaller than the blob (%d bytes)", (long long)vectors_stride, rp->vectors_size);
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    make_super_desc(sp, &sd);
+    RecalcParams P;
+    make_recalc_params(rp, sp, &P);
+    std::vector<RecalcJob> jobs((size_t)n);
+    for (int f = 0; f < n; f++) {
+        const int fn = first + f, nref = ref_frame_of_vd(rp->ad, rp->num_frames, fn);
+        RecalcJob &j = jobs[(size_t)f];
+        j.src = (const uint8_t *)dev_super + (long long)fn * sd.frame_bytes;
+        j.ref = nref >= 0 ? (const uint8_t *)dev_super + (long long)nref * sd.frame_bytes : nullptr;
+        j.old = (const uint8_t *)dev_old_vectors + (long long)f * old_stride;
+        j.out = (uint8_t *)dev_vectors + (long long)f * vectors_stride;
+        j.field_shift = nref >= 0 ? field_shift_tff(rp->fields, rp->tff_exists, rp->tff, rp->ad.nPel, rp->ad.nDeltaFrame % 2 != 0, fn, nref) : 0;
+    }
+    return launch_recalc(c, sd, P, jobs.data(), n);
+}
+
+int mvb200_compensate_batch(mvb200_ctx *ctx, const mvb200_compensate_params *cp, const mvb200_super_params *sp, const void *dev_super, int first, int n,
+                            const void *dev_vectors, int64_t vectors_stride, void *dev_dst) {
+    if (check_levels(sp))
+        return 1;
+    if (n <= 0)
+        return 0;
+    if (first < 0 || first + n > cp->num_frames)
+        return set_error("Compensate: frames [%d, %d) are outside the clip of %d frames", first, first + n, cp->num_frames);
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(sp, &sd);
+    make_clip_desc(sp, &cd);
+    for (int f = 0; f < n; f++) {
+        const int fn = first + f, nref = ref_frame_of_vd(cp->vd, cp->num_frames, fn);
+        const uint8_t *src = (const uint8_t *)dev_super + (long long)fn * sd.frame_bytes;
+        const uint8_t *ref = nref >= 0 ? (const uint8_t *)dev_super + (long long)nref * sd.frame_bytes : nullptr;
+        const int fs = nref >= 0 ? field_shift_tff(cp->fields, cp->tff_exists, cp->tff, cp->vd.nPel, (nref - fn) % 2 != 0, fn, nref) : 0;
+        if (launch_compensate(c, cp, sd, cd, src, ref, (const uint8_t *)dev_vectors + (long long)f * vectors_stride, fs, (uint8_t *)dev_dst + (long long)f * cd.frame_bytes))
+            return 1;
+    }
+    return 0;
 }
 
 // ------------------------------------------------ host-buffer clip pipeline
@@ -697,38 +804,7 @@ int mvb200_recalculate_frame(mvb200_ctx *ctx, const mvb200_recalculate_params *r
     uint8_t *dold = buf + sd.frame_bytes * 2, *dnew = dold + old_stride;
     MVB_CUDA_CHECK(cudaMemcpyAsync(dold, old_vectors, old_bytes, cudaMemcpyHostToDevice, c->stream));
     RecalcParams P;
-    memset(&P, 0, sizeof(P));
-    const mvb200_analysis_data &ad = rp->ad, &od = rp->old;
-    P.blkW = ad.nBlkSizeX;
-    P.blkH = ad.nBlkSizeY;
-    P.ovX = ad.nOverlapX;
-    P.ovY = ad.nOverlapY;
-    P.logPel = ad.nPel == 4 ? 2 : (ad.nPel == 2 ? 1 : 0);
-    P.chroma = rp->chroma;
-    P.bps = (ad.bitsPerSample + 7) / 8;
-    P.search = rp->search;
-    P.nSearchParam = rp->nSearchParam;
-    P.nLambda = rp->nLambda;
-    P.pnew = rp->pnew;
-    P.smooth = rp->smooth;
-    P.dctmode = rp->dctmode;
-    P.bits = sp->bits;
-    P.dct_cos = nullptr;
-    P.dct_scratch = nullptr;
-    P.dct_scratch_stride = 0;
-    P.divide = rp->divide;
-    P.thSAD = rp->thSAD;
-    P.verybigSAD = (long long)ad.nBlkSizeX * ad.nBlkSizeY * (1LL << ad.bitsPerSample);
-    P.nBlkX = ad.nBlkX;
-    P.nBlkY = ad.nBlkY;
-    P.vectors_size = rp->vectors_size;
-    P.oBlkX = od.nBlkX;
-    P.oBlkY = od.nBlkY;
-    P.oBlkW = od.nBlkSizeX;
-    P.oBlkH = od.nBlkSizeY;
-    P.oOvX = od.nOverlapX;
-    P.oOvY = od.nOverlapY;
-    P.oLogPel = od.nPel == 4 ? 2 : (od.nPel == 2 ? 1 : 0);
+    make_recalc_params(rp, sp, &P);
     RecalcJob j;
     j.src = buf;
     j.ref = ref_super ? buf + sd.frame_bytes : nullptr;

@@ -129,6 +129,10 @@ struct Ctx {
     int win_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     short *win_dev[2] = {nullptr, nullptr};
     bool win_valid = false;
+    // ... and of the last Compensate configuration
+    int cwin_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    short *cwin_dev[2] = {nullptr, nullptr};
+    bool cwin_valid = false;
     // host-buffer clip pipeline (mvb200_degrain_clip_host_async): copy streams + double-buffered clips
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};

@@ -161,6 +161,8 @@ def lib():
         L.mvb200_analyse_batch.argtypes = [vp, PP(AnalyseParams), PP(SuperParams), vp, i32, i32, vp, i64]
         L.mvb200_analyse_multi_batch.argtypes = [vp, PP(PP(AnalyseParams)), i32, PP(SuperParams), vp, i32, i32, PP(vp), i64]
         L.mvb200_degrain_batch.argtypes = [vp, PP(DegrainParams), PP(SuperParams), vp, vp, i32, i32, i32, PP(vp), i64, vp]
+        L.mvb200_recalculate_batch.argtypes = [vp, PP(RecalculateParams), PP(SuperParams), vp, i32, i32, vp, i64, vp, i64]
+        L.mvb200_compensate_batch.argtypes = [vp, PP(CompensateParams), PP(SuperParams), vp, i32, i32, vp, i64, vp]
         L.mvb200_degrain_clip_host_async.argtypes = [vp, PP(SuperParams), PP(PP(AnalyseParams)), i32, PP(DegrainParams), vp, vp, i32, i32, i32]
         L.mvb200_super_frame.argtypes = [vp, PP(SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
         L.mvb200_super_frame_pel.argtypes = [vp, PP(SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), i32, PP(vp), PP(C.c_ssize_t)]
