@@ -180,17 +180,7 @@ struct Cfg {
     // word layout, LDGSTS), so that it alone no longer sends the whole first step to global memory
     static constexpr bool ZB = MVB_ZB != 0 && BPS == 1; // (16-bit 16x16 blocks would drop from 9 to 8 chains per SM for its 1.5 KB)
     static constexpr int ZBOFF = BAROFF + 16;                                 // [zero block 0][zero block 1]
-#ifndef MVB_GB
-#define MVB_GB 1
-#endif
-    // GB: likewise the reference block at the global-motion candidate, when that candidate falls outside the next
-    // block's window (blocks that move against the global motion): rows of RW + 1 aligned words (any misalignment)
-    static constexpr bool GB = MVB_GB != 0 && ZB && CHROMA;
-    static constexpr int GBL = (RW + 1) * 4, GBC = (CRW + 1) * 4;             // row bytes: luma, chroma
-    static constexpr int GBBYTES = (BH * GBL + 2 * CH * GBC + 15) / 16 * 16;
-    static constexpr int GBOFF = ZBOFF + (ZB ? 2 * SRCB : 0);                 // [global block 0][global block 1]
-    static constexpr int RAWOFF = GBOFF + (GB ? 2 * GBBYTES : 0);             // raw lo/hi words of an unaligned source block (optional)
-    static_assert(!GB || (RW + 1 <= 8 && CRW + 1 <= 4 && BH % 4 == 0 && CH <= 8), "the GB lane mapping: 8 word slots per luma row, 4 per chroma row");
+    static constexpr int RAWOFF = ZBOFF + (ZB ? 2 * SRCB : 0);                // raw lo/hi words of an unaligned source block (optional)
     static constexpr int SMEM = r128(RAWOFF + 16), SMEM_RAW = r128(RAWOFF + 8 * SRCW + 16); // (+16: a row read fetches one word past the last block row)
     static_assert(BH % 4 == 0 && (BW * BPS) % 4 == 0, "block shape");
     static_assert(!CHROMA || (CH % 4 == 0 && (CW * BPS) % 4 == 0), "chroma block shape");
@@ -219,7 +209,6 @@ struct Cold {
     int wo[2][4];  // window origins of the two window buffers
     int cxmax, cymin, cymax; // CLD: limits of a chroma window origin that keep every LDGSTS address inside the plane
     int zb;                  // this level prefetches the zero-vector reference block (aligned source blocks, no field shift)
-    int gbv;                 // bit b: global-candidate block buffer b holds the block of the window buffer b's block
 };
 static_assert(sizeof(Cold) <= 256, "Cold");
 
@@ -242,7 +231,6 @@ struct Chain {
     int badcount, j, q;
     uint32_t sbuf; // shared-space address of the current window buffer
     uint32_t zbuf; // shared-space address of the current block's zero-vector reference block, or 0
-    uint32_t gbuf; // ... of the current block's global-candidate reference block, or 0
 
     __device__ __forceinline__ bool ok(int vx, int vy) const { return vx >= g.dxMin && vy >= g.dyMin && vx < g.dxMax && vy < g.dyMax; }
     __device__ __forceinline__ VEC clip(VEC v) const {
@@ -299,7 +287,6 @@ struct Chain {
     __device__ __forceinline__ void eval_step(const Cand &c, unsigned &mySy, unsigned &mySuv) const {
         const bool mine = j < NS && c.valid;
         const bool zlane = ZSLOT && C::ZB && j == 0 && zbuf != 0;
-        const bool glane = ZSLOT && C::GB && j == 1 && gbuf != 0;
         const int lvx = mine ? c.lvx : 0, lvy = mine ? c.lvy : 0, cvx = mine ? c.cvx : 0, cvy = mine ? c.cvy : 0;
         const int m = (1 << logPel) - 1;
         const int X = (g.x0 << logPel) + lvx, Y = (g.y0 << logPel) + lvy;
@@ -316,7 +303,7 @@ struct Chain {
             inside = inside && fxc >= wxc0 && fxc + C::CW <= wxc0 + C::CWB / BPS && fyc >= wyc0 && fyc + C::CH <= wyc0 + C::CWH;
             cbc = subc * C::CT + (fyc - wyc0) * C::CWB + (fxc - wxc0) * BPS;
         }
-        const unsigned outside = __ballot_sync(FULL, mine && !inside && !zlane && !glane);
+        const unsigned outside = __ballot_sync(FULL, mine && !inside && !zlane);
         unsigned aL = 0, aC = 0;
         if (outside == 0) {
             unsigned accL[C::LR], accC[2][C::CR]; // one accumulator per row: independent VABSDIFF4 chains
@@ -331,10 +318,6 @@ struct Chain {
                 al = zbuf + q * (C::RW * 4);
                 shl = 0;
                 lrow = 4 * (C::RW * 4);
-            }
-            if (glane) {                       // rows of RW + 1 words, the candidate's own misalignment (cbl's low bits)
-                al = gbuf + q * C::GBL;
-                lrow = 4 * C::GBL;
             }
 #pragma unroll
             for (int i = 0; i < C::LR; i++) {
@@ -362,11 +345,6 @@ struct Chain {
                     shc = 0;
                     crow = 4 * (C::CRW * 4);
                     cplane = C::CBYTES;
-                }
-                if (glane) {
-                    ac = gbuf + BH * C::GBL + q * C::GBC;
-                    crow = 4 * C::GBC;
-                    cplane = C::CH * C::GBC;
                 }
 #pragma unroll
                 for (int p = 0; p < 2; p++) {
@@ -845,7 +823,6 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
                 }
                 K.srcAligned = (((g0.hpad * BPS) | ((BW - P.ovX) * BPS) | (g1.hpad * BPS) | (((BW - P.ovX) >> LXR) * BPS)) & 3) == 0;
                 K.zb = C::ZB && K.srcAligned && fs == 0;
-                K.gbv = 0;
                 K.penaltyZero = P.pzero;
                 K.pglobal = P.global ? P.pglobal : P.pzero;
                 K.badrange = P.badrange;
@@ -981,7 +958,7 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
             return r;
         };
         // stages the window of the block with geometry gg around its clipped hierarchical predictor (hx, hy)
-        auto stage = [&](const Geom &gg, int hx, int hy, int buf, bool gb = false) {
+        auto stage = [&](const Geom &gg, int hx, int hy, int buf) {
             const int cx = min(max(hx, gg.dxMin), gg.dxMax - 1), cy = min(max(hy, gg.dyMin), gg.dyMax - 1);
             int wo[4];
             S.window_origin(gg, cx, cy, wo[0], wo[1], wo[2], wo[3]);
@@ -1009,42 +986,6 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
                         tma_load_3d(dst + C::LREG + C::CREG, &maps.plane[2], wo[2], K.row0_1 + wo[3], ref_frame, bar);
                     }
                 }
-            }
-            if (C::GB) {
-                // The global-motion candidate of that block, clipped the way epz() will clip it (first to the current
-                // block's bounds, then to its own): prefetched when it misses the window just placed.
-                bool want = false;
-                if (gb && K.zb) {
-                    const int m = (1 << S.logPel) - 1;
-                    const int gx = min(max(min(max(K.gmx, S.g.dxMin), S.g.dxMax - 1), gg.dxMin), gg.dxMax - 1);
-                    const int gy = min(max(min(max(K.gmy, S.g.dyMin), S.g.dyMax - 1), gg.dyMin), gg.dyMax - 1);
-                    const int X = (gg.x0 << S.logPel) + gx, Y = (gg.y0 << S.logPel) + gy;
-                    const int Xc = (gg.xc << S.logPel) + CH::cdiv(gx, LXR), Yc = (gg.yc << S.logPel) + CH::cdiv(gy, LYR);
-                    const int fx = X >> S.logPel, fy = Y >> S.logPel, fxc = Xc >> S.logPel, fyc = Yc >> S.logPel;
-                    want = !(fx >= wo[0] && fx + BW <= wo[0] + C::LWB / BPS && fy >= wo[1] && fy + BH <= wo[1] + C::LWH && fxc >= wo[2] &&
-                             fxc + C::CW <= wo[2] + C::CWB / BPS && fyc >= wo[3] && fyc + C::CH <= wo[3] + C::CWH);
-                    if (want) {
-                        const int pitch0 = K.pitch0, pitch1 = K.pitch1;
-                        const uint32_t d = smem0 + C::GBOFF + buf * C::GBBYTES;
-                        // luma: 8 word slots per row (RW + 1 used), 4 rows per instruction
-                        const int lcol = lane & 7, lr = lane >> 3;
-                        const uint8_t *pl = K.rbase[0] + (long long)((X & m) | ((Y & m) << S.logPel)) * K.sub0 + (long long)fy * pitch0 + ((fx * BPS) & ~3) + lcol * 4;
-                        if (lcol <= C::RW) {
-#pragma unroll
-                            for (int k = 0; k < BH / 4; k++)
-                                cp_async4(d + (4 * k + lr) * C::GBL + lcol * 4, pl + (long long)(4 * k + lr) * pitch0);
-                        }
-                        // chroma: 4 word slots per row (CRW + 1 used), 8 rows per instruction, one instruction per plane
-                        const int ccol = lane & 3, cr = lane >> 2;
-                        const long long oc = (long long)((Xc & m) | ((Yc & m) << S.logPel)) * K.sub1 + (long long)(fyc + cr) * pitch1 + ((fxc * BPS) & ~3) + ccol * 4;
-                        if (ccol <= C::CRW && cr < C::CH) {
-                            cp_async4(d + BH * C::GBL + cr * C::GBC + ccol * 4, K.rbase[1] + oc);
-                            cp_async4(d + BH * C::GBL + C::CH * C::GBC + cr * C::GBC + ccol * 4, K.rbase[2] + oc);
-                        }
-                    }
-                }
-                if (lane == 0)
-                    K.gbv = (K.gbv & ~(1 << buf)) | ((want ? 1 : 0) << buf);
             }
             if (C::CLD) {
                 // chroma windows: 16-byte rows, 12 rows per sub-plane, word w of a plane's window (sub-plane, row, column
@@ -1164,7 +1105,6 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
             phasebits ^= 1u << cbuf;
             S.sbuf = smem0 + cbuf * C::BUF;
             S.zbuf = (C::ZB && K.zb) ? smem0 + C::ZBOFF + (t & 1) * C::SRCB : 0u;
-            S.gbuf = (C::GB && !smallest && ((K.gbv >> cbuf) & 1)) ? smem0 + C::GBOFF + cbuf * C::GBBYTES : 0u;
             S.wx0 = K.wo[cbuf][0];
             S.wy0 = K.wo[cbuf][1];
             S.wxc0 = K.wo[cbuf][2];
@@ -1176,7 +1116,7 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
                 issue_src(gn.x0, gn.y0, gn.xc, gn.yc, (t + 1) & 1);
                 if (!smallest) {
                     const VEC hn = read_vec((t + 1) & 1);
-                    stage(gn, hn.x, hn.y, cbuf ^ 1, true);
+                    stage(gn, hn.x, hn.y, cbuf ^ 1);
                 }
             }
             S.epz(prx, pry, blkIdx);
