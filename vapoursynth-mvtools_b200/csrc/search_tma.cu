@@ -179,7 +179,8 @@ struct Cfg {
     // around the hierarchical predictor of fast motion -- is prefetched beside the source block (same position, same
     // word layout, LDGSTS), so that it alone no longer sends the whole first step to global memory
     static constexpr bool ZB = MVB_ZB != 0 && BPS == 1; // (16-bit 16x16 blocks would drop from 9 to 8 chains per SM for its 1.5 KB)
-    static constexpr int ZBOFF = BAROFF + 16;                                 // [zero block 0][zero block 1]
+    static constexpr int GEOOFF = BAROFF + 16;                                // the next block's Geom (8 ints), computed once at prefetch time
+    static constexpr int ZBOFF = GEOOFF + 32;                                 // [zero block 0][zero block 1]
     static constexpr int RAWOFF = ZBOFF + (ZB ? 2 * SRCB : 0);                // raw lo/hi words of an unaligned source block (optional)
     static constexpr int SMEM = r128(RAWOFF + 16), SMEM_RAW = r128(RAWOFF + 8 * SRCW + 16); // (+16: a row read fetches one word past the last block row)
     static_assert(BH % 4 == 0 && (BW * BPS) % 4 == 0, "block shape");
@@ -735,25 +736,16 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
     S.K = &K;
     S.penaltyNew = P.pnew;
 
-    // cooperative source-block load: word w of the block (luma rows, then U rows, then V rows) -> lane w % 32
-    int sw_plane[C::NSI], sw_row[C::NSI], sw_col[C::NSI];
+    // cooperative source-block load: word w of the block (luma rows, then U rows, then V rows) -> lane w % 32;
+    // bit k of sw_luma: this lane's k-th word is a luma word
+    unsigned sw_luma = 0;
 #pragma unroll
     for (int k = 0; k < C::NSI; k++) {
         int w = lane + 32 * k;
         w = w < C::SRCW ? w : 0;
-        const int lw = C::LBYTES / 4, cw = C::CBYTES / 4;
-        if (w < lw) {
-            sw_plane[k] = 0;
-            sw_row[k] = w / C::RW;
-            sw_col[k] = (w % C::RW) * 4;
-        } else {
-            const int w2 = w - lw;
-            sw_plane[k] = (CHROMA && w2 >= cw) ? 2 : 1;
-            const int w3 = (CHROMA && w2 >= cw) ? w2 - cw : w2;
-            sw_row[k] = w3 / C::CRW;
-            sw_col[k] = (w3 % C::CRW) * 4;
-        }
+        sw_luma |= (w < C::LBYTES / 4 ? 1u : 0u) << k;
     }
+    const long long refdelta = job.ref - job.src; // frames share one layout: a reference word lies this far from the source word
 
     for (int l = L - 1; l >= 0; l--) {
         S.logPel = l == 0 ? P.logPel : 0;
@@ -848,6 +840,20 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
         const int nBlk = nBlkX * nBlkY;
         const bool smallest = (l == L - 1);
 
+        // this lane's words of a source block at the level's origin: a block adds only its own offset (issue_src)
+        const uint8_t *srcp[C::NSI];
+#pragma unroll
+        for (int k = 0; k < C::NSI; k++) {
+            int w = lane + 32 * k;
+            w = w < C::SRCW ? w : 0;
+            constexpr int lw = C::LBYTES / 4, cw = C::CBYTES / 4;
+            if (w < lw) {
+                srcp[k] = K.sbase[0] + (long long)(w / C::RW) * K.pitch0 + (w % C::RW) * 4;
+            } else {
+                const int w2 = w - lw, pl = (CHROMA && w2 >= cw) ? 2 : 1, w3 = pl == 2 ? w2 - cw : w2;
+                srcp[k] = K.sbase[pl] + (long long)(w3 / C::CRW) * K.pitch1 + (w3 % C::CRW) * 4;
+            }
+        }
         auto block_geom = [&](int bx, int by, Geom &gg) {
             const int hp0 = K.hp0, vp0 = K.vp0;
             gg.x0 = hp0 + K.stepX * bx;
@@ -858,6 +864,28 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
             gg.dyMax = (K.ph0 - gg.y0 - BH - vp0 + K.vps) << S.logPel;
             gg.dxMin = -((gg.x0 - hp0 + K.hps) << S.logPel);
             gg.dyMin = -((gg.y0 - vp0 + K.vps) << S.logPel);
+        };
+        // a block's geometry is computed once, when the block is prefetched, and handed to the next iteration through
+        // shared memory (8 ints): one lane stores, every lane reloads after the end-of-block __syncwarp
+        auto store_geom = [&](const Geom &gg) {
+            __syncwarp(); // every lane has read the previous contents
+            if (lane == 0) {
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem0 + C::GEOOFF), "r"(gg.x0), "r"(gg.y0), "r"(gg.xc), "r"(gg.yc) : "memory");
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(smem0 + C::GEOOFF + 16), "r"(gg.dxMin), "r"(gg.dxMax), "r"(gg.dyMin), "r"(gg.dyMax) : "memory");
+            }
+        };
+        auto load_geom = [&](Geom &gg) {
+            unsigned a[4], b[4];
+            lds_vec(smem0 + C::GEOOFF, a);
+            lds_vec(smem0 + C::GEOOFF + 16, b);
+            gg.x0 = (int)a[0];
+            gg.y0 = (int)a[1];
+            gg.xc = (int)a[2];
+            gg.yc = (int)a[3];
+            gg.dxMin = (int)b[0];
+            gg.dxMax = (int)b[1];
+            gg.dyMin = (int)b[2];
+            gg.dyMax = (int)b[3];
         };
         // meander scan order (:1037-1055): successor of (bx, by, dir)
         auto succ = [&](int bx, int by, int dir, int &nbx, int &nby, int &ndir) {
@@ -875,16 +903,15 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
         auto issue_src = [&](int x0, int y0, int xc, int yc, int buf) {
             const bool aligned = K.srcAligned;
             const bool zb = K.zb != 0;
-            const int pitch0 = K.pitch0, pitch1 = K.pitch1;
+            const int orgl = y0 * K.pitch0 + x0 * BPS, orgc = yc * K.pitch1 + xc * BPS; // (a plane is far below 2 GB)
 #pragma unroll
             for (int k = 0; k < C::NSI; k++) {
                 if (lane + 32 * k < C::SRCW) {
-                    const int pl = sw_plane[k];
-                    const uint8_t *p = K.sbase[pl] + (long long)((pl == 0 ? y0 : yc) + sw_row[k]) * (pl == 0 ? pitch0 : pitch1) + (pl == 0 ? x0 : xc) * BPS + sw_col[k];
+                    const uint8_t *p = srcp[k] + (((sw_luma >> k) & 1u) ? orgl : orgc);
                     if (aligned) {
                         cp_async4(smem0 + C::SRCOFF + buf * C::SRCB + 4 * (lane + 32 * k), p);
                         if (C::ZB && zb) // same position in the reference frame: the block at the zero vector (sub-plane 0)
-                            cp_async4(smem0 + C::ZBOFF + buf * C::SRCB + 4 * (lane + 32 * k), K.rbase[pl] + (p - K.sbase[pl]));
+                            cp_async4(smem0 + C::ZBOFF + buf * C::SRCB + 4 * (lane + 32 * k), p + refdelta);
                     } else {
                         const unsigned *w = (const unsigned *)((unsigned long long)p & ~3ull);
                         cp_async4(smem0 + C::RAWOFF + 8 * (lane + 32 * k), w);
@@ -905,7 +932,7 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
                     if (lane + 32 * k < C::SRCW) {
                         unsigned lh[2];
                         lds_vec(smem0 + C::RAWOFF + 8 * (lane + 32 * k), lh);
-                        sts32(dst + 4 * (lane + 32 * k), __funnelshift_r(lh[0], lh[1], sw_plane[k] == 0 ? shl : shc));
+                        sts32(dst + 4 * (lane + 32 * k), __funnelshift_r(lh[0], lh[1], ((sw_luma >> k) & 1u) ? shl : shc));
                     }
                 __syncwarp();
             }
@@ -1029,6 +1056,7 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
             if (lane < 4)
                 sts32(slot_of_lane(1), (unsigned)w1);
             block_geom(0, 0, S.g);
+            store_geom(S.g);
             issue_src(S.g.x0, S.g.y0, S.g.xc, S.g.yc, 0);
             commit_src(S.g.x0, S.g.xc, 0); // (its __syncwarp also publishes the vector slots)
             if (!smallest) {
@@ -1056,7 +1084,7 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
                 succ(nbx, nby, ndir, n2x, n2y, n2d);
                 pv = fetch_word(t + 2 < nBlk, n2x, n2y, hasMore, nbx, nby, ndir);
             }
-            block_geom(bx, by, S.g);
+            load_geom(S.g); // = block_geom(bx, by): stored when this block was prefetched
             S.nLambda = by == 0 ? 0 : K.nLambdaLevel;
             S.predictor = S.clip(hier);
             // pobFetchPredictors, PlaneOfBlocks.cpp:419-463
@@ -1113,6 +1141,7 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
             if (hasMore) {
                 Geom gn;
                 block_geom(nbx, nby, gn);
+                store_geom(gn);
                 issue_src(gn.x0, gn.y0, gn.xc, gn.yc, (t + 1) & 1);
                 if (!smallest) {
                     const VEC hn = read_vec((t + 1) & 1);
