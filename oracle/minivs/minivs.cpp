@@ -233,6 +233,11 @@ int VS_CC queryVideoFormat(VSVideoFormat *format, int colorFamily, int sampleTyp
     return 1;
 }
 
+// inverse of VS_MAKE_VIDEO_ID (VapourSynth4.h)
+int VS_CC getVideoFormatByID(VSVideoFormat *format, uint32_t id, VSCore *core) {
+    return queryVideoFormat(format, (id >> 28) & 0xF, (id >> 24) & 0xF, (id >> 16) & 0xFF, (id >> 8) & 0xFF, id & 0xFF, core);
+}
+
 // ------------------------------------------------------------------- nodes
 
 void VS_CC freeNode(VSNode *node) {
@@ -628,6 +633,13 @@ VSMap *VS_CC invoke(VSPlugin *plugin, const char *name, const VSMap *args) {
     return out;
 }
 
+VSPlugin *VS_CC getPluginByID(const char *identifier, VSCore *core) {
+    for (VSPlugin *p : core->plugins)
+        if (p->id == identifier)
+            return p;
+    return nullptr;
+}
+
 int VS_CC apiGetAPIVersion(void) { return VAPOURSYNTH_API_VERSION; }
 
 void VS_CC logMessage(int msgType, const char *msg, VSCore *) {
@@ -659,6 +671,8 @@ VSAPI makeApi() {
     a.getFrameWidth = getFrameWidth;
     a.getFrameHeight = getFrameHeight;
     a.queryVideoFormat = queryVideoFormat;
+    a.getVideoFormatByID = getVideoFormatByID;
+    a.getPluginByID = getPluginByID;
     a.getFrame = getFrame;
     a.getFrameFilter = getFrameFilter;
     a.requestFrameFilter = requestFrameFilter;
