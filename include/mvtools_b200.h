@@ -18,6 +18,11 @@
  *   mvdegrainGetFrame  MVDegrains.cpp:85-330          mvb200_degrain_frame / _batch
  *   mvcompensateCreate/GetFrame MVCompensate.c:73-575 mvb200_compensate_init / _frame
  *   mvrecalculateCreate/GetFrame MVRecalculate.c:68-553 mvb200_recalculate_init / _frame
+ *   -- consumers of the vector clips --
+ *   mvscdetectionCreate/GetFrame MVSCDetection.c:43-131 mvb200_scdetection_init / _frame / _batch
+ *   mvmaskCreate/GetFrame        MVMask.c:74-344        mvb200_mask_init / _frame / _batch
+ *   mvfinestCreate/GetFrame      MVFinest.c:47-207      mvb200_finest_layout / _frame / _batch
+ *   mvflowCreate/GetFrame        MVFlow.cpp:157-593     mvb200_flow_init / _frame / _batch
  *
  * The VapourSynth plugin (vapoursynth-mvtools_b200/plugin, exporting
  * VapourSynthPluginInit2 like EntryPoint.c:28-50) is a thin host-side glue over
@@ -205,6 +210,55 @@ typedef struct mvb200_recalculate_params {
     int32_t vectors_size;
 } mvb200_recalculate_params;
 
+
+/* ------------------------------------------ SCDetection / Mask / Finest / Flow */
+/* Consumers of the vector clips.  Float arguments: NaN = "not given". */
+
+typedef struct mvb200_scdetection_params {
+    mvb200_analysis_data vd;
+    int64_t nSCD1;                /* scaled (scaleThSCD, MVAnalysisData.c:7-31) */
+    int32_t nSCD2;
+} mvb200_scdetection_params;
+
+typedef struct mvb200_mask_args {
+    double ml, gamma;             /* NaN = default (100.0, 1.0) */
+    int32_t kind;                 /* MVB200_UNSET = default (0) */
+    double time;                  /* NaN = default (100.0) */
+    int32_t ysc;                  /* MVB200_UNSET = default (0) */
+    int64_t thscd1;               /* MVB200_UNSET64 = default */
+    int32_t thscd2;               /* MVB200_UNSET = default */
+} mvb200_mask_args;
+
+typedef struct mvb200_mask_params {
+    mvb200_analysis_data vd;
+    int32_t kind, time256, nSceneChangeValue;
+    float ml, fGamma, fMaskNormFactor, fMaskNormFactor2, fHalfGamma; /* MVMask.c:299-302 (float arithmetic) */
+    int64_t nSCD1;
+    int32_t nSCD2;
+    int32_t clip_gray;            /* the input clip was GRAY8: the output is YUV444P8 (MVMask.c:323-324) */
+    int32_t nWidth, nHeight, nWidthUV, nHeightUV, nWidthB, nHeightB, nWidthBUV, nHeightBUV;
+} mvb200_mask_params;
+
+typedef struct mvb200_flow_args {
+    double time;                  /* NaN = default (100.0) */
+    int32_t mode, fields;         /* MVB200_UNSET = default (0) */
+    int64_t thscd1;
+    int32_t thscd2;
+    int32_t tff;                  /* MVB200_UNSET = not given */
+} mvb200_flow_args;
+
+typedef struct mvb200_flow_params {
+    mvb200_analysis_data vd;
+    int32_t time256, mode, fields, tff, tff_exists;
+    int64_t nSCD1;
+    int32_t nSCD2;
+    int32_t bits, ssw, ssh, gray, nplanes;
+    int32_t super_hpad, super_vpad, super_pel, super_levels;
+    /* MVFlow.cpp:529-548 */
+    int32_t nBlkXP, nBlkYP, nWidthP, nHeightP, nWidthPUV, nHeightPUV, nWidthUV, nHeightUV, nHPaddingUV, nVPaddingUV, VPitchY, VPitchUV;
+    int32_t num_frames;
+} mvb200_flow_params;
+
 /* ------------------------------------------------------------- host logic */
 /* (pure host code: usable without a GPU; restates the reference's *Create) */
 
@@ -227,6 +281,20 @@ MVB200_API int mvb200_compensate_init(const mvb200_compensate_args *a, const mvb
 
 /* MVRecalculate.c:263-553 */
 MVB200_API int mvb200_recalculate_init(const mvb200_recalculate_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *old, int num_frames, mvb200_recalculate_params *out);
+
+
+/* MVSCDetection.c:89-131.  thscd1 / thscd2: MVB200_UNSET64 / MVB200_UNSET = default. */
+MVB200_API int mvb200_scdetection_init(int64_t thscd1, int32_t thscd2, const mvb200_analysis_data *vd, mvb200_scdetection_params *out);
+
+/* MVMask.c:221-344.  The input clip's format: bits, log2 subsampling, gray. */
+MVB200_API int mvb200_mask_init(const mvb200_mask_args *a, const mvb200_analysis_data *vd, int clip_bits, int clip_ssw, int clip_ssh, int clip_gray, mvb200_mask_params *out);
+
+/* MVFlow.cpp:395-575.  `sp` describes the super clip, (clip_w, clip_h) the source clip. */
+MVB200_API int mvb200_flow_init(const mvb200_flow_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd, int num_frames, mvb200_flow_params *out);
+
+/* InitTables, SimpleResize.cpp:26-56: offsets[out] and weights[out] (14-bit) of the bilinear resizer the Mask / Flow
+ * filters upsize their per-block fields with (float arithmetic, restated on the host; uploaded once per configuration). */
+MVB200_API void mvb200_simple_resize_tables(int out, int in, int32_t *offsets, int32_t *weights);
 
 /* ---------------------------------------------------------------- context */
 
@@ -316,6 +384,36 @@ MVB200_API int mvb200_degrain_frame(mvb200_ctx *ctx, const mvb200_degrain_params
 MVB200_API int mvb200_compensate_frame(mvb200_ctx *ctx, const mvb200_compensate_params *cp, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *vectors, int field_shift, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
 
 MVB200_API int mvb200_recalculate_frame(mvb200_ctx *ctx, const mvb200_recalculate_params *rp, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *old_vectors, int field_shift, uint8_t *vectors_out);
+
+
+/* ------------------------------------- SCDetection / Mask / Finest / Flow entry points */
+
+/* mvscdetectionGetFrame (MVSCDetection.c:43-74): scene_change[i] = !fgopIsUsable(blob i) for n blobs (host or device
+ * blobs; the flags always land in HOST memory).  The plugin writes the flag as _SceneChangePrev / _SceneChangeNext. */
+MVB200_API int mvb200_scdetection_frame(mvb200_ctx *ctx, const mvb200_scdetection_params *p, const uint8_t *vectors, int32_t *scene_change);
+MVB200_API int mvb200_scdetection_batch(mvb200_ctx *ctx, const mvb200_scdetection_params *p, const void *dev_vectors, int64_t vectors_stride, int n, int32_t *scene_change);
+
+/* mvmaskGetFrame (MVMask.c:74-203).  The output is 8-bit, three planes (plane sizes nWidth x nHeight and
+ * nWidthUV x nHeightUV of the params); src_luma is only read for kind = 5 (luma is passed through). */
+MVB200_API int mvb200_mask_frame(mvb200_ctx *ctx, const mvb200_mask_params *p, const uint8_t *src_luma, ptrdiff_t src_stride, const uint8_t *vectors, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
+/* device resident: n blobs -> n masks; planes back to back with pitch round_up(w, 256) (mvb200_mask_layout);
+ * dev_src_luma (kind 5 only): n luma planes, src_pitch / src_frame_bytes apart. */
+MVB200_API void mvb200_mask_layout(const mvb200_mask_params *p, mvb200_frame_layout *l);
+MVB200_API int mvb200_mask_batch(mvb200_ctx *ctx, const mvb200_mask_params *p, const void *dev_src_luma, int64_t src_pitch, int64_t src_frame_bytes, const void *dev_vectors, int64_t vectors_stride, int n, void *dev_dst);
+
+/* mvfinestGetFrame (MVFinest.c:47-125): the pel^2 sub-planes of level 0 interleaved into one plane of
+ * (W + 2 hpad) pel x (H + 2 vpad) pel samples per plane (pel 1: level 0 as it is). */
+MVB200_API void mvb200_finest_layout(const mvb200_super_params *sp, mvb200_frame_layout *l);
+MVB200_API int mvb200_finest_frame(mvb200_ctx *ctx, const mvb200_super_params *sp, const uint8_t *const super[3], const ptrdiff_t super_stride[3], uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
+MVB200_API int mvb200_finest_batch(mvb200_ctx *ctx, const mvb200_super_params *sp, const void *dev_super, int n, void *dev_dst);
+
+/* mvflowGetFrame (MVFlow.cpp:157-368): per-pixel motion compensation of the reference frame by the upsized vector
+ * field.  The engine reads the pel sub-planes of the reference SUPER frame directly (the reference materialises them
+ * as an mv.Finest clip first; same samples).  *usable = 0 (scene change, invalid vectors or ref_super == NULL) leaves
+ * dst untouched: the reference returns the source frame itself then (MVFlow.cpp:362-366). */
+MVB200_API int mvb200_flow_frame(mvb200_ctx *ctx, const mvb200_flow_params *fp, const mvb200_super_params *sp, const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *vectors, int field_shift, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable);
+/* device resident, frames [first, first + n): unusable frames are copies of the source clip's frame (dev_src, clip layout). */
+MVB200_API int mvb200_flow_batch(mvb200_ctx *ctx, const mvb200_flow_params *fp, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int first, int n, const void *dev_vectors, int64_t vectors_stride, void *dev_dst);
 
 #ifdef __cplusplus
 }

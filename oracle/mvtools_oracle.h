@@ -35,6 +35,18 @@ MVO_API int mvo_compensate_frame(const mvb200_compensate_params *cp, const mvb20
 /* overInit, Overlap.cpp:40-125: 9 windows of nx*ny int16 */
 MVO_API void mvo_overlap_windows(int nx, int ny, int ox, int oy, int16_t *out9);
 
+/* ---- consumers of the vector clips (mvtools_oracle_flow.c) ---- */
+/* mvscdetectionGetFrame, MVSCDetection.c:43-74 */
+MVO_API int mvo_scdetection_frame(const mvb200_scdetection_params *p, const uint8_t *vectors, int32_t *scene_change);
+/* mvmaskGetFrame, MVMask.c:74-203 */
+MVO_API int mvo_mask_frame(const mvb200_mask_params *p, const uint8_t *src_luma, ptrdiff_t src_stride, const uint8_t *vectors, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
+/* mvfinestGetFrame, MVFinest.c:47-125 */
+MVO_API int mvo_finest_frame(const mvb200_super_params *sp, const uint8_t *const super[3], const ptrdiff_t super_stride[3], uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
+/* mvflowGetFrame, MVFlow.cpp:157-368 */
+MVO_API int mvo_flow_frame(const mvb200_flow_params *fp, const mvb200_super_params *sp, const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *vectors, int field_shift, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable);
+/* InitTables, SimpleResize.cpp:26-56 */
+MVO_API void mvo_simple_resize_tables(int out, int in, int32_t *offsets, int32_t *weights);
+
 /* kernels exposed for unit parity tests */
 MVO_API unsigned mvo_sad(const uint8_t *a, ptrdiff_t apitch, const uint8_t *b, ptrdiff_t bpitch, int w, int h, int bytes);
 MVO_API unsigned mvo_satd(const uint8_t *a, ptrdiff_t apitch, const uint8_t *b, ptrdiff_t bpitch, int w, int h, int bytes);

@@ -1,0 +1,495 @@
+/* TEST INFRASTRUCTURE -- CPU oracle, second part: the consumers of the vector clips that SURVEY.md
+ * section 8f ranks next (mv.SCDetection, mv.Mask, mv.Finest, mv.Flow).  A plain-C restatement of the
+ * reference's algorithms, every function citing the reference lines it follows
+ * (dubhater/vapoursynth-mvtools @ e516e90, paths under src/).  PINNED: tests/test_oracle_flow.py checks it
+ * against goldens produced by the compiled reference (oracle/_ref/libmvtools_ref.so) and, where that
+ * library is present, against the reference live.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may load this; the product
+ * (libmvtools_b200.so, the plugin) never does. */
+#include "mvtools_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct VEC {
+    int32_t x, y;
+    int64_t sad;
+} VEC;
+
+static VEC get_vec(const uint8_t *level0, int i) { /* VECTOR arrays are only 4-byte aligned inside the blob */
+    VEC v;
+    memcpy(&v, level0 + (size_t)i * 16, 16);
+    return v;
+}
+
+/* fgopUpdate, Fakery.c:110-121: levels are stored coarsest first, each with a 4-byte size header */
+static const uint8_t *blob_level0(const uint8_t *blob, const mvb200_analysis_data *vd, int *validity) {
+    int32_t v;
+    memcpy(&v, blob + 4, 4);
+    *validity = (v == 1); /* fgopGetValidity, Fakery.c:103-107 */
+    const uint8_t *p = blob + 8;
+    for (int i = vd->nLvCount - 1; i >= 1; i--) {
+        int32_t size;
+        memcpy(&size, p, 4);
+        p += size;
+    }
+    return p + 4;
+}
+
+/* fgopIsUsable, Fakery.c:144-146 with fpobIsSceneChange, Fakery.c:52-58 */
+static int is_usable(const uint8_t *blob, const mvb200_analysis_data *vd, int64_t th1, int th2) {
+    int validity;
+    const uint8_t *l0 = blob_level0(blob, vd, &validity);
+    int sum = 0;
+    for (int i = 0; i < vd->nBlkX * vd->nBlkY; i++)
+        sum += get_vec(l0, i).sad > th1 ? 1 : 0;
+    return !(sum > th2) && validity;
+}
+
+/* mvscdetectionGetFrame, MVSCDetection.c:43-74: the value of _SceneChangePrev / _SceneChangeNext */
+int mvo_scdetection_frame(const mvb200_scdetection_params *p, const uint8_t *vectors, int32_t *scene_change) {
+    *scene_change = !is_usable(vectors, &p->vd, p->nSCD1, p->nSCD2);
+    return 0;
+}
+
+/* ------------------------------------------------------------ SimpleResize */
+
+enum { WSHIFT = 14, WMAX = 1 << WSHIFT, WHALF = WMAX / 2 }; /* SimpleResize.h:31-35 */
+
+/* InitTables, SimpleResize.cpp:26-56 */
+void mvo_simple_resize_tables(int out, int in, int32_t *offsets, int32_t *weights) {
+    float leftmost = 0.5f, rightmost = in - 0.5f;
+    int leftmost_idx = (int)leftmost > 0 ? (int)leftmost : 0;
+    int rightmost_idx = (int)rightmost < in - 1 ? (int)rightmost : in - 1;
+    for (int i = 0; i < out; i++) {
+        float position = (i + 0.5f) * (float)in / (float)out;
+        float weight;
+        int offset;
+        if (position <= leftmost) {
+            offset = leftmost_idx;
+            weight = 0.0f;
+        } else if (position >= rightmost) {
+            offset = rightmost_idx - 1;
+            weight = 1.0f;
+        } else {
+            offset = (int)(position - leftmost);
+            weight = position - leftmost - offset;
+        }
+        offsets[i] = offset;
+        weights[i] = (int)(weight * WMAX);
+    }
+}
+
+typedef struct Resizer { /* simpleInit, SimpleResize.cpp:119-157 */
+    int dst_w, dst_h, src_w, src_h, limit_w, limit_h, pel;
+    int32_t *voff, *vwt, *hoff, *hwt;
+} Resizer;
+
+static void resizer_init(Resizer *r, int dst_w, int dst_h, int src_w, int src_h, int limit_w, int limit_h, int pel) {
+    r->dst_w = dst_w;
+    r->dst_h = dst_h;
+    r->src_w = src_w;
+    r->src_h = src_h;
+    r->limit_w = limit_w;
+    r->limit_h = limit_h;
+    r->pel = pel;
+    r->voff = malloc(sizeof(int32_t) * (size_t)dst_h);
+    r->vwt = malloc(sizeof(int32_t) * (size_t)dst_h);
+    r->hoff = malloc(sizeof(int32_t) * (size_t)dst_w);
+    r->hwt = malloc(sizeof(int32_t) * (size_t)dst_w);
+    mvo_simple_resize_tables(dst_w, src_w, r->hoff, r->hwt);
+    mvo_simple_resize_tables(dst_h, src_h, r->voff, r->vwt);
+}
+
+static void resizer_free(Resizer *r) {
+    free(r->voff);
+    free(r->vwt);
+    free(r->hoff);
+    free(r->hwt);
+}
+
+/* simpleResize<uint8_t>, SimpleResize.cpp:60-116 (no limiting for 8-bit data) */
+static void resize_u8(const Resizer *r, uint8_t *dst, ptrdiff_t dst_stride, const uint8_t *src, int src_stride) {
+    uint8_t *work = malloc((size_t)r->src_w);
+    for (int y = 0; y < r->dst_h; y++) {
+        int wb = r->vwt[y], wt = WMAX - wb;
+        const uint8_t *s1 = src + r->voff[y] * src_stride, *s2 = s1 + src_stride;
+        for (int x = 0; x < r->src_w; x++)
+            work[x] = (uint8_t)((s1[x] * wt + s2[x] * wb + WHALF) >> WSHIFT);
+        for (int x = 0; x < r->dst_w; x++) {
+            int wr = r->hwt[x], wl = WMAX - wr, o = r->hoff[x];
+            dst[x] = (uint8_t)((work[o] * wl + work[o + 1] * wr + WHALF) >> WSHIFT);
+        }
+        dst += dst_stride;
+    }
+    free(work);
+}
+
+/* simpleResize<int16_t>, SimpleResize.cpp:60-116: vectors are limited so that the position they point at stays
+ * inside the frame (the running minimum / maximum of :66-70,83-86,97-102,108-111) */
+static void resize_i16(const Resizer *r, int16_t *dst, int dst_stride, const int16_t *src, int src_stride, int horizontal_vectors) {
+    int pel = r->pel;
+    int minimum = 0, maximum = r->limit_h * pel - 1;
+    int hstep = horizontal_vectors ? pel : 0, vstep = horizontal_vectors ? 0 : pel;
+    int16_t *work = malloc(sizeof(int16_t) * (size_t)r->src_w);
+    for (int y = 0; y < r->dst_h; y++) {
+        int wb = r->vwt[y], wt = WMAX - wb;
+        const int16_t *s1 = src + r->voff[y] * src_stride, *s2 = s1 + src_stride;
+        for (int x = 0; x < r->src_w; x++)
+            work[x] = (int16_t)((s1[x] * wt + s2[x] * wb + WHALF) >> WSHIFT);
+        if (horizontal_vectors) {
+            minimum = 0;
+            maximum = r->limit_w * pel - 1;
+        }
+        for (int x = 0; x < r->dst_w; x++) {
+            int wr = r->hwt[x], wl = WMAX - wr, o = r->hoff[x];
+            int result = (work[o] * wl + work[o + 1] * wr + WHALF) >> WSHIFT;
+            result = result < maximum ? result : maximum; /* std::max(minimum, std::min(result, maximum)) */
+            result = result > minimum ? result : minimum;
+            minimum -= hstep;
+            maximum -= hstep;
+            dst[x] = (int16_t)result;
+        }
+        dst += dst_stride;
+        minimum -= vstep;
+        maximum -= vstep;
+    }
+    free(work);
+}
+
+/* ------------------------------------------------------------------- Mask */
+
+/* mvmaskLength, MVMask.c:65-71 */
+static uint8_t mask_length(VEC v, int pel, float fMaskNormFactor2, float fHalfGamma) {
+    double norme = (double)(v.x * v.x + v.y * v.y) / (pel * pel);
+    double l = 255 * pow(norme * fMaskNormFactor2, fHalfGamma);
+    return (uint8_t)((l > 255) ? 255 : l);
+}
+
+/* ByteNorm, MaskFun.cpp:129-133 */
+static uint8_t byte_norm(int64_t sad, double dSADNormFactor, double fGamma) {
+    double l = 255 * pow(sad * dSADNormFactor, fGamma);
+    return (uint8_t)((l > 255) ? 255 : l);
+}
+
+/* MakeSADMaskTime, MaskFun.cpp:136-160 */
+static void sad_mask_time(const uint8_t *l0, int nBlkX, int nBlkY, double dSADNormFactor, double fGamma, int nPel, uint8_t *mask, int pitch, int time256, int stepX, int stepY, int bits) {
+    memset(mask, 0, (size_t)nBlkY * pitch);
+    int time4096X = (256 - time256) * 16 / (stepX * nPel);
+    int time4096Y = (256 - time256) * 16 / (stepY * nPel);
+    for (int by = 0; by < nBlkY; by++)
+        for (int bx = 0; bx < nBlkX; bx++) {
+            VEC v = get_vec(l0, bx + by * nBlkX);
+            int bxi = bx - v.x * time4096X / 4096;
+            int byi = by - v.y * time4096Y / 4096;
+            if (bxi < 0 || bxi >= nBlkX || byi < 0 || byi >= nBlkY) {
+                bxi = bx;
+                byi = by;
+            }
+            int64_t sad = get_vec(l0, bxi + byi * nBlkX).sad >> (bits - 8);
+            mask[bx + by * pitch] = byte_norm(sad, dSADNormFactor, fGamma);
+        }
+}
+
+/* ByteOccMask, MaskFun.cpp:85-90 */
+static void byte_occ_mask(uint8_t *m, int occlusion, double occnorm, double fGamma) {
+    int v;
+    if (fGamma == 1.0)
+        v = (int)(255 * occlusion * occnorm);
+    else
+        v = (int)(255 * pow(occlusion * occnorm, fGamma));
+    v = v < 255 ? v : 255;
+    *m = *m > v ? *m : (uint8_t)v;
+}
+
+/* MakeVectorOcclusionMaskTime, MaskFun.cpp:92-126 */
+static void occlusion_mask_time(const uint8_t *l0, int isBackward, int nBlkX, int nBlkY, double dMaskNormDivider, double fGamma, int nPel, uint8_t *occ, int pitch, int time256, int stepX, int stepY) {
+    memset(occ, 0, (size_t)pitch * nBlkY);
+    int time4096X = time256 * 16 / (stepX * nPel);
+    int time4096Y = time256 * 16 / (stepY * nPel);
+    double occnormX = 80.0 / (dMaskNormDivider * stepX * nPel);
+    double occnormY = 80.0 / (dMaskNormDivider * stepY * nPel);
+    for (int by = 0; by < nBlkY; by++)
+        for (int bx = 0; bx < nBlkX; bx++) {
+            int i = bx + by * nBlkX;
+            VEC v = get_vec(l0, i);
+            if (bx < nBlkX - 1) {
+                int vx1 = get_vec(l0, i + 1).x;
+                if (vx1 < v.x) {
+                    int occlusion = v.x - vx1;
+                    int lo = bx + 1 - occlusion * time4096X / 4096;
+                    int minb = isBackward ? (lo > 0 ? lo : 0) : bx;
+                    int maxb = isBackward ? bx + 1 : (lo < nBlkX - 1 ? lo : nBlkX - 1);
+                    for (int bxi = minb; bxi <= maxb; bxi++)
+                        byte_occ_mask(&occ[bxi + by * pitch], occlusion, occnormX, fGamma);
+                }
+            }
+            if (by < nBlkY - 1) {
+                int vy1 = get_vec(l0, i + nBlkX).y;
+                if (vy1 < v.y) {
+                    int occlusion = v.y - vy1;
+                    int lo = by + 1 - occlusion * time4096Y / 4096;
+                    int minb = isBackward ? (lo > 0 ? lo : 0) : by;
+                    int maxb = isBackward ? by + 1 : (lo < nBlkY - 1 ? lo : nBlkY - 1);
+                    for (int byi = minb; byi <= maxb; byi++)
+                        byte_occ_mask(&occ[bx + byi * pitch], occlusion, occnormY, fGamma);
+                }
+            }
+        }
+}
+
+static int clamp255(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
+
+/* mvmaskGetFrame, MVMask.c:74-203 */
+int mvo_mask_frame(const mvb200_mask_params *p, const uint8_t *src_luma, ptrdiff_t src_stride, const uint8_t *vectors, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
+    const mvb200_analysis_data *vd = &p->vd;
+    const int kind = p->kind, nWidth = p->nWidth, nHeight = p->nHeight, nWidthUV = p->nWidthUV, nHeightUV = p->nHeightUV;
+    if (is_usable(vectors, vd, p->nSCD1, p->nSCD2)) {
+        int validity;
+        const uint8_t *l0 = blob_level0(vectors, vd, &validity);
+        const int nBlkX = vd->nBlkX, nBlkY = vd->nBlkY, n = nBlkX * nBlkY;
+        uint8_t *small = malloc((size_t)n), *smallV = malloc((size_t)n);
+        const int stepX = vd->nBlkSizeX - vd->nOverlapX, stepY = vd->nBlkSizeY - vd->nOverlapY;
+        if (kind == 0) {
+            for (int j = 0; j < n; j++)
+                small[j] = mask_length(get_vec(l0, j), vd->nPel, p->fMaskNormFactor2, p->fHalfGamma);
+        } else if (kind == 1) {
+            sad_mask_time(l0, nBlkX, nBlkY, 4.0 * p->fMaskNormFactor / (vd->nBlkSizeX * vd->nBlkSizeY), p->fGamma, vd->nPel, small, nBlkX, p->time256, stepX, stepY, 8 /* the clip is 8-bit, MVMask.c:318 */);
+        } else if (kind == 2) {
+            occlusion_mask_time(l0, vd->isBackward, nBlkX, nBlkY, 1.0 / p->fMaskNormFactor, p->fGamma, vd->nPel, small, nBlkX, p->time256, stepX, stepY);
+        } else if (kind == 3) {
+            for (int j = 0; j < n; j++)
+                small[j] = (uint8_t)clamp255((int)(get_vec(l0, j).x * p->fMaskNormFactor * 100 + 128));
+        } else if (kind == 4) {
+            for (int j = 0; j < n; j++)
+                small[j] = (uint8_t)clamp255((int)(get_vec(l0, j).y * p->fMaskNormFactor * 100 + 128));
+        } else {
+            for (int j = 0; j < n; j++) {
+                VEC v = get_vec(l0, j);
+                small[j] = (uint8_t)clamp255((int)(v.x * p->fMaskNormFactor * 100 + 128));
+                smallV[j] = (uint8_t)clamp255((int)(v.y * p->fMaskNormFactor * 100 + 128));
+            }
+        }
+        Resizer up, upUV;
+        resizer_init(&up, p->nWidthB, p->nHeightB, nBlkX, nBlkY, nWidth, nHeight, vd->nPel);
+        resizer_init(&upUV, p->nWidthBUV, p->nHeightBUV, nBlkX, nBlkY, nWidthUV, nHeightUV, vd->nPel);
+        if (kind == 5) {
+            for (int h = 0; h < nHeight; h++)
+                memcpy(dst[0] + h * dst_stride[0], src_luma + h * src_stride, (size_t)nWidth);
+        } else {
+            resize_u8(&up, dst[0], dst_stride[0], small, nBlkX);
+            for (int h = 0; h < nHeight && nWidth > p->nWidthB; h++) /* :158-161 (rows below nHeightB are rewritten next) */
+                for (int w = p->nWidthB; w < nWidth; w++)
+                    dst[0][h * dst_stride[0] + w] = dst[0][h * dst_stride[0] + p->nWidthB - 1];
+            for (int h = p->nHeightB; h < nHeight; h++) /* :162-163 */
+                memcpy(dst[0] + h * dst_stride[0], dst[0] + (p->nHeightB - 1) * dst_stride[0], (size_t)nWidth);
+        }
+        resize_u8(&upUV, dst[1], dst_stride[1], small, nBlkX);
+        if (kind == 5)
+            resize_u8(&upUV, dst[2], dst_stride[2], smallV, nBlkX);
+        else
+            for (int h = 0; h < p->nHeightBUV; h++)
+                memcpy(dst[2] + h * dst_stride[2], dst[1] + h * dst_stride[1], (size_t)p->nWidthBUV);
+        for (int pl = 1; pl < 3; pl++) { /* :175-185 */
+            for (int h = 0; h < nHeightUV && nWidthUV > p->nWidthBUV; h++)
+                for (int w = p->nWidthBUV; w < nWidthUV; w++)
+                    dst[pl][h * dst_stride[pl] + w] = dst[pl][h * dst_stride[pl] + p->nWidthBUV - 1];
+            for (int h = p->nHeightBUV; h < nHeightUV; h++)
+                memcpy(dst[pl] + h * dst_stride[pl], dst[pl] + (p->nHeightBUV - 1) * dst_stride[pl], (size_t)nWidthUV);
+        }
+        resizer_free(&up);
+        resizer_free(&upUV);
+        free(small);
+        free(smallV);
+    } else { /* :189-196 */
+        for (int h = 0; h < nHeight; h++) {
+            if (kind == 5)
+                memcpy(dst[0] + h * dst_stride[0], src_luma + h * src_stride, (size_t)nWidth);
+            else
+                memset(dst[0] + h * dst_stride[0], p->nSceneChangeValue, (size_t)nWidth);
+        }
+        for (int pl = 1; pl < 3; pl++)
+            for (int h = 0; h < nHeightUV; h++)
+                memset(dst[pl] + h * dst_stride[pl], p->nSceneChangeValue, (size_t)nWidthUV);
+    }
+    return 0;
+}
+
+/* ----------------------------------------------------------------- Finest */
+
+typedef struct FinestPlane {
+    int pw, ph; /* padded size of level 0 of this plane */
+} FinestPlane;
+
+static void finest_plane_dims(const mvb200_super_params *sp, int plane, FinestPlane *f) {
+    int xr = plane ? sp->xRatioUV : 1, yr = plane ? sp->yRatioUV : 1;
+    f->pw = sp->width / xr + 2 * (sp->hpad / xr); /* mvpInit via mvfInit, MVFrame.cpp:1775-1779: chroma padding = pad / ratio */
+    f->ph = sp->height / yr + 2 * (sp->vpad / yr);
+}
+
+/* mvfinestGetFrame, MVFinest.c:47-125 with Merge4PlanesToBig / Merge16PlanesToBig, MaskFun.cpp:196-336:
+ * dst(y * pel + sy, x * pel + sx) = sub-plane (sx, sy) at (x, y); sub-plane (sx, sy) starts
+ * (sx | sy << log2 pel) * padded_height rows into the plane (mvpGetAbsolutePointer, MVFrame.h / SURVEY.md a1).
+ * pel 1: the top (W + 2 hpad) x (H + 2 vpad) rows, i.e. level 0 (:75-77; the reference copies the LUMA size for
+ * every plane there, which overruns subsampled chroma planes -- the oracle copies each plane's own size). */
+int mvo_finest_frame(const mvb200_super_params *sp, const uint8_t *const super[3], const ptrdiff_t super_stride[3], uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
+    const int bps = (sp->bits + 7) / 8, pel = sp->pel, lp = pel == 4 ? 2 : (pel == 2 ? 1 : 0);
+    for (int pl = 0; pl < sp->nplanes; pl++) {
+        if (pl && !(sp->modeyuv & (MVB200_UPLANE | MVB200_VPLANE)))
+            continue;
+        FinestPlane f;
+        finest_plane_dims(sp, pl, &f);
+        for (int y = 0; y < f.ph * pel; y++)
+            for (int x = 0; x < f.pw * pel; x++) {
+                int idx = (x & (pel - 1)) | ((y & (pel - 1)) << lp);
+                const uint8_t *s = super[pl] + ((ptrdiff_t)idx * f.ph + (y >> lp)) * super_stride[pl] + (ptrdiff_t)(x >> lp) * bps;
+                memcpy(dst[pl] + (ptrdiff_t)y * dst_stride[pl] + (ptrdiff_t)x * bps, s, (size_t)bps);
+            }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------- Flow */
+
+/* MakeVectorSmallMasks (MaskFun.cpp:163-176) + CheckAndPadSmallY (:38-62) + the field shift of MVFlow.cpp:301-305 */
+static void small_vectors(const uint8_t *l0, int nBlkX, int nBlkY, int nBlkXP, int nBlkYP, int fieldShift, int16_t *vx, int16_t *vy) {
+    for (int by = 0; by < nBlkY; by++)
+        for (int bx = 0; bx < nBlkX; bx++) {
+            VEC v = get_vec(l0, bx + by * nBlkX);
+            vx[bx + by * nBlkXP] = (int16_t)v.x;
+            vy[bx + by * nBlkXP] = (int16_t)v.y;
+        }
+    if (nBlkXP > nBlkX)
+        for (int j = 0; j < nBlkY; j++) {
+            int16_t r = vx[j * nBlkXP + nBlkX - 1];
+            int16_t vxr = r < 0 ? r : 0, vyr = vy[j * nBlkXP + nBlkX - 1];
+            for (int dx = nBlkX; dx < nBlkXP; dx++) {
+                vx[j * nBlkXP + dx] = vxr;
+                vy[j * nBlkXP + dx] = vyr;
+            }
+        }
+    if (nBlkYP > nBlkY)
+        for (int i = 0; i < nBlkXP; i++) {
+            int16_t vxb = vx[nBlkXP * (nBlkY - 1) + i];
+            int16_t b = vy[nBlkXP * (nBlkY - 1) + i];
+            int16_t vyb = b < 0 ? b : 0;
+            for (int dy = nBlkY; dy < nBlkYP; dy++) {
+                vx[nBlkXP * dy + i] = vxb;
+                vy[nBlkXP * dy + i] = vyb;
+            }
+        }
+    for (int i = 0; i < nBlkXP * nBlkYP; i++)
+        vy[i] = (int16_t)(vy[i] + fieldShift);
+}
+
+/* VectorSmallMaskYToHalfUV, MaskFun.cpp:178-199 */
+static void small_to_uv(const int16_t *y, int n, int16_t *uv, int ratio) {
+    for (int i = 0; i < n; i++)
+        uv[i] = ratio == 2 ? (int16_t)(y[i] >> 1) : y[i];
+}
+
+static int ld_px(const uint8_t *p, int bps) { return bps == 1 ? p[0] : (p[0] | (p[1] << 8)); }
+
+/* flowFetch / flowShift, MVFlow.cpp:87-141, on a finest plane (`ref` points at the interior's first sample) */
+static void flow_plane(int mode, uint8_t *dst, ptrdiff_t dst_stride, const uint8_t *ref, ptrdiff_t ref_stride, const int16_t *VX, const int16_t *VY, int vpitch, int width, int height, int time256, int pel, int bps) {
+    int lp = pel == 4 ? 2 : (pel == 2 ? 1 : 0);
+    if (mode == 0) {
+        for (int h = 0; h < height; h++)
+            for (int w = 0; w < width; w++) {
+                int vx = (VX[h * vpitch + w] * time256 + 128) >> 8;
+                int vy = (VY[h * vpitch + w] * time256 + 128) >> 8;
+                const uint8_t *s = ref + ((ptrdiff_t)(h << lp) + vy) * ref_stride + ((ptrdiff_t)(w << lp) + vx) * bps;
+                memcpy(dst + h * dst_stride + (ptrdiff_t)w * bps, s, (size_t)bps);
+            }
+    } else {
+        int rounding = 128 << lp, shift = 8 + lp;
+        for (int h = 0; h < height; h++)
+            for (int w = 0; w < width; w++) {
+                int vx = (-VX[h * vpitch + w] * time256 + rounding) >> shift;
+                int vy = (-VY[h * vpitch + w] * time256 + rounding) >> shift;
+                int href = h + vy, wref = w + vx;
+                if (href >= 0 && href < height && wref >= 0 && wref < width)
+                    memcpy(dst + href * dst_stride + (ptrdiff_t)wref * bps, ref + (ptrdiff_t)(h << lp) * ref_stride + (ptrdiff_t)(w << lp) * bps, (size_t)bps);
+            }
+    }
+    (void)ld_px;
+}
+
+/* mvflowGetFrame, MVFlow.cpp:157-368.  ref_super: the super frame of the reference frame (the reference reads the
+ * mv.Finest clip made from it; built here the same way).  *usable = 0: the caller returns the source frame. */
+int mvo_flow_frame(const mvb200_flow_params *fp, const mvb200_super_params *sp, const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *vectors, int field_shift, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable) {
+    const mvb200_analysis_data *vd = &fp->vd;
+    *usable = ref_super != NULL && is_usable(vectors, vd, fp->nSCD1, fp->nSCD2);
+    if (!*usable)
+        return 0;
+    const int bps = (fp->bits + 7) / 8, pel = vd->nPel, pixel_max = (1 << fp->bits) - 1;
+    int validity;
+    const uint8_t *l0 = blob_level0(vectors, vd, &validity);
+    /* the finest planes */
+    uint8_t *fin[3] = {NULL, NULL, NULL};
+    ptrdiff_t fstride[3] = {0, 0, 0};
+    for (int pl = 0; pl < fp->nplanes; pl++) {
+        FinestPlane f;
+        finest_plane_dims(sp, pl, &f);
+        fstride[pl] = (ptrdiff_t)f.pw * pel * bps;
+        fin[pl] = malloc((size_t)fstride[pl] * f.ph * pel);
+    }
+    if (pel == 1) {
+        for (int pl = 0; pl < fp->nplanes; pl++) {
+            FinestPlane f;
+            finest_plane_dims(sp, pl, &f);
+            for (int y = 0; y < f.ph; y++)
+                memcpy(fin[pl] + y * fstride[pl], ref_super[pl] + y * ref_stride[pl], (size_t)f.pw * bps);
+        }
+    } else {
+        mvb200_super_params all = *sp;
+        all.modeyuv = MVB200_YUVPLANES;
+        mvo_finest_frame(&all, ref_super, ref_stride, fin, fstride);
+    }
+    const int nBlkXP = fp->nBlkXP, nBlkYP = fp->nBlkYP, ns = nBlkXP * nBlkYP;
+    int16_t *vxs = malloc(sizeof(int16_t) * (size_t)ns), *vys = malloc(sizeof(int16_t) * (size_t)ns);
+    small_vectors(l0, vd->nBlkX, vd->nBlkY, nBlkXP, nBlkYP, field_shift, vxs, vys);
+    Resizer up;
+    resizer_init(&up, fp->nWidthP, fp->nHeightP, nBlkXP, nBlkYP, vd->nWidth, vd->nHeight, pel);
+    int16_t *VX = malloc(sizeof(int16_t) * (size_t)fp->nHeightP * fp->VPitchY), *VY = malloc(sizeof(int16_t) * (size_t)fp->nHeightP * fp->VPitchY);
+    resize_i16(&up, VX, fp->VPitchY, vxs, nBlkXP, 1);
+    resize_i16(&up, VY, fp->VPitchY, vys, nBlkXP, 0);
+    if (fp->mode == 1)
+        for (int h = 0; h < vd->nHeight; h++)
+            for (int w = 0; w < vd->nWidth; w++)
+                memcpy(dst[0] + h * dst_stride[0] + (ptrdiff_t)w * bps, &pixel_max, (size_t)bps);
+    flow_plane(fp->mode, dst[0], dst_stride[0], fin[0] + (ptrdiff_t)vd->nVPadding * pel * fstride[0] + (ptrdiff_t)vd->nHPadding * pel * bps, fstride[0], VX, VY, fp->VPitchY, vd->nWidth, vd->nHeight, fp->time256, pel, bps);
+    if (fp->nplanes > 1) {
+        int16_t *vxuv = malloc(sizeof(int16_t) * (size_t)ns), *vyuv = malloc(sizeof(int16_t) * (size_t)ns);
+        small_to_uv(vxs, ns, vxuv, vd->xRatioUV);
+        small_to_uv(vys, ns, vyuv, vd->yRatioUV);
+        Resizer upUV;
+        resizer_init(&upUV, fp->nWidthPUV, fp->nHeightPUV, nBlkXP, nBlkYP, fp->nWidthUV, fp->nHeightUV, pel);
+        int16_t *VXUV = malloc(sizeof(int16_t) * (size_t)fp->nHeightPUV * fp->VPitchUV), *VYUV = malloc(sizeof(int16_t) * (size_t)fp->nHeightPUV * fp->VPitchUV);
+        resize_i16(&upUV, VXUV, fp->VPitchUV, vxuv, nBlkXP, 1);
+        resize_i16(&upUV, VYUV, fp->VPitchUV, vyuv, nBlkXP, 0);
+        for (int pl = 1; pl < 3; pl++) {
+            if (fp->mode == 1)
+                for (int h = 0; h < fp->nHeightUV; h++)
+                    for (int w = 0; w < fp->nWidthUV; w++)
+                        memcpy(dst[pl] + h * dst_stride[pl] + (ptrdiff_t)w * bps, &pixel_max, (size_t)bps);
+            flow_plane(fp->mode, dst[pl], dst_stride[pl], fin[pl] + (ptrdiff_t)fp->nVPaddingUV * pel * fstride[pl] + (ptrdiff_t)fp->nHPaddingUV * pel * bps, fstride[pl], VXUV, VYUV, fp->VPitchUV, fp->nWidthUV, fp->nHeightUV,
+                       fp->time256, pel, bps);
+        }
+        resizer_free(&upUV);
+        free(vxuv);
+        free(vyuv);
+        free(VXUV);
+        free(VYUV);
+    }
+    resizer_free(&up);
+    free(vxs);
+    free(vys);
+    free(VX);
+    free(VY);
+    for (int pl = 0; pl < 3; pl++)
+        free(fin[pl]);
+    return 0;
+}

@@ -30,6 +30,12 @@ def lib():
                                            PP(vp), PP(C.c_ssize_t)]
         L.mvo_overlap_windows.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp]
         L.mvo_overlap_windows.restype = None
+        L.mvo_scdetection_frame.argtypes = [PP(mb.ScdParams), vp, PP(C.c_int32)]
+        L.mvo_mask_frame.argtypes = [PP(mb.MaskParams), vp, C.c_ssize_t, vp, PP(vp), PP(C.c_ssize_t)]
+        L.mvo_finest_frame.argtypes = [PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
+        L.mvo_flow_frame.argtypes = [PP(mb.FlowParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), vp, C.c_int, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
+        L.mvo_simple_resize_tables.argtypes = [C.c_int, C.c_int, vp, vp]
+        L.mvo_simple_resize_tables.restype = None
         for n in ("mvo_sad", "mvo_satd"):
             f = getattr(L, n)
             f.restype = C.c_uint
@@ -118,3 +124,46 @@ def overlap_windows(nx, ny, ox, oy):
     out = np.zeros((9, ny, nx), dtype=np.int16)
     lib().mvo_overlap_windows(nx, ny, ox, oy, out.ctypes.data)
     return out
+
+
+# ---- consumers of the vector clips (mvtools_oracle_flow.c)
+
+def scdetection_frame(scp, vectors):
+    out = C.c_int32(0)
+    _check(lib().mvo_scdetection_frame(C.byref(scp), vectors.ctypes.data, C.byref(out)))
+    return out.value
+
+
+def mask_frame(mp, src_luma, vectors):
+    dst = mb.alloc_planes([mp.nWidth, mp.nWidthUV, mp.nWidthUV], [mp.nHeight, mp.nHeightUV, mp.nHeightUV], 8, fill=0xA5)
+    d, ds = mb.plane_ptrs(dst)
+    sl = None if src_luma is None else src_luma.ctypes.data
+    _check(lib().mvo_mask_frame(C.byref(mp), sl, 0 if src_luma is None else src_luma.strides[0], vectors.ctypes.data, d, ds))
+    return dst
+
+
+def finest_frame(sp, super_planes):
+    l = mb.finest_layout(sp)
+    dst = mb.alloc_planes(list(l.plane_w)[: sp.nplanes], list(l.plane_h)[: sp.nplanes], sp.bits, fill=0xA5)
+    s, ss = mb.plane_ptrs(super_planes)
+    d, ds = mb.plane_ptrs(dst)
+    _check(lib().mvo_finest_frame(C.byref(sp), s, ss, d, ds))
+    return dst
+
+
+def flow_frame(fp, sp, ref_super, vectors, field_shift=0):
+    w = [fp.vd.nWidth, fp.nWidthUV, fp.nWidthUV][: fp.nplanes]
+    h = [fp.vd.nHeight, fp.nHeightUV, fp.nHeightUV][: fp.nplanes]
+    dst = mb.alloc_planes(w, h, fp.bits, fill=0xA5)
+    r, rs = (None, None) if ref_super is None else mb.plane_ptrs(ref_super)
+    d, ds = mb.plane_ptrs(dst)
+    usable = C.c_int32(0)
+    _check(lib().mvo_flow_frame(C.byref(fp), C.byref(sp), r, rs, vectors.ctypes.data, field_shift, d, ds, C.byref(usable)))
+    return dst if usable.value else None
+
+
+def simple_resize_tables(out, in_):
+    off = np.zeros(out, dtype=np.int32)
+    wt = np.zeros(out, dtype=np.int32)
+    lib().mvo_simple_resize_tables(out, in_, off.ctypes.data, wt.ctypes.data)
+    return off, wt

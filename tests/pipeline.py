@@ -24,6 +24,10 @@ CASES = {
     "noise_badblocks_blk8": (dict(width=192, height=128, nframes=5, bits=8, pure_noise=True), dict(pel=2), dict(blksize=8, overlap=2, badsad=300, badrange=6), 1, dict(thscd1=16000, thscd2=255)),
     "trymany_nochroma_dct7_p16": (dict(width=192, height=128, nframes=5, bits=16), dict(pel=2), dict(blksize=16, overlap=4, trymany=1, chroma=0, dct=7, search=0, searchparam=3, global_=0), 1, dict()),
     "divide2_blk16_esa_neg_badrange": (dict(width=256, height=160, nframes=5, bits=8, pure_noise=True), dict(pel=2), dict(blksize=16, overlap=8, divide=2, badsad=500, badrange=-4, search=6, searchparam=3), 1, dict(thscd1=16000, thscd2=255)),
+    # blocks that cover neither the last columns nor the last rows (196 of 200, 148 of 152); plane widths are not multiples of
+    # the 64-byte stride alignment, which keeps the reference's vsh_bitblt on its row loop (MVMask.c:162-163 copies
+    # overlapping rows, and the single-memcpy shortcut for stride == row size would make that undefined behaviour)
+    "p8_420_blk16_ov4_uncovered": (dict(width=200, height=152, nframes=4, bits=8), dict(pel=2), dict(blksize=16, overlap=4), 1, {}),
     # dct 1..4: the FFTW DCT path (DCTFFTW.cpp); pinned against oracle/_ref, whose FFTW is oracle/shim/fftw_shim.c
     "dct1_blk8_p8": (dict(width=160, height=96, nframes=4, bits=8), dict(pel=2, hpad=8, vpad=8), dict(blksize=8, overlap=4, dct=1), 1, {}),
     "dct2_blk16_p16": (dict(width=160, height=96, nframes=4, bits=16, scene_cut=True), dict(pel=1, hpad=8, vpad=8), dict(blksize=16, dct=2, search=3, searchparam=1), 1, {}),

@@ -1,0 +1,139 @@
+"""Shared helpers for the consumers of the vector clips (mv.SCDetection, mv.Mask, mv.Finest,
+mv.Flow): run them on the seeded clips of pipeline.CASES through
+ (a) a VapourSynth plugin (the compiled reference by default) and the mini host,
+ (b) per-frame stage functions (the CPU oracle, or the CUDA C ABI),
+and hash every output the same way, so results can be compared or pinned as goldens
+(tests/golden/golden_flow.json, made by tests/golden/make_golden_flow.py)."""
+import functools
+
+import numpy as np
+
+import mvtools_b200 as mb
+import pipeline
+from pipeline import CASES, sha
+
+# case -> stages.  `vec`: which vector clip feeds the filter (0 = backward delta 1, 1 = forward delta 1).
+# Mask needs an 8-bit clip (MVMask.c:318); the reference's mv.Finest overruns subsampled chroma planes at pel = 1
+# (MVFinest.c:75-77 copies the luma size for every plane), so `finest` is only pinned for pel > 1 or 4:4:4 / gray.
+FLOW = {
+    "blk8_ov4_pel2_p8": dict(
+        mask=[dict(kind=0), dict(kind=1, gamma=2.0, time=30.0), dict(kind=2, ml=50.0), dict(kind=2, vec=1, gamma=0.7, time=60.0),
+              dict(kind=3), dict(kind=4, ml=20.0, vec=1), dict(kind=5, ysc=77), dict(kind=0, gamma=1.7, ml=30.0, thscd1=200, thscd2=40, ysc=200)],
+        flow=[dict(), dict(time=50.0, vec=1), dict(mode=1, time=70.0), dict(mode=1, vec=1, thscd1=250, thscd2=60)],
+        scd=[dict(), dict(vec=1, thscd1=150, thscd2=30)], finest=True),
+    "blk16_ov8_pel2_p16_r3": dict(flow=[dict(time=33.0), dict(mode=1, vec=1)], scd=[dict()], finest=True),
+    "p10_444_blk8_pel4_bicubic": dict(flow=[dict(time=80.0), dict(mode=1, time=45.0, vec=1)], finest=True, scd=[dict(thscd2=10)]),
+    "gray_blk4_pel1_rf0": dict(mask=[dict(kind=0), dict(kind=2, time=50.0), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=25.0)], finest=True, scd=[dict()]),
+    "c1_640x360_p8_blk8_pel1": dict(mask=[dict(kind=1), dict(kind=2, vec=1)], flow=[dict(time=60.0), dict(mode=1)], scd=[dict()]),
+    "p8_422_blk8x4_sharp0_rf1": dict(mask=[dict(kind=0, ml=10.0), dict(kind=1, time=0.0), dict(kind=2, vec=1, ml=10.0), dict(kind=5)], flow=[dict(vec=1), dict(mode=1, time=100.0)], finest=True,
+                                     scd=[dict(vec=1)]),
+    "noise_badblocks_blk8": dict(mask=[dict(kind=0, ysc=9), dict(kind=1, thscd1=16000, thscd2=255), dict(kind=2, thscd1=16000, thscd2=255, ml=400.0), dict(kind=5, thscd1=16000, thscd2=255, ml=3.0)],
+                                 flow=[dict(), dict(thscd1=16000, thscd2=255, time=90.0), dict(mode=1, thscd1=16000, thscd2=255, vec=1)], scd=[dict(), dict(thscd1=16000, thscd2=255)]),
+    "blk4_420_chroma2x2_pel2": dict(mask=[dict(kind=2, gamma=2.0)], flow=[dict(time=12.0), dict(mode=1)], finest=True),
+    # (no mask here: 256-sample rows equal the stride, and the reference's bottom-strip copy, MVMask.c:162-163, is an
+    # overlapping memcpy then -- undefined behaviour; the oracle and the engine replicate the last covered row, which is
+    # what the reference's row loop does for every other width)
+    "divide2_blk16_esa_neg_badrange": dict(flow=[dict(thscd1=16000, thscd2=255), dict(mode=1, thscd1=16000, thscd2=255, vec=1, time=40.0)], scd=[dict(thscd1=16000, thscd2=255)]),
+    "p8_420_blk16_ov4_uncovered": dict(mask=[dict(kind=0), dict(kind=1, ml=30.0), dict(kind=2, vec=1), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=66.0)], scd=[dict()], finest=True),
+}
+
+
+def _split(kw):
+    kw = dict(kw)
+    return kw.pop("vec", 0), kw
+
+
+@functools.lru_cache(maxsize=None)
+def inputs(case):
+    """(frames, super frames, [vectors of clip 0 per frame, vectors of clip 1 per frame]) computed by the CPU oracle
+    (itself pinned against the reference for these stages); inputs of the per-frame stage functions."""
+    import oracle
+    frames = pipeline.make_frames(CASES[case][0])
+    N = len(frames)
+    sp, aps, dp = pipeline.params_for(case)
+    if case in pipeline.PELCLIP:
+        raise ValueError("no flow stages for pelclip cases")
+    sups = [oracle.super_frame(sp, f) for f in frames]
+    vecs = []
+    for ap in aps[:2]:
+        row = []
+        for n in range(N):
+            r = pipeline.nref_of(ap, n, N)
+            row.append(oracle.analyse_frame(ap, sp, sups[n], sups[r] if r is not None else None))
+        vecs.append(row)
+    return frames, sups, vecs
+
+
+def flow_params_for(case):
+    """-> sp, aps, {stage: [params per variant]}"""
+    ck = CASES[case][0]
+    N = ck["nframes"]
+    sp, aps, dp = pipeline.params_for(case)
+    vds = [(ap.ad_divided if ap.divide else ap.ad) for ap in aps[:2]]
+    out = {"mask": [], "flow": [], "scd": []}
+    for kw in FLOW[case].get("mask", []):
+        v, kw = _split(kw)
+        out["mask"].append((v, mb.mask_params(vds[v], clip_bits=ck.get("bits", 8), clip_ssw=ck.get("ssw", 1), clip_ssh=ck.get("ssh", 1), clip_gray=ck.get("gray", False), **kw)))
+    for kw in FLOW[case].get("flow", []):
+        v, kw = _split(kw)
+        out["flow"].append((v, mb.flow_params(sp, vds[v], N, **kw)))
+    for kw in FLOW[case].get("scd", []):
+        v, kw = _split(kw)
+        out["scd"].append((v, mb.scdetection_params(vds[v], **kw)))
+    return sp, aps, out
+
+
+def run_engine_flow(case, scd_fn, mask_fn, finest_fn, flow_fn):
+    """Per-frame stage functions (oracle.* or Context.*) on the oracle-made inputs -> {stage: hashes}"""
+    frames, sups, vecs = inputs(case)
+    N = len(frames)
+    sp, aps, P = flow_params_for(case)
+    out = {"scd": [], "mask": [], "flow": [], "finest": []}
+    for v, scp in P["scd"]:
+        out["scd"].append([int(scd_fn(scp, vecs[v][n])) for n in range(N)])
+    for v, mp in P["mask"]:
+        out["mask"].append([[sha(p) for p in mask_fn(mp, frames[n][0], vecs[v][n])] for n in range(N)])
+    for v, fp in P["flow"]:
+        rows = []
+        for n in range(N):
+            r = pipeline.nref_of(aps[v], n, N)
+            d = flow_fn(fp, sp, sups[r] if r is not None else None, vecs[v][n])
+            rows.append([sha(p) for p in (d if d is not None else frames[n])])  # not usable: the source frame (MVFlow.cpp:362-366)
+        out["flow"].append(rows)
+    if FLOW[case].get("finest"):
+        out["finest"] = [[sha(p) for p in finest_fn(sp, sups[n])] for n in range(N)]
+    return out
+
+
+def run_reference_flow(case, plugin_path=None):
+    """The same stages through a VapourSynth plugin (default: the compiled reference) and the mini host."""
+    import minivs
+    ck, skw, akw, radius, dkw = CASES[case]
+    frames = pipeline.make_frames(ck)
+    N = len(frames)
+    core = minivs.Core()
+    mv = core.load(plugin_path or minivs.REF_PLUGIN)
+    clip = core.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1))
+    sup = mv.Super(clip, **skw)
+    vn = [mv.Analyse(sup, isb=isb, delta=1, **pipeline._fix(akw)) for isb in (1, 0)]
+    nplanes = 1 if ck.get("gray") else 3
+    out = {"scd": [], "mask": [], "flow": [], "finest": []}
+    for kw in FLOW[case].get("scd", []):
+        v, kw = _split(kw)
+        node = mv.SCDetection(clip, vn[v], **kw)
+        key = "_SceneChangeNext" if v == 0 else "_SceneChangePrev"  # isBackward -> Next (MVSCDetection.c:61-63)
+        out["scd"].append([int(node.get_frame(n).prop_int(key)) for n in range(N)])
+    for kw in FLOW[case].get("mask", []):
+        v, kw = _split(kw)
+        kw = {k: (float(x) if k in ("ml", "gamma", "time") else x) for k, x in kw.items()}
+        node = mv.Mask(clip, vn[v], **kw)
+        out["mask"].append([[sha(p) for p in node.get_frame(n).planes()] for n in range(N)])
+    for kw in FLOW[case].get("flow", []):
+        v, kw = _split(kw)
+        kw = {k: (float(x) if k == "time" else x) for k, x in kw.items()}
+        node = mv.Flow(clip, sup, vn[v], **kw)
+        out["flow"].append([[sha(p) for p in node.get_frame(n).planes()[:nplanes]] for n in range(N)])
+    if FLOW[case].get("finest"):
+        node = mv.Finest(sup)
+        out["finest"] = [[sha(p) for p in node.get_frame(n).planes()[:nplanes]] for n in range(N)]
+    return out

@@ -238,9 +238,6 @@ static void make_recalc_params(const mvb200_recalculate_params *rp, const mvb200
 
 using namespace mvb200;
 
-struct mvb200_ctx {
-    Ctx c;
-};
 
 extern "C" {
 

@@ -116,8 +116,8 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     long long launches = 0;
     // growable device scratch buffers
-    void *scratch[16] = {};
-    size_t scratch_bytes[16] = {};
+    void *scratch[24] = {};
+    size_t scratch_bytes[24] = {};
     // pinned host staging
     void *pinned = nullptr;
     size_t pinned_bytes = 0;
@@ -133,6 +133,10 @@ struct Ctx {
     int cwin_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     short *cwin_dev[2] = {nullptr, nullptr};
     bool cwin_valid = false;
+    // SimpleResize tables of the last Mask / Flow configuration (flow.cu), resident on the device
+    int rz_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int *rz_dev = nullptr;
+    bool rz_valid = false;
     // host-buffer clip pipeline (mvb200_degrain_clip_host_async): copy streams + double-buffered clips
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
@@ -156,3 +160,9 @@ struct Ctx {
 #endif // __CUDACC__
 
 } // namespace mvb200
+
+#ifdef __CUDACC__
+struct mvb200_ctx { // the opaque handle of the C ABI
+    mvb200::Ctx c;
+};
+#endif

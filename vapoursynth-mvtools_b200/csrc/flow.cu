@@ -1,0 +1,531 @@
+// The consumers of the vector clips that SURVEY.md section 8f ranks next: mv.SCDetection, mv.Mask, mv.Finest and
+// mv.Flow (MVSCDetection.c, MVMask.c + MaskFun.cpp, MVFinest.c, MVFlow.cpp + SimpleResize.cpp of the reference).
+//
+// All of them are HBM-bound per-pixel (or per-block) maps with no serial chain.  The reference stages full-size
+// intermediates (int16 vector planes, a pel-times upsized "finest" clip); here every output sample is computed from
+// the per-block field (a few KB, L1/L2 resident) and the reference SUPER frame in one pass: algorithmic bytes per
+// output frame are one read of the touched reference samples + one write of the output (Flow, fetch mode:
+// 2 P; Mask: P8 written only; Finest: S0 read + S0 written, S0 = the pel^2 level-0 sub-planes).
+// The per-thread arithmetic lives in flow_device.h (also compiled for the host by the emulation test).
+#include "engine.h"
+#include "flow_device.h"
+
+#include <cstring>
+#include <vector>
+
+namespace mvb200 {
+
+namespace {
+
+using namespace flowdev;
+
+// fgopIsUsable (Fakery.c:52-58,144-146) for blob blockIdx.x: usable[i] = valid && !(count(sad > nSCD1) > nSCD2) && haveRef
+__global__ void k_flow_scd(const uint8_t *vectors, long long stride, int nBlk, long long nSCD1, int nSCD2, int haveRef, int *usable) {
+    const uint8_t *blob = vectors + blockIdx.x * stride;
+    const int *l0 = blob_level0(blob, nBlk);
+    int cnt = 0;
+    for (int i = threadIdx.x; i < nBlk; i += blockDim.x)
+        cnt += vec_sad(l0 + 4 * i) > nSCD1 ? 1 : 0;
+    __shared__ int s;
+    if (threadIdx.x == 0)
+        s = 0;
+    __syncthreads();
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0)
+        atomicAdd(&s, cnt);
+    __syncthreads();
+    if (threadIdx.x == 0)
+        usable[blockIdx.x] = (((const int *)blob)[1] == 1) && !(s > nSCD2) && haveRef;
+}
+
+// ------------------------------------------------------------------- Flow
+
+struct SmallFields {
+    short *xY, *yY, *xUV, *yUV;
+};
+
+__global__ void k_small_vectors(const uint8_t *blob, int nBlkX, int nBlkY, int nBlkXP, int nBlkYP, int fieldShift, int xRatioUV, int yRatioUV, SmallFields out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nBlkXP * nBlkYP)
+        return;
+    const SmallVec s = small_vector(blob_level0(blob, nBlkX * nBlkY), nBlkX, nBlkY, k % nBlkXP, k / nBlkXP, fieldShift, xRatioUV, yRatioUV);
+    out.xY[k] = s.xY;
+    out.yY[k] = s.yY;
+    out.xUV[k] = s.xUV;
+    out.yUV[k] = s.yUV;
+}
+
+// fetch mode; an unusable frame is a copy of the source clip's frame when one is given (batch path)
+template <typename T>
+__global__ void k_flow_fetch(FlowPlane F, const uint8_t *__restrict__ ref_super, uint8_t *__restrict__ dst, long long dst_pitch, const uint8_t *__restrict__ src, const int *__restrict__ usable) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= F.W || y >= F.H)
+        return;
+    T *d = (T *)(dst + (long long)y * dst_pitch) + x;
+    if (!*usable) {
+        if (src)
+            *d = *((const T *)(src + (long long)y * dst_pitch) + x);
+        return;
+    }
+    *d = flow_fetch_sample<T>(F, ref_super, x, y);
+}
+
+// shift mode, pass 1: every source sample claims its destination; the largest source index wins (= the last writer
+// of the reference's raster loop)
+__global__ void k_flow_shift_mark(FlowPlane F, int *__restrict__ owner, const int *__restrict__ usable) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= F.W || y >= F.H || !*usable)
+        return;
+    const int t = flow_shift_target(F, x, y);
+    if (t >= 0)
+        atomicMax(owner + t, y * F.W + x + 1);
+}
+
+// pass 2: destinations nobody claimed keep the fill value (pixel_max, MVFlow.cpp:310-311)
+template <typename T>
+__global__ void k_flow_shift_resolve(FlowPlane F, const uint8_t *__restrict__ ref_super, uint8_t *__restrict__ dst, long long dst_pitch, const uint8_t *__restrict__ src, const int *__restrict__ owner, int pixel_max,
+                                     const int *__restrict__ usable) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= F.W || y >= F.H)
+        return;
+    T *d = (T *)(dst + (long long)y * dst_pitch) + x;
+    if (!*usable) {
+        if (src)
+            *d = *((const T *)(src + (long long)y * dst_pitch) + x);
+        return;
+    }
+    const int o = owner[y * F.W + x];
+    if (o == 0) {
+        *d = (T)pixel_max;
+        return;
+    }
+    const int sx = (o - 1) % F.W, sy = (o - 1) / F.W;
+    *d = finest_sample<T>(ref_super, F.S, F.logPel, (sx + F.S.hpad) << F.logPel, (sy + F.S.vpad) << F.logPel);
+}
+
+// ------------------------------------------------------------------- Mask
+
+__global__ void k_mask_small(MaskSmallParams P, const uint8_t *blob, int *small, int *smallV) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.nBlkX * P.nBlkY)
+        return;
+    const int *l0 = blob_level0(blob, P.nBlkX * P.nBlkY);
+    if (P.kind == 2) {
+        occlusion_contrib(l0, P.isBackward, P.nBlkX, P.nBlkY, 1.0 / P.fMaskNormFactor, P.fGamma, P.nPel, P.time256, P.stepX, P.stepY, j % P.nBlkX, j / P.nBlkX, [small](int idx, int val) { atomicMax(small + idx, val); });
+    } else {
+        mask_small_direct(P, l0, j, small, smallV);
+    }
+}
+
+__global__ void k_mask_plane(MaskPlane B, int kind, int ysc, int nBlkX, const int *__restrict__ small, const int *__restrict__ smallV, const uint8_t *__restrict__ src_luma, long long src_pitch, uint8_t *__restrict__ dst,
+                             long long dst_pitch, const int *__restrict__ usable) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= B.W || y >= B.H)
+        return;
+    dst[(long long)y * dst_pitch + x] = (uint8_t)mask_sample(B, kind, *usable, ysc, nBlkX, small, smallV, src_luma, src_pitch, x, y);
+}
+
+// ----------------------------------------------------------------- Finest
+
+template <typename T>
+__global__ void k_finest(SuperPlane S, int logPel, int W, int H, const uint8_t *__restrict__ super_frame, uint8_t *__restrict__ dst, long long dst_pitch) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H)
+        return;
+    *((T *)(dst + (long long)y * dst_pitch) + x) = finest_sample<T>(super_frame, S, logPel, x, y);
+}
+
+// ------------------------------------------------------------ host helpers
+
+constexpr int kSlotTables = 16, kSlotSmall = 17, kSlotStage = 18;
+
+int ilog2_pel(int pel) { return pel == 4 ? 2 : (pel == 2 ? 1 : 0); }
+
+SuperPlane make_super_plane(const SuperDesc &sd, int plane) {
+    SuperPlane S;
+    const mvb200_level_geom &g = sd.lv[plane][0];
+    S.pitch = sd.pitch[plane];
+    S.offset = sd.offset[plane];
+    S.sub_stride = sd.pitch[plane] * g.padded_h;
+    S.hpad = g.hpad;
+    S.vpad = g.vpad;
+    S.padded_w = g.padded_w;
+    S.padded_h = g.padded_h;
+    return S;
+}
+
+// The SimpleResize tables of (luma, chroma) upsizers with a common source size, resident on the device until the
+// configuration changes (first use: built on the host -- InitTables is float arithmetic -- and uploaded synchronously).
+int get_resize_tables(Ctx *c, int dw0, int dh0, int dw1, int dh1, int sw, int sh, ResizeTables t[2]) {
+    const int key[8] = {dw0, dh0, dw1, dh1, sw, sh, 1, 0};
+    const size_t n0 = (size_t)dw0 * 2 + (size_t)dh0 * 2, n1 = (size_t)dw1 * 2 + (size_t)dh1 * 2;
+    if (!c->rz_valid || memcmp(key, c->rz_key, sizeof(key)) != 0) {
+        std::vector<int32_t> host(n0 + n1);
+        int32_t *p = host.data();
+        mvb200_simple_resize_tables(dw0, sw, p, p + dw0);
+        mvb200_simple_resize_tables(dh0, sh, p + 2 * dw0, p + 2 * dw0 + dh0);
+        p += n0;
+        if (n1) {
+            mvb200_simple_resize_tables(dw1, sw, p, p + dw1);
+            mvb200_simple_resize_tables(dh1, sh, p + 2 * dw1, p + 2 * dw1 + dh1);
+        }
+        int *dev = (int *)c->get_scratch(kSlotTables, (n0 + n1) * sizeof(int32_t) + 256);
+        if (!dev)
+            return 1;
+        MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        MVB_CUDA_CHECK(cudaMemcpy(dev, host.data(), (n0 + n1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+        c->rz_dev = dev;
+        memcpy(c->rz_key, key, sizeof(key));
+        c->rz_valid = true;
+    }
+    const int *d = c->rz_dev;
+    t[0].hoff = d;
+    t[0].hwt = d + dw0;
+    t[0].voff = d + 2 * dw0;
+    t[0].vwt = d + 2 * dw0 + dh0;
+    d += n0;
+    t[1].hoff = d;
+    t[1].hwt = d + dw1;
+    t[1].voff = d + 2 * dw1;
+    t[1].vwt = d + 2 * dw1 + dh1;
+    return 0;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+} // namespace
+
+// mvflowGetFrame, MVFlow.cpp:157-368, for one frame on the device.  dev_ref_super == nullptr: not usable.
+// dev_src (clip layout, may be null): what an unusable frame becomes.  usable_dev: where the flag is left.
+static int launch_flow(Ctx *c, const mvb200_flow_params *fp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_ref_super, const uint8_t *dev_vectors, int field_shift, const uint8_t *dev_src, uint8_t *dev_dst, int **usable_dev) {
+    cudaStream_t st = c->stream;
+    const mvb200_analysis_data &vd = fp->vd;
+    const int ns = fp->nBlkXP * fp->nBlkYP;
+    const size_t field_bytes = align256((size_t)ns * sizeof(short));
+    const size_t owner_bytes = fp->mode == 1 ? align256((size_t)vd.nWidth * vd.nHeight * sizeof(int)) : 0;
+    uint8_t *scr = (uint8_t *)c->get_scratch(kSlotSmall, 256 + 4 * field_bytes + owner_bytes);
+    if (!scr)
+        return 1;
+    int *usable = (int *)scr;
+    SmallFields sf;
+    sf.xY = (short *)(scr + 256);
+    sf.yY = (short *)(scr + 256 + field_bytes);
+    sf.xUV = (short *)(scr + 256 + 2 * field_bytes);
+    sf.yUV = (short *)(scr + 256 + 3 * field_bytes);
+    int *owner = (int *)(scr + 256 + 4 * field_bytes);
+    *usable_dev = usable;
+    ResizeTables t[2];
+    if (get_resize_tables(c, fp->nWidthP, fp->nHeightP, fp->nplanes > 1 ? fp->nWidthPUV : 0, fp->nplanes > 1 ? fp->nHeightPUV : 0, fp->nBlkXP, fp->nBlkYP, t))
+        return 1;
+    k_flow_scd<<<1, 256, 0, st>>>(dev_vectors, 0, vd.nBlkX * vd.nBlkY, fp->nSCD1, fp->nSCD2, dev_ref_super != nullptr, usable);
+    c->launches++;
+    k_small_vectors<<<(ns + 255) / 256, 256, 0, st>>>(dev_vectors, vd.nBlkX, vd.nBlkY, fp->nBlkXP, fp->nBlkYP, field_shift, vd.xRatioUV, vd.yRatioUV, sf);
+    c->launches++;
+    const uint8_t *ref = dev_ref_super ? dev_ref_super : dev_vectors; // (never dereferenced when unusable)
+    for (int plane = 0; plane < fp->nplanes; plane++) {
+        FlowPlane F;
+        memset(&F, 0, sizeof(F));
+        F.plane = plane;
+        F.W = plane ? fp->nWidthUV : vd.nWidth;
+        F.H = plane ? fp->nHeightUV : vd.nHeight;
+        F.limitW = F.W;
+        F.limitH = F.H;
+        F.time256 = fp->time256;
+        F.pel = vd.nPel;
+        F.logPel = ilog2_pel(vd.nPel);
+        F.mode = fp->mode;
+        F.nBlkXP = fp->nBlkXP;
+        F.vxs = plane ? sf.xUV : sf.xY;
+        F.vys = plane ? sf.yUV : sf.yY;
+        F.t = t[plane ? 1 : 0];
+        F.S = make_super_plane(sd, plane);
+        uint8_t *dst = dev_dst + cd.offset[plane];
+        const uint8_t *src = dev_src ? dev_src + cd.offset[plane] : nullptr;
+        dim3 blk(32, 8), grid((F.W + 31) / 32, (F.H + 7) / 8);
+        if (fp->mode == 0) {
+            if (sd.bps == 1)
+                k_flow_fetch<uint8_t><<<grid, blk, 0, st>>>(F, ref, dst, cd.pitch[plane], src, usable);
+            else
+                k_flow_fetch<uint16_t><<<grid, blk, 0, st>>>(F, ref, dst, cd.pitch[plane], src, usable);
+            c->launches++;
+        } else {
+            MVB_CUDA_CHECK(cudaMemsetAsync(owner, 0, (size_t)F.W * F.H * sizeof(int), st));
+            k_flow_shift_mark<<<grid, blk, 0, st>>>(F, owner, usable);
+            if (sd.bps == 1)
+                k_flow_shift_resolve<uint8_t><<<grid, blk, 0, st>>>(F, ref, dst, cd.pitch[plane], src, owner, (1 << fp->bits) - 1, usable);
+            else
+                k_flow_shift_resolve<uint16_t><<<grid, blk, 0, st>>>(F, ref, dst, cd.pitch[plane], src, owner, (1 << fp->bits) - 1, usable);
+            c->launches += 2;
+        }
+    }
+    MVB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// mvmaskGetFrame, MVMask.c:74-203, for one frame on the device (dst: mvb200_mask_layout)
+static int launch_mask(Ctx *c, const mvb200_mask_params *mp, const mvb200_frame_layout &ml, const uint8_t *dev_src_luma, long long src_pitch, const uint8_t *dev_vectors, uint8_t *dev_dst) {
+    cudaStream_t st = c->stream;
+    const mvb200_analysis_data &vd = mp->vd;
+    const int n = vd.nBlkX * vd.nBlkY;
+    const size_t small_bytes = align256((size_t)n * sizeof(int));
+    uint8_t *scr = (uint8_t *)c->get_scratch(kSlotSmall, 256 + 2 * small_bytes);
+    if (!scr)
+        return 1;
+    int *usable = (int *)scr, *small = (int *)(scr + 256), *smallV = (int *)(scr + 256 + small_bytes);
+    ResizeTables t[2];
+    if (get_resize_tables(c, mp->nWidthB, mp->nHeightB, mp->nWidthBUV, mp->nHeightBUV, vd.nBlkX, vd.nBlkY, t))
+        return 1;
+    if (mp->kind == 5 && !dev_src_luma)
+        return set_error("Mask: kind=5 needs the source clip's luma plane");
+    k_flow_scd<<<1, 256, 0, st>>>(dev_vectors, 0, n, mp->nSCD1, mp->nSCD2, 1, usable);
+    c->launches++;
+    MaskSmallParams P;
+    memset(&P, 0, sizeof(P));
+    P.kind = mp->kind;
+    P.nBlkX = vd.nBlkX;
+    P.nBlkY = vd.nBlkY;
+    P.nPel = vd.nPel;
+    P.isBackward = vd.isBackward;
+    P.time256 = mp->time256;
+    P.stepX = vd.nBlkSizeX - vd.nOverlapX;
+    P.stepY = vd.nBlkSizeY - vd.nOverlapY;
+    P.blkSizeXY = vd.nBlkSizeX * vd.nBlkSizeY;
+    P.fGamma = mp->fGamma;
+    P.fMaskNormFactor = mp->fMaskNormFactor;
+    P.fMaskNormFactor2 = mp->fMaskNormFactor2;
+    P.fHalfGamma = mp->fHalfGamma;
+    if (mp->kind == 2)
+        MVB_CUDA_CHECK(cudaMemsetAsync(small, 0, (size_t)n * sizeof(int), st));
+    k_mask_small<<<(n + 127) / 128, 128, 0, st>>>(P, dev_vectors, small, smallV);
+    c->launches++;
+    for (int plane = 0; plane < 3; plane++) {
+        MaskPlane B;
+        B.plane = plane;
+        B.W = plane ? mp->nWidthUV : mp->nWidth;
+        B.H = plane ? mp->nHeightUV : mp->nHeight;
+        B.WB = plane ? mp->nWidthBUV : mp->nWidthB;
+        B.HB = plane ? mp->nHeightBUV : mp->nHeightB;
+        B.t = t[plane ? 1 : 0];
+        dim3 blk(32, 8), grid((B.W + 31) / 32, (B.H + 7) / 8);
+        k_mask_plane<<<grid, blk, 0, st>>>(B, mp->kind, mp->nSceneChangeValue, vd.nBlkX, small, smallV, dev_src_luma, src_pitch, dev_dst + ml.offset[plane], ml.pitch[plane], usable);
+        c->launches++;
+    }
+    MVB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// mvfinestGetFrame, MVFinest.c:47-125, for one frame on the device (dst: mvb200_finest_layout)
+static int launch_finest(Ctx *c, const mvb200_super_params *sp, const SuperDesc &sd, const mvb200_frame_layout &fl, const uint8_t *dev_super, uint8_t *dev_dst) {
+    const int lp = ilog2_pel(sp->pel);
+    for (int plane = 0; plane < sd.nplanes; plane++) {
+        if (plane && !(sp->modeyuv & (MVB200_UPLANE | MVB200_VPLANE)))
+            continue; // (the reference leaves planes the super clip does not carry untouched)
+        const SuperPlane S = make_super_plane(sd, plane);
+        const int W = S.padded_w * sp->pel, H = S.padded_h * sp->pel;
+        dim3 blk(32, 8), grid((W + 31) / 32, (H + 7) / 8);
+        if (sd.bps == 1)
+            k_finest<uint8_t><<<grid, blk, 0, c->stream>>>(S, lp, W, H, dev_super, dev_dst + fl.offset[plane], fl.pitch[plane]);
+        else
+            k_finest<uint16_t><<<grid, blk, 0, c->stream>>>(S, lp, W, H, dev_super, dev_dst + fl.offset[plane], fl.pitch[plane]);
+        c->launches++;
+    }
+    MVB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+static int blob_bytes_of(const uint8_t *host_blob) { return *(const int32_t *)host_blob; }
+
+} // namespace mvb200
+
+using namespace mvb200;
+
+extern "C" {
+
+int mvb200_scdetection_batch(mvb200_ctx *ctx, const mvb200_scdetection_params *p, const void *dev_vectors, int64_t vectors_stride, int n, int32_t *scene_change) {
+    if (n <= 0)
+        return 0;
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    int *flags = (int *)c->get_scratch(kSlotSmall, (size_t)n * sizeof(int));
+    if (!flags)
+        return 1;
+    k_flow_scd<<<n, 256, 0, c->stream>>>((const uint8_t *)dev_vectors, vectors_stride, p->vd.nBlkX * p->vd.nBlkY, p->nSCD1, p->nSCD2, 1, flags);
+    c->launches++;
+    MVB_CUDA_CHECK(cudaGetLastError());
+    MVB_CUDA_CHECK(cudaMemcpyAsync(scene_change, flags, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; i++)
+        scene_change[i] = !scene_change[i]; // the property is "scene change", the flag "usable" (MVSCDetection.c:63)
+    return 0;
+}
+
+int mvb200_scdetection_frame(mvb200_ctx *ctx, const mvb200_scdetection_params *p, const uint8_t *vectors, int32_t *scene_change) {
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)blob_bytes_of(vectors);
+    uint8_t *dev = (uint8_t *)c->get_scratch(kSlotStage, bytes + 256);
+    if (!dev)
+        return 1;
+    MVB_CUDA_CHECK(cudaMemcpyAsync(dev, vectors, bytes, cudaMemcpyHostToDevice, c->stream));
+    return mvb200_scdetection_batch(ctx, p, dev, 0, 1, scene_change);
+}
+
+int mvb200_mask_batch(mvb200_ctx *ctx, const mvb200_mask_params *p, const void *dev_src_luma, int64_t src_pitch, int64_t src_frame_bytes, const void *dev_vectors, int64_t vectors_stride, int n, void *dev_dst) {
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    mvb200_frame_layout ml;
+    mvb200_mask_layout(p, &ml);
+    for (int f = 0; f < n; f++)
+        if (launch_mask(c, p, ml, dev_src_luma ? (const uint8_t *)dev_src_luma + (long long)f * src_frame_bytes : nullptr, src_pitch, (const uint8_t *)dev_vectors + (long long)f * vectors_stride, (uint8_t *)dev_dst + (long long)f * ml.frame_bytes))
+            return 1;
+    return 0;
+}
+
+int mvb200_mask_frame(mvb200_ctx *ctx, const mvb200_mask_params *p, const uint8_t *src_luma, ptrdiff_t src_stride, const uint8_t *vectors, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    mvb200_frame_layout ml;
+    mvb200_mask_layout(p, &ml);
+    const size_t blob = (size_t)blob_bytes_of(vectors), luma_pitch = align256((size_t)p->nWidth), luma_bytes = p->kind == 5 ? luma_pitch * p->nHeight : 0;
+    uint8_t *buf = (uint8_t *)c->get_scratch(kSlotStage, (size_t)ml.frame_bytes + align256(blob) + luma_bytes + 256);
+    if (!buf)
+        return 1;
+    uint8_t *ddst = buf, *dvec = buf + ml.frame_bytes, *dluma = dvec + align256(blob);
+    MVB_CUDA_CHECK(cudaMemcpyAsync(dvec, vectors, blob, cudaMemcpyHostToDevice, c->stream));
+    if (p->kind == 5) {
+        if (!src_luma)
+            return set_error("Mask: kind=5 needs the source clip's luma plane");
+        MVB_CUDA_CHECK(cudaMemcpy2DAsync(dluma, luma_pitch, src_luma, (size_t)src_stride, (size_t)p->nWidth, (size_t)p->nHeight, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (launch_mask(c, p, ml, p->kind == 5 ? dluma : nullptr, (long long)luma_pitch, dvec, ddst))
+        return 1;
+    for (int pl = 0; pl < 3; pl++)
+        MVB_CUDA_CHECK(cudaMemcpy2DAsync(dst[pl], (size_t)dst_stride[pl], ddst + ml.offset[pl], (size_t)ml.pitch[pl], (size_t)ml.plane_w[pl], (size_t)ml.plane_h[pl], cudaMemcpyDeviceToHost, c->stream));
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int mvb200_finest_batch(mvb200_ctx *ctx, const mvb200_super_params *sp, const void *dev_super, int n, void *dev_dst) {
+    if (sp->levels > kDevMaxLevels)
+        return set_error("mvtools_b200: more than %d pyramid levels are not supported on the device", kDevMaxLevels);
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    make_super_desc(sp, &sd);
+    mvb200_frame_layout fl;
+    mvb200_finest_layout(sp, &fl);
+    for (int f = 0; f < n; f++)
+        if (launch_finest(c, sp, sd, fl, (const uint8_t *)dev_super + (long long)f * sd.frame_bytes, (uint8_t *)dev_dst + (long long)f * fl.frame_bytes))
+            return 1;
+    return 0;
+}
+
+int mvb200_finest_frame(mvb200_ctx *ctx, const mvb200_super_params *sp, const uint8_t *const super[3], const ptrdiff_t super_stride[3], uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
+    if (sp->levels > kDevMaxLevels)
+        return set_error("mvtools_b200: more than %d pyramid levels are not supported on the device", kDevMaxLevels);
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    make_super_desc(sp, &sd);
+    mvb200_frame_layout fl;
+    mvb200_finest_layout(sp, &fl);
+    uint8_t *buf = (uint8_t *)c->get_scratch(kSlotStage, (size_t)sd.frame_bytes + (size_t)fl.frame_bytes);
+    if (!buf)
+        return 1;
+    uint8_t *dsup = buf, *ddst = buf + sd.frame_bytes;
+    const bool chroma = (sp->modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) != 0;
+    for (int pl = 0; pl < sd.nplanes; pl++) { // only level 0 (the top pel^2 * padded_h rows of each plane) is read
+        if (pl && !chroma)
+            continue;
+        const mvb200_level_geom &g = sd.lv[pl][0];
+        MVB_CUDA_CHECK(cudaMemcpy2DAsync(dsup + sd.offset[pl], (size_t)sd.pitch[pl], super[pl], (size_t)super_stride[pl], (size_t)g.padded_w * sd.bps, (size_t)g.padded_h * sp->pel * sp->pel, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (launch_finest(c, sp, sd, fl, dsup, ddst))
+        return 1;
+    for (int pl = 0; pl < sd.nplanes; pl++) {
+        if (pl && !chroma)
+            continue;
+        const mvb200_level_geom &g = sd.lv[pl][0];
+        MVB_CUDA_CHECK(cudaMemcpy2DAsync(dst[pl], (size_t)dst_stride[pl], ddst + fl.offset[pl], (size_t)fl.pitch[pl], (size_t)g.padded_w * sp->pel * sd.bps, (size_t)g.padded_h * sp->pel, cudaMemcpyDeviceToHost, c->stream));
+    }
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int flow_check(const mvb200_flow_params *fp, const mvb200_super_params *sp) {
+    if (sp->levels > kDevMaxLevels)
+        return set_error("mvtools_b200: more than %d pyramid levels are not supported on the device", kDevMaxLevels);
+    if (fp->super_pel != sp->pel || fp->super_hpad != sp->hpad || fp->super_vpad != sp->vpad || fp->bits != sp->bits)
+        return set_error("Flow: the parameters were derived for another super clip");
+    return 0;
+}
+
+int mvb200_flow_batch(mvb200_ctx *ctx, const mvb200_flow_params *fp, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int first, int n, const void *dev_vectors, int64_t vectors_stride, void *dev_dst) {
+    if (flow_check(fp, sp))
+        return 1;
+    if (n <= 0)
+        return 0;
+    if (first < 0 || first + n > fp->num_frames)
+        return set_error("Flow: frames [%d, %d) are outside the clip of %d frames", first, first + n, fp->num_frames);
+    if (fp->fields && !fp->tff_exists && fp->vd.nPel > 1)
+        return set_error("Flow: _Field property not found in super frame. Therefore, you must pass tff argument.");
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(sp, &sd);
+    make_clip_desc(sp, &cd);
+    for (int f = 0; f < n; f++) {
+        const int fn = first + f, off = fp->vd.nDeltaFrame;
+        int nref = off > 0 ? (fp->vd.isBackward ? fn + off : fn - off) : -off; // MVFlow.cpp:186-193
+        if (nref < 0 || nref >= fp->num_frames)
+            nref = -1;
+        int fs = 0;
+        if (nref >= 0 && fp->fields && fp->vd.nPel > 1 && (nref - fn) % 2 != 0) { // :268-299 with an explicit tff
+            const int src_top = fp->tff ^ (fn % 2), ref_top = fp->tff ^ (nref % 2);
+            fs = (src_top && !ref_top) ? fp->vd.nPel / 2 : ((ref_top && !src_top) ? -(fp->vd.nPel / 2) : 0);
+        }
+        int *usable;
+        if (launch_flow(c, fp, sd, cd, nref >= 0 ? (const uint8_t *)dev_super + (long long)nref * sd.frame_bytes : nullptr, (const uint8_t *)dev_vectors + (long long)f * vectors_stride, fs,
+                        dev_src ? (const uint8_t *)dev_src + (long long)fn * cd.frame_bytes : nullptr, (uint8_t *)dev_dst + (long long)f * cd.frame_bytes, &usable))
+            return 1;
+    }
+    return 0;
+}
+
+int mvb200_flow_frame(mvb200_ctx *ctx, const mvb200_flow_params *fp, const mvb200_super_params *sp, const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *vectors, int field_shift, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable_out) {
+    if (flow_check(fp, sp))
+        return 1;
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(sp, &sd);
+    make_clip_desc(sp, &cd);
+    const size_t blob = (size_t)blob_bytes_of(vectors);
+    uint8_t *buf = (uint8_t *)c->get_scratch(kSlotStage, (size_t)sd.frame_bytes + (size_t)cd.frame_bytes + align256(blob) + 256);
+    if (!buf)
+        return 1;
+    uint8_t *dref = buf, *ddst = buf + sd.frame_bytes, *dvec = ddst + cd.frame_bytes;
+    MVB_CUDA_CHECK(cudaMemcpyAsync(dvec, vectors, blob, cudaMemcpyHostToDevice, c->stream));
+    if (ref_super)
+        for (int pl = 0; pl < fp->nplanes; pl++) { // level 0 only
+            const mvb200_level_geom &g = sd.lv[pl][0];
+            MVB_CUDA_CHECK(cudaMemcpy2DAsync(dref + sd.offset[pl], (size_t)sd.pitch[pl], ref_super[pl], (size_t)ref_stride[pl], (size_t)g.padded_w * sd.bps, (size_t)g.padded_h * sp->pel * sp->pel, cudaMemcpyHostToDevice, c->stream));
+        }
+    int *usable_dev = nullptr;
+    if (launch_flow(c, fp, sd, cd, ref_super ? dref : nullptr, dvec, field_shift, nullptr, ddst, &usable_dev))
+        return 1;
+    int usable = 0;
+    MVB_CUDA_CHECK(cudaMemcpyAsync(&usable, usable_dev, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    *usable_out = usable;
+    if (usable) {
+        for (int pl = 0; pl < fp->nplanes; pl++)
+            MVB_CUDA_CHECK(cudaMemcpy2DAsync(dst[pl], (size_t)dst_stride[pl], ddst + cd.offset[pl], (size_t)cd.pitch[pl], (size_t)cd.w[pl] * cd.bps, (size_t)cd.h[pl], cudaMemcpyDeviceToHost, c->stream));
+        MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+} // extern "C"

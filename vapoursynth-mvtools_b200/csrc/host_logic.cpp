@@ -6,6 +6,10 @@
 //   mvb200_super_geometry <- mvgofInit/Update  MVFrame.cpp:1852-1903, PlaneSuperOffset :1229-1247
 //   mvb200_analyse_init   <- mvanalyseCreate   MVAnalyse.c:267-624, gopInit GroupOfPlanes.c:25-56
 //   mvb200_degrain_init   <- mvdegrainCreate   MVDegrains.cpp:512-782, scaleThSCD MVAnalysisData.c:7-31
+//   mvb200_scdetection_init <- mvscdetectionCreate MVSCDetection.c:89-131
+//   mvb200_mask_init      <- mvmaskCreate      MVMask.c:221-344
+//   mvb200_flow_init      <- mvflowCreate      MVFlow.cpp:395-575
+//   mvb200_simple_resize_tables <- InitTables  SimpleResize.cpp:26-56
 #include "engine.h"
 
 #include <climits>
@@ -579,4 +583,170 @@ int mvb200_recalculate_init(const mvb200_recalculate_args *a, const mvb200_super
     return 0;
 }
 
+// ------------------------------------------- SCDetection / Mask / Finest / Flow
+
+int mvb200_scdetection_init(int64_t thscd1, int32_t thscd2, const mvb200_analysis_data *vd, mvb200_scdetection_params *d) {
+    memset(d, 0, sizeof(*d));
+    d->vd = *vd;
+    d->nSCD1 = GIVEN64(thscd1) ? thscd1 : 400; // MV_DEFAULT_SCD1/2, MVAnalysisData.h
+    d->nSCD2 = GIVEN(thscd2) ? thscd2 : 130;
+    return scale_thscd(&d->nSCD1, &d->nSCD2, &d->vd, "SCDetection");
+}
+
+int mvb200_mask_init(const mvb200_mask_args *a, const mvb200_analysis_data *vd, int clip_bits, int clip_ssw, int clip_ssh, int clip_gray, mvb200_mask_params *d) {
+    memset(d, 0, sizeof(*d));
+    // MVMask.c:230-258
+    d->ml = (a->ml == a->ml) ? (float)a->ml : 100.0f;
+    d->fGamma = (a->gamma == a->gamma) ? (float)a->gamma : 1.0f;
+    d->kind = GIVEN(a->kind) ? a->kind : 0;
+    const double time = (a->time == a->time) ? a->time : 100.0;
+    d->nSceneChangeValue = GIVEN(a->ysc) ? a->ysc : 0;
+    d->nSCD1 = GIVEN64(a->thscd1) ? a->thscd1 : 400;
+    d->nSCD2 = GIVEN(a->thscd2) ? a->thscd2 : 130;
+    // :261-279
+    if (d->fGamma < 0.0f)
+        return set_error("Mask: gamma must not be negative.");
+    if (d->kind < 0 || d->kind > 5)
+        return set_error("Mask: kind must 0, 1, 2, 3, 4, or 5.");
+    if (time < 0.0 || time > 100.0)
+        return set_error("Mask: time must be between 0.0 and 100.0 (inclusive).");
+    if (d->nSceneChangeValue < 0 || d->nSceneChangeValue > 255)
+        return set_error("Mask: ysc must be between 0 and 255 (inclusive).");
+    d->vd = *vd;
+    if (scale_thscd(&d->nSCD1, &d->nSCD2, &d->vd, "Mask"))
+        return 1;
+    // :299-311 (float arithmetic, as in the reference)
+    d->fMaskNormFactor = 1.0f / d->ml;
+    d->fMaskNormFactor2 = d->fMaskNormFactor * d->fMaskNormFactor;
+    d->fHalfGamma = d->fGamma * 0.5f;
+    d->nWidth = vd->nWidth;
+    d->nHeight = vd->nHeight;
+    d->nWidthB = vd->nBlkX * (vd->nBlkSizeX - vd->nOverlapX) + vd->nOverlapX;
+    d->nHeightB = vd->nBlkY * (vd->nBlkSizeY - vd->nOverlapY) + vd->nOverlapY;
+    d->nHeightUV = vd->nHeight / vd->yRatioUV;
+    d->nWidthUV = vd->nWidth / vd->xRatioUV;
+    d->nHeightBUV = d->nHeightB / vd->yRatioUV;
+    d->nWidthBUV = d->nWidthB / vd->xRatioUV;
+    // :317-322
+    if (clip_bits > 8 || clip_ssw > 1 || clip_ssh > 1)
+        return set_error("Mask: input clip must be GRAY8, YUV420P8, YUV422P8, YUV440P8, or YUV444P8, with constant dimensions.");
+    d->clip_gray = clip_gray != 0;
+    d->time256 = (int)(time * 256 / 100);
+    return 0;
+}
+
+int mvb200_flow_init(const mvb200_flow_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd, int num_frames, mvb200_flow_params *d) {
+    memset(d, 0, sizeof(*d));
+    // MVFlow.cpp:403-438
+    const double time = (a->time == a->time) ? a->time : 100.0;
+    d->mode = GIVEN(a->mode) ? a->mode : 0;
+    d->fields = GIVEN(a->fields) && a->fields != 0;
+    d->nSCD1 = GIVEN64(a->thscd1) ? a->thscd1 : 400;
+    d->nSCD2 = GIVEN(a->thscd2) ? a->thscd2 : 130;
+    d->tff = GIVEN(a->tff) && a->tff != 0;
+    d->tff_exists = GIVEN(a->tff);
+    if (time < 0.0 || time > 100.0)
+        return set_error("Flow: time must be between 0 and 100 %% (inclusive).");
+    if (d->mode < 0 || d->mode > 1)
+        return set_error("Flow: mode must be 0 or 1.");
+    d->time256 = (int)(time * 256.0 / 100.0);
+    d->vd = *vd;
+    if (scale_thscd(&d->nSCD1, &d->nSCD2, &d->vd, "Flow"))
+        return 1;
+    // :514-533
+    if (vd->nHeight != sp->height || vd->nWidth != sp->super_width - sp->hpad * 2 || vd->nPel != sp->pel)
+        return set_error("Flow: wrong source or super clip frame size.");
+    if (sp->bits > 16 || sp->ssw > 1 || sp->ssh > 1)
+        return set_error("Flow: input clip must be GRAY, 420, 422, 440, or 444, up to 16 bits, with constant dimensions.");
+    // :535-557
+    d->nBlkXP = vd->nBlkX;
+    d->nBlkYP = vd->nBlkY;
+    while (d->nBlkXP * (vd->nBlkSizeX - vd->nOverlapX) + vd->nOverlapX < vd->nWidth)
+        d->nBlkXP++;
+    while (d->nBlkYP * (vd->nBlkSizeY - vd->nOverlapY) + vd->nOverlapY < vd->nHeight)
+        d->nBlkYP++;
+    d->nWidthP = d->nBlkXP * (vd->nBlkSizeX - vd->nOverlapX) + vd->nOverlapX;
+    d->nHeightP = d->nBlkYP * (vd->nBlkSizeY - vd->nOverlapY) + vd->nOverlapY;
+    d->nWidthPUV = d->nWidthP / vd->xRatioUV;
+    d->nHeightPUV = d->nHeightP / vd->yRatioUV;
+    d->nHeightUV = vd->nHeight / vd->yRatioUV;
+    d->nWidthUV = vd->nWidth / vd->xRatioUV;
+    d->nHPaddingUV = vd->nHPadding / vd->xRatioUV;
+    d->nVPaddingUV = vd->nVPadding / vd->yRatioUV;
+    d->VPitchY = (d->nWidthP + 15) & (~15);
+    d->VPitchUV = (d->nWidthPUV + 15) & (~15);
+    d->bits = sp->bits;
+    d->ssw = sp->ssw;
+    d->ssh = sp->ssh;
+    d->gray = sp->gray;
+    d->nplanes = sp->nplanes;
+    d->super_hpad = sp->hpad;
+    d->super_vpad = sp->vpad;
+    d->super_pel = sp->pel;
+    d->super_levels = sp->levels;
+    d->num_frames = num_frames;
+    return 0;
+}
+
+// InitTables, SimpleResize.cpp:26-56 (single-precision arithmetic, evaluated in the reference's order)
+void mvb200_simple_resize_tables(int out, int in, int32_t *offsets, int32_t *weights) {
+    const float leftmost = 0.5f, rightmost = in - 0.5f;
+    const int leftmost_idx = (int)leftmost > 0 ? (int)leftmost : 0;
+    const int rightmost_idx = (int)rightmost < in - 1 ? (int)rightmost : in - 1;
+    for (int i = 0; i < out; i++) {
+        volatile float position = (i + 0.5f) * (float)in; // (volatile: no contraction / excess precision on any host)
+        position = position / (float)out;
+        float weight;
+        int offset;
+        if (position <= leftmost) {
+            offset = leftmost_idx;
+            weight = 0.0f;
+        } else if (position >= rightmost) {
+            offset = rightmost_idx - 1;
+            weight = 1.0f;
+        } else {
+            offset = (int)(position - leftmost);
+            volatile float t = position - leftmost;
+            weight = t - offset;
+        }
+        offsets[i] = offset;
+        weights[i] = (int)(weight * (1 << 14));
+    }
+}
+
+static long long round_up256(long long v) { return (v + 255) / 256 * 256; }
+
+void mvb200_mask_layout(const mvb200_mask_params *p, mvb200_frame_layout *l) {
+    memset(l, 0, sizeof(*l));
+    l->nplanes = 3;
+    l->bytes_per_sample = 1;
+    long long off = 0;
+    for (int i = 0; i < 3; i++) {
+        l->plane_w[i] = i ? p->nWidthUV : p->nWidth;
+        l->plane_h[i] = i ? p->nHeightUV : p->nHeight;
+        l->pitch[i] = round_up256(l->plane_w[i]);
+        l->offset[i] = off;
+        off += l->pitch[i] * l->plane_h[i];
+    }
+    l->frame_bytes = round_up256(off);
+}
+
+// mvfinestCreate, MVFinest.c:190-194: (W + 2 hpad) pel x (H + 2 vpad) pel; chroma planes by the subsampling
+void mvb200_finest_layout(const mvb200_super_params *sp, mvb200_frame_layout *l) {
+    memset(l, 0, sizeof(*l));
+    l->nplanes = sp->nplanes;
+    l->bytes_per_sample = (sp->bits + 7) / 8;
+    const int w = (sp->width + 2 * sp->hpad) * sp->pel, h = (sp->height + 2 * sp->vpad) * sp->pel;
+    long long off = 0;
+    for (int i = 0; i < sp->nplanes; i++) {
+        l->plane_w[i] = i ? w >> sp->ssw : w;
+        l->plane_h[i] = i ? h >> sp->ssh : h;
+        l->pitch[i] = round_up256((long long)l->plane_w[i] * l->bytes_per_sample);
+        l->offset[i] = off;
+        off += l->pitch[i] * l->plane_h[i];
+    }
+    l->frame_bytes = round_up256(off);
+}
+
 } // extern "C"
+

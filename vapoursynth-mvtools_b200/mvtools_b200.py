@@ -110,6 +110,33 @@ class RecalculateParams(C.Structure):
                             "ssw", "ssh", "gray", "num_frames", "vectors_size")]
 
 
+class ScdParams(C.Structure):
+    _fields_ = [("vd", AnalysisData), ("nSCD1", i64), ("nSCD2", i32)]
+
+
+class MaskArgs(C.Structure):
+    _fields_ = [("ml", C.c_double), ("gamma", C.c_double), ("kind", i32), ("time", C.c_double), ("ysc", i32), ("thscd1", i64), ("thscd2", i32)]
+
+
+class MaskParams(C.Structure):
+    _fields_ = [("vd", AnalysisData)] + [(n, i32) for n in ("kind", "time256", "nSceneChangeValue")] + \
+        [(n, C.c_float) for n in ("ml", "fGamma", "fMaskNormFactor", "fMaskNormFactor2", "fHalfGamma")] + \
+        [("nSCD1", i64), ("nSCD2", i32), ("clip_gray", i32)] + \
+        [(n, i32) for n in ("nWidth", "nHeight", "nWidthUV", "nHeightUV", "nWidthB", "nHeightB", "nWidthBUV", "nHeightBUV")]
+
+
+class FlowArgs(C.Structure):
+    _fields_ = [("time", C.c_double), ("mode", i32), ("fields", i32), ("thscd1", i64), ("thscd2", i32), ("tff", i32)]
+
+
+class FlowParams(C.Structure):
+    _fields_ = [("vd", AnalysisData)] + [(n, i32) for n in ("time256", "mode", "fields", "tff", "tff_exists")] + \
+        [("nSCD1", i64), ("nSCD2", i32)] + \
+        [(n, i32) for n in ("bits", "ssw", "ssh", "gray", "nplanes", "super_hpad", "super_vpad", "super_pel", "super_levels",
+                            "nBlkXP", "nBlkYP", "nWidthP", "nHeightP", "nWidthPUV", "nHeightPUV", "nWidthUV", "nHeightUV",
+                            "nHPaddingUV", "nVPaddingUV", "VPitchY", "VPitchUV", "num_frames")]
+
+
 class FrameLayout(C.Structure):
     _fields_ = [("nplanes", i32), ("bytes_per_sample", i32), ("plane_w", i32 * 3), ("plane_h", i32 * 3),
                 ("pitch", i64 * 3), ("offset", i64 * 3), ("frame_bytes", i64)]
@@ -171,6 +198,23 @@ def lib():
                                            PP(C.c_ssize_t), i32, vp]
         L.mvb200_degrain_frame.argtypes = [vp, PP(DegrainParams), PP(SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp),
                                            PP(C.c_ssize_t), PP(vp), PP(vp), PP(C.c_ssize_t)]
+        L.mvb200_scdetection_init.argtypes = [i64, i32, PP(AnalysisData), PP(ScdParams)]
+        L.mvb200_mask_init.argtypes = [PP(MaskArgs), PP(AnalysisData), i32, i32, i32, i32, PP(MaskParams)]
+        L.mvb200_flow_init.argtypes = [PP(FlowArgs), PP(SuperParams), PP(AnalysisData), i32, PP(FlowParams)]
+        L.mvb200_simple_resize_tables.argtypes = [i32, i32, vp, vp]
+        L.mvb200_simple_resize_tables.restype = None
+        L.mvb200_mask_layout.argtypes = [PP(MaskParams), PP(FrameLayout)]
+        L.mvb200_mask_layout.restype = None
+        L.mvb200_finest_layout.argtypes = [PP(SuperParams), PP(FrameLayout)]
+        L.mvb200_finest_layout.restype = None
+        L.mvb200_scdetection_frame.argtypes = [vp, PP(ScdParams), vp, PP(i32)]
+        L.mvb200_scdetection_batch.argtypes = [vp, PP(ScdParams), vp, i64, i32, PP(i32)]
+        L.mvb200_mask_frame.argtypes = [vp, PP(MaskParams), vp, C.c_ssize_t, vp, PP(vp), PP(C.c_ssize_t)]
+        L.mvb200_mask_batch.argtypes = [vp, PP(MaskParams), vp, i64, i64, vp, i64, i32, vp]
+        L.mvb200_finest_frame.argtypes = [vp, PP(SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
+        L.mvb200_finest_batch.argtypes = [vp, PP(SuperParams), vp, i32, vp]
+        L.mvb200_flow_frame.argtypes = [vp, PP(FlowParams), PP(SuperParams), PP(vp), PP(C.c_ssize_t), vp, i32, PP(vp), PP(C.c_ssize_t), PP(i32)]
+        L.mvb200_flow_batch.argtypes = [vp, PP(FlowParams), PP(SuperParams), vp, vp, i32, i32, vp, i64, vp]
         _LIB = L
     return _LIB
 
@@ -268,6 +312,61 @@ def recalculate_params(sp, old_vd, num_frames, **kw):
     out = RecalculateParams()
     _check(lib().mvb200_recalculate_init(C.byref(a), C.byref(sp), C.byref(old_vd), num_frames, C.byref(out)))
     return out
+
+
+def _opt(kw, name, unset, conv=int):
+    v = kw.pop(name, None)
+    return unset if v is None else conv(v)
+
+
+def scdetection_params(vd, thscd1=None, thscd2=None):
+    out = ScdParams()
+    _check(lib().mvb200_scdetection_init(UNSET64 if thscd1 is None else int(thscd1), UNSET if thscd2 is None else int(thscd2), C.byref(vd), C.byref(out)))
+    return out
+
+
+def mask_params(vd, clip_bits=8, clip_ssw=1, clip_ssh=1, clip_gray=False, **kw):
+    a = MaskArgs()
+    nan = float("nan")
+    a.ml, a.gamma, a.time = _opt(kw, "ml", nan, float), _opt(kw, "gamma", nan, float), _opt(kw, "time", nan, float)
+    a.kind, a.ysc, a.thscd2 = _opt(kw, "kind", UNSET), _opt(kw, "ysc", UNSET), _opt(kw, "thscd2", UNSET)
+    a.thscd1 = _opt(kw, "thscd1", UNSET64)
+    if kw:
+        raise TypeError("Mask: unknown argument(s) %s" % sorted(kw))
+    out = MaskParams()
+    _check(lib().mvb200_mask_init(C.byref(a), C.byref(vd), clip_bits, clip_ssw, clip_ssh, int(clip_gray), C.byref(out)))
+    return out
+
+
+def flow_params(sp, vd, num_frames, **kw):
+    a = FlowArgs()
+    a.time = _opt(kw, "time", float("nan"), float)
+    a.mode, a.fields, a.thscd2, a.tff = _opt(kw, "mode", UNSET), _opt(kw, "fields", UNSET), _opt(kw, "thscd2", UNSET), _opt(kw, "tff", UNSET)
+    a.thscd1 = _opt(kw, "thscd1", UNSET64)
+    if kw:
+        raise TypeError("Flow: unknown argument(s) %s" % sorted(kw))
+    out = FlowParams()
+    _check(lib().mvb200_flow_init(C.byref(a), C.byref(sp), C.byref(vd), num_frames, C.byref(out)))
+    return out
+
+
+def simple_resize_tables(out, in_):
+    off = np.zeros(out, dtype=np.int32)
+    wt = np.zeros(out, dtype=np.int32)
+    lib().mvb200_simple_resize_tables(out, in_, off.ctypes.data, wt.ctypes.data)
+    return off, wt
+
+
+def mask_layout(mp):
+    l = FrameLayout()
+    lib().mvb200_mask_layout(C.byref(mp), C.byref(l))
+    return l
+
+
+def finest_layout(sp):
+    l = FrameLayout()
+    lib().mvb200_finest_layout(C.byref(sp), C.byref(l))
+    return l
 
 
 def clip_layout(sp):
@@ -400,3 +499,35 @@ class Context:
         d, ds = plane_ptrs(dst)
         _check(lib().mvb200_degrain_frame(self._h, C.byref(dp), C.byref(sp), s, ss, refs, rstr, vecs, d, ds))
         return dst
+
+    # ---- consumers of the vector clips
+    def scdetection_frame(self, scp, vectors):
+        out = i32(0)
+        _check(lib().mvb200_scdetection_frame(self._h, C.byref(scp), vectors.ctypes.data, C.byref(out)))
+        return out.value
+
+    def mask_frame(self, mp, src_luma, vectors):
+        dst = alloc_planes([mp.nWidth, mp.nWidthUV, mp.nWidthUV], [mp.nHeight, mp.nHeightUV, mp.nHeightUV], 8, fill=0xA5)
+        d, ds = plane_ptrs(dst)
+        sl = None if src_luma is None else src_luma.ctypes.data
+        _check(lib().mvb200_mask_frame(self._h, C.byref(mp), sl, 0 if src_luma is None else src_luma.strides[0], vectors.ctypes.data, d, ds))
+        return dst
+
+    def finest_frame(self, sp, super_planes):
+        l = finest_layout(sp)
+        dst = alloc_planes(list(l.plane_w)[: sp.nplanes], list(l.plane_h)[: sp.nplanes], sp.bits, fill=0xA5)
+        s, ss = plane_ptrs(super_planes)
+        d, ds = plane_ptrs(dst)
+        _check(lib().mvb200_finest_frame(self._h, C.byref(sp), s, ss, d, ds))
+        return dst
+
+    def flow_frame(self, fp, sp, ref_super, vectors, field_shift=0):
+        """-> planes, or None when the vectors are not usable (the caller keeps the source frame)"""
+        w = [fp.vd.nWidth, fp.nWidthUV, fp.nWidthUV][: fp.nplanes]
+        h = [fp.vd.nHeight, fp.nHeightUV, fp.nHeightUV][: fp.nplanes]
+        dst = alloc_planes(w, h, fp.bits, fill=0xA5)
+        r, rs = (None, None) if ref_super is None else plane_ptrs(ref_super)
+        d, ds = plane_ptrs(dst)
+        usable = i32(0)
+        _check(lib().mvb200_flow_frame(self._h, C.byref(fp), C.byref(sp), r, rs, vectors.ctypes.data, field_shift, d, ds, C.byref(usable)))
+        return dst if usable.value else None
