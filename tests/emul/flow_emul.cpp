@@ -1,0 +1,144 @@
+// TEST INFRASTRUCTURE -- CPU emulation of the flow.cu kernels.
+//
+// The kernels of vapoursynth-mvtools_b200/csrc/flow.cu are index wrappers around the per-thread functions of
+// csrc/flow_device.h, with parameter blocks built by csrc/flow_setup.h.  This file includes those two headers as
+// host C++ and runs the functions "thread by thread" in plain loops (an atomicMax becomes a max), with the same
+// frame-level structure as the launchers: scene-change test -> per-block fields -> one pass per plane.  tests/
+// compare the result with the oracle bit for bit, which checks the kernels' index arithmetic without a GPU.
+// Nothing in the product links, loads or calls this file: the engine has no CPU path.
+#include "../../vapoursynth-mvtools_b200/csrc/flow_device.h"
+#include "../../vapoursynth-mvtools_b200/csrc/flow_setup.h"
+
+#include <cstring>
+#include <vector>
+
+using namespace mvb200::flowdev;
+
+#define EMUL_API extern "C" __attribute__((visibility("default")))
+
+static int usable_of(const uint8_t *blob, int nBlk, long long nSCD1, int nSCD2, int haveRef) { // k_flow_scd
+    const int *l0 = blob_level0(blob, nBlk);
+    int cnt = 0;
+    for (int i = 0; i < nBlk; i++)
+        cnt += vec_sad(l0 + 4 * i) > nSCD1 ? 1 : 0;
+    return (((const int *)blob)[1] == 1) && !(cnt > nSCD2) && haveRef;
+}
+
+EMUL_API int emul_scdetection_frame(const mvb200_scdetection_params *p, const uint8_t *vectors, int32_t *scene_change) {
+    *scene_change = !usable_of(vectors, p->vd.nBlkX * p->vd.nBlkY, p->nSCD1, p->nSCD2, 1);
+    return 0;
+}
+
+EMUL_API int emul_mask_frame(const mvb200_mask_params *mp, const uint8_t *src_luma, ptrdiff_t src_stride, const uint8_t *vectors, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
+    const mvb200_analysis_data &vd = mp->vd;
+    const int n = vd.nBlkX * vd.nBlkY;
+    const int usable = usable_of(vectors, n, mp->nSCD1, mp->nSCD2, 1);
+    std::vector<int32_t> tab(tables_ints(mp->nWidthB, mp->nHeightB) + tables_ints(mp->nWidthBUV, mp->nHeightBUV));
+    fill_tables(tab.data(), mp->nWidthB, mp->nHeightB, vd.nBlkX, vd.nBlkY);
+    fill_tables(tab.data() + tables_ints(mp->nWidthB, mp->nHeightB), mp->nWidthBUV, mp->nHeightBUV, vd.nBlkX, vd.nBlkY);
+    const ResizeTables t[2] = {tables_at(tab.data(), mp->nWidthB, mp->nHeightB), tables_at(tab.data() + tables_ints(mp->nWidthB, mp->nHeightB), mp->nWidthBUV, mp->nHeightBUV)};
+    std::vector<int> small(n, 0), smallV(n, 0);
+    const MaskSmallParams P = make_mask_small_params(mp);
+    const int *l0 = blob_level0(vectors, n);
+    int *sm = small.data();
+    for (int j = 0; j < n; j++) { // k_mask_small
+        if (P.kind == 2)
+            occlusion_contrib(l0, P.isBackward, P.nBlkX, P.nBlkY, 1.0 / P.fMaskNormFactor, P.fGamma, P.nPel, P.time256, P.stepX, P.stepY, j % P.nBlkX, j / P.nBlkX, [sm](int idx, int val) { sm[idx] = sm[idx] > val ? sm[idx] : val; });
+        else
+            mask_small_direct(P, l0, j, small.data(), smallV.data());
+    }
+    for (int plane = 0; plane < 3; plane++) { // k_mask_plane
+        const MaskPlane B = make_mask_plane(mp, plane, t[plane ? 1 : 0]);
+        for (int y = 0; y < B.H; y++)
+            for (int x = 0; x < B.W; x++)
+                dst[plane][y * dst_stride[plane] + x] = (uint8_t)mask_sample(B, mp->kind, usable, mp->nSceneChangeValue, vd.nBlkX, small.data(), smallV.data(), src_luma, src_stride, x, y);
+    }
+    return 0;
+}
+
+static void level0_geom(const mvb200_super_params *sp, int plane, mvb200_level_geom *g) {
+    mvb200_super_geom geom;
+    mvb200_super_geometry(sp, &geom);
+    *g = geom.lv[plane][0];
+}
+
+EMUL_API int emul_finest_frame(const mvb200_super_params *sp, const uint8_t *const super[3], const ptrdiff_t super_stride[3], uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
+    const int bps = (sp->bits + 7) / 8, lp = ilog2_pel(sp->pel);
+    for (int plane = 0; plane < sp->nplanes; plane++) { // k_finest
+        if (plane && !(sp->modeyuv & (MVB200_UPLANE | MVB200_VPLANE)))
+            continue;
+        mvb200_level_geom g;
+        level0_geom(sp, plane, &g);
+        const SuperPlane S = make_super_plane(super_stride[plane], 0, g);
+        const int W = S.padded_w * sp->pel, H = S.padded_h * sp->pel;
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++) {
+                if (bps == 1)
+                    dst[plane][y * dst_stride[plane] + x] = finest_sample<uint8_t>(super[plane], S, lp, x, y);
+                else
+                    *((uint16_t *)(dst[plane] + y * dst_stride[plane]) + x) = finest_sample<uint16_t>(super[plane], S, lp, x, y);
+            }
+    }
+    return 0;
+}
+
+EMUL_API int emul_flow_frame(const mvb200_flow_params *fp, const mvb200_super_params *sp, const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *vectors, int field_shift, uint8_t *const dst[3],
+                             const ptrdiff_t dst_stride[3], int32_t *usable_out) {
+    const mvb200_analysis_data &vd = fp->vd;
+    const int usable = usable_of(vectors, vd.nBlkX * vd.nBlkY, fp->nSCD1, fp->nSCD2, ref_super != nullptr);
+    *usable_out = usable;
+    if (!usable)
+        return 0;
+    const int ns = fp->nBlkXP * fp->nBlkYP, bps = (fp->bits + 7) / 8;
+    std::vector<short> xY(ns), yY(ns), xUV(ns), yUV(ns);
+    const int *l0 = blob_level0(vectors, vd.nBlkX * vd.nBlkY);
+    for (int k = 0; k < ns; k++) { // k_small_vectors
+        const SmallVec s = small_vector(l0, vd.nBlkX, vd.nBlkY, k % fp->nBlkXP, k / fp->nBlkXP, field_shift, vd.xRatioUV, vd.yRatioUV);
+        xY[k] = s.xY;
+        yY[k] = s.yY;
+        xUV[k] = s.xUV;
+        yUV[k] = s.yUV;
+    }
+    const size_t n0 = tables_ints(fp->nWidthP, fp->nHeightP), n1 = fp->nplanes > 1 ? tables_ints(fp->nWidthPUV, fp->nHeightPUV) : 0;
+    std::vector<int32_t> tab(n0 + n1);
+    fill_tables(tab.data(), fp->nWidthP, fp->nHeightP, fp->nBlkXP, fp->nBlkYP);
+    if (n1)
+        fill_tables(tab.data() + n0, fp->nWidthPUV, fp->nHeightPUV, fp->nBlkXP, fp->nBlkYP);
+    const ResizeTables t[2] = {tables_at(tab.data(), fp->nWidthP, fp->nHeightP), tables_at(tab.data() + n0, fp->nWidthPUV, fp->nHeightPUV)};
+    for (int plane = 0; plane < fp->nplanes; plane++) {
+        mvb200_level_geom g;
+        level0_geom(sp, plane, &g);
+        const FlowPlane F = make_flow_plane(fp, plane, plane ? xUV.data() : xY.data(), plane ? yUV.data() : yY.data(), t[plane ? 1 : 0], make_super_plane(ref_stride[plane], 0, g));
+        auto put = [&](int x, int y, int v) {
+            if (bps == 1)
+                dst[plane][y * dst_stride[plane] + x] = (uint8_t)v;
+            else
+                *((uint16_t *)(dst[plane] + y * dst_stride[plane]) + x) = (uint16_t)v;
+        };
+        if (fp->mode == 0) { // k_flow_fetch
+            for (int y = 0; y < F.H; y++)
+                for (int x = 0; x < F.W; x++)
+                    put(x, y, bps == 1 ? (int)flow_fetch_sample<uint8_t>(F, ref_super[plane], x, y) : (int)flow_fetch_sample<uint16_t>(F, ref_super[plane], x, y));
+        } else {
+            std::vector<int> owner((size_t)F.W * F.H, 0);
+            for (int y = 0; y < F.H; y++) // k_flow_shift_mark (atomicMax)
+                for (int x = 0; x < F.W; x++) {
+                    const int tgt = flow_shift_target(F, x, y);
+                    if (tgt >= 0 && owner[tgt] < y * F.W + x + 1)
+                        owner[tgt] = y * F.W + x + 1;
+                }
+            for (int y = 0; y < F.H; y++) // k_flow_shift_resolve
+                for (int x = 0; x < F.W; x++) {
+                    const int o = owner[y * F.W + x];
+                    if (o == 0) {
+                        put(x, y, (1 << fp->bits) - 1);
+                        continue;
+                    }
+                    const int sx = (o - 1) % F.W, sy = (o - 1) / F.W;
+                    put(x, y, bps == 1 ? (int)finest_sample<uint8_t>(ref_super[plane], F.S, F.logPel, (sx + F.S.hpad) << F.logPel, (sy + F.S.vpad) << F.logPel)
+                                       : (int)finest_sample<uint16_t>(ref_super[plane], F.S, F.logPel, (sx + F.S.hpad) << F.logPel, (sy + F.S.vpad) << F.logPel));
+                }
+        }
+    }
+    return 0;
+}

@@ -15,6 +15,10 @@ import pipeline
 HERE = os.path.dirname(os.path.abspath(__file__))
 REG = json.load(open(os.path.join(HERE, "golden", "registration.json")))
 GOLD = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+GOLD_FLOW = json.load(open(os.path.join(HERE, "golden", "golden_flow.json")))
+# functions of the reference (registration.json lists everything its build here registers) that this plugin does not
+# provide yet: the remaining SURVEY.md 8f rows (Depan needs complex FFTW and is not in the reference build either)
+NOT_YET = {"FlowBlur", "FlowInter", "FlowFPS", "BlockFPS"}
 
 
 def test_registration_is_the_references(built):
@@ -23,9 +27,12 @@ def test_registration_is_the_references(built):
     assert (p.identifier, p.namespace) == (REG["identifier"], REG["namespace"])
     mine = p.functions()
     for name, args in REG["functions"].items():
+        if name in NOT_YET:
+            assert name not in mine
+            continue
         assert name in mine, "mv.%s is not registered" % name
         assert mine[name] == args, "mv.%s: argument string differs from the reference" % name
-    assert set(mine) == set(REG["functions"])
+    assert set(mine) == set(REG["functions"]) - NOT_YET
 
 
 def test_registration_golden_is_current(have_ref):
@@ -57,6 +64,18 @@ def test_create_time_errors_through_the_plugin(built):
     with pytest.raises(minivs.Error) as e:
         mv.Super(clip, bogus=1)
     assert "does not take argument" in str(e.value)
+    # argument checks that come before any clip is touched (MVMask.c:261-279, MVFlow.cpp:427-436)
+    for call, msg in ((lambda: mv.Mask(clip, clip, kind=9), "Mask: kind must 0, 1, 2, 3, 4, or 5."),
+                      (lambda: mv.Mask(clip, clip, gamma=-0.5), "Mask: gamma must not be negative."),
+                      (lambda: mv.Mask(clip, clip, ysc=300), "Mask: ysc must be between 0 and 255 (inclusive)."),
+                      (lambda: mv.Flow(clip, clip, clip, mode=3), "Flow: mode must be 0 or 1."),
+                      (lambda: mv.Flow(clip, clip, clip, time=101.0), "Flow: time must be between 0 and 100 % (inclusive).")):
+        with pytest.raises(minivs.Error) as e:
+            call()
+        assert str(e.value) == msg
+    with pytest.raises(minivs.Error) as e:
+        mv.Finest(clip)
+    assert "required properties not found in first frame of super clip" in str(e.value)
 
 
 @pytest.mark.gpu
@@ -67,3 +86,13 @@ def test_script_through_plugin_matches_reference(built, case):
     for stage in ("super", "vectors", "degrain", "adata", "recalc", "compensate", "recalc_adata"):
         if stage in got:
             assert got[stage] == GOLD[case][stage], "%s: plugin %s differs from the reference plugin" % (case, stage)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "gray_blk4_pel1_rf0", "noise_badblocks_blk8", "p8_420_blk16_ov4_uncovered"])
+def test_flow_script_through_plugin_matches_reference(built, case):
+    """mv.SCDetection / mv.Mask / mv.Finest / mv.Flow of this plugin, driven like a .vpy script, give the reference plugin's bytes"""
+    import pipeline_flow
+    got = pipeline_flow.run_reference_flow(case, plugin_path=mb.PLUGIN_PATH)
+    for stage in ("scd", "mask", "flow", "finest"):
+        assert got[stage] == GOLD_FLOW[case][stage], "%s: plugin %s differs from the reference plugin" % (case, stage)

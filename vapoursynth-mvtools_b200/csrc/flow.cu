@@ -9,6 +9,7 @@
 // The per-thread arithmetic lives in flow_device.h (also compiled for the host by the emulation test).
 #include "engine.h"
 #include "flow_device.h"
+#include "flow_setup.h"
 
 #include <cstring>
 #include <vector>
@@ -139,36 +140,18 @@ __global__ void k_finest(SuperPlane S, int logPel, int W, int H, const uint8_t *
 
 constexpr int kSlotTables = 16, kSlotSmall = 17, kSlotStage = 18;
 
-int ilog2_pel(int pel) { return pel == 4 ? 2 : (pel == 2 ? 1 : 0); }
-
-SuperPlane make_super_plane(const SuperDesc &sd, int plane) {
-    SuperPlane S;
-    const mvb200_level_geom &g = sd.lv[plane][0];
-    S.pitch = sd.pitch[plane];
-    S.offset = sd.offset[plane];
-    S.sub_stride = sd.pitch[plane] * g.padded_h;
-    S.hpad = g.hpad;
-    S.vpad = g.vpad;
-    S.padded_w = g.padded_w;
-    S.padded_h = g.padded_h;
-    return S;
-}
+SuperPlane super_plane_of(const SuperDesc &sd, int plane) { return make_super_plane(sd.pitch[plane], sd.offset[plane], sd.lv[plane][0]); }
 
 // The SimpleResize tables of (luma, chroma) upsizers with a common source size, resident on the device until the
 // configuration changes (first use: built on the host -- InitTables is float arithmetic -- and uploaded synchronously).
 int get_resize_tables(Ctx *c, int dw0, int dh0, int dw1, int dh1, int sw, int sh, ResizeTables t[2]) {
     const int key[8] = {dw0, dh0, dw1, dh1, sw, sh, 1, 0};
-    const size_t n0 = (size_t)dw0 * 2 + (size_t)dh0 * 2, n1 = (size_t)dw1 * 2 + (size_t)dh1 * 2;
+    const size_t n0 = tables_ints(dw0, dh0), n1 = tables_ints(dw1, dh1);
     if (!c->rz_valid || memcmp(key, c->rz_key, sizeof(key)) != 0) {
         std::vector<int32_t> host(n0 + n1);
-        int32_t *p = host.data();
-        mvb200_simple_resize_tables(dw0, sw, p, p + dw0);
-        mvb200_simple_resize_tables(dh0, sh, p + 2 * dw0, p + 2 * dw0 + dh0);
-        p += n0;
-        if (n1) {
-            mvb200_simple_resize_tables(dw1, sw, p, p + dw1);
-            mvb200_simple_resize_tables(dh1, sh, p + 2 * dw1, p + 2 * dw1 + dh1);
-        }
+        fill_tables(host.data(), dw0, dh0, sw, sh);
+        if (n1)
+            fill_tables(host.data() + n0, dw1, dh1, sw, sh);
         int *dev = (int *)c->get_scratch(kSlotTables, (n0 + n1) * sizeof(int32_t) + 256);
         if (!dev)
             return 1;
@@ -178,16 +161,8 @@ int get_resize_tables(Ctx *c, int dw0, int dh0, int dw1, int dh1, int sw, int sh
         memcpy(c->rz_key, key, sizeof(key));
         c->rz_valid = true;
     }
-    const int *d = c->rz_dev;
-    t[0].hoff = d;
-    t[0].hwt = d + dw0;
-    t[0].voff = d + 2 * dw0;
-    t[0].vwt = d + 2 * dw0 + dh0;
-    d += n0;
-    t[1].hoff = d;
-    t[1].hwt = d + dw1;
-    t[1].voff = d + 2 * dw1;
-    t[1].vwt = d + 2 * dw1 + dh1;
+    t[0] = tables_at(c->rz_dev, dw0, dh0);
+    t[1] = tables_at(c->rz_dev + n0, dw1, dh1);
     return 0;
 }
 
@@ -223,22 +198,7 @@ static int launch_flow(Ctx *c, const mvb200_flow_params *fp, const SuperDesc &sd
     c->launches++;
     const uint8_t *ref = dev_ref_super ? dev_ref_super : dev_vectors; // (never dereferenced when unusable)
     for (int plane = 0; plane < fp->nplanes; plane++) {
-        FlowPlane F;
-        memset(&F, 0, sizeof(F));
-        F.plane = plane;
-        F.W = plane ? fp->nWidthUV : vd.nWidth;
-        F.H = plane ? fp->nHeightUV : vd.nHeight;
-        F.limitW = F.W;
-        F.limitH = F.H;
-        F.time256 = fp->time256;
-        F.pel = vd.nPel;
-        F.logPel = ilog2_pel(vd.nPel);
-        F.mode = fp->mode;
-        F.nBlkXP = fp->nBlkXP;
-        F.vxs = plane ? sf.xUV : sf.xY;
-        F.vys = plane ? sf.yUV : sf.yY;
-        F.t = t[plane ? 1 : 0];
-        F.S = make_super_plane(sd, plane);
+        const FlowPlane F = make_flow_plane(fp, plane, plane ? sf.xUV : sf.xY, plane ? sf.yUV : sf.yY, t[plane ? 1 : 0], super_plane_of(sd, plane));
         uint8_t *dst = dev_dst + cd.offset[plane];
         const uint8_t *src = dev_src ? dev_src + cd.offset[plane] : nullptr;
         dim3 blk(32, 8), grid((F.W + 31) / 32, (F.H + 7) / 8);
@@ -279,33 +239,13 @@ static int launch_mask(Ctx *c, const mvb200_mask_params *mp, const mvb200_frame_
         return set_error("Mask: kind=5 needs the source clip's luma plane");
     k_flow_scd<<<1, 256, 0, st>>>(dev_vectors, 0, n, mp->nSCD1, mp->nSCD2, 1, usable);
     c->launches++;
-    MaskSmallParams P;
-    memset(&P, 0, sizeof(P));
-    P.kind = mp->kind;
-    P.nBlkX = vd.nBlkX;
-    P.nBlkY = vd.nBlkY;
-    P.nPel = vd.nPel;
-    P.isBackward = vd.isBackward;
-    P.time256 = mp->time256;
-    P.stepX = vd.nBlkSizeX - vd.nOverlapX;
-    P.stepY = vd.nBlkSizeY - vd.nOverlapY;
-    P.blkSizeXY = vd.nBlkSizeX * vd.nBlkSizeY;
-    P.fGamma = mp->fGamma;
-    P.fMaskNormFactor = mp->fMaskNormFactor;
-    P.fMaskNormFactor2 = mp->fMaskNormFactor2;
-    P.fHalfGamma = mp->fHalfGamma;
+    const MaskSmallParams P = make_mask_small_params(mp);
     if (mp->kind == 2)
         MVB_CUDA_CHECK(cudaMemsetAsync(small, 0, (size_t)n * sizeof(int), st));
     k_mask_small<<<(n + 127) / 128, 128, 0, st>>>(P, dev_vectors, small, smallV);
     c->launches++;
     for (int plane = 0; plane < 3; plane++) {
-        MaskPlane B;
-        B.plane = plane;
-        B.W = plane ? mp->nWidthUV : mp->nWidth;
-        B.H = plane ? mp->nHeightUV : mp->nHeight;
-        B.WB = plane ? mp->nWidthBUV : mp->nWidthB;
-        B.HB = plane ? mp->nHeightBUV : mp->nHeightB;
-        B.t = t[plane ? 1 : 0];
+        const MaskPlane B = make_mask_plane(mp, plane, t[plane ? 1 : 0]);
         dim3 blk(32, 8), grid((B.W + 31) / 32, (B.H + 7) / 8);
         k_mask_plane<<<grid, blk, 0, st>>>(B, mp->kind, mp->nSceneChangeValue, vd.nBlkX, small, smallV, dev_src_luma, src_pitch, dev_dst + ml.offset[plane], ml.pitch[plane], usable);
         c->launches++;
@@ -320,7 +260,7 @@ static int launch_finest(Ctx *c, const mvb200_super_params *sp, const SuperDesc 
     for (int plane = 0; plane < sd.nplanes; plane++) {
         if (plane && !(sp->modeyuv & (MVB200_UPLANE | MVB200_VPLANE)))
             continue; // (the reference leaves planes the super clip does not carry untouched)
-        const SuperPlane S = make_super_plane(sd, plane);
+        const SuperPlane S = super_plane_of(sd, plane);
         const int W = S.padded_w * sp->pel, H = S.padded_h * sp->pel;
         dim3 blk(32, 8), grid((W + 31) / 32, (H + 7) / 8);
         if (sd.bps == 1)

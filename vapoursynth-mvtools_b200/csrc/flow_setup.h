@@ -1,0 +1,97 @@
+// Host-side construction of the parameter blocks the flow.cu kernels take (flow_device.h), from the C ABI's
+// parameter structs.  Shared by the launchers in flow.cu and by the CPU emulation test (tests/emul/flow_emul.cpp),
+// so that the test exercises the same set-up code as the product.
+#pragma once
+
+#include "../../include/mvtools_b200.h"
+#include "flow_device.h"
+
+#include <cstring>
+
+namespace mvb200 {
+namespace flowdev {
+
+inline int ilog2_pel(int pel) { return pel == 4 ? 2 : (pel == 2 ? 1 : 0); }
+
+// level 0 of one plane of a super frame: `pitch` / `offset` of the plane inside the frame buffer
+inline SuperPlane make_super_plane(long long pitch, long long offset, const mvb200_level_geom &g) {
+    SuperPlane S;
+    S.pitch = pitch;
+    S.offset = offset;
+    S.sub_stride = pitch * g.padded_h;
+    S.hpad = g.hpad;
+    S.vpad = g.vpad;
+    S.padded_w = g.padded_w;
+    S.padded_h = g.padded_h;
+    return S;
+}
+
+// where the four tables of an upsizer (dst_w x dst_h) live inside one int array: [hoff dw][hwt dw][voff dh][vwt dh]
+inline ResizeTables tables_at(const int *base, int dw, int dh) {
+    ResizeTables t;
+    t.hoff = base;
+    t.hwt = base + dw;
+    t.voff = base + 2 * dw;
+    t.vwt = base + 2 * dw + dh;
+    return t;
+}
+inline size_t tables_ints(int dw, int dh) { return (size_t)dw * 2 + (size_t)dh * 2; }
+// fills `host` (tables_ints(dw, dh) ints) for an upsizer from (sw x sh) blocks
+inline void fill_tables(int32_t *host, int dw, int dh, int sw, int sh) {
+    mvb200_simple_resize_tables(dw, sw, host, host + dw);
+    mvb200_simple_resize_tables(dh, sh, host + 2 * dw, host + 2 * dw + dh);
+}
+
+inline FlowPlane make_flow_plane(const mvb200_flow_params *fp, int plane, const short *vxs, const short *vys, const ResizeTables &t, const SuperPlane &S) {
+    FlowPlane F;
+    memset(&F, 0, sizeof(F));
+    F.plane = plane;
+    F.W = plane ? fp->nWidthUV : fp->vd.nWidth;
+    F.H = plane ? fp->nHeightUV : fp->vd.nHeight;
+    F.limitW = F.W; // simpleInit(..., nWidth, nHeight, ...) / (..., nWidthUV, nHeightUV, ...), MVFlow.cpp:561-563
+    F.limitH = F.H;
+    F.time256 = fp->time256;
+    F.pel = fp->vd.nPel;
+    F.logPel = ilog2_pel(fp->vd.nPel);
+    F.mode = fp->mode;
+    F.nBlkXP = fp->nBlkXP;
+    F.vxs = vxs;
+    F.vys = vys;
+    F.t = t;
+    F.S = S;
+    return F;
+}
+
+inline MaskSmallParams make_mask_small_params(const mvb200_mask_params *mp) {
+    const mvb200_analysis_data &vd = mp->vd;
+    MaskSmallParams P;
+    memset(&P, 0, sizeof(P));
+    P.kind = mp->kind;
+    P.nBlkX = vd.nBlkX;
+    P.nBlkY = vd.nBlkY;
+    P.nPel = vd.nPel;
+    P.isBackward = vd.isBackward;
+    P.time256 = mp->time256;
+    P.stepX = vd.nBlkSizeX - vd.nOverlapX;
+    P.stepY = vd.nBlkSizeY - vd.nOverlapY;
+    P.blkSizeXY = vd.nBlkSizeX * vd.nBlkSizeY;
+    P.fGamma = mp->fGamma;
+    P.fMaskNormFactor = mp->fMaskNormFactor;
+    P.fMaskNormFactor2 = mp->fMaskNormFactor2;
+    P.fHalfGamma = mp->fHalfGamma;
+    return P;
+}
+
+inline MaskPlane make_mask_plane(const mvb200_mask_params *mp, int plane, const ResizeTables &t) {
+    MaskPlane B;
+    B.plane = plane;
+    B.W = plane ? mp->nWidthUV : mp->nWidth;
+    B.H = plane ? mp->nHeightUV : mp->nHeight;
+    B.WB = plane ? mp->nWidthBUV : mp->nWidthB;
+    B.HB = plane ? mp->nHeightBUV : mp->nHeightB;
+    B.t = t;
+    return B;
+}
+
+} // namespace flowdev
+} // namespace mvb200

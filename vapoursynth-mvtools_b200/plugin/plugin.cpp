@@ -2,7 +2,7 @@
 //
 // Exports exactly what the reference's module exports (EntryPoint.c:28-50):
 // VapourSynthPluginInit2, which configures the plugin as "com.nodame.mvtools" / namespace
-// "mv" and registers Super, Analyse, Recalculate, Compensate and Degrain1..6 with the reference's
+// "mv" and registers Super, Analyse, Recalculate, Compensate, Degrain1..6, Mask, Finest, Flow and SCDetection with the reference's
 // byte-identical argument strings, so existing .vpy scripts load unchanged.  Every filter keeps the reference's
 // create-time validation (messages included, they come from mvb200_*_init), frame
 // properties (Super_*, MVTools_MVAnalysisData, MVTools_vectors) and request pattern; the
@@ -786,6 +786,414 @@ void VS_CC compCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const V
     vsapi->createVideoFilter(out, "Compensate", data->vi, compGetFrame, compFree, fmParallel, deps, 2, data, core);
 }
 
+// ------------------------------------------------------------ SCDetection
+// mvscdetectionCreate / GetFrame, MVSCDetection.c:43-131
+struct ScdData {
+    VSNode *node, *vectors;
+    const VSVideoInfo *vi;
+    mvb200_scdetection_params p;
+};
+
+const VSFrame *VS_CC scdGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    ScdData *d = (ScdData *)instanceData;
+    if (activationReason == arInitial) {
+        vsapi->requestFrameFilter(n, d->vectors, frameCtx);
+        vsapi->requestFrameFilter(n, d->node, frameCtx);
+    } else if (activationReason == arAllFramesReady) {
+        const VSFrame *src = vsapi->getFrameFilter(n, d->node, frameCtx);
+        VSFrame *dst = vsapi->copyFrame(src, core);
+        vsapi->freeFrame(src);
+        const VSFrame *mvn = vsapi->getFrameFilter(n, d->vectors, frameCtx);
+        int e = 0;
+        const uint8_t *vec = (const uint8_t *)vsapi->mapGetData(vsapi->getFramePropertiesRO(mvn), "MVTools_vectors", 0, &e);
+        std::string msg;
+        int rc = 1;
+        int32_t sc = 0;
+        if (e) {
+            msg = "MVTools_vectors property missing";
+        } else {
+            std::lock_guard<std::mutex> lock(g_engine_mutex);
+            mvb200_ctx *ctx = engine(msg);
+            rc = ctx ? mvb200_scdetection_frame(ctx, &d->p, vec, &sc) : 1;
+            if (ctx && rc)
+                msg = mvb200_last_error();
+        }
+        vsapi->freeFrame(mvn);
+        if (rc) {
+            vsapi->setFilterError(("SCDetection: " + msg).c_str(), frameCtx);
+            vsapi->freeFrame(dst);
+            return nullptr;
+        }
+        vsapi->mapSetInt(vsapi->getFramePropertiesRW(dst), d->p.vd.isBackward ? "_SceneChangeNext" : "_SceneChangePrev", sc, maReplace);
+        return dst;
+    }
+    return nullptr;
+}
+
+void VS_CC scdFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
+    ScdData *d = (ScdData *)instanceData;
+    vsapi->freeNode(d->node);
+    vsapi->freeNode(d->vectors);
+    delete d;
+}
+
+void VS_CC scdCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const VSAPI *vsapi) {
+    ScdData d;
+    memset(&d, 0, sizeof(d));
+    d.vectors = vsapi->mapGetNode(in, "vectors", 0, nullptr);
+    std::string msg;
+    mvb200_analysis_data vd;
+    if (!adataFromClip(d.vectors, vsapi, "SCDetection", "vectors", &vd, msg) || mvb200_scdetection_init(argInt64(vsapi, in, "thscd1"), argInt(vsapi, in, "thscd2"), &vd, &d.p)) {
+        vsapi->mapSetError(out, msg.empty() ? mvb200_last_error() : msg.c_str());
+        vsapi->freeNode(d.vectors);
+        return;
+    }
+    d.node = vsapi->mapGetNode(in, "clip", 0, nullptr);
+    d.vi = vsapi->getVideoInfo(d.node);
+    ScdData *data = new ScdData(d);
+    VSFilterDependency deps[2] = {{data->node, rpStrictSpatial}, {data->vectors, rpStrictSpatial}};
+    vsapi->createVideoFilter(out, "SCDetection", data->vi, scdGetFrame, scdFree, fmParallel, deps, 2, data, core);
+}
+
+// ------------------------------------------------------------------- Mask
+// mvmaskCreate / GetFrame, MVMask.c:74-344
+struct MaskData {
+    VSNode *node, *vectors;
+    VSVideoInfo vi;
+    mvb200_mask_params p;
+};
+
+const VSFrame *VS_CC maskGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    MaskData *d = (MaskData *)instanceData;
+    if (activationReason == arInitial) {
+        vsapi->requestFrameFilter(n, d->vectors, frameCtx);
+        vsapi->requestFrameFilter(n, d->node, frameCtx);
+    } else if (activationReason == arAllFramesReady) {
+        const VSFrame *src = vsapi->getFrameFilter(n, d->node, frameCtx);
+        VSFrame *dst = vsapi->newVideoFrame(&d->vi.format, d->vi.width, d->vi.height, src, core);
+        const VSFrame *mvn = vsapi->getFrameFilter(n, d->vectors, frameCtx);
+        int e = 0;
+        const uint8_t *vec = (const uint8_t *)vsapi->mapGetData(vsapi->getFramePropertiesRO(mvn), "MVTools_vectors", 0, &e);
+        std::string msg;
+        int rc = 1;
+        if (e) {
+            msg = "MVTools_vectors property missing";
+        } else if (d->vi.width != d->p.nWidth || d->vi.height != d->p.nHeight || (d->vi.width >> d->vi.format.subSamplingW) != d->p.nWidthUV || (d->vi.height >> d->vi.format.subSamplingH) != d->p.nHeightUV) {
+            msg = "the clip's dimensions or subsampling differ from the vectors' (the reference would write out of bounds)";
+        } else {
+            uint8_t *dp_[3];
+            ptrdiff_t ds[3];
+            planesRW(vsapi, dst, 3, dp_, ds);
+            std::lock_guard<std::mutex> lock(g_engine_mutex);
+            mvb200_ctx *ctx = engine(msg);
+            rc = ctx ? mvb200_mask_frame(ctx, &d->p, vsapi->getReadPtr(src, 0), vsapi->getStride(src, 0), vec, dp_, ds) : 1;
+            if (ctx && rc)
+                msg = mvb200_last_error();
+        }
+        vsapi->freeFrame(mvn);
+        vsapi->freeFrame(src);
+        if (rc) {
+            vsapi->setFilterError(("Mask: " + msg).c_str(), frameCtx);
+            vsapi->freeFrame(dst);
+            return nullptr;
+        }
+        return dst;
+    }
+    return nullptr;
+}
+
+void VS_CC maskFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
+    MaskData *d = (MaskData *)instanceData;
+    vsapi->freeNode(d->node);
+    vsapi->freeNode(d->vectors);
+    delete d;
+}
+
+double argFloat(const VSAPI *vsapi, const VSMap *in, const char *name) {
+    int err = 0;
+    double v = vsapi->mapGetFloat(in, name, 0, &err);
+    return err ? NAN : v;
+}
+
+void VS_CC maskCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const VSAPI *vsapi) {
+    mvb200_mask_args a;
+    a.ml = argFloat(vsapi, in, "ml");
+    a.gamma = argFloat(vsapi, in, "gamma");
+    a.kind = argInt(vsapi, in, "kind");
+    a.time = argFloat(vsapi, in, "time");
+    a.ysc = argInt(vsapi, in, "ysc");
+    a.thscd1 = argInt64(vsapi, in, "thscd1");
+    a.thscd2 = argInt(vsapi, in, "thscd2");
+    MaskData d;
+    memset(&d, 0, sizeof(d));
+    // the argument checks come before any clip is touched (MVMask.c:261-279): run them on a neutral vector description
+    {
+        mvb200_analysis_data probe;
+        memset(&probe, 0, sizeof(probe));
+        probe.nBlkSizeX = probe.nBlkSizeY = 8;
+        probe.nBlkX = probe.nBlkY = 2;
+        probe.xRatioUV = probe.yRatioUV = 1;
+        probe.bitsPerSample = 8;
+        mvb200_mask_args b = a;
+        b.thscd1 = MVB200_UNSET64;
+        if (mvb200_mask_init(&b, &probe, 8, 0, 0, 0, &d.p)) {
+            vsapi->mapSetError(out, mvb200_last_error());
+            return;
+        }
+    }
+    d.vectors = vsapi->mapGetNode(in, "vectors", 0, nullptr);
+    std::string msg;
+    mvb200_analysis_data vd;
+    if (!adataFromClip(d.vectors, vsapi, "Mask", "vectors", &vd, msg)) {
+        vsapi->mapSetError(out, msg.c_str());
+        vsapi->freeNode(d.vectors);
+        return;
+    }
+    {   // scaleThSCD's error precedes the format check (MVMask.c:288-297)
+        mvb200_scdetection_params t;
+        if (mvb200_scdetection_init(a.thscd1, a.thscd2, &vd, &t)) {
+            std::string m = mvb200_last_error();
+            m.replace(0, strlen("SCDetection"), "Mask");
+            vsapi->mapSetError(out, m.c_str());
+            vsapi->freeNode(d.vectors);
+            return;
+        }
+    }
+    d.node = vsapi->mapGetNode(in, "clip", 0, nullptr);
+    d.vi = *vsapi->getVideoInfo(d.node);
+    const bool fmtOk = vsh::isConstantVideoFormat(&d.vi) && d.vi.format.bitsPerSample <= 8 && d.vi.format.subSamplingW <= 1 && d.vi.format.subSamplingH <= 1 &&
+                       (d.vi.format.colorFamily == cfYUV || d.vi.format.colorFamily == cfGray);
+    if (!fmtOk || mvb200_mask_init(&a, &vd, d.vi.format.bitsPerSample, d.vi.format.subSamplingW, d.vi.format.subSamplingH, d.vi.format.colorFamily == cfGray, &d.p)) {
+        vsapi->mapSetError(out, fmtOk ? mvb200_last_error() : "Mask: input clip must be GRAY8, YUV420P8, YUV422P8, YUV440P8, or YUV444P8, with constant dimensions.");
+        vsapi->freeNode(d.node);
+        vsapi->freeNode(d.vectors);
+        return;
+    }
+    if (d.vi.format.colorFamily == cfGray)
+        vsapi->getVideoFormatByID(&d.vi.format, pfYUV444P8, core);
+    MaskData *data = new MaskData(d);
+    VSFilterDependency deps[2] = {{data->node, rpStrictSpatial}, {data->vectors, rpStrictSpatial}};
+    vsapi->createVideoFilter(out, "Mask", &data->vi, maskGetFrame, maskFree, fmParallel, deps, 2, data, core);
+}
+
+// ----------------------------------------------------------------- Finest
+// mvfinestCreate / GetFrame, MVFinest.c:47-207
+struct FinestData {
+    VSNode *super;
+    VSVideoInfo vi;
+    mvb200_super_params sp;
+};
+
+const VSFrame *VS_CC finestGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    FinestData *d = (FinestData *)instanceData;
+    if (activationReason == arInitial) {
+        vsapi->requestFrameFilter(n, d->super, frameCtx);
+    } else if (activationReason == arAllFramesReady) {
+        const VSFrame *ref = vsapi->getFrameFilter(n, d->super, frameCtx);
+        VSFrame *dst = vsapi->newVideoFrame(&d->vi.format, d->vi.width, d->vi.height, ref, core);
+        const uint8_t *sp_[3];
+        ptrdiff_t ss[3];
+        uint8_t *dp_[3];
+        ptrdiff_t ds[3];
+        planesRO(vsapi, ref, d->vi.format.numPlanes, sp_, ss);
+        planesRW(vsapi, dst, d->vi.format.numPlanes, dp_, ds);
+        std::string msg;
+        int rc = 0;
+        if (d->sp.pel == 1) { // :75-77, a plain copy of level 0 (each plane's own size: the reference copies the luma size for every plane)
+            for (int i = 0; i < d->vi.format.numPlanes; i++)
+                vsh::bitblt(dp_[i], ds[i], sp_[i], ss[i], (size_t)(i ? d->vi.width >> d->vi.format.subSamplingW : d->vi.width) * d->vi.format.bytesPerSample,
+                            (size_t)(i ? d->vi.height >> d->vi.format.subSamplingH : d->vi.height));
+        } else {
+            std::lock_guard<std::mutex> lock(g_engine_mutex);
+            mvb200_ctx *ctx = engine(msg);
+            rc = ctx ? mvb200_finest_frame(ctx, &d->sp, sp_, ss, dp_, ds) : 1;
+            if (ctx && rc)
+                msg = mvb200_last_error();
+        }
+        vsapi->freeFrame(ref);
+        if (rc) {
+            vsapi->setFilterError(("Finest: " + msg).c_str(), frameCtx);
+            vsapi->freeFrame(dst);
+            return nullptr;
+        }
+        return dst;
+    }
+    return nullptr;
+}
+
+void VS_CC finestFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
+    FinestData *d = (FinestData *)instanceData;
+    vsapi->freeNode(d->super);
+    delete d;
+}
+
+void VS_CC finestCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const VSAPI *vsapi) {
+    FinestData d;
+    memset(&d, 0, sizeof(d));
+    d.super = vsapi->mapGetNode(in, "super", 0, nullptr);
+    d.vi = *vsapi->getVideoInfo(d.super);
+    if (!formatOk(&d.vi)) {
+        vsapi->mapSetError(out, "Finest: input clip must be GRAY, 420, 422, 440, or 444, up to 16 bits, with constant dimensions.");
+        vsapi->freeNode(d.super);
+        return;
+    }
+    std::string msg;
+    if (!superFromClip(d.super, vsapi, "Finest", &d.sp, msg)) {
+        vsapi->mapSetError(out, msg.c_str());
+        vsapi->freeNode(d.super);
+        return;
+    }
+    d.vi.width = (d.sp.width + 2 * d.sp.hpad) * d.sp.pel; // :190-194
+    d.vi.height = (d.sp.height + 2 * d.sp.vpad) * d.sp.pel;
+    FinestData *data = new FinestData(d);
+    VSFilterDependency deps[1] = {{data->super, rpStrictSpatial}};
+    vsapi->createVideoFilter(out, "Finest", &data->vi, finestGetFrame, finestFree, fmParallel, deps, 1, data, core);
+}
+
+// ------------------------------------------------------------------- Flow
+// mvflowCreate / GetFrame, MVFlow.cpp:157-593.  The reference reads an mv.Finest clip made from `super`; the engine reads
+// the pel sub-planes of the super frame itself (same samples), so this filter requests super frames.
+struct FlowData {
+    VSNode *clip, *super, *vectors;
+    const VSVideoInfo *vi, *supervi;
+    mvb200_super_params sp;
+    mvb200_flow_params fp;
+};
+
+const VSFrame *VS_CC flowGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    FlowData *d = (FlowData *)instanceData;
+    const int offset = d->fp.vd.nDeltaFrame;
+    const int nref = offset > 0 ? (d->fp.vd.isBackward ? n + offset : n - offset) : -offset; // :163-170
+    const bool haveRef = nref >= 0 && nref < d->vi->numFrames;
+    const bool needField = d->fp.fields && d->fp.vd.nPel > 1 && (nref - n) % 2 != 0;
+    if (activationReason == arInitial) {
+        vsapi->requestFrameFilter(n, d->vectors, frameCtx);
+        if (haveRef) {
+            vsapi->requestFrameFilter(nref, d->super, frameCtx);
+            if (needField)
+                vsapi->requestFrameFilter(n, d->super, frameCtx);
+        }
+        vsapi->requestFrameFilter(n, d->clip, frameCtx);
+    } else if (activationReason == arAllFramesReady) {
+        const VSFrame *mvn = vsapi->getFrameFilter(n, d->vectors, frameCtx);
+        int e = 0;
+        const uint8_t *vec = (const uint8_t *)vsapi->mapGetData(vsapi->getFramePropertiesRO(mvn), "MVTools_vectors", 0, &e);
+        const VSFrame *ref = haveRef ? vsapi->getFrameFilter(nref, d->super, frameCtx) : nullptr;
+        VSFrame *dst = ref ? vsapi->newVideoFrame(&d->vi->format, d->vi->width, d->vi->height, ref, core) : nullptr;
+        std::string msg;
+        int rc = 1;
+        int32_t usable = 0;
+        int fieldShift = 0;
+        bool fieldOk = true;
+        if (ref && needField) {
+            const VSFrame *srcSuper = vsapi->getFrameFilter(n, d->super, frameCtx);
+            fieldOk = fieldShiftOf(vsapi, srcSuper, ref, n, nref, true, d->fp.tff_exists, d->fp.tff, d->fp.vd.nPel, true, &fieldShift);
+            vsapi->freeFrame(srcSuper);
+        }
+        if (e) {
+            msg = "MVTools_vectors property missing";
+        } else if (!fieldOk) {
+            msg = "_Field property not found in super frame. Therefore, you must pass tff argument.";
+        } else if (!ref) {
+            rc = 0; // out of range: the vectors are invalid, the source frame is returned
+        } else {
+            const uint8_t *rp_[3];
+            ptrdiff_t rs[3];
+            uint8_t *dp_[3];
+            ptrdiff_t ds[3];
+            planesRO(vsapi, ref, d->supervi->format.numPlanes, rp_, rs);
+            planesRW(vsapi, dst, d->vi->format.numPlanes, dp_, ds);
+            std::lock_guard<std::mutex> lock(g_engine_mutex);
+            mvb200_ctx *ctx = engine(msg);
+            rc = ctx ? mvb200_flow_frame(ctx, &d->fp, &d->sp, rp_, rs, vec, fieldShift, dp_, ds, &usable) : 1;
+            if (ctx && rc)
+                msg = mvb200_last_error();
+        }
+        vsapi->freeFrame(mvn);
+        vsapi->freeFrame(ref);
+        if (rc) {
+            vsapi->setFilterError(("Flow: " + msg).c_str(), frameCtx);
+            vsapi->freeFrame(dst);
+            return nullptr;
+        }
+        if (!usable) { // :362-366
+            vsapi->freeFrame(dst);
+            return vsapi->getFrameFilter(n, d->clip, frameCtx);
+        }
+        return dst;
+    }
+    return nullptr;
+}
+
+void VS_CC flowFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
+    FlowData *d = (FlowData *)instanceData;
+    vsapi->freeNode(d->clip);
+    vsapi->freeNode(d->super);
+    vsapi->freeNode(d->vectors);
+    delete d;
+}
+
+void VS_CC flowCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const VSAPI *vsapi) {
+    mvb200_flow_args a;
+    a.time = argFloat(vsapi, in, "time");
+    a.mode = argInt(vsapi, in, "mode");
+    a.fields = argInt(vsapi, in, "fields");
+    a.thscd1 = argInt64(vsapi, in, "thscd1");
+    a.thscd2 = argInt(vsapi, in, "thscd2");
+    a.tff = argInt(vsapi, in, "tff");
+    // argument checks before any clip is touched (MVFlow.cpp:427-436)
+    if (a.time == a.time && (a.time < 0.0 || a.time > 100.0)) {
+        vsapi->mapSetError(out, "Flow: time must be between 0 and 100 % (inclusive).");
+        return;
+    }
+    if (a.mode != MVB200_UNSET && (a.mode < 0 || a.mode > 1)) {
+        vsapi->mapSetError(out, "Flow: mode must be 0 or 1.");
+        return;
+    }
+    FlowData d;
+    memset(&d, 0, sizeof(d));
+    auto freeAll = [&]() {
+        vsapi->freeNode(d.clip);
+        vsapi->freeNode(d.super);
+        vsapi->freeNode(d.vectors);
+    };
+    d.super = vsapi->mapGetNode(in, "super", 0, nullptr);
+    d.supervi = vsapi->getVideoInfo(d.super);
+    std::string msg;
+    mvb200_analysis_data vd;
+    if (!superFromClip(d.super, vsapi, "Flow", &d.sp, msg)) {
+        vsapi->mapSetError(out, msg.c_str());
+        freeAll();
+        return;
+    }
+    d.vectors = vsapi->mapGetNode(in, "vectors", 0, nullptr);
+    if (!adataFromClip(d.vectors, vsapi, "Flow", "vectors", &vd, msg)) {
+        vsapi->mapSetError(out, msg.c_str());
+        freeAll();
+        return;
+    }
+    d.clip = vsapi->mapGetNode(in, "clip", 0, nullptr);
+    d.vi = vsapi->getVideoInfo(d.clip);
+    if (mvb200_flow_init(&a, &d.sp, &vd, d.vi->numFrames, &d.fp)) {
+        vsapi->mapSetError(out, mvb200_last_error());
+        freeAll();
+        return;
+    }
+    if (!formatOk(d.vi)) {
+        vsapi->mapSetError(out, "Flow: input clip must be GRAY, 420, 422, 440, or 444, up to 16 bits, with constant dimensions.");
+        freeAll();
+        return;
+    }
+    if (d.vi->width != vd.nWidth || d.vi->height != vd.nHeight || d.vi->format.bitsPerSample != d.sp.bits) {
+        vsapi->mapSetError(out, "Flow: wrong source or super clip frame size.");
+        freeAll();
+        return;
+    }
+    FlowData *data = new FlowData(d);
+    VSFilterDependency deps[3] = {{data->clip, rpStrictSpatial}, {data->super, rpGeneral}, {data->vectors, rpStrictSpatial}};
+    vsapi->createVideoFilter(out, "Flow", data->vi, flowGetFrame, flowFree, fmParallel, deps, 3, data, core);
+}
+
 } // namespace
 
 VS_EXTERNAL_API(void) VapourSynthPluginInit2(VSPlugin *plugin, const VSPLUGINAPI *vspapi) {
@@ -820,4 +1228,9 @@ VS_EXTERNAL_API(void) VapourSynthPluginInit2(VSPlugin *plugin, const VSPLUGINAPI
                              "chroma:int:opt;truemotion:int:opt;pnew:int:opt;overlap:int:opt;overlapv:int:opt;divide:int:opt;opt:int:opt;meander:int:opt;fields:int:opt;"
                              "tff:int:opt;dct:int:opt;",
                              "clip:vnode;", recalcCreate, nullptr, plugin);
+    // MVMask.c:347-362, MVFinest.c:210-216, MVFlow.cpp:596-610, MVSCDetection.c:134-142
+    vspapi->registerFunction("Mask", "clip:vnode;vectors:vnode;ml:float:opt;gamma:float:opt;kind:int:opt;time:float:opt;ysc:int:opt;thscd1:int:opt;thscd2:int:opt;opt:int:opt;", "clip:vnode;", maskCreate, nullptr, plugin);
+    vspapi->registerFunction("Finest", "super:vnode;opt:int:opt;", "clip:vnode;", finestCreate, nullptr, plugin);
+    vspapi->registerFunction("Flow", "clip:vnode;super:vnode;vectors:vnode;time:float:opt;mode:int:opt;fields:int:opt;thscd1:int:opt;thscd2:int:opt;opt:int:opt;tff:int:opt;", "clip:vnode;", flowCreate, nullptr, plugin);
+    vspapi->registerFunction("SCDetection", "clip:vnode;vectors:vnode;thscd1:int:opt;thscd2:int:opt;", "clip:vnode;", scdCreate, nullptr, plugin);
 }
