@@ -23,6 +23,7 @@
  *   mvmaskCreate/GetFrame        MVMask.c:74-344        mvb200_mask_init / _frame / _batch
  *   mvfinestCreate/GetFrame      MVFinest.c:47-207      mvb200_finest_layout / _frame / _batch
  *   mvflowCreate/GetFrame        MVFlow.cpp:157-593     mvb200_flow_init / _frame / _batch
+ *   mvflowinterCreate/GetFrame   MVFlowInter.c:83-690   mvb200_flowinter_init / _frame / _batch, mvb200_blend_frame
  *
  * The VapourSynth plugin (vapoursynth-mvtools_b200/plugin, exporting
  * VapourSynthPluginInit2 like EntryPoint.c:28-50) is a thin host-side glue over
@@ -259,6 +260,31 @@ typedef struct mvb200_flow_params {
     int32_t num_frames;
 } mvb200_flow_params;
 
+/* mv.FlowInter (MVFlowInter.c) and the per-frame core of mv.FlowFPS (MVFlowFPS.c): motion-compensated interpolation
+ * between a "left" frame and the frame `delta` later, at time256 / 256 of the way. */
+typedef struct mvb200_flowinter_args {
+    double time, ml;              /* NaN = default (50.0, 100.0) */
+    int32_t blend;                /* MVB200_UNSET = default (1) */
+    int64_t thscd1;
+    int32_t thscd2;
+} mvb200_flowinter_args;
+
+typedef struct mvb200_flowinter_params {
+    mvb200_analysis_data vd;      /* of mvbw (mvfw is checked to be similar) */
+    int32_t time256, blend;
+    double ml;                    /* MVFlowInter.c keeps a float, MVFlowFPS.c a double: stored widened */
+    int64_t nSCD1;
+    int32_t nSCD2;
+    /* which of FlowInterSimple (0) / FlowInter (1) / FlowInterExtra (2) runs when the extra vector pair (mvfw of the
+     * left frame, mvbw of the right frame) is usable, and which otherwise.  FlowInter: 2 / 1 (MVFlowInter.c:285,357);
+     * FlowFPS mask=0: 0 / 0, mask=1: 1 / 1, mask=2: 2 / 0 (MVFlowFPS.c:339-437) */
+    int32_t mode_primary, mode_fallback;
+    int32_t bits, ssw, ssh, gray, nplanes;
+    int32_t super_hpad, super_vpad, super_pel, super_levels;
+    int32_t nBlkXP, nBlkYP, nWidthP, nHeightP, nWidthPUV, nHeightPUV, nWidthUV, nHeightUV, nHPaddingUV, nVPaddingUV, VPitchY, VPitchUV;
+    int32_t num_frames;
+} mvb200_flowinter_params;
+
 /* ------------------------------------------------------------- host logic */
 /* (pure host code: usable without a GPU; restates the reference's *Create) */
 
@@ -291,6 +317,9 @@ MVB200_API int mvb200_mask_init(const mvb200_mask_args *a, const mvb200_analysis
 
 /* MVFlow.cpp:395-575.  `sp` describes the super clip, (clip_w, clip_h) the source clip. */
 MVB200_API int mvb200_flow_init(const mvb200_flow_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd, int num_frames, mvb200_flow_params *out);
+
+/* MVFlowInter.c:458-690.  vd_bw / vd_fw: the analysis data of mvbw / mvfw. */
+MVB200_API int mvb200_flowinter_init(const mvb200_flowinter_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd_bw, const mvb200_analysis_data *vd_fw, int num_frames, mvb200_flowinter_params *out);
 
 /* InitTables, SimpleResize.cpp:26-56: offsets[out] and weights[out] (14-bit) of the bilinear resizer the Mask / Flow
  * filters upsize their per-block fields with (float arithmetic, restated on the host; uploaded once per configuration). */
@@ -414,6 +443,22 @@ MVB200_API int mvb200_finest_batch(mvb200_ctx *ctx, const mvb200_super_params *s
 MVB200_API int mvb200_flow_frame(mvb200_ctx *ctx, const mvb200_flow_params *fp, const mvb200_super_params *sp, const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *vectors, int field_shift, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable);
 /* device resident, frames [first, first + n): unusable frames are copies of the source clip's frame (dev_src, clip layout). */
 MVB200_API int mvb200_flow_batch(mvb200_ctx *ctx, const mvb200_flow_params *fp, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int first, int n, const void *dev_vectors, int64_t vectors_stride, void *dev_dst);
+
+/* mvflowinterGetFrame (MVFlowInter.c:83-448) / the core of mvflowfpsGetFrame (MVFlowFPS.c:118-470) for one output
+ * frame: left_super / right_super are the super frames of frames nleft and nleft + delta; vec_b = mvbw of nleft,
+ * vec_f = mvfw of nleft + delta, vec_bb = mvbw of nleft + delta and vec_ff = mvfw of nleft (the "extra" pair, may be
+ * NULL when the mode never uses it).  *usable = 0 (scene change / invalid vectors): dst is left untouched and the
+ * caller blends the two SOURCE frames (mvb200_blend_frame) or returns the left one, as the reference does. */
+MVB200_API int mvb200_flowinter_frame(mvb200_ctx *ctx, const mvb200_flowinter_params *p, const mvb200_super_params *sp, int time256, const uint8_t *const left_super[3], const ptrdiff_t left_stride[3],
+                                      const uint8_t *const right_super[3], const ptrdiff_t right_stride[3], const uint8_t *vec_b, const uint8_t *vec_f, const uint8_t *vec_bb, const uint8_t *vec_ff,
+                                      uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable);
+/* Blend (MaskFun.cpp:349-373): dst = (src (256 - time256) + ref time256) >> 8 on frames of the clip `sp` describes */
+MVB200_API int mvb200_blend_frame(mvb200_ctx *ctx, const mvb200_super_params *sp, int time256, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const ref[3], const ptrdiff_t ref_stride[3],
+                                  uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
+/* mv.FlowInter over frames [first, first + n) of a device-resident clip: dev_bw / dev_fw hold the blobs of ALL
+ * num_frames frames (frame f's blob at f * vectors_stride); unusable frames are blended (or copied) from dev_src. */
+MVB200_API int mvb200_flowinter_batch(mvb200_ctx *ctx, const mvb200_flowinter_params *p, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int first, int n, const void *dev_bw, const void *dev_fw,
+                                      int64_t vectors_stride, void *dev_dst);
 
 #ifdef __cplusplus
 }

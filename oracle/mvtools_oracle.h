@@ -44,6 +44,11 @@ MVO_API int mvo_mask_frame(const mvb200_mask_params *p, const uint8_t *src_luma,
 MVO_API int mvo_finest_frame(const mvb200_super_params *sp, const uint8_t *const super[3], const ptrdiff_t super_stride[3], uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
 /* mvflowGetFrame, MVFlow.cpp:157-368 */
 MVO_API int mvo_flow_frame(const mvb200_flow_params *fp, const mvb200_super_params *sp, const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *vectors, int field_shift, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable);
+/* mvflowinterGetFrame, MVFlowInter.c:83-448 (also the core of mvflowfpsGetFrame) and Blend, MaskFun.cpp:349-373 */
+MVO_API int mvo_flowinter_frame(const mvb200_flowinter_params *p, const mvb200_super_params *sp, int time256, const uint8_t *const left_super[3], const ptrdiff_t left_stride[3], const uint8_t *const right_super[3],
+                                const ptrdiff_t right_stride[3], const uint8_t *vec_b, const uint8_t *vec_f, const uint8_t *vec_bb, const uint8_t *vec_ff, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable);
+MVO_API int mvo_blend_frame(const mvb200_super_params *sp, int time256, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const ref[3], const ptrdiff_t ref_stride[3], uint8_t *const dst[3],
+                            const ptrdiff_t dst_stride[3]);
 /* InitTables, SimpleResize.cpp:26-56 */
 MVO_API void mvo_simple_resize_tables(int out, int in, int32_t *offsets, int32_t *weights);
 

@@ -493,3 +493,212 @@ int mvo_flow_frame(const mvb200_flow_params *fp, const mvb200_super_params *sp, 
         free(fin[pl]);
     return 0;
 }
+
+/* -------------------------------------------------------------- FlowInter */
+
+/* CheckAndPadMaskSmall, MaskFun.cpp:65-82: the nBlkX x nBlkY mask (pitch nBlkXP) grown to nBlkXP x nBlkYP */
+static void pad_mask_small(uint8_t *m, int nBlkXP, int nBlkYP, int nBlkX, int nBlkY) {
+    if (nBlkXP > nBlkX)
+        for (int j = 0; j < nBlkY; j++)
+            for (int dx = nBlkX; dx < nBlkXP; dx++)
+                m[j * nBlkXP + dx] = m[j * nBlkXP + nBlkX - 1];
+    if (nBlkYP > nBlkY)
+        for (int i = 0; i < nBlkXP; i++)
+            for (int dy = nBlkY; dy < nBlkYP; dy++)
+                m[nBlkXP * dy + i] = m[nBlkXP * (nBlkY - 1) + i];
+}
+
+typedef struct InterFields { /* full-size planes of one plane type (luma or chroma) */
+    int16_t *VXB, *VYB, *VXF, *VYF, *VXBB, *VYBB, *VXFF, *VYFF;
+    uint8_t *MB, *MF;
+    int pitch;
+} InterFields;
+
+static int px(const uint8_t *p, int bps, ptrdiff_t i) { return bps == 1 ? p[i] : ((const uint16_t *)p)[i]; }
+static void put_px(uint8_t *p, int bps, ptrdiff_t i, int v) {
+    if (bps == 1)
+        p[i] = (uint8_t)v;
+    else
+        ((uint16_t *)p)[i] = (uint16_t)v;
+}
+static int imin(int a, int b) { return a < b ? a : b; }
+static int imax(int a, int b) { return a > b ? a : b; }
+
+/* FlowInterSimple / FlowInter / FlowInterExtra, MaskFun.cpp:376-546 (the C versions).  prefB / prefF point at the
+ * interior's first sample of the finest planes of the right / left frame; ref_pitch in samples. */
+static void flow_inter_plane(int method, uint8_t *dst, ptrdiff_t dst_stride, const uint8_t *prefB, const uint8_t *prefF, ptrdiff_t ref_pitch, const InterFields *f, int width, int height, int time256, int pel, int bps) {
+    const int lp = pel == 4 ? 2 : (pel == 2 ? 1 : 0);
+    for (int h = 0; h < height; h++) {
+        const int16_t *VXB = f->VXB + h * f->pitch, *VYB = f->VYB + h * f->pitch, *VXF = f->VXF + h * f->pitch, *VYF = f->VYF + h * f->pitch;
+        const uint8_t *MB = f->MB + h * f->pitch, *MF = f->MF + h * f->pitch;
+        const ptrdiff_t row = (ptrdiff_t)(h << lp) * ref_pitch;
+        for (int w = 0; w < width; w++) {
+            const ptrdiff_t at = row + (w << lp);
+            int out;
+            if (method == 0 && time256 == 128) { /* :464-485 */
+                int vxF = VXF[w] >> 1, vyF = VYF[w] >> 1, vxB = VXB[w] >> 1, vyB = VYB[w] >> 1;
+                int dstF = px(prefF, bps, at + vyF * ref_pitch + vxF), dstB = px(prefB, bps, at + vyB * ref_pitch + vxB);
+                out = (((dstF + dstB) << 8) + (dstB - dstF) * (MF[w] - MB[w])) >> 9;
+            } else {
+                int vxF = (VXF[w] * time256) >> 8, vyF = (VYF[w] * time256) >> 8;
+                int vxB = (VXB[w] * (256 - time256)) >> 8, vyB = (VYB[w] * (256 - time256)) >> 8;
+                int dstF = px(prefF, bps, at + vyF * ref_pitch + vxF), dstB = px(prefB, bps, at + vyB * ref_pitch + vxB);
+                if (method == 0) { /* :486-510 */
+                    out = (((dstF * (255 - MF[w]) + dstB * MF[w] + 255) >> 8) * (256 - time256) + ((dstB * (255 - MB[w]) + dstF * MB[w] + 255) >> 8) * time256) >> 8;
+                } else if (method == 1) { /* :376-418, 64-bit intermediates */
+                    int64_t dF = dstF, dB = dstB;
+                    int dstF0 = px(prefF, bps, at), dstB0 = px(prefB, bps, at);
+                    out = (int)((((dF * (255 - MF[w]) + ((MF[w] * (dB * (255 - MB[w]) + MB[w] * dstF0) + 255) >> 8) + 255) >> 8) * (256 - time256) +
+                                 ((dB * (255 - MB[w]) + ((MB[w] * (dF * (255 - MF[w]) + MF[w] * dstB0) + 255) >> 8) + 255) >> 8) * time256) >>
+                                8);
+                } else { /* :421-461 */
+                    const int16_t *VXBB = f->VXBB + h * f->pitch, *VYBB = f->VYBB + h * f->pitch, *VXFF = f->VXFF + h * f->pitch, *VYFF = f->VYFF + h * f->pitch;
+                    int vxFF = (VXFF[w] * time256) >> 8, vyFF = (VYFF[w] * time256) >> 8;
+                    int vxBB = (VXBB[w] * (256 - time256)) >> 8, vyBB = (VYBB[w] * (256 - time256)) >> 8;
+                    int dstFF = px(prefF, bps, at + vyFF * ref_pitch + vxFF), dstBB = px(prefB, bps, at + vyBB * ref_pitch + vxBB);
+                    int minfb = imin(dstB, dstF), maxfb = imax(dstB, dstF);
+                    int medianBB = imax(minfb, imin(dstBB, maxfb)), medianFF = imax(minfb, imin(dstFF, maxfb));
+                    out = (((medianBB * MF[w] + dstF * (255 - MF[w]) + 255) >> 8) * (256 - time256) + ((medianFF * MB[w] + dstB * (255 - MB[w]) + 255) >> 8) * time256) >> 8;
+                }
+            }
+            put_px(dst + h * dst_stride, bps, w, out);
+        }
+    }
+}
+
+static void finest_planes(const mvb200_super_params *sp, int nplanes, const uint8_t *const super[3], const ptrdiff_t stride[3], uint8_t *fin[3], ptrdiff_t fstride[3]) {
+    const int bps = (sp->bits + 7) / 8, pel = sp->pel;
+    mvb200_super_params all = *sp;
+    all.modeyuv = MVB200_YUVPLANES;
+    for (int pl = 0; pl < 3; pl++) {
+        fin[pl] = NULL;
+        fstride[pl] = 0;
+    }
+    for (int pl = 0; pl < nplanes; pl++) {
+        FinestPlane f;
+        finest_plane_dims(sp, pl, &f);
+        fstride[pl] = (ptrdiff_t)f.pw * pel * bps;
+        fin[pl] = malloc((size_t)fstride[pl] * f.ph * pel);
+        if (pel == 1)
+            for (int y = 0; y < f.ph; y++)
+                memcpy(fin[pl] + y * fstride[pl], super[pl] + y * stride[pl], (size_t)f.pw * bps);
+    }
+    if (pel > 1)
+        mvo_finest_frame(&all, super, stride, fin, fstride);
+}
+
+/* the full-size vector planes of one vector frame for luma (and chroma): MakeVectorSmallMasks + CheckAndPadSmallY +
+ * VectorSmallMaskYToHalfUV + simpleResize_int16_t, as in MVFlowInter.c:196-250 */
+static void full_vectors(const mvb200_flowinter_params *p, const uint8_t *blob, const Resizer *up, const Resizer *upUV, int16_t *VXY, int16_t *VYY, int16_t *VXUV, int16_t *VYUV) {
+    const mvb200_analysis_data *vd = &p->vd;
+    const int ns = p->nBlkXP * p->nBlkYP;
+    int validity;
+    const uint8_t *l0 = blob_level0(blob, vd, &validity);
+    int16_t *vxs = malloc(sizeof(int16_t) * (size_t)ns), *vys = malloc(sizeof(int16_t) * (size_t)ns);
+    small_vectors(l0, vd->nBlkX, vd->nBlkY, p->nBlkXP, p->nBlkYP, 0, vxs, vys);
+    resize_i16(up, VXY, p->VPitchY, vxs, p->nBlkXP, 1);
+    resize_i16(up, VYY, p->VPitchY, vys, p->nBlkXP, 0);
+    if (p->nplanes > 1) {
+        int16_t *vxuv = malloc(sizeof(int16_t) * (size_t)ns), *vyuv = malloc(sizeof(int16_t) * (size_t)ns);
+        small_to_uv(vxs, ns, vxuv, vd->xRatioUV);
+        small_to_uv(vys, ns, vyuv, vd->yRatioUV);
+        resize_i16(upUV, VXUV, p->VPitchUV, vxuv, p->nBlkXP, 1);
+        resize_i16(upUV, VYUV, p->VPitchUV, vyuv, p->nBlkXP, 0);
+        free(vxuv);
+        free(vyuv);
+    }
+    free(vxs);
+    free(vys);
+}
+
+/* mvflowinterGetFrame, MVFlowInter.c:83-448 (usable case), also the core of mvflowfpsGetFrame, MVFlowFPS.c:118-470 */
+int mvo_flowinter_frame(const mvb200_flowinter_params *p, const mvb200_super_params *sp, int time256, const uint8_t *const left_super[3], const ptrdiff_t left_stride[3], const uint8_t *const right_super[3],
+                        const ptrdiff_t right_stride[3], const uint8_t *vec_b, const uint8_t *vec_f, const uint8_t *vec_bb, const uint8_t *vec_ff, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable) {
+    const mvb200_analysis_data *vd = &p->vd;
+    *usable = left_super && right_super && vec_b && vec_f && is_usable(vec_f, vd, p->nSCD1, p->nSCD2) && is_usable(vec_b, vd, p->nSCD1, p->nSCD2);
+    if (!*usable)
+        return 0;
+    const int extra = vec_bb && vec_ff && is_usable(vec_ff, vd, p->nSCD1, p->nSCD2) && is_usable(vec_bb, vd, p->nSCD1, p->nSCD2);
+    const int method = extra ? p->mode_primary : p->mode_fallback;
+    const int bps = (p->bits + 7) / 8, pel = vd->nPel, nplanes = p->nplanes;
+    const int stepX = vd->nBlkSizeX - vd->nOverlapX, stepY = vd->nBlkSizeY - vd->nOverlapY;
+    uint8_t *finL[3], *finR[3];
+    ptrdiff_t fsL[3], fsR[3];
+    finest_planes(sp, nplanes, left_super, left_stride, finL, fsL);
+    finest_planes(sp, nplanes, right_super, right_stride, finR, fsR);
+    Resizer up, upUV;
+    resizer_init(&up, p->nWidthP, p->nHeightP, p->nBlkXP, p->nBlkYP, vd->nWidth, vd->nHeight, pel);
+    if (nplanes > 1)
+        resizer_init(&upUV, p->nWidthPUV, p->nHeightPUV, p->nBlkXP, p->nBlkYP, p->nWidthUV, p->nHeightUV, pel);
+    const size_t nY = (size_t)p->nHeightP * p->VPitchY, nUV = nplanes > 1 ? (size_t)p->nHeightPUV * p->VPitchUV : 1;
+    InterFields Y, UV;
+    memset(&Y, 0, sizeof(Y));
+    memset(&UV, 0, sizeof(UV));
+    Y.pitch = p->VPitchY;
+    UV.pitch = p->VPitchUV;
+    int16_t **ys[8] = {&Y.VXB, &Y.VYB, &Y.VXF, &Y.VYF, &Y.VXBB, &Y.VYBB, &Y.VXFF, &Y.VYFF}, **uvs[8] = {&UV.VXB, &UV.VYB, &UV.VXF, &UV.VYF, &UV.VXBB, &UV.VYBB, &UV.VXFF, &UV.VYFF};
+    for (int i = 0; i < 8; i++) {
+        *ys[i] = calloc(nY, sizeof(int16_t));
+        *uvs[i] = calloc(nUV, sizeof(int16_t));
+    }
+    Y.MB = calloc(nY, 1);
+    Y.MF = calloc(nY, 1);
+    UV.MB = calloc(nUV, 1);
+    UV.MF = calloc(nUV, 1);
+    full_vectors(p, vec_b, &up, &upUV, Y.VXB, Y.VYB, UV.VXB, UV.VYB);
+    full_vectors(p, vec_f, &up, &upUV, Y.VXF, Y.VYF, UV.VXF, UV.VYF);
+    if (method == 2) {
+        full_vectors(p, vec_bb, &up, &upUV, Y.VXBB, Y.VYBB, UV.VXBB, UV.VYBB);
+        full_vectors(p, vec_ff, &up, &upUV, Y.VXFF, Y.VYFF, UV.VXFF, UV.VYFF);
+    }
+    /* occlusion masks, :203-208 */
+    const int ns = p->nBlkXP * p->nBlkYP;
+    uint8_t *mB = calloc((size_t)ns, 1), *mF = calloc((size_t)ns, 1);
+    int validity;
+    occlusion_mask_time(blob_level0(vec_b, vd, &validity), 1, vd->nBlkX, vd->nBlkY, p->ml, 1.0, pel, mB, p->nBlkXP, 256 - time256, stepX, stepY);
+    occlusion_mask_time(blob_level0(vec_f, vd, &validity), 0, vd->nBlkX, vd->nBlkY, p->ml, 1.0, pel, mF, p->nBlkXP, time256, stepX, stepY);
+    pad_mask_small(mB, p->nBlkXP, p->nBlkYP, vd->nBlkX, vd->nBlkY);
+    pad_mask_small(mF, p->nBlkXP, p->nBlkYP, vd->nBlkX, vd->nBlkY);
+    resize_u8(&up, Y.MB, p->VPitchY, mB, p->nBlkXP);
+    resize_u8(&up, Y.MF, p->VPitchY, mF, p->nBlkXP);
+    if (nplanes > 1) {
+        resize_u8(&upUV, UV.MB, p->VPitchUV, mB, p->nBlkXP);
+        resize_u8(&upUV, UV.MF, p->VPitchUV, mF, p->nBlkXP);
+    }
+    for (int pl = 0; pl < nplanes; pl++) {
+        const int hp = pl ? p->nHPaddingUV : vd->nHPadding, vp = pl ? p->nVPaddingUV : vd->nVPadding;
+        const ptrdiff_t offR = (ptrdiff_t)vp * pel * fsR[pl] + (ptrdiff_t)hp * pel * bps, offL = (ptrdiff_t)vp * pel * fsL[pl] + (ptrdiff_t)hp * pel * bps;
+        flow_inter_plane(method, dst[pl], dst_stride[pl], finR[pl] + offR, finL[pl] + offL, fsL[pl] / bps, pl ? &UV : &Y, pl ? p->nWidthUV : vd->nWidth, pl ? p->nHeightUV : vd->nHeight, time256, pel, bps);
+    }
+    for (int i = 0; i < 8; i++) {
+        free(*ys[i]);
+        free(*uvs[i]);
+    }
+    free(Y.MB);
+    free(Y.MF);
+    free(UV.MB);
+    free(UV.MF);
+    free(mB);
+    free(mF);
+    resizer_free(&up);
+    if (nplanes > 1)
+        resizer_free(&upUV);
+    for (int pl = 0; pl < 3; pl++) {
+        free(finL[pl]);
+        free(finR[pl]);
+    }
+    return 0;
+}
+
+/* Blend, MaskFun.cpp:349-373 */
+int mvo_blend_frame(const mvb200_super_params *sp, int time256, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const ref[3], const ptrdiff_t ref_stride[3], uint8_t *const dst[3],
+                    const ptrdiff_t dst_stride[3]) {
+    const int bps = (sp->bits + 7) / 8;
+    for (int pl = 0; pl < sp->nplanes; pl++) {
+        const int w = pl ? sp->width >> sp->ssw : sp->width, h = pl ? sp->height >> sp->ssh : sp->height;
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++)
+                put_px(dst[pl] + y * dst_stride[pl], bps, x, (px(src[pl] + y * src_stride[pl], bps, x) * (256 - time256) + px(ref[pl] + y * ref_stride[pl], bps, x) * time256) >> 8);
+    }
+    return 0;
+}

@@ -34,6 +34,8 @@ def lib():
         L.mvo_mask_frame.argtypes = [PP(mb.MaskParams), vp, C.c_ssize_t, vp, PP(vp), PP(C.c_ssize_t)]
         L.mvo_finest_frame.argtypes = [PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
         L.mvo_flow_frame.argtypes = [PP(mb.FlowParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), vp, C.c_int, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
+        L.mvo_flowinter_frame.argtypes = [PP(mb.FlowInterParams), PP(mb.SuperParams), C.c_int, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, vp, vp, vp, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
+        L.mvo_blend_frame.argtypes = [PP(mb.SuperParams), C.c_int, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
         L.mvo_simple_resize_tables.argtypes = [C.c_int, C.c_int, vp, vp]
         L.mvo_simple_resize_tables.restype = None
         for n in ("mvo_sad", "mvo_satd"):
@@ -167,3 +169,25 @@ def simple_resize_tables(out, in_):
     wt = np.zeros(out, dtype=np.int32)
     lib().mvo_simple_resize_tables(out, in_, off.ctypes.data, wt.ctypes.data)
     return off, wt
+
+
+def flowinter_frame(p, sp, time256, left_super, right_super, vec_b, vec_f, vec_bb=None, vec_ff=None):
+    w = [p.vd.nWidth, p.nWidthUV, p.nWidthUV][: p.nplanes]
+    h = [p.vd.nHeight, p.nHeightUV, p.nHeightUV][: p.nplanes]
+    dst = mb.alloc_planes(w, h, p.bits, fill=0xA5)
+    l, ls = mb.plane_ptrs(left_super)
+    r, rs = mb.plane_ptrs(right_super)
+    d, ds = mb.plane_ptrs(dst)
+    usable = C.c_int32(0)
+    ptr = lambda v: None if v is None else v.ctypes.data
+    _check(lib().mvo_flowinter_frame(C.byref(p), C.byref(sp), time256, l, ls, r, rs, ptr(vec_b), ptr(vec_f), ptr(vec_bb), ptr(vec_ff), d, ds, C.byref(usable)))
+    return dst if usable.value else None
+
+
+def blend_frame(sp, time256, src, ref):
+    dst = mb.alloc_planes([a.shape[1] for a in src], [a.shape[0] for a in src], sp.bits, fill=0xA5)
+    s, ss = mb.plane_ptrs(src)
+    r, rs = mb.plane_ptrs(ref)
+    d, ds = mb.plane_ptrs(dst)
+    _check(lib().mvo_blend_frame(C.byref(sp), time256, s, ss, r, rs, d, ds))
+    return dst

@@ -142,3 +142,81 @@ EMUL_API int emul_flow_frame(const mvb200_flow_params *fp, const mvb200_super_pa
     }
     return 0;
 }
+
+EMUL_API int emul_flowinter_frame(const mvb200_flowinter_params *p, const mvb200_super_params *sp, int time256, const uint8_t *const left_super[3], const ptrdiff_t left_stride[3], const uint8_t *const right_super[3],
+                                  const ptrdiff_t right_stride[3], const uint8_t *vec_b, const uint8_t *vec_f, const uint8_t *vec_bb, const uint8_t *vec_ff, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable_out) {
+    const mvb200_analysis_data &vd = p->vd;
+    const int nb = vd.nBlkX * vd.nBlkY, ns = p->nBlkXP * p->nBlkYP, bps = (p->bits + 7) / 8;
+    const uint8_t *blobs[4] = {vec_b, vec_f, vec_bb, vec_ff};
+    int flags[4];
+    std::vector<short> fld[16];
+    for (int i = 0; i < 4; i++) { // k_flow_scd + k_small_vectors per blob
+        flags[i] = blobs[i] ? usable_of(blobs[i], nb, p->nSCD1, p->nSCD2, 1) : 0;
+        for (int k = 0; k < 4; k++)
+            fld[4 * i + k].assign(ns, 0);
+        if (!blobs[i])
+            continue;
+        const int *l0 = blob_level0(blobs[i], nb);
+        for (int k = 0; k < ns; k++) {
+            const SmallVec s = small_vector(l0, vd.nBlkX, vd.nBlkY, k % p->nBlkXP, k / p->nBlkXP, 0, vd.xRatioUV, vd.yRatioUV);
+            fld[4 * i][k] = s.xY;
+            fld[4 * i + 1][k] = s.yY;
+            fld[4 * i + 2][k] = s.xUV;
+            fld[4 * i + 3][k] = s.yUV;
+        }
+    }
+    *usable_out = flags[0] && flags[1];
+    if (!*usable_out)
+        return 0;
+    const int stepX = vd.nBlkSizeX - vd.nOverlapX, stepY = vd.nBlkSizeY - vd.nOverlapY;
+    std::vector<int> raw[2] = {std::vector<int>(nb, 0), std::vector<int>(nb, 0)}, mask[2] = {std::vector<int>(ns), std::vector<int>(ns)};
+    for (int m = 0; m < 2; m++) { // k_occ_small + k_pad_mask
+        int *r = raw[m].data();
+        const int *l0 = blob_level0(blobs[m], nb);
+        for (int j = 0; j < nb; j++)
+            occlusion_contrib(l0, m == 0, vd.nBlkX, vd.nBlkY, p->ml, 1.0, vd.nPel, m == 0 ? 256 - time256 : time256, stepX, stepY, j % vd.nBlkX, j / vd.nBlkX, [r](int idx, int val) { r[idx] = r[idx] > val ? r[idx] : val; });
+        for (int k = 0; k < ns; k++)
+            mask[m][k] = padded_mask_entry(r, vd.nBlkX, vd.nBlkY, k % p->nBlkXP, k / p->nBlkXP);
+    }
+    const size_t n0 = tables_ints(p->nWidthP, p->nHeightP), n1 = p->nplanes > 1 ? tables_ints(p->nWidthPUV, p->nHeightPUV) : 0;
+    std::vector<int32_t> tab(n0 + n1);
+    fill_tables(tab.data(), p->nWidthP, p->nHeightP, p->nBlkXP, p->nBlkYP);
+    if (n1)
+        fill_tables(tab.data() + n0, p->nWidthPUV, p->nHeightPUV, p->nBlkXP, p->nBlkYP);
+    const ResizeTables t[2] = {tables_at(tab.data(), p->nWidthP, p->nHeightP), tables_at(tab.data() + n0, p->nWidthPUV, p->nHeightPUV)};
+    const int method = (flags[2] && flags[3]) ? p->mode_primary : p->mode_fallback;
+    for (int plane = 0; plane < p->nplanes; plane++) { // k_flow_inter
+        const int u = plane ? 2 : 0;
+        const InterSmall v = {fld[0 + u].data(), fld[1 + u].data(), fld[4 + u].data(), fld[5 + u].data(), fld[8 + u].data(), fld[9 + u].data(), fld[12 + u].data(), fld[13 + u].data()};
+        mvb200_level_geom g;
+        level0_geom(sp, plane, &g);
+        // (both frames share one layout in the engine; the emulation asserts equal strides instead)
+        if (left_stride[plane] != right_stride[plane])
+            return 1;
+        const InterPlane P = make_inter_plane(p, time256, plane, v, mask[0].data(), mask[1].data(), t[plane ? 1 : 0], make_super_plane(left_stride[plane], 0, g));
+        for (int y = 0; y < P.H; y++)
+            for (int x = 0; x < P.W; x++) {
+                if (bps == 1)
+                    dst[plane][y * dst_stride[plane] + x] = (uint8_t)flow_inter_sample<uint8_t>(P, method, right_super[plane], left_super[plane], x, y);
+                else
+                    *((uint16_t *)(dst[plane] + y * dst_stride[plane]) + x) = (uint16_t)flow_inter_sample<uint16_t>(P, method, right_super[plane], left_super[plane], x, y);
+            }
+    }
+    return 0;
+}
+
+EMUL_API int emul_blend_frame(const mvb200_super_params *sp, int time256, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const ref[3], const ptrdiff_t ref_stride[3], uint8_t *const dst[3],
+                              const ptrdiff_t dst_stride[3]) {
+    const int bps = (sp->bits + 7) / 8;
+    for (int pl = 0; pl < sp->nplanes; pl++) { // k_blend
+        const int w = pl ? sp->width >> sp->ssw : sp->width, h = pl ? sp->height >> sp->ssh : sp->height;
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                if (bps == 1)
+                    dst[pl][y * dst_stride[pl] + x] = (uint8_t)blend_sample(src[pl][y * src_stride[pl] + x], ref[pl][y * ref_stride[pl] + x], time256);
+                else
+                    *((uint16_t *)(dst[pl] + y * dst_stride[pl]) + x) = (uint16_t)blend_sample(*((const uint16_t *)(src[pl] + y * src_stride[pl]) + x), *((const uint16_t *)(ref[pl] + y * ref_stride[pl]) + x), time256);
+            }
+    }
+    return 0;
+}

@@ -20,21 +20,23 @@ FLOW = {
         mask=[dict(kind=0), dict(kind=1, gamma=2.0, time=30.0), dict(kind=2, ml=50.0), dict(kind=2, vec=1, gamma=0.7, time=60.0),
               dict(kind=3), dict(kind=4, ml=20.0, vec=1), dict(kind=5, ysc=77), dict(kind=0, gamma=1.7, ml=30.0, thscd1=200, thscd2=40, ysc=200)],
         flow=[dict(), dict(time=50.0, vec=1), dict(mode=1, time=70.0), dict(mode=1, vec=1, thscd1=250, thscd2=60)],
-        scd=[dict(), dict(vec=1, thscd1=150, thscd2=30)], finest=True),
-    "blk16_ov8_pel2_p16_r3": dict(flow=[dict(time=33.0), dict(mode=1, vec=1)], scd=[dict()], finest=True),
-    "p10_444_blk8_pel4_bicubic": dict(flow=[dict(time=80.0), dict(mode=1, time=45.0, vec=1)], finest=True, scd=[dict(thscd2=10)]),
-    "gray_blk4_pel1_rf0": dict(mask=[dict(kind=0), dict(kind=2, time=50.0), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=25.0)], finest=True, scd=[dict()]),
-    "c1_640x360_p8_blk8_pel1": dict(mask=[dict(kind=1), dict(kind=2, vec=1)], flow=[dict(time=60.0), dict(mode=1)], scd=[dict()]),
+        scd=[dict(), dict(vec=1, thscd1=150, thscd2=30)], finest=True,
+        inter=[dict(), dict(time=25.0, ml=40.0), dict(time=80.0, blend=0, thscd1=250, thscd2=60), dict(time=0.0), dict(time=100.0)]),
+    "blk16_ov8_pel2_p16_r3": dict(flow=[dict(time=33.0), dict(mode=1, vec=1)], scd=[dict()], finest=True, inter=[dict(), dict(time=70.0, ml=20.0)]),
+    "p10_444_blk8_pel4_bicubic": dict(flow=[dict(time=80.0), dict(mode=1, time=45.0, vec=1)], finest=True, scd=[dict(thscd2=10)], inter=[dict(time=40.0)]),
+    "gray_blk4_pel1_rf0": dict(mask=[dict(kind=0), dict(kind=2, time=50.0), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=25.0)], finest=True, scd=[dict()], inter=[dict(time=60.0, ml=10.0)]),
+    "c1_640x360_p8_blk8_pel1": dict(mask=[dict(kind=1), dict(kind=2, vec=1)], flow=[dict(time=60.0), dict(mode=1)], scd=[dict()], inter=[dict(), dict(time=33.0, blend=0)]),
     "p8_422_blk8x4_sharp0_rf1": dict(mask=[dict(kind=0, ml=10.0), dict(kind=1, time=0.0), dict(kind=2, vec=1, ml=10.0), dict(kind=5)], flow=[dict(vec=1), dict(mode=1, time=100.0)], finest=True,
-                                     scd=[dict(vec=1)]),
+                                     scd=[dict(vec=1)], inter=[dict(time=45.0)]),
     "noise_badblocks_blk8": dict(mask=[dict(kind=0, ysc=9), dict(kind=1, thscd1=16000, thscd2=255), dict(kind=2, thscd1=16000, thscd2=255, ml=400.0), dict(kind=5, thscd1=16000, thscd2=255, ml=3.0)],
-                                 flow=[dict(), dict(thscd1=16000, thscd2=255, time=90.0), dict(mode=1, thscd1=16000, thscd2=255, vec=1)], scd=[dict(), dict(thscd1=16000, thscd2=255)]),
+                                 flow=[dict(), dict(thscd1=16000, thscd2=255, time=90.0), dict(mode=1, thscd1=16000, thscd2=255, vec=1)], scd=[dict(), dict(thscd1=16000, thscd2=255)],
+                                 inter=[dict(), dict(blend=0), dict(thscd1=16000, thscd2=255, ml=300.0, time=20.0)]),
     "blk4_420_chroma2x2_pel2": dict(mask=[dict(kind=2, gamma=2.0)], flow=[dict(time=12.0), dict(mode=1)], finest=True),
     # (no mask here: 256-sample rows equal the stride, and the reference's bottom-strip copy, MVMask.c:162-163, is an
     # overlapping memcpy then -- undefined behaviour; the oracle and the engine replicate the last covered row, which is
     # what the reference's row loop does for every other width)
     "divide2_blk16_esa_neg_badrange": dict(flow=[dict(thscd1=16000, thscd2=255), dict(mode=1, thscd1=16000, thscd2=255, vec=1, time=40.0)], scd=[dict(thscd1=16000, thscd2=255)]),
-    "p8_420_blk16_ov4_uncovered": dict(mask=[dict(kind=0), dict(kind=1, ml=30.0), dict(kind=2, vec=1), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=66.0)], scd=[dict()], finest=True),
+    "p8_420_blk16_ov4_uncovered": dict(mask=[dict(kind=0), dict(kind=1, ml=30.0), dict(kind=2, vec=1), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=66.0)], scd=[dict()], finest=True, inter=[dict(), dict(time=10.0, ml=50.0)]),
 }
 
 
@@ -70,7 +72,9 @@ def flow_params_for(case):
     N = ck["nframes"]
     sp, aps, dp = pipeline.params_for(case)
     vds = [(ap.ad_divided if ap.divide else ap.ad) for ap in aps[:2]]
-    out = {"mask": [], "flow": [], "scd": []}
+    out = {"mask": [], "flow": [], "scd": [], "inter": []}
+    for kw in FLOW[case].get("inter", []):
+        out["inter"].append(mb.flowinter_params(sp, vds[0], vds[1], N, **kw))
     for kw in FLOW[case].get("mask", []):
         v, kw = _split(kw)
         out["mask"].append((v, mb.mask_params(vds[v], clip_bits=ck.get("bits", 8), clip_ssw=ck.get("ssw", 1), clip_ssh=ck.get("ssh", 1), clip_gray=ck.get("gray", False), **kw)))
@@ -81,6 +85,26 @@ def flow_params_for(case):
         v, kw = _split(kw)
         out["scd"].append((v, mb.scdetection_params(vds[v], **kw)))
     return sp, aps, out
+
+
+def run_engine_inter(case, inter_fn, blend_fn):
+    """mv.FlowInter frame by frame (MVFlowInter.c:83-448): stage functions on the oracle-made inputs -> hashes"""
+    frames, sups, vecs = inputs(case)
+    N = len(frames)
+    sp, aps, P = flow_params_for(case)
+    out = []
+    for p in P["inter"]:
+        off = p.vd.nDeltaFrame
+        rows = []
+        for n in range(N):
+            d = None
+            if n + off < N:  # vec_b = mvbw(n), vec_f = mvfw(n + off), extra pair: mvbw(n + off), mvfw(n)
+                d = inter_fn(p, sp, p.time256, sups[n], sups[n + off], vecs[0][n], vecs[1][n + off], vecs[0][n + off], vecs[1][n])
+            if d is None:  # :412-447
+                d = blend_fn(sp, p.time256, frames[n], frames[min(n + off, N - 1)]) if p.blend else frames[n]
+            rows.append([sha(q) for q in d])
+        out.append(rows)
+    return out
 
 
 def run_engine_flow(case, scd_fn, mask_fn, finest_fn, flow_fn):
@@ -136,4 +160,9 @@ def run_reference_flow(case, plugin_path=None):
     if FLOW[case].get("finest"):
         node = mv.Finest(sup)
         out["finest"] = [[sha(p) for p in node.get_frame(n).planes()[:nplanes]] for n in range(N)]
+    out["inter"] = []
+    for kw in FLOW[case].get("inter", []):
+        kw = {k: (float(x) if k in ("time", "ml") else x) for k, x in kw.items()}
+        node = mv.FlowInter(clip, sup, vn[0], vn[1], **kw)
+        out["inter"].append([[sha(p) for p in node.get_frame(n).planes()[:nplanes]] for n in range(N)])
     return out

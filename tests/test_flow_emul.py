@@ -35,6 +35,8 @@ def emul():
         L.emul_mask_frame.argtypes = [PP(mb.MaskParams), vp, C.c_ssize_t, vp, PP(vp), PP(C.c_ssize_t)]
         L.emul_finest_frame.argtypes = [PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
         L.emul_flow_frame.argtypes = [PP(mb.FlowParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), vp, C.c_int, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
+        L.emul_flowinter_frame.argtypes = [PP(mb.FlowInterParams), PP(mb.SuperParams), C.c_int, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, vp, vp, vp, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
+        L.emul_blend_frame.argtypes = [PP(mb.SuperParams), C.c_int, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
         _LIB = L
     return _LIB
 
@@ -72,10 +74,33 @@ def flow(fp, sp, ref_super, vectors, field_shift=0):
     return dst if usable.value else None
 
 
+def inter(p, sp, time256, left_super, right_super, vec_b, vec_f, vec_bb=None, vec_ff=None):
+    w = [p.vd.nWidth, p.nWidthUV, p.nWidthUV][: p.nplanes]
+    h = [p.vd.nHeight, p.nHeightUV, p.nHeightUV][: p.nplanes]
+    dst = mb.alloc_planes(w, h, p.bits, fill=0xA5)
+    l, ls = mb.plane_ptrs(left_super)
+    r, rs = mb.plane_ptrs(right_super)
+    d, ds = mb.plane_ptrs(dst)
+    usable = C.c_int32(0)
+    ptr = lambda v: None if v is None else v.ctypes.data
+    assert emul().emul_flowinter_frame(C.byref(p), C.byref(sp), time256, l, ls, r, rs, ptr(vec_b), ptr(vec_f), ptr(vec_bb), ptr(vec_ff), d, ds, C.byref(usable)) == 0
+    return dst if usable.value else None
+
+
+def blend(sp, time256, src, ref):
+    dst = mb.alloc_planes([a.shape[1] for a in src], [a.shape[0] for a in src], sp.bits, fill=0xA5)
+    s, ss = mb.plane_ptrs(src)
+    r, rs = mb.plane_ptrs(ref)
+    d, ds = mb.plane_ptrs(dst)
+    assert emul().emul_blend_frame(C.byref(sp), time256, s, ss, r, rs, d, ds) == 0
+    return dst
+
+
 @pytest.mark.parametrize("case", sorted(pipeline_flow.FLOW))
 def test_kernel_arithmetic_matches_reference_goldens(built, case):
     got = pipeline_flow.run_engine_flow(case, scd, mask, finest, flow)
-    for stage in ("scd", "mask", "flow", "finest"):
+    got["inter"] = pipeline_flow.run_engine_inter(case, inter, blend)
+    for stage in ("scd", "mask", "flow", "finest", "inter"):
         assert got[stage] == GOLD[case][stage], "%s: emulated kernels' %s differs from the reference's golden hashes" % (case, stage)
 
 

@@ -23,8 +23,9 @@ def test_cuda_flow_matches_reference_goldens(gpu_ctx, case):
     ctx = gpu_ctx
     n0 = ctx.launch_count()
     got = pipeline_flow.run_engine_flow(case, ctx.scdetection_frame, ctx.mask_frame, ctx.finest_frame, ctx.flow_frame)
+    got["inter"] = pipeline_flow.run_engine_inter(case, ctx.flowinter_frame, ctx.blend_frame)
     assert ctx.launch_count() > n0, "no kernel was launched"
-    for stage in ("scd", "mask", "flow", "finest"):
+    for stage in ("scd", "mask", "flow", "finest", "inter"):
         assert got[stage] == GOLD[case][stage], "%s: CUDA %s differs from the reference's golden hashes" % (case, stage)
 
 
@@ -94,6 +95,13 @@ def test_flow_batch_entry_points_match_goldens(gpu_ctx, case):
         out = ddst.cpu().numpy()
         for n in range(N):
             assert [pipeline.sha(p) for p in _planes(out[n], ml)] == GOLD[case]["mask"][i][n], "mask variant %d frame %d" % (i, n)
+    for i, p in enumerate(P["inter"]):
+        ddst = torch.full((N, cl.frame_bytes), 0xA5, dtype=torch.uint8, device="cuda")
+        mb._check(L.mvb200_flowinter_batch(ctx.handle, C.byref(p), C.byref(sp), dsrc.data_ptr(), dsup.data_ptr(), 0, N, dvec[0].data_ptr(), dvec[1].data_ptr(), vs, ddst.data_ptr()))
+        ctx.synchronize()
+        out = ddst.cpu().numpy()
+        for n in range(N):
+            assert [pipeline.sha(q) for q in _planes(out[n], cl)] == GOLD[case]["inter"][i][n], "inter variant %d frame %d" % (i, n)
     if pipeline_flow.FLOW[case].get("finest"):
         fl = mb.finest_layout(sp)
         ddst = torch.full((N, fl.frame_bytes), 0xA5, dtype=torch.uint8, device="cuda")

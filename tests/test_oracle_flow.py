@@ -21,13 +21,15 @@ GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_
 
 def oracle_run(case):
     import oracle
-    return pipeline_flow.run_engine_flow(case, oracle.scdetection_frame, oracle.mask_frame, oracle.finest_frame, oracle.flow_frame)
+    out = pipeline_flow.run_engine_flow(case, oracle.scdetection_frame, oracle.mask_frame, oracle.finest_frame, oracle.flow_frame)
+    out["inter"] = pipeline_flow.run_engine_inter(case, oracle.flowinter_frame, oracle.blend_frame)
+    return out
 
 
 @pytest.mark.parametrize("case", sorted(pipeline_flow.FLOW))
 def test_flow_oracle_matches_golden(built, case):
     got = oracle_run(case)
-    for stage in ("scd", "mask", "flow", "finest"):
+    for stage in ("scd", "mask", "flow", "finest", "inter"):
         assert got[stage] == GOLD[case][stage], "%s: oracle %s differs from the reference's golden hashes" % (case, stage)
 
 

@@ -136,6 +136,50 @@ __global__ void k_finest(SuperPlane S, int logPel, int W, int H, const uint8_t *
     *((T *)(dst + (long long)y * dst_pitch) + x) = finest_sample<T>(super_frame, S, logPel, x, y);
 }
 
+// -------------------------------------------------------------- FlowInter
+
+// MakeVectorOcclusionMaskTime into a zeroed nBlkX x nBlkY int array (gamma = 1: MVFlowInter.c:203-206)
+__global__ void k_occ_small(const uint8_t *blob, int isBackward, int nBlkX, int nBlkY, double ml, int nPel, int time256, int stepX, int stepY, int *raw) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nBlkX * nBlkY)
+        return;
+    occlusion_contrib(blob_level0(blob, nBlkX * nBlkY), isBackward, nBlkX, nBlkY, ml, 1.0, nPel, time256, stepX, stepY, j % nBlkX, j / nBlkX, [raw](int idx, int val) { atomicMax(raw + idx, val); });
+}
+
+__global__ void k_pad_mask(const int *raw, int nBlkX, int nBlkY, int nBlkXP, int nBlkYP, int *out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nBlkXP * nBlkYP)
+        out[k] = padded_mask_entry(raw, nBlkX, nBlkY, k % nBlkXP, k / nBlkXP);
+}
+
+// flags: usable(vec_b), usable(vec_f), usable(vec_bb), usable(vec_ff).  Not usable: the blend of (or the copy from) the
+// SOURCE clip's frames when they are given (batch path), else dst is left alone.
+template <typename T>
+__global__ void k_flow_inter(InterPlane P, int mode_primary, int mode_fallback, const uint8_t *__restrict__ right_super, const uint8_t *__restrict__ left_super, uint8_t *__restrict__ dst, long long dst_pitch,
+                             const uint8_t *__restrict__ src, const uint8_t *__restrict__ ref, int blend, const int *__restrict__ flags) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= P.W || y >= P.H)
+        return;
+    T *d = (T *)(dst + (long long)y * dst_pitch) + x;
+    if (!(flags[0] && flags[1])) {
+        if (src) {
+            const int a = *((const T *)(src + (long long)y * dst_pitch) + x);
+            *d = (T)(blend ? blend_sample(a, *((const T *)(ref + (long long)y * dst_pitch) + x), P.time256) : a);
+        }
+        return;
+    }
+    *d = (T)flow_inter_sample<T>(P, (flags[2] && flags[3]) ? mode_primary : mode_fallback, right_super, left_super, x, y);
+}
+
+template <typename T>
+__global__ void k_blend(int W, int H, int time256, const uint8_t *__restrict__ src, const uint8_t *__restrict__ ref, uint8_t *__restrict__ dst, long long pitch) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H)
+        return;
+    const long long o = (long long)y * pitch;
+    *((T *)(dst + o) + x) = (T)blend_sample(*((const T *)(src + o) + x), *((const T *)(ref + o) + x), time256);
+}
+
 // ------------------------------------------------------------ host helpers
 
 constexpr int kSlotTables = 16, kSlotSmall = 17, kSlotStage = 18;
@@ -267,6 +311,72 @@ static int launch_finest(Ctx *c, const mvb200_super_params *sp, const SuperDesc 
             k_finest<uint8_t><<<grid, blk, 0, c->stream>>>(S, lp, W, H, dev_super, dev_dst + fl.offset[plane], fl.pitch[plane]);
         else
             k_finest<uint16_t><<<grid, blk, 0, c->stream>>>(S, lp, W, H, dev_super, dev_dst + fl.offset[plane], fl.pitch[plane]);
+        c->launches++;
+    }
+    MVB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// mvflowinterGetFrame (MVFlowInter.c:83-448) / the core of mvflowfpsGetFrame for one output frame on the device.
+// Any of the blobs / super frames may be null (frame out of range): the frame is then not usable.
+static int launch_flowinter(Ctx *c, const mvb200_flowinter_params *p, const SuperDesc &sd, const ClipDesc &cd, int time256, const uint8_t *left_super, const uint8_t *right_super, const uint8_t *vec_b, const uint8_t *vec_f,
+                            const uint8_t *vec_bb, const uint8_t *vec_ff, const uint8_t *dev_src, const uint8_t *dev_ref, uint8_t *dev_dst, int **flags_dev) {
+    cudaStream_t st = c->stream;
+    const mvb200_analysis_data &vd = p->vd;
+    const int ns = p->nBlkXP * p->nBlkYP, nb = vd.nBlkX * vd.nBlkY;
+    const size_t field_bytes = align256((size_t)ns * sizeof(short)), mask_bytes = align256((size_t)ns * sizeof(int)), raw_bytes = align256((size_t)nb * sizeof(int));
+    uint8_t *scr = (uint8_t *)c->get_scratch(kSlotSmall, 256 + 16 * field_bytes + 2 * mask_bytes + 2 * raw_bytes);
+    if (!scr)
+        return 1;
+    int *flags = (int *)scr;
+    *flags_dev = flags;
+    short *fld[16];
+    for (int i = 0; i < 16; i++)
+        fld[i] = (short *)(scr + 256 + i * field_bytes);
+    int *mask[2] = {(int *)(scr + 256 + 16 * field_bytes), (int *)(scr + 256 + 16 * field_bytes + mask_bytes)};
+    int *raw[2] = {(int *)(scr + 256 + 16 * field_bytes + 2 * mask_bytes), (int *)(scr + 256 + 16 * field_bytes + 2 * mask_bytes + raw_bytes)};
+    ResizeTables t[2];
+    if (get_resize_tables(c, p->nWidthP, p->nHeightP, p->nplanes > 1 ? p->nWidthPUV : 0, p->nplanes > 1 ? p->nHeightPUV : 0, p->nBlkXP, p->nBlkYP, t))
+        return 1;
+    const bool frames_ok = left_super && right_super && vec_b && vec_f;
+    const uint8_t *blobs[4] = {vec_b, vec_f, vec_bb, vec_ff};
+    for (int i = 0; i < 4; i++) {
+        const bool have = blobs[i] != nullptr && frames_ok;
+        if (have) {
+            k_flow_scd<<<1, 256, 0, st>>>(blobs[i], 0, nb, p->nSCD1, p->nSCD2, 1, flags + i);
+            c->launches++;
+            SmallFields sf = {fld[4 * i], fld[4 * i + 1], fld[4 * i + 2], fld[4 * i + 3]};
+            k_small_vectors<<<(ns + 255) / 256, 256, 0, st>>>(blobs[i], vd.nBlkX, vd.nBlkY, p->nBlkXP, p->nBlkYP, 0, vd.xRatioUV, vd.yRatioUV, sf);
+            c->launches++;
+        } else {
+            MVB_CUDA_CHECK(cudaMemsetAsync(flags + i, 0, sizeof(int), st));
+        }
+    }
+    if (frames_ok) {
+        const int stepX = vd.nBlkSizeX - vd.nOverlapX, stepY = vd.nBlkSizeY - vd.nOverlapY;
+        MVB_CUDA_CHECK(cudaMemsetAsync(raw[0], 0, 2 * raw_bytes, st));
+        k_occ_small<<<(nb + 127) / 128, 128, 0, st>>>(vec_b, 1, vd.nBlkX, vd.nBlkY, p->ml, vd.nPel, 256 - time256, stepX, stepY, raw[0]);
+        k_occ_small<<<(nb + 127) / 128, 128, 0, st>>>(vec_f, 0, vd.nBlkX, vd.nBlkY, p->ml, vd.nPel, time256, stepX, stepY, raw[1]);
+        k_pad_mask<<<(ns + 255) / 256, 256, 0, st>>>(raw[0], vd.nBlkX, vd.nBlkY, p->nBlkXP, p->nBlkYP, mask[0]);
+        k_pad_mask<<<(ns + 255) / 256, 256, 0, st>>>(raw[1], vd.nBlkX, vd.nBlkY, p->nBlkXP, p->nBlkYP, mask[1]);
+        c->launches += 4;
+    }
+    if (!frames_ok && !dev_src) { // nothing to write: the caller handles the unusable frame
+        MVB_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
+    for (int plane = 0; plane < p->nplanes; plane++) {
+        const int u = plane ? 2 : 0; // fields: [4 i + 0/1] = luma x / y, [4 i + 2/3] = chroma x / y of blob i (b, f, bb, ff)
+        const InterSmall v = {fld[0 + u], fld[1 + u], fld[4 + u], fld[5 + u], fld[8 + u], fld[9 + u], fld[12 + u], fld[13 + u]};
+        const InterPlane P = make_inter_plane(p, time256, plane, v, mask[0], mask[1], t[plane ? 1 : 0], super_plane_of(sd, plane));
+        uint8_t *dst = dev_dst + cd.offset[plane];
+        const uint8_t *src = dev_src ? dev_src + cd.offset[plane] : nullptr, *ref = dev_ref ? dev_ref + cd.offset[plane] : src;
+        const uint8_t *ls = left_super ? left_super : (const uint8_t *)flags, *rs = right_super ? right_super : (const uint8_t *)flags;
+        dim3 blk(32, 8), grid((P.W + 31) / 32, (P.H + 7) / 8);
+        if (sd.bps == 1)
+            k_flow_inter<uint8_t><<<grid, blk, 0, st>>>(P, p->mode_primary, p->mode_fallback, rs, ls, dst, cd.pitch[plane], src, ref, p->blend, flags);
+        else
+            k_flow_inter<uint16_t><<<grid, blk, 0, st>>>(P, p->mode_primary, p->mode_fallback, rs, ls, dst, cd.pitch[plane], src, ref, p->blend, flags);
         c->launches++;
     }
     MVB_CUDA_CHECK(cudaGetLastError());
@@ -465,6 +575,122 @@ int mvb200_flow_frame(mvb200_ctx *ctx, const mvb200_flow_params *fp, const mvb20
             MVB_CUDA_CHECK(cudaMemcpy2DAsync(dst[pl], (size_t)dst_stride[pl], ddst + cd.offset[pl], (size_t)cd.pitch[pl], (size_t)cd.w[pl] * cd.bps, (size_t)cd.h[pl], cudaMemcpyDeviceToHost, c->stream));
         MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     }
+    return 0;
+}
+
+static int flowinter_check(const mvb200_flowinter_params *p, const mvb200_super_params *sp) {
+    if (sp->levels > kDevMaxLevels)
+        return set_error("mvtools_b200: more than %d pyramid levels are not supported on the device", kDevMaxLevels);
+    if (p->super_pel != sp->pel || p->super_hpad != sp->hpad || p->super_vpad != sp->vpad || p->bits != sp->bits)
+        return set_error("FlowInter: the parameters were derived for another super clip");
+    return 0;
+}
+
+int mvb200_flowinter_batch(mvb200_ctx *ctx, const mvb200_flowinter_params *p, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int first, int n, const void *dev_bw, const void *dev_fw,
+                           int64_t vectors_stride, void *dev_dst) {
+    if (flowinter_check(p, sp))
+        return 1;
+    if (n <= 0)
+        return 0;
+    if (first < 0 || first + n > p->num_frames)
+        return set_error("FlowInter: frames [%d, %d) are outside the clip of %d frames", first, first + n, p->num_frames);
+    if (!dev_src)
+        return set_error("FlowInter: the batch entry point needs the source clip (unusable frames are made from it)");
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(sp, &sd);
+    make_clip_desc(sp, &cd);
+    const uint8_t *sup = (const uint8_t *)dev_super, *bw = (const uint8_t *)dev_bw, *fw = (const uint8_t *)dev_fw, *src = (const uint8_t *)dev_src;
+    for (int f = 0; f < n; f++) {
+        const int fn = first + f, off = p->vd.nDeltaFrame, fr = fn + off;
+        const bool in_range = fr < p->num_frames; // MVFlowInter.c:115
+        const int fref = fr < p->num_frames - 1 ? fr : p->num_frames - 1; // VSMIN(n + off, numFrames - 1), :421
+        int *flags;
+        if (launch_flowinter(c, p, sd, cd, p->time256, sup + (long long)fn * sd.frame_bytes, in_range ? sup + (long long)fr * sd.frame_bytes : nullptr, in_range ? bw + (long long)fn * vectors_stride : nullptr,
+                             in_range ? fw + (long long)fr * vectors_stride : nullptr, in_range ? bw + (long long)fr * vectors_stride : nullptr, in_range ? fw + (long long)fn * vectors_stride : nullptr,
+                             src + (long long)fn * cd.frame_bytes, src + (long long)fref * cd.frame_bytes, (uint8_t *)dev_dst + (long long)f * cd.frame_bytes, &flags))
+            return 1;
+    }
+    return 0;
+}
+
+int mvb200_flowinter_frame(mvb200_ctx *ctx, const mvb200_flowinter_params *p, const mvb200_super_params *sp, int time256, const uint8_t *const left_super[3], const ptrdiff_t left_stride[3],
+                           const uint8_t *const right_super[3], const ptrdiff_t right_stride[3], const uint8_t *vec_b, const uint8_t *vec_f, const uint8_t *vec_bb, const uint8_t *vec_ff, uint8_t *const dst[3],
+                           const ptrdiff_t dst_stride[3], int32_t *usable_out) {
+    if (flowinter_check(p, sp))
+        return 1;
+    *usable_out = 0;
+    if (!left_super || !right_super || !vec_b || !vec_f)
+        return 0;
+    if (time256 < 0 || time256 > 256)
+        return set_error("FlowInter: time256 = %d is outside [0, 256]", time256);
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(sp, &sd);
+    make_clip_desc(sp, &cd);
+    const uint8_t *host_blobs[4] = {vec_b, vec_f, vec_bb, vec_ff};
+    size_t blob_off[4], total = 0;
+    for (int i = 0; i < 4; i++) {
+        blob_off[i] = total;
+        total += host_blobs[i] ? align256((size_t)blob_bytes_of(host_blobs[i])) : 0;
+    }
+    uint8_t *buf = (uint8_t *)c->get_scratch(kSlotStage, 2 * (size_t)sd.frame_bytes + (size_t)cd.frame_bytes + total + 256);
+    if (!buf)
+        return 1;
+    uint8_t *dleft = buf, *dright = buf + sd.frame_bytes, *ddst = dright + sd.frame_bytes, *dvec = ddst + cd.frame_bytes;
+    const uint8_t *dev_blobs[4];
+    for (int i = 0; i < 4; i++) {
+        dev_blobs[i] = host_blobs[i] ? dvec + blob_off[i] : nullptr;
+        if (host_blobs[i])
+            MVB_CUDA_CHECK(cudaMemcpyAsync(dvec + blob_off[i], host_blobs[i], (size_t)blob_bytes_of(host_blobs[i]), cudaMemcpyHostToDevice, c->stream));
+    }
+    for (int pl = 0; pl < p->nplanes; pl++) { // level 0 only
+        const mvb200_level_geom &g = sd.lv[pl][0];
+        MVB_CUDA_CHECK(cudaMemcpy2DAsync(dleft + sd.offset[pl], (size_t)sd.pitch[pl], left_super[pl], (size_t)left_stride[pl], (size_t)g.padded_w * sd.bps, (size_t)g.padded_h * sp->pel * sp->pel, cudaMemcpyHostToDevice, c->stream));
+        MVB_CUDA_CHECK(cudaMemcpy2DAsync(dright + sd.offset[pl], (size_t)sd.pitch[pl], right_super[pl], (size_t)right_stride[pl], (size_t)g.padded_w * sd.bps, (size_t)g.padded_h * sp->pel * sp->pel, cudaMemcpyHostToDevice, c->stream));
+    }
+    int *flags_dev = nullptr;
+    if (launch_flowinter(c, p, sd, cd, time256, dleft, dright, dev_blobs[0], dev_blobs[1], dev_blobs[2], dev_blobs[3], nullptr, nullptr, ddst, &flags_dev))
+        return 1;
+    int flags[4] = {0, 0, 0, 0};
+    MVB_CUDA_CHECK(cudaMemcpyAsync(flags, flags_dev, sizeof(flags), cudaMemcpyDeviceToHost, c->stream));
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    *usable_out = flags[0] && flags[1];
+    if (*usable_out) {
+        for (int pl = 0; pl < p->nplanes; pl++)
+            MVB_CUDA_CHECK(cudaMemcpy2DAsync(dst[pl], (size_t)dst_stride[pl], ddst + cd.offset[pl], (size_t)cd.pitch[pl], (size_t)cd.w[pl] * cd.bps, (size_t)cd.h[pl], cudaMemcpyDeviceToHost, c->stream));
+        MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int mvb200_blend_frame(mvb200_ctx *ctx, const mvb200_super_params *sp, int time256, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const ref[3], const ptrdiff_t ref_stride[3], uint8_t *const dst[3],
+                       const ptrdiff_t dst_stride[3]) {
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    ClipDesc cd;
+    make_clip_desc(sp, &cd);
+    uint8_t *buf = (uint8_t *)c->get_scratch(kSlotStage, 3 * (size_t)cd.frame_bytes);
+    if (!buf)
+        return 1;
+    uint8_t *dsrc = buf, *dref = buf + cd.frame_bytes, *ddst = dref + cd.frame_bytes;
+    for (int pl = 0; pl < cd.nplanes; pl++) {
+        MVB_CUDA_CHECK(cudaMemcpy2DAsync(dsrc + cd.offset[pl], (size_t)cd.pitch[pl], src[pl], (size_t)src_stride[pl], (size_t)cd.w[pl] * cd.bps, (size_t)cd.h[pl], cudaMemcpyHostToDevice, c->stream));
+        MVB_CUDA_CHECK(cudaMemcpy2DAsync(dref + cd.offset[pl], (size_t)cd.pitch[pl], ref[pl], (size_t)ref_stride[pl], (size_t)cd.w[pl] * cd.bps, (size_t)cd.h[pl], cudaMemcpyHostToDevice, c->stream));
+        dim3 blk(32, 8), grid((cd.w[pl] + 31) / 32, (cd.h[pl] + 7) / 8);
+        if (cd.bps == 1)
+            k_blend<uint8_t><<<grid, blk, 0, c->stream>>>(cd.w[pl], cd.h[pl], time256, dsrc + cd.offset[pl], dref + cd.offset[pl], ddst + cd.offset[pl], cd.pitch[pl]);
+        else
+            k_blend<uint16_t><<<grid, blk, 0, c->stream>>>(cd.w[pl], cd.h[pl], time256, dsrc + cd.offset[pl], dref + cd.offset[pl], ddst + cd.offset[pl], cd.pitch[pl]);
+        c->launches++;
+        MVB_CUDA_CHECK(cudaMemcpy2DAsync(dst[pl], (size_t)dst_stride[pl], ddst + cd.offset[pl], (size_t)cd.pitch[pl], (size_t)cd.w[pl] * cd.bps, (size_t)cd.h[pl], cudaMemcpyDeviceToHost, c->stream));
+    }
+    MVB_CUDA_CHECK(cudaGetLastError());
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

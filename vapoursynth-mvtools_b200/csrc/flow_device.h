@@ -243,5 +243,68 @@ MVB_HD int flow_shift_target(const FlowPlane &F, int x, int y) {
     return -1;
 }
 
+// ------------------------------------------------------------------ FlowInter / FlowFPS
+
+// CheckAndPadMaskSmall, MaskFun.cpp:65-82: entry (i, j) of the nBlkXP x nBlkYP mask grown from nBlkX x nBlkY (right
+// fill first, then the bottom fill from the already filled last row: a clamp of both indices)
+MVB_HD int padded_mask_entry(const int *raw, int nBlkX, int nBlkY, int i, int j) {
+    return raw[(j < nBlkY ? j : nBlkY - 1) * nBlkX + (i < nBlkX ? i : nBlkX - 1)];
+}
+
+struct InterPlane {
+    int plane, W, H, limitW, limitH, pel, logPel, nBlkXP, time256;
+    const short *vxB, *vyB, *vxF, *vyF, *vxBB, *vyBB, *vxFF, *vyFF; // small fields of this plane
+    const int *maskB, *maskF;                                       // padded small occlusion masks
+    ResizeTables t;
+    SuperPlane S;
+};
+
+MVB_HD void inter_vector(const InterPlane &P, const short *vxs, const short *vys, int x, int y, int &VX, int &VY) {
+    const int voff = P.t.voff[y], vwt = P.t.vwt[y], hoff = P.t.hoff[x], hwt = P.t.hwt[x];
+    VX = (short)limit_vector(resize_sample<short>(vxs, P.nBlkXP, voff, vwt, hoff, hwt), x, P.limitW, P.pel);
+    VY = (short)limit_vector(resize_sample<short>(vys, P.nBlkXP, voff, vwt, hoff, hwt), y, P.limitH, P.pel);
+}
+
+// One output sample of FlowInterSimple (method 0) / FlowInter (1) / FlowInterExtra (2), MaskFun.cpp:376-546.
+// right_super = the frame the backward vectors point at (prefB), left_super = the current frame (prefF).
+template <typename T>
+MVB_HD int flow_inter_sample(const InterPlane &P, int method, const uint8_t *right_super, const uint8_t *left_super, int x, int y) {
+    const int voff = P.t.voff[y], vwt = P.t.vwt[y], hoff = P.t.hoff[x], hwt = P.t.hwt[x];
+    const int MB = resize_sample<int>(P.maskB, P.nBlkXP, voff, vwt, hoff, hwt) & 255;
+    const int MF = resize_sample<int>(P.maskF, P.nBlkXP, voff, vwt, hoff, hwt) & 255;
+    int VXB, VYB, VXF, VYF;
+    inter_vector(P, P.vxB, P.vyB, x, y, VXB, VYB);
+    inter_vector(P, P.vxF, P.vyF, x, y, VXF, VYF);
+    const int fx = (x + P.S.hpad) << P.logPel, fy = (y + P.S.vpad) << P.logPel, time256 = P.time256;
+    if (method == 0 && time256 == 128) { // :464-485
+        const int dstF = finest_sample<T>(left_super, P.S, P.logPel, fx + (VXF >> 1), fy + (VYF >> 1));
+        const int dstB = finest_sample<T>(right_super, P.S, P.logPel, fx + (VXB >> 1), fy + (VYB >> 1));
+        return (((dstF + dstB) << 8) + (dstB - dstF) * (MF - MB)) >> 9;
+    }
+    const int dstF = finest_sample<T>(left_super, P.S, P.logPel, fx + ((VXF * time256) >> 8), fy + ((VYF * time256) >> 8));
+    const int dstB = finest_sample<T>(right_super, P.S, P.logPel, fx + ((VXB * (256 - time256)) >> 8), fy + ((VYB * (256 - time256)) >> 8));
+    if (method == 0) // :486-510
+        return (((dstF * (255 - MF) + dstB * MF + 255) >> 8) * (256 - time256) + ((dstB * (255 - MB) + dstF * MB + 255) >> 8) * time256) >> 8;
+    if (method == 1) { // :376-418 (64-bit intermediates)
+        const long long dF = dstF, dB = dstB;
+        const int dstF0 = finest_sample<T>(left_super, P.S, P.logPel, fx, fy), dstB0 = finest_sample<T>(right_super, P.S, P.logPel, fx, fy);
+        return (int)((((dF * (255 - MF) + ((MF * (dB * (255 - MB) + MB * dstF0) + 255) >> 8) + 255) >> 8) * (256 - time256) +
+                      ((dB * (255 - MB) + ((MB * (dF * (255 - MF) + MF * dstB0) + 255) >> 8) + 255) >> 8) * time256) >>
+                     8);
+    }
+    int VXBB, VYBB, VXFF, VYFF; // :421-461
+    inter_vector(P, P.vxBB, P.vyBB, x, y, VXBB, VYBB);
+    inter_vector(P, P.vxFF, P.vyFF, x, y, VXFF, VYFF);
+    const int dstFF = finest_sample<T>(left_super, P.S, P.logPel, fx + ((VXFF * time256) >> 8), fy + ((VYFF * time256) >> 8));
+    const int dstBB = finest_sample<T>(right_super, P.S, P.logPel, fx + ((VXBB * (256 - time256)) >> 8), fy + ((VYBB * (256 - time256)) >> 8));
+    const int minfb = dstB < dstF ? dstB : dstF, maxfb = dstB > dstF ? dstB : dstF;
+    const int mBB = dstBB < maxfb ? dstBB : maxfb, mFF = dstFF < maxfb ? dstFF : maxfb;
+    const int medianBB = minfb > mBB ? minfb : mBB, medianFF = minfb > mFF ? minfb : mFF;
+    return (((medianBB * MF + dstF * (255 - MF) + 255) >> 8) * (256 - time256) + ((medianFF * MB + dstB * (255 - MB) + 255) >> 8) * time256) >> 8;
+}
+
+// Blend, MaskFun.cpp:349-373
+MVB_HD int blend_sample(int src, int ref, int time256) { return (src * (256 - time256) + ref * time256) >> 8; }
+
 } // namespace flowdev
 } // namespace mvb200

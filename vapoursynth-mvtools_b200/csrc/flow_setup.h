@@ -93,5 +93,36 @@ inline MaskPlane make_mask_plane(const mvb200_mask_params *mp, int plane, const 
     return B;
 }
 
+struct InterSmall { // the small fields of one plane type
+    const short *vxB, *vyB, *vxF, *vyF, *vxBB, *vyBB, *vxFF, *vyFF;
+};
+
+inline InterPlane make_inter_plane(const mvb200_flowinter_params *p, int time256, int plane, const InterSmall &v, const int *maskB, const int *maskF, const ResizeTables &t, const SuperPlane &S) {
+    InterPlane P;
+    memset(&P, 0, sizeof(P));
+    P.plane = plane;
+    P.W = plane ? p->nWidthUV : p->vd.nWidth;
+    P.H = plane ? p->nHeightUV : p->vd.nHeight;
+    P.limitW = P.W; // simpleInit, MVFlowInter.c:662-664
+    P.limitH = P.H;
+    P.pel = p->vd.nPel;
+    P.logPel = ilog2_pel(p->vd.nPel);
+    P.nBlkXP = p->nBlkXP;
+    P.time256 = time256;
+    P.vxB = v.vxB;
+    P.vyB = v.vyB;
+    P.vxF = v.vxF;
+    P.vyF = v.vyF;
+    P.vxBB = v.vxBB;
+    P.vyBB = v.vyBB;
+    P.vxFF = v.vxFF;
+    P.vyFF = v.vyFF;
+    P.maskB = maskB;
+    P.maskF = maskF;
+    P.t = t;
+    P.S = S;
+    return P;
+}
+
 } // namespace flowdev
 } // namespace mvb200

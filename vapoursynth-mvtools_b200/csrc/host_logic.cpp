@@ -688,6 +688,72 @@ int mvb200_flow_init(const mvb200_flow_args *a, const mvb200_super_params *sp, c
     return 0;
 }
 
+int mvb200_flowinter_init(const mvb200_flowinter_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd_bw, const mvb200_analysis_data *vd_fw, int num_frames, mvb200_flowinter_params *d) {
+    memset(d, 0, sizeof(*d));
+    // MVFlowInter.c:466-503 (time and ml are floats there)
+    const float time = (a->time == a->time) ? (float)a->time : 50.0f;
+    const float ml = (a->ml == a->ml) ? (float)a->ml : 100.0f;
+    d->blend = GIVEN(a->blend) ? a->blend != 0 : 1;
+    d->nSCD1 = GIVEN64(a->thscd1) ? a->thscd1 : 400;
+    d->nSCD2 = GIVEN(a->thscd2) ? a->thscd2 : 130;
+    if (time < 0.0f || time > 100.0f)
+        return set_error("FlowInter: time must be between 0 and 100 %% (inclusive).");
+    if (ml <= 0.0f)
+        return set_error("FlowInter: ml must be greater than 0.");
+    d->time256 = (int)(time * 256.0f / 100.0f);
+    d->ml = ml;
+    d->vd = *vd_bw;
+    // :537-580
+    if (scale_thscd(&d->nSCD1, &d->nSCD2, &d->vd, "FlowInter"))
+        return 1;
+    if (check_similarity(vd_bw, vd_fw, "FlowInter", "mvbw", "mvfw"))
+        return 1;
+    if (vd_bw->nDeltaFrame <= 0 || vd_fw->nDeltaFrame <= 0)
+        return set_error("FlowInter: cannot use motion vectors with absolute frame references.");
+    if (vd_fw->nDeltaFrame != vd_bw->nDeltaFrame)
+        return set_error("FlowInter: mvbw and mvfw must be generated with the same delta.");
+    if (!vd_bw->isBackward)
+        return set_error("FlowInter: mvbw must be generated with isb=True.");
+    if (vd_fw->isBackward)
+        return set_error("FlowInter: mvfw must be generated with isb=False.");
+    // :617-635
+    if (vd_bw->nHeight != sp->height || vd_bw->nWidth != sp->super_width - sp->hpad * 2 || vd_bw->nPel != sp->pel)
+        return set_error("FlowInter: wrong source or super clip frame size.");
+    if (sp->bits > 16 || sp->ssw > 1 || sp->ssh > 1)
+        return set_error("FlowInter: input clip must be GRAY, 420, 422, 440, or 444, up to 16 bits, with constant dimensions.");
+    d->mode_primary = 2;
+    d->mode_fallback = 1;
+    // :638-659
+    const mvb200_analysis_data *vd = vd_bw;
+    d->nBlkXP = vd->nBlkX;
+    d->nBlkYP = vd->nBlkY;
+    while (d->nBlkXP * (vd->nBlkSizeX - vd->nOverlapX) + vd->nOverlapX < vd->nWidth)
+        d->nBlkXP++;
+    while (d->nBlkYP * (vd->nBlkSizeY - vd->nOverlapY) + vd->nOverlapY < vd->nHeight)
+        d->nBlkYP++;
+    d->nWidthP = d->nBlkXP * (vd->nBlkSizeX - vd->nOverlapX) + vd->nOverlapX;
+    d->nHeightP = d->nBlkYP * (vd->nBlkSizeY - vd->nOverlapY) + vd->nOverlapY;
+    d->nWidthPUV = d->nWidthP / vd->xRatioUV;
+    d->nHeightPUV = d->nHeightP / vd->yRatioUV;
+    d->nHeightUV = vd->nHeight / vd->yRatioUV;
+    d->nWidthUV = vd->nWidth / vd->xRatioUV;
+    d->nHPaddingUV = vd->nHPadding / vd->xRatioUV;
+    d->nVPaddingUV = vd->nVPadding / vd->yRatioUV;
+    d->VPitchY = (d->nWidthP + 15) & (~15);
+    d->VPitchUV = (d->nWidthPUV + 15) & (~15);
+    d->bits = sp->bits;
+    d->ssw = sp->ssw;
+    d->ssh = sp->ssh;
+    d->gray = sp->gray;
+    d->nplanes = sp->nplanes;
+    d->super_hpad = sp->hpad;
+    d->super_vpad = sp->vpad;
+    d->super_pel = sp->pel;
+    d->super_levels = sp->levels;
+    d->num_frames = num_frames;
+    return 0;
+}
+
 // InitTables, SimpleResize.cpp:26-56 (single-precision arithmetic, evaluated in the reference's order)
 void mvb200_simple_resize_tables(int out, int in, int32_t *offsets, int32_t *weights) {
     const float leftmost = 0.5f, rightmost = in - 0.5f;

@@ -137,6 +137,18 @@ class FlowParams(C.Structure):
                             "nHPaddingUV", "nVPaddingUV", "VPitchY", "VPitchUV", "num_frames")]
 
 
+class FlowInterArgs(C.Structure):
+    _fields_ = [("time", C.c_double), ("ml", C.c_double), ("blend", i32), ("thscd1", i64), ("thscd2", i32)]
+
+
+class FlowInterParams(C.Structure):
+    _fields_ = [("vd", AnalysisData), ("time256", i32), ("blend", i32), ("ml", C.c_double), ("nSCD1", i64), ("nSCD2", i32),
+                ("mode_primary", i32), ("mode_fallback", i32)] + \
+        [(n, i32) for n in ("bits", "ssw", "ssh", "gray", "nplanes", "super_hpad", "super_vpad", "super_pel", "super_levels",
+                            "nBlkXP", "nBlkYP", "nWidthP", "nHeightP", "nWidthPUV", "nHeightPUV", "nWidthUV", "nHeightUV",
+                            "nHPaddingUV", "nVPaddingUV", "VPitchY", "VPitchUV", "num_frames")]
+
+
 class FrameLayout(C.Structure):
     _fields_ = [("nplanes", i32), ("bytes_per_sample", i32), ("plane_w", i32 * 3), ("plane_h", i32 * 3),
                 ("pitch", i64 * 3), ("offset", i64 * 3), ("frame_bytes", i64)]
@@ -215,6 +227,10 @@ def lib():
         L.mvb200_finest_batch.argtypes = [vp, PP(SuperParams), vp, i32, vp]
         L.mvb200_flow_frame.argtypes = [vp, PP(FlowParams), PP(SuperParams), PP(vp), PP(C.c_ssize_t), vp, i32, PP(vp), PP(C.c_ssize_t), PP(i32)]
         L.mvb200_flow_batch.argtypes = [vp, PP(FlowParams), PP(SuperParams), vp, vp, i32, i32, vp, i64, vp]
+        L.mvb200_flowinter_init.argtypes = [PP(FlowInterArgs), PP(SuperParams), PP(AnalysisData), PP(AnalysisData), i32, PP(FlowInterParams)]
+        L.mvb200_flowinter_frame.argtypes = [vp, PP(FlowInterParams), PP(SuperParams), i32, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, vp, vp, vp, PP(vp), PP(C.c_ssize_t), PP(i32)]
+        L.mvb200_blend_frame.argtypes = [vp, PP(SuperParams), i32, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
+        L.mvb200_flowinter_batch.argtypes = [vp, PP(FlowInterParams), PP(SuperParams), vp, vp, i32, i32, vp, vp, i64, vp]
         _LIB = L
     return _LIB
 
@@ -347,6 +363,18 @@ def flow_params(sp, vd, num_frames, **kw):
         raise TypeError("Flow: unknown argument(s) %s" % sorted(kw))
     out = FlowParams()
     _check(lib().mvb200_flow_init(C.byref(a), C.byref(sp), C.byref(vd), num_frames, C.byref(out)))
+    return out
+
+
+def flowinter_params(sp, vd_bw, vd_fw, num_frames, **kw):
+    a = FlowInterArgs()
+    a.time, a.ml = _opt(kw, "time", float("nan"), float), _opt(kw, "ml", float("nan"), float)
+    a.blend, a.thscd2 = _opt(kw, "blend", UNSET), _opt(kw, "thscd2", UNSET)
+    a.thscd1 = _opt(kw, "thscd1", UNSET64)
+    if kw:
+        raise TypeError("FlowInter: unknown argument(s) %s" % sorted(kw))
+    out = FlowInterParams()
+    _check(lib().mvb200_flowinter_init(C.byref(a), C.byref(sp), C.byref(vd_bw), C.byref(vd_fw), num_frames, C.byref(out)))
     return out
 
 
@@ -531,3 +559,24 @@ class Context:
         usable = i32(0)
         _check(lib().mvb200_flow_frame(self._h, C.byref(fp), C.byref(sp), r, rs, vectors.ctypes.data, field_shift, d, ds, C.byref(usable)))
         return dst if usable.value else None
+
+    def flowinter_frame(self, p, sp, time256, left_super, right_super, vec_b, vec_f, vec_bb=None, vec_ff=None):
+        """-> planes, or None when the vectors are not usable (the caller blends or keeps the source frame)"""
+        w = [p.vd.nWidth, p.nWidthUV, p.nWidthUV][: p.nplanes]
+        h = [p.vd.nHeight, p.nHeightUV, p.nHeightUV][: p.nplanes]
+        dst = alloc_planes(w, h, p.bits, fill=0xA5)
+        l, ls = plane_ptrs(left_super)
+        r, rs = plane_ptrs(right_super)
+        d, ds = plane_ptrs(dst)
+        usable = i32(0)
+        ptr = lambda v: None if v is None else v.ctypes.data
+        _check(lib().mvb200_flowinter_frame(self._h, C.byref(p), C.byref(sp), time256, l, ls, r, rs, ptr(vec_b), ptr(vec_f), ptr(vec_bb), ptr(vec_ff), d, ds, C.byref(usable)))
+        return dst if usable.value else None
+
+    def blend_frame(self, sp, time256, src, ref):
+        dst = alloc_planes([a.shape[1] for a in src], [a.shape[0] for a in src], sp.bits, fill=0xA5)
+        s, ss = plane_ptrs(src)
+        r, rs = plane_ptrs(ref)
+        d, ds = plane_ptrs(dst)
+        _check(lib().mvb200_blend_frame(self._h, C.byref(sp), time256, s, ss, r, rs, d, ds))
+        return dst

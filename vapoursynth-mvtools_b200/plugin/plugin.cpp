@@ -2,7 +2,7 @@
 //
 // Exports exactly what the reference's module exports (EntryPoint.c:28-50):
 // VapourSynthPluginInit2, which configures the plugin as "com.nodame.mvtools" / namespace
-// "mv" and registers Super, Analyse, Recalculate, Compensate, Degrain1..6, Mask, Finest, Flow and SCDetection with the reference's
+// "mv" and registers Super, Analyse, Recalculate, Compensate, Degrain1..6, Mask, Finest, Flow, FlowInter and SCDetection with the reference's
 // byte-identical argument strings, so existing .vpy scripts load unchanged.  Every filter keeps the reference's
 // create-time validation (messages included, they come from mvb200_*_init), frame
 // properties (Super_*, MVTools_MVAnalysisData, MVTools_vectors) and request pattern; the
@@ -1194,6 +1194,183 @@ void VS_CC flowCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const V
     vsapi->createVideoFilter(out, "Flow", data->vi, flowGetFrame, flowFree, fmParallel, deps, 3, data, core);
 }
 
+// -------------------------------------------------------------- FlowInter
+// mvflowinterCreate / GetFrame, MVFlowInter.c:83-713 (super frames are read where the reference reads its mv.Finest clip)
+struct FlowInterData {
+    VSNode *node, *super, *mvbw, *mvfw;
+    const VSVideoInfo *vi, *supervi;
+    mvb200_super_params sp, clipsp;
+    mvb200_flowinter_params p;
+};
+
+const uint8_t *vectorsOf(const VSAPI *vsapi, const VSFrame *f, bool *missing) {
+    int e = 0;
+    const uint8_t *v = (const uint8_t *)vsapi->mapGetData(vsapi->getFramePropertiesRO(f), "MVTools_vectors", 0, &e);
+    if (e)
+        *missing = true;
+    return e ? nullptr : v;
+}
+
+const VSFrame *VS_CC flowInterGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    FlowInterData *d = (FlowInterData *)instanceData;
+    const int off = d->p.vd.nDeltaFrame, N = d->vi->numFrames;
+    const bool inRange = n + off < N;
+    if (activationReason == arInitial) { // :89-105
+        if (inRange) {
+            vsapi->requestFrameFilter(n, d->mvfw, frameCtx);
+            vsapi->requestFrameFilter(n + off, d->mvfw, frameCtx);
+            vsapi->requestFrameFilter(n, d->mvbw, frameCtx);
+            vsapi->requestFrameFilter(n + off, d->mvbw, frameCtx);
+            vsapi->requestFrameFilter(n, d->super, frameCtx);
+            vsapi->requestFrameFilter(n + off, d->super, frameCtx);
+        }
+        vsapi->requestFrameFilter(n, d->node, frameCtx);
+        vsapi->requestFrameFilter(VSMIN(n + off, N - 1), d->node, frameCtx);
+    } else if (activationReason == arAllFramesReady) {
+        std::string msg;
+        int rc = 0;
+        int32_t usable = 0;
+        VSFrame *dst = nullptr;
+        if (inRange) {
+            const VSFrame *mvF = vsapi->getFrameFilter(n + off, d->mvfw, frameCtx), *mvB = vsapi->getFrameFilter(n, d->mvbw, frameCtx);
+            const VSFrame *mvFF = vsapi->getFrameFilter(n, d->mvfw, frameCtx), *mvBB = vsapi->getFrameFilter(n + off, d->mvbw, frameCtx);
+            const VSFrame *left = vsapi->getFrameFilter(n, d->super, frameCtx), *right = vsapi->getFrameFilter(n + off, d->super, frameCtx);
+            bool missing = false;
+            const uint8_t *vb = vectorsOf(vsapi, mvB, &missing), *vf = vectorsOf(vsapi, mvF, &missing), *vbb = vectorsOf(vsapi, mvBB, &missing), *vff = vectorsOf(vsapi, mvFF, &missing);
+            dst = vsapi->newVideoFrame(&d->vi->format, d->vi->width, d->vi->height, left, core);
+            if (missing) {
+                rc = 1;
+                msg = "MVTools_vectors property missing";
+            } else {
+                const uint8_t *lp[3], *rp[3];
+                ptrdiff_t ls[3], rs[3];
+                uint8_t *dp_[3];
+                ptrdiff_t ds[3];
+                planesRO(vsapi, left, d->supervi->format.numPlanes, lp, ls);
+                planesRO(vsapi, right, d->supervi->format.numPlanes, rp, rs);
+                planesRW(vsapi, dst, d->vi->format.numPlanes, dp_, ds);
+                std::lock_guard<std::mutex> lock(g_engine_mutex);
+                mvb200_ctx *ctx = engine(msg);
+                rc = ctx ? mvb200_flowinter_frame(ctx, &d->p, &d->sp, d->p.time256, lp, ls, rp, rs, vb, vf, vbb, vff, dp_, ds, &usable) : 1;
+                if (ctx && rc)
+                    msg = mvb200_last_error();
+            }
+            vsapi->freeFrame(mvF);
+            vsapi->freeFrame(mvB);
+            vsapi->freeFrame(mvFF);
+            vsapi->freeFrame(mvBB);
+            vsapi->freeFrame(left);
+            vsapi->freeFrame(right);
+        }
+        if (!rc && !usable) { // poor estimation, :412-447
+            vsapi->freeFrame(dst);
+            dst = nullptr;
+            const VSFrame *src = vsapi->getFrameFilter(n, d->node, frameCtx);
+            if (!d->p.blend)
+                return src; // like ChangeFPS
+            const VSFrame *ref = vsapi->getFrameFilter(VSMIN(n + off, N - 1), d->node, frameCtx);
+            dst = vsapi->newVideoFrame(&d->vi->format, d->vi->width, d->vi->height, src, core);
+            const uint8_t *sp_[3], *rp[3];
+            ptrdiff_t ss[3], rs[3];
+            uint8_t *dp_[3];
+            ptrdiff_t ds[3];
+            planesRO(vsapi, src, d->vi->format.numPlanes, sp_, ss);
+            planesRO(vsapi, ref, d->vi->format.numPlanes, rp, rs);
+            planesRW(vsapi, dst, d->vi->format.numPlanes, dp_, ds);
+            {
+                std::lock_guard<std::mutex> lock(g_engine_mutex);
+                mvb200_ctx *ctx = engine(msg);
+                rc = ctx ? mvb200_blend_frame(ctx, &d->clipsp, d->p.time256, sp_, ss, rp, rs, dp_, ds) : 1;
+                if (ctx && rc)
+                    msg = mvb200_last_error();
+            }
+            vsapi->freeFrame(src);
+            vsapi->freeFrame(ref);
+        }
+        if (rc) {
+            vsapi->setFilterError(("FlowInter: " + msg).c_str(), frameCtx);
+            vsapi->freeFrame(dst);
+            return nullptr;
+        }
+        return dst;
+    }
+    return nullptr;
+}
+
+void VS_CC flowInterFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
+    FlowInterData *d = (FlowInterData *)instanceData;
+    vsapi->freeNode(d->node);
+    vsapi->freeNode(d->super);
+    vsapi->freeNode(d->mvbw);
+    vsapi->freeNode(d->mvfw);
+    delete d;
+}
+
+void VS_CC flowInterCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const VSAPI *vsapi) {
+    mvb200_flowinter_args a;
+    a.time = argFloat(vsapi, in, "time");
+    a.ml = argFloat(vsapi, in, "ml");
+    a.blend = argInt(vsapi, in, "blend");
+    a.thscd1 = argInt64(vsapi, in, "thscd1");
+    a.thscd2 = argInt(vsapi, in, "thscd2");
+    // argument checks before any clip is touched (MVFlowInter.c:493-502; float comparisons as there)
+    if (a.time == a.time && ((float)a.time < 0.0f || (float)a.time > 100.0f)) {
+        vsapi->mapSetError(out, "FlowInter: time must be between 0 and 100 % (inclusive).");
+        return;
+    }
+    if (a.ml == a.ml && (float)a.ml <= 0.0f) {
+        vsapi->mapSetError(out, "FlowInter: ml must be greater than 0.");
+        return;
+    }
+    FlowInterData d;
+    memset(&d, 0, sizeof(d));
+    auto freeAll = [&]() {
+        vsapi->freeNode(d.node);
+        vsapi->freeNode(d.super);
+        vsapi->freeNode(d.mvbw);
+        vsapi->freeNode(d.mvfw);
+    };
+    d.super = vsapi->mapGetNode(in, "super", 0, nullptr);
+    d.supervi = vsapi->getVideoInfo(d.super);
+    std::string msg;
+    mvb200_analysis_data vdb, vdf;
+    if (!superFromClip(d.super, vsapi, "FlowInter", &d.sp, msg)) {
+        vsapi->mapSetError(out, msg.c_str());
+        freeAll();
+        return;
+    }
+    d.mvbw = vsapi->mapGetNode(in, "mvbw", 0, nullptr);
+    d.mvfw = vsapi->mapGetNode(in, "mvfw", 0, nullptr);
+    if (!adataFromClip(d.mvbw, vsapi, "FlowInter", "mvbw", &vdb, msg) || !adataFromClip(d.mvfw, vsapi, "FlowInter", "mvfw", &vdf, msg)) {
+        vsapi->mapSetError(out, msg.c_str());
+        freeAll();
+        return;
+    }
+    d.node = vsapi->mapGetNode(in, "clip", 0, nullptr);
+    d.vi = vsapi->getVideoInfo(d.node);
+    if (mvb200_flowinter_init(&a, &d.sp, &vdb, &vdf, d.vi->numFrames, &d.p)) {
+        vsapi->mapSetError(out, mvb200_last_error());
+        freeAll();
+        return;
+    }
+    if (!formatOk(d.vi)) {
+        vsapi->mapSetError(out, "FlowInter: input clip must be GRAY, 420, 422, 440, or 444, up to 16 bits, with constant dimensions.");
+        freeAll();
+        return;
+    }
+    if (d.vi->width != vdb.nWidth || d.vi->height != vdb.nHeight || d.vi->format.bitsPerSample != d.sp.bits) {
+        vsapi->mapSetError(out, "FlowInter: wrong source or super clip frame size.");
+        freeAll();
+        return;
+    }
+    // the source clip described as the engine describes clips (for the blend of unusable frames)
+    memset(&d.clipsp, 0, sizeof(d.clipsp));
+    d.clipsp = d.sp;
+    FlowInterData *data = new FlowInterData(d);
+    VSFilterDependency deps[4] = {{data->node, rpGeneral}, {data->super, rpGeneral}, {data->mvbw, rpGeneral}, {data->mvfw, rpGeneral}};
+    vsapi->createVideoFilter(out, "FlowInter", data->vi, flowInterGetFrame, flowInterFree, fmParallel, deps, 4, data, core);
+}
+
 } // namespace
 
 VS_EXTERNAL_API(void) VapourSynthPluginInit2(VSPlugin *plugin, const VSPLUGINAPI *vspapi) {
@@ -1233,4 +1410,6 @@ VS_EXTERNAL_API(void) VapourSynthPluginInit2(VSPlugin *plugin, const VSPLUGINAPI
     vspapi->registerFunction("Finest", "super:vnode;opt:int:opt;", "clip:vnode;", finestCreate, nullptr, plugin);
     vspapi->registerFunction("Flow", "clip:vnode;super:vnode;vectors:vnode;time:float:opt;mode:int:opt;fields:int:opt;thscd1:int:opt;thscd2:int:opt;opt:int:opt;tff:int:opt;", "clip:vnode;", flowCreate, nullptr, plugin);
     vspapi->registerFunction("SCDetection", "clip:vnode;vectors:vnode;thscd1:int:opt;thscd2:int:opt;", "clip:vnode;", scdCreate, nullptr, plugin);
+    // MVFlowInter.c:696-711
+    vspapi->registerFunction("FlowInter", "clip:vnode;super:vnode;mvbw:vnode;mvfw:vnode;time:float:opt;ml:float:opt;blend:int:opt;thscd1:int:opt;thscd2:int:opt;opt:int:opt;", "clip:vnode;", flowInterCreate, nullptr, plugin);
 }
