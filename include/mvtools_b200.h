@@ -24,6 +24,7 @@
  *   mvfinestCreate/GetFrame      MVFinest.c:47-207      mvb200_finest_layout / _frame / _batch
  *   mvflowCreate/GetFrame        MVFlow.cpp:157-593     mvb200_flow_init / _frame / _batch
  *   mvflowinterCreate/GetFrame   MVFlowInter.c:83-690   mvb200_flowinter_init / _frame / _batch, mvb200_blend_frame
+ *   mvflowfpsCreate/GetFrame     MVFlowFPS.c:86-928     mvb200_flowfps_init / _position + mvb200_flowinter_frame
  *
  * The VapourSynth plugin (vapoursynth-mvtools_b200/plugin, exporting
  * VapourSynthPluginInit2 like EntryPoint.c:28-50) is a thin host-side glue over
@@ -285,6 +286,24 @@ typedef struct mvb200_flowinter_params {
     int32_t num_frames;
 } mvb200_flowinter_params;
 
+/* mv.FlowFPS (MVFlowFPS.c:563-928): frame-rate conversion; the per-frame work is mvb200_flowinter_frame */
+typedef struct mvb200_flowfps_args {
+    int64_t num, den;             /* MVB200_UNSET64 = default (25, 1) */
+    int32_t mask;                 /* MVB200_UNSET = default (2) */
+    double ml;                    /* NaN = default (100.0) */
+    int32_t blend;
+    int64_t thscd1;
+    int32_t thscd2;
+} mvb200_flowfps_args;
+
+typedef struct mvb200_flowfps_params {
+    mvb200_flowinter_params inter; /* time256 is per output frame (mvb200_flowfps_position) */
+    int32_t maskmode;
+    int64_t fa, fb;               /* output frame n lies at n fa / fb in the input clip (MVFlowFPS.c:747-751) */
+    int64_t fps_num, fps_den;     /* of the output clip (setFPS, :547-561) */
+    int32_t num_frames_in, num_frames_out;
+} mvb200_flowfps_params;
+
 /* ------------------------------------------------------------- host logic */
 /* (pure host code: usable without a GPU; restates the reference's *Create) */
 
@@ -320,6 +339,13 @@ MVB200_API int mvb200_flow_init(const mvb200_flow_args *a, const mvb200_super_pa
 
 /* MVFlowInter.c:458-690.  vd_bw / vd_fw: the analysis data of mvbw / mvfw. */
 MVB200_API int mvb200_flowinter_init(const mvb200_flowinter_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd_bw, const mvb200_analysis_data *vd_fw, int num_frames, mvb200_flowinter_params *out);
+
+/* MVFlowFPS.c:563-800.  (fps_num, fps_den, clip_w, clip_h, num_frames) describe the input clip. */
+MVB200_API int mvb200_flowfps_init(const mvb200_flowfps_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd_bw, const mvb200_analysis_data *vd_fw, int64_t fps_num, int64_t fps_den, int clip_w, int clip_h,
+                                   int num_frames, mvb200_flowfps_params *out);
+/* MVFlowFPS.c:118-141: output frame n lies between input frames *nleft and *nleft + delta, *time256 / 256 of the way
+ * (0 and 256 mean "that input frame itself") */
+MVB200_API void mvb200_flowfps_position(const mvb200_flowfps_params *p, int n, int32_t *nleft, int32_t *time256);
 
 /* InitTables, SimpleResize.cpp:26-56: offsets[out] and weights[out] (14-bit) of the bilinear resizer the Mask / Flow
  * filters upsize their per-block fields with (float arithmetic, restated on the host; uploaded once per configuration). */

@@ -727,7 +727,69 @@ static thread_local std::string t_err;
 
 MVS_API const char *mvs_last_error() { return t_err.c_str(); }
 
-MVS_API void *mvs_core_create() { return new VSCore; }
+
+// ------------------------------------------------ built-in std.AssumeFPS
+// mv.FlowFPS / mv.BlockFPS finish by invoking std.AssumeFPS (MVFlowFPS.c:883-910): a pass-through that changes the
+// frame rate in the video info and stamps _DurationNum / _DurationDen on every frame, as VapourSynth's does.
+namespace {
+struct AssumeFPSData {
+    VSNode *node;
+    VSVideoInfo vi;
+};
+const VSFrame *VS_CC assumeFpsGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    AssumeFPSData *d = (AssumeFPSData *)instanceData;
+    if (activationReason == arInitial) {
+        vsapi->requestFrameFilter(n, d->node, frameCtx);
+    } else if (activationReason == arAllFramesReady) {
+        const VSFrame *src = vsapi->getFrameFilter(n, d->node, frameCtx);
+        VSFrame *dst = vsapi->copyFrame(src, core);
+        vsapi->freeFrame(src);
+        VSMap *props = vsapi->getFramePropertiesRW(dst);
+        vsapi->mapSetInt(props, "_DurationNum", d->vi.fpsDen, maReplace);
+        vsapi->mapSetInt(props, "_DurationDen", d->vi.fpsNum, maReplace);
+        return dst;
+    }
+    return nullptr;
+}
+void VS_CC assumeFpsFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
+    AssumeFPSData *d = (AssumeFPSData *)instanceData;
+    vsapi->freeNode(d->node);
+    delete d;
+}
+void VS_CC assumeFpsCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const VSAPI *vsapi) {
+    int err = 0;
+    AssumeFPSData *d = new AssumeFPSData;
+    d->node = vsapi->mapGetNode(in, "clip", 0, nullptr);
+    d->vi = *vsapi->getVideoInfo(d->node);
+    int64_t num = vsapi->mapGetInt(in, "fpsnum", 0, &err);
+    int64_t den = vsapi->mapGetInt(in, "fpsden", 0, &err);
+    if (err)
+        den = 1;
+    if (num <= 0 || den <= 0) {
+        vsapi->mapSetError(out, "AssumeFPS: invalid framerate specified");
+        vsapi->freeNode(d->node);
+        delete d;
+        return;
+    }
+    d->vi.fpsNum = num;
+    d->vi.fpsDen = den;
+    VSFilterDependency deps[1] = {{d->node, rpStrictSpatial}};
+    vsapi->createVideoFilter(out, "AssumeFPS", &d->vi, assumeFpsGetFrame, assumeFpsFree, fmParallel, deps, 1, d, core);
+}
+VSPlugin *makeStdPlugin(VSCore *core) {
+    VSPlugin *p = new VSPlugin;
+    p->core = core;
+    configPlugin("com.vapoursynth.std", "std", "minivs built-ins", 1, VAPOURSYNTH_API_VERSION, 0, p);
+    registerFunction("AssumeFPS", "clip:vnode;src:vnode:opt;fpsnum:int:opt;fpsden:int:opt;", "clip:vnode;", assumeFpsCreate, nullptr, p);
+    return p;
+}
+} // namespace
+
+MVS_API void *mvs_core_create() {
+    VSCore *core = new VSCore;
+    core->plugins.push_back(makeStdPlugin(core));
+    return core;
+}
 
 MVS_API void mvs_core_free(void *core) { delete (VSCore *)core; }
 

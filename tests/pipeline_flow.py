@@ -21,22 +21,23 @@ FLOW = {
               dict(kind=3), dict(kind=4, ml=20.0, vec=1), dict(kind=5, ysc=77), dict(kind=0, gamma=1.7, ml=30.0, thscd1=200, thscd2=40, ysc=200)],
         flow=[dict(), dict(time=50.0, vec=1), dict(mode=1, time=70.0), dict(mode=1, vec=1, thscd1=250, thscd2=60)],
         scd=[dict(), dict(vec=1, thscd1=150, thscd2=30)], finest=True,
-        inter=[dict(), dict(time=25.0, ml=40.0), dict(time=80.0, blend=0, thscd1=250, thscd2=60), dict(time=0.0), dict(time=100.0)]),
-    "blk16_ov8_pel2_p16_r3": dict(flow=[dict(time=33.0), dict(mode=1, vec=1)], scd=[dict()], finest=True, inter=[dict(), dict(time=70.0, ml=20.0)]),
-    "p10_444_blk8_pel4_bicubic": dict(flow=[dict(time=80.0), dict(mode=1, time=45.0, vec=1)], finest=True, scd=[dict(thscd2=10)], inter=[dict(time=40.0)]),
+        inter=[dict(), dict(time=25.0, ml=40.0), dict(time=80.0, blend=0, thscd1=250, thscd2=60), dict(time=0.0), dict(time=100.0)],
+        fps=[dict(num=50, den=1), dict(num=60, den=1, mask=0), dict(num=30000, den=1001, mask=1, ml=50.0), dict(num=50, den=1, mask=0), dict(num=40, den=1, mask=2, blend=0, thscd1=250, thscd2=60)]),
+    "blk16_ov8_pel2_p16_r3": dict(flow=[dict(time=33.0), dict(mode=1, vec=1)], scd=[dict()], finest=True, inter=[dict(), dict(time=70.0, ml=20.0)], fps=[dict(num=50, den=1, mask=0), dict(num=75, den=2, mask=1)]),
+    "p10_444_blk8_pel4_bicubic": dict(flow=[dict(time=80.0), dict(mode=1, time=45.0, vec=1)], finest=True, scd=[dict(thscd2=10)], inter=[dict(time=40.0)], fps=[dict(num=60, den=1)]),
     "gray_blk4_pel1_rf0": dict(mask=[dict(kind=0), dict(kind=2, time=50.0), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=25.0)], finest=True, scd=[dict()], inter=[dict(time=60.0, ml=10.0)]),
     "c1_640x360_p8_blk8_pel1": dict(mask=[dict(kind=1), dict(kind=2, vec=1)], flow=[dict(time=60.0), dict(mode=1)], scd=[dict()], inter=[dict(), dict(time=33.0, blend=0)]),
     "p8_422_blk8x4_sharp0_rf1": dict(mask=[dict(kind=0, ml=10.0), dict(kind=1, time=0.0), dict(kind=2, vec=1, ml=10.0), dict(kind=5)], flow=[dict(vec=1), dict(mode=1, time=100.0)], finest=True,
                                      scd=[dict(vec=1)], inter=[dict(time=45.0)]),
     "noise_badblocks_blk8": dict(mask=[dict(kind=0, ysc=9), dict(kind=1, thscd1=16000, thscd2=255), dict(kind=2, thscd1=16000, thscd2=255, ml=400.0), dict(kind=5, thscd1=16000, thscd2=255, ml=3.0)],
                                  flow=[dict(), dict(thscd1=16000, thscd2=255, time=90.0), dict(mode=1, thscd1=16000, thscd2=255, vec=1)], scd=[dict(), dict(thscd1=16000, thscd2=255)],
-                                 inter=[dict(), dict(blend=0), dict(thscd1=16000, thscd2=255, ml=300.0, time=20.0)]),
+                                 inter=[dict(), dict(blend=0), dict(thscd1=16000, thscd2=255, ml=300.0, time=20.0)], fps=[dict(num=60, den=1), dict(num=60, den=1, blend=0), dict(num=50, den=1, thscd1=16000, thscd2=255, mask=1)]),
     "blk4_420_chroma2x2_pel2": dict(mask=[dict(kind=2, gamma=2.0)], flow=[dict(time=12.0), dict(mode=1)], finest=True),
     # (no mask here: 256-sample rows equal the stride, and the reference's bottom-strip copy, MVMask.c:162-163, is an
     # overlapping memcpy then -- undefined behaviour; the oracle and the engine replicate the last covered row, which is
     # what the reference's row loop does for every other width)
     "divide2_blk16_esa_neg_badrange": dict(flow=[dict(thscd1=16000, thscd2=255), dict(mode=1, thscd1=16000, thscd2=255, vec=1, time=40.0)], scd=[dict(thscd1=16000, thscd2=255)]),
-    "p8_420_blk16_ov4_uncovered": dict(mask=[dict(kind=0), dict(kind=1, ml=30.0), dict(kind=2, vec=1), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=66.0)], scd=[dict()], finest=True, inter=[dict(), dict(time=10.0, ml=50.0)]),
+    "p8_420_blk16_ov4_uncovered": dict(mask=[dict(kind=0), dict(kind=1, ml=30.0), dict(kind=2, vec=1), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=66.0)], scd=[dict()], finest=True, inter=[dict(), dict(time=10.0, ml=50.0)], fps=[dict(num=35, den=1, mask=2), dict(num=20, den=1, mask=0)]),
 }
 
 
@@ -72,7 +73,9 @@ def flow_params_for(case):
     N = ck["nframes"]
     sp, aps, dp = pipeline.params_for(case)
     vds = [(ap.ad_divided if ap.divide else ap.ad) for ap in aps[:2]]
-    out = {"mask": [], "flow": [], "scd": [], "inter": []}
+    out = {"mask": [], "flow": [], "scd": [], "inter": [], "fps": []}
+    for kw in FLOW[case].get("fps", []):
+        out["fps"].append(mb.flowfps_params(sp, vds[0], vds[1], N, ck["width"], ck["height"], **kw))
     for kw in FLOW[case].get("inter", []):
         out["inter"].append(mb.flowinter_params(sp, vds[0], vds[1], N, **kw))
     for kw in FLOW[case].get("mask", []):
@@ -103,6 +106,35 @@ def run_engine_inter(case, inter_fn, blend_fn):
             if d is None:  # :412-447
                 d = blend_fn(sp, p.time256, frames[n], frames[min(n + off, N - 1)]) if p.blend else frames[n]
             rows.append([sha(q) for q in d])
+        out.append(rows)
+    return out
+
+
+def run_engine_fps(case, inter_fn, blend_fn):
+    """mv.FlowFPS output frame by output frame (MVFlowFPS.c:86-470) -> hashes"""
+    frames, sups, vecs = inputs(case)
+    N = len(frames)
+    sp, aps, P = flow_params_for(case)
+    out = []
+    for p in P["fps"]:
+        q, off = p.inter, p.inter.vd.nDeltaFrame
+        rows = []
+        for n in range(p.num_frames_out):
+            nleft, time256 = mb.flowfps_position(p, n)
+            nright = nleft + off
+            if time256 == 0:
+                d = frames[min(nleft, N - 1)]
+            elif time256 == 256:
+                d = frames[min(nright, N - 1)]
+            else:
+                d = None
+                if nleft < N and nright < N:
+                    extra = p.maskmode == 2
+                    d = inter_fn(q, sp, time256, sups[nleft], sups[nright], vecs[0][nleft], vecs[1][nright], vecs[0][nright] if extra else None, vecs[1][nleft] if extra else None)
+                if d is None:  # :470-520
+                    src = frames[min(nleft, N - 1)]
+                    d = blend_fn(sp, time256, src, frames[min(nright, N - 1)]) if q.blend else src
+            rows.append([sha(x) for x in d])
         out.append(rows)
     return out
 
@@ -165,4 +197,9 @@ def run_reference_flow(case, plugin_path=None):
         kw = {k: (float(x) if k in ("time", "ml") else x) for k, x in kw.items()}
         node = mv.FlowInter(clip, sup, vn[0], vn[1], **kw)
         out["inter"].append([[sha(p) for p in node.get_frame(n).planes()[:nplanes]] for n in range(N)])
+    out["fps"] = []
+    for kw in FLOW[case].get("fps", []):
+        kw = {k: (float(x) if k == "ml" else x) for k, x in kw.items()}
+        node = mv.FlowFPS(clip, sup, vn[0], vn[1], **kw)
+        out["fps"].append([[sha(p) for p in node.get_frame(n).planes()[:nplanes]] for n in range(node.num_frames)])
     return out

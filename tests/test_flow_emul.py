@@ -100,7 +100,8 @@ def blend(sp, time256, src, ref):
 def test_kernel_arithmetic_matches_reference_goldens(built, case):
     got = pipeline_flow.run_engine_flow(case, scd, mask, finest, flow)
     got["inter"] = pipeline_flow.run_engine_inter(case, inter, blend)
-    for stage in ("scd", "mask", "flow", "finest", "inter"):
+    got["fps"] = pipeline_flow.run_engine_fps(case, inter, blend)
+    for stage in ("scd", "mask", "flow", "finest", "inter", "fps"):
         assert got[stage] == GOLD[case][stage], "%s: emulated kernels' %s differs from the reference's golden hashes" % (case, stage)
 
 

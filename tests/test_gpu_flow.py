@@ -24,8 +24,9 @@ def test_cuda_flow_matches_reference_goldens(gpu_ctx, case):
     n0 = ctx.launch_count()
     got = pipeline_flow.run_engine_flow(case, ctx.scdetection_frame, ctx.mask_frame, ctx.finest_frame, ctx.flow_frame)
     got["inter"] = pipeline_flow.run_engine_inter(case, ctx.flowinter_frame, ctx.blend_frame)
+    got["fps"] = pipeline_flow.run_engine_fps(case, ctx.flowinter_frame, ctx.blend_frame)
     assert ctx.launch_count() > n0, "no kernel was launched"
-    for stage in ("scd", "mask", "flow", "finest", "inter"):
+    for stage in ("scd", "mask", "flow", "finest", "inter", "fps"):
         assert got[stage] == GOLD[case][stage], "%s: CUDA %s differs from the reference's golden hashes" % (case, stage)
 
 

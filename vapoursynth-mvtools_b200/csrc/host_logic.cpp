@@ -754,6 +754,119 @@ int mvb200_flowinter_init(const mvb200_flowinter_args *a, const mvb200_super_par
     return 0;
 }
 
+static int64_t gcd64(int64_t x, int64_t y) { // MVFlowFPS.c gcd()
+    while (y) {
+        int64_t t = x % y;
+        x = y;
+        y = t;
+    }
+    return x;
+}
+
+int mvb200_flowfps_init(const mvb200_flowfps_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd_bw, const mvb200_analysis_data *vd_fw, int64_t fps_num, int64_t fps_den, int clip_w, int clip_h, int num_frames,
+                        mvb200_flowfps_params *d) {
+    memset(d, 0, sizeof(*d));
+    mvb200_flowinter_params *q = &d->inter;
+    // MVFlowFPS.c:571-612
+    const int64_t num = GIVEN64(a->num) ? a->num : 25, den = GIVEN64(a->den) ? a->den : 1;
+    d->maskmode = GIVEN(a->mask) ? a->mask : 2;
+    q->ml = (a->ml == a->ml) ? a->ml : 100.0;
+    q->blend = GIVEN(a->blend) ? a->blend != 0 : 1;
+    q->nSCD1 = GIVEN64(a->thscd1) ? a->thscd1 : 400;
+    q->nSCD2 = GIVEN(a->thscd2) ? a->thscd2 : 130;
+    if (d->maskmode < 0 || d->maskmode > 2)
+        return set_error("FlowFPS: mask must be 0, 1, or 2.");
+    if (q->ml <= 0.0)
+        return set_error("FlowFPS: ml must be greater than 0.");
+    q->vd = *vd_bw;
+    // :650-690
+    if (scale_thscd(&q->nSCD1, &q->nSCD2, &q->vd, "FlowFPS"))
+        return 1;
+    if (check_similarity(vd_bw, vd_fw, "FlowFPS", "mvbw", "mvfw"))
+        return 1;
+    if (vd_bw->nDeltaFrame != vd_fw->nDeltaFrame)
+        return set_error("FlowFPS: mvbw and mvfw must be generated with the same delta.");
+    if (!vd_bw->isBackward)
+        return set_error("FlowFPS: mvbw must be generated with isb=True.");
+    if (vd_fw->isBackward)
+        return set_error("FlowFPS: mvfw must be generated with isb=False.");
+    // :725-756
+    if (fps_num == 0 || fps_den == 0)
+        return set_error("FlowFPS: The input clip must have a frame rate. Invoke AssumeFPS if necessary.");
+    int64_t numerator, denominator;
+    if (num != 0 && den != 0) {
+        numerator = num;
+        denominator = den;
+    } else {
+        numerator = fps_num * 2;
+        denominator = fps_den;
+    }
+    d->fa = denominator * fps_num;
+    d->fb = numerator * fps_den;
+    const int64_t g = gcd64(d->fa, d->fb);
+    d->fa /= g;
+    d->fb /= g;
+    if (numerator <= 0 || denominator <= 0) { // setFPS, :547-561
+        d->fps_num = 0;
+        d->fps_den = 1;
+    } else {
+        const int64_t x = gcd64(numerator, denominator);
+        d->fps_num = numerator / x;
+        d->fps_den = denominator / x;
+    }
+    d->num_frames_in = num_frames;
+    d->num_frames_out = (int)(1 + (num_frames - 1) * d->fb / d->fa);
+    // :759-800
+    if (vd_bw->nWidth != clip_w || vd_bw->nHeight != clip_h)
+        return set_error("FlowFPS: inconsistent source and vector frame size.");
+    if (vd_bw->nHeight != sp->height || vd_bw->nWidth != sp->super_width - sp->hpad * 2 || vd_bw->nPel != sp->pel)
+        return set_error("FlowFPS: wrong source or super clip frame size.");
+    if (!((vd_bw->nWidth + vd_bw->nHPadding * 2) == sp->super_width && (vd_bw->nHeight + vd_bw->nVPadding * 2) <= sp->super_height))
+        return set_error("FlowFPS: inconsistent clips frame size! Incomprehensible error messages are the best, right?");
+    if (sp->bits > 16 || sp->ssw > 1 || sp->ssh > 1)
+        return set_error("FlowFPS: input clip must be GRAY, 420, 422, 440, or 444, up to 16 bits, with constant dimensions.");
+    // which blend runs (MVFlowFPS.c:339-437): mask 2 -> Extra, or Simple when the extra vectors are unusable
+    q->mode_primary = d->maskmode == 2 ? 2 : (d->maskmode == 1 ? 1 : 0);
+    q->mode_fallback = d->maskmode == 1 ? 1 : 0;
+    const mvb200_analysis_data *vd = vd_bw;
+    q->nBlkXP = vd->nBlkX;
+    q->nBlkYP = vd->nBlkY;
+    while (q->nBlkXP * (vd->nBlkSizeX - vd->nOverlapX) + vd->nOverlapX < vd->nWidth)
+        q->nBlkXP++;
+    while (q->nBlkYP * (vd->nBlkSizeY - vd->nOverlapY) + vd->nOverlapY < vd->nHeight)
+        q->nBlkYP++;
+    q->nWidthP = q->nBlkXP * (vd->nBlkSizeX - vd->nOverlapX) + vd->nOverlapX;
+    q->nHeightP = q->nBlkYP * (vd->nBlkSizeY - vd->nOverlapY) + vd->nOverlapY;
+    q->nWidthPUV = q->nWidthP / vd->xRatioUV;
+    q->nHeightPUV = q->nHeightP / vd->yRatioUV;
+    q->nHeightUV = vd->nHeight / vd->yRatioUV;
+    q->nWidthUV = vd->nWidth / vd->xRatioUV;
+    q->nHPaddingUV = vd->nHPadding / vd->xRatioUV;
+    q->nVPaddingUV = vd->nVPadding / vd->yRatioUV;
+    q->VPitchY = (q->nWidthP + 15) & (~15);
+    q->VPitchUV = (q->nWidthPUV + 15) & (~15);
+    q->bits = sp->bits;
+    q->ssw = sp->ssw;
+    q->ssh = sp->ssh;
+    q->gray = sp->gray;
+    q->nplanes = sp->nplanes;
+    q->super_hpad = sp->hpad;
+    q->super_vpad = sp->vpad;
+    q->super_pel = sp->pel;
+    q->super_levels = sp->levels;
+    q->num_frames = num_frames;
+    return 0;
+}
+
+void mvb200_flowfps_position(const mvb200_flowfps_params *p, int n, int32_t *nleft, int32_t *time256) {
+    const int off = p->inter.vd.nDeltaFrame;
+    *nleft = (int)(n * p->fa / p->fb);
+    int t = (int)(((double)n * p->fa / p->fb - *nleft) * 256 + 0.5);
+    if (off > 1)
+        t = t / off;
+    *time256 = t;
+}
+
 // InitTables, SimpleResize.cpp:26-56 (single-precision arithmetic, evaluated in the reference's order)
 void mvb200_simple_resize_tables(int out, int in, int32_t *offsets, int32_t *weights) {
     const float leftmost = 0.5f, rightmost = in - 0.5f;

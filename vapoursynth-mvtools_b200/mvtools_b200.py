@@ -149,6 +149,15 @@ class FlowInterParams(C.Structure):
                             "nHPaddingUV", "nVPaddingUV", "VPitchY", "VPitchUV", "num_frames")]
 
 
+class FlowFPSArgs(C.Structure):
+    _fields_ = [("num", i64), ("den", i64), ("mask", i32), ("ml", C.c_double), ("blend", i32), ("thscd1", i64), ("thscd2", i32)]
+
+
+class FlowFPSParams(C.Structure):
+    _fields_ = [("inter", FlowInterParams), ("maskmode", i32), ("fa", i64), ("fb", i64), ("fps_num", i64), ("fps_den", i64),
+                ("num_frames_in", i32), ("num_frames_out", i32)]
+
+
 class FrameLayout(C.Structure):
     _fields_ = [("nplanes", i32), ("bytes_per_sample", i32), ("plane_w", i32 * 3), ("plane_h", i32 * 3),
                 ("pitch", i64 * 3), ("offset", i64 * 3), ("frame_bytes", i64)]
@@ -231,6 +240,9 @@ def lib():
         L.mvb200_flowinter_frame.argtypes = [vp, PP(FlowInterParams), PP(SuperParams), i32, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, vp, vp, vp, PP(vp), PP(C.c_ssize_t), PP(i32)]
         L.mvb200_blend_frame.argtypes = [vp, PP(SuperParams), i32, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
         L.mvb200_flowinter_batch.argtypes = [vp, PP(FlowInterParams), PP(SuperParams), vp, vp, i32, i32, vp, vp, i64, vp]
+        L.mvb200_flowfps_init.argtypes = [PP(FlowFPSArgs), PP(SuperParams), PP(AnalysisData), PP(AnalysisData), i64, i64, i32, i32, i32, PP(FlowFPSParams)]
+        L.mvb200_flowfps_position.argtypes = [PP(FlowFPSParams), i32, PP(i32), PP(i32)]
+        L.mvb200_flowfps_position.restype = None
         _LIB = L
     return _LIB
 
@@ -376,6 +388,24 @@ def flowinter_params(sp, vd_bw, vd_fw, num_frames, **kw):
     out = FlowInterParams()
     _check(lib().mvb200_flowinter_init(C.byref(a), C.byref(sp), C.byref(vd_bw), C.byref(vd_fw), num_frames, C.byref(out)))
     return out
+
+
+def flowfps_params(sp, vd_bw, vd_fw, num_frames, clip_w, clip_h, fps_num=25, fps_den=1, **kw):
+    a = FlowFPSArgs()
+    a.num, a.den, a.thscd1 = _opt(kw, "num", UNSET64), _opt(kw, "den", UNSET64), _opt(kw, "thscd1", UNSET64)
+    a.mask, a.blend, a.thscd2 = _opt(kw, "mask", UNSET), _opt(kw, "blend", UNSET), _opt(kw, "thscd2", UNSET)
+    a.ml = _opt(kw, "ml", float("nan"), float)
+    if kw:
+        raise TypeError("FlowFPS: unknown argument(s) %s" % sorted(kw))
+    out = FlowFPSParams()
+    _check(lib().mvb200_flowfps_init(C.byref(a), C.byref(sp), C.byref(vd_bw), C.byref(vd_fw), fps_num, fps_den, clip_w, clip_h, num_frames, C.byref(out)))
+    return out
+
+
+def flowfps_position(p, n):
+    nleft, t = i32(0), i32(0)
+    lib().mvb200_flowfps_position(C.byref(p), n, C.byref(nleft), C.byref(t))
+    return nleft.value, t.value
 
 
 def simple_resize_tables(out, in_):
