@@ -25,6 +25,7 @@
  *   mvflowCreate/GetFrame        MVFlow.cpp:157-593     mvb200_flow_init / _frame / _batch
  *   mvflowinterCreate/GetFrame   MVFlowInter.c:83-690   mvb200_flowinter_init / _frame / _batch, mvb200_blend_frame
  *   mvflowfpsCreate/GetFrame     MVFlowFPS.c:86-928     mvb200_flowfps_init / _position + mvb200_flowinter_frame
+ *   mvflowblurCreate/GetFrame    MVFlowBlur.c:144-545   mvb200_flowblur_init / _frame / _batch
  *
  * The VapourSynth plugin (vapoursynth-mvtools_b200/plugin, exporting
  * VapourSynthPluginInit2 like EntryPoint.c:28-50) is a thin host-side glue over
@@ -304,6 +305,25 @@ typedef struct mvb200_flowfps_params {
     int32_t num_frames_in, num_frames_out;
 } mvb200_flowfps_params;
 
+/* mv.FlowBlur (MVFlowBlur.c): motion blur of frame n along its forward and backward vectors */
+typedef struct mvb200_flowblur_args {
+    double blur;                  /* NaN = default (50.0) */
+    int32_t prec;                 /* MVB200_UNSET = default (1) */
+    int64_t thscd1;
+    int32_t thscd2;
+} mvb200_flowblur_args;
+
+typedef struct mvb200_flowblur_params {
+    mvb200_analysis_data vd;      /* of mvbw */
+    int32_t blur256, prec;
+    int64_t nSCD1;
+    int32_t nSCD2;
+    int32_t bits, ssw, ssh, gray, nplanes;
+    int32_t super_hpad, super_vpad, super_pel, super_levels;
+    int32_t nWidthUV, nHeightUV, nHPaddingUV, nVPaddingUV;
+    int32_t num_frames;
+} mvb200_flowblur_params;
+
 /* ------------------------------------------------------------- host logic */
 /* (pure host code: usable without a GPU; restates the reference's *Create) */
 
@@ -346,6 +366,9 @@ MVB200_API int mvb200_flowfps_init(const mvb200_flowfps_args *a, const mvb200_su
 /* MVFlowFPS.c:118-141: output frame n lies between input frames *nleft and *nleft + delta, *time256 / 256 of the way
  * (0 and 256 mean "that input frame itself") */
 MVB200_API void mvb200_flowfps_position(const mvb200_flowfps_params *p, int n, int32_t *nleft, int32_t *time256);
+
+/* MVFlowBlur.c:345-545 */
+MVB200_API int mvb200_flowblur_init(const mvb200_flowblur_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd_bw, const mvb200_analysis_data *vd_fw, int num_frames, mvb200_flowblur_params *out);
 
 /* InitTables, SimpleResize.cpp:26-56: offsets[out] and weights[out] (14-bit) of the bilinear resizer the Mask / Flow
  * filters upsize their per-block fields with (float arithmetic, restated on the host; uploaded once per configuration). */
@@ -485,6 +508,15 @@ MVB200_API int mvb200_blend_frame(mvb200_ctx *ctx, const mvb200_super_params *sp
  * num_frames frames (frame f's blob at f * vectors_stride); unusable frames are blended (or copied) from dev_src. */
 MVB200_API int mvb200_flowinter_batch(mvb200_ctx *ctx, const mvb200_flowinter_params *p, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int first, int n, const void *dev_bw, const void *dev_fw,
                                       int64_t vectors_stride, void *dev_dst);
+
+/* mvflowblurGetFrame (MVFlowBlur.c:144-337): super = the super frame of frame n, vec_b = mvbw of frame n - delta,
+ * vec_f = mvfw of frame n + delta (NULL when out of range).  *usable = 0: dst untouched, the caller returns the source. */
+MVB200_API int mvb200_flowblur_frame(mvb200_ctx *ctx, const mvb200_flowblur_params *p, const mvb200_super_params *sp, const uint8_t *const super[3], const ptrdiff_t super_stride[3], const uint8_t *vec_b, const uint8_t *vec_f,
+                                     uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable);
+/* frames [first, first + n) of a device-resident clip (blobs of all frames, frame f's at f * vectors_stride);
+ * unusable frames are copies of the source clip's frames */
+MVB200_API int mvb200_flowblur_batch(mvb200_ctx *ctx, const mvb200_flowblur_params *p, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int first, int n, const void *dev_bw, const void *dev_fw,
+                                     int64_t vectors_stride, void *dev_dst);
 
 #ifdef __cplusplus
 }

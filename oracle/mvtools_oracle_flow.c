@@ -702,3 +702,99 @@ int mvo_blend_frame(const mvb200_super_params *sp, int time256, const uint8_t *c
     }
     return 0;
 }
+
+/* --------------------------------------------------------------- FlowBlur */
+
+/* RealFlowBlur, MVFlowBlur.c:72-127 on a finest plane (`ref` points at the interior's first sample) */
+static void flow_blur_plane(uint8_t *dst, ptrdiff_t dst_stride, const uint8_t *ref, ptrdiff_t ref_pitch, const int16_t *VXB, const int16_t *VXF, const int16_t *VYB, const int16_t *VYF, int vpitch, int width, int height, int blur256, int prec,
+                            int pel, int bps) {
+    const int lp = pel == 4 ? 2 : (pel == 2 ? 1 : 0);
+    for (int h = 0; h < height; h++) {
+        const ptrdiff_t row = (ptrdiff_t)(h << lp) * ref_pitch;
+        for (int w = 0; w < width; w++) {
+            const ptrdiff_t at = row + (w << lp);
+            int bluredsum = px(ref, bps, at);
+            int vxF0 = VXF[h * vpitch + w] * blur256, vyF0 = VYF[h * vpitch + w] * blur256;
+            int mF = (imax(abs(vxF0), abs(vyF0)) / prec) >> 8;
+            if (mF > 0) {
+                vxF0 /= mF;
+                vyF0 /= mF;
+                int vxF = vxF0, vyF = vyF0;
+                for (int i = 0; i < mF; i++) {
+                    bluredsum += px(ref, bps, at + (vyF >> 8) * ref_pitch + (vxF >> 8));
+                    vxF += vxF0;
+                    vyF += vyF0;
+                }
+            }
+            int vxB0 = VXB[h * vpitch + w] * blur256, vyB0 = VYB[h * vpitch + w] * blur256;
+            int mB = (imax(abs(vxB0), abs(vyB0)) / prec) >> 8;
+            if (mB > 0) {
+                vxB0 /= mB;
+                vyB0 /= mB;
+                int vxB = vxB0, vyB = vyB0;
+                for (int i = 0; i < mB; i++) {
+                    bluredsum += px(ref, bps, at + (vyB >> 8) * ref_pitch + (vxB >> 8));
+                    vxB += vxB0;
+                    vyB += vyB0;
+                }
+            }
+            put_px(dst + h * dst_stride, bps, w, bluredsum / (mF + mB + 1));
+        }
+    }
+}
+
+/* mvflowblurGetFrame, MVFlowBlur.c:144-337.  vec_b = mvbw of frame n - delta, vec_f = mvfw of frame n + delta. */
+int mvo_flowblur_frame(const mvb200_flowblur_params *p, const mvb200_super_params *sp, const uint8_t *const super[3], const ptrdiff_t super_stride[3], const uint8_t *vec_b, const uint8_t *vec_f, uint8_t *const dst[3],
+                       const ptrdiff_t dst_stride[3], int32_t *usable) {
+    const mvb200_analysis_data *vd = &p->vd;
+    *usable = super && vec_b && vec_f && is_usable(vec_f, vd, p->nSCD1, p->nSCD2) && is_usable(vec_b, vd, p->nSCD1, p->nSCD2);
+    if (!*usable)
+        return 0;
+    const int bps = (p->bits + 7) / 8, pel = vd->nPel, nplanes = p->nplanes, nb = vd->nBlkX * vd->nBlkY;
+    uint8_t *fin[3];
+    ptrdiff_t fs[3];
+    finest_planes(sp, nplanes, super, super_stride, fin, fs);
+    Resizer up, upUV; /* simpleInit, :531-533: straight from nBlkX x nBlkY to the frame size, no padded field */
+    resizer_init(&up, vd->nWidth, vd->nHeight, vd->nBlkX, vd->nBlkY, vd->nWidth, vd->nHeight, pel);
+    if (nplanes > 1)
+        resizer_init(&upUV, p->nWidthUV, p->nHeightUV, vd->nBlkX, vd->nBlkY, p->nWidthUV, p->nHeightUV, pel);
+    const size_t nY = (size_t)vd->nWidth * vd->nHeight, nUV = nplanes > 1 ? (size_t)p->nWidthUV * p->nHeightUV : 1;
+    int16_t *full[2][4]; /* [b, f][xY, yY, xUV, yUV] */
+    const uint8_t *blobs[2] = {vec_b, vec_f};
+    for (int k = 0; k < 2; k++) {
+        int validity;
+        const uint8_t *l0 = blob_level0(blobs[k], vd, &validity);
+        int16_t *vxs = malloc(sizeof(int16_t) * (size_t)nb), *vys = malloc(sizeof(int16_t) * (size_t)nb), *vxuv = malloc(sizeof(int16_t) * (size_t)nb), *vyuv = malloc(sizeof(int16_t) * (size_t)nb);
+        small_vectors(l0, vd->nBlkX, vd->nBlkY, vd->nBlkX, vd->nBlkY, 0, vxs, vys);
+        small_to_uv(vxs, nb, vxuv, vd->xRatioUV);
+        small_to_uv(vys, nb, vyuv, vd->yRatioUV);
+        full[k][0] = calloc(nY, sizeof(int16_t));
+        full[k][1] = calloc(nY, sizeof(int16_t));
+        full[k][2] = calloc(nUV, sizeof(int16_t));
+        full[k][3] = calloc(nUV, sizeof(int16_t));
+        resize_i16(&up, full[k][0], vd->nWidth, vxs, vd->nBlkX, 1);
+        resize_i16(&up, full[k][1], vd->nWidth, vys, vd->nBlkX, 0);
+        if (nplanes > 1) {
+            resize_i16(&upUV, full[k][2], p->nWidthUV, vxuv, vd->nBlkX, 1);
+            resize_i16(&upUV, full[k][3], p->nWidthUV, vyuv, vd->nBlkX, 0);
+        }
+        free(vxs);
+        free(vys);
+        free(vxuv);
+        free(vyuv);
+    }
+    for (int pl = 0; pl < nplanes; pl++) {
+        const int hp = pl ? p->nHPaddingUV : vd->nHPadding, vp = pl ? p->nVPaddingUV : vd->nVPadding, u = pl ? 2 : 0;
+        const int W = pl ? p->nWidthUV : vd->nWidth, H = pl ? p->nHeightUV : vd->nHeight;
+        flow_blur_plane(dst[pl], dst_stride[pl], fin[pl] + (ptrdiff_t)vp * pel * fs[pl] + (ptrdiff_t)hp * pel * bps, fs[pl] / bps, full[0][u], full[1][u], full[0][u + 1], full[1][u + 1], W, W, H, p->blur256, p->prec, pel, bps);
+    }
+    for (int k = 0; k < 2; k++)
+        for (int i = 0; i < 4; i++)
+            free(full[k][i]);
+    resizer_free(&up);
+    if (nplanes > 1)
+        resizer_free(&upUV);
+    for (int pl = 0; pl < 3; pl++)
+        free(fin[pl]);
+    return 0;
+}

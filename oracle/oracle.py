@@ -36,6 +36,7 @@ def lib():
         L.mvo_flow_frame.argtypes = [PP(mb.FlowParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), vp, C.c_int, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
         L.mvo_flowinter_frame.argtypes = [PP(mb.FlowInterParams), PP(mb.SuperParams), C.c_int, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, vp, vp, vp, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
         L.mvo_blend_frame.argtypes = [PP(mb.SuperParams), C.c_int, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
+        L.mvo_flowblur_frame.argtypes = [PP(mb.FlowBlurParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), vp, vp, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
         L.mvo_simple_resize_tables.argtypes = [C.c_int, C.c_int, vp, vp]
         L.mvo_simple_resize_tables.restype = None
         for n in ("mvo_sad", "mvo_satd"):
@@ -191,3 +192,15 @@ def blend_frame(sp, time256, src, ref):
     d, ds = mb.plane_ptrs(dst)
     _check(lib().mvo_blend_frame(C.byref(sp), time256, s, ss, r, rs, d, ds))
     return dst
+
+
+def flowblur_frame(p, sp, super_planes, vec_b, vec_f):
+    w = [p.vd.nWidth, p.nWidthUV, p.nWidthUV][: p.nplanes]
+    h = [p.vd.nHeight, p.nHeightUV, p.nHeightUV][: p.nplanes]
+    dst = mb.alloc_planes(w, h, p.bits, fill=0xA5)
+    s, ss = mb.plane_ptrs(super_planes)
+    d, ds = mb.plane_ptrs(dst)
+    usable = C.c_int32(0)
+    ptr = lambda v: None if v is None else v.ctypes.data
+    _check(lib().mvo_flowblur_frame(C.byref(p), C.byref(sp), s, ss, ptr(vec_b), ptr(vec_f), d, ds, C.byref(usable)))
+    return dst if usable.value else None

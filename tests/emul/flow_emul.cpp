@@ -220,3 +220,46 @@ EMUL_API int emul_blend_frame(const mvb200_super_params *sp, int time256, const 
     }
     return 0;
 }
+
+EMUL_API int emul_flowblur_frame(const mvb200_flowblur_params *p, const mvb200_super_params *sp, const uint8_t *const super[3], const ptrdiff_t super_stride[3], const uint8_t *vec_b, const uint8_t *vec_f, uint8_t *const dst[3],
+                                 const ptrdiff_t dst_stride[3], int32_t *usable_out) {
+    const mvb200_analysis_data &vd = p->vd;
+    const int nb = vd.nBlkX * vd.nBlkY, bps = (p->bits + 7) / 8;
+    const uint8_t *blobs[2] = {vec_b, vec_f};
+    *usable_out = vec_b && vec_f && usable_of(vec_b, nb, p->nSCD1, p->nSCD2, 1) && usable_of(vec_f, nb, p->nSCD1, p->nSCD2, 1);
+    if (!*usable_out)
+        return 0;
+    std::vector<short> fld[8];
+    for (int i = 0; i < 2; i++) { // k_small_vectors (no padded field here)
+        const int *l0 = blob_level0(blobs[i], nb);
+        for (int k = 0; k < 4; k++)
+            fld[4 * i + k].assign(nb, 0);
+        for (int k = 0; k < nb; k++) {
+            const SmallVec s = small_vector(l0, vd.nBlkX, vd.nBlkY, k % vd.nBlkX, k / vd.nBlkX, 0, vd.xRatioUV, vd.yRatioUV);
+            fld[4 * i][k] = s.xY;
+            fld[4 * i + 1][k] = s.yY;
+            fld[4 * i + 2][k] = s.xUV;
+            fld[4 * i + 3][k] = s.yUV;
+        }
+    }
+    const size_t n0 = tables_ints(vd.nWidth, vd.nHeight), n1 = p->nplanes > 1 ? tables_ints(p->nWidthUV, p->nHeightUV) : 0;
+    std::vector<int32_t> tab(n0 + n1);
+    fill_tables(tab.data(), vd.nWidth, vd.nHeight, vd.nBlkX, vd.nBlkY);
+    if (n1)
+        fill_tables(tab.data() + n0, p->nWidthUV, p->nHeightUV, vd.nBlkX, vd.nBlkY);
+    const ResizeTables t[2] = {tables_at(tab.data(), vd.nWidth, vd.nHeight), tables_at(tab.data() + n0, p->nWidthUV, p->nHeightUV)};
+    for (int plane = 0; plane < p->nplanes; plane++) { // k_flow_blur
+        const int u = plane ? 2 : 0;
+        mvb200_level_geom g;
+        level0_geom(sp, plane, &g);
+        const BlurPlane P = make_blur_plane(p, plane, fld[0 + u].data(), fld[1 + u].data(), fld[4 + u].data(), fld[5 + u].data(), t[plane ? 1 : 0], make_super_plane(super_stride[plane], 0, g));
+        for (int y = 0; y < P.H; y++)
+            for (int x = 0; x < P.W; x++) {
+                if (bps == 1)
+                    dst[plane][y * dst_stride[plane] + x] = (uint8_t)flow_blur_sample<uint8_t>(P, super[plane], x, y);
+                else
+                    *((uint16_t *)(dst[plane] + y * dst_stride[plane]) + x) = (uint16_t)flow_blur_sample<uint16_t>(P, super[plane], x, y);
+            }
+    }
+    return 0;
+}

@@ -22,22 +22,23 @@ FLOW = {
         flow=[dict(), dict(time=50.0, vec=1), dict(mode=1, time=70.0), dict(mode=1, vec=1, thscd1=250, thscd2=60)],
         scd=[dict(), dict(vec=1, thscd1=150, thscd2=30)], finest=True,
         inter=[dict(), dict(time=25.0, ml=40.0), dict(time=80.0, blend=0, thscd1=250, thscd2=60), dict(time=0.0), dict(time=100.0)],
+        blur=[dict(), dict(blur=120.0, prec=2), dict(blur=200.0, thscd1=250, thscd2=60)],
         fps=[dict(num=50, den=1), dict(num=60, den=1, mask=0), dict(num=30000, den=1001, mask=1, ml=50.0), dict(num=50, den=1, mask=0), dict(num=40, den=1, mask=2, blend=0, thscd1=250, thscd2=60)]),
-    "blk16_ov8_pel2_p16_r3": dict(flow=[dict(time=33.0), dict(mode=1, vec=1)], scd=[dict()], finest=True, inter=[dict(), dict(time=70.0, ml=20.0)], fps=[dict(num=50, den=1, mask=0), dict(num=75, den=2, mask=1)]),
-    "p10_444_blk8_pel4_bicubic": dict(flow=[dict(time=80.0), dict(mode=1, time=45.0, vec=1)], finest=True, scd=[dict(thscd2=10)], inter=[dict(time=40.0)], fps=[dict(num=60, den=1)]),
-    "gray_blk4_pel1_rf0": dict(mask=[dict(kind=0), dict(kind=2, time=50.0), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=25.0)], finest=True, scd=[dict()], inter=[dict(time=60.0, ml=10.0)]),
+    "blk16_ov8_pel2_p16_r3": dict(flow=[dict(time=33.0), dict(mode=1, vec=1)], scd=[dict()], finest=True, inter=[dict(), dict(time=70.0, ml=20.0)], fps=[dict(num=50, den=1, mask=0), dict(num=75, den=2, mask=1)], blur=[dict(blur=80.0)]),
+    "p10_444_blk8_pel4_bicubic": dict(flow=[dict(time=80.0), dict(mode=1, time=45.0, vec=1)], finest=True, scd=[dict(thscd2=10)], inter=[dict(time=40.0)], fps=[dict(num=60, den=1)], blur=[dict(blur=150.0, prec=3)]),
+    "gray_blk4_pel1_rf0": dict(mask=[dict(kind=0), dict(kind=2, time=50.0), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=25.0)], finest=True, scd=[dict()], inter=[dict(time=60.0, ml=10.0)], blur=[dict()]),
     "c1_640x360_p8_blk8_pel1": dict(mask=[dict(kind=1), dict(kind=2, vec=1)], flow=[dict(time=60.0), dict(mode=1)], scd=[dict()], inter=[dict(), dict(time=33.0, blend=0)]),
     "p8_422_blk8x4_sharp0_rf1": dict(mask=[dict(kind=0, ml=10.0), dict(kind=1, time=0.0), dict(kind=2, vec=1, ml=10.0), dict(kind=5)], flow=[dict(vec=1), dict(mode=1, time=100.0)], finest=True,
                                      scd=[dict(vec=1)], inter=[dict(time=45.0)]),
     "noise_badblocks_blk8": dict(mask=[dict(kind=0, ysc=9), dict(kind=1, thscd1=16000, thscd2=255), dict(kind=2, thscd1=16000, thscd2=255, ml=400.0), dict(kind=5, thscd1=16000, thscd2=255, ml=3.0)],
                                  flow=[dict(), dict(thscd1=16000, thscd2=255, time=90.0), dict(mode=1, thscd1=16000, thscd2=255, vec=1)], scd=[dict(), dict(thscd1=16000, thscd2=255)],
-                                 inter=[dict(), dict(blend=0), dict(thscd1=16000, thscd2=255, ml=300.0, time=20.0)], fps=[dict(num=60, den=1), dict(num=60, den=1, blend=0), dict(num=50, den=1, thscd1=16000, thscd2=255, mask=1)]),
+                                 inter=[dict(), dict(blend=0), dict(thscd1=16000, thscd2=255, ml=300.0, time=20.0)], fps=[dict(num=60, den=1), dict(num=60, den=1, blend=0), dict(num=50, den=1, thscd1=16000, thscd2=255, mask=1)], blur=[dict(), dict(thscd1=16000, thscd2=255, blur=100.0)]),
     "blk4_420_chroma2x2_pel2": dict(mask=[dict(kind=2, gamma=2.0)], flow=[dict(time=12.0), dict(mode=1)], finest=True),
     # (no mask here: 256-sample rows equal the stride, and the reference's bottom-strip copy, MVMask.c:162-163, is an
     # overlapping memcpy then -- undefined behaviour; the oracle and the engine replicate the last covered row, which is
     # what the reference's row loop does for every other width)
     "divide2_blk16_esa_neg_badrange": dict(flow=[dict(thscd1=16000, thscd2=255), dict(mode=1, thscd1=16000, thscd2=255, vec=1, time=40.0)], scd=[dict(thscd1=16000, thscd2=255)]),
-    "p8_420_blk16_ov4_uncovered": dict(mask=[dict(kind=0), dict(kind=1, ml=30.0), dict(kind=2, vec=1), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=66.0)], scd=[dict()], finest=True, inter=[dict(), dict(time=10.0, ml=50.0)], fps=[dict(num=35, den=1, mask=2), dict(num=20, den=1, mask=0)]),
+    "p8_420_blk16_ov4_uncovered": dict(mask=[dict(kind=0), dict(kind=1, ml=30.0), dict(kind=2, vec=1), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=66.0)], scd=[dict()], finest=True, inter=[dict(), dict(time=10.0, ml=50.0)], fps=[dict(num=35, den=1, mask=2), dict(num=20, den=1, mask=0)], blur=[dict(blur=66.0)]),
 }
 
 
@@ -73,7 +74,9 @@ def flow_params_for(case):
     N = ck["nframes"]
     sp, aps, dp = pipeline.params_for(case)
     vds = [(ap.ad_divided if ap.divide else ap.ad) for ap in aps[:2]]
-    out = {"mask": [], "flow": [], "scd": [], "inter": [], "fps": []}
+    out = {"mask": [], "flow": [], "scd": [], "inter": [], "fps": [], "blur": []}
+    for kw in FLOW[case].get("blur", []):
+        out["blur"].append(mb.flowblur_params(sp, vds[0], vds[1], N, **kw))
     for kw in FLOW[case].get("fps", []):
         out["fps"].append(mb.flowfps_params(sp, vds[0], vds[1], N, ck["width"], ck["height"], **kw))
     for kw in FLOW[case].get("inter", []):
@@ -139,6 +142,22 @@ def run_engine_fps(case, inter_fn, blend_fn):
     return out
 
 
+def run_engine_blur(case, blur_fn):
+    """mv.FlowBlur frame by frame (MVFlowBlur.c:144-337): mvbw of n - delta and mvfw of n + delta -> hashes"""
+    frames, sups, vecs = inputs(case)
+    N = len(frames)
+    sp, aps, P = flow_params_for(case)
+    out = []
+    for p in P["blur"]:
+        off = p.vd.nDeltaFrame
+        rows = []
+        for n in range(N):
+            d = blur_fn(p, sp, sups[n], vecs[0][n - off], vecs[1][n + off]) if n - off >= 0 and n + off < N else None
+            rows.append([sha(q) for q in (d if d is not None else frames[n])])
+        out.append(rows)
+    return out
+
+
 def run_engine_flow(case, scd_fn, mask_fn, finest_fn, flow_fn):
     """Per-frame stage functions (oracle.* or Context.*) on the oracle-made inputs -> {stage: hashes}"""
     frames, sups, vecs = inputs(case)
@@ -197,6 +216,11 @@ def run_reference_flow(case, plugin_path=None):
         kw = {k: (float(x) if k in ("time", "ml") else x) for k, x in kw.items()}
         node = mv.FlowInter(clip, sup, vn[0], vn[1], **kw)
         out["inter"].append([[sha(p) for p in node.get_frame(n).planes()[:nplanes]] for n in range(N)])
+    out["blur"] = []
+    for kw in FLOW[case].get("blur", []):
+        kw = {k: (float(x) if k == "blur" else x) for k, x in kw.items()}
+        node = mv.FlowBlur(clip, sup, vn[0], vn[1], **kw)
+        out["blur"].append([[sha(p) for p in node.get_frame(n).planes()[:nplanes]] for n in range(N)])
     out["fps"] = []
     for kw in FLOW[case].get("fps", []):
         kw = {k: (float(x) if k == "ml" else x) for k, x in kw.items()}

@@ -37,6 +37,7 @@ def emul():
         L.emul_flow_frame.argtypes = [PP(mb.FlowParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), vp, C.c_int, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
         L.emul_flowinter_frame.argtypes = [PP(mb.FlowInterParams), PP(mb.SuperParams), C.c_int, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, vp, vp, vp, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
         L.emul_blend_frame.argtypes = [PP(mb.SuperParams), C.c_int, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
+        L.emul_flowblur_frame.argtypes = [PP(mb.FlowBlurParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), vp, vp, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
         _LIB = L
     return _LIB
 
@@ -87,6 +88,18 @@ def inter(p, sp, time256, left_super, right_super, vec_b, vec_f, vec_bb=None, ve
     return dst if usable.value else None
 
 
+def blur(p, sp, super_planes, vec_b, vec_f):
+    w = [p.vd.nWidth, p.nWidthUV, p.nWidthUV][: p.nplanes]
+    h = [p.vd.nHeight, p.nHeightUV, p.nHeightUV][: p.nplanes]
+    dst = mb.alloc_planes(w, h, p.bits, fill=0xA5)
+    s, ss = mb.plane_ptrs(super_planes)
+    d, ds = mb.plane_ptrs(dst)
+    usable = C.c_int32(0)
+    ptr = lambda v: None if v is None else v.ctypes.data
+    assert emul().emul_flowblur_frame(C.byref(p), C.byref(sp), s, ss, ptr(vec_b), ptr(vec_f), d, ds, C.byref(usable)) == 0
+    return dst if usable.value else None
+
+
 def blend(sp, time256, src, ref):
     dst = mb.alloc_planes([a.shape[1] for a in src], [a.shape[0] for a in src], sp.bits, fill=0xA5)
     s, ss = mb.plane_ptrs(src)
@@ -101,7 +114,8 @@ def test_kernel_arithmetic_matches_reference_goldens(built, case):
     got = pipeline_flow.run_engine_flow(case, scd, mask, finest, flow)
     got["inter"] = pipeline_flow.run_engine_inter(case, inter, blend)
     got["fps"] = pipeline_flow.run_engine_fps(case, inter, blend)
-    for stage in ("scd", "mask", "flow", "finest", "inter", "fps"):
+    got["blur"] = pipeline_flow.run_engine_blur(case, blur)
+    for stage in ("scd", "mask", "flow", "finest", "inter", "fps", "blur"):
         assert got[stage] == GOLD[case][stage], "%s: emulated kernels' %s differs from the reference's golden hashes" % (case, stage)
 
 

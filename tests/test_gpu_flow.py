@@ -25,8 +25,9 @@ def test_cuda_flow_matches_reference_goldens(gpu_ctx, case):
     got = pipeline_flow.run_engine_flow(case, ctx.scdetection_frame, ctx.mask_frame, ctx.finest_frame, ctx.flow_frame)
     got["inter"] = pipeline_flow.run_engine_inter(case, ctx.flowinter_frame, ctx.blend_frame)
     got["fps"] = pipeline_flow.run_engine_fps(case, ctx.flowinter_frame, ctx.blend_frame)
+    got["blur"] = pipeline_flow.run_engine_blur(case, ctx.flowblur_frame)
     assert ctx.launch_count() > n0, "no kernel was launched"
-    for stage in ("scd", "mask", "flow", "finest", "inter", "fps"):
+    for stage in ("scd", "mask", "flow", "finest", "inter", "fps", "blur"):
         assert got[stage] == GOLD[case][stage], "%s: CUDA %s differs from the reference's golden hashes" % (case, stage)
 
 
@@ -103,6 +104,13 @@ def test_flow_batch_entry_points_match_goldens(gpu_ctx, case):
         out = ddst.cpu().numpy()
         for n in range(N):
             assert [pipeline.sha(q) for q in _planes(out[n], cl)] == GOLD[case]["inter"][i][n], "inter variant %d frame %d" % (i, n)
+    for i, p in enumerate(P["blur"]):
+        ddst = torch.full((N, cl.frame_bytes), 0xA5, dtype=torch.uint8, device="cuda")
+        mb._check(L.mvb200_flowblur_batch(ctx.handle, C.byref(p), C.byref(sp), dsrc.data_ptr(), dsup.data_ptr(), 0, N, dvec[0].data_ptr(), dvec[1].data_ptr(), vs, ddst.data_ptr()))
+        ctx.synchronize()
+        out = ddst.cpu().numpy()
+        for n in range(N):
+            assert [pipeline.sha(q) for q in _planes(out[n], cl)] == GOLD[case]["blur"][i][n], "blur variant %d frame %d" % (i, n)
     if pipeline_flow.FLOW[case].get("finest"):
         fl = mb.finest_layout(sp)
         ddst = torch.full((N, fl.frame_bytes), 0xA5, dtype=torch.uint8, device="cuda")

@@ -18,7 +18,7 @@ GOLD = json.load(open(os.path.join(HERE, "golden", "golden.json")))
 GOLD_FLOW = json.load(open(os.path.join(HERE, "golden", "golden_flow.json")))
 # functions of the reference (registration.json lists everything its build here registers) that this plugin does not
 # provide yet: the remaining SURVEY.md 8f rows (Depan needs complex FFTW and is not in the reference build either)
-NOT_YET = {"FlowBlur", "BlockFPS"}
+NOT_YET = {"BlockFPS"}
 
 
 def test_registration_is_the_references(built):
@@ -71,6 +71,8 @@ def test_create_time_errors_through_the_plugin(built):
                       (lambda: mv.Flow(clip, clip, clip, mode=3), "Flow: mode must be 0 or 1."),
                       (lambda: mv.FlowInter(clip, clip, clip, clip, ml=0.0), "FlowInter: ml must be greater than 0."),
                       (lambda: mv.FlowFPS(clip, clip, clip, clip, mask=3), "FlowFPS: mask must be 0, 1, or 2."),
+                      (lambda: mv.FlowBlur(clip, clip, clip, clip, blur=201.0), "FlowBlur: blur must be between 0 and 200 % (inclusive)."),
+                      (lambda: mv.FlowBlur(clip, clip, clip, clip, prec=0), "FlowBlur: prec must be at least 1."),
                       (lambda: mv.FlowInter(clip, clip, clip, clip, time=-2.0), "FlowInter: time must be between 0 and 100 % (inclusive)."),
                       (lambda: mv.Flow(clip, clip, clip, time=101.0), "Flow: time must be between 0 and 100 % (inclusive).")):
         with pytest.raises(minivs.Error) as e:
@@ -97,5 +99,5 @@ def test_flow_script_through_plugin_matches_reference(built, case):
     """mv.SCDetection / mv.Mask / mv.Finest / mv.Flow of this plugin, driven like a .vpy script, give the reference plugin's bytes"""
     import pipeline_flow
     got = pipeline_flow.run_reference_flow(case, plugin_path=mb.PLUGIN_PATH)
-    for stage in ("scd", "mask", "flow", "finest", "inter", "fps"):
+    for stage in ("scd", "mask", "flow", "finest", "inter", "fps", "blur"):
         assert got[stage] == GOLD_FLOW[case][stage], "%s: plugin %s differs from the reference plugin" % (case, stage)

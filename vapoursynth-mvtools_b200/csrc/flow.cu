@@ -180,6 +180,21 @@ __global__ void k_blend(int W, int H, int time256, const uint8_t *__restrict__ s
     *((T *)(dst + o) + x) = (T)blend_sample(*((const T *)(src + o) + x), *((const T *)(ref + o) + x), time256);
 }
 
+// --------------------------------------------------------------- FlowBlur
+template <typename T>
+__global__ void k_flow_blur(BlurPlane P, const uint8_t *__restrict__ super_frame, uint8_t *__restrict__ dst, long long dst_pitch, const uint8_t *__restrict__ src, const int *__restrict__ flags) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= P.W || y >= P.H)
+        return;
+    T *d = (T *)(dst + (long long)y * dst_pitch) + x;
+    if (!(flags[0] && flags[1])) {
+        if (src)
+            *d = *((const T *)(src + (long long)y * dst_pitch) + x);
+        return;
+    }
+    *d = (T)flow_blur_sample<T>(P, super_frame, x, y);
+}
+
 // ------------------------------------------------------------ host helpers
 
 constexpr int kSlotTables = 16, kSlotSmall = 17, kSlotStage = 18;
@@ -377,6 +392,55 @@ static int launch_flowinter(Ctx *c, const mvb200_flowinter_params *p, const Supe
             k_flow_inter<uint8_t><<<grid, blk, 0, st>>>(P, p->mode_primary, p->mode_fallback, rs, ls, dst, cd.pitch[plane], src, ref, p->blend, flags);
         else
             k_flow_inter<uint16_t><<<grid, blk, 0, st>>>(P, p->mode_primary, p->mode_fallback, rs, ls, dst, cd.pitch[plane], src, ref, p->blend, flags);
+        c->launches++;
+    }
+    MVB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// mvflowblurGetFrame (MVFlowBlur.c:144-337) for one frame on the device; vec_b / vec_f null: not usable
+static int launch_flowblur(Ctx *c, const mvb200_flowblur_params *p, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *super_frame, const uint8_t *vec_b, const uint8_t *vec_f, const uint8_t *dev_src, uint8_t *dev_dst,
+                           int **flags_dev) {
+    cudaStream_t st = c->stream;
+    const mvb200_analysis_data &vd = p->vd;
+    const int nb = vd.nBlkX * vd.nBlkY;
+    const size_t field_bytes = align256((size_t)nb * sizeof(short));
+    uint8_t *scr = (uint8_t *)c->get_scratch(kSlotSmall, 256 + 8 * field_bytes);
+    if (!scr)
+        return 1;
+    int *flags = (int *)scr;
+    *flags_dev = flags;
+    short *fld[8];
+    for (int i = 0; i < 8; i++)
+        fld[i] = (short *)(scr + 256 + i * field_bytes);
+    ResizeTables t[2];
+    if (get_resize_tables(c, vd.nWidth, vd.nHeight, p->nplanes > 1 ? p->nWidthUV : 0, p->nplanes > 1 ? p->nHeightUV : 0, vd.nBlkX, vd.nBlkY, t))
+        return 1;
+    const bool ok = vec_b && vec_f;
+    const uint8_t *blobs[2] = {vec_b, vec_f};
+    for (int i = 0; i < 2; i++) {
+        if (ok) {
+            k_flow_scd<<<1, 256, 0, st>>>(blobs[i], 0, nb, p->nSCD1, p->nSCD2, 1, flags + i);
+            SmallFields sf = {fld[4 * i], fld[4 * i + 1], fld[4 * i + 2], fld[4 * i + 3]};
+            k_small_vectors<<<(nb + 255) / 256, 256, 0, st>>>(blobs[i], vd.nBlkX, vd.nBlkY, vd.nBlkX, vd.nBlkY, 0, vd.xRatioUV, vd.yRatioUV, sf);
+            c->launches += 2;
+        } else {
+            MVB_CUDA_CHECK(cudaMemsetAsync(flags + i, 0, sizeof(int), st));
+        }
+    }
+    if (!ok && !dev_src) {
+        MVB_CUDA_CHECK(cudaGetLastError());
+        return 0;
+    }
+    for (int plane = 0; plane < p->nplanes; plane++) {
+        const int u = plane ? 2 : 0;
+        const BlurPlane P = make_blur_plane(p, plane, fld[0 + u], fld[1 + u], fld[4 + u], fld[5 + u], t[plane ? 1 : 0], super_plane_of(sd, plane));
+        const uint8_t *src = dev_src ? dev_src + cd.offset[plane] : nullptr;
+        dim3 blk(32, 8), grid((P.W + 31) / 32, (P.H + 7) / 8);
+        if (sd.bps == 1)
+            k_flow_blur<uint8_t><<<grid, blk, 0, st>>>(P, super_frame, dev_dst + cd.offset[plane], cd.pitch[plane], src, flags);
+        else
+            k_flow_blur<uint16_t><<<grid, blk, 0, st>>>(P, super_frame, dev_dst + cd.offset[plane], cd.pitch[plane], src, flags);
         c->launches++;
     }
     MVB_CUDA_CHECK(cudaGetLastError());
@@ -691,6 +755,80 @@ int mvb200_blend_frame(mvb200_ctx *ctx, const mvb200_super_params *sp, int time2
     }
     MVB_CUDA_CHECK(cudaGetLastError());
     MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+static int flowblur_check(const mvb200_flowblur_params *p, const mvb200_super_params *sp) {
+    if (sp->levels > kDevMaxLevels)
+        return set_error("mvtools_b200: more than %d pyramid levels are not supported on the device", kDevMaxLevels);
+    if (p->super_pel != sp->pel || p->super_hpad != sp->hpad || p->super_vpad != sp->vpad || p->bits != sp->bits)
+        return set_error("FlowBlur: the parameters were derived for another super clip");
+    return 0;
+}
+
+int mvb200_flowblur_batch(mvb200_ctx *ctx, const mvb200_flowblur_params *p, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int first, int n, const void *dev_bw, const void *dev_fw, int64_t vectors_stride,
+                          void *dev_dst) {
+    if (flowblur_check(p, sp))
+        return 1;
+    if (n <= 0)
+        return 0;
+    if (first < 0 || first + n > p->num_frames)
+        return set_error("FlowBlur: frames [%d, %d) are outside the clip of %d frames", first, first + n, p->num_frames);
+    if (!dev_src)
+        return set_error("FlowBlur: the batch entry point needs the source clip (unusable frames are copies of it)");
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(sp, &sd);
+    make_clip_desc(sp, &cd);
+    for (int f = 0; f < n; f++) {
+        const int fn = first + f, off = p->vd.nDeltaFrame;
+        const bool in_range = fn - off >= 0 && fn + off < p->num_frames; // MVFlowBlur.c:173
+        int *flags;
+        if (launch_flowblur(c, p, sd, cd, (const uint8_t *)dev_super + (long long)fn * sd.frame_bytes, in_range ? (const uint8_t *)dev_bw + (long long)(fn - off) * vectors_stride : nullptr,
+                            in_range ? (const uint8_t *)dev_fw + (long long)(fn + off) * vectors_stride : nullptr, (const uint8_t *)dev_src + (long long)fn * cd.frame_bytes, (uint8_t *)dev_dst + (long long)f * cd.frame_bytes, &flags))
+            return 1;
+    }
+    return 0;
+}
+
+int mvb200_flowblur_frame(mvb200_ctx *ctx, const mvb200_flowblur_params *p, const mvb200_super_params *sp, const uint8_t *const super[3], const ptrdiff_t super_stride[3], const uint8_t *vec_b, const uint8_t *vec_f, uint8_t *const dst[3],
+                          const ptrdiff_t dst_stride[3], int32_t *usable_out) {
+    if (flowblur_check(p, sp))
+        return 1;
+    *usable_out = 0;
+    if (!super || !vec_b || !vec_f)
+        return 0;
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(sp, &sd);
+    make_clip_desc(sp, &cd);
+    const size_t bb = (size_t)blob_bytes_of(vec_b), bf = (size_t)blob_bytes_of(vec_f);
+    uint8_t *buf = (uint8_t *)c->get_scratch(kSlotStage, (size_t)sd.frame_bytes + (size_t)cd.frame_bytes + align256(bb) + align256(bf) + 256);
+    if (!buf)
+        return 1;
+    uint8_t *dsup = buf, *ddst = buf + sd.frame_bytes, *dvb = ddst + cd.frame_bytes, *dvf = dvb + align256(bb);
+    MVB_CUDA_CHECK(cudaMemcpyAsync(dvb, vec_b, bb, cudaMemcpyHostToDevice, c->stream));
+    MVB_CUDA_CHECK(cudaMemcpyAsync(dvf, vec_f, bf, cudaMemcpyHostToDevice, c->stream));
+    for (int pl = 0; pl < p->nplanes; pl++) { // level 0 only
+        const mvb200_level_geom &g = sd.lv[pl][0];
+        MVB_CUDA_CHECK(cudaMemcpy2DAsync(dsup + sd.offset[pl], (size_t)sd.pitch[pl], super[pl], (size_t)super_stride[pl], (size_t)g.padded_w * sd.bps, (size_t)g.padded_h * sp->pel * sp->pel, cudaMemcpyHostToDevice, c->stream));
+    }
+    int *flags_dev = nullptr;
+    if (launch_flowblur(c, p, sd, cd, dsup, dvb, dvf, nullptr, ddst, &flags_dev))
+        return 1;
+    int flags[2] = {0, 0};
+    MVB_CUDA_CHECK(cudaMemcpyAsync(flags, flags_dev, sizeof(flags), cudaMemcpyDeviceToHost, c->stream));
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    *usable_out = flags[0] && flags[1];
+    if (*usable_out) {
+        for (int pl = 0; pl < p->nplanes; pl++)
+            MVB_CUDA_CHECK(cudaMemcpy2DAsync(dst[pl], (size_t)dst_stride[pl], ddst + cd.offset[pl], (size_t)cd.pitch[pl], (size_t)cd.w[pl] * cd.bps, (size_t)cd.h[pl], cudaMemcpyDeviceToHost, c->stream));
+        MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
     return 0;
 }
 

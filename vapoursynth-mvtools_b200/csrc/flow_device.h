@@ -306,5 +306,42 @@ MVB_HD int flow_inter_sample(const InterPlane &P, int method, const uint8_t *rig
 // Blend, MaskFun.cpp:349-373
 MVB_HD int blend_sample(int src, int ref, int time256) { return (src * (256 - time256) + ref * time256) >> 8; }
 
+// ------------------------------------------------------------------ FlowBlur
+
+struct BlurPlane {
+    int plane, W, H, pel, logPel, nBlkX, blur256, prec;
+    const short *vxB, *vyB, *vxF, *vyF; // small fields (nBlkX x nBlkY, not padded: MVFlowBlur.c:243-244)
+    ResizeTables t;
+    SuperPlane S;
+};
+
+// RealFlowBlur, MVFlowBlur.c:72-127: the mean of the samples met along the forward and the backward vector
+template <typename T>
+MVB_HD int flow_blur_sample(const BlurPlane &P, const uint8_t *super_frame, int x, int y) {
+    const int voff = P.t.voff[y], vwt = P.t.vwt[y], hoff = P.t.hoff[x], hwt = P.t.hwt[x];
+    const int fx = (x + P.S.hpad) << P.logPel, fy = (y + P.S.vpad) << P.logPel;
+    int sum = finest_sample<T>(super_frame, P.S, P.logPel, fx, fy), count = 1;
+    for (int dir = 0; dir < 2; dir++) {
+        const short *vxs = dir ? P.vxB : P.vxF, *vys = dir ? P.vyB : P.vyF;
+        const int VX = (short)limit_vector(resize_sample<short>(vxs, P.nBlkX, voff, vwt, hoff, hwt), x, P.W, P.pel);
+        const int VY = (short)limit_vector(resize_sample<short>(vys, P.nBlkX, voff, vwt, hoff, hwt), y, P.H, P.pel);
+        int vx0 = VX * P.blur256, vy0 = VY * P.blur256;
+        const int ax = vx0 < 0 ? -vx0 : vx0, ay = vy0 < 0 ? -vy0 : vy0;
+        const int m = ((ax > ay ? ax : ay) / P.prec) >> 8;
+        if (m > 0) {
+            vx0 /= m;
+            vy0 /= m;
+            int vx = vx0, vy = vy0;
+            for (int i = 0; i < m; i++) {
+                sum += finest_sample<T>(super_frame, P.S, P.logPel, fx + (vx >> 8), fy + (vy >> 8));
+                vx += vx0;
+                vy += vy0;
+            }
+        }
+        count += m;
+    }
+    return sum / count;
+}
+
 } // namespace flowdev
 } // namespace mvb200

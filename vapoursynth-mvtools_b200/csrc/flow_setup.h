@@ -124,5 +124,25 @@ inline InterPlane make_inter_plane(const mvb200_flowinter_params *p, int time256
     return P;
 }
 
+inline BlurPlane make_blur_plane(const mvb200_flowblur_params *p, int plane, const short *vxB, const short *vyB, const short *vxF, const short *vyF, const ResizeTables &t, const SuperPlane &S) {
+    BlurPlane P;
+    memset(&P, 0, sizeof(P));
+    P.plane = plane;
+    P.W = plane ? p->nWidthUV : p->vd.nWidth; // also the resizer's limits (simpleInit, MVFlowBlur.c:531-533)
+    P.H = plane ? p->nHeightUV : p->vd.nHeight;
+    P.pel = p->vd.nPel;
+    P.logPel = ilog2_pel(p->vd.nPel);
+    P.nBlkX = p->vd.nBlkX;
+    P.blur256 = p->blur256;
+    P.prec = p->prec;
+    P.vxB = vxB;
+    P.vyB = vyB;
+    P.vxF = vxF;
+    P.vyF = vyF;
+    P.t = t;
+    P.S = S;
+    return P;
+}
+
 } // namespace flowdev
 } // namespace mvb200

@@ -867,6 +867,55 @@ void mvb200_flowfps_position(const mvb200_flowfps_params *p, int n, int32_t *nle
     *time256 = t;
 }
 
+int mvb200_flowblur_init(const mvb200_flowblur_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd_bw, const mvb200_analysis_data *vd_fw, int num_frames, mvb200_flowblur_params *d) {
+    memset(d, 0, sizeof(*d));
+    // MVFlowBlur.c:353-384 (blur is a float there)
+    const float blur = (a->blur == a->blur) ? (float)a->blur : 50.0f;
+    d->prec = GIVEN(a->prec) ? a->prec : 1;
+    d->nSCD1 = GIVEN64(a->thscd1) ? a->thscd1 : 400;
+    d->nSCD2 = GIVEN(a->thscd2) ? a->thscd2 : 130;
+    if (blur < 0.0f || blur > 200.0f)
+        return set_error("FlowBlur: blur must be between 0 and 200 %% (inclusive).");
+    if (d->prec < 1)
+        return set_error("FlowBlur: prec must be at least 1.");
+    d->blur256 = (int)(blur * 256.0f / 200.0f);
+    d->vd = *vd_bw;
+    // :418-461
+    if (scale_thscd(&d->nSCD1, &d->nSCD2, &d->vd, "FlowBlur"))
+        return 1;
+    if (check_similarity(vd_bw, vd_fw, "FlowBlur", "mvbw", "mvfw"))
+        return 1;
+    if (vd_bw->nDeltaFrame <= 0 || vd_fw->nDeltaFrame <= 0)
+        return set_error("FlowBlur: cannot use motion vectors with absolute frame references.");
+    if (vd_fw->nDeltaFrame != vd_bw->nDeltaFrame)
+        return set_error("FlowBlur: mvbw and mvfw must be generated with the same delta.");
+    if (!vd_bw->isBackward)
+        return set_error("FlowBlur: mvbw must be generated with isb=True.");
+    if (vd_fw->isBackward)
+        return set_error("FlowBlur: mvfw must be generated with isb=False.");
+    // :498-516
+    if (vd_bw->nHeight != sp->height || vd_bw->nWidth != sp->super_width - sp->hpad * 2 || vd_bw->nPel != sp->pel)
+        return set_error("FlowBlur: wrong source or super clip frame size.");
+    if (sp->bits > 16 || sp->ssw > 1 || sp->ssh > 1)
+        return set_error("FlowBlur: input clip must be GRAY, 420, 422, 440, or 444, up to 16 bits, with constant dimensions.");
+    // :519-529
+    d->nHeightUV = vd_bw->nHeight / vd_bw->yRatioUV;
+    d->nWidthUV = vd_bw->nWidth / vd_bw->xRatioUV;
+    d->nHPaddingUV = vd_bw->nHPadding / vd_bw->xRatioUV;
+    d->nVPaddingUV = vd_bw->nVPadding / vd_bw->yRatioUV;
+    d->bits = sp->bits;
+    d->ssw = sp->ssw;
+    d->ssh = sp->ssh;
+    d->gray = sp->gray;
+    d->nplanes = sp->nplanes;
+    d->super_hpad = sp->hpad;
+    d->super_vpad = sp->vpad;
+    d->super_pel = sp->pel;
+    d->super_levels = sp->levels;
+    d->num_frames = num_frames;
+    return 0;
+}
+
 // InitTables, SimpleResize.cpp:26-56 (single-precision arithmetic, evaluated in the reference's order)
 void mvb200_simple_resize_tables(int out, int in, int32_t *offsets, int32_t *weights) {
     const float leftmost = 0.5f, rightmost = in - 0.5f;

@@ -158,6 +158,16 @@ class FlowFPSParams(C.Structure):
                 ("num_frames_in", i32), ("num_frames_out", i32)]
 
 
+class FlowBlurArgs(C.Structure):
+    _fields_ = [("blur", C.c_double), ("prec", i32), ("thscd1", i64), ("thscd2", i32)]
+
+
+class FlowBlurParams(C.Structure):
+    _fields_ = [("vd", AnalysisData), ("blur256", i32), ("prec", i32), ("nSCD1", i64), ("nSCD2", i32)] + \
+        [(n, i32) for n in ("bits", "ssw", "ssh", "gray", "nplanes", "super_hpad", "super_vpad", "super_pel", "super_levels",
+                            "nWidthUV", "nHeightUV", "nHPaddingUV", "nVPaddingUV", "num_frames")]
+
+
 class FrameLayout(C.Structure):
     _fields_ = [("nplanes", i32), ("bytes_per_sample", i32), ("plane_w", i32 * 3), ("plane_h", i32 * 3),
                 ("pitch", i64 * 3), ("offset", i64 * 3), ("frame_bytes", i64)]
@@ -243,6 +253,9 @@ def lib():
         L.mvb200_flowfps_init.argtypes = [PP(FlowFPSArgs), PP(SuperParams), PP(AnalysisData), PP(AnalysisData), i64, i64, i32, i32, i32, PP(FlowFPSParams)]
         L.mvb200_flowfps_position.argtypes = [PP(FlowFPSParams), i32, PP(i32), PP(i32)]
         L.mvb200_flowfps_position.restype = None
+        L.mvb200_flowblur_init.argtypes = [PP(FlowBlurArgs), PP(SuperParams), PP(AnalysisData), PP(AnalysisData), i32, PP(FlowBlurParams)]
+        L.mvb200_flowblur_frame.argtypes = [vp, PP(FlowBlurParams), PP(SuperParams), PP(vp), PP(C.c_ssize_t), vp, vp, PP(vp), PP(C.c_ssize_t), PP(i32)]
+        L.mvb200_flowblur_batch.argtypes = [vp, PP(FlowBlurParams), PP(SuperParams), vp, vp, i32, i32, vp, vp, i64, vp]
         _LIB = L
     return _LIB
 
@@ -406,6 +419,18 @@ def flowfps_position(p, n):
     nleft, t = i32(0), i32(0)
     lib().mvb200_flowfps_position(C.byref(p), n, C.byref(nleft), C.byref(t))
     return nleft.value, t.value
+
+
+def flowblur_params(sp, vd_bw, vd_fw, num_frames, **kw):
+    a = FlowBlurArgs()
+    a.blur = _opt(kw, "blur", float("nan"), float)
+    a.prec, a.thscd2 = _opt(kw, "prec", UNSET), _opt(kw, "thscd2", UNSET)
+    a.thscd1 = _opt(kw, "thscd1", UNSET64)
+    if kw:
+        raise TypeError("FlowBlur: unknown argument(s) %s" % sorted(kw))
+    out = FlowBlurParams()
+    _check(lib().mvb200_flowblur_init(C.byref(a), C.byref(sp), C.byref(vd_bw), C.byref(vd_fw), num_frames, C.byref(out)))
+    return out
 
 
 def simple_resize_tables(out, in_):
@@ -610,3 +635,15 @@ class Context:
         d, ds = plane_ptrs(dst)
         _check(lib().mvb200_blend_frame(self._h, C.byref(sp), time256, s, ss, r, rs, d, ds))
         return dst
+
+    def flowblur_frame(self, p, sp, super_planes, vec_b, vec_f):
+        """-> planes, or None when the vectors are not usable (the caller keeps the source frame)"""
+        w = [p.vd.nWidth, p.nWidthUV, p.nWidthUV][: p.nplanes]
+        h = [p.vd.nHeight, p.nHeightUV, p.nHeightUV][: p.nplanes]
+        dst = alloc_planes(w, h, p.bits, fill=0xA5)
+        s, ss = plane_ptrs(super_planes)
+        d, ds = plane_ptrs(dst)
+        usable = i32(0)
+        ptr = lambda v: None if v is None else v.ctypes.data
+        _check(lib().mvb200_flowblur_frame(self._h, C.byref(p), C.byref(sp), s, ss, ptr(vec_b), ptr(vec_f), d, ds, C.byref(usable)))
+        return dst if usable.value else None

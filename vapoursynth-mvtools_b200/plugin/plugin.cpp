@@ -2,7 +2,7 @@
 //
 // Exports exactly what the reference's module exports (EntryPoint.c:28-50):
 // VapourSynthPluginInit2, which configures the plugin as "com.nodame.mvtools" / namespace
-// "mv" and registers Super, Analyse, Recalculate, Compensate, Degrain1..6, Mask, Finest, Flow, FlowInter, FlowFPS and SCDetection with the reference's
+// "mv" and registers Super, Analyse, Recalculate, Compensate, Degrain1..6, Mask, Finest, Flow, FlowInter, FlowFPS, FlowBlur and SCDetection with the reference's
 // byte-identical argument strings, so existing .vpy scripts load unchanged.  Every filter keeps the reference's
 // create-time validation (messages included, they come from mvb200_*_init), frame
 // properties (Super_*, MVTools_MVAnalysisData, MVTools_vectors) and request pattern; the
@@ -1579,6 +1579,141 @@ void VS_CC flowFpsCreate(const VSMap *in, VSMap *out, void *, VSCore *core, cons
     vsapi->freeNode(node);
 }
 
+// --------------------------------------------------------------- FlowBlur
+// mvflowblurCreate / GetFrame, MVFlowBlur.c:144-567
+struct FlowBlurData {
+    VSNode *node, *super, *mvbw, *mvfw;
+    const VSVideoInfo *vi, *supervi;
+    mvb200_super_params sp;
+    mvb200_flowblur_params p;
+};
+
+const VSFrame *VS_CC flowBlurGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    FlowBlurData *d = (FlowBlurData *)instanceData;
+    const int off = d->p.vd.nDeltaFrame;
+    const bool inRange = n - off >= 0 && n + off < d->vi->numFrames;
+    if (activationReason == arInitial) { // :150-160
+        if (inRange) {
+            vsapi->requestFrameFilter(n - off, d->mvbw, frameCtx);
+            vsapi->requestFrameFilter(n + off, d->mvfw, frameCtx);
+        }
+        vsapi->requestFrameFilter(n, d->super, frameCtx);
+        vsapi->requestFrameFilter(n, d->node, frameCtx);
+    } else if (activationReason == arAllFramesReady) {
+        std::string msg;
+        int rc = 0;
+        int32_t usable = 0;
+        VSFrame *dst = nullptr;
+        if (inRange) {
+            const VSFrame *mvF = vsapi->getFrameFilter(n + off, d->mvfw, frameCtx), *mvB = vsapi->getFrameFilter(n - off, d->mvbw, frameCtx);
+            const VSFrame *ref = vsapi->getFrameFilter(n, d->super, frameCtx);
+            bool missing = false;
+            const uint8_t *vb = vectorsOf(vsapi, mvB, &missing), *vf = vectorsOf(vsapi, mvF, &missing);
+            dst = vsapi->newVideoFrame(&d->vi->format, d->vi->width, d->vi->height, ref, core);
+            if (missing) {
+                rc = 1;
+                msg = "MVTools_vectors property missing";
+            } else {
+                const uint8_t *rp[3];
+                ptrdiff_t rs[3];
+                uint8_t *dp_[3];
+                ptrdiff_t ds[3];
+                planesRO(vsapi, ref, d->supervi->format.numPlanes, rp, rs);
+                planesRW(vsapi, dst, d->vi->format.numPlanes, dp_, ds);
+                std::lock_guard<std::mutex> lock(g_engine_mutex);
+                mvb200_ctx *ctx = engine(msg);
+                rc = ctx ? mvb200_flowblur_frame(ctx, &d->p, &d->sp, rp, rs, vb, vf, dp_, ds, &usable) : 1;
+                if (ctx && rc)
+                    msg = mvb200_last_error();
+            }
+            vsapi->freeFrame(mvF);
+            vsapi->freeFrame(mvB);
+            vsapi->freeFrame(ref);
+        }
+        if (rc) {
+            vsapi->setFilterError(("FlowBlur: " + msg).c_str(), frameCtx);
+            vsapi->freeFrame(dst);
+            return nullptr;
+        }
+        if (!usable) { // :331-335
+            vsapi->freeFrame(dst);
+            return vsapi->getFrameFilter(n, d->node, frameCtx);
+        }
+        return dst;
+    }
+    return nullptr;
+}
+
+void VS_CC flowBlurFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
+    FlowBlurData *d = (FlowBlurData *)instanceData;
+    vsapi->freeNode(d->node);
+    vsapi->freeNode(d->super);
+    vsapi->freeNode(d->mvbw);
+    vsapi->freeNode(d->mvfw);
+    delete d;
+}
+
+void VS_CC flowBlurCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const VSAPI *vsapi) {
+    mvb200_flowblur_args a;
+    a.blur = argFloat(vsapi, in, "blur");
+    a.prec = argInt(vsapi, in, "prec");
+    a.thscd1 = argInt64(vsapi, in, "thscd1");
+    a.thscd2 = argInt(vsapi, in, "thscd2");
+    // argument checks before any clip is touched (MVFlowBlur.c:374-382)
+    if (a.blur == a.blur && ((float)a.blur < 0.0f || (float)a.blur > 200.0f)) {
+        vsapi->mapSetError(out, "FlowBlur: blur must be between 0 and 200 % (inclusive).");
+        return;
+    }
+    if (a.prec != MVB200_UNSET && a.prec < 1) {
+        vsapi->mapSetError(out, "FlowBlur: prec must be at least 1.");
+        return;
+    }
+    FlowBlurData d;
+    memset(&d, 0, sizeof(d));
+    auto freeAll = [&]() {
+        vsapi->freeNode(d.node);
+        vsapi->freeNode(d.super);
+        vsapi->freeNode(d.mvbw);
+        vsapi->freeNode(d.mvfw);
+    };
+    d.super = vsapi->mapGetNode(in, "super", 0, nullptr);
+    d.supervi = vsapi->getVideoInfo(d.super);
+    std::string msg;
+    mvb200_analysis_data vdb, vdf;
+    if (!superFromClip(d.super, vsapi, "FlowBlur", &d.sp, msg)) {
+        vsapi->mapSetError(out, msg.c_str());
+        freeAll();
+        return;
+    }
+    d.mvbw = vsapi->mapGetNode(in, "mvbw", 0, nullptr);
+    d.mvfw = vsapi->mapGetNode(in, "mvfw", 0, nullptr);
+    if (!adataFromClip(d.mvbw, vsapi, "FlowBlur", "mvbw", &vdb, msg) || !adataFromClip(d.mvfw, vsapi, "FlowBlur", "mvfw", &vdf, msg)) {
+        vsapi->mapSetError(out, msg.c_str());
+        freeAll();
+        return;
+    }
+    d.node = vsapi->mapGetNode(in, "clip", 0, nullptr);
+    d.vi = vsapi->getVideoInfo(d.node);
+    if (mvb200_flowblur_init(&a, &d.sp, &vdb, &vdf, d.vi->numFrames, &d.p)) {
+        vsapi->mapSetError(out, mvb200_last_error());
+        freeAll();
+        return;
+    }
+    if (!formatOk(d.vi)) {
+        vsapi->mapSetError(out, "FlowBlur: input clip must be GRAY, 420, 422, 440, or 444, up to 16 bits, with constant dimensions.");
+        freeAll();
+        return;
+    }
+    if (d.vi->width != vdb.nWidth || d.vi->height != vdb.nHeight || d.vi->format.bitsPerSample != d.sp.bits) {
+        vsapi->mapSetError(out, "FlowBlur: wrong source or super clip frame size.");
+        freeAll();
+        return;
+    }
+    FlowBlurData *data = new FlowBlurData(d);
+    VSFilterDependency deps[4] = {{data->node, rpStrictSpatial}, {data->super, rpStrictSpatial}, {data->mvbw, rpGeneral}, {data->mvfw, rpGeneral}};
+    vsapi->createVideoFilter(out, "FlowBlur", data->vi, flowBlurGetFrame, flowBlurFree, fmParallel, deps, 4, data, core);
+}
+
 } // namespace
 
 VS_EXTERNAL_API(void) VapourSynthPluginInit2(VSPlugin *plugin, const VSPLUGINAPI *vspapi) {
@@ -1618,6 +1753,8 @@ VS_EXTERNAL_API(void) VapourSynthPluginInit2(VSPlugin *plugin, const VSPLUGINAPI
     vspapi->registerFunction("Finest", "super:vnode;opt:int:opt;", "clip:vnode;", finestCreate, nullptr, plugin);
     vspapi->registerFunction("Flow", "clip:vnode;super:vnode;vectors:vnode;time:float:opt;mode:int:opt;fields:int:opt;thscd1:int:opt;thscd2:int:opt;opt:int:opt;tff:int:opt;", "clip:vnode;", flowCreate, nullptr, plugin);
     vspapi->registerFunction("SCDetection", "clip:vnode;vectors:vnode;thscd1:int:opt;thscd2:int:opt;", "clip:vnode;", scdCreate, nullptr, plugin);
+    // MVFlowBlur.c:550-566
+    vspapi->registerFunction("FlowBlur", "clip:vnode;super:vnode;mvbw:vnode;mvfw:vnode;blur:float:opt;prec:int:opt;thscd1:int:opt;thscd2:int:opt;opt:int:opt;", "clip:vnode;", flowBlurCreate, nullptr, plugin);
     // MVFlowFPS.c:913-928
     vspapi->registerFunction("FlowFPS", "clip:vnode;super:vnode;mvbw:vnode;mvfw:vnode;num:int:opt;den:int:opt;mask:int:opt;ml:float:opt;blend:int:opt;thscd1:int:opt;thscd2:int:opt;opt:int:opt;", "clip:vnode;", flowFpsCreate, nullptr, plugin);
     // MVFlowInter.c:696-711
