@@ -180,8 +180,9 @@ def run_engine_flow(case, scd_fn, mask_fn, finest_fn, flow_fn):
     return out
 
 
-def run_reference_flow(case, plugin_path=None):
-    """The same stages through a VapourSynth plugin (default: the compiled reference) and the mini host."""
+def run_reference_flow(case, plugin_path=None, only=None):
+    """The same stages through a VapourSynth plugin (default: the compiled reference) and the mini host.
+    only: restrict to these stage names."""
     import minivs
     ck, skw, akw, radius, dkw = CASES[case]
     frames = pipeline.make_frames(ck)
@@ -193,36 +194,37 @@ def run_reference_flow(case, plugin_path=None):
     vn = [mv.Analyse(sup, isb=isb, delta=1, **pipeline._fix(akw)) for isb in (1, 0)]
     nplanes = 1 if ck.get("gray") else 3
     out = {"scd": [], "mask": [], "flow": [], "finest": []}
-    for kw in FLOW[case].get("scd", []):
+    want = lambda stage: FLOW[case].get(stage, []) if (only is None or stage in only) else []
+    for kw in want("scd"):
         v, kw = _split(kw)
         node = mv.SCDetection(clip, vn[v], **kw)
         key = "_SceneChangeNext" if v == 0 else "_SceneChangePrev"  # isBackward -> Next (MVSCDetection.c:61-63)
         out["scd"].append([int(node.get_frame(n).prop_int(key)) for n in range(N)])
-    for kw in FLOW[case].get("mask", []):
+    for kw in want("mask"):
         v, kw = _split(kw)
         kw = {k: (float(x) if k in ("ml", "gamma", "time") else x) for k, x in kw.items()}
         node = mv.Mask(clip, vn[v], **kw)
         out["mask"].append([[sha(p) for p in node.get_frame(n).planes()] for n in range(N)])
-    for kw in FLOW[case].get("flow", []):
+    for kw in want("flow"):
         v, kw = _split(kw)
         kw = {k: (float(x) if k == "time" else x) for k, x in kw.items()}
         node = mv.Flow(clip, sup, vn[v], **kw)
         out["flow"].append([[sha(p) for p in node.get_frame(n).planes()[:nplanes]] for n in range(N)])
-    if FLOW[case].get("finest"):
+    if want("finest"):
         node = mv.Finest(sup)
         out["finest"] = [[sha(p) for p in node.get_frame(n).planes()[:nplanes]] for n in range(N)]
     out["inter"] = []
-    for kw in FLOW[case].get("inter", []):
+    for kw in want("inter"):
         kw = {k: (float(x) if k in ("time", "ml") else x) for k, x in kw.items()}
         node = mv.FlowInter(clip, sup, vn[0], vn[1], **kw)
         out["inter"].append([[sha(p) for p in node.get_frame(n).planes()[:nplanes]] for n in range(N)])
     out["blur"] = []
-    for kw in FLOW[case].get("blur", []):
+    for kw in want("blur"):
         kw = {k: (float(x) if k == "blur" else x) for k, x in kw.items()}
         node = mv.FlowBlur(clip, sup, vn[0], vn[1], **kw)
         out["blur"].append([[sha(p) for p in node.get_frame(n).planes()[:nplanes]] for n in range(N)])
     out["fps"] = []
-    for kw in FLOW[case].get("fps", []):
+    for kw in want("fps"):
         kw = {k: (float(x) if k == "ml" else x) for k, x in kw.items()}
         node = mv.FlowFPS(clip, sup, vn[0], vn[1], **kw)
         out["fps"].append([[sha(p) for p in node.get_frame(n).planes()[:nplanes]] for n in range(node.num_frames)])

@@ -25,10 +25,37 @@ def test_cuda_flow_matches_reference_goldens(gpu_ctx, case):
     got = pipeline_flow.run_engine_flow(case, ctx.scdetection_frame, ctx.mask_frame, ctx.finest_frame, ctx.flow_frame)
     got["inter"] = pipeline_flow.run_engine_inter(case, ctx.flowinter_frame, ctx.blend_frame)
     got["fps"] = pipeline_flow.run_engine_fps(case, ctx.flowinter_frame, ctx.blend_frame)
-    got["blur"] = pipeline_flow.run_engine_blur(case, ctx.flowblur_frame)
     assert ctx.launch_count() > n0, "no kernel was launched"
-    for stage in ("scd", "mask", "flow", "finest", "inter", "fps", "blur"):
+    for stage in ("scd", "mask", "flow", "finest", "inter", "fps"):
         assert got[stage] == GOLD[case][stage], "%s: CUDA %s differs from the reference's golden hashes" % (case, stage)
+
+
+@pytest.mark.parametrize("case", sorted(c for c in pipeline_flow.FLOW if pipeline_flow.FLOW[c].get("blur")))
+def test_cuda_flowblur_matches_reference_goldens(gpu_ctx, case):
+    """mv.FlowBlur: per-frame entry point and the device-resident batch entry point"""
+    import torch
+    L = mb.lib()
+    ctx = gpu_ctx
+    assert pipeline_flow.run_engine_blur(case, ctx.flowblur_frame) == GOLD[case]["blur"]
+    frames, sups, vecs = pipeline_flow.inputs(case)
+    N = len(frames)
+    sp, aps, P = pipeline_flow.flow_params_for(case)
+    cl, sl = mb.clip_layout(sp), mb.super_layout(sp)
+    dsrc, dsup = _device_clip(frames, cl), _device_clip(sups, sl)
+    vs = (len(vecs[0][0]) + 255) // 256 * 256
+    dvec = []
+    for v in range(2):
+        host = np.zeros((N, vs), dtype=np.uint8)
+        for n in range(N):
+            host[n, : len(vecs[v][n])] = vecs[v][n]
+        dvec.append(torch.from_numpy(host).cuda())
+    for i, p in enumerate(P["blur"]):
+        ddst = torch.full((N, cl.frame_bytes), 0xA5, dtype=torch.uint8, device="cuda")
+        mb._check(L.mvb200_flowblur_batch(ctx.handle, C.byref(p), C.byref(sp), dsrc.data_ptr(), dsup.data_ptr(), 0, N, dvec[0].data_ptr(), dvec[1].data_ptr(), vs, ddst.data_ptr()))
+        ctx.synchronize()
+        out = ddst.cpu().numpy()
+        for n in range(N):
+            assert [pipeline.sha(q) for q in _planes(out[n], cl)] == GOLD[case]["blur"][i][n], "blur variant %d frame %d" % (i, n)
 
 
 @pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "p10_444_blk8_pel4_bicubic"])
@@ -104,13 +131,6 @@ def test_flow_batch_entry_points_match_goldens(gpu_ctx, case):
         out = ddst.cpu().numpy()
         for n in range(N):
             assert [pipeline.sha(q) for q in _planes(out[n], cl)] == GOLD[case]["inter"][i][n], "inter variant %d frame %d" % (i, n)
-    for i, p in enumerate(P["blur"]):
-        ddst = torch.full((N, cl.frame_bytes), 0xA5, dtype=torch.uint8, device="cuda")
-        mb._check(L.mvb200_flowblur_batch(ctx.handle, C.byref(p), C.byref(sp), dsrc.data_ptr(), dsup.data_ptr(), 0, N, dvec[0].data_ptr(), dvec[1].data_ptr(), vs, ddst.data_ptr()))
-        ctx.synchronize()
-        out = ddst.cpu().numpy()
-        for n in range(N):
-            assert [pipeline.sha(q) for q in _planes(out[n], cl)] == GOLD[case]["blur"][i][n], "blur variant %d frame %d" % (i, n)
     if pipeline_flow.FLOW[case].get("finest"):
         fl = mb.finest_layout(sp)
         ddst = torch.full((N, fl.frame_bytes), 0xA5, dtype=torch.uint8, device="cuda")
