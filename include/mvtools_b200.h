@@ -26,6 +26,7 @@
  *   mvflowinterCreate/GetFrame   MVFlowInter.c:83-690   mvb200_flowinter_init / _frame / _batch, mvb200_blend_frame
  *   mvflowfpsCreate/GetFrame     MVFlowFPS.c:86-928     mvb200_flowfps_init / _position + mvb200_flowinter_frame
  *   mvflowblurCreate/GetFrame    MVFlowBlur.c:144-545   mvb200_flowblur_init / _frame / _batch
+ *   mvblockfpsCreate/GetFrame    MVBlockFPS.c:240-1015  mvb200_blockfps_init / _position / _frame
  *
  * The VapourSynth plugin (vapoursynth-mvtools_b200/plugin, exporting
  * VapourSynthPluginInit2 like EntryPoint.c:28-50) is a thin host-side glue over
@@ -324,6 +325,29 @@ typedef struct mvb200_flowblur_params {
     int32_t num_frames;
 } mvb200_flowblur_params;
 
+/* mv.BlockFPS (MVBlockFPS.c): block-based frame-rate conversion */
+typedef struct mvb200_blockfps_args {
+    int64_t num, den;             /* MVB200_UNSET64 = default (25, 1) */
+    int32_t mode;                 /* MVB200_UNSET = default (3) */
+    double ml;                    /* NaN = default (100.0) */
+    int32_t blend;
+    int64_t thscd1;
+    int32_t thscd2;
+} mvb200_blockfps_args;
+
+typedef struct mvb200_blockfps_params {
+    mvb200_analysis_data vd;      /* of mvbw */
+    int32_t mode, blend;
+    double ml;
+    int64_t nSCD1;
+    int32_t nSCD2;
+    int32_t bits, ssw, ssh, gray, nplanes;
+    int32_t super_hpad, super_vpad, super_pel, super_modeyuv, super_levels;
+    int32_t nBlkXP, nBlkYP, nWidthP, nHeightP, nWidthPUV, nHeightPUV, nWidthUV, nHeightUV, nPitchY, nPitchUV;
+    int64_t fa, fb, fps_num, fps_den;
+    int32_t num_frames_in, num_frames_out;
+} mvb200_blockfps_params;
+
 /* ------------------------------------------------------------- host logic */
 /* (pure host code: usable without a GPU; restates the reference's *Create) */
 
@@ -369,6 +393,15 @@ MVB200_API void mvb200_flowfps_position(const mvb200_flowfps_params *p, int n, i
 
 /* MVFlowBlur.c:345-545 */
 MVB200_API int mvb200_flowblur_init(const mvb200_flowblur_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd_bw, const mvb200_analysis_data *vd_fw, int num_frames, mvb200_flowblur_params *out);
+
+/* MVBlockFPS.c:736-990 */
+MVB200_API int mvb200_blockfps_init(const mvb200_blockfps_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd_bw, const mvb200_analysis_data *vd_fw, int64_t fps_num, int64_t fps_den, int clip_w, int clip_h,
+                                    int num_frames, mvb200_blockfps_params *out);
+MVB200_API void mvb200_blockfps_position(const mvb200_blockfps_params *p, int n, int32_t *nleft, int32_t *time256); /* MVBlockFPS.c:275-289 */
+
+/* overInit, Overlap.cpp:40-125: the nine overlap windows (TL, TM, TR, ML, MM, MR, BL, BM, BR) of nx * ny int16 each,
+ * built on the host (the reference's cosf(double) expression); the Degrain / Compensate / BlockFPS kernels use them */
+MVB200_API void mvb200_overlap_windows(int nx, int ny, int ox, int oy, int16_t *out9);
 
 /* InitTables, SimpleResize.cpp:26-56: offsets[out] and weights[out] (14-bit) of the bilinear resizer the Mask / Flow
  * filters upsize their per-block fields with (float arithmetic, restated on the host; uploaded once per configuration). */
@@ -517,6 +550,12 @@ MVB200_API int mvb200_flowblur_frame(mvb200_ctx *ctx, const mvb200_flowblur_para
  * unusable frames are copies of the source clip's frames */
 MVB200_API int mvb200_flowblur_batch(mvb200_ctx *ctx, const mvb200_flowblur_params *p, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int first, int n, const void *dev_bw, const void *dev_fw,
                                      int64_t vectors_stride, void *dev_dst);
+
+/* mvblockfpsGetFrame (MVBlockFPS.c:240-640) for one output frame: left_super / right_super are the super frames of
+ * frames nleft and nleft + delta, vec_b = mvbw of nleft, vec_f = mvfw of nleft + delta.  *usable = 0: dst untouched
+ * (the caller blends the source frames with mvb200_blend_frame, or returns the left one). */
+MVB200_API int mvb200_blockfps_frame(mvb200_ctx *ctx, const mvb200_blockfps_params *p, const mvb200_super_params *sp, int time256, const uint8_t *const left_super[3], const ptrdiff_t left_stride[3],
+                                     const uint8_t *const right_super[3], const ptrdiff_t right_stride[3], const uint8_t *vec_b, const uint8_t *vec_f, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,9 @@ MVO_API int mvo_blend_frame(const mvb200_super_params *sp, int time256, const ui
 /* mvflowblurGetFrame, MVFlowBlur.c:144-337 */
 MVO_API int mvo_flowblur_frame(const mvb200_flowblur_params *p, const mvb200_super_params *sp, const uint8_t *const super[3], const ptrdiff_t super_stride[3], const uint8_t *vec_b, const uint8_t *vec_f, uint8_t *const dst[3],
                                const ptrdiff_t dst_stride[3], int32_t *usable);
+/* mvblockfpsGetFrame, MVBlockFPS.c:240-640 */
+MVO_API int mvo_blockfps_frame(const mvb200_blockfps_params *p, const mvb200_super_params *sp, int time256, const uint8_t *const left_super[3], const ptrdiff_t left_stride[3], const uint8_t *const right_super[3],
+                               const ptrdiff_t right_stride[3], const uint8_t *vec_b, const uint8_t *vec_f, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable);
 /* InitTables, SimpleResize.cpp:26-56 */
 MVO_API void mvo_simple_resize_tables(int out, int in, int32_t *offsets, int32_t *weights);
 

@@ -798,3 +798,228 @@ int mvo_flowblur_frame(const mvb200_flowblur_params *p, const mvb200_super_param
         free(fin[pl]);
     return 0;
 }
+
+/* --------------------------------------------------------------- BlockFPS */
+
+/* MakeSADMaskTime with the arguments BlockFPS passes (MVBlockFPS.c:419-420), gamma = 1 */
+/* (sad_mask_time above takes the bit depth: the SAD is scaled down to 8 bits, MaskFun.cpp:157) */
+
+typedef struct SuperPlaneView { /* level 0 of one plane of a super frame (mvpUpdate / mvpGetPointer, MVFrame.cpp:1356-1364,1732-1734) */
+    const uint8_t *base;
+    ptrdiff_t pitch;
+    int hpad, vpad, padded_h, pel, lp, bps;
+} SuperPlaneView;
+
+static const uint8_t *mvp_pointer(const SuperPlaneView *v, int nX, int nY) {
+    int ax = nX + v->hpad * v->pel, ay = nY + v->vpad * v->pel;
+    int idx = (ax & (v->pel - 1)) | ((ay & (v->pel - 1)) << v->lp);
+    return v->base + ((ptrdiff_t)idx * v->padded_h + (ay >> v->lp)) * v->pitch + (ptrdiff_t)(ax >> v->lp) * v->bps;
+}
+
+static int median3(int a, int b, int c) { /* MEDIAN, MVBlockFPS.c:101-110 */
+    int mn = imin(a, b), mx = imax(a, b);
+    return imax(mn, imin(mx, c));
+}
+
+/* RealResultBlock, MVBlockFPS.c:116-222 */
+static void result_block(uint8_t *pDst, ptrdiff_t dst_pitch, const uint8_t *pMCB, ptrdiff_t MCB_pitch, const uint8_t *pMCF, ptrdiff_t MCF_pitch, const uint8_t *pRef, ptrdiff_t ref_pitch, const uint8_t *pSrc, ptrdiff_t src_pitch,
+                         const uint8_t *maskB, int mask_pitch, const uint8_t *maskF, const uint8_t *pOcc, int bw, int bh, int time256, int mode, int bits) {
+    const int bps = (bits + 7) / 8;
+    for (int h = 0; h < bh; h++) {
+        for (int w = 0; w < bw; w++) {
+            int mcb = px(pMCB + h * MCB_pitch, bps, w), mcf = px(pMCF + h * MCF_pitch, bps, w), out;
+            if (mode == 0) {
+                out = (mcb * time256 + mcf * (256 - time256)) >> 8;
+            } else if (mode == 1) {
+                int mca = (mcb * time256 + mcf * (256 - time256)) >> 8;
+                out = median3(px(pRef + h * ref_pitch, bps, w), px(pSrc + h * src_pitch, bps, w), mca);
+            } else if (mode == 2) {
+                int avg = (px(pRef + h * ref_pitch, bps, w) * time256 + px(pSrc + h * src_pitch, bps, w) * (256 - time256)) >> 8;
+                out = median3(avg, mcb, mcf);
+            } else if (mode == 3 || mode == 6) {
+                int mB = maskB[h * mask_pitch + w], mF = maskF[h * mask_pitch + w];
+                out = (((mB * mcf + (255 - mB) * mcb + 255) >> 8) * time256 + ((mF * mcb + (255 - mF) * mcf + 255) >> 8) * (256 - time256)) >> 8;
+            } else if (mode == 4 || mode == 7) {
+                int mB = maskB[h * mask_pitch + w], mF = maskF[h * mask_pitch + w], occ = pOcc[h * mask_pitch + w];
+                int f = (mF * mcb + (255 - mF) * mcf + 255) >> 8;
+                int b = (mB * mcf + (255 - mB) * mcb + 255) >> 8;
+                int avg = (px(pRef + h * ref_pitch, bps, w) * time256 + px(pSrc + h * src_pitch, bps, w) * (256 - time256) + 255) >> 8;
+                int m = (b * time256 + f * (256 - time256)) >> 8;
+                out = (avg * occ + m * (255 - occ) + 255) >> 8;
+            } else {
+                out = pOcc[h * mask_pitch + w] << (bits - 8);
+            }
+            put_px(pDst + h * dst_pitch, bps, w, out);
+        }
+    }
+}
+
+static void blend_rect(uint8_t *dst, const uint8_t *src, const uint8_t *ref, int height, int width, ptrdiff_t dp, ptrdiff_t sp, ptrdiff_t rp, int time256, int bps) { /* Blend, MaskFun.cpp:349-373 */
+    for (int h = 0; h < height; h++)
+        for (int w = 0; w < width; w++)
+            put_px(dst + h * dp, bps, w, (px(src + h * sp, bps, w) * (256 - time256) + px(ref + h * rp, bps, w) * time256) >> 8);
+}
+
+/* mvblockfpsGetFrame, MVBlockFPS.c:240-640 (usable case) */
+int mvo_blockfps_frame(const mvb200_blockfps_params *p, const mvb200_super_params *sp, int time256, const uint8_t *const left_super[3], const ptrdiff_t left_stride[3], const uint8_t *const right_super[3],
+                       const ptrdiff_t right_stride[3], const uint8_t *vec_b, const uint8_t *vec_f, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable) {
+    const mvb200_analysis_data *vd = &p->vd;
+    *usable = left_super && right_super && vec_b && vec_f && is_usable(vec_f, vd, p->nSCD1, p->nSCD2) && is_usable(vec_b, vd, p->nSCD1, p->nSCD2);
+    if (!*usable)
+        return 0;
+    const int bits = p->bits, bps = (bits + 7) / 8, pel = vd->nPel, lp = pel == 4 ? 2 : (pel == 2 ? 1 : 0), mode = p->mode;
+    const int planes = (p->super_modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) ? 3 : 1;
+    const int xR[3] = {1, vd->xRatioUV, vd->xRatioUV}, yR[3] = {1, vd->yRatioUV, vd->yRatioUV};
+    const int nBlkX = vd->nBlkX, nBlkY = vd->nBlkY, nBlkXP = p->nBlkXP, nBlkYP = p->nBlkYP;
+    int W[3], H[3], bw[3], bh[3], ox[3], oy[3], WB[3], HB[3], pitchM[3] = {p->nPitchY, p->nPitchUV, p->nPitchUV};
+    for (int i = 0; i < 3; i++) {
+        W[i] = i ? p->nWidthUV : vd->nWidth;
+        H[i] = i ? p->nHeightUV : vd->nHeight;
+        bw[i] = vd->nBlkSizeX / xR[i];
+        bh[i] = vd->nBlkSizeY / yR[i];
+        ox[i] = vd->nOverlapX / xR[i];
+        oy[i] = vd->nOverlapY / yR[i];
+        WB[i] = (nBlkX * (vd->nBlkSizeX - vd->nOverlapX) + vd->nOverlapX) / xR[i];
+        HB[i] = (nBlkY * (vd->nBlkSizeY - vd->nOverlapY) + vd->nOverlapY) / yR[i];
+    }
+    int validity;
+    const uint8_t *l0B = blob_level0(vec_b, vd, &validity), *l0F = blob_level0(vec_f, vd, &validity);
+    /* masks, :393-440 */
+    uint8_t *MB[3] = {NULL, NULL, NULL}, *MF[3] = {NULL, NULL, NULL}, *MO[3] = {NULL, NULL, NULL};
+    MB[0] = calloc((size_t)p->nHeightP * pitchM[0], 1);
+    MF[0] = calloc((size_t)p->nHeightP * pitchM[0], 1);
+    MO[0] = calloc((size_t)p->nHeightP * pitchM[0], 1);
+    if (planes > 1) {
+        MB[1] = MB[2] = calloc((size_t)p->nHeightPUV * pitchM[1], 1);
+        MF[1] = MF[2] = calloc((size_t)p->nHeightPUV * pitchM[1], 1);
+        MO[1] = MO[2] = calloc((size_t)p->nHeightPUV * pitchM[1], 1);
+    }
+    if (mode >= 3) {
+        const int ns = nBlkXP * nBlkYP, stepX = vd->nBlkSizeX - vd->nOverlapX, stepY = vd->nBlkSizeY - vd->nOverlapY;
+        uint8_t *sB = calloc((size_t)ns, 1), *sF = calloc((size_t)ns, 1), *sO = calloc((size_t)ns, 1);
+        if (mode <= 5) {
+            occlusion_mask_time(l0F, 0, nBlkX, nBlkY, p->ml, 1.0, pel, sF, nBlkXP, time256, stepX, stepY);
+            occlusion_mask_time(l0B, 1, nBlkX, nBlkY, p->ml, 1.0, pel, sB, nBlkXP, 256 - time256, stepX, stepY);
+        } else {
+            sad_mask_time(l0F, nBlkX, nBlkY, 4.0 / (p->ml * vd->nBlkSizeX * vd->nBlkSizeY), 1.0, pel, sF, nBlkXP, time256, stepX, stepY, bits);
+            sad_mask_time(l0B, nBlkX, nBlkY, 4.0 / (p->ml * vd->nBlkSizeX * vd->nBlkSizeY), 1.0, pel, sB, nBlkXP, 256 - time256, stepX, stepY, bits);
+        }
+        pad_mask_small(sF, nBlkXP, nBlkYP, nBlkX, nBlkY);
+        pad_mask_small(sB, nBlkXP, nBlkYP, nBlkX, nBlkY);
+        Resizer up, upUV;
+        resizer_init(&up, p->nWidthP, p->nHeightP, nBlkXP, nBlkYP, vd->nWidth, vd->nHeight, pel);
+        resize_u8(&up, MF[0], pitchM[0], sF, nBlkXP);
+        resize_u8(&up, MB[0], pitchM[0], sB, nBlkXP);
+        if (planes > 1) {
+            resizer_init(&upUV, p->nWidthPUV, p->nHeightPUV, nBlkXP, nBlkYP, p->nWidthUV, p->nHeightUV, pel);
+            resize_u8(&upUV, MF[1], pitchM[1], sF, nBlkXP);
+            resize_u8(&upUV, MB[1], pitchM[1], sB, nBlkXP);
+        }
+        if (mode == 4 || mode == 5 || mode == 7 || mode == 8) {
+            for (int i = 0; i < ns; i++) /* MultMasks, :90-98 */
+                sO[i] = (uint8_t)((sF[i] * sB[i]) / 255);
+            resize_u8(&up, MO[0], pitchM[0], sO, nBlkXP);
+            if (planes > 1)
+                resize_u8(&upUV, MO[1], pitchM[1], sO, nBlkXP);
+        }
+        resizer_free(&up);
+        if (planes > 1)
+            resizer_free(&upUV);
+        free(sB);
+        free(sF);
+        free(sO);
+    }
+    /* plane views and the source / reference pointers at the interior (:443-452; chroma offsets are pad >> 1 whatever the subsampling) */
+    SuperPlaneView vB[3], vF[3];
+    const uint8_t *pRef[3], *pSrc[3];
+    for (int i = 0; i < planes; i++) {
+        FinestPlane f;
+        finest_plane_dims(sp, i, &f);
+        vB[i].base = right_super[i];
+        vB[i].pitch = right_stride[i];
+        vF[i].base = left_super[i];
+        vF[i].pitch = left_stride[i];
+        vB[i].hpad = vF[i].hpad = i ? sp->hpad / sp->xRatioUV : sp->hpad;
+        vB[i].vpad = vF[i].vpad = i ? sp->vpad / sp->yRatioUV : sp->vpad;
+        vB[i].padded_h = vF[i].padded_h = f.ph;
+        vB[i].pel = vF[i].pel = pel;
+        vB[i].lp = vF[i].lp = lp;
+        vB[i].bps = vF[i].bps = bps;
+        const int hp = i ? sp->hpad >> 1 : sp->hpad, vp = i ? sp->vpad >> 1 : sp->vpad;
+        pSrc[i] = left_super[i] + (ptrdiff_t)hp * bps + left_stride[i] * vp;
+        pRef[i] = right_super[i] + (ptrdiff_t)hp * bps + right_stride[i] * vp;
+    }
+    const int stepX0 = vd->nBlkSizeX - vd->nOverlapX, stepY0 = vd->nBlkSizeY - vd->nOverlapY;
+    if (vd->nOverlapX == 0 && vd->nOverlapY == 0) { /* :466-520 */
+        for (int i = 0; i < nBlkX * nBlkY; i++) {
+            const int bx = i % nBlkX, by = i / nBlkX;
+            VEC B = get_vec(l0B, i), F = get_vec(l0F, i);
+            for (int pl = 0; pl < planes; pl++) {
+                const int x0 = bx * bw[pl], y0 = by * bh[pl];
+                const uint8_t *mcb = mvp_pointer(&vB[pl], (bx * stepX0 * pel + ((B.x * (256 - time256)) >> 8)) / xR[pl], (by * stepY0 * pel + ((B.y * (256 - time256)) >> 8)) / yR[pl]);
+                const uint8_t *mcf = mvp_pointer(&vF[pl], (bx * stepX0 * pel + ((F.x * time256) >> 8)) / xR[pl], (by * stepY0 * pel + ((F.y * time256) >> 8)) / yR[pl]);
+                result_block(dst[pl] + y0 * dst_stride[pl] + (ptrdiff_t)x0 * bps, dst_stride[pl], mcb, vB[pl].pitch, mcf, vF[pl].pitch, pRef[pl] + y0 * right_stride[pl] + (ptrdiff_t)x0 * bps, right_stride[pl],
+                             pSrc[pl] + y0 * left_stride[pl] + (ptrdiff_t)x0 * bps, left_stride[pl], MB[pl] + y0 * pitchM[pl] + x0, pitchM[pl], MF[pl] + y0 * pitchM[pl] + x0, MO[pl] + y0 * pitchM[pl] + x0, bw[pl], bh[pl], time256, mode,
+                             bits);
+            }
+        }
+        for (int pl = 0; pl < planes; pl++) { /* the rest right of and below the blocks: time-weighted blend */
+            const int xr = bw[pl] * nBlkX, yb = bh[pl] * nBlkY;
+            blend_rect(dst[pl] + (ptrdiff_t)xr * bps, pSrc[pl] + (ptrdiff_t)xr * bps, pRef[pl] + (ptrdiff_t)xr * bps, yb, W[pl] - xr, dst_stride[pl], left_stride[pl], right_stride[pl], time256, bps);
+            blend_rect(dst[pl] + yb * dst_stride[pl], pSrc[pl] + yb * left_stride[pl], pRef[pl] + yb * right_stride[pl], H[pl] - yb, W[pl], dst_stride[pl], left_stride[pl], right_stride[pl], time256, bps);
+        }
+    } else { /* overlap, :521-606 */
+        int16_t *winY = malloc(sizeof(int16_t) * 9 * (size_t)bw[0] * bh[0]), *winUV = NULL;
+        mvo_overlap_windows(bw[0], bh[0], ox[0], oy[0], winY);
+        if (planes > 1) {
+            winUV = malloc(sizeof(int16_t) * 9 * (size_t)bw[1] * bh[1]);
+            mvo_overlap_windows(bw[1], bh[1], ox[1], oy[1], winUV);
+        }
+        uint8_t *tmp = malloc((size_t)bh[0] * bw[0] * bps);
+        for (int pl = 0; pl < planes; pl++) {
+            blend_rect(dst[pl] + (ptrdiff_t)WB[pl] * bps, pSrc[pl] + (ptrdiff_t)WB[pl] * bps, pRef[pl] + (ptrdiff_t)WB[pl] * bps, HB[pl], W[pl] - WB[pl], dst_stride[pl], left_stride[pl], right_stride[pl], time256, bps);
+            blend_rect(dst[pl] + dst_stride[pl] * HB[pl], pSrc[pl] + left_stride[pl] * HB[pl], pRef[pl] + right_stride[pl] * HB[pl], H[pl] - HB[pl], W[pl], dst_stride[pl], left_stride[pl], right_stride[pl], time256, bps);
+            uint32_t *acc = calloc((size_t)W[pl] * H[pl], sizeof(uint32_t)); /* DstTemp: uint16 (8-bit clips) or uint32 sums */
+            const int16_t *win9 = pl ? winUV : winY;
+            for (int by = 0; by < nBlkY; by++) {
+                const int wby = ((by + nBlkY - 3) / (nBlkY - 2)) * 3;
+                for (int bx = 0; bx < nBlkX; bx++) {
+                    const int wbx = bx == nBlkX - 1 ? 2 : (bx == 0 ? 0 : 1);
+                    const int16_t *win = win9 + (size_t)(wby + wbx) * bw[pl] * bh[pl];
+                    const int i = by * nBlkX + bx, x0 = bx * (bw[pl] - ox[pl]), y0 = by * (bh[pl] - oy[pl]);
+                    VEC B = get_vec(l0B, i), F = get_vec(l0F, i);
+                    const uint8_t *mcb = mvp_pointer(&vB[pl], (bx * stepX0 * pel + ((B.x * (256 - time256)) >> 8)) / xR[pl], (by * stepY0 * pel + ((B.y * (256 - time256)) >> 8)) / yR[pl]);
+                    const uint8_t *mcf = mvp_pointer(&vF[pl], (bx * stepX0 * pel + ((F.x * time256) >> 8)) / xR[pl], (by * stepY0 * pel + ((F.y * time256) >> 8)) / yR[pl]);
+                    result_block(tmp, (ptrdiff_t)bw[pl] * bps, mcb, vB[pl].pitch, mcf, vF[pl].pitch, pRef[pl] + y0 * right_stride[pl] + (ptrdiff_t)x0 * bps, right_stride[pl], pSrc[pl] + y0 * left_stride[pl] + (ptrdiff_t)x0 * bps,
+                                 left_stride[pl], MB[pl] + y0 * pitchM[pl] + x0, pitchM[pl], MF[pl] + y0 * pitchM[pl] + x0, MO[pl] + y0 * pitchM[pl] + x0, bw[pl], bh[pl], time256, mode, bits);
+                    for (int h = 0; h < bh[pl]; h++) /* overlaps_c, Overlap.cpp:144-158 */
+                        for (int w = 0; w < bw[pl]; w++) {
+                            uint32_t *a = &acc[(size_t)(y0 + h) * W[pl] + x0 + w];
+                            *a += (uint32_t)((px(tmp + (ptrdiff_t)h * bw[pl] * bps, bps, w) * win[h * bw[pl] + w]) >> 6);
+                            if (bps == 1)
+                                *a &= 0xffffu;
+                        }
+                }
+            }
+            const int pixelMax = (1 << bits) - 1;
+            for (int h = 0; h < HB[pl]; h++) /* ToPixels, Overlap.cpp:335-356 */
+                for (int w = 0; w < WB[pl]; w++) {
+                    int a = (int)((acc[(size_t)h * W[pl] + w] + 16) >> 5);
+                    put_px(dst[pl] + h * dst_stride[pl], bps, w, a > pixelMax ? pixelMax : a);
+                }
+            free(acc);
+        }
+        free(tmp);
+        free(winY);
+        free(winUV);
+    }
+    free(MB[0]);
+    free(MF[0]);
+    free(MO[0]);
+    if (planes > 1) {
+        free(MB[1]);
+        free(MF[1]);
+        free(MO[1]);
+    }
+    return 0;
+}

@@ -37,6 +37,7 @@ def lib():
         L.mvo_flowinter_frame.argtypes = [PP(mb.FlowInterParams), PP(mb.SuperParams), C.c_int, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, vp, vp, vp, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
         L.mvo_blend_frame.argtypes = [PP(mb.SuperParams), C.c_int, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
         L.mvo_flowblur_frame.argtypes = [PP(mb.FlowBlurParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), vp, vp, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
+        L.mvo_blockfps_frame.argtypes = [PP(mb.BlockFPSParams), PP(mb.SuperParams), C.c_int, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, vp, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
         L.mvo_simple_resize_tables.argtypes = [C.c_int, C.c_int, vp, vp]
         L.mvo_simple_resize_tables.restype = None
         for n in ("mvo_sad", "mvo_satd"):
@@ -203,4 +204,16 @@ def flowblur_frame(p, sp, super_planes, vec_b, vec_f):
     usable = C.c_int32(0)
     ptr = lambda v: None if v is None else v.ctypes.data
     _check(lib().mvo_flowblur_frame(C.byref(p), C.byref(sp), s, ss, ptr(vec_b), ptr(vec_f), d, ds, C.byref(usable)))
+    return dst if usable.value else None
+
+
+def blockfps_frame(p, sp, time256, left_super, right_super, vec_b, vec_f):
+    w = [p.vd.nWidth, p.nWidthUV, p.nWidthUV][: p.nplanes]
+    h = [p.vd.nHeight, p.nHeightUV, p.nHeightUV][: p.nplanes]
+    dst = mb.alloc_planes(w, h, p.bits, fill=0xA5)
+    l, ls = mb.plane_ptrs(left_super)
+    r, rs = mb.plane_ptrs(right_super)
+    d, ds = mb.plane_ptrs(dst)
+    usable = C.c_int32(0)
+    _check(lib().mvo_blockfps_frame(C.byref(p), C.byref(sp), time256, l, ls, r, rs, vec_b.ctypes.data, vec_f.ctypes.data, d, ds, C.byref(usable)))
     return dst if usable.value else None

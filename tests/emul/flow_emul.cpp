@@ -263,3 +263,61 @@ EMUL_API int emul_flowblur_frame(const mvb200_flowblur_params *p, const mvb200_s
     }
     return 0;
 }
+
+EMUL_API int emul_blockfps_frame(const mvb200_blockfps_params *p, const mvb200_super_params *sp, int time256, const uint8_t *const left_super[3], const ptrdiff_t left_stride[3], const uint8_t *const right_super[3],
+                                 const ptrdiff_t right_stride[3], const uint8_t *vec_b, const uint8_t *vec_f, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable_out) {
+    const mvb200_analysis_data &vd = p->vd;
+    const int nb = vd.nBlkX * vd.nBlkY, ns = p->nBlkXP * p->nBlkYP, bps = (p->bits + 7) / 8;
+    const int planes = (p->super_modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) ? 3 : 1;
+    *usable_out = vec_b && vec_f && usable_of(vec_b, nb, p->nSCD1, p->nSCD2, 1) && usable_of(vec_f, nb, p->nSCD1, p->nSCD2, 1);
+    if (!*usable_out)
+        return 0;
+    const int *l0B = blob_level0(vec_b, nb), *l0F = blob_level0(vec_f, nb);
+    std::vector<int> raw[2] = {std::vector<int>(nb, 0), std::vector<int>(nb, 0)}, mask[3] = {std::vector<int>(ns, 0), std::vector<int>(ns, 0), std::vector<int>(ns, 0)};
+    if (p->mode >= 3) {
+        const int stepX = vd.nBlkSizeX - vd.nOverlapX, stepY = vd.nBlkSizeY - vd.nOverlapY;
+        for (int m = 0; m < 2; m++) { // 0 = backward, 1 = forward
+            int *r = raw[m].data();
+            const int *l0 = m == 0 ? l0B : l0F;
+            const int t = m == 0 ? 256 - time256 : time256;
+            for (int j = 0; j < nb; j++) {
+                if (p->mode <= 5) // k_occ_small
+                    occlusion_contrib(l0, m == 0, vd.nBlkX, vd.nBlkY, p->ml, 1.0, vd.nPel, t, stepX, stepY, j % vd.nBlkX, j / vd.nBlkX, [r](int idx, int val) { r[idx] = r[idx] > val ? r[idx] : val; });
+                else // k_sad_small
+                    r[j] = sad_mask_entry(l0, vd.nBlkX, vd.nBlkY, j, 4.0 / (p->ml * vd.nBlkSizeX * vd.nBlkSizeY), vd.nPel, t, stepX, stepY, p->bits - 8);
+            }
+            for (int k = 0; k < ns; k++) // k_pad_mask
+                mask[m][k] = padded_mask_entry(r, vd.nBlkX, vd.nBlkY, k % p->nBlkXP, k / p->nBlkXP);
+        }
+        for (int k = 0; k < ns; k++) // k_mult_masks
+            mask[2][k] = (mask[1][k] * mask[0][k]) / 255;
+    }
+    const size_t n0 = tables_ints(p->nWidthP, p->nHeightP), n1 = planes > 1 ? tables_ints(p->nWidthPUV, p->nHeightPUV) : 0;
+    std::vector<int32_t> tab(n0 + n1);
+    fill_tables(tab.data(), p->nWidthP, p->nHeightP, p->nBlkXP, p->nBlkYP);
+    if (n1)
+        fill_tables(tab.data() + n0, p->nWidthPUV, p->nHeightPUV, p->nBlkXP, p->nBlkYP);
+    const ResizeTables t[2] = {tables_at(tab.data(), p->nWidthP, p->nHeightP), tables_at(tab.data() + n0, p->nWidthPUV, p->nHeightPUV)};
+    std::vector<int16_t> win[2];
+    win[0].resize((size_t)9 * vd.nBlkSizeX * vd.nBlkSizeY);
+    mvb200_overlap_windows(vd.nBlkSizeX, vd.nBlkSizeY, vd.nOverlapX, vd.nOverlapY, win[0].data());
+    if (planes > 1) {
+        win[1].resize((size_t)9 * (vd.nBlkSizeX / vd.xRatioUV) * (vd.nBlkSizeY / vd.yRatioUV));
+        mvb200_overlap_windows(vd.nBlkSizeX / vd.xRatioUV, vd.nBlkSizeY / vd.yRatioUV, vd.nOverlapX / vd.xRatioUV, vd.nOverlapY / vd.yRatioUV, win[1].data());
+    }
+    for (int plane = 0; plane < planes; plane++) { // k_blockfps
+        mvb200_level_geom g;
+        level0_geom(sp, plane, &g);
+        if (left_stride[plane] != right_stride[plane])
+            return 1;
+        const BfpsPlane P = make_bfps_plane(p, time256, plane, mask[0].data(), mask[1].data(), mask[2].data(), win[plane ? 1 : 0].data(), t[plane ? 1 : 0], make_super_plane(left_stride[plane], 0, g));
+        for (int y = 0; y < P.H; y++)
+            for (int x = 0; x < P.W; x++) {
+                if (bps == 1)
+                    dst[plane][y * dst_stride[plane] + x] = (uint8_t)bfps_sample<uint8_t>(P, l0B, l0F, right_super[plane], left_super[plane], x, y);
+                else
+                    *((uint16_t *)(dst[plane] + y * dst_stride[plane]) + x) = (uint16_t)bfps_sample<uint16_t>(P, l0B, l0F, right_super[plane], left_super[plane], x, y);
+            }
+    }
+    return 0;
+}

@@ -23,22 +23,24 @@ FLOW = {
         scd=[dict(), dict(vec=1, thscd1=150, thscd2=30)], finest=True,
         inter=[dict(), dict(time=25.0, ml=40.0), dict(time=80.0, blend=0, thscd1=250, thscd2=60), dict(time=0.0), dict(time=100.0)],
         blur=[dict(), dict(blur=120.0, prec=2), dict(blur=200.0, thscd1=250, thscd2=60)],
+        bfps=[dict(num=50, den=1), dict(num=60, den=1, mode=0), dict(num=60, den=1, mode=1), dict(num=60, den=1, mode=2), dict(num=40, den=1, mode=4, ml=30.0), dict(num=60, den=1, mode=5),
+              dict(num=60, den=1, mode=6, ml=50.0), dict(num=40, den=1, mode=7), dict(num=60, den=1, mode=8, blend=0, thscd1=250, thscd2=60)],
         fps=[dict(num=50, den=1), dict(num=60, den=1, mask=0), dict(num=30000, den=1001, mask=1, ml=50.0), dict(num=50, den=1, mask=0), dict(num=40, den=1, mask=2, blend=0, thscd1=250, thscd2=60)]),
-    "blk16_ov8_pel2_p16_r3": dict(flow=[dict(time=33.0), dict(mode=1, vec=1)], scd=[dict()], finest=True, inter=[dict(), dict(time=70.0, ml=20.0)], fps=[dict(num=50, den=1, mask=0), dict(num=75, den=2, mask=1)], blur=[dict(blur=80.0)]),
-    "p10_444_blk8_pel4_bicubic": dict(flow=[dict(time=80.0), dict(mode=1, time=45.0, vec=1)], finest=True, scd=[dict(thscd2=10)], inter=[dict(time=40.0)], fps=[dict(num=60, den=1)], blur=[dict(blur=150.0, prec=3)]),
-    "gray_blk4_pel1_rf0": dict(mask=[dict(kind=0), dict(kind=2, time=50.0), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=25.0)], finest=True, scd=[dict()], inter=[dict(time=60.0, ml=10.0)], blur=[dict()]),
-    "c1_640x360_p8_blk8_pel1": dict(mask=[dict(kind=1), dict(kind=2, vec=1)], flow=[dict(time=60.0), dict(mode=1)], scd=[dict()], inter=[dict(), dict(time=33.0, blend=0)]),
+    "blk16_ov8_pel2_p16_r3": dict(flow=[dict(time=33.0), dict(mode=1, vec=1)], scd=[dict()], finest=True, inter=[dict(), dict(time=70.0, ml=20.0)], fps=[dict(num=50, den=1, mask=0), dict(num=75, den=2, mask=1)], blur=[dict(blur=80.0)], bfps=[dict(num=60, den=1), dict(num=50, den=1, mode=7, ml=40.0), dict(num=40, den=1, mode=2)]),
+    "p10_444_blk8_pel4_bicubic": dict(flow=[dict(time=80.0), dict(mode=1, time=45.0, vec=1)], finest=True, scd=[dict(thscd2=10)], inter=[dict(time=40.0)], fps=[dict(num=60, den=1)], blur=[dict(blur=150.0, prec=3)], bfps=[dict(num=60, den=1, mode=4), dict(num=60, den=1, mode=1)]),
+    "gray_blk4_pel1_rf0": dict(mask=[dict(kind=0), dict(kind=2, time=50.0), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=25.0)], finest=True, scd=[dict()], inter=[dict(time=60.0, ml=10.0)], blur=[dict()], bfps=[dict(num=60, den=1), dict(num=60, den=1, mode=8)]),
+    "c1_640x360_p8_blk8_pel1": dict(mask=[dict(kind=1), dict(kind=2, vec=1)], flow=[dict(time=60.0), dict(mode=1)], scd=[dict()], inter=[dict(), dict(time=33.0, blend=0)], bfps=[dict(num=40, den=1), dict(num=40, den=1, mode=6), dict(num=40, den=1, mode=4)]),
     "p8_422_blk8x4_sharp0_rf1": dict(mask=[dict(kind=0, ml=10.0), dict(kind=1, time=0.0), dict(kind=2, vec=1, ml=10.0), dict(kind=5)], flow=[dict(vec=1), dict(mode=1, time=100.0)], finest=True,
-                                     scd=[dict(vec=1)], inter=[dict(time=45.0)]),
+                                     scd=[dict(vec=1)], inter=[dict(time=45.0)], bfps=[dict(num=60, den=1, mode=3), dict(num=60, den=1, mode=2)]),
     "noise_badblocks_blk8": dict(mask=[dict(kind=0, ysc=9), dict(kind=1, thscd1=16000, thscd2=255), dict(kind=2, thscd1=16000, thscd2=255, ml=400.0), dict(kind=5, thscd1=16000, thscd2=255, ml=3.0)],
                                  flow=[dict(), dict(thscd1=16000, thscd2=255, time=90.0), dict(mode=1, thscd1=16000, thscd2=255, vec=1)], scd=[dict(), dict(thscd1=16000, thscd2=255)],
-                                 inter=[dict(), dict(blend=0), dict(thscd1=16000, thscd2=255, ml=300.0, time=20.0)], fps=[dict(num=60, den=1), dict(num=60, den=1, blend=0), dict(num=50, den=1, thscd1=16000, thscd2=255, mask=1)], blur=[dict(), dict(thscd1=16000, thscd2=255, blur=100.0)]),
+                                 inter=[dict(), dict(blend=0), dict(thscd1=16000, thscd2=255, ml=300.0, time=20.0)], fps=[dict(num=60, den=1), dict(num=60, den=1, blend=0), dict(num=50, den=1, thscd1=16000, thscd2=255, mask=1)], blur=[dict(), dict(thscd1=16000, thscd2=255, blur=100.0)], bfps=[dict(num=60, den=1), dict(num=60, den=1, thscd1=16000, thscd2=255, mode=7), dict(num=60, den=1, blend=0)]),
     "blk4_420_chroma2x2_pel2": dict(mask=[dict(kind=2, gamma=2.0)], flow=[dict(time=12.0), dict(mode=1)], finest=True),
     # (no mask here: 256-sample rows equal the stride, and the reference's bottom-strip copy, MVMask.c:162-163, is an
     # overlapping memcpy then -- undefined behaviour; the oracle and the engine replicate the last covered row, which is
     # what the reference's row loop does for every other width)
     "divide2_blk16_esa_neg_badrange": dict(flow=[dict(thscd1=16000, thscd2=255), dict(mode=1, thscd1=16000, thscd2=255, vec=1, time=40.0)], scd=[dict(thscd1=16000, thscd2=255)]),
-    "p8_420_blk16_ov4_uncovered": dict(mask=[dict(kind=0), dict(kind=1, ml=30.0), dict(kind=2, vec=1), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=66.0)], scd=[dict()], finest=True, inter=[dict(), dict(time=10.0, ml=50.0)], fps=[dict(num=35, den=1, mask=2), dict(num=20, den=1, mask=0)], blur=[dict(blur=66.0)]),
+    "p8_420_blk16_ov4_uncovered": dict(mask=[dict(kind=0), dict(kind=1, ml=30.0), dict(kind=2, vec=1), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=66.0)], scd=[dict()], finest=True, inter=[dict(), dict(time=10.0, ml=50.0)], fps=[dict(num=35, den=1, mask=2), dict(num=20, den=1, mask=0)], blur=[dict(blur=66.0)], bfps=[dict(num=35, den=1), dict(num=35, den=1, mode=1), dict(num=35, den=1, mode=5)]),
 }
 
 
@@ -74,7 +76,9 @@ def flow_params_for(case):
     N = ck["nframes"]
     sp, aps, dp = pipeline.params_for(case)
     vds = [(ap.ad_divided if ap.divide else ap.ad) for ap in aps[:2]]
-    out = {"mask": [], "flow": [], "scd": [], "inter": [], "fps": [], "blur": []}
+    out = {"mask": [], "flow": [], "scd": [], "inter": [], "fps": [], "blur": [], "bfps": []}
+    for kw in FLOW[case].get("bfps", []):
+        out["bfps"].append(mb.blockfps_params(sp, vds[0], vds[1], N, ck["width"], ck["height"], **kw))
     for kw in FLOW[case].get("blur", []):
         out["blur"].append(mb.flowblur_params(sp, vds[0], vds[1], N, **kw))
     for kw in FLOW[case].get("fps", []):
@@ -158,6 +162,33 @@ def run_engine_blur(case, blur_fn):
     return out
 
 
+def run_engine_bfps(case, bfps_fn, blend_fn):
+    """mv.BlockFPS output frame by output frame (MVBlockFPS.c:240-680) -> hashes"""
+    frames, sups, vecs = inputs(case)
+    N = len(frames)
+    sp, aps, P = flow_params_for(case)
+    nplanes_used = 3 if (sp.modeyuv & 6) else 1
+    out = []
+    for p in P["bfps"]:
+        off = p.vd.nDeltaFrame
+        rows = []
+        for n in range(p.num_frames_out):
+            nleft, time256 = mb.blockfps_position(p, n)
+            nright = nleft + off
+            if time256 == 0:
+                d = frames[min(nleft, N - 1)]
+            elif time256 == 256:
+                d = frames[min(nright, N - 1)]
+            else:
+                d = bfps_fn(p, sp, time256, sups[nleft], sups[nright], vecs[0][nleft], vecs[1][nright]) if nleft < N and nright < N else None
+                if d is None:  # :640-670
+                    src = frames[min(nleft, N - 1)]
+                    d = blend_fn(sp, time256, src, frames[min(nright, N - 1)]) if p.blend else src
+            rows.append([sha(x) for x in d[:nplanes_used]])
+        out.append(rows)
+    return out
+
+
 def run_engine_flow(case, scd_fn, mask_fn, finest_fn, flow_fn):
     """Per-frame stage functions (oracle.* or Context.*) on the oracle-made inputs -> {stage: hashes}"""
     frames, sups, vecs = inputs(case)
@@ -223,6 +254,11 @@ def run_reference_flow(case, plugin_path=None, only=None):
         kw = {k: (float(x) if k == "blur" else x) for k, x in kw.items()}
         node = mv.FlowBlur(clip, sup, vn[0], vn[1], **kw)
         out["blur"].append([[sha(p) for p in node.get_frame(n).planes()[:nplanes]] for n in range(N)])
+    out["bfps"] = []
+    for kw in want("bfps"):
+        kw = {k: (float(x) if k == "ml" else x) for k, x in kw.items()}
+        node = mv.BlockFPS(clip, sup, vn[0], vn[1], **kw)
+        out["bfps"].append([[sha(p) for p in node.get_frame(n).planes()[:nplanes]] for n in range(node.num_frames)])
     out["fps"] = []
     for kw in want("fps"):
         kw = {k: (float(x) if k == "ml" else x) for k, x in kw.items()}

@@ -38,6 +38,7 @@ def emul():
         L.emul_flowinter_frame.argtypes = [PP(mb.FlowInterParams), PP(mb.SuperParams), C.c_int, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, vp, vp, vp, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
         L.emul_blend_frame.argtypes = [PP(mb.SuperParams), C.c_int, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t)]
         L.emul_flowblur_frame.argtypes = [PP(mb.FlowBlurParams), PP(mb.SuperParams), PP(vp), PP(C.c_ssize_t), vp, vp, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
+        L.emul_blockfps_frame.argtypes = [PP(mb.BlockFPSParams), PP(mb.SuperParams), C.c_int, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, vp, PP(vp), PP(C.c_ssize_t), PP(C.c_int32)]
         _LIB = L
     return _LIB
 
@@ -100,6 +101,18 @@ def blur(p, sp, super_planes, vec_b, vec_f):
     return dst if usable.value else None
 
 
+def bfps(p, sp, time256, left_super, right_super, vec_b, vec_f):
+    w = [p.vd.nWidth, p.nWidthUV, p.nWidthUV][: p.nplanes]
+    h = [p.vd.nHeight, p.nHeightUV, p.nHeightUV][: p.nplanes]
+    dst = mb.alloc_planes(w, h, p.bits, fill=0xA5)
+    l, ls = mb.plane_ptrs(left_super)
+    r, rs = mb.plane_ptrs(right_super)
+    d, ds = mb.plane_ptrs(dst)
+    usable = C.c_int32(0)
+    assert emul().emul_blockfps_frame(C.byref(p), C.byref(sp), time256, l, ls, r, rs, vec_b.ctypes.data, vec_f.ctypes.data, d, ds, C.byref(usable)) == 0
+    return dst if usable.value else None
+
+
 def blend(sp, time256, src, ref):
     dst = mb.alloc_planes([a.shape[1] for a in src], [a.shape[0] for a in src], sp.bits, fill=0xA5)
     s, ss = mb.plane_ptrs(src)
@@ -115,7 +128,8 @@ def test_kernel_arithmetic_matches_reference_goldens(built, case):
     got["inter"] = pipeline_flow.run_engine_inter(case, inter, blend)
     got["fps"] = pipeline_flow.run_engine_fps(case, inter, blend)
     got["blur"] = pipeline_flow.run_engine_blur(case, blur)
-    for stage in ("scd", "mask", "flow", "finest", "inter", "fps", "blur"):
+    got["bfps"] = pipeline_flow.run_engine_bfps(case, bfps, blend)
+    for stage in ("scd", "mask", "flow", "finest", "inter", "fps", "blur", "bfps"):
         assert got[stage] == GOLD[case][stage], "%s: emulated kernels' %s differs from the reference's golden hashes" % (case, stage)
 
 

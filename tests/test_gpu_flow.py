@@ -58,6 +58,13 @@ def test_cuda_flowblur_matches_reference_goldens(gpu_ctx, case):
             assert [pipeline.sha(q) for q in _planes(out[n], cl)] == GOLD[case]["blur"][i][n], "blur variant %d frame %d" % (i, n)
 
 
+@pytest.mark.parametrize("case", sorted(c for c in pipeline_flow.FLOW if pipeline_flow.FLOW[c].get("bfps")))
+def test_cuda_blockfps_matches_reference_goldens(gpu_ctx, case):
+    """mv.BlockFPS: every output frame of every variant (modes 0..8, with and without overlap)"""
+    ctx = gpu_ctx
+    assert pipeline_flow.run_engine_bfps(case, ctx.blockfps_frame, ctx.blend_frame) == GOLD[case]["bfps"]
+
+
 @pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "p10_444_blk8_pel4_bicubic"])
 def test_cuda_flow_matches_oracle_bytes(gpu_ctx, case):
     """byte-level comparison against the oracle (locates a mismatch instead of a hash); includes a field shift"""

@@ -25,13 +25,14 @@ def oracle_run(case):
     out["inter"] = pipeline_flow.run_engine_inter(case, oracle.flowinter_frame, oracle.blend_frame)
     out["fps"] = pipeline_flow.run_engine_fps(case, oracle.flowinter_frame, oracle.blend_frame)
     out["blur"] = pipeline_flow.run_engine_blur(case, oracle.flowblur_frame)
+    out["bfps"] = pipeline_flow.run_engine_bfps(case, oracle.blockfps_frame, oracle.blend_frame)
     return out
 
 
 @pytest.mark.parametrize("case", sorted(pipeline_flow.FLOW))
 def test_flow_oracle_matches_golden(built, case):
     got = oracle_run(case)
-    for stage in ("scd", "mask", "flow", "finest", "inter", "fps", "blur"):
+    for stage in ("scd", "mask", "flow", "finest", "inter", "fps", "blur", "bfps"):
         assert got[stage] == GOLD[case][stage], "%s: oracle %s differs from the reference's golden hashes" % (case, stage)
 
 

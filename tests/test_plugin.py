@@ -18,7 +18,7 @@ GOLD = json.load(open(os.path.join(HERE, "golden", "golden.json")))
 GOLD_FLOW = json.load(open(os.path.join(HERE, "golden", "golden_flow.json")))
 # functions of the reference (registration.json lists everything its build here registers) that this plugin does not
 # provide yet: the remaining SURVEY.md 8f rows (Depan needs complex FFTW and is not in the reference build either)
-NOT_YET = {"BlockFPS"}
+NOT_YET = set()
 
 
 def test_registration_is_the_references(built):
@@ -73,6 +73,7 @@ def test_create_time_errors_through_the_plugin(built):
                       (lambda: mv.FlowFPS(clip, clip, clip, clip, mask=3), "FlowFPS: mask must be 0, 1, or 2."),
                       (lambda: mv.FlowBlur(clip, clip, clip, clip, blur=201.0), "FlowBlur: blur must be between 0 and 200 % (inclusive)."),
                       (lambda: mv.FlowBlur(clip, clip, clip, clip, prec=0), "FlowBlur: prec must be at least 1."),
+                      (lambda: mv.BlockFPS(clip, clip, clip, clip, mode=9), "BlockFPS: mode must be between 0 and 8 (inclusive)."),
                       (lambda: mv.FlowInter(clip, clip, clip, clip, time=-2.0), "FlowInter: time must be between 0 and 100 % (inclusive)."),
                       (lambda: mv.Flow(clip, clip, clip, time=101.0), "Flow: time must be between 0 and 100 % (inclusive).")):
         with pytest.raises(minivs.Error) as e:
@@ -110,3 +111,11 @@ def test_flowblur_script_through_plugin_matches_reference(built, case):
     import pipeline_flow
     got = pipeline_flow.run_reference_flow(case, plugin_path=mb.PLUGIN_PATH, only=("blur",))
     assert got["blur"] == GOLD_FLOW[case]["blur"], "%s: plugin mv.FlowBlur differs from the reference plugin" % case
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "c1_640x360_p8_blk8_pel1", "noise_badblocks_blk8"])
+def test_blockfps_script_through_plugin_matches_reference(built, case):
+    import pipeline_flow
+    got = pipeline_flow.run_reference_flow(case, plugin_path=mb.PLUGIN_PATH, only=("bfps",))
+    assert got["bfps"] == GOLD_FLOW[case]["bfps"], "%s: plugin mv.BlockFPS differs from the reference plugin" % case

@@ -563,6 +563,16 @@ void overlap_windows(int nx, int ny, int ox, int oy, std::vector<short> &out) {
 
 void overlap_windows_host(int nx, int ny, int ox, int oy, std::vector<short> &out) { overlap_windows(nx, ny, ox, oy, out); }
 
+} // namespace mvb200
+
+extern "C" void mvb200_overlap_windows(int nx, int ny, int ox, int oy, int16_t *out9) {
+    std::vector<short> w;
+    mvb200::overlap_windows_host(nx, ny, ox, oy, w);
+    memcpy(out9, w.data(), w.size() * sizeof(short));
+}
+
+namespace mvb200 {
+
 int launch_degrain(Ctx *ctx, const mvb200_degrain_params *dp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, const uint8_t *dev_super, int num_frames,
                    int first, int n, const uint8_t *const *dev_vectors, long long vectors_stride, uint8_t *dev_dst) {
     if (n <= 0)

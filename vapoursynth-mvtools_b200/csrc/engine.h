@@ -137,6 +137,10 @@ struct Ctx {
     int rz_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int *rz_dev = nullptr;
     bool rz_valid = false;
+    // overlap windows of the last BlockFPS configuration
+    int bfw_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    short *bfw_dev[2] = {nullptr, nullptr};
+    bool bfw_valid = false;
     // host-buffer clip pipeline (mvb200_degrain_clip_host_async): copy streams + double-buffered clips
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};

@@ -195,6 +195,29 @@ __global__ void k_flow_blur(BlurPlane P, const uint8_t *__restrict__ super_frame
     *d = (T)flow_blur_sample<T>(P, super_frame, x, y);
 }
 
+// --------------------------------------------------------------- BlockFPS
+__global__ void k_sad_small(const uint8_t *blob, int nBlkX, int nBlkY, double dSADNormFactor, int nPel, int time256, int stepX, int stepY, int shift, int *raw) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nBlkX * nBlkY)
+        raw[j] = sad_mask_entry(blob_level0(blob, nBlkX * nBlkY), nBlkX, nBlkY, j, dSADNormFactor, nPel, time256, stepX, stepY, shift);
+}
+
+__global__ void k_mult_masks(const int *f, const int *b, int n, int *o) { // MultMasks, MVBlockFPS.c:90-98
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n)
+        o[k] = (f[k] * b[k]) / 255;
+}
+
+template <typename T>
+__global__ void k_blockfps(BfpsPlane P, const uint8_t *__restrict__ vec_b, const uint8_t *__restrict__ vec_f, const uint8_t *__restrict__ right_super, const uint8_t *__restrict__ left_super, uint8_t *__restrict__ dst,
+                           long long dst_pitch, const int *__restrict__ flags) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= P.W || y >= P.H || !(flags[0] && flags[1]))
+        return;
+    const int nb = P.nBlkX * P.nBlkY;
+    *((T *)(dst + (long long)y * dst_pitch) + x) = (T)bfps_sample<T>(P, blob_level0(vec_b, nb), blob_level0(vec_f, nb), right_super, left_super, x, y);
+}
+
 // ------------------------------------------------------------ host helpers
 
 constexpr int kSlotTables = 16, kSlotSmall = 17, kSlotStage = 18;
@@ -441,6 +464,80 @@ static int launch_flowblur(Ctx *c, const mvb200_flowblur_params *p, const SuperD
             k_flow_blur<uint8_t><<<grid, blk, 0, st>>>(P, super_frame, dev_dst + cd.offset[plane], cd.pitch[plane], src, flags);
         else
             k_flow_blur<uint16_t><<<grid, blk, 0, st>>>(P, super_frame, dev_dst + cd.offset[plane], cd.pitch[plane], src, flags);
+        c->launches++;
+    }
+    MVB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+void overlap_windows_host(int nx, int ny, int ox, int oy, std::vector<short> &out); // degrain.cu
+
+// mvblockfpsGetFrame (MVBlockFPS.c:240-640), usable case, for one output frame on the device
+static int launch_blockfps(Ctx *c, const mvb200_blockfps_params *p, const SuperDesc &sd, const ClipDesc &cd, int time256, const uint8_t *left_super, const uint8_t *right_super, const uint8_t *vec_b, const uint8_t *vec_f, uint8_t *dev_dst,
+                           int **flags_dev) {
+    cudaStream_t st = c->stream;
+    const mvb200_analysis_data &vd = p->vd;
+    const int ns = p->nBlkXP * p->nBlkYP, nb = vd.nBlkX * vd.nBlkY;
+    const int planes = (p->super_modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) ? 3 : 1;
+    const size_t mask_bytes = align256((size_t)ns * sizeof(int)), raw_bytes = align256((size_t)nb * sizeof(int));
+    uint8_t *scr = (uint8_t *)c->get_scratch(kSlotSmall, 256 + 3 * mask_bytes + 2 * raw_bytes);
+    if (!scr)
+        return 1;
+    int *flags = (int *)scr;
+    *flags_dev = flags;
+    int *mask[3] = {(int *)(scr + 256), (int *)(scr + 256 + mask_bytes), (int *)(scr + 256 + 2 * mask_bytes)}; // B, F, O
+    int *raw[2] = {(int *)(scr + 256 + 3 * mask_bytes), (int *)(scr + 256 + 3 * mask_bytes + raw_bytes)};
+    ResizeTables t[2];
+    if (get_resize_tables(c, p->nWidthP, p->nHeightP, planes > 1 ? p->nWidthPUV : 0, planes > 1 ? p->nHeightPUV : 0, p->nBlkXP, p->nBlkYP, t))
+        return 1;
+    const bool overlap = vd.nOverlapX || vd.nOverlapY;
+    if (overlap) { // the nine windows per plane type, resident until the configuration changes
+        const int key[8] = {vd.nBlkSizeX, vd.nBlkSizeY, vd.nOverlapX, vd.nOverlapY, planes > 1 ? vd.xRatioUV : 0, planes > 1 ? vd.yRatioUV : 0, 1, 0};
+        if (!c->bfw_valid || memcmp(key, c->bfw_key, sizeof(key)) != 0) {
+            std::vector<short> wl, wc;
+            overlap_windows_host(vd.nBlkSizeX, vd.nBlkSizeY, vd.nOverlapX, vd.nOverlapY, wl);
+            if (planes > 1)
+                overlap_windows_host(vd.nBlkSizeX / vd.xRatioUV, vd.nBlkSizeY / vd.yRatioUV, vd.nOverlapX / vd.xRatioUV, vd.nOverlapY / vd.yRatioUV, wc);
+            const size_t bl = wl.size() * sizeof(short), bc = wc.size() * sizeof(short), offc = align256(bl);
+            uint8_t *dev = (uint8_t *)c->get_scratch(19, offc + bc + 256);
+            if (!dev)
+                return 1;
+            MVB_CUDA_CHECK(cudaStreamSynchronize(st));
+            MVB_CUDA_CHECK(cudaMemcpy(dev, wl.data(), bl, cudaMemcpyHostToDevice));
+            if (bc)
+                MVB_CUDA_CHECK(cudaMemcpy(dev + offc, wc.data(), bc, cudaMemcpyHostToDevice));
+            c->bfw_dev[0] = (short *)dev;
+            c->bfw_dev[1] = (short *)(dev + offc);
+            memcpy(c->bfw_key, key, sizeof(key));
+            c->bfw_valid = true;
+        }
+    }
+    k_flow_scd<<<1, 256, 0, st>>>(vec_b, 0, nb, p->nSCD1, p->nSCD2, 1, flags);
+    k_flow_scd<<<1, 256, 0, st>>>(vec_f, 0, nb, p->nSCD1, p->nSCD2, 1, flags + 1);
+    c->launches += 2;
+    if (p->mode >= 3) { // :407-440
+        const int stepX = vd.nBlkSizeX - vd.nOverlapX, stepY = vd.nBlkSizeY - vd.nOverlapY;
+        if (p->mode <= 5) {
+            MVB_CUDA_CHECK(cudaMemsetAsync(raw[0], 0, 2 * raw_bytes, st));
+            k_occ_small<<<(nb + 127) / 128, 128, 0, st>>>(vec_b, 1, vd.nBlkX, vd.nBlkY, p->ml, vd.nPel, 256 - time256, stepX, stepY, raw[0]);
+            k_occ_small<<<(nb + 127) / 128, 128, 0, st>>>(vec_f, 0, vd.nBlkX, vd.nBlkY, p->ml, vd.nPel, time256, stepX, stepY, raw[1]);
+        } else {
+            const double f = 4.0 / (p->ml * vd.nBlkSizeX * vd.nBlkSizeY);
+            k_sad_small<<<(nb + 127) / 128, 128, 0, st>>>(vec_b, vd.nBlkX, vd.nBlkY, f, vd.nPel, 256 - time256, stepX, stepY, p->bits - 8, raw[0]);
+            k_sad_small<<<(nb + 127) / 128, 128, 0, st>>>(vec_f, vd.nBlkX, vd.nBlkY, f, vd.nPel, time256, stepX, stepY, p->bits - 8, raw[1]);
+        }
+        k_pad_mask<<<(ns + 255) / 256, 256, 0, st>>>(raw[0], vd.nBlkX, vd.nBlkY, p->nBlkXP, p->nBlkYP, mask[0]);
+        k_pad_mask<<<(ns + 255) / 256, 256, 0, st>>>(raw[1], vd.nBlkX, vd.nBlkY, p->nBlkXP, p->nBlkYP, mask[1]);
+        k_mult_masks<<<(ns + 255) / 256, 256, 0, st>>>(mask[1], mask[0], ns, mask[2]);
+        c->launches += 5;
+    }
+    for (int plane = 0; plane < planes; plane++) {
+        const BfpsPlane P = make_bfps_plane(p, time256, plane, mask[0], mask[1], mask[2], c->bfw_dev[plane ? 1 : 0], t[plane ? 1 : 0], super_plane_of(sd, plane));
+        dim3 blk(32, 8), grid((P.W + 31) / 32, (P.H + 7) / 8);
+        if (sd.bps == 1)
+            k_blockfps<uint8_t><<<grid, blk, 0, st>>>(P, vec_b, vec_f, right_super, left_super, dev_dst + cd.offset[plane], cd.pitch[plane], flags);
+        else
+            k_blockfps<uint16_t><<<grid, blk, 0, st>>>(P, vec_b, vec_f, right_super, left_super, dev_dst + cd.offset[plane], cd.pitch[plane], flags);
         c->launches++;
     }
     MVB_CUDA_CHECK(cudaGetLastError());
@@ -826,6 +923,51 @@ int mvb200_flowblur_frame(mvb200_ctx *ctx, const mvb200_flowblur_params *p, cons
     *usable_out = flags[0] && flags[1];
     if (*usable_out) {
         for (int pl = 0; pl < p->nplanes; pl++)
+            MVB_CUDA_CHECK(cudaMemcpy2DAsync(dst[pl], (size_t)dst_stride[pl], ddst + cd.offset[pl], (size_t)cd.pitch[pl], (size_t)cd.w[pl] * cd.bps, (size_t)cd.h[pl], cudaMemcpyDeviceToHost, c->stream));
+        MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    return 0;
+}
+
+int mvb200_blockfps_frame(mvb200_ctx *ctx, const mvb200_blockfps_params *p, const mvb200_super_params *sp, int time256, const uint8_t *const left_super[3], const ptrdiff_t left_stride[3], const uint8_t *const right_super[3],
+                          const ptrdiff_t right_stride[3], const uint8_t *vec_b, const uint8_t *vec_f, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable_out) {
+    if (sp->levels > kDevMaxLevels)
+        return set_error("mvtools_b200: more than %d pyramid levels are not supported on the device", kDevMaxLevels);
+    if (p->super_pel != sp->pel || p->super_hpad != sp->hpad || p->super_vpad != sp->vpad || p->bits != sp->bits)
+        return set_error("BlockFPS: the parameters were derived for another super clip");
+    *usable_out = 0;
+    if (!left_super || !right_super || !vec_b || !vec_f)
+        return 0;
+    if (time256 < 0 || time256 > 256)
+        return set_error("BlockFPS: time256 = %d is outside [0, 256]", time256);
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(sp, &sd);
+    make_clip_desc(sp, &cd);
+    const int planes = (p->super_modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) ? 3 : 1;
+    const size_t bb = (size_t)blob_bytes_of(vec_b), bf = (size_t)blob_bytes_of(vec_f);
+    uint8_t *buf = (uint8_t *)c->get_scratch(kSlotStage, 2 * (size_t)sd.frame_bytes + (size_t)cd.frame_bytes + align256(bb) + align256(bf) + 256);
+    if (!buf)
+        return 1;
+    uint8_t *dleft = buf, *dright = buf + sd.frame_bytes, *ddst = dright + sd.frame_bytes, *dvb = ddst + cd.frame_bytes, *dvf = dvb + align256(bb);
+    MVB_CUDA_CHECK(cudaMemcpyAsync(dvb, vec_b, bb, cudaMemcpyHostToDevice, c->stream));
+    MVB_CUDA_CHECK(cudaMemcpyAsync(dvf, vec_f, bf, cudaMemcpyHostToDevice, c->stream));
+    for (int pl = 0; pl < planes; pl++) { // level 0 only
+        const mvb200_level_geom &g = sd.lv[pl][0];
+        MVB_CUDA_CHECK(cudaMemcpy2DAsync(dleft + sd.offset[pl], (size_t)sd.pitch[pl], left_super[pl], (size_t)left_stride[pl], (size_t)g.padded_w * sd.bps, (size_t)g.padded_h * sp->pel * sp->pel, cudaMemcpyHostToDevice, c->stream));
+        MVB_CUDA_CHECK(cudaMemcpy2DAsync(dright + sd.offset[pl], (size_t)sd.pitch[pl], right_super[pl], (size_t)right_stride[pl], (size_t)g.padded_w * sd.bps, (size_t)g.padded_h * sp->pel * sp->pel, cudaMemcpyHostToDevice, c->stream));
+    }
+    int *flags_dev = nullptr;
+    if (launch_blockfps(c, p, sd, cd, time256, dleft, dright, dvb, dvf, ddst, &flags_dev))
+        return 1;
+    int flags[2] = {0, 0};
+    MVB_CUDA_CHECK(cudaMemcpyAsync(flags, flags_dev, sizeof(flags), cudaMemcpyDeviceToHost, c->stream));
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    *usable_out = flags[0] && flags[1];
+    if (*usable_out) {
+        for (int pl = 0; pl < planes; pl++)
             MVB_CUDA_CHECK(cudaMemcpy2DAsync(dst[pl], (size_t)dst_stride[pl], ddst + cd.offset[pl], (size_t)cd.pitch[pl], (size_t)cd.w[pl] * cd.bps, (size_t)cd.h[pl], cudaMemcpyDeviceToHost, c->stream));
         MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     }

@@ -343,5 +343,98 @@ MVB_HD int flow_blur_sample(const BlurPlane &P, const uint8_t *super_frame, int 
     return sum / count;
 }
 
+// ------------------------------------------------------------------ BlockFPS
+
+// MakeSADMaskTime (MaskFun.cpp:136-160) with gamma = 1 as BlockFPS calls it (MVBlockFPS.c:419-420): entry j
+MVB_HD int sad_mask_entry(const int *level0, int nBlkX, int nBlkY, int j, double dSADNormFactor, int nPel, int time256, int stepX, int stepY, int shift) {
+    const int time4096X = (256 - time256) * 16 / (stepX * nPel);
+    const int time4096Y = (256 - time256) * 16 / (stepY * nPel);
+    const int bx = j % nBlkX, by = j / nBlkX;
+    const int *v = level0 + 4 * j;
+    int bxi = bx - v[0] * time4096X / 4096;
+    int byi = by - v[1] * time4096Y / 4096;
+    if (bxi < 0 || bxi >= nBlkX || byi < 0 || byi >= nBlkY) {
+        bxi = bx;
+        byi = by;
+    }
+    const long long sad = vec_sad(level0 + 4 * (bxi + byi * nBlkX)) >> shift;
+    const double l = 255 * (sad * dSADNormFactor); // pow(x, 1.0) is x
+    return (int)(unsigned char)((l > 255) ? 255 : l);
+}
+
+struct BfpsPlane {
+    int plane, W, H, WB, HB, bw, bh, ox, oy, xR, yR, stepX0, stepY0, nBlkX, nBlkY, nBlkXP, pel, logPel, time256, mode, bits;
+    int refHpad, refVpad;             // where the reference puts the interior for its pRef / pSrc reads (MVBlockFPS.c:443-452)
+    const int *maskB, *maskF, *maskO; // padded small masks (nBlkXP x nBlkYP)
+    const short *win;                 // nine overlap windows of bw * bh, or null without overlap
+    ResizeTables t;
+    SuperPlane S;
+};
+
+MVB_HD int bfps_median(int a, int b, int c) { // MEDIAN, MVBlockFPS.c:101-110
+    const int mn = a < b ? a : b, mx = a > b ? a : b, m = mx < c ? mx : c;
+    return mn > m ? mn : m;
+}
+
+// RealResultBlock (MVBlockFPS.c:116-222): the sample block (bx, by) contributes at plane position (x, y)
+template <typename T>
+MVB_HD int bfps_result(const BfpsPlane &P, const int *l0B, const int *l0F, const uint8_t *right_super, const uint8_t *left_super, int bx, int by, int x, int y) {
+    const int i = by * P.nBlkX + bx, t = P.time256;
+    const int ix = x - bx * (P.bw - P.ox), iy = y - by * (P.bh - P.oy);
+    // mvpGetPointer at the time-scaled vector (C division toward zero for the chroma planes), then (ix, iy) inside that sub-plane
+    const int bxB = (bx * P.stepX0 * P.pel + ((l0B[4 * i] * (256 - t)) >> 8)) / P.xR + P.S.hpad * P.pel;
+    const int byB = (by * P.stepY0 * P.pel + ((l0B[4 * i + 1] * (256 - t)) >> 8)) / P.yR + P.S.vpad * P.pel;
+    const int bxF = (bx * P.stepX0 * P.pel + ((l0F[4 * i] * t) >> 8)) / P.xR + P.S.hpad * P.pel;
+    const int byF = (by * P.stepY0 * P.pel + ((l0F[4 * i + 1] * t) >> 8)) / P.yR + P.S.vpad * P.pel;
+    const int mcb = finest_sample<T>(right_super, P.S, P.logPel, bxB + (ix << P.logPel), byB + (iy << P.logPel));
+    const int mcf = finest_sample<T>(left_super, P.S, P.logPel, bxF + (ix << P.logPel), byF + (iy << P.logPel));
+    const int mode = P.mode;
+    if (mode == 0)
+        return (mcb * t + mcf * (256 - t)) >> 8;
+    const long long at = P.S.offset + (long long)(y + P.refVpad) * P.S.pitch + (long long)(x + P.refHpad) * (int)sizeof(T);
+    if (mode == 1 || mode == 2) {
+        const int ref = *(const T *)(right_super + at), src = *(const T *)(left_super + at);
+        if (mode == 1)
+            return bfps_median(ref, src, (mcb * t + mcf * (256 - t)) >> 8);
+        return bfps_median((ref * t + src * (256 - t)) >> 8, mcb, mcf);
+    }
+    const int voff = P.t.voff[y], vwt = P.t.vwt[y], hoff = P.t.hoff[x], hwt = P.t.hwt[x];
+    if (mode == 5 || mode == 8)
+        return (resize_sample<int>(P.maskO, P.nBlkXP, voff, vwt, hoff, hwt) & 255) << (P.bits - 8);
+    const int mB = resize_sample<int>(P.maskB, P.nBlkXP, voff, vwt, hoff, hwt) & 255, mF = resize_sample<int>(P.maskF, P.nBlkXP, voff, vwt, hoff, hwt) & 255;
+    if (mode == 3 || mode == 6)
+        return (((mB * mcf + (255 - mB) * mcb + 255) >> 8) * t + ((mF * mcb + (255 - mF) * mcf + 255) >> 8) * (256 - t)) >> 8;
+    const int occ = resize_sample<int>(P.maskO, P.nBlkXP, voff, vwt, hoff, hwt) & 255; // modes 4, 7
+    const int ref = *(const T *)(right_super + at), src = *(const T *)(left_super + at);
+    const int f = (mF * mcb + (255 - mF) * mcf + 255) >> 8, b = (mB * mcf + (255 - mB) * mcb + 255) >> 8;
+    const int avg = (ref * t + src * (256 - t) + 255) >> 8, m = (b * t + f * (256 - t)) >> 8;
+    return (avg * occ + m * (255 - occ) + 255) >> 8;
+}
+
+// mvblockfpsGetFrame, MVBlockFPS.c:466-606, as a gather: output sample (x, y) of a plane
+template <typename T>
+MVB_HD int bfps_sample(const BfpsPlane &P, const int *l0B, const int *l0F, const uint8_t *right_super, const uint8_t *left_super, int x, int y) {
+    if (x >= P.WB || y >= P.HB) { // right of / below the blocks: time-weighted blend of the two frames
+        const long long at = P.S.offset + (long long)(y + P.refVpad) * P.S.pitch + (long long)(x + P.refHpad) * (int)sizeof(T);
+        return blend_sample(*(const T *)(left_super + at), *(const T *)(right_super + at), P.time256);
+    }
+    if (!P.win)
+        return bfps_result<T>(P, l0B, l0F, right_super, left_super, x / P.bw, y / P.bh, x, y);
+    const int sx = P.bw - P.ox, sy = P.bh - P.oy;
+    const int bx1 = x / sx < P.nBlkX - 1 ? x / sx : P.nBlkX - 1, by1 = y / sy < P.nBlkY - 1 ? y / sy : P.nBlkY - 1;
+    const int bx0 = (bx1 >= 1 && x - bx1 * sx < P.ox) ? bx1 - 1 : bx1, by0 = (by1 >= 1 && y - by1 * sy < P.oy) ? by1 - 1 : by1;
+    unsigned acc = 0; // the reference's uint16 (8-bit clips) / uint32 accumulator: sums commute, the block order does not matter
+    for (int by = by0; by <= by1; by++)
+        for (int bx = bx0; bx <= bx1; bx++) {
+            const int v = bfps_result<T>(P, l0B, l0F, right_super, left_super, bx, by, x, y);
+            const int wby = ((by + P.nBlkY - 3) / (P.nBlkY - 2)) * 3, wbx = bx == P.nBlkX - 1 ? 2 : (bx == 0 ? 0 : 1);
+            acc += (unsigned)((v * (int)P.win[(wby + wbx) * P.bw * P.bh + (y - by * sy) * P.bw + (x - bx * sx)]) >> 6);
+            if (sizeof(T) == 1)
+                acc &= 0xffffu;
+        }
+    const int a = (int)((acc + 16) >> 5), pixelMax = (1 << P.bits) - 1; // ToPixels, Overlap.cpp:335-356
+    return a < pixelMax ? a : pixelMax;
+}
+
 } // namespace flowdev
 } // namespace mvb200

@@ -144,5 +144,41 @@ inline BlurPlane make_blur_plane(const mvb200_flowblur_params *p, int plane, con
     return P;
 }
 
+inline BfpsPlane make_bfps_plane(const mvb200_blockfps_params *p, int time256, int plane, const int *maskB, const int *maskF, const int *maskO, const short *win, const ResizeTables &t, const SuperPlane &S) {
+    const mvb200_analysis_data &vd = p->vd;
+    BfpsPlane P;
+    memset(&P, 0, sizeof(P));
+    P.plane = plane;
+    P.xR = plane ? vd.xRatioUV : 1;
+    P.yR = plane ? vd.yRatioUV : 1;
+    P.W = plane ? p->nWidthUV : vd.nWidth;
+    P.H = plane ? p->nHeightUV : vd.nHeight;
+    P.bw = vd.nBlkSizeX / P.xR;
+    P.bh = vd.nBlkSizeY / P.yR;
+    P.ox = vd.nOverlapX / P.xR;
+    P.oy = vd.nOverlapY / P.yR;
+    P.WB = (vd.nBlkX * (vd.nBlkSizeX - vd.nOverlapX) + vd.nOverlapX) / P.xR; // nWidth_B, MVBlockFPS.c:338-339
+    P.HB = (vd.nBlkY * (vd.nBlkSizeY - vd.nOverlapY) + vd.nOverlapY) / P.yR;
+    P.stepX0 = vd.nBlkSizeX - vd.nOverlapX;
+    P.stepY0 = vd.nBlkSizeY - vd.nOverlapY;
+    P.nBlkX = vd.nBlkX;
+    P.nBlkY = vd.nBlkY;
+    P.nBlkXP = p->nBlkXP;
+    P.pel = vd.nPel;
+    P.logPel = ilog2_pel(vd.nPel);
+    P.time256 = time256;
+    P.mode = p->mode;
+    P.bits = p->bits;
+    P.refHpad = plane ? p->super_hpad >> 1 : p->super_hpad; // (sic: >> 1 whatever the subsampling, :447-451)
+    P.refVpad = plane ? p->super_vpad >> 1 : p->super_vpad;
+    P.maskB = maskB;
+    P.maskF = maskF;
+    P.maskO = maskO;
+    P.win = (vd.nOverlapX || vd.nOverlapY) ? win : nullptr;
+    P.t = t;
+    P.S = S;
+    return P;
+}
+
 } // namespace flowdev
 } // namespace mvb200

@@ -916,6 +916,101 @@ int mvb200_flowblur_init(const mvb200_flowblur_args *a, const mvb200_super_param
     return 0;
 }
 
+int mvb200_blockfps_init(const mvb200_blockfps_args *a, const mvb200_super_params *sp, const mvb200_analysis_data *vd_bw, const mvb200_analysis_data *vd_fw, int64_t fps_num, int64_t fps_den, int clip_w, int clip_h, int num_frames,
+                         mvb200_blockfps_params *d) {
+    memset(d, 0, sizeof(*d));
+    // MVBlockFPS.c:744-782
+    const int64_t num = GIVEN64(a->num) ? a->num : 25, den = GIVEN64(a->den) ? a->den : 1;
+    d->mode = GIVEN(a->mode) ? a->mode : 3;
+    d->ml = (a->ml == a->ml) ? a->ml : 100.0;
+    d->blend = GIVEN(a->blend) ? a->blend != 0 : 1;
+    d->nSCD1 = GIVEN64(a->thscd1) ? a->thscd1 : 400;
+    d->nSCD2 = GIVEN(a->thscd2) ? a->thscd2 : 130;
+    if (d->mode < 0 || d->mode > 8)
+        return set_error("BlockFPS: mode must be between 0 and 8 (inclusive).");
+    d->vd = *vd_bw;
+    // :823-868
+    if (scale_thscd(&d->nSCD1, &d->nSCD2, &d->vd, "BlockFPS"))
+        return 1;
+    if (check_similarity(vd_bw, vd_fw, "BlockFPS", "mvbw", "mvfw"))
+        return 1;
+    if (vd_bw->nDeltaFrame <= 0 || vd_fw->nDeltaFrame <= 0)
+        return set_error("BlockFPS: cannot use motion vectors with absolute frame references.");
+    if (vd_bw->nDeltaFrame != vd_fw->nDeltaFrame)
+        return set_error("BlockFPS: mvbw and mvfw must be generated with the same delta.");
+    if (!vd_bw->isBackward)
+        return set_error("BlockFPS: mvbw must be generated with isb=True.");
+    if (vd_fw->isBackward)
+        return set_error("BlockFPS: mvfw must be generated with isb=False.");
+    // :875-910
+    if (fps_num == 0 || fps_den == 0)
+        return set_error("BlockFPS: The input clip must have a frame rate. Invoke AssumeFPS if necessary.");
+    int64_t numerator, denominator;
+    if (num != 0 && den != 0) {
+        numerator = num;
+        denominator = den;
+    } else {
+        numerator = fps_num * 2;
+        denominator = fps_den;
+    }
+    d->fa = denominator * fps_num;
+    d->fb = numerator * fps_den;
+    const int64_t g = gcd64(d->fa, d->fb);
+    d->fa /= g;
+    d->fb /= g;
+    if (numerator <= 0 || denominator <= 0) {
+        d->fps_num = 0;
+        d->fps_den = 1;
+    } else {
+        const int64_t x = gcd64(numerator, denominator);
+        d->fps_num = numerator / x;
+        d->fps_den = denominator / x;
+    }
+    d->num_frames_in = num_frames;
+    d->num_frames_out = (int)(1 + (num_frames - 1) * d->fb / d->fa);
+    // :913-935
+    if (vd_bw->nHeight != sp->height || vd_bw->nWidth != sp->super_width - sp->hpad * 2 || vd_bw->nWidth != clip_w || vd_bw->nHeight != clip_h || vd_bw->nPel != sp->pel)
+        return set_error("BlockFPS: wrong source or super clip frame size.");
+    if (sp->bits > 16 || sp->ssw > 1 || sp->ssh > 1)
+        return set_error("BlockFPS: input clip must be GRAY, 420, 422, 440, or 444, up to 16 bits, with constant dimensions.");
+    // :938-956
+    const mvb200_analysis_data *vd = vd_bw;
+    d->nBlkXP = vd->nBlkX;
+    d->nBlkYP = vd->nBlkY;
+    while (d->nBlkXP * (vd->nBlkSizeX - vd->nOverlapX) + vd->nOverlapX < vd->nWidth)
+        d->nBlkXP++;
+    while (d->nBlkYP * (vd->nBlkSizeY - vd->nOverlapY) + vd->nOverlapY < vd->nHeight)
+        d->nBlkYP++;
+    d->nWidthP = d->nBlkXP * (vd->nBlkSizeX - vd->nOverlapX) + vd->nOverlapX;
+    d->nHeightP = d->nBlkYP * (vd->nBlkSizeY - vd->nOverlapY) + vd->nOverlapY;
+    d->nWidthPUV = d->nWidthP / vd->xRatioUV;
+    d->nHeightPUV = d->nHeightP / vd->yRatioUV;
+    d->nHeightUV = vd->nHeight / vd->yRatioUV;
+    d->nWidthUV = vd->nWidth / vd->xRatioUV;
+    d->nPitchY = (d->nWidthP + 15) & (~15);
+    d->nPitchUV = (d->nWidthPUV + 15) & (~15);
+    d->bits = sp->bits;
+    d->ssw = sp->ssw;
+    d->ssh = sp->ssh;
+    d->gray = sp->gray;
+    d->nplanes = sp->nplanes;
+    d->super_hpad = sp->hpad;
+    d->super_vpad = sp->vpad;
+    d->super_pel = sp->pel;
+    d->super_modeyuv = sp->modeyuv;
+    d->super_levels = sp->levels;
+    return 0;
+}
+
+void mvb200_blockfps_position(const mvb200_blockfps_params *p, int n, int32_t *nleft, int32_t *time256) {
+    const int off = p->vd.nDeltaFrame;
+    *nleft = (int)(n * p->fa / p->fb);
+    int t = (int)(((double)n * p->fa / p->fb - *nleft) * 256 + 0.5);
+    if (off > 1)
+        t = t / off;
+    *time256 = t;
+}
+
 // InitTables, SimpleResize.cpp:26-56 (single-precision arithmetic, evaluated in the reference's order)
 void mvb200_simple_resize_tables(int out, int in, int32_t *offsets, int32_t *weights) {
     const float leftmost = 0.5f, rightmost = in - 0.5f;

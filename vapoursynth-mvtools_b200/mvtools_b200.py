@@ -168,6 +168,17 @@ class FlowBlurParams(C.Structure):
                             "nWidthUV", "nHeightUV", "nHPaddingUV", "nVPaddingUV", "num_frames")]
 
 
+class BlockFPSArgs(C.Structure):
+    _fields_ = [("num", i64), ("den", i64), ("mode", i32), ("ml", C.c_double), ("blend", i32), ("thscd1", i64), ("thscd2", i32)]
+
+
+class BlockFPSParams(C.Structure):
+    _fields_ = [("vd", AnalysisData), ("mode", i32), ("blend", i32), ("ml", C.c_double), ("nSCD1", i64), ("nSCD2", i32)] + \
+        [(n, i32) for n in ("bits", "ssw", "ssh", "gray", "nplanes", "super_hpad", "super_vpad", "super_pel", "super_modeyuv", "super_levels",
+                            "nBlkXP", "nBlkYP", "nWidthP", "nHeightP", "nWidthPUV", "nHeightPUV", "nWidthUV", "nHeightUV", "nPitchY", "nPitchUV")] + \
+        [(n, i64) for n in ("fa", "fb", "fps_num", "fps_den")] + [("num_frames_in", i32), ("num_frames_out", i32)]
+
+
 class FrameLayout(C.Structure):
     _fields_ = [("nplanes", i32), ("bytes_per_sample", i32), ("plane_w", i32 * 3), ("plane_h", i32 * 3),
                 ("pitch", i64 * 3), ("offset", i64 * 3), ("frame_bytes", i64)]
@@ -256,6 +267,10 @@ def lib():
         L.mvb200_flowblur_init.argtypes = [PP(FlowBlurArgs), PP(SuperParams), PP(AnalysisData), PP(AnalysisData), i32, PP(FlowBlurParams)]
         L.mvb200_flowblur_frame.argtypes = [vp, PP(FlowBlurParams), PP(SuperParams), PP(vp), PP(C.c_ssize_t), vp, vp, PP(vp), PP(C.c_ssize_t), PP(i32)]
         L.mvb200_flowblur_batch.argtypes = [vp, PP(FlowBlurParams), PP(SuperParams), vp, vp, i32, i32, vp, vp, i64, vp]
+        L.mvb200_blockfps_init.argtypes = [PP(BlockFPSArgs), PP(SuperParams), PP(AnalysisData), PP(AnalysisData), i64, i64, i32, i32, i32, PP(BlockFPSParams)]
+        L.mvb200_blockfps_position.argtypes = [PP(BlockFPSParams), i32, PP(i32), PP(i32)]
+        L.mvb200_blockfps_position.restype = None
+        L.mvb200_blockfps_frame.argtypes = [vp, PP(BlockFPSParams), PP(SuperParams), i32, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, vp, PP(vp), PP(C.c_ssize_t), PP(i32)]
         _LIB = L
     return _LIB
 
@@ -431,6 +446,24 @@ def flowblur_params(sp, vd_bw, vd_fw, num_frames, **kw):
     out = FlowBlurParams()
     _check(lib().mvb200_flowblur_init(C.byref(a), C.byref(sp), C.byref(vd_bw), C.byref(vd_fw), num_frames, C.byref(out)))
     return out
+
+
+def blockfps_params(sp, vd_bw, vd_fw, num_frames, clip_w, clip_h, fps_num=25, fps_den=1, **kw):
+    a = BlockFPSArgs()
+    a.num, a.den, a.thscd1 = _opt(kw, "num", UNSET64), _opt(kw, "den", UNSET64), _opt(kw, "thscd1", UNSET64)
+    a.mode, a.blend, a.thscd2 = _opt(kw, "mode", UNSET), _opt(kw, "blend", UNSET), _opt(kw, "thscd2", UNSET)
+    a.ml = _opt(kw, "ml", float("nan"), float)
+    if kw:
+        raise TypeError("BlockFPS: unknown argument(s) %s" % sorted(kw))
+    out = BlockFPSParams()
+    _check(lib().mvb200_blockfps_init(C.byref(a), C.byref(sp), C.byref(vd_bw), C.byref(vd_fw), fps_num, fps_den, clip_w, clip_h, num_frames, C.byref(out)))
+    return out
+
+
+def blockfps_position(p, n):
+    nleft, t = i32(0), i32(0)
+    lib().mvb200_blockfps_position(C.byref(p), n, C.byref(nleft), C.byref(t))
+    return nleft.value, t.value
 
 
 def simple_resize_tables(out, in_):
@@ -646,4 +679,16 @@ class Context:
         usable = i32(0)
         ptr = lambda v: None if v is None else v.ctypes.data
         _check(lib().mvb200_flowblur_frame(self._h, C.byref(p), C.byref(sp), s, ss, ptr(vec_b), ptr(vec_f), d, ds, C.byref(usable)))
+        return dst if usable.value else None
+
+    def blockfps_frame(self, p, sp, time256, left_super, right_super, vec_b, vec_f):
+        """-> planes, or None when the vectors are not usable"""
+        w = [p.vd.nWidth, p.nWidthUV, p.nWidthUV][: p.nplanes]
+        h = [p.vd.nHeight, p.nHeightUV, p.nHeightUV][: p.nplanes]
+        dst = alloc_planes(w, h, p.bits, fill=0xA5)
+        l, ls = plane_ptrs(left_super)
+        r, rs = plane_ptrs(right_super)
+        d, ds = plane_ptrs(dst)
+        usable = i32(0)
+        _check(lib().mvb200_blockfps_frame(self._h, C.byref(p), C.byref(sp), time256, l, ls, r, rs, vec_b.ctypes.data, vec_f.ctypes.data, d, ds, C.byref(usable)))
         return dst if usable.value else None

@@ -2,7 +2,7 @@
 //
 // Exports exactly what the reference's module exports (EntryPoint.c:28-50):
 // VapourSynthPluginInit2, which configures the plugin as "com.nodame.mvtools" / namespace
-// "mv" and registers Super, Analyse, Recalculate, Compensate, Degrain1..6, Mask, Finest, Flow, FlowInter, FlowFPS, FlowBlur and SCDetection with the reference's
+// "mv" and registers Super, Analyse, Recalculate, Compensate, Degrain1..6, Mask, Finest, Flow, FlowInter, FlowFPS, FlowBlur, BlockFPS and SCDetection with the reference's
 // byte-identical argument strings, so existing .vpy scripts load unchanged.  Every filter keeps the reference's
 // create-time validation (messages included, they come from mvb200_*_init), frame
 // properties (Super_*, MVTools_MVAnalysisData, MVTools_vectors) and request pattern; the
@@ -1714,6 +1714,202 @@ void VS_CC flowBlurCreate(const VSMap *in, VSMap *out, void *, VSCore *core, con
     vsapi->createVideoFilter(out, "FlowBlur", data->vi, flowBlurGetFrame, flowBlurFree, fmParallel, deps, 4, data, core);
 }
 
+// --------------------------------------------------------------- BlockFPS
+// mvblockfpsCreate / GetFrame, MVBlockFPS.c:240-1034
+struct BlockFPSData {
+    VSNode *node, *super, *mvbw, *mvfw;
+    VSVideoInfo vi;
+    const VSVideoInfo *oldvi, *supervi;
+    mvb200_super_params sp;
+    mvb200_blockfps_params p;
+};
+
+const VSFrame *VS_CC blockFpsGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    BlockFPSData *d = (BlockFPSData *)instanceData;
+    const int off = d->p.vd.nDeltaFrame, N = d->oldvi->numFrames;
+    int32_t nleft, time256;
+    mvb200_blockfps_position(&d->p, n, &nleft, &time256);
+    const int nright = nleft + off;
+    const bool inRange = nleft < N && nright < N;
+    if (activationReason == arInitial) { // :246-272
+        if (time256 == 0) {
+            vsapi->requestFrameFilter(VSMIN(nleft, N - 1), d->node, frameCtx);
+            return nullptr;
+        } else if (time256 == 256) {
+            vsapi->requestFrameFilter(VSMIN(nright, N - 1), d->node, frameCtx);
+            return nullptr;
+        }
+        if (inRange) {
+            vsapi->requestFrameFilter(nright, d->mvfw, frameCtx);
+            vsapi->requestFrameFilter(nleft, d->mvbw, frameCtx);
+            vsapi->requestFrameFilter(nleft, d->super, frameCtx);
+            vsapi->requestFrameFilter(nright, d->super, frameCtx);
+        }
+        vsapi->requestFrameFilter(VSMIN(nleft, N - 1), d->node, frameCtx);
+        if (d->p.blend)
+            vsapi->requestFrameFilter(VSMIN(nright, N - 1), d->node, frameCtx);
+    } else if (activationReason == arAllFramesReady) {
+        if (time256 == 0)
+            return vsapi->getFrameFilter(VSMIN(nleft, N - 1), d->node, frameCtx);
+        if (time256 == 256)
+            return vsapi->getFrameFilter(VSMIN(nright, N - 1), d->node, frameCtx);
+        const int planes = (d->sp.modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) ? 3 : 1;
+        std::string msg;
+        int rc = 0;
+        int32_t usable = 0;
+        VSFrame *dst = nullptr;
+        if (inRange) {
+            const VSFrame *mvF = vsapi->getFrameFilter(nright, d->mvfw, frameCtx), *mvB = vsapi->getFrameFilter(nleft, d->mvbw, frameCtx);
+            const VSFrame *left = vsapi->getFrameFilter(nleft, d->super, frameCtx), *right = vsapi->getFrameFilter(nright, d->super, frameCtx);
+            bool missing = false;
+            const uint8_t *vb = vectorsOf(vsapi, mvB, &missing), *vf = vectorsOf(vsapi, mvF, &missing);
+            dst = vsapi->newVideoFrame(&d->vi.format, d->vi.width, d->vi.height, left, core);
+            if (missing) {
+                rc = 1;
+                msg = "MVTools_vectors property missing";
+            } else {
+                const uint8_t *lp[3], *rp[3];
+                ptrdiff_t ls[3], rs[3];
+                uint8_t *dp_[3];
+                ptrdiff_t ds[3];
+                planesRO(vsapi, left, d->supervi->format.numPlanes, lp, ls);
+                planesRO(vsapi, right, d->supervi->format.numPlanes, rp, rs);
+                planesRW(vsapi, dst, d->vi.format.numPlanes, dp_, ds);
+                std::lock_guard<std::mutex> lock(g_engine_mutex);
+                mvb200_ctx *ctx = engine(msg);
+                rc = ctx ? mvb200_blockfps_frame(ctx, &d->p, &d->sp, time256, lp, ls, rp, rs, vb, vf, dp_, ds, &usable) : 1;
+                if (ctx && rc)
+                    msg = mvb200_last_error();
+            }
+            vsapi->freeFrame(mvF);
+            vsapi->freeFrame(mvB);
+            vsapi->freeFrame(left);
+            vsapi->freeFrame(right);
+        }
+        if (!rc && !usable) { // poor estimation, :636-670
+            vsapi->freeFrame(dst);
+            dst = nullptr;
+            const VSFrame *src = vsapi->getFrameFilter(VSMIN(nleft, N - 1), d->node, frameCtx);
+            if (!d->p.blend)
+                return src;
+            const VSFrame *ref = vsapi->getFrameFilter(VSMIN(nright, N - 1), d->node, frameCtx);
+            dst = vsapi->newVideoFrame(&d->vi.format, d->vi.width, d->vi.height, src, core);
+            const uint8_t *sp_[3], *rp[3];
+            ptrdiff_t ss[3], rs[3];
+            uint8_t *dp_[3];
+            ptrdiff_t ds[3];
+            planesRO(vsapi, src, d->vi.format.numPlanes, sp_, ss);
+            planesRO(vsapi, ref, d->vi.format.numPlanes, rp, rs);
+            planesRW(vsapi, dst, d->vi.format.numPlanes, dp_, ds);
+            mvb200_super_params used = d->sp; // only the planes the super clip carries are blended (:652)
+            used.nplanes = planes < d->sp.nplanes ? planes : d->sp.nplanes;
+            {
+                std::lock_guard<std::mutex> lock(g_engine_mutex);
+                mvb200_ctx *ctx = engine(msg);
+                rc = ctx ? mvb200_blend_frame(ctx, &used, time256, sp_, ss, rp, rs, dp_, ds) : 1;
+                if (ctx && rc)
+                    msg = mvb200_last_error();
+            }
+            vsapi->freeFrame(src);
+            vsapi->freeFrame(ref);
+        }
+        if (rc) {
+            vsapi->setFilterError(("BlockFPS: " + msg).c_str(), frameCtx);
+            vsapi->freeFrame(dst);
+            return nullptr;
+        }
+        return dst;
+    }
+    return nullptr;
+}
+
+void VS_CC blockFpsFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
+    BlockFPSData *d = (BlockFPSData *)instanceData;
+    vsapi->freeNode(d->node);
+    vsapi->freeNode(d->super);
+    vsapi->freeNode(d->mvbw);
+    vsapi->freeNode(d->mvfw);
+    delete d;
+}
+
+void VS_CC blockFpsCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const VSAPI *vsapi) {
+    mvb200_blockfps_args a;
+    a.num = argInt64(vsapi, in, "num");
+    a.den = argInt64(vsapi, in, "den");
+    a.mode = argInt(vsapi, in, "mode");
+    a.ml = argFloat(vsapi, in, "ml");
+    a.blend = argInt(vsapi, in, "blend");
+    a.thscd1 = argInt64(vsapi, in, "thscd1");
+    a.thscd2 = argInt(vsapi, in, "thscd2");
+    if (a.mode != MVB200_UNSET && (a.mode < 0 || a.mode > 8)) { // before any clip is touched (MVBlockFPS.c:779-782)
+        vsapi->mapSetError(out, "BlockFPS: mode must be between 0 and 8 (inclusive).");
+        return;
+    }
+    BlockFPSData d;
+    memset(&d, 0, sizeof(d));
+    auto freeAll = [&]() {
+        vsapi->freeNode(d.node);
+        vsapi->freeNode(d.super);
+        vsapi->freeNode(d.mvbw);
+        vsapi->freeNode(d.mvfw);
+    };
+    d.super = vsapi->mapGetNode(in, "super", 0, nullptr);
+    d.supervi = vsapi->getVideoInfo(d.super);
+    std::string msg;
+    mvb200_analysis_data vdb, vdf;
+    if (!superFromClip(d.super, vsapi, "BlockFPS", &d.sp, msg)) {
+        vsapi->mapSetError(out, msg.c_str());
+        freeAll();
+        return;
+    }
+    d.mvbw = vsapi->mapGetNode(in, "mvbw", 0, nullptr);
+    d.mvfw = vsapi->mapGetNode(in, "mvfw", 0, nullptr);
+    if (!adataFromClip(d.mvbw, vsapi, "BlockFPS", "mvbw", &vdb, msg) || !adataFromClip(d.mvfw, vsapi, "BlockFPS", "mvfw", &vdf, msg)) {
+        vsapi->mapSetError(out, msg.c_str());
+        freeAll();
+        return;
+    }
+    d.node = vsapi->mapGetNode(in, "clip", 0, nullptr);
+    d.oldvi = vsapi->getVideoInfo(d.node);
+    d.vi = *d.oldvi;
+    if (mvb200_blockfps_init(&a, &d.sp, &vdb, &vdf, d.vi.fpsNum, d.vi.fpsDen, d.vi.width, d.vi.height, d.vi.numFrames, &d.p)) {
+        vsapi->mapSetError(out, mvb200_last_error());
+        freeAll();
+        return;
+    }
+    if (!formatOk(&d.vi) || d.vi.format.bitsPerSample != d.sp.bits) {
+        vsapi->mapSetError(out, "BlockFPS: input clip must be GRAY, 420, 422, 440, or 444, up to 16 bits, with constant dimensions.");
+        freeAll();
+        return;
+    }
+    d.vi.fpsNum = d.p.fps_num;
+    d.vi.fpsDen = d.p.fps_den;
+    d.vi.numFrames = d.p.num_frames_out;
+    BlockFPSData *data = new BlockFPSData(d);
+    VSFilterDependency deps[4] = {{data->node, rpGeneral}, {data->super, rpGeneral}, {data->mvbw, rpGeneral}, {data->mvfw, rpGeneral}};
+    vsapi->createVideoFilter(out, "BlockFPS", &data->vi, blockFpsGetFrame, blockFpsFree, fmParallel, deps, 4, data, core);
+    // AssumeFPS sets the _DurationNum and _DurationDen properties (MVBlockFPS.c:990-1012)
+    VSPlugin *stdPlugin = vsapi->getPluginByID("com.vapoursynth.std", core);
+    VSMap *args = vsapi->createMap();
+    VSNode *node = vsapi->mapGetNode(out, "clip", 0, nullptr);
+    vsapi->mapSetNode(args, "clip", node, maReplace);
+    vsapi->freeNode(node);
+    vsapi->mapSetInt(args, "fpsnum", data->vi.fpsNum, maReplace);
+    vsapi->mapSetInt(args, "fpsden", data->vi.fpsDen, maReplace);
+    VSMap *ret = vsapi->invoke(stdPlugin, "AssumeFPS", args);
+    if (vsapi->mapGetError(ret)) {
+        vsapi->mapSetError(out, (std::string("BlockFPS: Failed to invoke AssumeFPS. Error message: ") + vsapi->mapGetError(ret)).c_str());
+        vsapi->freeMap(args);
+        vsapi->freeMap(ret);
+        return;
+    }
+    node = vsapi->mapGetNode(ret, "clip", 0, nullptr);
+    vsapi->freeMap(ret);
+    vsapi->freeMap(args);
+    vsapi->mapSetNode(out, "clip", node, maReplace);
+    vsapi->freeNode(node);
+}
+
 } // namespace
 
 VS_EXTERNAL_API(void) VapourSynthPluginInit2(VSPlugin *plugin, const VSPLUGINAPI *vspapi) {
@@ -1753,6 +1949,8 @@ VS_EXTERNAL_API(void) VapourSynthPluginInit2(VSPlugin *plugin, const VSPLUGINAPI
     vspapi->registerFunction("Finest", "super:vnode;opt:int:opt;", "clip:vnode;", finestCreate, nullptr, plugin);
     vspapi->registerFunction("Flow", "clip:vnode;super:vnode;vectors:vnode;time:float:opt;mode:int:opt;fields:int:opt;thscd1:int:opt;thscd2:int:opt;opt:int:opt;tff:int:opt;", "clip:vnode;", flowCreate, nullptr, plugin);
     vspapi->registerFunction("SCDetection", "clip:vnode;vectors:vnode;thscd1:int:opt;thscd2:int:opt;", "clip:vnode;", scdCreate, nullptr, plugin);
+    // MVBlockFPS.c:1017-1033
+    vspapi->registerFunction("BlockFPS", "clip:vnode;super:vnode;mvbw:vnode;mvfw:vnode;num:int:opt;den:int:opt;mode:int:opt;ml:float:opt;blend:int:opt;thscd1:int:opt;thscd2:int:opt;opt:int:opt;", "clip:vnode;", blockFpsCreate, nullptr, plugin);
     // MVFlowBlur.c:550-566
     vspapi->registerFunction("FlowBlur", "clip:vnode;super:vnode;mvbw:vnode;mvfw:vnode;blur:float:opt;prec:int:opt;thscd1:int:opt;thscd2:int:opt;opt:int:opt;", "clip:vnode;", flowBlurCreate, nullptr, plugin);
     // MVFlowFPS.c:913-928
