@@ -106,3 +106,62 @@ def test_scdetection_init(built):
     with pytest.raises(mb.Error) as e:
         mb.scdetection_params(vd, thscd1=99999)
     assert str(e.value) == "SCDetection: thscd1 can be at most 16320."
+
+
+def _two_vds(case="blk8_ov4_pel2_p8"):
+    sp, aps, dp = pipeline.params_for(case)
+    return sp, aps[0].ad, aps[1].ad
+
+
+def test_interpolation_filters_init_errors(built):
+    """create-time checks of mv.FlowInter / mv.FlowFPS / mv.FlowBlur / mv.BlockFPS: the reference's texts, in its order"""
+    sp, bw, fw = _two_vds()
+    W, H, N = 320, 192, 6
+    cases = [
+        (lambda: mb.flowinter_params(sp, bw, fw, N, time=100.5), "FlowInter: time must be between 0 and 100 % (inclusive)."),
+        (lambda: mb.flowinter_params(sp, bw, fw, N, ml=0.0), "FlowInter: ml must be greater than 0."),
+        (lambda: mb.flowinter_params(sp, fw, fw, N), "FlowInter: mvbw must be generated with isb=True."),
+        (lambda: mb.flowinter_params(sp, bw, bw, N), "FlowInter: mvfw must be generated with isb=False."),
+        (lambda: mb.flowinter_params(sp, bw, fw, N, thscd1=17000), "FlowInter: thscd1 can be at most 16320."),
+        (lambda: mb.flowfps_params(sp, bw, fw, N, W, H, mask=3), "FlowFPS: mask must be 0, 1, or 2."),
+        (lambda: mb.flowfps_params(sp, bw, fw, N, W, H, ml=-1.0), "FlowFPS: ml must be greater than 0."),
+        (lambda: mb.flowfps_params(sp, bw, fw, N, W, H, fps_num=0), "FlowFPS: The input clip must have a frame rate. Invoke AssumeFPS if necessary."),
+        (lambda: mb.flowfps_params(sp, bw, fw, N, W + 2, H), "FlowFPS: inconsistent source and vector frame size."),
+        (lambda: mb.flowfps_params(sp, fw, bw, N, W, H), "FlowFPS: mvbw must be generated with isb=True."),
+        (lambda: mb.flowblur_params(sp, bw, fw, N, blur=200.5), "FlowBlur: blur must be between 0 and 200 % (inclusive)."),
+        (lambda: mb.flowblur_params(sp, bw, fw, N, prec=0), "FlowBlur: prec must be at least 1."),
+        (lambda: mb.flowblur_params(sp, bw, bw, N), "FlowBlur: mvfw must be generated with isb=False."),
+        (lambda: mb.blockfps_params(sp, bw, fw, N, W, H, mode=9), "BlockFPS: mode must be between 0 and 8 (inclusive)."),
+        (lambda: mb.blockfps_params(sp, bw, fw, N, W, H + 2), "BlockFPS: wrong source or super clip frame size."),
+        (lambda: mb.blockfps_params(sp, bw, fw, N, W, H, fps_den=0), "BlockFPS: The input clip must have a frame rate. Invoke AssumeFPS if necessary."),
+    ]
+    for call, msg in cases:
+        with pytest.raises(mb.Error) as e:
+            call()
+        assert str(e.value) == msg
+    sp16, bw16, fw16 = _two_vds("blk16_ov8_pel2_p16_r3")
+    with pytest.raises(mb.Error) as e:
+        mb.flowinter_params(sp, bw, fw16, N)
+    assert str(e.value) == "FlowInter: mvbw and mvfw have different block sizes." or str(e.value).startswith("FlowInter: mvbw and mvfw have different")
+
+
+def test_fps_conversion_arithmetic(built):
+    """fa / fb, the output length and rate, and the position of every output frame (MVFlowFPS.c:118-141,737-756)"""
+    sp, bw, fw = _two_vds()
+    for (num, den, fn, fd, n_in) in ((50, 1, 25, 1, 6), (60, 1, 25, 1, 6), (30000, 1001, 25, 1, 9), (24, 1, 30000, 1001, 17), (0, 0, 25, 1, 5)):
+        p = mb.flowfps_params(sp, bw, fw, n_in, 320, 192, fps_num=fn, fps_den=fd, num=num, den=den)
+        numerator, denominator = (num, den) if num and den else (fn * 2, fd)
+        from math import gcd
+        fa, fb = denominator * fn, numerator * fd
+        g = gcd(fa, fb)
+        fa, fb = fa // g, fb // g
+        assert (p.fa, p.fb) == (fa, fb)
+        assert p.num_frames_out == 1 + (n_in - 1) * fb // fa
+        g2 = gcd(numerator, denominator)
+        assert (p.fps_num, p.fps_den) == (numerator // g2, denominator // g2)
+        q = mb.blockfps_params(sp, bw, fw, n_in, 320, 192, fps_num=fn, fps_den=fd, num=num, den=den)
+        assert (q.fa, q.fb, q.num_frames_out) == (p.fa, p.fb, p.num_frames_out)
+        for n in range(p.num_frames_out):
+            nleft, t = mb.flowfps_position(p, n)
+            assert nleft == n * fa // fb and t == int((n * fa / fb - nleft) * 256 + 0.5)
+            assert mb.blockfps_position(q, n) == (nleft, t)
