@@ -26,6 +26,9 @@ except Exception as e:
     print("variant $name F=$frames FAILED", e); print(open("gpurun_out/${TAG}_bench_${name}_$frames.err").read()[-600:])
 PY
 done
+echo "== flow kernels (device-resident throughput; tools/bench_flow.py)"
+timeout 300 python tools/bench_flow.py > gpurun_out/${TAG}_bench_flow.jsonl 2> gpurun_out/${TAG}_bench_flow.err
+cat gpurun_out/${TAG}_bench_flow.jsonl | cut -c1-200; tail -2 gpurun_out/${TAG}_bench_flow.err
 echo "== bench (reference arm)"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
 cat gpurun_out/${TAG}_bench_ref.json
