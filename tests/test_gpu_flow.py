@@ -184,3 +184,32 @@ def test_flow_full_size_1080p_properties(gpu_ctx):
         lv = g.lv[p][0]
         assert np.array_equal(fin[p][::2, ::2], sups[0][p][: lv.padded_h, : lv.padded_w])
     assert blob[1] == 1
+
+
+def test_interpolation_full_size_1080p_properties(gpu_ctx):
+    """1920x1080 YUV420P8, pel 2, blk 16 / overlap 8: with a zero vector field between two identical frames every
+    interpolation filter must return that frame, whatever its time / mode (all of them are convex blends of
+    motion-compensated samples); a full-size run of mv.FlowInter / mv.FlowBlur / mv.BlockFPS and their masks."""
+    ctx = gpu_ctx
+    W, H, N = 1920, 1080, 3
+    import clipgen
+    frames = clipgen.make_clip(W, H, 1, bits=8, scene_cut=False)
+    sp = mb.super_params(W, H, 8, 1, 1, pel=2)
+    sup = ctx.super_frame(sp, frames[0])
+    aps = [mb.analyse_params(sp, N, isb=isb, blksize=16, overlap=8) for isb in (1, 0)]
+    v0 = [ctx.analyse_frame(ap, sp, sup, sup) for ap in aps]
+    th = dict(thscd1=16000, thscd2=255)
+    ip = mb.flowinter_params(sp, aps[0].ad, aps[1].ad, N, time=37.0, **th)
+    out = ctx.flowinter_frame(ip, sp, ip.time256, sup, sup, v0[0], v0[1], v0[0], v0[1])
+    assert out is not None and all(np.array_equal(a, b) for a, b in zip(out, frames[0])), "FlowInter"
+    bp = mb.flowblur_params(sp, aps[0].ad, aps[1].ad, N, blur=100.0, **th)
+    out = ctx.flowblur_frame(bp, sp, sup, v0[0], v0[1])
+    assert out is not None and all(np.array_equal(a, b) for a, b in zip(out, frames[0])), "FlowBlur"
+    for mode in (0, 1, 2, 3, 4, 6, 7):
+        q = mb.blockfps_params(sp, aps[0].ad, aps[1].ad, N, W, H, num=60, den=1, mode=mode, **th)
+        out = ctx.blockfps_frame(q, sp, 100, sup, sup, v0[0], v0[1])
+        assert out is not None and all(np.array_equal(a, b) for a, b in zip(out, frames[0])), "BlockFPS mode %d" % mode
+    # the blend the filters fall back to at scene changes: time256 = 0 / 256 give the two frames themselves
+    other = [255 - p for p in frames[0]]
+    assert all(np.array_equal(a, b) for a, b in zip(ctx.blend_frame(sp, 0, frames[0], other), frames[0]))
+    assert all(np.array_equal(a, b) for a, b in zip(ctx.blend_frame(sp, 256, frames[0], other), other))
