@@ -1,0 +1,47 @@
+"""CPU test (no GPU) of the VapourSynth plugin's host-side glue: tests/mock builds the product's plugin.cpp, unchanged,
+against a stand-in engine whose per-frame entry points forward to the CPU oracle (tests/mock/mock_engine.cpp).  A script
+driven through that plugin by the mini host reproduces the reference's goldens only if the glue requests the right
+frames, picks the right reference frames / blobs / field shifts, attaches the right properties and takes the
+reference's fall-back paths at scene changes.  Test infrastructure only: the product plugin links libmvtools_b200.so
+(CUDA) and has no CPU path; the GPU tests in test_plugin.py drive the real one."""
+import json
+import os
+import subprocess
+
+import pytest
+
+import pipeline
+import pipeline_flow
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+GOLD_FLOW = json.load(open(os.path.join(HERE, "golden", "golden_flow.json")))
+
+
+@pytest.fixture(scope="module")
+def mock_plugin(built):
+    d = os.path.join(HERE, "mock")
+    so = os.path.join(d, "libmvtools_mockengine.so")
+    pkg = os.path.join(ROOT, "vapoursynth-mvtools_b200")
+    srcs = [os.path.join(pkg, "plugin", "plugin.cpp"), os.path.join(d, "mock_engine.cpp"), os.path.join(pkg, "csrc", "host_logic.cpp")]
+    deps = srcs + [os.path.join(ROOT, "include", "mvtools_b200.h"), os.path.join(ROOT, "oracle", "_ref", "liboracle.so")]
+    if not os.path.exists(so) or any(os.path.getmtime(p) > os.path.getmtime(so) for p in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-fvisibility=hidden", "-Wall", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "include", "vs"),
+                               "-shared", "-Wl,-Bsymbolic", "-o", so] + srcs + ["-L" + os.path.join(ROOT, "oracle", "_ref"), "-loracle", "-Wl,-rpath," + os.path.join(ROOT, "oracle", "_ref")])
+    return so
+
+
+@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "divide2_blk16_esa_neg_badrange", "pelclip2_p8", "noise_badblocks_blk8"])
+def test_hot_path_glue(mock_plugin, case):
+    got = pipeline.run_reference(case, plugin_path=mock_plugin)
+    for stage in ("super", "vectors", "degrain", "adata", "recalc", "compensate", "recalc_adata"):
+        if stage in got:
+            assert got[stage] == GOLD[case][stage], "%s: %s" % (case, stage)
+
+
+@pytest.mark.parametrize("case", sorted(pipeline_flow.FLOW))
+def test_flow_group_glue(mock_plugin, case):
+    got = pipeline_flow.run_reference_flow(case, plugin_path=mock_plugin)
+    for stage in ("scd", "mask", "flow", "finest", "inter", "fps", "blur", "bfps"):
+        assert got[stage] == GOLD_FLOW[case][stage], "%s: %s" % (case, stage)
