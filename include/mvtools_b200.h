@@ -489,6 +489,14 @@ MVB200_API int mvb200_super_frame_pel(mvb200_ctx *ctx, const mvb200_super_params
  * the default blob of gopWriteDefaultToArray, GroupOfPlanes.c:150-164, is written). */
 MVB200_API int mvb200_analyse_frame(mvb200_ctx *ctx, const mvb200_analyse_params *ap, const mvb200_super_params *sp, const uint8_t *const src_super[3], const ptrdiff_t src_stride[3], const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], int field_shift, uint8_t *vectors_out);
 
+/* Several frames of ONE mv.Analyse instance in one call (the plugin's look-ahead: a search is a serial chain, so the
+ * only way to use the GPU from a frame server is to have many frames' chains in flight).  `nframes` distinct host super
+ * frames are uploaded once (frames[3 i + p] / strides[3 i + p] = plane p of frame i); job k searches frame src_index[k]
+ * against frame ref_index[k] (< 0: no reference, the default blob of GroupOfPlanes.c:150-164) with field_shift[k], and
+ * writes ap->vectors_size bytes to vectors_out[k].  One launch, njobs chains. */
+MVB200_API int mvb200_analyse_frames(mvb200_ctx *ctx, const mvb200_analyse_params *ap, const mvb200_super_params *sp, int nframes, const uint8_t *const *frames, const ptrdiff_t *strides, int njobs, const int32_t *src_index,
+                                     const int32_t *ref_index, const int32_t *field_shift, uint8_t *const *vectors_out);
+
 /* refs[r] may be NULL (frame out of range); vectors[r] are host blobs. */
 MVB200_API int mvb200_degrain_frame(mvb200_ctx *ctx, const mvb200_degrain_params *dp, const mvb200_super_params *sp, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const *const ref_super /* [2r][3] flattened */, const ptrdiff_t *ref_stride /* [2r][3] */, const uint8_t *const *vectors /* [2r] */, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]);
 

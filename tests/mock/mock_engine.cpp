@@ -47,6 +47,17 @@ MVB200_API int mvb200_analyse_frame(mvb200_ctx *, const mvb200_analyse_params *a
                                     const ptrdiff_t ref_stride[3], int field_shift, uint8_t *vectors_out) {
     return fwd(mvo_analyse_frame(ap, sp, src_super, src_stride, ref_super, ref_stride, field_shift, vectors_out));
 }
+MVB200_API int mvb200_analyse_frames(mvb200_ctx *, const mvb200_analyse_params *ap, const mvb200_super_params *sp, int nframes, const uint8_t *const *frames, const ptrdiff_t *strides, int njobs, const int32_t *src_index,
+                                     const int32_t *ref_index, const int32_t *field_shift, uint8_t *const *vectors_out) {
+    for (int k = 0; k < njobs; k++) {
+        if (src_index[k] < 0 || src_index[k] >= nframes || ref_index[k] >= nframes)
+            return mvb200::set_error("mock: bad frame index");
+        const int r = ref_index[k];
+        if (fwd(mvo_analyse_frame(ap, sp, frames + 3 * src_index[k], strides + 3 * src_index[k], r >= 0 ? frames + 3 * r : nullptr, r >= 0 ? strides + 3 * r : nullptr, r >= 0 ? field_shift[k] : 0, vectors_out[k])))
+            return 1;
+    }
+    return 0;
+}
 MVB200_API int mvb200_degrain_frame(mvb200_ctx *, const mvb200_degrain_params *dp, const mvb200_super_params *sp, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const *const ref_super, const ptrdiff_t *ref_stride,
                                     const uint8_t *const *vectors, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
     return fwd(mvo_degrain_frame(dp, sp, src, src_stride, ref_super, ref_stride, vectors, dst, dst_stride));

@@ -45,3 +45,36 @@ def test_flow_group_glue(mock_plugin, case):
     got = pipeline_flow.run_reference_flow(case, plugin_path=mock_plugin)
     for stage in ("scd", "mask", "flow", "finest", "inter", "fps", "blur", "bfps"):
         assert got[stage] == GOLD_FLOW[case][stage], "%s: %s" % (case, stage)
+
+
+@pytest.mark.parametrize("window", [2, 3, 64])
+@pytest.mark.parametrize("case", ["blk16_ov8_pel2_p8_r3", "divide2_blk16_esa_neg_badrange", "noise_badblocks_blk8"])
+def test_analyse_lookahead_glue(mock_plugin, monkeypatch, case, window):
+    """MVB200_LOOKAHEAD: mv.Analyse searches a window of frames per engine call and serves the rest from its cache;
+    the vectors (and everything computed from them) must not change, whatever the window and the request order"""
+    monkeypatch.setenv("MVB200_LOOKAHEAD", str(window))
+    got = pipeline.run_reference(case, plugin_path=mock_plugin)
+    for stage in ("super", "vectors", "degrain", "adata", "recalc", "compensate"):
+        if stage in got:
+            assert got[stage] == GOLD[case][stage], "%s (window %d): %s" % (case, window, stage)
+
+
+def test_analyse_lookahead_batches_the_engine_calls(mock_plugin, monkeypatch):
+    """with a window of 4, six frames requested in order cost two window searches per vector clip, not six"""
+    import minivs
+    monkeypatch.setenv("MVB200_LOOKAHEAD", "4")
+    case = "blk8_ov4_pel2_p8"
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    core = minivs.Core()
+    mv = core.load(mock_plugin)
+    clip = core.source(frames, bits=8)
+    sup = mv.Super(clip, **skw)
+    vec = mv.Analyse(sup, isb=1, delta=1, **akw)
+    blobs = [vec.get_frame(n).prop_data("MVTools_vectors") for n in range(len(frames))]
+    sp, aps, dp = pipeline.params_for(case)
+    import numpy as np
+    assert [pipeline.sha(pipeline.mask_blob(np.frombuffer(b, dtype=np.uint8), aps[0])) for b in blobs] == [row[0] for row in GOLD[case]["vectors"]]
+    # out-of-order and repeated requests are served as well (cache hits, evictions, single-frame fall-back)
+    for n in (5, 0, 3, 3, 1):
+        assert vec.get_frame(n).prop_data("MVTools_vectors") == blobs[n]

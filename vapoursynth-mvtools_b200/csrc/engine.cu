@@ -698,6 +698,55 @@ int mvb200_analyse_frame(mvb200_ctx *ctx, const mvb200_analyse_params *ap, const
     return 0;
 }
 
+int mvb200_analyse_frames(mvb200_ctx *ctx, const mvb200_analyse_params *ap, const mvb200_super_params *sp, int nframes, const uint8_t *const *frames, const ptrdiff_t *strides, int njobs, const int32_t *src_index, const int32_t *ref_index,
+                          const int32_t *field_shift, uint8_t *const *vectors_out) {
+    if (check_analyse(ap, sp))
+        return 1;
+    if (njobs <= 0)
+        return 0;
+    if (nframes <= 0)
+        return set_error("Analyse: no frames given");
+    for (int k = 0; k < njobs; k++)
+        if (src_index[k] < 0 || src_index[k] >= nframes || ref_index[k] >= nframes)
+            return set_error("Analyse: job %d refers to a frame outside the %d given", k, nframes);
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    make_super_desc(sp, &sd);
+    const size_t blob = ((size_t)ap->vectors_size + 255) & ~(size_t)255;
+    uint8_t *buf = (uint8_t *)c->get_scratch(5, (size_t)sd.frame_bytes * nframes + blob * njobs);
+    if (!buf)
+        return 1;
+    int w[3], h[3];
+    super_plane_dims(sp, w, h);
+    const int nplanes_used = ap->chroma ? sd.nplanes : 1;
+    for (int i = 0; i < nframes; i++)
+        if (upload_planes(c, buf + (size_t)i * sd.frame_bytes, sd.pitch, sd.offset, w, h, sd.bps, nplanes_used, frames + 3 * i, strides + 3 * i))
+            return 1;
+    uint8_t *blobs = buf + (size_t)sd.frame_bytes * nframes;
+    SearchParams P;
+    make_search_params(ap, &P);
+    std::vector<SearchJob> jobs((size_t)njobs);
+    for (int k = 0; k < njobs; k++) {
+        SearchJob &j = jobs[k];
+        j.src = buf + (size_t)src_index[k] * sd.frame_bytes;
+        j.ref = ref_index[k] >= 0 ? buf + (size_t)ref_index[k] * sd.frame_bytes : nullptr;
+        j.out = blobs + (size_t)k * blob;
+        j.param = 0;
+        j.field_shift = ref_index[k] >= 0 ? field_shift[k] : 0;
+        j.src_index = src_index[k];
+        j.ref_index = ref_index[k] >= 0 ? ref_index[k] : 0;
+    }
+    mvb200_super_geom geom;
+    mvb200_super_geometry(sp, &geom);
+    if (launch_search(c, sd, geom, buf, nframes, &P, 1, jobs.data(), njobs))
+        return 1;
+    for (int k = 0; k < njobs; k++)
+        MVB_CUDA_CHECK(cudaMemcpyAsync(vectors_out[k], jobs[k].out, (size_t)ap->vectors_size, cudaMemcpyDeviceToHost, c->stream));
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int mvb200_degrain_frame(mvb200_ctx *ctx, const mvb200_degrain_params *dp, const mvb200_super_params *sp, const uint8_t *const src[3], const ptrdiff_t src_stride[3], const uint8_t *const *const ref_super, const ptrdiff_t *ref_stride, const uint8_t *const *vectors, uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
     if (check_levels(sp))
         return 1;

@@ -271,6 +271,7 @@ def lib():
         L.mvb200_blockfps_position.argtypes = [PP(BlockFPSParams), i32, PP(i32), PP(i32)]
         L.mvb200_blockfps_position.restype = None
         L.mvb200_blockfps_frame.argtypes = [vp, PP(BlockFPSParams), PP(SuperParams), i32, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, vp, PP(vp), PP(C.c_ssize_t), PP(i32)]
+        L.mvb200_analyse_frames.argtypes = [vp, PP(AnalyseParams), PP(SuperParams), i32, PP(vp), PP(C.c_ssize_t), i32, PP(i32), PP(i32), PP(i32), PP(vp)]
         _LIB = L
     return _LIB
 
@@ -692,3 +693,21 @@ class Context:
         usable = i32(0)
         _check(lib().mvb200_blockfps_frame(self._h, C.byref(p), C.byref(sp), time256, l, ls, r, rs, vec_b.ctypes.data, vec_f.ctypes.data, d, ds, C.byref(usable)))
         return dst if usable.value else None
+
+    def analyse_frames(self, ap, sp, super_frames, jobs):
+        """One engine call for several frames of one mv.Analyse instance: super_frames = list of plane lists (uploaded
+        once), jobs = [(src index, ref index or None, field shift)] -> list of blobs"""
+        nf, nj = len(super_frames), len(jobs)
+        planes = (C.c_void_p * (3 * nf))()
+        strides = (C.c_ssize_t * (3 * nf))()
+        for i, fr in enumerate(super_frames):
+            for p, a in enumerate(fr):
+                planes[3 * i + p] = a.ctypes.data
+                strides[3 * i + p] = a.strides[0]
+        src = (i32 * nj)(*[j[0] for j in jobs])
+        ref = (i32 * nj)(*[-1 if j[1] is None else j[1] for j in jobs])
+        fs = (i32 * nj)(*[j[2] for j in jobs])
+        outs = [np.empty(ap.vectors_size, dtype=np.uint8) for _ in jobs]
+        outp = (C.c_void_p * nj)(*[o.ctypes.data for o in outs])
+        _check(lib().mvb200_analyse_frames(self._h, C.byref(ap), C.byref(sp), nf, planes, strides, nj, src, ref, fs, outp))
+        return outs

@@ -21,6 +21,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -240,11 +242,31 @@ void VS_CC superCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const 
 }
 
 // ---------------------------------------------------------------- Analyse
+// Look-ahead (MVB200_LOOKAHEAD=<frames>, default 0 = off): a search is a strict serial chain, so ONE frame uses one warp of
+// the GPU.  With a window of B frames the filter requests the super frames of [n, n + B) (and their reference frames) on
+// a cache miss, searches all B chains in ONE engine call (mvb200_analyse_frames) and serves the following requests
+// from the cache: the frame server's usual in-order requests then cost one launch per B frames instead of one per frame.
+struct AnalyseCache {
+    std::mutex m;                                   // serialises window computations of this instance
+    std::map<int, std::vector<uint8_t>> blobs;      // frame -> MVTools_vectors
+    std::deque<int> order;                          // insertion order, for eviction
+    void put(int n, std::vector<uint8_t> &&v, size_t keep) {
+        if (blobs.emplace(n, std::move(v)).second)
+            order.push_back(n);
+        while (order.size() > keep) {
+            blobs.erase(order.front());
+            order.pop_front();
+        }
+    }
+};
+
 struct AnalyseData {
     VSNode *node;
     const VSVideoInfo *vi;
     mvb200_super_params sp;
     mvb200_analyse_params ap;
+    int lookahead;       // window length, 0 = one frame per call
+    AnalyseCache *cache; // owned; null without look-ahead
 };
 
 int refFrameOf(const mvb200_analyse_params &ap, int n) { // MVAnalyse.c:84-109
@@ -253,61 +275,173 @@ int refFrameOf(const mvb200_analyse_params &ap, int n) { // MVAnalyse.c:84-109
     return -ap.ad.nDeltaFrame;
 }
 
-const VSFrame *VS_CC analyseGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+// MVAnalyse.c:136-179: the vertical shift between fields of opposite parity; false = the _Field property is needed and missing
+bool analyseFieldShift(const AnalyseData *d, const VSAPI *vsapi, const VSFrame *src, const VSFrame *ref, int n, int nref, int *fieldShift) {
+    int err = 0;
+    *fieldShift = 0;
+    int srcTop = !!vsapi->mapGetInt(vsapi->getFramePropertiesRO(src), "_Field", 0, &err);
+    bool missing = err && d->ap.fields && !d->ap.tff_exists;
+    int refTop = 0;
+    if (ref) {
+        refTop = !!vsapi->mapGetInt(vsapi->getFramePropertiesRO(ref), "_Field", 0, &err);
+        missing = missing || (err && d->ap.fields && !d->ap.tff_exists);
+    }
+    if (missing)
+        return false;
+    if (d->ap.tff_exists) {
+        srcTop = d->ap.tff ^ (n % 2);
+        refTop = d->ap.tff ^ (nref % 2);
+    }
+    if (ref && d->ap.fields && d->ap.ad.nPel > 1 && (d->ap.ad.nDeltaFrame % 2))
+        *fieldShift = (srcTop && !refTop) ? d->ap.ad.nPel / 2 : ((refTop && !srcTop) ? -(d->ap.ad.nPel / 2) : 0);
+    return true;
+}
+
+// searches the window [n, end) in one engine call and fills the cache; returns false with msg set on failure
+bool analyseWindow(AnalyseData *d, const VSAPI *vsapi, VSFrameContext *frameCtx, int n, int end, std::string &msg) {
+    std::map<int, const VSFrame *> held; // distinct super frames of the window, by frame number
+    auto hold = [&](int k) {
+        auto it = held.find(k);
+        if (it == held.end())
+            it = held.emplace(k, vsapi->getFrameFilter(k, d->node, frameCtx)).first;
+        return it->second;
+    };
+    std::vector<int> jobFrame;
+    std::vector<int32_t> srcIdx, refIdx, shifts;
+    bool ok = true;
+    for (int k = n; k < end && ok; k++) {
+        if (d->cache->blobs.count(k))
+            continue;
+        const int nref = refFrameOf(d->ap, k);
+        const bool refOk = nref >= 0 && nref < d->vi->numFrames;
+        const VSFrame *src = hold(k), *ref = refOk ? hold(nref) : nullptr;
+        int fs = 0;
+        if (!analyseFieldShift(d, vsapi, src, ref, k, nref, &fs)) {
+            msg = "_Field property not found in input frame. Therefore, you must pass tff argument.";
+            ok = false;
+            break;
+        }
+        jobFrame.push_back(k);
+        srcIdx.push_back(k);
+        refIdx.push_back(refOk ? nref : -1);
+        shifts.push_back(fs);
+    }
+    if (ok && !jobFrame.empty()) {
+        std::map<int, int> slot; // frame number -> index in the upload list
+        std::vector<const uint8_t *> planes;
+        std::vector<ptrdiff_t> strides;
+        for (auto &h : held) {
+            slot[h.first] = (int)slot.size();
+            const uint8_t *p[3];
+            ptrdiff_t st[3];
+            planesRO(vsapi, h.second, d->vi->format.numPlanes, p, st);
+            planes.insert(planes.end(), p, p + 3);
+            strides.insert(strides.end(), st, st + 3);
+        }
+        for (size_t j = 0; j < jobFrame.size(); j++) {
+            srcIdx[j] = slot[srcIdx[j]];
+            refIdx[j] = refIdx[j] >= 0 ? slot[refIdx[j]] : -1;
+        }
+        std::vector<std::vector<uint8_t>> out(jobFrame.size(), std::vector<uint8_t>((size_t)d->ap.vectors_size));
+        std::vector<uint8_t *> outp;
+        for (auto &v : out)
+            outp.push_back(v.data());
+        int rc;
+        {
+            std::lock_guard<std::mutex> lock(g_engine_mutex);
+            mvb200_ctx *ctx = engine(msg);
+            rc = ctx ? mvb200_analyse_frames(ctx, &d->ap, &d->sp, (int)slot.size(), planes.data(), strides.data(), (int)jobFrame.size(), srcIdx.data(), refIdx.data(), shifts.data(), outp.data()) : 1;
+            if (ctx && rc)
+                msg = mvb200_last_error();
+        }
+        ok = rc == 0;
+        for (size_t j = 0; ok && j < jobFrame.size(); j++)
+            d->cache->put(jobFrame[j], std::move(out[j]), (size_t)d->lookahead * 4);
+    }
+    for (auto &h : held)
+        vsapi->freeFrame(h.second);
+    return ok;
+}
+
+const VSFrame *VS_CC analyseGetFrame(int n, int activationReason, void *instanceData, void **frameData, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
     AnalyseData *d = (AnalyseData *)instanceData;
     const int nref = refFrameOf(d->ap, n);
     const bool refOk = nref >= 0 && nref < d->vi->numFrames;
     if (activationReason == arInitial) {
+        // always what the reference requests (MVAnalyse.c:84-109): the single-frame path stays possible
         if (refOk) {
             vsapi->requestFrameFilter(n < nref ? n : nref, d->node, frameCtx);
             vsapi->requestFrameFilter(n < nref ? nref : n, d->node, frameCtx);
         } else {
             vsapi->requestFrameFilter(n, d->node, frameCtx);
         }
+        if (d->lookahead > 1) {
+            bool hit;
+            {
+                std::lock_guard<std::mutex> lock(d->cache->m);
+                hit = d->cache->blobs.count(n) != 0;
+            }
+            if (!hit) { // the rest of the window and its reference frames
+                const int end = n + d->lookahead < d->vi->numFrames ? n + d->lookahead : d->vi->numFrames;
+                for (int k = n + 1; k < end; k++) {
+                    vsapi->requestFrameFilter(k, d->node, frameCtx);
+                    const int r = refFrameOf(d->ap, k);
+                    if (r >= 0 && r < d->vi->numFrames)
+                        vsapi->requestFrameFilter(r, d->node, frameCtx);
+                }
+                *frameData = (void *)(intptr_t)end; // remembered for arAllFramesReady: the window was requested
+            }
+        }
     } else if (activationReason == arAllFramesReady) {
         const VSFrame *src = vsapi->getFrameFilter(n, d->node, frameCtx);
-        const VSFrame *ref = refOk ? vsapi->getFrameFilter(nref, d->node, frameCtx) : nullptr;
-        int err = 0;
-        int fieldShift = 0;
-        // MVAnalyse.c:136-179
-        int srcTop = !!vsapi->mapGetInt(vsapi->getFramePropertiesRO(src), "_Field", 0, &err);
-        bool missing = err && d->ap.fields && !d->ap.tff_exists;
-        int refTop = 0;
-        if (ref) {
-            refTop = !!vsapi->mapGetInt(vsapi->getFramePropertiesRO(ref), "_Field", 0, &err);
-            missing = missing || (err && d->ap.fields && !d->ap.tff_exists);
-        }
-        if (missing) {
-            vsapi->setFilterError("Analyse: _Field property not found in input frame. Therefore, you must pass tff argument.", frameCtx);
-            vsapi->freeFrame(src);
-            vsapi->freeFrame(ref);
-            return nullptr;
-        }
-        if (d->ap.tff_exists) {
-            srcTop = d->ap.tff ^ (n % 2);
-            refTop = d->ap.tff ^ (nref % 2);
-        }
-        if (ref && d->ap.fields && d->ap.ad.nPel > 1 && (d->ap.ad.nDeltaFrame % 2))
-            fieldShift = (srcTop && !refTop) ? d->ap.ad.nPel / 2 : ((refTop && !srcTop) ? -(d->ap.ad.nPel / 2) : 0);
-        std::vector<uint8_t> vectors((size_t)d->ap.vectors_size);
-        const uint8_t *sp_[3], *rp[3];
-        ptrdiff_t ss[3], rs[3];
-        planesRO(vsapi, src, d->vi->format.numPlanes, sp_, ss);
-        planesRO(vsapi, ref, d->vi->format.numPlanes, rp, rs);
+        std::vector<uint8_t> vectors;
         std::string msg;
-        int rc;
-        {
-            std::lock_guard<std::mutex> lock(g_engine_mutex);
-            mvb200_ctx *ctx = engine(msg);
-            rc = ctx ? mvb200_analyse_frame(ctx, &d->ap, &d->sp, sp_, ss, ref ? rp : nullptr, ref ? rs : nullptr, fieldShift, vectors.data()) : 1;
-            if (ctx && rc)
-                msg = mvb200_last_error();
+        bool have = false;
+        if (d->lookahead > 1) {
+            std::lock_guard<std::mutex> lock(d->cache->m);
+            auto it = d->cache->blobs.find(n);
+            const int end = (int)(intptr_t)*frameData;
+            if (it == d->cache->blobs.end() && end > n) { // miss, and this request holds the window's frames
+                if (!analyseWindow(d, vsapi, frameCtx, n, end, msg)) {
+                    vsapi->setFilterError(("Analyse: " + msg).c_str(), frameCtx);
+                    vsapi->freeFrame(src);
+                    return nullptr;
+                }
+                it = d->cache->blobs.find(n);
+            }
+            if (it != d->cache->blobs.end()) {
+                vectors = it->second;
+                have = true;
+            }
         }
-        vsapi->freeFrame(ref);
-        if (rc) {
-            vsapi->setFilterError(("Analyse: " + msg).c_str(), frameCtx);
-            vsapi->freeFrame(src);
-            return nullptr;
+        if (!have) { // one frame, one chain (also the fall-back when a cached blob was evicted in between)
+            const VSFrame *ref = refOk ? vsapi->getFrameFilter(nref, d->node, frameCtx) : nullptr;
+            int fieldShift = 0;
+            if (!analyseFieldShift(d, vsapi, src, ref, n, nref, &fieldShift)) {
+                vsapi->setFilterError("Analyse: _Field property not found in input frame. Therefore, you must pass tff argument.", frameCtx);
+                vsapi->freeFrame(src);
+                vsapi->freeFrame(ref);
+                return nullptr;
+            }
+            vectors.resize((size_t)d->ap.vectors_size);
+            const uint8_t *sp_[3], *rp[3];
+            ptrdiff_t ss[3], rs[3];
+            planesRO(vsapi, src, d->vi->format.numPlanes, sp_, ss);
+            planesRO(vsapi, ref, d->vi->format.numPlanes, rp, rs);
+            int rc;
+            {
+                std::lock_guard<std::mutex> lock(g_engine_mutex);
+                mvb200_ctx *ctx = engine(msg);
+                rc = ctx ? mvb200_analyse_frame(ctx, &d->ap, &d->sp, sp_, ss, ref ? rp : nullptr, ref ? rs : nullptr, fieldShift, vectors.data()) : 1;
+                if (ctx && rc)
+                    msg = mvb200_last_error();
+            }
+            vsapi->freeFrame(ref);
+            if (rc) {
+                vsapi->setFilterError(("Analyse: " + msg).c_str(), frameCtx);
+                vsapi->freeFrame(src);
+                return nullptr;
+            }
         }
         // the output frame is a copy of the super frame carrying the two properties (MVAnalyse.c:224-239)
         VSFrame *dst = vsapi->copyFrame(src, core);
@@ -324,6 +458,7 @@ const VSFrame *VS_CC analyseGetFrame(int n, int activationReason, void *instance
 void VS_CC analyseFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
     AnalyseData *d = (AnalyseData *)instanceData;
     vsapi->freeNode(d->node);
+    delete d->cache;
     delete d;
 }
 
@@ -351,6 +486,13 @@ void VS_CC analyseCreate(const VSMap *in, VSMap *out, void *, VSCore *core, cons
         vsapi->freeNode(d.node);
         return;
     }
+    const char *la = getenv("MVB200_LOOKAHEAD"); // frames searched per engine call (see AnalyseCache); default: one
+    d.lookahead = la ? atoi(la) : 0;
+    if (d.lookahead < 2)
+        d.lookahead = 0;
+    if (d.lookahead > 256)
+        d.lookahead = 256;
+    d.cache = d.lookahead ? new AnalyseCache : nullptr;
     AnalyseData *data = new AnalyseData(d);
     VSFilterDependency deps[1] = {{data->node, rpGeneral}};
     vsapi->createVideoFilter(out, "Analyse", data->vi, analyseGetFrame, analyseFree, fmParallel, deps, 1, data, core);
