@@ -30,41 +30,6 @@ def test_cuda_flow_matches_reference_goldens(gpu_ctx, case):
         assert got[stage] == GOLD[case][stage], "%s: CUDA %s differs from the reference's golden hashes" % (case, stage)
 
 
-@pytest.mark.parametrize("case", sorted(c for c in pipeline_flow.FLOW if pipeline_flow.FLOW[c].get("blur")))
-def test_cuda_flowblur_matches_reference_goldens(gpu_ctx, case):
-    """mv.FlowBlur: per-frame entry point and the device-resident batch entry point"""
-    import torch
-    L = mb.lib()
-    ctx = gpu_ctx
-    assert pipeline_flow.run_engine_blur(case, ctx.flowblur_frame) == GOLD[case]["blur"]
-    frames, sups, vecs = pipeline_flow.inputs(case)
-    N = len(frames)
-    sp, aps, P = pipeline_flow.flow_params_for(case)
-    cl, sl = mb.clip_layout(sp), mb.super_layout(sp)
-    dsrc, dsup = _device_clip(frames, cl), _device_clip(sups, sl)
-    vs = (len(vecs[0][0]) + 255) // 256 * 256
-    dvec = []
-    for v in range(2):
-        host = np.zeros((N, vs), dtype=np.uint8)
-        for n in range(N):
-            host[n, : len(vecs[v][n])] = vecs[v][n]
-        dvec.append(torch.from_numpy(host).cuda())
-    for i, p in enumerate(P["blur"]):
-        ddst = torch.full((N, cl.frame_bytes), 0xA5, dtype=torch.uint8, device="cuda")
-        mb._check(L.mvb200_flowblur_batch(ctx.handle, C.byref(p), C.byref(sp), dsrc.data_ptr(), dsup.data_ptr(), 0, N, dvec[0].data_ptr(), dvec[1].data_ptr(), vs, ddst.data_ptr()))
-        ctx.synchronize()
-        out = ddst.cpu().numpy()
-        for n in range(N):
-            assert [pipeline.sha(q) for q in _planes(out[n], cl)] == GOLD[case]["blur"][i][n], "blur variant %d frame %d" % (i, n)
-
-
-@pytest.mark.parametrize("case", sorted(c for c in pipeline_flow.FLOW if pipeline_flow.FLOW[c].get("bfps")))
-def test_cuda_blockfps_matches_reference_goldens(gpu_ctx, case):
-    """mv.BlockFPS: every output frame of every variant (modes 0..8, with and without overlap)"""
-    ctx = gpu_ctx
-    assert pipeline_flow.run_engine_bfps(case, ctx.blockfps_frame, ctx.blend_frame) == GOLD[case]["bfps"]
-
-
 @pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "p10_444_blk8_pel4_bicubic"])
 def test_cuda_flow_matches_oracle_bytes(gpu_ctx, case):
     """byte-level comparison against the oracle (locates a mismatch instead of a hash); includes a field shift"""
@@ -184,32 +149,3 @@ def test_flow_full_size_1080p_properties(gpu_ctx):
         lv = g.lv[p][0]
         assert np.array_equal(fin[p][::2, ::2], sups[0][p][: lv.padded_h, : lv.padded_w])
     assert blob[1] == 1
-
-
-def test_interpolation_full_size_1080p_properties(gpu_ctx):
-    """1920x1080 YUV420P8, pel 2, blk 16 / overlap 8: with a zero vector field between two identical frames every
-    interpolation filter must return that frame, whatever its time / mode (all of them are convex blends of
-    motion-compensated samples); a full-size run of mv.FlowInter / mv.FlowBlur / mv.BlockFPS and their masks."""
-    ctx = gpu_ctx
-    W, H, N = 1920, 1080, 3
-    import clipgen
-    frames = clipgen.make_clip(W, H, 1, bits=8, scene_cut=False)
-    sp = mb.super_params(W, H, 8, 1, 1, pel=2)
-    sup = ctx.super_frame(sp, frames[0])
-    aps = [mb.analyse_params(sp, N, isb=isb, blksize=16, overlap=8) for isb in (1, 0)]
-    v0 = [ctx.analyse_frame(ap, sp, sup, sup) for ap in aps]
-    th = dict(thscd1=16000, thscd2=255)
-    ip = mb.flowinter_params(sp, aps[0].ad, aps[1].ad, N, time=37.0, **th)
-    out = ctx.flowinter_frame(ip, sp, ip.time256, sup, sup, v0[0], v0[1], v0[0], v0[1])
-    assert out is not None and all(np.array_equal(a, b) for a, b in zip(out, frames[0])), "FlowInter"
-    bp = mb.flowblur_params(sp, aps[0].ad, aps[1].ad, N, blur=100.0, **th)
-    out = ctx.flowblur_frame(bp, sp, sup, v0[0], v0[1])
-    assert out is not None and all(np.array_equal(a, b) for a, b in zip(out, frames[0])), "FlowBlur"
-    for mode in (0, 1, 2, 3, 4, 6, 7):
-        q = mb.blockfps_params(sp, aps[0].ad, aps[1].ad, N, W, H, num=60, den=1, mode=mode, **th)
-        out = ctx.blockfps_frame(q, sp, 100, sup, sup, v0[0], v0[1])
-        assert out is not None and all(np.array_equal(a, b) for a, b in zip(out, frames[0])), "BlockFPS mode %d" % mode
-    # the blend the filters fall back to at scene changes: time256 = 0 / 256 give the two frames themselves
-    other = [255 - p for p in frames[0]]
-    assert all(np.array_equal(a, b) for a, b in zip(ctx.blend_frame(sp, 0, frames[0], other), frames[0]))
-    assert all(np.array_equal(a, b) for a, b in zip(ctx.blend_frame(sp, 256, frames[0], other), other))

@@ -334,27 +334,6 @@ def test_full_size_4k_satd_recalculate_compensate(gpu_ctx):
         assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("case", ["blk16_ov8_pel2_p8_r3", "blk16_ov8_pel2_p16_r3", "noise_badblocks_blk8", "divide2_blk16_esa_neg_badrange"])
-def test_analyse_frames_matches_goldens(gpu_ctx, case):
-    """mvb200_analyse_frames (the plugin's look-ahead: all frames of a vector clip searched in ONE engine call, the
-    super frames uploaded once) gives the reference's blobs"""
-    ctx = gpu_ctx
-    frames = pipeline.make_frames(pipeline.CASES[case][0])
-    N = len(frames)
-    sp, aps, dp = pipeline.params_for(case)
-    sups = [ctx.super_frame(sp, f) for f in frames]
-    for i, ap in enumerate(aps):
-        jobs = [(n, pipeline.nref_of(ap, n, N), 0) for n in range(N)]
-        blobs = ctx.analyse_frames(ap, sp, sups, jobs)
-        assert [pipeline.sha(pipeline.mask_blob(b, ap)) for b in blobs] == [row[i] for row in GOLD[case]["vectors"]], "vector clip %d" % i
-    # a sub-window with its own frame list (indices are positions in the list, not frame numbers)
-    ap = aps[0]
-    blobs = ctx.analyse_frames(ap, sp, [sups[2], sups[3], sups[1]], [(0, 1, 0), (2, 0, 0), (1, None, 0)])
-    assert np.array_equal(blobs[0], ctx.analyse_frame(ap, sp, sups[2], sups[3]))
-    assert np.array_equal(blobs[1], ctx.analyse_frame(ap, sp, sups[1], sups[2]))
-    assert np.array_equal(blobs[2], ctx.analyse_frame(ap, sp, sups[3], None))
-
-
 def test_smoke_entry(built):
     import __graft_entry__
     __graft_entry__.smoke()

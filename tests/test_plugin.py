@@ -103,30 +103,3 @@ def test_flow_script_through_plugin_matches_reference(built, case):
     got = pipeline_flow.run_reference_flow(case, plugin_path=mb.PLUGIN_PATH, only=stages)
     for stage in stages:
         assert got[stage] == GOLD_FLOW[case][stage], "%s: plugin %s differs from the reference plugin" % (case, stage)
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "noise_badblocks_blk8"])
-def test_flowblur_script_through_plugin_matches_reference(built, case):
-    import pipeline_flow
-    got = pipeline_flow.run_reference_flow(case, plugin_path=mb.PLUGIN_PATH, only=("blur",))
-    assert got["blur"] == GOLD_FLOW[case]["blur"], "%s: plugin mv.FlowBlur differs from the reference plugin" % case
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "c1_640x360_p8_blk8_pel1", "noise_badblocks_blk8"])
-def test_blockfps_script_through_plugin_matches_reference(built, case):
-    import pipeline_flow
-    got = pipeline_flow.run_reference_flow(case, plugin_path=mb.PLUGIN_PATH, only=("bfps",))
-    assert got["bfps"] == GOLD_FLOW[case]["bfps"], "%s: plugin mv.BlockFPS differs from the reference plugin" % case
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("case", ["blk16_ov8_pel2_p8_r3", "divide2_blk16_esa_neg_badrange"])
-def test_script_through_plugin_with_lookahead(built, monkeypatch, case):
-    """MVB200_LOOKAHEAD=4: mv.Analyse searches four frames per engine call; the script's results do not change"""
-    monkeypatch.setenv("MVB200_LOOKAHEAD", "4")
-    got = pipeline.run_reference(case, plugin_path=mb.PLUGIN_PATH)
-    for stage in ("super", "vectors", "degrain", "adata", "recalc", "compensate"):
-        if stage in got:
-            assert got[stage] == GOLD[case][stage], "%s: plugin %s differs from the reference plugin" % (case, stage)
