@@ -19,7 +19,7 @@ FLOW = {
     "blk8_ov4_pel2_p8": dict(
         mask=[dict(kind=0), dict(kind=1, gamma=2.0, time=30.0), dict(kind=2, ml=50.0), dict(kind=2, vec=1, gamma=0.7, time=60.0),
               dict(kind=3), dict(kind=4, ml=20.0, vec=1), dict(kind=5, ysc=77), dict(kind=0, gamma=1.7, ml=30.0, thscd1=200, thscd2=40, ysc=200)],
-        flow=[dict(), dict(time=50.0, vec=1), dict(mode=1, time=70.0), dict(mode=1, vec=1, thscd1=250, thscd2=60)],
+        flow=[dict(), dict(time=50.0, vec=1), dict(mode=1, time=70.0), dict(mode=1, vec=1, thscd1=250, thscd2=60), dict(fields=1, tff=1, time=80.0), dict(fields=1, tff=0, vec=1, mode=1)],
         scd=[dict(), dict(vec=1, thscd1=150, thscd2=30)], finest=True,
         inter=[dict(), dict(time=25.0, ml=40.0), dict(time=80.0, blend=0, thscd1=250, thscd2=60), dict(time=0.0), dict(time=100.0)],
         blur=[dict(), dict(blur=120.0, prec=2), dict(blur=200.0, thscd1=250, thscd2=60)],
@@ -203,7 +203,11 @@ def run_engine_flow(case, scd_fn, mask_fn, finest_fn, flow_fn):
         rows = []
         for n in range(N):
             r = pipeline.nref_of(aps[v], n, N)
-            d = flow_fn(fp, sp, sups[r] if r is not None else None, vecs[v][n])
+            fs = 0
+            if r is not None and fp.fields and fp.vd.nPel > 1 and (r - n) % 2:  # MVFlow.cpp:268-299 with an explicit tff
+                src_top, ref_top = fp.tff ^ (n % 2), fp.tff ^ (r % 2)
+                fs = fp.vd.nPel // 2 if (src_top and not ref_top) else (-(fp.vd.nPel // 2) if (ref_top and not src_top) else 0)
+            d = flow_fn(fp, sp, sups[r] if r is not None else None, vecs[v][n], fs)
             rows.append([sha(p) for p in (d if d is not None else frames[n])])  # not usable: the source frame (MVFlow.cpp:362-366)
         out["flow"].append(rows)
     if FLOW[case].get("finest"):
