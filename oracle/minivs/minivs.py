@@ -207,8 +207,8 @@ class Core:
             raise Error(lib().mvs_last_error().decode())
         return Plugin(p)
 
-    def source(self, frames, bits=8, ssw=1, ssh=1):
-        """frames: list of [Y,U,V] (or [Y]) numpy arrays."""
+    def source(self, frames, bits=8, ssw=1, ssh=1, props=None):
+        """frames: list of [Y,U,V] (or [Y]) numpy arrays; props: optional list (one dict of integer frame properties per frame)."""
         L = lib()
         nplanes = len(frames[0])
         h, w = frames[0][0].shape
@@ -220,6 +220,8 @@ class Core:
             for p, a in enumerate(fr):
                 a = np.ascontiguousarray(a)
                 L.mvs_source_set_plane(node, n, p, a.ctypes.data, a.strides[0])
+            for k, v in (props[n] if props else {}).items():
+                L.mvs_source_set_prop_int(node, n, k.encode(), int(v))
         return Node(node)
 
 

@@ -78,3 +78,40 @@ def test_analyse_lookahead_batches_the_engine_calls(mock_plugin, monkeypatch):
     # out-of-order and repeated requests are served as well (cache hits, evictions, single-frame fall-back)
     for n in (5, 0, 3, 3, 1):
         assert vec.get_frame(n).prop_data("MVTools_vectors") == blobs[n]
+
+
+def test_field_property_glue_matches_reference_live(mock_plugin, have_ref):
+    """field-separated clips: without a tff argument the filters read the _Field property of the frames
+    (MVAnalyse.c:136-179, MVCompensate.c, MVFlow.cpp:268-299); the plugin's glue against the compiled reference"""
+    if not have_ref:
+        pytest.skip("oracle/_ref/libmvtools_ref.so not built here (no /root/reference)")
+    import minivs
+    case = "blk8_ov4_pel2_p8"
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    N = len(frames)
+    props = [{"_Field": (n + 1) % 2} for n in range(N)]
+    outs = []
+    for path in (minivs.REF_PLUGIN, mock_plugin):
+        core = minivs.Core()
+        mv = core.load(path)
+        clip = core.source(frames, bits=8, props=props)
+        sup = mv.Super(clip, **skw)
+        vb = mv.Analyse(sup, isb=1, delta=1, fields=1, **akw)
+        vf = mv.Analyse(sup, isb=0, delta=1, fields=1, **akw)
+        comp = mv.Compensate(clip, sup, vb, fields=1)
+        flow = mv.Flow(clip, sup, vf, fields=1, time=60.0)
+        rec = mv.Recalculate(sup, vb, blksize=8, overlap=4, fields=1, thsad=50)
+        res = []
+        for n in range(N):
+            res.append((vb.get_frame(n).prop_data("MVTools_vectors"), vf.get_frame(n).prop_data("MVTools_vectors"), rec.get_frame(n).prop_data("MVTools_vectors"),
+                        [pipeline.sha(p) for p in comp.get_frame(n).planes()], [pipeline.sha(p) for p in flow.get_frame(n).planes()]))
+        outs.append(res)
+    assert outs[0] == outs[1]
+    # and the error when neither the property nor tff is there
+    core = minivs.Core()
+    mv = core.load(mock_plugin)
+    sup = mv.Super(core.source(frames, bits=8), **skw)
+    with pytest.raises(minivs.Error) as e:
+        mv.Analyse(sup, isb=1, fields=1, **akw).get_frame(1)
+    assert "_Field property not found in input frame" in str(e.value)
