@@ -474,6 +474,11 @@ MVB200_API int mvb200_compensate_batch(mvb200_ctx *ctx, const mvb200_compensate_
 MVB200_API int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap,
                                               const mvb200_degrain_params *dp, const void *host_src, void *host_dst, int n, int first, int count);
 
+/* Page-locked host memory for the buffers handed to mvb200_degrain_clip_host_async (pageable memory works too, but its
+ * copies are not asynchronous).  mvb200_pinned_alloc returns NULL on failure. */
+MVB200_API void *mvb200_pinned_alloc(size_t bytes);
+MVB200_API void mvb200_pinned_free(void *p);
+
 /* --------------------------------------------- host-buffer per-frame entry points */
 /* (what the VapourSynth plugin calls from GetFrame; H2D/D2H copies inside) */
 

@@ -89,7 +89,7 @@ class Frame:
         bps = self._info[5]
         buf = (C.c_uint8 * (stride * h)).from_address(L.mvs_frame_plane(self._p, p))
         a = np.frombuffer(buf, dtype=np.uint8).reshape(h, stride)[:, : w * bps]
-        a = np.ascontiguousarray(a)
+        a = np.array(a, copy=True, order="C")  # (always a copy: the frame may be freed before the array is read)
         return a.view(np.uint16) if bps == 2 else a
 
     def planes(self):

@@ -11,7 +11,9 @@
 #include "../../include/mvtools_b200.h"
 #include "../../oracle/mvtools_oracle.h"
 
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 
 struct mvb200_ctx {
     int dummy;
@@ -35,6 +37,96 @@ MVB200_API int mvb200_ctx_create(int, mvb200_ctx **out) {
 }
 MVB200_API void mvb200_ctx_destroy(mvb200_ctx *ctx) { delete ctx; }
 MVB200_API int mvb200_ctx_synchronize(mvb200_ctx *) { return 0; }
+MVB200_API void *mvb200_pinned_alloc(size_t bytes) { return malloc(bytes); }
+MVB200_API void mvb200_pinned_free(void *p) { free(p); }
+
+// the layouts of the device-resident clips, restated for the stand-in (the product's live in engine.cu)
+static long long round_up256(long long v) { return (v + 255) / 256 * 256; }
+MVB200_API void mvb200_clip_layout(const mvb200_super_params *p, mvb200_frame_layout *l) {
+    memset(l, 0, sizeof(*l));
+    l->nplanes = p->nplanes;
+    l->bytes_per_sample = (p->bits + 7) / 8;
+    long long off = 0;
+    for (int i = 0; i < p->nplanes; i++) {
+        l->plane_w[i] = i ? p->width >> p->ssw : p->width;
+        l->plane_h[i] = i ? p->height >> p->ssh : p->height;
+        l->pitch[i] = round_up256((long long)l->plane_w[i] * l->bytes_per_sample);
+        l->offset[i] = off;
+        off += l->pitch[i] * l->plane_h[i];
+    }
+    l->frame_bytes = round_up256(off);
+}
+
+// The clip pipeline on host memory, frame by frame through the oracle: Super of every frame of the segment, the nap
+// searches and DegrainN for frames [first, first + count).  Reference frames follow the analyse parameters with
+// num_frames = the segment length, as in the engine.
+MVB200_API int mvb200_degrain_clip_host_async(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const mvb200_degrain_params *dp, const void *host_src, void *host_dst, int n, int first,
+                                              int count) {
+    mvb200_frame_layout cl;
+    mvb200_clip_layout(sp, &cl);
+    mvb200_super_geom g;
+    mvb200_super_geometry(sp, &g);
+    const int bps = cl.bytes_per_sample;
+    std::vector<std::vector<uint8_t>> sup((size_t)n * 3);
+    ptrdiff_t sstride[3] = {0, 0, 0};
+    auto src_planes = [&](int f, const uint8_t *p[3], ptrdiff_t st[3]) {
+        for (int i = 0; i < 3; i++) {
+            p[i] = i < cl.nplanes ? (const uint8_t *)host_src + (size_t)cl.frame_bytes * f + cl.offset[i] : nullptr;
+            st[i] = i < cl.nplanes ? (ptrdiff_t)cl.pitch[i] : 0;
+        }
+    };
+    for (int f = 0; f < n; f++) {
+        const uint8_t *p[3];
+        ptrdiff_t st[3];
+        uint8_t *d[3] = {nullptr, nullptr, nullptr};
+        src_planes(f, p, st);
+        for (int i = 0; i < sp->nplanes; i++) {
+            sstride[i] = (ptrdiff_t)g.plane_w[i] * bps;
+            sup[(size_t)f * 3 + i].assign((size_t)sstride[i] * g.plane_h[i], 0);
+            d[i] = sup[(size_t)f * 3 + i].data();
+        }
+        if (fwd(mvo_super_frame(sp, p, st, d, sstride)))
+            return 1;
+    }
+    auto sup_planes = [&](int f, const uint8_t *p[3]) {
+        for (int i = 0; i < 3; i++)
+            p[i] = i < sp->nplanes ? sup[(size_t)f * 3 + i].data() : nullptr;
+    };
+    for (int k = 0; k < count; k++) {
+        const int f = first + k;
+        std::vector<std::vector<uint8_t>> blobs((size_t)nap);
+        std::vector<const uint8_t *> vecs((size_t)nap), refs((size_t)nap * 3, nullptr);
+        std::vector<ptrdiff_t> rstr((size_t)nap * 3, 0);
+        for (int i = 0; i < nap; i++) {
+            const int d = ap[i]->ad.nDeltaFrame;
+            int nref = d > 0 ? f + (ap[i]->ad.isBackward ? d : -d) : -d;
+            if (nref < 0 || nref >= n)
+                nref = -1;
+            const uint8_t *s[3], *r[3];
+            sup_planes(f, s);
+            if (nref >= 0)
+                sup_planes(nref, r);
+            blobs[i].assign((size_t)ap[i]->vectors_size, 0);
+            if (fwd(mvo_analyse_frame(ap[i], sp, s, sstride, nref >= 0 ? r : nullptr, nref >= 0 ? sstride : nullptr, 0, blobs[i].data())))
+                return 1;
+            vecs[i] = blobs[i].data();
+            if (nref >= 0)
+                for (int pl = 0; pl < sp->nplanes; pl++) {
+                    refs[(size_t)i * 3 + pl] = sup[(size_t)nref * 3 + pl].data();
+                    rstr[(size_t)i * 3 + pl] = sstride[pl];
+                }
+        }
+        const uint8_t *p[3];
+        ptrdiff_t st[3];
+        uint8_t *d[3];
+        src_planes(f, p, st);
+        for (int i = 0; i < 3; i++)
+            d[i] = i < cl.nplanes ? (uint8_t *)host_dst + (size_t)cl.frame_bytes * k + cl.offset[i] : nullptr;
+        if (fwd(mvo_degrain_frame(dp, sp, p, st, refs.data(), rstr.data(), vecs.data(), d, st)))
+            return 1;
+    }
+    return 0;
+}
 
 MVB200_API int mvb200_super_frame(mvb200_ctx *, const mvb200_super_params *p, const uint8_t *const src[3], const ptrdiff_t src_stride[3], uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
     return fwd(mvo_super_frame(p, src, src_stride, dst, dst_stride));

@@ -59,6 +59,32 @@ def test_analyse_lookahead_glue(mock_plugin, monkeypatch, case, window):
             assert got[stage] == GOLD[case][stage], "%s (window %d): %s" % (case, window, stage)
 
 
+@pytest.mark.parametrize("window", [2, 5])
+@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "gray_blk4_pel1_rf0", "p8_422_blk8x4_sharp0_rf1", "noise_badblocks_blk8", "c1_640x360_p8_blk8_pel1"])
+def test_degrain_fused_path_glue(mock_plugin, monkeypatch, case, window):
+    """MVB200_LOOKAHEAD: a DegrainN whose inputs are this plugin's own Super / Analyse nodes on the same clip runs windows of
+    frames through the engine's clip pipeline (source frames in, denoised frames out); its output must not change
+    (radius 1..3, 8 / 16 bit, gray, 4:2:2 with non-default sharp / rfilter and plane=0, scene changes, clip ends)"""
+    import minivs
+    monkeypatch.setenv("MVB200_LOOKAHEAD", str(window))
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    N = len(frames)
+    core = minivs.Core()
+    mv = core.load(mock_plugin)
+    clip = core.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1))
+    sup = mv.Super(clip, **skw)
+    vn = [mv.Analyse(sup, isb=isb, delta=d, **pipeline._fix(akw)) for d in range(1, radius + 1) for isb in (1, 0)]
+    dn = mv.invoke("Degrain%d" % radius, clip, sup, *vn, **dkw)
+    dn.set_cache(0)
+    before = (sup.computed(), [v.computed() for v in vn])  # what the filters' creation read (frame 0 of every input)
+    order = list(range(N)) + [N - 1, 0, N // 2]
+    for n in order:
+        assert [pipeline.sha(p) for p in dn.get_frame(n).planes()] == GOLD[case]["degrain"][n], "frame %d" % n
+    # the Super and Analyse nodes are not asked for a single frame on this path
+    assert (sup.computed(), [v.computed() for v in vn]) == before
+
+
 def test_analyse_lookahead_batches_the_engine_calls(mock_plugin, monkeypatch):
     """with a window of 4, six frames requested in order cost two window searches per vector clip, not six"""
     import minivs

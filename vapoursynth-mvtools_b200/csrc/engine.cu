@@ -567,6 +567,20 @@ int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *s
     return 0;
 }
 
+void *mvb200_pinned_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        set_error("mvtools_b200: cannot allocate %zu bytes of pinned host memory", bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void mvb200_pinned_free(void *p) {
+    if (p)
+        cudaFreeHost(p);
+}
+
 // ------------------------------------------------------- host-buffer path
 
 static int upload_planes(Ctx *c, uint8_t *dev_frame, const long long *pitch, const long long *offset, const int *w, const int *h, int bps, int nplanes, const uint8_t *const src[3], const ptrdiff_t stride[3]) {

@@ -44,6 +44,40 @@ mvb200_ctx *engine(std::string &err) {
     return g_ctx;
 }
 
+// The plugin's own Super / Analyse nodes, by node pointer (API 4: a VSNode* IS the node, every reference to it has the
+// same value).  mv.DegrainN looks its inputs up here to recognise the canonical script
+//     sup = Super(clip); v.. = Analyse(sup, ..); DegrainN(clip, sup, v..)
+// whose whole chain one engine call can run (see DegrainData::fused).
+enum { kNodeSuper = 1, kNodeAnalyse = 2 };
+struct NodeInfo {
+    int kind;
+    void *data;
+};
+std::mutex g_registry_mutex;
+std::map<VSNode *, NodeInfo> g_registry;
+
+// the node createVideoFilter just put into `out` (no reference is kept)
+VSNode *registerSelf(const VSAPI *vsapi, VSMap *out, int kind, void *data) {
+    VSNode *self = vsapi->mapGetNode(out, "clip", 0, nullptr);
+    if (!self)
+        return nullptr;
+    vsapi->freeNode(self);
+    std::lock_guard<std::mutex> lock(g_registry_mutex);
+    g_registry[self] = NodeInfo{kind, data};
+    return self;
+}
+
+void unregisterSelf(VSNode *self) {
+    std::lock_guard<std::mutex> lock(g_registry_mutex);
+    g_registry.erase(self);
+}
+
+int lookaheadFromEnv() { // MVB200_LOOKAHEAD: frames per engine call (2..256); anything else = off
+    const char *la = getenv("MVB200_LOOKAHEAD");
+    int v = la ? atoi(la) : 0;
+    return v < 2 ? 0 : (v > 256 ? 256 : v);
+}
+
 int argInt(const VSAPI *vsapi, const VSMap *in, const char *name) {
     int err = 0;
     int v = vsapi->mapGetIntSaturated(in, name, 0, &err);
@@ -129,6 +163,7 @@ struct SuperData {
     VSVideoInfo vi;
     mvb200_super_params sp;
     int usePelClip, pelPadded;
+    VSNode *self; // this filter's output node (registry key), not a reference
 };
 
 const VSFrame *VS_CC superGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
@@ -185,6 +220,7 @@ const VSFrame *VS_CC superGetFrame(int n, int activationReason, void *instanceDa
 
 void VS_CC superFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
     SuperData *d = (SuperData *)instanceData;
+    unregisterSelf(d->self);
     vsapi->freeNode(d->node);
     vsapi->freeNode(d->pelclip);
     delete d;
@@ -239,6 +275,7 @@ void VS_CC superCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const 
     SuperData *data = new SuperData(d);
     VSFilterDependency deps[1] = {{data->node, rpStrictSpatial}}; // (the reference declares the source clip only, MVSuper.c:270-272)
     vsapi->createVideoFilter(out, "Super", &data->vi, superGetFrame, superFree, fmParallel, deps, 1, data, core);
+    data->self = registerSelf(vsapi, out, kNodeSuper, data);
 }
 
 // ---------------------------------------------------------------- Analyse
@@ -267,6 +304,7 @@ struct AnalyseData {
     mvb200_analyse_params ap;
     int lookahead;       // window length, 0 = one frame per call
     AnalyseCache *cache; // owned; null without look-ahead
+    VSNode *self;        // this filter's output node (registry key), not a reference
 };
 
 int refFrameOf(const mvb200_analyse_params &ap, int n) { // MVAnalyse.c:84-109
@@ -457,6 +495,7 @@ const VSFrame *VS_CC analyseGetFrame(int n, int activationReason, void *instance
 
 void VS_CC analyseFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
     AnalyseData *d = (AnalyseData *)instanceData;
+    unregisterSelf(d->self);
     vsapi->freeNode(d->node);
     delete d->cache;
     delete d;
@@ -486,26 +525,148 @@ void VS_CC analyseCreate(const VSMap *in, VSMap *out, void *, VSCore *core, cons
         vsapi->freeNode(d.node);
         return;
     }
-    const char *la = getenv("MVB200_LOOKAHEAD"); // frames searched per engine call (see AnalyseCache); default: one
-    d.lookahead = la ? atoi(la) : 0;
-    if (d.lookahead < 2)
-        d.lookahead = 0;
-    if (d.lookahead > 256)
-        d.lookahead = 256;
+    d.lookahead = lookaheadFromEnv(); // frames searched per engine call (see AnalyseCache); default: one
     d.cache = d.lookahead ? new AnalyseCache : nullptr;
+    d.self = nullptr;
     AnalyseData *data = new AnalyseData(d);
     VSFilterDependency deps[1] = {{data->node, rpGeneral}};
     vsapi->createVideoFilter(out, "Analyse", data->vi, analyseGetFrame, analyseFree, fmParallel, deps, 1, data, core);
+    data->self = registerSelf(vsapi, out, kNodeAnalyse, data);
 }
 
 // ---------------------------------------------------------------- Degrain
+// Fused path (MVB200_LOOKAHEAD=<B>, default off): when the clip, the super clip and every vector clip of a DegrainN are
+// this plugin's own nodes wired as in the canonical script, the frames [n, n + B) are produced by ONE engine call over
+// the SOURCE frames of the window and its halo -- mvb200_degrain_clip_host_async: H2D of 3 MB source frames, Super,
+// 2r searches of B chains each, DegrainN, D2H -- instead of 1 + 2r + 1 per-frame calls that move 17.9 MB super frames
+// each way.  The Super / Analyse nodes are not even asked for those frames.  Results are identical (the engine's clip
+// pipeline is what the sharded bench runs; frames outside the window only serve as references).
+struct DegrainFused {
+    std::mutex m;
+    std::map<int, std::vector<uint8_t>> frames; // output frames in the clip layout
+    std::deque<int> order;
+    mvb200_analyse_params ap[2 * MVB200_MAX_RADIUS]; // copies: no dependence on the Analyse instances' lifetime
+    mvb200_frame_layout cl;
+    int window, halo;
+    void *hostSrc = nullptr, *hostDst = nullptr; // pinned staging, grown on demand
+    size_t hostSrcBytes = 0, hostDstBytes = 0;
+};
+
 struct DegrainData {
     VSNode *node, *super, *vectors[2 * MVB200_MAX_RADIUS];
     const VSVideoInfo *vi;
     mvb200_super_params sp;
     mvb200_degrain_params dp;
     int radius;
+    DegrainFused *fused; // owned; null = node-by-node evaluation
 };
+
+// runs the window [n, end) through the clip pipeline and caches its frames; false + msg on failure
+bool degrainFusedWindow(DegrainData *d, const VSAPI *vsapi, VSFrameContext *frameCtx, int n, int end, std::string &msg) {
+    DegrainFused *f = d->fused;
+    const int N = d->vi->numFrames, s0 = n - f->halo > 0 ? n - f->halo : 0, s1 = end + f->halo < N ? end + f->halo : N, seg = s1 - s0;
+    const size_t fb = (size_t)f->cl.frame_bytes;
+    std::lock_guard<std::mutex> lock(g_engine_mutex); // (also guards the staging buffers)
+    mvb200_ctx *ctx = engine(msg);
+    if (!ctx)
+        return false;
+    if (f->hostSrcBytes < fb * seg) {
+        mvb200_pinned_free(f->hostSrc);
+        f->hostSrc = mvb200_pinned_alloc(fb * seg);
+        f->hostSrcBytes = f->hostSrc ? fb * seg : 0;
+    }
+    if (f->hostDstBytes < fb * (end - n)) {
+        mvb200_pinned_free(f->hostDst);
+        f->hostDst = mvb200_pinned_alloc(fb * (end - n));
+        f->hostDstBytes = f->hostDst ? fb * (end - n) : 0;
+    }
+    if (!f->hostSrc || !f->hostDst) {
+        msg = mvb200_last_error();
+        return false;
+    }
+    for (int k = s0; k < s1; k++) { // pack the source frames into the clip layout
+        const VSFrame *fr = vsapi->getFrameFilter(k, d->node, frameCtx);
+        for (int p = 0; p < f->cl.nplanes; p++)
+            vsh::bitblt((uint8_t *)f->hostSrc + fb * (k - s0) + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], vsapi->getReadPtr(fr, p), vsapi->getStride(fr, p), (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample,
+                        (size_t)f->cl.plane_h[p]);
+        vsapi->freeFrame(fr);
+    }
+    const int R2 = d->radius * 2;
+    mvb200_analyse_params aps[2 * MVB200_MAX_RADIUS];
+    const mvb200_analyse_params *app[2 * MVB200_MAX_RADIUS];
+    for (int r = 0; r < R2; r++) { // the segment is the clip as far as the engine is concerned
+        aps[r] = f->ap[r];
+        aps[r].num_frames = seg;
+        app[r] = &aps[r];
+    }
+    if (mvb200_degrain_clip_host_async(ctx, &d->sp, app, R2, &d->dp, f->hostSrc, f->hostDst, seg, n - s0, end - n) || mvb200_ctx_synchronize(ctx)) {
+        msg = mvb200_last_error();
+        return false;
+    }
+    for (int k = n; k < end; k++) {
+        const uint8_t *p = (const uint8_t *)f->hostDst + fb * (k - n);
+        if (f->frames.emplace(k, std::vector<uint8_t>(p, p + fb)).second)
+            f->order.push_back(k);
+    }
+    while (f->order.size() > (size_t)f->window * 4) {
+        f->frames.erase(f->order.front());
+        f->order.pop_front();
+    }
+    return true;
+}
+
+const VSFrame *VS_CC degrainFusedGetFrame(int n, int activationReason, void *instanceData, void **frameData, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    DegrainData *d = (DegrainData *)instanceData;
+    DegrainFused *f = d->fused;
+    const int N = d->vi->numFrames;
+    if (activationReason == arInitial) {
+        vsapi->requestFrameFilter(n, d->node, frameCtx);
+        bool hit;
+        {
+            std::lock_guard<std::mutex> lock(f->m);
+            hit = f->frames.count(n) != 0;
+        }
+        if (!hit) { // the window's source frames and the halo the searches and the blend reach into
+            const int end = n + f->window < N ? n + f->window : N;
+            const int s0 = n - f->halo > 0 ? n - f->halo : 0, s1 = end + f->halo < N ? end + f->halo : N;
+            for (int k = s0; k < s1; k++)
+                if (k != n)
+                    vsapi->requestFrameFilter(k, d->node, frameCtx);
+            *frameData = (void *)(intptr_t)end;
+        }
+    } else if (activationReason == arAllFramesReady) {
+        const VSFrame *src = vsapi->getFrameFilter(n, d->node, frameCtx);
+        std::vector<uint8_t> frame;
+        std::string msg;
+        {
+            std::lock_guard<std::mutex> lock(f->m);
+            const int end = (int)(intptr_t)*frameData;
+            bool have = f->frames.count(n) != 0;
+            if (!have && end > n) // miss, and this request holds the window's source frames
+                have = degrainFusedWindow(d, vsapi, frameCtx, n, end, msg);
+            else if (!have)
+                msg = "internal: frame neither cached nor requested"; // (evicted between the two activations)
+            if (have)
+                frame = f->frames.find(n)->second;
+        }
+        if (frame.empty()) {
+            vsapi->setFilterError(("Degrain: " + msg).c_str(), frameCtx);
+            vsapi->freeFrame(src);
+            return nullptr;
+        }
+        VSFrame *dst = vsapi->newVideoFrame(&d->vi->format, d->vi->width, d->vi->height, src, core);
+        for (int p = 0; p < d->vi->format.numPlanes; p++) {
+            if (!d->dp.process[p]) { // planes the filter does not process are copies of the source (MVDegrains.cpp:211-214)
+                vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), vsapi->getReadPtr(src, p), vsapi->getStride(src, p), (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, (size_t)f->cl.plane_h[p]);
+                continue;
+            }
+            vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), frame.data() + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, (size_t)f->cl.plane_h[p]);
+        }
+        vsapi->freeFrame(src);
+        return dst;
+    }
+    return nullptr;
+}
 
 const VSFrame *VS_CC degrainGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
     DegrainData *d = (DegrainData *)instanceData;
@@ -577,6 +738,11 @@ void VS_CC degrainFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
     vsapi->freeNode(d->super);
     for (int r = 0; r < d->radius * 2; r++)
         vsapi->freeNode(d->vectors[r]);
+    if (d->fused) {
+        mvb200_pinned_free(d->fused->hostSrc);
+        mvb200_pinned_free(d->fused->hostDst);
+        delete d->fused;
+    }
     delete d;
 }
 
@@ -650,7 +816,43 @@ void VS_CC degrainCreate(const VSMap *in, VSMap *out, void *userData, VSCore *co
         freeAll();
         return;
     }
+    // the fused path: every input is one of this plugin's own nodes, wired as in the canonical script
+    const int window = lookaheadFromEnv();
+    if (window) {
+        std::lock_guard<std::mutex> lock(g_registry_mutex);
+        auto su = g_registry.find(d.super);
+        bool ok = su != g_registry.end() && su->second.kind == kNodeSuper;
+        const SuperData *S = ok ? (const SuperData *)su->second.data : nullptr;
+        ok = ok && S->node == d.node && !S->usePelClip && S->sp.width == d.sp.width && S->sp.height == d.sp.height && S->sp.bits == d.sp.bits && S->sp.pel == d.sp.pel && S->sp.hpad == d.sp.hpad &&
+             S->sp.vpad == d.sp.vpad && S->sp.levels == d.sp.levels && S->sp.modeyuv == d.sp.modeyuv;
+        DegrainFused *f = ok ? new DegrainFused : nullptr;
+        int halo = 0;
+        for (int r = 0; ok && r < 2 * radius; r++) {
+            auto an = g_registry.find(d.vectors[r]);
+            ok = an != g_registry.end() && an->second.kind == kNodeAnalyse;
+            const AnalyseData *A = ok ? (const AnalyseData *)an->second.data : nullptr;
+            ok = ok && A->node == d.super && !A->ap.fields && A->ap.ad.nDeltaFrame > 0 && A->ap.num_frames == d.vi->numFrames;
+            if (ok) {
+                f->ap[r] = A->ap;
+                halo = A->ap.ad.nDeltaFrame > halo ? A->ap.ad.nDeltaFrame : halo;
+            }
+        }
+        if (ok) {
+            d.sp = S->sp; // (with the Super's own sharp / rfilter: the frame properties do not carry them)
+            mvb200_clip_layout(&d.sp, &f->cl);
+            f->window = window;
+            f->halo = halo;
+            d.fused = f;
+        } else {
+            delete f;
+        }
+    }
     DegrainData *data = new DegrainData(d);
+    if (data->fused) { // only the source clip is read on this path
+        VSFilterDependency fdeps[1] = {{data->node, rpGeneral}};
+        vsapi->createVideoFilter(out, filter.c_str(), data->vi, degrainFusedGetFrame, degrainFree, fmParallel, fdeps, 1, data, core);
+        return;
+    }
     VSFilterDependency deps[14] = {{data->node, rpStrictSpatial}, {data->super, rpGeneral}};
     for (int r = 0; r < 12; r++)
         deps[2 + r] = {data->vectors[r], rpStrictSpatial};
