@@ -85,6 +85,35 @@ def test_degrain_fused_path_glue(mock_plugin, monkeypatch, case, window):
     assert (sup.computed(), [v.computed() for v in vn]) == before
 
 
+def test_lookahead_paths_under_concurrent_requests(mock_plugin, monkeypatch):
+    """fmParallel: several host threads pull frames at once (mini host's render); the window caches of mv.Analyse and of
+    the fused DegrainN must neither deadlock nor serve a wrong frame afterwards"""
+    import minivs
+    monkeypatch.setenv("MVB200_LOOKAHEAD", "3")
+    case = "blk16_ov8_pel2_p8_r3"
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    N = len(frames)
+    sp, aps, dp = pipeline.params_for(case)
+    for rounds in range(2):
+        core = minivs.Core()
+        mv = core.load(mock_plugin)
+        clip = core.source(frames, bits=8)
+        sup = mv.Super(clip, **skw)
+        vn = [mv.Analyse(sup, isb=isb, delta=d, **akw) for d in range(1, radius + 1) for isb in (1, 0)]
+        dn = mv.invoke("Degrain%d" % radius, clip, sup, *vn, **dkw)
+        comp = mv.Compensate(clip, sup, vn[0])  # a consumer that goes through the Analyse node (look-ahead cache)
+        for node in (dn, comp) + tuple(vn):
+            node.set_cache(0)
+        dn.render(0, N, 4)
+        comp.render(0, N, 4)
+        import numpy as np
+        for n in range(N):
+            assert [pipeline.sha(p) for p in dn.get_frame(n).planes()] == GOLD[case]["degrain"][n]
+            blob = np.frombuffer(vn[0].get_frame(n).prop_data("MVTools_vectors"), dtype=np.uint8)
+            assert pipeline.sha(pipeline.mask_blob(blob, aps[0])) == GOLD[case]["vectors"][n][0]
+
+
 def test_analyse_lookahead_batches_the_engine_calls(mock_plugin, monkeypatch):
     """with a window of 4, six frames requested in order cost two window searches per vector clip, not six"""
     import minivs

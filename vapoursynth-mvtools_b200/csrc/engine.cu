@@ -569,7 +569,7 @@ int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *s
 
 void *mvb200_pinned_alloc(size_t bytes) {
     void *p = nullptr;
-    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { // portable: the caller's thread may have another current device
         set_error("mvtools_b200: cannot allocate %zu bytes of pinned host memory", bytes);
         return nullptr;
     }
