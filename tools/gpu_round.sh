@@ -29,6 +29,9 @@ done
 echo "== flow kernels (device-resident throughput; tools/bench_flow.py)"
 timeout 300 python tools/bench_flow.py > gpurun_out/${TAG}_bench_flow.jsonl 2> gpurun_out/${TAG}_bench_flow.err
 cat gpurun_out/${TAG}_bench_flow.jsonl | cut -c1-200; tail -2 gpurun_out/${TAG}_bench_flow.err
+echo "== the plugin path: the canonical script through the mini host, look-ahead off / on (tools/bench_plugin.py)"
+timeout 600 python tools/bench_plugin.py --frames 96 --threads 8 --lookahead 0,32,88 > gpurun_out/${TAG}_bench_plugin.jsonl 2> gpurun_out/${TAG}_bench_plugin.err
+cat gpurun_out/${TAG}_bench_plugin.jsonl | cut -c1-200
 echo "== bench (reference arm)"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
 cat gpurun_out/${TAG}_bench_ref.json
