@@ -570,6 +570,16 @@ MVB200_API int mvb200_flowblur_batch(mvb200_ctx *ctx, const mvb200_flowblur_para
 MVB200_API int mvb200_blockfps_frame(mvb200_ctx *ctx, const mvb200_blockfps_params *p, const mvb200_super_params *sp, int time256, const uint8_t *const left_super[3], const ptrdiff_t left_stride[3],
                                      const uint8_t *const right_super[3], const ptrdiff_t right_stride[3], const uint8_t *vec_b, const uint8_t *vec_f, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable);
 
+/* The whole mv.Super -> 2 x mv.Analyse -> mv.FlowFPS chain for a window of OUTPUT frames in one call, on HOST buffers in
+ * the clip layout (the plugin's fused path for the canonical frame-rate conversion script).  host_src holds the n
+ * source frames [src_first, src_first + n) of the input clip (the window's left / right frames and a halo of 2 x delta
+ * frames after and delta before them, clipped to the clip: the caller computes it with mvb200_flowfps_position);
+ * frames [out_first, out_first + out_count) of the OUTPUT clip are written to host_dst.  ap_bw / ap_fw: the two
+ * mv.Analyse instances (their num_frames is replaced by n internally).  Unusable frames are blended / copied from the
+ * source frames as the filter does.  Synchronous. */
+MVB200_API int mvb200_flowfps_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowfps_params *p, const void *host_src, int src_first,
+                                        int n, int out_first, int out_count, void *host_dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -190,4 +190,110 @@ MVB200_API int mvb200_blockfps_frame(mvb200_ctx *, const mvb200_blockfps_params 
     return fwd(mvo_blockfps_frame(p, sp, time256, left_super, left_stride, right_super, right_stride, vec_b, vec_f, dst, dst_stride, usable));
 }
 
+// mvb200_flowfps_clip_host on host memory through the oracle, with the engine's conventions: the segment is the clip for
+// the two searches, output frames are placed by mvb200_flowfps_position
+MVB200_API int mvb200_flowfps_clip_host(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowfps_params *p, const void *host_src, int src_first, int n,
+                                        int out_first, int out_count, void *host_dst) {
+    mvb200_frame_layout cl;
+    mvb200_clip_layout(sp, &cl);
+    mvb200_super_geom g;
+    mvb200_super_geometry(sp, &g);
+    const int bps = cl.bytes_per_sample, off = p->inter.vd.nDeltaFrame, N = p->num_frames_in;
+    std::vector<std::vector<uint8_t>> sup((size_t)n * 3);
+    ptrdiff_t sstride[3] = {0, 0, 0};
+    auto src_planes = [&](int local, const uint8_t *q[3], ptrdiff_t st[3]) {
+        for (int i = 0; i < 3; i++) {
+            q[i] = i < cl.nplanes ? (const uint8_t *)host_src + (size_t)cl.frame_bytes * local + cl.offset[i] : nullptr;
+            st[i] = i < cl.nplanes ? (ptrdiff_t)cl.pitch[i] : 0;
+        }
+    };
+    for (int f = 0; f < n; f++) {
+        const uint8_t *q[3];
+        ptrdiff_t st[3];
+        uint8_t *d[3] = {nullptr, nullptr, nullptr};
+        src_planes(f, q, st);
+        for (int i = 0; i < sp->nplanes; i++) {
+            sstride[i] = (ptrdiff_t)g.plane_w[i] * bps;
+            sup[(size_t)f * 3 + i].assign((size_t)sstride[i] * g.plane_h[i], 0);
+            d[i] = sup[(size_t)f * 3 + i].data();
+        }
+        if (fwd(mvo_super_frame(sp, q, st, d, sstride)))
+            return 1;
+    }
+    auto sup_planes = [&](int local, const uint8_t *q[3]) {
+        for (int i = 0; i < 3; i++)
+            q[i] = i < sp->nplanes ? sup[(size_t)local * 3 + i].data() : nullptr;
+    };
+    const mvb200_analyse_params *aps[2] = {ap_bw, ap_fw};
+    std::vector<std::vector<uint8_t>> vec[2];
+    for (int k = 0; k < 2; k++) {
+        vec[k].resize((size_t)n);
+        for (int f = 0; f < n; f++) {
+            const int d = aps[k]->ad.nDeltaFrame;
+            int nref = f + (aps[k]->ad.isBackward ? d : -d);
+            if (nref < 0 || nref >= n)
+                nref = -1;
+            const uint8_t *s_[3], *r_[3];
+            sup_planes(f, s_);
+            if (nref >= 0)
+                sup_planes(nref, r_);
+            vec[k][f].assign((size_t)aps[k]->vectors_size, 0);
+            if (fwd(mvo_analyse_frame(aps[k], sp, s_, sstride, nref >= 0 ? r_ : nullptr, nref >= 0 ? sstride : nullptr, 0, vec[k][f].data())))
+                return 1;
+        }
+    }
+    for (int k = 0; k < out_count; k++) {
+        int32_t nleft, time256;
+        mvb200_flowfps_position(p, out_first + k, &nleft, &time256);
+        const int nright = nleft + off, fl = nleft < N - 1 ? nleft : N - 1, fr = nright < N - 1 ? nright : N - 1;
+        uint8_t *d[3];
+        ptrdiff_t dstr[3];
+        for (int i = 0; i < 3; i++) {
+            d[i] = i < cl.nplanes ? (uint8_t *)host_dst + (size_t)cl.frame_bytes * k + cl.offset[i] : nullptr;
+            dstr[i] = i < cl.nplanes ? (ptrdiff_t)cl.pitch[i] : 0;
+        }
+        auto in_seg = [&](int f) { return f >= src_first && f < src_first + n; };
+        const uint8_t *ql[3], *qr[3];
+        ptrdiff_t stl[3], str_[3];
+        if (!in_seg(fl) || !in_seg(fr))
+            return mvb200::set_error("mock: source frame outside the segment");
+        src_planes(fl - src_first, ql, stl);
+        src_planes(fr - src_first, qr, str_);
+        auto copy = [&](const uint8_t *const q[3], const ptrdiff_t st[3]) {
+            for (int i = 0; i < cl.nplanes; i++)
+                for (int y = 0; y < cl.plane_h[i]; y++)
+                    memcpy(d[i] + y * dstr[i], q[i] + y * st[i], (size_t)cl.plane_w[i] * bps);
+        };
+        if (time256 == 0) {
+            copy(ql, stl);
+            continue;
+        }
+        if (time256 == 256) {
+            copy(qr, str_);
+            continue;
+        }
+        int32_t usable = 0;
+        if (nleft < N && nright < N) {
+            if (!in_seg(nright))
+                return mvb200::set_error("mock: source frame outside the segment");
+            const int L = nleft - src_first, R = nright - src_first;
+            const uint8_t *sl[3], *sr[3];
+            sup_planes(L, sl);
+            sup_planes(R, sr);
+            const bool extra = p->maskmode == 2;
+            if (fwd(mvo_flowinter_frame(&p->inter, sp, time256, sl, sstride, sr, sstride, vec[0][L].data(), vec[1][R].data(), extra ? vec[0][R].data() : nullptr, extra ? vec[1][L].data() : nullptr, d, dstr, &usable)))
+                return 1;
+        }
+        if (!usable) {
+            if (p->inter.blend) {
+                if (fwd(mvo_blend_frame(sp, time256, ql, stl, qr, str_, d, dstr)))
+                    return 1;
+            } else {
+                copy(ql, stl);
+            }
+        }
+    }
+    return 0;
+}
+
 } // extern "C"

@@ -85,6 +85,32 @@ def test_degrain_fused_path_glue(mock_plugin, monkeypatch, case, window):
     assert (sup.computed(), [v.computed() for v in vn]) == before
 
 
+@pytest.mark.parametrize("window", [2, 7])
+@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "p10_444_blk8_pel4_bicubic", "noise_badblocks_blk8", "p8_420_blk16_ov4_uncovered"])
+def test_flowfps_fused_path_glue(mock_plugin, monkeypatch, case, window):
+    """MVB200_LOOKAHEAD: mv.FlowFPS fed by this plugin's own Super / Analyse nodes produces windows of OUTPUT frames with one
+    call of the engine's FlowFPS clip pipeline; every variant (mask 0 / 1 / 2, rates, blend on / off, scene changes)
+    must give the reference's frames, in order and out of order"""
+    import minivs
+    monkeypatch.setenv("MVB200_LOOKAHEAD", str(window))
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    nplanes = 1 if ck.get("gray") else 3
+    core = minivs.Core()
+    mv = core.load(mock_plugin)
+    clip = core.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1))
+    sup = mv.Super(clip, **skw)
+    vn = [mv.Analyse(sup, isb=isb, delta=1, **pipeline._fix(akw)) for isb in (1, 0)]
+    nodes = [mv.FlowFPS(clip, sup, vn[0], vn[1], **{k: (float(x) if k == "ml" else x) for k, x in kw.items()}) for kw in pipeline_flow.FLOW[case]["fps"]]
+    before = (sup.computed(), [v.computed() for v in vn])  # what the filters' creation read (frame 0 of every input)
+    for i, node in enumerate(nodes):
+        node.set_cache(0)
+        M = node.num_frames
+        for n in list(range(M)) + [M - 1, 0, M // 2]:
+            assert [pipeline.sha(p) for p in node.get_frame(n).planes()[:nplanes]] == GOLD_FLOW[case]["fps"][i][n], "variant %d frame %d" % (i, n)
+    assert (sup.computed(), [v.computed() for v in vn]) == before
+
+
 def test_lookahead_paths_under_concurrent_requests(mock_plugin, monkeypatch):
     """fmParallel: several host threads pull frames at once (mini host's render); the window caches of mv.Analyse and of
     the fused DegrainN must neither deadlock nor serve a wrong frame afterwards"""

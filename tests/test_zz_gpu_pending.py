@@ -126,3 +126,43 @@ def test_script_through_plugin_with_lookahead(built, monkeypatch, case):
     for stage in ("super", "vectors", "degrain", "adata", "recalc", "compensate"):
         if stage in got:
             assert got[stage] == GOLD_MAIN[case][stage], "%s: plugin %s differs from the reference plugin" % (case, stage)
+
+
+@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "noise_badblocks_blk8"])
+def test_flowfps_clip_host_matches_goldens(gpu_ctx, case):
+    """mvb200_flowfps_clip_host (Super -> 2 x Analyse -> FlowFPS for a window of output frames in one call, host buffers):
+    the whole clip at once, and a window in the middle with exactly the halo the plugin computes"""
+    L = mb.lib()
+    ctx = gpu_ctx
+    frames = pipeline.make_frames(pipeline.CASES[case][0])
+    N = len(frames)
+    sp, aps, P = pipeline_flow.flow_params_for(case)
+    cl = mb.clip_layout(sp)
+    host = np.zeros((N, cl.frame_bytes), dtype=np.uint8)
+    for n, fr in enumerate(frames):
+        for p, a in enumerate(fr):
+            rows = host[n, cl.offset[p]: cl.offset[p] + cl.pitch[p] * cl.plane_h[p]].reshape(cl.plane_h[p], cl.pitch[p])
+            rows[:, : a.shape[1] * a.itemsize] = a.view(np.uint8).reshape(a.shape[0], -1)
+    for i, p in enumerate(P["fps"]):
+        M = p.num_frames_out
+        out = np.zeros((M, cl.frame_bytes), dtype=np.uint8)
+        mb._check(L.mvb200_flowfps_clip_host(ctx.handle, C.byref(sp), C.byref(aps[0]), C.byref(aps[1]), C.byref(p), host.ctypes.data, 0, N, 0, M, out.ctypes.data))
+        for n in range(M):
+            assert [pipeline.sha(q) for q in _planes(out[n], cl)] == GOLD[case]["fps"][i][n], "variant %d frame %d" % (i, n)
+        # a window of three output frames from the middle, with the segment the plugin would pass
+        n0, n1, off = M // 2, min(M // 2 + 3, M), p.inter.vd.nDeltaFrame
+        lmin, lmax = mb.flowfps_position(p, n0)[0], mb.flowfps_position(p, n1 - 1)[0]
+        s0, s1 = max(0, lmin - off), min(N, lmax + 2 * off + 1)
+        s0 = min(s0, N - 1)
+        win = np.zeros((n1 - n0, cl.frame_bytes), dtype=np.uint8)
+        mb._check(L.mvb200_flowfps_clip_host(ctx.handle, C.byref(sp), C.byref(aps[0]), C.byref(aps[1]), C.byref(p), host[s0:].ctypes.data, s0, s1 - s0, n0, n1 - n0, win.ctypes.data))
+        for n in range(n0, n1):
+            assert [pipeline.sha(q) for q in _planes(win[n - n0], cl)] == GOLD[case]["fps"][i][n], "variant %d window frame %d" % (i, n)
+
+
+@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3"])
+def test_flowfps_script_through_plugin_with_lookahead(built, monkeypatch, case):
+    """MVB200_LOOKAHEAD=4: mv.FlowFPS on the plugin's own Super / Analyse nodes takes the fused path"""
+    monkeypatch.setenv("MVB200_LOOKAHEAD", "4")
+    got = pipeline_flow.run_reference_flow(case, plugin_path=mb.PLUGIN_PATH, only=("fps",))
+    assert got["fps"] == GOLD[case]["fps"], "%s: plugin mv.FlowFPS (fused) differs from the reference plugin" % case

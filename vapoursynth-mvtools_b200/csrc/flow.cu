@@ -974,4 +974,67 @@ int mvb200_blockfps_frame(mvb200_ctx *ctx, const mvb200_blockfps_params *p, cons
     return 0;
 }
 
+int mvb200_flowfps_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowfps_params *p, const void *host_src, int src_first, int n,
+                             int out_first, int out_count, void *host_dst) {
+    const mvb200_flowinter_params *q = &p->inter;
+    if (flowinter_check(q, sp))
+        return 1;
+    if (n <= 0 || out_count <= 0)
+        return 0;
+    if (src_first < 0 || src_first + n > p->num_frames_in || out_first < 0 || out_first + out_count > p->num_frames_out)
+        return set_error("FlowFPS: the window is outside the clip");
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(sp, &sd);
+    make_clip_desc(sp, &cd);
+    // the segment is the clip as far as the searches are concerned (references outside it: default vectors, only met by halo frames)
+    mvb200_analyse_params aps[2] = {*ap_bw, *ap_fw};
+    aps[0].num_frames = aps[1].num_frames = n;
+    const mvb200_analyse_params *app[2] = {&aps[0], &aps[1]};
+    const int64_t vstride = ((int64_t)(aps[0].vectors_size > aps[1].vectors_size ? aps[0].vectors_size : aps[1].vectors_size) + 255) / 256 * 256;
+    uint8_t *buf = (uint8_t *)c->get_scratch(kSlotStage, (size_t)cd.frame_bytes * (n + out_count) + (size_t)sd.frame_bytes * n + (size_t)vstride * n * 2 + 256);
+    if (!buf)
+        return 1;
+    uint8_t *dsrc = buf, *ddst = dsrc + (size_t)cd.frame_bytes * n, *dsup = ddst + (size_t)cd.frame_bytes * out_count, *dbw = dsup + (size_t)sd.frame_bytes * n, *dfw = dbw + (size_t)vstride * n;
+    MVB_CUDA_CHECK(cudaMemcpyAsync(dsrc, host_src, (size_t)cd.frame_bytes * n, cudaMemcpyHostToDevice, c->stream));
+    if (mvb200_super_batch(ctx, sp, dsrc, dsup, n))
+        return 1;
+    void *outs[2] = {dbw, dfw};
+    if (mvb200_analyse_multi_batch(ctx, app, 2, sp, dsup, 0, n, outs, vstride))
+        return 1;
+    const int off = q->vd.nDeltaFrame, N = p->num_frames_in;
+    for (int k = 0; k < out_count; k++) {
+        int32_t nleft, time256;
+        mvb200_flowfps_position(p, out_first + k, &nleft, &time256);
+        const int nright = nleft + off;
+        uint8_t *dst = ddst + (size_t)cd.frame_bytes * k;
+        auto local = [&](int f) { return f - src_first; };                 // position of source frame f in the segment
+        auto have = [&](int f) { return f >= src_first && f < src_first + n; };
+        const int fl = nleft < N - 1 ? nleft : N - 1, fr = nright < N - 1 ? nright : N - 1; // VSMIN(.., numFrames - 1), MVFlowFPS.c:137-141,474-486
+        if (time256 == 0 || time256 == 256) { // the input frame itself
+            const int f = time256 == 0 ? fl : fr;
+            if (!have(f))
+                return set_error("FlowFPS: source frame %d is not in the segment", f);
+            MVB_CUDA_CHECK(cudaMemcpyAsync(dst, dsrc + (size_t)cd.frame_bytes * local(f), (size_t)cd.frame_bytes, cudaMemcpyDeviceToDevice, c->stream));
+            continue;
+        }
+        if (!have(fl) || !have(fr))
+            return set_error("FlowFPS: source frames %d / %d are not in the segment", fl, fr);
+        const bool in_range = nleft < N && nright < N; // :156
+        const bool extra = p->maskmode == 2 && in_range;
+        if (in_range && (!have(nright) || (extra && !have(nright))))
+            return set_error("FlowFPS: source frame %d is not in the segment", nright);
+        int *flags;
+        if (launch_flowinter(c, q, sd, cd, time256, in_range ? dsup + (size_t)sd.frame_bytes * local(nleft) : nullptr, in_range ? dsup + (size_t)sd.frame_bytes * local(nright) : nullptr,
+                             in_range ? dbw + (size_t)vstride * local(nleft) : nullptr, in_range ? dfw + (size_t)vstride * local(nright) : nullptr, extra ? dbw + (size_t)vstride * local(nright) : nullptr,
+                             extra ? dfw + (size_t)vstride * local(nleft) : nullptr, dsrc + (size_t)cd.frame_bytes * local(fl), dsrc + (size_t)cd.frame_bytes * local(fr), dst, &flags))
+            return 1;
+    }
+    MVB_CUDA_CHECK(cudaMemcpyAsync(host_dst, ddst, (size_t)cd.frame_bytes * out_count, cudaMemcpyDeviceToHost, c->stream));
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 } // extern "C"

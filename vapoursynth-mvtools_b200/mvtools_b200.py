@@ -272,6 +272,11 @@ def lib():
         L.mvb200_blockfps_position.restype = None
         L.mvb200_blockfps_frame.argtypes = [vp, PP(BlockFPSParams), PP(SuperParams), i32, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, vp, PP(vp), PP(C.c_ssize_t), PP(i32)]
         L.mvb200_analyse_frames.argtypes = [vp, PP(AnalyseParams), PP(SuperParams), i32, PP(vp), PP(C.c_ssize_t), i32, PP(i32), PP(i32), PP(i32), PP(vp)]
+        L.mvb200_flowfps_clip_host.argtypes = [vp, PP(SuperParams), PP(AnalyseParams), PP(AnalyseParams), PP(FlowFPSParams), vp, i32, i32, i32, i32, vp]
+        L.mvb200_pinned_alloc.argtypes = [C.c_size_t]
+        L.mvb200_pinned_alloc.restype = vp
+        L.mvb200_pinned_free.argtypes = [vp]
+        L.mvb200_pinned_free.restype = None
         _LIB = L
     return _LIB
 

@@ -1719,13 +1719,123 @@ void VS_CC flowInterCreate(const VSMap *in, VSMap *out, void *, VSCore *core, co
 // mvflowfpsCreate / GetFrame, MVFlowFPS.c:86-928.  The reference wraps the vector clips in a helper filter that
 // attaches the upsized vector planes as frame properties; the engine upsizes inside the kernel, so the vector clips
 // are used as they are.
+// Fused path (MVB200_LOOKAHEAD=<B>, default off), as for DegrainN: when clip / super / mvbw / mvfw are this plugin's own
+// nodes wired as in the canonical script, a window of B OUTPUT frames is one mvb200_flowfps_clip_host call over the
+// source frames the window needs (its left / right frames, delta before and 2 x delta after them for the "extra" vectors).
+struct FlowFPSFused {
+    std::mutex m;
+    std::map<int, std::vector<uint8_t>> frames; // output frames in the clip layout
+    std::deque<int> order;
+    mvb200_analyse_params apBw, apFw;
+    mvb200_frame_layout cl;
+    int window;
+};
+
 struct FlowFPSData {
     VSNode *node, *super, *mvbw, *mvfw;
     VSVideoInfo vi;
     const VSVideoInfo *oldvi, *supervi;
     mvb200_super_params sp;
     mvb200_flowfps_params p;
+    FlowFPSFused *fused; // owned; null = node-by-node evaluation
 };
+
+// the source frames the output window [n, end) needs: [*s0, *s1)
+void flowFpsSegment(const FlowFPSData *d, int n, int end, int *s0, int *s1) {
+    const int off = d->p.inter.vd.nDeltaFrame, N = d->oldvi->numFrames;
+    int32_t lmin, lmax, t;
+    mvb200_flowfps_position(&d->p, n, &lmin, &t);
+    mvb200_flowfps_position(&d->p, end - 1, &lmax, &t);
+    *s0 = lmin - off > 0 ? lmin - off : 0;
+    *s1 = lmax + 2 * off + 1 < N ? lmax + 2 * off + 1 : N;
+    if (*s0 > N - 1)
+        *s0 = N - 1; // (output frames past the end are copies of the last input frame)
+}
+
+const VSFrame *VS_CC flowFpsFusedGetFrame(int n, int activationReason, void *instanceData, void **frameData, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    FlowFPSData *d = (FlowFPSData *)instanceData;
+    FlowFPSFused *f = d->fused;
+    const int N = d->oldvi->numFrames;
+    int32_t nleft, time256;
+    mvb200_flowfps_position(&d->p, n, &nleft, &time256);
+    const int propFrame = VSMIN(time256 == 256 ? nleft + d->p.inter.vd.nDeltaFrame : nleft, N - 1); // whose properties the output carries
+    if (activationReason == arInitial) {
+        vsapi->requestFrameFilter(propFrame, d->node, frameCtx);
+        bool hit;
+        {
+            std::lock_guard<std::mutex> lock(f->m);
+            hit = f->frames.count(n) != 0;
+        }
+        if (!hit) {
+            const int end = n + f->window < d->vi.numFrames ? n + f->window : d->vi.numFrames;
+            int s0, s1;
+            flowFpsSegment(d, n, end, &s0, &s1);
+            for (int k = s0; k < s1; k++)
+                if (k != propFrame)
+                    vsapi->requestFrameFilter(k, d->node, frameCtx);
+            *frameData = (void *)(intptr_t)end;
+        }
+    } else if (activationReason == arAllFramesReady) {
+        const VSFrame *src = vsapi->getFrameFilter(propFrame, d->node, frameCtx);
+        if (time256 == 0 || time256 == 256)
+            return src; // the input frame itself (MVFlowFPS.c:137-141)
+        std::vector<uint8_t> frame;
+        std::string msg;
+        {
+            std::lock_guard<std::mutex> lock(f->m);
+            const int end = (int)(intptr_t)*frameData;
+            bool have = f->frames.count(n) != 0;
+            if (!have && end > n) {
+                int s0, s1;
+                flowFpsSegment(d, n, end, &s0, &s1);
+                const size_t fb = (size_t)f->cl.frame_bytes;
+                std::vector<uint8_t> hostSrc(fb * (s1 - s0)), hostDst(fb * (end - n));
+                for (int k = s0; k < s1; k++) {
+                    const VSFrame *fr = vsapi->getFrameFilter(k, d->node, frameCtx);
+                    for (int p = 0; p < f->cl.nplanes; p++)
+                        vsh::bitblt(hostSrc.data() + fb * (k - s0) + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], vsapi->getReadPtr(fr, p), vsapi->getStride(fr, p), (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample,
+                                    (size_t)f->cl.plane_h[p]);
+                    vsapi->freeFrame(fr);
+                }
+                int rc;
+                {
+                    std::lock_guard<std::mutex> elock(g_engine_mutex);
+                    mvb200_ctx *ctx = engine(msg);
+                    rc = ctx ? mvb200_flowfps_clip_host(ctx, &d->sp, &f->apBw, &f->apFw, &d->p, hostSrc.data(), s0, s1 - s0, n, end - n, hostDst.data()) : 1;
+                    if (ctx && rc)
+                        msg = mvb200_last_error();
+                }
+                if (!rc) {
+                    for (int k = n; k < end; k++) {
+                        const uint8_t *p = hostDst.data() + fb * (k - n);
+                        if (f->frames.emplace(k, std::vector<uint8_t>(p, p + fb)).second)
+                            f->order.push_back(k);
+                    }
+                    while (f->order.size() > (size_t)f->window * 4) {
+                        f->frames.erase(f->order.front());
+                        f->order.pop_front();
+                    }
+                    have = true;
+                }
+            } else if (!have) {
+                msg = "internal: frame neither cached nor requested";
+            }
+            if (have)
+                frame = f->frames.find(n)->second;
+        }
+        if (frame.empty()) {
+            vsapi->setFilterError(("FlowFPS: " + msg).c_str(), frameCtx);
+            vsapi->freeFrame(src);
+            return nullptr;
+        }
+        VSFrame *dst = vsapi->newVideoFrame(&d->vi.format, d->vi.width, d->vi.height, src, core);
+        for (int p = 0; p < d->vi.format.numPlanes; p++)
+            vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), frame.data() + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, (size_t)f->cl.plane_h[p]);
+        vsapi->freeFrame(src);
+        return dst;
+    }
+    return nullptr;
+}
 
 const VSFrame *VS_CC flowFpsGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
     FlowFPSData *d = (FlowFPSData *)instanceData;
@@ -1837,6 +1947,7 @@ void VS_CC flowFpsFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
     vsapi->freeNode(d->super);
     vsapi->freeNode(d->mvbw);
     vsapi->freeNode(d->mvfw);
+    delete d->fused;
     delete d;
 }
 
@@ -1898,9 +2009,33 @@ void VS_CC flowFpsCreate(const VSMap *in, VSMap *out, void *, VSCore *core, cons
     d.vi.fpsNum = d.p.fps_num;
     d.vi.fpsDen = d.p.fps_den;
     d.vi.numFrames = d.p.num_frames_out;
+    const int window = lookaheadFromEnv();
+    if (window) { // the fused path: every input is one of this plugin's own nodes, wired as in the canonical script
+        std::lock_guard<std::mutex> lock(g_registry_mutex);
+        auto su = g_registry.find(d.super), bw = g_registry.find(d.mvbw), fw = g_registry.find(d.mvfw);
+        bool ok = su != g_registry.end() && su->second.kind == kNodeSuper && bw != g_registry.end() && bw->second.kind == kNodeAnalyse && fw != g_registry.end() && fw->second.kind == kNodeAnalyse;
+        if (ok) {
+            const SuperData *S = (const SuperData *)su->second.data;
+            const AnalyseData *B = (const AnalyseData *)bw->second.data, *F = (const AnalyseData *)fw->second.data;
+            ok = S->node == d.node && !S->usePelClip && S->sp.width == d.sp.width && S->sp.height == d.sp.height && S->sp.bits == d.sp.bits && S->sp.pel == d.sp.pel && S->sp.hpad == d.sp.hpad && S->sp.vpad == d.sp.vpad &&
+                 S->sp.levels == d.sp.levels && S->sp.modeyuv == d.sp.modeyuv && B->node == d.super && F->node == d.super && !B->ap.fields && !F->ap.fields && B->ap.ad.nDeltaFrame > 0 && !B->ap.divide && !F->ap.divide &&
+                 (S->sp.modeyuv & (MVB200_UPLANE | MVB200_VPLANE) || d.sp.gray);
+            if (ok) {
+                d.fused = new FlowFPSFused;
+                d.fused->apBw = B->ap;
+                d.fused->apFw = F->ap;
+                d.sp = S->sp;
+                mvb200_clip_layout(&d.sp, &d.fused->cl);
+                d.fused->window = window;
+            }
+        }
+    }
     FlowFPSData *data = new FlowFPSData(d);
     VSFilterDependency deps[4] = {{data->node, rpGeneral}, {data->super, rpGeneral}, {data->mvbw, rpGeneral}, {data->mvfw, rpGeneral}};
-    vsapi->createVideoFilter(out, "FlowFPS", &data->vi, flowFpsGetFrame, flowFpsFree, fmParallel, deps, 4, data, core);
+    if (data->fused)
+        vsapi->createVideoFilter(out, "FlowFPS", &data->vi, flowFpsFusedGetFrame, flowFpsFree, fmParallel, deps, 1, data, core);
+    else
+        vsapi->createVideoFilter(out, "FlowFPS", &data->vi, flowFpsGetFrame, flowFpsFree, fmParallel, deps, 4, data, core);
     // AssumeFPS sets the _DurationNum and _DurationDen properties (MVFlowFPS.c:883-910)
     VSPlugin *stdPlugin = vsapi->getPluginByID("com.vapoursynth.std", core);
     VSMap *args = vsapi->createMap();
