@@ -608,7 +608,7 @@ bool degrainFusedWindow(DegrainData *d, const VSAPI *vsapi, VSFrameContext *fram
         if (f->frames.emplace(k, std::vector<uint8_t>(p, p + fb)).second)
             f->order.push_back(k);
     }
-    while (f->order.size() > (size_t)f->window * 4) {
+    while (f->order.size() > (size_t)f->window * 2) { // the window being served and the previous one (the frame server caches the rest)
         f->frames.erase(f->order.front());
         f->order.pop_front();
     }
@@ -1811,7 +1811,7 @@ const VSFrame *VS_CC flowFpsFusedGetFrame(int n, int activationReason, void *ins
                         if (f->frames.emplace(k, std::vector<uint8_t>(p, p + fb)).second)
                             f->order.push_back(k);
                     }
-                    while (f->order.size() > (size_t)f->window * 4) {
+                    while (f->order.size() > (size_t)f->window * 2) { // the window being served and the previous one (the frame server caches the rest)
                         f->frames.erase(f->order.front());
                         f->order.pop_front();
                     }
