@@ -580,6 +580,13 @@ MVB200_API int mvb200_blockfps_frame(mvb200_ctx *ctx, const mvb200_blockfps_para
 MVB200_API int mvb200_flowfps_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowfps_params *p, const void *host_src, int src_first,
                                         int n, int out_first, int out_count, void *host_dst);
 
+/* mv.Super -> mv.Analyse -> mv.Compensate for output frames [out_first, out_first + out_count) in one call, on HOST
+ * buffers in the clip layout (the plugin's fused path).  host_src holds the n source frames [src_first, src_first + n):
+ * the output frames and delta frames on the side the vectors point to (more does not hurt).  ap / cp: the filters'
+ * parameters (their num_frames is replaced by n internally; relative delta only, no field shifts).  Synchronous. */
+MVB200_API int mvb200_compensate_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_compensate_params *cp, const void *host_src, int src_first, int n, int out_first,
+                                           int out_count, void *host_dst);
+
 #ifdef __cplusplus
 }
 #endif

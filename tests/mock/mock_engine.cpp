@@ -296,4 +296,54 @@ MVB200_API int mvb200_flowfps_clip_host(mvb200_ctx *, const mvb200_super_params 
     return 0;
 }
 
+MVB200_API int mvb200_compensate_clip_host(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_compensate_params *cp, const void *host_src, int src_first, int n, int out_first, int out_count,
+                                           void *host_dst) {
+    mvb200_frame_layout cl;
+    mvb200_clip_layout(sp, &cl);
+    mvb200_super_geom g;
+    mvb200_super_geometry(sp, &g);
+    const int bps = cl.bytes_per_sample;
+    std::vector<std::vector<uint8_t>> sup((size_t)n * 3);
+    ptrdiff_t sstride[3] = {0, 0, 0};
+    for (int f = 0; f < n; f++) {
+        const uint8_t *q[3];
+        ptrdiff_t st[3];
+        uint8_t *d[3] = {nullptr, nullptr, nullptr};
+        for (int i = 0; i < 3; i++) {
+            q[i] = i < cl.nplanes ? (const uint8_t *)host_src + (size_t)cl.frame_bytes * f + cl.offset[i] : nullptr;
+            st[i] = i < cl.nplanes ? (ptrdiff_t)cl.pitch[i] : 0;
+        }
+        for (int i = 0; i < sp->nplanes; i++) {
+            sstride[i] = (ptrdiff_t)g.plane_w[i] * bps;
+            sup[(size_t)f * 3 + i].assign((size_t)sstride[i] * g.plane_h[i], 0);
+            d[i] = sup[(size_t)f * 3 + i].data();
+        }
+        if (fwd(mvo_super_frame(sp, q, st, d, sstride)))
+            return 1;
+    }
+    for (int k = 0; k < out_count; k++) {
+        const int f = out_first - src_first + k, dlt = ap->ad.nDeltaFrame;
+        int nref = f + (ap->ad.isBackward ? dlt : -dlt);
+        if (nref < 0 || nref >= n)
+            nref = -1;
+        const uint8_t *s_[3], *r_[3];
+        for (int i = 0; i < 3; i++) {
+            s_[i] = i < sp->nplanes ? sup[(size_t)f * 3 + i].data() : nullptr;
+            r_[i] = i < sp->nplanes && nref >= 0 ? sup[(size_t)nref * 3 + i].data() : nullptr;
+        }
+        std::vector<uint8_t> blob((size_t)ap->vectors_size, 0);
+        if (fwd(mvo_analyse_frame(ap, sp, s_, sstride, nref >= 0 ? r_ : nullptr, nref >= 0 ? sstride : nullptr, 0, blob.data())))
+            return 1;
+        uint8_t *d[3];
+        ptrdiff_t dstr[3];
+        for (int i = 0; i < 3; i++) {
+            d[i] = i < cl.nplanes ? (uint8_t *)host_dst + (size_t)cl.frame_bytes * k + cl.offset[i] : nullptr;
+            dstr[i] = i < cl.nplanes ? (ptrdiff_t)cl.pitch[i] : 0;
+        }
+        if (fwd(mvo_compensate_frame(cp, sp, s_, sstride, nref >= 0 ? r_ : nullptr, nref >= 0 ? sstride : nullptr, blob.data(), 0, d, dstr)))
+            return 1;
+    }
+    return 0;
+}
+
 } // extern "C"

@@ -111,6 +111,30 @@ def test_flowfps_fused_path_glue(mock_plugin, monkeypatch, case, window):
     assert (sup.computed(), [v.computed() for v in vn]) == before
 
 
+@pytest.mark.parametrize("window", [2, 5])
+@pytest.mark.parametrize("case", sorted(pipeline.EXTRA))
+def test_compensate_fused_path_glue(mock_plugin, monkeypatch, case, window):
+    """MVB200_LOOKAHEAD: mv.Compensate on this plugin's own Super / Analyse nodes produces windows of frames with one call of
+    the engine's Compensate clip pipeline; the goldens' variants (time, thsad, scbehavior, scene-change thresholds)"""
+    import minivs
+    monkeypatch.setenv("MVB200_LOOKAHEAD", str(window))
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    N = len(frames)
+    nplanes = 1 if ck.get("gray") else 3
+    core = minivs.Core()
+    mv = core.load(mock_plugin)
+    clip = core.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1))
+    sup = mv.Super(clip, **skw)
+    vec = mv.Analyse(sup, isb=1, delta=1, **pipeline._fix(akw))
+    cn = mv.Compensate(clip, sup, vec, **pipeline.EXTRA[case]["comp"])
+    cn.set_cache(0)
+    before = (sup.computed(), vec.computed())
+    for n in list(range(N)) + [N - 1, 0, N // 2]:
+        assert [pipeline.sha(p) for p in cn.get_frame(n).planes()[:nplanes]] == GOLD[case]["compensate"][n], "frame %d" % n
+    assert (sup.computed(), vec.computed()) == before
+
+
 def test_lookahead_paths_under_concurrent_requests(mock_plugin, monkeypatch):
     """fmParallel: several host threads pull frames at once (mini host's render); the window caches of mv.Analyse and of
     the fused DegrainN must neither deadlock nor serve a wrong frame afterwards"""

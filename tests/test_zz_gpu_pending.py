@@ -166,3 +166,29 @@ def test_flowfps_script_through_plugin_with_lookahead(built, monkeypatch, case):
     monkeypatch.setenv("MVB200_LOOKAHEAD", "4")
     got = pipeline_flow.run_reference_flow(case, plugin_path=mb.PLUGIN_PATH, only=("fps",))
     assert got["fps"] == GOLD[case]["fps"], "%s: plugin mv.FlowFPS (fused) differs from the reference plugin" % case
+
+
+@pytest.mark.parametrize("case", ["c1_640x360_p8_blk8_pel1", "blk16_ov8_pel2_p16_r3", "noise_badblocks_blk8"])
+def test_compensate_clip_host_matches_goldens(gpu_ctx, case):
+    """mvb200_compensate_clip_host (Super -> Analyse -> Compensate for a window of frames in one call, host buffers):
+    the whole clip at once, and an inner window with a one-frame halo"""
+    L = mb.lib()
+    ctx = gpu_ctx
+    frames = pipeline.make_frames(pipeline.CASES[case][0])
+    N = len(frames)
+    sp, aps, dp = pipeline.params_for(case)
+    rp, cp = pipeline.extra_params_for(case)
+    cl = mb.clip_layout(sp)
+    host = np.zeros((N, cl.frame_bytes), dtype=np.uint8)
+    for n, fr in enumerate(frames):
+        for p, a in enumerate(fr):
+            rows = host[n, cl.offset[p]: cl.offset[p] + cl.pitch[p] * cl.plane_h[p]].reshape(cl.plane_h[p], cl.pitch[p])
+            rows[:, : a.shape[1] * a.itemsize] = a.view(np.uint8).reshape(a.shape[0], -1)
+    out = np.zeros((N, cl.frame_bytes), dtype=np.uint8)
+    mb._check(L.mvb200_compensate_clip_host(ctx.handle, C.byref(sp), C.byref(aps[0]), C.byref(cp), host.ctypes.data, 0, N, 0, N, out.ctypes.data))
+    for n in range(N):
+        assert [pipeline.sha(q) for q in _planes(out[n], cl)][: cp.nplanes] == GOLD_MAIN[case]["compensate"][n], "frame %d" % n
+    win = np.zeros((2, cl.frame_bytes), dtype=np.uint8)
+    mb._check(L.mvb200_compensate_clip_host(ctx.handle, C.byref(sp), C.byref(aps[0]), C.byref(cp), host[1:].ctypes.data, 1, 4, 2, 2, win.ctypes.data))
+    for n in (2, 3):
+        assert [pipeline.sha(q) for q in _planes(win[n - 2], cl)][: cp.nplanes] == GOLD_MAIN[case]["compensate"][n], "window frame %d" % n

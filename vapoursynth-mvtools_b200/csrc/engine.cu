@@ -581,6 +581,41 @@ void mvb200_pinned_free(void *p) {
         cudaFreeHost(p);
 }
 
+int mvb200_compensate_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_compensate_params *cp, const void *host_src, int src_first, int n, int out_first, int out_count,
+                                void *host_dst) {
+    if (check_levels(sp) || check_analyse(ap, sp))
+        return 1;
+    if (n <= 0 || out_count <= 0)
+        return 0;
+    if (out_first < src_first || out_first + out_count > src_first + n)
+        return set_error("Compensate: output frames [%d, %d) are outside the segment [%d, %d)", out_first, out_first + out_count, src_first, src_first + n);
+    if (ap->ad.nDeltaFrame <= 0 || ap->fields || cp->fields)
+        return set_error("Compensate: the clip pipeline handles relative references without field shifts only");
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(sp, &sd);
+    make_clip_desc(sp, &cd);
+    mvb200_analyse_params a = *ap; // the segment is the clip as far as the engine is concerned
+    a.num_frames = n;
+    mvb200_compensate_params q = *cp;
+    q.num_frames = n;
+    const int64_t vstride = ((int64_t)a.vectors_size + 255) / 256 * 256;
+    uint8_t *buf = (uint8_t *)c->get_scratch(5, (size_t)cd.frame_bytes * (n + out_count) + (size_t)sd.frame_bytes * n + (size_t)vstride * out_count + 256);
+    if (!buf)
+        return 1;
+    uint8_t *dsrc = buf, *ddst = dsrc + (size_t)cd.frame_bytes * n, *dsup = ddst + (size_t)cd.frame_bytes * out_count, *dvec = dsup + (size_t)sd.frame_bytes * n;
+    MVB_CUDA_CHECK(cudaMemcpyAsync(dsrc, host_src, (size_t)cd.frame_bytes * n, cudaMemcpyHostToDevice, c->stream));
+    const int first = out_first - src_first;
+    if (mvb200_super_batch(ctx, sp, dsrc, dsup, n) || mvb200_analyse_batch(ctx, &a, sp, dsup, first, out_count, dvec, vstride) ||
+        mvb200_compensate_batch(ctx, &q, sp, dsup, first, out_count, dvec, vstride, ddst))
+        return 1;
+    MVB_CUDA_CHECK(cudaMemcpyAsync(host_dst, ddst, (size_t)cd.frame_bytes * out_count, cudaMemcpyDeviceToHost, c->stream));
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 // ------------------------------------------------------- host-buffer path
 
 static int upload_planes(Ctx *c, uint8_t *dev_frame, const long long *pitch, const long long *offset, const int *w, const int *h, int bps, int nplanes, const uint8_t *const src[3], const ptrdiff_t stride[3]) {

@@ -277,6 +277,7 @@ def lib():
         L.mvb200_pinned_alloc.restype = vp
         L.mvb200_pinned_free.argtypes = [vp]
         L.mvb200_pinned_free.restype = None
+        L.mvb200_compensate_clip_host.argtypes = [vp, PP(SuperParams), PP(AnalyseParams), PP(CompensateParams), vp, i32, i32, i32, i32, vp]
         _LIB = L
     return _LIB
 

@@ -1008,12 +1008,103 @@ void VS_CC recalcCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const
 }
 
 // ------------------------------------------------------------- Compensate
+// Fused path (MVB200_LOOKAHEAD=<B>, default off), as for DegrainN: clip / super / vectors are this plugin's own nodes
+// wired as in the canonical script -> a window of B frames is one mvb200_compensate_clip_host call over source frames.
+struct CompFused {
+    std::mutex m;
+    std::map<int, std::vector<uint8_t>> frames; // output frames in the clip layout
+    std::deque<int> order;
+    mvb200_analyse_params ap;
+    mvb200_frame_layout cl;
+    int window, halo;
+};
+
 struct CompData {
     VSNode *node, *super, *vectors;
     const VSVideoInfo *vi, *supervi;
     mvb200_super_params sp;
     mvb200_compensate_params cp;
+    CompFused *fused; // owned; null = node-by-node evaluation
 };
+
+const VSFrame *VS_CC compFusedGetFrame(int n, int activationReason, void *instanceData, void **frameData, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    CompData *d = (CompData *)instanceData;
+    CompFused *f = d->fused;
+    const int N = d->vi->numFrames;
+    if (activationReason == arInitial) {
+        vsapi->requestFrameFilter(n, d->node, frameCtx);
+        bool hit;
+        {
+            std::lock_guard<std::mutex> lock(f->m);
+            hit = f->frames.count(n) != 0;
+        }
+        if (!hit) {
+            const int end = n + f->window < N ? n + f->window : N;
+            const int s0 = n - f->halo > 0 ? n - f->halo : 0, s1 = end + f->halo < N ? end + f->halo : N;
+            for (int k = s0; k < s1; k++)
+                if (k != n)
+                    vsapi->requestFrameFilter(k, d->node, frameCtx);
+            *frameData = (void *)(intptr_t)end;
+        }
+    } else if (activationReason == arAllFramesReady) {
+        const VSFrame *src = vsapi->getFrameFilter(n, d->node, frameCtx);
+        std::vector<uint8_t> frame;
+        std::string msg;
+        {
+            std::lock_guard<std::mutex> lock(f->m);
+            const int end = (int)(intptr_t)*frameData;
+            bool have = f->frames.count(n) != 0;
+            if (!have && end > n) {
+                const int s0 = n - f->halo > 0 ? n - f->halo : 0, s1 = end + f->halo < N ? end + f->halo : N;
+                const size_t fb = (size_t)f->cl.frame_bytes;
+                std::vector<uint8_t> hostSrc(fb * (s1 - s0)), hostDst(fb * (end - n));
+                for (int k = s0; k < s1; k++) {
+                    const VSFrame *fr = vsapi->getFrameFilter(k, d->node, frameCtx);
+                    for (int p = 0; p < f->cl.nplanes; p++)
+                        vsh::bitblt(hostSrc.data() + fb * (k - s0) + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], vsapi->getReadPtr(fr, p), vsapi->getStride(fr, p), (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample,
+                                    (size_t)f->cl.plane_h[p]);
+                    vsapi->freeFrame(fr);
+                }
+                int rc;
+                {
+                    std::lock_guard<std::mutex> elock(g_engine_mutex);
+                    mvb200_ctx *ctx = engine(msg);
+                    rc = ctx ? mvb200_compensate_clip_host(ctx, &d->sp, &f->ap, &d->cp, hostSrc.data(), s0, s1 - s0, n, end - n, hostDst.data()) : 1;
+                    if (ctx && rc)
+                        msg = mvb200_last_error();
+                }
+                if (!rc) {
+                    for (int k = n; k < end; k++) {
+                        const uint8_t *p = hostDst.data() + fb * (k - n);
+                        if (f->frames.emplace(k, std::vector<uint8_t>(p, p + fb)).second)
+                            f->order.push_back(k);
+                    }
+                    while (f->order.size() > (size_t)f->window * 2) {
+                        f->frames.erase(f->order.front());
+                        f->order.pop_front();
+                    }
+                    have = true;
+                }
+            } else if (!have) {
+                msg = "internal: frame neither cached nor requested";
+            }
+            if (have)
+                frame = f->frames.find(n)->second;
+        }
+        if (frame.empty()) {
+            vsapi->setFilterError(("Compensate: " + msg).c_str(), frameCtx);
+            vsapi->freeFrame(src);
+            return nullptr;
+        }
+        VSFrame *dst = vsapi->newVideoFrame(&d->vi->format, d->vi->width, d->vi->height, src, core);
+        const int planes = (d->cp.super_modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) ? d->vi->format.numPlanes : 1; // only the super clip's planes are produced
+        for (int p = 0; p < planes; p++)
+            vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), frame.data() + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, (size_t)f->cl.plane_h[p]);
+        vsapi->freeFrame(src);
+        return dst;
+    }
+    return nullptr;
+}
 
 const VSFrame *VS_CC compGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
     CompData *d = (CompData *)instanceData;
@@ -1072,6 +1163,7 @@ void VS_CC compFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
     vsapi->freeNode(d->node);
     vsapi->freeNode(d->super);
     vsapi->freeNode(d->vectors);
+    delete d->fused;
     delete d;
 }
 
@@ -1125,7 +1217,32 @@ void VS_CC compCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const V
         freeAll();
         return;
     }
+    const int window = lookaheadFromEnv();
+    if (window) { // the fused path: every input is one of this plugin's own nodes, wired as in the canonical script
+        std::lock_guard<std::mutex> lock(g_registry_mutex);
+        auto su = g_registry.find(d.super), an = g_registry.find(d.vectors);
+        if (su != g_registry.end() && su->second.kind == kNodeSuper && an != g_registry.end() && an->second.kind == kNodeAnalyse) {
+            const SuperData *S = (const SuperData *)su->second.data;
+            const AnalyseData *A = (const AnalyseData *)an->second.data;
+            const bool ok = S->node == d.node && !S->usePelClip && S->sp.width == d.sp.width && S->sp.height == d.sp.height && S->sp.bits == d.sp.bits && S->sp.pel == d.sp.pel && S->sp.hpad == d.sp.hpad &&
+                            S->sp.vpad == d.sp.vpad && S->sp.levels == d.sp.levels && S->sp.modeyuv == d.sp.modeyuv && A->node == d.super && !A->ap.fields && !d.cp.fields && A->ap.ad.nDeltaFrame > 0 &&
+                            A->ap.num_frames == d.vi->numFrames;
+            if (ok) {
+                d.fused = new CompFused;
+                d.fused->ap = A->ap;
+                d.sp = S->sp;
+                mvb200_clip_layout(&d.sp, &d.fused->cl);
+                d.fused->window = window;
+                d.fused->halo = A->ap.ad.nDeltaFrame;
+            }
+        }
+    }
     CompData *data = new CompData(d);
+    if (data->fused) { // only the source clip is read on this path
+        VSFilterDependency fdeps[1] = {{data->node, rpGeneral}};
+        vsapi->createVideoFilter(out, "Compensate", data->vi, compFusedGetFrame, compFree, fmParallel, fdeps, 1, data, core);
+        return;
+    }
     VSFilterDependency deps[2] = {{data->super, rpGeneral}, {data->vectors, rpGeneral}};
     vsapi->createVideoFilter(out, "Compensate", data->vi, compGetFrame, compFree, fmParallel, deps, 2, data, core);
 }
