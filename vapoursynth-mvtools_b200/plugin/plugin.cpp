@@ -78,6 +78,130 @@ int lookaheadFromEnv() { // MVB200_LOOKAHEAD: frames per engine call (2..256); a
     return v < 2 ? 0 : (v > 256 ? 256 : v);
 }
 
+// ---------------------------------------------------------------- fused windows
+// Shared by the fused paths of DegrainN / Compensate / FlowFPS (MVB200_LOOKAHEAD=<B>, default off): when a filter's
+// inputs are this plugin's own Super / Analyse nodes wired as in the canonical script, a window of B output frames is
+// produced by ONE engine call over SOURCE frames (a *_clip_host entry point: Super, the searches and the consumer all
+// run on the device) and served from a small cache; the Super / Analyse nodes are never asked for a frame.
+struct FusedCache {
+    std::mutex m;                               // serialises the window computations of one filter instance
+    std::map<int, std::vector<uint8_t>> frames; // output frames in the clip layout
+    std::deque<int> order;
+    mvb200_frame_layout cl;
+    int window = 0;
+    void *hostSrc = nullptr, *hostDst = nullptr; // pinned staging, grown on demand (used under g_engine_mutex)
+    size_t hostSrcBytes = 0, hostDstBytes = 0;
+    ~FusedCache() {
+        mvb200_pinned_free(hostSrc);
+        mvb200_pinned_free(hostDst);
+    }
+    bool staging(size_t srcBytes, size_t dstBytes) {
+        if (hostSrcBytes < srcBytes) {
+            mvb200_pinned_free(hostSrc);
+            hostSrc = mvb200_pinned_alloc(srcBytes);
+            hostSrcBytes = hostSrc ? srcBytes : 0;
+        }
+        if (hostDstBytes < dstBytes) {
+            mvb200_pinned_free(hostDst);
+            hostDst = mvb200_pinned_alloc(dstBytes);
+            hostDstBytes = hostDst ? dstBytes : 0;
+        }
+        return hostSrc && hostDst;
+    }
+    void store(int n, int end) { // the window's frames out of hostDst; keeps the window being served and the previous one
+        const size_t fb = (size_t)cl.frame_bytes;
+        for (int k = n; k < end; k++) {
+            const uint8_t *p = (const uint8_t *)hostDst + fb * (k - n);
+            if (frames.emplace(k, std::vector<uint8_t>(p, p + fb)).second)
+                order.push_back(k);
+        }
+        while (order.size() > (size_t)window * 2) {
+            frames.erase(order.front());
+            order.pop_front();
+        }
+    }
+};
+
+// One activation of a fused filter.  propFrame: the source frame the output frame takes its properties from (always
+// requested); segment(n, end, &s0, &s1): the source frames the output window [n, end) needs; run(ctx, hostSrc, s0, s1, n,
+// end, hostDst): the engine call (source frames [s0, s1) in the clip layout -> output frames [n, end)); planeMask: bit p
+// set = plane p comes from the engine, else it is a copy of the source frame's.
+template <class Segment, class Run>
+const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, const VSVideoInfo *outvi, int n, int propFrame, unsigned planeMask, int activationReason, void **frameData, VSFrameContext *frameCtx,
+                             VSCore *core, const VSAPI *vsapi, Segment segment, Run run) {
+    if (activationReason == arInitial) {
+        vsapi->requestFrameFilter(propFrame, clip, frameCtx);
+        bool hit;
+        {
+            std::lock_guard<std::mutex> lock(f->m);
+            hit = f->frames.count(n) != 0;
+        }
+        if (!hit) {
+            const int end = n + f->window < outvi->numFrames ? n + f->window : outvi->numFrames;
+            int s0, s1;
+            segment(n, end, &s0, &s1);
+            for (int k = s0; k < s1; k++)
+                if (k != propFrame)
+                    vsapi->requestFrameFilter(k, clip, frameCtx);
+            *frameData = (void *)(intptr_t)end; // remembered for arAllFramesReady: this request holds the window's frames
+        }
+        return nullptr;
+    }
+    if (activationReason != arAllFramesReady)
+        return nullptr;
+    const VSFrame *src = vsapi->getFrameFilter(propFrame, clip, frameCtx);
+    std::vector<uint8_t> frame;
+    std::string msg;
+    {
+        std::lock_guard<std::mutex> lock(f->m);
+        const int end = (int)(intptr_t)*frameData;
+        bool have = f->frames.count(n) != 0;
+        if (!have && end > n) {
+            int s0, s1;
+            segment(n, end, &s0, &s1);
+            const size_t fb = (size_t)f->cl.frame_bytes;
+            std::lock_guard<std::mutex> elock(g_engine_mutex); // (also guards the staging buffers)
+            mvb200_ctx *ctx = engine(msg);
+            if (ctx && !f->staging(fb * (s1 - s0), fb * (end - n)))
+                msg = mvb200_last_error();
+            else if (ctx) {
+                for (int k = s0; k < s1; k++) { // pack the source frames into the clip layout
+                    const VSFrame *fr = vsapi->getFrameFilter(k, clip, frameCtx);
+                    for (int p = 0; p < f->cl.nplanes; p++)
+                        vsh::bitblt((uint8_t *)f->hostSrc + fb * (k - s0) + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], vsapi->getReadPtr(fr, p), vsapi->getStride(fr, p),
+                                    (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, (size_t)f->cl.plane_h[p]);
+                    vsapi->freeFrame(fr);
+                }
+                if (run(ctx, f->hostSrc, s0, s1, n, end, f->hostDst)) {
+                    msg = mvb200_last_error();
+                } else {
+                    f->store(n, end);
+                    have = true;
+                }
+            }
+        } else if (!have) {
+            msg = "internal: frame neither cached nor requested"; // (evicted between the two activations)
+        }
+        if (have)
+            frame = f->frames.find(n)->second;
+    }
+    if (frame.empty()) {
+        vsapi->setFilterError((std::string(filter) + ": " + msg).c_str(), frameCtx);
+        vsapi->freeFrame(src);
+        return nullptr;
+    }
+    VSFrame *dst = vsapi->newVideoFrame(&outvi->format, outvi->width, outvi->height, src, core);
+    for (int p = 0; p < outvi->format.numPlanes; p++) {
+        const size_t row = (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, rows = (size_t)f->cl.plane_h[p];
+        if (planeMask & (1u << p))
+            vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), frame.data() + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], row, rows);
+        else
+            vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), vsapi->getReadPtr(src, p), vsapi->getStride(src, p), row, rows);
+    }
+    vsapi->freeFrame(src);
+    return dst;
+}
+
 int argInt(const VSAPI *vsapi, const VSMap *in, const char *name) {
     int err = 0;
     int v = vsapi->mapGetIntSaturated(in, name, 0, &err);
@@ -535,21 +659,13 @@ void VS_CC analyseCreate(const VSMap *in, VSMap *out, void *, VSCore *core, cons
 }
 
 // ---------------------------------------------------------------- Degrain
-// Fused path (MVB200_LOOKAHEAD=<B>, default off): when the clip, the super clip and every vector clip of a DegrainN are
-// this plugin's own nodes wired as in the canonical script, the frames [n, n + B) are produced by ONE engine call over
-// the SOURCE frames of the window and its halo -- mvb200_degrain_clip_host_async: H2D of 3 MB source frames, Super,
+// Fused path (see fusedGetFrame): ONE mvb200_degrain_clip_host_async call per window -- H2D of 3 MB source frames, Super,
 // 2r searches of B chains each, DegrainN, D2H -- instead of 1 + 2r + 1 per-frame calls that move 17.9 MB super frames
-// each way.  The Super / Analyse nodes are not even asked for those frames.  Results are identical (the engine's clip
-// pipeline is what the sharded bench runs; frames outside the window only serve as references).
-struct DegrainFused {
-    std::mutex m;
-    std::map<int, std::vector<uint8_t>> frames; // output frames in the clip layout
-    std::deque<int> order;
+// each way.  Results are identical (the engine's clip pipeline is what the sharded bench runs; frames outside the
+// window only serve as references).
+struct DegrainFused : FusedCache {
     mvb200_analyse_params ap[2 * MVB200_MAX_RADIUS]; // copies: no dependence on the Analyse instances' lifetime
-    mvb200_frame_layout cl;
-    int window, halo;
-    void *hostSrc = nullptr, *hostDst = nullptr; // pinned staging, grown on demand
-    size_t hostSrcBytes = 0, hostDstBytes = 0;
+    int halo;
 };
 
 struct DegrainData {
@@ -561,111 +677,29 @@ struct DegrainData {
     DegrainFused *fused; // owned; null = node-by-node evaluation
 };
 
-// runs the window [n, end) through the clip pipeline and caches its frames; false + msg on failure
-bool degrainFusedWindow(DegrainData *d, const VSAPI *vsapi, VSFrameContext *frameCtx, int n, int end, std::string &msg) {
-    DegrainFused *f = d->fused;
-    const int N = d->vi->numFrames, s0 = n - f->halo > 0 ? n - f->halo : 0, s1 = end + f->halo < N ? end + f->halo : N, seg = s1 - s0;
-    const size_t fb = (size_t)f->cl.frame_bytes;
-    std::lock_guard<std::mutex> lock(g_engine_mutex); // (also guards the staging buffers)
-    mvb200_ctx *ctx = engine(msg);
-    if (!ctx)
-        return false;
-    if (f->hostSrcBytes < fb * seg) {
-        mvb200_pinned_free(f->hostSrc);
-        f->hostSrc = mvb200_pinned_alloc(fb * seg);
-        f->hostSrcBytes = f->hostSrc ? fb * seg : 0;
-    }
-    if (f->hostDstBytes < fb * (end - n)) {
-        mvb200_pinned_free(f->hostDst);
-        f->hostDst = mvb200_pinned_alloc(fb * (end - n));
-        f->hostDstBytes = f->hostDst ? fb * (end - n) : 0;
-    }
-    if (!f->hostSrc || !f->hostDst) {
-        msg = mvb200_last_error();
-        return false;
-    }
-    for (int k = s0; k < s1; k++) { // pack the source frames into the clip layout
-        const VSFrame *fr = vsapi->getFrameFilter(k, d->node, frameCtx);
-        for (int p = 0; p < f->cl.nplanes; p++)
-            vsh::bitblt((uint8_t *)f->hostSrc + fb * (k - s0) + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], vsapi->getReadPtr(fr, p), vsapi->getStride(fr, p), (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample,
-                        (size_t)f->cl.plane_h[p]);
-        vsapi->freeFrame(fr);
-    }
-    const int R2 = d->radius * 2;
-    mvb200_analyse_params aps[2 * MVB200_MAX_RADIUS];
-    const mvb200_analyse_params *app[2 * MVB200_MAX_RADIUS];
-    for (int r = 0; r < R2; r++) { // the segment is the clip as far as the engine is concerned
-        aps[r] = f->ap[r];
-        aps[r].num_frames = seg;
-        app[r] = &aps[r];
-    }
-    if (mvb200_degrain_clip_host_async(ctx, &d->sp, app, R2, &d->dp, f->hostSrc, f->hostDst, seg, n - s0, end - n) || mvb200_ctx_synchronize(ctx)) {
-        msg = mvb200_last_error();
-        return false;
-    }
-    for (int k = n; k < end; k++) {
-        const uint8_t *p = (const uint8_t *)f->hostDst + fb * (k - n);
-        if (f->frames.emplace(k, std::vector<uint8_t>(p, p + fb)).second)
-            f->order.push_back(k);
-    }
-    while (f->order.size() > (size_t)f->window * 2) { // the window being served and the previous one (the frame server caches the rest)
-        f->frames.erase(f->order.front());
-        f->order.pop_front();
-    }
-    return true;
-}
-
 const VSFrame *VS_CC degrainFusedGetFrame(int n, int activationReason, void *instanceData, void **frameData, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
     DegrainData *d = (DegrainData *)instanceData;
     DegrainFused *f = d->fused;
     const int N = d->vi->numFrames;
-    if (activationReason == arInitial) {
-        vsapi->requestFrameFilter(n, d->node, frameCtx);
-        bool hit;
-        {
-            std::lock_guard<std::mutex> lock(f->m);
-            hit = f->frames.count(n) != 0;
+    unsigned mask = 0; // planes the filter does not process are copies of the source (MVDegrains.cpp:211-214)
+    for (int p = 0; p < 3; p++)
+        mask |= d->dp.process[p] ? 1u << p : 0u;
+    auto segment = [&](int w0, int w1, int *s0, int *s1) { // the window and the halo the searches and the blend reach into
+        *s0 = w0 - f->halo > 0 ? w0 - f->halo : 0;
+        *s1 = w1 + f->halo < N ? w1 + f->halo : N;
+    };
+    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst) {
+        const int R2 = d->radius * 2, seg = s1 - s0;
+        mvb200_analyse_params aps[2 * MVB200_MAX_RADIUS];
+        const mvb200_analyse_params *app[2 * MVB200_MAX_RADIUS];
+        for (int r = 0; r < R2; r++) { // the segment is the clip as far as the engine is concerned
+            aps[r] = f->ap[r];
+            aps[r].num_frames = seg;
+            app[r] = &aps[r];
         }
-        if (!hit) { // the window's source frames and the halo the searches and the blend reach into
-            const int end = n + f->window < N ? n + f->window : N;
-            const int s0 = n - f->halo > 0 ? n - f->halo : 0, s1 = end + f->halo < N ? end + f->halo : N;
-            for (int k = s0; k < s1; k++)
-                if (k != n)
-                    vsapi->requestFrameFilter(k, d->node, frameCtx);
-            *frameData = (void *)(intptr_t)end;
-        }
-    } else if (activationReason == arAllFramesReady) {
-        const VSFrame *src = vsapi->getFrameFilter(n, d->node, frameCtx);
-        std::vector<uint8_t> frame;
-        std::string msg;
-        {
-            std::lock_guard<std::mutex> lock(f->m);
-            const int end = (int)(intptr_t)*frameData;
-            bool have = f->frames.count(n) != 0;
-            if (!have && end > n) // miss, and this request holds the window's source frames
-                have = degrainFusedWindow(d, vsapi, frameCtx, n, end, msg);
-            else if (!have)
-                msg = "internal: frame neither cached nor requested"; // (evicted between the two activations)
-            if (have)
-                frame = f->frames.find(n)->second;
-        }
-        if (frame.empty()) {
-            vsapi->setFilterError(("Degrain: " + msg).c_str(), frameCtx);
-            vsapi->freeFrame(src);
-            return nullptr;
-        }
-        VSFrame *dst = vsapi->newVideoFrame(&d->vi->format, d->vi->width, d->vi->height, src, core);
-        for (int p = 0; p < d->vi->format.numPlanes; p++) {
-            if (!d->dp.process[p]) { // planes the filter does not process are copies of the source (MVDegrains.cpp:211-214)
-                vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), vsapi->getReadPtr(src, p), vsapi->getStride(src, p), (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, (size_t)f->cl.plane_h[p]);
-                continue;
-            }
-            vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), frame.data() + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, (size_t)f->cl.plane_h[p]);
-        }
-        vsapi->freeFrame(src);
-        return dst;
-    }
-    return nullptr;
+        return mvb200_degrain_clip_host_async(ctx, &d->sp, app, R2, &d->dp, hostSrc, hostDst, seg, w0 - s0, w1 - w0) || mvb200_ctx_synchronize(ctx);
+    };
+    return fusedGetFrame("Degrain", f, d->node, d->vi, n, n, mask, activationReason, frameData, frameCtx, core, vsapi, segment, run);
 }
 
 const VSFrame *VS_CC degrainGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
@@ -738,11 +772,7 @@ void VS_CC degrainFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
     vsapi->freeNode(d->super);
     for (int r = 0; r < d->radius * 2; r++)
         vsapi->freeNode(d->vectors[r]);
-    if (d->fused) {
-        mvb200_pinned_free(d->fused->hostSrc);
-        mvb200_pinned_free(d->fused->hostDst);
-        delete d->fused;
-    }
+    delete d->fused;
     delete d;
 }
 
@@ -1008,15 +1038,10 @@ void VS_CC recalcCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const
 }
 
 // ------------------------------------------------------------- Compensate
-// Fused path (MVB200_LOOKAHEAD=<B>, default off), as for DegrainN: clip / super / vectors are this plugin's own nodes
-// wired as in the canonical script -> a window of B frames is one mvb200_compensate_clip_host call over source frames.
-struct CompFused {
-    std::mutex m;
-    std::map<int, std::vector<uint8_t>> frames; // output frames in the clip layout
-    std::deque<int> order;
+// Fused path (see fusedGetFrame): a window of B frames is one mvb200_compensate_clip_host call over source frames.
+struct CompFused : FusedCache {
     mvb200_analyse_params ap;
-    mvb200_frame_layout cl;
-    int window, halo;
+    int halo;
 };
 
 struct CompData {
@@ -1031,79 +1056,15 @@ const VSFrame *VS_CC compFusedGetFrame(int n, int activationReason, void *instan
     CompData *d = (CompData *)instanceData;
     CompFused *f = d->fused;
     const int N = d->vi->numFrames;
-    if (activationReason == arInitial) {
-        vsapi->requestFrameFilter(n, d->node, frameCtx);
-        bool hit;
-        {
-            std::lock_guard<std::mutex> lock(f->m);
-            hit = f->frames.count(n) != 0;
-        }
-        if (!hit) {
-            const int end = n + f->window < N ? n + f->window : N;
-            const int s0 = n - f->halo > 0 ? n - f->halo : 0, s1 = end + f->halo < N ? end + f->halo : N;
-            for (int k = s0; k < s1; k++)
-                if (k != n)
-                    vsapi->requestFrameFilter(k, d->node, frameCtx);
-            *frameData = (void *)(intptr_t)end;
-        }
-    } else if (activationReason == arAllFramesReady) {
-        const VSFrame *src = vsapi->getFrameFilter(n, d->node, frameCtx);
-        std::vector<uint8_t> frame;
-        std::string msg;
-        {
-            std::lock_guard<std::mutex> lock(f->m);
-            const int end = (int)(intptr_t)*frameData;
-            bool have = f->frames.count(n) != 0;
-            if (!have && end > n) {
-                const int s0 = n - f->halo > 0 ? n - f->halo : 0, s1 = end + f->halo < N ? end + f->halo : N;
-                const size_t fb = (size_t)f->cl.frame_bytes;
-                std::vector<uint8_t> hostSrc(fb * (s1 - s0)), hostDst(fb * (end - n));
-                for (int k = s0; k < s1; k++) {
-                    const VSFrame *fr = vsapi->getFrameFilter(k, d->node, frameCtx);
-                    for (int p = 0; p < f->cl.nplanes; p++)
-                        vsh::bitblt(hostSrc.data() + fb * (k - s0) + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], vsapi->getReadPtr(fr, p), vsapi->getStride(fr, p), (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample,
-                                    (size_t)f->cl.plane_h[p]);
-                    vsapi->freeFrame(fr);
-                }
-                int rc;
-                {
-                    std::lock_guard<std::mutex> elock(g_engine_mutex);
-                    mvb200_ctx *ctx = engine(msg);
-                    rc = ctx ? mvb200_compensate_clip_host(ctx, &d->sp, &f->ap, &d->cp, hostSrc.data(), s0, s1 - s0, n, end - n, hostDst.data()) : 1;
-                    if (ctx && rc)
-                        msg = mvb200_last_error();
-                }
-                if (!rc) {
-                    for (int k = n; k < end; k++) {
-                        const uint8_t *p = hostDst.data() + fb * (k - n);
-                        if (f->frames.emplace(k, std::vector<uint8_t>(p, p + fb)).second)
-                            f->order.push_back(k);
-                    }
-                    while (f->order.size() > (size_t)f->window * 2) {
-                        f->frames.erase(f->order.front());
-                        f->order.pop_front();
-                    }
-                    have = true;
-                }
-            } else if (!have) {
-                msg = "internal: frame neither cached nor requested";
-            }
-            if (have)
-                frame = f->frames.find(n)->second;
-        }
-        if (frame.empty()) {
-            vsapi->setFilterError(("Compensate: " + msg).c_str(), frameCtx);
-            vsapi->freeFrame(src);
-            return nullptr;
-        }
-        VSFrame *dst = vsapi->newVideoFrame(&d->vi->format, d->vi->width, d->vi->height, src, core);
-        const int planes = (d->cp.super_modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) ? d->vi->format.numPlanes : 1; // only the super clip's planes are produced
-        for (int p = 0; p < planes; p++)
-            vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), frame.data() + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, (size_t)f->cl.plane_h[p]);
-        vsapi->freeFrame(src);
-        return dst;
-    }
-    return nullptr;
+    const unsigned mask = (d->cp.super_modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) ? 7u : 1u; // only the super clip's planes are produced
+    auto segment = [&](int w0, int w1, int *s0, int *s1) {
+        *s0 = w0 - f->halo > 0 ? w0 - f->halo : 0;
+        *s1 = w1 + f->halo < N ? w1 + f->halo : N;
+    };
+    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst) {
+        return mvb200_compensate_clip_host(ctx, &d->sp, &f->ap, &d->cp, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst);
+    };
+    return fusedGetFrame("Compensate", f, d->node, d->vi, n, n, mask, activationReason, frameData, frameCtx, core, vsapi, segment, run);
 }
 
 const VSFrame *VS_CC compGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
@@ -1836,16 +1797,10 @@ void VS_CC flowInterCreate(const VSMap *in, VSMap *out, void *, VSCore *core, co
 // mvflowfpsCreate / GetFrame, MVFlowFPS.c:86-928.  The reference wraps the vector clips in a helper filter that
 // attaches the upsized vector planes as frame properties; the engine upsizes inside the kernel, so the vector clips
 // are used as they are.
-// Fused path (MVB200_LOOKAHEAD=<B>, default off), as for DegrainN: when clip / super / mvbw / mvfw are this plugin's own
-// nodes wired as in the canonical script, a window of B OUTPUT frames is one mvb200_flowfps_clip_host call over the
-// source frames the window needs (its left / right frames, delta before and 2 x delta after them for the "extra" vectors).
-struct FlowFPSFused {
-    std::mutex m;
-    std::map<int, std::vector<uint8_t>> frames; // output frames in the clip layout
-    std::deque<int> order;
+// Fused path (see fusedGetFrame): a window of B OUTPUT frames is one mvb200_flowfps_clip_host call over the source
+// frames the window needs (its left / right frames, delta before and 2 x delta after them for the "extra" vectors).
+struct FlowFPSFused : FusedCache {
     mvb200_analyse_params apBw, apFw;
-    mvb200_frame_layout cl;
-    int window;
 };
 
 struct FlowFPSData {
@@ -1857,101 +1812,31 @@ struct FlowFPSData {
     FlowFPSFused *fused; // owned; null = node-by-node evaluation
 };
 
-// the source frames the output window [n, end) needs: [*s0, *s1)
-void flowFpsSegment(const FlowFPSData *d, int n, int end, int *s0, int *s1) {
-    const int off = d->p.inter.vd.nDeltaFrame, N = d->oldvi->numFrames;
-    int32_t lmin, lmax, t;
-    mvb200_flowfps_position(&d->p, n, &lmin, &t);
-    mvb200_flowfps_position(&d->p, end - 1, &lmax, &t);
-    *s0 = lmin - off > 0 ? lmin - off : 0;
-    *s1 = lmax + 2 * off + 1 < N ? lmax + 2 * off + 1 : N;
-    if (*s0 > N - 1)
-        *s0 = N - 1; // (output frames past the end are copies of the last input frame)
-}
-
 const VSFrame *VS_CC flowFpsFusedGetFrame(int n, int activationReason, void *instanceData, void **frameData, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
     FlowFPSData *d = (FlowFPSData *)instanceData;
     FlowFPSFused *f = d->fused;
-    const int N = d->oldvi->numFrames;
+    const int off = d->p.inter.vd.nDeltaFrame, N = d->oldvi->numFrames;
     int32_t nleft, time256;
     mvb200_flowfps_position(&d->p, n, &nleft, &time256);
-    const int propFrame = VSMIN(time256 == 256 ? nleft + d->p.inter.vd.nDeltaFrame : nleft, N - 1); // whose properties the output carries
-    if (activationReason == arInitial) {
-        vsapi->requestFrameFilter(propFrame, d->node, frameCtx);
-        bool hit;
-        {
-            std::lock_guard<std::mutex> lock(f->m);
-            hit = f->frames.count(n) != 0;
-        }
-        if (!hit) {
-            const int end = n + f->window < d->vi.numFrames ? n + f->window : d->vi.numFrames;
-            int s0, s1;
-            flowFpsSegment(d, n, end, &s0, &s1);
-            for (int k = s0; k < s1; k++)
-                if (k != propFrame)
-                    vsapi->requestFrameFilter(k, d->node, frameCtx);
-            *frameData = (void *)(intptr_t)end;
-        }
-    } else if (activationReason == arAllFramesReady) {
-        const VSFrame *src = vsapi->getFrameFilter(propFrame, d->node, frameCtx);
-        if (time256 == 0 || time256 == 256)
-            return src; // the input frame itself (MVFlowFPS.c:137-141)
-        std::vector<uint8_t> frame;
-        std::string msg;
-        {
-            std::lock_guard<std::mutex> lock(f->m);
-            const int end = (int)(intptr_t)*frameData;
-            bool have = f->frames.count(n) != 0;
-            if (!have && end > n) {
-                int s0, s1;
-                flowFpsSegment(d, n, end, &s0, &s1);
-                const size_t fb = (size_t)f->cl.frame_bytes;
-                std::vector<uint8_t> hostSrc(fb * (s1 - s0)), hostDst(fb * (end - n));
-                for (int k = s0; k < s1; k++) {
-                    const VSFrame *fr = vsapi->getFrameFilter(k, d->node, frameCtx);
-                    for (int p = 0; p < f->cl.nplanes; p++)
-                        vsh::bitblt(hostSrc.data() + fb * (k - s0) + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], vsapi->getReadPtr(fr, p), vsapi->getStride(fr, p), (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample,
-                                    (size_t)f->cl.plane_h[p]);
-                    vsapi->freeFrame(fr);
-                }
-                int rc;
-                {
-                    std::lock_guard<std::mutex> elock(g_engine_mutex);
-                    mvb200_ctx *ctx = engine(msg);
-                    rc = ctx ? mvb200_flowfps_clip_host(ctx, &d->sp, &f->apBw, &f->apFw, &d->p, hostSrc.data(), s0, s1 - s0, n, end - n, hostDst.data()) : 1;
-                    if (ctx && rc)
-                        msg = mvb200_last_error();
-                }
-                if (!rc) {
-                    for (int k = n; k < end; k++) {
-                        const uint8_t *p = hostDst.data() + fb * (k - n);
-                        if (f->frames.emplace(k, std::vector<uint8_t>(p, p + fb)).second)
-                            f->order.push_back(k);
-                    }
-                    while (f->order.size() > (size_t)f->window * 2) { // the window being served and the previous one (the frame server caches the rest)
-                        f->frames.erase(f->order.front());
-                        f->order.pop_front();
-                    }
-                    have = true;
-                }
-            } else if (!have) {
-                msg = "internal: frame neither cached nor requested";
-            }
-            if (have)
-                frame = f->frames.find(n)->second;
-        }
-        if (frame.empty()) {
-            vsapi->setFilterError(("FlowFPS: " + msg).c_str(), frameCtx);
-            vsapi->freeFrame(src);
-            return nullptr;
-        }
-        VSFrame *dst = vsapi->newVideoFrame(&d->vi.format, d->vi.width, d->vi.height, src, core);
-        for (int p = 0; p < d->vi.format.numPlanes; p++)
-            vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), frame.data() + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, (size_t)f->cl.plane_h[p]);
-        vsapi->freeFrame(src);
-        return dst;
+    const int propFrame = VSMIN(time256 == 256 ? nleft + off : nleft, N - 1); // whose properties the output carries
+    if (time256 == 0 || time256 == 256) { // the input frame itself (MVFlowFPS.c:93-101,137-141)
+        if (activationReason == arInitial)
+            vsapi->requestFrameFilter(propFrame, d->node, frameCtx);
+        return activationReason == arAllFramesReady ? vsapi->getFrameFilter(propFrame, d->node, frameCtx) : nullptr;
     }
-    return nullptr;
+    auto segment = [&](int w0, int w1, int *s0, int *s1) {
+        int32_t lmin, lmax, t;
+        mvb200_flowfps_position(&d->p, w0, &lmin, &t);
+        mvb200_flowfps_position(&d->p, w1 - 1, &lmax, &t);
+        *s0 = lmin - off > 0 ? lmin - off : 0;
+        *s1 = lmax + 2 * off + 1 < N ? lmax + 2 * off + 1 : N;
+        if (*s0 > N - 1)
+            *s0 = N - 1; // (output frames past the end are made of the last input frame)
+    };
+    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst) {
+        return mvb200_flowfps_clip_host(ctx, &d->sp, &f->apBw, &f->apFw, &d->p, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst);
+    };
+    return fusedGetFrame("FlowFPS", f, d->node, &d->vi, n, propFrame, 7u, activationReason, frameData, frameCtx, core, vsapi, segment, run);
 }
 
 const VSFrame *VS_CC flowFpsGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
