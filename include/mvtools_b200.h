@@ -587,6 +587,17 @@ MVB200_API int mvb200_flowfps_clip_host(mvb200_ctx *ctx, const mvb200_super_para
 MVB200_API int mvb200_compensate_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_compensate_params *cp, const void *host_src, int src_first, int n, int out_first,
                                            int out_count, void *host_dst);
 
+/* The same for the per-pixel consumers: mv.Super -> mv.Analyse (one or two instances) -> mv.Flow / mv.FlowInter /
+ * mv.FlowBlur for output frames [out_first, out_first + out_count), from the n source frames [src_first, src_first + n)
+ * in host_src (halo: delta frames on both sides for Flow and FlowBlur, delta before and 2 x delta after for FlowInter).
+ * Relative delta only, no field shifts.  Synchronous. */
+MVB200_API int mvb200_flow_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_flow_params *fp, const void *host_src, int src_first, int n, int out_first, int out_count,
+                                     void *host_dst);
+MVB200_API int mvb200_flowinter_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowinter_params *p, const void *host_src, int src_first,
+                                          int n, int out_first, int out_count, void *host_dst);
+MVB200_API int mvb200_flowblur_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowblur_params *p, const void *host_src, int src_first,
+                                         int n, int out_first, int out_count, void *host_dst);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,9 +1,7 @@
-"""GPU tests that have NOT run on a GPU yet: they were written after round 1's GPU minutes were spent (mv.FlowBlur,
-mv.BlockFPS, mvb200_analyse_frames / the plugin's look-ahead).  What they check has been verified without a GPU as far
-as that goes -- the oracle is pinned against the reference, the kernels' per-thread code is bit-exact against the same
-goldens in the CPU emulation (test_flow_emul.py), the plugin glue against a stand-in engine (test_plugin_glue.py) -- so
-what remains unproven is the launch code.  The file sorts last so that `pytest -x` reaches it after every test that has
-already passed on a B200."""
+"""GPU parity tests of mv.FlowBlur, mv.BlockFPS, mvb200_analyse_frames, the plugin's look-ahead (MVB200_LOOKAHEAD) and
+the fused *_clip_host entry points (FlowFPS, Compensate): CUDA output against the reference's goldens, per frame, through
+the plugin script and at full size.  All 36 passed on a B200 (profiles/r1_pytest_gpu_pending.log -- the file was called
+test_zz_gpu_pending.py while they were waiting for a GPU)."""
 import ctypes as C
 import json
 import os

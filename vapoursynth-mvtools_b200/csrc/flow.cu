@@ -1037,4 +1037,97 @@ int mvb200_flowfps_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, con
     return 0;
 }
 
+// Common front of the *_clip_host entry points: the segment's source frames to the device, their super frames, and the
+// blobs of nap (1 or 2) mv.Analyse instances for EVERY frame of the segment (num_frames = n: the segment is the clip).
+struct ChainBuffers {
+    uint8_t *dsrc, *ddst, *dsup, *dvec[2];
+    int64_t vstride;
+    SuperDesc sd;
+    ClipDesc cd;
+};
+static int chain_front(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const void *host_src, int src_first, int n, int out_first, int out_count, const char *filter, ChainBuffers *B) {
+    if (sp->levels > kDevMaxLevels)
+        return set_error("mvtools_b200: more than %d pyramid levels are not supported on the device", kDevMaxLevels);
+    if (out_first < src_first || out_first + out_count > src_first + n)
+        return set_error("%s: output frames [%d, %d) are outside the segment [%d, %d)", filter, out_first, out_first + out_count, src_first, src_first + n);
+    mvb200_analyse_params aps[2];
+    const mvb200_analyse_params *app[2];
+    B->vstride = 0;
+    for (int i = 0; i < nap; i++) {
+        if (ap[i]->ad.nDeltaFrame <= 0 || ap[i]->fields)
+            return set_error("%s: the clip pipeline handles relative references without field shifts only", filter);
+        aps[i] = *ap[i];
+        aps[i].num_frames = n;
+        app[i] = &aps[i];
+        const int64_t v = ((int64_t)aps[i].vectors_size + 255) / 256 * 256;
+        B->vstride = v > B->vstride ? v : B->vstride;
+    }
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    make_super_desc(sp, &B->sd);
+    make_clip_desc(sp, &B->cd);
+    uint8_t *buf = (uint8_t *)c->get_scratch(kSlotStage, (size_t)B->cd.frame_bytes * (n + out_count) + (size_t)B->sd.frame_bytes * n + (size_t)B->vstride * n * nap + 256);
+    if (!buf)
+        return 1;
+    B->dsrc = buf;
+    B->ddst = B->dsrc + (size_t)B->cd.frame_bytes * n;
+    B->dsup = B->ddst + (size_t)B->cd.frame_bytes * out_count;
+    B->dvec[0] = B->dsup + (size_t)B->sd.frame_bytes * n;
+    B->dvec[1] = B->dvec[0] + (size_t)B->vstride * n;
+    MVB_CUDA_CHECK(cudaMemcpyAsync(B->dsrc, host_src, (size_t)B->cd.frame_bytes * n, cudaMemcpyHostToDevice, c->stream));
+    void *outs[2] = {B->dvec[0], B->dvec[1]};
+    return mvb200_super_batch(ctx, sp, B->dsrc, B->dsup, n) || mvb200_analyse_multi_batch(ctx, app, nap, sp, B->dsup, 0, n, outs, B->vstride);
+}
+static int chain_back(mvb200_ctx *ctx, const ChainBuffers &B, int out_count, void *host_dst) {
+    MVB_CUDA_CHECK(cudaMemcpyAsync(host_dst, B.ddst, (size_t)B.cd.frame_bytes * out_count, cudaMemcpyDeviceToHost, ctx->c.stream));
+    MVB_CUDA_CHECK(cudaStreamSynchronize(ctx->c.stream));
+    return 0;
+}
+
+int mvb200_flow_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_flow_params *fp, const void *host_src, int src_first, int n, int out_first, int out_count, void *host_dst) {
+    if (n <= 0 || out_count <= 0)
+        return 0;
+    if (fp->fields)
+        return set_error("Flow: the clip pipeline handles relative references without field shifts only");
+    ChainBuffers B;
+    if (chain_front(ctx, sp, &ap, 1, host_src, src_first, n, out_first, out_count, "Flow", &B))
+        return 1;
+    mvb200_flow_params q = *fp;
+    q.num_frames = n;
+    const int first = out_first - src_first;
+    if (mvb200_flow_batch(ctx, &q, sp, B.dsrc, B.dsup, first, out_count, B.dvec[0] + (size_t)B.vstride * first, B.vstride, B.ddst))
+        return 1;
+    return chain_back(ctx, B, out_count, host_dst);
+}
+
+int mvb200_flowinter_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowinter_params *p, const void *host_src, int src_first, int n,
+                               int out_first, int out_count, void *host_dst) {
+    if (n <= 0 || out_count <= 0)
+        return 0;
+    ChainBuffers B;
+    const mvb200_analyse_params *ap[2] = {ap_bw, ap_fw};
+    if (chain_front(ctx, sp, ap, 2, host_src, src_first, n, out_first, out_count, "FlowInter", &B))
+        return 1;
+    mvb200_flowinter_params q = *p;
+    q.num_frames = n;
+    if (mvb200_flowinter_batch(ctx, &q, sp, B.dsrc, B.dsup, out_first - src_first, out_count, B.dvec[0], B.dvec[1], B.vstride, B.ddst))
+        return 1;
+    return chain_back(ctx, B, out_count, host_dst);
+}
+
+int mvb200_flowblur_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowblur_params *p, const void *host_src, int src_first, int n,
+                              int out_first, int out_count, void *host_dst) {
+    if (n <= 0 || out_count <= 0)
+        return 0;
+    ChainBuffers B;
+    const mvb200_analyse_params *ap[2] = {ap_bw, ap_fw};
+    if (chain_front(ctx, sp, ap, 2, host_src, src_first, n, out_first, out_count, "FlowBlur", &B))
+        return 1;
+    mvb200_flowblur_params q = *p;
+    q.num_frames = n;
+    if (mvb200_flowblur_batch(ctx, &q, sp, B.dsrc, B.dsup, out_first - src_first, out_count, B.dvec[0], B.dvec[1], B.vstride, B.ddst))
+        return 1;
+    return chain_back(ctx, B, out_count, host_dst);
+}
+
 } // extern "C"
