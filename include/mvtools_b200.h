@@ -590,11 +590,16 @@ MVB200_API int mvb200_compensate_clip_host(mvb200_ctx *ctx, const mvb200_super_p
 /* The same for the per-pixel consumers: mv.Super -> mv.Analyse (one or two instances) -> mv.Flow / mv.FlowInter /
  * mv.FlowBlur for output frames [out_first, out_first + out_count), from the n source frames [src_first, src_first + n)
  * in host_src (halo: delta frames on both sides for Flow and FlowBlur, delta before and 2 x delta after for FlowInter).
- * Relative delta only, no field shifts.  Synchronous. */
+ * Relative delta only, no field shifts.  Synchronous.  Replaces, for a window of frames, mvflowGetFrame (MVFlow.cpp:157-368),
+ * mvflowinterGetFrame (MVFlowInter.c:83-448) and mvflowblurGetFrame (MVFlowBlur.c:144-337) together with the
+ * mvsuperGetFrame / mvanalyseGetFrame calls that feed them.  usable_out (Flow and FlowInter, may be NULL): one flag per
+ * output frame, 1 = made from the vectors (the reference's frame then carries the properties of a SUPER frame: the
+ * reference frame's for Flow, frame n's for FlowInter), 0 = the copy / blend of source frames the reference returns at
+ * scene changes and clip ends (MVFlow.cpp:362-366, MVFlowInter.c:412-447). */
 MVB200_API int mvb200_flow_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_flow_params *fp, const void *host_src, int src_first, int n, int out_first, int out_count,
-                                     void *host_dst);
+                                     void *host_dst, int32_t *usable_out);
 MVB200_API int mvb200_flowinter_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowinter_params *p, const void *host_src, int src_first,
-                                          int n, int out_first, int out_count, void *host_dst);
+                                          int n, int out_first, int out_count, void *host_dst, int32_t *usable_out);
 MVB200_API int mvb200_flowblur_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowblur_params *p, const void *host_src, int src_first,
                                          int n, int out_first, int out_count, void *host_dst);
 

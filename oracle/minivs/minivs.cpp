@@ -180,6 +180,27 @@ void copyProps(const VSMap &src, VSMap &dst) {
     }
 }
 
+// copyMap of the API: values of src replace same-named keys of dst, other keys of dst stay
+void VS_CC copyMap(const VSMap *src, VSMap *dst) {
+    for (auto &e : src->kv) {
+        auto &out = dst->kv[e.first];
+        for (auto v : out) {
+            if (v.node)
+                g_api()->freeNode(v.node);
+            if (v.frame)
+                g_api()->freeFrame(v.frame);
+        }
+        out.clear();
+        for (auto v : e.second) {
+            if (v.node)
+                g_api()->addNodeRef(v.node);
+            if (v.frame)
+                g_api()->addFrameRef(v.frame);
+            out.push_back(v);
+        }
+    }
+}
+
 VSFrame *VS_CC newVideoFrame(const VSVideoFormat *format, int width, int height, const VSFrame *propSrc, VSCore *) {
     VSFrame *f = allocFrame(format, width, height);
     if (propSrc)
@@ -680,6 +701,7 @@ VSAPI makeApi() {
     a.createMap = createMap;
     a.freeMap = freeMap;
     a.clearMap = clearMap;
+    a.copyMap = copyMap;
     a.mapSetError = mapSetError;
     a.mapGetError = mapGetError;
     a.mapNumKeys = mapNumKeys;

@@ -347,3 +347,177 @@ MVB200_API int mvb200_compensate_clip_host(mvb200_ctx *, const mvb200_super_para
 }
 
 } // extern "C"
+
+// The front of the per-pixel consumers' clip calls on host memory: Super of every frame of the segment and the blobs of
+// nap mv.Analyse instances for every frame (the segment is the clip for the searches, as in the engine).
+namespace {
+struct MockSegment {
+    mvb200_frame_layout cl;
+    mvb200_super_geom g;
+    const mvb200_super_params *sp;
+    const uint8_t *host_src;
+    int n, bps;
+    std::vector<std::vector<uint8_t>> sup;
+    std::vector<std::vector<uint8_t>> vec[2];
+    ptrdiff_t sstride[3] = {0, 0, 0};
+    void src_planes(int local, const uint8_t *q[3], ptrdiff_t st[3]) const {
+        for (int i = 0; i < 3; i++) {
+            q[i] = i < cl.nplanes ? host_src + (size_t)cl.frame_bytes * local + cl.offset[i] : nullptr;
+            st[i] = i < cl.nplanes ? (ptrdiff_t)cl.pitch[i] : 0;
+        }
+    }
+    void sup_planes(int local, const uint8_t *q[3]) const {
+        for (int i = 0; i < 3; i++)
+            q[i] = i < sp->nplanes ? sup[(size_t)local * 3 + i].data() : nullptr;
+    }
+    void dst_planes(void *host_dst, int k, uint8_t *d[3], ptrdiff_t dstr[3]) const {
+        for (int i = 0; i < 3; i++) {
+            d[i] = i < cl.nplanes ? (uint8_t *)host_dst + (size_t)cl.frame_bytes * k + cl.offset[i] : nullptr;
+            dstr[i] = i < cl.nplanes ? (ptrdiff_t)cl.pitch[i] : 0;
+        }
+    }
+    void copy_src(int local, uint8_t *const d[3], const ptrdiff_t dstr[3]) const {
+        const uint8_t *q[3];
+        ptrdiff_t st[3];
+        src_planes(local, q, st);
+        for (int i = 0; i < cl.nplanes; i++)
+            for (int y = 0; y < cl.plane_h[i]; y++)
+                memcpy(d[i] + y * dstr[i], q[i] + y * st[i], (size_t)cl.plane_w[i] * bps);
+    }
+    int build(const mvb200_super_params *sp_, const mvb200_analyse_params *const *ap, int nap, const void *src, int n_) {
+        sp = sp_;
+        host_src = (const uint8_t *)src;
+        n = n_;
+        mvb200_clip_layout(sp, &cl);
+        mvb200_super_geometry(sp, &g);
+        bps = cl.bytes_per_sample;
+        sup.resize((size_t)n * 3);
+        for (int f = 0; f < n; f++) {
+            const uint8_t *q[3];
+            ptrdiff_t st[3];
+            uint8_t *d[3] = {nullptr, nullptr, nullptr};
+            src_planes(f, q, st);
+            for (int i = 0; i < sp->nplanes; i++) {
+                sstride[i] = (ptrdiff_t)g.plane_w[i] * bps;
+                sup[(size_t)f * 3 + i].assign((size_t)sstride[i] * g.plane_h[i], 0);
+                d[i] = sup[(size_t)f * 3 + i].data();
+            }
+            if (fwd(mvo_super_frame(sp, q, st, d, sstride)))
+                return 1;
+        }
+        for (int k = 0; k < nap; k++) {
+            vec[k].resize((size_t)n);
+            for (int f = 0; f < n; f++) {
+                const int d = ap[k]->ad.nDeltaFrame;
+                int nref = f + (ap[k]->ad.isBackward ? d : -d);
+                if (nref < 0 || nref >= n)
+                    nref = -1;
+                const uint8_t *s_[3], *r_[3];
+                sup_planes(f, s_);
+                if (nref >= 0)
+                    sup_planes(nref, r_);
+                vec[k][f].assign((size_t)ap[k]->vectors_size, 0);
+                if (fwd(mvo_analyse_frame(ap[k], sp, s_, sstride, nref >= 0 ? r_ : nullptr, nref >= 0 ? sstride : nullptr, 0, vec[k][f].data())))
+                    return 1;
+            }
+        }
+        return 0;
+    }
+};
+} // namespace
+
+extern "C" {
+
+MVB200_API int mvb200_flow_clip_host(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_flow_params *fp, const void *host_src, int src_first, int n, int out_first, int out_count,
+                                     void *host_dst, int32_t *usable_out) {
+    MockSegment S;
+    if (S.build(sp, &ap, 1, host_src, n))
+        return 1;
+    const int dlt = fp->vd.nDeltaFrame;
+    for (int k = 0; k < out_count; k++) {
+        const int f = out_first - src_first + k;
+        int nref = fp->vd.isBackward ? f + dlt : f - dlt;
+        if (nref < 0 || nref >= n)
+            nref = -1;
+        uint8_t *d[3];
+        ptrdiff_t dstr[3];
+        S.dst_planes(host_dst, k, d, dstr);
+        const uint8_t *r_[3];
+        int32_t usable = 0;
+        if (nref >= 0) {
+            S.sup_planes(nref, r_);
+            if (fwd(mvo_flow_frame(fp, sp, r_, S.sstride, S.vec[0][f].data(), 0, d, dstr, &usable)))
+                return 1;
+        }
+        if (!usable)
+            S.copy_src(f, d, dstr);
+        if (usable_out)
+            usable_out[k] = usable;
+    }
+    return 0;
+}
+
+MVB200_API int mvb200_flowinter_clip_host(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowinter_params *p, const void *host_src, int src_first,
+                                          int n, int out_first, int out_count, void *host_dst, int32_t *usable_out) {
+    MockSegment S;
+    const mvb200_analyse_params *aps[2] = {ap_bw, ap_fw};
+    if (S.build(sp, aps, 2, host_src, n))
+        return 1;
+    const int off = p->vd.nDeltaFrame;
+    for (int k = 0; k < out_count; k++) {
+        const int L = out_first - src_first + k, R = L + off, ref = R < n - 1 ? R : n - 1;
+        uint8_t *d[3];
+        ptrdiff_t dstr[3];
+        S.dst_planes(host_dst, k, d, dstr);
+        int32_t usable = 0;
+        if (R < n) {
+            const uint8_t *sl[3], *sr[3];
+            S.sup_planes(L, sl);
+            S.sup_planes(R, sr);
+            if (fwd(mvo_flowinter_frame(p, sp, p->time256, sl, S.sstride, sr, S.sstride, S.vec[0][L].data(), S.vec[1][R].data(), S.vec[0][R].data(), S.vec[1][L].data(), d, dstr, &usable)))
+                return 1;
+        }
+        if (usable_out)
+            usable_out[k] = usable;
+        if (!usable) {
+            if (p->blend) {
+                const uint8_t *ql[3], *qr[3];
+                ptrdiff_t stl[3], str_[3];
+                S.src_planes(L, ql, stl);
+                S.src_planes(ref, qr, str_);
+                if (fwd(mvo_blend_frame(sp, p->time256, ql, stl, qr, str_, d, dstr)))
+                    return 1;
+            } else {
+                S.copy_src(L, d, dstr);
+            }
+        }
+    }
+    return 0;
+}
+
+MVB200_API int mvb200_flowblur_clip_host(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowblur_params *p, const void *host_src, int src_first,
+                                         int n, int out_first, int out_count, void *host_dst) {
+    MockSegment S;
+    const mvb200_analyse_params *aps[2] = {ap_bw, ap_fw};
+    if (S.build(sp, aps, 2, host_src, n))
+        return 1;
+    const int off = p->vd.nDeltaFrame;
+    for (int k = 0; k < out_count; k++) {
+        const int f = out_first - src_first + k;
+        uint8_t *d[3];
+        ptrdiff_t dstr[3];
+        S.dst_planes(host_dst, k, d, dstr);
+        int32_t usable = 0;
+        if (f - off >= 0 && f + off < n) {
+            const uint8_t *s_[3];
+            S.sup_planes(f, s_);
+            if (fwd(mvo_flowblur_frame(p, sp, s_, S.sstride, S.vec[0][f - off].data(), S.vec[1][f + off].data(), d, dstr, &usable)))
+                return 1;
+        }
+        if (!usable)
+            S.copy_src(f, d, dstr);
+    }
+    return 0;
+}
+
+} // extern "C"

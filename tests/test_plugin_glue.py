@@ -135,6 +135,57 @@ def test_compensate_fused_path_glue(mock_plugin, monkeypatch, case, window):
     assert (sup.computed(), vec.computed()) == before
 
 
+@pytest.mark.parametrize("window", [2, 5])
+@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "p10_444_blk8_pel4_bicubic", "gray_blk4_pel1_rf0", "noise_badblocks_blk8", "p8_420_blk16_ov4_uncovered"])
+def test_flow_consumers_fused_path_glue(mock_plugin, monkeypatch, case, window):
+    """MVB200_LOOKAHEAD: mv.Flow / mv.FlowInter / mv.FlowBlur fed by this plugin's own Super / Analyse nodes produce windows
+    of frames with one call of the engine's clip pipelines (mvb200_flow_clip_host, _flowinter_, _flowblur_): the
+    reference's frames for every variant of the goldens (modes, times, scene changes, clip ends), in and out of order,
+    and the frame properties of the node-by-node evaluation (a compensated frame carries the REFERENCE frame's
+    properties, plus Super_* when that is frame 0)"""
+    import minivs
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    N = len(frames)
+    nplanes = 1 if ck.get("gray") else 3
+    tags = [{"Tag": 100 + n} for n in range(N)]
+    F = pipeline_flow.FLOW[case]
+
+    def build(fused):
+        if fused:
+            monkeypatch.setenv("MVB200_LOOKAHEAD", str(window))
+        else:
+            monkeypatch.delenv("MVB200_LOOKAHEAD", raising=False)
+        core = minivs.Core()
+        mv = core.load(mock_plugin)
+        clip = core.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1), props=tags)
+        sup = mv.Super(clip, **skw)
+        vn = [mv.Analyse(sup, isb=isb, delta=1, **pipeline._fix(akw)) for isb in (1, 0)]
+        nodes = []
+        for kw in F.get("flow", []):
+            v, kw = pipeline_flow._split(kw)
+            nodes.append(("flow", len([x for x in nodes if x[0] == "flow"]), bool(kw.get("fields")), mv.Flow(clip, sup, vn[v], **{k: (float(x) if k == "time" else x) for k, x in kw.items()})))
+        for i, kw in enumerate(F.get("inter", [])):
+            nodes.append(("inter", i, False, mv.FlowInter(clip, sup, vn[0], vn[1], **{k: (float(x) if k in ("time", "ml") else x) for k, x in kw.items()})))
+        for i, kw in enumerate(F.get("blur", [])):
+            nodes.append(("blur", i, False, mv.FlowBlur(clip, sup, vn[0], vn[1], **{k: (float(x) if k == "blur" else x) for k, x in kw.items()})))
+        return core, sup, vn, nodes
+
+    plain = build(False)
+    fused = build(True)
+    before = (fused[1].computed(), [v.computed() for v in fused[2]])  # what the filters' creation read (frame 0 of every input)
+    for (stage, i, fields, node), (_, _, _, ref) in zip(fused[3], plain[3]):
+        node.set_cache(0)
+        for n in list(range(N)) + [N - 1, 0, N // 2]:
+            fr, rf = node.get_frame(n), ref.get_frame(n)
+            assert [pipeline.sha(p) for p in fr.planes()[:nplanes]] == GOLD_FLOW[case][stage][i][n], "%s variant %d frame %d" % (stage, i, n)
+            for key in ("Tag", "Super_pel", "Super_height", "Super_levels"):
+                assert fr.prop_int(key) == rf.prop_int(key), "%s variant %d frame %d: property %s" % (stage, i, n, key)
+    # on the fused paths the Super and Analyse nodes are not asked for a single frame (mv.Flow with fields keeps the nodes)
+    if not any(fields for _, _, fields, _ in fused[3]):
+        assert (fused[1].computed(), [v.computed() for v in fused[2]]) == before
+
+
 def test_lookahead_paths_under_concurrent_requests(mock_plugin, monkeypatch):
     """fmParallel: several host threads pull frames at once (mini host's render); the window caches of mv.Analyse and of
     the fused DegrainN must neither deadlock nor serve a wrong frame afterwards"""

@@ -671,7 +671,8 @@ static int flow_check(const mvb200_flow_params *fp, const mvb200_super_params *s
     return 0;
 }
 
-int mvb200_flow_batch(mvb200_ctx *ctx, const mvb200_flow_params *fp, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int first, int n, const void *dev_vectors, int64_t vectors_stride, void *dev_dst) {
+// dev_usable (may be null): one int per frame, 1 = compensated, 0 = the copy of the source frame
+static int flow_batch(mvb200_ctx *ctx, const mvb200_flow_params *fp, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int first, int n, const void *dev_vectors, int64_t vectors_stride, void *dev_dst, int *dev_usable) {
     if (flow_check(fp, sp))
         return 1;
     if (n <= 0)
@@ -700,8 +701,14 @@ int mvb200_flow_batch(mvb200_ctx *ctx, const mvb200_flow_params *fp, const mvb20
         if (launch_flow(c, fp, sd, cd, nref >= 0 ? (const uint8_t *)dev_super + (long long)nref * sd.frame_bytes : nullptr, (const uint8_t *)dev_vectors + (long long)f * vectors_stride, fs,
                         dev_src ? (const uint8_t *)dev_src + (long long)fn * cd.frame_bytes : nullptr, (uint8_t *)dev_dst + (long long)f * cd.frame_bytes, &usable))
             return 1;
+        if (dev_usable) // (the flag lives in per-launch scratch: keep it before the next frame's launch reuses the slot)
+            MVB_CUDA_CHECK(cudaMemcpyAsync(dev_usable + f, usable, sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     }
     return 0;
+}
+
+int mvb200_flow_batch(mvb200_ctx *ctx, const mvb200_flow_params *fp, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int first, int n, const void *dev_vectors, int64_t vectors_stride, void *dev_dst) {
+    return flow_batch(ctx, fp, sp, dev_src, dev_super, first, n, dev_vectors, vectors_stride, dev_dst, nullptr);
 }
 
 int mvb200_flow_frame(mvb200_ctx *ctx, const mvb200_flow_params *fp, const mvb200_super_params *sp, const uint8_t *const ref_super[3], const ptrdiff_t ref_stride[3], const uint8_t *vectors, int field_shift, uint8_t *const dst[3], const ptrdiff_t dst_stride[3], int32_t *usable_out) {
@@ -747,8 +754,10 @@ static int flowinter_check(const mvb200_flowinter_params *p, const mvb200_super_
     return 0;
 }
 
-int mvb200_flowinter_batch(mvb200_ctx *ctx, const mvb200_flowinter_params *p, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int first, int n, const void *dev_bw, const void *dev_fw,
-                           int64_t vectors_stride, void *dev_dst) {
+// dev_flags (may be null): two ints per frame (backward / forward vectors usable); the frame is interpolated when both are
+// set, else it is the blend / copy of the source frames
+static int flowinter_batch(mvb200_ctx *ctx, const mvb200_flowinter_params *p, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int first, int n, const void *dev_bw, const void *dev_fw,
+                           int64_t vectors_stride, void *dev_dst, int *dev_flags) {
     if (flowinter_check(p, sp))
         return 1;
     if (n <= 0)
@@ -773,8 +782,15 @@ int mvb200_flowinter_batch(mvb200_ctx *ctx, const mvb200_flowinter_params *p, co
                              in_range ? fw + (long long)fr * vectors_stride : nullptr, in_range ? bw + (long long)fr * vectors_stride : nullptr, in_range ? fw + (long long)fn * vectors_stride : nullptr,
                              src + (long long)fn * cd.frame_bytes, src + (long long)fref * cd.frame_bytes, (uint8_t *)dev_dst + (long long)f * cd.frame_bytes, &flags))
             return 1;
+        if (dev_flags) // (per-launch scratch: keep the pair before the next frame's launch reuses the slot)
+            MVB_CUDA_CHECK(cudaMemcpyAsync(dev_flags + 2 * f, flags, 2 * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     }
     return 0;
+}
+
+int mvb200_flowinter_batch(mvb200_ctx *ctx, const mvb200_flowinter_params *p, const mvb200_super_params *sp, const void *dev_src, const void *dev_super, int first, int n, const void *dev_bw, const void *dev_fw,
+                           int64_t vectors_stride, void *dev_dst) {
+    return flowinter_batch(ctx, p, sp, dev_src, dev_super, first, n, dev_bw, dev_fw, vectors_stride, dev_dst, nullptr);
 }
 
 int mvb200_flowinter_frame(mvb200_ctx *ctx, const mvb200_flowinter_params *p, const mvb200_super_params *sp, int time256, const uint8_t *const left_super[3], const ptrdiff_t left_stride[3],
@@ -1041,6 +1057,7 @@ int mvb200_flowfps_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, con
 // blobs of nap (1 or 2) mv.Analyse instances for EVERY frame of the segment (num_frames = n: the segment is the clip).
 struct ChainBuffers {
     uint8_t *dsrc, *ddst, *dsup, *dvec[2];
+    int *dflags; // room for two per output frame
     int64_t vstride;
     SuperDesc sd;
     ClipDesc cd;
@@ -1066,7 +1083,7 @@ static int chain_front(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb
     MVB_CUDA_CHECK(cudaSetDevice(c->device));
     make_super_desc(sp, &B->sd);
     make_clip_desc(sp, &B->cd);
-    uint8_t *buf = (uint8_t *)c->get_scratch(kSlotStage, (size_t)B->cd.frame_bytes * (n + out_count) + (size_t)B->sd.frame_bytes * n + (size_t)B->vstride * n * nap + 256);
+    uint8_t *buf = (uint8_t *)c->get_scratch(kSlotStage, (size_t)B->cd.frame_bytes * (n + out_count) + (size_t)B->sd.frame_bytes * n + (size_t)B->vstride * n * nap + align256(2 * sizeof(int) * (size_t)out_count) + 256);
     if (!buf)
         return 1;
     B->dsrc = buf;
@@ -1074,6 +1091,7 @@ static int chain_front(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb
     B->dsup = B->ddst + (size_t)B->cd.frame_bytes * out_count;
     B->dvec[0] = B->dsup + (size_t)B->sd.frame_bytes * n;
     B->dvec[1] = B->dvec[0] + (size_t)B->vstride * n;
+    B->dflags = (int *)(B->dvec[0] + (size_t)B->vstride * n * nap);
     MVB_CUDA_CHECK(cudaMemcpyAsync(B->dsrc, host_src, (size_t)B->cd.frame_bytes * n, cudaMemcpyHostToDevice, c->stream));
     void *outs[2] = {B->dvec[0], B->dvec[1]};
     return mvb200_super_batch(ctx, sp, B->dsrc, B->dsup, n) || mvb200_analyse_multi_batch(ctx, app, nap, sp, B->dsup, 0, n, outs, B->vstride);
@@ -1084,7 +1102,8 @@ static int chain_back(mvb200_ctx *ctx, const ChainBuffers &B, int out_count, voi
     return 0;
 }
 
-int mvb200_flow_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_flow_params *fp, const void *host_src, int src_first, int n, int out_first, int out_count, void *host_dst) {
+int mvb200_flow_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_flow_params *fp, const void *host_src, int src_first, int n, int out_first, int out_count, void *host_dst,
+                          int32_t *usable_out) {
     if (n <= 0 || out_count <= 0)
         return 0;
     if (fp->fields)
@@ -1095,13 +1114,16 @@ int mvb200_flow_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const 
     mvb200_flow_params q = *fp;
     q.num_frames = n;
     const int first = out_first - src_first;
-    if (mvb200_flow_batch(ctx, &q, sp, B.dsrc, B.dsup, first, out_count, B.dvec[0] + (size_t)B.vstride * first, B.vstride, B.ddst))
+    if (flow_batch(ctx, &q, sp, B.dsrc, B.dsup, first, out_count, B.dvec[0] + (size_t)B.vstride * first, B.vstride, B.ddst, usable_out ? B.dflags : nullptr))
         return 1;
+    static_assert(sizeof(int) == sizeof(int32_t), "flags are copied out as they are");
+    if (usable_out)
+        MVB_CUDA_CHECK(cudaMemcpyAsync(usable_out, B.dflags, sizeof(int) * (size_t)out_count, cudaMemcpyDeviceToHost, ctx->c.stream));
     return chain_back(ctx, B, out_count, host_dst);
 }
 
 int mvb200_flowinter_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowinter_params *p, const void *host_src, int src_first, int n,
-                               int out_first, int out_count, void *host_dst) {
+                               int out_first, int out_count, void *host_dst, int32_t *usable_out) {
     if (n <= 0 || out_count <= 0)
         return 0;
     ChainBuffers B;
@@ -1110,9 +1132,16 @@ int mvb200_flowinter_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, c
         return 1;
     mvb200_flowinter_params q = *p;
     q.num_frames = n;
-    if (mvb200_flowinter_batch(ctx, &q, sp, B.dsrc, B.dsup, out_first - src_first, out_count, B.dvec[0], B.dvec[1], B.vstride, B.ddst))
+    if (flowinter_batch(ctx, &q, sp, B.dsrc, B.dsup, out_first - src_first, out_count, B.dvec[0], B.dvec[1], B.vstride, B.ddst, usable_out ? B.dflags : nullptr))
         return 1;
-    return chain_back(ctx, B, out_count, host_dst);
+    std::vector<int> pairs(usable_out ? 2 * (size_t)out_count : 0);
+    if (usable_out)
+        MVB_CUDA_CHECK(cudaMemcpyAsync(pairs.data(), B.dflags, sizeof(int) * pairs.size(), cudaMemcpyDeviceToHost, ctx->c.stream));
+    if (chain_back(ctx, B, out_count, host_dst)) // (synchronises the stream)
+        return 1;
+    for (int k = 0; usable_out && k < out_count; k++)
+        usable_out[k] = pairs[2 * k] && pairs[2 * k + 1];
+    return 0;
 }
 
 int mvb200_flowblur_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowblur_params *p, const void *host_src, int src_first, int n,

@@ -278,6 +278,9 @@ def lib():
         L.mvb200_pinned_free.argtypes = [vp]
         L.mvb200_pinned_free.restype = None
         L.mvb200_compensate_clip_host.argtypes = [vp, PP(SuperParams), PP(AnalyseParams), PP(CompensateParams), vp, i32, i32, i32, i32, vp]
+        L.mvb200_flow_clip_host.argtypes = [vp, PP(SuperParams), PP(AnalyseParams), PP(FlowParams), vp, i32, i32, i32, i32, vp, PP(i32)]
+        L.mvb200_flowinter_clip_host.argtypes = [vp, PP(SuperParams), PP(AnalyseParams), PP(AnalyseParams), PP(FlowInterParams), vp, i32, i32, i32, i32, vp, PP(i32)]
+        L.mvb200_flowblur_clip_host.argtypes = [vp, PP(SuperParams), PP(AnalyseParams), PP(AnalyseParams), PP(FlowBlurParams), vp, i32, i32, i32, i32, vp]
         _LIB = L
     return _LIB
 

@@ -86,6 +86,8 @@ int lookaheadFromEnv() { // MVB200_LOOKAHEAD: frames per engine call (2..256); a
 struct FusedCache {
     std::mutex m;                               // serialises the window computations of one filter instance
     std::map<int, std::vector<uint8_t>> frames; // output frames in the clip layout
+    std::map<int, int32_t> flags;               // per cached frame: the engine's "usable" flag, where the filter has one
+    std::vector<int32_t> runFlags;              // filled by the run callback (one per frame of the window), else empty
     std::deque<int> order;
     mvb200_frame_layout cl;
     int window = 0;
@@ -114,9 +116,13 @@ struct FusedCache {
             const uint8_t *p = (const uint8_t *)hostDst + fb * (k - n);
             if (frames.emplace(k, std::vector<uint8_t>(p, p + fb)).second)
                 order.push_back(k);
+            if ((size_t)(k - n) < runFlags.size())
+                flags[k] = runFlags[(size_t)(k - n)];
         }
+        runFlags.clear();
         while (order.size() > (size_t)window * 2) {
             frames.erase(order.front());
+            flags.erase(order.front());
             order.pop_front();
         }
     }
@@ -125,12 +131,16 @@ struct FusedCache {
 // One activation of a fused filter.  propFrame: the source frame the output frame takes its properties from (always
 // requested); segment(n, end, &s0, &s1): the source frames the output window [n, end) needs; run(ctx, hostSrc, s0, s1, n,
 // end, hostDst): the engine call (source frames [s0, s1) in the clip layout -> output frames [n, end)); planeMask: bit p
-// set = plane p comes from the engine, else it is a copy of the source frame's.
+// set = plane p comes from the engine, else it is a copy of the source frame's.  alsoFrame (-1: none): one more source
+// frame the caller reads after this returns (requested here so that no frame is requested twice); flagOut: the frame's
+// "usable" flag as the run callback left it in FusedCache::runFlags.
 template <class Segment, class Run>
 const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, const VSVideoInfo *outvi, int n, int propFrame, unsigned planeMask, int activationReason, void **frameData, VSFrameContext *frameCtx,
-                             VSCore *core, const VSAPI *vsapi, Segment segment, Run run) {
+                             VSCore *core, const VSAPI *vsapi, Segment segment, Run run, int alsoFrame = -1, int32_t *flagOut = nullptr) {
     if (activationReason == arInitial) {
         vsapi->requestFrameFilter(propFrame, clip, frameCtx);
+        if (alsoFrame >= 0 && alsoFrame != propFrame)
+            vsapi->requestFrameFilter(alsoFrame, clip, frameCtx);
         bool hit;
         {
             std::lock_guard<std::mutex> lock(f->m);
@@ -141,7 +151,7 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
             int s0, s1;
             segment(n, end, &s0, &s1);
             for (int k = s0; k < s1; k++)
-                if (k != propFrame)
+                if (k != propFrame && k != alsoFrame)
                     vsapi->requestFrameFilter(k, clip, frameCtx);
             *frameData = (void *)(intptr_t)end; // remembered for arAllFramesReady: this request holds the window's frames
         }
@@ -182,8 +192,12 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
         } else if (!have) {
             msg = "internal: frame neither cached nor requested"; // (evicted between the two activations)
         }
-        if (have)
+        if (have) {
             frame = f->frames.find(n)->second;
+            const auto fl = f->flags.find(n);
+            if (flagOut)
+                *flagOut = fl != f->flags.end() ? fl->second : 0;
+        }
     }
     if (frame.empty()) {
         vsapi->setFilterError((std::string(filter) + ": " + msg).c_str(), frameCtx);
@@ -290,6 +304,17 @@ struct SuperData {
     VSNode *self; // this filter's output node (registry key), not a reference
 };
 
+// the properties mv.Super attaches to frame 0 of a super clip (MVSuper.c:111-120)
+void setSuperProps(const VSAPI *vsapi, VSFrame *dst, const mvb200_super_params &sp) {
+    VSMap *props = vsapi->getFramePropertiesRW(dst);
+    vsapi->mapSetInt(props, "Super_height", sp.height, maReplace);
+    vsapi->mapSetInt(props, "Super_hpad", sp.hpad, maReplace);
+    vsapi->mapSetInt(props, "Super_vpad", sp.vpad, maReplace);
+    vsapi->mapSetInt(props, "Super_pel", sp.pel, maReplace);
+    vsapi->mapSetInt(props, "Super_modeyuv", sp.modeyuv, maReplace);
+    vsapi->mapSetInt(props, "Super_levels", sp.levels, maReplace);
+}
+
 const VSFrame *VS_CC superGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
     SuperData *d = (SuperData *)instanceData;
     if (activationReason == arInitial) {
@@ -328,15 +353,8 @@ const VSFrame *VS_CC superGetFrame(int n, int activationReason, void *instanceDa
             vsapi->freeFrame(dst);
             return nullptr;
         }
-        if (n == 0) { // MVSuper.c:111-120
-            VSMap *props = vsapi->getFramePropertiesRW(dst);
-            vsapi->mapSetInt(props, "Super_height", d->sp.height, maReplace);
-            vsapi->mapSetInt(props, "Super_hpad", d->sp.hpad, maReplace);
-            vsapi->mapSetInt(props, "Super_vpad", d->sp.vpad, maReplace);
-            vsapi->mapSetInt(props, "Super_pel", d->sp.pel, maReplace);
-            vsapi->mapSetInt(props, "Super_modeyuv", d->sp.modeyuv, maReplace);
-            vsapi->mapSetInt(props, "Super_levels", d->sp.levels, maReplace);
-        }
+        if (n == 0) // MVSuper.c:111-120
+            setSuperProps(vsapi, dst, d->sp);
         return dst;
     }
     return nullptr;
@@ -1472,15 +1490,81 @@ void VS_CC finestCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const
     vsapi->createVideoFilter(out, "Finest", &data->vi, finestGetFrame, finestFree, fmParallel, deps, 1, data, core);
 }
 
+// ------------------------------------------------- the canonical chain (fused paths of the per-pixel consumers)
+// True when `super` is this plugin's mv.Super of `clip` (no pelclip; chroma planes present unless the clip is gray) and
+// every vector clip is this plugin's mv.Analyse of that super clip with a relative delta, no field handling and no
+// divide: the chain one *_clip_host engine call runs from SOURCE frames.  *spOut / ap[i]: the nodes' own parameters.
+bool canonicalChain(VSNode *clip, VSNode *super, VSNode *const *vectors, int nvec, const mvb200_super_params &sp, int numFrames, mvb200_super_params *spOut, mvb200_analyse_params *ap) {
+    std::lock_guard<std::mutex> lock(g_registry_mutex);
+    const auto su = g_registry.find(super);
+    if (su == g_registry.end() || su->second.kind != kNodeSuper)
+        return false;
+    const SuperData *S = (const SuperData *)su->second.data;
+    if (S->node != clip || S->usePelClip || S->sp.width != sp.width || S->sp.height != sp.height || S->sp.bits != sp.bits || S->sp.pel != sp.pel || S->sp.hpad != sp.hpad || S->sp.vpad != sp.vpad || S->sp.levels != sp.levels ||
+        S->sp.modeyuv != sp.modeyuv || !((S->sp.modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) || sp.gray))
+        return false;
+    for (int i = 0; i < nvec; i++) {
+        const auto an = g_registry.find(vectors[i]);
+        if (an == g_registry.end() || an->second.kind != kNodeAnalyse)
+            return false;
+        const AnalyseData *A = (const AnalyseData *)an->second.data;
+        if (A->node != super || A->ap.fields || A->ap.divide || A->ap.ad.nDeltaFrame <= 0 || A->ap.num_frames != numFrames)
+            return false;
+        ap[i] = A->ap;
+    }
+    *spOut = S->sp;
+    return true;
+}
+
+// A fused frame that the reference would have made from a SUPER frame carries that frame's properties: those of source
+// frame `from` (read here; requested by fusedGetFrame as alsoFrame / propFrame) plus Super_* when it is frame 0.
+void superFrameProps(const VSAPI *vsapi, const VSFrame *out, VSNode *clip, int from, const mvb200_super_params &sp, VSFrameContext *frameCtx) {
+    VSFrame *w = const_cast<VSFrame *>(out); // (just created by fusedGetFrame, not shared yet)
+    const VSFrame *ref = vsapi->getFrameFilter(from, clip, frameCtx);
+    VSMap *props = vsapi->getFramePropertiesRW(w);
+    vsapi->clearMap(props);
+    vsapi->copyMap(vsapi->getFramePropertiesRO(ref), props);
+    vsapi->freeFrame(ref);
+    if (from == 0)
+        setSuperProps(vsapi, w, sp);
+}
+
 // ------------------------------------------------------------------- Flow
 // mvflowCreate / GetFrame, MVFlow.cpp:157-593.  The reference reads an mv.Finest clip made from `super`; the engine reads
 // the pel sub-planes of the super frame itself (same samples), so this filter requests super frames.
+// Fused path (see fusedGetFrame): a window of B frames is one mvb200_flow_clip_host call over source frames.
+struct FlowFused : FusedCache {
+    mvb200_analyse_params ap;
+};
+
 struct FlowData {
     VSNode *clip, *super, *vectors;
     const VSVideoInfo *vi, *supervi;
     mvb200_super_params sp;
     mvb200_flow_params fp;
+    FlowFused *fused; // owned; null = node-by-node evaluation
 };
+
+const VSFrame *VS_CC flowFusedGetFrame(int n, int activationReason, void *instanceData, void **frameData, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    FlowData *d = (FlowData *)instanceData;
+    FlowFused *f = d->fused;
+    const int off = d->fp.vd.nDeltaFrame, N = d->vi->numFrames;
+    const int nref = d->fp.vd.isBackward ? n + off : n - off;
+    const bool haveRef = nref >= 0 && nref < N;
+    auto segment = [&](int w0, int w1, int *s0, int *s1) {
+        *s0 = w0 - off > 0 ? w0 - off : 0;
+        *s1 = w1 + off < N ? w1 + off : N;
+    };
+    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst) {
+        f->runFlags.assign((size_t)(w1 - w0), 0);
+        return mvb200_flow_clip_host(ctx, &d->sp, &f->ap, &d->fp, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst, f->runFlags.data());
+    };
+    int32_t usable = 0;
+    const VSFrame *out = fusedGetFrame("Flow", f, d->clip, d->vi, n, n, 7u, activationReason, frameData, frameCtx, core, vsapi, segment, run, haveRef ? nref : -1, &usable);
+    if (out && usable && haveRef) // the reference builds a compensated frame on the reference frame's Finest frame (MVFlow.cpp:196-204)
+        superFrameProps(vsapi, out, d->clip, nref, d->sp, frameCtx);
+    return out;
+}
 
 const VSFrame *VS_CC flowGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
     FlowData *d = (FlowData *)instanceData;
@@ -1552,6 +1636,7 @@ void VS_CC flowFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
     vsapi->freeNode(d->clip);
     vsapi->freeNode(d->super);
     vsapi->freeNode(d->vectors);
+    delete d->fused;
     delete d;
 }
 
@@ -1611,19 +1696,60 @@ void VS_CC flowCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const V
         freeAll();
         return;
     }
+    const int window = lookaheadFromEnv();
+    mvb200_super_params ssp;
+    mvb200_analyse_params sap;
+    if (window && !d.fp.fields && canonicalChain(d.clip, d.super, &d.vectors, 1, d.sp, d.vi->numFrames, &ssp, &sap)) {
+        d.fused = new FlowFused;
+        d.fused->ap = sap;
+        d.sp = ssp;
+        mvb200_clip_layout(&d.sp, &d.fused->cl);
+        d.fused->window = window;
+    }
     FlowData *data = new FlowData(d);
+    if (data->fused) { // only the source clip is read on this path
+        VSFilterDependency fdeps[1] = {{data->clip, rpGeneral}};
+        vsapi->createVideoFilter(out, "Flow", data->vi, flowFusedGetFrame, flowFree, fmParallel, fdeps, 1, data, core);
+        return;
+    }
     VSFilterDependency deps[3] = {{data->clip, rpStrictSpatial}, {data->super, rpGeneral}, {data->vectors, rpStrictSpatial}};
     vsapi->createVideoFilter(out, "Flow", data->vi, flowGetFrame, flowFree, fmParallel, deps, 3, data, core);
 }
 
 // -------------------------------------------------------------- FlowInter
 // mvflowinterCreate / GetFrame, MVFlowInter.c:83-713 (super frames are read where the reference reads its mv.Finest clip)
+// Fused path (see fusedGetFrame): a window of B frames is one mvb200_flowinter_clip_host call over source frames (the
+// window, delta frames before it and 2 x delta after it for the "extra" vectors).
+struct FlowInterFused : FusedCache {
+    mvb200_analyse_params apBw, apFw;
+};
+
 struct FlowInterData {
     VSNode *node, *super, *mvbw, *mvfw;
     const VSVideoInfo *vi, *supervi;
     mvb200_super_params sp, clipsp;
     mvb200_flowinter_params p;
+    FlowInterFused *fused; // owned; null = node-by-node evaluation
 };
+
+const VSFrame *VS_CC flowInterFusedGetFrame(int n, int activationReason, void *instanceData, void **frameData, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    FlowInterData *d = (FlowInterData *)instanceData;
+    FlowInterFused *f = d->fused;
+    const int off = d->p.vd.nDeltaFrame, N = d->vi->numFrames;
+    auto segment = [&](int w0, int w1, int *s0, int *s1) {
+        *s0 = w0 - off > 0 ? w0 - off : 0;
+        *s1 = w1 + 2 * off < N ? w1 + 2 * off : N;
+    };
+    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst) {
+        f->runFlags.assign((size_t)(w1 - w0), 0);
+        return mvb200_flowinter_clip_host(ctx, &d->sp, &f->apBw, &f->apFw, &d->p, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst, f->runFlags.data());
+    };
+    int32_t usable = 0;
+    const VSFrame *out = fusedGetFrame("FlowInter", f, d->node, d->vi, n, n, 7u, activationReason, frameData, frameCtx, core, vsapi, segment, run, -1, &usable);
+    if (out && usable && n == 0) // an interpolated frame is built on super frame n (MVFlowInter.c:131): Super_* on frame 0
+        setSuperProps(vsapi, const_cast<VSFrame *>(out), d->sp);
+    return out;
+}
 
 const uint8_t *vectorsOf(const VSAPI *vsapi, const VSFrame *f, bool *missing) {
     int e = 0;
@@ -1725,6 +1851,7 @@ void VS_CC flowInterFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
     vsapi->freeNode(d->super);
     vsapi->freeNode(d->mvbw);
     vsapi->freeNode(d->mvfw);
+    delete d->fused;
     delete d;
 }
 
@@ -1788,9 +1915,24 @@ void VS_CC flowInterCreate(const VSMap *in, VSMap *out, void *, VSCore *core, co
     // the source clip described as the engine describes clips (for the blend of unusable frames)
     memset(&d.clipsp, 0, sizeof(d.clipsp));
     d.clipsp = d.sp;
+    const int window = lookaheadFromEnv();
+    mvb200_super_params ssp;
+    mvb200_analyse_params sap[2];
+    VSNode *vecs[2] = {d.mvbw, d.mvfw};
+    if (window && canonicalChain(d.node, d.super, vecs, 2, d.sp, d.vi->numFrames, &ssp, sap)) {
+        d.fused = new FlowInterFused;
+        d.fused->apBw = sap[0];
+        d.fused->apFw = sap[1];
+        d.sp = ssp;
+        mvb200_clip_layout(&d.sp, &d.fused->cl);
+        d.fused->window = window;
+    }
     FlowInterData *data = new FlowInterData(d);
     VSFilterDependency deps[4] = {{data->node, rpGeneral}, {data->super, rpGeneral}, {data->mvbw, rpGeneral}, {data->mvfw, rpGeneral}};
-    vsapi->createVideoFilter(out, "FlowInter", data->vi, flowInterGetFrame, flowInterFree, fmParallel, deps, 4, data, core);
+    if (data->fused) // only the source clip is read on this path
+        vsapi->createVideoFilter(out, "FlowInter", data->vi, flowInterFusedGetFrame, flowInterFree, fmParallel, deps, 1, data, core);
+    else
+        vsapi->createVideoFilter(out, "FlowInter", data->vi, flowInterGetFrame, flowInterFree, fmParallel, deps, 4, data, core);
 }
 
 // ---------------------------------------------------------------- FlowFPS
@@ -2062,12 +2204,33 @@ void VS_CC flowFpsCreate(const VSMap *in, VSMap *out, void *, VSCore *core, cons
 
 // --------------------------------------------------------------- FlowBlur
 // mvflowblurCreate / GetFrame, MVFlowBlur.c:144-567
+// Fused path (see fusedGetFrame): a window of B frames is one mvb200_flowblur_clip_host call over source frames.
+// (Frame 0 is never blurred -- it has no frame before it -- so no output ever carries super frame 0's Super_* properties.)
+struct FlowBlurFused : FusedCache {
+    mvb200_analyse_params apBw, apFw;
+};
+
 struct FlowBlurData {
     VSNode *node, *super, *mvbw, *mvfw;
     const VSVideoInfo *vi, *supervi;
     mvb200_super_params sp;
     mvb200_flowblur_params p;
+    FlowBlurFused *fused; // owned; null = node-by-node evaluation
 };
+
+const VSFrame *VS_CC flowBlurFusedGetFrame(int n, int activationReason, void *instanceData, void **frameData, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    FlowBlurData *d = (FlowBlurData *)instanceData;
+    FlowBlurFused *f = d->fused;
+    const int off = d->p.vd.nDeltaFrame, N = d->vi->numFrames;
+    auto segment = [&](int w0, int w1, int *s0, int *s1) {
+        *s0 = w0 - off > 0 ? w0 - off : 0;
+        *s1 = w1 + off < N ? w1 + off : N;
+    };
+    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst) {
+        return mvb200_flowblur_clip_host(ctx, &d->sp, &f->apBw, &f->apFw, &d->p, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst);
+    };
+    return fusedGetFrame("FlowBlur", f, d->node, d->vi, n, n, 7u, activationReason, frameData, frameCtx, core, vsapi, segment, run);
+}
 
 const VSFrame *VS_CC flowBlurGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
     FlowBlurData *d = (FlowBlurData *)instanceData;
@@ -2131,6 +2294,7 @@ void VS_CC flowBlurFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
     vsapi->freeNode(d->super);
     vsapi->freeNode(d->mvbw);
     vsapi->freeNode(d->mvfw);
+    delete d->fused;
     delete d;
 }
 
@@ -2190,7 +2354,24 @@ void VS_CC flowBlurCreate(const VSMap *in, VSMap *out, void *, VSCore *core, con
         freeAll();
         return;
     }
+    const int window = lookaheadFromEnv();
+    mvb200_super_params ssp;
+    mvb200_analyse_params sap[2];
+    VSNode *vecs[2] = {d.mvbw, d.mvfw};
+    if (window && canonicalChain(d.node, d.super, vecs, 2, d.sp, d.vi->numFrames, &ssp, sap)) {
+        d.fused = new FlowBlurFused;
+        d.fused->apBw = sap[0];
+        d.fused->apFw = sap[1];
+        d.sp = ssp;
+        mvb200_clip_layout(&d.sp, &d.fused->cl);
+        d.fused->window = window;
+    }
     FlowBlurData *data = new FlowBlurData(d);
+    if (data->fused) { // only the source clip is read on this path
+        VSFilterDependency fdeps[1] = {{data->node, rpGeneral}};
+        vsapi->createVideoFilter(out, "FlowBlur", data->vi, flowBlurFusedGetFrame, flowBlurFree, fmParallel, fdeps, 1, data, core);
+        return;
+    }
     VSFilterDependency deps[4] = {{data->node, rpStrictSpatial}, {data->super, rpStrictSpatial}, {data->mvbw, rpGeneral}, {data->mvfw, rpGeneral}};
     vsapi->createVideoFilter(out, "FlowBlur", data->vi, flowBlurGetFrame, flowBlurFree, fmParallel, deps, 4, data, core);
 }
