@@ -59,7 +59,7 @@ def test_flow_clip_host_matches_goldens(gpu_ctx, case):
             if pipeline.nref_of(aps[v], n, N) is None:
                 assert usable[n] == 0, "variant %d frame %d has no reference frame" % (i, n)
             if not usable[n]:
-                assert np.array_equal(out[n], host[n])
+                assert all(np.array_equal(a, b) for a, b in zip(_planes(out[n], cl), _planes(host[n], cl)))  # (pitch padding is not compared)
         d = fp.vd.nDeltaFrame
         n0, n1 = 2, min(4, N)
         s0, s1 = max(0, n0 - d), min(N, n1 + d)
