@@ -676,6 +676,33 @@ void VS_CC analyseCreate(const VSMap *in, VSMap *out, void *, VSCore *core, cons
     data->self = registerSelf(vsapi, out, kNodeAnalyse, data);
 }
 
+// ------------------------------------------------- the canonical chain (recognised by the fused paths)
+// True when `super` is this plugin's mv.Super of `clip` (no pelclip) and every vector clip is this plugin's mv.Analyse of
+// that super clip with a relative delta and no field handling: the chain one *_clip_host engine call runs from SOURCE
+// frames.  perPixel (the Flow* consumers): also chroma planes in the super clip unless the clip is gray, and no divide.
+// *spOut / ap[i]: the nodes' own parameters (the Super's own sharp / rfilter: the frame properties do not carry them).
+bool canonicalChain(VSNode *clip, VSNode *super, VSNode *const *vectors, int nvec, const mvb200_super_params &sp, int numFrames, bool perPixel, mvb200_super_params *spOut, mvb200_analyse_params *ap) {
+    std::lock_guard<std::mutex> lock(g_registry_mutex);
+    const auto su = g_registry.find(super);
+    if (su == g_registry.end() || su->second.kind != kNodeSuper)
+        return false;
+    const SuperData *S = (const SuperData *)su->second.data;
+    if (S->node != clip || S->usePelClip || S->sp.width != sp.width || S->sp.height != sp.height || S->sp.bits != sp.bits || S->sp.pel != sp.pel || S->sp.hpad != sp.hpad || S->sp.vpad != sp.vpad || S->sp.levels != sp.levels ||
+        S->sp.modeyuv != sp.modeyuv || (perPixel && !((S->sp.modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) || sp.gray)))
+        return false;
+    for (int i = 0; i < nvec; i++) {
+        const auto an = g_registry.find(vectors[i]);
+        if (an == g_registry.end() || an->second.kind != kNodeAnalyse)
+            return false;
+        const AnalyseData *A = (const AnalyseData *)an->second.data;
+        if (A->node != super || A->ap.fields || (perPixel && A->ap.divide) || A->ap.ad.nDeltaFrame <= 0 || A->ap.num_frames != numFrames)
+            return false;
+        ap[i] = A->ap;
+    }
+    *spOut = S->sp;
+    return true;
+}
+
 // ---------------------------------------------------------------- Degrain
 // Fused path (see fusedGetFrame): ONE mvb200_degrain_clip_host_async call per window -- H2D of 3 MB source frames, Super,
 // 2r searches of B chains each, DegrainN, D2H -- instead of 1 + 2r + 1 per-frame calls that move 17.9 MB super frames
@@ -867,26 +894,13 @@ void VS_CC degrainCreate(const VSMap *in, VSMap *out, void *userData, VSCore *co
     // the fused path: every input is one of this plugin's own nodes, wired as in the canonical script
     const int window = lookaheadFromEnv();
     if (window) {
-        std::lock_guard<std::mutex> lock(g_registry_mutex);
-        auto su = g_registry.find(d.super);
-        bool ok = su != g_registry.end() && su->second.kind == kNodeSuper;
-        const SuperData *S = ok ? (const SuperData *)su->second.data : nullptr;
-        ok = ok && S->node == d.node && !S->usePelClip && S->sp.width == d.sp.width && S->sp.height == d.sp.height && S->sp.bits == d.sp.bits && S->sp.pel == d.sp.pel && S->sp.hpad == d.sp.hpad &&
-             S->sp.vpad == d.sp.vpad && S->sp.levels == d.sp.levels && S->sp.modeyuv == d.sp.modeyuv;
-        DegrainFused *f = ok ? new DegrainFused : nullptr;
-        int halo = 0;
-        for (int r = 0; ok && r < 2 * radius; r++) {
-            auto an = g_registry.find(d.vectors[r]);
-            ok = an != g_registry.end() && an->second.kind == kNodeAnalyse;
-            const AnalyseData *A = ok ? (const AnalyseData *)an->second.data : nullptr;
-            ok = ok && A->node == d.super && !A->ap.fields && A->ap.ad.nDeltaFrame > 0 && A->ap.num_frames == d.vi->numFrames;
-            if (ok) {
-                f->ap[r] = A->ap;
-                halo = A->ap.ad.nDeltaFrame > halo ? A->ap.ad.nDeltaFrame : halo;
-            }
-        }
-        if (ok) {
-            d.sp = S->sp; // (with the Super's own sharp / rfilter: the frame properties do not carry them)
+        DegrainFused *f = new DegrainFused;
+        mvb200_super_params ssp;
+        if (canonicalChain(d.node, d.super, d.vectors, 2 * radius, d.sp, d.vi->numFrames, false, &ssp, f->ap)) {
+            int halo = 0;
+            for (int r = 0; r < 2 * radius; r++)
+                halo = f->ap[r].ad.nDeltaFrame > halo ? f->ap[r].ad.nDeltaFrame : halo;
+            d.sp = ssp;
             mvb200_clip_layout(&d.sp, &f->cl);
             f->window = window;
             f->halo = halo;
@@ -1197,24 +1211,15 @@ void VS_CC compCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const V
         return;
     }
     const int window = lookaheadFromEnv();
-    if (window) { // the fused path: every input is one of this plugin's own nodes, wired as in the canonical script
-        std::lock_guard<std::mutex> lock(g_registry_mutex);
-        auto su = g_registry.find(d.super), an = g_registry.find(d.vectors);
-        if (su != g_registry.end() && su->second.kind == kNodeSuper && an != g_registry.end() && an->second.kind == kNodeAnalyse) {
-            const SuperData *S = (const SuperData *)su->second.data;
-            const AnalyseData *A = (const AnalyseData *)an->second.data;
-            const bool ok = S->node == d.node && !S->usePelClip && S->sp.width == d.sp.width && S->sp.height == d.sp.height && S->sp.bits == d.sp.bits && S->sp.pel == d.sp.pel && S->sp.hpad == d.sp.hpad &&
-                            S->sp.vpad == d.sp.vpad && S->sp.levels == d.sp.levels && S->sp.modeyuv == d.sp.modeyuv && A->node == d.super && !A->ap.fields && !d.cp.fields && A->ap.ad.nDeltaFrame > 0 &&
-                            A->ap.num_frames == d.vi->numFrames;
-            if (ok) {
-                d.fused = new CompFused;
-                d.fused->ap = A->ap;
-                d.sp = S->sp;
-                mvb200_clip_layout(&d.sp, &d.fused->cl);
-                d.fused->window = window;
-                d.fused->halo = A->ap.ad.nDeltaFrame;
-            }
-        }
+    mvb200_super_params ssp;
+    mvb200_analyse_params sap;
+    if (window && !d.cp.fields && canonicalChain(d.node, d.super, &d.vectors, 1, d.sp, d.vi->numFrames, false, &ssp, &sap)) { // the fused path
+        d.fused = new CompFused;
+        d.fused->ap = sap;
+        d.sp = ssp;
+        mvb200_clip_layout(&d.sp, &d.fused->cl);
+        d.fused->window = window;
+        d.fused->halo = sap.ad.nDeltaFrame;
     }
     CompData *data = new CompData(d);
     if (data->fused) { // only the source clip is read on this path
@@ -1490,32 +1495,7 @@ void VS_CC finestCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const
     vsapi->createVideoFilter(out, "Finest", &data->vi, finestGetFrame, finestFree, fmParallel, deps, 1, data, core);
 }
 
-// ------------------------------------------------- the canonical chain (fused paths of the per-pixel consumers)
-// True when `super` is this plugin's mv.Super of `clip` (no pelclip; chroma planes present unless the clip is gray) and
-// every vector clip is this plugin's mv.Analyse of that super clip with a relative delta, no field handling and no
-// divide: the chain one *_clip_host engine call runs from SOURCE frames.  *spOut / ap[i]: the nodes' own parameters.
-bool canonicalChain(VSNode *clip, VSNode *super, VSNode *const *vectors, int nvec, const mvb200_super_params &sp, int numFrames, mvb200_super_params *spOut, mvb200_analyse_params *ap) {
-    std::lock_guard<std::mutex> lock(g_registry_mutex);
-    const auto su = g_registry.find(super);
-    if (su == g_registry.end() || su->second.kind != kNodeSuper)
-        return false;
-    const SuperData *S = (const SuperData *)su->second.data;
-    if (S->node != clip || S->usePelClip || S->sp.width != sp.width || S->sp.height != sp.height || S->sp.bits != sp.bits || S->sp.pel != sp.pel || S->sp.hpad != sp.hpad || S->sp.vpad != sp.vpad || S->sp.levels != sp.levels ||
-        S->sp.modeyuv != sp.modeyuv || !((S->sp.modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) || sp.gray))
-        return false;
-    for (int i = 0; i < nvec; i++) {
-        const auto an = g_registry.find(vectors[i]);
-        if (an == g_registry.end() || an->second.kind != kNodeAnalyse)
-            return false;
-        const AnalyseData *A = (const AnalyseData *)an->second.data;
-        if (A->node != super || A->ap.fields || A->ap.divide || A->ap.ad.nDeltaFrame <= 0 || A->ap.num_frames != numFrames)
-            return false;
-        ap[i] = A->ap;
-    }
-    *spOut = S->sp;
-    return true;
-}
-
+// ------------------------------------------------- fused paths of the per-pixel consumers
 // A fused frame that the reference would have made from a SUPER frame carries that frame's properties: those of source
 // frame `from` (read here; requested by fusedGetFrame as alsoFrame / propFrame) plus Super_* when it is frame 0.
 void superFrameProps(const VSAPI *vsapi, const VSFrame *out, VSNode *clip, int from, const mvb200_super_params &sp, VSFrameContext *frameCtx) {
@@ -1699,7 +1679,7 @@ void VS_CC flowCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const V
     const int window = lookaheadFromEnv();
     mvb200_super_params ssp;
     mvb200_analyse_params sap;
-    if (window && !d.fp.fields && canonicalChain(d.clip, d.super, &d.vectors, 1, d.sp, d.vi->numFrames, &ssp, &sap)) {
+    if (window && !d.fp.fields && canonicalChain(d.clip, d.super, &d.vectors, 1, d.sp, d.vi->numFrames, true, &ssp, &sap)) {
         d.fused = new FlowFused;
         d.fused->ap = sap;
         d.sp = ssp;
@@ -1919,7 +1899,7 @@ void VS_CC flowInterCreate(const VSMap *in, VSMap *out, void *, VSCore *core, co
     mvb200_super_params ssp;
     mvb200_analyse_params sap[2];
     VSNode *vecs[2] = {d.mvbw, d.mvfw};
-    if (window && canonicalChain(d.node, d.super, vecs, 2, d.sp, d.vi->numFrames, &ssp, sap)) {
+    if (window && canonicalChain(d.node, d.super, vecs, 2, d.sp, d.vi->numFrames, true, &ssp, sap)) {
         d.fused = new FlowInterFused;
         d.fused->apBw = sap[0];
         d.fused->apFw = sap[1];
@@ -2154,25 +2134,16 @@ void VS_CC flowFpsCreate(const VSMap *in, VSMap *out, void *, VSCore *core, cons
     d.vi.fpsDen = d.p.fps_den;
     d.vi.numFrames = d.p.num_frames_out;
     const int window = lookaheadFromEnv();
-    if (window) { // the fused path: every input is one of this plugin's own nodes, wired as in the canonical script
-        std::lock_guard<std::mutex> lock(g_registry_mutex);
-        auto su = g_registry.find(d.super), bw = g_registry.find(d.mvbw), fw = g_registry.find(d.mvfw);
-        bool ok = su != g_registry.end() && su->second.kind == kNodeSuper && bw != g_registry.end() && bw->second.kind == kNodeAnalyse && fw != g_registry.end() && fw->second.kind == kNodeAnalyse;
-        if (ok) {
-            const SuperData *S = (const SuperData *)su->second.data;
-            const AnalyseData *B = (const AnalyseData *)bw->second.data, *F = (const AnalyseData *)fw->second.data;
-            ok = S->node == d.node && !S->usePelClip && S->sp.width == d.sp.width && S->sp.height == d.sp.height && S->sp.bits == d.sp.bits && S->sp.pel == d.sp.pel && S->sp.hpad == d.sp.hpad && S->sp.vpad == d.sp.vpad &&
-                 S->sp.levels == d.sp.levels && S->sp.modeyuv == d.sp.modeyuv && B->node == d.super && F->node == d.super && !B->ap.fields && !F->ap.fields && B->ap.ad.nDeltaFrame > 0 && !B->ap.divide && !F->ap.divide &&
-                 (S->sp.modeyuv & (MVB200_UPLANE | MVB200_VPLANE) || d.sp.gray);
-            if (ok) {
-                d.fused = new FlowFPSFused;
-                d.fused->apBw = B->ap;
-                d.fused->apFw = F->ap;
-                d.sp = S->sp;
-                mvb200_clip_layout(&d.sp, &d.fused->cl);
-                d.fused->window = window;
-            }
-        }
+    mvb200_super_params ssp;
+    mvb200_analyse_params sap[2];
+    VSNode *vecs[2] = {d.mvbw, d.mvfw};
+    if (window && canonicalChain(d.node, d.super, vecs, 2, d.sp, d.oldvi->numFrames, true, &ssp, sap)) { // the fused path
+        d.fused = new FlowFPSFused;
+        d.fused->apBw = sap[0];
+        d.fused->apFw = sap[1];
+        d.sp = ssp;
+        mvb200_clip_layout(&d.sp, &d.fused->cl);
+        d.fused->window = window;
     }
     FlowFPSData *data = new FlowFPSData(d);
     VSFilterDependency deps[4] = {{data->node, rpGeneral}, {data->super, rpGeneral}, {data->mvbw, rpGeneral}, {data->mvfw, rpGeneral}};
@@ -2358,7 +2329,7 @@ void VS_CC flowBlurCreate(const VSMap *in, VSMap *out, void *, VSCore *core, con
     mvb200_super_params ssp;
     mvb200_analyse_params sap[2];
     VSNode *vecs[2] = {d.mvbw, d.mvfw};
-    if (window && canonicalChain(d.node, d.super, vecs, 2, d.sp, d.vi->numFrames, &ssp, sap)) {
+    if (window && canonicalChain(d.node, d.super, vecs, 2, d.sp, d.vi->numFrames, true, &ssp, sap)) {
         d.fused = new FlowBlurFused;
         d.fused->apBw = sap[0];
         d.fused->apFw = sap[1];
