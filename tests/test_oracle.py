@@ -41,6 +41,34 @@ def test_oracle_matches_compiled_reference(have_ref, case):
     assert ref == {k: GOLD[case][k] for k in ref}, "committed goldens are stale: re-run tests/golden/make_golden.py"
 
 
+def test_reference_refine_overrun_is_confined(have_ref):
+    """A reference artefact the restatement does not reproduce: when the padded width of the super clip is a multiple of
+    the 64-byte stride alignment (no slack after a row), the reference's SIMD refine kernels write past the last row of
+    level 0's last pel plane (MVFrame.cpp:462-493) -- into the first bytes of level 1, the corner of its top-left padding.
+    Everything else of the super frame, and the vectors searched on it, are identical."""
+    if not have_ref:
+        pytest.skip("oracle/_ref/libmvtools_ref.so not built here (no /root/reference)")
+    import minivs
+    import oracle
+    import mvtools_b200 as mb
+    import clipgen
+    W, H, hpad = 160, 64, 16  # 160 + 2 * 16 = 192 = 3 * 64
+    frames = clipgen.make_clip(W, H, 3, bits=8)
+    core = minivs.Core()
+    mv = core.load(minivs.REF_PLUGIN)
+    sup = mv.Super(core.source(frames, bits=8), pel=2, hpad=hpad, vpad=16)
+    sp = mb.super_params(W, H, 8, 1, 1, pel=2, hpad=hpad, vpad=16)
+    level1_row0 = 4 * (H + 2 * 16)  # four pel planes of level 0 above it
+    for n in range(3):
+        ref, got = sup.get_frame(n).planes(), oracle.super_frame(sp, frames[n])
+        for p, (a, b) in enumerate(zip(ref, got)):
+            bad = np.argwhere(a != b)
+            if p == 0:
+                assert all(r == level1_row0 and c < 12 for r, c in bad.tolist()), bad[:4]
+            else:
+                assert bad.size == 0  # chroma planes: 96 bytes wide in a 128-byte stride
+
+
 def test_analysis_data_prop_matches_reference(built):
     """MVTools_MVAnalysisData (84 bytes) as derived by mvb200_analyse_init vs the reference's prop
     (the 12 never-initialised / host-specific bytes masked)."""

@@ -1,4 +1,6 @@
-"""GPU tests that have NOT run on a GPU yet: the fused clip calls of the per-pixel consumers (mvb200_flow_clip_host,
+"""GPU tests that have NOT run on a GPU yet: (1) the block shapes / penalty options of pipeline.LATE (64x32, 64x64, 128x64,
+128x128, 16x2, 16x8, 32x16 blocks, search 7, explicit lambda / pnew / plevel / pzero / pglobal / lsad / levels) through
+the per-frame entry points -- the oracle is pinned against the reference on them; (2) the fused clip calls of the per-pixel consumers (mvb200_flow_clip_host,
 mvb200_flowinter_clip_host, mvb200_flowblur_clip_host) and the plugin's fused paths built on them were written after
 round 1's GPU minutes were spent.  They are compositions of pieces that HAVE passed on a B200 (mvb200_super_batch,
 mvb200_analyse_multi_batch, mvb200_flow_batch / _flowinter_batch / _flowblur_batch -- the same composition as
@@ -21,7 +23,18 @@ pytestmark = pytest.mark.gpu
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "golden_flow.json")))
+GOLD_MAIN = json.load(open(os.path.join(HERE, "golden", "golden.json")))
 CASES = ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "noise_badblocks_blk8"]
+
+
+@pytest.mark.parametrize("case", sorted(pipeline.LATE))
+def test_cuda_matches_reference_goldens_late_cases(gpu_ctx, case):
+    """per-frame host-buffer entry points on the LATE cases: bit-exact against the reference's goldens"""
+    ctx = gpu_ctx
+    got = pipeline.run_engine(case, ctx.super_frame, ctx.analyse_frame, ctx.degrain_frame, ctx.recalculate_frame, ctx.compensate_frame)
+    for stage in ("super", "vectors", "degrain", "recalc", "compensate"):
+        if stage in got:
+            assert got[stage] == GOLD_MAIN[case][stage], "%s: CUDA %s differs from the reference" % (case, stage)
 
 
 def _host_clip(case):
