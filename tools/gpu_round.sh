@@ -43,5 +43,9 @@ echo "== ncu --set full: search kernel (one launch)"
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_search_tma -c 1 -f -o gpurun_out/${TAG}_prof_search \
     python tools/gpu_prof.py ${PROF_FRAMES:-296} > gpurun_out/${TAG}_prof_search.log 2>&1
 echo "search prof exit $?"
+echo "== ncu --set full: the per-pixel flow kernels (one launch each; DESIGN.md 4.5 expects them near the HBM roofline)"
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:'k_flow_fetch|k_flow_inter|k_flow_blur|k_blockfps|k_mask_plane|k_finest' -c 6 -f -o gpurun_out/${TAG}_prof_flow \
+    python tools/bench_flow.py --frames 16 --reps 1 > gpurun_out/${TAG}_prof_flow.log 2>&1
+echo "flow prof exit $?"
 find gpurun_out -size +40M -print -delete
 du -sh gpurun_out; ls -la gpurun_out | tail -25
