@@ -40,6 +40,14 @@ FLOW = {
     # overlapping memcpy then -- undefined behaviour; the oracle and the engine replicate the last covered row, which is
     # what the reference's row loop does for every other width)
     "divide2_blk16_esa_neg_badrange": dict(flow=[dict(thscd1=16000, thscd2=255), dict(mode=1, thscd1=16000, thscd2=255, vec=1, time=40.0)], scd=[dict(thscd1=16000, thscd2=255)]),
+    # pipeline.LATE cases (large and flat blocks): GPU tests in test_zz_gpu_pending.py
+    "blk64_420_ov32_r2": dict(mask=[dict(kind=0), dict(kind=1, time=40.0), dict(kind=2, vec=1, ml=60.0), dict(kind=5)], flow=[dict(time=70.0), dict(mode=1, vec=1)], scd=[dict()], finest=True,
+                              inter=[dict(), dict(time=30.0, ml=50.0, blend=0)], fps=[dict(num=50, den=1), dict(num=40, den=1, mask=1)], blur=[dict(blur=90.0)], bfps=[dict(num=50, den=1), dict(num=50, den=1, mode=4), dict(num=40, den=1, mode=7, ml=60.0)]),
+    "blk16x8_ov8x4_p10": dict(flow=[dict(), dict(mode=1, vec=1, time=35.0)], scd=[dict(vec=1)], finest=True, inter=[dict(time=60.0)], fps=[dict(num=60, den=1, mask=0)], blur=[dict()], bfps=[dict(num=60, den=1), dict(num=60, den=1, mode=2)]),
+    # (no flow / inter / fps with 128-wide blocks: the reference corrupts its heap there -- glibc aborts with "double free or
+    # corruption" -- whenever the vector field is narrower than 8 blocks, which its SIMD SimpleResize rows assume)
+    "blk128x64_gray_p8": dict(mask=[dict(kind=0), dict(kind=2, time=70.0), dict(kind=3), dict(kind=4, vec=1)], scd=[dict()], finest=True, blur=[dict(blur=60.0, prec=2)], bfps=[dict(num=45, den=1), dict(num=45, den=1, mode=6)]),
+    "blk64x32_ov_vertical_p8": dict(mask=[dict(kind=1), dict(kind=2, ml=80.0)], flow=[dict(), dict(mode=1, time=20.0, vec=1)], scd=[dict()], inter=[dict(time=45.0, ml=30.0)], fps=[dict(num=45, den=1)]),
     "p8_420_blk16_ov4_uncovered": dict(mask=[dict(kind=0), dict(kind=1, ml=30.0), dict(kind=2, vec=1), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=66.0)], scd=[dict()], finest=True, inter=[dict(), dict(time=10.0, ml=50.0)], fps=[dict(num=35, den=1, mask=2), dict(num=20, den=1, mask=0)], blur=[dict(blur=66.0)], bfps=[dict(num=35, den=1), dict(num=35, den=1, mode=1), dict(num=35, den=1, mode=5)]),
 }
 

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "golden_flow.json")))
 
 
-@pytest.mark.parametrize("case", sorted(pipeline_flow.FLOW))
+@pytest.mark.parametrize("case", sorted(c for c in pipeline_flow.FLOW if c not in pipeline.LATE))  # (LATE: test_zz_gpu_pending.py)
 def test_cuda_flow_matches_reference_goldens(gpu_ctx, case):
     ctx = gpu_ctx
     n0 = ctx.launch_count()

@@ -22,7 +22,7 @@ GOLD_MAIN = json.load(open(os.path.join(HERE, "golden", "golden.json")))
 GOLD_FLOW = GOLD
 
 
-@pytest.mark.parametrize("case", sorted(c for c in pipeline_flow.FLOW if pipeline_flow.FLOW[c].get("blur")))
+@pytest.mark.parametrize("case", sorted(c for c in pipeline_flow.FLOW if pipeline_flow.FLOW[c].get("blur") and c not in pipeline.LATE))
 def test_cuda_flowblur_matches_reference_goldens(gpu_ctx, case):
     """mv.FlowBlur: per-frame entry point and the device-resident batch entry point"""
     import torch
@@ -49,7 +49,7 @@ def test_cuda_flowblur_matches_reference_goldens(gpu_ctx, case):
         for n in range(N):
             assert [pipeline.sha(q) for q in _planes(out[n], cl)] == GOLD[case]["blur"][i][n], "blur variant %d frame %d" % (i, n)
 
-@pytest.mark.parametrize("case", sorted(c for c in pipeline_flow.FLOW if pipeline_flow.FLOW[c].get("bfps")))
+@pytest.mark.parametrize("case", sorted(c for c in pipeline_flow.FLOW if pipeline_flow.FLOW[c].get("bfps") and c not in pipeline.LATE))
 def test_cuda_blockfps_matches_reference_goldens(gpu_ctx, case):
     """mv.BlockFPS: every output frame of every variant (modes 0..8, with and without overlap)"""
     ctx = gpu_ctx

@@ -37,6 +37,20 @@ def test_cuda_matches_reference_goldens_late_cases(gpu_ctx, case):
             assert got[stage] == GOLD_MAIN[case][stage], "%s: CUDA %s differs from the reference" % (case, stage)
 
 
+@pytest.mark.parametrize("case", sorted(c for c in pipeline_flow.FLOW if c in pipeline.LATE))
+def test_cuda_flow_group_matches_reference_goldens_late_cases(gpu_ctx, case):
+    """the vector-clip consumers on the LATE cases (64x64, 64x32, 16x8, 128x64 blocks): per-frame entry points against the
+    reference's goldens (the kernels' per-thread code already reproduces them in the CPU emulation, test_flow_emul.py)"""
+    ctx = gpu_ctx
+    got = pipeline_flow.run_engine_flow(case, ctx.scdetection_frame, ctx.mask_frame, ctx.finest_frame, ctx.flow_frame)
+    got["inter"] = pipeline_flow.run_engine_inter(case, ctx.flowinter_frame, ctx.blend_frame)
+    got["fps"] = pipeline_flow.run_engine_fps(case, ctx.flowinter_frame, ctx.blend_frame)
+    got["blur"] = pipeline_flow.run_engine_blur(case, ctx.flowblur_frame)
+    got["bfps"] = pipeline_flow.run_engine_bfps(case, ctx.blockfps_frame, ctx.blend_frame)
+    for stage in ("scd", "mask", "flow", "finest", "inter", "fps", "blur", "bfps"):
+        assert got[stage] == GOLD[case][stage], "%s: CUDA %s differs from the reference's golden hashes" % (case, stage)
+
+
 def _host_clip(case):
     frames = pipeline.make_frames(pipeline.CASES[case][0])
     sp, aps, P = pipeline_flow.flow_params_for(case)
