@@ -576,9 +576,10 @@ MVB200_API int mvb200_blockfps_frame(mvb200_ctx *ctx, const mvb200_blockfps_para
  * frames after and delta before them, clipped to the clip: the caller computes it with mvb200_flowfps_position);
  * frames [out_first, out_first + out_count) of the OUTPUT clip are written to host_dst.  ap_bw / ap_fw: the two
  * mv.Analyse instances (their num_frames is replaced by n internally).  Unusable frames are blended / copied from the
- * source frames as the filter does.  Synchronous. */
+ * source frames as the filter does; usable_out (may be NULL): 1 = the frame was interpolated from the vectors (the
+ * reference's frame then carries the LEFT super frame's properties), 0 = an input frame, a blend or a copy.  Synchronous. */
 MVB200_API int mvb200_flowfps_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowfps_params *p, const void *host_src, int src_first,
-                                        int n, int out_first, int out_count, void *host_dst);
+                                        int n, int out_first, int out_count, void *host_dst, int32_t *usable_out);
 
 /* mv.Super -> mv.Analyse -> mv.Compensate for output frames [out_first, out_first + out_count) in one call, on HOST
  * buffers in the clip layout (the plugin's fused path).  host_src holds the n source frames [src_first, src_first + n):
@@ -602,6 +603,15 @@ MVB200_API int mvb200_flowinter_clip_host(mvb200_ctx *ctx, const mvb200_super_pa
                                           int n, int out_first, int out_count, void *host_dst, int32_t *usable_out);
 MVB200_API int mvb200_flowblur_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowblur_params *p, const void *host_src, int src_first,
                                          int n, int out_first, int out_count, void *host_dst);
+
+/* The same for mv.BlockFPS (mvblockfpsGetFrame, MVBlockFPS.c:240-680, with the mvsuperGetFrame / mvanalyseGetFrame calls
+ * that feed it): output frames [out_first, out_first + out_count) of the rate-converted clip from the n source frames
+ * [src_first, src_first + n) -- every window frame's left and right source frames (mvb200_blockfps_position; no further
+ * halo: the two searches only look at each other's frame).  usable_out (may be NULL): 1 = interpolated from the vectors
+ * (the reference's frame then carries the LEFT super frame's properties), 0 = an input frame itself, or the blend /
+ * copy of the source frames the reference returns for poor estimations (:636-670). */
+MVB200_API int mvb200_blockfps_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_blockfps_params *p, const void *host_src, int src_first,
+                                         int n, int out_first, int out_count, void *host_dst, int32_t *usable_out);
 
 #ifdef __cplusplus
 }

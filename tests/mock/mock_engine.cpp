@@ -193,7 +193,9 @@ MVB200_API int mvb200_blockfps_frame(mvb200_ctx *, const mvb200_blockfps_params 
 // mvb200_flowfps_clip_host on host memory through the oracle, with the engine's conventions: the segment is the clip for
 // the two searches, output frames are placed by mvb200_flowfps_position
 MVB200_API int mvb200_flowfps_clip_host(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowfps_params *p, const void *host_src, int src_first, int n,
-                                        int out_first, int out_count, void *host_dst) {
+                                        int out_first, int out_count, void *host_dst, int32_t *usable_out) {
+    for (int k = 0; usable_out && k < out_count; k++)
+        usable_out[k] = 0;
     mvb200_frame_layout cl;
     mvb200_clip_layout(sp, &cl);
     mvb200_super_geom g;
@@ -284,6 +286,8 @@ MVB200_API int mvb200_flowfps_clip_host(mvb200_ctx *, const mvb200_super_params 
             if (fwd(mvo_flowinter_frame(&p->inter, sp, time256, sl, sstride, sr, sstride, vec[0][L].data(), vec[1][R].data(), extra ? vec[0][R].data() : nullptr, extra ? vec[1][L].data() : nullptr, d, dstr, &usable)))
                 return 1;
         }
+        if (usable_out)
+            usable_out[k] = usable;
         if (!usable) {
             if (p->inter.blend) {
                 if (fwd(mvo_blend_frame(sp, time256, ql, stl, qr, str_, d, dstr)))
@@ -516,6 +520,59 @@ MVB200_API int mvb200_flowblur_clip_host(mvb200_ctx *, const mvb200_super_params
         }
         if (!usable)
             S.copy_src(f, d, dstr);
+    }
+    return 0;
+}
+
+MVB200_API int mvb200_blockfps_clip_host(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_blockfps_params *p, const void *host_src, int src_first,
+                                         int n, int out_first, int out_count, void *host_dst, int32_t *usable_out) {
+    MockSegment S;
+    const mvb200_analyse_params *aps[2] = {ap_bw, ap_fw};
+    if (S.build(sp, aps, 2, host_src, n))
+        return 1;
+    const int off = p->vd.nDeltaFrame, N = p->num_frames_in;
+    auto in_seg = [&](int f) { return f >= src_first && f < src_first + n; };
+    for (int k = 0; k < out_count; k++) {
+        int32_t nleft, time256;
+        mvb200_blockfps_position(p, out_first + k, &nleft, &time256);
+        const int nright = nleft + off, fl = nleft < N - 1 ? nleft : N - 1, fr = nright < N - 1 ? nright : N - 1;
+        uint8_t *d[3];
+        ptrdiff_t dstr[3];
+        S.dst_planes(host_dst, k, d, dstr);
+        if (usable_out)
+            usable_out[k] = 0;
+        if (time256 == 0 || time256 == 256) {
+            const int f = time256 == 0 ? fl : fr;
+            if (!in_seg(f))
+                return mvb200::set_error("mock: source frame outside the segment");
+            S.copy_src(f - src_first, d, dstr);
+            continue;
+        }
+        if (!in_seg(fl) || !in_seg(fr))
+            return mvb200::set_error("mock: source frame outside the segment");
+        int32_t usable = 0;
+        if (nleft < N && nright < N) {
+            const int L = nleft - src_first, R = nright - src_first;
+            const uint8_t *sl[3], *sr[3];
+            S.sup_planes(L, sl);
+            S.sup_planes(R, sr);
+            if (fwd(mvo_blockfps_frame(p, sp, time256, sl, S.sstride, sr, S.sstride, S.vec[0][L].data(), S.vec[1][R].data(), d, dstr, &usable)))
+                return 1;
+        }
+        if (usable_out)
+            usable_out[k] = usable;
+        if (!usable) {
+            if (p->blend) {
+                const uint8_t *ql[3], *qr[3];
+                ptrdiff_t stl[3], str_[3];
+                S.src_planes(fl - src_first, ql, stl);
+                S.src_planes(fr - src_first, qr, str_);
+                if (fwd(mvo_blend_frame(sp, time256, ql, stl, qr, str_, d, dstr)))
+                    return 1;
+            } else {
+                S.copy_src(fl - src_first, d, dstr);
+            }
+        }
     }
     return 0;
 }

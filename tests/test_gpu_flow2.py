@@ -144,7 +144,7 @@ def test_flowfps_clip_host_matches_goldens(gpu_ctx, case):
     for i, p in enumerate(P["fps"]):
         M = p.num_frames_out
         out = np.zeros((M, cl.frame_bytes), dtype=np.uint8)
-        mb._check(L.mvb200_flowfps_clip_host(ctx.handle, C.byref(sp), C.byref(aps[0]), C.byref(aps[1]), C.byref(p), host.ctypes.data, 0, N, 0, M, out.ctypes.data))
+        mb._check(L.mvb200_flowfps_clip_host(ctx.handle, C.byref(sp), C.byref(aps[0]), C.byref(aps[1]), C.byref(p), host.ctypes.data, 0, N, 0, M, out.ctypes.data, None))
         for n in range(M):
             assert [pipeline.sha(q) for q in _planes(out[n], cl)] == GOLD[case]["fps"][i][n], "variant %d frame %d" % (i, n)
         # a window of three output frames from the middle, with the segment the plugin would pass
@@ -153,7 +153,7 @@ def test_flowfps_clip_host_matches_goldens(gpu_ctx, case):
         s0, s1 = max(0, lmin - off), min(N, lmax + 2 * off + 1)
         s0 = min(s0, N - 1)
         win = np.zeros((n1 - n0, cl.frame_bytes), dtype=np.uint8)
-        mb._check(L.mvb200_flowfps_clip_host(ctx.handle, C.byref(sp), C.byref(aps[0]), C.byref(aps[1]), C.byref(p), host[s0:].ctypes.data, s0, s1 - s0, n0, n1 - n0, win.ctypes.data))
+        mb._check(L.mvb200_flowfps_clip_host(ctx.handle, C.byref(sp), C.byref(aps[0]), C.byref(aps[1]), C.byref(p), host[s0:].ctypes.data, s0, s1 - s0, n0, n1 - n0, win.ctypes.data, None))
         for n in range(n0, n1):
             assert [pipeline.sha(q) for q in _planes(win[n - n0], cl)] == GOLD[case]["fps"][i][n], "variant %d window frame %d" % (i, n)
 

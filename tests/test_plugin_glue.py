@@ -103,11 +103,24 @@ def test_flowfps_fused_path_glue(mock_plugin, monkeypatch, case, window):
     vn = [mv.Analyse(sup, isb=isb, delta=1, **pipeline._fix(akw)) for isb in (1, 0)]
     nodes = [mv.FlowFPS(clip, sup, vn[0], vn[1], **{k: (float(x) if k == "ml" else x) for k, x in kw.items()}) for kw in pipeline_flow.FLOW[case]["fps"]]
     before = (sup.computed(), [v.computed() for v in vn])  # what the filters' creation read (frame 0 of every input)
+    # the node-by-node evaluation of the same script, for the frame properties (Super_* on frames built on super frame 0)
+    monkeypatch.delenv("MVB200_LOOKAHEAD")
+    core2 = minivs.Core()
+    mv2 = core2.load(mock_plugin)
+    clip2 = core2.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1))
+    sup2 = mv2.Super(clip2, **skw)
+    vn2 = [mv2.Analyse(sup2, isb=isb, delta=1, **pipeline._fix(akw)) for isb in (1, 0)]
+    plain = [mv2.FlowFPS(clip2, sup2, vn2[0], vn2[1], **{k: (float(x) if k == "ml" else x) for k, x in kw.items()}) for kw in pipeline_flow.FLOW[case]["fps"]]
     for i, node in enumerate(nodes):
         node.set_cache(0)
         M = node.num_frames
         for n in list(range(M)) + [M - 1, 0, M // 2]:
-            assert [pipeline.sha(p) for p in node.get_frame(n).planes()[:nplanes]] == GOLD_FLOW[case]["fps"][i][n], "variant %d frame %d" % (i, n)
+            fr = node.get_frame(n)
+            assert [pipeline.sha(p) for p in fr.planes()[:nplanes]] == GOLD_FLOW[case]["fps"][i][n], "variant %d frame %d" % (i, n)
+            if n < 3:
+                rf = plain[i].get_frame(n)
+                for key in ("Super_pel", "Super_levels", "_DurationNum", "_DurationDen"):
+                    assert fr.prop_int(key) == rf.prop_int(key), "variant %d frame %d: property %s" % (i, n, key)
     assert (sup.computed(), [v.computed() for v in vn]) == before
 
 
@@ -184,6 +197,45 @@ def test_flow_consumers_fused_path_glue(mock_plugin, monkeypatch, case, window):
     # on the fused paths the Super and Analyse nodes are not asked for a single frame (mv.Flow with fields keeps the nodes)
     if not any(fields for _, _, fields, _ in fused[3]):
         assert (fused[1].computed(), [v.computed() for v in fused[2]]) == before
+
+
+@pytest.mark.parametrize("window", [2, 7])
+@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "gray_blk4_pel1_rf0", "noise_badblocks_blk8", "p8_420_blk16_ov4_uncovered", "blk64_420_ov32_r2"])
+def test_blockfps_fused_path_glue(mock_plugin, monkeypatch, case, window):
+    """MVB200_LOOKAHEAD: mv.BlockFPS fed by this plugin's own Super / Analyse nodes produces windows of OUTPUT frames with one
+    call of the engine's BlockFPS clip pipeline (mvb200_blockfps_clip_host): every variant of the goldens (modes 0..8,
+    rates, blend on / off, scene changes), in and out of order, with the node-by-node evaluation's frame properties"""
+    import minivs
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    nplanes = 1 if ck.get("gray") else 3
+    tags = [{"Tag": 100 + n} for n in range(len(frames))]
+
+    def build(fused):
+        if fused:
+            monkeypatch.setenv("MVB200_LOOKAHEAD", str(window))
+        else:
+            monkeypatch.delenv("MVB200_LOOKAHEAD", raising=False)
+        core = minivs.Core()
+        mv = core.load(mock_plugin)
+        clip = core.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1), props=tags)
+        sup = mv.Super(clip, **skw)
+        vn = [mv.Analyse(sup, isb=isb, delta=1, **pipeline._fix(akw)) for isb in (1, 0)]
+        nodes = [mv.BlockFPS(clip, sup, vn[0], vn[1], **{k: (float(x) if k == "ml" else x) for k, x in kw.items()}) for kw in pipeline_flow.FLOW[case]["bfps"]]
+        return core, sup, vn, nodes
+
+    plain = build(False)
+    fused = build(True)
+    before = (fused[1].computed(), [v.computed() for v in fused[2]])  # what the filters' creation read (frame 0 of every input)
+    for i, (node, ref) in enumerate(zip(fused[3], plain[3])):
+        node.set_cache(0)
+        M = node.num_frames
+        for n in list(range(M)) + [M - 1, 0, M // 2]:
+            fr, rf = node.get_frame(n), ref.get_frame(n)
+            assert [pipeline.sha(p) for p in fr.planes()[:nplanes]] == GOLD_FLOW[case]["bfps"][i][n], "variant %d frame %d" % (i, n)
+            for key in ("Tag", "Super_pel", "Super_levels", "_DurationNum", "_DurationDen"):
+                assert fr.prop_int(key) == rf.prop_int(key), "variant %d frame %d: property %s" % (i, n, key)
+    assert (fused[1].computed(), [v.computed() for v in fused[2]]) == before
 
 
 def test_lookahead_paths_under_concurrent_requests(mock_plugin, monkeypatch):

@@ -1,7 +1,7 @@
 """GPU tests that have NOT run on a GPU yet: (1) the block shapes / penalty options of pipeline.LATE (64x32, 64x64, 128x64,
 128x128, 16x2, 16x8, 32x16 blocks, search 7, explicit lambda / pnew / plevel / pzero / pglobal / lsad / levels) through
 the per-frame entry points -- the oracle is pinned against the reference on them; (2) the fused clip calls of the per-pixel consumers (mvb200_flow_clip_host,
-mvb200_flowinter_clip_host, mvb200_flowblur_clip_host) and the plugin's fused paths built on them were written after
+mvb200_flowinter_clip_host, mvb200_flowblur_clip_host, mvb200_blockfps_clip_host) and the plugin's fused paths built on them were written after
 round 1's GPU minutes were spent.  They are compositions of pieces that HAVE passed on a B200 (mvb200_super_batch,
 mvb200_analyse_multi_batch, mvb200_flow_batch / _flowinter_batch / _flowblur_batch -- the same composition as
 mvb200_flowfps_clip_host, test_gpu_flow2.py) and the plugin glue around them is tested on the CPU against a stand-in
@@ -132,6 +132,39 @@ def test_flowblur_clip_host_matches_goldens(gpu_ctx, case):
         win = np.zeros((n1 - n0, cl.frame_bytes), dtype=np.uint8)
         mb._check(L.mvb200_flowblur_clip_host(gpu_ctx.handle, C.byref(sp), C.byref(aps[0]), C.byref(aps[1]), C.byref(p), host[s0:].ctypes.data, s0, s1 - s0, n0, n1 - n0, win.ctypes.data))
         _check_frames(win, cl, GOLD[case]["blur"][i], n0, "variant %d window" % i)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_blockfps_clip_host_matches_goldens(gpu_ctx, case):
+    """mvb200_blockfps_clip_host (Super -> 2 x Analyse -> BlockFPS for a window of OUTPUT frames): the whole clip, and a
+    window from the middle with the segment the plugin passes (its frames' left and right source frames)"""
+    L = mb.lib()
+    host, sp, aps, P, cl = _host_clip(case)
+    N = host.shape[0]
+    for i, p in enumerate(P["bfps"]):
+        M = p.num_frames_out
+        out = np.zeros((M, cl.frame_bytes), dtype=np.uint8)
+        usable = (C.c_int32 * M)()
+        mb._check(L.mvb200_blockfps_clip_host(gpu_ctx.handle, C.byref(sp), C.byref(aps[0]), C.byref(aps[1]), C.byref(p), host.ctypes.data, 0, N, 0, M, out.ctypes.data, usable))
+        _check_frames(out, cl, GOLD[case]["bfps"][i], 0, "variant %d" % i)
+        for n in range(M):
+            nleft, time256 = mb.blockfps_position(p, n)
+            if time256 in (0, 256) or nleft + p.vd.nDeltaFrame >= N:
+                assert usable[n] == 0, "variant %d frame %d is an input frame / has no right frame" % (i, n)
+        n0, n1, off = M // 2, min(M // 2 + 3, M), p.vd.nDeltaFrame
+        lmin, lmax = mb.blockfps_position(p, n0)[0], mb.blockfps_position(p, n1 - 1)[0]
+        s0, s1 = min(lmin, N - 1), min(N, lmax + off + 1)
+        win = np.zeros((n1 - n0, cl.frame_bytes), dtype=np.uint8)
+        mb._check(L.mvb200_blockfps_clip_host(gpu_ctx.handle, C.byref(sp), C.byref(aps[0]), C.byref(aps[1]), C.byref(p), host[s0:].ctypes.data, s0, s1 - s0, n0, n1 - n0, win.ctypes.data, None))
+        _check_frames(win, cl, GOLD[case]["bfps"][i], n0, "variant %d window" % i)
+
+
+@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3"])
+def test_blockfps_script_through_plugin_with_lookahead(built, monkeypatch, case):
+    """MVB200_LOOKAHEAD=4: mv.BlockFPS on the plugin's own Super / Analyse nodes takes the fused path"""
+    monkeypatch.setenv("MVB200_LOOKAHEAD", "4")
+    got = pipeline_flow.run_reference_flow(case, plugin_path=mb.PLUGIN_PATH, only=("bfps",))
+    assert got["bfps"] == GOLD[case]["bfps"], "%s: plugin mv.BlockFPS (fused) differs from the reference plugin" % case
 
 
 @pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3"])

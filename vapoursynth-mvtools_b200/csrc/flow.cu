@@ -180,6 +180,18 @@ __global__ void k_blend(int W, int H, int time256, const uint8_t *__restrict__ s
     *((T *)(dst + o) + x) = (T)blend_sample(*((const T *)(src + o) + x), *((const T *)(ref + o) + x), time256);
 }
 
+// What the reference returns when the vectors are not usable (MVBlockFPS.c:636-670): the blend of the two source frames, or
+// the left one.  flags (may be null = unconditionally): two ints, both set = the frame was interpolated, leave it.
+template <typename T>
+__global__ void k_fallback(int W, int H, int time256, int blend, const uint8_t *__restrict__ src, const uint8_t *__restrict__ ref, uint8_t *__restrict__ dst, long long pitch, const int *__restrict__ flags) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= W || y >= H || (flags && flags[0] && flags[1]))
+        return;
+    const long long o = (long long)y * pitch;
+    const int a = *((const T *)(src + o) + x);
+    *((T *)(dst + o) + x) = (T)(blend ? blend_sample(a, *((const T *)(ref + o) + x), time256) : a);
+}
+
 // --------------------------------------------------------------- FlowBlur
 template <typename T>
 __global__ void k_flow_blur(BlurPlane P, const uint8_t *__restrict__ super_frame, uint8_t *__restrict__ dst, long long dst_pitch, const uint8_t *__restrict__ src, const int *__restrict__ flags) {
@@ -991,7 +1003,7 @@ int mvb200_blockfps_frame(mvb200_ctx *ctx, const mvb200_blockfps_params *p, cons
 }
 
 int mvb200_flowfps_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_flowfps_params *p, const void *host_src, int src_first, int n,
-                             int out_first, int out_count, void *host_dst) {
+                             int out_first, int out_count, void *host_dst, int32_t *usable_out) {
     const mvb200_flowinter_params *q = &p->inter;
     if (flowinter_check(q, sp))
         return 1;
@@ -1010,10 +1022,13 @@ int mvb200_flowfps_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, con
     aps[0].num_frames = aps[1].num_frames = n;
     const mvb200_analyse_params *app[2] = {&aps[0], &aps[1]};
     const int64_t vstride = ((int64_t)(aps[0].vectors_size > aps[1].vectors_size ? aps[0].vectors_size : aps[1].vectors_size) + 255) / 256 * 256;
-    uint8_t *buf = (uint8_t *)c->get_scratch(kSlotStage, (size_t)cd.frame_bytes * (n + out_count) + (size_t)sd.frame_bytes * n + (size_t)vstride * n * 2 + 256);
+    uint8_t *buf = (uint8_t *)c->get_scratch(kSlotStage, (size_t)cd.frame_bytes * (n + out_count) + (size_t)sd.frame_bytes * n + (size_t)vstride * n * 2 + align256(2 * sizeof(int) * (size_t)out_count) + 256);
     if (!buf)
         return 1;
     uint8_t *dsrc = buf, *ddst = dsrc + (size_t)cd.frame_bytes * n, *dsup = ddst + (size_t)cd.frame_bytes * out_count, *dbw = dsup + (size_t)sd.frame_bytes * n, *dfw = dbw + (size_t)vstride * n;
+    int *dflags = (int *)(dfw + (size_t)vstride * n); // two per output frame: both set = interpolated from the vectors
+    if (usable_out)
+        MVB_CUDA_CHECK(cudaMemsetAsync(dflags, 0, 2 * sizeof(int) * (size_t)out_count, c->stream));
     MVB_CUDA_CHECK(cudaMemcpyAsync(dsrc, host_src, (size_t)cd.frame_bytes * n, cudaMemcpyHostToDevice, c->stream));
     if (mvb200_super_batch(ctx, sp, dsrc, dsup, n))
         return 1;
@@ -1047,9 +1062,16 @@ int mvb200_flowfps_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, con
                              in_range ? dbw + (size_t)vstride * local(nleft) : nullptr, in_range ? dfw + (size_t)vstride * local(nright) : nullptr, extra ? dbw + (size_t)vstride * local(nright) : nullptr,
                              extra ? dfw + (size_t)vstride * local(nleft) : nullptr, dsrc + (size_t)cd.frame_bytes * local(fl), dsrc + (size_t)cd.frame_bytes * local(fr), dst, &flags))
             return 1;
+        if (usable_out) // (per-launch scratch: keep the pair before the next frame's launch reuses the slot)
+            MVB_CUDA_CHECK(cudaMemcpyAsync(dflags + 2 * k, flags, 2 * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
     }
+    std::vector<int> pairs(usable_out ? 2 * (size_t)out_count : 0);
+    if (usable_out)
+        MVB_CUDA_CHECK(cudaMemcpyAsync(pairs.data(), dflags, sizeof(int) * pairs.size(), cudaMemcpyDeviceToHost, c->stream));
     MVB_CUDA_CHECK(cudaMemcpyAsync(host_dst, ddst, (size_t)cd.frame_bytes * out_count, cudaMemcpyDeviceToHost, c->stream));
     MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int k = 0; usable_out && k < out_count; k++)
+        usable_out[k] = pairs[2 * k] && pairs[2 * k + 1];
     return 0;
 }
 
@@ -1062,7 +1084,9 @@ struct ChainBuffers {
     SuperDesc sd;
     ClipDesc cd;
 };
-static int chain_front(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const void *host_src, int src_first, int n, int out_first, int out_count, const char *filter, ChainBuffers *B) {
+// (out_buffers: output frames to make room for when they are not frames [out_first, out_first + out_count) of the source clip -- a rate conversion)
+static int chain_front(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const void *host_src, int src_first, int n, int out_first, int out_count, const char *filter, ChainBuffers *B,
+                       int out_buffers = -1) {
     if (sp->levels > kDevMaxLevels)
         return set_error("mvtools_b200: more than %d pyramid levels are not supported on the device", kDevMaxLevels);
     if (out_first < src_first || out_first + out_count > src_first + n)
@@ -1079,6 +1103,8 @@ static int chain_front(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb
         const int64_t v = ((int64_t)aps[i].vectors_size + 255) / 256 * 256;
         B->vstride = v > B->vstride ? v : B->vstride;
     }
+    if (out_buffers >= 0)
+        out_count = out_buffers;
     Ctx *c = &ctx->c;
     MVB_CUDA_CHECK(cudaSetDevice(c->device));
     make_super_desc(sp, &B->sd);
@@ -1157,6 +1183,75 @@ int mvb200_flowblur_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, co
     if (mvb200_flowblur_batch(ctx, &q, sp, B.dsrc, B.dsup, out_first - src_first, out_count, B.dvec[0], B.dvec[1], B.vstride, B.ddst))
         return 1;
     return chain_back(ctx, B, out_count, host_dst);
+}
+
+int mvb200_blockfps_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap_bw, const mvb200_analyse_params *ap_fw, const mvb200_blockfps_params *p, const void *host_src, int src_first, int n,
+                              int out_first, int out_count, void *host_dst, int32_t *usable_out) {
+    if (p->super_pel != sp->pel || p->super_hpad != sp->hpad || p->super_vpad != sp->vpad || p->bits != sp->bits)
+        return set_error("BlockFPS: the parameters were derived for another super clip");
+    if (n <= 0 || out_count <= 0)
+        return 0;
+    if (src_first < 0 || src_first + n > p->num_frames_in || out_first < 0 || out_first + out_count > p->num_frames_out)
+        return set_error("BlockFPS: the window is outside the clip");
+    ChainBuffers B;
+    const mvb200_analyse_params *ap[2] = {ap_bw, ap_fw};
+    // (chain_front's own window test compares output with source frame numbers; they are different clips here)
+    if (chain_front(ctx, sp, ap, 2, host_src, src_first, n, src_first, 0, "BlockFPS", &B, out_count))
+        return 1;
+    Ctx *c = &ctx->c;
+    const ClipDesc &cd = B.cd;
+    const int off = p->vd.nDeltaFrame, N = p->num_frames_in;
+    const int planes = (p->super_modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) ? 3 : 1; // the planes the reference writes (:652)
+    auto local = [&](int f) { return f - src_first; }; // position of source frame f in the segment
+    auto have = [&](int f) { return f >= src_first && f < src_first + n; };
+    for (int k = 0; k < out_count; k++) {
+        int32_t nleft, time256;
+        mvb200_blockfps_position(p, out_first + k, &nleft, &time256);
+        const int nright = nleft + off;
+        uint8_t *dst = B.ddst + (size_t)cd.frame_bytes * k;
+        const int fl = nleft < N - 1 ? nleft : N - 1, fr = nright < N - 1 ? nright : N - 1; // VSMIN(.., numFrames - 1), MVBlockFPS.c:246-272
+        if (time256 == 0 || time256 == 256) { // the input frame itself
+            const int f = time256 == 0 ? fl : fr;
+            if (!have(f))
+                return set_error("BlockFPS: source frame %d is not in the segment", f);
+            MVB_CUDA_CHECK(cudaMemcpyAsync(dst, B.dsrc + (size_t)cd.frame_bytes * local(f), (size_t)cd.frame_bytes, cudaMemcpyDeviceToDevice, c->stream));
+            MVB_CUDA_CHECK(cudaMemsetAsync(B.dflags + 2 * k, 0, 2 * sizeof(int), c->stream));
+            continue;
+        }
+        if (!have(fl) || !have(fr))
+            return set_error("BlockFPS: source frames %d / %d are not in the segment", fl, fr);
+        const uint8_t *src = B.dsrc + (size_t)cd.frame_bytes * local(fl), *ref = B.dsrc + (size_t)cd.frame_bytes * local(fr);
+        const bool in_range = nleft < N && nright < N; // :275
+        int *flags = nullptr;
+        if (in_range) {
+            if (launch_blockfps(c, p, B.sd, cd, time256, B.dsup + (size_t)B.sd.frame_bytes * local(nleft), B.dsup + (size_t)B.sd.frame_bytes * local(nright), B.dvec[0] + (size_t)B.vstride * local(nleft),
+                                B.dvec[1] + (size_t)B.vstride * local(nright), dst, &flags))
+                return 1;
+            MVB_CUDA_CHECK(cudaMemcpyAsync(B.dflags + 2 * k, flags, 2 * sizeof(int), cudaMemcpyDeviceToDevice, c->stream)); // (per-launch scratch)
+        } else {
+            MVB_CUDA_CHECK(cudaMemsetAsync(B.dflags + 2 * k, 0, 2 * sizeof(int), c->stream));
+        }
+        // frames the vectors cannot make (scene change, clip end): the blend of the source frames, or the left one
+        if (planes < cd.nplanes) // (planes the reference leaves uninitialised: the left frame's here)
+            MVB_CUDA_CHECK(cudaMemcpyAsync(dst + cd.offset[planes], src + cd.offset[planes], (size_t)(cd.frame_bytes - cd.offset[planes]), cudaMemcpyDeviceToDevice, c->stream));
+        for (int pl = 0; pl < planes && pl < cd.nplanes; pl++) {
+            dim3 blk(32, 8), grid((cd.w[pl] + 31) / 32, (cd.h[pl] + 7) / 8);
+            if (cd.bps == 1)
+                k_fallback<uint8_t><<<grid, blk, 0, c->stream>>>(cd.w[pl], cd.h[pl], time256, p->blend, src + cd.offset[pl], ref + cd.offset[pl], dst + cd.offset[pl], cd.pitch[pl], flags);
+            else
+                k_fallback<uint16_t><<<grid, blk, 0, c->stream>>>(cd.w[pl], cd.h[pl], time256, p->blend, src + cd.offset[pl], ref + cd.offset[pl], dst + cd.offset[pl], cd.pitch[pl], flags);
+            c->launches++;
+        }
+        MVB_CUDA_CHECK(cudaGetLastError());
+    }
+    std::vector<int> pairs(usable_out ? 2 * (size_t)out_count : 0);
+    if (usable_out)
+        MVB_CUDA_CHECK(cudaMemcpyAsync(pairs.data(), B.dflags, sizeof(int) * pairs.size(), cudaMemcpyDeviceToHost, c->stream));
+    if (chain_back(ctx, B, out_count, host_dst)) // (synchronises the stream)
+        return 1;
+    for (int k = 0; usable_out && k < out_count; k++)
+        usable_out[k] = pairs[2 * k] && pairs[2 * k + 1];
+    return 0;
 }
 
 } // extern "C"

@@ -272,7 +272,7 @@ def lib():
         L.mvb200_blockfps_position.restype = None
         L.mvb200_blockfps_frame.argtypes = [vp, PP(BlockFPSParams), PP(SuperParams), i32, PP(vp), PP(C.c_ssize_t), PP(vp), PP(C.c_ssize_t), vp, vp, PP(vp), PP(C.c_ssize_t), PP(i32)]
         L.mvb200_analyse_frames.argtypes = [vp, PP(AnalyseParams), PP(SuperParams), i32, PP(vp), PP(C.c_ssize_t), i32, PP(i32), PP(i32), PP(i32), PP(vp)]
-        L.mvb200_flowfps_clip_host.argtypes = [vp, PP(SuperParams), PP(AnalyseParams), PP(AnalyseParams), PP(FlowFPSParams), vp, i32, i32, i32, i32, vp]
+        L.mvb200_flowfps_clip_host.argtypes = [vp, PP(SuperParams), PP(AnalyseParams), PP(AnalyseParams), PP(FlowFPSParams), vp, i32, i32, i32, i32, vp, PP(i32)]
         L.mvb200_pinned_alloc.argtypes = [C.c_size_t]
         L.mvb200_pinned_alloc.restype = vp
         L.mvb200_pinned_free.argtypes = [vp]
@@ -280,6 +280,7 @@ def lib():
         L.mvb200_compensate_clip_host.argtypes = [vp, PP(SuperParams), PP(AnalyseParams), PP(CompensateParams), vp, i32, i32, i32, i32, vp]
         L.mvb200_flow_clip_host.argtypes = [vp, PP(SuperParams), PP(AnalyseParams), PP(FlowParams), vp, i32, i32, i32, i32, vp, PP(i32)]
         L.mvb200_flowinter_clip_host.argtypes = [vp, PP(SuperParams), PP(AnalyseParams), PP(AnalyseParams), PP(FlowInterParams), vp, i32, i32, i32, i32, vp, PP(i32)]
+        L.mvb200_blockfps_clip_host.argtypes = [vp, PP(SuperParams), PP(AnalyseParams), PP(AnalyseParams), PP(BlockFPSParams), vp, i32, i32, i32, i32, vp, PP(i32)]
         L.mvb200_flowblur_clip_host.argtypes = [vp, PP(SuperParams), PP(AnalyseParams), PP(AnalyseParams), PP(FlowBlurParams), vp, i32, i32, i32, i32, vp]
         _LIB = L
     return _LIB

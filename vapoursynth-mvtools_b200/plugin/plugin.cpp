@@ -1956,9 +1956,14 @@ const VSFrame *VS_CC flowFpsFusedGetFrame(int n, int activationReason, void *ins
             *s0 = N - 1; // (output frames past the end are made of the last input frame)
     };
     auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst) {
-        return mvb200_flowfps_clip_host(ctx, &d->sp, &f->apBw, &f->apFw, &d->p, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst);
+        f->runFlags.assign((size_t)(w1 - w0), 0);
+        return mvb200_flowfps_clip_host(ctx, &d->sp, &f->apBw, &f->apFw, &d->p, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst, f->runFlags.data());
     };
-    return fusedGetFrame("FlowFPS", f, d->node, &d->vi, n, propFrame, 7u, activationReason, frameData, frameCtx, core, vsapi, segment, run);
+    int32_t usable = 0;
+    const VSFrame *out = fusedGetFrame("FlowFPS", f, d->node, &d->vi, n, propFrame, 7u, activationReason, frameData, frameCtx, core, vsapi, segment, run, -1, &usable);
+    if (out && usable && nleft == 0) // an interpolated frame is built on the left super frame (MVFlowFPS.c:162): Super_* on frame 0
+        setSuperProps(vsapi, const_cast<VSFrame *>(out), d->sp);
+    return out;
 }
 
 const VSFrame *VS_CC flowFpsGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
@@ -2349,13 +2354,50 @@ void VS_CC flowBlurCreate(const VSMap *in, VSMap *out, void *, VSCore *core, con
 
 // --------------------------------------------------------------- BlockFPS
 // mvblockfpsCreate / GetFrame, MVBlockFPS.c:240-1034
+// Fused path (see fusedGetFrame): a window of B OUTPUT frames is one mvb200_blockfps_clip_host call over the source
+// frames the window needs (every output frame's left and right frames; the two searches look at each other's frame).
+struct BlockFPSFused : FusedCache {
+    mvb200_analyse_params apBw, apFw;
+};
+
 struct BlockFPSData {
     VSNode *node, *super, *mvbw, *mvfw;
     VSVideoInfo vi;
     const VSVideoInfo *oldvi, *supervi;
     mvb200_super_params sp;
     mvb200_blockfps_params p;
+    BlockFPSFused *fused; // owned; null = node-by-node evaluation
 };
+
+const VSFrame *VS_CC blockFpsFusedGetFrame(int n, int activationReason, void *instanceData, void **frameData, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    BlockFPSData *d = (BlockFPSData *)instanceData;
+    BlockFPSFused *f = d->fused;
+    const int off = d->p.vd.nDeltaFrame, N = d->oldvi->numFrames;
+    int32_t nleft, time256;
+    mvb200_blockfps_position(&d->p, n, &nleft, &time256);
+    const int propFrame = VSMIN(time256 == 256 ? nleft + off : nleft, N - 1); // whose properties the output carries
+    if (time256 == 0 || time256 == 256) { // the input frame itself (MVBlockFPS.c:246-253)
+        if (activationReason == arInitial)
+            vsapi->requestFrameFilter(propFrame, d->node, frameCtx);
+        return activationReason == arAllFramesReady ? vsapi->getFrameFilter(propFrame, d->node, frameCtx) : nullptr;
+    }
+    auto segment = [&](int w0, int w1, int *s0, int *s1) {
+        int32_t lmin, lmax, t;
+        mvb200_blockfps_position(&d->p, w0, &lmin, &t);
+        mvb200_blockfps_position(&d->p, w1 - 1, &lmax, &t);
+        *s0 = lmin < N - 1 ? lmin : N - 1; // (output frames past the end are made of the last input frame)
+        *s1 = lmax + off + 1 < N ? lmax + off + 1 : N;
+    };
+    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst) {
+        f->runFlags.assign((size_t)(w1 - w0), 0);
+        return mvb200_blockfps_clip_host(ctx, &d->sp, &f->apBw, &f->apFw, &d->p, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst, f->runFlags.data());
+    };
+    int32_t usable = 0;
+    const VSFrame *out = fusedGetFrame("BlockFPS", f, d->node, &d->vi, n, propFrame, 7u, activationReason, frameData, frameCtx, core, vsapi, segment, run, -1, &usable);
+    if (out && usable && nleft == 0) // an interpolated frame is built on the left super frame (MVBlockFPS.c:287): Super_* on frame 0
+        setSuperProps(vsapi, const_cast<VSFrame *>(out), d->sp);
+    return out;
+}
 
 const VSFrame *VS_CC blockFpsGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
     BlockFPSData *d = (BlockFPSData *)instanceData;
@@ -2462,6 +2504,7 @@ void VS_CC blockFpsFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
     vsapi->freeNode(d->super);
     vsapi->freeNode(d->mvbw);
     vsapi->freeNode(d->mvfw);
+    delete d->fused;
     delete d;
 }
 
@@ -2518,9 +2561,25 @@ void VS_CC blockFpsCreate(const VSMap *in, VSMap *out, void *, VSCore *core, con
     d.vi.fpsNum = d.p.fps_num;
     d.vi.fpsDen = d.p.fps_den;
     d.vi.numFrames = d.p.num_frames_out;
+    d.fused = nullptr;
+    const int window = lookaheadFromEnv();
+    mvb200_super_params ssp;
+    mvb200_analyse_params sap[2];
+    VSNode *vecs[2] = {d.mvbw, d.mvfw};
+    if (window && canonicalChain(d.node, d.super, vecs, 2, d.sp, d.oldvi->numFrames, true, &ssp, sap)) { // the fused path
+        d.fused = new BlockFPSFused;
+        d.fused->apBw = sap[0];
+        d.fused->apFw = sap[1];
+        d.sp = ssp;
+        mvb200_clip_layout(&d.sp, &d.fused->cl);
+        d.fused->window = window;
+    }
     BlockFPSData *data = new BlockFPSData(d);
     VSFilterDependency deps[4] = {{data->node, rpGeneral}, {data->super, rpGeneral}, {data->mvbw, rpGeneral}, {data->mvfw, rpGeneral}};
-    vsapi->createVideoFilter(out, "BlockFPS", &data->vi, blockFpsGetFrame, blockFpsFree, fmParallel, deps, 4, data, core);
+    if (data->fused) // only the source clip is read on this path
+        vsapi->createVideoFilter(out, "BlockFPS", &data->vi, blockFpsFusedGetFrame, blockFpsFree, fmParallel, deps, 1, data, core);
+    else
+        vsapi->createVideoFilter(out, "BlockFPS", &data->vi, blockFpsGetFrame, blockFpsFree, fmParallel, deps, 4, data, core);
     // AssumeFPS sets the _DurationNum and _DurationDen properties (MVBlockFPS.c:990-1012)
     VSPlugin *stdPlugin = vsapi->getPluginByID("com.vapoursynth.std", core);
     VSMap *args = vsapi->createMap();
