@@ -312,8 +312,8 @@ const VSFrame *computeFrame(VSNode *node, int n, std::string &err) {
         return addFrameRef(node->sourceFrames[idx]);
     }
     VSFrameContext ctx;
-    void *frameData = nullptr;
-    const VSFrame *r = node->getFrame(n, arInitial, node->instanceData, &frameData, &ctx, node->core, g_api());
+    void *frameData[4] = {nullptr, nullptr, nullptr, nullptr}; // (API 4: four pointers per request, zeroed)
+    const VSFrame *r = node->getFrame(n, arInitial, node->instanceData, frameData, &ctx, node->core, g_api());
     if (ctx.hasError) {
         err = ctx.error;
         if (r)
@@ -334,7 +334,7 @@ const VSFrame *computeFrame(VSNode *node, int n, std::string &err) {
         ctx.ready[rq] = f;
     }
     if (!failed) {
-        r = node->getFrame(n, arAllFramesReady, node->instanceData, &frameData, &ctx, node->core, g_api());
+        r = node->getFrame(n, arAllFramesReady, node->instanceData, frameData, &ctx, node->core, g_api());
         if (ctx.hasError) {
             err = ctx.error;
             if (r)
@@ -344,6 +344,8 @@ const VSFrame *computeFrame(VSNode *node, int n, std::string &err) {
             err = node->name + ": getFrame returned no frame and no error";
         }
     }
+    if (failed) // a requested frame failed: the filter gets the chance to release what it keeps in frameData
+        node->getFrame(n, arError, node->instanceData, frameData, &ctx, node->core, g_api());
     for (auto &e : ctx.ready)
         freeFrame(e.second);
     node->computed.fetch_add(1);

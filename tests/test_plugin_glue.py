@@ -238,11 +238,13 @@ def test_blockfps_fused_path_glue(mock_plugin, monkeypatch, case, window):
     assert (fused[1].computed(), [v.computed() for v in fused[2]]) == before
 
 
-def test_lookahead_paths_under_concurrent_requests(mock_plugin, monkeypatch):
+@pytest.mark.parametrize("window,threads", [(3, 4), (2, 8)])
+def test_lookahead_paths_under_concurrent_requests(mock_plugin, monkeypatch, window, threads):
     """fmParallel: several host threads pull frames at once (mini host's render); the window caches of mv.Analyse and of
-    the fused DegrainN must neither deadlock nor serve a wrong frame afterwards"""
+    the fused DegrainN must neither deadlock nor serve a wrong frame afterwards.  With more threads than the cache has
+    windows, a frame that was cached when a request started is evicted before the request finishes: the request keeps it."""
     import minivs
-    monkeypatch.setenv("MVB200_LOOKAHEAD", "3")
+    monkeypatch.setenv("MVB200_LOOKAHEAD", str(window))
     case = "blk16_ov8_pel2_p8_r3"
     ck, skw, akw, radius, dkw = pipeline.CASES[case]
     frames = pipeline.make_frames(ck)
@@ -258,8 +260,8 @@ def test_lookahead_paths_under_concurrent_requests(mock_plugin, monkeypatch):
         comp = mv.Compensate(clip, sup, vn[0])  # a consumer that goes through the Analyse node (look-ahead cache)
         for node in (dn, comp) + tuple(vn):
             node.set_cache(0)
-        dn.render(0, N, 4)
-        comp.render(0, N, 4)
+        dn.render(0, N, threads)
+        comp.render(0, N, threads)
         import numpy as np
         for n in range(N):
             assert [pipeline.sha(p) for p in dn.get_frame(n).planes()] == GOLD[case]["degrain"][n]

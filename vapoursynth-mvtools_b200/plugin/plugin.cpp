@@ -23,6 +23,7 @@
 #include <cstring>
 #include <deque>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -83,11 +84,22 @@ int lookaheadFromEnv() { // MVB200_LOOKAHEAD: frames per engine call (2..256); a
 // inputs are this plugin's own Super / Analyse nodes wired as in the canonical script, a window of B output frames is
 // produced by ONE engine call over SOURCE frames (a *_clip_host entry point: Super, the searches and the consumer all
 // run on the device) and served from a small cache; the Super / Analyse nodes are never asked for a frame.
+struct FusedEntry {
+    std::vector<uint8_t> bytes; // an output frame in the clip layout
+    int32_t flag = 0;           // the engine's "usable" flag, where the filter has one
+};
+
+// What one frame request keeps between its two activations (frameData[0]): the end of the window it asked the source
+// frames for, or -- on a cache hit -- the cached frame itself, which other threads' windows may evict in the meantime.
+struct FusedRequest {
+    int end = 0;
+    std::shared_ptr<const FusedEntry> held;
+};
+
 struct FusedCache {
-    std::mutex m;                               // serialises the window computations of one filter instance
-    std::map<int, std::vector<uint8_t>> frames; // output frames in the clip layout
-    std::map<int, int32_t> flags;               // per cached frame: the engine's "usable" flag, where the filter has one
-    std::vector<int32_t> runFlags;              // filled by the run callback (one per frame of the window), else empty
+    std::mutex m;                                              // serialises the window computations of one filter instance
+    std::map<int, std::shared_ptr<const FusedEntry>> frames;   // output frames by number
+    std::vector<int32_t> runFlags;                             // filled by the run callback (one per frame of the window), else empty
     std::deque<int> order;
     mvb200_frame_layout cl;
     int window = 0;
@@ -113,16 +125,18 @@ struct FusedCache {
     void store(int n, int end) { // the window's frames out of hostDst; keeps the window being served and the previous one
         const size_t fb = (size_t)cl.frame_bytes;
         for (int k = n; k < end; k++) {
+            if (frames.count(k))
+                continue;
             const uint8_t *p = (const uint8_t *)hostDst + fb * (k - n);
-            if (frames.emplace(k, std::vector<uint8_t>(p, p + fb)).second)
-                order.push_back(k);
-            if ((size_t)(k - n) < runFlags.size())
-                flags[k] = runFlags[(size_t)(k - n)];
+            auto e = std::make_shared<FusedEntry>();
+            e->bytes.assign(p, p + fb);
+            e->flag = (size_t)(k - n) < runFlags.size() ? runFlags[(size_t)(k - n)] : 0;
+            frames.emplace(k, std::move(e));
+            order.push_back(k);
         }
         runFlags.clear();
         while (order.size() > (size_t)window * 2) {
             frames.erase(order.front());
-            flags.erase(order.front());
             order.pop_front();
         }
     }
@@ -141,31 +155,35 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
         vsapi->requestFrameFilter(propFrame, clip, frameCtx);
         if (alsoFrame >= 0 && alsoFrame != propFrame)
             vsapi->requestFrameFilter(alsoFrame, clip, frameCtx);
-        bool hit;
+        FusedRequest *rq = new FusedRequest;
         {
             std::lock_guard<std::mutex> lock(f->m);
-            hit = f->frames.count(n) != 0;
+            const auto hit = f->frames.find(n);
+            if (hit != f->frames.end())
+                rq->held = hit->second;
         }
-        if (!hit) {
-            const int end = n + f->window < outvi->numFrames ? n + f->window : outvi->numFrames;
+        if (!rq->held) {
+            rq->end = n + f->window < outvi->numFrames ? n + f->window : outvi->numFrames;
             int s0, s1;
-            segment(n, end, &s0, &s1);
+            segment(n, rq->end, &s0, &s1);
             for (int k = s0; k < s1; k++)
                 if (k != propFrame && k != alsoFrame)
                     vsapi->requestFrameFilter(k, clip, frameCtx);
-            *frameData = (void *)(intptr_t)end; // remembered for arAllFramesReady: this request holds the window's frames
         }
+        frameData[0] = rq;
         return nullptr;
     }
-    if (activationReason != arAllFramesReady)
+    std::unique_ptr<FusedRequest> rq((FusedRequest *)frameData[0]); // (released on every exit, arError included)
+    frameData[0] = nullptr;
+    if (activationReason != arAllFramesReady || !rq)
         return nullptr;
     const VSFrame *src = vsapi->getFrameFilter(propFrame, clip, frameCtx);
-    std::vector<uint8_t> frame;
+    std::shared_ptr<const FusedEntry> entry = rq->held;
     std::string msg;
-    {
+    if (!entry) {
         std::lock_guard<std::mutex> lock(f->m);
-        const int end = (int)(intptr_t)*frameData;
-        bool have = f->frames.count(n) != 0;
+        const int end = rq->end;
+        bool have = f->frames.count(n) != 0; // (another request's window may have produced it in the meantime)
         if (!have && end > n) {
             int s0, s1;
             segment(n, end, &s0, &s1);
@@ -190,16 +208,14 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
                 }
             }
         } else if (!have) {
-            msg = "internal: frame neither cached nor requested"; // (evicted between the two activations)
+            msg = "internal: frame neither cached nor requested";
         }
-        if (have) {
-            frame = f->frames.find(n)->second;
-            const auto fl = f->flags.find(n);
-            if (flagOut)
-                *flagOut = fl != f->flags.end() ? fl->second : 0;
-        }
+        if (have)
+            entry = f->frames.find(n)->second;
     }
-    if (frame.empty()) {
+    if (entry && flagOut)
+        *flagOut = entry->flag;
+    if (!entry) {
         vsapi->setFilterError((std::string(filter) + ": " + msg).c_str(), frameCtx);
         vsapi->freeFrame(src);
         return nullptr;
@@ -208,7 +224,7 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
     for (int p = 0; p < outvi->format.numPlanes; p++) {
         const size_t row = (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, rows = (size_t)f->cl.plane_h[p];
         if (planeMask & (1u << p))
-            vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), frame.data() + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], row, rows);
+            vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), entry->bytes.data() + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], row, rows);
         else
             vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), vsapi->getReadPtr(src, p), vsapi->getStride(src, p), row, rows);
     }
