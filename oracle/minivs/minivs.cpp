@@ -109,6 +109,7 @@ struct VSNode {
     std::vector<VSNode *> deps; // referenced for lifetime only
     // source clip
     std::vector<const VSFrame *> sourceFrames;
+    std::map<int, int> sourceDelayMs; // test aid: fetching these frames of a source clip takes this long
     // cache
     std::mutex m;
     std::condition_variable cv;
@@ -309,6 +310,9 @@ const VSFrame *evalFrame(VSNode *node, int n, std::string &err);
 const VSFrame *computeFrame(VSNode *node, int n, std::string &err) {
     if (!node->getFrame) { // source clip
         int idx = n < 0 ? 0 : (n >= (int)node->sourceFrames.size() ? (int)node->sourceFrames.size() - 1 : n);
+        const auto slow = node->sourceDelayMs.find(idx);
+        if (slow != node->sourceDelayMs.end())
+            std::this_thread::sleep_for(std::chrono::milliseconds(slow->second));
         return addFrameRef(node->sourceFrames[idx]);
     }
     VSFrameContext ctx;
@@ -911,6 +915,9 @@ MVS_API void mvs_source_set_prop_int(void *node, int n, const char *key, int64_t
     VSFrame *f = const_cast<VSFrame *>(((VSNode *)node)->sourceFrames[n]);
     mapSetInt(&f->props, key, v, maReplace);
 }
+
+// (set before any frame is requested)
+MVS_API void mvs_source_set_delay(void *node, int n, int ms) { ((VSNode *)node)->sourceDelayMs[n] = ms; }
 
 MVS_API void mvs_node_free(void *node) { freeNode((VSNode *)node); }
 MVS_API void mvs_node_set_cache(void *node, int size) { ((VSNode *)node)->cacheSize = (size_t)size; }

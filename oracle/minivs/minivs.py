@@ -45,6 +45,7 @@ def lib():
             "mvs_source_create": (vp, [vp, i32, i32, i32, i32, i32, i32, i32]),
             "mvs_source_set_plane": (None, [vp, i32, i32, vp, i64]),
             "mvs_source_set_prop_int": (None, [vp, i32, cp, i64]),
+            "mvs_source_set_delay": (None, [vp, i32, i32]),
             "mvs_node_free": (None, [vp]),
             "mvs_node_set_cache": (None, [vp, i32]),
             "mvs_node_computed": (C.c_long, [vp]),
@@ -207,8 +208,9 @@ class Core:
             raise Error(lib().mvs_last_error().decode())
         return Plugin(p)
 
-    def source(self, frames, bits=8, ssw=1, ssh=1, props=None):
-        """frames: list of [Y,U,V] (or [Y]) numpy arrays; props: optional list (one dict of integer frame properties per frame)."""
+    def source(self, frames, bits=8, ssw=1, ssh=1, props=None, delay_ms=None):
+        """frames: list of [Y,U,V] (or [Y]) numpy arrays; props: optional list (one dict of integer frame properties per frame);
+        delay_ms: optional {frame: milliseconds} -- fetching those frames is slow (to order concurrent requests in a test)."""
         L = lib()
         nplanes = len(frames[0])
         h, w = frames[0][0].shape
@@ -222,6 +224,8 @@ class Core:
                 L.mvs_source_set_plane(node, n, p, a.ctypes.data, a.strides[0])
             for k, v in (props[n] if props else {}).items():
                 L.mvs_source_set_prop_int(node, n, k.encode(), int(v))
+        for n, ms in (delay_ms or {}).items():
+            L.mvs_source_set_delay(node, int(n), int(ms))
         return Node(node)
 
 

@@ -269,6 +269,41 @@ def test_lookahead_paths_under_concurrent_requests(mock_plugin, monkeypatch, win
             assert pipeline.sha(pipeline.mask_blob(blob, aps[0])) == GOLD[case]["vectors"][n][0]
 
 
+def test_fused_request_survives_the_eviction_of_its_frame(mock_plugin, monkeypatch):
+    """A request that finds its frame in the window cache keeps it: while that request waits for the (here: slow) source
+    frame it takes its properties from, other requests' windows push the frame out of the cache (two windows are kept)."""
+    import threading
+    import time
+    import clipgen
+    import minivs
+    monkeypatch.setenv("MVB200_LOOKAHEAD", "2")
+    frames = clipgen.make_clip(96, 64, 10, bits=8)
+    core = minivs.Core()
+    mv = core.load(mock_plugin)
+    clip = core.source(frames, bits=8, delay_ms={1: 1500})
+    sup = mv.Super(clip, pel=1)
+    vn = [mv.Analyse(sup, isb=isb, delta=1, blksize=8) for isb in (1, 0)]
+    dn = mv.Degrain1(clip, sup, vn[0], vn[1])
+    dn.set_cache(0)
+    first = [p.copy() for p in dn.get_frame(1).planes()]  # the window [1, 3) is computed and cached
+    result = {}
+
+    def late():
+        try:
+            result["planes"] = dn.get_frame(1).planes()  # a cache hit that then waits 1.5 s for source frame 1
+        except Exception as e:  # noqa: BLE001
+            result["error"] = str(e)
+
+    t = threading.Thread(target=late)
+    t.start()
+    time.sleep(0.3)
+    dn.get_frame(4)  # windows [4, 6) and [6, 8): four newer frames, [1, 3) is evicted (neither needs source frame 1)
+    dn.get_frame(6)
+    t.join()
+    assert "error" not in result, result.get("error")
+    assert all((a == b).all() for a, b in zip(result["planes"], first))
+
+
 def test_analyse_lookahead_batches_the_engine_calls(mock_plugin, monkeypatch):
     """with a window of 4, six frames requested in order cost two window searches per vector clip, not six"""
     import minivs
