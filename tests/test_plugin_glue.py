@@ -269,6 +269,61 @@ def test_lookahead_paths_under_concurrent_requests(mock_plugin, monkeypatch, win
             assert pipeline.sha(pipeline.mask_blob(blob, aps[0])) == GOLD[case]["vectors"][n][0]
 
 
+def test_non_canonical_chains_keep_the_node_by_node_evaluation(mock_plugin, monkeypatch):
+    """MVB200_LOOKAHEAD set, but the script is not the canonical chain: vectors searched on ANOTHER Super node of the same
+    clip, a vector clip with divide feeding mv.Flow, a consumer with fields -- the fused paths must decline (the Super /
+    Analyse nodes are asked for frames) and the results stay the reference's"""
+    import minivs
+    monkeypatch.setenv("MVB200_LOOKAHEAD", "4")
+    # (a) another Super instance
+    case = "blk8_ov4_pel2_p8"
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    N = len(frames)
+    core = minivs.Core()
+    mv = core.load(mock_plugin)
+    clip = core.source(frames, bits=8)
+    sup, sup2 = mv.Super(clip, **skw), mv.Super(clip, **skw)
+    vn = [mv.Analyse(sup2, isb=isb, delta=1, **akw) for isb in (1, 0)]
+    dn = mv.Degrain1(clip, sup, vn[0], vn[1])
+    inter = mv.FlowInter(clip, sup, vn[0], vn[1])
+    before = sup.computed()
+    for n in range(N):
+        assert [pipeline.sha(p) for p in dn.get_frame(n).planes()] == GOLD[case]["degrain"][n]
+        assert [pipeline.sha(p) for p in inter.get_frame(n).planes()] == GOLD_FLOW[case]["inter"][0][n]
+    assert sup.computed() > before
+    # a consumer with fields on the canonical nodes
+    sup3 = mv.Super(clip, **skw)
+    v3 = mv.Analyse(sup3, isb=1, delta=1, **akw)
+    kw = dict(pipeline_flow.FLOW[case]["flow"][4])  # fields=1, tff=1
+    assert kw.get("fields") == 1 and "vec" not in kw
+    fl = mv.Flow(clip, sup3, v3, **{k: (float(x) if k == "time" else x) for k, x in kw.items()})
+    before = v3.computed()
+    for n in range(N):
+        assert [pipeline.sha(p) for p in fl.get_frame(n).planes()] == GOLD_FLOW[case]["flow"][4][n]
+    assert v3.computed() > before
+    # (b) divide: mv.Flow declines, mv.Compensate (a block filter) does not
+    case = "divide2_blk16_esa_neg_badrange"
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    core = minivs.Core()
+    mv = core.load(mock_plugin)
+    clip = core.source(frames, bits=8)
+    sup = mv.Super(clip, **skw)
+    vec = mv.Analyse(sup, isb=1, delta=1, **pipeline._fix(akw))
+    kw = dict(pipeline_flow.FLOW[case]["flow"][0])
+    fl = mv.Flow(clip, sup, vec, **kw)
+    before = vec.computed()  # (the vector clip: creating the filters already made its look-ahead read the super frames)
+    for n in range(len(frames)):
+        assert [pipeline.sha(p) for p in fl.get_frame(n).planes()] == GOLD_FLOW[case]["flow"][0][n]
+    assert vec.computed() > before
+    comp = mv.Compensate(clip, sup, vec, **pipeline.EXTRA[case]["comp"])
+    before = vec.computed()
+    for n in range(len(frames)):
+        assert [pipeline.sha(p) for p in comp.get_frame(n).planes()] == GOLD[case]["compensate"][n]
+    assert vec.computed() == before
+
+
 def test_fused_request_survives_the_eviction_of_its_frame(mock_plugin, monkeypatch):
     """A request that finds its frame in the window cache keeps it: while that request waits for the (here: slow) source
     frame it takes its properties from, other requests' windows push the frame out of the cache (two windows are kept)."""
