@@ -6,7 +6,7 @@ set -e
 cd "$(dirname "$0")/.."
 ASAN=$(g++ -print-file-name=libasan.so)
 cp oracle/_ref/liboracle.so /tmp/liboracle.normal
-trap 'cp /tmp/liboracle.normal oracle/_ref/liboracle.so; rm -f tests/emul/libflow_emul.so' EXIT
+trap 'cp /tmp/liboracle.normal oracle/_ref/liboracle.so; rm -f tests/emul/libflow_emul.so tests/mock/libmvtools_mockengine.so' EXIT   # (the test fixtures rebuild the normal ones)
 (cd tests/emul && g++ -std=c++17 -O1 -g -fsanitize=address -fno-omit-frame-pointer -fPIC -fvisibility=hidden -ffp-contract=off -shared -o libflow_emul.so flow_emul.cpp \
     -L../../vapoursynth-mvtools_b200 -lmvtools_b200 -Wl,-rpath,"$PWD/../../vapoursynth-mvtools_b200" && touch libflow_emul.so)
 (cd oracle && gcc -std=gnu11 -O1 -g -fsanitize=address -fno-omit-frame-pointer -fPIC -fvisibility=hidden -ffp-contract=off -shared -o _ref/liboracle.so mvtools_oracle.c mvtools_oracle_flow.c -lm)
@@ -16,5 +16,4 @@ LD_PRELOAD=$ASAN ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/test_flow_em
 ROOT=$PWD; PKG=$ROOT/vapoursynth-mvtools_b200
 g++ -std=c++17 -O1 -g -fsanitize=address -fno-omit-frame-pointer -fPIC -fvisibility=hidden -Wall -I$ROOT/include -I$ROOT/include/vs -shared -Wl,-Bsymbolic \
     -o tests/mock/libmvtools_mockengine.so $PKG/plugin/plugin.cpp tests/mock/mock_engine.cpp $PKG/csrc/host_logic.cpp -L$ROOT/oracle/_ref -loracle -Wl,-rpath,$ROOT/oracle/_ref
-LD_PRELOAD=$ASAN ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/test_plugin_glue.py -q -k "fused or lookahead or concurrent or canonical" || true
-rm -f tests/mock/libmvtools_mockengine.so   # (the test fixture rebuilds the normal one)
+LD_PRELOAD=$ASAN ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/test_plugin_glue.py -q -k "fused or lookahead or concurrent or canonical"
