@@ -26,6 +26,28 @@ GOLD_MAIN = json.load(open(os.path.join(HERE, "golden", "golden.json")))
 CASES = ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "noise_badblocks_blk8"]
 
 
+@pytest.mark.parametrize("case", ["c1_640x360_p8_blk8_pel1", "blk16_ov8_pel2_p8_r3", "blk16_ov8_pel2_p16_r3", "divide2_blk16_esa_neg_badrange", "p8_422_blk8x4_sharp0_rf1",
+                                  "pelclip2_p8", "pelclip4_padded_p16"])
+def test_script_through_plugin_with_lookahead_32(built, monkeypatch, case):
+    """test_plugin.py's hot-path scripts with the look-ahead at 32 (longer than the clips): windows clipped to the clip, fused
+    DegrainN / Compensate where the script is canonical, node-by-node otherwise (pelclip)"""
+    monkeypatch.setenv("MVB200_LOOKAHEAD", "32")
+    got = pipeline.run_reference(case, plugin_path=mb.PLUGIN_PATH)
+    for stage in ("super", "vectors", "degrain", "adata", "recalc", "compensate", "recalc_adata"):
+        if stage in got:
+            assert got[stage] == GOLD_MAIN[case][stage], "%s: plugin %s differs from the reference plugin" % (case, stage)
+
+
+@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "gray_blk4_pel1_rf0", "noise_badblocks_blk8", "p8_420_blk16_ov4_uncovered"])
+def test_flow_script_through_plugin_with_lookahead_32(built, monkeypatch, case):
+    """test_plugin.py's flow-group scripts with the look-ahead at 32: every consumer on its fused path"""
+    monkeypatch.setenv("MVB200_LOOKAHEAD", "32")
+    stages = ("scd", "mask", "flow", "finest", "inter", "fps", "blur", "bfps")
+    got = pipeline_flow.run_reference_flow(case, plugin_path=mb.PLUGIN_PATH, only=stages)
+    for stage in stages:
+        assert got[stage] == GOLD[case][stage], "%s: plugin %s differs from the reference plugin" % (case, stage)
+
+
 @pytest.mark.parametrize("case", sorted(pipeline.LATE))
 def test_cuda_matches_reference_goldens_late_cases(gpu_ctx, case):
     """per-frame host-buffer entry points on the LATE cases: bit-exact against the reference's goldens"""
@@ -48,25 +70,3 @@ def test_cuda_flow_group_matches_reference_goldens_late_cases(gpu_ctx, case):
     got["bfps"] = pipeline_flow.run_engine_bfps(case, ctx.blockfps_frame, ctx.blend_frame)
     for stage in ("scd", "mask", "flow", "finest", "inter", "fps", "blur", "bfps"):
         assert got[stage] == GOLD[case][stage], "%s: CUDA %s differs from the reference's golden hashes" % (case, stage)
-
-
-@pytest.mark.parametrize("case", ["c1_640x360_p8_blk8_pel1", "blk16_ov8_pel2_p8_r3", "blk16_ov8_pel2_p16_r3", "divide2_blk16_esa_neg_badrange", "p8_422_blk8x4_sharp0_rf1",
-                                  "pelclip2_p8", "pelclip4_padded_p16"])
-def test_script_through_plugin_with_lookahead_32(built, monkeypatch, case):
-    """test_plugin.py's hot-path scripts with the look-ahead at 32 (longer than the clips): windows clipped to the clip, fused
-    DegrainN / Compensate where the script is canonical, node-by-node otherwise (pelclip)"""
-    monkeypatch.setenv("MVB200_LOOKAHEAD", "32")
-    got = pipeline.run_reference(case, plugin_path=mb.PLUGIN_PATH)
-    for stage in ("super", "vectors", "degrain", "adata", "recalc", "compensate", "recalc_adata"):
-        if stage in got:
-            assert got[stage] == GOLD_MAIN[case][stage], "%s: plugin %s differs from the reference plugin" % (case, stage)
-
-
-@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "gray_blk4_pel1_rf0", "noise_badblocks_blk8", "p8_420_blk16_ov4_uncovered"])
-def test_flow_script_through_plugin_with_lookahead_32(built, monkeypatch, case):
-    """test_plugin.py's flow-group scripts with the look-ahead at 32: every consumer on its fused path"""
-    monkeypatch.setenv("MVB200_LOOKAHEAD", "32")
-    stages = ("scd", "mask", "flow", "finest", "inter", "fps", "blur", "bfps")
-    got = pipeline_flow.run_reference_flow(case, plugin_path=mb.PLUGIN_PATH, only=stages)
-    for stage in stages:
-        assert got[stage] == GOLD[case][stage], "%s: plugin %s differs from the reference plugin" % (case, stage)
