@@ -51,6 +51,9 @@ LATE = {
     "blk32x16_penalties_levels2": (dict(width=288, height=160, nframes=5, bits=8, noise_sigma=6.0), dict(pel=2, levels=3, hpad=8, vpad=8), dict(blksize=32, blksizev=16, overlap=8, overlapv=4, levels=2, truemotion=0, pnew=40, plevel=2,
                                    pzero=20, pglobal=10, lsad=400, pelsearch=1, search=2, searchparam=3, **{"lambda": 700}), 1, {}),
     "blk128x64_gray_p8": (dict(width=448, height=256, nframes=4, bits=8, gray=True), dict(pel=1), dict(blksize=128, blksizev=64, overlap=64, overlapv=32), 1, {}),
+    # 4:4:0 (chroma halved vertically only), the one subsampling the cases above do not have
+    "p8_440_blk8_ov4_r2": (dict(width=184, height=128, nframes=5, bits=8, ssw=0, ssh=1), dict(pel=2, hpad=8, vpad=8), dict(blksize=8, overlap=4), 2, {}),
+    "p16_440_blk16x8_pel1": (dict(width=208, height=96, nframes=4, bits=16, ssw=0, ssh=1), dict(pel=1, hpad=8, vpad=8), dict(blksize=16, blksizev=8, search=5, searchparam=2), 1, dict(limit=3000)),
 }
 CASES.update(LATE)
 
@@ -73,6 +76,7 @@ EXTRA = {
     "blk64_420_ov32_r2": dict(recalc=dict(blksize=32, overlap=16, thsad=120, search=4, searchparam=1), comp=dict(time=40.0)),
     "blk16x8_ov8x4_p10": dict(recalc=dict(blksize=8, blksizev=4, overlap=4, overlapv=2, thsad=60), comp=dict(thsad=5000)),
     "blk128x64_gray_p8": dict(recalc=dict(blksize=64, blksizev=32, overlap=32, overlapv=16, thsad=200, chroma=0), comp=dict()),
+    "p8_440_blk8_ov4_r2": dict(recalc=dict(blksize=8, overlap=4, thsad=80), comp=dict(time=60.0)),
 }
 
 

@@ -32,7 +32,7 @@ def mock_plugin(built):
     return so
 
 
-@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "divide2_blk16_esa_neg_badrange", "pelclip2_p8", "noise_badblocks_blk8", "blk64_420_ov32_r2", "blk32x16_penalties_levels2"])
+@pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "divide2_blk16_esa_neg_badrange", "pelclip2_p8", "noise_badblocks_blk8", "blk64_420_ov32_r2", "blk32x16_penalties_levels2", "p8_440_blk8_ov4_r2"])
 def test_hot_path_glue(mock_plugin, case):
     got = pipeline.run_reference(case, plugin_path=mock_plugin)
     for stage in ("super", "vectors", "degrain", "adata", "recalc", "compensate", "recalc_adata"):
