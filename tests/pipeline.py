@@ -58,6 +58,11 @@ LATE = {
     "r6_blk8_ov4_p8": (dict(width=136, height=96, nframes=14, bits=8), dict(pel=2, hpad=8, vpad=8), dict(blksize=8, overlap=4), 6, dict(thsad=500, thsadc=300, limit=30, limitc=40)),
     "r5_blk16_p16_422": (dict(width=144, height=96, nframes=9, bits=16, ssw=1, ssh=0, scene_cut=True), dict(pel=1, hpad=8, vpad=8), dict(blksize=16, overlap=8), 5, dict(plane=4)),
     "r4_gray_blk8x4": (dict(width=120, height=80, nframes=7, bits=8, gray=True), dict(pel=2, hpad=8, vpad=8), dict(blksize=8, blksizev=4, overlap=2, overlapv=2), 4, {}),
+    # the SATD mixing modes the cases above leave out (dct 5 and 7 are there)
+    "dct6_blk8_p8": (dict(width=136, height=96, nframes=4, bits=8, noise_sigma=8.0), dict(pel=2, hpad=8, vpad=8), dict(blksize=8, overlap=4, dct=6), 1, {}),
+    "dct8_blk16_p16": (dict(width=144, height=96, nframes=4, bits=16), dict(pel=2, hpad=8, vpad=8), dict(blksize=16, dct=8, search=5, searchparam=2), 1, {}),
+    "dct9_blk8x4_p8": (dict(width=136, height=80, nframes=4, bits=8, scene_cut=True), dict(pel=1, hpad=8, vpad=8), dict(blksize=8, blksizev=4, dct=9), 1, {}),
+    "dct10_blk4_p10": (dict(width=104, height=64, nframes=4, bits=10, ssw=0, ssh=0, noise_sigma=10.0), dict(pel=2, hpad=8, vpad=8), dict(blksize=4, dct=10, search=3, searchparam=1), 1, {}),
 }
 CASES.update(LATE)
 

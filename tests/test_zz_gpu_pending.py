@@ -1,5 +1,5 @@
 """GPU tests that have NOT run on a GPU yet: the block shapes / penalty options of pipeline.LATE (64x32, 64x64, 128x64,
-128x128, 16x2, 16x8, 32x16 blocks, search 7, explicit lambda / pnew / plevel / pzero / pglobal / lsad / levels, 4:4:0, Degrain4..6) through
+128x128, 16x2, 16x8, 32x16 blocks, search 7, explicit lambda / pnew / plevel / pzero / pglobal / lsad / levels, 4:4:0, Degrain4..6, dct 6 / 8 / 9 / 10) through
 the per-frame entry points, and the flow group on four of them.  They were added after round 1's GPU minutes were spent:
 the oracle is pinned against the reference on them, the plugin glue reproduces them through the stand-in engine and the
 flow kernels' per-thread code reproduces them in the CPU emulation (test_flow_emul.py); what remains unproven is the
