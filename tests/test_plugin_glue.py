@@ -416,3 +416,42 @@ def test_field_property_glue_matches_reference_live(mock_plugin, have_ref):
     with pytest.raises(minivs.Error) as e:
         mv.Analyse(sup, isb=1, fields=1, **akw).get_frame(1)
     assert "_Field property not found in input frame" in str(e.value)
+
+
+@pytest.mark.parametrize("lookahead", [None, "3"])
+def test_static_reference_frame_glue_matches_reference_live(mock_plugin, have_ref, monkeypatch, lookahead):
+    """delta < 0: every frame is searched against ONE fixed frame (-delta; MVAnalyse.c:84-109) -- the vector clip, and
+    Compensate / Flow / Mask / SCDetection / Recalculate on it, against the compiled reference; also with the look-ahead
+    set (windows of mv.Analyse share the reference frame; the fused paths decline absolute references)"""
+    if not have_ref:
+        pytest.skip("oracle/_ref/libmvtools_ref.so not built here (no /root/reference)")
+    import minivs
+    if lookahead:
+        monkeypatch.setenv("MVB200_LOOKAHEAD", lookahead)
+    else:
+        monkeypatch.delenv("MVB200_LOOKAHEAD", raising=False)
+    case = "blk8_ov4_pel2_p8"
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    N = len(frames)
+    outs = []
+    for path in (minivs.REF_PLUGIN, mock_plugin):
+        core = minivs.Core()
+        mv = core.load(path)
+        clip = core.source(frames, bits=8)
+        sup = mv.Super(clip, **skw)
+        vec = mv.Analyse(sup, isb=0, delta=-2, **akw)
+        comp = mv.Compensate(clip, sup, vec)
+        flow = mv.Flow(clip, sup, vec, time=70.0)
+        mask = mv.Mask(clip, vec, kind=1)
+        scd = mv.SCDetection(clip, vec)
+        rec = mv.Recalculate(sup, vec, blksize=8, overlap=4, thsad=50)
+        res = []
+        for n in range(N):
+            res.append((vec.get_frame(n).prop_data("MVTools_vectors"), rec.get_frame(n).prop_data("MVTools_vectors"), [pipeline.sha(p) for p in comp.get_frame(n).planes()],
+                        [pipeline.sha(p) for p in flow.get_frame(n).planes()], [pipeline.sha(p) for p in mask.get_frame(n).planes()], scd.get_frame(n).prop_int("_SceneChangePrev")))
+        outs.append(res)
+    for n in range(N):
+        for k, what in enumerate(("vectors", "recalculated vectors", "Compensate", "Flow", "Mask", "SCDetection")):
+            assert outs[0][n][k] == outs[1][n][k], "frame %d: %s" % (n, what)
+
