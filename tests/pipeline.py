@@ -63,6 +63,8 @@ LATE = {
     "dct8_blk16_p16": (dict(width=144, height=96, nframes=4, bits=16), dict(pel=2, hpad=8, vpad=8), dict(blksize=16, dct=8, search=5, searchparam=2), 1, {}),
     "dct9_blk8x4_p8": (dict(width=136, height=80, nframes=4, bits=8, scene_cut=True), dict(pel=1, hpad=8, vpad=8), dict(blksize=8, blksizev=4, dct=9), 1, {}),
     "dct10_blk4_p10": (dict(width=104, height=64, nframes=4, bits=10, ssw=0, ssh=0, noise_sigma=10.0), dict(pel=2, hpad=8, vpad=8), dict(blksize=4, dct=10, search=3, searchparam=1), 1, {}),
+    # a luma-only super clip (mv.Super(chroma=False)): searches without chroma, DegrainN of the luma plane
+    "super_nochroma_blk8_r2": (dict(width=152, height=96, nframes=6, bits=8), dict(pel=2, hpad=8, vpad=8, chroma=0), dict(blksize=8, overlap=4, chroma=0), 2, dict(plane=0)),
 }
 CASES.update(LATE)
 

@@ -61,7 +61,7 @@ def test_analyse_lookahead_glue(mock_plugin, monkeypatch, case, window):
 
 @pytest.mark.parametrize("window", [2, 5])
 @pytest.mark.parametrize("case", ["blk8_ov4_pel2_p8", "blk16_ov8_pel2_p16_r3", "gray_blk4_pel1_rf0", "p8_422_blk8x4_sharp0_rf1", "noise_badblocks_blk8", "c1_640x360_p8_blk8_pel1", "r6_blk8_ov4_p8", "r5_blk16_p16_422",
-                                  "r4_gray_blk8x4", "p8_440_blk8_ov4_r2"])
+                                  "r4_gray_blk8x4", "p8_440_blk8_ov4_r2", "super_nochroma_blk8_r2"])
 def test_degrain_fused_path_glue(mock_plugin, monkeypatch, case, window):
     """MVB200_LOOKAHEAD: a DegrainN whose inputs are this plugin's own Super / Analyse nodes on the same clip runs windows of
     frames through the engine's clip pipeline (source frames in, denoised frames out); its output must not change
