@@ -1,5 +1,5 @@
 """Differential fuzz of the CPU oracle against the compiled reference (oracle/_ref, build container only): random clip
-formats, block shapes, search types, SATD modes, penalties, divide, radius -- Super / Analyse / DegrainN hashes compared
+formats, block shapes, search types, SATD modes, penalties, divide, radius -- Super / Analyse / DegrainN / Recalculate / Compensate hashes compared
 through tests/pipeline.py.  Test infrastructure (a tool, not part of the suite):
 
     python tools/fuzz_oracle.py [seed] [iterations]
@@ -46,19 +46,28 @@ for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 30):
     if rnd.random() < 0.4: dkw = dict(thsad=rnd.choice([100, 400, 2000]), limit=rnd.choice([5, 50, 255]))
     name = "fuzz%d" % it
     pipeline.CASES[name] = (ck, skw, akw, radius, dkw)
+    if rnd.random() < 0.6:  # mv.Recalculate / mv.Compensate on vector clip 0
+        rb = rnd.choice([s_ for s_ in shapes if s_[0] <= bw and s_[1] <= bh and not (s_[1] == 2 and fmt.get("ssh", 1) == 1 and not fmt.get("gray"))] or [(bw, bh)])
+        rkw = dict(blksize=rb[0], blksizev=rb[1], thsad=rnd.choice([20, 200, 2000]), search=rnd.choice([0, 1, 2, 3, 4, 5, 6, 7]), searchparam=rnd.choice([1, 2]), smooth=rnd.choice([0, 1]),
+                   chroma=akw["chroma"], truemotion=rnd.choice([0, 1]), dct=rnd.choice([0, 0, 5, 8]))
+        if rb[1] >= 4 and rnd.random() < 0.5:
+            rkw.update(overlap=rb[0] // 2, overlapv=rb[1] // 2 - (rb[1] // 2) % (2 if fmt.get("ssh", 1) == 1 and not fmt.get("gray") else 1))
+        if rnd.random() < 0.2 and rb[0] >= 8 and rb[1] >= 8 and not rkw.get("overlap", 0) % 4 and not rkw.get("overlapv", 0) % 4:
+            rkw["divide"] = rnd.choice([1, 2])
+        pipeline.EXTRA[name] = dict(recalc=rkw, comp=dict(time=round(rnd.uniform(0, 100), 1), thsad=rnd.choice([100, 10000]), scbehavior=rnd.choice([0, 1])))
     try:
         ref = pipeline.run_reference(name)
     except Exception as e:
         print(name, "reference declined:", str(e)[:100]); continue
     try:
-        got = pipeline.run_engine(name, oracle.super_frame, oracle.analyse_frame, oracle.degrain_frame)
+        got = pipeline.run_engine(name, oracle.super_frame, oracle.analyse_frame, oracle.degrain_frame, oracle.recalculate_frame, oracle.compensate_frame)
     except Exception as e:
         print(name, "ORACLE ERROR", str(e)[:200], ck, skw, akw); bad += 1; continue
-    mism = [st for st in ("super", "vectors", "degrain") if got[st] != ref[st]]
+    mism = [st for st in ("super", "vectors", "degrain", "recalc", "compensate") if st in ref and got.get(st) != ref[st]]
     if mism == ["super"]:
         cwid = W if fmt.get("ssw", 1) == 0 or fmt.get("gray") else W // 2 + 8 - 16
         slack = min((-(w + 16) * ((bits + 7) // 8)) % 64 or 64 for w in (W, cwid))
-        if (bits == 8 and pel == 4 and skw["sharp"] > 0) or (pel > 1 and slack < 12):
+        if (bits == 8 and pel == 4) or (pel > 1 and slack < 12):
             print(name, "known reference artefact in the super frame (8-bit pel 4 last column / stride slack %d)" % slack)
             continue
     if mism:
