@@ -3,6 +3,8 @@ formats, block shapes, search types, SATD modes, penalties, divide, radius -- Su
 through tests/pipeline.py.  Test infrastructure (a tool, not part of the suite):
 
     python tools/fuzz_oracle.py [seed] [iterations]
+    FUZZ_GLUE=1 python tools/fuzz_oracle.py ...   (the same scripts through the product's plugin glue + create-time logic
+                                                  over the stand-in engine of tests/mock, against the reference plugin)
 
 Known reference artefacts are reported as such, not as mismatches: the SIMD refine kernels' overrun
 when a plane has < 12 bytes of stride slack, and -- 8-bit, pel 4 -- the last column of the 3/4-pel planes, which the
@@ -63,7 +65,13 @@ for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 30):
         got = pipeline.run_engine(name, oracle.super_frame, oracle.analyse_frame, oracle.degrain_frame, oracle.recalculate_frame, oracle.compensate_frame)
     except Exception as e:
         print(name, "ORACLE ERROR", str(e)[:200], ck, skw, akw); bad += 1; continue
-    mism = [st for st in ("super", "vectors", "degrain", "recalc", "compensate") if st in ref and got.get(st) != ref[st]]
+    if os.environ.get("FUZZ_GLUE"):  # the product's plugin.cpp + host_logic.cpp over the stand-in engine (tests/mock), as a script
+        got = pipeline.run_reference(name, plugin_path=os.path.join(R, "tests", "mock", "libmvtools_mockengine.so"))
+        ref = {k: v for k, v in ref.items()}
+        keys = ("super", "vectors", "degrain", "recalc", "compensate", "adata", "recalc_adata")
+    else:
+        keys = ("super", "vectors", "degrain", "recalc", "compensate")
+    mism = [st for st in keys if st in ref and got.get(st) != ref[st]]
     if mism == ["super"]:
         cwid = W if fmt.get("ssw", 1) == 0 or fmt.get("gray") else W // 2 + 8 - 16
         slack = min((-(w + 16) * ((bits + 7) // 8)) % 64 or 64 for w in (W, cwid))
