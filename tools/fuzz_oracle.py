@@ -5,6 +5,8 @@ through tests/pipeline.py.  Test infrastructure (a tool, not part of the suite):
     python tools/fuzz_oracle.py [seed] [iterations]
     FUZZ_GLUE=1 python tools/fuzz_oracle.py ...   (the same scripts through the product's plugin glue + create-time logic
                                                   over the stand-in engine of tests/mock, against the reference plugin)
+    FUZZ_GLUE=gpu python tools/fuzz_oracle.py ... (on a GPU box: the PRODUCT plugin, CUDA engine, against the reference plugin
+                                                  -- oracle/_ref travels with the snapshot)
 
 Known reference artefacts are reported as such, not as mismatches: the SIMD refine kernels' overrun
 when a plane has < 12 bytes of stride slack, and -- 8-bit, pel 4 -- the last column of the 3/4-pel planes, which the
@@ -66,7 +68,8 @@ for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 30):
     except Exception as e:
         print(name, "ORACLE ERROR", str(e)[:200], ck, skw, akw); bad += 1; continue
     if os.environ.get("FUZZ_GLUE"):  # the product's plugin.cpp + host_logic.cpp over the stand-in engine (tests/mock), as a script
-        got = pipeline.run_reference(name, plugin_path=os.path.join(R, "tests", "mock", "libmvtools_mockengine.so"))
+        so = os.path.join(R, "vapoursynth-mvtools_b200", "libmvtools.so") if os.environ["FUZZ_GLUE"] == "gpu" else os.path.join(R, "tests", "mock", "libmvtools_mockengine.so")
+        got = pipeline.run_reference(name, plugin_path=so)
         ref = {k: v for k, v in ref.items()}
         keys = ("super", "vectors", "degrain", "recalc", "compensate", "adata", "recalc_adata")
     else:

@@ -10,6 +10,9 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gp
 echo "== pytest -m gpu"
 timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1
 echo "pytest exit $?"; tail -3 gpurun_out/${TAG}_pytest_gpu.log
+echo "== differential fuzz on the GPU: random scripts through the product plugin against the compiled reference plugin"
+FUZZ_GLUE=gpu timeout 300 python tools/fuzz_oracle.py 1 60 > gpurun_out/${TAG}_fuzz_gpu.log 2>&1; tail -3 gpurun_out/${TAG}_fuzz_gpu.log | cut -c1-300
+MVB200_LOOKAHEAD=16 FUZZ_GLUE=gpu timeout 300 python tools/fuzz_oracle.py 2 60 > gpurun_out/${TAG}_fuzz_gpu_lookahead.log 2>&1; tail -3 gpurun_out/${TAG}_fuzz_gpu_lookahead.log | cut -c1-300
 echo "== bench (b200 arm, default library)"
 timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 echo "bench exit $?"; cat gpurun_out/${TAG}_bench.json; tail -3 gpurun_out/${TAG}_bench.err
