@@ -1,4 +1,4 @@
-// TEST INFRASTRUCTURE -- not part of the product path.
+// A frame-server stand-in (test and measurement harness) -- not part of the product path.
 //
 // minivs: a minimal, self-contained VapourSynth API-4 *host* (the side that a
 // real VapourSynth core plays).  No VapourSynth runtime exists in the build
@@ -23,6 +23,7 @@
 #include <VapourSynth4.h>
 
 #include <dlfcn.h>
+#include <malloc.h>
 
 #include <atomic>
 #include <chrono>
@@ -814,6 +815,10 @@ VSPlugin *makeStdPlugin(VSCore *core) {
 } // namespace
 
 MVS_API void *mvs_core_create() {
+    // VapourSynth recycles frame memory through a pool; the nearest plain-malloc equivalent: keep freed frame buffers in
+    // the heap instead of returning every multi-megabyte frame to the kernel (mmap / munmap and page faults per frame)
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
     VSCore *core = new VSCore;
     core->plugins.push_back(makeStdPlugin(core));
     return core;
@@ -909,6 +914,15 @@ MVS_API void mvs_source_set_plane(void *node, int n, int plane, const uint8_t *d
     size_t row = (size_t)f->pw(plane) * f->fmt.bytesPerSample;
     for (int y = 0; y < f->ph(plane); y++)
         memcpy(f->plane[plane] + (size_t)y * f->stride[plane], data + (size_t)y * stride, row);
+}
+
+// frame n of a source clip becomes another reference to frame m (long cyclic clips without the memory)
+MVS_API void mvs_source_alias(void *node, int n, int m) {
+    VSNode *nd = (VSNode *)node;
+    if (n == m)
+        return;
+    freeFrame(nd->sourceFrames[n]);
+    nd->sourceFrames[n] = addFrameRef(nd->sourceFrames[m]);
 }
 
 MVS_API void mvs_source_set_prop_int(void *node, int n, const char *key, int64_t v) {

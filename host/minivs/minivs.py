@@ -1,4 +1,5 @@
-"""TEST INFRASTRUCTURE: ctypes binding of the mini VapourSynth host (libminivs.so).
+"""ctypes binding of the mini VapourSynth host (libminivs.so) -- a frame-server stand-in (this image has no VapourSynth):
+it loads a VapourSynth API-4 plugin (this repo's libmvtools.so, or the compiled reference) and drives it the way vspipe would.
 
 Gives tests a tiny imitation of the VapourSynth Python API:
     core = Core(); mv = core.load(path_to_plugin)
@@ -22,7 +23,7 @@ cfGray, cfYUV = 1, 3
 def lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(_HERE, "..", "_ref", "libminivs.so")
+        path = os.path.join(_HERE, "libminivs.so")
         L = C.CDLL(os.path.abspath(path), mode=C.RTLD_GLOBAL)
         vp, cp, i32, i64 = C.c_void_p, C.c_char_p, C.c_int, C.c_int64
         sig = {
@@ -44,6 +45,7 @@ def lib():
             "mvs_invoke": (vp, [vp, cp, vp]),
             "mvs_source_create": (vp, [vp, i32, i32, i32, i32, i32, i32, i32]),
             "mvs_source_set_plane": (None, [vp, i32, i32, vp, i64]),
+            "mvs_source_alias": (None, [vp, i32, i32]),
             "mvs_source_set_prop_int": (None, [vp, i32, cp, i64]),
             "mvs_source_set_delay": (None, [vp, i32, i32]),
             "mvs_node_free": (None, [vp]),
@@ -210,8 +212,10 @@ class Core:
 
     def source(self, frames, bits=8, ssw=1, ssh=1, props=None, delay_ms=None):
         """frames: list of [Y,U,V] (or [Y]) numpy arrays; props: optional list (one dict of integer frame properties per frame);
-        delay_ms: optional {frame: milliseconds} -- fetching those frames is slow (to order concurrent requests in a test)."""
+        delay_ms: optional {frame: milliseconds} -- fetching those frames is slow (to order concurrent requests in a test).
+        A frame that IS (same list object) an earlier frame of the list shares that frame's memory (cyclic clips)."""
         L = lib()
+        seen = {}
         nplanes = len(frames[0])
         h, w = frames[0][0].shape
         node = L.mvs_source_create(self._p, cfGray if nplanes == 1 else cfYUV, bits,
@@ -219,6 +223,10 @@ class Core:
         if not node:
             raise Error(L.mvs_last_error().decode())
         for n, fr in enumerate(frames):
+            if id(fr) in seen and not props:
+                L.mvs_source_alias(node, n, seen[id(fr)])
+                continue
+            seen[id(fr)] = n
             for p, a in enumerate(fr):
                 a = np.ascontiguousarray(a)
                 L.mvs_source_set_plane(node, n, p, a.ctypes.data, a.strides[0])
@@ -229,4 +237,4 @@ class Core:
         return Node(node)
 
 
-REF_PLUGIN = os.path.abspath(os.path.join(_HERE, "..", "_ref", "libmvtools_ref.so"))
+REF_PLUGIN = os.path.abspath(os.path.join(_HERE, "..", "..", "oracle", "_ref", "libmvtools_ref.so"))

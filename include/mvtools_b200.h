@@ -421,6 +421,31 @@ MVB200_API void *mvb200_ctx_stream(mvb200_ctx *ctx);
 /* number of kernels this context has launched so far */
 MVB200_API int64_t mvb200_ctx_launch_count(mvb200_ctx *ctx);
 
+/* Completion marker for the asynchronous entry points (mvb200_degrain_clip_host_async): mvb200_ctx_record() marks
+ * everything enqueued on the context so far (its compute stream and both copy streams).  The reference has no
+ * counterpart -- its GetFrame functions are synchronous (MVDegrains.cpp:85-330); this is what lets the plugin keep the next
+ * window of frames in flight on the GPU while the frame server's threads still collect the current one.
+ * mvb200_event_wait blocks the calling thread until that work is done; mvb200_event_query returns 0 when done, 1 while
+ * pending; both may be called from any thread without holding whatever lock serialises the context's other calls. */
+typedef struct mvb200_event mvb200_event;
+MVB200_API int mvb200_ctx_record(mvb200_ctx *ctx, mvb200_event **out);
+MVB200_API int mvb200_event_wait(mvb200_event *ev);
+MVB200_API int mvb200_event_query(mvb200_event *ev);
+MVB200_API void mvb200_event_destroy(mvb200_event *ev);
+
+/* Which search kernel a mv.Analyse configuration runs on and how many of its serial search chains (one per frame and
+ * vector clip: doPobSearchMVs walks a plane's blocks strictly in order, PlaneOfBlocks.cpp:971-1131) fill the GPU once.
+ * kernel: 0 = generic (every option), 1 = register-blocked, 2 = TMA-staged windows (the production kernel).  Pure host
+ * code: sm_count <= 0 assumes a B200 (148 SMs).  Callers size their batches with it: frames per launch =
+ * chains_per_wave / number of vector clips. */
+typedef struct mvb200_search_plan {
+    int32_t kernel;
+    int32_t chains_per_sm;
+    int32_t chains_per_wave;
+    int32_t smem_per_chain;
+} mvb200_search_plan;
+MVB200_API int mvb200_search_plan_query(const mvb200_analyse_params *ap, const mvb200_super_params *sp, int sm_count, mvb200_search_plan *out);
+
 /* Device frame layout used by the *_batch functions: planes are stored one after
  * another, each with its own pitch (bytes), frames one after another.
  * pitch[p] = round_up(plane_w[p]*bytes, 256); offsets are from the frame start. */

@@ -4,7 +4,7 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in ("vapoursynth-mvtools_b200", "oracle", os.path.join("oracle", "minivs"), "tests", ""):
+for p in ("vapoursynth-mvtools_b200", "oracle", os.path.join("host", "minivs"), "tests", ""):
     q = os.path.join(ROOT, p)
     if q not in sys.path:
         sys.path.insert(0, q)
@@ -19,7 +19,7 @@ def built():
     """The in-tree shared libraries; built once per session if missing (nvcc works without a GPU)."""
     import mvtools_b200 as mb
     need = [mb.LIB_PATH, mb.PLUGIN_PATH, os.path.join(ROOT, "oracle", "_ref", "liboracle.so"),
-            os.path.join(ROOT, "oracle", "_ref", "libminivs.so")]
+            os.path.join(ROOT, "host", "minivs", "libminivs.so")]
     if not all(os.path.exists(p) for p in need):
         import __graft_entry__
         __graft_entry__.build()

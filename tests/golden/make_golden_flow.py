@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
-for p in ("vapoursynth-mvtools_b200", "oracle", os.path.join("oracle", "minivs"), "tests"):
+for p in ("vapoursynth-mvtools_b200", "oracle", os.path.join("host", "minivs"), "tests"):
     sys.path.insert(0, os.path.join(ROOT, p))
 import pipeline_flow  # noqa: E402
 

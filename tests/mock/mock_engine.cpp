@@ -11,9 +11,12 @@
 #include "../../include/mvtools_b200.h"
 #include "../../oracle/mvtools_oracle.h"
 
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+
+static std::atomic<long> g_clip_calls{0}; // mvb200_degrain_clip_host_async calls so far (the glue tests count the windows)
 
 struct mvb200_ctx {
     int dummy;
@@ -37,6 +40,26 @@ MVB200_API int mvb200_ctx_create(int, mvb200_ctx **out) {
 }
 MVB200_API void mvb200_ctx_destroy(mvb200_ctx *ctx) { delete ctx; }
 MVB200_API int mvb200_ctx_synchronize(mvb200_ctx *) { return 0; }
+// the stand-in computes synchronously: an event is complete when it is recorded
+struct mvb200_event {
+    int dummy;
+};
+MVB200_API int mvb200_ctx_record(mvb200_ctx *, mvb200_event **out) {
+    *out = new mvb200_event{0};
+    return 0;
+}
+MVB200_API long mvb200_mock_clip_calls(void) { return g_clip_calls.load(); }
+MVB200_API int mvb200_event_wait(mvb200_event *) { return 0; }
+MVB200_API int mvb200_event_query(mvb200_event *) { return 0; }
+MVB200_API void mvb200_event_destroy(mvb200_event *ev) { delete ev; }
+// the automatic window of the fused paths: small here, so that the default configuration exercises several windows per test clip
+MVB200_API int mvb200_search_plan_query(const mvb200_analyse_params *, const mvb200_super_params *, int, mvb200_search_plan *out) {
+    out->kernel = 0;
+    out->chains_per_sm = 1;
+    out->chains_per_wave = 6;
+    out->smem_per_chain = 0;
+    return 0;
+}
 MVB200_API void *mvb200_pinned_alloc(size_t bytes) { return malloc(bytes); }
 MVB200_API void mvb200_pinned_free(void *p) { free(p); }
 
@@ -62,6 +85,7 @@ MVB200_API void mvb200_clip_layout(const mvb200_super_params *p, mvb200_frame_la
 // num_frames = the segment length, as in the engine.
 MVB200_API int mvb200_degrain_clip_host_async(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const mvb200_degrain_params *dp, const void *host_src, void *host_dst, int n, int first,
                                               int count) {
+    g_clip_calls++;
     mvb200_frame_layout cl;
     mvb200_clip_layout(sp, &cl);
     mvb200_super_geom g;

@@ -105,7 +105,7 @@ def test_flowfps_fused_path_glue(mock_plugin, monkeypatch, case, window):
     nodes = [mv.FlowFPS(clip, sup, vn[0], vn[1], **{k: (float(x) if k == "ml" else x) for k, x in kw.items()}) for kw in pipeline_flow.FLOW[case]["fps"]]
     before = (sup.computed(), [v.computed() for v in vn])  # what the filters' creation read (frame 0 of every input)
     # the node-by-node evaluation of the same script, for the frame properties (Super_* on frames built on super frame 0)
-    monkeypatch.delenv("MVB200_LOOKAHEAD")
+    monkeypatch.setenv("MVB200_LOOKAHEAD", "0")
     core2 = minivs.Core()
     mv2 = core2.load(mock_plugin)
     clip2 = core2.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1))
@@ -169,7 +169,7 @@ def test_flow_consumers_fused_path_glue(mock_plugin, monkeypatch, case, window):
         if fused:
             monkeypatch.setenv("MVB200_LOOKAHEAD", str(window))
         else:
-            monkeypatch.delenv("MVB200_LOOKAHEAD", raising=False)
+            monkeypatch.setenv("MVB200_LOOKAHEAD", "0")
         core = minivs.Core()
         mv = core.load(mock_plugin)
         clip = core.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1), props=tags)
@@ -216,7 +216,7 @@ def test_blockfps_fused_path_glue(mock_plugin, monkeypatch, case, window):
         if fused:
             monkeypatch.setenv("MVB200_LOOKAHEAD", str(window))
         else:
-            monkeypatch.delenv("MVB200_LOOKAHEAD", raising=False)
+            monkeypatch.setenv("MVB200_LOOKAHEAD", "0")
         core = minivs.Core()
         mv = core.load(mock_plugin)
         clip = core.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1), props=tags)
@@ -268,6 +268,40 @@ def test_lookahead_paths_under_concurrent_requests(mock_plugin, monkeypatch, win
             assert [pipeline.sha(p) for p in dn.get_frame(n).planes()] == GOLD[case]["degrain"][n]
             blob = np.frombuffer(vn[0].get_frame(n).prop_data("MVTools_vectors"), dtype=np.uint8)
             assert pipeline.sha(pipeline.mask_blob(blob, aps[0])) == GOLD[case]["vectors"][n][0]
+
+
+@pytest.mark.parametrize("window,threads", [(3, 1), (3, 4), (4, 2)])
+def test_fused_windows_are_aligned_pipelined_and_computed_once(mock_plugin, monkeypatch, window, threads):
+    """The fused DegrainN cuts the clip into aligned windows; frames pulled in order by any number of threads cost exactly one
+    engine call per window (the request that first touches window k also enqueues window k + 1 -- nobody recomputes it), and
+    the automatic window (MVB200_LOOKAHEAD unset) gives the same frames."""
+    import ctypes
+    import minivs
+    case = "blk16_ov8_pel2_p8_r3"
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    N = len(frames)
+    calls = ctypes.CDLL(mock_plugin).mvb200_mock_clip_calls
+    calls.restype = ctypes.c_long
+    for la in (str(window), None):
+        if la is None:
+            monkeypatch.delenv("MVB200_LOOKAHEAD", raising=False)
+        else:
+            monkeypatch.setenv("MVB200_LOOKAHEAD", la)
+        core = minivs.Core()
+        mv = core.load(mock_plugin)
+        clip = core.source(frames, bits=8)
+        sup = mv.Super(clip, **skw)
+        vn = [mv.Analyse(sup, isb=isb, delta=d, **akw) for d in range(1, radius + 1) for isb in (1, 0)]
+        dn = mv.invoke("Degrain%d" % radius, clip, sup, *vn, **dkw)
+        dn.set_cache(0)
+        before = calls()
+        dn.render(0, N, threads)
+        made = calls() - before
+        B = window if la else 16  # (the stand-in's plan: the automatic window is the 16-frame minimum)
+        assert made == (N + B - 1) // B, "window %s: %d engine calls for %d frames" % (la, made, N)
+        for n in range(N):
+            assert [pipeline.sha(p) for p in dn.get_frame(n).planes()] == GOLD[case]["degrain"][n]
 
 
 def test_non_canonical_chains_keep_the_node_by_node_evaluation(mock_plugin, monkeypatch):

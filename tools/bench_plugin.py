@@ -13,7 +13,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in ("vapoursynth-mvtools_b200", os.path.join("oracle", "minivs")):
+for p in ("vapoursynth-mvtools_b200", os.path.join("host", "minivs")):
     sys.path.insert(0, os.path.join(ROOT, p))
 
 
@@ -33,7 +33,7 @@ def one_run(plugin, frames_n, w, h, threads, radius=3):
         v.set_cache(8 + 2 * threads)
     out = mv.invoke("Degrain%d" % radius, clip, sup, *vecs)
     out.set_cache(0)
-    warm = min(8, frames_n // 4)
+    warm = frames_n // 4
     out.render(0, warm, threads)
     t = out.render(warm, frames_n, threads)
     return (frames_n - warm) / t
@@ -44,7 +44,7 @@ def main():
     ap.add_argument("--frames", type=int, default=96)
     ap.add_argument("--size", default="1920x1080")
     ap.add_argument("--threads", type=int, default=8)
-    ap.add_argument("--lookahead", default="0,32,96")
+    ap.add_argument("--lookahead", default="auto,32")
     ap.add_argument("--plugin", default=None)
     ap.add_argument("--child", default=None)
     a = ap.parse_args()
@@ -55,12 +55,12 @@ def main():
     import minivs
     import mvtools_b200 as mb
     runs = [("reference", minivs.REF_PLUGIN, None)] if os.path.exists(minivs.REF_PLUGIN) else []
-    for la in a.lookahead.split(","):
+    for la in a.lookahead.split(","):  # "auto" = MVB200_LOOKAHEAD unset: the plugin's default
         runs.append(("b200 lookahead=%s" % la, a.plugin or mb.PLUGIN_PATH, la))
     for name, plugin, la in runs:
         env = dict(os.environ)
         env.pop("MVB200_LOOKAHEAD", None)
-        if la and int(la) > 1:
+        if la and la != "auto":
             env["MVB200_LOOKAHEAD"] = la
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", plugin, "--frames", str(a.frames), "--size", a.size, "--threads", str(a.threads)], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
         try:

@@ -16,7 +16,7 @@ import random
 import sys
 
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in ("vapoursynth-mvtools_b200", "oracle", "oracle/minivs", "tests"):
+for p in ("vapoursynth-mvtools_b200", "oracle", "host/minivs", "tests"):
     sys.path.insert(0, R + "/" + p)
 import pipeline, oracle
 rnd = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 1)

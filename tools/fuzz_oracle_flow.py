@@ -13,7 +13,7 @@ R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def one(seed):
-    for p in ("vapoursynth-mvtools_b200", "oracle", os.path.join("oracle", "minivs"), "tests"):
+    for p in ("vapoursynth-mvtools_b200", "oracle", os.path.join("host", "minivs"), "tests"):
         sys.path.insert(0, os.path.join(R, p))
     import pipeline
     import pipeline_flow

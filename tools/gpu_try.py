@@ -1,7 +1,7 @@
 """Scratch GPU experiment: batch path timing of Super / Analyse xK / DegrainN (not a bench)."""
 import os, sys, time, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in ("vapoursynth-mvtools_b200", "oracle", "oracle/minivs"):
+for p in ("vapoursynth-mvtools_b200", "oracle", "host/minivs"):
     sys.path.insert(0, os.path.join(ROOT, p))
 import numpy as np, torch
 import clipgen, mvtools_b200 as mb

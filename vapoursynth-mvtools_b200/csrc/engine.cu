@@ -58,8 +58,12 @@ void make_super_desc(const mvb200_super_params *sp, SuperDesc *d) {
 void *Ctx::get_scratch(int slot, size_t bytes) {
     if (bytes <= scratch_bytes[slot])
         return scratch[slot];
-    // device memory may still be in use by queued kernels: drain first
+    // device memory may still be in use by queued kernels or copies: drain first
     cudaStreamSynchronize(stream);
+    if (copy_in)
+        cudaStreamSynchronize(copy_in);
+    if (copy_out)
+        cudaStreamSynchronize(copy_out);
     if (scratch[slot])
         cudaFree(scratch[slot]);
     scratch[slot] = nullptr;
@@ -110,6 +114,8 @@ int Ctx::staging_posted() {
     MVB_CUDA_CHECK(cudaEventRecord(staging_ev, stream));
     return 0;
 }
+
+constexpr int kMaxFramesPerLaunch = 32768;
 
 static int check_levels(const mvb200_super_params *sp) {
     if (sp->levels > kDevMaxLevels)
@@ -316,6 +322,98 @@ int mvb200_ctx_synchronize(mvb200_ctx *ctx) {
 
 void *mvb200_ctx_stream(mvb200_ctx *ctx) { return (void *)ctx->c.stream; }
 
+} // extern "C"
+
+struct mvb200_event {
+    int device;
+    int n;
+    cudaEvent_t ev[3];
+};
+
+extern "C" {
+
+int mvb200_ctx_record(mvb200_ctx *ctx, mvb200_event **out) {
+    *out = nullptr;
+    Ctx &c = ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c.device));
+    mvb200_event *e = new mvb200_event{c.device, 0, {nullptr, nullptr, nullptr}};
+    cudaStream_t streams[3] = {c.stream, c.copy_in, c.copy_out};
+    for (cudaStream_t s : streams) {
+        if (!s)
+            continue;
+        cudaError_t err = cudaEventCreateWithFlags(&e->ev[e->n], cudaEventDisableTiming);
+        if (err == cudaSuccess) {
+            e->n++;
+            err = cudaEventRecord(e->ev[e->n - 1], s);
+        }
+        if (err != cudaSuccess) {
+            mvb200_event_destroy(e);
+            return set_error("mvtools_b200: cannot record an event (%s)", cudaGetErrorString(err));
+        }
+    }
+    *out = e;
+    return 0;
+}
+
+int mvb200_event_wait(mvb200_event *ev) {
+    if (!ev)
+        return 0;
+    for (int i = 0; i < ev->n; i++)
+        MVB_CUDA_CHECK(cudaEventSynchronize(ev->ev[i]));
+    return 0;
+}
+
+int mvb200_event_query(mvb200_event *ev) {
+    if (!ev)
+        return 0;
+    for (int i = 0; i < ev->n; i++) {
+        const cudaError_t e = cudaEventQuery(ev->ev[i]);
+        if (e == cudaErrorNotReady)
+            return 1;
+        if (e != cudaSuccess) {
+            set_error("mvtools_b200: CUDA error %s behind an event (%s)", cudaGetErrorName(e), cudaGetErrorString(e));
+            return -1;
+        }
+    }
+    return 0;
+}
+
+void mvb200_event_destroy(mvb200_event *ev) {
+    if (!ev)
+        return;
+    for (int i = 0; i < ev->n; i++)
+        cudaEventDestroy(ev->ev[i]);
+    delete ev;
+}
+
+int mvb200_search_plan_query(const mvb200_analyse_params *ap, const mvb200_super_params *sp, int sm_count, mvb200_search_plan *out) {
+    memset(out, 0, sizeof(*out));
+    if (check_analyse(ap, sp))
+        return 1;
+    SuperDesc sd;
+    make_super_desc(sp, &sd);
+    SearchParams P;
+    make_search_params(ap, &P);
+    const int sms = sm_count > 0 ? sm_count : 148;
+    const char *force = getenv("MVB200_FORCE_GENERIC");
+    const char *notma = getenv("MVB200_NO_TMA");
+    const bool generic_only = force && force[0] == '1';
+    int smem = 0;
+    const int tma = (generic_only || (notma && notma[0] == '1')) ? 0 : tma_plan(sd, &P, 1, &smem);
+    if (tma > 0) {
+        out->kernel = 2;
+        out->chains_per_sm = tma;
+        out->smem_per_chain = smem;
+    } else {
+        // one-warp CTAs without shared memory: the register file (<= 255 registers per thread) holds 8 of them per SM
+        // at the least, 16 at the register counts these kernels compile to
+        out->kernel = (!generic_only && fast_applies(sd, &P, 1)) ? 1 : 0;
+        out->chains_per_sm = 16;
+    }
+    out->chains_per_wave = out->chains_per_sm * sms;
+    return 0;
+}
+
 int64_t mvb200_ctx_launch_count(mvb200_ctx *ctx) { return ctx->c.launches; }
 
 void mvb200_clip_layout(const mvb200_super_params *p, mvb200_frame_layout *l) {
@@ -360,7 +458,13 @@ int mvb200_super_batch(mvb200_ctx *ctx, const mvb200_super_params *p, const void
     ClipDesc cd;
     make_super_desc(p, &sd);
     make_clip_desc(p, &cd);
-    return launch_super(&ctx->c, p, sd, cd, (const uint8_t *)dev_src, (uint8_t *)dev_super, n);
+    // the frame index travels in grid.z / grid.y of the kernels (<= 65535): longer ranges go in pieces
+    for (int f0 = 0; f0 < n; f0 += kMaxFramesPerLaunch) {
+        const int c = n - f0 < kMaxFramesPerLaunch ? n - f0 : kMaxFramesPerLaunch;
+        if (launch_super(&ctx->c, p, sd, cd, (const uint8_t *)dev_src + (long long)f0 * cd.frame_bytes, (uint8_t *)dev_super + (long long)f0 * sd.frame_bytes, c))
+            return 1;
+    }
+    return 0;
 }
 
 int mvb200_analyse_multi_batch(mvb200_ctx *ctx, const mvb200_analyse_params *const *ap, int nap, const mvb200_super_params *sp, const void *dev_super, int first, int n, void *const *dev_vectors, int64_t vectors_stride) {
@@ -369,10 +473,17 @@ int mvb200_analyse_multi_batch(mvb200_ctx *ctx, const mvb200_analyse_params *con
     make_super_desc(sp, &sd);
     std::vector<SearchParams> params((size_t)nap);
     std::vector<SearchJob> jobs;
+    if (nap <= 0 || n <= 0)
+        return 0;
     jobs.reserve((size_t)nap * n);
     for (int i = 0; i < nap; i++) {
         if (check_analyse(ap[i], sp))
             return 1;
+        // the instances describe ONE resident super clip: its length sizes the tensor maps and bounds every frame index
+        if (ap[i]->num_frames != ap[0]->num_frames)
+            return set_error("Analyse: the instances of one launch disagree on the clip length (%d / %d frames)", ap[0]->num_frames, ap[i]->num_frames);
+        if (first < 0 || first + n > ap[i]->num_frames)
+            return set_error("Analyse: frames [%d, %d) are outside the clip of %d frames", first, first + n, ap[i]->num_frames);
         if (vectors_stride < ap[i]->vectors_size)
             return set_error("Analyse: vectors_stride (%lld) is smaller than the blob (%d bytes)", (long long)vectors_stride, ap[i]->vectors_size);
         make_search_params(ap[i], &params[i]);
@@ -411,7 +522,15 @@ int mvb200_degrain_batch(mvb200_ctx *ctx, const mvb200_degrain_params *dp, const
     ClipDesc cd;
     make_super_desc(sp, &sd);
     make_clip_desc(sp, &cd);
-    return launch_degrain(&ctx->c, dp, sd, cd, (const uint8_t *)dev_src, (const uint8_t *)dev_super, num_frames, first, n, (const uint8_t *const *)dev_vectors, vectors_stride, (uint8_t *)dev_dst);
+    for (int f0 = 0; f0 < n; f0 += kMaxFramesPerLaunch) { // (grid.y / grid.z carry the frame index)
+        const int c = n - f0 < kMaxFramesPerLaunch ? n - f0 : kMaxFramesPerLaunch;
+        const uint8_t *vec[2 * MVB200_MAX_RADIUS];
+        for (int r = 0; r < 2 * dp->radius; r++)
+            vec[r] = (const uint8_t *)dev_vectors[r] + (long long)f0 * vectors_stride;
+        if (launch_degrain(&ctx->c, dp, sd, cd, (const uint8_t *)dev_src, (const uint8_t *)dev_super, num_frames, first + f0, c, vec, vectors_stride, (uint8_t *)dev_dst + (long long)f0 * cd.frame_bytes))
+            return 1;
+    }
+    return 0;
 }
 
 // mv.Recalculate / mv.Compensate over frames [first, first + n) of a device-resident super clip (the counterparts of
@@ -433,6 +552,13 @@ int mvb200_recalculate_batch(mvb200_ctx *ctx, const mvb200_recalculate_params *r
     make_super_desc(sp, &sd);
     RecalcParams P;
     make_recalc_params(rp, sp, &P);
+    if (n > kMaxFramesPerLaunch) { // (grid.y carries the frame index)
+        for (int f0 = 0; f0 < n; f0 += kMaxFramesPerLaunch)
+            if (mvb200_recalculate_batch(ctx, rp, sp, dev_super, first + f0, n - f0 < kMaxFramesPerLaunch ? n - f0 : kMaxFramesPerLaunch, (const uint8_t *)dev_old_vectors + (long long)f0 * old_stride, old_stride,
+                                         (uint8_t *)dev_vectors + (long long)f0 * vectors_stride, vectors_stride))
+                return 1;
+        return 0;
+    }
     std::vector<RecalcJob> jobs((size_t)n);
     for (int f = 0; f < n; f++) {
         const int fn = first + f, nref = ref_frame_of_vd(rp->ad, rp->num_frames, fn);

@@ -105,6 +105,10 @@ int launch_search_tma(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &ge
                       const SuperDesc *dev_sd, const SearchParams *dev_params, const SearchJob *dev_jobs, int njobs, int *hist, int hist_ints, bool *handled);
 int launch_search_fast(Ctx *ctx, const SuperDesc &sd, const SearchParams *host_params, int nparams, const SuperDesc *dev_sd, const SearchParams *dev_params,
                        const SearchJob *dev_jobs, int njobs, int *hist, int hist_ints, bool *handled);
+// pure host (mvb200_search_plan_query): chains per SM of the TMA kernel for these parameter sets (0: it does not apply) and
+// whether the register-blocked kernel applies
+int tma_plan(const SuperDesc &sd, const SearchParams *host_params, int nparams, int *smem_per_chain);
+bool fast_applies(const SuperDesc &sd, const SearchParams *host_params, int nparams);
 int launch_recalc(Ctx *ctx, const SuperDesc &sd, const RecalcParams &P, const RecalcJob *host_jobs, int njobs);
 int launch_compensate(Ctx *ctx, const mvb200_compensate_params *cp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src_super, const uint8_t *dev_ref_super, const uint8_t *dev_vectors, int field_shift, uint8_t *dev_dst);
 int launch_degrain(Ctx *ctx, const mvb200_degrain_params *dp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, const uint8_t *dev_super, int num_frames, int first, int n, const uint8_t *const *dev_vectors, long long vectors_stride, uint8_t *dev_dst);

@@ -1055,8 +1055,13 @@ int mvb200_flowfps_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, con
             return set_error("FlowFPS: source frames %d / %d are not in the segment", fl, fr);
         const bool in_range = nleft < N && nright < N; // :156
         const bool extra = p->maskmode == 2 && in_range;
-        if (in_range && (!have(nright) || (extra && !have(nright))))
+        if (in_range && !have(nright))
             return set_error("FlowFPS: source frame %d is not in the segment", nright);
+        // the extra pair -- mvbw of the right frame, mvfw of the left one -- was searched against frames nright + off and
+        // nleft - off: inside the clip they must be inside the segment too, or the segment's searches gave default vectors
+        // where the whole clip's would not
+        if (extra && ((nright + off < N && !have(nright + off)) || (nleft - off >= 0 && !have(nleft - off))))
+            return set_error("FlowFPS: the segment [%d, %d) does not hold frames %d / %d the extra vectors of frames %d / %d refer to", src_first, src_first + n, nleft - off, nright + off, nleft, nright);
         int *flags;
         if (launch_flowinter(c, q, sd, cd, time256, in_range ? dsup + (size_t)sd.frame_bytes * local(nleft) : nullptr, in_range ? dsup + (size_t)sd.frame_bytes * local(nright) : nullptr,
                              in_range ? dbw + (size_t)vstride * local(nleft) : nullptr, in_range ? dfw + (size_t)vstride * local(nright) : nullptr, extra ? dbw + (size_t)vstride * local(nright) : nullptr,
@@ -1085,12 +1090,21 @@ struct ChainBuffers {
     ClipDesc cd;
 };
 // (out_buffers: output frames to make room for when they are not frames [out_first, out_first + out_count) of the source clip -- a rate conversion)
+// reach_back / reach_fwd: how far before / after an output frame the vectors it is made of refer (the frames they were searched
+// against).  The segment's searches see the segment as the whole clip, so inside the real clip those frames must be inside
+// the segment -- else a vector clip silently holds default vectors where the whole clip's search would not.
 static int chain_front(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const void *host_src, int src_first, int n, int out_first, int out_count, const char *filter, ChainBuffers *B,
-                       int out_buffers = -1) {
+                       int reach_back, int reach_fwd, int out_buffers = -1) {
     if (sp->levels > kDevMaxLevels)
         return set_error("mvtools_b200: more than %d pyramid levels are not supported on the device", kDevMaxLevels);
     if (out_first < src_first || out_first + out_count > src_first + n)
         return set_error("%s: output frames [%d, %d) are outside the segment [%d, %d)", filter, out_first, out_first + out_count, src_first, src_first + n);
+    if (out_count > 0) {
+        const int realN = ap[0]->num_frames;
+        const int need0 = out_first - reach_back > 0 ? out_first - reach_back : 0, need1 = out_first + out_count + reach_fwd < realN ? out_first + out_count + reach_fwd : realN;
+        if (need0 < src_first || need1 > src_first + n)
+            return set_error("%s: the segment [%d, %d) does not hold the frames [%d, %d) that the vectors of output frames [%d, %d) refer to", filter, src_first, src_first + n, need0, need1, out_first, out_first + out_count);
+    }
     mvb200_analyse_params aps[2];
     const mvb200_analyse_params *app[2];
     B->vstride = 0;
@@ -1135,7 +1149,8 @@ int mvb200_flow_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const 
     if (fp->fields)
         return set_error("Flow: the clip pipeline handles relative references without field shifts only");
     ChainBuffers B;
-    if (chain_front(ctx, sp, &ap, 1, host_src, src_first, n, out_first, out_count, "Flow", &B))
+    const int d = ap->ad.nDeltaFrame;
+    if (chain_front(ctx, sp, &ap, 1, host_src, src_first, n, out_first, out_count, "Flow", &B, ap->ad.isBackward ? 0 : d, ap->ad.isBackward ? d : 0))
         return 1;
     mvb200_flow_params q = *fp;
     q.num_frames = n;
@@ -1154,7 +1169,8 @@ int mvb200_flowinter_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, c
         return 0;
     ChainBuffers B;
     const mvb200_analyse_params *ap[2] = {ap_bw, ap_fw};
-    if (chain_front(ctx, sp, ap, 2, host_src, src_first, n, out_first, out_count, "FlowInter", &B))
+    // frames n and n + off; their extra vectors (mvfw of n, mvbw of n + off) were searched against n - off and n + 2 off
+    if (chain_front(ctx, sp, ap, 2, host_src, src_first, n, out_first, out_count, "FlowInter", &B, p->vd.nDeltaFrame, 2 * p->vd.nDeltaFrame))
         return 1;
     mvb200_flowinter_params q = *p;
     q.num_frames = n;
@@ -1176,7 +1192,7 @@ int mvb200_flowblur_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, co
         return 0;
     ChainBuffers B;
     const mvb200_analyse_params *ap[2] = {ap_bw, ap_fw};
-    if (chain_front(ctx, sp, ap, 2, host_src, src_first, n, out_first, out_count, "FlowBlur", &B))
+    if (chain_front(ctx, sp, ap, 2, host_src, src_first, n, out_first, out_count, "FlowBlur", &B, p->vd.nDeltaFrame, p->vd.nDeltaFrame))
         return 1;
     mvb200_flowblur_params q = *p;
     q.num_frames = n;
@@ -1196,7 +1212,7 @@ int mvb200_blockfps_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, co
     ChainBuffers B;
     const mvb200_analyse_params *ap[2] = {ap_bw, ap_fw};
     // (chain_front's own window test compares output with source frame numbers; they are different clips here)
-    if (chain_front(ctx, sp, ap, 2, host_src, src_first, n, src_first, 0, "BlockFPS", &B, out_count))
+    if (chain_front(ctx, sp, ap, 2, host_src, src_first, n, src_first, 0, "BlockFPS", &B, 0, 0, out_count))
         return 1;
     Ctx *c = &ctx->c;
     const ClipDesc &cd = B.cd;

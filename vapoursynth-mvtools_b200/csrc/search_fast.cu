@@ -695,6 +695,18 @@ static int fast_config(const SearchParams &P, const SuperDesc &sd, int *nw, int 
     return (*nw) * 4 + (P.bps == 2 ? 2 : 0) + *pack;
 }
 
+bool fast_applies(const SuperDesc &sd, const SearchParams *host_params, int nparams) {
+    int key = -2;
+    for (int i = 0; i < nparams; i++) {
+        int n = 0, p = 0;
+        const int k = fast_config(host_params[i], sd, &n, &p);
+        if (k < 0 || (key != -2 && k != key))
+            return false;
+        key = k;
+    }
+    return key >= 0;
+}
+
 int launch_search_fast(Ctx *ctx, const SuperDesc &sd, const SearchParams *host_params, int nparams, const SuperDesc *dev_sd, const SearchParams *dev_params,
                        const SearchJob *dev_jobs, int njobs, int *hist, int hist_ints, bool *handled) {
     *handled = false;

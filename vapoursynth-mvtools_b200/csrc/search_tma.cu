@@ -23,6 +23,8 @@
 
 #include <cuda.h>
 
+#include <atomic>
+
 #ifndef MVB_TMA_MIN_BLOCKS
 #define MVB_TMA_MIN_BLOCKS 12 // chains (warps) per SM: caps registers at 168 (16 chains at 128 registers measured slower: instruction-cache and LSU pressure)
 #endif
@@ -1190,11 +1192,13 @@ EncodeTiledFn get_encode_fn() {
 
 template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
 int launch_cfg(Ctx *ctx, const SuperDesc &sd, const uint8_t *frames_base, int nframes, const SuperDesc *dev_sd, const SearchParams *dev_params, const SearchJob *dev_jobs,
-               int njobs, int *hist, int hist_ints, const mvb200_super_geom &geom, int pel, bool need_raw) {
+               int njobs, int *hist, int hist_ints, const mvb200_super_geom &geom, int pel, bool need_raw, bool *handled) {
     using C = Cfg<BPS, BW, BH, LXR, LYR, CHROMA>;
     EncodeTiledFn enc = get_encode_fn();
-    if (!enc)
-        return set_error("mvtools_b200: cuTensorMapEncodeTiled is not available from this driver");
+    if (!enc) {
+        *handled = false;
+        return 0;
+    }
     TmaMaps maps;
     memset(&maps, 0, sizeof(maps));
     const CUtensorMapDataType dt = BPS == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
@@ -1207,8 +1211,10 @@ int launch_cfg(Ctx *ctx, const SuperDesc &sd, const uint8_t *frames_base, int nf
             cuuint32_t estr[3] = {1, 1, 1};
             CUresult r = enc(&maps.plane[p], dt, 3, (void *)(frames_base + sd.offset[p]), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS)
-                return set_error("mvtools_b200: cuTensorMapEncodeTiled failed (%d) for plane %d", (int)r, p);
+            if (r != CUDA_SUCCESS) { // (a layout the tensor-map encoder rejects: the register-blocked kernel takes the job)
+                *handled = false;
+                return 0;
+            }
         }
         if (pel == 2) { // level 0 as {x, row, sub-plane, frame}: one tile load brings the window of all four sub-planes
             const mvb200_level_geom &g0 = sd.lv[p][0];
@@ -1218,21 +1224,59 @@ int launch_cfg(Ctx *ctx, const SuperDesc &sd, const uint8_t *frames_base, int nf
             cuuint32_t estr[4] = {1, 1, 1, 1};
             CUresult r = enc(&maps.plane4[p], dt, 4, (void *)(frames_base + sd.offset[p] + (long long)g0.row0 * sd.pitch[p]), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS)
-                return set_error("mvtools_b200: cuTensorMapEncodeTiled (4-D) failed (%d) for plane %d", (int)r, p);
+            if (r != CUDA_SUCCESS) {
+                *handled = false;
+                return 0;
+            }
         }
     }
     auto kern = k_search_tma<BPS, BW, BH, LXR, LYR, CHROMA>;
-    static bool configured = false;
-    if (!configured) {
+    // function attributes are per device: one bit per device ordinal (a second context on another GPU of the same process)
+    static std::atomic<unsigned long long> configured{0};
+    const unsigned long long devbit = 1ull << (ctx->device & 63);
+    if (!(configured.load(std::memory_order_acquire) & devbit)) {
         MVB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_RAW));
         MVB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        configured = true;
+        configured.fetch_or(devbit, std::memory_order_release);
     }
     kern<<<njobs, 32, need_raw ? C::SMEM_RAW : C::SMEM, ctx->stream>>>(maps, dev_sd, dev_params, dev_jobs, njobs, hist, hist_ints, geom.plane_h[CHROMA ? 1 : 0]);
     ctx->launches++;
     MVB_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+// The compiled configurations, in the order of TMA_CONFIGS below; -1 when a parameter set needs another kernel.
+#define TMA_CONFIGS(X) X(0, 1, 16, 16, 1, 1, true) X(1, 2, 16, 16, 1, 1, true) X(2, 1, 8, 8, 1, 1, true) X(3, 2, 8, 8, 1, 1, true) X(4, 1, 16, 16, 0, 0, false) X(5, 1, 8, 8, 0, 0, false)
+
+static int tma_match(const SuperDesc &sd, const SearchParams *host_params, int nparams, bool *need_raw) {
+    const SearchParams &P0 = host_params[0];
+    for (int i = 0; i < nparams; i++) {
+        const SearchParams &P = host_params[i];
+        auto okType = [](int t) { return t == 3 || t == 4 || t == 5; };
+        if (P.dctmode != 0 || P.tryMany || !okType(P.search) || !okType(P.search_coarse) || P.pel > 2)
+            return -1;
+        if (P.blkW != P0.blkW || P.blkH != P0.blkH || P.chroma != P0.chroma || P.bps != P0.bps || P.pel != P0.pel)
+            return -1;
+    }
+    // the winner's vector travels as two 16-bit halves of one shuffle
+    if ((sd.lv[0][0].padded_w << P0.logPel) >= 32768 || (sd.lv[0][0].padded_h << P0.logPel) >= 32768)
+        return -1;
+    const int bw = P0.blkW, bh = P0.blkH, bps = P0.bps, lx = sd.logxR, ly = sd.logyR;
+    // source blocks that are not 4-byte aligned in some level need the raw staging area (same test as K.srcAligned)
+    *need_raw = false;
+    for (int i = 0; i < nparams; i++)
+        for (int l = 0; l < host_params[i].levels; l++) {
+            const int stepX = bw - host_params[i].ovX, c = P0.chroma ? 1 : 0;
+            if ((((sd.lv[0][l].hpad * bps) | (stepX * bps) | (sd.lv[c][l].hpad * bps) | ((stepX >> (c ? lx : 0)) * bps)) & 3) != 0)
+                *need_raw = true;
+        }
+    const bool chroma = P0.chroma;
+#define MATCH(ID_, BPS_, BW_, BH_, LX_, LY_, CH_)                                                            \
+    if (bps == BPS_ && bw == BW_ && bh == BH_ && chroma == CH_ && (!CH_ || (lx == LX_ && ly == LY_))) \
+        return ID_;
+    TMA_CONFIGS(MATCH)
+#undef MATCH
+    return -1;
 }
 
 } // namespace
@@ -1243,40 +1287,37 @@ int launch_search_tma(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &ge
     *handled = false;
     if (!frames_base || nframes <= 0)
         return 0;
-    const SearchParams &P0 = host_params[0];
-    for (int i = 0; i < nparams; i++) {
-        const SearchParams &P = host_params[i];
-        auto okType = [](int t) { return t == 3 || t == 4 || t == 5; };
-        if (P.dctmode != 0 || P.tryMany || !okType(P.search) || !okType(P.search_coarse) || P.pel > 2)
-            return 0;
-        if (P.blkW != P0.blkW || P.blkH != P0.blkH || P.chroma != P0.chroma || P.bps != P0.bps || P.pel != P0.pel)
-            return 0;
-    }
-    // the winner's vector travels as two 16-bit halves of one shuffle
-    if ((sd.lv[0][0].padded_w << P0.logPel) >= 32768 || (sd.lv[0][0].padded_h << P0.logPel) >= 32768)
-        return 0;
-    const int bw = P0.blkW, bh = P0.blkH, bps = P0.bps, lx = sd.logxR, ly = sd.logyR;
-    // source blocks that are not 4-byte aligned in some level need the raw staging area (same test as K.srcAligned)
     bool need_raw = false;
-    for (int i = 0; i < nparams; i++)
-        for (int l = 0; l < host_params[i].levels; l++) {
-            const int stepX = bw - host_params[i].ovX, c = P0.chroma ? 1 : 0;
-            if ((((sd.lv[0][l].hpad * bps) | (stepX * bps) | (sd.lv[c][l].hpad * bps) | ((stepX >> (c ? lx : 0)) * bps)) & 3) != 0)
-                need_raw = true;
-        }
-    const bool chroma = P0.chroma;
-#define TRY(BPS_, BW_, BH_, LX_, LY_, CH_)                                                                                                                       \
-    if (!*handled && bps == BPS_ && bw == BW_ && bh == BH_ && chroma == CH_ && (!CH_ || (lx == LX_ && ly == LY_))) {                                             \
-        *handled = true;                                                                                                                                          \
-        return launch_cfg<BPS_, BW_, BH_, LX_, LY_, CH_>(ctx, sd, frames_base, nframes, dev_sd, dev_params, dev_jobs, njobs, hist, hist_ints, geom, P0.pel, need_raw); \
-    }
-    TRY(1, 16, 16, 1, 1, true)
-    TRY(2, 16, 16, 1, 1, true)
-    TRY(1, 8, 8, 1, 1, true)
-    TRY(2, 8, 8, 1, 1, true)
-    TRY(1, 16, 16, 0, 0, false)
-    TRY(1, 8, 8, 0, 0, false)
+    const int id = tma_match(sd, host_params, nparams, &need_raw);
+    if (id < 0)
+        return 0;
+    if (!get_encode_fn()) // (the driver is older than the tensor-map API: the register-blocked kernel takes the job)
+        return 0;
+    *handled = true;
+#define TRY(ID_, BPS_, BW_, BH_, LX_, LY_, CH_) \
+    if (id == ID_)                              \
+        return launch_cfg<BPS_, BW_, BH_, LX_, LY_, CH_>(ctx, sd, frames_base, nframes, dev_sd, dev_params, dev_jobs, njobs, hist, hist_ints, geom, host_params[0].pel, need_raw, handled);
+    TMA_CONFIGS(TRY)
 #undef TRY
+    return 0;
+}
+
+// Pure host: chains (CTAs of one warp) per SM the TMA kernel runs for these parameter sets -- the smaller of the register
+// cap it is compiled for (__launch_bounds__) and what 227 KB of shared memory per SM hold (1 KB is reserved per CTA) --
+// or 0 when the kernel does not apply.
+int tma_plan(const SuperDesc &sd, const SearchParams *host_params, int nparams, int *smem_per_chain) {
+    bool need_raw = false;
+    const int id = tma_match(sd, host_params, nparams, &need_raw);
+    *smem_per_chain = 0;
+#define PLAN(ID_, BPS_, BW_, BH_, LX_, LY_, CH_)                                  \
+    if (id == ID_) {                                                              \
+        using C = Cfg<BPS_, BW_, BH_, LX_, LY_, CH_>;                             \
+        *smem_per_chain = need_raw ? C::SMEM_RAW : C::SMEM;                       \
+        const int by_smem = (227 * 1024) / (*smem_per_chain + 1024);              \
+        return by_smem < C::MINB ? by_smem : C::MINB;                             \
+    }
+    TMA_CONFIGS(PLAN)
+#undef PLAN
     return 0;
 }
 

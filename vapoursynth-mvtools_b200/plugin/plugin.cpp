@@ -17,7 +17,9 @@
 
 #include <mvtools_b200.h>
 
+#include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -27,6 +29,8 @@
 #include <mutex>
 #include <string>
 #include <vector>
+
+#include <unistd.h>
 
 namespace {
 
@@ -73,84 +77,141 @@ void unregisterSelf(VSNode *self) {
     g_registry.erase(self);
 }
 
-int lookaheadFromEnv() { // MVB200_LOOKAHEAD: frames per engine call (2..256); anything else = off
+// MVB200_LOOKAHEAD: frames per engine call.  Unset = automatic (-1: the window that fills the GPU's search-chain slots once,
+// see fusedWindowFrames / analyseWindowFrames); 0 or 1 = off (one frame per call, the reference's own granularity); N = N frames.
+int lookaheadFromEnv() {
     const char *la = getenv("MVB200_LOOKAHEAD");
-    int v = la ? atoi(la) : 0;
-    return v < 2 ? 0 : (v > 256 ? 256 : v);
+    if (!la || !*la)
+        return -1;
+    const int v = atoi(la);
+    return v < 2 ? 0 : (v > 4096 ? 4096 : v);
+}
+
+// Pinned host memory one fused filter instance may hold for its windows (MVB200_PINNED_MB; default: an eighth of the
+// machine's memory, between 2 and 32 GiB).
+int64_t pinnedBudget() {
+    const char *mb = getenv("MVB200_PINNED_MB");
+    if (mb && atoll(mb) > 0)
+        return atoll(mb) << 20;
+    const int64_t phys = (int64_t)sysconf(_SC_PHYS_PAGES) * (int64_t)sysconf(_SC_PAGE_SIZE);
+    const int64_t lo = (int64_t)2 << 30, hi = (int64_t)32 << 30;
+    const int64_t b = phys / 8;
+    return b < lo ? lo : (b > hi ? hi : b);
 }
 
 // ---------------------------------------------------------------- fused windows
-// Shared by the fused paths of DegrainN / Compensate / FlowFPS (MVB200_LOOKAHEAD=<B>, default off): when a filter's
-// inputs are this plugin's own Super / Analyse nodes wired as in the canonical script, a window of B output frames is
-// produced by ONE engine call over SOURCE frames (a *_clip_host entry point: Super, the searches and the consumer all
-// run on the device) and served from a small cache; the Super / Analyse nodes are never asked for a frame.
-struct FusedEntry {
-    std::vector<uint8_t> bytes; // an output frame in the clip layout
-    int32_t flag = 0;           // the engine's "usable" flag, where the filter has one
+// Shared by the fused paths of DegrainN / Compensate / Flow* / BlockFPS: when a filter's inputs are this plugin's own
+// Super / Analyse nodes wired as in the canonical script, the Super / Analyse nodes are never asked for a frame.  The
+// output clip is cut into ALIGNED windows of B frames; a window is produced by ONE engine call over SOURCE frames (a
+// *_clip_host entry point: Super, the searches and the consumer all run on the device).  A search is a strict serial chain
+// (one warp per frame and vector clip), so B is chosen to fill the GPU's chain slots once (mvb200_search_plan_query), and
+// the windows are pipelined: the request that first touches window k also gathers the source frames of window k + 1 and
+// enqueues it before it waits for its own frame, so the GPU works on the next window while the frame server's threads
+// collect the current one (DegrainN: the engine call is asynchronous; the copies of neighbouring windows overlap the
+// kernels).  No request ever waits for another REQUEST to be scheduled -- a request that finds its window not yet
+// enqueued holds the window's source frames itself and packs / enqueues it (cooperatively with the other requests in
+// the same position) -- so a frame server with few threads cannot deadlock; requests only wait for the GPU.
+struct PinnedPool { // window buffers are recycled: page-locking gigabytes per window would cost more than the copies
+    std::mutex m;
+    std::vector<std::pair<void *, size_t>> free_;
+    ~PinnedPool() {
+        for (auto &b : free_)
+            mvb200_pinned_free(b.first);
+    }
+    void *get(size_t bytes, size_t *got) {
+        {
+            std::lock_guard<std::mutex> lock(m);
+            for (size_t i = 0; i < free_.size(); i++)
+                if (free_[i].second >= bytes) {
+                    void *p = free_[i].first;
+                    *got = free_[i].second;
+                    free_.erase(free_.begin() + (ptrdiff_t)i);
+                    return p;
+                }
+            if (!free_.empty()) { // too small for this window: replace the smallest one
+                mvb200_pinned_free(free_.back().first);
+                free_.pop_back();
+            }
+        }
+        *got = bytes;
+        return mvb200_pinned_alloc(bytes);
+    }
+    void put(void *p, size_t bytes) {
+        if (!p)
+            return;
+        std::lock_guard<std::mutex> lock(m);
+        free_.emplace_back(p, bytes);
+    }
 };
 
-// What one frame request keeps between its two activations (frameData[0]): the end of the window it asked the source
-// frames for, or -- on a cache hit -- the cached frame itself, which other threads' windows may evict in the meantime.
+struct FusedWindow {
+    enum State { Idle = 0, Packing, Launching, Running, Ready, Failed };
+    int w0 = 0, w1 = 0, s0 = 0, s1 = 0; // output frames [w0, w1) are made of source frames [s0, s1)
+    std::mutex m;
+    std::condition_variable cv;
+    std::atomic<int> state{Idle};
+    bool prefetchClaimed = false; // (under FusedCache::m) some request already gathers this window's source frames ahead of time
+    int packNext = 0, packDone = 0;
+    std::string err;
+    void *hostSrc = nullptr, *hostDst = nullptr; // in the clip layout, frame_bytes apart
+    size_t srcBytes = 0, dstBytes = 0;
+    std::vector<int32_t> flags; // the engine's "usable" flag per output frame, where the filter has one
+    mvb200_event *done = nullptr;
+    std::shared_ptr<PinnedPool> pool;
+    ~FusedWindow() {
+        if (done) {
+            mvb200_event_wait(done); // the GPU may still be writing hostDst
+            mvb200_event_destroy(done);
+        }
+        if (pool) {
+            pool->put(hostSrc, srcBytes);
+            pool->put(hostDst, dstBytes);
+        }
+    }
+};
+
+// What one frame request keeps between its two activations (frameData[0]): its own window (so that it survives the
+// cache's eviction while the request waits for frames) and the windows whose source frames this request holds.
 struct FusedRequest {
-    int end = 0;
-    std::shared_ptr<const FusedEntry> held;
+    std::shared_ptr<FusedWindow> win;
+    std::vector<std::shared_ptr<FusedWindow>> hold;
 };
 
 struct FusedCache {
-    std::mutex m;                                              // serialises the window computations of one filter instance
-    std::map<int, std::shared_ptr<const FusedEntry>> frames;   // output frames by number
-    std::vector<int32_t> runFlags;                             // filled by the run callback (one per frame of the window), else empty
-    std::deque<int> order;
+    std::mutex m;                                           // guards `windows` and the windows' prefetchClaimed
+    std::map<int, std::shared_ptr<FusedWindow>> windows;    // by window index (frame / window)
+    std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
     mvb200_frame_layout cl;
     int window = 0;
-    void *hostSrc = nullptr, *hostDst = nullptr; // pinned staging, grown on demand (used under g_engine_mutex)
-    size_t hostSrcBytes = 0, hostDstBytes = 0;
-    ~FusedCache() {
-        mvb200_pinned_free(hostSrc);
-        mvb200_pinned_free(hostDst);
-    }
-    bool staging(size_t srcBytes, size_t dstBytes) {
-        if (hostSrcBytes < srcBytes) {
-            mvb200_pinned_free(hostSrc);
-            hostSrc = mvb200_pinned_alloc(srcBytes);
-            hostSrcBytes = hostSrc ? srcBytes : 0;
-        }
-        if (hostDstBytes < dstBytes) {
-            mvb200_pinned_free(hostDst);
-            hostDst = mvb200_pinned_alloc(dstBytes);
-            hostDstBytes = hostDst ? dstBytes : 0;
-        }
-        return hostSrc && hostDst;
-    }
-    void store(int n, int end) { // the window's frames out of hostDst; keeps the window being served and the previous one
-        const size_t fb = (size_t)cl.frame_bytes;
-        for (int k = n; k < end; k++) {
-            if (frames.count(k))
-                continue;
-            const uint8_t *p = (const uint8_t *)hostDst + fb * (k - n);
-            auto e = std::make_shared<FusedEntry>();
-            e->bytes.assign(p, p + fb);
-            e->flag = (size_t)(k - n) < runFlags.size() ? runFlags[(size_t)(k - n)] : 0;
-            frames.emplace(k, std::move(e));
-            order.push_back(k);
-        }
-        runFlags.clear();
-        while (order.size() > (size_t)window * 2) {
-            frames.erase(order.front());
-            order.pop_front();
-        }
-    }
+    int depth = 1; // windows enqueued ahead of the one being served
 };
 
+// Frames per window: MVB200_LOOKAHEAD if given, else what fills the search kernel's chain slots once with nvec vector
+// clips per frame (at least 16), within the pinned-memory budget (three windows alive: served, running, recycled).
+int fusedWindowFrames(int la, const mvb200_analyse_params *ap, const mvb200_super_params *sp, int nvec, int64_t frameBytes) {
+    if (la > 0)
+        return la;
+    mvb200_search_plan plan;
+    int frames = 64;
+    if (mvb200_search_plan_query(ap, sp, 0, &plan) == 0 && plan.chains_per_wave > 0)
+        frames = (plan.chains_per_wave + nvec - 1) / (nvec > 0 ? nvec : 1);
+    const int64_t cap = pinnedBudget() / (6 * (frameBytes > 0 ? frameBytes : 1));
+    if (frames > cap)
+        frames = (int)cap;
+    return frames < 16 ? 16 : frames;
+}
+
 // One activation of a fused filter.  propFrame: the source frame the output frame takes its properties from (always
-// requested); segment(n, end, &s0, &s1): the source frames the output window [n, end) needs; run(ctx, hostSrc, s0, s1, n,
-// end, hostDst): the engine call (source frames [s0, s1) in the clip layout -> output frames [n, end)); planeMask: bit p
-// set = plane p comes from the engine, else it is a copy of the source frame's.  alsoFrame (-1: none): one more source
-// frame the caller reads after this returns (requested here so that no frame is requested twice); flagOut: the frame's
-// "usable" flag as the run callback left it in FusedCache::runFlags.
+// requested); segment(w0, w1, &s0, &s1): the source frames the output window [w0, w1) needs; run(ctx, hostSrc, s0, s1, w0,
+// w1, hostDst, flags): ENQUEUES the engine call (source frames [s0, s1) in the clip layout -> output frames [w0, w1); flags:
+// one "usable" flag per output frame, zeroed) -- it may return before the work is done, completion is an engine event;
+// planeMask: bit p set = plane p comes from the engine, else it is a copy of the source frame's.  alsoFrame (-1: none):
+// one more source frame the caller reads after this returns (requested here so that no frame is requested twice);
+// flagOut: the frame's "usable" flag.
 template <class Segment, class Run>
 const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, const VSVideoInfo *outvi, int n, int propFrame, unsigned planeMask, int activationReason, void **frameData, VSFrameContext *frameCtx,
                              VSCore *core, const VSAPI *vsapi, Segment segment, Run run, int alsoFrame = -1, int32_t *flagOut = nullptr) {
+    const int B = f->window, N = outvi->numFrames;
     if (activationReason == arInitial) {
         vsapi->requestFrameFilter(propFrame, clip, frameCtx);
         if (alsoFrame >= 0 && alsoFrame != propFrame)
@@ -158,73 +219,142 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
         FusedRequest *rq = new FusedRequest;
         {
             std::lock_guard<std::mutex> lock(f->m);
-            const auto hit = f->frames.find(n);
-            if (hit != f->frames.end())
-                rq->held = hit->second;
+            const int k = n / B;
+            auto get = [&](int idx) -> std::shared_ptr<FusedWindow> & {
+                std::shared_ptr<FusedWindow> &w = f->windows[idx];
+                if (!w) {
+                    w = std::make_shared<FusedWindow>();
+                    w->pool = f->pool;
+                    w->w0 = idx * B;
+                    w->w1 = w->w0 + B < N ? w->w0 + B : N;
+                    segment(w->w0, w->w1, &w->s0, &w->s1);
+                }
+                return w;
+            };
+            rq->win = get(k);
+            if (rq->win->state.load() < FusedWindow::Running) // not enqueued yet: this request may have to do it
+                rq->hold.push_back(rq->win);
+            for (int a = 1; a <= f->depth && (int64_t)(k + a) * B < N; a++) { // ... and the windows after it, once
+                std::shared_ptr<FusedWindow> &w = get(k + a);
+                if (w->state.load() == FusedWindow::Idle && !w->prefetchClaimed) {
+                    w->prefetchClaimed = true;
+                    rq->hold.push_back(w);
+                }
+            }
+            // keep the window being served, the ones ahead of it and one behind; requests in flight keep their own alive
+            for (auto it = f->windows.begin(); it != f->windows.end();)
+                it = (it->first < k - 1 || it->first > k + f->depth + 1) ? f->windows.erase(it) : std::next(it);
         }
-        if (!rq->held) {
-            rq->end = n + f->window < outvi->numFrames ? n + f->window : outvi->numFrames;
-            int s0, s1;
-            segment(n, rq->end, &s0, &s1);
-            for (int k = s0; k < s1; k++)
-                if (k != propFrame && k != alsoFrame)
-                    vsapi->requestFrameFilter(k, clip, frameCtx);
-        }
+        int requestedEnd = -1; // the windows are in ascending order: their segments overlap by the halo at most
+        for (auto &w : rq->hold)
+            for (int s = w->s0 > requestedEnd ? w->s0 : requestedEnd; s < w->s1; s++) {
+                if (s != propFrame && s != alsoFrame)
+                    vsapi->requestFrameFilter(s, clip, frameCtx);
+                requestedEnd = s + 1;
+            }
         frameData[0] = rq;
         return nullptr;
     }
     std::unique_ptr<FusedRequest> rq((FusedRequest *)frameData[0]); // (released on every exit, arError included)
     frameData[0] = nullptr;
-    if (activationReason != arAllFramesReady || !rq)
+    if (!rq)
         return nullptr;
-    const VSFrame *src = vsapi->getFrameFilter(propFrame, clip, frameCtx);
-    std::shared_ptr<const FusedEntry> entry = rq->held;
-    std::string msg;
-    if (!entry) {
-        std::lock_guard<std::mutex> lock(f->m);
-        const int end = rq->end;
-        bool have = f->frames.count(n) != 0; // (another request's window may have produced it in the meantime)
-        if (!have && end > n) {
-            int s0, s1;
-            segment(n, end, &s0, &s1);
-            const size_t fb = (size_t)f->cl.frame_bytes;
-            std::lock_guard<std::mutex> elock(g_engine_mutex); // (also guards the staging buffers)
-            mvb200_ctx *ctx = engine(msg);
-            if (ctx && !f->staging(fb * (s1 - s0), fb * (end - n)))
-                msg = mvb200_last_error();
-            else if (ctx) {
-                for (int k = s0; k < s1; k++) { // pack the source frames into the clip layout
-                    const VSFrame *fr = vsapi->getFrameFilter(k, clip, frameCtx);
-                    for (int p = 0; p < f->cl.nplanes; p++)
-                        vsh::bitblt((uint8_t *)f->hostSrc + fb * (k - s0) + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], vsapi->getReadPtr(fr, p), vsapi->getStride(fr, p),
-                                    (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, (size_t)f->cl.plane_h[p]);
-                    vsapi->freeFrame(fr);
-                }
-                if (run(ctx, f->hostSrc, s0, s1, n, end, f->hostDst)) {
-                    msg = mvb200_last_error();
-                } else {
-                    f->store(n, end);
-                    have = true;
+    if (activationReason != arAllFramesReady) {
+        std::lock_guard<std::mutex> lock(f->m); // a failed request's look-ahead claims go back
+        for (auto &w : rq->hold)
+            if (w != rq->win && w->state.load() == FusedWindow::Idle)
+                w->prefetchClaimed = false;
+        return nullptr;
+    }
+    const size_t fb = (size_t)f->cl.frame_bytes;
+    // every window this request holds the source frames of: pack it (together with the other requests that hold it) and
+    // enqueue it -- the own window first, the look-ahead windows behind it on the engine's streams
+    for (auto &w : rq->hold) {
+        std::unique_lock<std::mutex> wl(w->m);
+        if (w->state.load() == FusedWindow::Idle) {
+            size_t gs = 0, gd = 0;
+            w->hostSrc = w->pool->get(fb * (size_t)(w->s1 - w->s0), &gs);
+            w->srcBytes = gs;
+            w->hostDst = w->hostSrc ? w->pool->get(fb * (size_t)(w->w1 - w->w0), &gd) : nullptr;
+            w->dstBytes = gd;
+            w->flags.assign((size_t)(w->w1 - w->w0), 0);
+            if (!w->hostSrc || !w->hostDst) {
+                w->err = mvb200_last_error();
+                w->state.store(FusedWindow::Failed);
+                w->cv.notify_all();
+                continue;
+            }
+            w->state.store(FusedWindow::Packing);
+        }
+        const int count = w->s1 - w->s0;
+        while (w->state.load() == FusedWindow::Packing || w->state.load() == FusedWindow::Launching) {
+            if (w->state.load() == FusedWindow::Launching || w->packNext >= count) { // every frame is taken: the thread that packs the last one enqueues the window
+                w->cv.wait(wl);
+                continue;
+            }
+            const int i = w->packNext++;
+            wl.unlock();
+            const VSFrame *fr = vsapi->getFrameFilter(w->s0 + i, clip, frameCtx);
+            for (int p = 0; p < f->cl.nplanes; p++)
+                vsh::bitblt((uint8_t *)w->hostSrc + fb * (size_t)i + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], vsapi->getReadPtr(fr, p), vsapi->getStride(fr, p),
+                            (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, (size_t)f->cl.plane_h[p]);
+            vsapi->freeFrame(fr);
+            wl.lock();
+            if (++w->packDone < count)
+                continue;
+            w->state.store(FusedWindow::Launching);
+            wl.unlock();
+            std::string msg;
+            bool ok = false;
+            mvb200_event *ev = nullptr;
+            {
+                std::lock_guard<std::mutex> elock(g_engine_mutex);
+                mvb200_ctx *ctx = engine(msg);
+                if (ctx) {
+                    ok = run(ctx, w->hostSrc, w->s0, w->s1, w->w0, w->w1, w->hostDst, w->flags.data()) == 0 && mvb200_ctx_record(ctx, &ev) == 0;
+                    if (!ok)
+                        msg = mvb200_last_error();
                 }
             }
-        } else if (!have) {
-            msg = "internal: frame neither cached nor requested";
+            wl.lock();
+            w->done = ev;
+            w->err = msg;
+            w->state.store(ok ? FusedWindow::Running : FusedWindow::Failed);
+            w->cv.notify_all();
         }
-        if (have)
-            entry = f->frames.find(n)->second;
     }
-    if (entry && flagOut)
-        *flagOut = entry->flag;
-    if (!entry) {
+    const VSFrame *src = vsapi->getFrameFilter(propFrame, clip, frameCtx);
+    FusedWindow *w = rq->win.get();
+    std::string msg;
+    int st = w->state.load();
+    if (st == FusedWindow::Running) {
+        if (mvb200_event_wait(w->done)) { // (any number of threads may wait for the same event)
+            std::lock_guard<std::mutex> wl(w->m);
+            w->err = mvb200_last_error();
+            w->state.store(FusedWindow::Failed);
+        } else {
+            int expect = FusedWindow::Running;
+            w->state.compare_exchange_strong(expect, FusedWindow::Ready);
+        }
+        st = w->state.load();
+    }
+    if (st != FusedWindow::Ready) {
+        {
+            std::lock_guard<std::mutex> wl(w->m);
+            msg = st == FusedWindow::Failed ? w->err : "internal: window neither enqueued nor held";
+        }
         vsapi->setFilterError((std::string(filter) + ": " + msg).c_str(), frameCtx);
         vsapi->freeFrame(src);
         return nullptr;
     }
+    if (flagOut)
+        *flagOut = w->flags[(size_t)(n - w->w0)];
+    const uint8_t *bytes = (const uint8_t *)w->hostDst + fb * (size_t)(n - w->w0);
     VSFrame *dst = vsapi->newVideoFrame(&outvi->format, outvi->width, outvi->height, src, core);
     for (int p = 0; p < outvi->format.numPlanes; p++) {
         const size_t row = (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, rows = (size_t)f->cl.plane_h[p];
         if (planeMask & (1u << p))
-            vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), entry->bytes.data() + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], row, rows);
+            vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), bytes + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], row, rows);
         else
             vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), vsapi->getReadPtr(src, p), vsapi->getStride(src, p), row, rows);
     }
@@ -683,7 +813,17 @@ void VS_CC analyseCreate(const VSMap *in, VSMap *out, void *, VSCore *core, cons
         vsapi->freeNode(d.node);
         return;
     }
-    d.lookahead = lookaheadFromEnv(); // frames searched per engine call (see AnalyseCache); default: one
+    // frames searched per engine call (see AnalyseCache).  Automatic: a request holds the window's SUPER frames (pel^2 + 1/3
+    // times the size of a source frame each), so the window stays well below what fills the GPU -- the fused paths do that
+    d.lookahead = lookaheadFromEnv();
+    if (d.lookahead < 0) {
+        mvb200_search_plan plan;
+        d.lookahead = 32;
+        if (mvb200_search_plan_query(&d.ap, &d.sp, 0, &plan) == 0 && plan.chains_per_wave < d.lookahead)
+            d.lookahead = plan.chains_per_wave < 2 ? 0 : plan.chains_per_wave;
+        if (d.lookahead > d.vi->numFrames)
+            d.lookahead = d.vi->numFrames < 2 ? 0 : d.vi->numFrames;
+    }
     d.cache = d.lookahead ? new AnalyseCache : nullptr;
     d.self = nullptr;
     AnalyseData *data = new AnalyseData(d);
@@ -749,7 +889,7 @@ const VSFrame *VS_CC degrainFusedGetFrame(int n, int activationReason, void *ins
         *s0 = w0 - f->halo > 0 ? w0 - f->halo : 0;
         *s1 = w1 + f->halo < N ? w1 + f->halo : N;
     };
-    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst) {
+    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst, int32_t *flags) {
         const int R2 = d->radius * 2, seg = s1 - s0;
         mvb200_analyse_params aps[2 * MVB200_MAX_RADIUS];
         const mvb200_analyse_params *app[2 * MVB200_MAX_RADIUS];
@@ -758,7 +898,7 @@ const VSFrame *VS_CC degrainFusedGetFrame(int n, int activationReason, void *ins
             aps[r].num_frames = seg;
             app[r] = &aps[r];
         }
-        return mvb200_degrain_clip_host_async(ctx, &d->sp, app, R2, &d->dp, hostSrc, hostDst, seg, w0 - s0, w1 - w0) || mvb200_ctx_synchronize(ctx);
+        return mvb200_degrain_clip_host_async(ctx, &d->sp, app, R2, &d->dp, hostSrc, hostDst, seg, w0 - s0, w1 - w0); // (asynchronous: fusedGetFrame records the completion event)
     };
     return fusedGetFrame("Degrain", f, d->node, d->vi, n, n, mask, activationReason, frameData, frameCtx, core, vsapi, segment, run);
 }
@@ -918,7 +1058,7 @@ void VS_CC degrainCreate(const VSMap *in, VSMap *out, void *userData, VSCore *co
                 halo = f->ap[r].ad.nDeltaFrame > halo ? f->ap[r].ad.nDeltaFrame : halo;
             d.sp = ssp;
             mvb200_clip_layout(&d.sp, &f->cl);
-            f->window = window;
+            f->window = fusedWindowFrames(window, f->ap, &d.sp, 2 * radius, f->cl.frame_bytes);
             f->halo = halo;
             d.fused = f;
         } else {
@@ -1109,7 +1249,7 @@ const VSFrame *VS_CC compFusedGetFrame(int n, int activationReason, void *instan
         *s0 = w0 - f->halo > 0 ? w0 - f->halo : 0;
         *s1 = w1 + f->halo < N ? w1 + f->halo : N;
     };
-    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst) {
+    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst, int32_t *flags) {
         return mvb200_compensate_clip_host(ctx, &d->sp, &f->ap, &d->cp, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst);
     };
     return fusedGetFrame("Compensate", f, d->node, d->vi, n, n, mask, activationReason, frameData, frameCtx, core, vsapi, segment, run);
@@ -1234,7 +1374,7 @@ void VS_CC compCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const V
         d.fused->ap = sap;
         d.sp = ssp;
         mvb200_clip_layout(&d.sp, &d.fused->cl);
-        d.fused->window = window;
+        d.fused->window = fusedWindowFrames(window, &sap, &d.sp, 1, d.fused->cl.frame_bytes);
         d.fused->halo = sap.ad.nDeltaFrame;
     }
     CompData *data = new CompData(d);
@@ -1551,9 +1691,8 @@ const VSFrame *VS_CC flowFusedGetFrame(int n, int activationReason, void *instan
         *s0 = w0 - off > 0 ? w0 - off : 0;
         *s1 = w1 + off < N ? w1 + off : N;
     };
-    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst) {
-        f->runFlags.assign((size_t)(w1 - w0), 0);
-        return mvb200_flow_clip_host(ctx, &d->sp, &f->ap, &d->fp, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst, f->runFlags.data());
+    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst, int32_t *flags) {
+        return mvb200_flow_clip_host(ctx, &d->sp, &f->ap, &d->fp, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst, flags);
     };
     int32_t usable = 0;
     const VSFrame *out = fusedGetFrame("Flow", f, d->clip, d->vi, n, n, 7u, activationReason, frameData, frameCtx, core, vsapi, segment, run, haveRef ? nref : -1, &usable);
@@ -1700,7 +1839,7 @@ void VS_CC flowCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const V
         d.fused->ap = sap;
         d.sp = ssp;
         mvb200_clip_layout(&d.sp, &d.fused->cl);
-        d.fused->window = window;
+        d.fused->window = fusedWindowFrames(window, &sap, &d.sp, 1, d.fused->cl.frame_bytes);
     }
     FlowData *data = new FlowData(d);
     if (data->fused) { // only the source clip is read on this path
@@ -1736,9 +1875,8 @@ const VSFrame *VS_CC flowInterFusedGetFrame(int n, int activationReason, void *i
         *s0 = w0 - off > 0 ? w0 - off : 0;
         *s1 = w1 + 2 * off < N ? w1 + 2 * off : N;
     };
-    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst) {
-        f->runFlags.assign((size_t)(w1 - w0), 0);
-        return mvb200_flowinter_clip_host(ctx, &d->sp, &f->apBw, &f->apFw, &d->p, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst, f->runFlags.data());
+    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst, int32_t *flags) {
+        return mvb200_flowinter_clip_host(ctx, &d->sp, &f->apBw, &f->apFw, &d->p, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst, flags);
     };
     int32_t usable = 0;
     const VSFrame *out = fusedGetFrame("FlowInter", f, d->node, d->vi, n, n, 7u, activationReason, frameData, frameCtx, core, vsapi, segment, run, -1, &usable);
@@ -1921,7 +2059,7 @@ void VS_CC flowInterCreate(const VSMap *in, VSMap *out, void *, VSCore *core, co
         d.fused->apFw = sap[1];
         d.sp = ssp;
         mvb200_clip_layout(&d.sp, &d.fused->cl);
-        d.fused->window = window;
+        d.fused->window = fusedWindowFrames(window, sap, &d.sp, 2, d.fused->cl.frame_bytes);
     }
     FlowInterData *data = new FlowInterData(d);
     VSFilterDependency deps[4] = {{data->node, rpGeneral}, {data->super, rpGeneral}, {data->mvbw, rpGeneral}, {data->mvfw, rpGeneral}};
@@ -1971,9 +2109,8 @@ const VSFrame *VS_CC flowFpsFusedGetFrame(int n, int activationReason, void *ins
         if (*s0 > N - 1)
             *s0 = N - 1; // (output frames past the end are made of the last input frame)
     };
-    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst) {
-        f->runFlags.assign((size_t)(w1 - w0), 0);
-        return mvb200_flowfps_clip_host(ctx, &d->sp, &f->apBw, &f->apFw, &d->p, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst, f->runFlags.data());
+    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst, int32_t *flags) {
+        return mvb200_flowfps_clip_host(ctx, &d->sp, &f->apBw, &f->apFw, &d->p, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst, flags);
     };
     int32_t usable = 0;
     const VSFrame *out = fusedGetFrame("FlowFPS", f, d->node, &d->vi, n, propFrame, 7u, activationReason, frameData, frameCtx, core, vsapi, segment, run, -1, &usable);
@@ -2164,7 +2301,7 @@ void VS_CC flowFpsCreate(const VSMap *in, VSMap *out, void *, VSCore *core, cons
         d.fused->apFw = sap[1];
         d.sp = ssp;
         mvb200_clip_layout(&d.sp, &d.fused->cl);
-        d.fused->window = window;
+        d.fused->window = fusedWindowFrames(window, sap, &d.sp, 2, d.fused->cl.frame_bytes);
     }
     FlowFPSData *data = new FlowFPSData(d);
     VSFilterDependency deps[4] = {{data->node, rpGeneral}, {data->super, rpGeneral}, {data->mvbw, rpGeneral}, {data->mvfw, rpGeneral}};
@@ -2218,7 +2355,7 @@ const VSFrame *VS_CC flowBlurFusedGetFrame(int n, int activationReason, void *in
         *s0 = w0 - off > 0 ? w0 - off : 0;
         *s1 = w1 + off < N ? w1 + off : N;
     };
-    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst) {
+    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst, int32_t *flags) {
         return mvb200_flowblur_clip_host(ctx, &d->sp, &f->apBw, &f->apFw, &d->p, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst);
     };
     return fusedGetFrame("FlowBlur", f, d->node, d->vi, n, n, 7u, activationReason, frameData, frameCtx, core, vsapi, segment, run);
@@ -2356,7 +2493,7 @@ void VS_CC flowBlurCreate(const VSMap *in, VSMap *out, void *, VSCore *core, con
         d.fused->apFw = sap[1];
         d.sp = ssp;
         mvb200_clip_layout(&d.sp, &d.fused->cl);
-        d.fused->window = window;
+        d.fused->window = fusedWindowFrames(window, sap, &d.sp, 2, d.fused->cl.frame_bytes);
     }
     FlowBlurData *data = new FlowBlurData(d);
     if (data->fused) { // only the source clip is read on this path
@@ -2404,9 +2541,8 @@ const VSFrame *VS_CC blockFpsFusedGetFrame(int n, int activationReason, void *in
         *s0 = lmin < N - 1 ? lmin : N - 1; // (output frames past the end are made of the last input frame)
         *s1 = lmax + off + 1 < N ? lmax + off + 1 : N;
     };
-    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst) {
-        f->runFlags.assign((size_t)(w1 - w0), 0);
-        return mvb200_blockfps_clip_host(ctx, &d->sp, &f->apBw, &f->apFw, &d->p, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst, f->runFlags.data());
+    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst, int32_t *flags) {
+        return mvb200_blockfps_clip_host(ctx, &d->sp, &f->apBw, &f->apFw, &d->p, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst, flags);
     };
     int32_t usable = 0;
     const VSFrame *out = fusedGetFrame("BlockFPS", f, d->node, &d->vi, n, propFrame, 7u, activationReason, frameData, frameCtx, core, vsapi, segment, run, -1, &usable);
@@ -2588,7 +2724,7 @@ void VS_CC blockFpsCreate(const VSMap *in, VSMap *out, void *, VSCore *core, con
         d.fused->apFw = sap[1];
         d.sp = ssp;
         mvb200_clip_layout(&d.sp, &d.fused->cl);
-        d.fused->window = window;
+        d.fused->window = fusedWindowFrames(window, sap, &d.sp, 2, d.fused->cl.frame_bytes);
     }
     BlockFPSData *data = new BlockFPSData(d);
     VSFilterDependency deps[4] = {{data->node, rpGeneral}, {data->super, rpGeneral}, {data->mvbw, rpGeneral}, {data->mvfw, rpGeneral}};
