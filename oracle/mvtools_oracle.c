@@ -326,6 +326,19 @@ static void average2(uint8_t *d, const uint8_t *a, const uint8_t *b, ptrdiff_t p
     }
 }
 
+/* The 3/4-pel planes of an 8-bit clip, with the reference's default opt=1 on x86-64: Average2 over nPaddedWidth - 1 columns
+ * (MVFrame.cpp:1519-1526) runs Average2_avx2 (MVFrame.cpp:1496-1503, MVFrame_AVX2.cpp:19-33), whose 32-byte steps also write
+ * the LAST column unless nPaddedWidth - 1 is a multiple of 32: avg(the sample after plane a's row, b's last sample).  The
+ * sample after the row is stride slack that mvsuper's memset and the SIMD passes leave at 0 (a frame stride wider than
+ * the row: every VapourSynth stride except super widths that are multiples of the 64-byte alignment).  The C loop
+ * (opt=0, and every 16-bit clip) leaves the column at the memset's 0. */
+static void average2_last_column_avx2(uint8_t *d, const uint8_t *b, ptrdiff_t pitch, int w, int h) {
+    if ((w - 1) % 32 == 0)
+        return;
+    for (int j = 0; j < h; j++)
+        d[(ptrdiff_t)j * pitch + w - 1] = (uint8_t)((b[(ptrdiff_t)j * pitch + w - 1] + 1) >> 1);
+}
+
 /* mvpRefine, MVFrame.cpp:1386-1527 */
 static void refine_plane(uint8_t *base, ptrdiff_t pitch, const Lv *g, int bps, int bits, int sharp) {
     int pel = g->pel;
@@ -357,6 +370,12 @@ static void refine_plane(uint8_t *base, ptrdiff_t pitch, const Lv *g, int bps, i
         average2(P[13], P[12], P[14], pitch, w, h, bps);
         average2(P[7], P[4] + bps, P[6], pitch, w - 1, h, bps);
         average2(P[15], P[12] + bps, P[14], pitch, w - 1, h, bps);
+        if (bps == 1) {
+            average2_last_column_avx2(P[3], P[2], pitch, w, h);
+            average2_last_column_avx2(P[11], P[10], pitch, w, h);
+            average2_last_column_avx2(P[7], P[6], pitch, w, h);
+            average2_last_column_avx2(P[15], P[14], pitch, w, h);
+        }
     }
 }
 

@@ -54,6 +54,9 @@ LATE = {
     # 4:4:0 (chroma halved vertically only), the one subsampling the cases above do not have
     "p8_440_blk8_ov4_r2": (dict(width=184, height=128, nframes=5, bits=8, ssw=0, ssh=1), dict(pel=2, hpad=8, vpad=8), dict(blksize=8, overlap=4), 2, {}),
     "p16_440_blk16x8_pel1": (dict(width=208, height=96, nframes=4, bits=16, ssw=0, ssh=1), dict(pel=1, hpad=8, vpad=8), dict(blksize=16, blksizev=8, search=5, searchparam=2), 1, dict(limit=3000)),
+    # 8-bit, pel 4: the last column of the 3/4-pel planes as the reference's default (opt=1, AVX2 Average2) path writes it
+    # (MVFrame.cpp:1519-1526): pinned for mv.Super, mv.Finest and everything computed from the super clip
+    "p8_420_blk8_pel4": (dict(width=168, height=96, nframes=4, bits=8), dict(pel=4), dict(blksize=8, overlap=4), 1, {}),
     # Degrain4..6 (the cases above stop at radius 3)
     "r6_blk8_ov4_p8": (dict(width=136, height=96, nframes=14, bits=8), dict(pel=2, hpad=8, vpad=8), dict(blksize=8, overlap=4), 6, dict(thsad=500, thsadc=300, limit=30, limitc=40)),
     "r5_blk16_p16_422": (dict(width=144, height=96, nframes=9, bits=16, ssw=1, ssh=0, scene_cut=True), dict(pel=1, hpad=8, vpad=8), dict(blksize=16, overlap=8), 5, dict(plane=4)),

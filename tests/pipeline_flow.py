@@ -50,6 +50,7 @@ FLOW = {
     "blk64x32_ov_vertical_p8": dict(mask=[dict(kind=1), dict(kind=2, ml=80.0)], flow=[dict(), dict(mode=1, time=20.0, vec=1)], scd=[dict()], inter=[dict(time=45.0, ml=30.0)], fps=[dict(num=45, den=1)]),
     "p8_440_blk8_ov4_r2": dict(mask=[dict(kind=0), dict(kind=2, vec=1), dict(kind=5)], flow=[dict(time=55.0), dict(mode=1, vec=1)], scd=[dict()], finest=True, inter=[dict(), dict(time=30.0, ml=60.0)],
                                fps=[dict(num=50, den=1), dict(num=40, den=1, mask=1)], blur=[dict(blur=70.0)], bfps=[dict(num=50, den=1), dict(num=50, den=1, mode=4)]),
+    "p8_420_blk8_pel4": dict(flow=[dict(time=40.0), dict(mode=1, vec=1)], finest=True, scd=[dict()], inter=[dict(time=30.0)], blur=[dict()], bfps=[dict(num=50, den=1)]),
     "p8_420_blk16_ov4_uncovered": dict(mask=[dict(kind=0), dict(kind=1, ml=30.0), dict(kind=2, vec=1), dict(kind=5)], flow=[dict(), dict(mode=1, vec=1, time=66.0)], scd=[dict()], finest=True, inter=[dict(), dict(time=10.0, ml=50.0)], fps=[dict(num=35, den=1, mask=2), dict(num=20, den=1, mask=0)], blur=[dict(blur=66.0)], bfps=[dict(num=35, den=1), dict(num=35, den=1, mode=1), dict(num=35, den=1, mode=5)]),
 }
 

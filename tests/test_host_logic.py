@@ -22,9 +22,23 @@ def test_library_exports_every_declared_symbol(built):
     assert b"mvtools_b200" in mb.lib().mvb200_version()
 
 
+def _exported(path):
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", path], stdout=subprocess.PIPE, text=True, check=True).stdout
+    return sorted(line.split()[-1] for line in out.splitlines() if line.strip())
+
+
 def test_plugin_exports_entry_point(built):
+    """exactly one export, like the reference module (EntryPoint.c:28-29; -fvisibility=hidden, meson.build:15): no libstdc++
+    or template symbols leak into a host that loads other C++ plugins"""
     L = C.CDLL(mb.PLUGIN_PATH)
     assert hasattr(L, "VapourSynthPluginInit2")
+    assert _exported(mb.PLUGIN_PATH) == ["VapourSynthPluginInit2"]
+
+
+def test_engine_exports_only_the_c_abi(built):
+    names = _exported(mb.LIB_PATH)
+    assert names and all(n.startswith("mvb200_") for n in names), [n for n in names if not n.startswith("mvb200_")][:5]
 
 
 def test_super_geometry_matches_survey_table(built):

@@ -147,6 +147,16 @@ def test_compensate_fused_path_glue(mock_plugin, monkeypatch, case, window):
     for n in list(range(N)) + [N - 1, 0, N // 2]:
         assert [pipeline.sha(p) for p in cn.get_frame(n).planes()[:nplanes]] == GOLD[case]["compensate"][n], "frame %d" % n
     assert (sup.computed(), vec.computed()) == before
+    # frame properties: the node-by-node path builds the output on super frame n, so frame 0 carries Super_* (MVCompensate.c:113)
+    monkeypatch.setenv("MVB200_LOOKAHEAD", "0")
+    core2 = minivs.Core()
+    mv2 = core2.load(mock_plugin)
+    clip2 = core2.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1))
+    sup2 = mv2.Super(clip2, **skw)
+    plain = mv2.Compensate(clip2, sup2, mv2.Analyse(sup2, isb=1, delta=1, **pipeline._fix(akw)), **pipeline.EXTRA[case]["comp"])
+    for n in (0, 1):
+        for key in ("Super_pel", "Super_levels", "Super_hpad", "Super_modeyuv"):
+            assert cn.get_frame(n).prop_int(key) == plain.get_frame(n).prop_int(key), "frame %d: property %s" % (n, key)
 
 
 @pytest.mark.parametrize("window", [2, 5])

@@ -319,17 +319,19 @@ __global__ void k_refine_diag(uint8_t *__restrict__ dst_base, const uint8_t *__r
 
 template <typename T>
 __global__ void k_avg2(uint8_t *__restrict__ dst_base, const uint8_t *__restrict__ a_base, const uint8_t *__restrict__ b_base,
-                       long long pitch_bytes, long long frame_bytes, int w, int h) {
+                       long long pitch_bytes, long long frame_bytes, int w, int h, int last_column) {
     int x = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y * blockDim.y + threadIdx.y;
-    if (x >= w || y >= h)
+    if (x >= w + last_column || y >= h)
         return;
     long long sp = pitch_bytes / (long long)sizeof(T);
     long long o = (long long)y * sp + x;
     const T *a = (const T *)(a_base + (long long)blockIdx.z * frame_bytes);
     const T *b = (const T *)(b_base + (long long)blockIdx.z * frame_bytes);
     T *d = (T *)(dst_base + (long long)blockIdx.z * frame_bytes);
-    d[o] = (T)((ld(a, o) + ld(b, o) + 1) >> 1);
+    // last_column: the column after the w averaged ones, as the reference's AVX2 Average2 leaves it in an 8-bit clip --
+    // avg(the 0 after plane a's row, b's sample); see the launch site
+    d[o] = (T)(((x < w ? ld(a, o) : 0) + ld(b, o) + 1) >> 1);
 }
 
 // mvpRefineExtPel2 / Pel4, MVFrame.cpp:1530-1614: sub-plane i = (sx, sy) of level 0 is the (sx, sy) phase of a
@@ -418,8 +420,13 @@ int super_typed(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, con
                 refine_hv(iD, iV, 0);
             ctx->launches += 3;
             if (p->pel == 4) {
+                // The 3/4-pel planes average w - 1 columns (MVFrame.cpp:1519-1526).  In an 8-bit clip the reference's default
+                // path (opt=1: Average2_avx2, MVFrame_AVX2.cpp:19-33, 32-byte steps) also writes the last column unless
+                // w - 1 is a multiple of 32: avg(the zeroed stride slack after plane a's row, b's last sample).  The C loop
+                // (16-bit clips) leaves it at the frame's initial 0.
                 auto avg = [&](int d, const uint8_t *a, const uint8_t *b, int ww, int hh) {
-                    k_avg2<T><<<grid2d(ww, hh, n, blk), blk, 0, st>>>(P(d), a, b, pitch, sd.frame_bytes, ww, hh);
+                    const int last = (bps == 1 && ww == w - 1 && (w - 1) % 32 != 0) ? 1 : 0;
+                    k_avg2<T><<<grid2d(ww + last, hh, n, blk), blk, 0, st>>>(P(d), a, b, pitch, sd.frame_bytes, ww, hh, last);
                     ctx->launches++;
                 };
                 avg(1, P(0), P(2), w, h);

@@ -184,6 +184,10 @@ class FrameLayout(C.Structure):
                 ("pitch", i64 * 3), ("offset", i64 * 3), ("frame_bytes", i64)]
 
 
+class SearchPlan(C.Structure):
+    _fields_ = [("kernel", i32), ("chains_per_sm", i32), ("chains_per_wave", i32), ("smem_per_chain", i32)]
+
+
 class Error(RuntimeError):
     pass
 
@@ -226,6 +230,12 @@ def lib():
         L.mvb200_ctx_stream.restype = vp
         L.mvb200_ctx_launch_count.argtypes = [vp]
         L.mvb200_ctx_launch_count.restype = i64
+        L.mvb200_search_plan_query.argtypes = [PP(AnalyseParams), PP(SuperParams), i32, PP(SearchPlan)]
+        L.mvb200_ctx_record.argtypes = [vp, PP(vp)]
+        L.mvb200_event_wait.argtypes = [vp]
+        L.mvb200_event_query.argtypes = [vp]
+        L.mvb200_event_destroy.argtypes = [vp]
+        L.mvb200_event_destroy.restype = None
         L.mvb200_super_batch.argtypes = [vp, PP(SuperParams), vp, vp, i32]
         L.mvb200_analyse_batch.argtypes = [vp, PP(AnalyseParams), PP(SuperParams), vp, i32, i32, vp, i64]
         L.mvb200_analyse_multi_batch.argtypes = [vp, PP(PP(AnalyseParams)), i32, PP(SuperParams), vp, i32, i32, PP(vp), i64]

@@ -374,6 +374,25 @@ int64_t argInt64(const VSAPI *vsapi, const VSMap *in, const char *name) {
     return err ? MVB200_UNSET64 : v;
 }
 
+// The MVTools_vectors blob of a vector frame (GroupOfPlanes.c:76-85: its first int is its own size in bytes).  *err is set when
+// the property is missing or when it is shorter than it claims to be -- the engine trusts that size.
+const uint8_t *vectorBlob(const VSAPI *vsapi, const VSFrame *f, int *err) {
+    int e = 0;
+    const VSMap *props = vsapi->getFramePropertiesRO(f);
+    const uint8_t *v = (const uint8_t *)vsapi->mapGetData(props, "MVTools_vectors", 0, &e);
+    if (!e) {
+        const int size = vsapi->mapGetDataSize(props, "MVTools_vectors", 0, nullptr);
+        int32_t claimed = 0;
+        if (size >= 4)
+            memcpy(&claimed, v, 4);
+        if (size < 8 || claimed > size)
+            e = 1;
+    }
+    if (e)
+        *err = e;
+    return e ? nullptr : v;
+}
+
 bool formatOk(const VSVideoInfo *vi) {
     return vsh::isConstantVideoFormat(vi) && vi->format.bitsPerSample <= 16 && vi->format.sampleType == stInteger && vi->format.subSamplingW <= 1 &&
            vi->format.subSamplingH <= 1 && (vi->format.colorFamily == cfYUV || vi->format.colorFamily == cfGray);
@@ -930,7 +949,7 @@ const VSFrame *VS_CC degrainGetFrame(int n, int activationReason, void *instance
         for (int r = 0; r < R2; r++) {
             vecFrames[r] = vsapi->getFrameFilter(n, d->vectors[r], frameCtx);
             int err = 0;
-            vecs[r] = (const uint8_t *)vsapi->mapGetData(vsapi->getFramePropertiesRO(vecFrames[r]), "MVTools_vectors", 0, &err);
+            vecs[r] = vectorBlob(vsapi, vecFrames[r], &err);
             bad = bad || err;
             int nref = n + d->dp.vd[r].nDeltaFrame * (d->dp.vd[r].isBackward ? 1 : -1);
             if (nref >= 0 && nref < d->vi->numFrames)
@@ -1149,7 +1168,7 @@ const VSFrame *VS_CC recalcGetFrame(int n, int activationReason, void *instanceD
         const VSFrame *ref = refOk ? vsapi->getFrameFilter(nref, d->node, frameCtx) : nullptr;
         const VSFrame *mvn = vsapi->getFrameFilter(n, d->vectors, frameCtx);
         int e = 0;
-        const uint8_t *old = (const uint8_t *)vsapi->mapGetData(vsapi->getFramePropertiesRO(mvn), "MVTools_vectors", 0, &e);
+        const uint8_t *old = vectorBlob(vsapi, mvn, &e);
         int fieldShift = 0;
         std::string msg;
         int rc = 1;
@@ -1252,7 +1271,10 @@ const VSFrame *VS_CC compFusedGetFrame(int n, int activationReason, void *instan
     auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst, int32_t *flags) {
         return mvb200_compensate_clip_host(ctx, &d->sp, &f->ap, &d->cp, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst);
     };
-    return fusedGetFrame("Compensate", f, d->node, d->vi, n, n, mask, activationReason, frameData, frameCtx, core, vsapi, segment, run);
+    const VSFrame *out = fusedGetFrame("Compensate", f, d->node, d->vi, n, n, mask, activationReason, frameData, frameCtx, core, vsapi, segment, run);
+    if (out && n == 0) // the reference builds the output on super frame n (MVCompensate.c:113): frame 0 carries the Super_* properties
+        setSuperProps(vsapi, const_cast<VSFrame *>(out), d->sp);
+    return out;
 }
 
 const VSFrame *VS_CC compGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
@@ -1272,7 +1294,7 @@ const VSFrame *VS_CC compGetFrame(int n, int activationReason, void *instanceDat
         const VSFrame *mvn = vsapi->getFrameFilter(n, d->vectors, frameCtx);
         VSFrame *dst = vsapi->newVideoFrame(&d->vi->format, d->vi->width, d->vi->height, src, core);
         int e = 0;
-        const uint8_t *vec = (const uint8_t *)vsapi->mapGetData(vsapi->getFramePropertiesRO(mvn), "MVTools_vectors", 0, &e);
+        const uint8_t *vec = vectorBlob(vsapi, mvn, &e);
         int fieldShift = 0;
         std::string msg;
         int rc = 1;
@@ -1406,7 +1428,7 @@ const VSFrame *VS_CC scdGetFrame(int n, int activationReason, void *instanceData
         vsapi->freeFrame(src);
         const VSFrame *mvn = vsapi->getFrameFilter(n, d->vectors, frameCtx);
         int e = 0;
-        const uint8_t *vec = (const uint8_t *)vsapi->mapGetData(vsapi->getFramePropertiesRO(mvn), "MVTools_vectors", 0, &e);
+        const uint8_t *vec = vectorBlob(vsapi, mvn, &e);
         std::string msg;
         int rc = 1;
         int32_t sc = 0;
@@ -1474,7 +1496,7 @@ const VSFrame *VS_CC maskGetFrame(int n, int activationReason, void *instanceDat
         VSFrame *dst = vsapi->newVideoFrame(&d->vi.format, d->vi.width, d->vi.height, src, core);
         const VSFrame *mvn = vsapi->getFrameFilter(n, d->vectors, frameCtx);
         int e = 0;
-        const uint8_t *vec = (const uint8_t *)vsapi->mapGetData(vsapi->getFramePropertiesRO(mvn), "MVTools_vectors", 0, &e);
+        const uint8_t *vec = vectorBlob(vsapi, mvn, &e);
         std::string msg;
         int rc = 1;
         if (e) {
@@ -1718,7 +1740,7 @@ const VSFrame *VS_CC flowGetFrame(int n, int activationReason, void *instanceDat
     } else if (activationReason == arAllFramesReady) {
         const VSFrame *mvn = vsapi->getFrameFilter(n, d->vectors, frameCtx);
         int e = 0;
-        const uint8_t *vec = (const uint8_t *)vsapi->mapGetData(vsapi->getFramePropertiesRO(mvn), "MVTools_vectors", 0, &e);
+        const uint8_t *vec = vectorBlob(vsapi, mvn, &e);
         const VSFrame *ref = haveRef ? vsapi->getFrameFilter(nref, d->super, frameCtx) : nullptr;
         VSFrame *dst = ref ? vsapi->newVideoFrame(&d->vi->format, d->vi->width, d->vi->height, ref, core) : nullptr;
         std::string msg;
@@ -1887,7 +1909,7 @@ const VSFrame *VS_CC flowInterFusedGetFrame(int n, int activationReason, void *i
 
 const uint8_t *vectorsOf(const VSAPI *vsapi, const VSFrame *f, bool *missing) {
     int e = 0;
-    const uint8_t *v = (const uint8_t *)vsapi->mapGetData(vsapi->getFramePropertiesRO(f), "MVTools_vectors", 0, &e);
+    const uint8_t *v = vectorBlob(vsapi, f, &e);
     if (e)
         *missing = true;
     return e ? nullptr : v;
