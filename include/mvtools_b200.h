@@ -414,6 +414,10 @@ typedef struct mvb200_ctx mvb200_ctx;
 /* Binds a context to CUDA device `device` (own stream, scratch pools).  Fails if
  * the device is missing or is not compute capability 10.x. */
 MVB200_API int mvb200_ctx_create(int device, mvb200_ctx **out);
+/* Number of CUDA devices this engine can run on (compute capability 10.x), for callers that spread independent frame
+ * windows over every GPU of a box (the plugin's fused paths: one context per device, no data-path collective -- frames are
+ * independent units, readme.rst:36).  0 when there is none (and mvb200_last_error says why). */
+MVB200_API int mvb200_device_count(void);
 MVB200_API void mvb200_ctx_destroy(mvb200_ctx *ctx);
 MVB200_API int mvb200_ctx_synchronize(mvb200_ctx *ctx);
 /* the cudaStream_t the context launches on (for CUDA-event timing by the caller) */

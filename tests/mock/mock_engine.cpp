@@ -16,6 +16,7 @@
 #include <cstring>
 #include <vector>
 
+static std::atomic<long> g_ctx_created{0}; // mvb200_ctx_create calls so far (one context per device the plugin uses)
 static std::atomic<long> g_clip_calls{0}; // mvb200_degrain_clip_host_async calls so far (the glue tests count the windows)
 
 struct mvb200_ctx {
@@ -36,9 +37,16 @@ extern "C" {
 
 MVB200_API int mvb200_ctx_create(int, mvb200_ctx **out) {
     *out = new mvb200_ctx{0};
+    g_ctx_created++;
     return 0;
 }
 MVB200_API void mvb200_ctx_destroy(mvb200_ctx *ctx) { delete ctx; }
+// MVB200_MOCK_DEVICES: how many "devices" the stand-in pretends to have (the plugin then spreads its windows over them)
+MVB200_API int mvb200_device_count(void) {
+    const char *e = getenv("MVB200_MOCK_DEVICES");
+    return e ? atoi(e) : 1;
+}
+MVB200_API long mvb200_mock_contexts(void) { return g_ctx_created.load(); }
 MVB200_API int mvb200_ctx_synchronize(mvb200_ctx *) { return 0; }
 // the stand-in computes synchronously: an event is complete when it is recorded
 struct mvb200_event {

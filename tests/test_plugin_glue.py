@@ -314,6 +314,45 @@ def test_fused_windows_are_aligned_pipelined_and_computed_once(mock_plugin, monk
             assert [pipeline.sha(p) for p in dn.get_frame(n).planes()] == GOLD[case]["degrain"][n]
 
 
+def test_fused_windows_spread_over_every_device(mock_plugin):
+    """With several devices (here: the stand-in pretends to have three) the windows of a fused filter go round the engine
+    contexts, one per device, and as many windows as there are devices are enqueued ahead; the frames do not change.
+    (A child process: the plugin reads the device list once per process.)"""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes, json, os, sys
+sys.path[:0] = [%r, %r, %r]
+import minivs, pipeline
+case = "blk16_ov8_pel2_p8_r3"
+ck, skw, akw, radius, dkw = pipeline.CASES[case]
+frames = pipeline.make_frames(ck)
+core = minivs.Core()
+mv = core.load(%r)
+clip = core.source(frames, bits=8)
+sup = mv.Super(clip, **skw)
+vn = [mv.Analyse(sup, isb=isb, delta=d, **akw) for d in range(1, radius + 1) for isb in (1, 0)]
+dn = mv.invoke("Degrain%%d" %% radius, clip, sup, *vn, **dkw)
+dn.set_cache(0)
+dn.render(0, len(frames), 4)
+L = ctypes.CDLL(%r)
+L.mvb200_mock_contexts.restype = ctypes.c_long
+L.mvb200_mock_clip_calls.restype = ctypes.c_long
+print(json.dumps({"contexts": L.mvb200_mock_contexts(), "calls": L.mvb200_mock_clip_calls(),
+                  "frames": [[pipeline.sha(p) for p in dn.get_frame(n).planes()] for n in range(len(frames))]}))
+''' % (os.path.join(ROOT, "vapoursynth-mvtools_b200"), os.path.join(ROOT, "host", "minivs"), HERE, mock_plugin, mock_plugin)
+    env = dict(os.environ, MVB200_MOCK_DEVICES="3", MVB200_LOOKAHEAD="2")
+    env.pop("MVB200_DEVICE", None)
+    env.pop("MVB200_DEVICES", None)
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = json.loads(r.stdout.strip().splitlines()[-1])
+    case = "blk16_ov8_pel2_p8_r3"
+    assert got["frames"] == GOLD[case]["degrain"]
+    assert got["contexts"] == 3, "windows were not spread over the three devices"
+    assert got["calls"] >= 4
+
+
 def test_non_canonical_chains_keep_the_node_by_node_evaluation(mock_plugin, monkeypatch):
     """MVB200_LOOKAHEAD set, but the script is not the canonical chain: vectors searched on ANOTHER Super node of the same
     clip, a vector clip with divide feeding mv.Flow, a consumer with fields -- the fused paths must decline (the Super /

@@ -272,6 +272,22 @@ int mvb200_ctx_create(int device, mvb200_ctx **out) {
     return 0;
 }
 
+int mvb200_device_count(void) {
+    int count = 0;
+    const cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        set_error("mvtools_b200: no CUDA device available (%s)", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return 0;
+    }
+    int usable = 0;
+    for (int d = 0; d < count; d++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10)
+            usable = d + 1; // (device ordinals are used as they are: count up to the last usable one)
+    }
+    return usable;
+}
+
 void mvb200_ctx_destroy(mvb200_ctx *ctx) {
     if (!ctx)
         return;

@@ -20,6 +20,8 @@
 //                 *Wiener :1019-1111, Average2 :1180-1197, driver mvpRefine :1386-1527
 #include "engine.h"
 
+#include <cstdlib>
+
 namespace mvb200 {
 
 namespace {
@@ -292,6 +294,136 @@ __global__ void k_refine_hv_w(uint8_t *__restrict__ dst_base, const uint8_t *__r
     *d = out;
 }
 
+// ---- level 0 of a pel-2 super frame in ONE pass -------------------------------------------------------------------------
+// mvfFillPlane + PadReferenceFrame + mvpRefine (MVFrame.cpp:1367-1371, 1264-1318, 1386-1494) for level 0: the reference
+// copies the source plane into the frame, replicates its borders, then filters the padded plane three times (H from P0,
+// V from P0, D from V -- or the bilinear diagonal from P0).  Every sample of the four sub-planes is a pure function of
+// the SOURCE plane (a padded sample is the clamped source sample), so one CTA stages a (TH + 5) x (TW + 8) source tile
+// in shared memory once and writes the tile of all four sub-planes: the source is read once and nothing is read back
+// from the super frame (the separate passes read P0 three times and V once, after a memset of the whole frame).
+// One 32-bit word (4 / 2 samples) per thread and step; rows of the super frame start 4-byte aligned and W * bps, hpad * bps
+// are whole words (checked by the caller).  The threads of the last tile column also clear the row tails [W * bps, pitch).
+template <int SHARP>
+__device__ __forceinline__ int refine_tap(int t0, int t1, int t2, int t3, int t4, int t5, int i, int n, int pixelMax) {
+    if (i >= n - 1)
+        return t2;
+    const int avg = (t2 + t3 + 1) >> 1;
+    if (SHARP == 0)
+        return avg;
+    if (SHARP == 1) // HorizontalBicubic / VerticalBicubic, MVFrame.cpp:1115-1176
+        return (i >= 1 && i < n - 3) ? min(pixelMax, max(0, (-t1 - t4 + (t2 + t3) * 9 + 8) >> 4)) : avg;
+    if (!(i >= 2 && i < n - 4)) // Wiener, MVFrame.cpp:1019-1111
+        return avg;
+    int m2 = (t2 + t3) * 4;
+    m2 -= t1 + t4;
+    m2 *= 5;
+    const int m0 = (t0 + t5 + m2 + 16) >> 5;
+    return max(0, min(m0, pixelMax));
+}
+
+template <typename T, int SHARP>
+__global__ void __launch_bounds__(256) k_super0_pel2(const uint8_t *__restrict__ src_base, long long src_pitch, long long src_frame, uint8_t *__restrict__ lvl0, long long pitch,
+                                                     long long frame_bytes, long long sub_bytes, int w, int h, int hpad, int vpad, int bits) {
+    constexpr int SPW = 4 / (int)sizeof(T), SH = 8 * (int)sizeof(T);
+    constexpr unsigned MASK = sizeof(T) == 1 ? 0xffu : 0xffffu;
+    constexpr int TW = 64, TH = 32;           // samples x rows of one output tile (per sub-plane)
+    constexpr int PW = (TW + 8) / SPW;        // words of a staged row: samples x0 - 4 .. x0 + TW + 3
+    constexpr int PR = TH + 5;                // staged rows: y0 - 2 .. y0 + TH + 2
+    __shared__ unsigned sP[PR][PW + 1];
+    __shared__ unsigned sV[TH][PW + 1];
+    const int W = w + 2 * hpad, Hh = h + 2 * vpad;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int pixelMax = (1 << bits) - 1;
+    const uint8_t *src = src_base + (long long)blockIdx.z * src_frame;
+    uint8_t *out = lvl0 + (long long)blockIdx.z * frame_bytes;
+    const int tid = threadIdx.x;
+
+    // ---- phase A: the source tile, borders replicated by clamping the coordinates (also beyond the padded plane: never used)
+    for (int k = tid; k < PR * PW; k += 256) {
+        const int r = k / PW, cw = k - r * PW;
+        const int y = min(max(y0 - 2 + r - vpad, 0), h - 1);
+        const int x = x0 - 4 + cw * SPW - hpad; // source column of the word's first sample
+        const uint8_t *row = src + (long long)y * src_pitch;
+        unsigned v;
+        if (x >= 0 && x + SPW <= w) {
+            v = __ldg((const unsigned *)(row + (long long)x * (int)sizeof(T)));
+        } else {
+            v = 0;
+#pragma unroll
+            for (int j = 0; j < SPW; j++)
+                v |= (unsigned)((const T *)row)[min(max(x + j, 0), w - 1)] << (SH * j);
+        }
+        sP[r][cw] = v;
+    }
+    __syncthreads();
+    auto sample = [&](const unsigned(*tile)[PW + 1], int r, int c) -> int { // sample c (0 = x0 - 4) of staged row r
+        return (int)((tile[r][c / SPW] >> (SH * (c % SPW))) & MASK);
+    };
+    // ---- phase B: V over the whole staged width (D filters it horizontally), rows y0 .. y0 + TH - 1
+    for (int k = tid; k < TH * PW; k += 256) {
+        const int r = k / PW, cw = k - r * PW;
+        const int y = y0 + r;
+        unsigned t[6];
+#pragma unroll
+        for (int q = 0; q < 6; q++)
+            t[q] = sP[r + q][cw];
+        unsigned v = 0;
+#pragma unroll
+        for (int j = 0; j < SPW; j++) {
+            const int a0 = (t[0] >> (SH * j)) & MASK, a1 = (t[1] >> (SH * j)) & MASK, a2 = (t[2] >> (SH * j)) & MASK, a3 = (t[3] >> (SH * j)) & MASK, a4 = (t[4] >> (SH * j)) & MASK,
+                      a5 = (t[5] >> (SH * j)) & MASK;
+            v |= (unsigned)refine_tap<SHARP>(a0, a1, a2, a3, a4, a5, y, Hh, pixelMax) << (SH * j);
+        }
+        sV[r][cw] = v;
+        const int x = x0 - 4 + cw * SPW;
+        if (cw >= 4 / SPW && cw < PW - 4 / SPW && x < W && y < Hh)
+            *(unsigned *)(out + 2 * sub_bytes + (long long)y * pitch + (long long)x * (int)sizeof(T)) = v;
+    }
+    __syncthreads();
+    // ---- phase C: P0 (the padded plane itself), H and D
+    constexpr int OW = TW / SPW;
+    for (int k = tid; k < TH * OW; k += 256) {
+        const int r = k / OW, ow = k - r * OW;
+        const int y = y0 + r, x = x0 + ow * SPW;
+        if (x >= W || y >= Hh)
+            continue;
+        const int c = 4 + ow * SPW; // staged column of the word's first sample
+        unsigned vh = 0, vd = 0;
+#pragma unroll
+        for (int j = 0; j < SPW; j++) {
+            const int cc = c + j;
+            const int hval = refine_tap<SHARP>(sample(sP, r + 2, cc - 2), sample(sP, r + 2, cc - 1), sample(sP, r + 2, cc), sample(sP, r + 2, cc + 1), sample(sP, r + 2, cc + 2), sample(sP, r + 2, cc + 3),
+                                               x + j, W, pixelMax);
+            int dval;
+            if (SHARP == 0) { // DiagonalBilinear, MVFrame.cpp:536-572
+                const int p00 = sample(sP, r + 2, cc), p01 = sample(sP, r + 2, cc + 1), p10 = sample(sP, r + 3, cc), p11 = sample(sP, r + 3, cc + 1);
+                if (y < Hh - 1)
+                    dval = (x + j < W - 1) ? (p00 + p01 + p10 + p11 + 2) >> 2 : (p00 + p10 + 1) >> 1;
+                else
+                    dval = (x + j < W - 1) ? (p00 + p01 + 1) >> 1 : p00;
+            } else {
+                dval = refine_tap<SHARP>(sample(sV, r, cc - 2), sample(sV, r, cc - 1), sample(sV, r, cc), sample(sV, r, cc + 1), sample(sV, r, cc + 2), sample(sV, r, cc + 3), x + j, W, pixelMax);
+            }
+            vh |= (unsigned)hval << (SH * j);
+            vd |= (unsigned)dval << (SH * j);
+        }
+        const long long o = (long long)y * pitch + (long long)x * (int)sizeof(T);
+        *(unsigned *)(out + o) = sP[r + 2][c / SPW];
+        *(unsigned *)(out + sub_bytes + o) = vh;
+        *(unsigned *)(out + 3 * sub_bytes + o) = vd;
+    }
+    // ---- the row tails of the four sub-planes stay zero (MVSuper.c:75 clears the whole frame)
+    if (x0 + TW >= W) {
+        const int tail_words = (int)((pitch - (long long)W * (int)sizeof(T)) / 4);
+        const int rows = min(TH, Hh - y0);
+        for (int k = tid; k < 4 * rows * tail_words; k += 256) {
+            const int sp = k / (rows * tail_words), rem = k - sp * rows * tail_words;
+            const int r = rem / tail_words, cw = rem - r * tail_words;
+            *(unsigned *)(out + sp * sub_bytes + (long long)(y0 + r) * pitch + (long long)W * (int)sizeof(T) + 4ll * cw) = 0u;
+        }
+    }
+}
+
 template <typename T>
 __global__ void k_refine_diag(uint8_t *__restrict__ dst_base, const uint8_t *__restrict__ src_base, long long pitch_bytes,
                               long long frame_bytes, int w, int h) {
@@ -356,9 +488,29 @@ int super_typed(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, con
     cudaStream_t st = ctx->stream;
     const dim3 blk(64, 4);
     const int bps = sd.bps;
-    // MVSuper.c:75 -- the whole super frame starts zeroed (the gaps between levels stay zero)
-    MVB_CUDA_CHECK(cudaMemsetAsync(dev_super, 0, (size_t)sd.frame_bytes * n, st));
-    ctx->launches++;
+    // MVSuper.c:75 -- the whole super frame starts zeroed (the gaps between levels stay zero).  A plane whose level 0 is
+    // written by the fused kernel (every byte of its rows, tails included) only needs its upper levels cleared.
+    const bool no_fused = getenv("MVB200_NO_FUSED_SUPER") != nullptr; // (A/B switch: the separate passes)
+    auto fused_plane = [&](int plane) {
+        const mvb200_level_geom &g = sd.lv[plane][0];
+        return !no_fused && p->pel == 2 && !pelclip && (p->modeyuv & (1 << plane)) && (g.width * bps) % 4 == 0 && (g.hpad * bps) % 4 == 0 && g.width >= 4 && g.height >= 1;
+    };
+    {
+        bool all_fused = true;
+        for (int plane = 0; plane < sd.nplanes; plane++)
+            all_fused = all_fused && fused_plane(plane);
+        if (!all_fused) {
+            MVB_CUDA_CHECK(cudaMemsetAsync(dev_super, 0, (size_t)sd.frame_bytes * n, st));
+        } else {
+            for (int plane = 0; plane < sd.nplanes; plane++) {
+                const long long begin = sd.offset[plane] + (long long)sd.lv[plane][0].padded_h * 4 * sd.pitch[plane]; // after the four sub-planes of level 0
+                const long long end = plane + 1 < sd.nplanes ? sd.offset[plane + 1] : sd.frame_bytes;
+                if (end > begin)
+                    MVB_CUDA_CHECK(cudaMemset2DAsync(dev_super + begin, (size_t)sd.frame_bytes, 0, (size_t)(end - begin), (size_t)n, st));
+            }
+        }
+        ctx->launches++;
+    }
     for (int plane = 0; plane < sd.nplanes; plane++) {
         if (!(p->modeyuv & (1 << plane)))
             continue;
@@ -368,7 +520,21 @@ int super_typed(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, con
         auto interior = [&](int l) { return level_base(l) + (long long)sd.lv[plane][l].vpad * pitch + (long long)sd.lv[plane][l].hpad * bps; };
         const mvb200_level_geom &g0 = sd.lv[plane][0];
         const bool words0 = (g0.width * bps) % 4 == 0 && (g0.hpad * bps) % 4 == 0; // level 0: whole 32-bit words per row segment
-        if (words0)
+        const bool fused0 = fused_plane(plane);
+        if (fused0) {
+            const dim3 g((g0.padded_w + 63) / 64, (g0.padded_h + 31) / 32, n);
+            const long long sub = pitch * g0.padded_h;
+#define MVB_SUPER0(SHARP_)                                                                                                                                                         \
+    k_super0_pel2<T, SHARP_><<<g, 256, 0, st>>>(dev_src + cd.offset[plane], cd.pitch[plane], cd.frame_bytes, level_base(0), pitch, sd.frame_bytes, sub, g0.width, g0.height, g0.hpad, \
+                                                g0.vpad, sd.bits)
+            if (p->sharp == 0)
+                MVB_SUPER0(0);
+            else if (p->sharp == 1)
+                MVB_SUPER0(1);
+            else
+                MVB_SUPER0(2);
+#undef MVB_SUPER0
+        } else if (words0)
             k_fill_w<<<grid2d(g0.width * bps / 4, g0.height, n, blk), blk, 0, st>>>(dev_src + cd.offset[plane], cd.pitch[plane], cd.frame_bytes, interior(0), pitch, sd.frame_bytes,
                                                                                   g0.width * bps / 4, g0.height);
         else
@@ -382,6 +548,8 @@ int super_typed(Ctx *ctx, const mvb200_super_params *p, const SuperDesc &sd, con
             k_pad<T><<<grid2d(g1.padded_w, g1.padded_h, n, blk), blk, 0, st>>>(level_base(l + 1), pitch, sd.frame_bytes, g1.hpad, g1.vpad, g1.width, g1.height);
             ctx->launches += 2;
         }
+        if (fused0)
+            continue; // level 0 is complete: padded plane and the three half-pel planes
         if (words0)
             k_pad_w<T><<<grid2d(g0.padded_w * bps / 4, 2 * g0.vpad + g0.height, n, blk), blk, 0, st>>>(level_base(0), pitch, sd.frame_bytes, g0.hpad, g0.vpad, g0.width, g0.height);
         else

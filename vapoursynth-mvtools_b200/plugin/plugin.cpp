@@ -34,19 +34,70 @@
 
 namespace {
 
-std::mutex g_engine_mutex;
-mvb200_ctx *g_ctx = nullptr;
+// One engine context (own CUDA streams and scratch) per device, each guarded by its own mutex.  Device 0 of the list does the
+// per-frame work; the fused windows go round the whole list (frames are independent units: a window carries its own halo).
+//   MVB200_DEVICES=0,2,3  the devices to use        MVB200_DEVICE=1  a single device (what a multi-process launcher sets per rank)
+//   neither: every device the engine can run on
+constexpr int kMaxDevices = 16;
+struct EngineSlot {
+    std::mutex m; // serialises this context's calls (the engine context is not re-entrant)
+    mvb200_ctx *ctx = nullptr;
+    int device = 0;
+    bool failed = false;
+    std::string err;
+};
+EngineSlot g_engines[kMaxDevices];
+std::once_flag g_devices_once;
+int g_ndev = 1;
 
-// returns nullptr and fills err on failure
-mvb200_ctx *engine(std::string &err) {
-    if (!g_ctx) {
-        const char *dev = getenv("MVB200_DEVICE");
-        if (mvb200_ctx_create(dev ? atoi(dev) : 0, &g_ctx)) {
-            err = mvb200_last_error();
-            g_ctx = nullptr;
+void listDevices() {
+    int n = 0;
+    if (const char *list = getenv("MVB200_DEVICES")) {
+        for (const char *p = list; *p && n < kMaxDevices;) {
+            char *end = nullptr;
+            const long d = strtol(p, &end, 10);
+            if (end == p)
+                break;
+            g_engines[n++].device = (int)d;
+            p = *end == ',' ? end + 1 : end;
+        }
+    } else if (const char *one = getenv("MVB200_DEVICE")) {
+        g_engines[n++].device = atoi(one);
+    } else {
+        const int count = mvb200_device_count();
+        for (int d = 0; d < count && n < kMaxDevices; d++)
+            g_engines[n++].device = d;
+    }
+    if (n == 0)
+        g_engines[n++].device = 0; // (no usable device: creating the context reports why)
+    g_ndev = n;
+}
+
+int deviceCount() {
+    std::call_once(g_devices_once, listDevices);
+    return g_ndev;
+}
+
+// The context of slot `which` (created on first use), with the slot's mutex to hold around every call on it;
+// returns nullptr and fills err on failure.  Call with the slot's mutex held.
+mvb200_ctx *engineOf(EngineSlot &e, std::string &err) {
+    if (!e.ctx && !e.failed) {
+        if (mvb200_ctx_create(e.device, &e.ctx)) {
+            e.err = mvb200_last_error();
+            e.ctx = nullptr;
+            e.failed = true;
         }
     }
-    return g_ctx;
+    if (!e.ctx)
+        err = e.err;
+    return e.ctx;
+}
+
+// the per-frame paths: device slot 0
+std::mutex &g_engine_mutex = g_engines[0].m;
+mvb200_ctx *engine(std::string &err) {
+    deviceCount();
+    return engineOf(g_engines[0], err);
 }
 
 // The plugin's own Super / Analyse nodes, by node pointer (API 4: a VSNode* IS the node, every reference to it has the
@@ -155,6 +206,7 @@ struct FusedWindow {
     std::string err;
     void *hostSrc = nullptr, *hostDst = nullptr; // in the clip layout, frame_bytes apart
     size_t srcBytes = 0, dstBytes = 0;
+    int slot = 0;               // which engine context (device) computes this window
     std::vector<int32_t> flags; // the engine's "usable" flag per output frame, where the filter has one
     mvb200_event *done = nullptr;
     std::shared_ptr<PinnedPool> pool;
@@ -183,7 +235,7 @@ struct FusedCache {
     std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
     mvb200_frame_layout cl;
     int window = 0;
-    int depth = 1; // windows enqueued ahead of the one being served
+    int depth = deviceCount(); // windows enqueued ahead of the one being served: one per device
 };
 
 // Frames per window: MVB200_LOOKAHEAD if given, else what fills the search kernel's chain slots once with nvec vector
@@ -191,11 +243,12 @@ struct FusedCache {
 int fusedWindowFrames(int la, const mvb200_analyse_params *ap, const mvb200_super_params *sp, int nvec, int64_t frameBytes) {
     if (la > 0)
         return la;
+    const int ndev = deviceCount();
     mvb200_search_plan plan;
     int frames = 64;
     if (mvb200_search_plan_query(ap, sp, 0, &plan) == 0 && plan.chains_per_wave > 0)
         frames = (plan.chains_per_wave + nvec - 1) / (nvec > 0 ? nvec : 1);
-    const int64_t cap = pinnedBudget() / (6 * (frameBytes > 0 ? frameBytes : 1));
+    const int64_t cap = pinnedBudget() / (2 * (ndev + 2) * (frameBytes > 0 ? frameBytes : 1)); // windows alive: one per device, the one being served, one recycled
     if (frames > cap)
         frames = (int)cap;
     return frames < 16 ? 16 : frames;
@@ -225,6 +278,7 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
                 if (!w) {
                     w = std::make_shared<FusedWindow>();
                     w->pool = f->pool;
+                    w->slot = idx % deviceCount();
                     w->w0 = idx * B;
                     w->w1 = w->w0 + B < N ? w->w0 + B : N;
                     segment(w->w0, w->w1, &w->s0, &w->s1);
@@ -308,8 +362,9 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
             bool ok = false;
             mvb200_event *ev = nullptr;
             {
-                std::lock_guard<std::mutex> elock(g_engine_mutex);
-                mvb200_ctx *ctx = engine(msg);
+                EngineSlot &es = g_engines[w->slot];
+                std::lock_guard<std::mutex> elock(es.m);
+                mvb200_ctx *ctx = engineOf(es, msg);
                 if (ctx) {
                     ok = run(ctx, w->hostSrc, w->s0, w->s1, w->w0, w->w1, w->hostDst, w->flags.data()) == 0 && mvb200_ctx_record(ctx, &ev) == 0;
                     if (!ok)
