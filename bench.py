@@ -227,34 +227,64 @@ def fill_host_clip(hv, frames, cl):
             rows[:, : a.shape[1] * a.itemsize] = a.view(np.uint8).reshape(a.shape[0], -1)
 
 
-def plugin_leg(cfg, args, mb, plan, world, rank, local, barrier, total_frames, gold):
-    """e2e through libmvtools.so under the API-4 host: W warm-up steps, K timed steps of F_out frames; then the output check."""
+def plugin_window(plan_q, nvec):
+    """Frames per look-ahead window of the plugin's fused paths in its default configuration (plugin.cpp fusedWindowFrames:
+    what fills the search kernel's chain slots once, at most 768) -- only used to ALIGN the timed region, see plugin_leg."""
+    return max(16, min(768, -(-plan_q.chains_per_wave // max(nvec, 1))))
+
+
+def plugin_leg(cfg, args, mb, plan, world, rank, local, barrier, total_frames, gold, window):
+    """e2e through libmvtools.so under the API-4 host, default environment.
+    Weak-scaling configs: STEADY STATE -- one long clip; W warm-up steps, then K timed steps.  The plugin works in aligned
+    windows and keeps the next window in flight, so a timed region that started or ended inside a window would inherit (or
+    give away) part of a window's work: the step is rounded up to whole windows, the region starts on a window boundary
+    and the clip continues for a window past it.
+    A fixed batch (c5): COLD START -- the engine is warmed on another instance of the script, then a fresh instance renders
+    exactly the batch, first request to last frame (pipeline fill and drain included)."""
     import minivs
     os.environ["MVB200_DEVICE"] = str(local)
-    F_out, OFF = plan["count"], plan["offset"]
+    F_out, OFF, lo = plan["count"], plan["offset"], plan["lo"]
     threads = max(4, (os.cpu_count() or 4) // world)
-    core = minivs.Core()
-    mv = core.load(mb.PLUGIN_PATH)
-    # this rank's clip: (W + K) copies of its shard's frames back to back would break the temporal continuity the searches see,
-    # so the clip simply continues the cyclic synthetic clip: step s of this rank covers global frames first + s * stride ...
-    steps = args.warmup_e2e + args.steps
-    lo = plan["lo"]
-    n_local = OFF + steps * F_out + (plan["local_frames"] - OFF - F_out)
-    out, keep = build_script(mv, core, cfg, make_frames(cfg, n_local, first=lo))
-    out.set_cache(0)
-    if cfg["kind"] != "degrain":  # node-by-node evaluation reads the super / vector clips through the host's caches
-        keep[1].set_cache(64 + 2 * threads)
-        for v in keep[2:]:
-            v.set_cache(8 + 2 * threads)
-    t_warm = out.render(OFF, OFF + args.warmup_e2e * F_out, threads) if args.warmup_e2e else 0.0
-    barrier()
-    t = out.render(OFF + args.warmup_e2e * F_out, OFF + steps * F_out, threads)
-    barrier()
+    fused = cfg["kind"] == "degrain"
+
+    def script(n_local, first):
+        core = minivs.Core()
+        mv = core.load(mb.PLUGIN_PATH)
+        out, keep = build_script(mv, core, cfg, make_frames(cfg, n_local, first=first))
+        out.set_cache(0)
+        if not fused:  # node-by-node evaluation reads the super / vector clips through the host's caches
+            keep[1].set_cache(64 + 2 * threads)
+            for v in keep[2:]:
+                v.set_cache(8 + 2 * threads)
+        return core, out, keep
+
+    if cfg.get("fixed_total"):
+        tail = plan["local_frames"] - OFF - F_out
+        warm = script(OFF + min(F_out, 2 * window) + tail, lo)
+        warm[1].render(OFF, OFF + min(F_out, 2 * window), threads)
+        del warm
+        core, out, keep = script(plan["local_frames"], lo)
+        barrier()
+        t = out.render(OFF, OFF + F_out, threads)
+        barrier()
+        frames_timed, first_timed, protocol = F_out, OFF, "cold start: a fresh script instance renders the whole batch once (engine warmed on another instance)"
+    else:
+        step = -(-F_out // window) * window if fused else F_out
+        base = -(-OFF // window) * window if fused else OFF  # the first rendered frame: a window boundary at or after the halo
+        n_local = base + (args.warmup_e2e + args.steps) * step + (window if fused else 0) + REACH
+        core, out, keep = script(n_local, lo)
+        if args.warmup_e2e:
+            out.render(base, base + args.warmup_e2e * step, threads)
+        barrier()
+        t = out.render(base + args.warmup_e2e * step, base + (args.warmup_e2e + args.steps) * step, threads)
+        barrier()
+        frames_timed, first_timed = args.steps * step, base
+        protocol = "steady state: %d warm-up + %d timed steps of %d frames (whole look-ahead windows of %d) on one long clip" % (args.warmup_e2e, args.steps, step, window)
     # ---- output check (untimed): sampled frames against reference-derived digests
     checked, bad = 0, []
     if gold is not None:
         cyc = cfg.get("distinct", DISTINCT)
-        picks = sorted(set([OFF, OFF + 1, OFF + 2] + [OFF + k for k in (cyc // 2 - 2, cyc // 2 - 1, cyc // 2, cyc // 2 + 1, cyc - 2, cyc - 1, cyc, cyc + 1) if k < F_out]))
+        picks = sorted(set(first_timed + k for k in (0, 1, 2, cyc // 2 - 2, cyc // 2 - 1, cyc // 2, cyc // 2 + 1, cyc - 2, cyc - 1, cyc, cyc + 1) if k < F_out))
         for n in picks:
             want = expected_digest(gold, lo + n, 1 << 30)
             if want is None:
@@ -262,7 +292,7 @@ def plugin_leg(cfg, args, mb, plan, world, rank, local, barrier, total_frames, g
             checked += 1
             if frame_digest(cfg, out.get_frame(n)) != want:
                 bad.append(lo + n)
-    return dict(seconds=t, warm_seconds=t_warm, threads=threads, checked=checked, bad=bad)
+    return dict(seconds=t, frames=frames_timed, threads=threads, checked=checked, bad=bad, protocol=protocol)
 
 
 def run_gpu_arm(args, cfg):
@@ -376,7 +406,12 @@ def run_gpu_arm(args, cfg):
     search_ms = stage_ms[stages[1][0]]
     value = (total if cfg.get("fixed_total") else world * F_out) * args.steps / (region_ms / 1e3)
 
-    # ---- the clip-level C ABI with pinned host buffers (round 1's e2e; DegrainN pipelines only)
+    # ---- the clip-level C ABI with pinned host buffers (round 1's e2e; DegrainN pipelines only).  The resident leg's device
+    # buffers go first: the engine allocates its own clips, and a 4K batch does not fit twice.
+    del dsup, dvec, ddst, dsrc, outs
+    if kind == "mc":
+        del drec
+    torch.cuda.empty_cache()
     c_abi = None
     if kind == "degrain":
         host_outs = [torch.zeros((F_out, cl.frame_bytes), dtype=torch.uint8).pin_memory() for _ in range(2)]
@@ -402,19 +437,25 @@ def run_gpu_arm(args, cfg):
         del host_outs
     clocks_dev = sampler.stop() if rank == 0 else None
 
-    # ---- e2e through the drop-in plugin (the headline): free this leg's device memory first, the plugin has its own context
-    del dsup, dvec, ddst, dsrc, outs
-    if kind == "mc":
-        del drec
+    # ---- e2e through the drop-in plugin (the headline); the plugin has its own context(s): this one's memory goes first
+    del host
+    ctx.close()
     torch.cuda.empty_cache()
     gold = load_golden(args.config)
+    cl_frame_bytes, sl_frame_bytes = int(cl.frame_bytes), int(sl.frame_bytes)
     sampler2 = ClockSampler(local)
     if rank == 0:
         sampler2.start()
-    pl = plugin_leg(cfg, args, mb, plan, world, rank, local, barrier, total, gold)
+    def host_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    pl = plugin_leg(cfg, args, mb, plan, world, rank, local, host_barrier, total, gold, plugin_window(plan_q, len(aps)))
     clocks_e2e = sampler2.stop() if rank == 0 else None
     e2e_s = max_over_ranks(pl["seconds"])
-    e2e_value = (total if cfg.get("fixed_total") else world * F_out) * args.steps / e2e_s
+    e2e_frames = total if cfg.get("fixed_total") else world * pl["frames"]
+    e2e_value = e2e_frames / e2e_s
     nbad = max_over_ranks(float(len(pl["bad"])))
     nchecked = -max_over_ranks(-float(pl["checked"]))  # the minimum over ranks
     if world > 1:
@@ -451,7 +492,6 @@ def run_gpu_arm(args, cfg):
                     "source": "profiles/" + prof_name}
     except (OSError, KeyError, ValueError):
         pass
-    frames_total = total if cfg.get("fixed_total") else world * F_out
     line = {
         "metric": cfg["metric"], "value": value, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": region_ms / args.steps, "higher_is_better": True,
@@ -464,8 +504,10 @@ def run_gpu_arm(args, cfg):
                    "stage_ms": stage_ms},
         "e2e": {"value": e2e_value, "unit": "frames/s", "through": "libmvtools.so (VapourSynthPluginInit2) under host/minivs, default environment, %d host threads per rank" % pl["threads"],
                 "timer": "wall clock around the host's render of K steps (the plugin owns its CUDA context), max over ranks",
-                "h2d_bytes_per_step": int(F_out * cl.frame_bytes), "d2h_bytes_per_step": int(F_out * cl.frame_bytes) if kind != "analyse" else int(F_out * (aps[0].vectors_size + sl.frame_bytes)),
-                "seconds": e2e_s, "frames": frames_total * args.steps, "warmup_steps": args.warmup_e2e, "c_abi": c_abi,
+                "protocol": pl["protocol"],
+                "h2d_bytes_per_step": int(pl["frames"] // max(args.steps, 1) * cl_frame_bytes) if not cfg.get("fixed_total") else int(F_out * cl_frame_bytes),
+                "d2h_bytes_per_step": (int(pl["frames"] // max(args.steps, 1) * cl_frame_bytes) if not cfg.get("fixed_total") else int(F_out * cl_frame_bytes)) if kind != "analyse" else int(F_out * (aps[0].vectors_size + sl_frame_bytes)),
+                "seconds": e2e_s, "frames": e2e_frames, "warmup_steps": args.warmup_e2e, "c_abi": c_abi,
                 "c_abi_note": "mvb200_degrain_clip_host_async with pinned host buffers, CUDA events (round 1's e2e)" if c_abi else None},
         "output_check": {"frames_checked_per_rank": int(nchecked), "mismatches": int(nbad),
                          "against": "sha256 of the compiled reference's output (tests/golden/bench_digest.json)" if gold is not None else "no golden digest for this config"},
@@ -492,7 +534,6 @@ def run_gpu_arm(args, cfg):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
-    ctx.synchronize()
     torch.cuda.synchronize()
     if nbad:
         raise SystemExit("bench.py: %d sampled output frame(s) differ from the reference-derived digests" % int(nbad))

@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--lookahead", default="auto,32")
     ap.add_argument("--plugin", default=None)
     ap.add_argument("--child", default=None)
+    ap.add_argument("--no-reference", action="store_true")
     a = ap.parse_args()
     w, h = (int(x) for x in a.size.split("x"))
     if a.child:
@@ -54,7 +55,7 @@ def main():
         return
     import minivs
     import mvtools_b200 as mb
-    runs = [("reference", minivs.REF_PLUGIN, None)] if os.path.exists(minivs.REF_PLUGIN) else []
+    runs = [("reference", minivs.REF_PLUGIN, None)] if os.path.exists(minivs.REF_PLUGIN) and not a.no_reference else []
     for la in a.lookahead.split(","):  # "auto" = MVB200_LOOKAHEAD unset: the plugin's default
         runs.append(("b200 lookahead=%s" % la, a.plugin or mb.PLUGIN_PATH, la))
     for name, plugin, la in runs:

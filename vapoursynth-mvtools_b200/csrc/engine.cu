@@ -68,7 +68,7 @@ void *Ctx::get_scratch(int slot, size_t bytes) {
         cudaFree(scratch[slot]);
     scratch[slot] = nullptr;
     scratch_bytes[slot] = 0;
-    size_t want = bytes + bytes / 4 + 4096;
+    size_t want = bytes + std::min<size_t>(bytes / 4, (size_t)256 << 20) + 4096; // (growth slack, bounded: clips of a 4K batch are tens of GB)
     void *p = nullptr;
     if (cudaMalloc(&p, want) != cudaSuccess) {
         set_error("mvtools_b200: out of device memory (%zu bytes of scratch)", want);

@@ -162,7 +162,7 @@ int64_t pinnedBudget() {
 // kernels).  No request ever waits for another REQUEST to be scheduled -- a request that finds its window not yet
 // enqueued holds the window's source frames itself and packs / enqueues it (cooperatively with the other requests in
 // the same position) -- so a frame server with few threads cannot deadlock; requests only wait for the GPU.
-struct PinnedPool { // window buffers are recycled: page-locking gigabytes per window would cost more than the copies
+struct PinnedPool { // window buffers are recycled (process-wide: a script's filters, and a re-created script, share them): page-locking gigabytes per window would cost more than the copies
     std::mutex m;
     std::vector<std::pair<void *, size_t>> free_;
     ~PinnedPool() {
@@ -191,9 +191,21 @@ struct PinnedPool { // window buffers are recycled: page-locking gigabytes per w
         if (!p)
             return;
         std::lock_guard<std::mutex> lock(m);
+        size_t held = bytes;
+        for (auto &b : free_)
+            held += b.second;
+        if ((int64_t)held > pinnedBudget()) { // (more idle buffers than any filter may hold: give it back)
+            mvb200_pinned_free(p);
+            return;
+        }
         free_.emplace_back(p, bytes);
     }
 };
+
+std::shared_ptr<PinnedPool> sharedPinnedPool() {
+    static std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
+    return pool;
+}
 
 struct FusedWindow {
     enum State { Idle = 0, Packing, Launching, Running, Ready, Failed };
@@ -232,7 +244,7 @@ struct FusedRequest {
 struct FusedCache {
     std::mutex m;                                           // guards `windows` and the windows' prefetchClaimed
     std::map<int, std::shared_ptr<FusedWindow>> windows;    // by window index (frame / window)
-    std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
+    std::shared_ptr<PinnedPool> pool = sharedPinnedPool();
     mvb200_frame_layout cl;
     int window = 0;
     int depth = deviceCount(); // windows enqueued ahead of the one being served: one per device
