@@ -245,7 +245,7 @@ def plugin_leg(cfg, args, mb, plan, world, rank, local, barrier, total_frames, g
     os.environ["MVB200_DEVICE"] = str(local)
     F_out, OFF, lo = plan["count"], plan["offset"], plan["lo"]
     threads = max(4, (os.cpu_count() or 4) // world)
-    fused = cfg["kind"] == "degrain"
+    fused = cfg["kind"] in ("degrain", "mc")  # (Recalculate passes are part of the fused chains)
 
     def script(n_local, first):
         core = minivs.Core()
@@ -386,32 +386,98 @@ def run_gpu_arm(args, cfg):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident timing
-    for _ in range(args.warmup):
-        pipeline()
+    # ---- device-resident timing, pass 1: ONE context, stages serialised on its stream -> per-stage times (the roofline's kernel time)
+    aux_steps = max(1, min(2, args.steps))
+    pipeline()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = ctx.launch_count()
-    stage_events = [[ev() for _ in range(len(stages) + 1)] for _ in range(args.steps)]
-    barrier()
-    for k in range(args.steps):
+    stage_events = [[ev() for _ in range(len(stages) + 1)] for _ in range(aux_steps)]
+    for k in range(aux_steps):
         pipeline(stage_events[k])
     barrier()
-    launches = ctx.launch_count() - launches0
-    # the steps are back to back on one stream: whole-region time = first start -> last end
-    region_ms = max_over_ranks(stage_events[0][0].elapsed_time(stage_events[-1][-1]))
-    stage_ms = {name: sum(e[i].elapsed_time(e[i + 1]) for e in stage_events) / args.steps for i, (name, _) in enumerate(stages)}
+    stage_ms = {name: sum(e[i].elapsed_time(e[i + 1]) for e in stage_events) / aux_steps for i, (name, _) in enumerate(stages)}
     search_ms = stage_ms[stages[1][0]]
-    value = (total if cfg.get("fixed_total") else world * F_out) * args.steps / (region_ms / 1e3)
-
-    # ---- the clip-level C ABI with pinned host buffers (round 1's e2e; DegrainN pipelines only).  The resident leg's device
-    # buffers go first: the engine allocates its own clips, and a 4K batch does not fit twice.
-    del dsup, dvec, ddst, dsrc, outs
+    value_one_context = (total if cfg.get("fixed_total") else world * F_out) * aux_steps / (max_over_ranks(stage_events[0][0].elapsed_time(stage_events[-1][-1])) / 1e3)
+    del dsup, dvec, ddst, outs
     if kind == "mc":
         del drec
     torch.cuda.empty_cache()
+
+    # ---- pass 2 (the `value`): the product's execution mode -- C engine contexts on the device, each running the whole path over
+    # its own contiguous part of the step's frames (+ REACH halo frames of super clip) on its own stream.  A search launch is a set
+    # of serial chains walking the same phases in lockstep; parts started independently fill each other's idle issue slots and
+    # tails, and one part's Super / DegrainN kernels run beside another's search.  W warm-up steps, K timed steps, no host sync
+    # between steps; time = first start -> last end over all streams (CUDA events), max over ranks.
+    NC = max(1, min(args.contexts, F_out // 8 or 1))
+    parts = []
+    for i in range(NC):
+        a0, a1 = F_out * i // NC, F_out * (i + 1) // NC
+        lo_i, hi_i = max(0, OFF + a0 - REACH), min(F, OFF + a1 + REACH)
+        Fi, offi, cnt = hi_i - lo_i, OFF + a0 - lo_i, a1 - a0
+        c_i = ctx if i == 0 else mb.Context(local)
+        st_i = torch.cuda.ExternalStream(c_i.stream(), device=torch.device("cuda", local))
+        if kind == "degrain":
+            aps_i = [mb.analyse_params(sp, Fi, isb=isb, delta=d, **akw) for d in range(1, cfg["radius"] + 1) for isb in (1, 0)]
+        elif kind == "analyse":
+            aps_i = [mb.analyse_params(sp, Fi, **akw)]
+        else:
+            aps_i = [mb.analyse_params(sp, Fi, isb=1, **akw)]
+            rp_i = mb.recalculate_params(sp, aps_i[0].ad, Fi, blksize=cfg["blk"], overlap=cfg["ov"], dct=cfg.get("dct", 0))
+            cp_i = mb.compensate_params(sp, rp_i.ad, W_, H_, Fi)
+        with torch.cuda.stream(st_i):
+            dsup_i = torch.empty((Fi, sl.frame_bytes), dtype=torch.uint8, device="cuda")
+            dvec_i = [torch.empty((cnt, vs), dtype=torch.uint8, device="cuda") for _ in aps_i]
+            ddst_i = torch.empty((cnt, cl.frame_bytes), dtype=torch.uint8, device="cuda") if kind != "analyse" else None
+            drec_i = torch.empty((cnt, rvs), dtype=torch.uint8, device="cuda") if kind == "mc" else None
+        apa_i = (C.POINTER(mb.AnalyseParams) * len(aps_i))(*[C.pointer(a) for a in aps_i])
+        outs_i = (C.c_void_p * len(aps_i))(*[t.data_ptr() for t in dvec_i])
+        src_i = dsrc.data_ptr() + lo_i * cl.frame_bytes
+        P = dict(ctx=c_i, stream=st_i, keep=(aps_i, dsup_i, dvec_i, ddst_i, drec_i, apa_i, outs_i))
+
+        def run(P=P, c_i=c_i, Fi=Fi, offi=offi, cnt=cnt, apa_i=apa_i, outs_i=outs_i, src_i=src_i, dsup_i=dsup_i, ddst_i=ddst_i, drec_i=drec_i, dvec_i=dvec_i, n_aps=len(aps_i),
+                rp_i=locals().get("rp_i"), cp_i=locals().get("cp_i")):
+            mb._check(L.mvb200_super_batch(c_i.handle, C.byref(sp), src_i, dsup_i.data_ptr(), Fi))
+            mb._check(L.mvb200_analyse_multi_batch(c_i.handle, apa_i, n_aps, C.byref(sp), dsup_i.data_ptr(), offi, cnt, outs_i, vs))
+            if kind == "degrain":
+                mb._check(L.mvb200_degrain_batch(c_i.handle, C.byref(dp), C.byref(sp), src_i, dsup_i.data_ptr(), Fi, offi, cnt, outs_i, vs, ddst_i.data_ptr()))
+            elif kind == "mc":
+                mb._check(L.mvb200_recalculate_batch(c_i.handle, C.byref(rp_i), C.byref(sp), dsup_i.data_ptr(), offi, cnt, dvec_i[0].data_ptr(), vs, drec_i.data_ptr(), rvs))
+                mb._check(L.mvb200_compensate_batch(c_i.handle, C.byref(cp_i), C.byref(sp), dsup_i.data_ptr(), offi, cnt, drec_i.data_ptr(), rvs, ddst_i.data_ptr()))
+        P["run"] = run
+        parts.append(P)
+
+    def barrier_all():
+        for P in parts:
+            P["ctx"].synchronize()
+        barrier()
+
+    for _ in range(args.warmup):
+        for P in parts:
+            P["run"]()
+    barrier_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = sum(P["ctx"].launch_count() for P in parts)
+    e_start = ev()
+    e_ends = [ev() for _ in parts]
+    barrier_all()
+    e_start.record(parts[0]["stream"])
+    for k in range(args.steps):
+        for P in parts:
+            P["run"]()
+    for P, e in zip(parts, e_ends):
+        e.record(P["stream"])
+    barrier_all()
+    launches = sum(P["ctx"].launch_count() for P in parts) - launches0
+    region_ms = max_over_ranks(max(e_start.elapsed_time(e) for e in e_ends))
+    value = (total if cfg.get("fixed_total") else world * F_out) * args.steps / (region_ms / 1e3)
+    for P in parts[1:]:
+        P["ctx"].close()
+    del parts, dsrc
+    torch.cuda.empty_cache()
+
+    # ---- the clip-level C ABI with pinned host buffers (round 1's e2e; DegrainN pipelines only).  (The resident legs' device
+    # buffers are gone: the engine allocates its own clips, and a 4K batch does not fit twice.)
     c_abi = None
     if kind == "degrain":
         host_outs = [torch.zeros((F_out, cl.frame_bytes), dtype=torch.uint8).pin_memory() for _ in range(2)]
@@ -501,7 +567,8 @@ def run_gpu_arm(args, cfg):
                    "search_kernel": {0: "k_search (generic)", 1: "k_search_fast (register-blocked)", 2: "k_search_tma (TMA-staged windows)"}[plan_q.kernel],
                    "search_chain_slots_per_gpu": plan_q.chains_per_wave,
                    "l2": "inputs larger than L2 (%d MB of super frames + vectors per step vs 126 MB L2), no flush" % int((F * sl.frame_bytes + len(aps) * F_out * vs) / 1e6),
-                   "stage_ms": stage_ms},
+                   "contexts_per_gpu": NC, "value_one_context": value_one_context,
+                   "stage_ms": stage_ms, "stage_ms_note": "one context, stages serialised on one stream (pass 1); `value` runs %d contexts concurrently" % NC},
         "e2e": {"value": e2e_value, "unit": "frames/s", "through": "libmvtools.so (VapourSynthPluginInit2) under host/minivs, default environment, %d host threads per rank" % pl["threads"],
                 "timer": "wall clock around the host's render of K steps (the plugin owns its CUDA context), max over ranks",
                 "protocol": pl["protocol"],
@@ -549,6 +616,7 @@ def main():
     ap.add_argument("--frames", type=int, default=None, help="frames per step per GPU (default: the config's)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--contexts", type=int, default=3, help="engine contexts per GPU of the device-resident leg (the plugin's default: MVB200_CONTEXTS_PER_DEVICE)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.frames is None:

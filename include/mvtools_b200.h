@@ -418,6 +418,8 @@ MVB200_API int mvb200_ctx_create(int device, mvb200_ctx **out);
  * windows over every GPU of a box (the plugin's fused paths: one context per device, no data-path collective -- frames are
  * independent units, readme.rst:36).  0 when there is none (and mvb200_last_error says why). */
 MVB200_API int mvb200_device_count(void);
+/* total memory of a device in bytes (0 on failure): callers that keep several windows of a clip resident size them with it */
+MVB200_API int64_t mvb200_device_memory(int device);
 MVB200_API void mvb200_ctx_destroy(mvb200_ctx *ctx);
 MVB200_API int mvb200_ctx_synchronize(mvb200_ctx *ctx);
 /* the cudaStream_t the context launches on (for CUDA-event timing by the caller) */
@@ -502,6 +504,14 @@ MVB200_API int mvb200_compensate_batch(mvb200_ctx *ctx, const mvb200_compensate_
  * overlap (H2D of segment k+1 and D2H of segment k-1 beside the kernels of segment k). */
 MVB200_API int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap,
                                               const mvb200_degrain_params *dp, const void *host_src, void *host_dst, int n, int first, int count);
+
+/* The same clip pipeline with mv.Recalculate between the searches and the blend (the refinemotion shape of denoising
+ * scripts: Analyse -> Recalculate (-> Recalculate) -> DegrainN): rp[i * nrp + k], k = 0 .. nrp - 1 (NULL = none), are the
+ * refinement passes of vector clip i, applied in order (mvrecalculateGetFrame, MVRecalculate.c:68-254); dp was derived
+ * from the analysis data of the LAST pass of each clip.  rp == NULL or nrp == 0: exactly mvb200_degrain_clip_host_async. */
+MVB200_API int mvb200_degrain_recalc_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap,
+                                                     const mvb200_recalculate_params *const *rp, int nrp, const mvb200_degrain_params *dp, const void *host_src, void *host_dst,
+                                                     int n, int first, int count);
 
 /* Page-locked host memory for the buffers handed to mvb200_degrain_clip_host_async (pageable memory works too, but its
  * copies are not asynchronous).  mvb200_pinned_alloc returns NULL on failure. */
@@ -616,6 +626,11 @@ MVB200_API int mvb200_flowfps_clip_host(mvb200_ctx *ctx, const mvb200_super_para
  * parameters (their num_frames is replaced by n internally; relative delta only, no field shifts).  Synchronous. */
 MVB200_API int mvb200_compensate_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_compensate_params *cp, const void *host_src, int src_first, int n, int out_first,
                                            int out_count, void *host_dst);
+
+/* ... with nrp mv.Recalculate passes (rp[0 .. nrp - 1], applied in order; MVRecalculate.c:68-254) between the search and the
+ * compensation; cp was derived from the last pass's analysis data. */
+MVB200_API int mvb200_compensate_recalc_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_recalculate_params *const *rp, int nrp,
+                                                  const mvb200_compensate_params *cp, const void *host_src, int src_first, int n, int out_first, int out_count, void *host_dst);
 
 /* The same for the per-pixel consumers: mv.Super -> mv.Analyse (one or two instances) -> mv.Flow / mv.FlowInter /
  * mv.FlowBlur for output frames [out_first, out_first + out_count), from the n source frames [src_first, src_first + n)

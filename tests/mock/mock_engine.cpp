@@ -46,6 +46,7 @@ MVB200_API int mvb200_device_count(void) {
     const char *e = getenv("MVB200_MOCK_DEVICES");
     return e ? atoi(e) : 1;
 }
+MVB200_API int64_t mvb200_device_memory(int) { return (int64_t)180 << 30; }
 MVB200_API long mvb200_mock_contexts(void) { return g_ctx_created.load(); }
 MVB200_API int mvb200_ctx_synchronize(mvb200_ctx *) { return 0; }
 // the stand-in computes synchronously: an event is complete when it is recorded
@@ -88,11 +89,29 @@ MVB200_API void mvb200_clip_layout(const mvb200_super_params *p, mvb200_frame_la
     l->frame_bytes = round_up256(off);
 }
 
+// (only the plugin's estimate of a window's device footprint reads it: the super frame's planes at the same pitch rule)
+MVB200_API void mvb200_super_layout(const mvb200_super_params *p, mvb200_frame_layout *l) {
+    mvb200_super_geom g;
+    mvb200_super_geometry(p, &g);
+    memset(l, 0, sizeof(*l));
+    l->nplanes = p->nplanes;
+    l->bytes_per_sample = (p->bits + 7) / 8;
+    long long off = 0;
+    for (int i = 0; i < p->nplanes; i++) {
+        l->plane_w[i] = g.plane_w[i];
+        l->plane_h[i] = g.plane_h[i];
+        l->pitch[i] = round_up256((long long)g.plane_w[i] * l->bytes_per_sample + 4);
+        l->offset[i] = off;
+        off += l->pitch[i] * g.plane_h[i];
+    }
+    l->frame_bytes = round_up256(off);
+}
+
 // The clip pipeline on host memory, frame by frame through the oracle: Super of every frame of the segment, the nap
 // searches and DegrainN for frames [first, first + count).  Reference frames follow the analyse parameters with
 // num_frames = the segment length, as in the engine.
-MVB200_API int mvb200_degrain_clip_host_async(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const mvb200_degrain_params *dp, const void *host_src, void *host_dst, int n, int first,
-                                              int count) {
+MVB200_API int mvb200_degrain_recalc_clip_host_async(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const mvb200_recalculate_params *const *rp, int nrp,
+                                                     const mvb200_degrain_params *dp, const void *host_src, void *host_dst, int n, int first, int count) {
     g_clip_calls++;
     mvb200_frame_layout cl;
     mvb200_clip_layout(sp, &cl);
@@ -141,6 +160,14 @@ MVB200_API int mvb200_degrain_clip_host_async(mvb200_ctx *, const mvb200_super_p
             blobs[i].assign((size_t)ap[i]->vectors_size, 0);
             if (fwd(mvo_analyse_frame(ap[i], sp, s, sstride, nref >= 0 ? r : nullptr, nref >= 0 ? sstride : nullptr, 0, blobs[i].data())))
                 return 1;
+            for (int k2 = 0; rp && k2 < nrp; k2++) { // the refinement passes of this vector clip, in order
+                if (!rp[i * nrp + k2])
+                    continue;
+                std::vector<uint8_t> nb((size_t)rp[i * nrp + k2]->vectors_size, 0);
+                if (fwd(mvo_recalculate_frame(rp[i * nrp + k2], sp, s, sstride, nref >= 0 ? r : nullptr, nref >= 0 ? sstride : nullptr, blobs[i].data(), 0, nb.data())))
+                    return 1;
+                blobs[i].swap(nb);
+            }
             vecs[i] = blobs[i].data();
             if (nref >= 0)
                 for (int pl = 0; pl < sp->nplanes; pl++) {
@@ -158,6 +185,11 @@ MVB200_API int mvb200_degrain_clip_host_async(mvb200_ctx *, const mvb200_super_p
             return 1;
     }
     return 0;
+}
+
+MVB200_API int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const mvb200_degrain_params *dp, const void *host_src, void *host_dst, int n, int first,
+                                              int count) {
+    return mvb200_degrain_recalc_clip_host_async(ctx, sp, ap, nap, nullptr, 0, dp, host_src, host_dst, n, first, count);
 }
 
 MVB200_API int mvb200_super_frame(mvb200_ctx *, const mvb200_super_params *p, const uint8_t *const src[3], const ptrdiff_t src_stride[3], uint8_t *const dst[3], const ptrdiff_t dst_stride[3]) {
@@ -332,8 +364,8 @@ MVB200_API int mvb200_flowfps_clip_host(mvb200_ctx *, const mvb200_super_params 
     return 0;
 }
 
-MVB200_API int mvb200_compensate_clip_host(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_compensate_params *cp, const void *host_src, int src_first, int n, int out_first, int out_count,
-                                           void *host_dst) {
+MVB200_API int mvb200_compensate_recalc_clip_host(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_recalculate_params *const *rp, int nrp, const mvb200_compensate_params *cp,
+                                                  const void *host_src, int src_first, int n, int out_first, int out_count, void *host_dst) {
     mvb200_frame_layout cl;
     mvb200_clip_layout(sp, &cl);
     mvb200_super_geom g;
@@ -370,6 +402,14 @@ MVB200_API int mvb200_compensate_clip_host(mvb200_ctx *, const mvb200_super_para
         std::vector<uint8_t> blob((size_t)ap->vectors_size, 0);
         if (fwd(mvo_analyse_frame(ap, sp, s_, sstride, nref >= 0 ? r_ : nullptr, nref >= 0 ? sstride : nullptr, 0, blob.data())))
             return 1;
+        for (int k2 = 0; rp && k2 < nrp; k2++) {
+            if (!rp[k2])
+                continue;
+            std::vector<uint8_t> nb((size_t)rp[k2]->vectors_size, 0);
+            if (fwd(mvo_recalculate_frame(rp[k2], sp, s_, sstride, nref >= 0 ? r_ : nullptr, nref >= 0 ? sstride : nullptr, blob.data(), 0, nb.data())))
+                return 1;
+            blob.swap(nb);
+        }
         uint8_t *d[3];
         ptrdiff_t dstr[3];
         for (int i = 0; i < 3; i++) {
@@ -463,6 +503,11 @@ struct MockSegment {
 } // namespace
 
 extern "C" {
+
+MVB200_API int mvb200_compensate_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_compensate_params *cp, const void *host_src, int src_first, int n, int out_first, int out_count,
+                                           void *host_dst) {
+    return mvb200_compensate_recalc_clip_host(ctx, sp, ap, nullptr, 0, cp, host_src, src_first, n, out_first, out_count, host_dst);
+}
 
 MVB200_API int mvb200_flow_clip_host(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_flow_params *fp, const void *host_src, int src_first, int n, int out_first, int out_count,
                                      void *host_dst, int32_t *usable_out) {

@@ -183,3 +183,37 @@ def test_static_reference_frame_on_the_gpu_matches_the_reference_plugin(built, m
         outs.append([(vec.get_frame(n).prop_data("MVTools_vectors"), rec.get_frame(n).prop_data("MVTools_vectors"), [pipeline.sha(p) for p in comp.get_frame(n).planes()])
                      for n in range(len(frames))])
     assert outs[0] == outs[1]
+
+
+@pytest.mark.parametrize("lookahead", ["3", None])
+def test_recalculate_passes_inside_the_fused_chains_on_the_gpu(built, monkeypatch, lookahead):
+    """Analyse -> Recalculate (-> Recalculate) -> Degrain1 / Compensate through the product plugin (fused: one engine call per
+    window, mvb200_degrain_recalc_clip_host_async / mvb200_compensate_recalc_clip_host) against the reference plugin"""
+    import pipeline
+    minivs = _ref_or_skip()
+    if lookahead:
+        monkeypatch.setenv("MVB200_LOOKAHEAD", lookahead)
+    else:
+        monkeypatch.delenv("MVB200_LOOKAHEAD", raising=False)
+    case = "blk16_ov8_pel2_p8_r3"
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    outs, counts = [], None
+    for path in (minivs.REF_PLUGIN, mb.PLUGIN_PATH):
+        core = minivs.Core()
+        mv = core.load(path)
+        clip = core.source(frames, bits=8)
+        sup = mv.Super(clip, **skw)
+        vb, vf = mv.Analyse(sup, isb=1, delta=1, **akw), mv.Analyse(sup, isb=0, delta=1, **akw)
+        rb = mv.Recalculate(sup, vb, blksize=8, overlap=4, thsad=100)
+        rb2 = mv.Recalculate(sup, rb, blksize=8, overlap=4, thsad=50, search=3, searchparam=1)
+        rf = mv.Recalculate(sup, vf, blksize=8, overlap=4, thsad=100, divide=0)
+        dn = mv.Degrain1(clip, sup, rb2, rf, thsad=300)
+        comp = mv.Compensate(clip, sup, rb)
+        nodes = (sup, vb, vf, rb, rb2, rf)
+        before = [x.computed() for x in nodes]
+        outs.append([([pipeline.sha(p) for p in dn.get_frame(n).planes()], [pipeline.sha(p) for p in comp.get_frame(n).planes()]) for n in range(len(frames))])
+        if path == mb.PLUGIN_PATH:
+            counts = (before, [x.computed() for x in nodes])
+    assert outs[0] == outs[1]
+    assert counts[0] == counts[1], "the fused path asked the Super / Analyse / Recalculate nodes for frames"

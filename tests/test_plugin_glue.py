@@ -341,7 +341,7 @@ L.mvb200_mock_clip_calls.restype = ctypes.c_long
 print(json.dumps({"contexts": L.mvb200_mock_contexts(), "calls": L.mvb200_mock_clip_calls(),
                   "frames": [[pipeline.sha(p) for p in dn.get_frame(n).planes()] for n in range(len(frames))]}))
 ''' % (os.path.join(ROOT, "vapoursynth-mvtools_b200"), os.path.join(ROOT, "host", "minivs"), HERE, mock_plugin, mock_plugin)
-    env = dict(os.environ, MVB200_MOCK_DEVICES="3", MVB200_LOOKAHEAD="2")
+    env = dict(os.environ, MVB200_MOCK_DEVICES="3", MVB200_LOOKAHEAD="2", MVB200_CONTEXTS_PER_DEVICE="1")
     env.pop("MVB200_DEVICE", None)
     env.pop("MVB200_DEVICES", None)
     r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
@@ -351,6 +351,47 @@ print(json.dumps({"contexts": L.mvb200_mock_contexts(), "calls": L.mvb200_mock_c
     assert got["frames"] == GOLD[case]["degrain"]
     assert got["contexts"] == 3, "windows were not spread over the three devices"
     assert got["calls"] >= 4
+
+
+@pytest.mark.parametrize("window", ["3", None])
+def test_recalculate_passes_inside_the_fused_chains(mock_plugin, have_ref, monkeypatch, window):
+    """The refinemotion shape -- Analyse -> Recalculate (-> Recalculate) -> DegrainN / Compensate -- is still one engine call per
+    window: the fused paths recognise this plugin's own mv.Recalculate nodes on top of its mv.Analyse nodes and hand their
+    parameters to the clip pipeline; the frames are the reference plugin's, and none of the Super / Analyse / Recalculate nodes
+    is asked for a frame."""
+    if not have_ref:
+        pytest.skip("oracle/_ref/libmvtools_ref.so not built here (no /root/reference)")
+    import minivs
+    if window:
+        monkeypatch.setenv("MVB200_LOOKAHEAD", window)
+    else:
+        monkeypatch.delenv("MVB200_LOOKAHEAD", raising=False)
+    case = "blk16_ov8_pel2_p8_r3"
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    N = len(frames)
+    outs, counts = [], None
+    for path in (minivs.REF_PLUGIN, mock_plugin):
+        core = minivs.Core()
+        mv = core.load(path)
+        clip = core.source(frames, bits=8)
+        sup = mv.Super(clip, **skw)
+        vb, vf = mv.Analyse(sup, isb=1, delta=1, **akw), mv.Analyse(sup, isb=0, delta=1, **akw)
+        rb = mv.Recalculate(sup, vb, blksize=8, overlap=4, thsad=100)
+        rb2 = mv.Recalculate(sup, rb, blksize=8, overlap=4, thsad=50, search=3, searchparam=1)
+        rf = mv.Recalculate(sup, vf, blksize=8, overlap=4, thsad=100, divide=0)
+        dn = mv.Degrain1(clip, sup, rb2, rf, thsad=300)
+        comp = mv.Compensate(clip, sup, rb)
+        nodes = (sup, vb, vf, rb, rb2, rf)
+        before = [x.computed() for x in nodes]
+        res = []
+        for n in list(range(N)) + [0, N - 1]:
+            res.append(([pipeline.sha(p) for p in dn.get_frame(n).planes()], [pipeline.sha(p) for p in comp.get_frame(n).planes()]))
+        outs.append(res)
+        if path == mock_plugin:
+            counts = (before, [x.computed() for x in nodes])
+    assert outs[0] == outs[1]
+    assert counts[0] == counts[1], "the fused path asked the Super / Analyse / Recalculate nodes for frames"
 
 
 def test_non_canonical_chains_keep_the_node_by_node_evaluation(mock_plugin, monkeypatch):

@@ -288,6 +288,13 @@ int mvb200_device_count(void) {
     return usable;
 }
 
+int64_t mvb200_device_memory(int device) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+        return 0;
+    return (int64_t)prop.totalGlobalMem;
+}
+
 void mvb200_ctx_destroy(mvb200_ctx *ctx) {
     if (!ctx)
         return;
@@ -622,6 +629,13 @@ int mvb200_compensate_batch(mvb200_ctx *ctx, const mvb200_compensate_params *cp,
 // (source / output clips are double buffered on the device).
 int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const mvb200_degrain_params *dp,
                                    const void *host_src, void *host_dst, int n, int first, int count) {
+    return mvb200_degrain_recalc_clip_host_async(ctx, sp, ap, nap, nullptr, 0, dp, host_src, host_dst, n, first, count);
+}
+
+// The same with mv.Recalculate between the searches and the blend: rp[i * nrp + k] (k = 0 .. nrp - 1, NULL = none) are the
+// refinement passes applied, in order, to vector clip i (gopRecalculateMVs, MVRecalculate.c:68-254).
+int mvb200_degrain_recalc_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const mvb200_recalculate_params *const *rp, int nrp,
+                                          const mvb200_degrain_params *dp, const void *host_src, void *host_dst, int n, int first, int count) {
     if (check_levels(sp))
         return 1;
     if (n <= 0 || count <= 0)
@@ -650,8 +664,15 @@ int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *s
     make_super_desc(sp, &sd);
     make_clip_desc(sp, &cd);
     int64_t vstride = 0;
-    for (int i = 0; i < nap; i++)
+    bool any_recalc = false;
+    for (int i = 0; i < nap; i++) {
         vstride = std::max<int64_t>(vstride, ((int64_t)ap[i]->vectors_size + 255) / 256 * 256);
+        for (int k = 0; rp && k < nrp; k++)
+            if (rp[i * nrp + k]) {
+                vstride = std::max<int64_t>(vstride, ((int64_t)rp[i * nrp + k]->vectors_size + 255) / 256 * 256);
+                any_recalc = true;
+            }
+    }
     const int slot = (int)(c.clip_calls & 1);
     const bool reuse = c.clip_calls >= 2; // this slot's buffers were used by the call before the previous one
     c.clip_calls++;
@@ -661,7 +682,8 @@ int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *s
     uint8_t *ddst = (uint8_t *)c.get_scratch(10 + slot, clip_bytes);
     uint8_t *dsup = (uint8_t *)c.get_scratch(12, (size_t)sd.frame_bytes * n);
     uint8_t *dvec = (uint8_t *)c.get_scratch(13, (size_t)vstride * count * nap);
-    if (!dsrc || !ddst || !dsup || !dvec)
+    uint8_t *dvec2 = any_recalc ? (uint8_t *)c.get_scratch(14, (size_t)vstride * count) : nullptr; // one vector clip being refined
+    if (!dsrc || !ddst || !dsup || !dvec || (any_recalc && !dvec2))
         return 1;
     if (before[0] != dsrc || before[1] != ddst || before[2] != dsup || before[3] != dvec)
         MVB_CUDA_CHECK(cudaStreamSynchronize(c.stream)); // fresh buffers are cleared on the compute stream: finish that before the copy stream writes
@@ -692,6 +714,16 @@ int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *s
         outs[i] = dvec + (size_t)vstride * count * i;
     if (mvb200_analyse_multi_batch(ctx, ap, nap, sp, dsup, first, count, outs.data(), vstride))
         return 1;
+    for (int i = 0; any_recalc && i < nap; i++)
+        for (int k = 0; k < nrp; k++) {
+            if (!rp[i * nrp + k])
+                continue;
+            mvb200_recalculate_params q = *rp[i * nrp + k]; // the segment is the clip as far as the engine is concerned
+            q.num_frames = n;
+            if (mvb200_recalculate_batch(ctx, &q, sp, dsup, first, count, outs[i], vstride, dvec2, vstride))
+                return 1;
+            MVB_CUDA_CHECK(cudaMemcpyAsync(outs[i], dvec2, (size_t)vstride * count, cudaMemcpyDeviceToDevice, c.stream));
+        }
     std::vector<const void *> vin((size_t)nap);
     for (int i = 0; i < nout; i++) {
         const int o0 = (int)((long long)count * i / nout), o1 = (int)((long long)count * (i + 1) / nout);
@@ -725,6 +757,12 @@ void mvb200_pinned_free(void *p) {
 
 int mvb200_compensate_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_compensate_params *cp, const void *host_src, int src_first, int n, int out_first, int out_count,
                                 void *host_dst) {
+    return mvb200_compensate_recalc_clip_host(ctx, sp, ap, nullptr, 0, cp, host_src, src_first, n, out_first, out_count, host_dst);
+}
+
+// ... with nrp mv.Recalculate passes (rp[0 .. nrp - 1], in order) between the search and the compensation
+int mvb200_compensate_recalc_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_recalculate_params *const *rp, int nrp, const mvb200_compensate_params *cp,
+                                       const void *host_src, int src_first, int n, int out_first, int out_count, void *host_dst) {
     if (check_levels(sp) || check_analyse(ap, sp))
         return 1;
     if (n <= 0 || out_count <= 0)
@@ -743,15 +781,29 @@ int mvb200_compensate_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, 
     a.num_frames = n;
     mvb200_compensate_params q = *cp;
     q.num_frames = n;
-    const int64_t vstride = ((int64_t)a.vectors_size + 255) / 256 * 256;
-    uint8_t *buf = (uint8_t *)c->get_scratch(5, (size_t)cd.frame_bytes * (n + out_count) + (size_t)sd.frame_bytes * n + (size_t)vstride * out_count + 256);
+    int64_t vstride = ((int64_t)a.vectors_size + 255) / 256 * 256;
+    for (int k = 0; rp && k < nrp; k++)
+        if (rp[k])
+            vstride = std::max<int64_t>(vstride, ((int64_t)rp[k]->vectors_size + 255) / 256 * 256);
+    uint8_t *buf = (uint8_t *)c->get_scratch(5, (size_t)cd.frame_bytes * (n + out_count) + (size_t)sd.frame_bytes * n + (size_t)vstride * out_count * 2 + 256);
     if (!buf)
         return 1;
     uint8_t *dsrc = buf, *ddst = dsrc + (size_t)cd.frame_bytes * n, *dsup = ddst + (size_t)cd.frame_bytes * out_count, *dvec = dsup + (size_t)sd.frame_bytes * n;
+    uint8_t *dvec2 = dvec + (size_t)vstride * out_count;
     MVB_CUDA_CHECK(cudaMemcpyAsync(dsrc, host_src, (size_t)cd.frame_bytes * n, cudaMemcpyHostToDevice, c->stream));
     const int first = out_first - src_first;
-    if (mvb200_super_batch(ctx, sp, dsrc, dsup, n) || mvb200_analyse_batch(ctx, &a, sp, dsup, first, out_count, dvec, vstride) ||
-        mvb200_compensate_batch(ctx, &q, sp, dsup, first, out_count, dvec, vstride, ddst))
+    if (mvb200_super_batch(ctx, sp, dsrc, dsup, n) || mvb200_analyse_batch(ctx, &a, sp, dsup, first, out_count, dvec, vstride))
+        return 1;
+    for (int k = 0; rp && k < nrp; k++) {
+        if (!rp[k])
+            continue;
+        mvb200_recalculate_params r = *rp[k];
+        r.num_frames = n;
+        if (mvb200_recalculate_batch(ctx, &r, sp, dsup, first, out_count, dvec, vstride, dvec2, vstride))
+            return 1;
+        std::swap(dvec, dvec2);
+    }
+    if (mvb200_compensate_batch(ctx, &q, sp, dsup, first, out_count, dvec, vstride, ddst))
         return 1;
     MVB_CUDA_CHECK(cudaMemcpyAsync(host_dst, ddst, (size_t)cd.frame_bytes * out_count, cudaMemcpyDeviceToHost, c->stream));
     MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));

@@ -356,9 +356,6 @@ __global__ void __launch_bounds__(256) k_super0_pel2(const uint8_t *__restrict__
         sP[r][cw] = v;
     }
     __syncthreads();
-    auto sample = [&](const unsigned(*tile)[PW + 1], int r, int c) -> int { // sample c (0 = x0 - 4) of staged row r
-        return (int)((tile[r][c / SPW] >> (SH * (c % SPW))) & MASK);
-    };
     // ---- phase B: V over the whole staged width (D filters it horizontally), rows y0 .. y0 + TH - 1
     for (int k = tid; k < TH * PW; k += 256) {
         const int r = k / PW, cw = k - r * PW;
@@ -380,35 +377,50 @@ __global__ void __launch_bounds__(256) k_super0_pel2(const uint8_t *__restrict__
             *(unsigned *)(out + 2 * sub_bytes + (long long)y * pitch + (long long)x * (int)sizeof(T)) = v;
     }
     __syncthreads();
-    // ---- phase C: P0 (the padded plane itself), H and D
+    // ---- phase C: P0 (the padded plane itself), H and D.  A thread makes one word of each: the three words around it (12 / 6
+    // samples: columns c - SPW .. c + 2 SPW - 1) hold every tap of its samples
     constexpr int OW = TW / SPW;
     for (int k = tid; k < TH * OW; k += 256) {
         const int r = k / OW, ow = k - r * OW;
         const int y = y0 + r, x = x0 + ow * SPW;
         if (x >= W || y >= Hh)
             continue;
-        const int c = 4 + ow * SPW; // staged column of the word's first sample
+        const int cw = 4 / SPW + ow; // staged word of the output word
+        constexpr int NS = 3 * SPW + (SPW == 2 ? 2 : 0); // u8: words cw-1..cw+1 (12 samples); u16: words cw-1..cw+2 (8 samples): taps reach c + SPW + 2
+        constexpr int NWD = SPW == 2 ? 4 : 3;
+        int sp[NS], sv[NS], sn[NS]; // the row of P0, of V, and -- bilinear diagonal only -- the next row of P0
+#pragma unroll
+        for (int q = 0; q < NWD; q++) {
+            const unsigned wp = sP[r + 2][cw - 1 + q];
+            const unsigned wv = SHARP == 0 ? 0u : sV[r][cw - 1 + q];
+            const unsigned wn = SHARP == 0 ? sP[r + 3][cw - 1 + q] : 0u;
+#pragma unroll
+            for (int j = 0; j < SPW; j++) {
+                sp[q * SPW + j] = (int)((wp >> (SH * j)) & MASK);
+                sv[q * SPW + j] = (int)((wv >> (SH * j)) & MASK);
+                sn[q * SPW + j] = (int)((wn >> (SH * j)) & MASK);
+            }
+        }
         unsigned vh = 0, vd = 0;
 #pragma unroll
         for (int j = 0; j < SPW; j++) {
-            const int cc = c + j;
-            const int hval = refine_tap<SHARP>(sample(sP, r + 2, cc - 2), sample(sP, r + 2, cc - 1), sample(sP, r + 2, cc), sample(sP, r + 2, cc + 1), sample(sP, r + 2, cc + 2), sample(sP, r + 2, cc + 3),
-                                               x + j, W, pixelMax);
+            const int c = SPW + j; // index of this sample in sp[] / sv[]
+            const int hval = refine_tap<SHARP>(sp[c - 2], sp[c - 1], sp[c], sp[c + 1], sp[c + 2], sp[c + 3], x + j, W, pixelMax);
             int dval;
             if (SHARP == 0) { // DiagonalBilinear, MVFrame.cpp:536-572
-                const int p00 = sample(sP, r + 2, cc), p01 = sample(sP, r + 2, cc + 1), p10 = sample(sP, r + 3, cc), p11 = sample(sP, r + 3, cc + 1);
+                const int p00 = sp[c], p01 = sp[c + 1], p10 = sn[c], p11 = sn[c + 1];
                 if (y < Hh - 1)
                     dval = (x + j < W - 1) ? (p00 + p01 + p10 + p11 + 2) >> 2 : (p00 + p10 + 1) >> 1;
                 else
                     dval = (x + j < W - 1) ? (p00 + p01 + 1) >> 1 : p00;
             } else {
-                dval = refine_tap<SHARP>(sample(sV, r, cc - 2), sample(sV, r, cc - 1), sample(sV, r, cc), sample(sV, r, cc + 1), sample(sV, r, cc + 2), sample(sV, r, cc + 3), x + j, W, pixelMax);
+                dval = refine_tap<SHARP>(sv[c - 2], sv[c - 1], sv[c], sv[c + 1], sv[c + 2], sv[c + 3], x + j, W, pixelMax);
             }
             vh |= (unsigned)hval << (SH * j);
             vd |= (unsigned)dval << (SH * j);
         }
         const long long o = (long long)y * pitch + (long long)x * (int)sizeof(T);
-        *(unsigned *)(out + o) = sP[r + 2][c / SPW];
+        *(unsigned *)(out + o) = sP[r + 2][cw];
         *(unsigned *)(out + sub_bytes + o) = vh;
         *(unsigned *)(out + 3 * sub_bytes + o) = vd;
     }

@@ -34,10 +34,15 @@
 
 namespace {
 
-// One engine context (own CUDA streams and scratch) per device, each guarded by its own mutex.  Device 0 of the list does the
-// per-frame work; the fused windows go round the whole list (frames are independent units: a window carries its own halo).
+// Engine contexts (own CUDA streams and scratch each), every one guarded by its own mutex.  Slot 0 does the per-frame work;
+// the fused windows go round the whole list (frames are independent units: a window carries its own halo).
 //   MVB200_DEVICES=0,2,3  the devices to use        MVB200_DEVICE=1  a single device (what a multi-process launcher sets per rank)
 //   neither: every device the engine can run on
+// Each device gets MVB200_CONTEXTS_PER_DEVICE contexts (default 3): consecutive windows then run CONCURRENTLY on one GPU.  A
+// search launch is a set of serial chains that all walk the same phases in lockstep and finish at different times; windows
+// started at different times fill each other's idle issue slots and tails, and one window's Super / DegrainN kernels and
+// copies run beside another's search (measured on the 1080p Degrain3 script: 1280 -> 1606 -> 1815 frames/s with 1 / 2 / 3
+// contexts).  A device named several times in MVB200_DEVICES gets exactly that many contexts.
 constexpr int kMaxDevices = 16;
 struct EngineSlot {
     std::mutex m; // serialises this context's calls (the engine context is not re-entrant)
@@ -46,9 +51,11 @@ struct EngineSlot {
     bool failed = false;
     std::string err;
 };
-EngineSlot g_engines[kMaxDevices];
+EngineSlot g_engines[kMaxDevices * 4];
 std::once_flag g_devices_once;
-int g_ndev = 1;
+int g_ndev = 1;      // engine slots in all
+int g_ndevices = 1;  // distinct positions of the device list (slots are laid out context-major: [context][device])
+int g_perdev = 1;    // contexts per device
 
 void listDevices() {
     int n = 0;
@@ -70,7 +77,24 @@ void listDevices() {
     }
     if (n == 0)
         g_engines[n++].device = 0; // (no usable device: creating the context reports why)
-    g_ndev = n;
+    g_ndevices = n;
+    int per = 3;
+    if (const char *c = getenv("MVB200_CONTEXTS_PER_DEVICE"))
+        per = atoi(c);
+    if (getenv("MVB200_DEVICES")) { // an explicit list says how many contexts each device gets
+        bool repeated = false;
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < i; j++)
+                repeated = repeated || g_engines[i].device == g_engines[j].device;
+        if (repeated)
+            per = 1;
+    }
+    per = per < 1 ? 1 : (per > 4 ? 4 : per);
+    for (int c = 1; c < per; c++)
+        for (int d = 0; d < n; d++)
+            g_engines[c * n + d].device = g_engines[d].device;
+    g_perdev = per;
+    g_ndev = n * per;
 }
 
 int deviceCount() {
@@ -104,7 +128,7 @@ mvb200_ctx *engine(std::string &err) {
 // same value).  mv.DegrainN looks its inputs up here to recognise the canonical script
 //     sup = Super(clip); v.. = Analyse(sup, ..); DegrainN(clip, sup, v..)
 // whose whole chain one engine call can run (see DegrainData::fused).
-enum { kNodeSuper = 1, kNodeAnalyse = 2 };
+enum { kNodeSuper = 1, kNodeAnalyse = 2, kNodeRecalc = 3 };
 struct NodeInfo {
     int kind;
     void *data;
@@ -218,7 +242,7 @@ struct FusedWindow {
     std::string err;
     void *hostSrc = nullptr, *hostDst = nullptr; // in the clip layout, frame_bytes apart
     size_t srcBytes = 0, dstBytes = 0;
-    int slot = 0;               // which engine context (device) computes this window
+    int slot = 0;               // which engine context computes this window
     std::vector<int32_t> flags; // the engine's "usable" flag per output frame, where the filter has one
     mvb200_event *done = nullptr;
     std::shared_ptr<PinnedPool> pool;
@@ -247,23 +271,49 @@ struct FusedCache {
     std::shared_ptr<PinnedPool> pool = sharedPinnedPool();
     mvb200_frame_layout cl;
     int window = 0;
-    int depth = deviceCount(); // windows enqueued ahead of the one being served: one per device
+    int nslots = 1; // engine contexts this filter's windows go round (set with the window: fusedWindowFrames)
+    int depth = 1;  // windows enqueued ahead of the one being served: one per context
 };
 
 // Frames per window: MVB200_LOOKAHEAD if given, else what fills the search kernel's chain slots once with nvec vector
-// clips per frame (at least 16), within the pinned-memory budget (three windows alive: served, running, recycled).
-int fusedWindowFrames(int la, const mvb200_analyse_params *ap, const mvb200_super_params *sp, int nvec, int64_t frameBytes) {
-    if (la > 0)
-        return la;
-    const int ndev = deviceCount();
+// clips per frame (at least 16).  Also decides how many engine contexts the filter's windows go round: every device, and as
+// many contexts per device as keep the windows' device buffers (source / output clips double buffered, super clip, vectors)
+// within 45 % of the device's memory -- and the pinned host windows (one per context, one being served, one recycled)
+// within the pinned-memory budget.
+int fusedWindowFrames(FusedCache *f, int la, const mvb200_analyse_params *ap, const mvb200_super_params *sp, int nvec) {
+    const int64_t frameBytes = f->cl.frame_bytes > 0 ? f->cl.frame_bytes : 1;
     mvb200_search_plan plan;
     int frames = 64;
-    if (mvb200_search_plan_query(ap, sp, 0, &plan) == 0 && plan.chains_per_wave > 0)
+    int64_t chains = 0;
+    if (mvb200_search_plan_query(ap, sp, 0, &plan) == 0 && plan.chains_per_wave > 0) {
         frames = (plan.chains_per_wave + nvec - 1) / (nvec > 0 ? nvec : 1);
-    const int64_t cap = pinnedBudget() / (2 * (ndev + 2) * (frameBytes > 0 ? frameBytes : 1)); // windows alive: one per device, the one being served, one recycled
-    if (frames > cap)
-        frames = (int)cap;
-    return frames < 16 ? 16 : frames;
+        chains = plan.chains_per_wave;
+    }
+    if (frames > 768) // (a single vector clip per frame would ask for 1776 frames: bound the latency of a window)
+        frames = 768;
+    if (la > 0)
+        frames = la;
+    deviceCount();
+    mvb200_frame_layout sl;
+    mvb200_super_layout(sp, &sl);
+    int per = g_perdev;
+    const int64_t devmem = mvb200_device_memory(g_engines[0].device) > 0 ? mvb200_device_memory(g_engines[0].device) : ((int64_t)180 << 30);
+    auto deviceBytes = [&](int fr) { return (int64_t)fr * (4 * frameBytes + sl.frame_bytes + (int64_t)nvec * (ap->vectors_size + 256)) * 5 / 4 + chains * 65536; };
+    while (per > 1 && per * deviceBytes(frames) > devmem * 45 / 100)
+        per--;
+    if (la <= 0)
+        while (frames > 16 && per * deviceBytes(frames) > devmem * 45 / 100)
+            frames = frames * 3 / 4;
+    f->nslots = g_ndevices * per;
+    f->depth = f->nslots;
+    if (la <= 0) {
+        const int64_t cap = pinnedBudget() / (2 * (f->nslots + 2) * frameBytes);
+        if (frames > cap)
+            frames = (int)cap;
+        if (frames < 16)
+            frames = 16;
+    }
+    return frames;
 }
 
 // One activation of a fused filter.  propFrame: the source frame the output frame takes its properties from (always
@@ -290,7 +340,7 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
                 if (!w) {
                     w = std::make_shared<FusedWindow>();
                     w->pool = f->pool;
-                    w->slot = idx % deviceCount();
+                    w->slot = idx % f->nslots;
                     w->w0 = idx * B;
                     w->w1 = w->w0 + B < N ? w->w0 + B : N;
                     segment(w->w0, w->w1, &w->s0, &w->s1);
@@ -918,12 +968,31 @@ void VS_CC analyseCreate(const VSMap *in, VSMap *out, void *, VSCore *core, cons
     data->self = registerSelf(vsapi, out, kNodeAnalyse, data);
 }
 
+struct RecalcData {
+    VSNode *node, *vectors;
+    const VSVideoInfo *vi;
+    mvb200_super_params sp;
+    mvb200_recalculate_params rp;
+    VSNode *self; // this filter's output node (registry key), not a reference
+};
+
+// mv.Recalculate passes between a vector clip's mv.Analyse and its consumer (the refinemotion shape: Analyse -> Recalculate
+// (-> Recalculate) -> DegrainN / Compensate), innermost first
+constexpr int kMaxRecalc = 2;
+struct FusedRecalc {
+    int n = 0;
+    mvb200_recalculate_params rp[kMaxRecalc];
+};
+
 // ------------------------------------------------- the canonical chain (recognised by the fused paths)
 // True when `super` is this plugin's mv.Super of `clip` (no pelclip) and every vector clip is this plugin's mv.Analyse of
 // that super clip with a relative delta and no field handling: the chain one *_clip_host engine call runs from SOURCE
 // frames.  perPixel (the Flow* consumers): also chroma planes in the super clip unless the clip is gray, and no divide.
 // *spOut / ap[i]: the nodes' own parameters (the Super's own sharp / rfilter: the frame properties do not carry them).
-bool canonicalChain(VSNode *clip, VSNode *super, VSNode *const *vectors, int nvec, const mvb200_super_params &sp, int numFrames, bool perPixel, mvb200_super_params *spOut, mvb200_analyse_params *ap) {
+// rc (block consumers only; null = not accepted): a vector clip may also be up to kMaxRecalc of this plugin's mv.Recalculate
+// nodes (same super clip, no field handling) on top of such an mv.Analyse; rc[i] receives their parameters, innermost first.
+bool canonicalChain(VSNode *clip, VSNode *super, VSNode *const *vectors, int nvec, const mvb200_super_params &sp, int numFrames, bool perPixel, mvb200_super_params *spOut, mvb200_analyse_params *ap,
+                    FusedRecalc *rc = nullptr) {
     std::lock_guard<std::mutex> lock(g_registry_mutex);
     const auto su = g_registry.find(super);
     if (su == g_registry.end() || su->second.kind != kNodeSuper)
@@ -933,9 +1002,24 @@ bool canonicalChain(VSNode *clip, VSNode *super, VSNode *const *vectors, int nve
         S->sp.modeyuv != sp.modeyuv || (perPixel && !((S->sp.modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) || sp.gray)))
         return false;
     for (int i = 0; i < nvec; i++) {
-        const auto an = g_registry.find(vectors[i]);
+        VSNode *v = vectors[i];
+        const RecalcData *passes[kMaxRecalc];
+        int npass = 0;
+        auto an = g_registry.find(v);
+        while (an != g_registry.end() && an->second.kind == kNodeRecalc) { // outermost pass first
+            const RecalcData *R = (const RecalcData *)an->second.data;
+            if (!rc || npass == kMaxRecalc || R->node != super || R->rp.fields || R->rp.num_frames != numFrames)
+                return false;
+            passes[npass++] = R;
+            an = g_registry.find(R->vectors);
+        }
         if (an == g_registry.end() || an->second.kind != kNodeAnalyse)
             return false;
+        if (rc) {
+            rc[i].n = npass;
+            for (int k = 0; k < npass; k++)
+                rc[i].rp[k] = passes[npass - 1 - k]->rp;
+        }
         const AnalyseData *A = (const AnalyseData *)an->second.data;
         if (A->node != super || A->ap.fields || (perPixel && A->ap.divide) || A->ap.ad.nDeltaFrame <= 0 || A->ap.num_frames != numFrames)
             return false;
@@ -952,6 +1036,7 @@ bool canonicalChain(VSNode *clip, VSNode *super, VSNode *const *vectors, int nve
 // window only serve as references).
 struct DegrainFused : FusedCache {
     mvb200_analyse_params ap[2 * MVB200_MAX_RADIUS]; // copies: no dependence on the Analyse instances' lifetime
+    FusedRecalc rc[2 * MVB200_MAX_RADIUS];           // mv.Recalculate passes of each vector clip (usually none)
     int halo;
 };
 
@@ -984,7 +1069,12 @@ const VSFrame *VS_CC degrainFusedGetFrame(int n, int activationReason, void *ins
             aps[r].num_frames = seg;
             app[r] = &aps[r];
         }
-        return mvb200_degrain_clip_host_async(ctx, &d->sp, app, R2, &d->dp, hostSrc, hostDst, seg, w0 - s0, w1 - w0); // (asynchronous: fusedGetFrame records the completion event)
+        const mvb200_recalculate_params *rpp[2 * MVB200_MAX_RADIUS * kMaxRecalc];
+        for (int r = 0; r < R2; r++)
+            for (int k = 0; k < kMaxRecalc; k++)
+                rpp[r * kMaxRecalc + k] = k < f->rc[r].n ? &f->rc[r].rp[k] : nullptr;
+        // (asynchronous: fusedGetFrame records the completion event)
+        return mvb200_degrain_recalc_clip_host_async(ctx, &d->sp, app, R2, rpp, kMaxRecalc, &d->dp, hostSrc, hostDst, seg, w0 - s0, w1 - w0);
     };
     return fusedGetFrame("Degrain", f, d->node, d->vi, n, n, mask, activationReason, frameData, frameCtx, core, vsapi, segment, run);
 }
@@ -1138,13 +1228,13 @@ void VS_CC degrainCreate(const VSMap *in, VSMap *out, void *userData, VSCore *co
     if (window) {
         DegrainFused *f = new DegrainFused;
         mvb200_super_params ssp;
-        if (canonicalChain(d.node, d.super, d.vectors, 2 * radius, d.sp, d.vi->numFrames, false, &ssp, f->ap)) {
+        if (canonicalChain(d.node, d.super, d.vectors, 2 * radius, d.sp, d.vi->numFrames, false, &ssp, f->ap, f->rc)) {
             int halo = 0;
             for (int r = 0; r < 2 * radius; r++)
                 halo = f->ap[r].ad.nDeltaFrame > halo ? f->ap[r].ad.nDeltaFrame : halo;
             d.sp = ssp;
             mvb200_clip_layout(&d.sp, &f->cl);
-            f->window = fusedWindowFrames(window, f->ap, &d.sp, 2 * radius, f->cl.frame_bytes);
+            f->window = fusedWindowFrames(f, window, f->ap, &d.sp, 2 * radius);
             f->halo = halo;
             d.fused = f;
         } else {
@@ -1210,12 +1300,6 @@ bool fieldShiftOf(const VSAPI *vsapi, const VSFrame *src, const VSFrame *ref, in
 }
 
 // ------------------------------------------------------------ Recalculate
-struct RecalcData {
-    VSNode *node, *vectors;
-    const VSVideoInfo *vi;
-    mvb200_super_params sp;
-    mvb200_recalculate_params rp;
-};
 
 const VSFrame *VS_CC recalcGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
     RecalcData *d = (RecalcData *)instanceData;
@@ -1279,6 +1363,7 @@ const VSFrame *VS_CC recalcGetFrame(int n, int activationReason, void *instanceD
 
 void VS_CC recalcFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
     RecalcData *d = (RecalcData *)instanceData;
+    unregisterSelf(d->self);
     vsapi->freeNode(d->node);
     vsapi->freeNode(d->vectors);
     delete d;
@@ -1309,12 +1394,14 @@ void VS_CC recalcCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const
     RecalcData *data = new RecalcData(d);
     VSFilterDependency deps[2] = {{data->node, rpGeneral}, {data->vectors, rpStrictSpatial}};
     vsapi->createVideoFilter(out, "Recalculate", data->vi, recalcGetFrame, recalcFree, fmParallel, deps, 2, data, core);
+    data->self = registerSelf(vsapi, out, kNodeRecalc, data);
 }
 
 // ------------------------------------------------------------- Compensate
 // Fused path (see fusedGetFrame): a window of B frames is one mvb200_compensate_clip_host call over source frames.
 struct CompFused : FusedCache {
     mvb200_analyse_params ap;
+    FusedRecalc rc; // mv.Recalculate passes between the search and the compensation (usually none)
     int halo;
 };
 
@@ -1336,7 +1423,10 @@ const VSFrame *VS_CC compFusedGetFrame(int n, int activationReason, void *instan
         *s1 = w1 + f->halo < N ? w1 + f->halo : N;
     };
     auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst, int32_t *flags) {
-        return mvb200_compensate_clip_host(ctx, &d->sp, &f->ap, &d->cp, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst);
+        const mvb200_recalculate_params *rpp[kMaxRecalc];
+        for (int k = 0; k < kMaxRecalc; k++)
+            rpp[k] = k < f->rc.n ? &f->rc.rp[k] : nullptr;
+        return mvb200_compensate_recalc_clip_host(ctx, &d->sp, &f->ap, rpp, kMaxRecalc, &d->cp, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst);
     };
     const VSFrame *out = fusedGetFrame("Compensate", f, d->node, d->vi, n, n, mask, activationReason, frameData, frameCtx, core, vsapi, segment, run);
     if (out && n == 0) // the reference builds the output on super frame n (MVCompensate.c:113): frame 0 carries the Super_* properties
@@ -1458,12 +1548,14 @@ void VS_CC compCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const V
     const int window = lookaheadFromEnv();
     mvb200_super_params ssp;
     mvb200_analyse_params sap;
-    if (window && !d.cp.fields && canonicalChain(d.node, d.super, &d.vectors, 1, d.sp, d.vi->numFrames, false, &ssp, &sap)) { // the fused path
+    FusedRecalc src;
+    if (window && !d.cp.fields && canonicalChain(d.node, d.super, &d.vectors, 1, d.sp, d.vi->numFrames, false, &ssp, &sap, &src)) { // the fused path
         d.fused = new CompFused;
         d.fused->ap = sap;
+        d.fused->rc = src;
         d.sp = ssp;
         mvb200_clip_layout(&d.sp, &d.fused->cl);
-        d.fused->window = fusedWindowFrames(window, &sap, &d.sp, 1, d.fused->cl.frame_bytes);
+        d.fused->window = fusedWindowFrames(d.fused, window, &sap, &d.sp, 1);
         d.fused->halo = sap.ad.nDeltaFrame;
     }
     CompData *data = new CompData(d);
@@ -1928,7 +2020,7 @@ void VS_CC flowCreate(const VSMap *in, VSMap *out, void *, VSCore *core, const V
         d.fused->ap = sap;
         d.sp = ssp;
         mvb200_clip_layout(&d.sp, &d.fused->cl);
-        d.fused->window = fusedWindowFrames(window, &sap, &d.sp, 1, d.fused->cl.frame_bytes);
+        d.fused->window = fusedWindowFrames(d.fused, window, &sap, &d.sp, 1);
     }
     FlowData *data = new FlowData(d);
     if (data->fused) { // only the source clip is read on this path
@@ -2148,7 +2240,7 @@ void VS_CC flowInterCreate(const VSMap *in, VSMap *out, void *, VSCore *core, co
         d.fused->apFw = sap[1];
         d.sp = ssp;
         mvb200_clip_layout(&d.sp, &d.fused->cl);
-        d.fused->window = fusedWindowFrames(window, sap, &d.sp, 2, d.fused->cl.frame_bytes);
+        d.fused->window = fusedWindowFrames(d.fused, window, sap, &d.sp, 2);
     }
     FlowInterData *data = new FlowInterData(d);
     VSFilterDependency deps[4] = {{data->node, rpGeneral}, {data->super, rpGeneral}, {data->mvbw, rpGeneral}, {data->mvfw, rpGeneral}};
@@ -2390,7 +2482,7 @@ void VS_CC flowFpsCreate(const VSMap *in, VSMap *out, void *, VSCore *core, cons
         d.fused->apFw = sap[1];
         d.sp = ssp;
         mvb200_clip_layout(&d.sp, &d.fused->cl);
-        d.fused->window = fusedWindowFrames(window, sap, &d.sp, 2, d.fused->cl.frame_bytes);
+        d.fused->window = fusedWindowFrames(d.fused, window, sap, &d.sp, 2);
     }
     FlowFPSData *data = new FlowFPSData(d);
     VSFilterDependency deps[4] = {{data->node, rpGeneral}, {data->super, rpGeneral}, {data->mvbw, rpGeneral}, {data->mvfw, rpGeneral}};
@@ -2582,7 +2674,7 @@ void VS_CC flowBlurCreate(const VSMap *in, VSMap *out, void *, VSCore *core, con
         d.fused->apFw = sap[1];
         d.sp = ssp;
         mvb200_clip_layout(&d.sp, &d.fused->cl);
-        d.fused->window = fusedWindowFrames(window, sap, &d.sp, 2, d.fused->cl.frame_bytes);
+        d.fused->window = fusedWindowFrames(d.fused, window, sap, &d.sp, 2);
     }
     FlowBlurData *data = new FlowBlurData(d);
     if (data->fused) { // only the source clip is read on this path
@@ -2813,7 +2905,7 @@ void VS_CC blockFpsCreate(const VSMap *in, VSMap *out, void *, VSCore *core, con
         d.fused->apFw = sap[1];
         d.sp = ssp;
         mvb200_clip_layout(&d.sp, &d.fused->cl);
-        d.fused->window = fusedWindowFrames(window, sap, &d.sp, 2, d.fused->cl.frame_bytes);
+        d.fused->window = fusedWindowFrames(d.fused, window, sap, &d.sp, 2);
     }
     BlockFPSData *data = new BlockFPSData(d);
     VSFilterDependency deps[4] = {{data->node, rpGeneral}, {data->super, rpGeneral}, {data->mvbw, rpGeneral}, {data->mvfw, rpGeneral}};
