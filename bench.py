@@ -402,48 +402,67 @@ def run_gpu_arm(args, cfg):
         del drec
     torch.cuda.empty_cache()
 
-    # ---- pass 2 (the `value`): the product's execution mode -- C engine contexts on the device, each running the whole path over
-    # its own contiguous part of the step's frames (+ REACH halo frames of super clip) on its own stream.  A search launch is a set
-    # of serial chains walking the same phases in lockstep; parts started independently fill each other's idle issue slots and
-    # tails, and one part's Super / DegrainN kernels run beside another's search.  W warm-up steps, K timed steps, no host sync
-    # between steps; time = first start -> last end over all streams (CUDA events), max over ranks.
-    NC = max(1, min(args.contexts, F_out // 8 or 1))
-    parts = []
-    for i in range(NC):
-        a0, a1 = F_out * i // NC, F_out * (i + 1) // NC
-        lo_i, hi_i = max(0, OFF + a0 - REACH), min(F, OFF + a1 + REACH)
-        Fi, offi, cnt = hi_i - lo_i, OFF + a0 - lo_i, a1 - a0
-        c_i = ctx if i == 0 else mb.Context(local)
-        st_i = torch.cuda.ExternalStream(c_i.stream(), device=torch.device("cuda", local))
-        if kind == "degrain":
-            aps_i = [mb.analyse_params(sp, Fi, isb=isb, delta=d, **akw) for d in range(1, cfg["radius"] + 1) for isb in (1, 0)]
-        elif kind == "analyse":
-            aps_i = [mb.analyse_params(sp, Fi, **akw)]
-        else:
-            aps_i = [mb.analyse_params(sp, Fi, isb=1, **akw)]
-            rp_i = mb.recalculate_params(sp, aps_i[0].ad, Fi, blksize=cfg["blk"], overlap=cfg["ov"], dct=cfg.get("dct", 0))
-            cp_i = mb.compensate_params(sp, rp_i.ad, W_, H_, Fi)
+    # ---- pass 2 (the `value`): the product's execution mode -- the step's frames flow through C engine contexts on the device as
+    # WINDOWS (the plugin's own window size: what fills the search kernel's chain slots once), window j on context j mod C, each
+    # context running Super -> searches -> DegrainN of its windows back to back on its own stream.  A search launch is a set of
+    # serial chains of very different lengths: one launch alone ends in a long tail of a few slow chains (a wave of 1776 chains
+    # takes 201 ms, the average chain 150 ms).  With several windows in flight the next window's chains take the slots the moment
+    # they free up, and one window's Super / DegrainN kernels run beside another's search.  W warm-up steps, K timed steps, all
+    # enqueued without a host sync in between; time = first start -> last end over all streams (CUDA events), max over ranks.
+    NC = max(1, args.contexts)
+    S = max(8, min(plugin_window(plan_q, len(aps)), F_out))
+    bounds = list(range(0, F_out, S)) + [F_out]
+    ctxs = [ctx] + [mb.Context(local) for _ in range(NC - 1)]
+    streams = [torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", local)) for c in ctxs]
+    bufs = []
+    for c_i, st_i in zip(ctxs, streams):
         with torch.cuda.stream(st_i):
-            dsup_i = torch.empty((Fi, sl.frame_bytes), dtype=torch.uint8, device="cuda")
-            dvec_i = [torch.empty((cnt, vs), dtype=torch.uint8, device="cuda") for _ in aps_i]
-            ddst_i = torch.empty((cnt, cl.frame_bytes), dtype=torch.uint8, device="cuda") if kind != "analyse" else None
-            drec_i = torch.empty((cnt, rvs), dtype=torch.uint8, device="cuda") if kind == "mc" else None
-        apa_i = (C.POINTER(mb.AnalyseParams) * len(aps_i))(*[C.pointer(a) for a in aps_i])
-        outs_i = (C.c_void_p * len(aps_i))(*[t.data_ptr() for t in dvec_i])
-        src_i = dsrc.data_ptr() + lo_i * cl.frame_bytes
-        P = dict(ctx=c_i, stream=st_i, keep=(aps_i, dsup_i, dvec_i, ddst_i, drec_i, apa_i, outs_i))
+            bufs.append(dict(sup=torch.empty((S + 2 * REACH, sl.frame_bytes), dtype=torch.uint8, device="cuda"),
+                             vec=[torch.empty((S, vs), dtype=torch.uint8, device="cuda") for _ in aps],
+                             rec=torch.empty((S, rvs), dtype=torch.uint8, device="cuda") if kind == "mc" else None))
+    ddst_all = torch.empty((F_out, cl.frame_bytes), dtype=torch.uint8, device="cuda") if kind != "analyse" else None
+    torch.cuda.synchronize()
+    params_for = {}
 
-        def run(P=P, c_i=c_i, Fi=Fi, offi=offi, cnt=cnt, apa_i=apa_i, outs_i=outs_i, src_i=src_i, dsup_i=dsup_i, ddst_i=ddst_i, drec_i=drec_i, dvec_i=dvec_i, n_aps=len(aps_i),
-                rp_i=locals().get("rp_i"), cp_i=locals().get("cp_i")):
-            mb._check(L.mvb200_super_batch(c_i.handle, C.byref(sp), src_i, dsup_i.data_ptr(), Fi))
-            mb._check(L.mvb200_analyse_multi_batch(c_i.handle, apa_i, n_aps, C.byref(sp), dsup_i.data_ptr(), offi, cnt, outs_i, vs))
+    def window_params(Fi):
+        if Fi not in params_for:
             if kind == "degrain":
-                mb._check(L.mvb200_degrain_batch(c_i.handle, C.byref(dp), C.byref(sp), src_i, dsup_i.data_ptr(), Fi, offi, cnt, outs_i, vs, ddst_i.data_ptr()))
-            elif kind == "mc":
-                mb._check(L.mvb200_recalculate_batch(c_i.handle, C.byref(rp_i), C.byref(sp), dsup_i.data_ptr(), offi, cnt, dvec_i[0].data_ptr(), vs, drec_i.data_ptr(), rvs))
-                mb._check(L.mvb200_compensate_batch(c_i.handle, C.byref(cp_i), C.byref(sp), dsup_i.data_ptr(), offi, cnt, drec_i.data_ptr(), rvs, ddst_i.data_ptr()))
-        P["run"] = run
-        parts.append(P)
+                aps_i = [mb.analyse_params(sp, Fi, isb=isb, delta=d, **akw) for d in range(1, cfg["radius"] + 1) for isb in (1, 0)]
+                extra = None
+            elif kind == "analyse":
+                aps_i, extra = [mb.analyse_params(sp, Fi, **akw)], None
+            else:
+                aps_i = [mb.analyse_params(sp, Fi, isb=1, **akw)]
+                rp_i = mb.recalculate_params(sp, aps_i[0].ad, Fi, blksize=cfg["blk"], overlap=cfg["ov"], dct=cfg.get("dct", 0))
+                extra = (rp_i, mb.compensate_params(sp, rp_i.ad, W_, H_, Fi))
+            params_for[Fi] = (aps_i, (C.POINTER(mb.AnalyseParams) * len(aps_i))(*[C.pointer(a) for a in aps_i]), extra)
+        return params_for[Fi]
+
+    windows = []
+    for j in range(len(bounds) - 1):
+        a0, a1 = bounds[j], bounds[j + 1]
+        lo_i, hi_i = max(0, OFF + a0 - REACH), min(F, OFF + a1 + REACH)
+        windows.append(dict(slot=j % NC, Fi=hi_i - lo_i, off=OFF + a0 - lo_i, cnt=a1 - a0, src=dsrc.data_ptr() + lo_i * cl.frame_bytes, dst=a0))
+
+    def run_window(wd):
+        c_i, B = ctxs[wd["slot"]], bufs[wd["slot"]]
+        aps_i, apa_i, extra = window_params(wd["Fi"])
+        outs_i = (C.c_void_p * len(aps_i))(*[t.data_ptr() for t in B["vec"]])
+        mb._check(L.mvb200_super_batch(c_i.handle, C.byref(sp), wd["src"], B["sup"].data_ptr(), wd["Fi"]))
+        mb._check(L.mvb200_analyse_multi_batch(c_i.handle, apa_i, len(aps_i), C.byref(sp), B["sup"].data_ptr(), wd["off"], wd["cnt"], outs_i, vs))
+        if kind == "degrain":
+            mb._check(L.mvb200_degrain_batch(c_i.handle, C.byref(dp), C.byref(sp), wd["src"], B["sup"].data_ptr(), wd["Fi"], wd["off"], wd["cnt"], outs_i, vs,
+                                             ddst_all.data_ptr() + wd["dst"] * cl.frame_bytes))
+        elif kind == "mc":
+            mb._check(L.mvb200_recalculate_batch(c_i.handle, C.byref(extra[0]), C.byref(sp), B["sup"].data_ptr(), wd["off"], wd["cnt"], B["vec"][0].data_ptr(), vs, B["rec"].data_ptr(), rvs))
+            mb._check(L.mvb200_compensate_batch(c_i.handle, C.byref(extra[1]), C.byref(sp), B["sup"].data_ptr(), wd["off"], wd["cnt"], B["rec"].data_ptr(), rvs,
+                                                ddst_all.data_ptr() + wd["dst"] * cl.frame_bytes))
+
+    parts = [dict(ctx=c_i, stream=st_i) for c_i, st_i in zip(ctxs, streams)]
+
+    def run_step():
+        for wd in windows:
+            run_window(wd)
 
     def barrier_all():
         for P in parts:
@@ -451,8 +470,7 @@ def run_gpu_arm(args, cfg):
         barrier()
 
     for _ in range(args.warmup):
-        for P in parts:
-            P["run"]()
+        run_step()
     barrier_all()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -463,8 +481,7 @@ def run_gpu_arm(args, cfg):
     barrier_all()
     e_start.record(parts[0]["stream"])
     for k in range(args.steps):
-        for P in parts:
-            P["run"]()
+        run_step()
     for P, e in zip(parts, e_ends):
         e.record(P["stream"])
     barrier_all()
@@ -473,7 +490,7 @@ def run_gpu_arm(args, cfg):
     value = (total if cfg.get("fixed_total") else world * F_out) * args.steps / (region_ms / 1e3)
     for P in parts[1:]:
         P["ctx"].close()
-    del parts, dsrc
+    del parts, dsrc, bufs, ddst_all, windows
     torch.cuda.empty_cache()
 
     # ---- the clip-level C ABI with pinned host buffers (round 1's e2e; DegrainN pipelines only).  (The resident legs' device
@@ -567,8 +584,8 @@ def run_gpu_arm(args, cfg):
                    "search_kernel": {0: "k_search (generic)", 1: "k_search_fast (register-blocked)", 2: "k_search_tma (TMA-staged windows)"}[plan_q.kernel],
                    "search_chain_slots_per_gpu": plan_q.chains_per_wave,
                    "l2": "inputs larger than L2 (%d MB of super frames + vectors per step vs 126 MB L2), no flush" % int((F * sl.frame_bytes + len(aps) * F_out * vs) / 1e6),
-                   "contexts_per_gpu": NC, "value_one_context": value_one_context,
-                   "stage_ms": stage_ms, "stage_ms_note": "one context, stages serialised on one stream (pass 1); `value` runs %d contexts concurrently" % NC},
+                   "contexts_per_gpu": NC, "window_frames": S, "value_one_context": value_one_context,
+                   "stage_ms": stage_ms, "stage_ms_note": "one context, the whole step in one launch per stage, serialised on one stream (pass 1); `value` streams windows of %d frames through %d contexts" % (S, NC)},
         "e2e": {"value": e2e_value, "unit": "frames/s", "through": "libmvtools.so (VapourSynthPluginInit2) under host/minivs, default environment, %d host threads per rank" % pl["threads"],
                 "timer": "wall clock around the host's render of K steps (the plugin owns its CUDA context), max over ranks",
                 "protocol": pl["protocol"],
@@ -616,7 +633,7 @@ def main():
     ap.add_argument("--frames", type=int, default=None, help="frames per step per GPU (default: the config's)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--contexts", type=int, default=3, help="engine contexts per GPU of the device-resident leg (the plugin's default: MVB200_CONTEXTS_PER_DEVICE)")
+    ap.add_argument("--contexts", type=int, default=4, help="engine contexts per GPU of the device-resident leg (the plugin's default: MVB200_CONTEXTS_PER_DEVICE)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.frames is None:

@@ -38,11 +38,13 @@ namespace {
 // the fused windows go round the whole list (frames are independent units: a window carries its own halo).
 //   MVB200_DEVICES=0,2,3  the devices to use        MVB200_DEVICE=1  a single device (what a multi-process launcher sets per rank)
 //   neither: every device the engine can run on
-// Each device gets MVB200_CONTEXTS_PER_DEVICE contexts (default 3): consecutive windows then run CONCURRENTLY on one GPU.  A
-// search launch is a set of serial chains that all walk the same phases in lockstep and finish at different times; windows
-// started at different times fill each other's idle issue slots and tails, and one window's Super / DegrainN kernels and
-// copies run beside another's search (measured on the 1080p Degrain3 script: 1280 -> 1606 -> 1815 frames/s with 1 / 2 / 3
-// contexts).  A device named several times in MVB200_DEVICES gets exactly that many contexts.
+// Each device gets MVB200_CONTEXTS_PER_DEVICE contexts (default 4): consecutive windows then run CONCURRENTLY on one GPU.  A
+// search launch is a set of serial chains of very different lengths: alone it ends in a long tail of a few slow chains (a
+// wave of 1776 chains takes 201 ms, the average chain 150 ms).  With several windows in flight the next window's chains take
+// the slots the moment they free up, and one window's Super / DegrainN kernels and copies run beside another's search
+// (measured on the 1080p Degrain3 script, profiles/r2_plugin_context_sweep.txt: 1327 / 1580 / 1759 / 1978 frames/s with
+// 1 / 2 / 3 / 4 contexts; what counts is the number of frames in flight -- 4 contexts with half-size windows give what 2 give
+// with whole ones).  A device named several times in MVB200_DEVICES gets exactly that many contexts.
 constexpr int kMaxDevices = 16;
 struct EngineSlot {
     std::mutex m; // serialises this context's calls (the engine context is not re-entrant)
@@ -51,7 +53,7 @@ struct EngineSlot {
     bool failed = false;
     std::string err;
 };
-EngineSlot g_engines[kMaxDevices * 4];
+EngineSlot g_engines[kMaxDevices * 8];
 std::once_flag g_devices_once;
 int g_ndev = 1;      // engine slots in all
 int g_ndevices = 1;  // distinct positions of the device list (slots are laid out context-major: [context][device])
@@ -78,7 +80,7 @@ void listDevices() {
     if (n == 0)
         g_engines[n++].device = 0; // (no usable device: creating the context reports why)
     g_ndevices = n;
-    int per = 3;
+    int per = 4;
     if (const char *c = getenv("MVB200_CONTEXTS_PER_DEVICE"))
         per = atoi(c);
     if (getenv("MVB200_DEVICES")) { // an explicit list says how many contexts each device gets
@@ -89,7 +91,7 @@ void listDevices() {
         if (repeated)
             per = 1;
     }
-    per = per < 1 ? 1 : (per > 4 ? 4 : per);
+    per = per < 1 ? 1 : (per > 8 ? 8 : per);
     for (int c = 1; c < per; c++)
         for (int d = 0; d < n; d++)
             g_engines[c * n + d].device = g_engines[d].device;
