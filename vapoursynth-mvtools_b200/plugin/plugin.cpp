@@ -18,6 +18,7 @@
 #include <mvtools_b200.h>
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstdio>
@@ -240,7 +241,9 @@ struct FusedWindow {
     std::condition_variable cv;
     std::atomic<int> state{Idle};
     bool prefetchClaimed = false; // (under FusedCache::m) some request already gathers this window's source frames ahead of time
-    int packNext = 0, packDone = 0;
+    std::atomic<int> packNext{0}, packDone{0};
+    std::vector<const VSFrame *> srcFrames; // references to the window's source frames, released one by one as they are packed
+    const VSAPI *vsapi = nullptr;
     std::string err;
     void *hostSrc = nullptr, *hostDst = nullptr; // in the clip layout, frame_bytes apart
     size_t srcBytes = 0, dstBytes = 0;
@@ -249,6 +252,9 @@ struct FusedWindow {
     mvb200_event *done = nullptr;
     std::shared_ptr<PinnedPool> pool;
     ~FusedWindow() {
+        for (const VSFrame *fr : srcFrames) // (a window that was published but never packed)
+            if (fr && vsapi)
+                vsapi->freeFrame(fr);
         if (done) {
             mvb200_event_wait(done); // the GPU may still be writing hostDst
             mvb200_event_destroy(done);
@@ -270,6 +276,7 @@ struct FusedRequest {
 struct FusedCache {
     std::mutex m;                                           // guards `windows` and the windows' prefetchClaimed
     std::map<int, std::shared_ptr<FusedWindow>> windows;    // by window index (frame / window)
+    std::vector<std::shared_ptr<FusedWindow>> packing;      // windows whose source frames wait to be copied into their pinned buffers
     std::shared_ptr<PinnedPool> pool = sharedPinnedPool();
     mvb200_frame_layout cl;
     int window = 0;
@@ -385,61 +392,97 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
         return nullptr;
     }
     const size_t fb = (size_t)f->cl.frame_bytes;
-    // every window this request holds the source frames of: pack it (together with the other requests that hold it) and
-    // enqueue it -- the own window first, the look-ahead windows behind it on the engine's streams
+    // (1) every window this request holds the source frames of and nobody has taken yet: take references to its frames and
+    // publish it for packing (the frames then belong to the window, not to this request)
     for (auto &w : rq->hold) {
         std::unique_lock<std::mutex> wl(w->m);
-        if (w->state.load() == FusedWindow::Idle) {
-            size_t gs = 0, gd = 0;
-            w->hostSrc = w->pool->get(fb * (size_t)(w->s1 - w->s0), &gs);
-            w->srcBytes = gs;
-            w->hostDst = w->hostSrc ? w->pool->get(fb * (size_t)(w->w1 - w->w0), &gd) : nullptr;
-            w->dstBytes = gd;
-            w->flags.assign((size_t)(w->w1 - w->w0), 0);
-            if (!w->hostSrc || !w->hostDst) {
-                w->err = mvb200_last_error();
-                w->state.store(FusedWindow::Failed);
-                w->cv.notify_all();
-                continue;
-            }
-            w->state.store(FusedWindow::Packing);
+        if (w->state.load() != FusedWindow::Idle)
+            continue;
+        size_t gs = 0, gd = 0;
+        w->hostSrc = w->pool->get(fb * (size_t)(w->s1 - w->s0), &gs);
+        w->srcBytes = gs;
+        w->hostDst = w->hostSrc ? w->pool->get(fb * (size_t)(w->w1 - w->w0), &gd) : nullptr;
+        w->dstBytes = gd;
+        w->flags.assign((size_t)(w->w1 - w->w0), 0);
+        if (!w->hostSrc || !w->hostDst) {
+            w->err = mvb200_last_error();
+            w->state.store(FusedWindow::Failed);
+            w->cv.notify_all();
+            continue;
         }
         const int count = w->s1 - w->s0;
-        while (w->state.load() == FusedWindow::Packing || w->state.load() == FusedWindow::Launching) {
-            if (w->state.load() == FusedWindow::Launching || w->packNext >= count) { // every frame is taken: the thread that packs the last one enqueues the window
-                w->cv.wait(wl);
-                continue;
-            }
-            const int i = w->packNext++;
-            wl.unlock();
-            const VSFrame *fr = vsapi->getFrameFilter(w->s0 + i, clip, frameCtx);
-            for (int p = 0; p < f->cl.nplanes; p++)
-                vsh::bitblt((uint8_t *)w->hostSrc + fb * (size_t)i + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], vsapi->getReadPtr(fr, p), vsapi->getStride(fr, p),
-                            (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, (size_t)f->cl.plane_h[p]);
-            vsapi->freeFrame(fr);
-            wl.lock();
-            if (++w->packDone < count)
-                continue;
-            w->state.store(FusedWindow::Launching);
-            wl.unlock();
-            std::string msg;
-            bool ok = false;
-            mvb200_event *ev = nullptr;
-            {
-                EngineSlot &es = g_engines[w->slot];
-                std::lock_guard<std::mutex> elock(es.m);
-                mvb200_ctx *ctx = engineOf(es, msg);
-                if (ctx) {
-                    ok = run(ctx, w->hostSrc, w->s0, w->s1, w->w0, w->w1, w->hostDst, w->flags.data()) == 0 && mvb200_ctx_record(ctx, &ev) == 0;
-                    if (!ok)
-                        msg = mvb200_last_error();
+        w->vsapi = vsapi;
+        w->srcFrames.resize((size_t)count);
+        for (int i = 0; i < count; i++)
+            w->srcFrames[(size_t)i] = vsapi->getFrameFilter(w->s0 + i, clip, frameCtx);
+        w->state.store(FusedWindow::Packing);
+        wl.unlock();
+        std::lock_guard<std::mutex> lock(f->m);
+        f->packing.push_back(w);
+    }
+    // (2) pack: EVERY request of this filter copies frames of whatever windows wait for it into their pinned buffers (a window
+    // is a gigabyte: one thread would need longer for it than the GPU for the window before); the thread that packs a window's
+    // last frame enqueues it on its engine context
+    auto packSome = [&]() -> bool {
+        std::shared_ptr<FusedWindow> w;
+        {
+            std::lock_guard<std::mutex> lock(f->m);
+            for (auto it = f->packing.begin(); it != f->packing.end();) {
+                if ((*it)->packNext.load() >= (*it)->s1 - (*it)->s0) {
+                    it = f->packing.erase(it); // every frame is taken
+                } else {
+                    w = *it;
+                    break;
                 }
             }
+        }
+        if (!w)
+            return false;
+        const int count = w->s1 - w->s0;
+        const int i = w->packNext.fetch_add(1);
+        if (i >= count)
+            return true;
+        const VSFrame *fr = w->srcFrames[(size_t)i];
+        for (int p = 0; p < f->cl.nplanes; p++)
+            vsh::bitblt((uint8_t *)w->hostSrc + fb * (size_t)i + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], vsapi->getReadPtr(fr, p), vsapi->getStride(fr, p),
+                        (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, (size_t)f->cl.plane_h[p]);
+        w->srcFrames[(size_t)i] = nullptr;
+        vsapi->freeFrame(fr);
+        if (w->packDone.fetch_add(1) + 1 < count)
+            return true;
+        w->state.store(FusedWindow::Launching);
+        std::string msg;
+        bool ok = false;
+        mvb200_event *ev = nullptr;
+        {
+            EngineSlot &es = g_engines[w->slot];
+            std::lock_guard<std::mutex> elock(es.m);
+            mvb200_ctx *ctx = engineOf(es, msg);
+            if (ctx) {
+                ok = run(ctx, w->hostSrc, w->s0, w->s1, w->w0, w->w1, w->hostDst, w->flags.data()) == 0 && mvb200_ctx_record(ctx, &ev) == 0;
+                if (!ok)
+                    msg = mvb200_last_error();
+            }
+        }
+        std::lock_guard<std::mutex> wl(w->m);
+        w->done = ev;
+        w->err = msg;
+        w->state.store(ok ? FusedWindow::Running : FusedWindow::Failed);
+        w->cv.notify_all();
+        return true;
+    };
+    while (packSome()) {
+    }
+    // (3) this request's own window may still be in other threads' hands (its last frames being packed, or being enqueued)
+    {
+        FusedWindow *own = rq->win.get();
+        std::unique_lock<std::mutex> wl(own->m);
+        while (own->state.load() == FusedWindow::Packing || own->state.load() == FusedWindow::Launching) {
+            wl.unlock();
+            const bool worked = packSome();
             wl.lock();
-            w->done = ev;
-            w->err = msg;
-            w->state.store(ok ? FusedWindow::Running : FusedWindow::Failed);
-            w->cv.notify_all();
+            if (!worked && (own->state.load() == FusedWindow::Packing || own->state.load() == FusedWindow::Launching))
+                own->cv.wait_for(wl, std::chrono::milliseconds(1));
         }
     }
     const VSFrame *src = vsapi->getFrameFilter(propFrame, clip, frameCtx);
