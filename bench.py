@@ -411,16 +411,7 @@ def run_gpu_arm(args, cfg):
     # enqueued without a host sync in between; time = first start -> last end over all streams (CUDA events), max over ranks.
     NC = max(1, args.contexts)
     S = max(8, min(plugin_window(plan_q, len(aps)), F_out))
-    # the first C windows of a step are S/C, 2S/C, ... S frames long: contexts that start together on equal windows would also end
-    # together (the tails coincide again); uneven first windows de-phase them for good, as a frame server's pacing does in the plugin
-    bounds, pos, j = [0], 0, 0
-    while pos < F_out:
-        size = max(8, S * (j + 1) // NC) if j < NC else S
-        pos = min(F_out, pos + size)
-        if F_out - pos < 8:
-            pos = F_out
-        bounds.append(pos)
-        j += 1
+    bounds = list(range(0, F_out, S)) + [F_out]
     ctxs = [ctx] + [mb.Context(local) for _ in range(NC - 1)]
     streams = [torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", local)) for c in ctxs]
     bufs = []
@@ -538,9 +529,8 @@ def run_gpu_arm(args, cfg):
     sampler2 = ClockSampler(local)
     if rank == 0:
         sampler2.start()
-    def host_barrier():
-        torch.cuda.synchronize()
-        if world > 1:
+    def host_barrier():  # (no device synchronisation here: the plugin's windows in flight must stay in flight across the boundary
+        if world > 1:    #  between the warm-up and the timed steps -- a drained pipeline would hand the timed region finished windows)
             dist.barrier()
 
     pl = plugin_leg(cfg, args, mb, plan, world, rank, local, host_barrier, total, gold, plugin_window(plan_q, len(aps)))

@@ -57,6 +57,11 @@ LATE = {
     # 8-bit, pel 4: the last column of the 3/4-pel planes as the reference's default (opt=1, AVX2 Average2) path writes it
     # (MVFrame.cpp:1519-1526): pinned for mv.Super, mv.Finest and everything computed from the super clip
     "p8_420_blk8_pel4": (dict(width=168, height=96, nframes=4, bits=8), dict(pel=4), dict(blksize=8, overlap=4), 1, {}),
+    # dct=5 (SATD luma cost) with the default search types: the configurations the TMA search kernel's SATD lane layout serves
+    # (4x4 Hadamard tiles per lane); UMH + a low badsad send steps through the global-memory path and the bad-block search
+    "satd_dct5_blk8_hex": (dict(width=192, height=128, nframes=5, bits=8), dict(pel=2), dict(blksize=8, overlap=4, dct=5), 1, {}),
+    "satd_dct5_blk16_umh_noise": (dict(width=256, height=160, nframes=5, bits=8, noise_sigma=8.0, scene_cut=True), dict(pel=2), dict(blksize=16, overlap=8, dct=5, search=5, searchparam=4, badsad=400), 2, {}),
+    "satd_dct5_blk8_pel1_esa": (dict(width=160, height=96, nframes=4, bits=8), dict(pel=1, hpad=8, vpad=8), dict(blksize=8, dct=5, search=3, searchparam=2), 1, {}),
     # Degrain4..6 (the cases above stop at radius 3)
     "r6_blk8_ov4_p8": (dict(width=136, height=96, nframes=14, bits=8), dict(pel=2, hpad=8, vpad=8), dict(blksize=8, overlap=4), 6, dict(thsad=500, thsadc=300, limit=30, limitc=40)),
     "r5_blk16_p16_422": (dict(width=144, height=96, nframes=9, bits=16, ssw=1, ssh=0, scene_cut=True), dict(pel=1, hpad=8, vpad=8), dict(blksize=16, overlap=8), 5, dict(plane=4)),

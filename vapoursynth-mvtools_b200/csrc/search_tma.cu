@@ -137,8 +137,17 @@ __constant__ int t_hex4[16][2] = {{-4, 2}, {-4, 1}, {-4, 0}, {-4, -1}, {-4, -2},
 
 constexpr int r128(int v) { return (v + 127) / 128 * 128; }
 
-template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
+// SATD_ (dct = 5, pobLumaSAD<5>: the luma cost is Satd_C, SADFunctions.cpp:581-710): the four lanes of a candidate no longer take
+// rows q, q + 4, ... of the block but whole 4x4 Hadamard tiles -- lane q owns tiles q * T .. q * T + T - 1 of the block's TCxTR tile
+// grid (16x16: tile row q, all four tile columns; 8x8: the one tile (q & 1, q >> 1)).  Chroma stays a SAD.
+template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA, bool SATD_ = false>
 struct Cfg {
+    static constexpr bool SATD = SATD_;
+    static_assert(!SATD_ || BPS == 1, "the SATD lane layout is written for 8-bit samples");
+    static constexpr int TC = BW / 4, TR = BH / 4, T = (TC * TR) / 4; // tile grid, tiles per lane
+    static constexpr int SRW = T < TC ? T : TC;                        // words (tile columns) a lane reads per row
+    static_assert(!SATD_ || (TC * TR) % 4 == 0, "tiles per lane");
+    static_assert(!SATD_ || T <= TC, "a lane's tiles lie in one tile row");
     static constexpr int CW = BW >> LXR, CH = BH >> LYR;
     static constexpr int R = 4; // guaranteed luma window radius in full pixels
     static constexpr int RCX = R >> LXR, RCY = R >> LYR;
@@ -168,7 +177,7 @@ struct Cfg {
     static constexpr int CRW = CHROMA ? CW * BPS / 4 : 1, CR = CHROMA ? CH / 4 : 1; // same for one chroma plane
     static constexpr int LBYTES = BW * BH * BPS, CBYTES = CHROMA ? CW * CH * BPS : 0;
     static constexpr int SRCW = (LBYTES + 2 * CBYTES) / 4, NSI = (SRCW + 31) / 32; // source block words, per lane for the cooperative load
-    static constexpr bool PACK = BPS == 1 && BW * BH <= 256 && 2 * CW * CH <= 256;
+    static constexpr bool PACK = !SATD_ && BPS == 1 && BW * BH <= 256 && 2 * CW * CH <= 256; // (a SATD does not fit 16 bits)
     static constexpr bool SRC_SMEM = BPS == 2 && BW * BH >= 256; // too many registers: read source rows from shared memory
     static constexpr int SRCB = r128(LBYTES + 2 * CBYTES);                   // one source-block buffer
     static constexpr int SRCOFF = 2 * BUF;                                   // [src 0][src 1]
@@ -215,14 +224,15 @@ struct Cold {
 };
 static_assert(sizeof(Cold) <= 256, "Cold");
 
-template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
+template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA, bool SATD_ = false>
 struct Chain {
-    using C = Cfg<BPS, BW, BH, LXR, LYR, CHROMA>;
+    using C = Cfg<BPS, BW, BH, LXR, LYR, CHROMA, SATD_>;
     static constexpr long long INF = 0x7fffffffffffffffLL;
     static constexpr unsigned FULL = 0xffffffffu;
 
     // ---- source block rows of this lane (rows q, q+4, ...), unless C::SRC_SMEM
-    unsigned srcL[C::SRC_SMEM ? 1 : C::LR][C::RW], srcC[2][C::SRC_SMEM ? 1 : C::CR][C::CRW];
+    // (SATD: rows 4 * trow + i, i = 0 .. 3, of the lane's tile row, words tcol .. tcol + SRW - 1)
+    unsigned srcL[C::SRC_SMEM ? 1 : (C::SATD ? 4 : C::LR)][C::SATD ? C::SRW : C::RW], srcC[2][C::SRC_SMEM ? 1 : C::CR][C::CRW];
     uint32_t srcbuf; // shared-space address of the current source block
     Cold *K;
     int logPel, penaltyNew;
@@ -257,6 +267,35 @@ struct Chain {
         return __funnelshift_r(__ldg(w), __ldg(w + 1), sh);
     }
     __device__ __forceinline__ static unsigned absd(unsigned a, unsigned b) { return BPS == 1 ? __vsadu4(a, b) : __vsadu2(a, b); }
+
+    // Real_Satd_4x4_C (SADFunctions.cpp:605-641) on one tile held as four words of source and four of reference samples; the same
+    // 32-bit pseudo-SIMD arithmetic (two 16-bit sums per register, abs2), so the result is the reference's bit for bit
+    __device__ __forceinline__ static unsigned abs2(unsigned a) {
+        const unsigned s = ((a >> 15) & 0x10001u) * 0xffffu;
+        return (a + s) ^ s;
+    }
+    __device__ __forceinline__ static unsigned satd_tile(const unsigned s0, const unsigned s1, const unsigned s2, const unsigned s3, const unsigned r0, const unsigned r1, const unsigned r2,
+                                                         const unsigned r3) {
+        const unsigned sv[4] = {s0, s1, s2, s3}, rv[4] = {r0, r1, r2, r3};
+        unsigned t0[4], t1[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const unsigned a0 = (sv[i] & 0xffu) - (rv[i] & 0xffu), a1 = ((sv[i] >> 8) & 0xffu) - ((rv[i] >> 8) & 0xffu);
+            const unsigned a2 = ((sv[i] >> 16) & 0xffu) - ((rv[i] >> 16) & 0xffu), a3 = (sv[i] >> 24) - (rv[i] >> 24);
+            const unsigned b0 = (a0 + a1) + ((a0 - a1) << 16), b1 = (a2 + a3) + ((a2 - a3) << 16);
+            t0[i] = b0 + b1;
+            t1[i] = b0 - b1;
+        }
+        unsigned sum = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const unsigned *t = h ? t1 : t0;
+            const unsigned u0 = t[0] + t[1], u1 = t[0] - t[1], u2 = t[2] + t[3], u3 = t[2] - t[3];
+            const unsigned a = abs2(u0 + u2) + abs2(u0 - u2) + abs2(u1 + u3) + abs2(u1 - u3);
+            sum += (a & 0xffffu) + (a >> 16);
+        }
+        return sum >> 1;
+    }
 
     // window placement for a block whose (clipped) centre vector is (cx, cy)
     __device__ __forceinline__ void window_origin(const Geom &gg, int cx, int cy, int &ox, int &oy, int &oxc, int &oyc) const {
@@ -322,8 +361,30 @@ struct Chain {
                 shl = 0;
                 lrow = 4 * (C::RW * 4);
             }
+            if constexpr (C::SATD) {
+                // this lane's tiles: rows 4 * trow .. + 3, words tcol .. tcol + SRW - 1 of the candidate block
+                const int trow = (q * C::T) / C::TC, tcol = (q * C::T) % C::TC;
+                uint32_t at = sbuf + (cbl & ~3) + 4 * trow * C::LWB + 4 * tcol;
+                int trs = C::LWB;
+                if (zlane) {
+                    at = zbuf + 4 * trow * (C::RW * 4) + 4 * tcol;
+                    trs = C::RW * 4;
+                }
+                unsigned ref[4][C::SRW];
 #pragma unroll
-            for (int i = 0; i < C::LR; i++) {
+                for (int i = 0; i < 4; i++) {
+                    unsigned r[C::SRW + 1];
+                    lds_row(at + i * trs, r);
+#pragma unroll
+                    for (int w = 0; w < C::SRW; w++)
+                        ref[i][w] = __funnelshift_r(r[w], r[w + 1], shl);
+                }
+#pragma unroll
+                for (int w = 0; w < C::SRW; w++)
+                    aL += satd_tile(srcL[0][w], srcL[1][w], srcL[2][w], srcL[3][w], ref[0][w], ref[1][w], ref[2][w], ref[3][w]);
+            }
+#pragma unroll
+            for (int i = 0; i < (C::SATD ? 0 : C::LR); i++) {
                 unsigned r[C::RW + 1], sw[C::RW];
                 if (ZSLOT && C::ZB)
                     lds_row(al + i * lrow, r);
@@ -337,7 +398,7 @@ struct Chain {
                     accL[i] += absd(__funnelshift_r(r[w], r[w + 1], shl), C::SRC_SMEM ? sw[w] : srcL[i][w]);
             }
 #pragma unroll
-            for (int i = 0; i < C::LR; i++)
+            for (int i = 0; i < (C::SATD ? 0 : C::LR); i++)
                 aL += accL[i];
             if (CHROMA) {
                 uint32_t ac = sbuf + C::LREG + (cbc & ~3) + q * C::CWB;
@@ -381,8 +442,29 @@ struct Chain {
             const uint8_t *lw = (const uint8_t *)(la & ~3ull);
             const unsigned shl = ((unsigned)la & 3u) * 8u;
             unsigned accL[C::LR], accC[2][C::CR];
+            if constexpr (C::SATD) {
+                const int trow = (q * C::T) / C::TC, tcol = (q * C::T) % C::TC;
+                const unsigned long long ta = (unsigned long long)(K->rbase[0] + (long long)subl * K->sub0 + (long long)(fy + 4 * trow) * pitch0 + fx * BPS + 4 * tcol);
+                const uint8_t *tw = (const uint8_t *)(ta & ~3ull);
+                const unsigned sht = ((unsigned)ta & 3u) * 8u;
+                unsigned ref[4][C::SRW];
 #pragma unroll
-            for (int i = 0; i < C::LR; i++) {
+                for (int i = 0; i < 4; i++) {
+                    const unsigned *rw = (const unsigned *)(tw + (long long)i * pitch0);
+                    unsigned r[C::SRW + 1];
+#pragma unroll
+                    for (int w = 0; w <= C::SRW; w++)
+                        r[w] = __ldg(rw + w);
+#pragma unroll
+                    for (int w = 0; w < C::SRW; w++)
+                        ref[i][w] = __funnelshift_r(r[w], r[w + 1], sht);
+                }
+#pragma unroll
+                for (int w = 0; w < C::SRW; w++)
+                    aL += satd_tile(srcL[0][w], srcL[1][w], srcL[2][w], srcL[3][w], ref[0][w], ref[1][w], ref[2][w], ref[3][w]);
+            }
+#pragma unroll
+            for (int i = 0; i < (C::SATD ? 0 : C::LR); i++) {
                 const unsigned *rw = (const unsigned *)(lw + (long long)(4 * i) * pitch0);
                 unsigned r[C::RW + 1], sw[C::RW];
 #pragma unroll
@@ -396,7 +478,7 @@ struct Chain {
                     accL[i] += absd(__funnelshift_r(r[w], r[w + 1], shl), C::SRC_SMEM ? sw[w] : srcL[i][w]);
             }
 #pragma unroll
-            for (int i = 0; i < C::LR; i++)
+            for (int i = 0; i < (C::SATD ? 0 : C::LR); i++)
                 aL += accL[i];
             if (CHROMA) {
                 const long long oc = (long long)subc * K->sub1 + (long long)(fyc + q) * pitch1 + fxc * BPS;
@@ -694,11 +776,11 @@ struct Chain {
     }
 };
 
-template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
-__global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)) k_search_tma(const __grid_constant__ TmaMaps maps, const SuperDesc *__restrict__ sdp, const SearchParams *__restrict__ params,
+template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA, bool SATD_ = false>
+__global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA, SATD_>::MINB)) k_search_tma(const __grid_constant__ TmaMaps maps, const SuperDesc *__restrict__ sdp, const SearchParams *__restrict__ params,
                                                    const SearchJob *__restrict__ jobs, int njobs, int *__restrict__ hist_all, int hist_ints, int chroma_rows) {
-    using C = Cfg<BPS, BW, BH, LXR, LYR, CHROMA>;
-    using CH = Chain<BPS, BW, BH, LXR, LYR, CHROMA>;
+    using C = Cfg<BPS, BW, BH, LXR, LYR, CHROMA, SATD_>;
+    using CH = Chain<BPS, BW, BH, LXR, LYR, CHROMA, SATD_>;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     const int chain = blockIdx.x;
     if (chain >= njobs)
@@ -939,9 +1021,15 @@ __global__ void __launch_bounds__(32, (Cfg<BPS, BW, BH, LXR, LYR, CHROMA>::MINB)
                 __syncwarp();
             }
             S.srcbuf = dst;
+            if constexpr (C::SATD) { // the lane's tile row: rows 4 * trow .. + 3, words tcol .. tcol + SRW - 1
+                const int trow = (S.q * C::T) / C::TC, tcol = (S.q * C::T) % C::TC;
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    lds_vec(dst + (4 * trow + i) * (C::RW * 4) + 4 * tcol, S.srcL[i]);
+            }
             if (!C::SRC_SMEM) {
 #pragma unroll
-                for (int i = 0; i < C::LR; i++)
+                for (int i = 0; i < (C::SATD ? 0 : C::LR); i++)
                     lds_vec(dst + (S.q + 4 * i) * (C::RW * 4), S.srcL[i]);
                 if (CHROMA) {
 #pragma unroll
@@ -1190,10 +1278,10 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA>
+template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA, bool SATD_>
 int launch_cfg(Ctx *ctx, const SuperDesc &sd, const uint8_t *frames_base, int nframes, const SuperDesc *dev_sd, const SearchParams *dev_params, const SearchJob *dev_jobs,
                int njobs, int *hist, int hist_ints, const mvb200_super_geom &geom, int pel, bool need_raw, bool *handled) {
-    using C = Cfg<BPS, BW, BH, LXR, LYR, CHROMA>;
+    using C = Cfg<BPS, BW, BH, LXR, LYR, CHROMA, SATD_>;
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         *handled = false;
@@ -1230,7 +1318,7 @@ int launch_cfg(Ctx *ctx, const SuperDesc &sd, const uint8_t *frames_base, int nf
             }
         }
     }
-    auto kern = k_search_tma<BPS, BW, BH, LXR, LYR, CHROMA>;
+    auto kern = k_search_tma<BPS, BW, BH, LXR, LYR, CHROMA, SATD_>;
     // function attributes are per device: one bit per device ordinal (a second context on another GPU of the same process)
     static std::atomic<unsigned long long> configured{0};
     const unsigned long long devbit = 1ull << (ctx->device & 63);
@@ -1246,16 +1334,19 @@ int launch_cfg(Ctx *ctx, const SuperDesc &sd, const uint8_t *frames_base, int nf
 }
 
 // The compiled configurations, in the order of TMA_CONFIGS below; -1 when a parameter set needs another kernel.
-#define TMA_CONFIGS(X) X(0, 1, 16, 16, 1, 1, true) X(1, 2, 16, 16, 1, 1, true) X(2, 1, 8, 8, 1, 1, true) X(3, 2, 8, 8, 1, 1, true) X(4, 1, 16, 16, 0, 0, false) X(5, 1, 8, 8, 0, 0, false)
+// (ID, bytes per sample, block, log2 chroma subsampling, chroma, SATD luma cost: dct = 5)
+#define TMA_CONFIGS(X)                                                                                                                                                         \
+    X(0, 1, 16, 16, 1, 1, true, false) X(1, 2, 16, 16, 1, 1, true, false) X(2, 1, 8, 8, 1, 1, true, false) X(3, 2, 8, 8, 1, 1, true, false) X(4, 1, 16, 16, 0, 0, false, false) \
+    X(5, 1, 8, 8, 0, 0, false, false) X(6, 1, 16, 16, 1, 1, true, true) X(7, 1, 8, 8, 1, 1, true, true)
 
 static int tma_match(const SuperDesc &sd, const SearchParams *host_params, int nparams, bool *need_raw) {
     const SearchParams &P0 = host_params[0];
     for (int i = 0; i < nparams; i++) {
         const SearchParams &P = host_params[i];
         auto okType = [](int t) { return t == 3 || t == 4 || t == 5; };
-        if (P.dctmode != 0 || P.tryMany || !okType(P.search) || !okType(P.search_coarse) || P.pel > 2)
+        if ((P.dctmode != 0 && P.dctmode != 5) || P.tryMany || !okType(P.search) || !okType(P.search_coarse) || P.pel > 2)
             return -1;
-        if (P.blkW != P0.blkW || P.blkH != P0.blkH || P.chroma != P0.chroma || P.bps != P0.bps || P.pel != P0.pel)
+        if (P.blkW != P0.blkW || P.blkH != P0.blkH || P.chroma != P0.chroma || P.bps != P0.bps || P.pel != P0.pel || P.dctmode != P0.dctmode)
             return -1;
     }
     // the winner's vector travels as two 16-bit halves of one shuffle
@@ -1270,9 +1361,9 @@ static int tma_match(const SuperDesc &sd, const SearchParams *host_params, int n
             if ((((sd.lv[0][l].hpad * bps) | (stepX * bps) | (sd.lv[c][l].hpad * bps) | ((stepX >> (c ? lx : 0)) * bps)) & 3) != 0)
                 *need_raw = true;
         }
-    const bool chroma = P0.chroma;
-#define MATCH(ID_, BPS_, BW_, BH_, LX_, LY_, CH_)                                                            \
-    if (bps == BPS_ && bw == BW_ && bh == BH_ && chroma == CH_ && (!CH_ || (lx == LX_ && ly == LY_))) \
+    const bool chroma = P0.chroma, satd = P0.dctmode == 5;
+#define MATCH(ID_, BPS_, BW_, BH_, LX_, LY_, CH_, SATD_)                                                                      \
+    if (bps == BPS_ && bw == BW_ && bh == BH_ && chroma == CH_ && satd == SATD_ && (!CH_ || (lx == LX_ && ly == LY_))) \
         return ID_;
     TMA_CONFIGS(MATCH)
 #undef MATCH
@@ -1294,9 +1385,9 @@ int launch_search_tma(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &ge
     if (!get_encode_fn()) // (the driver is older than the tensor-map API: the register-blocked kernel takes the job)
         return 0;
     *handled = true;
-#define TRY(ID_, BPS_, BW_, BH_, LX_, LY_, CH_) \
-    if (id == ID_)                              \
-        return launch_cfg<BPS_, BW_, BH_, LX_, LY_, CH_>(ctx, sd, frames_base, nframes, dev_sd, dev_params, dev_jobs, njobs, hist, hist_ints, geom, host_params[0].pel, need_raw, handled);
+#define TRY(ID_, BPS_, BW_, BH_, LX_, LY_, CH_, SATD_) \
+    if (id == ID_)                                     \
+        return launch_cfg<BPS_, BW_, BH_, LX_, LY_, CH_, SATD_>(ctx, sd, frames_base, nframes, dev_sd, dev_params, dev_jobs, njobs, hist, hist_ints, geom, host_params[0].pel, need_raw, handled);
     TMA_CONFIGS(TRY)
 #undef TRY
     return 0;
@@ -1309,9 +1400,9 @@ int tma_plan(const SuperDesc &sd, const SearchParams *host_params, int nparams, 
     bool need_raw = false;
     const int id = tma_match(sd, host_params, nparams, &need_raw);
     *smem_per_chain = 0;
-#define PLAN(ID_, BPS_, BW_, BH_, LX_, LY_, CH_)                                  \
+#define PLAN(ID_, BPS_, BW_, BH_, LX_, LY_, CH_, SATD_)                           \
     if (id == ID_) {                                                              \
-        using C = Cfg<BPS_, BW_, BH_, LX_, LY_, CH_>;                             \
+        using C = Cfg<BPS_, BW_, BH_, LX_, LY_, CH_, SATD_>;                      \
         *smem_per_chain = need_raw ? C::SMEM_RAW : C::SMEM;                       \
         const int by_smem = (227 * 1024) / (*smem_per_chain + 1024);              \
         return by_smem < C::MINB ? by_smem : C::MINB;                             \
