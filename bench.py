@@ -404,10 +404,9 @@ def run_gpu_arm(args, cfg):
 
     # ---- pass 2 (the `value`): the product's execution mode -- the step's frames flow through C engine contexts on the device as
     # WINDOWS (the plugin's own window size: what fills the search kernel's chain slots once), window j on context j mod C, each
-    # context running Super -> searches -> DegrainN of its windows back to back on its own stream.  A search launch is a set of
-    # serial chains of very different lengths: one launch alone ends in a long tail of a few slow chains (a wave of 1776 chains
-    # takes 201 ms, the average chain 150 ms).  With several windows in flight the next window's chains take the slots the moment
-    # they free up, and one window's Super / DegrainN kernels run beside another's search.  W warm-up steps, K timed steps, all
+    # context running Super -> searches -> DegrainN of its windows back to back on its own stream: one window's Super / DegrainN
+    # kernels run beside the other's search, and the next window's search chains take the slots the moment the slow chains of the
+    # previous one leave them.  W warm-up steps, K timed steps, all
     # enqueued without a host sync in between; time = first start -> last end over all streams (CUDA events), max over ranks.
     NC = max(1, args.contexts)
     S = max(8, min(plugin_window(plan_q, len(aps)), F_out))
@@ -632,7 +631,7 @@ def main():
     ap.add_argument("--frames", type=int, default=None, help="frames per step per GPU (default: the config's)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--contexts", type=int, default=4, help="engine contexts per GPU of the device-resident leg (the plugin's default: MVB200_CONTEXTS_PER_DEVICE)")
+    ap.add_argument("--contexts", type=int, default=2, help="engine contexts per GPU of the device-resident leg (the plugin's default: MVB200_CONTEXTS_PER_DEVICE)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.frames is None:

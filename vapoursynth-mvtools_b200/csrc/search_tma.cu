@@ -1,4 +1,4 @@
-// The production search kernel for the default mv.Analyse configurations (dct=0, no
+// The production search kernel for the default mv.Analyse configurations (dct=0 or dct=5 / SATD on 8-bit clips, no
 // trymany, search types exhaustive / hex2 / UMH, pel <= 2, compile-time block shapes).
 // Same semantics -- bit for bit -- as the generic kernel (search.cu).  One warp owns one
 // serial search chain (one (frame, direction, delta) instance); what makes it fast on sm_100a:

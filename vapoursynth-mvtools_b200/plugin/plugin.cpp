@@ -39,13 +39,11 @@ namespace {
 // the fused windows go round the whole list (frames are independent units: a window carries its own halo).
 //   MVB200_DEVICES=0,2,3  the devices to use        MVB200_DEVICE=1  a single device (what a multi-process launcher sets per rank)
 //   neither: every device the engine can run on
-// Each device gets MVB200_CONTEXTS_PER_DEVICE contexts (default 4): consecutive windows then run CONCURRENTLY on one GPU.  A
-// search launch is a set of serial chains of very different lengths: alone it ends in a long tail of a few slow chains (a
-// wave of 1776 chains takes 201 ms, the average chain 150 ms).  With several windows in flight the next window's chains take
-// the slots the moment they free up, and one window's Super / DegrainN kernels and copies run beside another's search
-// (measured on the 1080p Degrain3 script, profiles/r2_plugin_context_sweep.txt: 1327 / 1580 / 1759 / 1978 frames/s with
-// 1 / 2 / 3 / 4 contexts; what counts is the number of frames in flight -- 4 contexts with half-size windows give what 2 give
-// with whole ones).  A device named several times in MVB200_DEVICES gets exactly that many contexts.
+// Each device gets MVB200_CONTEXTS_PER_DEVICE contexts (default 2): consecutive windows then run CONCURRENTLY on one GPU -- one
+// window's copies, Super and DegrainN kernels beside the other's search, and the next window's search chains take the slots the
+// moment the slow chains of the previous one leave them.  Steady state of the 1080p Degrain3 script over 60 windows
+// (profiles/r2_plugin_long_runs.txt): 1298 / 1493 / 1491 frames/s with 1 / 2 / 4 contexts -- two are enough, more only cost
+// device memory.  A device named several times in MVB200_DEVICES gets exactly that many contexts.
 constexpr int kMaxDevices = 16;
 struct EngineSlot {
     std::mutex m; // serialises this context's calls (the engine context is not re-entrant)
@@ -81,7 +79,7 @@ void listDevices() {
     if (n == 0)
         g_engines[n++].device = 0; // (no usable device: creating the context reports why)
     g_ndevices = n;
-    int per = 4;
+    int per = 2;
     if (const char *c = getenv("MVB200_CONTEXTS_PER_DEVICE"))
         per = atoi(c);
     if (getenv("MVB200_DEVICES")) { // an explicit list says how many contexts each device gets
