@@ -122,17 +122,22 @@ __device__ __forceinline__ void hadamard4(int &d0, int &d1, int &d2, int &d3, in
     d3 = t1 - t3;
 }
 
-// per-lane partial SATD: one lane per 4x4 tile.  Satd_C, SADFunctions.cpp:605-710: every
-// 8x4 (or lone 4x4) tile is halved; each 4x4 half is even, so halving per 4x4 is identical.
+// per-lane partial SATD, NOT yet halved.  Satd_C, SADFunctions.cpp:605-710: every 8x4 (or lone 4x4) tile's sum of absolute
+// Hadamard coefficients is halved; each 4x4 half is even, so the block's SATD is (sum over all tiles) >> 1 -- the callers halve the
+// warp sum.  One lane per tile ROW (four adjacent lanes per 4x4 tile: 16 lanes busy on an 8x8 block, where one lane per tile kept
+// 4 busy): a lane transforms its row horizontally, the vertical transform is two butterfly exchanges between the tile's four lanes.
+// Called by all 32 lanes (full-mask shuffles).
 __device__ unsigned lane_satd(const uint8_t *a, long long ap, const uint8_t *b, long long bp, int w, int h, int bps, int lane) {
-    int tx = w >> 2, tiles = tx * (h >> 2);
+    const int tx = w >> 2, units = tx * (h >> 2) * 4;
     unsigned acc = 0;
-    for (int t = lane; t < tiles; t += 32) {
-        int ox = (t % tx) * 4, oy = (t / tx) * 4;
-        int m[4][4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const uint8_t *pa = a + (oy + r) * ap + ox * bps, *pb = b + (oy + r) * bp + ox * bps;
+    for (int u0 = 0; u0 < units; u0 += 32) {
+        const int u = u0 + lane;
+        const bool live = u < units;
+        const int t = (live ? u : 0) >> 2, r = u & 3;
+        const int ox = (t % tx) * 4, oy = (t / tx) * 4 + r;
+        int m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+        if (live) {
+            const uint8_t *pa = a + oy * ap + ox * bps, *pb = b + oy * bp + ox * bps;
             int d0, d1, d2, d3;
             if (bps == 1) {
                 unsigned va = ldu32(pa), vb = ldu32(pb);
@@ -147,16 +152,18 @@ __device__ unsigned lane_satd(const uint8_t *a, long long ap, const uint8_t *b, 
                 d2 = (int)(va2 & 0xffff) - (int)(vb2 & 0xffff);
                 d3 = (int)(va2 >> 16) - (int)(vb2 >> 16);
             }
-            hadamard4(m[r][0], m[r][1], m[r][2], m[r][3], d0, d1, d2, d3);
+            hadamard4(m0, m1, m2, m3, d0, d1, d2, d3);
         }
-        unsigned s = 0;
+        // vertical HADAMARD4 over the tile's rows r = 0..3 (lanes 4k .. 4k + 3): rows (0,1) and (2,3) first, then the pairs
+        int v[4] = {m0, m1, m2, m3};
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            int a0, a1, a2, a3;
-            hadamard4(a0, a1, a2, a3, m[0][c], m[1][c], m[2][c], m[3][c]);
-            s += (unsigned)(abs(a0) + abs(a1) + abs(a2) + abs(a3));
+            int o = __shfl_xor_sync(0xffffffffu, v[c], 1);
+            v[c] = (r & 1) ? o - v[c] : v[c] + o; // even row: t0 + t1 (t2 + t3), odd row: t0 - t1 (t2 - t3)
+            o = __shfl_xor_sync(0xffffffffu, v[c], 2);
+            v[c] = (r & 2) ? o - v[c] : v[c] + o; // rows 0, 1: sums, rows 2, 3: differences of the pairs
+            acc += (unsigned)abs(v[c]);
         }
-        acc += s >> 1;
     }
     return acc;
 }
@@ -232,7 +239,7 @@ __device__ long long luma_sad(State &S, const uint8_t *pRef) {
     long long sp = S.src[0].pitch, rp = S.ref[0].pitch;
     int d = S.dctmode;
     if (d == 5)
-        return wsum(lane_satd(S.pSrc[0], sp, pRef, rp, S.blkW, S.blkH, S.bps, S.lane));
+        return wsum(lane_satd(S.pSrc[0], sp, pRef, rp, S.blkW, S.blkH, S.bps, S.lane)) >> 1;
     long long sad = wsum(lane_sad(S.pSrc[0], sp, pRef, rp, S.blkW * S.bps, S.blkH, S.bps, S.lane));
     if (d == 0)
         return sad;
@@ -261,7 +268,7 @@ __device__ long long luma_sad(State &S, const uint8_t *pRef) {
     }
     if (d == 6) {
         if (S.dctweight16 > 0) {
-            long long dctsad = wsum(lane_satd(S.pSrc[0], sp, pRef, rp, S.blkW, S.blkH, S.bps, S.lane));
+            long long dctsad = wsum(lane_satd(S.pSrc[0], sp, pRef, rp, S.blkW, S.blkH, S.bps, S.lane)) >> 1;
             sad = (sad * (16 - S.dctweight16) + dctsad * S.dctweight16) / 16;
         }
         return sad;
@@ -269,7 +276,7 @@ __device__ long long luma_sad(State &S, const uint8_t *pRef) {
     if (d == 9) {
         if (S.dctweight16 > 1) {
             int half = S.dctweight16 / 2;
-            long long dctsad = wsum(lane_satd(S.pSrc[0], sp, pRef, rp, S.blkW, S.blkH, S.bps, S.lane));
+            long long dctsad = wsum(lane_satd(S.pSrc[0], sp, pRef, rp, S.blkW, S.blkH, S.bps, S.lane)) >> 1;
             sad = (sad * (16 - half) + dctsad * half) / 16;
         }
         return sad;
@@ -277,7 +284,7 @@ __device__ long long luma_sad(State &S, const uint8_t *pRef) {
     int refLuma = (int)wsum(lane_luma(pRef, rp, S.blkW * S.bps, S.blkH, S.bps, S.lane));
     int shift = d == 10 ? 4 : 5;
     if (abs(S.srcLuma - refLuma) > ((S.srcLuma + refLuma) >> shift)) {
-        long long dctsad = wsum(lane_satd(S.pSrc[0], sp, pRef, rp, S.blkW, S.blkH, S.bps, S.lane));
+        long long dctsad = wsum(lane_satd(S.pSrc[0], sp, pRef, rp, S.blkW, S.blkH, S.bps, S.lane)) >> 1;
         if (d == 7)
             sad = sad / 2 + dctsad / 2;
         else if (d == 8)
