@@ -227,10 +227,17 @@ def fill_host_clip(hv, frames, cl):
             rows[:, : a.shape[1] * a.itemsize] = a.view(np.uint8).reshape(a.shape[0], -1)
 
 
-def plugin_window(plan_q, nvec):
-    """Frames per look-ahead window of the plugin's fused paths in its default configuration (plugin.cpp fusedWindowFrames:
-    what fills the search kernel's chain slots once, at most 768) -- only used to ALIGN the timed region, see plugin_leg."""
-    return max(16, min(768, -(-plan_q.chains_per_wave // max(nvec, 1))))
+def plugin_window(mb, aps, sp, kind, device):
+    """Frames per window of the plugin's fused paths in its default configuration on one device: the engine's own answer
+    (mvb200_window_plan_query, which plugin.cpp fusedWindowFrames calls with the same arguments) -- used to size the resident
+    leg's windows and to ALIGN the timed region of the plugin leg, see plugin_leg."""
+    L = mb.lib()
+    cl, sl = mb.clip_layout(sp), mb.super_layout(sp)
+    out_bytes = sl.frame_bytes + (aps[0].vectors_size + 255) // 256 * 256 if kind == "analyse" else cl.frame_bytes
+    per = int(os.environ.get("MVB200_CONTEXTS_PER_DEVICE", "2") or 2)
+    wp = mb.WindowPlan()
+    mb._check(L.mvb200_window_plan_query(C.byref(aps[0]), C.byref(sp), len(aps), -1, cl.frame_bytes, out_bytes, 1, per, 0, L.mvb200_device_memory(device), C.byref(wp)))
+    return int(wp.frames)
 
 
 def plugin_leg(cfg, args, mb, plan, world, rank, local, barrier, total_frames, gold, window):
@@ -245,17 +252,12 @@ def plugin_leg(cfg, args, mb, plan, world, rank, local, barrier, total_frames, g
     os.environ["MVB200_DEVICE"] = str(local)
     F_out, OFF, lo = plan["count"], plan["offset"], plan["lo"]
     threads = max(4, (os.cpu_count() or 4) // world)
-    fused = cfg["kind"] in ("degrain", "mc")  # (Recalculate passes are part of the fused chains)
 
     def script(n_local, first):
         core = minivs.Core()
         mv = core.load(mb.PLUGIN_PATH)
         out, keep = build_script(mv, core, cfg, make_frames(cfg, n_local, first=first))
-        out.set_cache(0)
-        if not fused:  # node-by-node evaluation reads the super / vector clips through the host's caches
-            keep[1].set_cache(64 + 2 * threads)
-            for v in keep[2:]:
-                v.set_cache(8 + 2 * threads)
+        out.set_cache(0)  # (every config's consumer is computed in windows from the source frames: nothing upstream is read through a cache)
         return core, out, keep
 
     if cfg.get("fixed_total"):
@@ -269,9 +271,9 @@ def plugin_leg(cfg, args, mb, plan, world, rank, local, barrier, total_frames, g
         barrier()
         frames_timed, first_timed, protocol = F_out, OFF, "cold start: a fresh script instance renders the whole batch once (engine warmed on another instance)"
     else:
-        step = -(-F_out // window) * window if fused else F_out
-        base = -(-OFF // window) * window if fused else OFF  # the first rendered frame: a window boundary at or after the halo
-        n_local = base + (args.warmup_e2e + args.steps) * step + (window if fused else 0) + REACH
+        step = -(-F_out // window) * window
+        base = -(-OFF // window) * window  # the first rendered frame: a window boundary at or after the halo
+        n_local = base + (args.warmup_e2e + args.steps) * step + window + REACH
         core, out, keep = script(n_local, lo)
         if args.warmup_e2e:
             out.render(base, base + args.warmup_e2e * step, threads)
@@ -409,7 +411,8 @@ def run_gpu_arm(args, cfg):
     # previous one leave them.  W warm-up steps, K timed steps, all
     # enqueued without a host sync in between; time = first start -> last end over all streams (CUDA events), max over ranks.
     NC = max(1, args.contexts)
-    S = max(8, min(plugin_window(plan_q, len(aps)), F_out))
+    PW = plugin_window(mb, aps, sp, kind, local)
+    S = max(8, min(PW, F_out))
     bounds = list(range(0, F_out, S)) + [F_out]
     ctxs = [ctx] + [mb.Context(local) for _ in range(NC - 1)]
     streams = [torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", local)) for c in ctxs]
@@ -532,7 +535,7 @@ def run_gpu_arm(args, cfg):
         if world > 1:    #  between the warm-up and the timed steps -- a drained pipeline would hand the timed region finished windows)
             dist.barrier()
 
-    pl = plugin_leg(cfg, args, mb, plan, world, rank, local, host_barrier, total, gold, plugin_window(plan_q, len(aps)))
+    pl = plugin_leg(cfg, args, mb, plan, world, rank, local, host_barrier, total, gold, PW)
     clocks_e2e = sampler2.stop() if rank == 0 else None
     e2e_s = max_over_ranks(pl["seconds"])
     e2e_frames = total if cfg.get("fixed_total") else world * pl["frames"]

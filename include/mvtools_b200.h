@@ -452,6 +452,20 @@ typedef struct mvb200_search_plan {
 } mvb200_search_plan;
 MVB200_API int mvb200_search_plan_query(const mvb200_analyse_params *ap, const mvb200_super_params *sp, int sm_count, mvb200_search_plan *out);
 
+/* How a caller that streams windows of frames through the *_clip_host entry points should size them (the plugin's fused paths and
+ * bench.py share this): frames per window = what fills the search kernel's chain slots once with nvec vector clips per frame (at
+ * most 768), or `lookahead` when > 0; engine contexts per device = contexts_per_device reduced until the windows' device buffers
+ * (source / output clips double buffered, super clip, vectors) fit 45 % of device_memory; then the window shrinks until the pinned
+ * host windows (one per context, one being served, one recycled; src_frame_bytes + out_frame_bytes each per frame) fit
+ * pinned_budget (<= 0: an eighth of the machine's memory, between 2 and 32 GiB). */
+typedef struct mvb200_window_plan {
+    int32_t frames;               /* frames per window */
+    int32_t contexts_per_device;  /* engine contexts to create on each device */
+    int64_t pinned_budget;        /* the budget that was applied */
+} mvb200_window_plan;
+MVB200_API int mvb200_window_plan_query(const mvb200_analyse_params *ap, const mvb200_super_params *sp, int nvec, int lookahead, int64_t src_frame_bytes, int64_t out_frame_bytes, int ndevices,
+                                        int contexts_per_device, int64_t pinned_budget, int64_t device_memory, mvb200_window_plan *out);
+
 /* Device frame layout used by the *_batch functions: planes are stored one after
  * another, each with its own pitch (bytes), frames one after another.
  * pitch[p] = round_up(plane_w[p]*bytes, 256); offsets are from the frame start. */
@@ -626,6 +640,16 @@ MVB200_API int mvb200_flowfps_clip_host(mvb200_ctx *ctx, const mvb200_super_para
  * parameters (their num_frames is replaced by n internally; relative delta only, no field shifts).  Synchronous. */
 MVB200_API int mvb200_compensate_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_compensate_params *cp, const void *host_src, int src_first, int n, int out_first,
                                            int out_count, void *host_dst);
+
+/* A window of a VECTOR clip from source frames: mv.Super of the n source frames [src_first, src_first + n) in host_src and
+ * mv.Analyse of frames [out_first, out_first + out_count) (halo: delta frames on the side the vectors point to).  Writes, per
+ * output frame, the SUPER frame (the pixels an mv.Analyse frame carries, MVAnalyse.c:224: super layout, mvb200_super_layout)
+ * into host_super (out_count frames, frame_bytes apart) and the MVTools_vectors blob into host_vectors (vectors_stride apart, >=
+ * ap->vectors_size).  Replaces mvsuperGetFrame + mvanalyseGetFrame (MVSuper.c:43-126, MVAnalyse.c:76-254) for a window of a
+ * script whose vector clip is read by something else than this library's fused consumers.  Relative delta, no field shifts.
+ * Synchronous. */
+MVB200_API int mvb200_analyse_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const void *host_src, int src_first, int n, int out_first, int out_count,
+                                        void *host_super, void *host_vectors, int64_t vectors_stride);
 
 /* ... with nrp mv.Recalculate passes (rp[0 .. nrp - 1], applied in order; MVRecalculate.c:68-254) between the search and the
  * compensation; cp was derived from the last pass's analysis data. */

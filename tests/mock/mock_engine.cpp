@@ -47,6 +47,14 @@ MVB200_API int mvb200_device_count(void) {
     return e ? atoi(e) : 1;
 }
 MVB200_API int64_t mvb200_device_memory(int) { return (int64_t)180 << 30; }
+// (the stand-in's window plan: the 16-frame minimum unless the look-ahead is given; every context the plugin asks for)
+MVB200_API int mvb200_window_plan_query(const mvb200_analyse_params *, const mvb200_super_params *, int, int lookahead, int64_t, int64_t, int, int contexts_per_device, int64_t pinned_budget, int64_t,
+                                        mvb200_window_plan *out) {
+    out->frames = lookahead > 0 ? lookahead : 16;
+    out->contexts_per_device = contexts_per_device < 1 ? 1 : contexts_per_device;
+    out->pinned_budget = pinned_budget;
+    return 0;
+}
 MVB200_API long mvb200_mock_contexts(void) { return g_ctx_created.load(); }
 MVB200_API int mvb200_ctx_synchronize(mvb200_ctx *) { return 0; }
 // the stand-in computes synchronously: an event is complete when it is recorded
@@ -360,6 +368,53 @@ MVB200_API int mvb200_flowfps_clip_host(mvb200_ctx *, const mvb200_super_params 
                 copy(ql, stl);
             }
         }
+    }
+    return 0;
+}
+
+// A window of a vector clip from source frames, frame by frame through the oracle: the super frames of the output range (super
+// layout) and their blobs.
+MVB200_API int mvb200_analyse_clip_host(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const void *host_src, int src_first, int n, int out_first, int out_count, void *host_super,
+                                        void *host_vectors, int64_t vectors_stride) {
+    mvb200_frame_layout cl, sl;
+    mvb200_clip_layout(sp, &cl);
+    mvb200_super_layout(sp, &sl);
+    mvb200_super_geom g;
+    mvb200_super_geometry(sp, &g);
+    const int bps = cl.bytes_per_sample;
+    std::vector<std::vector<uint8_t>> sup((size_t)n * 3);
+    ptrdiff_t sstride[3] = {0, 0, 0};
+    for (int f = 0; f < n; f++) {
+        const uint8_t *q[3];
+        ptrdiff_t st[3];
+        uint8_t *d[3] = {nullptr, nullptr, nullptr};
+        for (int i = 0; i < 3; i++) {
+            q[i] = i < cl.nplanes ? (const uint8_t *)host_src + (size_t)cl.frame_bytes * f + cl.offset[i] : nullptr;
+            st[i] = i < cl.nplanes ? (ptrdiff_t)cl.pitch[i] : 0;
+        }
+        for (int i = 0; i < sp->nplanes; i++) {
+            sstride[i] = (ptrdiff_t)g.plane_w[i] * bps;
+            sup[(size_t)f * 3 + i].assign((size_t)sstride[i] * g.plane_h[i], 0);
+            d[i] = sup[(size_t)f * 3 + i].data();
+        }
+        if (fwd(mvo_super_frame(sp, q, st, d, sstride)))
+            return 1;
+    }
+    for (int k = 0; k < out_count; k++) {
+        const int f = out_first - src_first + k, dlt = ap->ad.nDeltaFrame;
+        int nref = f + (ap->ad.isBackward ? dlt : -dlt);
+        if (nref < 0 || nref >= n)
+            nref = -1;
+        const uint8_t *s_[3], *r_[3];
+        for (int i = 0; i < 3; i++) {
+            s_[i] = i < sp->nplanes ? sup[(size_t)f * 3 + i].data() : nullptr;
+            r_[i] = i < sp->nplanes && nref >= 0 ? sup[(size_t)nref * 3 + i].data() : nullptr;
+        }
+        if (fwd(mvo_analyse_frame(ap, sp, s_, sstride, nref >= 0 ? r_ : nullptr, nref >= 0 ? sstride : nullptr, 0, (uint8_t *)host_vectors + (size_t)vectors_stride * k)))
+            return 1;
+        for (int i = 0; i < sp->nplanes; i++)
+            for (int y = 0; y < g.plane_h[i]; y++)
+                memcpy((uint8_t *)host_super + (size_t)sl.frame_bytes * k + sl.offset[i] + (size_t)sl.pitch[i] * y, sup[(size_t)f * 3 + i].data() + (size_t)sstride[i] * y, (size_t)sstride[i]);
     }
     return 0;
 }

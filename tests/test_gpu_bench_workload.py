@@ -217,3 +217,37 @@ def test_recalculate_passes_inside_the_fused_chains_on_the_gpu(built, monkeypatc
             counts = (before, [x.computed() for x in nodes])
     assert outs[0] == outs[1]
     assert counts[0] == counts[1], "the fused path asked the Super / Analyse / Recalculate nodes for frames"
+
+
+@pytest.mark.parametrize("lookahead", ["3", None])
+@pytest.mark.parametrize("case", ["c1_640x360_p8_blk8_pel1", "blk16_ov8_pel2_p16_r3", "gray_blk4_pel1_rf0", "divide2_blk16_esa_neg_badrange", "super_nochroma_blk8_r2", "p8_420_blk8_pel4"])
+def test_vector_clip_windows_from_source_frames_on_the_gpu(built, monkeypatch, case, lookahead):
+    """a vector clip read directly (here also by mv.SCDetection): windows of vector frames from ONE mvb200_analyse_clip_host call over
+    source frames -- pixels (the super frame), vectors and properties against the goldens"""
+    import json
+    import minivs
+    import pipeline
+    gold = json.load(open(os.path.join(bench.ROOT, "tests", "golden", "golden.json")))
+    if lookahead:
+        monkeypatch.setenv("MVB200_LOOKAHEAD", lookahead)
+    else:
+        monkeypatch.delenv("MVB200_LOOKAHEAD", raising=False)
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    n_frames = len(frames)
+    sp, aps, dp = pipeline.params_for(case)
+    core = minivs.Core()
+    mv = core.load(mb.PLUGIN_PATH)
+    clip = core.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1))
+    sup = mv.Super(clip, **skw)
+    vec = mv.Analyse(sup, isb=1, delta=1, **pipeline._fix(akw))
+    scd = mv.SCDetection(clip, vec)
+    vec.set_cache(0)
+    for n in list(range(n_frames)) + [n_frames - 1, 0, n_frames // 2]:
+        fr = vec.get_frame(n)
+        assert [pipeline.sha(p) for p in fr.planes()] == gold[case]["super"][n], "frame %d: pixels" % n
+        blob = np.frombuffer(fr.prop_data("MVTools_vectors"), dtype=np.uint8)
+        assert pipeline.sha(pipeline.mask_blob(blob, aps[0])) == gold[case]["vectors"][n][0], "frame %d: vectors" % n
+        assert (fr.prop_int("Super_pel") is not None) == (n == 0)
+        scd.get_frame(n)
+    assert sup.computed() <= 2

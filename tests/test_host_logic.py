@@ -126,3 +126,33 @@ def test_compute_fails_loudly_without_gpu(built):
     with pytest.raises(mb.Error) as e:
         mb.Context(0)
     assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_window_plan_query(built):
+    """The window sizing the plugin's fused paths and bench.py share (host arithmetic only, no device needed)."""
+    import ctypes as C
+    L = mb.lib()
+
+    def plan(w, h, bits, blk, ov, nvec, lookahead=-1, contexts=2, budget=0, devmem=180 << 30, ndev=1):
+        sp = mb.super_params(w, h, bits, 1, 1, pel=2)
+        ap = mb.analyse_params(sp, 1000, blksize=blk, overlap=ov)
+        cl = mb.clip_layout(sp)
+        q, wp = mb.SearchPlan(), mb.WindowPlan()
+        assert L.mvb200_search_plan_query(C.byref(ap), C.byref(sp), 0, C.byref(q)) == 0
+        assert L.mvb200_window_plan_query(C.byref(ap), C.byref(sp), nvec, lookahead, cl.frame_bytes, cl.frame_bytes, ndev, contexts, budget, devmem, C.byref(wp)) == 0
+        return q, wp, cl
+
+    q, wp, cl = plan(1920, 1080, 8, 16, 8, 6, budget=32 << 30)
+    assert wp.frames == -(-q.chains_per_wave // 6) == 296 and wp.contexts_per_device == 2  # the headline: one wave of chain slots
+    q, wp, cl = plan(1920, 1080, 8, 16, 8, 1, budget=32 << 30)
+    assert wp.frames == 768  # a single vector clip: bounded latency
+    q, wp, cl = plan(1920, 1080, 8, 16, 8, 6, lookahead=40)
+    assert wp.frames == 40  # an explicit look-ahead is taken as given
+    q, wp, cl = plan(1920, 1080, 8, 16, 8, 6, budget=2 << 30)
+    assert wp.frames == (2 << 30) // (4 * 2 * cl.frame_bytes) and wp.pinned_budget == 2 << 30  # the pinned windows fit the budget
+    q, wp8, cl = plan(1920, 1080, 8, 16, 8, 6, budget=2 << 30, ndev=8)
+    assert wp8.frames < wp.frames  # more contexts, more windows in flight
+    q, wp, cl = plan(3840, 2160, 16, 16, 8, 6, budget=32 << 30, devmem=40 << 30)
+    assert wp.contexts_per_device == 1 and 16 <= wp.frames < 296  # a small device: one context, a shorter window
+    q, wp, cl = plan(1920, 1080, 8, 16, 8, 6)
+    assert wp.pinned_budget >= 2 << 30 and wp.pinned_budget <= 32 << 30

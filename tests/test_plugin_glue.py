@@ -394,6 +394,41 @@ def test_recalculate_passes_inside_the_fused_chains(mock_plugin, have_ref, monke
     assert counts[0] == counts[1], "the fused path asked the Super / Analyse / Recalculate nodes for frames"
 
 
+@pytest.mark.parametrize("window", ["3", None])
+@pytest.mark.parametrize("case", ["c1_640x360_p8_blk8_pel1", "blk16_ov8_pel2_p16_r3", "gray_blk4_pel1_rf0", "divide2_blk16_esa_neg_badrange", "super_nochroma_blk8_r2"])
+def test_vector_clip_windows_from_source_frames(mock_plugin, monkeypatch, case, window):
+    """A vector clip that is read directly (the script's output, mv.Mask, mv.SCDetection, another plugin): when its super clip is
+    this plugin's own mv.Super, windows of vector frames come from ONE engine call over SOURCE frames (mvb200_analyse_clip_host) --
+    pixels (the super frame), MVTools_vectors, MVTools_MVAnalysisData and Super_* identical to the goldens / the node-by-node
+    evaluation, and the Super node is asked for frame 0 only (the single chain that serves the script-building reads)."""
+    import minivs
+    import numpy as np
+    if window:
+        monkeypatch.setenv("MVB200_LOOKAHEAD", window)
+    else:
+        monkeypatch.delenv("MVB200_LOOKAHEAD", raising=False)
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    N = len(frames)
+    sp, aps, dp = pipeline.params_for(case)
+    core = minivs.Core()
+    mv = core.load(mock_plugin)
+    clip = core.source(frames, bits=ck.get("bits", 8), ssw=ck.get("ssw", 1), ssh=ck.get("ssh", 1))
+    sup = mv.Super(clip, **skw)
+    vec = mv.Analyse(sup, isb=1, delta=1, **pipeline._fix(akw))
+    scd = mv.SCDetection(clip, vec)  # a consumer that reads the vector clip frame by frame
+    vec.set_cache(0)
+    for n in list(range(N)) + [N - 1, 0, N // 2]:
+        fr = vec.get_frame(n)
+        assert [pipeline.sha(p) for p in fr.planes()] == GOLD[case]["super"][n], "frame %d: pixels" % n
+        blob = np.frombuffer(fr.prop_data("MVTools_vectors"), dtype=np.uint8)
+        assert pipeline.sha(pipeline.mask_blob(blob, aps[0])) == GOLD[case]["vectors"][n][0], "frame %d: vectors" % n
+        assert fr.prop_data("MVTools_MVAnalysisData") is not None
+        assert (fr.prop_int("Super_pel") is not None) == (n == 0), "frame %d: Super_* properties" % n
+        scd.get_frame(n)
+    assert sup.computed() <= 2, "the Super node was asked for more than the frames of the single chain of frame 0"
+
+
 def test_non_canonical_chains_keep_the_node_by_node_evaluation(mock_plugin, monkeypatch):
     """MVB200_LOOKAHEAD set, but the script is not the canonical chain: vectors searched on ANOTHER Super node of the same
     clip, a vector clip with divide feeding mv.Flow, a consumer with fields -- the fused paths must decline (the Super /

@@ -6,6 +6,8 @@
 
 #include <algorithm>
 
+#include <unistd.h>
+
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -286,6 +288,50 @@ int mvb200_device_count(void) {
             usable = d + 1; // (device ordinals are used as they are: count up to the last usable one)
     }
     return usable;
+}
+
+int mvb200_window_plan_query(const mvb200_analyse_params *ap, const mvb200_super_params *sp, int nvec, int lookahead, int64_t src_frame_bytes, int64_t out_frame_bytes, int ndevices,
+                             int contexts_per_device, int64_t pinned_budget, int64_t device_memory, mvb200_window_plan *out) {
+    memset(out, 0, sizeof(*out));
+    mvb200_search_plan plan;
+    if (mvb200_search_plan_query(ap, sp, 0, &plan))
+        return 1;
+    if (nvec < 1)
+        nvec = 1;
+    if (pinned_budget <= 0) {
+        const int64_t phys = (int64_t)sysconf(_SC_PHYS_PAGES) * (int64_t)sysconf(_SC_PAGE_SIZE);
+        const int64_t lo = (int64_t)2 << 30, hi = (int64_t)32 << 30;
+        pinned_budget = phys / 8 < lo ? lo : (phys / 8 > hi ? hi : phys / 8);
+    }
+    if (device_memory <= 0)
+        device_memory = (int64_t)180 << 30;
+    int frames = (plan.chains_per_wave + nvec - 1) / nvec;
+    if (frames > 768) // (a single vector clip per frame would ask for 1776 frames: bound the latency of a window)
+        frames = 768;
+    if (lookahead > 0)
+        frames = lookahead;
+    mvb200_frame_layout sl;
+    mvb200_super_layout(sp, &sl);
+    const int64_t chains = plan.chains_per_wave;
+    auto device_bytes = [&](int fr) { return (int64_t)fr * (4 * src_frame_bytes + sl.frame_bytes + (int64_t)nvec * (ap->vectors_size + 256)) * 5 / 4 + chains * 65536; };
+    int per = contexts_per_device < 1 ? 1 : contexts_per_device;
+    while (per > 1 && per * device_bytes(frames) > device_memory * 45 / 100)
+        per--;
+    if (lookahead <= 0) {
+        while (frames > 16 && per * device_bytes(frames) > device_memory * 45 / 100)
+            frames = frames * 3 / 4;
+        const int nslots = (ndevices < 1 ? 1 : ndevices) * per;
+        const int64_t per_frame = src_frame_bytes + (out_frame_bytes > 0 ? out_frame_bytes : src_frame_bytes);
+        const int64_t cap = pinned_budget / ((nslots + 2) * (per_frame > 0 ? per_frame : 1));
+        if (frames > cap)
+            frames = (int)cap;
+        if (frames < 16)
+            frames = 16;
+    }
+    out->frames = frames;
+    out->contexts_per_device = per;
+    out->pinned_budget = pinned_budget;
+    return 0;
 }
 
 int64_t mvb200_device_memory(int device) {
@@ -806,6 +852,51 @@ int mvb200_compensate_recalc_clip_host(mvb200_ctx *ctx, const mvb200_super_param
     if (mvb200_compensate_batch(ctx, &q, sp, dsup, first, out_count, dvec, vstride, ddst))
         return 1;
     MVB_CUDA_CHECK(cudaMemcpyAsync(host_dst, ddst, (size_t)cd.frame_bytes * out_count, cudaMemcpyDeviceToHost, c->stream));
+    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// A window of a vector clip from source frames: Super of the segment, Analyse of [out_first, out_first + out_count); the super
+// frames and the blobs of the output range go back to the host.
+int mvb200_analyse_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const void *host_src, int src_first, int n, int out_first, int out_count,
+                             void *host_super, void *host_vectors, int64_t vectors_stride) {
+    if (check_levels(sp) || check_analyse(ap, sp))
+        return 1;
+    if (n <= 0 || out_count <= 0)
+        return 0;
+    if (out_first < src_first || out_first + out_count > src_first + n)
+        return set_error("Analyse: output frames [%d, %d) are outside the segment [%d, %d)", out_first, out_first + out_count, src_first, src_first + n);
+    if (ap->ad.nDeltaFrame <= 0 || ap->fields)
+        return set_error("Analyse: the clip pipeline handles relative references without field shifts only");
+    if (vectors_stride < ap->vectors_size)
+        return set_error("Analyse: vectors_stride (%lld) is smaller than the blob (%d bytes)", (long long)vectors_stride, ap->vectors_size);
+    {   // inside the real clip the frames the vectors refer to must be inside the segment (else: silent default vectors)
+        const int d = ap->ad.nDeltaFrame, realN = ap->num_frames;
+        const int need0 = ap->ad.isBackward ? out_first : (out_first - d > 0 ? out_first - d : 0);
+        const int need1 = ap->ad.isBackward ? (out_first + out_count + d < realN ? out_first + out_count + d : realN) : out_first + out_count;
+        if (need0 < src_first || need1 > src_first + n)
+            return set_error("Analyse: the segment [%d, %d) does not hold the frames [%d, %d) that the vectors of output frames [%d, %d) refer to", src_first, src_first + n, need0, need1, out_first,
+                             out_first + out_count);
+    }
+    Ctx *c = &ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c->device));
+    SuperDesc sd;
+    ClipDesc cd;
+    make_super_desc(sp, &sd);
+    make_clip_desc(sp, &cd);
+    mvb200_analyse_params a = *ap; // the segment is the clip as far as the engine is concerned
+    a.num_frames = n;
+    const int64_t vstride = ((int64_t)a.vectors_size + 255) / 256 * 256;
+    uint8_t *buf = (uint8_t *)c->get_scratch(5, (size_t)cd.frame_bytes * n + (size_t)sd.frame_bytes * n + (size_t)vstride * out_count + 256);
+    if (!buf)
+        return 1;
+    uint8_t *dsrc = buf, *dsup = dsrc + (size_t)cd.frame_bytes * n, *dvec = dsup + (size_t)sd.frame_bytes * n;
+    MVB_CUDA_CHECK(cudaMemcpyAsync(dsrc, host_src, (size_t)cd.frame_bytes * n, cudaMemcpyHostToDevice, c->stream));
+    const int first = out_first - src_first;
+    if (mvb200_super_batch(ctx, sp, dsrc, dsup, n) || mvb200_analyse_batch(ctx, &a, sp, dsup, first, out_count, dvec, vstride))
+        return 1;
+    MVB_CUDA_CHECK(cudaMemcpyAsync(host_super, dsup + (size_t)sd.frame_bytes * first, (size_t)sd.frame_bytes * out_count, cudaMemcpyDeviceToHost, c->stream));
+    MVB_CUDA_CHECK(cudaMemcpy2DAsync(host_vectors, (size_t)vectors_stride, dvec, (size_t)vstride, (size_t)a.vectors_size, (size_t)out_count, cudaMemcpyDeviceToHost, c->stream));
     MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return 0;
 }

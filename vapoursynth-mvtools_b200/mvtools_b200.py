@@ -188,6 +188,10 @@ class SearchPlan(C.Structure):
     _fields_ = [("kernel", i32), ("chains_per_sm", i32), ("chains_per_wave", i32), ("smem_per_chain", i32)]
 
 
+class WindowPlan(C.Structure):
+    _fields_ = [("frames", i32), ("contexts_per_device", i32), ("pinned_budget", i64)]
+
+
 class Error(RuntimeError):
     pass
 
@@ -231,6 +235,9 @@ def lib():
         L.mvb200_ctx_launch_count.argtypes = [vp]
         L.mvb200_ctx_launch_count.restype = i64
         L.mvb200_search_plan_query.argtypes = [PP(AnalyseParams), PP(SuperParams), i32, PP(SearchPlan)]
+        L.mvb200_window_plan_query.argtypes = [PP(AnalyseParams), PP(SuperParams), i32, i32, i64, i64, i32, i32, i64, i64, PP(WindowPlan)]
+        L.mvb200_device_memory.argtypes = [i32]
+        L.mvb200_device_memory.restype = i64
         L.mvb200_ctx_record.argtypes = [vp, PP(vp)]
         L.mvb200_event_wait.argtypes = [vp]
         L.mvb200_event_query.argtypes = [vp]

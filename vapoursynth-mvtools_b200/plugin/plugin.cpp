@@ -10,8 +10,12 @@
 // include/mvtools_b200.h.  There is no CPU code path here: if the CUDA context cannot be
 // created the filter's frame request fails with that error.
 //
-// One engine context (one CUDA stream + scratch) per process, guarded by a mutex: VapourSynth
-// calls getFrame concurrently (fmParallel) and the engine context is not re-entrant.
+// VapourSynth calls getFrame concurrently (fmParallel).  The reference spends every host core on each frame; a search on the GPU
+// is one warp per frame and vector clip, so this plugin works in WINDOWS of frames instead (fusedGetFrame below): consumers fed by
+// this plugin's own Super / Analyse / Recalculate nodes produce a window of output frames with one engine call from the source
+// frames, keep the next windows in flight on two engine contexts per GPU and on every visible GPU, and serve the frame server's
+// threads from the windows' pinned buffers.  Everything else is evaluated node by node on engine context 0 (mv.Analyse with its
+// own look-ahead window), each engine context guarded by its own mutex (a context is not re-entrant).
 #include <VapourSynth4.h>
 #include <VSHelper4.h>
 
@@ -25,6 +29,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -277,6 +282,10 @@ struct FusedCache {
     std::vector<std::shared_ptr<FusedWindow>> packing;      // windows whose source frames wait to be copied into their pinned buffers
     std::shared_ptr<PinnedPool> pool = sharedPinnedPool();
     mvb200_frame_layout cl;
+    // the output frames' layout and bytes per frame in a window's output buffer when they differ from the source clip's (a
+    // vector clip's frames are super frames); outExtra more bytes per frame follow the frames (the vector blobs)
+    mvb200_frame_layout out{};
+    size_t outFrameBytes = 0, outExtra = 0;
     int window = 0;
     int nslots = 1; // engine contexts this filter's windows go round (set with the window: fusedWindowFrames)
     int depth = 1;  // windows enqueued ahead of the one being served: one per context
@@ -288,39 +297,17 @@ struct FusedCache {
 // within 45 % of the device's memory -- and the pinned host windows (one per context, one being served, one recycled)
 // within the pinned-memory budget.
 int fusedWindowFrames(FusedCache *f, int la, const mvb200_analyse_params *ap, const mvb200_super_params *sp, int nvec) {
-    const int64_t frameBytes = f->cl.frame_bytes > 0 ? f->cl.frame_bytes : 1;
-    mvb200_search_plan plan;
-    int frames = 64;
-    int64_t chains = 0;
-    if (mvb200_search_plan_query(ap, sp, 0, &plan) == 0 && plan.chains_per_wave > 0) {
-        frames = (plan.chains_per_wave + nvec - 1) / (nvec > 0 ? nvec : 1);
-        chains = plan.chains_per_wave;
-    }
-    if (frames > 768) // (a single vector clip per frame would ask for 1776 frames: bound the latency of a window)
-        frames = 768;
-    if (la > 0)
-        frames = la;
     deviceCount();
-    mvb200_frame_layout sl;
-    mvb200_super_layout(sp, &sl);
-    int per = g_perdev;
-    const int64_t devmem = mvb200_device_memory(g_engines[0].device) > 0 ? mvb200_device_memory(g_engines[0].device) : ((int64_t)180 << 30);
-    auto deviceBytes = [&](int fr) { return (int64_t)fr * (4 * frameBytes + sl.frame_bytes + (int64_t)nvec * (ap->vectors_size + 256)) * 5 / 4 + chains * 65536; };
-    while (per > 1 && per * deviceBytes(frames) > devmem * 45 / 100)
-        per--;
-    if (la <= 0)
-        while (frames > 16 && per * deviceBytes(frames) > devmem * 45 / 100)
-            frames = frames * 3 / 4;
-    f->nslots = g_ndevices * per;
-    f->depth = f->nslots;
-    if (la <= 0) {
-        const int64_t cap = pinnedBudget() / (2 * (f->nslots + 2) * frameBytes);
-        if (frames > cap)
-            frames = (int)cap;
-        if (frames < 16)
-            frames = 16;
+    const char *mb = getenv("MVB200_PINNED_MB");
+    mvb200_window_plan plan;
+    if (mvb200_window_plan_query(ap, sp, nvec, la, f->cl.frame_bytes, f->outFrameBytes ? (int64_t)(f->outFrameBytes + f->outExtra) : f->cl.frame_bytes, g_ndevices, g_perdev,
+                                 mb && atoll(mb) > 0 ? atoll(mb) << 20 : 0, mvb200_device_memory(g_engines[0].device), &plan)) {
+        f->nslots = f->depth = 1;
+        return la > 0 ? la : 64;
     }
-    return frames;
+    f->nslots = g_ndevices * plan.contexts_per_device;
+    f->depth = f->nslots;
+    return plan.frames;
 }
 
 // One activation of a fused filter.  propFrame: the source frame the output frame takes its properties from (always
@@ -330,9 +317,11 @@ int fusedWindowFrames(FusedCache *f, int la, const mvb200_analyse_params *ap, co
 // planeMask: bit p set = plane p comes from the engine, else it is a copy of the source frame's.  alsoFrame (-1: none):
 // one more source frame the caller reads after this returns (requested here so that no frame is requested twice);
 // flagOut: the frame's "usable" flag.
+// post (optional): called with the finished output frame and the window's output buffer, to attach what is not pixels.
 template <class Segment, class Run>
 const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, const VSVideoInfo *outvi, int n, int propFrame, unsigned planeMask, int activationReason, void **frameData, VSFrameContext *frameCtx,
-                             VSCore *core, const VSAPI *vsapi, Segment segment, Run run, int alsoFrame = -1, int32_t *flagOut = nullptr) {
+                             VSCore *core, const VSAPI *vsapi, Segment segment, Run run, int alsoFrame = -1, int32_t *flagOut = nullptr,
+                             const std::function<void(VSFrame *, const uint8_t *hostDst, int w0, int w1)> &post = nullptr) {
     const int B = f->window, N = outvi->numFrames;
     if (activationReason == arInitial) {
         vsapi->requestFrameFilter(propFrame, clip, frameCtx);
@@ -399,7 +388,7 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
         size_t gs = 0, gd = 0;
         w->hostSrc = w->pool->get(fb * (size_t)(w->s1 - w->s0), &gs);
         w->srcBytes = gs;
-        w->hostDst = w->hostSrc ? w->pool->get(fb * (size_t)(w->w1 - w->w0), &gd) : nullptr;
+        w->hostDst = w->hostSrc ? w->pool->get(((f->outFrameBytes ? f->outFrameBytes : fb) + f->outExtra) * (size_t)(w->w1 - w->w0), &gd) : nullptr;
         w->dstBytes = gd;
         w->flags.assign((size_t)(w->w1 - w->w0), 0);
         if (!w->hostSrc || !w->hostDst) {
@@ -509,15 +498,18 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
     }
     if (flagOut)
         *flagOut = w->flags[(size_t)(n - w->w0)];
-    const uint8_t *bytes = (const uint8_t *)w->hostDst + fb * (size_t)(n - w->w0);
+    const mvb200_frame_layout &ol = f->outFrameBytes ? f->out : f->cl;
+    const uint8_t *bytes = (const uint8_t *)w->hostDst + (f->outFrameBytes ? f->outFrameBytes : fb) * (size_t)(n - w->w0);
     VSFrame *dst = vsapi->newVideoFrame(&outvi->format, outvi->width, outvi->height, src, core);
     for (int p = 0; p < outvi->format.numPlanes; p++) {
-        const size_t row = (size_t)f->cl.plane_w[p] * f->cl.bytes_per_sample, rows = (size_t)f->cl.plane_h[p];
+        const size_t row = (size_t)ol.plane_w[p] * ol.bytes_per_sample, rows = (size_t)ol.plane_h[p];
         if (planeMask & (1u << p))
-            vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), bytes + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], row, rows);
+            vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), bytes + ol.offset[p], (ptrdiff_t)ol.pitch[p], row, rows);
         else
             vsh::bitblt(vsapi->getWritePtr(dst, p), vsapi->getStride(dst, p), vsapi->getReadPtr(src, p), vsapi->getStride(src, p), row, rows);
     }
+    if (post)
+        post(dst, (const uint8_t *)w->hostDst, w->w0, w->w1);
     vsapi->freeFrame(src);
     return dst;
 }
@@ -772,6 +764,12 @@ struct AnalyseData {
     int lookahead;       // window length, 0 = one frame per call
     AnalyseCache *cache; // owned; null without look-ahead
     VSNode *self;        // this filter's output node (registry key), not a reference
+    // fused path (see analyseFusedGetFrame): the super clip is this plugin's own mv.Super of `clip`
+    FusedCache *fused;   // owned; null = the super clip is read frame by frame
+    VSNode *clip;        // the Super's source clip (a reference of our own)
+    mvb200_super_params ssp; // the Super node's own parameters (sharp / rfilter are not in the frame properties)
+    mvb200_frame_layout sl;
+    int64_t vstride;
 };
 
 int refFrameOf(const mvb200_analyse_params &ap, int n) { // MVAnalyse.c:84-109
@@ -960,10 +958,61 @@ const VSFrame *VS_CC analyseGetFrame(int n, int activationReason, void *instance
     return nullptr;
 }
 
+// Fused path of a vector clip that something else than this plugin's fused consumers reads (another plugin, mv.Mask,
+// mv.SCDetection, a script that outputs the vectors): when the super clip is this plugin's own mv.Super, a window of vector frames
+// is ONE mvb200_analyse_clip_host call over SOURCE frames -- Super and the searches on the device, the super frames (the pixels an
+// mv.Analyse frame carries, MVAnalyse.c:224) and the blobs back -- instead of the Super node's frames one by one, down and up again.
+const VSFrame *VS_CC analyseGetFrame(int n, int activationReason, void *instanceData, void **frameData, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi);
+
+const VSFrame *VS_CC analyseFusedGetFrame(int n, int activationReason, void *instanceData, void **frameData, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
+    AnalyseData *d = (AnalyseData *)instanceData;
+    FusedCache *f = d->fused;
+    // Frame 0 is what every consumer reads when the script is BUILT (adataFromVectorClip, MVAnalysisData.c:42-63): while no window
+    // holds it, it is searched on its own from the super clip (one chain) instead of starting a whole window nobody may ever read
+    // (the fused consumers never come back for frames).  frameData[1] remembers the choice between the two activations.
+    if (activationReason == arInitial) {
+        bool single = false;
+        if (n == 0) {
+            std::lock_guard<std::mutex> lock(f->m);
+            const auto it = f->windows.find(0);
+            single = it == f->windows.end() || it->second->state.load() == FusedWindow::Idle;
+        }
+        frameData[1] = single ? (void *)1 : nullptr;
+    }
+    if (frameData[1])
+        return analyseGetFrame(n, activationReason, instanceData, frameData, frameCtx, core, vsapi);
+    const int N = d->vi->numFrames, delta = d->ap.ad.nDeltaFrame;
+    auto segment = [&](int w0, int w1, int *s0, int *s1) { // the window and the frames its vectors refer to
+        *s0 = d->ap.ad.isBackward ? w0 : (w0 - delta > 0 ? w0 - delta : 0);
+        *s1 = d->ap.ad.isBackward ? (w1 + delta < N ? w1 + delta : N) : w1;
+    };
+    auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst, int32_t *) {
+        uint8_t *blobs = (uint8_t *)hostDst + (size_t)d->sl.frame_bytes * (size_t)(w1 - w0);
+        return mvb200_analyse_clip_host(ctx, &d->ssp, &d->ap, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst, blobs, d->vstride);
+    };
+    const unsigned mask = (d->ssp.modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) ? 7u : 1u;
+    auto post = [&](VSFrame *dst, const uint8_t *hostDst, int w0, int w1) {
+        if (n == 0) // the frame is a copy of super frame n (MVAnalyse.c:224), which carries Super_* on frame 0 (MVSuper.c:111-120)
+            setSuperProps(vsapi, dst, d->ssp);
+        if (!(mask & 2u)) // a luma-only super clip: the reference's super frames keep their zeroed chroma planes (MVSuper.c:75)
+            for (int p = 1; p < d->vi->format.numPlanes; p++)
+                memset(vsapi->getWritePtr(dst, p), 0, (size_t)vsapi->getStride(dst, p) * (size_t)vsapi->getFrameHeight(dst, p));
+        VSMap *props = vsapi->getFramePropertiesRW(dst);
+        const mvb200_analysis_data *ad = d->ap.divide ? &d->ap.ad_divided : &d->ap.ad;
+        const uint8_t *blob = hostDst + (size_t)d->sl.frame_bytes * (size_t)(w1 - w0) + (size_t)d->vstride * (size_t)(n - w0);
+        vsapi->mapSetData(props, "MVTools_MVAnalysisData", (const char *)ad, sizeof(*ad), dtBinary, maReplace);
+        vsapi->mapSetData(props, "MVTools_vectors", (const char *)blob, d->ap.vectors_size, dtBinary, maReplace);
+    };
+    return fusedGetFrame("Analyse", f, d->clip, d->vi, n, n, 7u, activationReason, frameData, frameCtx, core, vsapi, segment, run, -1, nullptr, post);
+}
+
 void VS_CC analyseFree(void *instanceData, VSCore *, const VSAPI *vsapi) {
     AnalyseData *d = (AnalyseData *)instanceData;
     unregisterSelf(d->self);
     vsapi->freeNode(d->node);
+    if (d->clip)
+        vsapi->freeNode(d->clip);
+    delete d->fused;
     delete d->cache;
     delete d;
 }
@@ -1005,9 +1054,39 @@ void VS_CC analyseCreate(const VSMap *in, VSMap *out, void *, VSCore *core, cons
     }
     d.cache = d.lookahead ? new AnalyseCache : nullptr;
     d.self = nullptr;
+    d.fused = nullptr;
+    d.clip = nullptr;
+    if (d.lookahead && !d.ap.fields && d.ap.ad.nDeltaFrame > 0) { // the fused path: the super clip is this plugin's own mv.Super (no pelclip)
+        std::lock_guard<std::mutex> lock(g_registry_mutex);
+        const auto su = g_registry.find(d.node);
+        if (su != g_registry.end() && su->second.kind == kNodeSuper) {
+            const SuperData *S = (const SuperData *)su->second.data;
+            const VSVideoInfo *cvi = vsapi->getVideoInfo(S->node);
+            if (!S->usePelClip && cvi->numFrames == d.vi->numFrames) {
+                d.clip = vsapi->addNodeRef(S->node);
+                d.ssp = S->sp;
+                mvb200_super_layout(&d.ssp, &d.sl);
+                d.vstride = ((int64_t)d.ap.vectors_size + 255) / 256 * 256;
+                d.fused = new FusedCache;
+                mvb200_clip_layout(&d.ssp, &d.fused->cl);
+                d.fused->out = d.sl;
+                d.fused->outFrameBytes = (size_t)d.sl.frame_bytes;
+                d.fused->outExtra = (size_t)d.vstride;
+                d.fused->window = fusedWindowFrames(d.fused, lookaheadFromEnv(), &d.ap, &d.ssp, 1);
+                d.lookahead = 0; // (the windows replace the look-ahead over super frames; frame 0 alone is searched as one chain)
+                delete d.cache;
+                d.cache = nullptr;
+            }
+        }
+    }
     AnalyseData *data = new AnalyseData(d);
-    VSFilterDependency deps[1] = {{data->node, rpGeneral}};
-    vsapi->createVideoFilter(out, "Analyse", data->vi, analyseGetFrame, analyseFree, fmParallel, deps, 1, data, core);
+    if (data->fused) { // the Super's source clip is what the windows read; the super clip only for frame 0 at script-building time
+        VSFilterDependency fdeps[2] = {{data->clip, rpGeneral}, {data->node, rpGeneral}};
+        vsapi->createVideoFilter(out, "Analyse", data->vi, analyseFusedGetFrame, analyseFree, fmParallel, fdeps, 2, data, core);
+    } else {
+        VSFilterDependency deps[1] = {{data->node, rpGeneral}};
+        vsapi->createVideoFilter(out, "Analyse", data->vi, analyseGetFrame, analyseFree, fmParallel, deps, 1, data, core);
+    }
     data->self = registerSelf(vsapi, out, kNodeAnalyse, data);
 }
 
