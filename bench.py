@@ -273,15 +273,32 @@ def plugin_leg(cfg, args, mb, plan, world, rank, local, barrier, total_frames, g
     else:
         step = -(-F_out // window) * window
         base = -(-OFF // window) * window  # the first rendered frame: a window boundary at or after the halo
-        n_local = base + (args.warmup_e2e + args.steps) * step + window + REACH
+        # warm-up: the requested steps, and at least the windows it takes for the plugin's pinned buffers to be in circulation (one
+        # per engine context, one being served, one recycled, one more); then window by window until two consecutive windows take
+        # the same time within 25 % (page-locking the windows' gigabytes is a start-up cost of seconds: a small configuration
+        # renders a dozen windows before the last buffer exists), at most 24 more
+        warm_min = max(args.warmup_e2e * step, (int(os.environ.get("MVB200_CONTEXTS_PER_DEVICE", "2") or 2) + 3) * window) if args.warmup_e2e else 0
+        warm_min = -(-warm_min // window) * window
+        warm_max = warm_min + (24 * window if args.warmup_e2e else 0)
+        n_local = base + warm_max + args.steps * step + window + REACH
         core, out, keep = script(n_local, lo)
-        if args.warmup_e2e:
-            out.render(base, base + args.warmup_e2e * step, threads)
+        pos, prev = base, None
+        if warm_min > window:
+            out.render(base, base + warm_min - window, threads)
+            pos = base + warm_min - window
+        while pos < base + warm_max:
+            tw = out.render(pos, pos + window, threads)
+            pos += window
+            if pos - base >= warm_min and prev is not None and abs(tw - prev) <= 0.25 * max(tw, prev):
+                break
+            prev = tw
+        warm = pos - base
         barrier()
-        t = out.render(base + args.warmup_e2e * step, base + (args.warmup_e2e + args.steps) * step, threads)
+        t = out.render(pos, pos + args.steps * step, threads)
         barrier()
-        frames_timed, first_timed = args.steps * step, base
-        protocol = "steady state: %d warm-up + %d timed steps of %d frames (whole look-ahead windows of %d) on one long clip" % (args.warmup_e2e, args.steps, step, window)
+        frames_timed, first_timed = args.steps * step, pos
+        protocol = "steady state: %d warm-up frames (%d windows, until two consecutive windows took the same time), then %d timed steps of %d frames (whole look-ahead windows of %d) on one long clip" % (
+            warm, warm // window, args.steps, step, window)
     # ---- output check (untimed): sampled frames against reference-derived digests
     checked, bad = 0, []
     if gold is not None:

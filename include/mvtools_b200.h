@@ -656,6 +656,15 @@ MVB200_API int mvb200_analyse_clip_host(mvb200_ctx *ctx, const mvb200_super_para
 MVB200_API int mvb200_compensate_recalc_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_recalculate_params *const *rp, int nrp,
                                                   const mvb200_compensate_params *cp, const void *host_src, int src_first, int n, int out_first, int out_count, void *host_dst);
 
+/* The two above without the final wait: the call returns when the work is enqueued on the context (the source frames move
+ * host -> device in pieces on a copy stream beside the previous call's kernels, the output pieces leave on another one);
+ * the host buffers (pinned memory for truly asynchronous copies) are valid after mvb200_ctx_synchronize() or after an
+ * event recorded behind the call (mvb200_ctx_record / mvb200_event_wait).  This is what the plugin's windows use. */
+MVB200_API int mvb200_compensate_recalc_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_recalculate_params *const *rp, int nrp,
+                                                        const mvb200_compensate_params *cp, const void *host_src, int src_first, int n, int out_first, int out_count, void *host_dst);
+MVB200_API int mvb200_analyse_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const void *host_src, int src_first, int n, int out_first, int out_count,
+                                              void *host_super, void *host_vectors, int64_t vectors_stride);
+
 /* The same for the per-pixel consumers: mv.Super -> mv.Analyse (one or two instances) -> mv.Flow / mv.FlowInter /
  * mv.FlowBlur for output frames [out_first, out_first + out_count), from the n source frames [src_first, src_first + n)
  * in host_src (halo: delta frames on both sides for Flow and FlowBlur, delta before and 2 x delta after for FlowInter).

@@ -16,6 +16,8 @@
 #include <cstring>
 #include <vector>
 
+#include <unistd.h>
+
 static std::atomic<long> g_ctx_created{0}; // mvb200_ctx_create calls so far (one context per device the plugin uses)
 static std::atomic<long> g_clip_calls{0}; // mvb200_degrain_clip_host_async calls so far (the glue tests count the windows)
 
@@ -77,7 +79,12 @@ MVB200_API int mvb200_search_plan_query(const mvb200_analyse_params *, const mvb
     out->smem_per_chain = 0;
     return 0;
 }
-MVB200_API void *mvb200_pinned_alloc(size_t bytes) { return malloc(bytes); }
+static std::atomic<int> g_pinned_allocs{0};
+MVB200_API int mvb200_mock_pinned_allocs() { return g_pinned_allocs.load(); }
+MVB200_API void *mvb200_pinned_alloc(size_t bytes) {
+    g_pinned_allocs.fetch_add(1);
+    return malloc(bytes);
+}
 MVB200_API void mvb200_pinned_free(void *p) { free(p); }
 
 // the layouts of the device-resident clips, restated for the stand-in (the product's live in engine.cu)
@@ -376,6 +383,11 @@ MVB200_API int mvb200_flowfps_clip_host(mvb200_ctx *, const mvb200_super_params 
 // layout) and their blobs.
 MVB200_API int mvb200_analyse_clip_host(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const void *host_src, int src_first, int n, int out_first, int out_count, void *host_super,
                                         void *host_vectors, int64_t vectors_stride) {
+    if (const char *nc = getenv("MVB200_MOCK_NOCOMPUTE")) { // (tools/bench_glue.py: the plugin's host plumbing alone, outputs left as they are; the value = a call's latency in ms)
+        if (atoi(nc) > 1)
+            usleep((useconds_t)atoi(nc) * 1000);
+        return 0;
+    }
     mvb200_frame_layout cl, sl;
     mvb200_clip_layout(sp, &cl);
     mvb200_super_layout(sp, &sl);
@@ -710,3 +722,13 @@ MVB200_API int mvb200_blockfps_clip_host(mvb200_ctx *, const mvb200_super_params
 }
 
 } // extern "C"
+
+// (the stand-in computes at once: "asynchronous" is the synchronous call)
+MVB200_API int mvb200_compensate_recalc_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_recalculate_params *const *rp, int nrp,
+                                                        const mvb200_compensate_params *cp, const void *host_src, int src_first, int n, int out_first, int out_count, void *host_dst) {
+    return mvb200_compensate_recalc_clip_host(ctx, sp, ap, rp, nrp, cp, host_src, src_first, n, out_first, out_count, host_dst);
+}
+MVB200_API int mvb200_analyse_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const void *host_src, int src_first, int n, int out_first, int out_count,
+                                              void *host_super, void *host_vectors, int64_t vectors_stride) {
+    return mvb200_analyse_clip_host(ctx, sp, ap, host_src, src_first, n, out_first, out_count, host_super, host_vectors, vectors_stride);
+}

@@ -5,6 +5,7 @@
 #include "engine.h"
 
 #include <algorithm>
+#include <functional>
 
 #include <unistd.h>
 
@@ -678,18 +679,20 @@ int mvb200_degrain_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *s
     return mvb200_degrain_recalc_clip_host_async(ctx, sp, ap, nap, nullptr, 0, dp, host_src, host_dst, n, first, count);
 }
 
-// The same with mv.Recalculate between the searches and the blend: rp[i * nrp + k] (k = 0 .. nrp - 1, NULL = none) are the
-// refinement passes applied, in order, to vector clip i (gopRecalculateMVs, MVRecalculate.c:68-254).
-int mvb200_degrain_recalc_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const mvb200_recalculate_params *const *rp, int nrp,
-                                          const mvb200_degrain_params *dp, const void *host_src, void *host_dst, int n, int first, int count) {
-    if (check_levels(sp))
-        return 1;
-    if (n <= 0 || count <= 0)
-        return 0;
-    if (first < 0 || first + count > n)
-        return set_error("mvtools_b200: output range [%d, %d) is outside the segment of %d frames", first, first + count, n);
-    if (nap != dp->radius * 2)
-        return set_error("mvtools_b200: Degrain%d needs %d vector clips, %d given", dp->radius, dp->radius * 2, nap);
+// What the fused clip calls share (clip_pipeline below): a segment of n source frames in HOST memory goes to the device in
+// pieces on a copy stream, every frame gets its super frame, `search` enqueues the searches (and Recalculate passes) over the
+// super clip, `consume(o0, o1)` enqueues the consumer of output frames [o0, o1) of the range into the (double buffered) device
+// output, `download(o0, o1)` enqueues that piece's copies to the host on the other copy stream.  Asynchronous; consecutive calls
+// on one context overlap: the H2D copy of segment k+1 and the D2H copy of segment k-1 run beside the kernels of segment k.
+struct ClipWork {
+    size_t dst_bytes = 0;                                  // device output buffer for the whole range
+    std::function<int(uint8_t *dsrc, uint8_t *dsup)> search;
+    std::function<int(uint8_t *dsrc, uint8_t *dsup, uint8_t *ddst, int o0, int o1)> consume;
+    std::function<int(const uint8_t *ddst, int o0, int o1, cudaStream_t copy_out)> download;
+    bool super_is_output = false; // download reads the super clip itself (a vector clip's frames): the super clip is double buffered too
+};
+
+static int clip_pipeline(mvb200_ctx *ctx, const mvb200_super_params *sp, const void *host_src, int n, int count, const ClipWork &work) {
     Ctx &c = ctx->c;
     MVB_CUDA_CHECK(cudaSetDevice(c.device));
     if (!c.copy_in) {
@@ -709,6 +712,73 @@ int mvb200_degrain_recalc_clip_host_async(mvb200_ctx *ctx, const mvb200_super_pa
     ClipDesc cd;
     make_super_desc(sp, &sd);
     make_clip_desc(sp, &cd);
+    const int slot = (int)(c.clip_calls & 1);
+    const bool reuse = c.clip_calls >= 2; // this slot's buffers were used by the call before the previous one
+    c.clip_calls++;
+    const size_t clip_bytes = (size_t)cd.frame_bytes * n;
+    const int sup_slot = work.super_is_output ? 15 + slot : 12;
+    void *before[3] = {c.scratch[8 + slot], c.scratch[10 + slot], c.scratch[sup_slot]};
+    uint8_t *dsrc = (uint8_t *)c.get_scratch(8 + slot, clip_bytes);
+    uint8_t *ddst = (uint8_t *)c.get_scratch(10 + slot, work.dst_bytes ? work.dst_bytes : 256);
+    uint8_t *dsup = (uint8_t *)c.get_scratch(sup_slot, (size_t)sd.frame_bytes * n);
+    if (!dsrc || !ddst || !dsup)
+        return 1;
+    if (before[0] != dsrc || before[1] != ddst || before[2] != dsup)
+        MVB_CUDA_CHECK(cudaStreamSynchronize(c.stream)); // fresh buffers are cleared on the compute stream: finish that before the copy stream writes
+    // The segment moves in up to kClipChunks pieces so that only a piece's copy -- not the whole segment's -- is exposed
+    // before the first kernel and after the last one: Super of piece i runs while piece i+1 is still arriving, and the
+    // output frames of piece i leave while piece i+1 is being computed.  (Between consecutive calls the copies already
+    // overlap the neighbouring segments' kernels.)
+    const int nin = n >= 8 * kClipChunks ? kClipChunks : 1, nout = count >= 8 * kClipChunks ? kClipChunks : 1;
+    // H2D: once the kernels that last read this slot's source clip are done
+    if (reuse)
+        MVB_CUDA_CHECK(cudaStreamWaitEvent(c.copy_in, c.ev_compute[slot], 0));
+    // compute: after the D2H that last read this slot's output (and, piece by piece, after this segment's H2D)
+    if (reuse)
+        MVB_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_d2h[slot], 0));
+    for (int i = 0; i < nin; i++) {
+        const int f0 = (int)((long long)n * i / nin), f1 = (int)((long long)n * (i + 1) / nin);
+        MVB_CUDA_CHECK(cudaMemcpyAsync(dsrc + (size_t)cd.frame_bytes * f0, (const uint8_t *)host_src + (size_t)cd.frame_bytes * f0, (size_t)cd.frame_bytes * (f1 - f0),
+                                       cudaMemcpyHostToDevice, c.copy_in));
+        MVB_CUDA_CHECK(cudaEventRecord(c.ev_piece_in[i], c.copy_in));
+        MVB_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_piece_in[i], 0));
+        // every frame of the segment gets its super frame: the frames outside the output range are references
+        if (mvb200_super_batch(ctx, sp, dsrc + (size_t)cd.frame_bytes * f0, dsup + (size_t)sd.frame_bytes * f0, f1 - f0))
+            return 1;
+    }
+    MVB_CUDA_CHECK(cudaEventRecord(c.ev_h2d[slot], c.copy_in));
+    if (work.search && work.search(dsrc, dsup))
+        return 1;
+    for (int i = 0; i < nout; i++) {
+        const int o0 = (int)((long long)count * i / nout), o1 = (int)((long long)count * (i + 1) / nout);
+        if (work.consume && work.consume(dsrc, dsup, ddst, o0, o1))
+            return 1;
+        MVB_CUDA_CHECK(cudaEventRecord(i == nout - 1 ? c.ev_compute[slot] : c.ev_piece_out[i], c.stream));
+        // D2H of the piece
+        MVB_CUDA_CHECK(cudaStreamWaitEvent(c.copy_out, i == nout - 1 ? c.ev_compute[slot] : c.ev_piece_out[i], 0));
+        if (work.download(work.super_is_output ? dsup : ddst, o0, o1, c.copy_out))
+            return 1;
+    }
+    MVB_CUDA_CHECK(cudaEventRecord(c.ev_d2h[slot], c.copy_out));
+    return 0;
+}
+
+// The same with mv.Recalculate between the searches and the blend: rp[i * nrp + k] (k = 0 .. nrp - 1, NULL = none) are the
+// refinement passes applied, in order, to vector clip i (gopRecalculateMVs, MVRecalculate.c:68-254).
+int mvb200_degrain_recalc_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const mvb200_recalculate_params *const *rp, int nrp,
+                                          const mvb200_degrain_params *dp, const void *host_src, void *host_dst, int n, int first, int count) {
+    if (check_levels(sp))
+        return 1;
+    if (n <= 0 || count <= 0)
+        return 0;
+    if (first < 0 || first + count > n)
+        return set_error("mvtools_b200: output range [%d, %d) is outside the segment of %d frames", first, first + count, n);
+    if (nap != dp->radius * 2)
+        return set_error("mvtools_b200: Degrain%d needs %d vector clips, %d given", dp->radius, dp->radius * 2, nap);
+    Ctx &c = ctx->c;
+    MVB_CUDA_CHECK(cudaSetDevice(c.device));
+    ClipDesc cd;
+    make_clip_desc(sp, &cd);
     int64_t vstride = 0;
     bool any_recalc = false;
     for (int i = 0; i < nap; i++) {
@@ -719,72 +789,41 @@ int mvb200_degrain_recalc_clip_host_async(mvb200_ctx *ctx, const mvb200_super_pa
                 any_recalc = true;
             }
     }
-    const int slot = (int)(c.clip_calls & 1);
-    const bool reuse = c.clip_calls >= 2; // this slot's buffers were used by the call before the previous one
-    c.clip_calls++;
-    const size_t clip_bytes = (size_t)cd.frame_bytes * n;
-    void *before[4] = {c.scratch[8 + slot], c.scratch[10 + slot], c.scratch[12], c.scratch[13]};
-    uint8_t *dsrc = (uint8_t *)c.get_scratch(8 + slot, clip_bytes);
-    uint8_t *ddst = (uint8_t *)c.get_scratch(10 + slot, clip_bytes);
-    uint8_t *dsup = (uint8_t *)c.get_scratch(12, (size_t)sd.frame_bytes * n);
     uint8_t *dvec = (uint8_t *)c.get_scratch(13, (size_t)vstride * count * nap);
     uint8_t *dvec2 = any_recalc ? (uint8_t *)c.get_scratch(14, (size_t)vstride * count) : nullptr; // one vector clip being refined
-    if (!dsrc || !ddst || !dsup || !dvec || (any_recalc && !dvec2))
+    if (!dvec || (any_recalc && !dvec2))
         return 1;
-    if (before[0] != dsrc || before[1] != ddst || before[2] != dsup || before[3] != dvec)
-        MVB_CUDA_CHECK(cudaStreamSynchronize(c.stream)); // fresh buffers are cleared on the compute stream: finish that before the copy stream writes
-    // The segment moves in up to kClipChunks pieces so that only a piece's copy -- not the whole segment's -- is exposed
-    // before the first kernel and after the last one: Super of piece i runs while piece i+1 is still arriving, and the
-    // denoised frames of piece i leave while piece i+1 is being blended.  (Between consecutive calls the copies already
-    // overlap the neighbouring segments' kernels.)
-    const int nin = n >= 8 * kClipChunks ? kClipChunks : 1, nout = count >= 8 * kClipChunks ? kClipChunks : 1;
-    // H2D: once the kernels that last read this slot's source clip are done
-    if (reuse)
-        MVB_CUDA_CHECK(cudaStreamWaitEvent(c.copy_in, c.ev_compute[slot], 0));
-    // compute: after the D2H that last read this slot's output clip (and, piece by piece, after this segment's H2D)
-    if (reuse)
-        MVB_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_d2h[slot], 0));
-    for (int i = 0; i < nin; i++) {
-        const int f0 = (int)((long long)n * i / nin), f1 = (int)((long long)n * (i + 1) / nin);
-        MVB_CUDA_CHECK(cudaMemcpyAsync(dsrc + (size_t)cd.frame_bytes * f0, (const uint8_t *)host_src + (size_t)cd.frame_bytes * f0, (size_t)cd.frame_bytes * (f1 - f0),
-                                       cudaMemcpyHostToDevice, c.copy_in));
-        MVB_CUDA_CHECK(cudaEventRecord(c.ev_piece_in[i], c.copy_in));
-        MVB_CUDA_CHECK(cudaStreamWaitEvent(c.stream, c.ev_piece_in[i], 0));
-        // every frame of the segment gets its super frame: the frames outside [first, first + count) are references
-        if (mvb200_super_batch(ctx, sp, dsrc + (size_t)cd.frame_bytes * f0, dsup + (size_t)sd.frame_bytes * f0, f1 - f0))
-            return 1;
-    }
-    MVB_CUDA_CHECK(cudaEventRecord(c.ev_h2d[slot], c.copy_in));
     std::vector<void *> outs((size_t)nap);
     for (int i = 0; i < nap; i++)
         outs[i] = dvec + (size_t)vstride * count * i;
-    if (mvb200_analyse_multi_batch(ctx, ap, nap, sp, dsup, first, count, outs.data(), vstride))
-        return 1;
-    for (int i = 0; any_recalc && i < nap; i++)
-        for (int k = 0; k < nrp; k++) {
-            if (!rp[i * nrp + k])
-                continue;
-            mvb200_recalculate_params q = *rp[i * nrp + k]; // the segment is the clip as far as the engine is concerned
-            q.num_frames = n;
-            if (mvb200_recalculate_batch(ctx, &q, sp, dsup, first, count, outs[i], vstride, dvec2, vstride))
-                return 1;
-            MVB_CUDA_CHECK(cudaMemcpyAsync(outs[i], dvec2, (size_t)vstride * count, cudaMemcpyDeviceToDevice, c.stream));
-        }
-    std::vector<const void *> vin((size_t)nap);
-    for (int i = 0; i < nout; i++) {
-        const int o0 = (int)((long long)count * i / nout), o1 = (int)((long long)count * (i + 1) / nout);
+    ClipWork work;
+    work.dst_bytes = (size_t)cd.frame_bytes * count;
+    work.search = [&](uint8_t *, uint8_t *dsup) -> int {
+        if (mvb200_analyse_multi_batch(ctx, ap, nap, sp, dsup, first, count, outs.data(), vstride))
+            return 1;
+        for (int i = 0; any_recalc && i < nap; i++)
+            for (int k = 0; k < nrp; k++) {
+                if (!rp[i * nrp + k])
+                    continue;
+                mvb200_recalculate_params q = *rp[i * nrp + k]; // the segment is the clip as far as the engine is concerned
+                q.num_frames = n;
+                if (mvb200_recalculate_batch(ctx, &q, sp, dsup, first, count, outs[i], vstride, dvec2, vstride))
+                    return 1;
+                MVB_CUDA_CHECK(cudaMemcpyAsync(outs[i], dvec2, (size_t)vstride * count, cudaMemcpyDeviceToDevice, c.stream));
+            }
+        return 0;
+    };
+    work.consume = [&](uint8_t *dsrc, uint8_t *dsup, uint8_t *ddst, int o0, int o1) -> int {
+        std::vector<const void *> vin((size_t)nap);
         for (int k = 0; k < nap; k++)
             vin[k] = (const uint8_t *)outs[k] + (size_t)vstride * o0;
-        if (mvb200_degrain_batch(ctx, dp, sp, dsrc, dsup, n, first + o0, o1 - o0, vin.data(), vstride, ddst + (size_t)cd.frame_bytes * o0))
-            return 1;
-        MVB_CUDA_CHECK(cudaEventRecord(i == nout - 1 ? c.ev_compute[slot] : c.ev_piece_out[i], c.stream));
-        // D2H of the piece
-        MVB_CUDA_CHECK(cudaStreamWaitEvent(c.copy_out, i == nout - 1 ? c.ev_compute[slot] : c.ev_piece_out[i], 0));
-        MVB_CUDA_CHECK(cudaMemcpyAsync((uint8_t *)host_dst + (size_t)cd.frame_bytes * o0, ddst + (size_t)cd.frame_bytes * o0, (size_t)cd.frame_bytes * (o1 - o0),
-                                       cudaMemcpyDeviceToHost, c.copy_out));
-    }
-    MVB_CUDA_CHECK(cudaEventRecord(c.ev_d2h[slot], c.copy_out));
-    return 0;
+        return mvb200_degrain_batch(ctx, dp, sp, dsrc, dsup, n, first + o0, o1 - o0, vin.data(), vstride, ddst + (size_t)cd.frame_bytes * o0);
+    };
+    work.download = [&](const uint8_t *ddst, int o0, int o1, cudaStream_t s) -> int {
+        MVB_CUDA_CHECK(cudaMemcpyAsync((uint8_t *)host_dst + (size_t)cd.frame_bytes * o0, ddst + (size_t)cd.frame_bytes * o0, (size_t)cd.frame_bytes * (o1 - o0), cudaMemcpyDeviceToHost, s));
+        return 0;
+    };
+    return clip_pipeline(ctx, sp, host_src, n, count, work);
 }
 
 void *mvb200_pinned_alloc(size_t bytes) {
@@ -809,6 +848,15 @@ int mvb200_compensate_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, 
 // ... with nrp mv.Recalculate passes (rp[0 .. nrp - 1], in order) between the search and the compensation
 int mvb200_compensate_recalc_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_recalculate_params *const *rp, int nrp, const mvb200_compensate_params *cp,
                                        const void *host_src, int src_first, int n, int out_first, int out_count, void *host_dst) {
+    if (mvb200_compensate_recalc_clip_host_async(ctx, sp, ap, rp, nrp, cp, host_src, src_first, n, out_first, out_count, host_dst))
+        return 1;
+    return mvb200_ctx_synchronize(ctx);
+}
+
+// Asynchronous (like mvb200_degrain_recalc_clip_host_async): returns when the work is enqueued; host_dst is valid after
+// mvb200_ctx_synchronize() or an event recorded after the call; consecutive calls on one context overlap their copies.
+int mvb200_compensate_recalc_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const mvb200_recalculate_params *const *rp, int nrp,
+                                             const mvb200_compensate_params *cp, const void *host_src, int src_first, int n, int out_first, int out_count, void *host_dst) {
     if (check_levels(sp) || check_analyse(ap, sp))
         return 1;
     if (n <= 0 || out_count <= 0)
@@ -819,9 +867,7 @@ int mvb200_compensate_recalc_clip_host(mvb200_ctx *ctx, const mvb200_super_param
         return set_error("Compensate: the clip pipeline handles relative references without field shifts only");
     Ctx *c = &ctx->c;
     MVB_CUDA_CHECK(cudaSetDevice(c->device));
-    SuperDesc sd;
     ClipDesc cd;
-    make_super_desc(sp, &sd);
     make_clip_desc(sp, &cd);
     mvb200_analyse_params a = *ap; // the segment is the clip as far as the engine is concerned
     a.num_frames = n;
@@ -831,35 +877,48 @@ int mvb200_compensate_recalc_clip_host(mvb200_ctx *ctx, const mvb200_super_param
     for (int k = 0; rp && k < nrp; k++)
         if (rp[k])
             vstride = std::max<int64_t>(vstride, ((int64_t)rp[k]->vectors_size + 255) / 256 * 256);
-    uint8_t *buf = (uint8_t *)c->get_scratch(5, (size_t)cd.frame_bytes * (n + out_count) + (size_t)sd.frame_bytes * n + (size_t)vstride * out_count * 2 + 256);
-    if (!buf)
+    uint8_t *dvec = (uint8_t *)c->get_scratch(13, (size_t)vstride * out_count);
+    uint8_t *dvec2 = (uint8_t *)c->get_scratch(14, (size_t)vstride * out_count);
+    if (!dvec || !dvec2)
         return 1;
-    uint8_t *dsrc = buf, *ddst = dsrc + (size_t)cd.frame_bytes * n, *dsup = ddst + (size_t)cd.frame_bytes * out_count, *dvec = dsup + (size_t)sd.frame_bytes * n;
-    uint8_t *dvec2 = dvec + (size_t)vstride * out_count;
-    MVB_CUDA_CHECK(cudaMemcpyAsync(dsrc, host_src, (size_t)cd.frame_bytes * n, cudaMemcpyHostToDevice, c->stream));
     const int first = out_first - src_first;
-    if (mvb200_super_batch(ctx, sp, dsrc, dsup, n) || mvb200_analyse_batch(ctx, &a, sp, dsup, first, out_count, dvec, vstride))
-        return 1;
-    for (int k = 0; rp && k < nrp; k++) {
-        if (!rp[k])
-            continue;
-        mvb200_recalculate_params r = *rp[k];
-        r.num_frames = n;
-        if (mvb200_recalculate_batch(ctx, &r, sp, dsup, first, out_count, dvec, vstride, dvec2, vstride))
+    ClipWork work;
+    work.dst_bytes = (size_t)cd.frame_bytes * out_count;
+    work.search = [&](uint8_t *, uint8_t *dsup) -> int {
+        if (mvb200_analyse_batch(ctx, &a, sp, dsup, first, out_count, dvec, vstride))
             return 1;
-        std::swap(dvec, dvec2);
-    }
-    if (mvb200_compensate_batch(ctx, &q, sp, dsup, first, out_count, dvec, vstride, ddst))
-        return 1;
-    MVB_CUDA_CHECK(cudaMemcpyAsync(host_dst, ddst, (size_t)cd.frame_bytes * out_count, cudaMemcpyDeviceToHost, c->stream));
-    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    return 0;
+        for (int k = 0; rp && k < nrp; k++) {
+            if (!rp[k])
+                continue;
+            mvb200_recalculate_params r = *rp[k];
+            r.num_frames = n;
+            if (mvb200_recalculate_batch(ctx, &r, sp, dsup, first, out_count, dvec, vstride, dvec2, vstride))
+                return 1;
+            std::swap(dvec, dvec2);
+        }
+        return 0;
+    };
+    work.consume = [&](uint8_t *, uint8_t *dsup, uint8_t *ddst, int o0, int o1) -> int {
+        return mvb200_compensate_batch(ctx, &q, sp, dsup, first + o0, o1 - o0, dvec + (size_t)vstride * o0, vstride, ddst + (size_t)cd.frame_bytes * o0);
+    };
+    work.download = [&](const uint8_t *ddst, int o0, int o1, cudaStream_t s) -> int {
+        MVB_CUDA_CHECK(cudaMemcpyAsync((uint8_t *)host_dst + (size_t)cd.frame_bytes * o0, ddst + (size_t)cd.frame_bytes * o0, (size_t)cd.frame_bytes * (o1 - o0), cudaMemcpyDeviceToHost, s));
+        return 0;
+    };
+    return clip_pipeline(ctx, sp, host_src, n, out_count, work);
 }
 
 // A window of a vector clip from source frames: Super of the segment, Analyse of [out_first, out_first + out_count); the super
 // frames and the blobs of the output range go back to the host.
 int mvb200_analyse_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const void *host_src, int src_first, int n, int out_first, int out_count,
                              void *host_super, void *host_vectors, int64_t vectors_stride) {
+    if (mvb200_analyse_clip_host_async(ctx, sp, ap, host_src, src_first, n, out_first, out_count, host_super, host_vectors, vectors_stride))
+        return 1;
+    return mvb200_ctx_synchronize(ctx);
+}
+
+int mvb200_analyse_clip_host_async(mvb200_ctx *ctx, const mvb200_super_params *sp, const mvb200_analyse_params *ap, const void *host_src, int src_first, int n, int out_first, int out_count,
+                                   void *host_super, void *host_vectors, int64_t vectors_stride) {
     if (check_levels(sp) || check_analyse(ap, sp))
         return 1;
     if (n <= 0 || out_count <= 0)
@@ -881,24 +940,29 @@ int mvb200_analyse_clip_host(mvb200_ctx *ctx, const mvb200_super_params *sp, con
     Ctx *c = &ctx->c;
     MVB_CUDA_CHECK(cudaSetDevice(c->device));
     SuperDesc sd;
-    ClipDesc cd;
     make_super_desc(sp, &sd);
-    make_clip_desc(sp, &cd);
     mvb200_analyse_params a = *ap; // the segment is the clip as far as the engine is concerned
     a.num_frames = n;
     const int64_t vstride = ((int64_t)a.vectors_size + 255) / 256 * 256;
-    uint8_t *buf = (uint8_t *)c->get_scratch(5, (size_t)cd.frame_bytes * n + (size_t)sd.frame_bytes * n + (size_t)vstride * out_count + 256);
-    if (!buf)
-        return 1;
-    uint8_t *dsrc = buf, *dsup = dsrc + (size_t)cd.frame_bytes * n, *dvec = dsup + (size_t)sd.frame_bytes * n;
-    MVB_CUDA_CHECK(cudaMemcpyAsync(dsrc, host_src, (size_t)cd.frame_bytes * n, cudaMemcpyHostToDevice, c->stream));
     const int first = out_first - src_first;
-    if (mvb200_super_batch(ctx, sp, dsrc, dsup, n) || mvb200_analyse_batch(ctx, &a, sp, dsup, first, out_count, dvec, vstride))
-        return 1;
-    MVB_CUDA_CHECK(cudaMemcpyAsync(host_super, dsup + (size_t)sd.frame_bytes * first, (size_t)sd.frame_bytes * out_count, cudaMemcpyDeviceToHost, c->stream));
-    MVB_CUDA_CHECK(cudaMemcpy2DAsync(host_vectors, (size_t)vectors_stride, dvec, (size_t)vstride, (size_t)a.vectors_size, (size_t)out_count, cudaMemcpyDeviceToHost, c->stream));
-    MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    return 0;
+    ClipWork work;
+    work.super_is_output = true;                    // the output frames ARE the super frames: nothing to consume,
+    work.dst_bytes = (size_t)vstride * out_count;   // the double-buffered output holds the blobs
+    uint8_t *dvec_cur = nullptr;
+    work.search = [&](uint8_t *, uint8_t *) -> int { return 0; };
+    work.consume = [&](uint8_t *, uint8_t *dsup, uint8_t *ddst, int o0, int o1) -> int {
+        if (o0 != 0) // (the search is one launch over the whole range: it runs before the first piece leaves)
+            return 0;
+        dvec_cur = ddst;
+        return mvb200_analyse_batch(ctx, &a, sp, dsup, first, out_count, ddst, vstride);
+    };
+    work.download = [&](const uint8_t *dsup, int o0, int o1, cudaStream_t s) -> int {
+        MVB_CUDA_CHECK(cudaMemcpyAsync((uint8_t *)host_super + (size_t)sd.frame_bytes * o0, dsup + (size_t)sd.frame_bytes * (first + o0), (size_t)sd.frame_bytes * (o1 - o0), cudaMemcpyDeviceToHost, s));
+        MVB_CUDA_CHECK(cudaMemcpy2DAsync((uint8_t *)host_vectors + (size_t)vectors_stride * o0, (size_t)vectors_stride, dvec_cur + (size_t)vstride * o0, (size_t)vstride, (size_t)a.vectors_size,
+                                         (size_t)(o1 - o0), cudaMemcpyDeviceToHost, s));
+        return 0;
+    };
+    return clip_pipeline(ctx, sp, host_src, n, out_count, work);
 }
 
 // ------------------------------------------------------- host-buffer path

@@ -199,19 +199,32 @@ struct PinnedPool { // window buffers are recycled (process-wide: a script's fil
         for (auto &b : free_)
             mvb200_pinned_free(b.first);
     }
+    // best fit: a window's source and output buffers differ in size (halo frames; a vector clip's super frames), and a first
+    // fit would hand the large ones to the small requests and then page-lock new large ones window after window
     void *get(size_t bytes, size_t *got) {
         {
             std::lock_guard<std::mutex> lock(m);
-            for (size_t i = 0; i < free_.size(); i++)
-                if (free_[i].second >= bytes) {
-                    void *p = free_[i].first;
-                    *got = free_[i].second;
-                    free_.erase(free_.begin() + (ptrdiff_t)i);
-                    return p;
-                }
-            if (!free_.empty()) { // too small for this window: replace the smallest one
-                mvb200_pinned_free(free_.back().first);
-                free_.pop_back();
+            size_t best = free_.size(), held = 0;
+            for (size_t i = 0; i < free_.size(); i++) {
+                held += free_[i].second;
+                if (free_[i].second >= bytes && (best == free_.size() || free_[i].second < free_[best].second))
+                    best = i;
+            }
+            if (best != free_.size()) {
+                void *p = free_[best].first;
+                *got = free_[best].second;
+                free_.erase(free_.begin() + (ptrdiff_t)best);
+                return p;
+            }
+            // nothing fits: make room within the budget by giving back the smallest idle buffers
+            while (!free_.empty() && (int64_t)(held + bytes) > pinnedBudget()) {
+                size_t smallest = 0;
+                for (size_t i = 1; i < free_.size(); i++)
+                    if (free_[i].second < free_[smallest].second)
+                        smallest = i;
+                held -= free_[smallest].second;
+                mvb200_pinned_free(free_[smallest].first);
+                free_.erase(free_.begin() + (ptrdiff_t)smallest);
             }
         }
         *got = bytes;
@@ -276,7 +289,53 @@ struct FusedRequest {
     std::vector<std::shared_ptr<FusedWindow>> hold;
 };
 
+// MVB200_STATS=1: where the host threads of a fused filter spent their time, printed to stderr when the filter is freed
+// (nanoseconds summed over threads; "wait" is time blocked on the GPU, everything else is host work).
+struct FusedStats {
+    std::atomic<int64_t> request{0}, collect{0}, pack{0}, launch{0}, waitOwn{0}, waitEvent{0}, serve{0}, frames{0}, windows{0};
+    const bool on = getenv("MVB200_STATS") != nullptr;
+    const int every = on ? atoi(getenv("MVB200_STATS")) : 0; // > 1: also a line every that many windows (what happened since the last one)
+    int64_t last[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, lastT = 0;
+    std::mutex m;
+    static int64_t now() { return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+    void print(const char *name, int window, bool delta) {
+        std::lock_guard<std::mutex> lock(m);
+        const int64_t cur[9] = {request.load(), collect.load(), pack.load(), launch.load(), waitOwn.load(), waitEvent.load(), serve.load(), frames.load(), windows.load()};
+        const int64_t t = now();
+        double v[9];
+        for (int i = 0; i < 9; i++)
+            v[i] = (double)(cur[i] - (delta ? last[i] : 0));
+        if (delta)
+            fprintf(stderr, "[mvtools-b200] %s: +%.0f frames, +%.0f windows of %d in %.1f ms; ", name, v[7], v[8], window, lastT ? (t - lastT) / 1e6 : 0.0);
+        else
+            fprintf(stderr, "[mvtools-b200] %s: %.0f frames in %.0f windows of %d; ", name, v[7], v[8], window);
+        fprintf(stderr, "host ms (summed over threads): request %.1f, collect %.1f, pack %.1f, launch %.1f, wait for packing / enqueueing %.1f, wait for the GPU %.1f, serve %.1f\n", v[0] / 1e6, v[1] / 1e6,
+                v[2] / 1e6, v[3] / 1e6, v[4] / 1e6, v[5] / 1e6, v[6] / 1e6);
+        if (delta) {
+            memcpy(last, cur, sizeof(last));
+            lastT = t;
+        }
+    }
+};
+struct StatTimer {
+    std::atomic<int64_t> *acc;
+    int64_t t0;
+    StatTimer(FusedStats &st, std::atomic<int64_t> &a) : acc(st.on ? &a : nullptr), t0(st.on ? FusedStats::now() : 0) {}
+    void stop() {
+        if (acc)
+            acc->fetch_add(FusedStats::now() - t0);
+        acc = nullptr;
+    }
+    ~StatTimer() { stop(); }
+};
+
 struct FusedCache {
+    FusedStats stats;
+    const char *name = "";
+    ~FusedCache() {
+        if (stats.on && stats.frames.load())
+            stats.print(name, window, false);
+    }
     std::mutex m;                                           // guards `windows` and the windows' prefetchClaimed
     std::map<int, std::shared_ptr<FusedWindow>> windows;    // by window index (frame / window)
     std::vector<std::shared_ptr<FusedWindow>> packing;      // windows whose source frames wait to be copied into their pinned buffers
@@ -324,6 +383,8 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
                              const std::function<void(VSFrame *, const uint8_t *hostDst, int w0, int w1)> &post = nullptr) {
     const int B = f->window, N = outvi->numFrames;
     if (activationReason == arInitial) {
+        StatTimer tRequest(f->stats, f->stats.request);
+        f->name = filter;
         vsapi->requestFrameFilter(propFrame, clip, frameCtx);
         if (alsoFrame >= 0 && alsoFrame != propFrame)
             vsapi->requestFrameFilter(alsoFrame, clip, frameCtx);
@@ -385,6 +446,7 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
         std::unique_lock<std::mutex> wl(w->m);
         if (w->state.load() != FusedWindow::Idle)
             continue;
+        StatTimer tCollect(f->stats, f->stats.collect);
         size_t gs = 0, gd = 0;
         w->hostSrc = w->pool->get(fb * (size_t)(w->s1 - w->s0), &gs);
         w->srcBytes = gs;
@@ -429,6 +491,7 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
         const int i = w->packNext.fetch_add(1);
         if (i >= count)
             return true;
+        StatTimer tPack(f->stats, f->stats.pack);
         const VSFrame *fr = w->srcFrames[(size_t)i];
         for (int p = 0; p < f->cl.nplanes; p++)
             vsh::bitblt((uint8_t *)w->hostSrc + fb * (size_t)i + f->cl.offset[p], (ptrdiff_t)f->cl.pitch[p], vsapi->getReadPtr(fr, p), vsapi->getStride(fr, p),
@@ -438,6 +501,10 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
         if (w->packDone.fetch_add(1) + 1 < count)
             return true;
         w->state.store(FusedWindow::Launching);
+        tPack.stop();
+        StatTimer tLaunch(f->stats, f->stats.launch);
+        if (f->stats.on && (f->stats.windows.fetch_add(1) + 1) % (f->stats.every > 1 ? f->stats.every : (1 << 30)) == 0)
+            f->stats.print(filter, f->window, true);
         std::string msg;
         bool ok = false;
         mvb200_event *ev = nullptr;
@@ -462,6 +529,7 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
     }
     // (3) this request's own window may still be in other threads' hands (its last frames being packed, or being enqueued)
     {
+        StatTimer tWaitOwn(f->stats, f->stats.waitOwn);
         FusedWindow *own = rq->win.get();
         std::unique_lock<std::mutex> wl(own->m);
         while (own->state.load() == FusedWindow::Packing || own->state.load() == FusedWindow::Launching) {
@@ -477,6 +545,7 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
     std::string msg;
     int st = w->state.load();
     if (st == FusedWindow::Running) {
+        StatTimer tWaitEvent(f->stats, f->stats.waitEvent);
         if (mvb200_event_wait(w->done)) { // (any number of threads may wait for the same event)
             std::lock_guard<std::mutex> wl(w->m);
             w->err = mvb200_last_error();
@@ -496,6 +565,8 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
         vsapi->freeFrame(src);
         return nullptr;
     }
+    StatTimer tServe(f->stats, f->stats.serve);
+    f->stats.frames.fetch_add(1);
     if (flagOut)
         *flagOut = w->flags[(size_t)(n - w->w0)];
     const mvb200_frame_layout &ol = f->outFrameBytes ? f->out : f->cl;
@@ -988,7 +1059,7 @@ const VSFrame *VS_CC analyseFusedGetFrame(int n, int activationReason, void *ins
     };
     auto run = [&](mvb200_ctx *ctx, const void *hostSrc, int s0, int s1, int w0, int w1, void *hostDst, int32_t *) {
         uint8_t *blobs = (uint8_t *)hostDst + (size_t)d->sl.frame_bytes * (size_t)(w1 - w0);
-        return mvb200_analyse_clip_host(ctx, &d->ssp, &d->ap, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst, blobs, d->vstride);
+        return mvb200_analyse_clip_host_async(ctx, &d->ssp, &d->ap, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst, blobs, d->vstride);
     };
     const unsigned mask = (d->ssp.modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) ? 7u : 1u;
     auto post = [&](VSFrame *dst, const uint8_t *hostDst, int w0, int w1) {
@@ -1548,7 +1619,7 @@ const VSFrame *VS_CC compFusedGetFrame(int n, int activationReason, void *instan
         const mvb200_recalculate_params *rpp[kMaxRecalc];
         for (int k = 0; k < kMaxRecalc; k++)
             rpp[k] = k < f->rc.n ? &f->rc.rp[k] : nullptr;
-        return mvb200_compensate_recalc_clip_host(ctx, &d->sp, &f->ap, rpp, kMaxRecalc, &d->cp, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst);
+        return mvb200_compensate_recalc_clip_host_async(ctx, &d->sp, &f->ap, rpp, kMaxRecalc, &d->cp, hostSrc, s0, s1 - s0, w0, w1 - w0, hostDst);
     };
     const VSFrame *out = fusedGetFrame("Compensate", f, d->node, d->vi, n, n, mask, activationReason, frameData, frameCtx, core, vsapi, segment, run);
     if (out && n == 0) // the reference builds the output on super frame n (MVCompensate.c:113): frame 0 carries the Super_* properties
