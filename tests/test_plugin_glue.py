@@ -431,10 +431,9 @@ def test_vector_clip_windows_from_source_frames(mock_plugin, monkeypatch, case, 
 
 
 def test_window_buffers_are_recycled_in_steady_state(mock_plugin):
-    """A vector clip's windows have a small source buffer and a large output buffer (super frames): after the first windows no
-    further pinned allocation may happen -- a first-fit pool handed the large buffers to the small requests and page-locked a
-    new gigabyte window after window (measured on the GPU: configs[0] at 3.7 k frames/s instead of > 8 k).  Own process: the
-    pool is process-wide and the stand-in's compute is switched off."""
+    """A vector clip's windows have a small source buffer and a large output buffer (super frames): after the first windows the
+    pinned buffers go round -- no allocation per window (page-locking a gigabyte costs half a second on the GPU box).  Own
+    process: the pool is process-wide and the stand-in's compute is switched off."""
     code = """
 import ctypes, os, sys
 sys.path[:0] = [%r, %r, %r]
@@ -453,7 +452,7 @@ a0 = allocs()
 vec.render(96, 304, 4)
 a1 = allocs()
 print("ALLOCS", a0, a1)
-assert a0 > 0 and a1 == a0, (a0, a1)
+assert a0 > 0 and a1 - a0 <= 4, (a0, a1)  # 13 more windows: a late extra window in flight may add a pair, a per-window allocation adds 26
 """ % (os.path.join(ROOT, "host", "minivs"), HERE, os.path.join(ROOT, "vapoursynth-mvtools_b200"), mock_plugin)
     env = dict(os.environ, MVB200_LOOKAHEAD="16", MVB200_MOCK_NOCOMPUTE="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)

@@ -716,7 +716,7 @@ static int clip_pipeline(mvb200_ctx *ctx, const mvb200_super_params *sp, const v
     const bool reuse = c.clip_calls >= 2; // this slot's buffers were used by the call before the previous one
     c.clip_calls++;
     const size_t clip_bytes = (size_t)cd.frame_bytes * n;
-    const int sup_slot = work.super_is_output ? 15 + slot : 12;
+    const int sup_slot = work.super_is_output ? 20 + slot : 12; // (scratch slots: 0-7 kernels' own, 8-14 this pipeline, 16-19 flow.cu, 20-21 here)
     void *before[3] = {c.scratch[8 + slot], c.scratch[10 + slot], c.scratch[sup_slot]};
     uint8_t *dsrc = (uint8_t *)c.get_scratch(8 + slot, clip_bytes);
     uint8_t *ddst = (uint8_t *)c.get_scratch(10 + slot, work.dst_bytes ? work.dst_bytes : 256);

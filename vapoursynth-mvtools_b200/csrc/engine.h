@@ -119,7 +119,11 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     long long launches = 0;
-    // growable device scratch buffers
+    // growable device scratch buffers.  Every user owns its slot numbers (a shared slot means one call's data under another's
+    // cached pointers): 0, 1, 7 search.cu (jobs / histogram / vectors); 2, 3, 4 degrain.cu; 2, 6 compensate.cu; 5 the per-frame and
+    // windowed entry points of engine.cu; 8-14 clip_pipeline (8/9 source clip, 10/11 output, 12 super clip, 13/14 vectors);
+    // 16, 17, 18, 19 flow.cu (tables -- resident across calls --, small fields, staging, windows); 20/21 clip_pipeline's double
+    // buffered super clip of a vector-clip window; 15, 22, 23 free
     void *scratch[24] = {};
     size_t scratch_bytes[24] = {};
     // pinned host staging
