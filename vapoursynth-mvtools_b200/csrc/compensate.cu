@@ -164,9 +164,9 @@ int launch_compensate(Ctx *ctx, const mvb200_compensate_params *cp, const SuperD
             if (!dev)
                 return 1;
             MVB_CUDA_CHECK(cudaStreamSynchronize(st)); // (also past the clearing of a fresh scratch buffer)
-            MVB_CUDA_CHECK(cudaMemcpy(dev, wl.data(), bl, cudaMemcpyHostToDevice));
+            MVB_CUDA_CHECK(upload_table(ctx, dev, wl.data(), bl));
             if (bc)
-                MVB_CUDA_CHECK(cudaMemcpy(dev + offc, wc.data(), bc, cudaMemcpyHostToDevice));
+                MVB_CUDA_CHECK(upload_table(ctx, dev + offc, wc.data(), bc));
             ctx->cwin_dev[0] = (short *)dev;
             ctx->cwin_dev[1] = (short *)(dev + offc);
             memcpy(ctx->cwin_key, key, sizeof(key));

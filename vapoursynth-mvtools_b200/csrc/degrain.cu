@@ -629,9 +629,9 @@ int launch_degrain(Ctx *ctx, const mvb200_degrain_params *dp, const SuperDesc &s
             if (!dev)
                 return 1;
             MVB_CUDA_CHECK(cudaStreamSynchronize(st)); // (also past the clearing of a fresh scratch buffer)
-            MVB_CUDA_CHECK(cudaMemcpy(dev, wl.data(), bl, cudaMemcpyHostToDevice));
+            MVB_CUDA_CHECK(upload_table(ctx, dev, wl.data(), bl));
             if (bc)
-                MVB_CUDA_CHECK(cudaMemcpy(dev + offc, wc.data(), bc, cudaMemcpyHostToDevice));
+                MVB_CUDA_CHECK(upload_table(ctx, dev + offc, wc.data(), bc));
             ctx->win_dev[0] = (short *)dev;
             ctx->win_dev[1] = (short *)(dev + offc);
             memcpy(ctx->win_key, key, sizeof(key));

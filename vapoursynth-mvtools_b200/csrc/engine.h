@@ -161,6 +161,20 @@ struct Ctx {
     int staging_posted(); // after the upload out of it was enqueued on `stream`
 };
 
+// Upload of a small host-built table (overlap windows, resize tables) into device scratch, complete on return.  Through the
+// context's stream: a synchronous cudaMemcpy from pageable memory may return before its DMA has reached the device, and a
+// kernel on this NON-BLOCKING stream is not ordered behind the legacy stream's copy -- that was the rare wrong first frame of a
+// configuration with large tables (blk 128x64: 147 KB of windows).  -DMVB_SYNC_TABLE_UPLOAD rebuilds the old behaviour for
+// tools/stress_tables.py.
+inline cudaError_t upload_table(Ctx *c, void *dev, const void *host, size_t bytes) {
+#ifdef MVB_SYNC_TABLE_UPLOAD
+    return cudaMemcpy(dev, host, bytes, cudaMemcpyHostToDevice);
+#else
+    cudaError_t e = cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(c->stream);
+#endif
+}
+
 #define MVB_CUDA_CHECK(call)                                                                          \
     do {                                                                                              \
         cudaError_t e_ = (call);                                                                      \

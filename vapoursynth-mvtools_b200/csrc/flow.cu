@@ -250,7 +250,7 @@ int get_resize_tables(Ctx *c, int dw0, int dh0, int dw1, int dh1, int sw, int sh
         if (!dev)
             return 1;
         MVB_CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        MVB_CUDA_CHECK(cudaMemcpy(dev, host.data(), (n0 + n1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+        MVB_CUDA_CHECK(upload_table(c, dev, host.data(), (n0 + n1) * sizeof(int32_t)));
         c->rz_dev = dev;
         memcpy(c->rz_key, key, sizeof(key));
         c->rz_valid = true;
@@ -515,9 +515,9 @@ static int launch_blockfps(Ctx *c, const mvb200_blockfps_params *p, const SuperD
             if (!dev)
                 return 1;
             MVB_CUDA_CHECK(cudaStreamSynchronize(st));
-            MVB_CUDA_CHECK(cudaMemcpy(dev, wl.data(), bl, cudaMemcpyHostToDevice));
+            MVB_CUDA_CHECK(upload_table(c, dev, wl.data(), bl));
             if (bc)
-                MVB_CUDA_CHECK(cudaMemcpy(dev + offc, wc.data(), bc, cudaMemcpyHostToDevice));
+                MVB_CUDA_CHECK(upload_table(c, dev + offc, wc.data(), bc));
             c->bfw_dev[0] = (short *)dev;
             c->bfw_dev[1] = (short *)(dev + offc);
             memcpy(c->bfw_key, key, sizeof(key));
