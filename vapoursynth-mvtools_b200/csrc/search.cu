@@ -1134,8 +1134,17 @@ int launch_recalc(Ctx *ctx, const SuperDesc &sd, const RecalcParams &P_in, const
     if (ctx->staging_posted())
         return 1;
     const int n = P.nBlkX * P.nBlkY;
-    k_recalc<<<dim3(n, njobs), 32, 0, ctx->stream>>>((const SuperDesc *)dev, (const RecalcParams *)(dev + off_p), (const RecalcJob *)(dev + off_j));
-    ctx->launches++;
+    // the specialised kernel when the new grid is one of its compiled configurations; MVB200_FORCE_GENERIC=1 / MVB200_NO_TMA=1
+    // keep the generic one (the tests cover both)
+    bool handled = false;
+    const char *force = getenv("MVB200_FORCE_GENERIC"), *notma = getenv("MVB200_NO_TMA");
+    if (!(force && force[0] == '1') && !(notma && notma[0] == '1'))
+        if (launch_recalc_tma(ctx, sd, P, (const SuperDesc *)dev, (const RecalcParams *)(dev + off_p), (const RecalcJob *)(dev + off_j), njobs, &handled))
+            return 1;
+    if (!handled) {
+        k_recalc<<<dim3(n, njobs), 32, 0, ctx->stream>>>((const SuperDesc *)dev, (const RecalcParams *)(dev + off_p), (const RecalcJob *)(dev + off_j));
+        ctx->launches++;
+    }
     if (P.divide) {
         k_recalc_divide<<<dim3((n + 127) / 128, njobs), 128, 0, ctx->stream>>>((const RecalcParams *)(dev + off_p), (const RecalcJob *)(dev + off_j));
         ctx->launches++;

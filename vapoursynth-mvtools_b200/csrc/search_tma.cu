@@ -1333,6 +1333,171 @@ int launch_cfg(Ctx *ctx, const SuperDesc &sd, const uint8_t *frames_base, int nf
     return 0;
 }
 
+
+// ------------------------------------------------------------------ Recalculate with the chain's candidate layout
+// doPobRecalculateMVs (PlaneOfBlocks.cpp:1158-1424): a block's predictor comes from the OLD vector field, there is no neighbour
+// predictor and no bad-block path, so blocks are independent -- one warp per block, four per CTA.  What a block does is what a
+// chain's block does after its predictors: one candidate (the predictor, cost = its SAD / SATD, no penalty), then, above
+// thSAD, pobRefine around it -- so the warp runs Chain's own eval_step / refine (8 candidates x 4 lanes per step, REDUX arg-min,
+// the SATD tile layout for dct = 5) with no staged window: every candidate reads the reference frame through the global path.
+// The generic k_recalc (search.cu) evaluated one candidate at a time with one lane per 4x4 tile or row group; it stays for
+// the configurations this kernel is not compiled for (and other search types / dct modes).
+template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA, bool SATD_>
+__global__ void __launch_bounds__(128) k_recalc_tma(const SuperDesc *__restrict__ sdp, const RecalcParams *__restrict__ pp, const RecalcJob *__restrict__ jobs) {
+    using C = Cfg<BPS, BW, BH, LXR, LYR, CHROMA, SATD_>;
+    using CH = Chain<BPS, BW, BH, LXR, LYR, CHROMA, SATD_>;
+    static_assert(!C::SRC_SMEM, "the source block lives in registers here");
+    __shared__ Cold cold[4];
+    const SuperDesc &sd = *sdp;
+    const RecalcParams &P = *pp;
+    const RecalcJob job = jobs[blockIdx.y];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = P.nBlkX * P.nBlkY;
+    const int blkIdx = blockIdx.x * 4 + warp;
+    if (blkIdx >= n)
+        return;
+    int *hdr = (int *)job.out;
+    VEC *res = (VEC *)(job.out + 12);
+    const int old_valid = __ldg((const int *)job.old + 1) == 1;
+    const bool live = job.ref != nullptr && old_valid;
+    if (blkIdx == 0 && lane == 0) {
+        hdr[0] = P.vectors_size;
+        hdr[1] = live ? 1 : 0;
+        hdr[2] = 4 + n * 16;
+        if (P.divide)
+            *(int *)(job.out + 12 + n * 16) = 4 + n * 16 * 4;
+    }
+    const int by = blkIdx / P.nBlkX, bx = blkIdx - by * P.nBlkX;
+    if (!live) { // gopWriteDefaultToArray, GroupOfPlanes.c:150-164
+        VEC d;
+        d.x = 0;
+        d.y = 0;
+        d.sad = P.verybigSAD;
+        if (lane == 0)
+            stvec(&res[blkIdx], d);
+        if (P.divide && lane < 4) {
+            VEC *q = (VEC *)(job.out + 12 + n * 16 + 4);
+            stvec(&q[(by * 2 + (lane >> 1)) * (P.nBlkX * 2) + bx * 2 + (lane & 1)], d);
+        }
+        return;
+    }
+    const mvb200_level_geom &g0 = sd.lv[0][0];
+    const mvb200_level_geom &g1 = sd.lv[CHROMA ? 1 : 0][0];
+    Cold &K = cold[warp];
+    if (lane == 0) {
+#pragma unroll
+        for (int p = 0; p < 3; p++) {
+            const int qp = (CHROMA || p == 0) ? p : 0;
+            const long long off = sd.offset[qp] + (long long)sd.lv[qp][0].row0 * sd.pitch[qp];
+            K.sbase[p] = job.src + off;
+            K.rbase[p] = job.ref + off;
+        }
+        K.pitch0 = (int)sd.pitch[0];
+        K.pitch1 = (int)sd.pitch[CHROMA ? 1 : 0];
+        K.sub0 = K.pitch0 * g0.padded_h;
+        K.sub1 = K.pitch1 * g1.padded_h;
+        K.searchType = P.search;
+        K.searchParam = P.nSearchParam;
+    }
+    __syncwarp();
+    CH S;
+    S.j = lane >> 2;
+    S.q = lane & 3;
+    S.K = &K;
+    S.logPel = P.logPel;
+    S.penaltyNew = P.pnew;
+    S.badcount = 0;
+    S.srcbuf = 0;
+    S.sbuf = 0;
+    S.zbuf = 0;
+    S.wx0 = S.wy0 = S.wxc0 = S.wyc0 = 1 << 20; // no staged window: no candidate is "inside"
+    const int stepX = BW - P.ovX, stepY = BH - P.ovY;
+    S.g.x0 = g0.hpad + stepX * bx;
+    S.g.y0 = g0.vpad + stepY * by;
+    S.g.xc = g1.hpad + (stepX >> LXR) * bx;
+    S.g.yc = g1.vpad + (stepY >> LYR) * by;
+    S.g.dxMax = (g0.padded_w - S.g.x0 - BW) << P.logPel; // :1274-1277, the whole padded plane
+    S.g.dyMax = (g0.padded_h - S.g.y0 - BH) << P.logPel;
+    S.g.dxMin = -(S.g.x0 << P.logPel);
+    S.g.dyMin = -(S.g.y0 << P.logPel);
+    S.nLambda = by == 0 ? 0 : P.nLambda / ((1 << P.logPel) * (1 << P.logPel));
+    // this lane's rows (or tiles) of the source block
+    {
+        const uint8_t *sl = K.sbase[0] + (long long)S.g.y0 * K.pitch0 + S.g.x0 * BPS;
+        if constexpr (C::SATD) {
+            const int trow = (S.q * C::T) / C::TC, tcol = (S.q * C::T) % C::TC;
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int w = 0; w < C::SRW; w++)
+                    S.srcL[i][w] = CH::ldg_un(sl + (long long)(4 * trow + i) * K.pitch0 + 4 * (tcol + w));
+        } else {
+#pragma unroll
+            for (int i = 0; i < C::LR; i++)
+#pragma unroll
+                for (int w = 0; w < C::RW; w++)
+                    S.srcL[i][w] = CH::ldg_un(sl + (long long)(S.q + 4 * i) * K.pitch0 + 4 * w);
+        }
+        if (CHROMA) {
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                const uint8_t *sc = K.sbase[1 + p] + (long long)S.g.yc * K.pitch1 + S.g.xc * BPS;
+#pragma unroll
+                for (int i = 0; i < C::CR; i++)
+#pragma unroll
+                    for (int w = 0; w < C::CRW; w++)
+                        S.srcC[p][i][w] = CH::ldg_un(sc + (long long)(S.q + 4 * i) * K.pitch1 + 4 * w);
+            }
+        }
+    }
+    // predictor from the old field (:1279-1330)
+    const VEC *oldv = (const VEC *)(job.old + __ldg((const int *)job.old) - 16 * P.oBlkX * P.oBlkY);
+    const int nStepXold = P.oBlkW - P.oOvX, nStepYold = P.oBlkH - P.oOvY;
+    const int centerX = BW / 2 + stepX * bx;
+    const int blkxold = (centerX - P.oBlkW / 2) / nStepXold;
+    const int centerY = BH / 2 + stepY * by;
+    const int blkyold = (centerY - P.oBlkH / 2) / nStepYold;
+    const int deltaX = max(0, centerX - (P.oBlkW / 2 + nStepXold * blkxold));
+    const int deltaY = max(0, centerY - (P.oBlkH / 2 + nStepYold * blkyold));
+    const int bx1 = min(P.oBlkX - 1, max(0, blkxold)), bx2 = min(P.oBlkX - 1, max(0, blkxold + 1));
+    const int by1 = min(P.oBlkY - 1, max(0, blkyold)), by2 = min(P.oBlkY - 1, max(0, blkyold + 1));
+    VEC vo;
+    if (P.smooth == 1) {
+        const VEC v1 = ldvec(&oldv[bx1 + by1 * P.oBlkX]), v2 = ldvec(&oldv[bx2 + by1 * P.oBlkX]), v3 = ldvec(&oldv[bx1 + by2 * P.oBlkX]), v4 = ldvec(&oldv[bx2 + by2 * P.oBlkX]);
+        const int a_x = v1.x * nStepXold + deltaX * (v2.x - v1.x);
+        const int a_y = v1.y * nStepXold + deltaX * (v2.y - v1.y);
+        const long long a_s = v1.sad * nStepXold + deltaX * (v2.sad - v1.sad);
+        const int b_x = v3.x * nStepXold + deltaX * (v4.x - v3.x);
+        const int b_y = v3.y * nStepXold + deltaX * (v4.y - v3.y);
+        const long long b_s = v3.sad * nStepXold + deltaX * (v4.sad - v3.sad);
+        vo.x = (a_x + deltaY * (b_x - a_x) / nStepYold) / nStepXold;
+        vo.y = (a_y + deltaY * (b_y - a_y) / nStepYold) / nStepXold;
+        vo.sad = (a_s + deltaY * (b_s - a_s) / nStepYold) / nStepXold;
+    } else {
+        const bool rx = deltaX * 2 >= nStepXold, ry = deltaY * 2 >= nStepYold;
+        vo = ldvec(&oldv[(rx ? bx2 : bx1) + (ry ? by2 : by1) * P.oBlkX]);
+    }
+    vo.x = (vo.x << P.logPel) >> P.oLogPel;
+    vo.y = (vo.y << P.logPel) >> P.oLogPel;
+    S.predictor = S.clip(vo);
+    S.predictor.sad = vo.sad * (BW * BH) / (P.oBlkW * P.oBlkH);
+    S.best = S.predictor;
+    // the predictor itself: one candidate in slot 0, cost = its SAD (:1340-1346)
+    typename CH::Cand c;
+    c.lvx = c.cvx = S.predictor.x;
+    c.lvy = c.cvy = S.predictor.y;
+    c.valid = S.j == 0;
+    unsigned sy, suv;
+    S.template eval_step<1>(c, sy, suv);
+    const unsigned s0 = __shfl_sync(CH::FULL, sy, 0), s1 = __shfl_sync(CH::FULL, suv, 0);
+    S.best.sad = (long long)s0 + s1;
+    S.nMinCost = S.best.sad;
+    if (S.best.sad > P.thSAD)
+        S.refine();
+    if (lane == 0)
+        stvec(&res[blkIdx], S.best);
+}
+
 // The compiled configurations, in the order of TMA_CONFIGS below; -1 when a parameter set needs another kernel.
 // (ID, bytes per sample, block, log2 chroma subsampling, chroma, SATD luma cost: dct = 5)
 #define TMA_CONFIGS(X)                                                                                                                                                         \
@@ -1390,6 +1555,42 @@ int launch_search_tma(Ctx *ctx, const SuperDesc &sd, const mvb200_super_geom &ge
         return launch_cfg<BPS_, BW_, BH_, LX_, LY_, CH_, SATD_>(ctx, sd, frames_base, nframes, dev_sd, dev_params, dev_jobs, njobs, hist, hist_ints, geom, host_params[0].pel, need_raw, handled);
     TMA_CONFIGS(TRY)
 #undef TRY
+    return 0;
+}
+
+namespace {
+template <int BPS, int BW, int BH, int LXR, int LYR, bool CHROMA, bool SATD_>
+bool recalc_launch(Ctx *ctx, int n, int njobs, const SuperDesc *dev_sd, const RecalcParams *dev_params, const RecalcJob *dev_jobs) {
+    if constexpr (Cfg<BPS, BW, BH, LXR, LYR, CHROMA, SATD_>::SRC_SMEM) {
+        return false; // (16-bit 16x16: the chain reads its source rows from shared memory; the generic kernel takes these)
+    } else {
+        k_recalc_tma<BPS, BW, BH, LXR, LYR, CHROMA, SATD_><<<dim3((n + 3) / 4, njobs), 128, 0, ctx->stream>>>(dev_sd, dev_params, dev_jobs);
+        return true;
+    }
+}
+} // namespace
+
+// Recalculate on the chain's candidate layout (k_recalc_tma) when the new grid is one of the compiled configurations; *handled
+// stays false otherwise and launch_recalc runs the generic kernel.
+int launch_recalc_tma(Ctx *ctx, const SuperDesc &sd, const RecalcParams &P, const SuperDesc *dev_sd, const RecalcParams *dev_params, const RecalcJob *dev_jobs, int njobs, bool *handled) {
+    *handled = false;
+    auto okType = [](int t) { return t == 3 || t == 4 || t == 5; };
+    if ((P.dctmode != 0 && P.dctmode != 5) || !okType(P.search) || P.logPel > 1)
+        return 0;
+    if ((sd.lv[0][0].padded_w << P.logPel) >= 32768 || (sd.lv[0][0].padded_h << P.logPel) >= 32768)
+        return 0;
+    const int bps = P.bps, bw = P.blkW, bh = P.blkH, lx = sd.logxR, ly = sd.logyR;
+    const bool chroma = P.chroma != 0, satd = P.dctmode == 5;
+    const int n = P.nBlkX * P.nBlkY;
+#define RECALC(ID_, BPS_, BW_, BH_, LX_, LY_, CH_, SATD_)                                                                       \
+    if (!*handled && bps == BPS_ && bw == BW_ && bh == BH_ && chroma == CH_ && satd == SATD_ && (!CH_ || (lx == LX_ && ly == LY_))) \
+        *handled = recalc_launch<BPS_, BW_, BH_, LX_, LY_, CH_, SATD_>(ctx, n, njobs, dev_sd, dev_params, dev_jobs);
+    TMA_CONFIGS(RECALC)
+#undef RECALC
+    if (*handled) {
+        ctx->launches++;
+        MVB_CUDA_CHECK(cudaGetLastError());
+    }
     return 0;
 }
 
