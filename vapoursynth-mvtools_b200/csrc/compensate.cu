@@ -6,6 +6,7 @@
 // <= 4 blocks covering it.
 #include "engine.h"
 
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -35,34 +36,41 @@ struct CompPlane {
 
 __device__ __forceinline__ const VEC4 *level0(const uint8_t *blob, int nBlk) { return (const VEC4 *)(blob + __ldg((const int *)blob) - 16 * nBlk); }
 
-// fgopIsUsable (Fakery.c:52-58,144-146): one CTA
-__global__ void k_comp_scd(CompDev D, int *usable) {
-    const VEC4 *v = level0(D.vectors, D.nBlkX * D.nBlkY);
-    int valid = ((const int *)D.vectors)[1] == 1;
-    int n = D.nBlkX * D.nBlkY, cnt = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
-        cnt += v[i].sad() > D.nSCD1 ? 1 : 0;
-    __shared__ int s;
-    if (threadIdx.x == 0)
-        s = 0;
-    __syncthreads();
+// fgopIsUsable (Fakery.c:52-58,144-146), first half: the number of blocks whose SAD exceeds thscd1, counted by many CTAs
+// (grid = (chunks, frames); one CTA scanning a 4K frame's 130 000 vectors alone took 300 us, longer than the compensation
+// itself).  count[f] must be zero before the launch.
+__global__ void k_comp_count(int nBlk, long long nSCD1, const uint8_t *__restrict__ vectors, long long vstride, int *__restrict__ count) {
+    const uint8_t *blob = vectors + (long long)blockIdx.y * vstride;
+    const VEC4 *v = level0(blob, nBlk);
+    int cnt = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nBlk; i += gridDim.x * blockDim.x)
+        cnt += v[i].sad() > nSCD1 ? 1 : 0;
     cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if ((threadIdx.x & 31) == 0)
-        atomicAdd(&s, cnt);
-    __syncthreads();
-    if (threadIdx.x == 0)
-        *usable = valid && !(s > D.nSCD2) && D.haveRef;
+    if ((threadIdx.x & 31) == 0 && cnt)
+        atomicAdd(&count[blockIdx.y], cnt);
 }
 
+// ... second half, by every consumer thread: usable = valid blob && count <= thscd2 && a reference frame exists
+__device__ __forceinline__ bool comp_usable(const CompDev &D, const int *count) { return ((const int *)D.vectors)[1] == 1 && !(*count > D.nSCD2) && D.haveRef; }
+
+// A frame of a batch (blockIdx.z): which frames it reads, MVCompensate.c:80-87,188-223
+struct CompBatch {
+    const uint8_t *sup;
+    uint8_t *dst;
+    const uint8_t *vectors;
+    long long sup_frame_bytes, dst_frame_bytes, vstride;
+    int first, num_frames, delta, backward;
+};
+
 template <typename T>
-__global__ void k_compensate(CompDev D, CompPlane B, const uint8_t *__restrict__ src_super, const uint8_t *__restrict__ ref_super, uint8_t *__restrict__ dst, const int *__restrict__ usable) {
+__device__ __forceinline__ void compensate_sample(const CompDev &D, const CompPlane &B, const uint8_t *__restrict__ src_super, const uint8_t *__restrict__ ref_super, uint8_t *__restrict__ dst, const int *__restrict__ count) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= B.W || y >= B.H)
         return;
     T *drow = (T *)(dst + B.dst_off + (long long)y * B.dst_pitch);
     const long long interior = B.sup_off + (long long)(y + B.vpad) * B.sup_pitch + (long long)(x + B.hpad) * (int)sizeof(T);
-    if (!*usable) { // MVCompensate.c:348-364: whole-frame copy of the source (or reference) super frame's interior
+    if (!comp_usable(D, count)) { // MVCompensate.c:348-364: whole-frame copy of the source (or reference) super frame's interior
         const uint8_t *s = (!D.scBehavior && D.haveRef) ? ref_super : src_super;
         drow[x] = *(const T *)(s + interior);
         return;
@@ -122,9 +130,30 @@ __global__ void k_compensate(CompDev D, CompPlane B, const uint8_t *__restrict__
     drow[x] = (T)out;
 }
 
+template <typename T>
+__global__ void k_compensate(CompDev D, CompPlane B, const uint8_t *__restrict__ src_super, const uint8_t *__restrict__ ref_super, uint8_t *__restrict__ dst, const int *__restrict__ count) {
+    compensate_sample<T>(D, B, src_super, ref_super, dst, count);
+}
+
+// the frames of a batch in one launch (grid.z = frame; relative or static reference, no field shift)
+template <typename T>
+__global__ void k_compensate_batch(CompDev D, CompPlane B, CompBatch Q, const int *__restrict__ count) {
+    const int f = blockIdx.z, fn = Q.first + f;
+    int nref = Q.delta > 0 ? fn + (Q.backward ? Q.delta : -Q.delta) : -Q.delta;
+    if (nref < 0 || nref >= Q.num_frames)
+        nref = -1;
+    const uint8_t *src = Q.sup + (long long)fn * Q.sup_frame_bytes;
+    D.haveRef = nref >= 0;
+    D.vectors = Q.vectors + (long long)f * Q.vstride;
+    compensate_sample<T>(D, B, src, nref >= 0 ? Q.sup + (long long)nref * Q.sup_frame_bytes : src, Q.dst + (long long)f * Q.dst_frame_bytes, count + f);
+}
+
 } // namespace
 
-int launch_compensate(Ctx *ctx, const mvb200_compensate_params *cp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src_super, const uint8_t *dev_ref_super, const uint8_t *dev_vectors, int field_shift, uint8_t *dev_dst) {
+// dev_ref_super == nullptr and batch == nullptr: a frame without a reference.  batch != nullptr: n frames [first, first + n)
+// of the resident super clip `dev_src_super` in one launch per plane (dev_vectors / dev_dst: the first frame's).
+static int compensate_launch(Ctx *ctx, const mvb200_compensate_params *cp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src_super, const uint8_t *dev_ref_super, const uint8_t *dev_vectors, int field_shift,
+                             uint8_t *dev_dst, bool batch, int first, int n, long long vstride) {
     cudaStream_t st = ctx->stream;
     const mvb200_analysis_data &vd = cp->vd;
     CompDev D;
@@ -142,11 +171,25 @@ int launch_compensate(Ctx *ctx, const mvb200_compensate_params *cp, const SuperD
     D.nSCD1 = cp->nSCD1;
     D.nSCD2 = cp->nSCD2;
     D.vectors = dev_vectors;
-    int *usable = (int *)ctx->get_scratch(2, sizeof(int));
-    if (!usable)
+    int *count = (int *)ctx->get_scratch(2, sizeof(int) * (size_t)n);
+    if (!count)
         return 1;
-    k_comp_scd<<<1, 256, 0, st>>>(D, usable);
+    MVB_CUDA_CHECK(cudaMemsetAsync(count, 0, sizeof(int) * (size_t)n, st));
+    const int nBlk = vd.nBlkX * vd.nBlkY;
+    k_comp_count<<<dim3((unsigned)std::min(64, (nBlk + 255) / 256), (unsigned)n), 256, 0, st>>>(nBlk, cp->nSCD1, dev_vectors, vstride, count);
     ctx->launches++;
+    CompBatch Q;
+    memset(&Q, 0, sizeof(Q));
+    Q.sup = dev_src_super;
+    Q.dst = dev_dst;
+    Q.vectors = dev_vectors;
+    Q.sup_frame_bytes = sd.frame_bytes;
+    Q.dst_frame_bytes = cd.frame_bytes;
+    Q.vstride = vstride;
+    Q.first = first;
+    Q.num_frames = cp->num_frames;
+    Q.delta = vd.nDeltaFrame;
+    Q.backward = vd.isBackward;
     const bool overlap = cp->nOverlapX[0] > 0 || cp->nOverlapY[0] > 0;
     const int num_planes = (cp->super_modeyuv & (MVB200_UPLANE | MVB200_VPLANE)) ? 3 : 1;
     short *dev_win[2] = {nullptr, nullptr};
@@ -200,15 +243,31 @@ int launch_compensate(Ctx *ctx, const mvb200_compensate_params *cp, const SuperD
         B.sup_off = sd.offset[plane];
         B.sup_sub = sd.pitch[plane] * g.padded_h;
         B.win = overlap ? dev_win[plane ? 1 : 0] : nullptr;
-        dim3 blk(32, 8), grid((B.W + 31) / 32, (B.H + 7) / 8);
-        if (sd.bps == 1)
-            k_compensate<uint8_t><<<grid, blk, 0, st>>>(D, B, dev_src_super, dev_ref_super ? dev_ref_super : dev_src_super, dev_dst, usable);
-        else
-            k_compensate<uint16_t><<<grid, blk, 0, st>>>(D, B, dev_src_super, dev_ref_super ? dev_ref_super : dev_src_super, dev_dst, usable);
+        dim3 blk(32, 8), grid((B.W + 31) / 32, (B.H + 7) / 8, batch ? (unsigned)n : 1u);
+        if (batch) {
+            if (sd.bps == 1)
+                k_compensate_batch<uint8_t><<<grid, blk, 0, st>>>(D, B, Q, count);
+            else
+                k_compensate_batch<uint16_t><<<grid, blk, 0, st>>>(D, B, Q, count);
+        } else if (sd.bps == 1) {
+            k_compensate<uint8_t><<<grid, blk, 0, st>>>(D, B, dev_src_super, dev_ref_super ? dev_ref_super : dev_src_super, dev_dst, count);
+        } else {
+            k_compensate<uint16_t><<<grid, blk, 0, st>>>(D, B, dev_src_super, dev_ref_super ? dev_ref_super : dev_src_super, dev_dst, count);
+        }
         ctx->launches++;
     }
     MVB_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+int launch_compensate(Ctx *ctx, const mvb200_compensate_params *cp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src_super, const uint8_t *dev_ref_super, const uint8_t *dev_vectors, int field_shift, uint8_t *dev_dst) {
+    return compensate_launch(ctx, cp, sd, cd, dev_src_super, dev_ref_super, dev_vectors, field_shift, dev_dst, false, 0, 1, 0);
+}
+
+// Frames [first, first + n) of a resident super clip (no field handling: the caller checks cp->fields): one launch per plane
+int launch_compensate_batch(Ctx *ctx, const mvb200_compensate_params *cp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_super, int first, int n, const uint8_t *dev_vectors, long long vectors_stride,
+                            uint8_t *dev_dst) {
+    return compensate_launch(ctx, cp, sd, cd, dev_super, dev_super, dev_vectors, 0, dev_dst, true, first, n, vectors_stride);
 }
 
 } // namespace mvb200

@@ -656,6 +656,15 @@ int mvb200_compensate_batch(mvb200_ctx *ctx, const mvb200_compensate_params *cp,
     ClipDesc cd;
     make_super_desc(sp, &sd);
     make_clip_desc(sp, &cd);
+    if (!cp->fields) { // no field shifts: the frames of the batch in one launch per plane (chunks of kMaxFramesPerLaunch: grid.z)
+        for (int f0 = 0; f0 < n; f0 += kMaxFramesPerLaunch) {
+            const int m = std::min(kMaxFramesPerLaunch, n - f0);
+            if (launch_compensate_batch(c, cp, sd, cd, (const uint8_t *)dev_super, first + f0, m, (const uint8_t *)dev_vectors + (long long)f0 * vectors_stride, vectors_stride,
+                                        (uint8_t *)dev_dst + (long long)f0 * cd.frame_bytes))
+                return 1;
+        }
+        return 0;
+    }
     for (int f = 0; f < n; f++) {
         const int fn = first + f, nref = ref_frame_of_vd(cp->vd, cp->num_frames, fn);
         const uint8_t *src = (const uint8_t *)dev_super + (long long)fn * sd.frame_bytes;

@@ -112,6 +112,7 @@ bool fast_applies(const SuperDesc &sd, const SearchParams *host_params, int npar
 int launch_recalc(Ctx *ctx, const SuperDesc &sd, const RecalcParams &P, const RecalcJob *host_jobs, int njobs);
 int launch_recalc_tma(Ctx *ctx, const SuperDesc &sd, const RecalcParams &P, const SuperDesc *dev_sd, const RecalcParams *dev_params, const RecalcJob *dev_jobs, int njobs, bool *handled);
 int launch_compensate(Ctx *ctx, const mvb200_compensate_params *cp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src_super, const uint8_t *dev_ref_super, const uint8_t *dev_vectors, int field_shift, uint8_t *dev_dst);
+int launch_compensate_batch(Ctx *ctx, const mvb200_compensate_params *cp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_super, int first, int n, const uint8_t *dev_vectors, long long vectors_stride, uint8_t *dev_dst);
 int launch_degrain(Ctx *ctx, const mvb200_degrain_params *dp, const SuperDesc &sd, const ClipDesc &cd, const uint8_t *dev_src, const uint8_t *dev_super, int num_frames, int first, int n, const uint8_t *const *dev_vectors, long long vectors_stride, uint8_t *dev_dst);
 
 constexpr int kClipChunks = 4;
