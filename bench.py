@@ -228,19 +228,19 @@ def fill_host_clip(hv, frames, cl):
 
 
 def plugin_window(mb, aps, sp, kind, device):
-    """Frames per window of the plugin's fused paths in its default configuration on one device: the engine's own answer
+    """(frames per window, engine contexts) of the plugin's fused paths in its default configuration on one device: the engine's own answer
     (mvb200_window_plan_query, which plugin.cpp fusedWindowFrames calls with the same arguments) -- used to size the resident
     leg's windows and to ALIGN the timed region of the plugin leg, see plugin_leg."""
     L = mb.lib()
     cl, sl = mb.clip_layout(sp), mb.super_layout(sp)
     out_bytes = sl.frame_bytes + (aps[0].vectors_size + 255) // 256 * 256 if kind == "analyse" else cl.frame_bytes
-    per = int(os.environ.get("MVB200_CONTEXTS_PER_DEVICE", "2") or 2)
+    per = int(os.environ.get("MVB200_CONTEXTS_PER_DEVICE", "0") or 0)  # (unset: the plan chooses)
     wp = mb.WindowPlan()
     mb._check(L.mvb200_window_plan_query(C.byref(aps[0]), C.byref(sp), len(aps), -1, cl.frame_bytes, out_bytes, 1, per, 0, L.mvb200_device_memory(device), C.byref(wp)))
-    return int(wp.frames)
+    return int(wp.frames), int(wp.contexts_per_device)
 
 
-def plugin_leg(cfg, args, mb, plan, world, rank, local, barrier, total_frames, gold, window):
+def plugin_leg(cfg, args, mb, plan, world, rank, local, barrier, total_frames, gold, window, contexts=2):
     """e2e through libmvtools.so under the API-4 host, default environment.
     Weak-scaling configs: STEADY STATE -- one long clip; W warm-up steps, then K timed steps.  The plugin works in aligned
     windows and keeps the next window in flight, so a timed region that started or ended inside a window would inherit (or
@@ -277,7 +277,7 @@ def plugin_leg(cfg, args, mb, plan, world, rank, local, barrier, total_frames, g
         # per engine context, one being served, one recycled, one more); then window by window until two consecutive windows take
         # the same time within 25 % (page-locking the windows' gigabytes is a start-up cost of seconds: a small configuration
         # renders a dozen windows before the last buffer exists), at most 24 more
-        warm_min = max(args.warmup_e2e * step, (int(os.environ.get("MVB200_CONTEXTS_PER_DEVICE", "2") or 2) + 3) * window) if args.warmup_e2e else 0
+        warm_min = max(args.warmup_e2e * step, (contexts + 3) * window) if args.warmup_e2e else 0
         warm_min = -(-warm_min // window) * window
         warm_max = warm_min + (24 * window if args.warmup_e2e else 0)
         n_local = base + warm_max + args.steps * step + window + REACH
@@ -427,8 +427,8 @@ def run_gpu_arm(args, cfg):
     # kernels run beside the other's search, and the next window's search chains take the slots the moment the slow chains of the
     # previous one leave them.  W warm-up steps, K timed steps, all
     # enqueued without a host sync in between; time = first start -> last end over all streams (CUDA events), max over ranks.
-    NC = max(1, args.contexts)
-    PW = plugin_window(mb, aps, sp, kind, local)
+    PW, plan_contexts = plugin_window(mb, aps, sp, kind, local)
+    NC = max(1, args.contexts if args.contexts else plan_contexts)
     S = max(8, min(PW, F_out))
     bounds = list(range(0, F_out, S)) + [F_out]
     ctxs = [ctx] + [mb.Context(local) for _ in range(NC - 1)]
@@ -552,7 +552,7 @@ def run_gpu_arm(args, cfg):
         if world > 1:    #  between the warm-up and the timed steps -- a drained pipeline would hand the timed region finished windows)
             dist.barrier()
 
-    pl = plugin_leg(cfg, args, mb, plan, world, rank, local, host_barrier, total, gold, PW)
+    pl = plugin_leg(cfg, args, mb, plan, world, rank, local, host_barrier, total, gold, PW, plan_contexts)
     clocks_e2e = sampler2.stop() if rank == 0 else None
     e2e_s = max_over_ranks(pl["seconds"])
     e2e_frames = total if cfg.get("fixed_total") else world * pl["frames"]
@@ -651,7 +651,7 @@ def main():
     ap.add_argument("--frames", type=int, default=None, help="frames per step per GPU (default: the config's)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--contexts", type=int, default=2, help="engine contexts per GPU of the device-resident leg (the plugin's default: MVB200_CONTEXTS_PER_DEVICE)")
+    ap.add_argument("--contexts", type=int, default=0, help="engine contexts per GPU of the device-resident leg (0: what the engine's window plan says, the plugin's own choice)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.frames is None:

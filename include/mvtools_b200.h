@@ -453,11 +453,14 @@ typedef struct mvb200_search_plan {
 MVB200_API int mvb200_search_plan_query(const mvb200_analyse_params *ap, const mvb200_super_params *sp, int sm_count, mvb200_search_plan *out);
 
 /* How a caller that streams windows of frames through the *_clip_host entry points should size them (the plugin's fused paths and
- * bench.py share this): frames per window = what fills the search kernel's chain slots once with nvec vector clips per frame (at
- * most 768), or `lookahead` when > 0; engine contexts per device = contexts_per_device reduced until the windows' device buffers
- * (source / output clips double buffered, super clip, vectors) fit 45 % of device_memory; then the window shrinks until the pinned
- * host windows (one per context, one being served, one recycled; src_frame_bytes + out_frame_bytes each per frame) fit
- * pinned_budget (<= 0: an eighth of the machine's memory, between 2 and 32 GiB). */
+ * bench.py share this).  A window of nvec vector clips per frame that fills the search kernel's chain slots once has
+ * chains_per_wave / nvec frames (at most 768); two such waves in flight per device are what pays.  The windows' device buffers
+ * (source / output clips double buffered, super clip, vectors) must fit 60 % of device_memory and the pinned host windows (one per
+ * context, one being served, one recycled; src_frame_bytes + out_frame_bytes per frame) pinned_budget (<= 0: an eighth of the
+ * machine's memory, between 2 and 32 GiB).  lookahead > 0: the window length is given.  contexts_per_device > 0: the number of
+ * engine contexts per device is given (reduced only when the device cannot hold them); <= 0: chosen here, 1 to 4 -- a configuration
+ * whose window cannot be a whole wave (4K frames: the window is what the pinned budget allows) gets more, smaller windows on more
+ * contexts, since the chains in flight are contexts x window. */
 typedef struct mvb200_window_plan {
     int32_t frames;               /* frames per window */
     int32_t contexts_per_device;  /* engine contexts to create on each device */

@@ -53,7 +53,7 @@ MVB200_API int64_t mvb200_device_memory(int) { return (int64_t)180 << 30; }
 MVB200_API int mvb200_window_plan_query(const mvb200_analyse_params *, const mvb200_super_params *, int, int lookahead, int64_t, int64_t, int, int contexts_per_device, int64_t pinned_budget, int64_t,
                                         mvb200_window_plan *out) {
     out->frames = lookahead > 0 ? lookahead : 16;
-    out->contexts_per_device = contexts_per_device < 1 ? 1 : contexts_per_device;
+    out->contexts_per_device = contexts_per_device < 1 ? 2 : contexts_per_device; // (unset: two, the engine's usual answer)
     out->pinned_budget = pinned_budget;
     return 0;
 }

@@ -153,6 +153,16 @@ def test_window_plan_query(built):
     q, wp8, cl = plan(1920, 1080, 8, 16, 8, 6, budget=2 << 30, ndev=8)
     assert wp8.frames < wp.frames  # more contexts, more windows in flight
     q, wp, cl = plan(3840, 2160, 16, 16, 8, 6, budget=32 << 30, devmem=40 << 30)
-    assert wp.contexts_per_device == 1 and 16 <= wp.frames < 296  # a small device: one context, a shorter window
+    assert wp.contexts_per_device == 2 and 16 <= wp.frames < 100  # a small device: the contexts that were asked for, shorter windows
+    q, wp, cl = plan(3840, 2160, 16, 16, 8, 6, budget=32 << 30, devmem=4 << 30)
+    assert wp.contexts_per_device == 1 and wp.frames == 16  # ... that cannot even hold two minimal windows: one context
+    # the number of contexts left to the plan (0): two waves of chains in flight per device are the target
+    q, wp, cl = plan(1920, 1080, 8, 16, 8, 6, contexts=0, budget=32 << 30)
+    assert (wp.frames, wp.contexts_per_device) == (296, 2)  # whole waves: two contexts
+    q, wp4, cl = plan(3840, 2160, 8, 8, 0, 1, contexts=0, budget=24 << 30)
+    q, wp1, cl = plan(3840, 2160, 8, 8, 0, 1, contexts=1, budget=24 << 30)
+    # 4K, one vector clip per frame: a window is what the pinned budget allows, far from a wave -- more, smaller windows
+    assert wp4.contexts_per_device == 4 and wp4.frames < wp1.frames and 4 * wp4.frames > 1.8 * wp1.frames
+    assert (4 + 2) * wp4.frames * 2 * cl.frame_bytes <= 24 << 30
     q, wp, cl = plan(1920, 1080, 8, 16, 8, 6)
     assert wp.pinned_budget >= 2 << 30 and wp.pinned_budget <= 32 << 30

@@ -299,6 +299,8 @@ int mvb200_window_plan_query(const mvb200_analyse_params *ap, const mvb200_super
         return 1;
     if (nvec < 1)
         nvec = 1;
+    if (ndevices < 1)
+        ndevices = 1;
     if (pinned_budget <= 0) {
         const int64_t phys = (int64_t)sysconf(_SC_PHYS_PAGES) * (int64_t)sysconf(_SC_PAGE_SIZE);
         const int64_t lo = (int64_t)2 << 30, hi = (int64_t)32 << 30;
@@ -306,29 +308,63 @@ int mvb200_window_plan_query(const mvb200_analyse_params *ap, const mvb200_super
     }
     if (device_memory <= 0)
         device_memory = (int64_t)180 << 30;
-    int frames = (plan.chains_per_wave + nvec - 1) / nvec;
-    if (frames > 768) // (a single vector clip per frame would ask for 1776 frames: bound the latency of a window)
-        frames = 768;
-    if (lookahead > 0)
-        frames = lookahead;
+    const int64_t wave = plan.chains_per_wave > 0 ? plan.chains_per_wave : 1;
+    int frames0 = (int)((wave + nvec - 1) / nvec); // one window fills the chain slots once
+    if (frames0 > 768) // (a single vector clip per frame would ask for 1776 frames: bound the latency of a window)
+        frames0 = 768;
     mvb200_frame_layout sl;
     mvb200_super_layout(sp, &sl);
-    const int64_t chains = plan.chains_per_wave;
-    auto device_bytes = [&](int fr) { return (int64_t)fr * (4 * src_frame_bytes + sl.frame_bytes + (int64_t)nvec * (ap->vectors_size + 256)) * 5 / 4 + chains * 65536; };
-    int per = contexts_per_device < 1 ? 1 : contexts_per_device;
-    while (per > 1 && per * device_bytes(frames) > device_memory * 45 / 100)
-        per--;
-    if (lookahead <= 0) {
-        while (frames > 16 && per * device_bytes(frames) > device_memory * 45 / 100)
-            frames = frames * 3 / 4;
-        const int nslots = (ndevices < 1 ? 1 : ndevices) * per;
-        const int64_t per_frame = src_frame_bytes + (out_frame_bytes > 0 ? out_frame_bytes : src_frame_bytes);
-        const int64_t cap = pinned_budget / ((nslots + 2) * (per_frame > 0 ? per_frame : 1));
-        if (frames > cap)
-            frames = (int)cap;
-        if (frames < 16)
-            frames = 16;
+    if (out_frame_bytes <= 0)
+        out_frame_bytes = src_frame_bytes;
+    // device bytes of one context working on windows of fr frames: source / output clips double buffered, the super clip (twice
+    // when the output frames are super frames), the vectors, a quarter of growth slack, the searches' histograms
+    const int64_t per_frame_dev = (2 * src_frame_bytes + 2 * out_frame_bytes + sl.frame_bytes + (int64_t)nvec * (ap->vectors_size + 256)) * 5 / 4;
+    const int64_t fixed_dev = wave * 65536;
+    const int64_t per_frame_pinned = src_frame_bytes + out_frame_bytes > 0 ? src_frame_bytes + out_frame_bytes : 1;
+    const int64_t dev_limit = device_memory * 3 / 5;
+    // frames per window when `per` contexts per device work side by side: within the device limit and the pinned budget (one
+    // window per context, one being served, one recycled)
+    auto frames_for = [&](int per, int want) -> int {
+        int64_t fr = want;
+        const int64_t by_dev = (dev_limit / per - fixed_dev) / (per_frame_dev > 0 ? per_frame_dev : 1);
+        const int64_t by_pin = pinned_budget / (((int64_t)ndevices * per + 2) * per_frame_pinned);
+        fr = fr < by_dev ? fr : by_dev;
+        fr = fr < by_pin ? fr : by_pin;
+        return (int)(fr < 0 ? 0 : fr);
+    };
+    int per, frames;
+    if (lookahead > 0) { // the window is given: only the number of contexts is adapted to the device
+        per = contexts_per_device > 0 ? contexts_per_device : 2;
+        frames = lookahead;
+        while (per > 1 && per * ((int64_t)frames * per_frame_dev + fixed_dev) > dev_limit)
+            per--;
+    } else if (contexts_per_device > 0) { // the number of contexts is given (reduced only if the device cannot hold them)
+        per = contexts_per_device;
+        while (per > 1 && frames_for(per, frames0) < 16)
+            per--;
+        frames = frames_for(per, frames0);
+    } else {
+        // automatic: two waves of chains in flight per device are what pays (the second hides the first one's tail and the other
+        // stages); a configuration whose window cannot be a whole wave (4K: a window is the pinned budget) gets
+        // more, smaller windows on more contexts -- in flight = contexts x window, under the same budgets.  At most 4.
+        per = 1;
+        frames = frames_for(1, frames0);
+        int64_t best = -1;
+        for (int c = 1; c <= 4; c++) {
+            const int fr = frames_for(c, frames0);
+            if (fr < 16 && c > 1)
+                break;
+            int64_t score = (int64_t)c * fr * nvec;
+            score = score < 2 * wave ? score : 2 * wave;
+            if (score > best + best / 16) { // (a further context must buy more than 6 % more chains in flight)
+                best = score;
+                per = c;
+                frames = fr;
+            }
+        }
     }
+    if (frames < 16)
+        frames = 16;
     out->frames = frames;
     out->contexts_per_device = per;
     out->pinned_budget = pinned_budget;

@@ -61,7 +61,8 @@ EngineSlot g_engines[kMaxDevices * 8];
 std::once_flag g_devices_once;
 int g_ndev = 1;      // engine slots in all
 int g_ndevices = 1;  // distinct positions of the device list (slots are laid out context-major: [context][device])
-int g_perdev = 1;    // contexts per device
+int g_perdev = 1;    // contexts per device the slots are laid out for (8 unless the device list repeats devices)
+int g_perdev_asked = 0; // MVB200_CONTEXTS_PER_DEVICE (0: unset -- the window plan chooses, mvb200_window_plan_query)
 
 void listDevices() {
     int n = 0;
@@ -84,18 +85,19 @@ void listDevices() {
     if (n == 0)
         g_engines[n++].device = 0; // (no usable device: creating the context reports why)
     g_ndevices = n;
-    int per = 2;
-    if (const char *c = getenv("MVB200_CONTEXTS_PER_DEVICE"))
-        per = atoi(c);
+    int per = 8; // slots for up to 8 contexts per device; a filter uses as many as its window plan says
+    if (const char *c = getenv("MVB200_CONTEXTS_PER_DEVICE")) {
+        g_perdev_asked = atoi(c) < 1 ? 1 : (atoi(c) > 8 ? 8 : atoi(c));
+        per = g_perdev_asked;
+    }
     if (getenv("MVB200_DEVICES")) { // an explicit list says how many contexts each device gets
         bool repeated = false;
         for (int i = 0; i < n; i++)
             for (int j = 0; j < i; j++)
                 repeated = repeated || g_engines[i].device == g_engines[j].device;
         if (repeated)
-            per = 1;
+            per = g_perdev_asked = 1;
     }
-    per = per < 1 ? 1 : (per > 8 ? 8 : per);
     for (int c = 1; c < per; c++)
         for (int d = 0; d < n; d++)
             g_engines[c * n + d].device = g_engines[d].device;
@@ -359,7 +361,7 @@ int fusedWindowFrames(FusedCache *f, int la, const mvb200_analyse_params *ap, co
     deviceCount();
     const char *mb = getenv("MVB200_PINNED_MB");
     mvb200_window_plan plan;
-    if (mvb200_window_plan_query(ap, sp, nvec, la, f->cl.frame_bytes, f->outFrameBytes ? (int64_t)(f->outFrameBytes + f->outExtra) : f->cl.frame_bytes, g_ndevices, g_perdev,
+    if (mvb200_window_plan_query(ap, sp, nvec, la, f->cl.frame_bytes, f->outFrameBytes ? (int64_t)(f->outFrameBytes + f->outExtra) : f->cl.frame_bytes, g_ndevices, g_perdev_asked,
                                  mb && atoll(mb) > 0 ? atoll(mb) << 20 : 0, mvb200_device_memory(g_engines[0].device), &plan)) {
         f->nslots = f->depth = 1;
         return la > 0 ? la : 64;
