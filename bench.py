@@ -262,8 +262,9 @@ def plugin_leg(cfg, args, mb, plan, world, rank, local, barrier, total_frames, g
 
     if cfg.get("fixed_total"):
         tail = plan["local_frames"] - OFF - F_out
-        warm = script(OFF + min(F_out, 2 * window) + tail, lo)
-        warm[1].render(OFF, OFF + min(F_out, 2 * window), threads)
+        nwarm = min(F_out, (contexts + 3) * window)  # (every context's scratch and the pinned windows in circulation: both are per process)
+        warm = script(OFF + nwarm + tail, lo)
+        warm[1].render(OFF, OFF + nwarm, threads)
         del warm
         core, out, keep = script(plan["local_frames"], lo)
         barrier()
@@ -463,8 +464,8 @@ def run_gpu_arm(args, cfg):
         lo_i, hi_i = max(0, OFF + a0 - REACH), min(F, OFF + a1 + REACH)
         windows.append(dict(slot=j % NC, Fi=hi_i - lo_i, off=OFF + a0 - lo_i, cnt=a1 - a0, src=dsrc.data_ptr() + lo_i * cl.frame_bytes, dst=a0))
 
-    def run_window(wd):
-        c_i, B = ctxs[wd["slot"]], bufs[wd["slot"]]
+    def run_window(wd, slot):
+        c_i, B = ctxs[slot], bufs[slot]
         aps_i, apa_i, extra = window_params(wd["Fi"])
         outs_i = (C.c_void_p * len(aps_i))(*[t.data_ptr() for t in B["vec"]])
         mb._check(L.mvb200_super_batch(c_i.handle, C.byref(sp), wd["src"], B["sup"].data_ptr(), wd["Fi"]))
@@ -479,16 +480,19 @@ def run_gpu_arm(args, cfg):
 
     parts = [dict(ctx=c_i, stream=st_i) for c_i, st_i in zip(ctxs, streams)]
 
+    turn = [0]  # windows go round the contexts ACROSS steps (a step of two windows would keep to two contexts otherwise)
+
     def run_step():
         for wd in windows:
-            run_window(wd)
+            run_window(wd, turn[0] % NC)
+            turn[0] += 1
 
     def barrier_all():
         for P in parts:
             P["ctx"].synchronize()
         barrier()
 
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, -(-NC // len(windows)))):  # (every context runs at least one window before the timed region)
         run_step()
     barrier_all()
     sampler = ClockSampler(local)
