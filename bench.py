@@ -281,7 +281,10 @@ def plugin_leg(cfg, args, mb, plan, world, rank, local, barrier, total_frames, g
         warm_min = max(args.warmup_e2e * step, (contexts + 3) * window) if args.warmup_e2e else 0
         warm_min = -(-warm_min // window) * window
         warm_max = warm_min + (24 * window if args.warmup_e2e else 0)
-        n_local = base + warm_max + args.steps * step + window + REACH
+        # timed: the K steps, and at least four times the windows the plugin keeps in flight (they straddle both ends of the
+        # region: a region of four windows with four in flight measured 596 - 803 frames/s on the same box, run to run)
+        timed = max(args.steps * step, 4 * contexts * window)
+        n_local = base + warm_max + timed + window + REACH
         core, out, keep = script(n_local, lo)
         pos, prev = base, None
         if warm_min > window:
@@ -295,11 +298,11 @@ def plugin_leg(cfg, args, mb, plan, world, rank, local, barrier, total_frames, g
             prev = tw
         warm = pos - base
         barrier()
-        t = out.render(pos, pos + args.steps * step, threads)
+        t = out.render(pos, pos + timed, threads)
         barrier()
-        frames_timed, first_timed = args.steps * step, pos
-        protocol = "steady state: %d warm-up frames (%d windows, until two consecutive windows took the same time), then %d timed steps of %d frames (whole look-ahead windows of %d) on one long clip" % (
-            warm, warm // window, args.steps, step, window)
+        frames_timed, first_timed = timed, pos
+        protocol = "steady state: %d warm-up frames (%d windows, until two consecutive windows took the same time), then %d timed frames (%d steps of %d frames, at least 4 x %d contexts x windows of %d) on one long clip" % (
+            warm, warm // window, timed, args.steps, step, contexts, window)
     # ---- output check (untimed): sampled frames against reference-derived digests
     checked, bad = 0, []
     if gold is not None:
