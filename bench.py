@@ -434,6 +434,7 @@ def run_gpu_arm(args, cfg):
     PW, plan_contexts = plugin_window(mb, aps, sp, kind, local)
     NC = max(1, args.contexts if args.contexts else plan_contexts)
     S = max(8, min(PW, F_out))
+    window_frames = S
     bounds = list(range(0, F_out, S)) + [F_out]
     ctxs = [ctx] + [mb.Context(local) for _ in range(NC - 1)]
     streams = [torch.cuda.ExternalStream(c.stream(), device=torch.device("cuda", local)) for c in ctxs]
@@ -609,8 +610,8 @@ def run_gpu_arm(args, cfg):
                    "search_kernel": {0: "k_search (generic)", 1: "k_search_fast (register-blocked)", 2: "k_search_tma (TMA-staged windows)"}[plan_q.kernel],
                    "search_chain_slots_per_gpu": plan_q.chains_per_wave,
                    "l2": "inputs larger than L2 (%d MB of super frames + vectors per step vs 126 MB L2), no flush" % int((F * sl.frame_bytes + len(aps) * F_out * vs) / 1e6),
-                   "contexts_per_gpu": NC, "window_frames": S, "value_one_context": value_one_context,
-                   "stage_ms": stage_ms, "stage_ms_note": "one context, the whole step in one launch per stage, serialised on one stream (pass 1); `value` streams windows of %d frames through %d contexts" % (S, NC)},
+                   "contexts_per_gpu": NC, "window_frames": window_frames, "value_one_context": value_one_context,
+                   "stage_ms": stage_ms, "stage_ms_note": "one context, the whole step in one launch per stage, serialised on one stream (pass 1); `value` streams windows of %d frames through %d contexts" % (window_frames, NC)},
         "e2e": {"value": e2e_value, "unit": "frames/s", "through": "libmvtools.so (VapourSynthPluginInit2) under host/minivs, default environment, %d host threads per rank" % pl["threads"],
                 "timer": "wall clock around the host's render of K steps (the plugin owns its CUDA context), max over ranks",
                 "protocol": pl["protocol"],
