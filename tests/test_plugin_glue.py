@@ -354,6 +354,50 @@ print(json.dumps({"contexts": L.mvb200_mock_contexts(), "calls": L.mvb200_mock_c
     assert got["calls"] >= 4
 
 
+def test_fused_windows_on_four_contexts_of_one_device(mock_plugin):
+    """The window plan may ask for up to four engine contexts on one device (4K clips: more, smaller windows): four windows are
+    enqueued ahead, eight host threads pull frames, windows are evicted while requests hold them -- every frame is still the
+    golden's, for a fused DegrainN and for a vector clip read directly.  (A child process: the device list is read once.)"""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes, json, os, sys
+sys.path[:0] = [%r, %r, %r]
+import numpy as np
+import minivs, pipeline
+case = "blk16_ov8_pel2_p8_r3"
+ck, skw, akw, radius, dkw = pipeline.CASES[case]
+frames = pipeline.make_frames(ck)
+sp, aps, dp = pipeline.params_for(case)
+core = minivs.Core()
+mv = core.load(%r)
+clip = core.source(frames, bits=8)
+sup = mv.Super(clip, **skw)
+vn = [mv.Analyse(sup, isb=isb, delta=d, **akw) for d in range(1, radius + 1) for isb in (1, 0)]
+dn = mv.invoke("Degrain%%d" %% radius, clip, sup, *vn, **dkw)
+for node in [dn] + vn:
+    node.set_cache(0)
+for rounds in range(3):
+    dn.render(0, len(frames), 8)
+    vn[0].render(0, len(frames), 8)
+L = ctypes.CDLL(%r)
+L.mvb200_mock_contexts.restype = ctypes.c_long
+print(json.dumps({"contexts": L.mvb200_mock_contexts(),
+                  "frames": [[pipeline.sha(p) for p in dn.get_frame(n).planes()] for n in range(len(frames))],
+                  "vectors": [pipeline.sha(pipeline.mask_blob(np.frombuffer(vn[0].get_frame(n).prop_data("MVTools_vectors"), dtype=np.uint8), aps[0])) for n in range(len(frames))]}))
+''' % (os.path.join(ROOT, "vapoursynth-mvtools_b200"), os.path.join(ROOT, "host", "minivs"), HERE, mock_plugin, mock_plugin)
+    env = dict(os.environ, MVB200_LOOKAHEAD="2", MVB200_CONTEXTS_PER_DEVICE="4")
+    for k in ("MVB200_DEVICE", "MVB200_DEVICES", "MVB200_MOCK_DEVICES"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = json.loads(r.stdout.strip().splitlines()[-1])
+    case = "blk16_ov8_pel2_p8_r3"
+    assert got["frames"] == GOLD[case]["degrain"]
+    assert got["vectors"] == [v[0] for v in GOLD[case]["vectors"]]
+    assert got["contexts"] == 4, "the windows did not go round four contexts"
+
+
 @pytest.mark.parametrize("window", ["3", None])
 def test_recalculate_passes_inside_the_fused_chains(mock_plugin, have_ref, monkeypatch, window):
     """The refinemotion shape -- Analyse -> Recalculate (-> Recalculate) -> DegrainN / Compensate -- is still one engine call per
