@@ -127,7 +127,10 @@ MVB200_API void mvb200_super_layout(const mvb200_super_params *p, mvb200_frame_l
 // num_frames = the segment length, as in the engine.
 MVB200_API int mvb200_degrain_recalc_clip_host_async(mvb200_ctx *, const mvb200_super_params *sp, const mvb200_analyse_params *const *ap, int nap, const mvb200_recalculate_params *const *rp, int nrp,
                                                      const mvb200_degrain_params *dp, const void *host_src, void *host_dst, int n, int first, int count) {
-    g_clip_calls++;
+    const long call = ++g_clip_calls;
+    if (const char *fail = getenv("MVB200_MOCK_FAIL_CLIP_CALL")) // (the glue's error path: the k-th window's engine call fails)
+        if (atol(fail) == call)
+            return mvb200::set_error("mock: injected failure of clip call %ld", call);
     mvb200_frame_layout cl;
     mvb200_clip_layout(sp, &cl);
     mvb200_super_geom g;

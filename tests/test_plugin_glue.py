@@ -354,6 +354,46 @@ print(json.dumps({"contexts": L.mvb200_mock_contexts(), "calls": L.mvb200_mock_c
     assert got["calls"] >= 4
 
 
+def test_a_failed_window_reports_its_error_and_nothing_else_breaks(mock_plugin, monkeypatch):
+    """The engine call of ONE window fails (the stand-in injects it): every frame of that window raises the engine's message through
+    the frame server -- no hang, no crash, no frame from a half-written buffer --, the other windows' frames are the golden's, and
+    a later request for the failed window's frames fails again rather than serving stale data."""
+    import minivs
+    monkeypatch.setenv("MVB200_LOOKAHEAD", "3")
+    monkeypatch.setenv("MVB200_MOCK_FAIL_CLIP_CALL", str(ctypes_calls(mock_plugin) + 2))  # the second window of this script
+    case = "blk16_ov8_pel2_p8_r3"
+    ck, skw, akw, radius, dkw = pipeline.CASES[case]
+    frames = pipeline.make_frames(ck)
+    N = len(frames)
+    core = minivs.Core()
+    mv = core.load(mock_plugin)
+    clip = core.source(frames, bits=8)
+    sup = mv.Super(clip, **skw)
+    vn = [mv.Analyse(sup, isb=isb, delta=d, **akw) for d in range(1, radius + 1) for isb in (1, 0)]
+    dn = mv.invoke("Degrain%d" % radius, clip, sup, *vn, **dkw)
+    dn.set_cache(0)
+    failed, good = [], []
+    for n in range(N):
+        try:
+            fr = dn.get_frame(n)
+        except minivs.Error as e:
+            assert "injected failure" in str(e) and str(e).startswith("Degrain%d: " % radius), str(e)
+            failed.append(n)
+            continue
+        assert [pipeline.sha(p) for p in fr.planes()] == GOLD[case]["degrain"][n], "frame %d" % n
+        good.append(n)
+    assert failed == [3, 4, 5], (failed, good)  # exactly the second window of three frames
+    with pytest.raises(minivs.Error):
+        dn.get_frame(4)
+
+
+def ctypes_calls(so):
+    import ctypes
+    f = ctypes.CDLL(so).mvb200_mock_clip_calls
+    f.restype = ctypes.c_long
+    return f()
+
+
 def test_fused_windows_on_four_contexts_of_one_device(mock_plugin):
     """The window plan may ask for up to four engine contexts on one device (4K clips: more, smaller windows): four windows are
     enqueued ahead, eight host threads pull frames, windows are evicted while requests hold them -- every frame is still the

@@ -1271,7 +1271,8 @@ const VSFrame *VS_CC degrainFusedGetFrame(int n, int activationReason, void *ins
         // (asynchronous: fusedGetFrame records the completion event)
         return mvb200_degrain_recalc_clip_host_async(ctx, &d->sp, app, R2, rpp, kMaxRecalc, &d->dp, hostSrc, hostDst, seg, w0 - s0, w1 - w0);
     };
-    return fusedGetFrame("Degrain", f, d->node, d->vi, n, n, mask, activationReason, frameData, frameCtx, core, vsapi, segment, run);
+    static const char *const names[] = {"Degrain", "Degrain1", "Degrain2", "Degrain3", "Degrain4", "Degrain5", "Degrain6"}; // (the filter's own name in messages, as at create time)
+    return fusedGetFrame(names[d->radius >= 1 && d->radius <= 6 ? d->radius : 0], f, d->node, d->vi, n, n, mask, activationReason, frameData, frameCtx, core, vsapi, segment, run);
 }
 
 const VSFrame *VS_CC degrainGetFrame(int n, int activationReason, void *instanceData, void **, VSFrameContext *frameCtx, VSCore *core, const VSAPI *vsapi) {
