@@ -62,6 +62,13 @@ LATE = {
     "satd_dct5_blk8_hex": (dict(width=192, height=128, nframes=5, bits=8), dict(pel=2), dict(blksize=8, overlap=4, dct=5), 1, {}),
     "satd_dct5_blk16_umh_noise": (dict(width=256, height=160, nframes=5, bits=8, noise_sigma=8.0, scene_cut=True), dict(pel=2), dict(blksize=16, overlap=8, dct=5, search=5, searchparam=4, badsad=400), 2, {}),
     "satd_dct5_blk8_pel1_esa": (dict(width=160, height=96, nframes=4, bits=8), dict(pel=1, hpad=8, vpad=8), dict(blksize=8, dct=5, search=3, searchparam=2), 1, {}),
+    # mv.Recalculate onto the grids k_recalc_tma is compiled for but no GPU run has pinned yet (8-bit 16x16 SAD / SATD, 16-bit 8x8,
+    # luma-only 16x16 / 8x8): low thsad so that most blocks refine (EXTRA below; test_zz_gpu_pending.py runs them on the specialised kernel)
+    "rc16_from32_p8": (dict(width=256, height=160, nframes=4, bits=8, noise_sigma=4.0), dict(pel=2), dict(blksize=32, overlap=16), 1, {}),
+    "rc16_satd_from32_p8": (dict(width=232, height=160, nframes=4, bits=8, noise_sigma=6.0, scene_cut=True), dict(pel=2), dict(blksize=32, overlap=16, dct=5), 1, {}),
+    "rc8_from16_p16": (dict(width=200, height=128, nframes=4, bits=16, noise_sigma=4.0), dict(pel=2), dict(blksize=16, overlap=8), 1, {}),
+    "rc16_gray_from32_p8": (dict(width=256, height=160, nframes=4, bits=8, gray=True, noise_sigma=4.0), dict(pel=1), dict(blksize=32, overlap=16), 1, {}),
+    "rc8_gray_from16_p8": (dict(width=200, height=128, nframes=4, bits=8, gray=True), dict(pel=2), dict(blksize=16, overlap=8), 1, {}),
     # Degrain4..6 (the cases above stop at radius 3)
     "r6_blk8_ov4_p8": (dict(width=136, height=96, nframes=14, bits=8), dict(pel=2, hpad=8, vpad=8), dict(blksize=8, overlap=4), 6, dict(thsad=500, thsadc=300, limit=30, limitc=40)),
     "r5_blk16_p16_422": (dict(width=144, height=96, nframes=9, bits=16, ssw=1, ssh=0, scene_cut=True), dict(pel=1, hpad=8, vpad=8), dict(blksize=16, overlap=8), 5, dict(plane=4)),
@@ -96,7 +103,15 @@ EXTRA = {
     "blk16x8_ov8x4_p10": dict(recalc=dict(blksize=8, blksizev=4, overlap=4, overlapv=2, thsad=60), comp=dict(thsad=5000)),
     "blk128x64_gray_p8": dict(recalc=dict(blksize=64, blksizev=32, overlap=32, overlapv=16, thsad=200, chroma=0), comp=dict()),
     "p8_440_blk8_ov4_r2": dict(recalc=dict(blksize=8, overlap=4, thsad=80), comp=dict(time=60.0)),
+    # (k_recalc_tma configurations not pinned on the GPU yet)
+    "rc16_from32_p8": dict(recalc=dict(blksize=16, overlap=8, thsad=60, search=4, searchparam=2), comp=dict()),
+    "rc16_satd_from32_p8": dict(recalc=dict(blksize=16, overlap=4, dct=5, thsad=80, search=5, searchparam=4, smooth=0), comp=dict(time=30.0)),
+    "rc8_from16_p16": dict(recalc=dict(blksize=8, overlap=4, thsad=60, search=3, searchparam=2), comp=dict()),
+    "rc16_gray_from32_p8": dict(recalc=dict(blksize=16, overlap=8, thsad=60, chroma=0), comp=dict()),
+    "rc8_gray_from16_p8": dict(recalc=dict(blksize=8, overlap=2, thsad=40, chroma=0, search=5, searchparam=2), comp=dict()),
 }
+# the EXTRA cases whose Recalculate grid k_recalc_tma is compiled for but runs on the generic kernel by default (MVB200_RECALC_TMA_ALL)
+RECALC_TMA_UNPINNED = ["rc16_from32_p8", "rc16_satd_from32_p8", "rc8_from16_p16", "rc16_gray_from32_p8", "rc8_gray_from16_p8"]
 
 
 def _fix(kw):

@@ -70,3 +70,16 @@ def test_cuda_flow_group_matches_reference_goldens_late_cases(gpu_ctx, case):
     got["bfps"] = pipeline_flow.run_engine_bfps(case, ctx.blockfps_frame, ctx.blend_frame)
     for stage in ("scd", "mask", "flow", "finest", "inter", "fps", "blur", "bfps"):
         assert got[stage] == GOLD[case][stage], "%s: CUDA %s differs from the reference's golden hashes" % (case, stage)
+
+
+@pytest.mark.xfail(reason="k_recalc_tma on configurations no GPU run has pinned yet (MVB200_RECALC_TMA_ALL=1): the round's GPU budget ended before this test could run; "
+                          "XPASS = the configuration can join the default set in csrc/search_tma.cu launch_recalc_tma", strict=False)
+@pytest.mark.parametrize("case", pipeline.RECALC_TMA_UNPINNED)
+def test_recalculate_on_the_specialised_kernel_unpinned_configurations(gpu_ctx, monkeypatch, case):
+    """mv.Recalculate of the 8-bit 16x16 (SAD / SATD), 16-bit 8x8 and luma-only grids through k_recalc_tma instead of the generic kernel
+    (which test_cuda_matches_reference_goldens_late_cases runs on the same cases by default): identical blobs and compensated frames."""
+    monkeypatch.setenv("MVB200_RECALC_TMA_ALL", "1")
+    ctx = gpu_ctx
+    got = pipeline.run_engine(case, ctx.super_frame, ctx.analyse_frame, ctx.degrain_frame, ctx.recalculate_frame, ctx.compensate_frame)
+    for stage in ("recalc", "compensate"):
+        assert got[stage] == GOLD_MAIN[case][stage], "%s: CUDA %s differs from the reference" % (case, stage)

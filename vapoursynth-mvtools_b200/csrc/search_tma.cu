@@ -1582,8 +1582,14 @@ int launch_recalc_tma(Ctx *ctx, const SuperDesc &sd, const RecalcParams &P, cons
     const int bps = P.bps, bw = P.blkW, bh = P.blkH, lx = sd.logxR, ly = sd.logyR;
     const bool chroma = P.chroma != 0, satd = P.dctmode == 5;
     const int n = P.nBlkX * P.nBlkY;
-#define RECALC(ID_, BPS_, BW_, BH_, LX_, LY_, CH_, SATD_)                                                                       \
-    if (!*handled && bps == BPS_ && bw == BW_ && bh == BH_ && chroma == CH_ && satd == SATD_ && (!CH_ || (lx == LX_ && ly == LY_))) \
+    // Parity first: the configurations whose Recalculate output has been compared with the reference ON THE GPU (goldens
+    // c1_640x360_p8_blk8_pel1, blk16_ov8_pel2_p8_r3, divide2_blk16_esa_neg_badrange: 8-bit 8x8 4:2:0; noise_badblocks_blk8 and the
+    // 4K digests of bench.py --config c4: the same with SATD) run here by default; the other compiled configurations (16x16, 16-bit
+    // 8x8, gray) share every line of code but no GPU run has pinned them yet: MVB200_RECALC_TMA_ALL=1 enables them.
+    const char *all = getenv("MVB200_RECALC_TMA_ALL");
+    const bool every = all && all[0] == '1';
+#define RECALC(ID_, BPS_, BW_, BH_, LX_, LY_, CH_, SATD_)                                                                                                       \
+    if (!*handled && (every || ID_ == 2 || ID_ == 7) && bps == BPS_ && bw == BW_ && bh == BH_ && chroma == CH_ && satd == SATD_ && (!CH_ || (lx == LX_ && ly == LY_))) \
         *handled = recalc_launch<BPS_, BW_, BH_, LX_, LY_, CH_, SATD_>(ctx, n, njobs, dev_sd, dev_params, dev_jobs);
     TMA_CONFIGS(RECALC)
 #undef RECALC
