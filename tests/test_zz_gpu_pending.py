@@ -75,11 +75,23 @@ def test_cuda_flow_group_matches_reference_goldens_late_cases(gpu_ctx, case):
 @pytest.mark.xfail(reason="k_recalc_tma on configurations no GPU run has pinned yet (MVB200_RECALC_TMA_ALL=1): the round's GPU budget ended before this test could run; "
                           "XPASS = the configuration can join the default set in csrc/search_tma.cu launch_recalc_tma", strict=False)
 @pytest.mark.parametrize("case", pipeline.RECALC_TMA_UNPINNED)
-def test_recalculate_on_the_specialised_kernel_unpinned_configurations(gpu_ctx, monkeypatch, case):
+def test_recalculate_on_the_specialised_kernel_unpinned_configurations(case):
     """mv.Recalculate of the 8-bit 16x16 (SAD / SATD), 16-bit 8x8 and luma-only grids through k_recalc_tma instead of the generic kernel
-    (which test_cuda_matches_reference_goldens_late_cases runs on the same cases by default): identical blobs and compensated frames."""
-    monkeypatch.setenv("MVB200_RECALC_TMA_ALL", "1")
-    ctx = gpu_ctx
-    got = pipeline.run_engine(case, ctx.super_frame, ctx.analyse_frame, ctx.degrain_frame, ctx.recalculate_frame, ctx.compensate_frame)
-    for stage in ("recalc", "compensate"):
-        assert got[stage] == GOLD_MAIN[case][stage], "%s: CUDA %s differs from the reference" % (case, stage)
+    (which test_cuda_matches_reference_goldens_late_cases runs on the same cases by default): identical blobs and compensated frames.
+    In a child process: a kernel that has never run must not be able to take this session's CUDA context with it."""
+    import subprocess
+    import sys
+    code = r'''
+import json, os, sys
+sys.path[:0] = [%r, %r, %r]
+import mvtools_b200 as mb, pipeline
+case = %r
+gold = json.load(open(%r))
+ctx = mb.Context(0)
+got = pipeline.run_engine(case, ctx.super_frame, ctx.analyse_frame, ctx.degrain_frame, ctx.recalculate_frame, ctx.compensate_frame)
+bad = [st for st in ("recalc", "compensate") if got[st] != gold[case][st]]
+print("BAD", bad)
+sys.exit(1 if bad else 0)
+''' % (os.path.join(os.path.dirname(HERE), "vapoursynth-mvtools_b200"), os.path.join(os.path.dirname(HERE), "oracle"), HERE, case, os.path.join(HERE, "golden", "golden.json"))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, MVB200_RECALC_TMA_ALL="1"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-1500:]
