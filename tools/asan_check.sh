@@ -16,4 +16,7 @@ LD_PRELOAD=$ASAN ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/test_flow_em
 ROOT=$PWD; PKG=$ROOT/vapoursynth-mvtools_b200
 g++ -std=c++17 -O1 -g -fsanitize=address -fno-omit-frame-pointer -fPIC -fvisibility=hidden -Wall -I$ROOT/include -I$ROOT/include/vs -shared -Wl,-Bsymbolic \
     -o tests/mock/libmvtools_mockengine.so $PKG/plugin/plugin.cpp tests/mock/mock_engine.cpp $PKG/csrc/host_logic.cpp -L$ROOT/oracle/_ref -loracle -Wl,-rpath,$ROOT/oracle/_ref
-LD_PRELOAD=$ASAN ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/test_plugin_glue.py -q -k "fused or lookahead or concurrent or canonical"
+# (not the tests that also load the compiled REFERENCE plugin: it throws and catches std::out_of_range inside selectSADFunction, and a
+# preloaded ASan cannot intercept __cxa_throw of a libstdc++ that arrives by dlopen -- "CHECK failed: real___cxa_throw != 0")
+LD_PRELOAD=$ASAN ASAN_OPTIONS=detect_leaks=0 python -m pytest tests/test_plugin_glue.py -q \
+    -k "(fused or lookahead or concurrent or canonical or vector_clip or four_contexts or failed_window or recycled) and not recalculate_passes and not _live"
