@@ -333,10 +333,10 @@ struct StatTimer {
 
 struct FusedCache {
     FusedStats stats;
-    const char *name = "";
+    std::atomic<const char *> name{""}; // (every request stores the same literal)
     ~FusedCache() {
         if (stats.on && stats.frames.load())
-            stats.print(name, window, false);
+            stats.print(name.load(), window, false);
     }
     std::mutex m;                                           // guards `windows` and the windows' prefetchClaimed
     std::map<int, std::shared_ptr<FusedWindow>> windows;    // by window index (frame / window)
@@ -386,7 +386,7 @@ const VSFrame *fusedGetFrame(const char *filter, FusedCache *f, VSNode *clip, co
     const int B = f->window, N = outvi->numFrames;
     if (activationReason == arInitial) {
         StatTimer tRequest(f->stats, f->stats.request);
-        f->name = filter;
+        f->name.store(filter, std::memory_order_relaxed);
         vsapi->requestFrameFilter(propFrame, clip, frameCtx);
         if (alsoFrame >= 0 && alsoFrame != propFrame)
             vsapi->requestFrameFilter(alsoFrame, clip, frameCtx);
